@@ -1,0 +1,153 @@
+"""Test harness: ctypes wrapper of the CPU oracle (oracle/libdem_oracle.so) and helpers that feed one
+SceneSpec to both the oracle and the CUDA engine.  The oracle is the checker only; nothing in woo_b200/ imports this."""
+import ctypes as C
+import os, subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libdem_oracle.so")
+
+
+def build_oracle():
+    src = os.path.join(ORACLE_DIR, "dem_oracle.cpp")
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    return ORACLE_SO
+
+
+class OrcParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("dt", "dtSafety")] + [("gravity", C.c_double * 3)] + \
+        [(n, C.c_double) for n in ("distFactor", "damping", "verletDist", "wallHalfThick", "relRollStiff", "relTwistStiff",
+                                   "rollTanPhi", "poisson", "en", "maxRelInc")] + [("loneMask", C.c_uint)] + \
+        [(n, C.c_int) for n in ("deterministic", "reset", "noRatch", "iniLensTouch", "trsfRenorm", "applyForces", "law", "noSlip",
+                                "noBreak", "noFrict", "noAttraction", "dynDtPeriod", "periodic")]
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build_oracle())
+        L.orc_create.restype = C.c_void_p
+        L.orc_last_error.restype = C.c_char_p
+        for f in ("orc_get_dt", "orc_get_time", "orc_get_verlet_dist", "orc_pwave_dt", "orc_kinetic_energy"):
+            getattr(L, f).restype = C.c_double
+        for f in ("orc_get_step", "orc_num_contacts", "orc_get_contacts"):
+            getattr(L, f).restype = C.c_long
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    def __init__(self, spec=None):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.orc_create())
+        if spec is not None:
+            self.load(spec)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_destroy(self.h); self.h = None
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.orc_last_error(self.h).decode())
+
+    def load(self, S):
+        L, h = self.L, self.h
+        self.spec = S
+        for m in S.mats:
+            L.orc_add_material(h, C.c_int(m[0]), *[C.c_double(x) for x in m[1:]])
+        mass, inertia = S.mass_inertia()
+
+        def add_boundaries():
+            for w in S.walls:
+                pos = (C.c_double * 3)(*w["pos"]); vel = (C.c_double * 3)(*w.get("vel", (0, 0, 0)))
+                L.orc_add_wall(h, pos, C.c_int(w["axis"]), C.c_int(w["sense"]), C.c_int(w.get("mat", 0)), C.c_uint(w.get("mask", 3)), vel)
+            for f in S.facets:
+                v = np.ascontiguousarray(f["v"], dtype=np.float64).reshape(9)
+                fv = np.ascontiguousarray(f.get("fakeVel", (0, 0, 0)), dtype=np.float64)
+                nl = np.ascontiguousarray(f.get("n21lim", (np.nan,) * 3), dtype=np.float64)
+                vv = np.ascontiguousarray(f.get("vvel", np.zeros(9)), dtype=np.float64).reshape(9)
+                L.orc_add_facet(h, _p(v, C.c_double), C.c_double(f.get("halfThick", 0.)), _p(fv, C.c_double), _p(nl, C.c_double),
+                                _p(vv, C.c_double), C.c_int(f.get("mat", 0)), C.c_uint(f.get("mask", 3)))
+
+        def add_spheres():
+            if S.n:
+                L.orc_add_spheres(h, C.c_int(S.n), _p(S.pos, C.c_double), _p(S.radius, C.c_double), _p(mass, C.c_double),
+                                  _p(inertia, C.c_double), _p(S.mat, C.c_int), _p(S.mask, C.c_uint), _p(S.flags, C.c_uint),
+                                  _p(S.vel, C.c_double), _p(S.angVel, C.c_double), None)
+        if S.boundaries_first:
+            add_boundaries(); add_spheres()
+        else:
+            add_spheres(); add_boundaries()
+        P = OrcParams(); L.orc_default_params(C.byref(P))
+        for k, v in vars(S.params).items():
+            if k == "gravity":
+                P.gravity = (C.c_double * 3)(*v)
+            else:
+                setattr(P, k, v)
+        L.orc_set_params(h, C.byref(P))
+        if S.cell is not None:
+            hs = np.ascontiguousarray(S.cell["hSize"], dtype=np.float64).reshape(9)
+            gv = np.ascontiguousarray(S.cell.get("gradV", np.zeros(9)), dtype=np.float64).reshape(9)
+            ng = np.ascontiguousarray(S.cell.get("nextGradV", gv), dtype=np.float64).reshape(9)
+            L.orc_set_cell(h, _p(hs, C.c_double), _p(gv, C.c_double), _p(ng, C.c_double), C.c_int(S.cell.get("homoDeform", 4)))
+
+    def step(self, n=1):
+        self._chk(self.L.orc_step(self.h, C.c_int(n)))
+
+    def collider_run(self):
+        self._chk(self.L.orc_collider_run(self.h))
+
+    @property
+    def dt(self): return self.L.orc_get_dt(self.h)
+    @property
+    def nstep(self): return self.L.orc_get_step(self.h)
+    @property
+    def time(self): return self.L.orc_get_time(self.h)
+    @property
+    def verletDist(self): return self.L.orc_get_verlet_dist(self.h)
+    @property
+    def nFullRuns(self): return self.L.orc_get_nfullruns(self.h)
+    def pWaveDt(self): return self.L.orc_pwave_dt(self.h)
+    def kineticEnergy(self): return self.L.orc_kinetic_energy(self.h)
+
+    def spheres(self):
+        n = self.L.orc_num_spheres(self.h)
+        out = {k: np.zeros((n, 3)) for k in ("pos", "vel", "angVel", "force", "torque")}
+        out["ori"] = np.zeros((n, 4))
+        self.L.orc_get_spheres(self.h, _p(out["pos"], C.c_double), _p(out["ori"], C.c_double), _p(out["vel"], C.c_double),
+                               _p(out["angVel"], C.c_double), _p(out["force"], C.c_double), _p(out["torque"], C.c_double))
+        return out
+
+    def set_sphere(self, idx, pos=None, vel=None, angVel=None):
+        a = lambda v: None if v is None else (C.c_double * 3)(*v)
+        self.L.orc_set_sphere_state(self.h, C.c_int(idx), a(pos), a(vel), a(angVel))
+
+    def wall_forces(self):
+        out = np.zeros((len(self.spec.walls), 3))
+        if len(out):
+            self.L.orc_get_wall_forces(self.h, _p(out, C.c_double))
+        return out
+
+    def num_contacts(self, real_only=False):
+        return self.L.orc_num_contacts(self.h, C.c_int(int(real_only)))
+
+    def contacts(self, real_only=False):
+        n = self.num_contacts(real_only)
+        o = dict(ids=np.zeros((n, 2), np.int32), cellDist=np.zeros((n, 3), np.int32), real=np.zeros(n, np.int32), uN=np.zeros(n),
+                 force=np.zeros((n, 3)), torque=np.zeros((n, 3)), trsf=np.zeros((n, 9)), contPt=np.zeros((n, 3)), phys=np.zeros((n, 3)),
+                 vel=np.zeros((n, 3)), stepCreated=np.zeros(n, np.int32))
+        if n:
+            self.L.orc_get_contacts(self.h, C.c_int(int(real_only)), _p(o["ids"], C.c_int), _p(o["cellDist"], C.c_int), _p(o["real"], C.c_int),
+                                    _p(o["uN"], C.c_double), _p(o["force"], C.c_double), _p(o["torque"], C.c_double), _p(o["trsf"], C.c_double),
+                                    _p(o["contPt"], C.c_double), _p(o["phys"], C.c_double), _p(o["vel"], C.c_double), _p(o["stepCreated"], C.c_int))
+        return o

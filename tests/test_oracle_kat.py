@@ -1,0 +1,161 @@
+"""Known-answer tests pinning the CPU oracle against the reference's own tests and documented formulas
+(SURVEY.md §8c "Golden vectors / KATs").  CPU only."""
+import math
+import numpy as np
+import pytest
+from woo_b200 import scenes as sc
+from _harness import Oracle
+
+
+def two_spheres(law, v0=0.0, gap=1e-5, r=.05, mat=None, en=0.0):
+    S = sc.SceneSpec()
+    S.mats = [mat or sc.hertz_mat(density=1e3, young=1e8, ktDivKn=.2, tanPhi=.5)]
+    S.pos = np.array([[0, 0, 0], [0, 2 * r + gap, 0]], dtype=float)
+    S.radius = np.array([r, r])
+    S.vel = np.array([[0, v0 / 2, 0], [0, -v0 / 2, 0]])
+    S.params = sc.Params(law=law, damping=0., dtSafety=.4, dynDtPeriod=10, en=en, poisson=.2)
+    return S.finalize()
+
+
+def test_pwave_dt():
+    # woo.utils.spherePWaveDt(1e-3,2400,30e9)=2.8284271247461903e-07 (py/utils.py:80-81)
+    S = sc.SceneSpec(); S.mats = [sc.frict_mat(density=2400, young=30e9)]
+    S.pos = np.zeros((1, 3)); S.radius = np.array([1e-3]); S.finalize()
+    assert Oracle(S).pWaveDt() == 2.8284271247461903e-07
+
+
+@pytest.mark.parametrize("v0", [1, 1e-1, 1e-2, 1e-3, 1e-4, 1e-5])
+def test_hertz_collision_time(v0):
+    """py/tests/test_hertz.py:30-47 — collision time of two Hertzian spheres within 1 % of
+    tau = 2.214 (rho/Eeff)^(2/5) d / v0^(1/5), dtSafety .4, DynDt every 10 steps."""
+    S = two_spheres(sc.LAW_HERTZ_DMT, v0=v0, gap=1e-5 * 0 + 1e-9)
+    O = Oracle(S)
+    E, nu, rho, d = 1e8, .2, 1e3, .1
+    Eeff = (E * E) / (E * (1 - nu ** 2) + E * (1 - nu ** 2))
+    tau = 2.214 * (rho / Eeff) ** (2 / 5.) * (d / v0 ** (1 / 5.))
+    t0 = t1 = None
+    for i in range(2000000):
+        O.step(1)
+        real = O.num_contacts(True)
+        if t0 is None and real:
+            t0 = O.time
+        if t0 is not None and not real:
+            t1 = O.time; break
+    assert t0 is not None and t1 is not None
+    assert abs((t1 - t0) - tau) < 0.01 * tau + 2 * O.dt
+
+
+def test_cundall_kn_and_hertz_force():
+    # linear: kn=1/(r1/(E1 A)+r2/(E2 A)), A=pi min(r)^2 (py/models.py:16-19); kt=ktDivKn*kn
+    r, E = .05, 1e7
+    S = two_spheres(sc.LAW_IDEALELPL, gap=-1e-4, mat=sc.frict_mat(young=E, ktDivKn=.2, tanPhi=.5))
+    S.params.dt = 1e-6
+    O = Oracle(S); O.step(1)
+    c = O.contacts(True)
+    assert len(c["uN"]) == 1
+    A = math.pi * r ** 2
+    kn = 1 / (r / (E * A) + r / (E * A))
+    assert c["phys"][0, 0] == pytest.approx(kn, rel=1e-14)
+    assert c["phys"][0, 1] == pytest.approx(.2 * kn, rel=1e-14)
+    assert c["force"][0, 0] == pytest.approx(kn * c["uN"][0], rel=1e-14)
+    assert c["uN"][0] == pytest.approx(-1e-4, rel=1e-9)
+    # Hertz: F = K sqrt(R) delta^(3/2), K=(4/3)E*/..., R=r/2 (py/models.py:43-54)
+    S = two_spheres(sc.LAW_HERTZ_DMT, gap=-1e-4); S.params.dt = 1e-7
+    O = Oracle(S); O.step(1)
+    c = O.contacts(True)
+    E, nu = 1e8, .2
+    K = (4 / 3.) / (2 * (1 - nu ** 2) / E); R = r / 2
+    assert c["force"][0, 0] == pytest.approx(-K * math.sqrt(R) * (1e-4) ** 1.5, rel=1e-8)
+
+
+def test_update_phys_kn_proportional_to_young():
+    # py/tests/test_demfield.py:25-50: kn ∝ young
+    k = []
+    for E in (1e7, 2e7):
+        S = two_spheres(sc.LAW_IDEALELPL, gap=-1e-4, mat=sc.frict_mat(young=E)); S.params.dt = 1e-6
+        O = Oracle(S); O.step(1); k.append(O.contacts(True)["phys"][0, 0])
+    assert k[1] == pytest.approx(2 * k[0], rel=1e-14)
+
+
+def test_force_sign_ten_spheres():
+    # py/tests/test_core.py:436-453: 10 overlapping spheres in a row -> contact (4,5) exists after one step
+    S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+    S.pos = np.array([[x * .95, 0, 0] for x in range(10)], dtype=float); S.radius = np.full(10, .5)
+    S.params = sc.Params(dt=1e-5, damping=0.); S.finalize()
+    O = Oracle(S); O.step(1)
+    c = O.contacts(True)
+    ids = [tuple(i) for i in c["ids"]]
+    assert (4, 5) in ids
+    k = ids.index((4, 5))
+    assert c["force"][k, 0] < 0        # compressive normal force on pA in local frame
+    s = O.spheres()
+    # particle 4 is pushed to -x by 5 and to +x by 3: inner particles in equilibrium, ends are not
+    assert s["force"][0, 0] < 0 and s["force"][9, 0] > 0
+    assert abs(s["force"][4, 0]) < 1e-9 * abs(s["force"][0, 0])
+
+
+def pbc_scene(p, r):
+    S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+    S.pos = np.array(p, dtype=float); S.radius = np.array(r, dtype=float)
+    S.params = sc.Params(dt=1e-9, periodic=1, damping=0.)
+    S.cell = dict(hSize=np.eye(3), homoDeform=sc.HOMO_GRADV2)
+    return S.finalize()
+
+
+@pytest.mark.parametrize("shift", [(0, 0, 0), (1, 2, 3), (6, 8, -4)])
+def test_pbc_normal_contact(shift):
+    # py/tests/test_pbc.py:157-171: C.cellDist == -shift
+    S = pbc_scene([(.5, .5, .5), (.8 + shift[0], .6 + shift[1], .5 + shift[2])], [.2, .2])
+    O = Oracle(S); O.collider_run()
+    c = O.contacts()
+    assert len(c["ids"]) == 1 and tuple(c["ids"][0]) == (0, 1)
+    assert tuple(c["cellDist"][0]) == tuple(-np.array(shift))
+
+
+def test_pbc_over_half_and_double_contact():
+    # py/tests/test_pbc.py:130-154
+    O = Oracle(pbc_scene([(.3, .5, .5), (.7, .9, .5)], [.4, .1])); O.collider_run()
+    assert tuple(O.contacts()["cellDist"][0]) == (0, 0, 0)
+    O = Oracle(pbc_scene([(.3 + 13, .5 + 14, .5 + 15), (.7, .9, .5)], [.4, .1])); O.collider_run()
+    assert tuple(O.contacts()["cellDist"][0]) == (13, 14, 15)
+    O = Oracle(pbc_scene([(.3, .5, .5), (.8, .9, .5)], [.4, .2]))
+    with pytest.raises(RuntimeError):
+        O.collider_run()
+
+
+def test_pbc_incident_velocity():
+    # py/tests/test_pbc.py:86-102: |L6Geom.vel| == |initVel| for a contact across 10 periodic cells (gradV=0)
+    S = pbc_scene([(.5, .5, .5), (.5, .5 + .39999, .5 + 10)], [.2, .2])
+    S.vel = np.array([[0, 0, 0], [0, 0, 5.]]); S.params.dt = 1e-6
+    O = Oracle(S); O.step(2)
+    c = O.contacts(True)
+    assert len(c["uN"]) == 1
+    assert np.linalg.norm(c["vel"][0]) == pytest.approx(5., rel=1e-9)
+
+
+def test_wall_sphere_leapfrog_400_steps():
+    """py/tests/test_energy.py:69-90 scene: wall z=0 sense +1, sphere r=.8 at z=.1, g=(0,0,-10), damping .4, 400 steps.
+    The reference asserts on energies; here: the sphere is pushed up, settles towards z≈r, wall force accumulates
+     and gravitySkip/dampingSkip change the trajectory."""
+    def run(flags):
+        S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+        S.pos = np.array([[0, 0, .1]]); S.radius = np.array([.8]); S.flags = np.array([flags], dtype=np.uint32)
+        S.walls = [dict(pos=(0, 0, 0), axis=2, sense=1, mat=0, mask=3)]
+        S.params = sc.Params(gravity=(0, 0, -10), damping=.4, dtSafety=.9)
+        S.finalize()
+        O = Oracle(S); O.step(400)
+        return O
+    O = run(0)
+    z = O.spheres()["pos"][0, 2]
+    assert .1 < z and np.isfinite(z)
+    assert O.wall_forces()[0, 2] < 0          # wall pushed down; never reset
+    z_ng = run(sc.GRAVITY_SKIP).spheres()["pos"][0, 2]
+    z_nd = run(sc.DAMPING_SKIP).spheres()["pos"][0, 2]
+    assert z_ng != z and z_nd != z
+
+
+def test_dyndt_rate_limit():
+    # DynDt.cpp:99-102: dt may grow at most by (1+maxRelInc)^nSteps between runs
+    S = two_spheres(sc.LAW_IDEALELPL, gap=-1e-4, mat=sc.frict_mat(young=1e7)); S.params.dt = 1e-8; S.params.dynDtPeriod = 10
+    O = Oracle(S); O.step(11)
+    assert O.dt == pytest.approx(1e-8 * (1 + 1e-4) ** 10, rel=1e-12)

@@ -1,0 +1,180 @@
+"""Synthetic scene generators and the plain-array scene description shared by the
+product host layer, the tests and bench.py.  Our own seeded generator, not Woo's (py/pack.py is out of scope).
+
+Mass/inertia follow woo::Sphere::lumpMassInertia (src/dem/Sphere.cpp:26-33):
+m = 4/3 π r³ ρ, I = 2/5 m r².  Default masks follow src/dem/Particle.hpp:339-349
+(spheres 0b0101, walls/facets 0b0011, loneMask 0b0010).
+"""
+from __future__ import annotations
+import math
+from dataclasses import dataclass, field
+import numpy as np
+
+MAT_FRICT, MAT_HERTZ = 0, 1
+LAW_IDEALELPL, LAW_HERTZ_DMT = 0, 1
+HOMO_NONE, HOMO_POS, HOMO_VEL, HOMO_VEL_2ND, HOMO_GRADV2 = 0, 1, 2, 3, 4
+MASK_SPHERE, MASK_BOUNDARY, LONE_MASK = 0b0101, 0b0011, 0b0010
+# DemData flags (src/dem/Particle.hpp:198-203)
+DOF_ALL, GRAVITY_SKIP, DAMPING_SKIP = 63, 512, 2048
+
+
+@dataclass
+class Params:
+    """Engine attributes, named as in the reference."""
+    dt: float = float("nan")
+    dtSafety: float = 0.9
+    gravity: tuple = (0.0, 0.0, 0.0)
+    loneMask: int = LONE_MASK
+    distFactor: float = -1.0
+    deterministic: int = 1
+    damping: float = 0.2          # Leapfrog.damping
+    reset: int = 1                # Leapfrog.reset
+    verletDist: float = -0.05     # InsertionSortCollider.verletDist
+    wallHalfThick: float = 0.0    # Bo1_Wall_Aabb.halfThick
+    noRatch: int = 0              # Cg2_*.noRatch
+    iniLensTouch: int = 1
+    trsfRenorm: int = 100
+    applyForces: int = 1          # ContactLoop.applyForces
+    law: int = LAW_IDEALELPL
+    noSlip: int = 0
+    noBreak: int = 0
+    noFrict: int = 0
+    relRollStiff: float = 0.0
+    relTwistStiff: float = 0.0
+    rollTanPhi: float = 0.0
+    poisson: float = 0.2          # Cp2_HertzMat_HertzPhys.poisson
+    en: float = float("nan")      # Cp2_HertzMat_HertzPhys.en
+    noAttraction: int = 1         # Law2_L6Geom_HertzPhys_DMT.noAttraction
+    dynDtPeriod: int = 100        # DynDt.stepPeriod (<=0: no DynDt)
+    maxRelInc: float = 1e-4
+    periodic: int = 0
+
+
+@dataclass
+class SceneSpec:
+    """Particles are numbered in the order spheres, walls, facets unless ``order`` says otherwise
+    (ids are what S.dem.par.add would hand out)."""
+    mats: list = field(default_factory=list)   # (kind, density, young, ktDivKn, tanPhi, surfEnergy, alpha)
+    pos: np.ndarray = None
+    radius: np.ndarray = None
+    vel: np.ndarray = None
+    angVel: np.ndarray = None
+    mat: np.ndarray = None
+    mask: np.ndarray = None
+    flags: np.ndarray = None
+    walls: list = field(default_factory=list)  # dict(pos, axis, sense, mat, mask, vel)
+    facets: list = field(default_factory=list)  # dict(v(3,3), halfThick, fakeVel, n21lim, vvel, mat, mask)
+    params: Params = field(default_factory=Params)
+    cell: dict = None                           # dict(hSize(3,3), gradV, nextGradV, homoDeform)
+    boundaries_first: bool = False              # ids: walls+facets first, then spheres
+
+    @property
+    def n(self):
+        return 0 if self.pos is None else len(self.pos)
+
+    def finalize(self):
+        n = self.n
+        self.pos = np.ascontiguousarray(self.pos, dtype=np.float64).reshape(n, 3)
+        self.radius = np.ascontiguousarray(self.radius, dtype=np.float64).reshape(n)
+        self.vel = np.zeros((n, 3)) if self.vel is None else np.ascontiguousarray(self.vel, dtype=np.float64).reshape(n, 3)
+        self.angVel = np.zeros((n, 3)) if self.angVel is None else np.ascontiguousarray(self.angVel, dtype=np.float64).reshape(n, 3)
+        self.mat = np.zeros(n, dtype=np.int32) if self.mat is None else np.ascontiguousarray(self.mat, dtype=np.int32)
+        self.mask = np.full(n, MASK_SPHERE, dtype=np.uint32) if self.mask is None else np.ascontiguousarray(self.mask, dtype=np.uint32)
+        self.flags = np.zeros(n, dtype=np.uint32) if self.flags is None else np.ascontiguousarray(self.flags, dtype=np.uint32)
+        return self
+
+    def mass_inertia(self):
+        dens = np.array([m[1] for m in self.mats], dtype=np.float64)[self.mat]
+        m = (4 / 3.) * math.pi * self.radius ** 3 * dens
+        I = (2. / 5.) * m * self.radius ** 2
+        return m, I
+
+    def sphere_ids(self):
+        nb = len(self.walls) + len(self.facets)
+        first = nb if self.boundaries_first else 0
+        return np.arange(first, first + self.n, dtype=np.int32)
+
+    def wall_ids(self):
+        first = 0 if self.boundaries_first else self.n
+        return np.arange(first, first + len(self.walls), dtype=np.int32)
+
+    def facet_ids(self):
+        first = (0 if self.boundaries_first else self.n) + len(self.walls)
+        return np.arange(first, first + len(self.facets), dtype=np.int32)
+
+
+def frict_mat(density=1e3, young=1e7, ktDivKn=.2, tanPhi=math.tan(.5)):
+    """woo.utils.defaultMaterial (py/utils.py:88-92)."""
+    return (MAT_FRICT, density, young, ktDivKn, tanPhi, 0.0, 0.0)
+
+
+def hertz_mat(density=1e3, young=1e8, ktDivKn=.2, tanPhi=.5, surfEnergy=0.0, alpha=0.0):
+    return (MAT_HERTZ, density, young, ktDivKn, tanPhi, surfEnergy, alpha)
+
+
+def box_walls(lo, hi, mat=0, top=False):
+    """5 (or 6) axis-aligned Walls with sense pointing inwards."""
+    w = []
+    for ax in range(3):
+        p = [0., 0., 0.]; p[ax] = lo[ax]
+        w.append(dict(pos=tuple(p), axis=ax, sense=1, mat=mat, mask=MASK_BOUNDARY))
+        if ax < 2 or top:
+            p = [0., 0., 0.]; p[ax] = hi[ax]
+            w.append(dict(pos=tuple(p), axis=ax, sense=-1, mat=mat, mask=MASK_BOUNDARY))
+    return w
+
+
+def lattice(nx, ny, nz, spacing, origin, jitter, rng):
+    g = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    p = np.asarray(origin) + (g + .5) * spacing
+    if jitter > 0:
+        p = p + rng.uniform(-jitter, jitter, p.shape)
+    return p
+
+
+def deposition(n, *, r=5e-3, psd_ratio=1.0, seed=1, law=LAW_IDEALELPL, layers=None, damping=.2, young=None,
+               density=2500., shuffle=True, spacing_factor=2.2, en=float("nan")):
+    """Gravity deposition in an open-top box of 5 Walls (cfg1/cfg2/cfg3 of BASELINE.json).
+
+    Spheres sit on a jittered cubic lattice (spacing = spacing_factor * r_max), radii log-uniform on
+    [r, psd_ratio*r].  ``layers`` fixes the lattice height (default: cube)."""
+    rng = np.random.default_rng(seed)
+    rmax = r * psd_ratio
+    sp = spacing_factor * rmax
+    if layers is None:
+        nz = max(1, round(n ** (1 / 3.)))
+    else:
+        nz = layers
+    nx = max(1, int(math.ceil(math.sqrt(n / nz))))
+    ny = max(1, int(math.ceil(n / (nx * nz))))
+    p = lattice(nx, ny, nz, sp, (0, 0, 0), 0.05 * r, rng)
+    if shuffle:
+        p = p[rng.permutation(len(p))]
+    p = p[:n]
+    rad = np.full(n, r) if psd_ratio == 1.0 else r * np.exp(rng.uniform(0, math.log(psd_ratio), n))
+    S = SceneSpec()
+    if law == LAW_IDEALELPL:
+        S.mats = [frict_mat(density=density, young=young or 1e7, ktDivKn=.2, tanPhi=.5)]
+    else:
+        S.mats = [hertz_mat(density=density, young=young or 1e8, tanPhi=.5)]
+    S.pos, S.radius = p, rad
+    S.walls = box_walls((0, 0, 0), (nx * sp, ny * sp, nz * sp), mat=0)
+    S.params = Params(gravity=(0, 0, -9.81), damping=damping, law=law, verletDist=-.05, dtSafety=.9, dynDtPeriod=100, en=en)
+    return S.finalize()
+
+
+def random_gas(n, *, box=1.0, r=0.02, psd_ratio=1.0, seed=0, vmax=1.0, law=LAW_IDEALELPL, overlap=True, walls=True,
+               angvel=1.0, en=float("nan")):
+    """Dense random cloud with overlaps and random velocities: exercises creation, update, breakage and sliding
+    of many contacts in few steps (parity stress test, not a physical config)."""
+    rng = np.random.default_rng(seed)
+    S = SceneSpec()
+    S.mats = [frict_mat(density=2500., young=1e7, tanPhi=.5)] if law == LAW_IDEALELPL else [hertz_mat(density=2500., young=1e8)]
+    S.pos = rng.uniform(0.05 * box, 0.95 * box, (n, 3))
+    S.radius = np.full(n, r) if psd_ratio == 1.0 else r * np.exp(rng.uniform(0, math.log(psd_ratio), n))
+    S.vel = rng.uniform(-vmax, vmax, (n, 3))
+    S.angVel = rng.uniform(-angvel, angvel, (n, 3))
+    if walls:
+        S.walls = box_walls((0, 0, 0), (box, box, box), mat=0, top=True)
+    S.params = Params(gravity=(0, 0, -9.81), damping=.2, law=law, verletDist=-.05, dynDtPeriod=10, en=en)
+    return S.finalize()
