@@ -1,0 +1,237 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the DEM hot path on B200 (BASELINE.json metric), one JSON line on stdout.
+
+A "step" is one Scene step (Leapfrog -> collider -> ContactLoop -> DynDt) over the whole packing.
+Workload at N GPUs: BASELINE.json configs[1] — 1M polydisperse spheres (PSD 1:4, log-uniform radii) settled under gravity
+in a box of 5 walls, linear IdealElPl law; synthetic (woo_b200.scenes.deposition, seed 2).  For N>1 every rank owns one such
+slab-shaped box (weak scaling, no data-path collective in this round; see DESIGN.md "Multi-GPU").
+value  = particle-steps/s with the state resident in HBM (CUDA events on the engine's stream, max over ranks).
+e2e    = same metric through the C-ABI call wdem_step_e2e with pinned HOST buffers: per step H2D of pos/vel/angVel,
+         one step, D2H of pos/vel + kinetic energy.
+--impl reference: the CPU restatement oracle (the reference itself cannot be built here: Eigen/Boost/TBB missing) on all
+host threads, on a bounded sample (pre-settled 20k-sphere packing of the same PSD/material, tests/golden/cfg2_sample_20k.npz).
+"""
+import argparse, json, os, subprocess, sys, threading, time
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_FULL = 1_000_000
+LAYERS = 40
+SETTLE_STEPS = int(os.environ.get("WDEM_BENCH_SETTLE", "20000"))
+SAMPLE = os.path.join(ROOT, "tests", "golden", "cfg2_sample_20k.npz")
+# algorithmic bytes (SURVEY.md §8d / DESIGN.md)
+B_P, B_C, B_Q, B_R, B_PAIR = 348, 552, 72, 200, 496
+B_C_KERNEL = 480   # contact kernel's share of B_C (552 minus the 72 B read by the reduce kernel)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(n, seed):
+    from woo_b200 import scenes as sc
+    return sc.deposition(n, r=1e-3, psd_ratio=4.0, seed=seed, law=sc.LAW_IDEALELPL, layers=LAYERS, damping=.2, young=1e7, density=2500.)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from woo_b200.engine import Engine
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    n = args.n
+    S = workload(n, seed=2 + rank)
+    E = Engine(S.params, device=local).load(S)
+    # settle (untimed preparation of the dense packing; includes many collider full runs)
+    t0 = time.time()
+    done = 0
+    while done < args.settle:
+        k = min(2000, args.settle - done); E.step(k); done += k
+    st = E.stats
+    settle_s = time.time() - t0
+    # warm-up
+    E.step(max(args.warmup, 3))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local); clocks.start()
+    # ---- timed region 1: K steps, state resident in HBM; per-phase CUDA events on the engine's stream
+    E.set_profiling(True)
+    barrier()
+    w0 = time.time()
+    st = E.step(args.steps)
+    barrier()
+    wall = time.time() - w0
+    E.set_profiling(False)
+    dev_ms = st.device_ms
+    stats = st.asdict()
+    # ---- timed region 2: end to end through the C-ABI with pinned host buffers
+    s = E.spheres()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    tp, tv, tw = pin(s["pos"]), pin(s["vel"]), pin(s["angVel"])
+    po, vo = torch.empty_like(tp).pin_memory(), torch.empty_like(tv).pin_memory()
+    ke = min(args.steps, args.e2e_steps)
+    for _ in range(3):
+        E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy()); tp.copy_(po); tv.copy_(vo)
+    barrier()
+    e0 = time.time()
+    for _ in range(ke):
+        ek, _st = E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy())
+        tp.copy_(po); tv.copy_(vo)     # the step's output is the next step's host-side input
+    barrier()
+    e2e_s = time.time() - e0
+    ck = clocks.stop()
+    # ---- reduce over ranks (max of times)
+    t = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([stats["sum_real"], stats["sum_potential_evaluated"], stats["n_rebuilds"], stats["n_launches"], stats["n_real"], stats["n_contacts"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, wall_ms = [float(x) for x in t.cpu()]
+    sum_real, sum_pot, n_reb, n_launch, n_real, n_con = [float(x) for x in cnt.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    K = args.steps
+    ntot = n * world
+    value = ntot * K / (dev_ms * 1e-3)
+    # dominant kernel: fused contact kernel (Cg2+Cp2+Law2), per launch = per step (rank 0's numbers)
+    ms_contact = stats["ms_contact"] / K
+    bytes_contact = (B_C_KERNEL * stats["sum_real"] + B_Q * stats["sum_potential_evaluated"]) / K
+    ach = bytes_contact / (ms_contact * 1e-3) / 1e9 if ms_contact > 0 else 0.
+    step_bytes = (n * B_P * K + B_C * stats["sum_real"] + B_Q * stats["sum_potential_evaluated"] + stats["n_rebuilds"] * (n * B_R + B_PAIR * stats["n_contacts"])) / K
+    out = {
+        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: 1M polydisperse spheres (PSD 1:4) settled under gravity, Leapfrog+collider+ContactLoop(Cg2_Sphere_Sphere/Wall_Sphere_L6Geom, Cp2_FrictMat_FrictPhys, Law2_L6Geom_FrictPhys_IdealElPl)+DynDt",
+                   "n_spheres_per_gpu": n, "settle_steps": args.settle, "real_contacts": n_real, "candidate_contacts": n_con, "rebuilds_in_timed_region": n_reb,
+                   "l2_policy": "inputs larger than L2 (per-step working set %.0f MB > 126 MB)" % (step_bytes / 1e6), "parallelism": "1 slab box per GPU" if world > 1 else "single GPU",
+                   "settle_wall_s": round(settle_s, 1)},
+        "roofline": {"bound": "hbm", "kernel": "k_contact_ss<IdealElPl>", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": bytes_contact, "ms_per_launch": ms_contact,
+                     "step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9, "frac": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9 / peak},
+                     "phase_ms_per_step": {k: stats[k] / K for k in ("ms_integrate", "ms_rebuild", "ms_contact", "ms_reduce", "ms_dyndt")}},
+        "e2e": {"value": ntot * ke / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": int(n * 72), "d2h_bytes_per_step": int(n * 48 + 8), "steps": ke,
+                "api": "wdem_step_e2e (C-ABI, pinned host buffers)"},
+        "gpu_launches": int(n_launch), "clocks": ck, "wall_ms_per_step": wall_ms / K,
+    }
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args.cpu_steps)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_sample():
+    from woo_b200 import scenes as sc
+    if not os.path.exists(SAMPLE):
+        return None
+    d = np.load(SAMPLE)
+    S = workload(len(d["radius"]), seed=2)
+    S.pos, S.radius, S.vel, S.angVel = d["pos"], d["radius"], d["vel"], d["angVel"]
+    S.walls = sc.box_walls(tuple(d["lo"]), tuple(d["hi"]), mat=0)
+    S.params.dt = float(d["dt"])
+    return S.finalize()
+
+
+def cpu_baseline(steps, warmup=3):
+    """The CPU oracle (kind 'port': the reference cannot be compiled here) on all host threads, bounded sample."""
+    from _harness import Oracle, lib
+    S = load_sample()
+    sample = "pre-settled 20k-sphere PSD 1:4 packing (tests/golden/cfg2_sample_20k.npz), same material/law as the 1M workload"
+    if S is None:
+        S = workload(20000, seed=2); sample = "20k-sphere PSD 1:4 lattice (unsettled: golden sample missing)"
+    S.params.deterministic = 0      # the reference's default: parallel force application (ContactLoop.cpp:195-198)
+    O = Oracle(S)
+    cores = lib().orc_num_threads()
+    O.step(warmup)
+    t0 = time.time(); O.step(steps); dt = time.time() - t0
+    return {"value": S.n * steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample, "steps": steps,
+            "real_contacts": int(O.num_contacts(True)), "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, max(args.warmup, 3)
+    # bounded: the CPU arm times min(K, cpu_steps) steps per "step sample"
+    k = min(K, args.cpu_steps)
+    cb = cpu_baseline(k, W)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = {"impl": "reference", "metric": "particle-steps/s", "value": cb["value"], "unit": "particle-steps/s", "n_gpus": world, "steps": k, "warmup": W,
+           "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "cfg2 sample: " + cb["sample"]},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=N_FULL, help="spheres per GPU (default: the 1M workload)")
+    ap.add_argument("--settle", type=int, default=SETTLE_STEPS)
+    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--cpu-steps", type=int, default=200)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,132 @@
+/* wdem.h — C-ABI of the B200 DEM hot-path engine (libwdem.so).
+ *
+ * Drop-in boundary for woodem/woo's per-timestep DEM loop
+ *     [Leapfrog, InsertionSortCollider, ContactLoop(Cg2_*, Cp2_*, Law2_*), DynDt]
+ * (reference: py/utils.py:122-129 defaultEngines; Scene::doOneStep src/core/Scene.cpp:366-432).
+ * One handle owns all device state of one DemField on one GPU.  Plain pointers and sizes only; every call
+ * returns 0 on success and a non-zero code otherwise, with the message available from wdem_last_error().
+ * No C++ exception crosses this boundary (the C++ engine GpuDemLoop converts non-zero to std::runtime_error,
+ * which is what the reference's engines throw out of run(): src/core/Scene.cpp:110-117).
+ *
+ * All host arrays are row-major, float64 unless stated; vectors are xyz triples, quaternions are (x,y,z,w)
+ * (Eigen coeffs() order), matrices are row-major 3x3.  Spheres are addressed by *upload index* on download.
+ *
+ * There is no CPU fallback: every entry point fails with WDEM_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef WDEM_H
+#define WDEM_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wdem_engine* wdem_handle;
+
+enum { WDEM_OK = 0, WDEM_ERR_INVALID = 1, WDEM_ERR_CUDA = 2, WDEM_ERR_UNSUPPORTED = 3, WDEM_ERR_RUNTIME = 4 };
+enum { WDEM_MAT_FRICT = 0, WDEM_MAT_HERTZ = 1 };          /* FrictMat (FrictMat.hpp:20-31), HertzMat (Hertz.hpp:9-16) */
+enum { WDEM_LAW_IDEALELPL = 0, WDEM_LAW_HERTZ_DMT = 1 };  /* Law2_L6Geom_FrictPhys_IdealElPl / Law2_L6Geom_HertzPhys_DMT */
+enum { WDEM_HOMO_NONE = 0, WDEM_HOMO_POS = 1, WDEM_HOMO_VEL = 2, WDEM_HOMO_VEL_2ND = 3, WDEM_HOMO_GRADV2 = 4 }; /* Cell.hpp */
+
+/* Engine attributes; field names are the reference's attribute names.  Replaces the attribute
+ * reads each reference engine does in its run():
+ *   Leapfrog.{damping,reset}                     src/dem/Leapfrog.hpp:50-53
+ *   InsertionSortCollider.verletDist             src/dem/Collision.hpp:94;  Bo1_Wall_Aabb.halfThick Wall.hpp
+ *   Cg2_*.{noRatch,iniLensTouch,trsfRenorm}      src/dem/L6Geom.hpp:35-45   (approxMask must be 0)
+ *   ContactLoop.applyForces                      src/dem/ContactLoop.hpp:115-127
+ *   Law2_L6Geom_FrictPhys_IdealElPl.*            src/dem/IdealElPl.hpp:17-24
+ *   Cp2_HertzMat_HertzPhys.{poisson,en}          src/dem/Hertz.hpp:58-59
+ *   Law2_L6Geom_HertzPhys_DMT.noAttraction       src/dem/Hertz.hpp:96
+ *   DynDt.{stepPeriod,maxRelInc}                 src/dem/DynDt.hpp:21-23, src/core/Engine.hpp:149
+ *   Scene.{dt,dtSafety}, DemField.{gravity,loneMask,distFactor}   Scene.hpp:191-205, Particle.hpp:359-361 */
+typedef struct wdem_config {
+  double dt, dtSafety;
+  double gravity[3];
+  double distFactor;
+  double damping;
+  double verletDist;
+  double wallHalfThick;
+  double relRollStiff, relTwistStiff, rollTanPhi;
+  double poisson, en;
+  double maxRelInc;
+  uint32_t loneMask;
+  int32_t reset;
+  int32_t noRatch, iniLensTouch, trsfRenorm;
+  int32_t applyForces;
+  int32_t law;
+  int32_t noSlip, noBreak, noFrict;
+  int32_t noAttraction;
+  int32_t dynDtPeriod;
+  int32_t periodic;
+  int32_t device;      /* CUDA device ordinal */
+  int32_t reserved[7];
+} wdem_config;
+
+/* Counters of the last wdem_step call (cumulative ones say so). */
+typedef struct wdem_stats {
+  int64_t n_spheres, n_contacts, n_real;      /* after the last step */
+  int64_t n_rebuilds;                         /* collider full runs inside this call */
+  int64_t n_full_runs_total;                  /* InsertionSortCollider.nFullRuns (cumulative) */
+  int64_t n_launches;                         /* kernels launched inside this call (ours + CUB at rebuilds) */
+  int64_t step;                               /* Scene.step after the call */
+  double dt, time;                            /* Scene.dt / Scene.time after the call */
+  double device_ms;                           /* CUDA-event time of the whole call on the engine's stream */
+  double ms_integrate, ms_contact, ms_reduce, ms_rebuild, ms_dyndt;  /* per-phase event times (if profiling enabled) */
+  int64_t sum_contacts, sum_real, sum_potential_evaluated;           /* summed over the steps of this call (roofline accounting) */
+} wdem_stats;
+
+int wdem_default_config(wdem_config* cfg);
+int wdem_create(const wdem_config* cfg, wdem_handle* out);
+int wdem_destroy(wdem_handle h);
+const char* wdem_last_error(wdem_handle h);  /* h may be NULL: message of the last failed wdem_create */
+int wdem_set_config(wdem_handle h, const wdem_config* cfg);  /* re-read attributes (as the reference does each run()) */
+int wdem_set_profiling(wdem_handle h, int per_phase_events);
+
+/* Materials: replaces the shared_ptr<Material> each Particle carries (Particle.hpp:91-97). */
+int wdem_upload_materials(wdem_handle h, int n, const int32_t* kind, const double* density, const double* young,
+                          const double* ktDivKn, const double* tanPhi, const double* surfEnergy, const double* alpha);
+/* Spheres: Node{pos,ori} + DemData{vel,angVel,mass,inertia,flags} + Sphere::radius + Particle{id,mask,material}
+ * (core/Field.hpp:102-103, dem/Particle.hpp:281-292,91-97, dem/Sphere.hpp:25).  ori/vel/angVel/flags/mask may be NULL. */
+int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const double* pos, const double* ori, const double* vel,
+                        const double* angVel, const double* mass, const double* inertia, const double* radius,
+                        const uint32_t* flags, const uint32_t* mask, const int32_t* matId);
+/* Walls (dem/Wall.hpp): static; vel may be NULL. */
+int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* pos, const int32_t* axis, const int32_t* sense,
+                      const double* vel, const uint32_t* mask, const int32_t* matId);
+/* Facets (dem/Facet.hpp): verts 9 per facet, vvel 9 per facet (node velocities; NULL = 0), fakeVel 3, n21lim 3 (NaN = none). */
+int wdem_upload_facets(wdem_handle h, int n, const int32_t* ids, const double* verts, const double* vvel, const double* fakeVel,
+                       const double* halfThick, const double* n21lim, const uint32_t* mask, const int32_t* matId);
+/* Periodic cell (core/Cell.hpp): Cell.setHSize + gradV/nextGradV/homoDeform. */
+int wdem_set_cell(wdem_handle h, const double* hSize, const double* gradV, const double* nextGradV, int homoDeform);
+int wdem_set_next_gradv(wdem_handle h, const double* nextGradV);
+int wdem_get_cell(wdem_handle h, double* hSize);
+
+/* nsteps times Scene::doOneStep restricted to this engine group (Scene.cpp:366-432): cell.integrateAndUpdate,
+ * Leapfrog, collider, ContactLoop, DynDt, epilogue (step++, time+=dt, dt=nextDt). stats may be NULL. */
+int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats);
+/* End-to-end variant for the public API benchmark: uploads pos/vel/angVel (host, upload order), steps, downloads pos/vel. */
+int wdem_step_e2e(wdem_handle h, int64_t nsteps, const double* pos_in, const double* vel_in, const double* angVel_in,
+                  double* pos_out, double* vel_out, double* ek_out, wdem_stats* stats);
+
+/* Downloads, in upload order; any pointer may be NULL. */
+int wdem_download_state(wdem_handle h, double* pos, double* ori, double* vel, double* angVel);
+int wdem_download_forces(wdem_handle h, double* force, double* torque);
+int wdem_set_state(wdem_handle h, int64_t first, int64_t n, const double* pos, const double* vel, const double* angVel);
+int64_t wdem_num_contacts(wdem_handle h, int realOnly);
+/* Contacts sorted by canonical key (id1,id2): boundary first, sphere-sphere lower id first. Returns the count (<0: error).
+ * ids 2/contact, cellDist 3, real 1, uN 1, forceLocal 3, torqueLocal 3, trsf 9 (column-major), contPt 3, phys 3 (kn,kt,tanPhi),
+ * stepCreated 1. */
+int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t* ids, int32_t* cellDist, int32_t* real, double* uN,
+                               double* forceLocal, double* torqueLocal, double* trsf, double* contPt, double* phys,
+                               int32_t* stepCreated);
+/* DemField::critDt -> DemFuncs::pWaveDt (Funcs.cpp:151-175). */
+int wdem_crit_dt(wdem_handle h, double* dt);
+/* Σ ½ m v² + ½ ω·I·ω  (DemData::getEk_any, Particle.cpp:247-265), device reduction. */
+int wdem_kinetic_energy(wdem_handle h, double* ek);
+int wdem_get_scalars(wdem_handle h, double* dt, double* time, int64_t* step, double* verletDist, int64_t* nFullRuns);
+/* Device-level info for bench.py: bytes allocated, stream pointer (cudaStream_t) */
+int wdem_device_info(wdem_handle h, int64_t* bytes_allocated, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

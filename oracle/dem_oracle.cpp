@@ -1033,25 +1033,28 @@ struct Scene {
   // DynDt (DynDt.cpp:16-113) and pWaveDt (Funcs.cpp:151-175)
   // ------------------------------------------------------------------------------------------
   Real critDtStiffness() {
-    std::vector<V3> ktrans(sph.size()), krot(sph.size());
-    for (auto& kv : con) {
-      const Contact& C = kv.second; if (!C.isReal()) continue;
-      V3 n = quatRotate(C.ori, V3(1, 0, 0));
-      V3 n2(n.x * n.x, n.y * n.y, n.z * n.z);
-      for (int side = 0; side < 2; side++) {
-        int id = side == 0 ? C.idA : C.idB; const PRef& p = par[id];
-        if (p.kind != SHAPE_SPHERE) continue;  // walls/facets are not in dem.nodes
-        ktrans[p.idx] += n2 * (C.kn - C.kt) + V3(C.kt, C.kt, C.kt);
-        krot[p.idx] += pow2(C.lens[side]) * C.kt * V3(n2[1] + n2[2], n2[2] + n2[0], n2[0] + n2[1]);
-      }
-    }
+    // DynDt::nodalStiffAdd walks p->contacts, a std::map keyed by the OTHER particle's id (Particle.hpp:36) => ascending other id
+    struct Inc { int other; const Contact* C; int side; };
+    std::vector<std::vector<Inc>> inc(par.size());
+    for (auto& kv : con) { const Contact& C = kv.second; if (!C.isReal()) continue; inc[C.idA].push_back({C.idB, &C, 0}); inc[C.idB].push_back({C.idA, &C, 1}); }
     Real ret = Inf;
-    for (size_t i = 0; i < sph.size(); i++) {
-      const Sphere& s = sph[i];
+    for (size_t id = 0; id < par.size(); id++) {
+      const PRef& p = par[id];
+      if (p.kind != SHAPE_SPHERE) continue;  // walls/facets are not in dem.nodes
+      const Sphere& s = sph[p.idx];
       if ((s.flags & DOF_ALL) == DOF_ALL) continue;
+      std::sort(inc[id].begin(), inc[id].end(), [](const Inc& a, const Inc& b) { return a.other < b.other; });
+      V3 ktrans, krot;
+      for (const Inc& e : inc[id]) {
+        const Contact& C = *e.C;
+        V3 n = quatRotate(C.ori, V3(1, 0, 0));
+        V3 n2(n.x * n.x, n.y * n.y, n.z * n.z);
+        ktrans += n2 * (C.kn - C.kt) + V3(C.kt, C.kt, C.kt);
+        krot += pow2(C.lens[e.side]) * C.kt * V3(n2[1] + n2[2], n2[2] + n2[0], n2[0] + n2[1]);
+      }
       Real r = Inf;
-      for (int k = 0; k < 3; k++) if (ktrans[i][k] != 0 && s.mass > 0. && !(s.flags & (1u << k))) r = std::min(r, s.mass / std::abs(ktrans[i][k]));
-      for (int k = 0; k < 3; k++) if (krot[i][k] != 0 && s.inertia > 0. && !(s.flags & (1u << (k + 3)))) r = std::min(r, s.inertia / std::abs(krot[i][k]));
+      for (int k = 0; k < 3; k++) if (ktrans[k] != 0 && s.mass > 0. && !(s.flags & (1u << k))) r = std::min(r, s.mass / std::abs(ktrans[k]));
+      for (int k = 0; k < 3; k++) if (krot[k] != 0 && s.inertia > 0. && !(s.flags & (1u << (k + 3)))) r = std::min(r, s.inertia / std::abs(krot[k]));
       ret = std::min(ret, 2 * r);
     }
     return std::sqrt(ret);

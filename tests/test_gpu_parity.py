@@ -1,0 +1,80 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on seeded scenes."""
+import numpy as np
+import pytest
+from woo_b200 import scenes as sc
+from _harness import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_for(S):
+    from woo_b200.engine import Engine
+    return Engine(S.params).load(S)
+
+
+def compare(S, nsteps, check_every=1, exact=True, label=""):
+    O = Oracle(S); E = engine_for(S)
+    done = 0
+    while done < nsteps:
+        k = min(check_every, nsteps - done)
+        O.step(k); E.step(k); done += k
+        so, sg = O.spheres(), E.spheres()
+        co, cg = O.contacts(True), E.contacts(True)
+        # bit-exact: the set of real contacts
+        assert [tuple(x) for x in co["ids"]] == [tuple(x) for x in cg["ids"]], f"{label}: real contact set differs at step {done}"
+        assert O.nFullRuns == E.scalars()["nFullRuns"], f"{label}: collider full runs differ at step {done}"
+        assert O.dt == E.scalars()["dt"]
+        if exact:
+            for k_ in ("pos", "vel", "angVel", "force", "torque"):
+                assert np.array_equal(so[k_], sg[k_]), f"{label}: {k_} not bit-identical at step {done} (max diff {np.abs(so[k_]-sg[k_]).max()})"
+            for k_ in ("uN", "force", "contPt", "trsf", "phys"):
+                assert np.array_equal(co[k_], cg[k_]), f"{label}: contact {k_} not bit-identical at step {done}"
+        else:
+            scale = np.abs(co["force"]).max() if len(co["force"]) else 1.
+            assert np.allclose(co["force"], cg["force"], rtol=1e-10, atol=1e-10 * scale)
+            assert np.allclose(so["force"], sg["force"], rtol=1e-10, atol=1e-10 * scale)
+        # orientation: tolerance only (sin/cos differ by ulps between glibc and CUDA)
+        assert np.allclose(so["ori"], sg["ori"], rtol=0, atol=1e-12)
+    return O, E
+
+
+@pytest.mark.parametrize("law", [sc.LAW_IDEALELPL, sc.LAW_HERTZ_DMT])
+def test_two_spheres_head_on(law):
+    S = sc.SceneSpec()
+    S.mats = [sc.frict_mat()] if law == sc.LAW_IDEALELPL else [sc.hertz_mat()]
+    S.pos = np.array([[0, 0, 0], [0, .10001, 0.001]]); S.radius = np.array([.05, .05])
+    S.vel = np.array([[0, .5, 0], [0, -.5, 0.1]]); S.angVel = np.array([[1., 2, 3], [-3, 2, 1]])
+    S.params = sc.Params(law=law, damping=0., dtSafety=.4, dynDtPeriod=10, en=.5 if law else float("nan"))
+    compare(S.finalize(), 600, check_every=50, label="two-spheres")
+
+
+@pytest.mark.parametrize("law", [sc.LAW_IDEALELPL, sc.LAW_HERTZ_DMT])
+@pytest.mark.parametrize("psd", [1.0, 4.0])
+def test_random_gas_bitwise(law, psd):
+    S = sc.random_gas(400, box=.5, r=.02, psd_ratio=psd, seed=3, law=law, en=.7 if law else float("nan"))
+    compare(S, 300, check_every=25, label=f"gas law={law} psd={psd}")
+
+
+def test_deposition_cfg1_small():
+    S = sc.deposition(2000, seed=1)
+    compare(S, 400, check_every=100, label="deposition-2k")
+
+
+def test_blocked_dofs_and_skips():
+    S = sc.random_gas(200, box=.4, r=.02, seed=5)
+    S.flags[::7] = sc.DOF_ALL; S.flags[1::7] = 1 | 8; S.flags[2::7] = sc.GRAVITY_SKIP; S.flags[3::7] = sc.DAMPING_SKIP
+    compare(S, 200, check_every=50, label="flags")
+
+
+def test_law_flags():
+    for kw in (dict(noSlip=1), dict(noFrict=1), dict(noRatch=1), dict(trsfRenorm=7), dict(damping=0.), dict(relRollStiff=.3, relTwistStiff=.2, rollTanPhi=.4)):
+        S = sc.random_gas(200, box=.4, r=.02, seed=7)
+        for k, v in kw.items():
+            setattr(S.params, k, v)
+        compare(S, 120, check_every=40, label=str(kw))
+
+
+def test_verlet_zero_and_fixed():
+    for vd in (0., .004):
+        S = sc.random_gas(150, box=.35, r=.02, seed=11); S.params.verletDist = vd
+        compare(S, 60, check_every=20, label=f"verletDist={vd}")

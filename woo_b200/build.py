@@ -1,0 +1,43 @@
+"""Builds libwdem.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.  --fmad=false is part of the
+numerical contract (bit parity with the reference's non-FMA x86-64 arithmetic)."""
+import os, subprocess, shutil, sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libwdem.so")
+SOURCES = ["wdem_engine.cu"]
+DEPS = ["wdem_engine.cu", "wdem_kernels.cuh", "wdem_math.cuh", os.path.join("..", "..", "include", "wdem.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-Wno-deprecated-declarations",
+              "-diag-suppress", "177"]
+
+
+def nvcc():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found: the woo_b200 engine cannot be built (there is no CPU fallback)")
+    return p
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    env.pop("CXX", None); env.pop("CC", None)
+    cmd += ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd, env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="-f" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "-v" in sys.argv else [])

@@ -1,0 +1,67 @@
+"""ctypes binding of the C-ABI in include/wdem.h (libwdem.so).  Thin: no compute here, no CPU fallback — if the
+library cannot be built/loaded or there is no sm_100 device, calls raise."""
+import ctypes as C
+import os
+import numpy as np
+from . import build as _build
+
+_LIB = None
+
+
+class WdemConfig(C.Structure):
+    _fields_ = [("dt", C.c_double), ("dtSafety", C.c_double), ("gravity", C.c_double * 3), ("distFactor", C.c_double),
+                ("damping", C.c_double), ("verletDist", C.c_double), ("wallHalfThick", C.c_double), ("relRollStiff", C.c_double),
+                ("relTwistStiff", C.c_double), ("rollTanPhi", C.c_double), ("poisson", C.c_double), ("en", C.c_double),
+                ("maxRelInc", C.c_double), ("loneMask", C.c_uint32), ("reset", C.c_int32), ("noRatch", C.c_int32),
+                ("iniLensTouch", C.c_int32), ("trsfRenorm", C.c_int32), ("applyForces", C.c_int32), ("law", C.c_int32),
+                ("noSlip", C.c_int32), ("noBreak", C.c_int32), ("noFrict", C.c_int32), ("noAttraction", C.c_int32),
+                ("dynDtPeriod", C.c_int32), ("periodic", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class WdemStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("n_spheres", "n_contacts", "n_real", "n_rebuilds", "n_full_runs_total", "n_launches", "step")] + \
+        [(n, C.c_double) for n in ("dt", "time", "device_ms", "ms_integrate", "ms_contact", "ms_reduce", "ms_rebuild", "ms_dyndt")] + \
+        [(n, C.c_int64) for n in ("sum_contacts", "sum_real", "sum_potential_evaluated")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+EXPORTS = ["wdem_default_config", "wdem_create", "wdem_destroy", "wdem_last_error", "wdem_set_config", "wdem_set_profiling",
+           "wdem_upload_materials", "wdem_upload_spheres", "wdem_upload_walls", "wdem_upload_facets", "wdem_set_cell",
+           "wdem_set_next_gradv", "wdem_get_cell", "wdem_step", "wdem_step_e2e", "wdem_download_state", "wdem_download_forces",
+           "wdem_set_state", "wdem_num_contacts", "wdem_download_contacts", "wdem_crit_dt", "wdem_kinetic_energy", "wdem_get_scalars",
+           "wdem_device_info"]
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build=True):
+    global _LIB
+    if _LIB is None:
+        if build:
+            _build.build()
+        if not os.path.exists(_build.LIB):
+            raise RuntimeError("libwdem.so is missing: build it with `python -m woo_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(_build.LIB)
+        L.wdem_last_error.restype = C.c_char_p
+        L.wdem_last_error.argtypes = [C.c_void_p]
+        L.wdem_num_contacts.restype = C.c_int64
+        L.wdem_download_contacts.restype = C.c_int64
+        _LIB = L
+    return _LIB
+
+
+def ptr(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a if shape is None else a.reshape(shape)

@@ -1,0 +1,770 @@
+// wdem_engine.cu — host orchestration + C-ABI (include/wdem.h) of the B200 DEM hot-path engine.
+// One step = Scene::doOneStep restricted to [Leapfrog, InsertionSortCollider, ContactLoop, DynDt]
+// (reference: src/core/Scene.cpp:366-432, py/utils.py:122-129).  All compute is in wdem_kernels.cuh; CUB is used only
+// inside collider full runs (radix sort / scans).  No CPU fallback: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+#include "../../include/wdem.h"
+#include "wdem_kernels.cuh"
+
+using namespace wd;
+
+namespace {
+thread_local std::string g_createError;
+
+struct CudaErr { std::string msg; int code; };
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = (call);                                                                             \
+    if (e__ != cudaSuccess) throw CudaErr{std::string(#call) + ": " + cudaGetErrorString(e__), WDEM_ERR_CUDA}; \
+  } while (0)
+struct EngErr { std::string msg; int code; };
+
+template <class T>
+struct DBuf {  // growable device buffer
+  T* p = nullptr; size_t cap = 0;
+  void ensure(size_t n, int64_t& total, bool keep = false, cudaStream_t st = 0) {
+    if (n <= cap) return;
+    size_t ncap = std::max(n, cap + cap / 2);
+    T* q = nullptr;
+    CK(cudaMalloc(&q, ncap * sizeof(T)));
+    if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (p) { CK(cudaStreamSynchronize(st)); CK(cudaFree(p)); total -= (int64_t)(cap * sizeof(T)); }
+    p = q; cap = ncap; total += (int64_t)(ncap * sizeof(T));
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct SphereStore {
+  DBuf<double4> posr, velm, angi, ori; DBuf<double> f[6], l[3]; DBuf<uint32_t> flags, mask; DBuf<int32_t> mat, id, up;
+  void ensure(size_t n, int64_t& tot) {
+    posr.ensure(n, tot); velm.ensure(n, tot); angi.ensure(n, tot); ori.ensure(n, tot);
+    for (auto& b : f) b.ensure(n, tot); for (auto& b : l) b.ensure(n, tot);
+    flags.ensure(n, tot); mask.ensure(n, tot); mat.ensure(n, tot); id.ensure(n, tot); up.ensure(n, tot);
+  }
+  Spheres view() { Spheres S; S.posr = posr.p; S.velm = velm.p; S.angi = angi.p; S.ori = ori.p; S.fx = f[0].p; S.fy = f[1].p; S.fz = f[2].p; S.tx = f[3].p; S.ty = f[4].p; S.tz = f[5].p;
+    S.lx = l[0].p; S.ly = l[1].p; S.lz = l[2].p; S.flags = flags.p; S.mask = mask.p; S.mat = mat.p; S.id = id.p; S.up = up.p; return S; }
+  void release() { posr.release(); velm.release(); angi.release(); ori.release(); for (auto& b : f) b.release(); for (auto& b : l) b.release(); flags.release(); mask.release(); mat.release(); id.release(); up.release(); }
+};
+
+struct ContactStore {
+  DBuf<int2> pair; DBuf<uint32_t> flags; DBuf<int32_t> stepCreated, cd[3]; DBuf<double> t[6], fl[3], ph[5], tq[3]; DBuf<double4> cp, Fg, Tg;
+  size_t cap = 0;
+  void ensure(size_t n, int64_t& tot, bool hertz, bool rolling, bool periodic, bool keep = false, cudaStream_t st = 0) {
+    if (n <= cap) return;
+    n = std::max(n, cap + cap / 2);
+    pair.ensure(n, tot, keep, st); flags.ensure(n, tot, keep, st); stepCreated.ensure(n, tot, keep, st);
+    if (periodic) for (auto& b : cd) b.ensure(n, tot, keep, st);
+    for (auto& b : t) b.ensure(n, tot, keep, st); for (auto& b : fl) b.ensure(n, tot, keep, st);
+    for (int k = 0; k < (hertz ? 5 : 3); k++) ph[k].ensure(n, tot, keep, st);
+    if (rolling) { for (auto& b : tq) b.ensure(n, tot, keep, st); Tg.ensure(n, tot, keep, st); }
+    cp.ensure(n, tot, keep, st); Fg.ensure(n, tot, keep, st);
+    cap = n;
+  }
+  Contacts view() { Contacts C; C.pair = pair.p; C.flags = flags.p; C.stepCreated = stepCreated.p; C.cdx = cd[0].p; C.cdy = cd[1].p; C.cdz = cd[2].p;
+    C.t0x = t[0].p; C.t0y = t[1].p; C.t0z = t[2].p; C.t1x = t[3].p; C.t1y = t[4].p; C.t1z = t[5].p; C.cp = cp.p; C.fn = fl[0].p; C.ft0 = fl[1].p; C.ft1 = fl[2].p;
+    for (int k = 0; k < 5; k++) C.ph[k] = ph[k].p; C.tq0 = tq[0].p; C.tq1 = tq[1].p; C.tq2 = tq[2].p; C.Fg = Fg.p; C.Tg = Tg.p; return C; }
+  void release() { pair.release(); flags.release(); stepCreated.release(); for (auto& b : cd) b.release(); for (auto& b : t) b.release(); for (auto& b : fl) b.release(); for (auto& b : ph) b.release(); for (auto& b : tq) b.release(); cp.release(); Fg.release(); Tg.release(); cap = 0; }
+};
+
+struct CsrStore { DBuf<int> rowStart; DBuf<uint32_t> rowEntry; DBuf<int32_t> rowOther; bool valid = false; void release() { rowStart.release(); rowEntry.release(); rowOther.release(); } };
+
+// ---- host-side 3x3 helpers for the periodic cell (src/core/Cell.cpp:81-120), row-major m33
+m33 mIdent() { m33 r; for (int i = 0; i < 9; i++) r.m[i] = (i % 4 == 0) ? 1. : 0.; return r; }
+m33 mZero() { m33 r; for (int i = 0; i < 9; i++) r.m[i] = 0.; return r; }
+m33 mAdd(const m33& a, const m33& b) { m33 r; for (int i = 0; i < 9; i++) r.m[i] = a.m[i] + b.m[i]; return r; }
+m33 mSub(const m33& a, const m33& b) { m33 r; for (int i = 0; i < 9; i++) r.m[i] = a.m[i] - b.m[i]; return r; }
+m33 mScale(const m33& a, double s) { m33 r; for (int i = 0; i < 9; i++) r.m[i] = a.m[i] * s; return r; }
+m33 mT(const m33& a) { m33 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[3 * i + j] = a.m[3 * j + i]; return r; }
+m33 mMul(const m33& a, const m33& b) { m33 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[3 * i + j] = (a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j]) + a.m[3 * i + 2] * b.m[6 + j]; return r; }
+double mDet(const m33& a) { const double* m = a.m; return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]); }
+m33 mInv(const m33& a) {
+  const double* m = a.m; double id = 1. / mDet(a); m33 r;
+  r.m[0] = (m[4] * m[8] - m[5] * m[7]) * id; r.m[1] = (m[2] * m[7] - m[1] * m[8]) * id; r.m[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  r.m[3] = (m[5] * m[6] - m[3] * m[8]) * id; r.m[4] = (m[0] * m[8] - m[2] * m[6]) * id; r.m[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  r.m[6] = (m[3] * m[7] - m[4] * m[6]) * id; r.m[7] = (m[1] * m[6] - m[0] * m[7]) * id; r.m[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return r;
+}
+d3 hLevi(const m33& a) { return mk3(a.m[5] - a.m[7], a.m[6] - a.m[2], a.m[1] - a.m[3]); }  // Math.hpp:223-228
+
+struct HostCell {
+  m33 hSize = mIdent(), trsf = mIdent(), gradV = mZero(), nextGradV = mZero(), pprevHsize = mIdent();
+  d3 spinVec = mk3(0, 0, 0), size = mk3(1, 1, 1); bool hasShear = false; int homoDeform = WDEM_HOMO_GRADV2;
+  void integrateAndUpdate(double dt) {  // Cell.cpp:81-120
+    m33 inc = mScale(gradV, dt);
+    trsf = mAdd(trsf, mMul(inc, trsf));
+    m33 prev = hSize;
+    if (homoDeform == WDEM_HOMO_GRADV2) {
+      m33 A = mInv(mSub(mIdent(), mScale(mScale(gradV, dt), .5)));
+      m33 B = mAdd(mIdent(), mScale(mScale(gradV, dt), .5));
+      hSize = mMul(mMul(A, B), hSize);
+    } else hSize = mAdd(hSize, mMul(inc, hSize));
+    pprevHsize = mScale(mAdd(prev, hSize), .5);
+    if (mDet(hSize) == 0) throw EngErr{"Cell is degenerate (zero volume).", WDEM_ERR_RUNTIME};
+    for (int i = 0; i < 3; i++) { d3 b = mk3(hSize.m[i], hSize.m[3 + i], hSize.m[6 + i]); setc(size, i, nrm(b)); }
+    hasShear = (hSize.m[1] != 0 || hSize.m[2] != 0 || hSize.m[3] != 0 || hSize.m[5] != 0 || hSize.m[6] != 0 || hSize.m[7] != 0);
+  }
+  void setNextGradV() { gradV = nextGradV; m33 W = mScale(mSub(gradV, mT(gradV)), .5); spinVec = .5 * hLevi(W); }  // Cell.cpp:60-66
+};
+}  // namespace
+
+struct wdem_engine {
+  wdem_config cfg;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  int64_t bytes = 0;
+  bool profiling = false;
+  // particles
+  int n = 0; SphereStore sph[2]; int cur = 0; DBuf<int> id2slot, up2slot; int maxId = -1; bool up2slotValid = false;
+  std::vector<Material> hMats; DBuf<Material> dMats;
+  std::vector<Wall> hWalls; DBuf<Wall> dWalls;
+  int nFacets = 0; DBuf<int32_t> dFacetIds;
+  double minRadius = INFINITY, pwaveDt = INFINITY;
+  std::vector<double> hRadius; std::vector<int32_t> hMatOfSphere;
+  // contacts
+  ContactStore con[2]; int curC = 0; long long nSS = 0, nWS = 0, nFS = 0, nOrph = 0, nC = 0;
+  CsrStore csr[2]; int curR = 0;
+  // scratch
+  DBuf<uint32_t> keys, keysAlt; DBuf<int> idx, idxAlt, cellStart, counts, offsets; DBuf<unsigned char> cubTemp; DBuf<double> blk;
+  DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt;
+  Counters* dCnt = nullptr; Counters* hCnt = nullptr;
+  // scene scalars
+  double dt = NAN, time = 0, nextDt = NAN, verletDist = NAN; long long step = 0, nFullRuns = 0; bool conDirty = true;
+  long long dynStepLast = -1, dynStepPrev = -1;
+  HostCell cell;
+  long long launches = 0;
+  Spheres S() { return sph[cur].view(); }
+};
+
+namespace {
+
+inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
+
+void validateConfig(const wdem_config& c) {
+  if (c.law != WDEM_LAW_IDEALELPL && c.law != WDEM_LAW_HERTZ_DMT) throw EngErr{"unknown law", WDEM_ERR_INVALID};
+  if (!c.iniLensTouch) throw EngErr{"Cg2_*.iniLensTouch=False is not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+  if (c.distFactor > 1.) throw EngErr{"DemField.distFactor>1 is not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+  if (c.dynDtPeriod > 0 && 1. + c.maxRelInc == 1.) throw EngErr{"DynDt: maxRelInc too small (1.0+maxRelInc==1.0)", WDEM_ERR_INVALID};  // DynDt.cpp:12-14
+  if (c.periodic) throw EngErr{"periodic cell: not implemented in this build of the GPU engine yet", WDEM_ERR_UNSUPPORTED};
+}
+
+StepU makeUniforms(wdem_engine* E) {
+  const wdem_config& c = E->cfg;
+  StepU u; memset(&u, 0, sizeof(u));
+  u.dt = E->dt; u.damping = c.damping; u.gravity = mk3(c.gravity[0], c.gravity[1], c.gravity[2]);
+  u.hasGravity = (c.gravity[0] != 0 || c.gravity[1] != 0 || c.gravity[2] != 0); u.reset = c.reset;
+  u.maxD2 = E->verletDist * E->verletDist;
+  u.periodic = c.periodic; u.homoDeform = c.periodic ? E->cell.homoDeform : -1;
+  u.hSize = E->cell.hSize;
+  u.shiftVelM = mZero();
+  if (c.periodic) {
+    const HostCell& ce = E->cell;
+    if (ce.homoDeform == WDEM_HOMO_VEL || ce.homoDeform == WDEM_HOMO_VEL_2ND) u.shiftVelM = mMul(ce.gradV, ce.hSize);
+    else if (ce.homoDeform == WDEM_HOMO_GRADV2) u.shiftVelM = mMul(ce.gradV, ce.pprevHsize);
+    u.gradV = ce.gradV; u.nextGradV = ce.nextGradV; u.dGradV = mSub(ce.nextGradV, ce.gradV); u.midGradV = mScale(mAdd(ce.gradV, ce.nextGradV), .5);
+    u.spinVec = ce.spinVec;
+    if (ce.homoDeform == WDEM_HOMO_GRADV2) {  // Leapfrog.cpp:114-127
+      m33 s4 = mScale(mScale(mAdd(ce.nextGradV, ce.gradV), E->dt), .25);
+      u.ImLL4hInv = mInv(mSub(mIdent(), s4)); u.IpLL4h = mAdd(mIdent(), s4); u.LmL = mSub(ce.nextGradV, ce.gradV);
+      d3 a = hLevi(mScale(mSub(ce.gradV, mT(ce.gradV)), .5)), b = hLevi(mScale(mSub(ce.nextGradV, mT(ce.nextGradV)), .5));
+      u.deltaSpinVec = (-.5) * a + .5 * b;
+    }
+  }
+  u.step = E->step; u.renormNow = (c.trsfRenorm > 0 && (E->step % c.trsfRenorm) == 0); u.noRatch = c.noRatch;
+  u.absDistFactor = std::abs(c.distFactor);
+  u.law = c.law; u.noSlip = c.noSlip; u.noBreak = c.noBreak; u.noFrict = c.noFrict; u.noAttraction = c.noAttraction;
+  u.rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.); u.relRollStiff = c.relRollStiff; u.relTwistStiff = c.relTwistStiff; u.rollTanPhi = c.rollTanPhi;
+  u.poisson = c.poisson; u.en = c.en;
+  u.viscAlpha = (c.en > 0 && c.en < 1.) ? (-std::sqrt(5.) * std::log(c.en) / (std::sqrt(std::log(c.en) * std::log(c.en) + M_PI * M_PI))) : 0.;
+  return u;
+}
+
+void checkDeviceError(wdem_engine* E) {
+  const Counters& h = *E->hCnt;
+  if (h.error == ERR_NONE) return;
+  std::string pr = "##" + std::to_string(h.errA) + "+" + std::to_string(h.errB);
+  switch (h.error) {
+    case ERR_NAN_FORCE: throw EngErr{"NaN force in contact " + pr + " (IdealElPl.cpp:79-83)", WDEM_ERR_RUNTIME};
+    case ERR_NAN_POS: throw EngErr{"NaN position of particle #" + std::to_string(h.errA), WDEM_ERR_RUNTIME};
+    case ERR_NO_PHYS: throw EngErr{"ContactLoop: " + pr + ": no Contact.phys created (Cp2_HertzMat_HertzPhys needs HertzMat on both particles; ContactLoop.cpp:181)", WDEM_ERR_RUNTIME};
+    case ERR_SCHWARZ: throw EngErr{"Law2_L6Geom_HertzPhys_DMT: Schwarz model (alpha!=0 and gamma!=0) is out of scope " + pr, WDEM_ERR_UNSUPPORTED};
+    default: throw EngErr{"device error " + std::to_string(h.error) + " " + pr, WDEM_ERR_RUNTIME};
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Collider full run (replaces InsertionSortCollider::run's fullRun branch, InsertionSortCollider.cpp:407-613)
+// -------------------------------------------------------------------------------------------------
+void rebuild(wdem_engine* E) {
+  const wdem_config& c = E->cfg;
+  cudaStream_t st = E->stream;
+  const int n = E->n;
+  const bool hertz = c.law == WDEM_LAW_HERTZ_DMT, rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.);
+  const double vd = E->verletDist;
+  int64_t& tot = E->bytes;
+  long long nSS = 0, nWS = 0, nOrphOut = 0;
+  ContactStore& Nst = E->con[1 - E->curC];
+  ContactStore& Ost = E->con[E->curC];
+  CsrStore& Ocsr = E->csr[E->curR];
+  CsrStore& Ncsr = E->csr[1 - E->curR];
+  OldCsr oc; oc.valid = Ocsr.valid ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
+  const int* perm = nullptr;
+  Grid g; memset(&g, 0, sizeof(g));
+  if (n > 0) {
+    // 1. bounds of sphere centres + max radius
+    const int nb = nblk(n, 256);
+    E->blk.ensure((size_t)nb * 7, tot);
+    k_bounds<<<nb, 256, 0, st>>>(E->S().posr, n, E->blk.p); E->launches++;
+    std::vector<double> hb((size_t)nb * 7);
+    CK(cudaMemcpyAsync(hb.data(), E->blk.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, rmax = 0;
+    for (int b = 0; b < nb; b++) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], hb[7 * b + k]); hi[k] = std::max(hi[k], hb[7 * b + 3 + k]); } rmax = std::max(rmax, hb[7 * b + 6]); }
+    for (int k = 0; k < 3; k++) if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) throw EngErr{"non-finite particle position at collider run", WDEM_ERR_RUNTIME};
+    // 2. grid: cell edge ~ smallest enlarged AABB, but no more than ~8 cells per sphere
+    double cell = 2 * (E->minRadius + vd);
+    double vol = std::max(hi[0] - lo[0], cell) * std::max(hi[1] - lo[1], cell) * std::max(hi[2] - lo[2], cell);
+    cell = std::max(cell, std::cbrt(vol / (8.0 * n)));
+    g.cell = cell; g.inv = 1. / cell; g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+    g.nx = std::max(1, (int)std::floor((hi[0] - lo[0]) * g.inv) + 1); g.ny = std::max(1, (int)std::floor((hi[1] - lo[1]) * g.inv) + 1); g.nz = std::max(1, (int)std::floor((hi[2] - lo[2]) * g.inv) + 1);
+    const long long ncells = (long long)g.nx * g.ny * g.nz;
+    if (ncells > (1ll << 31) - 2) throw EngErr{"collider grid too large", WDEM_ERR_RUNTIME};
+    // 3. cell keys, radix sort, reorder all sphere arrays into cell order
+    E->keys.ensure(n, tot); E->keysAlt.ensure(n, tot); E->idx.ensure(n, tot); E->idxAlt.ensure(n, tot);
+    k_cellkeys<<<nb, 256, 0, st>>>(E->S().posr, n, g, E->keys.p, E->idx.p); E->launches++;
+    int keyBits = 1; while ((1ll << keyBits) < ncells) keyBits++;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, E->keys.p, E->keysAlt.p, E->idx.p, E->idxAlt.p, n, 0, keyBits, st);
+    E->cubTemp.ensure(tb, tot);
+    cub::DeviceRadixSort::SortPairs(E->cubTemp.p, tb, E->keys.p, E->keysAlt.p, E->idx.p, E->idxAlt.p, n, 0, keyBits, st); E->launches += 4;
+    SphereStore& dst = E->sph[1 - E->cur];
+    dst.ensure(n, tot);
+    k_reorder<<<nb, 256, 0, st>>>(dst.view(), E->S(), E->idxAlt.p, n, E->id2slot.p); E->launches++;
+    E->cur = 1 - E->cur; E->up2slotValid = false;
+    perm = E->idxAlt.p;
+    // 4. cellStart[k] = #spheres with key<k
+    E->cellStart.ensure((size_t)ncells + 1, tot);
+    CK(cudaMemsetAsync(E->cellStart.p, 0, ((size_t)ncells + 1) * sizeof(int), st));
+    k_cellends<<<nb, 256, 0, st>>>(E->keysAlt.p, n, E->cellStart.p); E->launches++;
+    tb = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, tb, E->cellStart.p, E->cellStart.p, cub::Max(), (int)(ncells + 1), st);
+    E->cubTemp.ensure(tb, tot);
+    cub::DeviceScan::InclusiveScan(E->cubTemp.p, tb, E->cellStart.p, E->cellStart.p, cub::Max(), (int)(ncells + 1), st); E->launches += 2;
+    // 5. count candidates: [SS by sphere | WS by sphere]
+    const int nWalls = (int)E->hWalls.size();
+    E->counts.ensure((size_t)2 * n + 1, tot); E->offsets.ensure((size_t)2 * n + 1, tot);
+    Contacts dummy; memset(&dummy, 0, sizeof(dummy));
+    const int nb128 = nblk(n, 128);
+    k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, c.law, rolling, E->step); E->launches++;
+    if (nWalls) { k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, dummy, oc, perm, c.law, rolling, E->step); E->launches++; }
+    else CK(cudaMemsetAsync(E->counts.p + n, 0, (size_t)n * sizeof(int), st));
+    CK(cudaMemsetAsync(E->counts.p + 2 * n, 0, sizeof(int), st));
+    tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, E->counts.p, E->offsets.p, 2 * n + 1, st);
+    E->cubTemp.ensure(tb, tot);
+    cub::DeviceScan::ExclusiveSum(E->cubTemp.p, tb, E->counts.p, E->offsets.p, 2 * n + 1, st); E->launches += 2;
+    int hOff[2];
+    CK(cudaMemcpyAsync(&hOff[0], E->offsets.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hOff[1], E->offsets.p + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    nSS = hOff[0]; nWS = hOff[1] - hOff[0];
+    if (hOff[1] < 0 || (long long)hOff[1] >= (1ll << 30)) throw EngErr{"too many potential contacts for one device", WDEM_ERR_RUNTIME};
+    // 6. fill pairs + carry history
+    const long long nC0 = nSS + nWS;
+    Nst.ensure((size_t)std::max<long long>(nC0, 1), tot, hertz, rolling, c.periodic);
+    Contacts N = Nst.view(), O = Ost.view();
+    k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, N, O, oc, perm, c.law, rolling, E->step); E->launches++;
+    if (nWalls) { k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, N, O, oc, perm, c.law, rolling, E->step); E->launches++; }
+    // 6b. orphans: real contacts of the previous table that no candidate claimed (AABBs separated while real)
+    long long nOrph = 0;
+    if (oc.valid && E->nC > 0) {
+      E->orphCnt.ensure(1, tot);
+      CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
+      const int32_t* oldSid = E->sph[1 - E->cur].id.p;
+      k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, c.law, rolling, c.periodic, E->orphCnt.p, 0); E->launches++;
+      int hN = 0; CK(cudaMemcpyAsync(&hN, E->orphCnt.p, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+      if (hN > 0) {
+        nOrph = hN;
+        Nst.ensure((size_t)(nC0 + nOrph), tot, hertz, rolling, c.periodic, /*keep*/ true, st);
+        N = Nst.view();
+        CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
+        k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, c.law, rolling, c.periodic, E->orphCnt.p, 1); E->launches++;
+      }
+    }
+    const long long nC = nC0 + nOrph;
+    nOrphOut = nOrph;
+    // 7. per-particle incidence rows sorted by the other particle's id
+    const long long nK = 2 * nC;
+    Ncsr.rowStart.ensure((size_t)n + 2, tot); Ncsr.rowEntry.ensure((size_t)std::max<long long>(nK, 1), tot); Ncsr.rowOther.ensure((size_t)std::max<long long>(nK, 1), tot);
+    if (nC > 0) {
+      E->ckeys.ensure(nK, tot); E->ckeysAlt.ensure(nK, tot); E->cvals.ensure(nK, tot);
+      k_csr_emit<<<nblk(nC, 256), 256, 0, st>>>(N, nC, E->S().id, E->dWalls.p, E->dFacetIds.p, E->ckeys.p, E->cvals.p); E->launches++;
+      int slotBits = 1; while ((1ll << slotBits) <= n) slotBits++;
+      tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, E->ckeys.p, E->ckeysAlt.p, E->cvals.p, Ncsr.rowEntry.p, (int)nK, 0, 32 + slotBits, st);
+      E->cubTemp.ensure(tb, tot);
+      cub::DeviceRadixSort::SortPairs(E->cubTemp.p, tb, E->ckeys.p, E->ckeysAlt.p, E->cvals.p, Ncsr.rowEntry.p, (int)nK, 0, 32 + slotBits, st); E->launches += 8;
+      k_rowstart<<<nblk(std::max<long long>(n + 1, std::min<long long>(nK, 1 << 22)), 256), 256, 0, st>>>(E->ckeysAlt.p, nK, n, Ncsr.rowStart.p, Ncsr.rowOther.p); E->launches++;
+    } else CK(cudaMemsetAsync(Ncsr.rowStart.p, 0, ((size_t)n + 2) * sizeof(int), st));
+    Ncsr.valid = true;
+  }
+  E->nSS = nSS; E->nWS = nWS; E->nFS = 0; E->nOrph = nOrphOut; E->nC = nSS + nWS + nOrphOut;
+  E->curC = 1 - E->curC; E->curR = 1 - E->curR;
+  E->nFullRuns++;
+}
+
+void ensureVerletAndDt(wdem_engine* E) {
+  const wdem_config& c = E->cfg;
+  // AabbCollider::setVerletDist (Collision.cpp:164-184)
+  if (std::isnan(E->verletDist)) {
+    if (c.verletDist >= 0) E->verletDist = c.verletDist;
+    else if (std::isfinite(E->minRadius)) E->verletDist = std::abs(c.verletDist) * E->minRadius;
+    else E->verletDist = 0.;
+  }
+  // Scene::doOneStep (Scene.cpp:380-398): dt = dtSafety * critDt when unset
+  if (std::isnan(E->dt) || std::isinf(E->dt) || E->dt < 0) {
+    if (std::isinf(E->pwaveDt)) throw EngErr{"Failed to obtain meaningful dt from engines and fields automatically", WDEM_ERR_RUNTIME};
+    E->dt = c.dtSafety * E->pwaveDt;
+  }
+}
+
+void fetchCounters(wdem_engine* E) {
+  CK(cudaMemcpyAsync(E->hCnt, E->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+}
+
+double dynDtCrit(wdem_engine* E) {
+  const int n = E->n; if (n == 0) return INFINITY;
+  const int nb = nblk(n, 256);
+  E->blk.ensure((size_t)std::max(nb, 1) * 7, E->bytes);
+  CsrStore& R = E->csr[E->curR];
+  k_dyndt<<<nb, 256, 0, E->stream>>>(E->S(), n, E->con[E->curC].view(), R.rowStart.p, R.rowEntry.p, E->cfg.law, E->blk.p); E->launches++;
+  std::vector<double> hb(nb);
+  CK(cudaMemcpyAsync(hb.data(), E->blk.p, nb * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  double r = INFINITY; for (double v : hb) r = std::min(r, v);
+  return std::sqrt(r);
+}
+double pown(double x, unsigned n) { unsigned d = n >> 1, r = n & 1; double a = d == 0 ? 1 : pown(x * x, d); double b = r == 0 ? 1 : x; return a * b; }  // Math.hpp:161-176
+
+void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
+  const wdem_config& c = E->cfg;
+  cudaStream_t st = E->stream;
+  ensureVerletAndDt(E);
+  if (c.periodic) E->cell.integrateAndUpdate(E->dt);
+  StepU u = makeUniforms(E);
+  const int n = E->n;
+  const bool prof = E->profiling;
+  if (prof) CK(cudaEventRecord(E->evp[0], st));
+  if (n > 0) { k_leapfrog<<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt); E->launches++; }
+  if (prof) CK(cudaEventRecord(E->evp[1], st));
+  // collider: full run if contacts are dirty / verletDist==0 / any sphere moved farther than verletDist
+  bool full = E->conDirty || E->verletDist == 0;
+  fetchCounters(E);
+  checkDeviceError(E);
+  if (E->hCnt->dirty) full = true;
+  if (full) {
+    rebuild(E);
+    E->conDirty = false;
+    CK(cudaMemsetAsync(&E->dCnt->dirty, 0, sizeof(int), st));
+    if (stats) stats->n_rebuilds++;
+  }
+  if (prof) CK(cudaEventRecord(E->evp[2], st));
+  Contacts C = E->con[E->curC].view();
+  if (E->nSS > 0) {
+    if (c.law == 0) k_contact_ss<0><<<nblk(E->nSS, 128), 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt);
+    else k_contact_ss<1><<<nblk(E->nSS, 128), 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt);
+    E->launches++;
+  }
+  if (E->nWS > 0) {
+    if (c.law == 0) k_contact_ws<0><<<nblk(E->nWS, 128), 128, 0, st>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt);
+    else k_contact_ws<1><<<nblk(E->nWS, 128), 128, 0, st>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt);
+    E->launches++;
+  }
+  if (E->nOrph > 0) {
+    const long long f0 = E->nSS + E->nWS + E->nFS;
+    if (c.law == 0) k_contact_orphans<0><<<nblk(E->nOrph, 128), 128, 0, st>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt);
+    else k_contact_orphans<1><<<nblk(E->nOrph, 128), 128, 0, st>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt);
+    E->launches++;
+  }
+  if (prof) CK(cudaEventRecord(E->evp[3], st));
+  if (n > 0 && c.applyForces) {
+    CsrStore& R = E->csr[E->curR];
+    k_reduce<<<nblk(n, 256), 256, 0, st>>>(E->S(), n, C, R.rowStart.p, R.rowEntry.p, u); E->launches++;
+  }
+  if (prof) CK(cudaEventRecord(E->evp[4], st));
+  // DynDt (PeriodicEngine::isActivated, Engine.cpp:170-195 with stepModulo/initRun defaults; DynDt::run DynDt.cpp:90-113)
+  if (c.dynDtPeriod > 0) {
+    bool initNow = E->dynStepLast < 0;
+    if (initNow) E->dynStepLast = E->step;
+    if ((E->step - E->dynStepLast >= c.dynDtPeriod) || (E->step % c.dynDtPeriod == 0)) {
+      E->dynStepPrev = E->dynStepLast; E->dynStepLast = E->step;
+      double crDt = dynDtCrit(E);
+      if (!std::isinf(crDt)) {
+        int nSteps = (int)(E->step - E->dynStepPrev);
+        double maxNewDt = E->dt * pown(1. + c.maxRelInc, (unsigned)nSteps);
+        double nDt = std::min(crDt * c.dtSafety, maxNewDt);
+        if (nDt != E->dt) E->nextDt = nDt;
+      }
+    }
+  }
+  if (prof) {
+    CK(cudaEventRecord(E->evp[5], st)); CK(cudaEventSynchronize(E->evp[5]));
+    float ms;
+    for (int k = 0; k < 5; k++) { CK(cudaEventElapsedTime(&ms, E->evp[k], E->evp[k + 1])); phaseMs[k] += ms; }
+  }
+  // epilogue (Scene.cpp:428-432)
+  if (c.periodic) E->cell.setNextGradV();
+  E->step++; E->time += E->dt;
+  if (!std::isnan(E->nextDt)) { E->dt = E->nextDt; E->nextDt = NAN; }
+}
+
+template <class F>
+int guarded(wdem_handle h, F&& f) {
+  if (!h) return WDEM_ERR_INVALID;
+  try {
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) { h->err = "cudaSetDevice failed (no usable CUDA device; this engine has no CPU fallback)"; return WDEM_ERR_CUDA; }
+    f();
+    return WDEM_OK;
+  } catch (CudaErr& e) { h->err = e.msg; return e.code; }
+  catch (EngErr& e) { h->err = e.msg; return e.code; }
+  catch (std::exception& e) { h->err = e.what(); return WDEM_ERR_RUNTIME; }
+}
+
+void countContacts(wdem_engine* E, long long& nReal, long long& nAlive) {
+  nReal = nAlive = 0;
+  if (E->nC == 0) return;
+  E->cntScratch.ensure(2, E->bytes);
+  CK(cudaMemsetAsync(E->cntScratch.p, 0, 2 * sizeof(unsigned long long), E->stream));
+  k_count_flags<<<nblk(E->nC, 256), 256, 0, E->stream>>>(E->con[E->curC].flags.p, E->nC, E->cntScratch.p);
+  unsigned long long h[2];
+  CK(cudaMemcpyAsync(h, E->cntScratch.p, sizeof(h), cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  nReal = (long long)h[0]; nAlive = (long long)h[1];
+}
+
+void ensureUp2Slot(wdem_engine* E) {
+  if (E->up2slotValid || E->n == 0) return;
+  E->up2slot.ensure(E->n, E->bytes);
+  k_up2slot<<<nblk(E->n, 256), 256, 0, E->stream>>>(E->S().up, E->n, E->up2slot.p);
+  E->up2slotValid = true;
+}
+
+template <class T>
+std::vector<T> d2h(const T* p, size_t n, cudaStream_t st) {
+  std::vector<T> v(n);
+  if (n) { CK(cudaMemcpyAsync(v.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+  return v;
+}
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+int wdem_default_config(wdem_config* c) {
+  if (!c) return WDEM_ERR_INVALID;
+  memset(c, 0, sizeof(*c));
+  c->dt = NAN; c->dtSafety = 0.9; c->distFactor = -1.; c->damping = 0.2; c->verletDist = -0.05; c->poisson = 0.2; c->en = NAN; c->maxRelInc = 1e-4;
+  c->loneMask = 2; c->reset = 1; c->iniLensTouch = 1; c->trsfRenorm = 100; c->applyForces = 1; c->law = WDEM_LAW_IDEALELPL; c->noAttraction = 1; c->dynDtPeriod = 100;
+  return WDEM_OK;
+}
+
+const char* wdem_last_error(wdem_handle h) { return h ? h->err.c_str() : g_createError.c_str(); }
+
+int wdem_create(const wdem_config* cfg, wdem_handle* out) {
+  if (!cfg || !out) return WDEM_ERR_INVALID;
+  *out = nullptr;
+  wdem_engine* E = nullptr;
+  try {
+    validateConfig(*cfg);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaErr{"no CUDA device available: the B200 DEM engine has no CPU fallback", WDEM_ERR_CUDA};
+    if (cfg->device < 0 || cfg->device >= ndev) throw EngErr{"invalid device ordinal", WDEM_ERR_INVALID};
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) throw CudaErr{std::string("device '") + prop.name + "' is not sm_100 (this library carries sm_100a code only)", WDEM_ERR_CUDA};
+    E = new wdem_engine(); E->cfg = *cfg; E->dt = cfg->dt;
+    CK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&E->ev0)); CK(cudaEventCreate(&E->ev1));
+    for (auto& e : E->evp) CK(cudaEventCreate(&e));
+    CK(cudaMalloc(&E->dCnt, sizeof(Counters))); CK(cudaMemset(E->dCnt, 0, sizeof(Counters)));
+    CK(cudaMallocHost(&E->hCnt, sizeof(Counters))); memset(E->hCnt, 0, sizeof(Counters));
+    *out = E;
+    return WDEM_OK;
+  } catch (CudaErr& e) { g_createError = e.msg; delete E; return e.code; }
+  catch (EngErr& e) { g_createError = e.msg; delete E; return e.code; }
+}
+
+int wdem_destroy(wdem_handle h) {
+  if (!h) return WDEM_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release();
+  h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacetIds.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
+  h->orphCnt.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release();
+  if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt);
+  if (h->ev0) cudaEventDestroy(h->ev0); if (h->ev1) cudaEventDestroy(h->ev1); for (auto& e : h->evp) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return WDEM_OK;
+}
+
+int wdem_set_config(wdem_handle h, const wdem_config* cfg) {
+  return guarded(h, [&] {
+    if (!cfg) throw EngErr{"null config", WDEM_ERR_INVALID};
+    validateConfig(*cfg);
+    if (cfg->law != h->cfg.law && h->nC > 0) throw EngErr{"cannot change the contact law while contacts exist", WDEM_ERR_UNSUPPORTED};
+    int dev = h->cfg.device; bool newDt = !(cfg->dt == h->cfg.dt || (std::isnan(cfg->dt) && std::isnan(h->cfg.dt)));
+    h->cfg = *cfg; h->cfg.device = dev;
+    if (newDt) h->dt = cfg->dt;
+  });
+}
+int wdem_set_profiling(wdem_handle h, int on) { return guarded(h, [&] { h->profiling = on != 0; }); }
+
+int wdem_upload_materials(wdem_handle h, int n, const int32_t* kind, const double* density, const double* young, const double* ktDivKn, const double* tanPhi,
+                          const double* surfEnergy, const double* alpha) {
+  return guarded(h, [&] {
+    if (n <= 0 || !kind || !density || !young || !ktDivKn || !tanPhi) throw EngErr{"wdem_upload_materials: bad arguments", WDEM_ERR_INVALID};
+    h->hMats.resize(n);
+    for (int i = 0; i < n; i++) { Material m; m.kind = kind[i]; m.pad = 0; m.density = density[i]; m.young = young[i]; m.ktDivKn = ktDivKn[i]; m.tanPhi = tanPhi[i]; m.surfEnergy = surfEnergy ? surfEnergy[i] : 0.; m.alpha = alpha ? alpha[i] : 0.; h->hMats[i] = m; }
+    h->dMats.ensure(n, h->bytes);
+    CK(cudaMemcpyAsync(h->dMats.p, h->hMats.data(), n * sizeof(Material), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const double* pos, const double* ori, const double* vel, const double* angVel, const double* mass,
+                        const double* inertia, const double* radius, const uint32_t* flags, const uint32_t* mask, const int32_t* matId) {
+  return guarded(h, [&] {
+    if (n < 0 || n > (1ll << 30) || (n > 0 && (!pos || !mass || !inertia || !radius))) throw EngErr{"wdem_upload_spheres: bad arguments", WDEM_ERR_INVALID};
+    if (h->hMats.empty()) throw EngErr{"wdem_upload_spheres: upload materials first", WDEM_ERR_INVALID};
+    // DemField::selfTest-like checks (Particle.cpp:566-625)
+    std::vector<double4> posr(n), velm(n), angi(n), q(n); std::vector<uint32_t> fl(n), mk(n); std::vector<int32_t> mt(n), id(n), up(n);
+    int maxId = h->maxId; double minR = INFINITY, pw = INFINITY;
+    for (auto& w : h->hWalls) maxId = std::max(maxId, w.id);
+    for (int64_t i = 0; i < n; i++) {
+      id[i] = ids ? ids[i] : (int32_t)i; up[i] = (int32_t)i;
+      if (id[i] < 0) throw EngErr{"negative particle id", WDEM_ERR_INVALID};
+      maxId = std::max(maxId, id[i]);
+      fl[i] = flags ? flags[i] : 0u; mk[i] = mask ? mask[i] : 5u; mt[i] = matId ? matId[i] : 0;
+      if (mt[i] < 0 || mt[i] >= (int)h->hMats.size()) throw EngErr{"sphere material index out of range", WDEM_ERR_INVALID};
+      if (fl[i] & (64u | 128u)) throw EngErr{"clumps are not supported by the GPU engine (DemData.flags has CLUMP bits)", WDEM_ERR_UNSUPPORTED};
+      if (!(radius[i] > 0)) throw EngErr{"sphere #" + std::to_string(id[i]) + ": radius must be positive", WDEM_ERR_INVALID};
+      if ((fl[i] & 7u) != 7u && !(mass[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive mass with free translational DOFs", WDEM_ERR_INVALID};
+      if ((fl[i] & 56u) != 56u && !(inertia[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive inertia with free rotational DOFs", WDEM_ERR_INVALID};
+      posr[i] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], radius[i]);
+      velm[i] = make_double4(vel ? vel[3 * i] : 0, vel ? vel[3 * i + 1] : 0, vel ? vel[3 * i + 2] : 0, mass[i]);
+      angi[i] = make_double4(angVel ? angVel[3 * i] : 0, angVel ? angVel[3 * i + 1] : 0, angVel ? angVel[3 * i + 2] : 0, inertia[i]);
+      q[i] = ori ? make_double4(ori[4 * i], ori[4 * i + 1], ori[4 * i + 2], ori[4 * i + 3]) : make_double4(0, 0, 0, 1);
+      minR = std::min(minR, radius[i]);
+      const Material& m = h->hMats[mt[i]];
+      pw = std::min(pw, radius[i] / (1. * std::sqrt(m.young / m.density)));  // DemFuncs::pWaveDt (Funcs.cpp:151-175)
+    }
+    h->n = (int)n; h->minRadius = minR; h->pwaveDt = pw; h->maxId = maxId;
+    h->cur = 0;
+    SphereStore& s = h->sph[0];
+    s.ensure(std::max<int64_t>(n, 1), h->bytes);
+    cudaStream_t st = h->stream;
+    auto H2D = [&](void* d, const void* src, size_t b) { if (b) CK(cudaMemcpyAsync(d, src, b, cudaMemcpyHostToDevice, st)); };
+    H2D(s.posr.p, posr.data(), n * sizeof(double4)); H2D(s.velm.p, velm.data(), n * sizeof(double4)); H2D(s.angi.p, angi.data(), n * sizeof(double4)); H2D(s.ori.p, q.data(), n * sizeof(double4));
+    for (auto& b : s.f) if (n) CK(cudaMemsetAsync(b.p, 0, n * sizeof(double), st));
+    for (auto& b : s.l) if (n) CK(cudaMemsetAsync(b.p, 0, n * sizeof(double), st));
+    H2D(s.flags.p, fl.data(), n * 4); H2D(s.mask.p, mk.data(), n * 4); H2D(s.mat.p, mt.data(), n * 4); H2D(s.id.p, id.data(), n * 4); H2D(s.up.p, up.data(), n * 4);
+    h->id2slot.ensure((size_t)maxId + 2, h->bytes);
+    CK(cudaMemsetAsync(h->id2slot.p, 0xFF, ((size_t)maxId + 2) * sizeof(int), st));
+    CK(cudaStreamSynchronize(st));
+    h->conDirty = true; h->nC = h->nSS = h->nWS = h->nFS = 0; h->csr[0].valid = h->csr[1].valid = false; h->up2slotValid = false;
+    h->verletDist = NAN;
+  });
+}
+
+int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* pos, const int32_t* axis, const int32_t* sense, const double* vel, const uint32_t* mask,
+                      const int32_t* matId) {
+  return guarded(h, [&] {
+    if (n < 0 || (n > 0 && (!ids || !pos || !axis || !sense))) throw EngErr{"wdem_upload_walls: bad arguments", WDEM_ERR_INVALID};
+    h->hWalls.resize(n);
+    for (int i = 0; i < n; i++) {
+      Wall w; memset(&w, 0, sizeof(w));
+      for (int k = 0; k < 3; k++) { w.pos[k] = pos[3 * i + k]; w.vel[k] = vel ? vel[3 * i + k] : 0.; }
+      w.axis = axis[i]; w.sense = sense[i]; w.mask = mask ? mask[i] : 3u; w.mat = matId ? matId[i] : 0; w.id = ids[i];
+      if (w.axis < 0 || w.axis > 2 || w.sense < -1 || w.sense > 1) throw EngErr{"Wall.axis must be 0..2 and Wall.sense -1,0,1", WDEM_ERR_INVALID};
+      if (w.mat < 0 || w.mat >= (int)h->hMats.size()) throw EngErr{"wall material index out of range", WDEM_ERR_INVALID};
+      h->hWalls[i] = w;
+    }
+    h->dWalls.ensure(std::max(n, 1), h->bytes);
+    if (n) CK(cudaMemcpyAsync(h->dWalls.p, h->hWalls.data(), n * sizeof(Wall), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->conDirty = true;
+  });
+}
+
+int wdem_upload_facets(wdem_handle h, int n, const int32_t*, const double*, const double*, const double*, const double*, const double*, const uint32_t*, const int32_t*) {
+  return guarded(h, [&] { if (n > 0) throw EngErr{"facets: not implemented in this build of the GPU engine yet", WDEM_ERR_UNSUPPORTED}; });
+}
+
+int wdem_set_cell(wdem_handle h, const double* hSize, const double* gradV, const double* nextGradV, int homoDeform) {
+  return guarded(h, [&] {
+    if (!hSize) throw EngErr{"wdem_set_cell: hSize required", WDEM_ERR_INVALID};
+    HostCell& c = h->cell;
+    for (int i = 0; i < 9; i++) { c.hSize.m[i] = hSize[i]; c.gradV.m[i] = gradV ? gradV[i] : 0.; c.nextGradV.m[i] = nextGradV ? nextGradV[i] : c.gradV.m[i]; }
+    c.pprevHsize = c.hSize; c.trsf = mIdent(); c.homoDeform = homoDeform;
+    if (homoDeform < 0 || homoDeform > 4) throw EngErr{"Cell.homoDeform must be in {0,1,2,3,4}.", WDEM_ERR_INVALID};
+    c.integrateAndUpdate(0);
+  });
+}
+int wdem_set_next_gradv(wdem_handle h, const double* g) { return guarded(h, [&] { for (int i = 0; i < 9; i++) h->cell.nextGradV.m[i] = g[i]; }); }
+int wdem_get_cell(wdem_handle h, double* hSize) { return guarded(h, [&] { for (int i = 0; i < 9; i++) hSize[i] = h->cell.hSize.m[i]; }); }
+
+int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats) {
+  return guarded(h, [&] {
+    wdem_stats local; memset(&local, 0, sizeof(local));
+    float phase[5] = {0, 0, 0, 0, 0};
+    long long l0 = h->launches;
+    CK(cudaMemsetAsync(h->dCnt, 0, 4 * sizeof(unsigned long long), h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int64_t s = 0; s < nsteps; s++) oneStep(h, &local, phase);
+    CK(cudaEventRecord(h->ev1, h->stream));
+    fetchCounters(h);
+    CK(cudaEventSynchronize(h->ev1));
+    checkDeviceError(h);
+    float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (stats) {
+      local.device_ms = ms; local.n_spheres = h->n; local.n_full_runs_total = h->nFullRuns; local.n_launches = h->launches - l0; local.step = h->step; local.dt = h->dt; local.time = h->time;
+      local.ms_integrate = phase[0]; local.ms_rebuild = phase[1]; local.ms_contact = phase[2]; local.ms_reduce = phase[3]; local.ms_dyndt = phase[4];
+      long long nr, na; countContacts(h, nr, na); local.n_contacts = na; local.n_real = nr;
+      local.sum_real = (int64_t)h->hCnt->nReal; local.sum_potential_evaluated = (int64_t)h->hCnt->nPotEval - (int64_t)h->hCnt->nReal; local.sum_contacts = (int64_t)h->hCnt->nPotEval;
+      *stats = local;
+    }
+  });
+}
+
+int wdem_set_state(wdem_handle h, int64_t first, int64_t cnt, const double* pos, const double* vel, const double* angVel) {
+  return guarded(h, [&] {
+    if (first < 0 || cnt < 0 || first + cnt > h->n) throw EngErr{"wdem_set_state: range out of bounds", WDEM_ERR_INVALID};
+    if (cnt == 0) return;
+    ensureUp2Slot(h);
+    h->ioBuf.ensure((size_t)h->n * 19, h->bytes);
+    double *dp = nullptr, *dv = nullptr, *dw = nullptr;
+    if (pos) { dp = h->ioBuf.p; CK(cudaMemcpyAsync(dp, pos, cnt * 24, cudaMemcpyHostToDevice, h->stream)); }
+    if (vel) { dv = h->ioBuf.p + 3 * cnt; CK(cudaMemcpyAsync(dv, vel, cnt * 24, cudaMemcpyHostToDevice, h->stream)); }
+    if (angVel) { dw = h->ioBuf.p + 6 * cnt; CK(cudaMemcpyAsync(dw, angVel, cnt * 24, cudaMemcpyHostToDevice, h->stream)); }
+    k_scatter_state<<<nblk(cnt, 256), 256, 0, h->stream>>>(h->S(), h->n, h->up2slot.p, first, cnt, dp, dv, dw);
+    CK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+static void downloadInto(wdem_handle h, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque) {
+  const int n = h->n; if (n == 0) return;
+  h->ioBuf.ensure((size_t)n * 19, h->bytes);
+  double* d = h->ioBuf.p;
+  double *dpos = pos ? d : nullptr, *dori = ori ? d + 3 * (size_t)n : nullptr, *dvel = vel ? d + 7 * (size_t)n : nullptr, *dw = angVel ? d + 10 * (size_t)n : nullptr,
+         *df = force ? d + 13 * (size_t)n : nullptr, *dt_ = torque ? d + 16 * (size_t)n : nullptr;
+  k_gather_state<<<nblk(n, 256), 256, 0, h->stream>>>(h->S(), n, dpos, dori, dvel, dw, df, dt_);
+  auto D2H = [&](double* dst, double* src, size_t cnt) { if (dst) CK(cudaMemcpyAsync(dst, src, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); };
+  D2H(pos, dpos, 3 * (size_t)n); D2H(ori, dori, 4 * (size_t)n); D2H(vel, dvel, 3 * (size_t)n); D2H(angVel, dw, 3 * (size_t)n); D2H(force, df, 3 * (size_t)n); D2H(torque, dt_, 3 * (size_t)n);
+  CK(cudaStreamSynchronize(h->stream));
+}
+int wdem_download_state(wdem_handle h, double* pos, double* ori, double* vel, double* angVel) { return guarded(h, [&] { downloadInto(h, pos, ori, vel, angVel, nullptr, nullptr); }); }
+int wdem_download_forces(wdem_handle h, double* force, double* torque) { return guarded(h, [&] { downloadInto(h, nullptr, nullptr, nullptr, nullptr, force, torque); }); }
+
+int wdem_kinetic_energy(wdem_handle h, double* ek) {
+  return guarded(h, [&] {
+    const int n = h->n; double e = 0;
+    if (n) {
+      const int nb = nblk(n, 256); h->blk.ensure((size_t)nb * 7, h->bytes);
+      k_ekin<<<nb, 256, 0, h->stream>>>(h->S(), n, h->blk.p);
+      auto hb = d2h(h->blk.p, nb, h->stream);
+      for (double v : hb) e += v;
+    }
+    *ek = e;
+  });
+}
+
+int wdem_step_e2e(wdem_handle h, int64_t nsteps, const double* pos_in, const double* vel_in, const double* angVel_in, double* pos_out, double* vel_out, double* ek_out,
+                  wdem_stats* stats) {
+  int rc = wdem_set_state(h, 0, h ? h->n : 0, pos_in, vel_in, angVel_in);
+  if (rc) return rc;
+  rc = wdem_step(h, nsteps, stats);
+  if (rc) return rc;
+  rc = wdem_download_state(h, pos_out, nullptr, vel_out, nullptr);
+  if (rc) return rc;
+  if (ek_out) rc = wdem_kinetic_energy(h, ek_out);
+  return rc;
+}
+
+int64_t wdem_num_contacts(wdem_handle h, int realOnly) {
+  long long nr = 0, na = 0;
+  int rc = guarded(h, [&] { countContacts(h, nr, na); });
+  if (rc) return -1;
+  return realOnly ? nr : na;
+}
+
+int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t* ids, int32_t* cellDist, int32_t* real, double* uN, double* forceLocal, double* torqueLocal,
+                               double* trsf, double* contPt, double* phys, int32_t* stepCreated) {
+  int64_t nOut = 0;
+  int rc = guarded(h, [&] {
+    const long long nC = h->nC; if (nC == 0) return;
+    cudaStream_t st = h->stream; ContactStore& cs = h->con[h->curC];
+    auto pair = d2h(cs.pair.p, nC, st); auto flags = d2h(cs.flags.p, nC, st); auto sid = d2h(h->S().id, h->n, st);
+    std::vector<std::vector<double>> t(6), f(3), ph(5), tq(3);
+    for (int k = 0; k < 6; k++) t[k] = d2h(cs.t[k].p, nC, st);
+    for (int k = 0; k < 3; k++) f[k] = d2h(cs.fl[k].p, nC, st);
+    const bool hertz = h->cfg.law == WDEM_LAW_HERTZ_DMT, rolling = (h->cfg.relRollStiff > 0. && h->cfg.rollTanPhi > 0.);
+    for (int k = 0; k < (hertz ? 5 : 3); k++) ph[k] = d2h(cs.ph[k].p, nC, st);
+    if (rolling) for (int k = 0; k < 3; k++) tq[k] = d2h(cs.tq[k].p, nC, st);
+    auto cp = d2h(cs.cp.p, nC, st); auto sc = d2h(cs.stepCreated.p, nC, st);
+    struct Row { uint64_t key; long long c; };
+    std::vector<Row> rows; rows.reserve(nC);
+    for (long long c = 0; c < nC; c++) {
+      if (flags[c] & CF_DEAD) continue;
+      if (realOnly && !(flags[c] & CF_REAL)) continue;
+      int a = (cf_kind(flags[c]) == KIND_SS) ? sid[pair[c].x] : h->hWalls[pair[c].x].id, b = sid[pair[c].y];
+      rows.push_back(Row{((uint64_t)(uint32_t)a << 32) | (uint32_t)b, c});
+    }
+    std::sort(rows.begin(), rows.end(), [](const Row& x, const Row& y) { return x.key < y.key; });
+    nOut = (int64_t)rows.size();
+    if (cap < nOut) { if (cap > 0) throw EngErr{"wdem_download_contacts: capacity too small", WDEM_ERR_INVALID}; return; }
+    for (int64_t i = 0; i < nOut; i++) {
+      const long long c = rows[i].c; const bool isReal = flags[c] & CF_REAL;
+      if (ids) { ids[2 * i] = (int32_t)(rows[i].key >> 32); ids[2 * i + 1] = (int32_t)(rows[i].key & 0xFFFFFFFFu); }
+      if (cellDist) { cellDist[3 * i] = cellDist[3 * i + 1] = cellDist[3 * i + 2] = 0; }
+      if (real) real[i] = isReal;
+      if (uN) uN[i] = isReal ? cp[c].w : NAN;
+      if (forceLocal) for (int k = 0; k < 3; k++) forceLocal[3 * i + k] = isReal ? f[k][c] : 0.;
+      if (torqueLocal) for (int k = 0; k < 3; k++) torqueLocal[3 * i + k] = (isReal && rolling) ? tq[k][c] : 0.;
+      if (trsf) {
+        d3 c0 = mk3(t[0][c], t[1][c], t[2][c]), c1 = mk3(t[3][c], t[4][c], t[5][c]); d3 c2 = cross(c0, c1);
+        double* o = trsf + 9 * i;
+        if (isReal) { o[0] = c0.x; o[1] = c0.y; o[2] = c0.z; o[3] = c1.x; o[4] = c1.y; o[5] = c1.z; o[6] = c2.x; o[7] = c2.y; o[8] = c2.z; }
+        else for (int k = 0; k < 9; k++) o[k] = (k % 4 == 0) ? 1. : 0.;
+      }
+      if (contPt) { contPt[3 * i] = isReal ? cp[c].x : NAN; contPt[3 * i + 1] = isReal ? cp[c].y : NAN; contPt[3 * i + 2] = isReal ? cp[c].z : NAN; }
+      if (phys) {
+        if (!isReal) { phys[3 * i] = phys[3 * i + 1] = phys[3 * i + 2] = NAN; }
+        else if (!hertz) { phys[3 * i] = ph[0][c]; phys[3 * i + 1] = ph[1][c]; phys[3 * i + 2] = ph[2][c]; }
+        else { double u_ = cp[c].w; phys[3 * i] = (3 / 2.) * ph[0][c] * std::sqrt(-u_); phys[3 * i + 1] = ph[1][c] * std::sqrt(u_ < 0 ? -u_ : 0); phys[3 * i + 2] = ph[2][c]; }
+      }
+      if (stepCreated) stepCreated[i] = sc[c];
+    }
+  });
+  return rc ? -1 : nOut;
+}
+
+int wdem_crit_dt(wdem_handle h, double* dt) { return guarded(h, [&] { *dt = h->pwaveDt; }); }
+int wdem_get_scalars(wdem_handle h, double* dt, double* time, int64_t* step, double* verletDist, int64_t* nFullRuns) {
+  return guarded(h, [&] { if (dt) *dt = h->dt; if (time) *time = h->time; if (step) *step = h->step; if (verletDist) *verletDist = h->verletDist; if (nFullRuns) *nFullRuns = h->nFullRuns; });
+}
+int wdem_device_info(wdem_handle h, int64_t* bytes, void** stream) { return guarded(h, [&] { if (bytes) *bytes = h->bytes; if (stream) *stream = (void*)h->stream; }); }
+
+}  // extern "C"

@@ -1,0 +1,795 @@
+// wdem_kernels.cuh — hand-written sm_100a kernels of the DEM hot path (float64, HBM/L2-bound; no tensor cores).
+// Reference semantics are cited per function as file:line relative to the woodem/woo tree.
+#pragma once
+#include <stdint.h>
+#include "wdem_math.cuh"
+
+namespace wd {
+
+// DemData flags (src/dem/Particle.hpp:198-203)
+enum { F_DOF_ALL = 63, F_GRAVITY_SKIP = 512, F_DAMPING_SKIP = 2048 };
+// contact flags
+enum { CF_REAL = 1, CF_ORPHAN = 2, CF_DEAD = 4, CF_CLAIMED = 8, CF_KIND_SHIFT = 4, CF_KIND_MASK = 3u << 4 };
+__host__ __device__ __forceinline__ int cf_kind(uint32_t f) { return (int)((f >> 4) & 3u); }
+enum { KIND_SS = 0, KIND_WS = 1, KIND_FS = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// Device views
+// ------------------------------------------------------------------------------------------------
+struct Spheres {          // one slot per sphere; slots are re-ordered by grid cell at every collider full run
+  double4* posr;          // x,y,z,radius      (32 B: one sector per gather)
+  double4* velm;          // vx,vy,vz,mass
+  double4* angi;          // wx,wy,wz,inertia
+  double4* ori;           // quaternion x,y,z,w
+  double *fx, *fy, *fz, *tx, *ty, *tz;   // force / torque (streamed only)
+  double *lx, *ly, *lz;   // position at the last collider full run (Aabb::nodeLastPos)
+  uint32_t* flags;        // DemData.flags
+  uint32_t* mask;         // Particle.mask
+  int32_t* mat;           // material index
+  int32_t* id;            // Particle.id
+  int32_t* up;            // upload index (for downloads)
+};
+
+struct Wall { double pos[3]; double vel[3]; int32_t axis, sense; uint32_t mask; int32_t mat; int32_t id; int32_t pad; };
+struct Material { int32_t kind; int32_t pad; double density, young, ktDivKn, tanPhi, surfEnergy, alpha; };
+
+struct Contacts {         // SoA planes, one entry per candidate pair (real or potential)
+  int2* pair;             // SS: (slotA, slotB) with id[slotA] < id[slotB]; WS: (wall index, slot); FS: (facet index, slot)
+  uint32_t* flags;
+  int32_t* stepCreated;
+  int32_t *cdx, *cdy, *cdz;            // Contact.cellDist (periodic only)
+  double *t0x, *t0y, *t0z, *t1x, *t1y, *t1z;  // L6Geom.trsf columns 0 and 1 (column 2 = c0 x c1, recomputed bit-identically)
+  double4* cp;            // contact point xyz (CGeom.node.pos), w = uN
+  double *fn, *ft0, *ft1; // CPhys.force in the local frame
+  double* ph[5];          // linear: kn, kt, tanPhi ; Hertz: kn0=K*sqrt(R), kt0, tanPhi, alpha_sqrtMK, Fna=4*pi*R*gamma
+  double *tq0, *tq1, *tq2;  // CPhys.torque (only with rolling/twisting resistance)
+  double4* Fg;            // global force on pA (xyz), w = 1 if the contact is real in this step else 0
+  double4* Tg;            // global contact torque on pA (rolling resistance only)
+};
+
+struct StepU {            // per-step uniforms
+  double dt, damping; d3 gravity; int hasGravity, reset; double maxD2;
+  int periodic, homoDeform;
+  m33 hSize;              // Cell.hSize (intrShiftPos)
+  m33 shiftVelM;          // gradV*pprevHsize (GRADV2) or gradV*hSize (VEL, VEL_2ND) or 0  (Cell::intrShiftVel)
+  m33 gradV, nextGradV, dGradV, midGradV, ImLL4hInv, IpLL4h, LmL; d3 spinVec, deltaSpinVec;
+  long long step; int renormNow; int noRatch;
+  double absDistFactor;
+  int law; int noSlip, noBreak, noFrict, noAttraction; int rolling; double relRollStiff, relTwistStiff, rollTanPhi;
+  double poisson, en, viscAlpha;  // viscAlpha = -sqrt(5) ln(en)/sqrt(ln(en)^2+pi^2), host-computed (Hertz.cpp:69)
+};
+
+struct Counters { unsigned long long nReal, nPotEval, nCreated, nBroken; int dirty; int error; int errA, errB; };
+enum { ERR_NONE = 0, ERR_NAN_FORCE = 1, ERR_NAN_POS = 2, ERR_NO_PHYS = 3, ERR_SCHWARZ = 4, ERR_FACET_IMPOSSIBLE = 5, ERR_AMBIGUOUS_PERI = 6 };
+
+__device__ __forceinline__ double signd(double f) { return f < 0 ? -1. : (f > 0 ? 1. : 0.); }  // Mathr::Sign (Math.hpp:145)
+
+// ------------------------------------------------------------------------------------------------
+// Leapfrog::run, spherical branch (src/dem/Leapfrog.cpp:104-255; helpers :33-48, :258-297) fused with the
+// Verlet-distance dirtiness test of AabbCollider::aabbIsDirty (src/dem/Collision.cpp:80-123).
+// Streaming kernel: one thread per sphere.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_leapfrog(Spheres S, int n, StepU u, Counters* cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 pr = S.posr[i], vm = S.velm[i], ai = S.angi[i], qo = S.ori[i];
+  const uint32_t fl = S.flags[i];
+  d3 f = mk3(S.fx[i], S.fy[i], S.fz[i]);
+  d3 t = mk3(S.tx[i], S.ty[i], S.tz[i]);
+  d3 pos = xyz(pr), vel = xyz(vm), w = xyz(ai);
+  const double mass = vm.w, inertia = ai.w, dt = u.dt;
+  const bool blockedAll = (fl & F_DOF_ALL) == F_DOF_ALL, blockedNone = (fl & F_DOF_ALL) == 0;
+  const bool damp = (u.damping != 0. && !(fl & F_DAMPING_SKIP));
+  d3 linAccel = mk3(0, 0, 0), angAccel = mk3(0, 0, 0);
+  if (!blockedAll) {
+    if (blockedNone) linAccel = f / mass;                                  // computeAccel :37-42
+    else {
+      if (!(fl & 1u)) linAccel.x += f.x / mass;
+      if (!(fl & 2u)) linAccel.y += f.y / mass;
+      if (!(fl & 4u)) linAccel.z += f.z / mass;
+    }
+    d3 pfv, pfw;
+    if (u.periodic) {                                                      // Cell::pprevFluctVel / pprevFluctAngVel (Cell.cpp:36-57)
+      if (u.homoDeform == 2 || u.homoDeform == 3) pfv = vel - mulMV(u.gradV, pos);
+      else if (u.homoDeform == 4) pfv = vel - mulMV(u.gradV, pos - (dt / 2) * vel);
+      else pfv = vel;
+      pfw = (u.homoDeform == 4) ? w - u.spinVec : w;
+    } else { pfv = vel; pfw = w; }
+    if (damp) {                                                            // nonviscDamp2nd :33-35
+      linAccel.x *= 1 - u.damping * signd(f.x * (pfv.x + 0.5 * dt * linAccel.x));
+      linAccel.y *= 1 - u.damping * signd(f.y * (pfv.y + 0.5 * dt * linAccel.y));
+      linAccel.z *= 1 - u.damping * signd(f.z * (pfv.z + 0.5 * dt * linAccel.z));
+    }
+    if (u.periodic && u.homoDeform == 4) vel = mulMV(u.ImLL4hInv, (mulMV(u.LmL, pos) + mulMV(u.IpLL4h, vel)) + linAccel * dt);
+    else vel = vel + dt * linAccel;
+    if (inertia != 0.) {
+      if (blockedNone) angAccel = mk3(t.x / inertia, t.y / inertia, t.z / inertia);
+      else {
+        if (!(fl & 8u)) angAccel.x += t.x / inertia;
+        if (!(fl & 16u)) angAccel.y += t.y / inertia;
+        if (!(fl & 32u)) angAccel.z += t.z / inertia;
+      }
+      if (damp) {
+        angAccel.x *= 1 - u.damping * signd(t.x * (pfw.x + 0.5 * dt * angAccel.x));
+        angAccel.y *= 1 - u.damping * signd(t.y * (pfw.y + 0.5 * dt * angAccel.y));
+        angAccel.z *= 1 - u.damping * signd(t.z * (pfw.z + 0.5 * dt * angAccel.z));
+      }
+      w = w + dt * angAccel;
+      if (u.periodic && u.homoDeform == 4) w = w - u.deltaSpinVec;
+    }
+  } else if (u.periodic && u.homoDeform == 4) vel = mulMV(u.ImLL4hInv, mulMV(u.LmL, pos) + mulMV(u.IpLL4h, vel));
+  if (u.periodic && u.homoDeform != 4) {                                   // applyPeriodicCorrections :258-273
+    if (u.homoDeform == 2 || u.homoDeform == 3) {
+      if (u.homoDeform == 3) vel = vel + mulMV(u.midGradV, vel - (dt / 2.) * linAccel) * dt;
+      vel = vel + mulMV(u.dGradV, pos);
+    } else if (u.homoDeform == 1) pos = pos + mulMV(u.nextGradV, pos) * dt;
+  }
+  pos = pos + vel * dt;                                                    // leapfrogTranslate :275-278
+  // leapfrogSphericalRotate :280-297 (orientation of a sphere feeds no contact functor: tolerance-level parity)
+  if (w.x != 0. || w.y != 0. || w.z != 0.) {
+    double angle = nrm(w); d3 ax = w / angle;
+    double ha = 0.5 * (angle * dt), sn, cs;
+    sincos(ha, &sn, &cs);
+    double qw = cs, qx = sn * ax.x, qy = sn * ax.y, qz = sn * ax.z;
+    double ow = qo.w, ox = qo.x, oy = qo.y, oz = qo.z;
+    qo.w = qw * ow - qx * ox - qy * oy - qz * oz;
+    qo.x = qw * ox + qx * ow + qy * oz - qz * oy;
+    qo.y = qw * oy + qy * ow + qz * ox - qx * oz;
+    qo.z = qw * oz + qz * ow + qx * oy - qy * ox;
+  }
+  {
+    double nn = sqrt(((qo.x * qo.x + qo.y * qo.y) + qo.z * qo.z) + qo.w * qo.w);
+    qo.x /= nn; qo.y /= nn; qo.z /= nn; qo.w /= nn;
+  }
+  S.posr[i] = make_double4(pos.x, pos.y, pos.z, pr.w);
+  S.velm[i] = make_double4(vel.x, vel.y, vel.z, mass);
+  S.angi[i] = make_double4(w.x, w.y, w.z, inertia);
+  S.ori[i] = qo;
+  // Verlet test (Collision.cpp:113-121): d2 > maxD2 strictly
+  d3 dl = mk3(S.lx[i], S.ly[i], S.lz[i]) - pos;
+  double d2 = fmax(0., sqn(dl));
+  if (d2 > u.maxD2) cnt->dirty = 1;
+  if (!(d2 == d2)) { cnt->dirty = 1; cnt->error = ERR_NAN_POS; cnt->errA = S.id[i]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared tail of the three Cg2 functors: Cg2_Any_Any_L6Geom__Base::handleSpheresLikeContact
+// (src/dem/L6Geom.cpp:49-216, approxMask==0) -> Cp2 (once) -> Law2 -> global force output.
+// ------------------------------------------------------------------------------------------------
+struct MatPair { double young1, young2, ktDivKn1, ktDivKn2, tanPhi1, tanPhi2, surf1, surf2, alpha1, alpha2; int kind1, kind2; };
+
+template <int LAW>
+__device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uint32_t fl, const StepU& u, d3 pos1, d3 vel1, d3 w1, d3 pos2,
+                                             d3 vel2, d3 w2, d3 shiftVel2, d3 normal, d3 contPt, double uN, double r1, double r2,
+                                             const Material* mats, int matA, int matB, double massA, double massB, Counters* cnt,
+                                             int idA, int idB, unsigned& nRealOut) {
+  const bool wasReal = fl & CF_REAL;
+  d3 c0, c1, c2, gvel = mk3(0, 0, 0), gang = mk3(0, 0, 0);
+  double kn, kt, tanPhi, p3 = 0, p4 = 0, ftA = 0, ftB = 0, tq0 = 0, tq1 = 0, tq2 = 0;
+  if (!wasReal) {
+    // ---- create geometry (L6Geom.cpp:51-70) + L6Geom::setInitialLocalCoords (L6Geom.cpp:25-36)
+    c0 = normal;
+    d3 ly = cross(c0, fabs(c0.y) < fabs(c0.z) ? mk3(0, 1, 0) : mk3(0, 0, 1));
+    ly = ly - c0 * dot(ly, c0);
+    ly = ly / nrm(ly);
+    c1 = ly;
+    c2 = cross(c0, c1);
+    // iniLensTouch=true: lens=(|r1|,|r2|); contA = pi*min(r)^2 (or the positive one)
+    double l0 = fabs(r1), l1 = fabs(r2);
+    double rr = (r1 > 0 && r2 > 0) ? fmin(r1, r2) : (r1 > 0 ? r1 : r2);
+    double A = M_PI * (rr * rr);
+    // ---- Cp2 (ContactLoop.cpp:179-181)
+    const Material m1 = mats[matA], m2 = mats[matB];
+    if (LAW == 0) {  // Cp2_FrictMat_FrictPhys::updateFrictPhys (FrictMat.cpp:20-44)
+      kn = 1 / (1 / (m1.young * A / l0) + 1 / (m2.young * A / l1));
+      kt = .5 * (m1.ktDivKn + m2.ktDivKn) * kn;
+      tanPhi = fmin(m1.tanPhi, m2.tanPhi);
+      C.ph[0][c] = kn; C.ph[1][c] = kt; C.ph[2][c] = tanPhi;
+    } else {         // Cp2_HertzMat_HertzPhys::go (Hertz.cpp:34-77)
+      if (m1.kind != 1 || m2.kind != 1) { cnt->error = ERR_NO_PHYS; cnt->errA = idA; cnt->errB = idB; return; }
+      const double nu1 = u.poisson, nu2 = u.poisson, E1 = m1.young, E2 = m2.young;
+      double K = (4 / 3.) * 1. / ((1 - nu1 * nu1) / E1 + (1 - nu2 * nu2) / E2);
+      double R = 1. / (1. / l0 + 1. / l1);
+      double kn0 = K * sqrt(R);
+      double gamma = fmin(m1.surfEnergy, m2.surfEnergy);
+      double alpha = .5 * (m1.alpha + m2.alpha);
+      if (!(alpha == 0. || gamma == 0.)) { cnt->error = ERR_SCHWARZ; cnt->errA = idA; cnt->errB = idB; return; }
+      double G1 = E1 / (2 * (1 + nu1)), G2 = E2 / (2 * (1 + nu2));
+      double G = .5 * (G1 + G2);
+      double nu = .5 * (nu1 + nu2);
+      double kt0 = 2 * sqrt(4 * R) * G / (2 - nu);
+      tanPhi = fmin(m1.tanPhi, m2.tanPhi);
+      double asmk = 0.0;
+      if (u.en > 0 && u.en < 1.) {
+        double mbar = (massA <= 0 && massB > 0) ? massB : ((massA > 0 && massB <= 0) ? massA : (massA * massB) / (massA + massB));
+        asmk = fmax(0., u.viscAlpha * sqrt(mbar * kn0));
+      }
+      // ph[4] = Fna = 4*pi*R*gamma (Hertz.cpp:113) when alpha==0; alpha!=0 implies gamma==0 here (Fna=0) and is flagged by -1:
+      // the noAttraction clamp applies only when alpha==0 (Hertz.cpp:177)
+      kn = kn0; kt = kt0; p3 = asmk; p4 = (alpha == 0.) ? (4 * M_PI * R * gamma) : -1.0;
+      C.ph[0][c] = kn0; C.ph[1][c] = kt0; C.ph[2][c] = tanPhi; C.ph[3][c] = asmk; C.ph[4][c] = p4;
+    }
+    C.stepCreated[c] = (int)u.step;
+    atomicAdd(&cnt->nCreated, 1ull);
+  } else {
+    // ---- update geometry (L6Geom.cpp:72-216)
+    const d3 prevN = mk3(C.t0x[c], C.t0y[c], C.t0z[c]);
+    const d3 prev1 = mk3(C.t1x[c], C.t1y[c], C.t1z[c]);
+    const double4 pcp = C.cp[c];
+    const d3 prevContPt = xyz(pcp);
+    const double dt = u.dt;
+    d3 normRotVec = cross(prevN, normal);
+    d3 midN = .5 * (prevN + normal);
+    double nm = nrm(midN);
+    if (nm == 0) midN = normal; else midN = midN / nm;
+    d3 normTwistVec = midN * dt * .5 * dot(midN, w1 + w2);
+    d3 rot = normRotVec + normTwistVec;
+    d3 mid1 = prev1 - cross(prev1, rot) / 2.;
+    d3 mid2 = cross(midN, mid1);
+    c0 = normal;
+    c1 = prev1 - cross(mid1, rot);
+    c2 = cross(c0, c1);
+    if (u.renormNow) {                                                     // L6Geom.cpp:124-129
+      c0 = c0 / nrm(c0);
+      c1 = c1 - c0 * dot(c1, c0);
+      c1 = c1 / nrm(c1);
+      c2 = cross(c0, c1);
+    }
+    d3 midContPt = .5 * (prevContPt + contPt);
+    d3 midPos1 = pos1 - (dt / 2.) * vel1;
+    d3 v2s = vel2 + shiftVel2;
+    d3 midPos2 = pos2 - (dt / 2.) * v2s;
+    d3 c1x = (u.noRatch && r1 > 0) ? (r1 * midN) : (midContPt - midPos1);
+    d3 c2x = (u.noRatch && r2 > 0) ? ((-r2) * midN) : (midContPt - midPos2);
+    d3 relVel = (v2s + cross(w2, c2x)) - (vel1 + cross(w1, c1x));
+    gvel = mk3(dot(midN, relVel), dot(mid1, relVel), dot(mid2, relVel));
+    if (u.rolling) { d3 dw = w2 - w1; gang = mk3(dot(midN, dw), dot(mid1, dw), dot(mid2, dw)); }
+    kn = C.ph[0][c]; kt = C.ph[1][c]; tanPhi = C.ph[2][c];
+    if (LAW == 1) { p3 = C.ph[3][c]; p4 = C.ph[4][c]; }
+    ftA = C.ft0[c]; ftB = C.ft1[c];
+    // CPhys.torque is zeroed at the top of the law every step (IdealElPl.cpp:43), so it carries no history
+  }
+  // ---- Law2
+  double Fn; bool keep = true;
+  if (LAW == 0) {  // Law2_L6Geom_FrictPhys_IdealElPl::go (IdealElPl.cpp:15-125), iniEqlb/trackEnergy unsupported
+    if (uN > 0 && !u.noBreak) keep = false;
+    else {
+      Fn = kn * uN;
+      if (u.noFrict || tanPhi == 0.) { ftA = 0; ftB = 0; }
+      else {
+        ftA += (u.dt * kt) * gvel.y; ftB += (u.dt * kt) * gvel.z;
+        double maxFt = fabs(Fn) * tanPhi;
+        double sq = ftA * ftA + ftB * ftB;
+        if (sq > maxFt * maxFt && !u.noSlip) {
+          double FtNorm = sqrt(sq);
+          double ratio = maxFt / FtNorm;
+          if (FtNorm == 0.) ratio = 0.;
+          ftA *= ratio; ftB *= ratio;
+        }
+        if (!(Fn == Fn) || !(ftA == ftA) || !(ftB == ftB)) { cnt->error = ERR_NAN_FORCE; cnt->errA = idA; cnt->errB = idB; }
+      }
+      if (u.rolling) {                                                     // IdealElPl.cpp:94-123
+        double charLen = fabs(r1) + fabs(r2);
+        double kr = kn * charLen;
+        if (u.relTwistStiff > 0) {
+          tq0 += u.dt * u.relTwistStiff * kr * gang.x;
+          double maxTt = fabs(Fn * u.rollTanPhi * charLen);
+          if (fabs(tq0) > maxTt) tq0 = copysign(maxTt, tq0);
+        }
+        tq1 += (u.dt * kr) * gang.y; tq2 += (u.dt * kr) * gang.z;
+        double maxTr = fmax(0., fabs(Fn) * u.rollTanPhi * charLen);
+        double sq = tq1 * tq1 + tq2 * tq2;
+        if (sq > maxTr * maxTr) { double TrNorm = sqrt(sq); double ratio = maxTr / TrNorm; if (TrNorm == 0.) ratio = 0.; tq1 *= ratio; tq2 *= ratio; }
+      }
+    }
+  } else {         // Law2_L6Geom_HertzPhys_DMT::go, Hertz/DMT branch (Hertz.cpp:85-114,170-210)
+    const double kn0 = kn, kt0 = kt, asmk = p3;
+    const bool alphaZero = !(p4 < 0);
+    const double Fna = alphaZero ? p4 : 0.;
+    if (uN > 0) keep = false;
+    else {
+      double s = sqrt(-uN);
+      double Fne = -kn0 * ((s * s) * s);
+      double eta = (asmk > 0 ? asmk * sqrt(sqrt(fmax(-uN, 0.))) : 0.);
+      double Fnv = eta * gvel.x;
+      if (alphaZero && u.noAttraction && Fne + Fnv > 0) Fnv = -Fne;
+      Fn = Fne + Fna + Fnv;
+      double ktc = kt0 * sqrt(uN < 0 ? -uN : 0);
+      ftA += (u.dt * ktc) * gvel.y; ftB += (u.dt * ktc) * gvel.z;
+      double maxFt = fabs(fmin(0., Fn) * tanPhi);
+      double sq = ftA * ftA + ftB * ftB;
+      if (sq > maxFt * maxFt) { double FtNorm = sqrt(sq); double ratio = maxFt / FtNorm; ftA *= ratio; ftB *= ratio; }
+      else { ftA += eta * gvel.y; ftB += eta * gvel.z; }
+      if (!(Fn == Fn) || !(ftA == ftA) || !(ftB == ftB)) { cnt->error = ERR_NAN_FORCE; cnt->errA = idA; cnt->errB = idB; }
+    }
+  }
+  if (!keep) {
+    // ContactContainer::requestRemoval -> Contact::reset (ContactContainer.cpp:164-174): geom/phys dropped; the pair stays a potential
+    // contact while its (frozen) AABBs overlap, i.e. unless it is an orphan (InsertionSortCollider.hpp:213-218)
+    uint32_t nf = (fl & ~CF_REAL) | ((fl & CF_ORPHAN) ? CF_DEAD : 0);
+    C.flags[c] = nf;
+    C.Fg[c] = make_double4(0, 0, 0, 0);
+    if (wasReal) atomicAdd(&cnt->nBroken, 1ull);
+    return;
+  }
+  // ---- store state
+  C.t0x[c] = c0.x; C.t0y[c] = c0.y; C.t0z[c] = c0.z;
+  C.t1x[c] = c1.x; C.t1y[c] = c1.y; C.t1z[c] = c1.z;
+  C.cp[c] = make_double4(contPt.x, contPt.y, contPt.z, uN);
+  C.fn[c] = Fn; C.ft0[c] = ftA; C.ft1[c] = ftB;
+  if (!wasReal) C.flags[c] = fl | CF_REAL;
+  // ---- Contact::getForceTorqueBranch (Contact.cpp:24-35): F = ori * phys.force, ori = Quaternionr(trsf)
+  q4 q = quatFromCols(c0, c1, c2);
+  d3 Fglob = quatRotate(q, mk3(Fn, ftA, ftB));
+  C.Fg[c] = make_double4(Fglob.x, Fglob.y, Fglob.z, 1.0);
+  if (u.rolling) {
+    C.tq0[c] = tq0; C.tq1[c] = tq1; C.tq2[c] = tq2;
+    d3 Tg = (tq0 == 0. && tq1 == 0. && tq2 == 0.) ? mk3(0, 0, 0) : quatRotate(q, mk3(tq0, tq1, tq2));
+    C.Tg[c] = make_double4(Tg.x, Tg.y, Tg.z, 0);
+  }
+  nRealOut = 1;
+}
+
+__device__ __forceinline__ void block_count(unsigned isReal, unsigned evald, Counters* cnt) {
+  unsigned r = __reduce_add_sync(0xffffffffu, isReal), e = __reduce_add_sync(0xffffffffu, evald);
+  if ((threadIdx.x & 31) == 0) { if (r) atomicAdd(&cnt->nReal, (unsigned long long)r); if (e) atomicAdd(&cnt->nPotEval, (unsigned long long)e); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ContactLoop::run body for Sphere+Sphere (src/dem/ContactLoop.cpp:134-216) with Cg2_Sphere_Sphere_L6Geom::go
+// (src/dem/Sphere.cpp:92-117) fused with Cp2 and Law2.  One thread per candidate pair.
+// ------------------------------------------------------------------------------------------------
+template <int LAW>
+__device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint32_t fl, const Spheres& S, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
+  const int2 pr = C.pair[c];
+  const double4 pa = S.posr[pr.x], pb = S.posr[pr.y];
+  d3 shift2 = mk3(0, 0, 0), shiftVel2 = mk3(0, 0, 0);
+  if (u.periodic) {
+    d3 cd = mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]);
+    shift2 = mulMV(u.hSize, cd); shiftVel2 = mulMV(u.shiftVelM, cd);
+  }
+  const d3 p1 = xyz(pa), p2 = xyz(pb) + shift2;
+  const double r1 = pa.w, r2 = pb.w;
+  d3 relPos = p2 - p1;
+  double d2 = sqn(relPos);
+  double rs = u.absDistFactor * (r1 + r2);
+  double unDistSq = d2 - rs * rs;
+  if (unDistSq > 0 && !(fl & CF_REAL)) return;
+  double dist = sqrt(d2);
+  double uN = dist - (r1 + r2);
+  d3 normal = relPos / dist;
+  d3 contPt = p1 + (r1 + 0.5 * uN) * normal;
+  d3 v1 = mk3(0, 0, 0), v2 = v1, w1 = v1, w2 = v1; double mA = 0, mB = 0;
+  if (fl & CF_REAL) {
+    double4 a = S.velm[pr.x], b = S.velm[pr.y]; v1 = xyz(a); v2 = xyz(b);
+    a = S.angi[pr.x]; b = S.angi[pr.y]; w1 = xyz(a); w2 = xyz(b);
+  } else if (LAW == 1) { mA = S.velm[pr.x].w; mB = S.velm[pr.y].w; }
+  int matA = 0, matB = 0;
+  if (!(fl & CF_REAL)) { matA = S.mat[pr.x]; matB = S.mat[pr.y]; }
+  contact_tail<LAW>(C, c, fl, u, p1, v1, w1, p2, v2, w2, shiftVel2, normal, contPt, uN, r1, r2, mats, matA, matB, mA, mB, cnt, S.id[pr.x], S.id[pr.y], isReal);
+}
+
+template <int LAW>
+__global__ void __launch_bounds__(128) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt) {
+  long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned isReal = 0, evald = 0;
+  if (c < first + n) {
+    const uint32_t fl = C.flags[c];
+    if (!(fl & CF_DEAD)) { evald = 1; contact_ss<LAW>(C, c, fl, S, mats, u, cnt, isReal); }
+  }
+  block_count(isReal, evald, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wall+Sphere: Cg2_Wall_Sphere_L6Geom::go (src/dem/Wall.cpp:50-84)
+// ------------------------------------------------------------------------------------------------
+template <int LAW>
+__device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint32_t fl, const Spheres& S, const Wall* walls, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
+  const int2 pr = C.pair[c];
+  const Wall W = walls[pr.x];
+  const double4 pb = S.posr[pr.y];
+  d3 shift2 = mk3(0, 0, 0), shiftVel2 = mk3(0, 0, 0);
+  if (u.periodic) {
+    d3 cd = mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]);
+    shift2 = mulMV(u.hSize, cd); shiftVel2 = mulMV(u.shiftVelM, cd);
+  }
+  const d3 wallPos = mk3(W.pos[0], W.pos[1], W.pos[2]);
+  const d3 spherePos = xyz(pb) + shift2;
+  const double radius = pb.w; const int ax = W.axis;
+  double dist = comp(spherePos, ax) - comp(wallPos, ax);
+  if (!(fl & CF_REAL) && fabs(dist) > radius) return;
+  d3 contPt = spherePos; setc(contPt, ax, comp(wallPos, ax));
+  d3 normal = mk3(0, 0, 0);
+  double nax;
+  if (W.sense == 0) {
+    if (!(fl & CF_REAL)) nax = dist > 0 ? 1. : -1.;
+    else nax = (ax == 0 ? C.t0x[c] : (ax == 1 ? C.t0y[c] : C.t0z[c]));
+  } else nax = (W.sense == 1 ? 1. : -1.);
+  setc(normal, ax, nax);
+  double uN = nax * dist - radius;
+  d3 v2 = mk3(0, 0, 0), w2 = v2; double mB = 0;
+  if (fl & CF_REAL) { double4 b = S.velm[pr.y]; v2 = xyz(b); b = S.angi[pr.y]; w2 = xyz(b); }
+  else if (LAW == 1) mB = S.velm[pr.y].w;
+  int matB = (fl & CF_REAL) ? 0 : S.mat[pr.y];
+  contact_tail<LAW>(C, c, fl, u, wallPos, mk3(W.vel[0], W.vel[1], W.vel[2]), mk3(0, 0, 0), spherePos, v2, w2, shiftVel2, normal, contPt, uN, -radius, radius,
+                    mats, W.mat, matB, 0., mB, cnt, W.id, S.id[pr.y], isReal);
+}
+
+template <int LAW>
+__global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Material* mats, StepU u, Counters* cnt) {
+  long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned isReal = 0, evald = 0;
+  if (c < first + n) {
+    const uint32_t fl = C.flags[c];
+    if (!(fl & CF_DEAD)) { evald = 1; contact_ws<LAW>(C, c, fl, S, walls, mats, u, cnt, isReal); }
+  }
+  block_count(isReal, evald, cnt);
+}
+
+// Orphans: contacts that are real although their AABBs no longer overlap (the collider never removes a real contact,
+// InsertionSortCollider.cpp:78-113); rare, kept in a mixed-kind tail segment.
+template <int LAW>
+__global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Material* mats, StepU u, Counters* cnt) {
+  long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned isReal = 0, evald = 0;
+  if (c < first + n) {
+    const uint32_t fl = C.flags[c];
+    if (!(fl & CF_DEAD)) {
+      evald = 1;
+      const int kind = cf_kind(fl);
+      if (kind == KIND_SS) contact_ss<LAW>(C, c, fl, S, mats, u, cnt, isReal);
+      else if (kind == KIND_WS) contact_ws<LAW>(C, c, fl, S, walls, mats, u, cnt, isReal);
+    }
+  }
+  block_count(isReal, evald, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-particle force/torque: ContactLoop::applyForceUninodal + Contact::getForceTorqueBranch + DemData::addForceTorque
+// (ContactLoop.cpp:270-276, Contact.cpp:24-35, Particle.hpp:249) as a deterministic segmented reduction over the
+// particle's incidence row (ascending id of the other particle), fused with Leapfrog's force reset (Leapfrog.cpp:240-245).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 pr = S.posr[i];
+  const d3 pos = xyz(pr);
+  d3 F, T;
+  if (u.reset) {
+    const uint32_t fl = S.flags[i];
+    F = (u.hasGravity && !(fl & F_GRAVITY_SKIP)) ? (S.velm[i].w * u.gravity) : mk3(0, 0, 0);
+    T = mk3(0, 0, 0);
+  } else { F = mk3(S.fx[i], S.fy[i], S.fz[i]); T = mk3(S.tx[i], S.ty[i], S.tz[i]); }
+  const int e0 = rowStart[i], e1 = rowStart[i + 1];
+  for (int e = e0; e < e1; e++) {
+    const uint32_t ent = rowEntry[e];
+    const uint32_t c = ent >> 1;
+    const double4 fg = C.Fg[c];
+    if (fg.w == 0.) continue;
+    const double4 cp = C.cp[c];
+    d3 Fc = xyz(fg), xc;
+    if (ent & 1u) {  // this particle is pB: sign=-1, branch from pos+shift2
+      Fc = Fc * (-1.);
+      d3 p = pos;
+      if (u.periodic) p = pos + mulMV(u.hSize, mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]));
+      xc = xyz(cp) - p;
+    } else xc = xyz(cp) - pos;
+    d3 Tc = cross(xc, Fc);
+    if (u.rolling) { double4 tg = C.Tg[c]; d3 tt = xyz(tg); if (ent & 1u) tt = tt * (-1.); Tc = Tc + tt; }
+    F = F + Fc; T = T + Tc;
+  }
+  S.fx[i] = F.x; S.fy[i] = F.y; S.fz[i] = F.z;
+  S.tx[i] = T.x; S.ty[i] = T.y; S.tz[i] = T.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DynDt::nodalCritDtSq (src/dem/DynDt.cpp:16-58): per-sphere stiffness sums over real contacts -> min of 2*m/k.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, int law,
+                                              double* blockMin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double ret = INFINITY;
+  if (i < n) {
+    const uint32_t fl = S.flags[i];
+    if ((fl & F_DOF_ALL) != F_DOF_ALL) {
+      d3 ktr = mk3(0, 0, 0), krot = mk3(0, 0, 0);
+      const double myR = S.posr[i].w;
+      for (int e = rowStart[i]; e < rowStart[i + 1]; e++) {
+        const uint32_t ent = rowEntry[e]; const uint32_t c = ent >> 1;
+        const uint32_t cfl = C.flags[c];
+        if (!(cfl & CF_REAL)) continue;
+        d3 c0 = mk3(C.t0x[c], C.t0y[c], C.t0z[c]), c1 = mk3(C.t1x[c], C.t1y[c], C.t1z[c]);
+        d3 c2 = cross(c0, c1);
+        d3 nrmv = quatRotate(quatFromCols(c0, c1, c2), mk3(1, 0, 0));
+        d3 n2 = mk3(nrmv.x * nrmv.x, nrmv.y * nrmv.y, nrmv.z * nrmv.z);
+        double kn, kt;
+        if (law == 0) { kn = C.ph[0][c]; kt = C.ph[1][c]; }
+        else { double uN = C.cp[c].w; kn = (3 / 2.) * C.ph[0][c] * sqrt(-uN); kt = C.ph[1][c] * sqrt(uN < 0 ? -uN : 0); }
+        // lens[ix] (iniLensTouch): SS: own radius; WS/FS: the sphere's radius on both sides (L6Geom.cpp:61, Wall.cpp:82)
+        double len = myR;
+        if (cf_kind(cfl) == KIND_SS) { int2 pr = C.pair[c]; len = (ent & 1u) ? S.posr[pr.y].w : S.posr[pr.x].w; }
+        ktr = ktr + (n2 * (kn - kt) + mk3(kt, kt, kt));
+        krot = krot + (len * len) * kt * mk3(n2.y + n2.z, n2.z + n2.x, n2.x + n2.y);
+      }
+      const double mass = S.velm[i].w, inertia = S.angi[i].w;
+      if (ktr.x != 0 && mass > 0. && !(fl & 1u)) ret = fmin(ret, mass / fabs(ktr.x));
+      if (ktr.y != 0 && mass > 0. && !(fl & 2u)) ret = fmin(ret, mass / fabs(ktr.y));
+      if (ktr.z != 0 && mass > 0. && !(fl & 4u)) ret = fmin(ret, mass / fabs(ktr.z));
+      if (krot.x != 0 && inertia > 0. && !(fl & 8u)) ret = fmin(ret, inertia / fabs(krot.x));
+      if (krot.y != 0 && inertia > 0. && !(fl & 16u)) ret = fmin(ret, inertia / fabs(krot.y));
+      if (krot.z != 0 && inertia > 0. && !(fl & 32u)) ret = fmin(ret, inertia / fabs(krot.z));
+      ret = 2 * ret;
+    }
+  }
+  __shared__ double sm[256];
+  sm[threadIdx.x] = ret; __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sm[threadIdx.x] = fmin(sm[threadIdx.x], sm[threadIdx.x + s]); __syncthreads(); }
+  if (threadIdx.x == 0) blockMin[blockIdx.x] = sm[0];
+}
+
+// kinetic energy Σ ½ m v·v + ½ I ω·ω (aperiodic: DemData::getEk_any, Particle.cpp:247-265); per-block partial sums, fixed order
+__global__ void __launch_bounds__(256) k_ekin(Spheres S, int n, double* blockSum) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0;
+  if (i < n) { double4 v = S.velm[i], w = S.angi[i]; e = .5 * (v.w * sqn(xyz(v))); if (!isinf(w.w)) e += .5 * w.w * sqn(xyz(w)); }
+  __shared__ double sm[256];
+  sm[threadIdx.x] = e; __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0) blockSum[blockIdx.x] = sm[0];
+}
+
+// ================================================================================================
+// Broad phase (replaces InsertionSortCollider::run, src/dem/InsertionSortCollider.cpp:386-613): at every full run the set of
+// potential contacts is rebuilt as { (i,j) : enlarged AABBs overlap (closed intervals, spatialOverlap :67-73) and
+// Collider::mayCollide (Collision.cpp:21-43) } from a uniform grid over radix-sorted cell keys.
+// ================================================================================================
+struct Grid { double ox, oy, oz, inv; int nx, ny, nz; double cell; };
+
+__global__ void __launch_bounds__(256) k_bounds(const double4* __restrict__ posr, int n, double* blk /*7 per block*/) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[7] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0};
+  if (i < n) { double4 p = posr[i]; v[0] = v[3] = p.x; v[1] = v[4] = p.y; v[2] = v[5] = p.z; v[6] = p.w; }
+  __shared__ double sm[7][256];
+  for (int k = 0; k < 7; k++) sm[k][threadIdx.x] = v[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      for (int k = 0; k < 3; k++) sm[k][threadIdx.x] = fmin(sm[k][threadIdx.x], sm[k][threadIdx.x + s]);
+      for (int k = 3; k < 7; k++) sm[k][threadIdx.x] = fmax(sm[k][threadIdx.x], sm[k][threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) for (int k = 0; k < 7; k++) blk[7 * blockIdx.x + k] = sm[k][0];
+}
+
+__device__ __forceinline__ int cellCoord(double x, double o, double inv, int n) {
+  int c = (int)floor((x - o) * inv);
+  return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+__global__ void __launch_bounds__(256) k_cellkeys(const double4* __restrict__ posr, int n, Grid g, uint32_t* keys, int* idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = posr[i];
+  int ix = cellCoord(p.x, g.ox, g.inv, g.nx), iy = cellCoord(p.y, g.oy, g.inv, g.ny), iz = cellCoord(p.z, g.oz, g.inv, g.nz);
+  keys[i] = (uint32_t)((iz * g.ny + iy) * g.nx + ix);
+  idx[i] = i;
+}
+
+// gather all per-sphere arrays into cell order; also refreshes lastPos (Aabb::nodeLastPos, Collision.cpp:138-141)
+__global__ void __launch_bounds__(256) k_reorder(Spheres dst, Spheres src, const int* __restrict__ perm, int n, int* id2slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int o = perm[i];
+  double4 p = src.posr[o];
+  dst.posr[i] = p; dst.velm[i] = src.velm[o]; dst.angi[i] = src.angi[o]; dst.ori[i] = src.ori[o];
+  dst.fx[i] = src.fx[o]; dst.fy[i] = src.fy[o]; dst.fz[i] = src.fz[o];
+  dst.tx[i] = src.tx[o]; dst.ty[i] = src.ty[o]; dst.tz[i] = src.tz[o];
+  dst.lx[i] = p.x; dst.ly[i] = p.y; dst.lz[i] = p.z;
+  dst.flags[i] = src.flags[o]; dst.mask[i] = src.mask[o]; dst.mat[i] = src.mat[o];
+  int id = src.id[o]; dst.id[i] = id; dst.up[i] = src.up[o];
+  id2slot[id] = i;
+}
+
+// cellStart[k] = number of spheres with key < k : scatter run ends, then inclusive max-scan (done by the host with cub)
+__global__ void __launch_bounds__(256) k_cellends(const uint32_t* __restrict__ keys, int n, int* cellStart) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == n - 1 || keys[i] != keys[i + 1]) cellStart[keys[i] + 1] = i + 1;
+}
+
+__device__ __forceinline__ bool aabbOverlapSS(double4 a, double4 b, double vd) {
+  // Bo1_Sphere_Aabb::goGeneric + AabbCollider::updateAabb (Sphere.cpp:52-66, Collision.cpp:156-159): min=(pos-r)-vd, max=(pos+r)+vd
+  return ((a.x - a.w) - vd <= (b.x + b.w) + vd) && ((a.x + a.w) + vd >= (b.x - b.w) - vd) &&
+         ((a.y - a.w) - vd <= (b.y + b.w) + vd) && ((a.y + a.w) + vd >= (b.y - b.w) - vd) &&
+         ((a.z - a.w) - vd <= (b.z + b.w) + vd) && ((a.z + a.w) + vd >= (b.z - b.w) - vd);
+}
+__device__ __forceinline__ bool mayCollide(uint32_t mA, uint32_t mB, uint32_t lone) { return (mA & mB) && !(mA & mB & lone); }  // Collision.cpp:21-43
+
+struct OldCsr {  // incidence rows of the previous contact table (for history carry-over)
+  const int* rowStart; const uint32_t* rowEntry; const int32_t* rowOther; int valid;
+};
+
+__device__ __forceinline__ void copy_history(const Contacts& N, long long cn, const Contacts& O, long long co, int law, int rolling, int periodic) {
+  N.t0x[cn] = O.t0x[co]; N.t0y[cn] = O.t0y[co]; N.t0z[cn] = O.t0z[co];
+  N.t1x[cn] = O.t1x[co]; N.t1y[cn] = O.t1y[co]; N.t1z[cn] = O.t1z[co];
+  N.cp[cn] = O.cp[co];
+  N.fn[cn] = O.fn[co]; N.ft0[cn] = O.ft0[co]; N.ft1[cn] = O.ft1[co];
+  N.ph[0][cn] = O.ph[0][co]; N.ph[1][cn] = O.ph[1][co]; N.ph[2][cn] = O.ph[2][co];
+  if (law == 1) { N.ph[3][cn] = O.ph[3][co]; N.ph[4][cn] = O.ph[4][co]; }
+  if (rolling) { N.tq0[cn] = O.tq0[co]; N.tq1[cn] = O.tq1[co]; N.tq2[cn] = O.tq2[co]; }
+  N.stepCreated[cn] = O.stepCreated[co];
+  if (periodic) { N.cdx[cn] = O.cdx[co]; N.cdy[cn] = O.cdy[co]; N.cdz[cn] = O.cdz[co]; }
+}
+
+// find the previous contact between the sphere in (old) slot `oslot` and the particle with id `otherId`
+__device__ __forceinline__ long long find_old(const OldCsr& oc, int oslot, int otherId) {
+  if (!oc.valid) return -1;
+  for (int e = oc.rowStart[oslot]; e < oc.rowStart[oslot + 1]; e++) if (oc.rowOther[e] == otherId) return (long long)(oc.rowEntry[e] >> 1);
+  return -1;
+}
+
+// Sphere+Sphere candidates.  Ownership: the pair is emitted by the sphere with the larger radius (ties: larger slot), whose search
+// box (own AABB grown by its own half-extent) necessarily contains the centre of the other.  FILL=false counts, FILL=true writes
+// pairs (canonical pA = lower id) and carries L6Geom/FrictPhys history of contacts that were real (sorted-row lookup).
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_pairs_ss(Spheres S, int n, Grid g, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
+                                                 const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
+                                                 int law, int rolling, long long stepNow) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 pi = S.posr[i];
+  const double H = 2 * (pi.w + vd) * (1 + 1e-12) + 1e-300;
+  const int x0 = cellCoord(pi.x - H, g.ox, g.inv, g.nx), x1 = cellCoord(pi.x + H, g.ox, g.inv, g.nx);
+  const int y0 = cellCoord(pi.y - H, g.oy, g.inv, g.ny), y1 = cellCoord(pi.y + H, g.oy, g.inv, g.ny);
+  const int z0 = cellCoord(pi.z - H, g.oz, g.inv, g.nz), z1 = cellCoord(pi.z + H, g.oz, g.inv, g.nz);
+  const uint32_t mi = S.mask[i];
+  int cntLocal = 0;
+  long long out = FILL ? offsets[i] : 0;
+  int idI = 0, oslotI = 0;
+  if (FILL) { idI = S.id[i]; oslotI = perm ? perm[i] : i; }
+  for (int iz = z0; iz <= z1; iz++)
+    for (int iy = y0; iy <= y1; iy++) {
+      const int k0 = (iz * g.ny + iy) * g.nx;
+      const int jb = cellStart[k0 + x0], je = cellStart[k0 + x1 + 1];
+      for (int j = jb; j < je; j++) {
+        if (j == i) continue;
+        const double4 pj = S.posr[j];
+        if (!(pj.w < pi.w || (pj.w == pi.w && j < i))) continue;
+        if (!aabbOverlapSS(pi, pj, vd)) continue;
+        if (!mayCollide(mi, S.mask[j], loneMask)) continue;
+        if (FILL) {
+          const int idJ = S.id[j];
+          const long long c = out + cntLocal;
+          const bool iIsA = idI < idJ;
+          N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
+          long long co = find_old(oc, oslotI, idJ);
+          uint32_t fl = 0;
+          if (co >= 0 && (O.flags[co] & CF_REAL)) { copy_history(N, c, O, co, law, rolling, 0); fl = CF_REAL; N.Fg[c] = O.Fg[co]; O.flags[co] |= CF_CLAIMED; }
+          else { N.stepCreated[c] = (int)stepNow; N.Fg[c] = make_double4(0, 0, 0, 0); }
+          N.flags[c] = fl | (KIND_SS << CF_KIND_SHIFT);
+        }
+        cntLocal++;
+      }
+    }
+  if (!FILL) counts[i] = cntLocal;
+}
+
+// Wall+Sphere candidates: Bo1_Wall_Aabb (Wall.cpp:25-38): the wall box is the plane coordinate (± halfThick) ± verletDist on its axis, infinite elsewhere.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_pairs_ws(Spheres S, int n, const Wall* __restrict__ walls, int nWalls, double vd, double wallHalfThick, uint32_t loneMask,
+                                                 int* counts, const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
+                                                 int law, int rolling, long long stepNow) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 pi = S.posr[i];
+  const uint32_t mi = S.mask[i];
+  int cntLocal = 0;
+  long long out = FILL ? offsets[i] : 0;
+  const int oslotI = FILL ? (perm ? perm[i] : i) : 0;
+  for (int w = 0; w < nWalls; w++) {
+    const Wall W = walls[w];
+    const double pc = comp(xyz(pi), W.axis);
+    double wmin = W.pos[W.axis], wmax = wmin;
+    if (wallHalfThick > 0) { wmin -= wallHalfThick; wmax += wallHalfThick; }
+    wmin = wmin - vd; wmax = wmax + vd;
+    if (!(((pc - pi.w) - vd <= wmax) && ((pc + pi.w) + vd >= wmin))) continue;
+    if (!mayCollide(mi, W.mask, loneMask)) continue;
+    if (FILL) {
+      const long long c = out + cntLocal;
+      N.pair[c] = make_int2(w, i);
+      long long co = find_old(oc, oslotI, W.id);
+      uint32_t fl = 0;
+      if (co >= 0 && (O.flags[co] & CF_REAL)) { copy_history(N, c, O, co, law, rolling, 0); fl = CF_REAL; N.Fg[c] = O.Fg[co]; O.flags[co] |= CF_CLAIMED; }
+      else { N.stepCreated[c] = (int)stepNow; N.Fg[c] = make_double4(0, 0, 0, 0); }
+      N.flags[c] = fl | (KIND_WS << CF_KIND_SHIFT);
+    }
+    cntLocal++;
+  }
+  if (!FILL) counts[i] = cntLocal;
+}
+
+// incidence keys for the per-particle rows: (slot << 32 | other id) -> (contact << 1 | side)
+__global__ void __launch_bounds__(256) k_csr_emit(Contacts C, long long nTot, const int32_t* __restrict__ sid, const Wall* __restrict__ walls,
+                                                 const int32_t* __restrict__ facetIds, unsigned long long* keys, uint32_t* vals) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nTot) return;
+  const int2 pr = C.pair[c];
+  const int kind = cf_kind(C.flags[c]);
+  if (kind == KIND_SS) {
+    keys[2 * c] = ((unsigned long long)(uint32_t)pr.x << 32) | (uint32_t)sid[pr.y];
+    keys[2 * c + 1] = ((unsigned long long)(uint32_t)pr.y << 32) | (uint32_t)sid[pr.x];
+  } else {
+    const int bid = (kind == KIND_WS) ? walls[pr.x].id : facetIds[pr.x];
+    keys[2 * c] = 0xFFFFFFFFFFFFFFFFull;  // boundary side: walls/facets receive nothing through this path (ContactLoop.cpp:272)
+    keys[2 * c + 1] = ((unsigned long long)(uint32_t)pr.y << 32) | (uint32_t)bid;
+  }
+  vals[2 * c] = (uint32_t)(c << 1);
+  vals[2 * c + 1] = (uint32_t)(c << 1) | 1u;
+}
+
+// old real contacts nobody claimed during the fill = orphans: count, then append behind the grid candidates
+__global__ void __launch_bounds__(256) k_orphans(Contacts O, long long nOld, Contacts N, long long nNewBase, const int32_t* __restrict__ oldSid, const int* __restrict__ id2slot,
+                                                int law, int rolling, int periodic, int* counter, int doAppend) {
+  long long co = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= nOld) return;
+  const uint32_t fl = O.flags[co];
+  if (!(fl & CF_REAL) || (fl & (CF_CLAIMED | CF_DEAD))) return;
+  const int k = atomicAdd(counter, 1);
+  if (!doAppend) return;
+  const long long c = nNewBase + k;
+  const int kind = cf_kind(fl);
+  int2 pr = O.pair[co];
+  pr.y = id2slot[oldSid[pr.y]];
+  if (kind == KIND_SS) pr.x = id2slot[oldSid[pr.x]];
+  N.pair[c] = pr;
+  copy_history(N, c, O, co, law, rolling, periodic);
+  N.Fg[c] = O.Fg[co];
+  N.flags[c] = CF_REAL | CF_ORPHAN | (fl & CF_KIND_MASK);
+}
+
+__global__ void __launch_bounds__(256) k_rowstart(const unsigned long long* __restrict__ keys, long long nKeys, int n, int* rowStart, int32_t* rowOther) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= n) {  // lower_bound of (t<<32)
+    const unsigned long long target = (unsigned long long)t << 32;
+    long long lo = 0, hi = nKeys;
+    while (lo < hi) { long long mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+    rowStart[t] = (int)lo;
+  }
+  for (long long e = t; e < nKeys; e += (long long)gridDim.x * blockDim.x) rowOther[e] = (int32_t)(uint32_t)(keys[e] & 0xFFFFFFFFull);
+}
+
+// scatter per-slot data into upload order (downloads)
+__global__ void __launch_bounds__(256) k_gather_state(Spheres S, int n, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long u = S.up[i];
+  if (pos) { double4 p = S.posr[i]; pos[3 * u] = p.x; pos[3 * u + 1] = p.y; pos[3 * u + 2] = p.z; }
+  if (ori) { double4 q = S.ori[i]; ori[4 * u] = q.x; ori[4 * u + 1] = q.y; ori[4 * u + 2] = q.z; ori[4 * u + 3] = q.w; }
+  if (vel) { double4 v = S.velm[i]; vel[3 * u] = v.x; vel[3 * u + 1] = v.y; vel[3 * u + 2] = v.z; }
+  if (angVel) { double4 w = S.angi[i]; angVel[3 * u] = w.x; angVel[3 * u + 1] = w.y; angVel[3 * u + 2] = w.z; }
+  if (force) { force[3 * u] = S.fx[i]; force[3 * u + 1] = S.fy[i]; force[3 * u + 2] = S.fz[i]; }
+  if (torque) { torque[3 * u] = S.tx[i]; torque[3 * u + 1] = S.ty[i]; torque[3 * u + 2] = S.tz[i]; }
+}
+__global__ void __launch_bounds__(256) k_scatter_state(Spheres S, int n, const int* __restrict__ up2slot, long long first, long long cnt, const double* pos, const double* vel,
+                                                      const double* angVel) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  const int i = up2slot[first + t];
+  if (pos) { double4 p = S.posr[i]; p.x = pos[3 * t]; p.y = pos[3 * t + 1]; p.z = pos[3 * t + 2]; S.posr[i] = p; }
+  if (vel) { double4 v = S.velm[i]; v.x = vel[3 * t]; v.y = vel[3 * t + 1]; v.z = vel[3 * t + 2]; S.velm[i] = v; }
+  if (angVel) { double4 w = S.angi[i]; w.x = angVel[3 * t]; w.y = angVel[3 * t + 1]; w.z = angVel[3 * t + 2]; S.angi[i] = w; }
+}
+__global__ void __launch_bounds__(256) k_up2slot(const int32_t* __restrict__ up, int n, int* up2slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) up2slot[up[i]] = i;
+}
+__global__ void __launch_bounds__(256) k_count_flags(const uint32_t* __restrict__ flags, long long n, unsigned long long* out /*[0]=real,[1]=alive*/) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned r = 0, a = 0;
+  if (c < n) { uint32_t f = flags[c]; r = (f & CF_REAL) ? 1 : 0; a = (f & CF_DEAD) ? 0 : 1; }
+  r = __reduce_add_sync(0xffffffffu, r); a = __reduce_add_sync(0xffffffffu, a);
+  if ((threadIdx.x & 31) == 0) { if (r) atomicAdd(&out[0], (unsigned long long)r); if (a) atomicAdd(&out[1], (unsigned long long)a); }
+}
+
+}  // namespace wd

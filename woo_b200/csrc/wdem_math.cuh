@@ -1,0 +1,79 @@
+// wdem_math.cuh — float64 3-vector / quaternion helpers for the sm_100a DEM kernels.
+// Operation order is part of the contract: the translation unit is compiled with --fmad=false and every
+// reduction is left-to-right ((c0+c1)+c2), see DESIGN.md "Eigen semantics".  IEEE div/sqrt (fp64 default).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace wd {
+
+struct d3 {
+  double x, y, z;
+};
+__host__ __device__ __forceinline__ d3 mk3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ d3 operator-(d3 a, d3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ d3 operator-(d3 a) { return mk3(-a.x, -a.y, -a.z); }
+__host__ __device__ __forceinline__ d3 operator*(d3 a, double s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ d3 operator*(double s, d3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+__host__ __device__ __forceinline__ d3 operator/(d3 a, double s) { return mk3(a.x / s, a.y / s, a.z / s); }
+__host__ __device__ __forceinline__ double dot(d3 a, d3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__host__ __device__ __forceinline__ double sqn(d3 a) { return dot(a, a); }
+__host__ __device__ __forceinline__ double nrm(d3 a) { return sqrt(sqn(a)); }
+__host__ __device__ __forceinline__ d3 cross(d3 a, d3 b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__host__ __device__ __forceinline__ double comp(d3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+__host__ __device__ __forceinline__ void setc(d3& a, int i, double v) { if (i == 0) a.x = v; else if (i == 1) a.y = v; else a.z = v; }
+__host__ __device__ __forceinline__ d3 xyz(double4 v) { return mk3(v.x, v.y, v.z); }
+
+struct q4 { double w, x, y, z; };
+
+// Eigen Quaternion(Matrix3) from columns c0,c1,c2 (L6Geom.cpp:68,215: node.ori=Quaternionr(trsf))
+__host__ __device__ __forceinline__ q4 quatFromCols(d3 c0, d3 c1, d3 c2) {
+  // m(i,j) = cj[i]
+  const double m00 = c0.x, m10 = c0.y, m20 = c0.z, m01 = c1.x, m11 = c1.y, m21 = c1.z, m02 = c2.x, m12 = c2.y, m22 = c2.z;
+  q4 q;
+  double t = (m00 + m11) + m22;
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (m21 - m12) * t;
+    q.y = (m02 - m20) * t;
+    q.z = (m10 - m01) * t;
+  } else {
+    int i = 0;
+    if (m11 > m00) i = 1;
+    if (m22 > (i == 0 ? m00 : m11)) i = 2;
+    if (i == 0) {  // j=1,k=2
+      t = sqrt(m00 - m11 - m22 + 1.0);
+      q.x = 0.5 * t; t = 0.5 / t;
+      q.w = (m21 - m12) * t; q.y = (m10 + m01) * t; q.z = (m20 + m02) * t;
+    } else if (i == 1) {  // j=2,k=0
+      t = sqrt(m11 - m22 - m00 + 1.0);
+      q.y = 0.5 * t; t = 0.5 / t;
+      q.w = (m02 - m20) * t; q.z = (m21 + m12) * t; q.x = (m01 + m10) * t;
+    } else {  // i=2: j=0,k=1
+      t = sqrt(m22 - m00 - m11 + 1.0);
+      q.z = 0.5 * t; t = 0.5 / t;
+      q.w = (m10 - m01) * t; q.x = (m02 + m20) * t; q.y = (m12 + m21) * t;
+    }
+  }
+  return q;
+}
+// Eigen QuaternionBase::_transformVector (Contact.cpp:30-31, DynDt.cpp:29)
+__host__ __device__ __forceinline__ d3 quatRotate(q4 q, d3 v) {
+  d3 qv = mk3(q.x, q.y, q.z);
+  d3 uv = cross(qv, v);
+  uv = uv + uv;
+  return (v + q.w * uv) + cross(qv, uv);
+}
+
+struct m33 { double m[9]; };  // row-major, host-prepared uniforms
+__host__ __device__ __forceinline__ d3 mulMV(const m33& M, d3 v) {
+  return mk3((M.m[0] * v.x + M.m[1] * v.y) + M.m[2] * v.z, (M.m[3] * v.x + M.m[4] * v.y) + M.m[5] * v.z,
+             (M.m[6] * v.x + M.m[7] * v.y) + M.m[8] * v.z);
+}
+
+}  // namespace wd

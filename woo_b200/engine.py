@@ -1,0 +1,183 @@
+"""Host-side handle of the CUDA DEM engine over the C-ABI (array level).  The reference-facing plugin layer
+(GpuDemLoop engine + Scene/DemField mirror) sits on top of this in woo_b200/dem.py."""
+import ctypes as C
+import numpy as np
+from . import capi
+from .capi import WdemConfig, WdemStats, ptr, f64
+
+
+class WdemError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One DemField on one GPU.  Mirrors the C-ABI 1:1; arrays in, arrays out."""
+
+    def __init__(self, params=None, device=0, **kw):
+        self.L = capi.load()
+        self.cfg = WdemConfig()
+        self.L.wdem_default_config(C.byref(self.cfg))
+        self.cfg.device = device
+        if params is not None:
+            self._apply(vars(params))
+        self._apply(kw)
+        self.h = C.c_void_p()
+        rc = self.L.wdem_create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise WdemError(self.L.wdem_last_error(None).decode())
+        self._keep = []
+
+    def _apply(self, d):
+        for k, v in d.items():
+            if k == "gravity":
+                self.cfg.gravity = (C.c_double * 3)(*v)
+            elif k == "deterministic":
+                continue        # the GPU force reduction is always deterministic (S.deterministic semantics)
+            elif hasattr(self.cfg, k):
+                setattr(self.cfg, k, v)
+            else:
+                raise AttributeError("unknown engine attribute %r" % k)
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise WdemError(self.L.wdem_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wdem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_config(self, **kw):
+        self._apply(kw)
+        self._chk(self.L.wdem_set_config(self.h, C.byref(self.cfg)))
+
+    def set_profiling(self, on=True):
+        self._chk(self.L.wdem_set_profiling(self.h, C.c_int(int(on))))
+
+    # ---- uploads
+    def upload_materials(self, mats):
+        a = np.array(mats, dtype=np.float64).reshape(len(mats), 7)
+        kind = np.ascontiguousarray(a[:, 0], dtype=np.int32)
+        cols = [np.ascontiguousarray(a[:, i]) for i in range(1, 7)]
+        self._chk(self.L.wdem_upload_materials(self.h, C.c_int(len(mats)), ptr(kind), *[ptr(c) for c in cols]))
+
+    def upload_spheres(self, ids, pos, radius, mass, inertia, mat=None, mask=None, flags=None, vel=None, angVel=None, ori=None):
+        n = len(radius)
+        self.n = n
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int32)
+        mat = None if mat is None else np.ascontiguousarray(mat, dtype=np.int32)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+        flags = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint32)
+        args = [f64(pos), f64(ori), f64(vel), f64(angVel), f64(mass), f64(inertia), f64(radius)]
+        self._chk(self.L.wdem_upload_spheres(self.h, C.c_int64(n), ptr(ids), *[ptr(a) for a in args], ptr(flags), ptr(mask), ptr(mat)))
+
+    def upload_walls(self, ids, walls):
+        n = len(walls)
+        if n == 0:
+            return
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        pos = f64([w["pos"] for w in walls]); vel = f64([w.get("vel", (0, 0, 0)) for w in walls])
+        axis = np.array([w["axis"] for w in walls], dtype=np.int32); sense = np.array([w["sense"] for w in walls], dtype=np.int32)
+        mask = np.array([w.get("mask", 3) for w in walls], dtype=np.uint32); mat = np.array([w.get("mat", 0) for w in walls], dtype=np.int32)
+        self._chk(self.L.wdem_upload_walls(self.h, C.c_int(n), ptr(ids), ptr(pos), ptr(axis), ptr(sense), ptr(vel), ptr(mask), ptr(mat)))
+
+    def upload_facets(self, ids, facets):
+        n = len(facets)
+        if n == 0:
+            return
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        v = f64([np.asarray(f["v"]).reshape(9) for f in facets]); vv = f64([np.asarray(f.get("vvel", np.zeros(9))).reshape(9) for f in facets])
+        fk = f64([f.get("fakeVel", (0, 0, 0)) for f in facets]); ht = f64([f.get("halfThick", 0.) for f in facets])
+        nl = f64([f.get("n21lim", (np.nan,) * 3) for f in facets])
+        mask = np.array([f.get("mask", 3) for f in facets], dtype=np.uint32); mat = np.array([f.get("mat", 0) for f in facets], dtype=np.int32)
+        self._chk(self.L.wdem_upload_facets(self.h, C.c_int(n), ptr(ids), ptr(v), ptr(vv), ptr(fk), ptr(ht), ptr(nl), ptr(mask), ptr(mat)))
+
+    def set_cell(self, hSize, gradV=None, nextGradV=None, homoDeform=4):
+        self._chk(self.L.wdem_set_cell(self.h, ptr(f64(hSize)), ptr(f64(gradV)), ptr(f64(nextGradV)), C.c_int(homoDeform)))
+
+    def load(self, S):
+        """Upload a woo_b200.scenes.SceneSpec."""
+        self.spec = S
+        self.upload_materials(S.mats)
+        m, I = S.mass_inertia()
+        self.upload_spheres(S.sphere_ids(), S.pos, S.radius, m, I, S.mat, S.mask, S.flags, S.vel, S.angVel)
+        self.upload_walls(S.wall_ids(), S.walls)
+        self.upload_facets(S.facet_ids(), S.facets)
+        if S.cell is not None:
+            self.set_cell(S.cell["hSize"], S.cell.get("gradV"), S.cell.get("nextGradV"), S.cell.get("homoDeform", 4))
+        return self
+
+    # ---- stepping
+    def step(self, n=1):
+        st = WdemStats()
+        self._chk(self.L.wdem_step(self.h, C.c_int64(n), C.byref(st)))
+        self.stats = st
+        return st
+
+    def step_e2e(self, n, pos, vel, angVel, pos_out, vel_out):
+        st = WdemStats(); ek = C.c_double()
+        self._chk(self.L.wdem_step_e2e(self.h, C.c_int64(n), ptr(pos), ptr(vel), ptr(angVel), ptr(pos_out), ptr(vel_out), C.byref(ek), C.byref(st)))
+        self.stats = st
+        return ek.value, st
+
+    # ---- downloads
+    def spheres(self):
+        n = self.n
+        o = {k: np.zeros((n, 3)) for k in ("pos", "vel", "angVel", "force", "torque")}
+        o["ori"] = np.zeros((n, 4))
+        self._chk(self.L.wdem_download_state(self.h, ptr(o["pos"]), ptr(o["ori"]), ptr(o["vel"]), ptr(o["angVel"])))
+        self._chk(self.L.wdem_download_forces(self.h, ptr(o["force"]), ptr(o["torque"])))
+        return o
+
+    def set_state(self, first, pos=None, vel=None, angVel=None):
+        a = [f64(x) for x in (pos, vel, angVel)]
+        n = next(len(x) for x in a if x is not None)
+        self._chk(self.L.wdem_set_state(self.h, C.c_int64(first), C.c_int64(n), *[ptr(x) for x in a]))
+
+    def num_contacts(self, real_only=False):
+        n = self.L.wdem_num_contacts(self.h, C.c_int(int(real_only)))
+        if n < 0:
+            self._chk(1)
+        return n
+
+    def contacts(self, real_only=False):
+        n = self.L.wdem_download_contacts(self.h, C.c_int(int(real_only)), C.c_int64(0), *([None] * 10))
+        if n < 0:
+            self._chk(1)
+        o = dict(ids=np.zeros((n, 2), np.int32), cellDist=np.zeros((n, 3), np.int32), real=np.zeros(n, np.int32), uN=np.zeros(n),
+                 force=np.zeros((n, 3)), torque=np.zeros((n, 3)), trsf=np.zeros((n, 9)), contPt=np.zeros((n, 3)), phys=np.zeros((n, 3)),
+                 stepCreated=np.zeros(n, np.int32))
+        if n:
+            m = self.L.wdem_download_contacts(self.h, C.c_int(int(real_only)), C.c_int64(n), ptr(o["ids"]), ptr(o["cellDist"]), ptr(o["real"]),
+                                              ptr(o["uN"]), ptr(o["force"]), ptr(o["torque"]), ptr(o["trsf"]), ptr(o["contPt"]), ptr(o["phys"]),
+                                              ptr(o["stepCreated"]))
+            if m < 0:
+                self._chk(1)
+        return o
+
+    def kinetic_energy(self):
+        e = C.c_double()
+        self._chk(self.L.wdem_kinetic_energy(self.h, C.byref(e)))
+        return e.value
+
+    def crit_dt(self):
+        e = C.c_double()
+        self._chk(self.L.wdem_crit_dt(self.h, C.byref(e)))
+        return e.value
+
+    def scalars(self):
+        dt, t, vd = C.c_double(), C.c_double(), C.c_double(); st, nf = C.c_int64(), C.c_int64()
+        self._chk(self.L.wdem_get_scalars(self.h, C.byref(dt), C.byref(t), C.byref(st), C.byref(vd), C.byref(nf)))
+        return dict(dt=dt.value, time=t.value, step=st.value, verletDist=vd.value, nFullRuns=nf.value)
+
+    def device_info(self):
+        b = C.c_int64(); s = C.c_void_p()
+        self._chk(self.L.wdem_device_info(self.h, C.byref(b), C.byref(s)))
+        return dict(bytes=b.value, stream=s.value)
