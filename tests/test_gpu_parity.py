@@ -78,3 +78,22 @@ def test_verlet_zero_and_fixed():
     for vd in (0., .004):
         S = sc.random_gas(150, box=.35, r=.02, seed=11); S.params.verletDist = vd
         compare(S, 60, check_every=20, label=f"verletDist={vd}")
+
+
+@pytest.mark.parametrize("law", [sc.LAW_IDEALELPL, sc.LAW_HERTZ_DMT])
+def test_facet_box(law):
+    S = sc.facet_box_scene(300, seed=2, law=law, en=.6 if law else float("nan"))
+    compare(S, 200, check_every=25, label=f"facet-box law={law}")
+
+
+def test_facet_variants():
+    for kw in (dict(halfThick=.004), dict(fakeVel=(.3, -.2, .1)), dict(fakeVel=(float("nan"), 0, 0)), dict(random_n21lim=False, div=1)):
+        S = sc.facet_box_scene(200, seed=4, **kw)
+        compare(S, 120, check_every=30, label=f"facets {kw}")
+
+
+def test_mixed_walls_facets_ids_first():
+    S = sc.facet_box_scene(250, seed=9, div=2)
+    S.walls = sc.box_walls((-.05, -.05, -.05), (.45, .45, .45), mat=0, top=True)
+    S.boundaries_first = True
+    compare(S, 150, check_every=50, label="mixed")

@@ -127,7 +127,7 @@ struct wdem_engine {
   int n = 0; SphereStore sph[2]; int cur = 0; DBuf<int> id2slot, up2slot; int maxId = -1; bool up2slotValid = false;
   std::vector<Material> hMats; DBuf<Material> dMats;
   std::vector<Wall> hWalls; DBuf<Wall> dWalls;
-  int nFacets = 0; DBuf<int32_t> dFacetIds;
+  std::vector<Facet> hFacets; DBuf<Facet> dFacets; DBuf<int> fgCellStart, fgCellFacet; FacetGrid fgrid; bool fgridValid = false;
   double minRadius = INFINITY, pwaveDt = INFINITY;
   std::vector<double> hRadius; std::vector<int32_t> hMatOfSphere;
   // contacts
@@ -135,7 +135,7 @@ struct wdem_engine {
   CsrStore csr[2]; int curR = 0;
   // scratch
   DBuf<uint32_t> keys, keysAlt; DBuf<int> idx, idxAlt, cellStart, counts, offsets; DBuf<unsigned char> cubTemp; DBuf<double> blk;
-  DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt;
+  DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt;
   Counters* dCnt = nullptr; Counters* hCnt = nullptr;
   // scene scalars
   double dt = NAN, time = 0, nextDt = NAN, verletDist = NAN; long long step = 0, nFullRuns = 0; bool conDirty = true;
@@ -201,6 +201,8 @@ void checkDeviceError(wdem_engine* E) {
   }
 }
 
+void buildFacetGrid(wdem_engine* E);
+
 // -------------------------------------------------------------------------------------------------
 // Collider full run (replaces InsertionSortCollider::run's fullRun branch, InsertionSortCollider.cpp:407-613)
 // -------------------------------------------------------------------------------------------------
@@ -211,7 +213,9 @@ void rebuild(wdem_engine* E) {
   const bool hertz = c.law == WDEM_LAW_HERTZ_DMT, rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.);
   const double vd = E->verletDist;
   int64_t& tot = E->bytes;
-  long long nSS = 0, nWS = 0, nOrphOut = 0;
+  long long nSS = 0, nWS = 0, nFS = 0, nOrphOut = 0;
+  if (!E->fgridValid) buildFacetGrid(E);
+  const int nFacets = (int)E->hFacets.size();
   ContactStore& Nst = E->con[1 - E->curC];
   ContactStore& Ost = E->con[E->curC];
   CsrStore& Ocsr = E->csr[E->curR];
@@ -261,65 +265,113 @@ void rebuild(wdem_engine* E) {
     cub::DeviceScan::InclusiveScan(E->cubTemp.p, tb, E->cellStart.p, E->cellStart.p, cub::Max(), (int)(ncells + 1), st); E->launches += 2;
     // 5. count candidates: [SS by sphere | WS by sphere]
     const int nWalls = (int)E->hWalls.size();
-    E->counts.ensure((size_t)2 * n + 1, tot); E->offsets.ensure((size_t)2 * n + 1, tot);
+    E->counts.ensure((size_t)3 * n + 1, tot); E->offsets.ensure((size_t)3 * n + 1, tot);
     Contacts dummy; memset(&dummy, 0, sizeof(dummy));
     const int nb128 = nblk(n, 128);
-    k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, c.law, rolling, E->step); E->launches++;
-    if (nWalls) { k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, dummy, oc, perm, c.law, rolling, E->step); E->launches++; }
+    E->rowCount.ensure((size_t)n + 1, tot);
+    CK(cudaMemsetAsync(E->rowCount.p, 0, ((size_t)n + 1) * sizeof(int), st));
+    k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++;
+    if (nWalls) { k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++; }
     else CK(cudaMemsetAsync(E->counts.p + n, 0, (size_t)n * sizeof(int), st));
-    CK(cudaMemsetAsync(E->counts.p + 2 * n, 0, sizeof(int), st));
+    if (nFacets) { k_pairs_fs<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, E->counts.p + 2 * n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++; }
+    else CK(cudaMemsetAsync(E->counts.p + 2 * n, 0, (size_t)n * sizeof(int), st));
+    CK(cudaMemsetAsync(E->counts.p + 3 * n, 0, sizeof(int), st));
     tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, E->counts.p, E->offsets.p, 2 * n + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, E->counts.p, E->offsets.p, 3 * n + 1, st);
     E->cubTemp.ensure(tb, tot);
-    cub::DeviceScan::ExclusiveSum(E->cubTemp.p, tb, E->counts.p, E->offsets.p, 2 * n + 1, st); E->launches += 2;
-    int hOff[2];
+    cub::DeviceScan::ExclusiveSum(E->cubTemp.p, tb, E->counts.p, E->offsets.p, 3 * n + 1, st); E->launches += 2;
+    int hOff[3];
     CK(cudaMemcpyAsync(&hOff[0], E->offsets.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&hOff[1], E->offsets.p + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hOff[2], E->offsets.p + 3 * n, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    nSS = hOff[0]; nWS = hOff[1] - hOff[0];
-    if (hOff[1] < 0 || (long long)hOff[1] >= (1ll << 30)) throw EngErr{"too many potential contacts for one device", WDEM_ERR_RUNTIME};
+    nSS = hOff[0]; nWS = hOff[1] - hOff[0]; nFS = hOff[2] - hOff[1];
+    if (hOff[2] < 0 || (long long)hOff[2] >= (1ll << 30)) throw EngErr{"too many potential contacts for one device", WDEM_ERR_RUNTIME};
     // 6. fill pairs + carry history
-    const long long nC0 = nSS + nWS;
+    const long long nC0 = nSS + nWS + nFS;
     Nst.ensure((size_t)std::max<long long>(nC0, 1), tot, hertz, rolling, c.periodic);
     Contacts N = Nst.view(), O = Ost.view();
-    k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, N, O, oc, perm, c.law, rolling, E->step); E->launches++;
-    if (nWalls) { k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, N, O, oc, perm, c.law, rolling, E->step); E->launches++; }
+    E->srcOld.ensure((size_t)std::max<long long>(nC0, 1), tot);
+    k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, N, O, oc, perm, nullptr, E->srcOld.p); E->launches++;
+    if (nWalls) { k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, N, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
+    if (nFacets) { k_pairs_fs<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, nullptr, E->offsets.p + 2 * n, N, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
+    if (nC0 > 0) { k_carry<<<nblk(nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, c.law, rolling, c.periodic, E->step); E->launches++; }
     // 6b. orphans: real contacts of the previous table that no candidate claimed (AABBs separated while real)
     long long nOrph = 0;
     if (oc.valid && E->nC > 0) {
       E->orphCnt.ensure(1, tot);
       CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
       const int32_t* oldSid = E->sph[1 - E->cur].id.p;
-      k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, c.law, rolling, c.periodic, E->orphCnt.p, 0); E->launches++;
+      k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 0); E->launches++;
       int hN = 0; CK(cudaMemcpyAsync(&hN, E->orphCnt.p, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
       if (hN > 0) {
         nOrph = hN;
         Nst.ensure((size_t)(nC0 + nOrph), tot, hertz, rolling, c.periodic, /*keep*/ true, st);
         N = Nst.view();
         CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
-        k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, c.law, rolling, c.periodic, E->orphCnt.p, 1); E->launches++;
+        k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 1); E->launches++;
       }
     }
     const long long nC = nC0 + nOrph;
     nOrphOut = nOrph;
-    // 7. per-particle incidence rows sorted by the other particle's id
+    // 7. per-particle incidence rows sorted by the other particle's id: scan of row counts, cursor fill, per-row sort
     const long long nK = 2 * nC;
     Ncsr.rowStart.ensure((size_t)n + 2, tot); Ncsr.rowEntry.ensure((size_t)std::max<long long>(nK, 1), tot); Ncsr.rowOther.ensure((size_t)std::max<long long>(nK, 1), tot);
+    tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, E->rowCount.p, Ncsr.rowStart.p, n + 1, st);
+    E->cubTemp.ensure(tb, tot);
+    cub::DeviceScan::ExclusiveSum(E->cubTemp.p, tb, E->rowCount.p, Ncsr.rowStart.p, n + 1, st); E->launches += 2;
     if (nC > 0) {
-      E->ckeys.ensure(nK, tot); E->ckeysAlt.ensure(nK, tot); E->cvals.ensure(nK, tot);
-      k_csr_emit<<<nblk(nC, 256), 256, 0, st>>>(N, nC, E->S().id, E->dWalls.p, E->dFacetIds.p, E->ckeys.p, E->cvals.p); E->launches++;
-      int slotBits = 1; while ((1ll << slotBits) <= n) slotBits++;
-      tb = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, tb, E->ckeys.p, E->ckeysAlt.p, E->cvals.p, Ncsr.rowEntry.p, (int)nK, 0, 32 + slotBits, st);
-      E->cubTemp.ensure(tb, tot);
-      cub::DeviceRadixSort::SortPairs(E->cubTemp.p, tb, E->ckeys.p, E->ckeysAlt.p, E->cvals.p, Ncsr.rowEntry.p, (int)nK, 0, 32 + slotBits, st); E->launches += 8;
-      k_rowstart<<<nblk(std::max<long long>(n + 1, std::min<long long>(nK, 1 << 22)), 256), 256, 0, st>>>(E->ckeysAlt.p, nK, n, Ncsr.rowStart.p, Ncsr.rowOther.p); E->launches++;
-    } else CK(cudaMemsetAsync(Ncsr.rowStart.p, 0, ((size_t)n + 2) * sizeof(int), st));
+      CK(cudaMemsetAsync(E->rowCount.p, 0, ((size_t)n + 1) * sizeof(int), st));   // reused as the per-row cursor
+      k_csr_fill<<<nblk(nC, 256), 256, 0, st>>>(N, nC, E->S().id, E->dWalls.p, E->dFacets.p, Ncsr.rowStart.p, E->rowCount.p, Ncsr.rowEntry.p, Ncsr.rowOther.p); E->launches++;
+      k_row_sort<<<nb128, 128, 0, st>>>(n, Ncsr.rowStart.p, Ncsr.rowEntry.p, Ncsr.rowOther.p); E->launches++;
+    }
     Ncsr.valid = true;
   }
-  E->nSS = nSS; E->nWS = nWS; E->nFS = 0; E->nOrph = nOrphOut; E->nC = nSS + nWS + nOrphOut;
+  E->nSS = nSS; E->nWS = nWS; E->nFS = nFS; E->nOrph = nOrphOut; E->nC = nSS + nWS + nFS + nOrphOut;
   E->curC = 1 - E->curC; E->curR = 1 - E->curR;
   E->nFullRuns++;
+}
+
+// Static facets are binned once on the host (they never move in this engine: Impose/clump motion is out of scope).
+void buildFacetGrid(wdem_engine* E) {
+  const int nf = (int)E->hFacets.size();
+  FacetGrid& g = E->fgrid; memset(&g, 0, sizeof(g));
+  if (nf == 0) { E->fgridValid = true; return; }
+  const double vd = E->verletDist;
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  std::vector<double> ext; ext.reserve(nf);
+  for (auto& f : E->hFacets) { double e = 0; for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], f.bmin[k] - vd); hi[k] = std::max(hi[k], f.bmax[k] + vd); e = std::max(e, f.bmax[k] - f.bmin[k]); } ext.push_back(e); }
+  std::nth_element(ext.begin(), ext.begin() + nf / 2, ext.end());
+  double cell = std::max(ext[nf / 2] + 2 * vd, 1e-300);
+  double vol = std::max(hi[0] - lo[0], cell) * std::max(hi[1] - lo[1], cell) * std::max(hi[2] - lo[2], cell);
+  cell = std::max(cell, std::cbrt(vol / (16.0 * nf + 64)));
+  g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2]; g.inv = 1. / cell;
+  g.nx = std::max(1, (int)std::floor((hi[0] - lo[0]) * g.inv) + 1); g.ny = std::max(1, (int)std::floor((hi[1] - lo[1]) * g.inv) + 1); g.nz = std::max(1, (int)std::floor((hi[2] - lo[2]) * g.inv) + 1);
+  auto cc = [&](double x, double o, int n) { int c = (int)std::floor((x - o) * g.inv); return c < 0 ? 0 : (c >= n ? n - 1 : c); };
+  const size_t ncell = (size_t)g.nx * g.ny * g.nz;
+  std::vector<int> start(ncell + 1, 0);
+  for (int pass = 0; pass < 2; pass++) {
+    std::vector<int> fill;
+    std::vector<int> list;
+    if (pass == 1) { for (size_t k = 0; k < ncell; k++) start[k + 1] += start[k]; fill.assign(start.begin(), start.end() - 1); list.resize(start[ncell]); }
+    for (int f = 0; f < nf; f++) {
+      const Facet& F = E->hFacets[f];
+      int x0 = cc(F.bmin[0] - vd, g.ox, g.nx), x1 = cc(F.bmax[0] + vd, g.ox, g.nx), y0 = cc(F.bmin[1] - vd, g.oy, g.ny), y1 = cc(F.bmax[1] + vd, g.oy, g.ny), z0 = cc(F.bmin[2] - vd, g.oz, g.nz), z1 = cc(F.bmax[2] + vd, g.oz, g.nz);
+      for (int iz = z0; iz <= z1; iz++) for (int iy = y0; iy <= y1; iy++) for (int ix = x0; ix <= x1; ix++) {
+        size_t k = ((size_t)iz * g.ny + iy) * g.nx + ix;
+        if (pass == 0) start[k + 1]++; else list[fill[k]++] = f;
+      }
+    }
+    if (pass == 1) {
+      E->fgCellStart.ensure(ncell + 1, E->bytes); E->fgCellFacet.ensure(std::max<size_t>(list.size(), 1), E->bytes);
+      CK(cudaMemcpyAsync(E->fgCellStart.p, start.data(), (ncell + 1) * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+      if (!list.empty()) CK(cudaMemcpyAsync(E->fgCellFacet.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, E->stream));
+      CK(cudaStreamSynchronize(E->stream));
+    }
+  }
+  g.cellStart = E->fgCellStart.p; g.cellFacet = E->fgCellFacet.p;
+  E->fgridValid = true;
 }
 
 void ensureVerletAndDt(wdem_engine* E) {
@@ -390,10 +442,15 @@ void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
     else k_contact_ws<1><<<nblk(E->nWS, 128), 128, 0, st>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt);
     E->launches++;
   }
+  if (E->nFS > 0) {
+    if (c.law == 0) k_contact_fs<0><<<nblk(E->nFS, 128), 128, 0, st>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt);
+    else k_contact_fs<1><<<nblk(E->nFS, 128), 128, 0, st>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt);
+    E->launches++;
+  }
   if (E->nOrph > 0) {
     const long long f0 = E->nSS + E->nWS + E->nFS;
-    if (c.law == 0) k_contact_orphans<0><<<nblk(E->nOrph, 128), 128, 0, st>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt);
-    else k_contact_orphans<1><<<nblk(E->nOrph, 128), 128, 0, st>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt);
+    if (c.law == 0) k_contact_orphans<0><<<nblk(E->nOrph, 128), 128, 0, st>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt);
+    else k_contact_orphans<1><<<nblk(E->nOrph, 128), 128, 0, st>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt);
     E->launches++;
   }
   if (prof) CK(cudaEventRecord(E->evp[3], st));
@@ -511,8 +568,8 @@ int wdem_destroy(wdem_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release();
-  h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacetIds.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
-  h->orphCnt.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release();
+  h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
+  h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release();
   if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt);
   if (h->ev0) cudaEventDestroy(h->ev0); if (h->ev1) cudaEventDestroy(h->ev1); for (auto& e : h->evp) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -553,6 +610,7 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
     std::vector<double4> posr(n), velm(n), angi(n), q(n); std::vector<uint32_t> fl(n), mk(n); std::vector<int32_t> mt(n), id(n), up(n);
     int maxId = h->maxId; double minR = INFINITY, pw = INFINITY;
     for (auto& w : h->hWalls) maxId = std::max(maxId, w.id);
+    for (auto& f : h->hFacets) maxId = std::max(maxId, f.id);
     for (int64_t i = 0; i < n; i++) {
       id[i] = ids ? ids[i] : (int32_t)i; up[i] = (int32_t)i;
       if (id[i] < 0) throw EngErr{"negative particle id", WDEM_ERR_INVALID};
@@ -585,7 +643,7 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
     CK(cudaMemsetAsync(h->id2slot.p, 0xFF, ((size_t)maxId + 2) * sizeof(int), st));
     CK(cudaStreamSynchronize(st));
     h->conDirty = true; h->nC = h->nSS = h->nWS = h->nFS = 0; h->csr[0].valid = h->csr[1].valid = false; h->up2slotValid = false;
-    h->verletDist = NAN;
+    h->verletDist = NAN; h->fgridValid = false;
   });
 }
 
@@ -609,8 +667,29 @@ int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* po
   });
 }
 
-int wdem_upload_facets(wdem_handle h, int n, const int32_t*, const double*, const double*, const double*, const double*, const double*, const uint32_t*, const int32_t*) {
-  return guarded(h, [&] { if (n > 0) throw EngErr{"facets: not implemented in this build of the GPU engine yet", WDEM_ERR_UNSUPPORTED}; });
+int wdem_upload_facets(wdem_handle h, int n, const int32_t* ids, const double* verts, const double* vvel, const double* fakeVel, const double* halfThick, const double* n21lim,
+                       const uint32_t* mask, const int32_t* matId) {
+  return guarded(h, [&] {
+    if (n < 0 || (n > 0 && (!ids || !verts))) throw EngErr{"wdem_upload_facets: bad arguments", WDEM_ERR_INVALID};
+    h->hFacets.resize(n);
+    for (int i = 0; i < n; i++) {
+      Facet f; memset(&f, 0, sizeof(f));
+      for (int k = 0; k < 9; k++) { f.v[k] = verts[9 * i + k]; f.vvel[k] = vvel ? vvel[9 * i + k] : 0.; }
+      for (int k = 0; k < 3; k++) { f.fakeVel[k] = fakeVel ? fakeVel[3 * i + k] : 0.; f.n21lim[k] = n21lim ? n21lim[3 * i + k] : NAN; }
+      f.halfThick = halfThick ? halfThick[i] : 0.; f.mask = mask ? mask[i] : 3u; f.mat = matId ? matId[i] : 0; f.id = ids[i];
+      if (f.mat < 0 || f.mat >= (int)h->hMats.size()) throw EngErr{"facet material index out of range", WDEM_ERR_INVALID};
+      // Bo1_Facet_Aabb::go (Facet.cpp:275-298), aperiodic
+      for (int k = 0; k < 3; k++) {
+        f.bmin[k] = f.v[k] - f.halfThick; f.bmax[k] = f.v[k] + f.halfThick;
+        for (int j = 1; j < 3; j++) { f.bmin[k] = std::min(f.bmin[k], f.v[3 * j + k] - f.halfThick); f.bmax[k] = std::max(f.bmax[k], f.v[3 * j + k] + f.halfThick); }
+      }
+      h->hFacets[i] = f;
+    }
+    h->dFacets.ensure(std::max(n, 1), h->bytes);
+    if (n) CK(cudaMemcpyAsync(h->dFacets.p, h->hFacets.data(), n * sizeof(Facet), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->conDirty = true; h->fgridValid = false;
+  });
 }
 
 int wdem_set_cell(wdem_handle h, const double* hSize, const double* gradV, const double* nextGradV, int homoDeform) {
@@ -729,7 +808,8 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
     for (long long c = 0; c < nC; c++) {
       if (flags[c] & CF_DEAD) continue;
       if (realOnly && !(flags[c] & CF_REAL)) continue;
-      int a = (cf_kind(flags[c]) == KIND_SS) ? sid[pair[c].x] : h->hWalls[pair[c].x].id, b = sid[pair[c].y];
+      const int kd = cf_kind(flags[c]);
+      int a = (kd == KIND_SS) ? sid[pair[c].x] : (kd == KIND_WS ? h->hWalls[pair[c].x].id : h->hFacets[pair[c].x].id), b = sid[pair[c].y];
       rows.push_back(Row{((uint64_t)(uint32_t)a << 32) | (uint32_t)b, c});
     }
     std::sort(rows.begin(), rows.end(), [](const Row& x, const Row& y) { return x.key < y.key; });

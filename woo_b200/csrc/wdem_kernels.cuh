@@ -31,6 +31,8 @@ struct Spheres {          // one slot per sphere; slots are re-ordered by grid c
 };
 
 struct Wall { double pos[3]; double vel[3]; int32_t axis, sense; uint32_t mask; int32_t mat; int32_t id; int32_t pad; };
+struct Facet { double v[9]; double vvel[9]; double fakeVel[3]; double halfThick; double n21lim[3]; double bmin[3], bmax[3]; uint32_t mask; int32_t mat; int32_t id; int32_t pad; };
+struct FacetGrid { double ox, oy, oz, inv; int nx, ny, nz; const int* cellStart; const int* cellFacet; };
 struct Material { int32_t kind; int32_t pad; double density, young, ktDivKn, tanPhi, surfEnergy, alpha; };
 
 struct Contacts {         // SoA planes, one entry per candidate pair (real or potential)
@@ -426,10 +428,133 @@ __global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first,
   block_count(isReal, evald, cnt);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Facet+Sphere: Cg2_Facet_Sphere_L6Geom::go (src/dem/Facet.cpp:333-391) with Facet::getNormal/getOuterVectors (:74-77,:113-118),
+// interpolatePtLinAngVel (:161-177), adjustBoundaryContactGeom(_impl) (:220-265), CompUtils::closestSegmentPt /
+// triangleBarycentrics (src/supp/base/CompUtils.cpp:59-65,94-112).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ d3 ld3(const double* p) { return mk3(p[0], p[1], p[2]); }
+__device__ __forceinline__ d3 closestSegmentPt(d3 P, d3 A, d3 B) {
+  d3 BA = B - A;
+  if (sqn(BA) == 0.) return A;
+  double u = (dot(P, BA) - dot(A, BA)) / (sqn(BA));
+  return A + fmin(1., fmax(0., u)) * BA;
+}
+__device__ __forceinline__ d3 triangleBarycentrics(d3 x, d3 A, d3 B, d3 Cc) {
+  d3 vB = B - A, vC = Cc - A, vX = x - A;
+  double m00 = dot(vB, vB), m01 = dot(vC, vB), m10 = dot(vB, vC), m11 = dot(vC, vC);
+  double invdet = 1. / (m00 * m11 - m10 * m01);   // Eigen 2x2: inverse = adj * (1/det)
+  double i00 = m11 * invdet, i10 = -m10 * invdet, i01 = -m01 * invdet, i11 = m00 * invdet;
+  double b0 = dot(vX, vB), b1 = dot(vX, vC);
+  double u = i00 * b0 + i01 * b1, v = i10 * b0 + i11 * b1;
+  return mk3(1 - u - v, u, v);
+}
+__device__ __forceinline__ void facetAdjustImpl(d3 fN, d3 edgePt, d3 unitOutVec, d3 otherCenter, double nnLim, d3& normal, d3& contPt) {
+  if (nnLim != nnLim) return;
+  double nn = dot(normal, fN);
+  if ((nn >= 0 && nnLim > 0 && nn >= nnLim) || (nn < 0 && nnLim < 0 && nn <= nnLim)) return;
+  double noLim = (fabs(nnLim) >= 1. ? 1. : sqrt(1. - nnLim * nnLim));
+  double nno0, nno1;
+  if ((nnLim >= 0 && nn <= -noLim) || (nnLim <= 0 && nn >= noLim)) { nno0 = -nnLim; nno1 = 0; } else { nno0 = nnLim; nno1 = noLim; }
+  normal = nno0 * fN + nno1 * unitOutVec;
+  contPt = otherCenter - normal * (dot(otherCenter - edgePt, normal));
+}
+
+template <int LAW>
+__device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint32_t fl, const Spheres& S, const Facet* facets, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
+  const int2 pr = C.pair[c];
+  const Facet* F = facets + pr.x;
+  const double4 pb = S.posr[pr.y];
+  d3 shift2 = mk3(0, 0, 0), shiftVel2 = mk3(0, 0, 0);
+  if (u.periodic) {
+    d3 cd = mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]);
+    shift2 = mulMV(u.hSize, cd); shiftVel2 = mulMV(u.shiftVelM, cd);
+  }
+  const d3 sC = xyz(pb) + shift2;
+  const double radius = pb.w, ht = F->halfThick;
+  const d3 v0 = ld3(F->v), v1 = ld3(F->v + 3), v2 = ld3(F->v + 6);
+  const d3 nn = cross(v1 - v0, v2 - v0);
+  const d3 fNormal = nn / nrm(nn);
+  double planeDist = dot(sC - v0, fNormal);
+  const bool real = fl & CF_REAL;
+  if (fabs(planeDist) > (radius + ht) && !real) return;
+  d3 fC = sC - planeDist * fNormal;
+  d3 o0 = cross(v1 - v0, nn), o1 = cross(v2 - v1, nn), o2 = cross(v0 - v2, nn);
+  double l0 = dot(o0, fC - v0), l1 = dot(o1, fC - v1), l2 = dot(o2, fC - v2);
+  int w = (l0 > 0 ? 1 : 0) + (l1 > 0 ? 2 : 0) + (l2 > 0 ? 4 : 0);
+  d3 contPt;
+  switch (w) {
+    case 0: contPt = fC; break;
+    case 1: contPt = closestSegmentPt(fC, v0, v1); break;
+    case 2: contPt = closestSegmentPt(fC, v1, v2); break;
+    case 4: contPt = closestSegmentPt(fC, v2, v0); break;
+    case 3: contPt = v1; break;
+    case 5: contPt = v0; break;
+    case 6: contPt = v2; break;
+    default: cnt->error = ERR_FACET_IMPOSSIBLE; cnt->errA = F->id; cnt->errB = S.id[pr.y]; return;
+  }
+  d3 normal = sC - contPt;
+  if (sqn(normal) > (radius + ht) * (radius + ht) && !real) return;
+  double dist = nrm(normal);
+  if (dist != 0) normal = normal / dist;
+  else {
+    if (real) { d3 c0 = mk3(C.t0x[c], C.t0y[c], C.t0z[c]), c1 = mk3(C.t1x[c], C.t1y[c], C.t1z[c]); normal = quatRotate(quatFromCols(c0, c1, cross(c0, c1)), mk3(1, 0, 0)); }
+    else normal = mk3(1, 0, 0);
+  }
+  if (w > 0) {  // Facet::adjustBoundaryContactGeom (Facet.cpp:220-237); edgeNums (Facet.cpp:374)
+    const int e0 = (w == 1 || w == 3) ? 0 : ((w == 2 || w == 6) ? 1 : 2);
+    const int e1 = (w == 3) ? 1 : ((w == 5) ? 0 : ((w == 6) ? 2 : -1));
+    const d3 oe0 = e0 == 0 ? o0 : (e0 == 1 ? o1 : o2);
+    const d3 ve0 = e0 == 0 ? v0 : (e0 == 1 ? v1 : v2);
+    const double n0 = F->n21lim[e0];
+    if (!(n0 != n0)) {
+      if (e1 < 0) facetAdjustImpl(fNormal, ve0, oe0 / nrm(oe0), sC, n0, normal, contPt);
+      else {
+        const double n1 = F->n21lim[e1];
+        if (!(n1 != n1)) {
+          const d3 oe1 = e1 == 0 ? o0 : (e1 == 1 ? o1 : o2);
+          const d3 ve1 = e1 == 0 ? v0 : (e1 == 1 ? v1 : v2);
+          d3 out0 = oe0 / nrm(oe0), out1 = oe1 / nrm(oe1);
+          double p0 = dot(out0, normal), pMin = dot(out0, out1), pMax = 1.;
+          double t01 = (p0 - pMin) / (pMax - pMin);
+          facetAdjustImpl(fNormal, ve1, (t01 * out0 + (1 - t01) * out1), sC, (t01 * n0 + (1 - t01) * n1), normal, contPt);
+        }
+      }
+    }
+  }
+  if (ht > 0) contPt = contPt + normal * ht;
+  double uN = dist - radius - ht;
+  // Facet::interpolatePtLinAngVel
+  const d3 vv0 = ld3(F->vvel), vv1 = ld3(F->vvel + 3), vv2 = ld3(F->vvel + 6), fk = ld3(F->fakeVel);
+  d3 a = triangleBarycentrics(contPt, v0, v1, v2);
+  d3 linVel = (a.x * vv0 + a.y * vv1) + a.z * vv2;
+  d3 angVel = (cross(v0 - contPt, vv0) + cross(v1 - contPt, vv1)) + cross(v2 - contPt, vv2);
+  if (!(fk.x == 0. && fk.y == 0. && fk.z == 0.)) {
+    if (!(fk.x != fk.x)) linVel = linVel + fk;
+    else linVel = dot(linVel, fNormal) * fNormal;
+  }
+  d3 vs = mk3(0, 0, 0), ws = vs; double mB = 0;
+  if (real) { double4 b = S.velm[pr.y]; vs = xyz(b); b = S.angi[pr.y]; ws = xyz(b); }
+  else if (LAW == 1) mB = S.velm[pr.y].w;
+  int matB = real ? 0 : S.mat[pr.y];
+  contact_tail<LAW>(C, c, fl, u, contPt, linVel, angVel, sC, vs, ws, shiftVel2, normal, contPt, uN, fmax(ht, radius), radius, mats, F->mat, matB, 0., mB, cnt, F->id, S.id[pr.y], isReal);
+}
+
+template <int LAW>
+__global__ void __launch_bounds__(128) k_contact_fs(Contacts C, long long first, long long n, Spheres S, const Facet* facets, const Material* mats, StepU u, Counters* cnt) {
+  long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned isReal = 0, evald = 0;
+  if (c < first + n) {
+    const uint32_t fl = C.flags[c];
+    if (!(fl & CF_DEAD)) { evald = 1; contact_fs<LAW>(C, c, fl, S, facets, mats, u, cnt, isReal); }
+  }
+  block_count(isReal, evald, cnt);
+}
+
 // Orphans: contacts that are real although their AABBs no longer overlap (the collider never removes a real contact,
 // InsertionSortCollider.cpp:78-113); rare, kept in a mixed-kind tail segment.
 template <int LAW>
-__global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Material* mats, StepU u, Counters* cnt) {
+__global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Facet* facets, const Material* mats, StepU u, Counters* cnt) {
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
   if (c < first + n) {
@@ -439,6 +564,7 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
       const int kind = cf_kind(fl);
       if (kind == KIND_SS) contact_ss<LAW>(C, c, fl, S, mats, u, cnt, isReal);
       else if (kind == KIND_WS) contact_ws<LAW>(C, c, fl, S, walls, mats, u, cnt, isReal);
+      else contact_fs<LAW>(C, c, fl, S, facets, mats, u, cnt, isReal);
     }
   }
   block_count(isReal, evald, cnt);
@@ -635,7 +761,7 @@ __device__ __forceinline__ long long find_old(const OldCsr& oc, int oslot, int o
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_pairs_ss(Spheres S, int n, Grid g, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
                                                  const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
-                                                 int law, int rolling, long long stepNow) {
+                                                 int* __restrict__ rowCount, int* __restrict__ srcOld) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double4 pi = S.posr[i];
@@ -664,22 +790,21 @@ __global__ void __launch_bounds__(128) k_pairs_ss(Spheres S, int n, Grid g, cons
           const bool iIsA = idI < idJ;
           N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
           long long co = find_old(oc, oslotI, idJ);
-          uint32_t fl = 0;
-          if (co >= 0 && (O.flags[co] & CF_REAL)) { copy_history(N, c, O, co, law, rolling, 0); fl = CF_REAL; N.Fg[c] = O.Fg[co]; O.flags[co] |= CF_CLAIMED; }
-          else { N.stepCreated[c] = (int)stepNow; N.Fg[c] = make_double4(0, 0, 0, 0); }
-          N.flags[c] = fl | (KIND_SS << CF_KIND_SHIFT);
-        }
+          if (co >= 0 && !(O.flags[co] & CF_REAL)) co = -1;
+          srcOld[c] = (int)co;
+          N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
+        } else atomicAdd(&rowCount[j], 1);
         cntLocal++;
       }
     }
-  if (!FILL) counts[i] = cntLocal;
+  if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
 }
 
 // Wall+Sphere candidates: Bo1_Wall_Aabb (Wall.cpp:25-38): the wall box is the plane coordinate (± halfThick) ± verletDist on its axis, infinite elsewhere.
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_pairs_ws(Spheres S, int n, const Wall* __restrict__ walls, int nWalls, double vd, double wallHalfThick, uint32_t loneMask,
                                                  int* counts, const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
-                                                 int law, int rolling, long long stepNow) {
+                                                 int* __restrict__ rowCount, int* __restrict__ srcOld) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double4 pi = S.posr[i];
@@ -699,64 +824,123 @@ __global__ void __launch_bounds__(128) k_pairs_ws(Spheres S, int n, const Wall* 
       const long long c = out + cntLocal;
       N.pair[c] = make_int2(w, i);
       long long co = find_old(oc, oslotI, W.id);
-      uint32_t fl = 0;
-      if (co >= 0 && (O.flags[co] & CF_REAL)) { copy_history(N, c, O, co, law, rolling, 0); fl = CF_REAL; N.Fg[c] = O.Fg[co]; O.flags[co] |= CF_CLAIMED; }
-      else { N.stepCreated[c] = (int)stepNow; N.Fg[c] = make_double4(0, 0, 0, 0); }
-      N.flags[c] = fl | (KIND_WS << CF_KIND_SHIFT);
+      if (co >= 0 && !(O.flags[co] & CF_REAL)) co = -1;
+      srcOld[c] = (int)co;
+      N.flags[c] = (KIND_WS << CF_KIND_SHIFT);
     }
     cntLocal++;
   }
-  if (!FILL) counts[i] = cntLocal;
+  if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
 }
 
-// incidence keys for the per-particle rows: (slot << 32 | other id) -> (contact << 1 | side)
-__global__ void __launch_bounds__(256) k_csr_emit(Contacts C, long long nTot, const int32_t* __restrict__ sid, const Wall* __restrict__ walls,
-                                                 const int32_t* __restrict__ facetIds, unsigned long long* keys, uint32_t* vals) {
+// Facet+Sphere candidates: Bo1_Facet_Aabb (Facet.cpp:275-298): vertex min/max ± halfThick, then ± verletDist.  Facets are static and are
+// binned once (host) into a uniform grid; each sphere visits the bins its enlarged AABB touches and emits a facet from the single bin
+// that holds the lower corner of the intersection of the two boxes (no duplicates).
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_pairs_fs(Spheres S, int n, const Facet* __restrict__ facets, FacetGrid fg, double vd, uint32_t loneMask, int* counts,
+                                                 const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
+                                                 int* __restrict__ rowCount, int* __restrict__ srcOld) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 pi = S.posr[i];
+  const uint32_t mi = S.mask[i];
+  const double smin[3] = {(pi.x - pi.w) - vd, (pi.y - pi.w) - vd, (pi.z - pi.w) - vd}, smax[3] = {(pi.x + pi.w) + vd, (pi.y + pi.w) + vd, (pi.z + pi.w) + vd};
+  const int x0 = cellCoord(smin[0], fg.ox, fg.inv, fg.nx), x1 = cellCoord(smax[0], fg.ox, fg.inv, fg.nx);
+  const int y0 = cellCoord(smin[1], fg.oy, fg.inv, fg.ny), y1 = cellCoord(smax[1], fg.oy, fg.inv, fg.ny);
+  const int z0 = cellCoord(smin[2], fg.oz, fg.inv, fg.nz), z1 = cellCoord(smax[2], fg.oz, fg.inv, fg.nz);
+  int cntLocal = 0;
+  long long out = FILL ? offsets[i] : 0;
+  const int oslotI = FILL ? (perm ? perm[i] : i) : 0;
+  for (int iz = z0; iz <= z1; iz++)
+    for (int iy = y0; iy <= y1; iy++)
+      for (int ix = x0; ix <= x1; ix++) {
+        const int k = (iz * fg.ny + iy) * fg.nx + ix;
+        for (int e = fg.cellStart[k]; e < fg.cellStart[k + 1]; e++) {
+          const int f = fg.cellFacet[e];
+          const Facet* F = facets + f;
+          const double fbmin[3] = {F->bmin[0] - vd, F->bmin[1] - vd, F->bmin[2] - vd}, fbmax[3] = {F->bmax[0] + vd, F->bmax[1] + vd, F->bmax[2] + vd};
+          if (!(smin[0] <= fbmax[0] && smax[0] >= fbmin[0] && smin[1] <= fbmax[1] && smax[1] >= fbmin[1] && smin[2] <= fbmax[2] && smax[2] >= fbmin[2])) continue;
+          // unique bin of the pair
+          if (cellCoord(fmax(smin[0], fbmin[0]), fg.ox, fg.inv, fg.nx) != ix || cellCoord(fmax(smin[1], fbmin[1]), fg.oy, fg.inv, fg.ny) != iy ||
+              cellCoord(fmax(smin[2], fbmin[2]), fg.oz, fg.inv, fg.nz) != iz) continue;
+          if (!mayCollide(mi, F->mask, loneMask)) continue;
+          if (FILL) {
+            const long long c = out + cntLocal;
+            N.pair[c] = make_int2(f, i);
+            long long co = find_old(oc, oslotI, F->id);
+            if (co >= 0 && !(O.flags[co] & CF_REAL)) co = -1;
+            srcOld[c] = (int)co;
+            N.flags[c] = (KIND_FS << CF_KIND_SHIFT);
+          }
+          cntLocal++;
+        }
+      }
+  if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
+}
+
+// carry L6Geom/FrictPhys history of contacts that were real into the new table: one thread per NEW contact (coalesced writes)
+__global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Contacts O, const int* __restrict__ srcOld, int law, int rolling, int periodic, long long stepNow) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nTot) return;
-  const int2 pr = C.pair[c];
-  const int kind = cf_kind(C.flags[c]);
-  if (kind == KIND_SS) {
-    keys[2 * c] = ((unsigned long long)(uint32_t)pr.x << 32) | (uint32_t)sid[pr.y];
-    keys[2 * c + 1] = ((unsigned long long)(uint32_t)pr.y << 32) | (uint32_t)sid[pr.x];
+  if (c >= nNew) return;
+  const int co = srcOld[c];
+  if (co >= 0) {
+    copy_history(N, c, O, co, law, rolling, periodic);
+    N.Fg[c] = O.Fg[co];
+    N.flags[c] |= CF_REAL;
+    O.flags[co] |= CF_CLAIMED;
   } else {
-    const int bid = (kind == KIND_WS) ? walls[pr.x].id : facetIds[pr.x];
-    keys[2 * c] = 0xFFFFFFFFFFFFFFFFull;  // boundary side: walls/facets receive nothing through this path (ContactLoop.cpp:272)
-    keys[2 * c + 1] = ((unsigned long long)(uint32_t)pr.y << 32) | (uint32_t)bid;
+    N.stepCreated[c] = (int)stepNow;
+    N.Fg[c] = make_double4(0, 0, 0, 0);
   }
-  vals[2 * c] = (uint32_t)(c << 1);
-  vals[2 * c + 1] = (uint32_t)(c << 1) | 1u;
 }
 
-// old real contacts nobody claimed during the fill = orphans: count, then append behind the grid candidates
+// old real contacts nobody claimed = orphans: count (and add their incidences to the row counts), then append behind the grid candidates
 __global__ void __launch_bounds__(256) k_orphans(Contacts O, long long nOld, Contacts N, long long nNewBase, const int32_t* __restrict__ oldSid, const int* __restrict__ id2slot,
-                                                int law, int rolling, int periodic, int* counter, int doAppend) {
+                                                int law, int rolling, int periodic, int* counter, int* __restrict__ rowCount, int doAppend) {
   long long co = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (co >= nOld) return;
   const uint32_t fl = O.flags[co];
   if (!(fl & CF_REAL) || (fl & (CF_CLAIMED | CF_DEAD))) return;
   const int k = atomicAdd(counter, 1);
-  if (!doAppend) return;
-  const long long c = nNewBase + k;
   const int kind = cf_kind(fl);
   int2 pr = O.pair[co];
   pr.y = id2slot[oldSid[pr.y]];
   if (kind == KIND_SS) pr.x = id2slot[oldSid[pr.x]];
+  if (!doAppend) { atomicAdd(&rowCount[pr.y], 1); if (kind == KIND_SS) atomicAdd(&rowCount[pr.x], 1); return; }
+  const long long c = nNewBase + k;
   N.pair[c] = pr;
   copy_history(N, c, O, co, law, rolling, periodic);
   N.Fg[c] = O.Fg[co];
   N.flags[c] = CF_REAL | CF_ORPHAN | (fl & CF_KIND_MASK);
 }
 
-__global__ void __launch_bounds__(256) k_rowstart(const unsigned long long* __restrict__ keys, long long nKeys, int n, int* rowStart, int32_t* rowOther) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t <= n) {  // lower_bound of (t<<32)
-    const unsigned long long target = (unsigned long long)t << 32;
-    long long lo = 0, hi = nKeys;
-    while (lo < hi) { long long mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
-    rowStart[t] = (int)lo;
+// per-particle incidence rows: rowStart = exclusive scan of rowCount (host: cub), then fill through per-row cursors and sort each row by the
+// other particle's id (the canonical summation order).  Replaces a global 64-bit radix sort.
+__global__ void __launch_bounds__(256) k_csr_fill(Contacts C, long long nTot, const int32_t* __restrict__ sid, const Wall* __restrict__ walls, const Facet* __restrict__ facets,
+                                                 const int* __restrict__ rowStart, int* __restrict__ cursor, uint32_t* __restrict__ rowEntry, int32_t* __restrict__ rowOther) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nTot) return;
+  const int2 pr = C.pair[c];
+  const int kind = cf_kind(C.flags[c]);
+  int idA;
+  if (kind == KIND_SS) {
+    idA = sid[pr.x];
+    const int p = rowStart[pr.x] + atomicAdd(&cursor[pr.x], 1);
+    rowEntry[p] = (uint32_t)(c << 1); rowOther[p] = sid[pr.y];
+  } else idA = (kind == KIND_WS) ? walls[pr.x].id : facets[pr.x].id;
+  const int p = rowStart[pr.y] + atomicAdd(&cursor[pr.y], 1);
+  rowEntry[p] = (uint32_t)(c << 1) | 1u; rowOther[p] = idA;
+}
+__global__ void __launch_bounds__(128) k_row_sort(int n, const int* __restrict__ rowStart, uint32_t* __restrict__ rowEntry, int32_t* __restrict__ rowOther) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = rowStart[i], e = rowStart[i + 1];
+  for (int a = b + 1; a < e; a++) {  // insertion sort (rows hold ~8 entries)
+    const int32_t ko = rowOther[a]; const uint32_t ke = rowEntry[a];
+    int q = a - 1;
+    while (q >= b && rowOther[q] > ko) { rowOther[q + 1] = rowOther[q]; rowEntry[q + 1] = rowEntry[q]; q--; }
+    rowOther[q + 1] = ko; rowEntry[q + 1] = ke;
   }
-  for (long long e = t; e < nKeys; e += (long long)gridDim.x * blockDim.x) rowOther[e] = (int32_t)(uint32_t)(keys[e] & 0xFFFFFFFFull);
 }
 
 // scatter per-slot data into upload order (downloads)

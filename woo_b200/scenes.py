@@ -178,3 +178,43 @@ def random_gas(n, *, box=1.0, r=0.02, psd_ratio=1.0, seed=0, vmax=1.0, law=LAW_I
         S.walls = box_walls((0, 0, 0), (box, box, box), mat=0, top=True)
     S.params = Params(gravity=(0, 0, -9.81), damping=.2, law=law, verletDist=-.05, dynDtPeriod=10, en=en)
     return S.finalize()
+
+
+def quad_facets(p0, p1, p2, p3, nu, nv, **kw):
+    """Triangulate the parallelogram p0,p1,p2,p3 (p0->p1 = u, p0->p3 = v) into 2*nu*nv facets."""
+    p0, p1, p3 = np.asarray(p0, float), np.asarray(p1, float), np.asarray(p3, float)
+    u, v = (p1 - p0) / nu, (p3 - p0) / nv
+    out = []
+    for i in range(nu):
+        for j in range(nv):
+            a = p0 + i * u + j * v; b = a + u; c = a + u + v; d = a + v
+            out.append(dict(v=np.array([a, b, c]), **kw)); out.append(dict(v=np.array([a, c, d]), **kw))
+    return out
+
+
+def facet_box_scene(n=300, *, box=.4, r=.02, psd_ratio=2.0, seed=0, law=LAW_IDEALELPL, div=3, halfThick=0.0, fakeVel=(0, 0, 0),
+                    random_n21lim=True, vmax=1.0, en=float("nan")):
+    """Spheres thrown into an open box made of triangulated facets (floor + 4 sides): exercises face/edge/vertex regions of
+    Cg2_Facet_Sphere_L6Geom, halfThick, fakeVel and the n21lim neighbour-angle adjustment (values are synthetic)."""
+    rng = np.random.default_rng(seed)
+    S = SceneSpec()
+    S.mats = [frict_mat(density=2500., young=1e7, tanPhi=.5)] if law == LAW_IDEALELPL else [hertz_mat(density=2500., young=1e8)]
+    b = box
+    kw = dict(halfThick=halfThick, fakeVel=fakeVel, mat=0, mask=MASK_BOUNDARY)
+    F = quad_facets((0, 0, 0), (b, 0, 0), (b, b, 0), (0, b, 0), div, div, **kw)
+    F += quad_facets((0, 0, 0), (0, 0, b), (0, b, b), (0, b, 0), div, div, **kw)
+    F += quad_facets((b, 0, 0), (b, b, 0), (b, b, b), (b, 0, b), div, div, **kw)
+    F += quad_facets((0, 0, 0), (b, 0, 0), (b, 0, b), (0, 0, b), div, div, **kw)
+    F += quad_facets((0, b, 0), (0, b, b), (b, b, b), (b, b, 0), div, div, **kw)
+    for f in F:
+        if random_n21lim:
+            nl = rng.uniform(-1, 1, 3); nl[rng.uniform(size=3) < .3] = np.nan
+            f["n21lim"] = nl
+        if rng.uniform() < .2:
+            f["vvel"] = rng.uniform(-.2, .2, 9)
+    S.facets = F
+    S.pos = rng.uniform(-.2 * r, b + .2 * r, (n, 3)); S.pos[:, 2] = rng.uniform(-.2 * r, .6 * b, n)
+    S.radius = np.full(n, r) if psd_ratio == 1.0 else r * np.exp(rng.uniform(0, math.log(psd_ratio), n))
+    S.vel = rng.uniform(-vmax, vmax, (n, 3)); S.angVel = rng.uniform(-1, 1, (n, 3))
+    S.params = Params(gravity=(0, 0, -9.81), damping=.2, law=law, verletDist=-.05, dynDtPeriod=10, en=en)
+    return S.finalize()
