@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_FULL = 1_000_000
 LAYERS = 40
-SETTLE_STEPS = int(os.environ.get("WDEM_BENCH_SETTLE", "20000"))
+SETTLE_STEPS = int(os.environ.get("WDEM_BENCH_SETTLE", "6000"))
 SAMPLE = os.path.join(ROOT, "tests", "golden", "cfg2_sample_20k.npz")
 # algorithmic bytes (SURVEY.md §8d / DESIGN.md)
 B_P, B_C, B_Q, B_R, B_PAIR = 348, 552, 72, 200, 496
@@ -76,6 +76,31 @@ def workload(n, seed):
     return sc.deposition(n, r=1e-3, psd_ratio=4.0, seed=seed, law=sc.LAW_IDEALELPL, layers=LAYERS, damping=.2, young=1e7, density=2500.)
 
 
+def workload_tiled(n, tiles_x=None):
+    """cfg2 at full size without hours of settling: the committed pre-settled 20k-sphere PSD 1:4 bed (tests/golden/cfg2_sample_20k.npz,
+    made by scripts/make_cpu_sample.py with the same generator/material/law) is tiled in x and y inside one box of 5 walls; the former
+    side walls of the tiles become internal planes across which spheres of neighbouring tiles touch; the bed re-settles in the untimed
+    preparation phase (--settle steps)."""
+    from woo_b200 import scenes as sc
+    d = np.load(SAMPLE)
+    m = len(d["radius"])
+    tiles = max(1, n // m)
+    tx = tiles_x or int(np.ceil(np.sqrt(2 * tiles)))
+    while tiles % tx:
+        tx += 1
+    ty = tiles // tx
+    L = d["hi"] - d["lo"]
+    off = np.array([[i * L[0], j * L[1], 0.] for i in range(tx) for j in range(ty)])
+    S = workload(m, seed=2)
+    S.pos = (d["pos"][None, :, :] + off[:, None, :]).reshape(-1, 3)
+    S.radius = np.tile(d["radius"], tiles); S.vel = np.tile(d["vel"], (tiles, 1)); S.angVel = np.tile(d["angVel"], (tiles, 1))
+    S.mat = S.mask = S.flags = None
+    lo = d["lo"]; hi = np.array([lo[0] + tx * L[0], lo[1] + ty * L[1], d["hi"][2]])
+    S.walls = sc.box_walls(tuple(lo), tuple(hi), mat=0)
+    S.params.dt = float(d["dt"])
+    return S.finalize(), dict(tiles=tiles, tiles_x=tx, tiles_y=ty)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -85,13 +110,18 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     n = args.n
-    S = workload(n, seed=2 + rank)
+    if args.lattice or not os.path.exists(SAMPLE):
+        S = workload(n, seed=2 + rank); tiling = None
+    else:
+        S, tiling = workload_tiled(n); n = S.n
     E = Engine(S.params, device=local).load(S)
     # settle (untimed preparation of the dense packing; includes many collider full runs)
     t0 = time.time()
     done = 0
     while done < args.settle:
-        k = min(2000, args.settle - done); E.step(k); done += k
+        k = min(2000, args.settle - done); st_ = E.step(k); done += k
+        if rank == 0:
+            print("settle %d: rebuilds %d/%d, %.3f ms/step, real %d, Ek %.4g" % (done, st_.n_rebuilds, k, st_.device_ms / k, st_.n_real, E.kinetic_energy()), file=sys.stderr, flush=True)
     st = E.stats
     settle_s = time.time() - t0
     # warm-up
@@ -153,7 +183,7 @@ def run_gpu(args):
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg2: 1M polydisperse spheres (PSD 1:4) settled under gravity, Leapfrog+collider+ContactLoop(Cg2_Sphere_Sphere/Wall_Sphere_L6Geom, Cp2_FrictMat_FrictPhys, Law2_L6Geom_FrictPhys_IdealElPl)+DynDt",
-                   "n_spheres_per_gpu": n, "settle_steps": args.settle, "real_contacts": n_real, "candidate_contacts": n_con, "rebuilds_in_timed_region": n_reb,
+                   "n_spheres_per_gpu": n, "initial_state": ("tiled pre-settled 20k bed (tests/golden/cfg2_sample_20k.npz) %dx%d, re-settled" % (tiling["tiles_x"], tiling["tiles_y"])) if tiling else "jittered lattice", "settle_steps": args.settle, "real_contacts": n_real, "candidate_contacts": n_con, "rebuilds_in_timed_region": n_reb,
                    "l2_policy": "inputs larger than L2 (per-step working set %.0f MB > 126 MB)" % (step_bytes / 1e6), "parallelism": "1 slab box per GPU" if world > 1 else "single GPU",
                    "settle_wall_s": round(settle_s, 1)},
         "roofline": {"bound": "hbm", "kernel": "k_contact_ss<IdealElPl>", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
@@ -222,7 +252,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", type=int, default=N_FULL, help="spheres per GPU (default: the 1M workload)")
-    ap.add_argument("--settle", type=int, default=SETTLE_STEPS)
+    ap.add_argument("--settle", type=int, default=SETTLE_STEPS, help="untimed preparation steps before warm-up")
+    ap.add_argument("--lattice", action="store_true", help="start from the jittered lattice instead of the tiled pre-settled bed")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true")

@@ -120,6 +120,11 @@ class Oracle:
     def pWaveDt(self): return self.L.orc_pwave_dt(self.h)
     def kineticEnergy(self): return self.L.orc_kinetic_energy(self.h)
 
+    def cell_hsize(self):
+        h = np.zeros((3, 3))
+        self.L.orc_get_cell(self.h, _p(h, C.c_double))
+        return h
+
     def spheres(self):
         n = self.L.orc_num_spheres(self.h)
         out = {k: np.zeros((n, 3)) for k in ("pos", "vel", "angVel", "force", "torque")}

@@ -97,3 +97,61 @@ def test_mixed_walls_facets_ids_first():
     S.walls = sc.box_walls((-.05, -.05, -.05), (.45, .45, .45), mat=0, top=True)
     S.boundaries_first = True
     compare(S, 150, check_every=50, label="mixed")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# periodic cell (B4/I2: spatialOverlapPeri, cellDist, Cell.integrateAndUpdate, GRADV2 Leapfrog)
+# ---------------------------------------------------------------------------------------------------------------
+def compare_potential(O, E):
+    co, cg = O.contacts(False), E.contacts(False)
+    assert [tuple(x) for x in co["ids"]] == [tuple(x) for x in cg["ids"]], "potential contact set differs"
+    assert np.array_equal(co["cellDist"], cg["cellDist"]), "cellDist differs"
+
+
+@pytest.mark.parametrize("shift", [(0, 0, 0), (1, 2, 3), (6, 8, -4)])
+def test_pbc_celldist_kat(shift):
+    # py/tests/test_pbc.py:157-171 on the GPU: C.cellDist == -shift
+    S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+    S.pos = np.array([(.5, .5, .5), (.8 + shift[0], .6 + shift[1], .5 + shift[2])]); S.radius = np.array([.2, .2])
+    S.params = sc.Params(dt=1e-9, periodic=1, damping=0.)
+    S.cell = dict(hSize=np.eye(3), homoDeform=sc.HOMO_GRADV2)
+    E = engine_for(S.finalize()); E.step(1)
+    c = E.contacts(False)
+    assert [tuple(x) for x in c["ids"]] == [(0, 1)] and tuple(c["cellDist"][0]) == tuple(-np.array(shift))
+
+
+def test_pbc_ambiguous_raises():
+    # py/tests/test_pbc.py:145-154
+    from woo_b200.engine import WdemError
+    S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+    S.pos = np.array([(.3, .5, .5), (.8, .9, .5)]); S.radius = np.array([.4, .2])
+    S.params = sc.Params(dt=1e-9, periodic=1, damping=0.)
+    S.cell = dict(hSize=np.eye(3), homoDeform=sc.HOMO_GRADV2)
+    E = engine_for(S.finalize())
+    with pytest.raises(WdemError, match="ambiguous periodic contact"):
+        E.step(1)
+
+
+@pytest.mark.parametrize("law", [sc.LAW_IDEALELPL, sc.LAW_HERTZ_DMT])
+@pytest.mark.parametrize("homo", [sc.HOMO_GRADV2, sc.HOMO_VEL_2ND, sc.HOMO_VEL, sc.HOMO_POS, sc.HOMO_NONE])
+def test_periodic_shear_bitwise(law, homo):
+    g = [[0, 2.0, 0], [0, 0, 0], [0, 0, 0]]
+    S = sc.periodic_gas(400, cell=(.5, .4, .45), r=.02, psd_ratio=2.0, seed=13, law=law, gradV=g, homoDeform=homo, en=.7 if law else float("nan"))
+    O, E = compare(S, 200, check_every=25, label=f"peri-shear law={law} homo={homo}")
+    compare_potential(O, E)
+    assert np.array_equal(np.asarray(O.cell_hsize()), np.asarray(E.cell_hsize()))
+    assert O.kineticEnergy() == pytest.approx(E.kinetic_energy(), rel=1e-12)
+
+
+def test_periodic_preskewed_compression():
+    g = [[-1.0, .5, 0], [0, -1.0, 0], [.3, 0, -1.0]]
+    S = sc.periodic_gas(300, cell=(.45, .45, .45), r=.02, psd_ratio=3.0, seed=17, gradV=g, shear0=.3)
+    O, E = compare(S, 150, check_every=25, label="peri-skew-compress")
+    compare_potential(O, E)
+
+
+def test_periodic_with_walls():
+    S = sc.periodic_gas(300, cell=(.4, .4, .5), r=.02, psd_ratio=2.0, seed=19, walls=True)
+    S.params.gravity = (0, 0, -9.81)
+    O, E = compare(S, 150, check_every=25, label="peri-walls")
+    compare_potential(O, E)

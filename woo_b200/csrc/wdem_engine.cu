@@ -97,7 +97,7 @@ d3 hLevi(const m33& a) { return mk3(a.m[5] - a.m[7], a.m[6] - a.m[2], a.m[1] - a
 
 struct HostCell {
   m33 hSize = mIdent(), trsf = mIdent(), gradV = mZero(), nextGradV = mZero(), pprevHsize = mIdent();
-  d3 spinVec = mk3(0, 0, 0), size = mk3(1, 1, 1); bool hasShear = false; int homoDeform = WDEM_HOMO_GRADV2;
+  d3 spinVec = mk3(0, 0, 0), size = mk3(1, 1, 1), cosv = mk3(1, 1, 1); m33 unshearTrsf = mIdent(); bool hasShear = false; int homoDeform = WDEM_HOMO_GRADV2;
   void integrateAndUpdate(double dt) {  // Cell.cpp:81-120
     m33 inc = mScale(gradV, dt);
     trsf = mAdd(trsf, mMul(inc, trsf));
@@ -109,7 +109,13 @@ struct HostCell {
     } else hSize = mAdd(hSize, mMul(inc, hSize));
     pprevHsize = mScale(mAdd(prev, hSize), .5);
     if (mDet(hSize) == 0) throw EngErr{"Cell is degenerate (zero volume).", WDEM_ERR_RUNTIME};
-    for (int i = 0; i < 3; i++) { d3 b = mk3(hSize.m[i], hSize.m[3 + i], hSize.m[6 + i]); setc(size, i, nrm(b)); }
+    m33 Hn; d3 hcol[3];
+    for (int i = 0; i < 3; i++) {
+      d3 b = mk3(hSize.m[i], hSize.m[3 + i], hSize.m[6 + i]); double l = nrm(b); setc(size, i, l);
+      b = b / l; hcol[i] = b; Hn.m[i] = b.x; Hn.m[3 + i] = b.y; Hn.m[6 + i] = b.z;
+    }
+    for (int i = 0; i < 3; i++) setc(cosv, i, sqn(cross(hcol[(i + 1) % 3], hcol[(i + 2) % 3])));
+    unshearTrsf = mInv(Hn);   // _shearTrsf=Hnorm; _unshearTrsf=_shearTrsf.inverse() (Cell.cpp:104-106)
     hasShear = (hSize.m[1] != 0 || hSize.m[2] != 0 || hSize.m[3] != 0 || hSize.m[5] != 0 || hSize.m[6] != 0 || hSize.m[7] != 0);
   }
   void setNextGradV() { gradV = nextGradV; m33 W = mScale(mSub(gradV, mT(gradV)), .5); spinVec = .5 * hLevi(W); }  // Cell.cpp:60-66
@@ -154,7 +160,6 @@ void validateConfig(const wdem_config& c) {
   if (!c.iniLensTouch) throw EngErr{"Cg2_*.iniLensTouch=False is not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
   if (c.distFactor > 1.) throw EngErr{"DemField.distFactor>1 is not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
   if (c.dynDtPeriod > 0 && 1. + c.maxRelInc == 1.) throw EngErr{"DynDt: maxRelInc too small (1.0+maxRelInc==1.0)", WDEM_ERR_INVALID};  // DynDt.cpp:12-14
-  if (c.periodic) throw EngErr{"periodic cell: not implemented in this build of the GPU engine yet", WDEM_ERR_UNSUPPORTED};
 }
 
 StepU makeUniforms(wdem_engine* E) {
@@ -197,6 +202,8 @@ void checkDeviceError(wdem_engine* E) {
     case ERR_NAN_POS: throw EngErr{"NaN position of particle #" + std::to_string(h.errA), WDEM_ERR_RUNTIME};
     case ERR_NO_PHYS: throw EngErr{"ContactLoop: " + pr + ": no Contact.phys created (Cp2_HertzMat_HertzPhys needs HertzMat on both particles; ContactLoop.cpp:181)", WDEM_ERR_RUNTIME};
     case ERR_SCHWARZ: throw EngErr{"Law2_L6Geom_HertzPhys_DMT: Schwarz model (alpha!=0 and gamma!=0) is out of scope " + pr, WDEM_ERR_UNSUPPORTED};
+    case ERR_AMBIGUOUS_PERI: throw EngErr{"InsertionSortCollider: ambiguous periodic contact " + pr + " (particle too large for the cell; InsertionSortCollider.cpp:979-981)", WDEM_ERR_RUNTIME};
+    case ERR_FACET_IMPOSSIBLE: throw EngErr{"Cg2_Facet_Sphere_L6Geom: impossible sphere-facet intersection " + pr + " (Facet.cpp:358)", WDEM_ERR_RUNTIME};
     default: throw EngErr{"device error " + std::to_string(h.error) + " " + pr, WDEM_ERR_RUNTIME};
   }
 }
@@ -223,28 +230,48 @@ void rebuild(wdem_engine* E) {
   OldCsr oc; oc.valid = Ocsr.valid ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
   const int* perm = nullptr;
   Grid g; memset(&g, 0, sizeof(g));
+  PeriU pu; memset(&pu, 0, sizeof(pu)); PGrid pg; memset(&pg, 0, sizeof(pg));
+  if (c.periodic) {
+    if (nFacets) throw EngErr{"Facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    if (!E->hWalls.empty() && E->cell.hasShear) throw EngErr{"Walls not supported in skewed periodic boundary conditions.", WDEM_ERR_RUNTIME};  // Wall.cpp:30
+    pu.unshear = E->cell.unshearTrsf; pu.size = E->cell.size; pu.cosv = E->cell.cosv; pu.hasShear = E->cell.hasShear ? 1 : 0;
+  }
   if (n > 0) {
-    // 1. bounds of sphere centres + max radius
     const int nb = nblk(n, 256);
-    E->blk.ensure((size_t)nb * 7, tot);
-    k_bounds<<<nb, 256, 0, st>>>(E->S().posr, n, E->blk.p); E->launches++;
-    std::vector<double> hb((size_t)nb * 7);
-    CK(cudaMemcpyAsync(hb.data(), E->blk.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, rmax = 0;
-    for (int b = 0; b < nb; b++) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], hb[7 * b + k]); hi[k] = std::max(hi[k], hb[7 * b + 3 + k]); } rmax = std::max(rmax, hb[7 * b + 6]); }
-    for (int k = 0; k < 3; k++) if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) throw EngErr{"non-finite particle position at collider run", WDEM_ERR_RUNTIME};
-    // 2. grid: cell edge ~ smallest enlarged AABB, but no more than ~8 cells per sphere
-    double cell = 2 * (E->minRadius + vd);
-    double vol = std::max(hi[0] - lo[0], cell) * std::max(hi[1] - lo[1], cell) * std::max(hi[2] - lo[2], cell);
-    cell = std::max(cell, std::cbrt(vol / (8.0 * n)));
-    g.cell = cell; g.inv = 1. / cell; g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
-    g.nx = std::max(1, (int)std::floor((hi[0] - lo[0]) * g.inv) + 1); g.ny = std::max(1, (int)std::floor((hi[1] - lo[1]) * g.inv) + 1); g.nz = std::max(1, (int)std::floor((hi[2] - lo[2]) * g.inv) + 1);
-    const long long ncells = (long long)g.nx * g.ny * g.nz;
-    if (ncells > (1ll << 31) - 2) throw EngErr{"collider grid too large", WDEM_ERR_RUNTIME};
-    // 3. cell keys, radix sort, reorder all sphere arrays into cell order
+    long long ncells = 0;
     E->keys.ensure(n, tot); E->keysAlt.ensure(n, tot); E->idx.ensure(n, tot); E->idxAlt.ensure(n, tot);
-    k_cellkeys<<<nb, 256, 0, st>>>(E->S().posr, n, g, E->keys.p, E->idx.p); E->launches++;
+    if (!c.periodic) {
+      // 1. bounds of sphere centres
+      E->blk.ensure((size_t)nb * 7, tot);
+      k_bounds<<<nb, 256, 0, st>>>(E->S().posr, n, E->blk.p); E->launches++;
+      std::vector<double> hb((size_t)nb * 7);
+      CK(cudaMemcpyAsync(hb.data(), E->blk.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+      for (int b = 0; b < nb; b++) for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], hb[7 * b + k]); hi[k] = std::max(hi[k], hb[7 * b + 3 + k]); }
+      for (int k = 0; k < 3; k++) if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) throw EngErr{"non-finite particle position at collider run", WDEM_ERR_RUNTIME};
+      // 2. grid: cell edge ~ smallest enlarged AABB, but no more than ~8 cells per sphere
+      double cell = 2 * (E->minRadius + vd);
+      double vol = std::max(hi[0] - lo[0], cell) * std::max(hi[1] - lo[1], cell) * std::max(hi[2] - lo[2], cell);
+      cell = std::max(cell, std::cbrt(vol / (8.0 * n)));
+      g.cell = cell; g.inv = 1. / cell; g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+      g.nx = std::max(1, (int)std::floor((hi[0] - lo[0]) * g.inv) + 1); g.ny = std::max(1, (int)std::floor((hi[1] - lo[1]) * g.inv) + 1); g.nz = std::max(1, (int)std::floor((hi[2] - lo[2]) * g.inv) + 1);
+      ncells = (long long)g.nx * g.ny * g.nz;
+      if (ncells > (1ll << 31) - 2) throw EngErr{"collider grid too large", WDEM_ERR_RUNTIME};
+      // 3. cell keys
+      k_cellkeys<<<nb, 256, 0, st>>>(E->S().posr, n, g, E->keys.p, E->idx.p); E->launches++;
+    } else {
+      // periodic: nc[k] cells along each (unsheared) cell axis; the hash wraps, positions do not
+      const d3 sz = E->cell.size;
+      double cell = 2 * (E->minRadius + vd);
+      cell = std::max(cell, std::cbrt((sz.x * sz.y * sz.z) / (8.0 * n)));
+      auto nc = [&](double s) { return (int)std::min(1024., std::max(1., std::floor(s / cell))); };
+      pg.nx = nc(sz.x); pg.ny = nc(sz.y); pg.nz = nc(sz.z);
+      pg.invx = pg.nx / sz.x; pg.invy = pg.ny / sz.y; pg.invz = pg.nz / sz.z;
+      ncells = (long long)pg.nx * pg.ny * pg.nz;
+      k_cellkeys_peri<<<nb, 256, 0, st>>>(E->S().posr, n, pg, pu, E->keys.p, E->idx.p); E->launches++;
+    }
+    // radix sort by cell, reorder all sphere arrays into cell order
     int keyBits = 1; while ((1ll << keyBits) < ncells) keyBits++;
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, E->keys.p, E->keysAlt.p, E->idx.p, E->idxAlt.p, n, 0, keyBits, st);
@@ -270,8 +297,14 @@ void rebuild(wdem_engine* E) {
     const int nb128 = nblk(n, 128);
     E->rowCount.ensure((size_t)n + 1, tot);
     CK(cudaMemsetAsync(E->rowCount.p, 0, ((size_t)n + 1) * sizeof(int), st));
-    k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++;
-    if (nWalls) { k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++; }
+    if (!c.periodic) k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr);
+    else k_pairs_ss_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, pg, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
+    E->launches++;
+    if (nWalls) {
+      if (!c.periodic) k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr);
+      else k_pairs_ws_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
+      E->launches++;
+    }
     else CK(cudaMemsetAsync(E->counts.p + n, 0, (size_t)n * sizeof(int), st));
     if (nFacets) { k_pairs_fs<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, E->counts.p + 2 * n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++; }
     else CK(cudaMemsetAsync(E->counts.p + 2 * n, 0, (size_t)n * sizeof(int), st));
@@ -292,8 +325,14 @@ void rebuild(wdem_engine* E) {
     Nst.ensure((size_t)std::max<long long>(nC0, 1), tot, hertz, rolling, c.periodic);
     Contacts N = Nst.view(), O = Ost.view();
     E->srcOld.ensure((size_t)std::max<long long>(nC0, 1), tot);
-    k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, N, O, oc, perm, nullptr, E->srcOld.p); E->launches++;
-    if (nWalls) { k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, N, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
+    if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, N, O, oc, perm, nullptr, E->srcOld.p);
+    else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, pg, pu, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, N, oc, perm, nullptr, E->srcOld.p, E->dCnt);
+    E->launches++;
+    if (nWalls) {
+      if (!c.periodic) k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, N, O, oc, perm, nullptr, E->srcOld.p);
+      else k_pairs_ws_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, N, oc, perm, nullptr, E->srcOld.p, E->dCnt);
+      E->launches++;
+    }
     if (nFacets) { k_pairs_fs<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, nullptr, E->offsets.p + 2 * n, N, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
     if (nC0 > 0) { k_carry<<<nblk(nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, c.law, rolling, c.periodic, E->step); E->launches++; }
     // 6b. orphans: real contacts of the previous table that no candidate claimed (AABBs separated while real)
@@ -762,7 +801,7 @@ int wdem_kinetic_energy(wdem_handle h, double* ek) {
     const int n = h->n; double e = 0;
     if (n) {
       const int nb = nblk(n, 256); h->blk.ensure((size_t)nb * 7, h->bytes);
-      k_ekin<<<nb, 256, 0, h->stream>>>(h->S(), n, h->blk.p);
+      k_ekin<<<nb, 256, 0, h->stream>>>(h->S(), n, makeUniforms(h), h->blk.p);
       auto hb = d2h(h->blk.p, nb, h->stream);
       for (double v : hb) e += v;
     }
@@ -803,6 +842,8 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
     for (int k = 0; k < (hertz ? 5 : 3); k++) ph[k] = d2h(cs.ph[k].p, nC, st);
     if (rolling) for (int k = 0; k < 3; k++) tq[k] = d2h(cs.tq[k].p, nC, st);
     auto cp = d2h(cs.cp.p, nC, st); auto sc = d2h(cs.stepCreated.p, nC, st);
+    std::vector<int32_t> cdv[3];
+    if (h->cfg.periodic) for (int k = 0; k < 3; k++) cdv[k] = d2h(cs.cd[k].p, nC, st);
     struct Row { uint64_t key; long long c; };
     std::vector<Row> rows; rows.reserve(nC);
     for (long long c = 0; c < nC; c++) {
@@ -818,7 +859,7 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
     for (int64_t i = 0; i < nOut; i++) {
       const long long c = rows[i].c; const bool isReal = flags[c] & CF_REAL;
       if (ids) { ids[2 * i] = (int32_t)(rows[i].key >> 32); ids[2 * i + 1] = (int32_t)(rows[i].key & 0xFFFFFFFFu); }
-      if (cellDist) { cellDist[3 * i] = cellDist[3 * i + 1] = cellDist[3 * i + 2] = 0; }
+      if (cellDist) for (int k = 0; k < 3; k++) cellDist[3 * i + k] = h->cfg.periodic ? cdv[k][c] : 0;
       if (real) real[i] = isReal;
       if (uN) uN[i] = isReal ? cp[c].w : NAN;
       if (forceLocal) for (int k = 0; k < 3; k++) forceLocal[3 * i + k] = isReal ? f[k][c] : 0.;

@@ -654,10 +654,19 @@ __global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, con
 }
 
 // kinetic energy Σ ½ m v·v + ½ I ω·ω (aperiodic: DemData::getEk_any, Particle.cpp:247-265); per-block partial sums, fixed order
-__global__ void __launch_bounds__(256) k_ekin(Spheres S, int n, double* blockSum) {
+__global__ void __launch_bounds__(256) k_ekin(Spheres S, int n, StepU u, double* blockSum) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0;
-  if (i < n) { double4 v = S.velm[i], w = S.angi[i]; e = .5 * (v.w * sqn(xyz(v))); if (!isinf(w.w)) e += .5 * w.w * sqn(xyz(w)); }
+  if (i < n) {
+    double4 v = S.velm[i], w = S.angi[i];
+    d3 fv = xyz(v), fw = xyz(w);
+    if (u.periodic) {   // Cell::pprevFluctVel / pprevFluctAngVel (Cell.cpp:36-57)
+      const d3 pos = xyz(S.posr[i]);
+      if (u.homoDeform == 2 || u.homoDeform == 3) fv = fv - mulMV(u.gradV, pos);
+      else if (u.homoDeform == 4) { fv = fv - mulMV(u.gradV, pos - (u.dt / 2) * fv); fw = fw - u.spinVec; }
+    }
+    e = .5 * (v.w * sqn(fv)); if (!isinf(w.w)) e += .5 * w.w * sqn(fw);
+  }
   __shared__ double sm[256];
   sm[threadIdx.x] = e; __syncthreads();
   for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s]; __syncthreads(); }
@@ -789,9 +798,7 @@ __global__ void __launch_bounds__(128) k_pairs_ss(Spheres S, int n, Grid g, cons
           const long long c = out + cntLocal;
           const bool iIsA = idI < idJ;
           N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
-          long long co = find_old(oc, oslotI, idJ);
-          if (co >= 0 && !(O.flags[co] & CF_REAL)) co = -1;
-          srcOld[c] = (int)co;
+          srcOld[c] = (int)find_old(oc, oslotI, idJ);
           N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
         } else atomicAdd(&rowCount[j], 1);
         cntLocal++;
@@ -823,9 +830,7 @@ __global__ void __launch_bounds__(128) k_pairs_ws(Spheres S, int n, const Wall* 
     if (FILL) {
       const long long c = out + cntLocal;
       N.pair[c] = make_int2(w, i);
-      long long co = find_old(oc, oslotI, W.id);
-      if (co >= 0 && !(O.flags[co] & CF_REAL)) co = -1;
-      srcOld[c] = (int)co;
+      srcOld[c] = (int)find_old(oc, oslotI, W.id);
       N.flags[c] = (KIND_WS << CF_KIND_SHIFT);
     }
     cntLocal++;
@@ -867,9 +872,7 @@ __global__ void __launch_bounds__(128) k_pairs_fs(Spheres S, int n, const Facet*
           if (FILL) {
             const long long c = out + cntLocal;
             N.pair[c] = make_int2(f, i);
-            long long co = find_old(oc, oslotI, F->id);
-            if (co >= 0 && !(O.flags[co] & CF_REAL)) co = -1;
-            srcOld[c] = (int)co;
+            srcOld[c] = (int)find_old(oc, oslotI, F->id);
             N.flags[c] = (KIND_FS << CF_KIND_SHIFT);
           }
           cntLocal++;
@@ -878,17 +881,172 @@ __global__ void __launch_bounds__(128) k_pairs_fs(Spheres S, int n, const Facet*
   if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
 }
 
+// ================================================================================================
+// Periodic broad phase (replaces insertionSortPeri/handleBoundInversionPeri/spatialOverlapPeri, InsertionSortCollider.cpp:637-1060):
+// AABBs live in the cell's unsheared coordinates (Bo1_Sphere_Aabb::goGeneric, Sphere.cpp:67-81), overlap is per-axis periodic and yields
+// the integer cellDist.  Positions are never wrapped (InsertionSortCollider.hpp:28-29); only the grid hash wraps.
+// ================================================================================================
+struct PeriU { m33 unshear; d3 size; d3 cosv; int hasShear; };   // Cell::unshearPt, getSize, getCos, hasShear (Cell.hpp:82-97)
+struct PGrid { double invx, invy, invz; int nx, ny, nz; };       // nc[k] cells of size[k]/nc[k] along each cell axis
+
+__device__ __forceinline__ void periAabb(const PeriU& pu, double4 p, double vd, d3& mn, d3& mx) {
+  d3 half = mk3(p.w, p.w, p.w);
+  if (pu.hasShear) {  // Cell::shearAlignedExtents (Cell.cpp:68-79): sequential += in the order ax=0,1,2
+    const d3 perp = half;
+    half.y += .5 * perp.y * (1 / pu.cosv.x - 1); half.z += .5 * perp.z * (1 / pu.cosv.x - 1);
+    half.z += .5 * perp.z * (1 / pu.cosv.y - 1); half.x += .5 * perp.x * (1 / pu.cosv.y - 1);
+    half.x += .5 * perp.x * (1 / pu.cosv.z - 1); half.y += .5 * perp.y * (1 / pu.cosv.z - 1);
+  }
+  const d3 u = mulMV(pu.unshear, xyz(p));
+  mn = u - half; mx = u + half;
+  if (vd > 0) { mx = mk3(mx.x + vd, mx.y + vd, mx.z + vd); mn = mk3(mn.x - vd, mn.y - vd, mn.z - vd); }  // AabbCollider::updateAabb (Collision.cpp:156-159)
+}
+__device__ __forceinline__ double cellWrapRel(double x, double x0, double x1, int& period) {  // InsertionSortCollider.cpp:624-628
+  double xNorm = (x - x0) / (x1 - x0);
+  double fl = floor(xNorm);
+  period = (int)fl;
+  return (xNorm - fl) * (x1 - x0);
+}
+// spatialOverlapPeri_axis, "new algorithm" (InsertionSortCollider.cpp:897-1026). Returns 0/1, or -1 for the ambiguous double contact.
+__device__ __forceinline__ int overlapPeriAxis(double min1, double max1, double min2, double max2, double dim, int& period) {
+  if (isinf(min1) || isinf(min2)) { period = 0; return 1; }
+  int pmn1_2, pmx1_2, pmn2_1, pmx2_1;
+  double mn1_2 = cellWrapRel(min1, min2, min2 + dim, pmn1_2); (void)cellWrapRel(max1, min2, min2 + dim, pmx1_2);
+  double mn2_1 = cellWrapRel(min2, min1, min1 + dim, pmn2_1); (void)cellWrapRel(max2, min1, min1 + dim, pmx2_1);
+  if (pmn1_2 != pmx1_2 && pmn2_1 != pmx2_1) return -1;
+  if (pmn2_1 == pmx2_1) { period = -pmn2_1; return mn2_1 < (max1 - min1) ? 1 : 0; }
+  period = pmn1_2; return mn1_2 < (max2 - min2) ? 1 : 0;
+}
+// spatialOverlapPeri (InsertionSortCollider.cpp:1042-1060), box 1 belonging to the particle with the lower id
+__device__ __forceinline__ int overlapPeri(d3 mn1, d3 mx1, d3 mn2, d3 mx2, d3 size, int per[3]) {
+  int r = overlapPeriAxis(mn1.x, mx1.x, mn2.x, mx2.x, size.x, per[0]); if (r <= 0) return r;
+  r = overlapPeriAxis(mn1.y, mx1.y, mn2.y, mx2.y, size.y, per[1]); if (r <= 0) return r;
+  return overlapPeriAxis(mn1.z, mx1.z, mn2.z, mx2.z, size.z, per[2]);
+}
+__device__ __forceinline__ int imod(int a, int n) { int m = a % n; return m < 0 ? m + n : m; }
+__device__ __forceinline__ double wrap01(double u, double size) { double xn = u / size; xn -= floor(xn); return xn * size; }
+
+__global__ void __launch_bounds__(256) k_cellkeys_peri(const double4* __restrict__ posr, int n, PGrid g, PeriU pu, uint32_t* keys, int* idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const d3 u = mulMV(pu.unshear, xyz(posr[i]));
+  int ix = min(g.nx - 1, max(0, (int)floor(wrap01(u.x, pu.size.x) * g.invx)));
+  int iy = min(g.ny - 1, max(0, (int)floor(wrap01(u.y, pu.size.y) * g.invy)));
+  int iz = min(g.nz - 1, max(0, (int)floor(wrap01(u.z, pu.size.z) * g.invz)));
+  keys[i] = (uint32_t)((iz * g.ny + iy) * g.nx + ix);
+  idx[i] = i;
+}
+
+// Sphere+Sphere candidates in a periodic cell; same ownership rule as k_pairs_ss (the larger sphere searches), cells wrap.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_pairs_ss_peri(Spheres S, int n, PGrid g, PeriU pu, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
+                                                      const int* __restrict__ offsets, Contacts N, OldCsr oc, const int* __restrict__ perm,
+                                                      int* __restrict__ rowCount, int* __restrict__ srcOld, Counters* cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 pi = S.posr[i];
+  d3 mnI, mxI; periAabb(pu, pi, vd, mnI, mxI);
+  const d3 ui = mulMV(pu.unshear, xyz(pi));
+  const double cx = wrap01(ui.x, pu.size.x), cy = wrap01(ui.y, pu.size.y), cz = wrap01(ui.z, pu.size.z);
+  // |Δcentre| <= half_i + half_j <= 2*half_i = extent of the own box (radius_j <= radius_i); small relative + absolute slack
+  const double Hx = (mxI.x - mnI.x) * (1 + 1e-9) + 1e-9 / g.invx, Hy = (mxI.y - mnI.y) * (1 + 1e-9) + 1e-9 / g.invy, Hz = (mxI.z - mnI.z) * (1 + 1e-9) + 1e-9 / g.invz;
+  int x0 = (int)floor((cx - Hx) * g.invx), x1 = (int)floor((cx + Hx) * g.invx); if (x1 - x0 + 1 >= g.nx) { x0 = 0; x1 = g.nx - 1; }
+  int y0 = (int)floor((cy - Hy) * g.invy), y1 = (int)floor((cy + Hy) * g.invy); if (y1 - y0 + 1 >= g.ny) { y0 = 0; y1 = g.ny - 1; }
+  int z0 = (int)floor((cz - Hz) * g.invz), z1 = (int)floor((cz + Hz) * g.invz); if (z1 - z0 + 1 >= g.nz) { z0 = 0; z1 = g.nz - 1; }
+  // the x range wraps into at most two runs of consecutive cells
+  const int wx0 = imod(x0, g.nx), wx1 = imod(x1, g.nx);
+  const int nseg = (wx0 <= wx1) ? 1 : 2;
+  const uint32_t mi = S.mask[i];
+  const int idI = S.id[i];
+  const int oslotI = FILL ? (perm ? perm[i] : i) : 0;
+  int cntLocal = 0;
+  long long out = FILL ? offsets[i] : 0;
+  for (int iz = z0; iz <= z1; iz++)
+    for (int iy = y0; iy <= y1; iy++) {
+      const int k0 = (imod(iz, g.nz) * g.ny + imod(iy, g.ny)) * g.nx;
+      for (int seg = 0; seg < nseg; seg++) {
+        const int sa = (nseg == 1) ? wx0 : (seg == 0 ? wx0 : 0), sb = (nseg == 1) ? wx1 : (seg == 0 ? g.nx - 1 : wx1);
+        const int jb = cellStart[k0 + sa], je = cellStart[k0 + sb + 1];
+        for (int j = jb; j < je; j++) {
+          if (j == i) continue;
+          const double4 pj = S.posr[j];
+          if (!(pj.w < pi.w || (pj.w == pi.w && j < i))) continue;
+          if (!mayCollide(mi, S.mask[j], loneMask)) continue;
+          d3 mnJ, mxJ; periAabb(pu, pj, vd, mnJ, mxJ);
+          const int idJ = S.id[j];
+          const bool iIsA = idI < idJ;
+          int per[3];
+          const int ov = iIsA ? overlapPeri(mnI, mxI, mnJ, mxJ, pu.size, per) : overlapPeri(mnJ, mxJ, mnI, mxI, pu.size, per);
+          if (ov < 0) { cnt->error = ERR_AMBIGUOUS_PERI; cnt->errA = iIsA ? idI : idJ; cnt->errB = iIsA ? idJ : idI; continue; }
+          if (!ov) continue;
+          if (FILL) {
+            const long long c = out + cntLocal;
+            N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
+            N.cdx[c] = per[0]; N.cdy[c] = per[1]; N.cdz[c] = per[2];
+            srcOld[c] = (int)find_old(oc, oslotI, idJ);
+            N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
+          } else atomicAdd(&rowCount[j], 1);
+          cntLocal++;
+        }
+      }
+    }
+  if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
+}
+
+// Wall+Sphere candidates in a (non-skewed) periodic cell: the wall box is infinite on two axes (period 0 there) and takes part in the
+// periodic overlap test on its own axis.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_pairs_ws_peri(Spheres S, int n, const Wall* __restrict__ walls, int nWalls, PeriU pu, double vd, double wallHalfThick, uint32_t loneMask,
+                                                      int* counts, const int* __restrict__ offsets, Contacts N, OldCsr oc, const int* __restrict__ perm,
+                                                      int* __restrict__ rowCount, int* __restrict__ srcOld, Counters* cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 pi = S.posr[i];
+  d3 mnI, mxI; periAabb(pu, pi, vd, mnI, mxI);
+  const uint32_t mi = S.mask[i];
+  const int idI = S.id[i];
+  int cntLocal = 0;
+  long long out = FILL ? offsets[i] : 0;
+  const int oslotI = FILL ? (perm ? perm[i] : i) : 0;
+  for (int w = 0; w < nWalls; w++) {
+    const Wall W = walls[w];
+    if (!mayCollide(mi, W.mask, loneMask)) continue;
+    double wmin = W.pos[W.axis], wmax = wmin;
+    if (wallHalfThick > 0) { wmin -= wallHalfThick; wmax += wallHalfThick; }
+    if (vd > 0) { wmax = wmax + vd; wmin = wmin - vd; }
+    const double smin = comp(mnI, W.axis), smax = comp(mxI, W.axis), dim = comp(pu.size, W.axis);
+    int period;
+    const bool wallLo = W.id < idI;
+    const int ov = wallLo ? overlapPeriAxis(wmin, wmax, smin, smax, dim, period) : overlapPeriAxis(smin, smax, wmin, wmax, dim, period);
+    if (ov < 0) { cnt->error = ERR_AMBIGUOUS_PERI; cnt->errA = W.id; cnt->errB = idI; continue; }
+    if (!ov) continue;
+    if (FILL) {
+      const long long c = out + cntLocal;
+      N.pair[c] = make_int2(w, i);
+      const int cd = wallLo ? period : -period;   // canonical pA = wall (Contact::swapOrder negates cellDist, Contact.cpp:12-16)
+      N.cdx[c] = W.axis == 0 ? cd : 0; N.cdy[c] = W.axis == 1 ? cd : 0; N.cdz[c] = W.axis == 2 ? cd : 0;
+      srcOld[c] = (int)find_old(oc, oslotI, W.id);
+      N.flags[c] = (KIND_WS << CF_KIND_SHIFT);
+    }
+    cntLocal++;
+  }
+  if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
+}
+
 // carry L6Geom/FrictPhys history of contacts that were real into the new table: one thread per NEW contact (coalesced writes)
 __global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Contacts O, const int* __restrict__ srcOld, int law, int rolling, int periodic, long long stepNow) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nNew) return;
   const int co = srcOld[c];
-  if (co >= 0) {
+  if (co >= 0 && (O.flags[co] & CF_REAL)) {
     copy_history(N, c, O, co, law, rolling, periodic);
     N.Fg[c] = O.Fg[co];
     N.flags[c] |= CF_REAL;
     O.flags[co] |= CF_CLAIMED;
   } else {
+    // a potential contact that survives a full run keeps the cellDist it was created with (handleBoundInversionPeri only creates
+    // when !hasInter, InsertionSortCollider.cpp:844-893)
+    if (periodic && co >= 0) { N.cdx[c] = O.cdx[co]; N.cdy[c] = O.cdy[co]; N.cdz[c] = O.cdz[co]; }
     N.stepCreated[c] = (int)stepNow;
     N.Fg[c] = make_double4(0, 0, 0, 0);
   }

@@ -167,6 +167,11 @@ class Engine:
         self._chk(self.L.wdem_kinetic_energy(self.h, C.byref(e)))
         return e.value
 
+    def cell_hsize(self):
+        h = np.zeros((3, 3))
+        self._chk(self.L.wdem_get_cell(self.h, ptr(h)))
+        return h
+
     def crit_dt(self):
         e = C.c_double()
         self._chk(self.L.wdem_crit_dt(self.h, C.byref(e)))

@@ -218,3 +218,32 @@ def facet_box_scene(n=300, *, box=.4, r=.02, psd_ratio=2.0, seed=0, law=LAW_IDEA
     S.vel = rng.uniform(-vmax, vmax, (n, 3)); S.angVel = rng.uniform(-1, 1, (n, 3))
     S.params = Params(gravity=(0, 0, -9.81), damping=.2, law=law, verletDist=-.05, dynDtPeriod=10, en=en)
     return S.finalize()
+
+
+def periodic_gas(n, *, cell=(.5, .5, .5), r=.02, psd_ratio=1.0, seed=0, vmax=1.0, law=LAW_IDEALELPL, gradV=None, homoDeform=HOMO_GRADV2,
+                 shear0=0.0, scatter=2, walls=False, en=float("nan"), mean_field=True):
+    """Random overlapping cloud in a periodic cell (cfg4 of BASELINE.json in small): positions are NOT wrapped — a fraction is shifted by
+    whole cell vectors (``scatter`` periods each way) so that non-zero Contact.cellDist occurs from the first collider run.
+    ``shear0`` pre-skews the cell (hSize[0,1]); ``gradV`` (3x3) drives it; initial velocities = fluctuation + gradV·x (mean field)."""
+    rng = np.random.default_rng(seed)
+    S = SceneSpec()
+    S.mats = [frict_mat(density=2500., young=1e7, tanPhi=.5)] if law == LAW_IDEALELPL else [hertz_mat(density=2500., young=1e8)]
+    H = np.diag(np.asarray(cell, dtype=np.float64)); H[0, 1] = shear0 * cell[1]
+    g = np.zeros((3, 3)) if gradV is None else np.asarray(gradV, dtype=np.float64).reshape(3, 3)
+    frac = rng.uniform(0, 1, (n, 3))
+    if walls:   # walls at z=0.1 and z=0.9 of the cell height (non-skewed cells only)
+        frac[:, 2] = rng.uniform(.12, .88, n)
+    shift = rng.integers(-scatter, scatter + 1, (n, 3)) if scatter > 0 else np.zeros((n, 3))
+    if walls:
+        shift[:, 2] = 0
+    S.pos = (frac + shift) @ H.T
+    S.radius = np.full(n, r) if psd_ratio == 1.0 else r * np.exp(rng.uniform(0, math.log(psd_ratio), n))
+    S.vel = rng.uniform(-vmax, vmax, (n, 3))
+    if mean_field:
+        S.vel = S.vel + S.pos @ g.T
+    S.angVel = rng.uniform(-1, 1, (n, 3))
+    if walls:
+        S.walls = [dict(pos=(0, 0, .1 * cell[2]), axis=2, sense=1, mat=0, mask=MASK_BOUNDARY), dict(pos=(0, 0, .9 * cell[2]), axis=2, sense=-1, mat=0, mask=MASK_BOUNDARY)]
+    S.params = Params(gravity=(0, 0, 0), damping=.1, law=law, verletDist=-.05, dynDtPeriod=10, en=en, periodic=1)
+    S.cell = dict(hSize=H, gradV=g, nextGradV=g, homoDeform=homoDeform)
+    return S.finalize()
