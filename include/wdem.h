@@ -123,6 +123,26 @@ int wdem_crit_dt(wdem_handle h, double* dt);
 /* Σ ½ m v² + ½ ω·I·ω  (DemData::getEk_any, Particle.cpp:247-265), device reduction. */
 int wdem_kinetic_energy(wdem_handle h, double* ek);
 int wdem_get_scalars(wdem_handle h, double* dt, double* time, int64_t* step, double* verletDist, int64_t* nFullRuns);
+/* ---- Slab decomposition over several GPUs.  The reference has no distributed DEM; its nearest interface is the shared-memory
+ * loop over all particles/contacts (`#pragma omp parallel for`, Leapfrog.cpp:144-147, ContactLoop.cpp:134-137), which this replaces for scenes that do not
+ * fit / should not run on one GPU.  One handle = one subdomain (1-D slab along `axis`, periodic scenes: along the cell axis, ring-closed).
+ * Every subdomain uploads the walls/facets/materials of the whole scene and ANY subset of the spheres with scene-wide unique ids (the first collider
+ * run migrates them to their owners); then all subdomains call wdem_step with the same arguments.  Per step the owners refresh pos/vel/angVel of
+ * their ghosts (72 B each); at collider full runs spheres migrate together with the history of their contacts and ghosts are re-selected.
+ * Transport: NCCL (one process per GPU; the 128-byte id from rank 0 must be distributed by the caller, e.g. torch.distributed) or an in-process
+ * group (one host thread per handle; any mix of devices, also several subdomains on one GPU). */
+int wdem_comm_unique_id(char* out128);
+int wdem_comm_init_nccl(wdem_handle h, int rank, int world, const char* id128);
+void* wdem_local_group_create(int world);
+int wdem_local_group_destroy(void* group);
+int wdem_comm_init_local(wdem_handle h, void* group, int rank);
+/* cuts: world-1 ascending slab boundaries along axis (absolute coordinates; periodic: fractions of the cell size). globalMaxId: largest Particle.id of the scene. */
+int wdem_set_domain(wdem_handle h, int axis, int ncuts, const double* cuts, int64_t globalMaxId);
+int64_t wdem_num_owned(wdem_handle h);
+/* Owned spheres in subdomain order with their ids (any pointer but ids may be NULL); arrays sized by wdem_num_owned. */
+int wdem_download_owned(wdem_handle h, int32_t* ids, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque);
+int wdem_domain_stats(wdem_handle h, int64_t* nOwned, int64_t* nGhosts, int64_t* migratedOut, int64_t* migratedIn, int64_t* rowsIn);
+
 /* Device-level info for bench.py: bytes allocated, stream pointer (cudaStream_t) */
 int wdem_device_info(wdem_handle h, int64_t* bytes_allocated, void** stream);
 

@@ -12,8 +12,8 @@ def engine_for(S):
     return Engine(S.params).load(S)
 
 
-def compare(S, nsteps, check_every=1, exact=True, label=""):
-    O = Oracle(S); E = engine_for(S)
+def compare(S, nsteps, check_every=1, exact=True, label="", make=None):
+    O = Oracle(S); E = (make or engine_for)(S)
     done = 0
     while done < nsteps:
         k = min(check_every, nsteps - done)
@@ -155,3 +155,48 @@ def test_periodic_with_walls():
     S.params.gravity = (0, 0, -9.81)
     O, E = compare(S, 150, check_every=25, label="peri-walls")
     compare_potential(O, E)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# slab decomposition: several subdomains on this one GPU (in-process transport), bit-identical to the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def cluster(world, axis=0, scramble=False):
+    from woo_b200.domain import LocalCluster
+    return lambda S: LocalCluster(S, world, axis=axis, scramble=scramble)
+
+
+@pytest.mark.parametrize("law", [sc.LAW_IDEALELPL, sc.LAW_HERTZ_DMT])
+@pytest.mark.parametrize("world", [2, 3])
+def test_decomposed_gas(law, world):
+    S = sc.random_gas(500, box=.5, r=.02, psd_ratio=3.0, seed=21, law=law, en=.7 if law else float("nan"))
+    O, E = compare(S, 300, check_every=25, label=f"decomposed gas world={world} law={law}", make=cluster(world))
+    st = E.domain_stats()
+    assert sum(d["migrated_in"] for d in st) > 0 and sum(d["rows_in"] for d in st) > 0, "test did not exercise migration with history: %r" % st
+    assert sum(d["ghosts"] for d in st) > 0
+
+
+def test_decomposed_scrambled_start_and_axes():
+    for axis in (1, 2):
+        S = sc.random_gas(300, box=.4, r=.02, psd_ratio=2.0, seed=23)
+        compare(S, 120, check_every=30, label=f"decomposed scrambled axis={axis}", make=cluster(3, axis=axis, scramble=True))
+
+
+def test_decomposed_deposition():
+    S = sc.deposition(2000, seed=1)
+    compare(S, 400, check_every=100, label="decomposed deposition", make=cluster(4))
+
+
+def test_decomposed_facets_and_flags():
+    S = sc.facet_box_scene(300, seed=2)
+    S.flags[::7] = sc.DOF_ALL; S.flags[1::7] = 1 | 8
+    compare(S, 150, check_every=25, label="decomposed facets", make=cluster(2))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_decomposed_periodic_shear(world):
+    g = [[0, 2.0, 0], [0, 0, 0], [0, 0, 0]]
+    S = sc.periodic_gas(500, cell=(.6, .4, .45), r=.02, psd_ratio=2.0, seed=29, gradV=g)
+    O, E = compare(S, 200, check_every=25, label=f"decomposed periodic world={world}", make=cluster(world))
+    compare_potential(O, E)
+    S = sc.periodic_gas(300, cell=(.45, .45, .45), r=.02, psd_ratio=3.0, seed=17, gradV=[[-1.0, .5, 0], [0, -1.0, 0], [.3, 0, -1.0]], shear0=.3)
+    compare(S, 100, check_every=25, label="decomposed periodic skew", make=cluster(world, axis=1))

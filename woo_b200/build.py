@@ -6,10 +6,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwdem.so")
 SOURCES = ["wdem_engine.cu"]
-DEPS = ["wdem_engine.cu", "wdem_kernels.cuh", "wdem_math.cuh", os.path.join("..", "..", "include", "wdem.h")]
+DEPS = ["wdem_engine.cu", "wdem_kernels.cuh", "wdem_domain.cuh", "wdem_comm.h", "wdem_math.cuh", os.path.join("..", "..", "include", "wdem.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-Wno-deprecated-declarations",
               "-diag-suppress", "177"]
+
+
+def nccl_flags():
+    """NCCL for the slab decomposition (halo exchange / migration).  Prefer the copy PyTorch ships (the one torch.distributed loads in the
+    same process, so that only one NCCL lives in a rank); fall back to the system library."""
+    import importlib.util
+    spec = importlib.util.find_spec("nvidia.nccl")
+    if spec and spec.submodule_search_locations:
+        root = list(spec.submodule_search_locations)[0]
+        inc, lib = os.path.join(root, "include"), os.path.join(root, "lib")
+        if os.path.exists(os.path.join(inc, "nccl.h")) and os.path.exists(os.path.join(lib, "libnccl.so.2")):
+            return ["-I", inc, "-L", lib, "-l:libnccl.so.2", "-Xlinker", "-rpath=" + lib]
+    return ["-lnccl"]
 
 
 def nvcc():
@@ -29,7 +42,7 @@ def needs_build():
 def build(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + nccl_flags()
     env = dict(os.environ)
     env.pop("CXX", None); env.pop("CC", None)
     cmd += ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []

@@ -31,7 +31,8 @@ EXPORTS = ["wdem_default_config", "wdem_create", "wdem_destroy", "wdem_last_erro
            "wdem_upload_materials", "wdem_upload_spheres", "wdem_upload_walls", "wdem_upload_facets", "wdem_set_cell",
            "wdem_set_next_gradv", "wdem_get_cell", "wdem_step", "wdem_step_e2e", "wdem_download_state", "wdem_download_forces",
            "wdem_set_state", "wdem_num_contacts", "wdem_download_contacts", "wdem_crit_dt", "wdem_kinetic_energy", "wdem_get_scalars",
-           "wdem_device_info"]
+           "wdem_device_info", "wdem_comm_unique_id", "wdem_comm_init_nccl", "wdem_local_group_create", "wdem_local_group_destroy",
+           "wdem_comm_init_local", "wdem_set_domain", "wdem_num_owned", "wdem_download_owned", "wdem_domain_stats"]
 
 
 def lib_path():
@@ -50,6 +51,8 @@ def load(build=True):
         L.wdem_last_error.argtypes = [C.c_void_p]
         L.wdem_num_contacts.restype = C.c_int64
         L.wdem_download_contacts.restype = C.c_int64
+        L.wdem_num_owned.restype = C.c_int64
+        L.wdem_local_group_create.restype = C.c_void_p
         _LIB = L
     return _LIB
 

@@ -1,0 +1,268 @@
+// wdem_domain.cuh — kernels of the 1-D slab decomposition: ownership, migration of spheres together with the history
+// rows of their real contacts, ghost export at collider full runs, and the per-step ghost refresh (pos, vel, angVel).
+// Cross-slab pairs are evaluated on both sides from bit-identical inputs (ghost = bit copy, history created in the same step on both
+// sides), so both replicas of a contact stay bit-identical; forces are reduced only into owned spheres — no reverse exchange.
+#pragma once
+#include "wdem_kernels.cuh"
+
+namespace wd {
+
+#define WDEM_MAX_RANKS 16
+
+struct DomainU {
+  int rank, world, axis, periodic;
+  double bounds[WDEM_MAX_RANKS + 1];   // slab r = [bounds[r], bounds[r+1]) in the slab coordinate (periodic: wrapped unsheared coordinate)
+  double reach;                        // (largest half-extent + verletDist): how far an owned box of any rank sticks out of its slab
+  double vd;
+  double dim;                          // periodic: cell size along the slab axis
+  PeriU pu;
+};
+
+__device__ __forceinline__ double slabCoord(const DomainU& D, double4 p) {
+  if (!D.periodic) return comp(xyz(p), D.axis);
+  const d3 u = mulMV(D.pu.unshear, xyz(p));
+  return wrap01(comp(u, D.axis), D.dim);
+}
+__device__ __forceinline__ int ownerOf(const DomainU& D, double x) {
+  int r = 0;
+  while (r + 1 < D.world && x >= D.bounds[r + 1]) r++;
+  return r;
+}
+// half-extent of the sphere's enlarged AABB along the slab axis
+__device__ __forceinline__ double slabHalf(const DomainU& D, double4 p) {
+  if (!D.periodic) return p.w + D.vd;
+  d3 mn, mx; periAabb(D.pu, p, D.vd, mn, mx);
+  return .5 * (comp(mx, D.axis) - comp(mn, D.axis));
+}
+
+// key 0: stays owned; 1+r: emigrates to rank r; world+1: ghost of the previous generation (dropped)
+__global__ void __launch_bounds__(256) k_dom_classify(Spheres S, int n, DomainU D, uint32_t* keys, int* slots) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t key;
+  if (S.flags[i] & F_GHOST) key = D.world + 1;
+  else { const int o = ownerOf(D, slabCoord(D, S.posr[i])); key = (o == D.rank) ? 0u : (uint32_t)(1 + o); }
+  keys[i] = key; slots[i] = i;
+}
+// first index of every key in the sorted key array (start[] pre-filled with n)
+__global__ void __launch_bounds__(256) k_dom_starts(const uint32_t* __restrict__ keys, int n, int* start) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0 || keys[i] != keys[i - 1]) start[keys[i]] = i;
+}
+__global__ void k_fill_int(int* p, int n, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+struct PRec {   // a migrating sphere: Node + DemData + Sphere + Particle fields
+  double4 posr, velm, angi, ori; double f[6]; uint32_t flags, mask; int32_t mat, id, up, pad;
+};
+struct GRec {   // a ghost: what the contact functors read
+  double4 posr, velm, angi; uint32_t flags, mask; int32_t mat, id;
+};
+struct CRec {   // history row of a real contact keyed by particle ids
+  int32_t idA, idB; uint32_t flags; int32_t stepCreated; int32_t cd[3]; int32_t pad;
+  double t[6]; double4 cp; double fl[3]; double ph[5]; double tq[3]; double4 Fg;
+};
+
+__global__ void __launch_bounds__(256) k_dom_pack_particles(Spheres S, const int* __restrict__ slots, int first, int cnt, PRec* out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  const int i = slots[first + k];
+  PRec r;
+  r.posr = S.posr[i]; r.velm = S.velm[i]; r.angi = S.angi[i]; r.ori = S.ori[i];
+  r.f[0] = S.fx[i]; r.f[1] = S.fy[i]; r.f[2] = S.fz[i]; r.f[3] = S.tx[i]; r.f[4] = S.ty[i]; r.f[5] = S.tz[i];
+  r.flags = S.flags[i]; r.mask = S.mask[i]; r.mat = S.mat[i]; r.id = S.id[i]; r.up = S.up[i]; r.pad = 0;
+  out[k] = r;
+}
+__global__ void __launch_bounds__(256) k_dom_unpack_particles(Spheres S, int first, int cnt, const PRec* __restrict__ in) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  const int i = first + k;
+  const PRec r = in[k];
+  S.posr[i] = r.posr; S.velm[i] = r.velm; S.angi[i] = r.angi; S.ori[i] = r.ori;
+  S.fx[i] = r.f[0]; S.fy[i] = r.f[1]; S.fz[i] = r.f[2]; S.tx[i] = r.f[3]; S.ty[i] = r.f[4]; S.tz[i] = r.f[5];
+  S.lx[i] = r.posr.x; S.ly[i] = r.posr.y; S.lz[i] = r.posr.z;
+  S.flags[i] = (r.flags & ~(F_GHOST | F_ARRIVED)) | F_ARRIVED; S.mask[i] = r.mask; S.mat[i] = r.mat; S.id[i] = r.id; S.up[i] = r.up;
+}
+// kept spheres: gather in (stable) slot order into the new generation
+__global__ void __launch_bounds__(256) k_dom_gather_kept(Spheres dst, Spheres src, const int* __restrict__ slots, int cnt) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  const int o = slots[k];
+  dst.posr[k] = src.posr[o]; dst.velm[k] = src.velm[o]; dst.angi[k] = src.angi[o]; dst.ori[k] = src.ori[o];
+  dst.fx[k] = src.fx[o]; dst.fy[k] = src.fy[o]; dst.fz[k] = src.fz[o]; dst.tx[k] = src.tx[o]; dst.ty[k] = src.ty[o]; dst.tz[k] = src.tz[o];
+  dst.lx[k] = src.lx[o]; dst.ly[k] = src.ly[o]; dst.lz[k] = src.lz[o];
+  dst.flags[k] = src.flags[o] & ~(F_GHOST | F_ARRIVED); dst.mask[k] = src.mask[o]; dst.mat[k] = src.mat[o]; dst.id[k] = src.id[o]; dst.up[k] = src.up[o];
+}
+
+// history rows of emigrants: count, then pack (one thread per emigrant walks its incidence row of the previous table)
+__global__ void __launch_bounds__(128) k_dom_count_rows(const int* __restrict__ slots, int first, int cnt, OldCsr oc, const uint32_t* __restrict__ oflags, int* rowCnt) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  int c = 0;
+  if (oc.valid) { const int s = slots[first + k]; for (int e = oc.rowStart[s]; e < oc.rowStart[s + 1]; e++) { const uint32_t f = oflags[oc.rowEntry[e] >> 1]; if ((f & CF_REAL) && !(f & CF_DEAD)) c++; } }
+  rowCnt[k] = c;
+}
+__device__ __forceinline__ void crec_from(const Contacts& O, long long co, int idA, int idB, int law, int rolling, int periodic, CRec& r) {
+  r.idA = idA; r.idB = idB; r.flags = O.flags[co]; r.stepCreated = O.stepCreated[co]; r.pad = 0;
+  r.cd[0] = periodic ? O.cdx[co] : 0; r.cd[1] = periodic ? O.cdy[co] : 0; r.cd[2] = periodic ? O.cdz[co] : 0;
+  r.t[0] = O.t0x[co]; r.t[1] = O.t0y[co]; r.t[2] = O.t0z[co]; r.t[3] = O.t1x[co]; r.t[4] = O.t1y[co]; r.t[5] = O.t1z[co];
+  r.cp = O.cp[co]; r.fl[0] = O.fn[co]; r.fl[1] = O.ft0[co]; r.fl[2] = O.ft1[co];
+  for (int k = 0; k < 3; k++) r.ph[k] = O.ph[k][co];
+  r.ph[3] = law == 1 ? O.ph[3][co] : 0.; r.ph[4] = law == 1 ? O.ph[4][co] : 0.;
+  r.tq[0] = rolling ? O.tq0[co] : 0.; r.tq[1] = rolling ? O.tq1[co] : 0.; r.tq[2] = rolling ? O.tq2[co] : 0.;
+  r.Fg = O.Fg[co];
+}
+__global__ void __launch_bounds__(128) k_dom_pack_rows(const int* __restrict__ slots, int first, int cnt, OldCsr oc, Contacts O, const int32_t* __restrict__ sid,
+                                                      const Wall* __restrict__ walls, const Facet* __restrict__ facets, const int* __restrict__ rowOff, int law, int rolling,
+                                                      int periodic, CRec* out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt || !oc.valid) return;
+  const int s = slots[first + k];
+  int w = rowOff[k];
+  for (int e = oc.rowStart[s]; e < oc.rowStart[s + 1]; e++) {
+    const long long co = oc.rowEntry[e] >> 1;
+    const uint32_t f = O.flags[co];
+    if (!(f & CF_REAL) || (f & CF_DEAD)) continue;
+    const int2 pr = O.pair[co]; const int kind = cf_kind(f);
+    const int idA = kind == KIND_SS ? sid[pr.x] : (kind == KIND_WS ? walls[pr.x].id : facets[pr.x].id);
+    crec_from(O, co, idA, sid[pr.y], law, rolling, periodic, out[w]);
+    out[w].pad = pr.x;   // wall / facet index for boundary rows
+    w++;
+  }
+}
+// received rows are appended behind the previous table (so that k_carry can index them) and keyed for the lookup
+__global__ void __launch_bounds__(256) k_dom_unpack_rows(Contacts O, long long base, int cnt, const CRec* __restrict__ in, int law, int rolling, int periodic,
+                                                        unsigned long long* keys, int* vals) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  const CRec r = in[k];
+  const long long co = base + k;
+  O.pair[co] = make_int2(r.pad, -1);
+  O.flags[co] = (r.flags & (CF_KIND_MASK | CF_REAL)) | CF_CLAIMED;   // never an orphan candidate: the sender keeps or drops it by its own rules
+  O.stepCreated[co] = r.stepCreated;
+  if (periodic) { O.cdx[co] = r.cd[0]; O.cdy[co] = r.cd[1]; O.cdz[co] = r.cd[2]; }
+  O.t0x[co] = r.t[0]; O.t0y[co] = r.t[1]; O.t0z[co] = r.t[2]; O.t1x[co] = r.t[3]; O.t1y[co] = r.t[4]; O.t1z[co] = r.t[5];
+  O.cp[co] = r.cp; O.fn[co] = r.fl[0]; O.ft0[co] = r.fl[1]; O.ft1[co] = r.fl[2];
+  for (int q = 0; q < 3; q++) O.ph[q][co] = r.ph[q];
+  if (law == 1) { O.ph[3][co] = r.ph[3]; O.ph[4][co] = r.ph[4]; }
+  if (rolling) { O.tq0[co] = r.tq[0]; O.tq1[co] = r.tq[1]; O.tq2[co] = r.tq[2]; }
+  O.Fg[co] = r.Fg;
+  keys[k] = ((unsigned long long)(uint32_t)r.idA << 32) | (uint32_t)r.idB;
+  vals[k] = (int)co;
+}
+
+// ghost export: bit r of mask[i] set if the enlarged box of owned sphere i can overlap the enlarged box of a sphere owned by rank r
+__global__ void __launch_bounds__(256) k_dom_export_mask(Spheres S, int nOwn, DomainU D, uint32_t* mask, int* perRank) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t m = 0;
+  if (i < nOwn) {
+    const double4 p = S.posr[i];
+    const double x = slabCoord(D, p), h = slabHalf(D, p) + D.reach;
+    for (int r = 0; r < D.world; r++) {
+      if (r == D.rank) continue;
+      const double lo = D.bounds[r], hi = D.bounds[r + 1];
+      bool hit;
+      if (!D.periodic) hit = (x + h >= lo) && (x - h <= hi);
+      else {
+        if (x >= lo && x < hi) hit = true;
+        else { const double d1 = wrap01(lo - x, D.dim), d2 = wrap01(x - hi, D.dim); hit = fmin(d1, d2) <= h; }
+      }
+      if (hit) m |= 1u << r;
+    }
+    mask[i] = m;
+  }
+  for (int r = 0; r < D.world; r++) {
+    const unsigned c = __reduce_add_sync(0xffffffffu, (m >> r) & 1u);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&perRank[r], (int)c);
+  }
+}
+__global__ void __launch_bounds__(256) k_dom_export_flag(const uint32_t* __restrict__ mask, int nOwn, int r, int* flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nOwn) flag[i] = (mask[i] >> r) & 1u;
+}
+__global__ void __launch_bounds__(256) k_dom_pack_ghosts(Spheres S, int nOwn, const uint32_t* __restrict__ mask, int r, const int* __restrict__ off, GRec* out, int32_t* exportId) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nOwn || !((mask[i] >> r) & 1u)) return;
+  GRec g; g.posr = S.posr[i]; g.velm = S.velm[i]; g.angi = S.angi[i]; g.flags = (S.flags[i] & ~F_ARRIVED) | F_GHOST; g.mask = S.mask[i]; g.mat = S.mat[i]; g.id = S.id[i];
+  out[off[i]] = g; exportId[off[i]] = g.id;
+}
+__global__ void __launch_bounds__(256) k_dom_unpack_ghosts(Spheres S, int first, int cnt, const GRec* __restrict__ in, int32_t* importId) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  const int i = first + k; const GRec g = in[k];
+  S.posr[i] = g.posr; S.velm[i] = g.velm; S.angi[i] = g.angi; S.ori[i] = make_double4(0, 0, 0, 1);
+  S.fx[i] = S.fy[i] = S.fz[i] = S.tx[i] = S.ty[i] = S.tz[i] = 0.;
+  S.lx[i] = g.posr.x; S.ly[i] = g.posr.y; S.lz[i] = g.posr.z;
+  S.flags[i] = g.flags | F_GHOST; S.mask[i] = g.mask; S.mat[i] = g.mat; S.id[i] = g.id; S.up[i] = -1;
+  importId[k] = g.id;
+}
+// slot of each sphere of the new (pre-sort) generation in the arrays the previous contact table / CSR refer to (-1: was not here)
+__global__ void __launch_bounds__(256) k_dom_orig_slot(const int32_t* __restrict__ id, int n, const int* __restrict__ id2slot, int* origSlot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) origSlot[i] = id2slot[id[i]];
+}
+__global__ void __launch_bounds__(256) k_dom_clear_id2slot(const int32_t* __restrict__ id, int n, int* id2slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) id2slot[id[i]] = -1;
+}
+__global__ void __launch_bounds__(256) k_dom_compose(const int* __restrict__ origSlot, const int* __restrict__ perm, int n, int* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = origSlot[perm[i]];
+}
+__global__ void __launch_bounds__(256) k_dom_ids_to_slots(const int32_t* __restrict__ ids, int n, const int* __restrict__ id2slot, int* slots) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) slots[i] = id2slot[ids[i]];
+}
+
+// per-step ghost refresh: 9 doubles per exported sphere
+__global__ void __launch_bounds__(256) k_halo_pack(Spheres S, const int* __restrict__ slots, int n, double* buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = slots[k];
+  const double4 p = S.posr[i], v = S.velm[i], w = S.angi[i];
+  double* o = buf + 9ll * k;
+  o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = v.x; o[4] = v.y; o[5] = v.z; o[6] = w.x; o[7] = w.y; o[8] = w.z;
+}
+__global__ void __launch_bounds__(256) k_halo_unpack(Spheres S, const int* __restrict__ slots, int n, const double* __restrict__ buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = slots[k];
+  const double* o = buf + 9ll * k;
+  double4 p = S.posr[i], v = S.velm[i], w = S.angi[i];
+  p.x = o[0]; p.y = o[1]; p.z = o[2]; v.x = o[3]; v.y = o[4]; v.z = o[5]; w.x = o[6]; w.y = o[7]; w.z = o[8];
+  S.posr[i] = p; S.velm[i] = v; S.angi[i] = w;
+}
+
+// contacts counted once over all ranks: by the owner of the sphere that is pA (sphere-sphere) / of the sphere (boundary contacts)
+__global__ void __launch_bounds__(256) k_count_contacts_owned(Contacts C, long long n, const uint32_t* __restrict__ sflags, unsigned long long* out) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned r = 0, a = 0;
+  if (c < n) {
+    const uint32_t f = C.flags[c]; const int2 pr = C.pair[c];
+    const int s = cf_kind(f) == KIND_SS ? pr.x : pr.y;
+    if (!(sflags[s] & F_GHOST)) { r = (f & CF_REAL) ? 1 : 0; a = (f & CF_DEAD) ? 0 : 1; }
+  }
+  r = __reduce_add_sync(0xffffffffu, r); a = __reduce_add_sync(0xffffffffu, a);
+  if ((threadIdx.x & 31) == 0) { if (r) atomicAdd(&out[0], (unsigned long long)r); if (a) atomicAdd(&out[1], (unsigned long long)a); }
+}
+
+// owned spheres, compacted, with their ids (downloads in decomposed runs)
+__global__ void __launch_bounds__(256) k_gather_owned(Spheres S, int n, const int* __restrict__ off, int32_t* ids, double* pos, double* ori, double* vel, double* angVel, double* force,
+                                                     double* torque) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (S.flags[i] & F_GHOST)) return;
+  const long long u = off[i];
+  ids[u] = S.id[i];
+  if (pos) { double4 p = S.posr[i]; pos[3 * u] = p.x; pos[3 * u + 1] = p.y; pos[3 * u + 2] = p.z; }
+  if (ori) { double4 q = S.ori[i]; ori[4 * u] = q.x; ori[4 * u + 1] = q.y; ori[4 * u + 2] = q.z; ori[4 * u + 3] = q.w; }
+  if (vel) { double4 v = S.velm[i]; vel[3 * u] = v.x; vel[3 * u + 1] = v.y; vel[3 * u + 2] = v.z; }
+  if (angVel) { double4 w = S.angi[i]; angVel[3 * u] = w.x; angVel[3 * u + 1] = w.y; angVel[3 * u + 2] = w.z; }
+  if (force) { force[3 * u] = S.fx[i]; force[3 * u + 1] = S.fy[i]; force[3 * u + 2] = S.fz[i]; }
+  if (torque) { torque[3 * u] = S.tx[i]; torque[3 * u + 1] = S.ty[i]; torque[3 * u + 2] = S.tz[i]; }
+}
+__global__ void __launch_bounds__(256) k_owned_flag(const uint32_t* __restrict__ sflags, int n, int* flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (sflags[i] & F_GHOST) ? 0 : 1;
+}
+
+}  // namespace wd

@@ -14,6 +14,8 @@
 #include <vector>
 #include "../../include/wdem.h"
 #include "wdem_kernels.cuh"
+#include "wdem_domain.cuh"
+#include "wdem_comm.h"
 
 using namespace wd;
 
@@ -45,10 +47,10 @@ struct DBuf {  // growable device buffer
 
 struct SphereStore {
   DBuf<double4> posr, velm, angi, ori; DBuf<double> f[6], l[3]; DBuf<uint32_t> flags, mask; DBuf<int32_t> mat, id, up;
-  void ensure(size_t n, int64_t& tot) {
-    posr.ensure(n, tot); velm.ensure(n, tot); angi.ensure(n, tot); ori.ensure(n, tot);
-    for (auto& b : f) b.ensure(n, tot); for (auto& b : l) b.ensure(n, tot);
-    flags.ensure(n, tot); mask.ensure(n, tot); mat.ensure(n, tot); id.ensure(n, tot); up.ensure(n, tot);
+  void ensure(size_t n, int64_t& tot, bool keep = false, cudaStream_t st = 0) {
+    posr.ensure(n, tot, keep, st); velm.ensure(n, tot, keep, st); angi.ensure(n, tot, keep, st); ori.ensure(n, tot, keep, st);
+    for (auto& b : f) b.ensure(n, tot, keep, st); for (auto& b : l) b.ensure(n, tot, keep, st);
+    flags.ensure(n, tot, keep, st); mask.ensure(n, tot, keep, st); mat.ensure(n, tot, keep, st); id.ensure(n, tot, keep, st); up.ensure(n, tot, keep, st);
   }
   Spheres view() { Spheres S; S.posr = posr.p; S.velm = velm.p; S.angi = angi.p; S.ori = ori.p; S.fx = f[0].p; S.fy = f[1].p; S.fz = f[2].p; S.tx = f[3].p; S.ty = f[4].p; S.tz = f[5].p;
     S.lx = l[0].p; S.ly = l[1].p; S.lz = l[2].p; S.flags = flags.p; S.mask = mask.p; S.mat = mat.p; S.id = id.p; S.up = up.p; return S; }
@@ -122,8 +124,25 @@ struct HostCell {
 };
 }  // namespace
 
+// Slab decomposition state of one subdomain; inactive (comm == nullptr) in single-domain runs.
+struct DomainState {
+  int axis = 0; std::vector<double> cuts;   // world-1 interior boundaries: absolute coordinates, or fractions of the cell size if periodic
+  int nOwn = 0; int globalMaxId = -1; bool globalsValid = false; double rmaxGlobal = 0;
+  std::vector<size_t> sendCnt, recvCnt; size_t nSendTot = 0, nRecvTot = 0;   // ghosts exported to / imported from every rank
+  DBuf<int> sendSlot, recvSlot; DBuf<int32_t> exportId, importId, oldIds; DBuf<double> haloSend, haloRecv;
+  DBuf<uint32_t> dkeys, dkeysAlt, emask; DBuf<int> dslots, dslotsAlt, dstart, origSlot, perm2, rowCnt, rowOff, perRank, flag, off;
+  DBuf<char> sendBuf, recvBuf; DBuf<unsigned long long> immKeys, immKeysAlt; DBuf<int> immVals, immValsAlt; int nImm = 0;
+  long long migratedOut = 0, migratedIn = 0, rowsIn = 0;
+  void release() {
+    sendSlot.release(); recvSlot.release(); exportId.release(); importId.release(); oldIds.release(); haloSend.release(); haloRecv.release(); dkeys.release(); dkeysAlt.release();
+    emask.release(); dslots.release(); dslotsAlt.release(); dstart.release(); origSlot.release(); perm2.release(); rowCnt.release(); rowOff.release(); perRank.release();
+    flag.release(); off.release(); sendBuf.release(); recvBuf.release(); immKeys.release(); immKeysAlt.release(); immVals.release(); immValsAlt.release();
+  }
+};
+
 struct wdem_engine {
   wdem_config cfg;
+  Transport* comm = nullptr; DomainState dom;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string err;
@@ -197,6 +216,7 @@ void checkDeviceError(wdem_engine* E) {
   const Counters& h = *E->hCnt;
   if (h.error == ERR_NONE) return;
   std::string pr = "##" + std::to_string(h.errA) + "+" + std::to_string(h.errB);
+  if (E->comm) pr += " [subdomain " + std::to_string(E->comm->rank) + "; the ids are those of the failing subdomain]";
   switch (h.error) {
     case ERR_NAN_FORCE: throw EngErr{"NaN force in contact " + pr + " (IdealElPl.cpp:79-83)", WDEM_ERR_RUNTIME};
     case ERR_NAN_POS: throw EngErr{"NaN position of particle #" + std::to_string(h.errA), WDEM_ERR_RUNTIME};
@@ -211,11 +231,217 @@ void checkDeviceError(wdem_engine* E) {
 void buildFacetGrid(wdem_engine* E);
 
 // -------------------------------------------------------------------------------------------------
+// Slab decomposition: host orchestration of migration, ghost export and the per-step ghost refresh.
+// -------------------------------------------------------------------------------------------------
+template <class T> T* as(DBuf<char>& b, size_t byteOff = 0) { return reinterpret_cast<T*>(b.p + byteOff); }
+
+PeriU makePeriU(wdem_engine* E) {
+  PeriU pu; memset(&pu, 0, sizeof(pu));
+  if (E->cfg.periodic) { pu.unshear = E->cell.unshearTrsf; pu.size = E->cell.size; pu.cosv = E->cell.cosv; pu.hasShear = E->cell.hasShear ? 1 : 0; }
+  return pu;
+}
+
+DomainU makeDomainU(wdem_engine* E) {
+  DomainU D; memset(&D, 0, sizeof(D));
+  const int W = E->comm->world;
+  D.rank = E->comm->rank; D.world = W; D.axis = E->dom.axis; D.periodic = E->cfg.periodic; D.vd = E->verletDist; D.pu = makePeriU(E);
+  D.dim = E->cfg.periodic ? comp(E->cell.size, D.axis) : 0.;
+  D.bounds[0] = E->cfg.periodic ? 0. : -INFINITY; D.bounds[W] = E->cfg.periodic ? D.dim : INFINITY;
+  for (int r = 1; r < W; r++) D.bounds[r] = E->cfg.periodic ? E->dom.cuts[r - 1] * D.dim : E->dom.cuts[r - 1];
+  // largest half-extent of an enlarged box along the slab axis
+  double h = E->dom.rmaxGlobal;
+  if (E->cfg.periodic && E->cell.hasShear) {  // Cell::shearAlignedExtents (Cell.cpp:68-79) of the largest sphere
+    const d3 c = E->cell.cosv; double hx = h, hy = h, hz = h;
+    hy += .5 * h * (1 / c.x - 1); hz += .5 * h * (1 / c.x - 1); hz += .5 * h * (1 / c.y - 1); hx += .5 * h * (1 / c.y - 1); hx += .5 * h * (1 / c.z - 1); hy += .5 * h * (1 / c.z - 1);
+    h = D.axis == 0 ? hx : (D.axis == 1 ? hy : hz);
+  }
+  D.reach = (h + E->verletDist) * (1 + 1e-9);
+  return D;
+}
+
+// values every subdomain must agree on: smallest radius (verletDist), p-wave dt, largest radius (ghost reach)
+void syncGlobals(wdem_engine* E) {
+  if (!E->comm || E->dom.globalsValid) return;
+  const int W = E->comm->world;
+  double mine[3] = {E->minRadius, E->pwaveDt, E->dom.rmaxGlobal};
+  int64_t m64[3]; memcpy(m64, mine, sizeof(mine));
+  std::vector<int64_t> all((size_t)3 * W);
+  E->comm->allgather64(m64, 3, all.data(), E->stream);
+  for (int r = 0; r < W; r++) { double v[3]; memcpy(v, &all[(size_t)3 * r], sizeof(v)); E->minRadius = std::min(E->minRadius, v[0]); E->pwaveDt = std::min(E->pwaveDt, v[1]); E->dom.rmaxGlobal = std::max(E->dom.rmaxGlobal, v[2]); }
+  E->dom.globalsValid = true;
+}
+
+void sortPairs32(wdem_engine* E, uint32_t* k, uint32_t* kAlt, int* v, int* vAlt, int n, int bits) {
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, k, kAlt, v, vAlt, n, 0, bits, E->stream);
+  E->cubTemp.ensure(tb, E->bytes);
+  cub::DeviceRadixSort::SortPairs(E->cubTemp.p, tb, k, kAlt, v, vAlt, n, 0, bits, E->stream);
+}
+void exclusiveSum(wdem_engine* E, const int* in, int* out, int n) {
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, E->stream);
+  E->cubTemp.ensure(tb, E->bytes);
+  cub::DeviceScan::ExclusiveSum(E->cubTemp.p, tb, in, out, n, E->stream);
+}
+
+// Runs at the start of every collider full run of a decomposed scene, on all subdomains in the same step:
+//   1. owned spheres whose slab coordinate left the slab migrate (full state + the history rows of their real contacts);
+//   2. ghosts of the previous generation are dropped; every owned sphere whose enlarged AABB can reach a box owned by rank r is exported to r.
+// Leaves the new generation (owned first, then ghosts; unsorted) in the current sphere store.
+void domainExchange(wdem_engine* E) {
+  Transport* T = E->comm; DomainState& M = E->dom;
+  const int W = T->world, R = T->rank; cudaStream_t st = E->stream; int64_t& tot = E->bytes;
+  const wdem_config& c = E->cfg;
+  const bool hertz = c.law == WDEM_LAW_HERTZ_DMT, rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.);
+  const int n = E->n;
+  const DomainU D = makeDomainU(E);
+  SphereStore& Ast = E->sph[E->cur]; SphereStore& Bst = E->sph[1 - E->cur];
+  Spheres A = Ast.view();
+  ContactStore& Ost = E->con[E->curC]; CsrStore& Ocsr = E->csr[E->curR];
+  OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = (Ocsr.valid && E->nC > 0) ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
+  // ---- 1. classify and group by destination
+  std::vector<int> start(W + 3, 0);
+  const size_t nn = std::max(n, 1);
+  M.dkeys.ensure(nn, tot); M.dkeysAlt.ensure(nn, tot); M.dslots.ensure(nn, tot); M.dslotsAlt.ensure(nn, tot); M.dstart.ensure(W + 3, tot);
+  if (n > 0) {
+    k_dom_classify<<<nblk(n, 256), 256, 0, st>>>(A, n, D, M.dkeys.p, M.dslots.p);
+    int bits = 1; while ((1 << bits) < W + 2) bits++;
+    sortPairs32(E, M.dkeys.p, M.dkeysAlt.p, M.dslots.p, M.dslotsAlt.p, n, bits);
+    k_fill_int<<<1, 64, 0, st>>>(M.dstart.p, W + 3, n);
+    k_dom_starts<<<nblk(n, 256), 256, 0, st>>>(M.dkeysAlt.p, n, M.dstart.p);
+    CK(cudaMemcpyAsync(start.data(), M.dstart.p, (W + 3) * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    start[W + 2] = n;
+    for (int k = W + 1; k >= 0; k--) if (start[k] == n) start[k] = start[k + 1];
+    E->launches += 7;
+  }
+  const int nKeep = start[1] - start[0], nE = start[W + 1] - start[1];
+  // ---- 2. emigrants: particle records and history rows
+  std::vector<int> hRowOff(nE + 1, 0);
+  if (nE > 0) {
+    M.rowCnt.ensure(nE + 1, tot); M.rowOff.ensure(nE + 1, tot);
+    k_dom_count_rows<<<nblk(nE, 128), 128, 0, st>>>(M.dslotsAlt.p, start[1], nE, oc, Ost.flags.p, M.rowCnt.p);
+    CK(cudaMemsetAsync(M.rowCnt.p + nE, 0, sizeof(int), st));
+    exclusiveSum(E, M.rowCnt.p, M.rowOff.p, nE + 1);
+    CK(cudaMemcpyAsync(hRowOff.data(), M.rowOff.p, (nE + 1) * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    E->launches += 3;
+  }
+  std::vector<int64_t> mine(2 * W, 0), all((size_t)2 * W * W, 0);
+  for (int r = 0; r < W; r++) {
+    const int a = start[1 + r] - start[1], b = start[2 + r] - start[1];
+    mine[2 * r] = b - a; mine[2 * r + 1] = hRowOff[b] - hRowOff[a];
+  }
+  T->allgather64(mine.data(), 2 * W, all.data(), st);
+  std::vector<size_t> sOffP(W, 0), sBytP(W, 0), rOffP(W, 0), rBytP(W, 0), sOffR(W, 0), sBytR(W, 0), rOffR(W, 0), rBytR(W, 0);
+  size_t nImmP = 0, nImmR = 0, accP = 0, accR = 0;
+  for (int r = 0; r < W; r++) {
+    sOffP[r] = (size_t)(start[1 + r] - start[1]) * sizeof(PRec); sBytP[r] = (size_t)mine[2 * r] * sizeof(PRec);
+    sOffR[r] = (size_t)hRowOff[start[1 + r] - start[1]] * sizeof(CRec); sBytR[r] = (size_t)mine[2 * r + 1] * sizeof(CRec);
+    const size_t np = (size_t)all[(size_t)r * 2 * W + 2 * R], nr = (size_t)all[(size_t)r * 2 * W + 2 * R + 1];
+    rOffP[r] = accP * sizeof(PRec); rBytP[r] = np * sizeof(PRec); accP += np;
+    rOffR[r] = accR * sizeof(CRec); rBytR[r] = nr * sizeof(CRec); accR += nr;
+  }
+  nImmP = accP; nImmR = accR;
+  const size_t sendRowsBase = (size_t)nE * sizeof(PRec), recvRowsBase = nImmP * sizeof(PRec);
+  M.sendBuf.ensure(sendRowsBase + (size_t)hRowOff[nE] * sizeof(CRec) + 64, tot); M.recvBuf.ensure(recvRowsBase + nImmR * sizeof(CRec) + 64, tot);
+  if (nE > 0) {
+    k_dom_pack_particles<<<nblk(nE, 256), 256, 0, st>>>(A, M.dslotsAlt.p, start[1], nE, as<PRec>(M.sendBuf));
+    if (hRowOff[nE] > 0)
+      k_dom_pack_rows<<<nblk(nE, 128), 128, 0, st>>>(M.dslotsAlt.p, start[1], nE, oc, Ost.view(), A.id, E->dWalls.p, E->dFacets.p, M.rowOff.p, c.law, rolling, c.periodic, as<CRec>(M.sendBuf, sendRowsBase));
+    E->launches += 2;
+  }
+  T->alltoallv(M.sendBuf.p, sOffP.data(), sBytP.data(), M.recvBuf.p, rOffP.data(), rBytP.data(), st);
+  T->alltoallv(M.sendBuf.p + sendRowsBase, sOffR.data(), sBytR.data(), M.recvBuf.p + recvRowsBase, rOffR.data(), rBytR.data(), st);
+  // ---- 3. new owned set = kept + immigrants
+  const int nOwn = nKeep + (int)nImmP;
+  Bst.ensure((size_t)std::max(nOwn + (int)M.nRecvTot + 1024, 1), tot);
+  Spheres B = Bst.view();
+  if (nKeep > 0) { k_dom_gather_kept<<<nblk(nKeep, 256), 256, 0, st>>>(B, A, M.dslotsAlt.p + start[0], nKeep); E->launches++; }
+  if (nImmP > 0) { k_dom_unpack_particles<<<nblk(nImmP, 256), 256, 0, st>>>(B, nKeep, (int)nImmP, as<PRec>(M.recvBuf)); E->launches++; }
+  // ---- 4. immigrant history rows: appended behind the previous table, keyed by (idA,idB)
+  M.nImm = (int)nImmR;
+  if (nImmR > 0) {
+    Ost.ensure((size_t)(E->nC + nImmR), tot, hertz, rolling, c.periodic, /*keep*/ true, st);
+    M.immKeys.ensure(nImmR, tot); M.immKeysAlt.ensure(nImmR, tot); M.immVals.ensure(nImmR, tot); M.immValsAlt.ensure(nImmR, tot);
+    k_dom_unpack_rows<<<nblk(nImmR, 256), 256, 0, st>>>(Ost.view(), E->nC, (int)nImmR, as<CRec>(M.recvBuf, recvRowsBase), c.law, rolling, c.periodic, M.immKeys.p, M.immVals.p);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, M.immKeys.p, M.immKeysAlt.p, M.immVals.p, M.immValsAlt.p, (int)nImmR, 0, 64, st);
+    E->cubTemp.ensure(tb, tot);
+    cub::DeviceRadixSort::SortPairs(E->cubTemp.p, tb, M.immKeys.p, M.immKeysAlt.p, M.immVals.p, M.immValsAlt.p, (int)nImmR, 0, 64, st);
+    E->launches += 4;
+  }
+  // ---- 5. ghost export
+  M.perRank.ensure(WDEM_MAX_RANKS, tot); M.emask.ensure((size_t)std::max(nOwn, 1), tot);
+  CK(cudaMemsetAsync(M.perRank.p, 0, WDEM_MAX_RANKS * sizeof(int), st));
+  std::vector<int> hPer(WDEM_MAX_RANKS, 0);
+  if (nOwn > 0) {
+    k_dom_export_mask<<<nblk(nOwn, 256), 256, 0, st>>>(B, nOwn, D, M.emask.p, M.perRank.p); E->launches++;
+    CK(cudaMemcpyAsync(hPer.data(), M.perRank.p, WDEM_MAX_RANKS * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  }
+  std::vector<int64_t> gm(W, 0), ga((size_t)W * W, 0);
+  for (int r = 0; r < W; r++) gm[r] = hPer[r];
+  T->allgather64(gm.data(), W, ga.data(), st);
+  M.sendCnt.assign(W, 0); M.recvCnt.assign(W, 0);
+  std::vector<size_t> sOffG(W, 0), sBytG(W, 0), rOffG(W, 0), rBytG(W, 0);
+  size_t accS = 0, accG = 0;
+  for (int r = 0; r < W; r++) {
+    M.sendCnt[r] = (size_t)gm[r]; M.recvCnt[r] = (size_t)ga[(size_t)r * W + R];
+    sOffG[r] = accS * sizeof(GRec); sBytG[r] = M.sendCnt[r] * sizeof(GRec); accS += M.sendCnt[r];
+    rOffG[r] = accG * sizeof(GRec); rBytG[r] = M.recvCnt[r] * sizeof(GRec); accG += M.recvCnt[r];
+  }
+  M.nSendTot = accS; M.nRecvTot = accG;
+  M.sendBuf.ensure(accS * sizeof(GRec) + 64, tot); M.recvBuf.ensure(accG * sizeof(GRec) + 64, tot);
+  M.exportId.ensure(std::max<size_t>(accS, 1), tot); M.importId.ensure(std::max<size_t>(accG, 1), tot);
+  if (accS > 0) {
+    M.flag.ensure((size_t)nOwn + 1, tot); M.off.ensure((size_t)nOwn + 1, tot);
+    size_t base = 0;
+    for (int r = 0; r < W; r++) {
+      if (!M.sendCnt[r]) continue;
+      k_dom_export_flag<<<nblk(nOwn, 256), 256, 0, st>>>(M.emask.p, nOwn, r, M.flag.p);
+      exclusiveSum(E, M.flag.p, M.off.p, nOwn);
+      k_dom_pack_ghosts<<<nblk(nOwn, 256), 256, 0, st>>>(B, nOwn, M.emask.p, r, M.off.p, as<GRec>(M.sendBuf) + base, M.exportId.p + base);
+      base += M.sendCnt[r]; E->launches += 4;
+    }
+  }
+  T->alltoallv(M.sendBuf.p, sOffG.data(), sBytG.data(), M.recvBuf.p, rOffG.data(), rBytG.data(), st);
+  const int nNew = nOwn + (int)accG;
+  Bst.ensure((size_t)std::max(nNew, 1), tot, /*keep*/ true, st); B = Bst.view();
+  if (accG > 0) { k_dom_unpack_ghosts<<<nblk(accG, 256), 256, 0, st>>>(B, nOwn, (int)accG, as<GRec>(M.recvBuf), M.importId.p); E->launches++; }
+  // ---- 6. bookkeeping for the history lookup of the full run that follows
+  M.oldIds.ensure(nn, tot); M.origSlot.ensure((size_t)std::max(nNew, 1), tot);
+  if (n > 0) CK(cudaMemcpyAsync(M.oldIds.p, A.id, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (nNew > 0) { k_dom_orig_slot<<<nblk(nNew, 256), 256, 0, st>>>(B.id, nNew, E->id2slot.p, M.origSlot.p); E->launches++; }
+  if (n > 0) { k_dom_clear_id2slot<<<nblk(n, 256), 256, 0, st>>>(A.id, n, E->id2slot.p); E->launches++; }
+  E->n = nNew; E->cur = 1 - E->cur; M.nOwn = nOwn; E->up2slotValid = false;
+  M.migratedOut += nE; M.migratedIn += (long long)nImmP; M.rowsIn += (long long)nImmR;
+}
+
+// after the full run: exported / imported ids -> slots of the sorted generation
+void domainFinishRebuild(wdem_engine* E) {
+  DomainState& M = E->dom; cudaStream_t st = E->stream;
+  M.sendSlot.ensure(std::max<size_t>(M.nSendTot, 1), E->bytes); M.recvSlot.ensure(std::max<size_t>(M.nRecvTot, 1), E->bytes);
+  if (M.nSendTot) { k_dom_ids_to_slots<<<nblk(M.nSendTot, 256), 256, 0, st>>>(M.exportId.p, (int)M.nSendTot, E->id2slot.p, M.sendSlot.p); E->launches++; }
+  if (M.nRecvTot) { k_dom_ids_to_slots<<<nblk(M.nRecvTot, 256), 256, 0, st>>>(M.importId.p, (int)M.nRecvTot, E->id2slot.p, M.recvSlot.p); E->launches++; }
+  M.haloSend.ensure(std::max<size_t>(M.nSendTot * 9, 1), E->bytes); M.haloRecv.ensure(std::max<size_t>(M.nRecvTot * 9, 1), E->bytes);
+}
+
+// per step (no full run): owners send pos, vel, angVel of the spheres they exported; 72 B per ghost
+void haloExchange(wdem_engine* E) {
+  DomainState& M = E->dom; Transport* T = E->comm; cudaStream_t st = E->stream; const int W = T->world;
+  if (M.nSendTot) { k_halo_pack<<<nblk(M.nSendTot, 256), 256, 0, st>>>(E->S(), M.sendSlot.p, (int)M.nSendTot, M.haloSend.p); E->launches++; }
+  std::vector<size_t> sOff(W, 0), sByt(W, 0), rOff(W, 0), rByt(W, 0);
+  size_t a = 0, b = 0;
+  for (int r = 0; r < W; r++) { sOff[r] = a * 72; sByt[r] = M.sendCnt[r] * 72; a += M.sendCnt[r]; rOff[r] = b * 72; rByt[r] = M.recvCnt[r] * 72; b += M.recvCnt[r]; }
+  T->alltoallv((const char*)M.haloSend.p, sOff.data(), sByt.data(), (char*)M.haloRecv.p, rOff.data(), rByt.data(), st);
+  if (M.nRecvTot) { k_halo_unpack<<<nblk(M.nRecvTot, 256), 256, 0, st>>>(E->S(), M.recvSlot.p, (int)M.nRecvTot, M.haloRecv.p); E->launches++; }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Collider full run (replaces InsertionSortCollider::run's fullRun branch, InsertionSortCollider.cpp:407-613)
 // -------------------------------------------------------------------------------------------------
 void rebuild(wdem_engine* E) {
   const wdem_config& c = E->cfg;
   cudaStream_t st = E->stream;
+  if (E->comm) domainExchange(E);   // migration + ghosts; leaves the new (unsorted) generation in the current store
   const int n = E->n;
   const bool hertz = c.law == WDEM_LAW_HERTZ_DMT, rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.);
   const double vd = E->verletDist;
@@ -227,7 +453,8 @@ void rebuild(wdem_engine* E) {
   ContactStore& Ost = E->con[E->curC];
   CsrStore& Ocsr = E->csr[E->curR];
   CsrStore& Ncsr = E->csr[1 - E->curR];
-  OldCsr oc; oc.valid = Ocsr.valid ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
+  OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = Ocsr.valid ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
+  if (E->comm && E->dom.nImm > 0) { oc.immKeys = E->dom.immKeysAlt.p; oc.immVals = E->dom.immValsAlt.p; oc.nImm = E->dom.nImm; }
   const int* perm = nullptr;
   Grid g; memset(&g, 0, sizeof(g));
   PeriU pu; memset(&pu, 0, sizeof(pu)); PGrid pg; memset(&pg, 0, sizeof(pg));
@@ -282,6 +509,11 @@ void rebuild(wdem_engine* E) {
     k_reorder<<<nb, 256, 0, st>>>(dst.view(), E->S(), E->idxAlt.p, n, E->id2slot.p); E->launches++;
     E->cur = 1 - E->cur; E->up2slotValid = false;
     perm = E->idxAlt.p;
+    if (E->comm) {   // slots of the previous table's generation: through the pre-sort generation built by domainExchange
+      E->dom.perm2.ensure(n, tot);
+      k_dom_compose<<<nb, 256, 0, st>>>(E->dom.origSlot.p, E->idxAlt.p, n, E->dom.perm2.p); E->launches++;
+      perm = E->dom.perm2.p;
+    }
     // 4. cellStart[k] = #spheres with key<k
     E->cellStart.ensure((size_t)ncells + 1, tot);
     CK(cudaMemsetAsync(E->cellStart.p, 0, ((size_t)ncells + 1) * sizeof(int), st));
@@ -340,15 +572,16 @@ void rebuild(wdem_engine* E) {
     if (oc.valid && E->nC > 0) {
       E->orphCnt.ensure(1, tot);
       CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
-      const int32_t* oldSid = E->sph[1 - E->cur].id.p;
-      k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 0); E->launches++;
+      const int32_t* oldSid = E->comm ? E->dom.oldIds.p : E->sph[1 - E->cur].id.p;
+      const uint32_t* sfl = E->comm ? E->S().flags : nullptr;
+      k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, sfl, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 0); E->launches++;
       int hN = 0; CK(cudaMemcpyAsync(&hN, E->orphCnt.p, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
       if (hN > 0) {
         nOrph = hN;
         Nst.ensure((size_t)(nC0 + nOrph), tot, hertz, rolling, c.periodic, /*keep*/ true, st);
         N = Nst.view();
         CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
-        k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 1); E->launches++;
+        k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, sfl, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 1); E->launches++;
       }
     }
     const long long nC = nC0 + nOrph;
@@ -370,6 +603,7 @@ void rebuild(wdem_engine* E) {
   E->nSS = nSS; E->nWS = nWS; E->nFS = nFS; E->nOrph = nOrphOut; E->nC = nSS + nWS + nFS + nOrphOut;
   E->curC = 1 - E->curC; E->curR = 1 - E->curR;
   E->nFullRuns++;
+  if (E->comm) domainFinishRebuild(E);
 }
 
 // Static facets are binned once on the host (they never move in this engine: Impose/clump motion is out of scope).
@@ -415,6 +649,7 @@ void buildFacetGrid(wdem_engine* E) {
 
 void ensureVerletAndDt(wdem_engine* E) {
   const wdem_config& c = E->cfg;
+  syncGlobals(E);
   // AabbCollider::setVerletDist (Collision.cpp:164-184)
   if (std::isnan(E->verletDist)) {
     if (c.verletDist >= 0) E->verletDist = c.verletDist;
@@ -445,6 +680,14 @@ double dynDtCrit(wdem_engine* E) {
   double r = INFINITY; for (double v : hb) r = std::min(r, v);
   return std::sqrt(r);
 }
+double dynDtCritGlobal(wdem_engine* E) {
+  double r = dynDtCrit(E);
+  if (!E->comm) return r;
+  const int W = E->comm->world; int64_t m; memcpy(&m, &r, 8); std::vector<int64_t> all(W);
+  E->comm->allgather64(&m, 1, all.data(), E->stream);
+  for (int k = 0; k < W; k++) { double v; memcpy(&v, &all[k], 8); r = std::min(r, v); }
+  return r;
+}
 double pown(double x, unsigned n) { unsigned d = n >> 1, r = n & 1; double a = d == 0 ? 1 : pown(x * x, d); double b = r == 0 ? 1 : x; return a * b; }  // Math.hpp:161-176
 
 void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
@@ -460,6 +703,7 @@ void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
   if (prof) CK(cudaEventRecord(E->evp[1], st));
   // collider: full run if contacts are dirty / verletDist==0 / any sphere moved farther than verletDist
   bool full = E->conDirty || E->verletDist == 0;
+  if (E->comm) E->comm->allreduceMaxInt(&E->dCnt->dirty, 2, st);   // (dirty, error): every subdomain rebuilds / fails in the same step
   fetchCounters(E);
   checkDeviceError(E);
   if (E->hCnt->dirty) full = true;
@@ -468,7 +712,7 @@ void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
     E->conDirty = false;
     CK(cudaMemsetAsync(&E->dCnt->dirty, 0, sizeof(int), st));
     if (stats) stats->n_rebuilds++;
-  }
+  } else if (E->comm) haloExchange(E);
   if (prof) CK(cudaEventRecord(E->evp[2], st));
   Contacts C = E->con[E->curC].view();
   if (E->nSS > 0) {
@@ -493,9 +737,10 @@ void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
     E->launches++;
   }
   if (prof) CK(cudaEventRecord(E->evp[3], st));
-  if (n > 0 && c.applyForces) {
+  const int nNow = E->n;   // a full run of a decomposed scene changes the local sphere count (migration, ghosts)
+  if (nNow > 0 && c.applyForces) {
     CsrStore& R = E->csr[E->curR];
-    k_reduce<<<nblk(n, 256), 256, 0, st>>>(E->S(), n, C, R.rowStart.p, R.rowEntry.p, u); E->launches++;
+    k_reduce<<<nblk(nNow, 256), 256, 0, st>>>(E->S(), nNow, C, R.rowStart.p, R.rowEntry.p, u); E->launches++;
   }
   if (prof) CK(cudaEventRecord(E->evp[4], st));
   // DynDt (PeriodicEngine::isActivated, Engine.cpp:170-195 with stepModulo/initRun defaults; DynDt::run DynDt.cpp:90-113)
@@ -504,7 +749,7 @@ void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
     if (initNow) E->dynStepLast = E->step;
     if ((E->step - E->dynStepLast >= c.dynDtPeriod) || (E->step % c.dynDtPeriod == 0)) {
       E->dynStepPrev = E->dynStepLast; E->dynStepLast = E->step;
-      double crDt = dynDtCrit(E);
+      double crDt = dynDtCritGlobal(E);
       if (!std::isinf(crDt)) {
         int nSteps = (int)(E->step - E->dynStepPrev);
         double maxNewDt = E->dt * pown(1. + c.maxRelInc, (unsigned)nSteps);
@@ -531,9 +776,10 @@ int guarded(wdem_handle h, F&& f) {
     if (cudaSetDevice(h->cfg.device) != cudaSuccess) { h->err = "cudaSetDevice failed (no usable CUDA device; this engine has no CPU fallback)"; return WDEM_ERR_CUDA; }
     f();
     return WDEM_OK;
-  } catch (CudaErr& e) { h->err = e.msg; return e.code; }
-  catch (EngErr& e) { h->err = e.msg; return e.code; }
-  catch (std::exception& e) { h->err = e.what(); return WDEM_ERR_RUNTIME; }
+  } catch (CudaErr& e) { h->err = e.msg; if (h->comm) h->comm->abort(); return e.code; }
+  catch (EngErr& e) { h->err = e.msg; if (h->comm) h->comm->abort(); return e.code; }
+  catch (CommErr& e) { h->err = e.msg; if (h->comm) h->comm->abort(); return WDEM_ERR_RUNTIME; }
+  catch (std::exception& e) { h->err = e.what(); if (h->comm) h->comm->abort(); return WDEM_ERR_RUNTIME; }
 }
 
 void countContacts(wdem_engine* E, long long& nReal, long long& nAlive) {
@@ -541,7 +787,8 @@ void countContacts(wdem_engine* E, long long& nReal, long long& nAlive) {
   if (E->nC == 0) return;
   E->cntScratch.ensure(2, E->bytes);
   CK(cudaMemsetAsync(E->cntScratch.p, 0, 2 * sizeof(unsigned long long), E->stream));
-  k_count_flags<<<nblk(E->nC, 256), 256, 0, E->stream>>>(E->con[E->curC].flags.p, E->nC, E->cntScratch.p);
+  if (E->comm) k_count_contacts_owned<<<nblk(E->nC, 256), 256, 0, E->stream>>>(E->con[E->curC].view(), E->nC, E->S().flags, E->cntScratch.p);
+  else k_count_flags<<<nblk(E->nC, 256), 256, 0, E->stream>>>(E->con[E->curC].flags.p, E->nC, E->cntScratch.p);
   unsigned long long h[2];
   CK(cudaMemcpyAsync(h, E->cntScratch.p, sizeof(h), cudaMemcpyDeviceToHost, E->stream));
   CK(cudaStreamSynchronize(E->stream));
@@ -609,6 +856,7 @@ int wdem_destroy(wdem_handle h) {
   for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release();
   h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
   h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release();
+  h->dom.release(); delete h->comm; h->comm = nullptr;
   if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt);
   if (h->ev0) cudaEventDestroy(h->ev0); if (h->ev1) cudaEventDestroy(h->ev1); for (auto& e : h->evp) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -678,8 +926,11 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
     for (auto& b : s.f) if (n) CK(cudaMemsetAsync(b.p, 0, n * sizeof(double), st));
     for (auto& b : s.l) if (n) CK(cudaMemsetAsync(b.p, 0, n * sizeof(double), st));
     H2D(s.flags.p, fl.data(), n * 4); H2D(s.mask.p, mk.data(), n * 4); H2D(s.mat.p, mt.data(), n * 4); H2D(s.id.p, id.data(), n * 4); H2D(s.up.p, up.data(), n * 4);
-    h->id2slot.ensure((size_t)maxId + 2, h->bytes);
-    CK(cudaMemsetAsync(h->id2slot.p, 0xFF, ((size_t)maxId + 2) * sizeof(int), st));
+    const int idCap = std::max(maxId, h->dom.globalMaxId);
+    h->id2slot.ensure((size_t)idCap + 2, h->bytes);
+    CK(cudaMemsetAsync(h->id2slot.p, 0xFF, ((size_t)idCap + 2) * sizeof(int), st));
+    h->dom.nOwn = (int)n; h->dom.globalsValid = false; h->dom.rmaxGlobal = 0; for (int64_t i = 0; i < n; i++) h->dom.rmaxGlobal = std::max(h->dom.rmaxGlobal, radius[i]);
+    h->dom.nSendTot = h->dom.nRecvTot = 0; h->dom.nImm = 0;
     CK(cudaStreamSynchronize(st));
     h->conDirty = true; h->nC = h->nSS = h->nWS = h->nFS = 0; h->csr[0].valid = h->csr[1].valid = false; h->up2slotValid = false;
     h->verletDist = NAN; h->fgridValid = false;
@@ -753,12 +1004,13 @@ int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats) {
     CK(cudaEventRecord(h->ev0, h->stream));
     for (int64_t s = 0; s < nsteps; s++) oneStep(h, &local, phase);
     CK(cudaEventRecord(h->ev1, h->stream));
+    if (h->comm) h->comm->allreduceMaxInt(&h->dCnt->dirty, 2, h->stream);
     fetchCounters(h);
     CK(cudaEventSynchronize(h->ev1));
     checkDeviceError(h);
     float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     if (stats) {
-      local.device_ms = ms; local.n_spheres = h->n; local.n_full_runs_total = h->nFullRuns; local.n_launches = h->launches - l0; local.step = h->step; local.dt = h->dt; local.time = h->time;
+      local.device_ms = ms; local.n_spheres = h->comm ? h->dom.nOwn : h->n; local.n_full_runs_total = h->nFullRuns; local.n_launches = h->launches - l0; local.step = h->step; local.dt = h->dt; local.time = h->time;
       local.ms_integrate = phase[0]; local.ms_rebuild = phase[1]; local.ms_contact = phase[2]; local.ms_reduce = phase[3]; local.ms_dyndt = phase[4];
       long long nr, na; countContacts(h, nr, na); local.n_contacts = na; local.n_real = nr;
       local.sum_real = (int64_t)h->hCnt->nReal; local.sum_potential_evaluated = (int64_t)h->hCnt->nPotEval - (int64_t)h->hCnt->nReal; local.sum_contacts = (int64_t)h->hCnt->nPotEval;
@@ -769,6 +1021,7 @@ int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats) {
 
 int wdem_set_state(wdem_handle h, int64_t first, int64_t cnt, const double* pos, const double* vel, const double* angVel) {
   return guarded(h, [&] {
+    if (h->comm) throw EngErr{"wdem_set_state: not available in decomposed runs (spheres migrate between subdomains)", WDEM_ERR_UNSUPPORTED};
     if (first < 0 || cnt < 0 || first + cnt > h->n) throw EngErr{"wdem_set_state: range out of bounds", WDEM_ERR_INVALID};
     if (cnt == 0) return;
     ensureUp2Slot(h);
@@ -783,6 +1036,7 @@ int wdem_set_state(wdem_handle h, int64_t first, int64_t cnt, const double* pos,
 }
 
 static void downloadInto(wdem_handle h, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque) {
+  if (h->comm) throw EngErr{"decomposed run: use wdem_download_owned (upload order is not defined across subdomains)", WDEM_ERR_UNSUPPORTED};
   const int n = h->n; if (n == 0) return;
   h->ioBuf.ensure((size_t)n * 19, h->bytes);
   double* d = h->ioBuf.p;
@@ -835,6 +1089,7 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
     const long long nC = h->nC; if (nC == 0) return;
     cudaStream_t st = h->stream; ContactStore& cs = h->con[h->curC];
     auto pair = d2h(cs.pair.p, nC, st); auto flags = d2h(cs.flags.p, nC, st); auto sid = d2h(h->S().id, h->n, st);
+    std::vector<uint32_t> sfl; if (h->comm) sfl = d2h(h->S().flags, h->n, st);
     std::vector<std::vector<double>> t(6), f(3), ph(5), tq(3);
     for (int k = 0; k < 6; k++) t[k] = d2h(cs.t[k].p, nC, st);
     for (int k = 0; k < 3; k++) f[k] = d2h(cs.fl[k].p, nC, st);
@@ -850,6 +1105,7 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
       if (flags[c] & CF_DEAD) continue;
       if (realOnly && !(flags[c] & CF_REAL)) continue;
       const int kd = cf_kind(flags[c]);
+      if (h->comm && (sfl[kd == KIND_SS ? pair[c].x : pair[c].y] & F_GHOST)) continue;   // reported by the subdomain owning pA (sphere-sphere) / the sphere
       int a = (kd == KIND_SS) ? sid[pair[c].x] : (kd == KIND_WS ? h->hWalls[pair[c].x].id : h->hFacets[pair[c].x].id), b = sid[pair[c].y];
       rows.push_back(Row{((uint64_t)(uint32_t)a << 32) | (uint32_t)b, c});
     }
@@ -886,6 +1142,66 @@ int wdem_crit_dt(wdem_handle h, double* dt) { return guarded(h, [&] { *dt = h->p
 int wdem_get_scalars(wdem_handle h, double* dt, double* time, int64_t* step, double* verletDist, int64_t* nFullRuns) {
   return guarded(h, [&] { if (dt) *dt = h->dt; if (time) *time = h->time; if (step) *step = h->step; if (verletDist) *verletDist = h->verletDist; if (nFullRuns) *nFullRuns = h->nFullRuns; });
 }
+// ---- slab decomposition
+int wdem_comm_unique_id(char* out128) {
+  if (!out128) return WDEM_ERR_INVALID;
+  ncclUniqueId id; static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  if (ncclGetUniqueId(&id) != ncclSuccess) return WDEM_ERR_RUNTIME;
+  memcpy(out128, &id, 128); return WDEM_OK;
+}
+int wdem_comm_init_nccl(wdem_handle h, int rank, int world, const char* id128) {
+  return guarded(h, [&] {
+    if (!id128 || world < 1 || world > WDEM_MAX_RANKS || rank < 0 || rank >= world) throw EngErr{"wdem_comm_init_nccl: bad arguments", WDEM_ERR_INVALID};
+    if (h->comm) throw EngErr{"communicator already set", WDEM_ERR_INVALID};
+    ncclUniqueId id; memcpy(&id, id128, 128);
+    h->comm = new NcclTransport(rank, world, id);
+  });
+}
+void* wdem_local_group_create(int world) { return (world >= 1 && world <= WDEM_MAX_RANKS) ? new LocalGroup(world) : nullptr; }
+int wdem_local_group_destroy(void* g) { delete (LocalGroup*)g; return WDEM_OK; }
+int wdem_comm_init_local(wdem_handle h, void* group, int rank) {
+  return guarded(h, [&] {
+    LocalGroup* G = (LocalGroup*)group;
+    if (!G || rank < 0 || rank >= G->world) throw EngErr{"wdem_comm_init_local: bad arguments", WDEM_ERR_INVALID};
+    if (h->comm) throw EngErr{"communicator already set", WDEM_ERR_INVALID};
+    h->comm = new LocalTransport(G, rank);
+  });
+}
+int wdem_set_domain(wdem_handle h, int axis, int ncuts, const double* cuts, int64_t globalMaxId) {
+  return guarded(h, [&] {
+    if (!h->comm) throw EngErr{"wdem_set_domain: initialise the communicator first", WDEM_ERR_INVALID};
+    if (axis < 0 || axis > 2 || ncuts != h->comm->world - 1 || (ncuts > 0 && !cuts)) throw EngErr{"wdem_set_domain: need world-1 cuts along axis 0..2", WDEM_ERR_INVALID};
+    for (int k = 0; k < ncuts; k++) if (!(cuts[k] == cuts[k]) || (k > 0 && cuts[k] < cuts[k - 1])) throw EngErr{"wdem_set_domain: cuts must be ascending", WDEM_ERR_INVALID};
+    if (h->cfg.noBreak) throw EngErr{"Law2.noBreak is not supported in decomposed runs (separated real contacts are not exchanged)", WDEM_ERR_UNSUPPORTED};
+    h->dom.axis = axis; h->dom.cuts.assign(cuts, cuts + ncuts); h->dom.globalMaxId = (int)globalMaxId; h->conDirty = true;
+  });
+}
+int64_t wdem_num_owned(wdem_handle h) { return h ? (h->comm ? h->dom.nOwn : h->n) : -1; }
+int wdem_download_owned(wdem_handle h, int32_t* ids, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque) {
+  return guarded(h, [&] {
+    const int n = h->n; if (n == 0 || !ids) return;
+    cudaStream_t st = h->stream;
+    const int nOwn = h->comm ? h->dom.nOwn : n;
+    h->ioBuf.ensure((size_t)n * 20 + 8, h->bytes); h->counts.ensure((size_t)n + 1, h->bytes); h->offsets.ensure((size_t)n + 1, h->bytes);
+    k_owned_flag<<<nblk(n, 256), 256, 0, st>>>(h->S().flags, n, h->counts.p);
+    exclusiveSum(h, h->counts.p, h->offsets.p, n);
+    double* d = h->ioBuf.p; const size_t m = (size_t)nOwn;
+    double *dpos = pos ? d : nullptr, *dori = ori ? d + 3 * m : nullptr, *dvel = vel ? d + 7 * m : nullptr, *dw = angVel ? d + 10 * m : nullptr, *df = force ? d + 13 * m : nullptr,
+           *dt_ = torque ? d + 16 * m : nullptr;
+    int32_t* dids = (int32_t*)(d + 19 * m);
+    k_gather_owned<<<nblk(n, 256), 256, 0, st>>>(h->S(), n, h->offsets.p, dids, dpos, dori, dvel, dw, df, dt_);
+    auto D2H = [&](void* dst, void* src, size_t bytes) { if (dst) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)); };
+    D2H(ids, dids, m * 4); D2H(pos, dpos, 24 * m); D2H(ori, dori, 32 * m); D2H(vel, dvel, 24 * m); D2H(angVel, dw, 24 * m); D2H(force, df, 24 * m); D2H(torque, dt_, 24 * m);
+    CK(cudaStreamSynchronize(st));
+  });
+}
+int wdem_domain_stats(wdem_handle h, int64_t* nOwned, int64_t* nGhosts, int64_t* migratedOut, int64_t* migratedIn, int64_t* rowsIn) {
+  return guarded(h, [&] {
+    if (nOwned) *nOwned = h->comm ? h->dom.nOwn : h->n; if (nGhosts) *nGhosts = h->comm ? h->n - h->dom.nOwn : 0;
+    if (migratedOut) *migratedOut = h->dom.migratedOut; if (migratedIn) *migratedIn = h->dom.migratedIn; if (rowsIn) *rowsIn = h->dom.rowsIn;
+  });
+}
+
 int wdem_device_info(wdem_handle h, int64_t* bytes, void** stream) { return guarded(h, [&] { if (bytes) *bytes = h->bytes; if (stream) *stream = (void*)h->stream; }); }
 
 }  // extern "C"

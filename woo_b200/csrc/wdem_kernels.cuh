@@ -8,6 +8,9 @@ namespace wd {
 
 // DemData flags (src/dem/Particle.hpp:198-203)
 enum { F_DOF_ALL = 63, F_GRAVITY_SKIP = 512, F_DAMPING_SKIP = 2048 };
+// engine-internal bits kept in the same word (DemData.flags uses bits 0..11): ghost copy of a sphere owned by another subdomain;
+// sphere that migrated into this subdomain at the current collider full run
+enum : uint32_t { F_GHOST = 1u << 30, F_ARRIVED = 1u << 29 };
 // contact flags
 enum { CF_REAL = 1, CF_ORPHAN = 2, CF_DEAD = 4, CF_CLAIMED = 8, CF_KIND_SHIFT = 4, CF_KIND_MASK = 3u << 4 };
 __host__ __device__ __forceinline__ int cf_kind(uint32_t f) { return (int)((f >> 4) & 3u); }
@@ -74,8 +77,9 @@ __device__ __forceinline__ double signd(double f) { return f < 0 ? -1. : (f > 0 
 __global__ void __launch_bounds__(256) k_leapfrog(Spheres S, int n, StepU u, Counters* cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double4 pr = S.posr[i], vm = S.velm[i], ai = S.angi[i], qo = S.ori[i];
   const uint32_t fl = S.flags[i];
+  if (fl & F_GHOST) return;   // integrated by its owner; refreshed by the halo exchange
+  double4 pr = S.posr[i], vm = S.velm[i], ai = S.angi[i], qo = S.ori[i];
   d3 f = mk3(S.fx[i], S.fy[i], S.fz[i]);
   d3 t = mk3(S.tx[i], S.ty[i], S.tz[i]);
   d3 pos = xyz(pr), vel = xyz(vm), w = xyz(ai);
@@ -578,11 +582,12 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
 __global__ void __launch_bounds__(256) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const uint32_t fl = S.flags[i];
+  if (fl & F_GHOST) return;   // forces are reduced by the owner only
   const double4 pr = S.posr[i];
   const d3 pos = xyz(pr);
   d3 F, T;
   if (u.reset) {
-    const uint32_t fl = S.flags[i];
     F = (u.hasGravity && !(fl & F_GRAVITY_SKIP)) ? (S.velm[i].w * u.gravity) : mk3(0, 0, 0);
     T = mk3(0, 0, 0);
   } else { F = mk3(S.fx[i], S.fy[i], S.fz[i]); T = mk3(S.tx[i], S.ty[i], S.tz[i]); }
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, con
   double ret = INFINITY;
   if (i < n) {
     const uint32_t fl = S.flags[i];
-    if ((fl & F_DOF_ALL) != F_DOF_ALL) {
+    if ((fl & F_DOF_ALL) != F_DOF_ALL && !(fl & F_GHOST)) {
       d3 ktr = mk3(0, 0, 0), krot = mk3(0, 0, 0);
       const double myR = S.posr[i].w;
       for (int e = rowStart[i]; e < rowStart[i + 1]; e++) {
@@ -657,7 +662,7 @@ __global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, con
 __global__ void __launch_bounds__(256) k_ekin(Spheres S, int n, StepU u, double* blockSum) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0;
-  if (i < n) {
+  if (i < n && !(S.flags[i] & F_GHOST)) {
     double4 v = S.velm[i], w = S.angi[i];
     d3 fv = xyz(v), fw = xyz(w);
     if (u.periodic) {   // Cell::pprevFluctVel / pprevFluctAngVel (Cell.cpp:36-57)
@@ -743,6 +748,8 @@ __device__ __forceinline__ bool mayCollide(uint32_t mA, uint32_t mB, uint32_t lo
 
 struct OldCsr {  // incidence rows of the previous contact table (for history carry-over)
   const int* rowStart; const uint32_t* rowEntry; const int32_t* rowOther; int valid;
+  // history rows that arrived with spheres migrating in from another subdomain (sorted by key (idA<<32|idB)); see wdem_domain.cuh
+  const unsigned long long* immKeys; const int* immVals; int nImm;
 };
 
 __device__ __forceinline__ void copy_history(const Contacts& N, long long cn, const Contacts& O, long long co, int law, int rolling, int periodic) {
@@ -759,9 +766,19 @@ __device__ __forceinline__ void copy_history(const Contacts& N, long long cn, co
 
 // find the previous contact between the sphere in (old) slot `oslot` and the particle with id `otherId`
 __device__ __forceinline__ long long find_old(const OldCsr& oc, int oslot, int otherId) {
-  if (!oc.valid) return -1;
+  if (!oc.valid || oslot < 0) return -1;
   for (int e = oc.rowStart[oslot]; e < oc.rowStart[oslot + 1]; e++) if (oc.rowOther[e] == otherId) return (long long)(oc.rowEntry[e] >> 1);
   return -1;
+}
+// same, falling back to the rows that migrated in when one of the two spheres arrived in this full run
+__device__ __forceinline__ long long find_old2(const OldCsr& oc, int oslot, int otherId, uint32_t arrivedBits, int idA, int idB) {
+  long long co = find_old(oc, oslot, otherId);
+  if (co < 0 && oc.nImm > 0 && (arrivedBits & F_ARRIVED)) {
+    const unsigned long long key = ((unsigned long long)(uint32_t)idA << 32) | (uint32_t)idB;
+    int lo = 0, hi = oc.nImm - 1;
+    while (lo <= hi) { const int mid = (lo + hi) >> 1; const unsigned long long k = oc.immKeys[mid]; if (k == key) return oc.immVals[mid]; if (k < key) lo = mid + 1; else hi = mid - 1; }
+  }
+  return co;
 }
 
 // Sphere+Sphere candidates.  Ownership: the pair is emitted by the sphere with the larger radius (ties: larger slot), whose search
@@ -779,6 +796,7 @@ __global__ void __launch_bounds__(128) k_pairs_ss(Spheres S, int n, Grid g, cons
   const int y0 = cellCoord(pi.y - H, g.oy, g.inv, g.ny), y1 = cellCoord(pi.y + H, g.oy, g.inv, g.ny);
   const int z0 = cellCoord(pi.z - H, g.oz, g.inv, g.nz), z1 = cellCoord(pi.z + H, g.oz, g.inv, g.nz);
   const uint32_t mi = S.mask[i];
+  const uint32_t fi = S.flags[i];
   int cntLocal = 0;
   long long out = FILL ? offsets[i] : 0;
   int idI = 0, oslotI = 0;
@@ -793,12 +811,13 @@ __global__ void __launch_bounds__(128) k_pairs_ss(Spheres S, int n, Grid g, cons
         if (!(pj.w < pi.w || (pj.w == pi.w && j < i))) continue;
         if (!aabbOverlapSS(pi, pj, vd)) continue;
         if (!mayCollide(mi, S.mask[j], loneMask)) continue;
+        if ((fi & F_GHOST) && (S.flags[j] & F_GHOST)) continue;   // ghost-ghost pairs belong to other subdomains
         if (FILL) {
           const int idJ = S.id[j];
           const long long c = out + cntLocal;
           const bool iIsA = idI < idJ;
           N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
-          srcOld[c] = (int)find_old(oc, oslotI, idJ);
+          srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
           N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
         } else atomicAdd(&rowCount[j], 1);
         cntLocal++;
@@ -816,6 +835,8 @@ __global__ void __launch_bounds__(128) k_pairs_ws(Spheres S, int n, const Wall* 
   if (i >= n) return;
   const double4 pi = S.posr[i];
   const uint32_t mi = S.mask[i];
+  const uint32_t fi = S.flags[i];
+  if (fi & F_GHOST) { if (!FILL) counts[i] = 0; return; }   // boundary contacts of a ghost are its owner's business
   int cntLocal = 0;
   long long out = FILL ? offsets[i] : 0;
   const int oslotI = FILL ? (perm ? perm[i] : i) : 0;
@@ -830,7 +851,7 @@ __global__ void __launch_bounds__(128) k_pairs_ws(Spheres S, int n, const Wall* 
     if (FILL) {
       const long long c = out + cntLocal;
       N.pair[c] = make_int2(w, i);
-      srcOld[c] = (int)find_old(oc, oslotI, W.id);
+      srcOld[c] = (int)find_old2(oc, oslotI, W.id, fi, W.id, S.id[i]);
       N.flags[c] = (KIND_WS << CF_KIND_SHIFT);
     }
     cntLocal++;
@@ -849,6 +870,8 @@ __global__ void __launch_bounds__(128) k_pairs_fs(Spheres S, int n, const Facet*
   if (i >= n) return;
   const double4 pi = S.posr[i];
   const uint32_t mi = S.mask[i];
+  const uint32_t fi = S.flags[i];
+  if (fi & F_GHOST) { if (!FILL) counts[i] = 0; return; }
   const double smin[3] = {(pi.x - pi.w) - vd, (pi.y - pi.w) - vd, (pi.z - pi.w) - vd}, smax[3] = {(pi.x + pi.w) + vd, (pi.y + pi.w) + vd, (pi.z + pi.w) + vd};
   const int x0 = cellCoord(smin[0], fg.ox, fg.inv, fg.nx), x1 = cellCoord(smax[0], fg.ox, fg.inv, fg.nx);
   const int y0 = cellCoord(smin[1], fg.oy, fg.inv, fg.ny), y1 = cellCoord(smax[1], fg.oy, fg.inv, fg.ny);
@@ -872,7 +895,7 @@ __global__ void __launch_bounds__(128) k_pairs_fs(Spheres S, int n, const Facet*
           if (FILL) {
             const long long c = out + cntLocal;
             N.pair[c] = make_int2(f, i);
-            srcOld[c] = (int)find_old(oc, oslotI, F->id);
+            srcOld[c] = (int)find_old2(oc, oslotI, F->id, fi, F->id, S.id[i]);
             N.flags[c] = (KIND_FS << CF_KIND_SHIFT);
           }
           cntLocal++;
@@ -957,6 +980,7 @@ __global__ void __launch_bounds__(128) k_pairs_ss_peri(Spheres S, int n, PGrid g
   const int wx0 = imod(x0, g.nx), wx1 = imod(x1, g.nx);
   const int nseg = (wx0 <= wx1) ? 1 : 2;
   const uint32_t mi = S.mask[i];
+  const uint32_t fi = S.flags[i];
   const int idI = S.id[i];
   const int oslotI = FILL ? (perm ? perm[i] : i) : 0;
   int cntLocal = 0;
@@ -972,6 +996,7 @@ __global__ void __launch_bounds__(128) k_pairs_ss_peri(Spheres S, int n, PGrid g
           const double4 pj = S.posr[j];
           if (!(pj.w < pi.w || (pj.w == pi.w && j < i))) continue;
           if (!mayCollide(mi, S.mask[j], loneMask)) continue;
+          if ((fi & F_GHOST) && (S.flags[j] & F_GHOST)) continue;
           d3 mnJ, mxJ; periAabb(pu, pj, vd, mnJ, mxJ);
           const int idJ = S.id[j];
           const bool iIsA = idI < idJ;
@@ -983,7 +1008,7 @@ __global__ void __launch_bounds__(128) k_pairs_ss_peri(Spheres S, int n, PGrid g
             const long long c = out + cntLocal;
             N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
             N.cdx[c] = per[0]; N.cdy[c] = per[1]; N.cdz[c] = per[2];
-            srcOld[c] = (int)find_old(oc, oslotI, idJ);
+            srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
             N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
           } else atomicAdd(&rowCount[j], 1);
           cntLocal++;
@@ -1004,6 +1029,8 @@ __global__ void __launch_bounds__(128) k_pairs_ws_peri(Spheres S, int n, const W
   const double4 pi = S.posr[i];
   d3 mnI, mxI; periAabb(pu, pi, vd, mnI, mxI);
   const uint32_t mi = S.mask[i];
+  const uint32_t fi = S.flags[i];
+  if (fi & F_GHOST) { if (!FILL) counts[i] = 0; return; }
   const int idI = S.id[i];
   int cntLocal = 0;
   long long out = FILL ? offsets[i] : 0;
@@ -1025,7 +1052,7 @@ __global__ void __launch_bounds__(128) k_pairs_ws_peri(Spheres S, int n, const W
       N.pair[c] = make_int2(w, i);
       const int cd = wallLo ? period : -period;   // canonical pA = wall (Contact::swapOrder negates cellDist, Contact.cpp:12-16)
       N.cdx[c] = W.axis == 0 ? cd : 0; N.cdy[c] = W.axis == 1 ? cd : 0; N.cdz[c] = W.axis == 2 ? cd : 0;
-      srcOld[c] = (int)find_old(oc, oslotI, W.id);
+      srcOld[c] = (int)find_old2(oc, oslotI, W.id, fi, W.id, idI);
       N.flags[c] = (KIND_WS << CF_KIND_SHIFT);
     }
     cntLocal++;
@@ -1054,16 +1081,22 @@ __global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Conta
 
 // old real contacts nobody claimed = orphans: count (and add their incidences to the row counts), then append behind the grid candidates
 __global__ void __launch_bounds__(256) k_orphans(Contacts O, long long nOld, Contacts N, long long nNewBase, const int32_t* __restrict__ oldSid, const int* __restrict__ id2slot,
-                                                int law, int rolling, int periodic, int* counter, int* __restrict__ rowCount, int doAppend) {
+                                                const uint32_t* __restrict__ sflags, int law, int rolling, int periodic, int* counter, int* __restrict__ rowCount, int doAppend) {
   long long co = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (co >= nOld) return;
   const uint32_t fl = O.flags[co];
   if (!(fl & CF_REAL) || (fl & (CF_CLAIMED | CF_DEAD))) return;
-  const int k = atomicAdd(counter, 1);
   const int kind = cf_kind(fl);
   int2 pr = O.pair[co];
   pr.y = id2slot[oldSid[pr.y]];
   if (kind == KIND_SS) pr.x = id2slot[oldSid[pr.x]];
+  // decomposed runs: a partner left this subdomain, or the pair is now ghost-ghost / a ghost's boundary contact -> not ours any more
+  if (pr.y < 0 || (kind == KIND_SS && pr.x < 0)) return;
+  if (sflags) {
+    const bool gy = sflags[pr.y] & F_GHOST;
+    if (kind == KIND_SS ? (gy && (sflags[pr.x] & F_GHOST)) : gy) return;
+  }
+  const int k = atomicAdd(counter, 1);
   if (!doAppend) { atomicAdd(&rowCount[pr.y], 1); if (kind == KIND_SS) atomicAdd(&rowCount[pr.x], 1); return; }
   const long long c = nNewBase + k;
   N.pair[c] = pr;

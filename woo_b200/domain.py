@@ -1,0 +1,194 @@
+"""Host side of the slab decomposition: one Engine handle per subdomain.
+
+* ``LocalCluster``  — all subdomains in this process, one host thread each (in-process transport; several subdomains may share a GPU).
+* ``DistributedEngine`` — one subdomain per process under torchrun; halo exchange / migration over NCCL inside the C-ABI library, the
+  128-byte NCCL id is broadcast with torch.distributed.
+
+Both take a whole-scene SceneSpec; every subdomain uploads the boundaries/materials and the spheres of its slab.  Results are assembled
+by particle id, so they can be compared with a single-domain run bit for bit (forces are reduced per particle in ascending-id order of the
+contact partner, independent of the decomposition).
+"""
+import ctypes as C
+import threading
+import numpy as np
+from . import capi
+from .capi import ptr
+from .engine import Engine, WdemError
+
+
+def slab_coord(S, axis):
+    """Coordinate along which slabs are cut: position (aperiodic) or fraction of the cell along the unsheared axis (periodic)."""
+    if not S.params.periodic:
+        return S.pos[:, axis]
+    H = np.asarray(S.cell["hSize"], dtype=np.float64).reshape(3, 3)
+    size = np.linalg.norm(H, axis=0)
+    u = S.pos @ np.linalg.inv(H / size).T
+    f = u[:, axis] / size[axis]
+    return f - np.floor(f)
+
+
+def quantile_cuts(S, world, axis):
+    """world-1 boundaries with equal sphere counts per slab (SURVEY §8e "particle-count quantiles")."""
+    x = np.sort(slab_coord(S, axis))
+    return np.array([.5 * (x[len(x) * k // world - 1] + x[len(x) * k // world]) for k in range(1, world)], dtype=np.float64)
+
+
+def owner_of(S, cuts, axis):
+    return np.searchsorted(np.asarray(cuts), slab_coord(S, axis), side="right")
+
+
+def _load_part(E, S, sel):
+    E.spec = S
+    E.upload_materials(S.mats)
+    m, I = S.mass_inertia()
+    ids = S.sphere_ids()
+    E.upload_spheres(ids[sel], S.pos[sel], S.radius[sel], m[sel], I[sel], S.mat[sel], S.mask[sel], S.flags[sel], S.vel[sel], S.angVel[sel])
+    E.upload_walls(S.wall_ids(), S.walls)
+    E.upload_facets(S.facet_ids(), S.facets)
+    if S.cell is not None:
+        E.set_cell(S.cell["hSize"], S.cell.get("gradV"), S.cell.get("nextGradV"), S.cell.get("homoDeform", 4))
+
+
+def _set_domain(E, axis, cuts, max_id):
+    cuts = np.ascontiguousarray(cuts, dtype=np.float64)
+    E._chk(E.L.wdem_set_domain(E.h, C.c_int(axis), C.c_int(len(cuts)), ptr(cuts), C.c_int64(int(max_id))))
+
+
+def _owned(E):
+    n = E.L.wdem_num_owned(E.h)
+    o = {k: np.zeros((n, 3)) for k in ("pos", "vel", "angVel", "force", "torque")}
+    o["ori"] = np.zeros((n, 4)); o["ids"] = np.zeros(n, np.int32)
+    E._chk(E.L.wdem_download_owned(E.h, ptr(o["ids"]), ptr(o["pos"]), ptr(o["ori"]), ptr(o["vel"]), ptr(o["angVel"]), ptr(o["force"]), ptr(o["torque"])))
+    return o
+
+
+def _domain_stats(E):
+    v = [C.c_int64() for _ in range(5)]
+    E._chk(E.L.wdem_domain_stats(E.h, *[C.byref(x) for x in v]))
+    return dict(zip(("owned", "ghosts", "migrated_out", "migrated_in", "rows_in"), [x.value for x in v]))
+
+
+def _max_id(S):
+    return S.n + len(S.walls) + len(S.facets) - 1
+
+
+class LocalCluster:
+    """``world`` subdomains of one scene inside this process."""
+
+    def __init__(self, S, world, axis=0, cuts=None, devices=None, scramble=False):
+        self.S, self.world, self.axis = S, world, axis
+        self.L = capi.load()
+        self.group = C.c_void_p(self.L.wdem_local_group_create(C.c_int(world)))
+        self.cuts = quantile_cuts(S, world, axis) if cuts is None else np.asarray(cuts, dtype=np.float64)
+        own = owner_of(S, self.cuts, axis)
+        if scramble:      # deliberately wrong initial placement: the first collider run must migrate everything home
+            own = (own + 1 + np.arange(S.n) % max(world - 1, 1)) % world
+        devices = devices or [0] * world
+        self.E = []
+        for r in range(world):
+            E = Engine(S.params, device=devices[r])
+            E._chk(self.L.wdem_comm_init_local(E.h, self.group, C.c_int(r)))
+            _set_domain(E, axis, self.cuts, _max_id(S))
+            _load_part(E, S, np.nonzero(own == r)[0])
+            self.E.append(E)
+
+    def close(self):
+        for E in self.E:
+            E.close()
+        self.E = []
+        if self.group:
+            self.L.wdem_local_group_destroy(self.group); self.group = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _all(self, fn):
+        out, err = [None] * self.world, [None] * self.world
+
+        def run(r):
+            try:
+                out[r] = fn(self.E[r])
+            except Exception as e:   # noqa: BLE001 - re-raised below
+                err[r] = e
+        th = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for e in err:
+            if e is not None and "another subdomain failed" not in str(e):
+                raise e
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+    def step(self, n=1):
+        self.stats = self._all(lambda E: E.step(n))
+        return self.stats
+
+    def spheres(self):
+        parts = [_owned(E) for E in self.E]
+        ids = np.concatenate([p["ids"] for p in parts])
+        order = np.argsort(ids, kind="stable")
+        assert len(ids) == self.S.n and np.array_equal(ids[order], self.S.sphere_ids()), "spheres lost or duplicated across subdomains"
+        return {k: np.concatenate([p[k] for p in parts])[order] for k in parts[0] if k != "ids"}
+
+    def contacts(self, real_only=False):
+        parts = [E.contacts(real_only) for E in self.E]
+        ids = np.concatenate([p["ids"] for p in parts])
+        key = ids[:, 0].astype(np.int64) << 32 | ids[:, 1].astype(np.int64)
+        order = np.argsort(key, kind="stable")
+        return {k: np.concatenate([p[k] for p in parts])[order] for k in parts[0]}
+
+    def scalars(self):
+        s = [E.scalars() for E in self.E]
+        assert all(x == s[0] for x in s), "subdomains disagree on dt/step/verletDist/nFullRuns: %r" % (s,)
+        return s[0]
+
+    def kinetic_energy(self):
+        return sum(E.kinetic_energy() for E in self.E)
+
+    def cell_hsize(self):
+        return self.E[0].cell_hsize()
+
+    def domain_stats(self):
+        return [_domain_stats(E) for E in self.E]
+
+
+class DistributedEngine:
+    """One subdomain per process (torchrun: RANK/WORLD_SIZE/LOCAL_RANK); torch.distributed must be initialised by the caller."""
+
+    def __init__(self, S, axis=0, cuts=None, device=None, sel=None):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        device = torch.cuda.current_device() if device is None else device
+        self.E = E = Engine(S.params, device=device)
+        L = E.L
+        idbuf = C.create_string_buffer(128)
+        if self.rank == 0:
+            E._chk(L.wdem_comm_unique_id(idbuf))
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda(device); dist.broadcast(t, 0); t = t.cpu()
+        else:
+            dist.broadcast(t, 0)
+        E._chk(L.wdem_comm_init_nccl(E.h, C.c_int(self.rank), C.c_int(self.world), bytes(t.numpy().tobytes())))
+        self.cuts = quantile_cuts(S, self.world, axis) if cuts is None else np.asarray(cuts, dtype=np.float64)
+        _set_domain(E, axis, self.cuts, S.global_max_id if hasattr(S, "global_max_id") else _max_id(S))
+        if sel is None:
+            sel = np.nonzero(owner_of(S, self.cuts, axis) == self.rank)[0]
+        _load_part(E, S, sel)
+
+    def step(self, n=1):
+        return self.E.step(n)
+
+    def owned(self):
+        return _owned(self.E)
+
+    def domain_stats(self):
+        return _domain_stats(self.E)

@@ -67,6 +67,8 @@ class SceneSpec:
     params: Params = field(default_factory=Params)
     cell: dict = None                           # dict(hSize(3,3), gradV, nextGradV, homoDeform)
     boundaries_first: bool = False              # ids: walls+facets first, then spheres
+    ids: np.ndarray = None                      # explicit sphere ids (a part of a larger scene; needs boundaries_first)
+    global_max_id: int = None                   # largest Particle.id of the whole scene when this spec holds only a part
 
     @property
     def n(self):
@@ -90,6 +92,8 @@ class SceneSpec:
         return m, I
 
     def sphere_ids(self):
+        if self.ids is not None:
+            return np.ascontiguousarray(self.ids, dtype=np.int32)
         nb = len(self.walls) + len(self.facets)
         first = nb if self.boundaries_first else 0
         return np.arange(first, first + self.n, dtype=np.int32)
