@@ -2,12 +2,14 @@
 """bench.py — particle-steps/s of the DEM hot path on B200 (BASELINE.json metric), one JSON line on stdout.
 
 A "step" is one Scene step (Leapfrog -> collider -> ContactLoop -> DynDt) over the whole packing.
-Workload at N GPUs: BASELINE.json configs[1] — 1M polydisperse spheres (PSD 1:4, log-uniform radii) settled under gravity
-in a box of 5 walls, linear IdealElPl law; synthetic (woo_b200.scenes.deposition, seed 2).  For N>1 every rank owns one such
-slab-shaped box (weak scaling, no data-path collective in this round; see DESIGN.md "Multi-GPU").
+Workload: BASELINE.json configs[1] — 1M polydisperse spheres (PSD 1:4, log-uniform radii) per GPU, dense bed settling under gravity in a box of
+5 walls, linear IdealElPl law; synthetic: the committed pre-settled 20k-sphere bed (tests/golden/cfg2_sample_20k.npz, made by
+scripts/make_cpu_sample.py with woo_b200.scenes.deposition seed 2) tiled 10x5 per GPU and re-settled in the untimed preparation phase.
+For N>1 it is ONE box N times as long, cut into N x-slabs (weak scaling): per step every rank refreshes the pos/vel/angVel of its ghosts
+and at collider full runs spheres migrate with their contact history, all over NCCL inside libwdem.so (DESIGN.md "Multi-GPU").
 value  = particle-steps/s with the state resident in HBM (CUDA events on the engine's stream, max over ranks).
-e2e    = same metric through the C-ABI call wdem_step_e2e with pinned HOST buffers: per step H2D of pos/vel/angVel,
-         one step, D2H of pos/vel + kinetic energy.
+e2e    = same metric through the C-ABI with pinned HOST buffers: per step H2D of pos/vel/angVel, one step, D2H of pos/vel (+ids/angVel
+         when decomposed) and the kinetic energy.
 --impl reference: the CPU restatement oracle (the reference itself cannot be built here: Eigen/Boost/TBB missing) on all
 host threads, on a bounded sample (pre-settled 20k-sphere packing of the same PSD/material, tests/golden/cfg2_sample_20k.npz).
 """
@@ -101,6 +103,33 @@ def workload_tiled(n, tiles_x=None):
     return S.finalize(), dict(tiles=tiles, tiles_x=tx, tiles_y=ty)
 
 
+def workload_slab(n, rank, world):
+    """The part of the N-GPU scene that rank `rank` uploads: the tiled bed of workload_tiled() repeated `world` times along x inside ONE box
+    of 5 walls; slab boundaries are the tile-group boundaries.  Sphere ids are scene-wide (walls take ids 0..4)."""
+    from woo_b200 import scenes as sc
+    d = np.load(SAMPLE)
+    m = len(d["radius"]); tiles = max(1, n // m)
+    tx = int(np.ceil(np.sqrt(2 * tiles)))
+    while tiles % tx:
+        tx += 1
+    ty = tiles // tx
+    L = d["hi"] - d["lo"]
+    off = np.array([[(rank * tx + i) * L[0], j * L[1], 0.] for i in range(tx) for j in range(ty)])
+    S = workload(m, seed=2)
+    S.pos = (d["pos"][None, :, :] + off[:, None, :]).reshape(-1, 3)
+    S.radius = np.tile(d["radius"], tiles); S.vel = np.tile(d["vel"], (tiles, 1)); S.angVel = np.tile(d["angVel"], (tiles, 1))
+    S.mat = S.mask = S.flags = None
+    lo = d["lo"]; hi = np.array([lo[0] + world * tx * L[0], lo[1] + ty * L[1], d["hi"][2]])
+    S.walls = sc.box_walls(tuple(lo), tuple(hi), mat=0)
+    S.params.dt = float(d["dt"])
+    nloc = m * tiles; nb = len(S.walls)
+    S.boundaries_first = True
+    S.ids = (nb + rank * nloc + np.arange(nloc)).astype(np.int32)
+    S.global_max_id = nb + world * nloc - 1
+    cuts = np.array([lo[0] + k * tx * L[0] for k in range(1, world)], dtype=np.float64)
+    return S.finalize(), dict(tiles=tiles * world, tiles_x=tx * world, tiles_y=ty, cuts=cuts)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -110,11 +139,19 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     n = args.n
-    if args.lattice or not os.path.exists(SAMPLE):
+    D = None
+    if world > 1:
+        # one scene, slab-decomposed along x: one subdomain per GPU, halo exchange + migration over NCCL (woo_b200/domain.py)
+        from woo_b200.domain import DistributedEngine
+        S, tiling = workload_slab(n, rank, world); n = S.n
+        D = DistributedEngine(S, axis=0, cuts=tiling["cuts"], device=local, sel=np.arange(S.n))
+        E = D.E
+    elif args.lattice or not os.path.exists(SAMPLE):
         S = workload(n, seed=2 + rank); tiling = None
+        E = Engine(S.params, device=local).load(S)
     else:
         S, tiling = workload_tiled(n); n = S.n
-    E = Engine(S.params, device=local).load(S)
+        E = Engine(S.params, device=local).load(S)
     # settle (untimed preparation of the dense packing; includes many collider full runs)
     t0 = time.time()
     done = 0
@@ -144,20 +181,43 @@ def run_gpu(args):
     dev_ms = st.device_ms
     stats = st.asdict()
     # ---- timed region 2: end to end through the C-ABI with pinned host buffers
-    s = E.spheres()
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    tp, tv, tw = pin(s["pos"]), pin(s["vel"]), pin(s["angVel"])
-    po, vo = torch.empty_like(tp).pin_memory(), torch.empty_like(tv).pin_memory()
     ke = min(args.steps, args.e2e_steps)
-    for _ in range(3):
-        E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy()); tp.copy_(po); tv.copy_(vo)
-    barrier()
-    e0 = time.time()
-    for _ in range(ke):
-        ek, _st = E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy())
-        tp.copy_(po); tv.copy_(vo)     # the step's output is the next step's host-side input
-    barrier()
-    e2e_s = time.time() - e0
+    if D is None:
+        s = E.spheres()
+        tp, tv, tw = pin(s["pos"]), pin(s["vel"]), pin(s["angVel"])
+        po, vo = torch.empty_like(tp).pin_memory(), torch.empty_like(tv).pin_memory()
+        for _ in range(3):
+            E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy()); tp.copy_(po); tv.copy_(vo)
+        barrier()
+        e0 = time.time()
+        for _ in range(ke):
+            ek, _st = E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy())
+            tp.copy_(po); tv.copy_(vo)     # the step's output is the next step's host-side input
+        barrier()
+        e2e_s = time.time() - e0
+        h2d, d2h = int(n * 72), int(n * 48 + 8)
+    else:
+        # decomposed: every rank round-trips the spheres it owns, addressed by id (the owned set changes when spheres migrate)
+        o = D.owned(); m = len(o["ids"]); cap = int(m * 1.05) + 4096
+        buf = lambda w, dt=np.float64: torch.from_numpy(np.zeros((cap, w) if w > 1 else cap, dtype=dt)).pin_memory()
+        ii, pi_, vi, wi = buf(1, np.int32), buf(3), buf(3), buf(3)
+        io, po, vo, wo = buf(1, np.int32), buf(3), buf(3), buf(3)
+        ii.numpy()[:m] = o["ids"]; pi_.numpy()[:m] = o["pos"]; vi.numpy()[:m] = o["vel"]; wi.numpy()[:m] = o["angVel"]
+
+        def one(m):
+            m2, ek, _st = D.step_e2e(1, ii.numpy()[:m], pi_.numpy()[:m], vi.numpy()[:m], wi.numpy()[:m], io.numpy(), po.numpy(), vo.numpy(), wo.numpy())
+            ii[:m2].copy_(io[:m2]); pi_[:m2].copy_(po[:m2]); vi[:m2].copy_(vo[:m2]); wi[:m2].copy_(wo[:m2])
+            return m2
+        for _ in range(3):
+            m = one(m)
+        barrier()
+        e0 = time.time()
+        for _ in range(ke):
+            m = one(m)
+        barrier()
+        e2e_s = time.time() - e0
+        h2d, d2h = int(m * 76), int(m * 76 + 8)
     ck = clocks.stop()
     # ---- reduce over ranks (max of times)
     t = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device="cuda")
@@ -184,14 +244,14 @@ def run_gpu(args):
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg2: 1M polydisperse spheres (PSD 1:4) settled under gravity, Leapfrog+collider+ContactLoop(Cg2_Sphere_Sphere/Wall_Sphere_L6Geom, Cp2_FrictMat_FrictPhys, Law2_L6Geom_FrictPhys_IdealElPl)+DynDt",
                    "n_spheres_per_gpu": n, "initial_state": ("tiled pre-settled 20k bed (tests/golden/cfg2_sample_20k.npz) %dx%d, re-settled" % (tiling["tiles_x"], tiling["tiles_y"])) if tiling else "jittered lattice", "settle_steps": args.settle, "real_contacts": n_real, "candidate_contacts": n_con, "rebuilds_in_timed_region": n_reb,
-                   "l2_policy": "inputs larger than L2 (per-step working set %.0f MB > 126 MB)" % (step_bytes / 1e6), "parallelism": "1 slab box per GPU" if world > 1 else "single GPU",
+                   "l2_policy": "inputs larger than L2 (per-step working set %.0f MB > 126 MB)" % (step_bytes / 1e6), "parallelism": ("%d x-slabs of one box, 1 per GPU; ghosts refreshed per step and spheres migrated at collider runs over NCCL" % world) if world > 1 else "single GPU",
                    "settle_wall_s": round(settle_s, 1)},
         "roofline": {"bound": "hbm", "kernel": "k_contact_ss<IdealElPl>", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "algorithmic_bytes_per_launch": bytes_contact, "ms_per_launch": ms_contact,
                      "step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9, "frac": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9 / peak},
                      "phase_ms_per_step": {k: stats[k] / K for k in ("ms_integrate", "ms_rebuild", "ms_contact", "ms_reduce", "ms_dyndt")}},
-        "e2e": {"value": ntot * ke / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": int(n * 72), "d2h_bytes_per_step": int(n * 48 + 8), "steps": ke,
-                "api": "wdem_step_e2e (C-ABI, pinned host buffers)"},
+        "e2e": {"value": ntot * ke / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
+                "api": "wdem_step_e2e (C-ABI, pinned host buffers)" if D is None else "wdem_set_owned + wdem_step + wdem_download_owned per rank (C-ABI, pinned host buffers)"},
         "gpu_launches": int(n_launch), "clocks": ck, "wall_ms_per_step": wall_ms / K,
     }
     if world == 1 and not args.no_cpu:

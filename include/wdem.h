@@ -141,6 +141,8 @@ int wdem_set_domain(wdem_handle h, int axis, int ncuts, const double* cuts, int6
 int64_t wdem_num_owned(wdem_handle h);
 /* Owned spheres in subdomain order with their ids (any pointer but ids may be NULL); arrays sized by wdem_num_owned. */
 int wdem_download_owned(wdem_handle h, int32_t* ids, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque);
+/* Overwrite pos/vel/angVel (any may be NULL) of owned spheres addressed by Particle.id; fails if an id is not owned here. */
+int wdem_set_owned(wdem_handle h, int64_t n, const int32_t* ids, const double* pos, const double* vel, const double* angVel);
 int wdem_domain_stats(wdem_handle h, int64_t* nOwned, int64_t* nGhosts, int64_t* migratedOut, int64_t* migratedIn, int64_t* rowsIn);
 
 /* Device-level info for bench.py: bytes allocated, stream pointer (cudaStream_t) */

@@ -260,6 +260,17 @@ __global__ void __launch_bounds__(256) k_gather_owned(Spheres S, int n, const in
   if (force) { force[3 * u] = S.fx[i]; force[3 * u + 1] = S.fy[i]; force[3 * u + 2] = S.fz[i]; }
   if (torque) { torque[3 * u] = S.tx[i]; torque[3 * u + 1] = S.ty[i]; torque[3 * u + 2] = S.tz[i]; }
 }
+// host-supplied state of owned spheres addressed by Particle.id (end-to-end path of decomposed runs)
+__global__ void __launch_bounds__(256) k_scatter_owned(Spheres S, const int* __restrict__ id2slot, const int32_t* __restrict__ ids, long long cnt, const double* pos,
+                                                      const double* vel, const double* angVel, int* missing) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  const int i = id2slot[ids[t]];
+  if (i < 0 || (S.flags[i] & F_GHOST)) { atomicAdd(missing, 1); return; }
+  if (pos) { double4 p = S.posr[i]; p.x = pos[3 * t]; p.y = pos[3 * t + 1]; p.z = pos[3 * t + 2]; S.posr[i] = p; }
+  if (vel) { double4 v = S.velm[i]; v.x = vel[3 * t]; v.y = vel[3 * t + 1]; v.z = vel[3 * t + 2]; S.velm[i] = v; }
+  if (angVel) { double4 w = S.angi[i]; w.x = angVel[3 * t]; w.y = angVel[3 * t + 1]; w.z = angVel[3 * t + 2]; S.angi[i] = w; }
+}
 __global__ void __launch_bounds__(256) k_owned_flag(const uint32_t* __restrict__ sflags, int n, int* flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flag[i] = (sflags[i] & F_GHOST) ? 0 : 1;

@@ -1195,6 +1195,25 @@ int wdem_download_owned(wdem_handle h, int32_t* ids, double* pos, double* ori, d
     CK(cudaStreamSynchronize(st));
   });
 }
+int wdem_set_owned(wdem_handle h, int64_t n, const int32_t* ids, const double* pos, const double* vel, const double* angVel) {
+  return guarded(h, [&] {
+    if (n < 0 || (n > 0 && !ids)) throw EngErr{"wdem_set_owned: bad arguments", WDEM_ERR_INVALID};
+    if (n == 0) return;
+    if (h->conDirty) throw EngErr{"wdem_set_owned: step at least once first (ownership is settled by the first collider run)", WDEM_ERR_INVALID};
+    cudaStream_t st = h->stream;
+    h->ioBuf.ensure((size_t)n * 10 + 8, h->bytes); h->orphCnt.ensure(1, h->bytes);
+    double* d = h->ioBuf.p; int32_t* dids = (int32_t*)(d + 9 * (size_t)n);
+    double *dp = nullptr, *dv = nullptr, *dw = nullptr;
+    CK(cudaMemcpyAsync(dids, ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (pos) { dp = d; CK(cudaMemcpyAsync(dp, pos, (size_t)n * 24, cudaMemcpyHostToDevice, st)); }
+    if (vel) { dv = d + 3 * (size_t)n; CK(cudaMemcpyAsync(dv, vel, (size_t)n * 24, cudaMemcpyHostToDevice, st)); }
+    if (angVel) { dw = d + 6 * (size_t)n; CK(cudaMemcpyAsync(dw, angVel, (size_t)n * 24, cudaMemcpyHostToDevice, st)); }
+    CK(cudaMemsetAsync(h->orphCnt.p, 0, sizeof(int), st));
+    k_scatter_owned<<<nblk(n, 256), 256, 0, st>>>(h->S(), h->id2slot.p, dids, n, dp, dv, dw, h->orphCnt.p);
+    int miss = 0; CK(cudaMemcpyAsync(&miss, h->orphCnt.p, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    if (miss) throw EngErr{"wdem_set_owned: " + std::to_string(miss) + " ids are not owned by this subdomain", WDEM_ERR_INVALID};
+  });
+}
 int wdem_domain_stats(wdem_handle h, int64_t* nOwned, int64_t* nGhosts, int64_t* migratedOut, int64_t* migratedIn, int64_t* rowsIn) {
   return guarded(h, [&] {
     if (nOwned) *nOwned = h->comm ? h->dom.nOwn : h->n; if (nGhosts) *nGhosts = h->comm ? h->n - h->dom.nOwn : 0;

@@ -62,6 +62,10 @@ def _owned(E):
     return o
 
 
+def _set_owned(E, ids, pos=None, vel=None, angVel=None):
+    E._chk(E.L.wdem_set_owned(E.h, C.c_int64(len(ids)), ptr(ids), ptr(pos), ptr(vel), ptr(angVel)))
+
+
 def _domain_stats(E):
     v = [C.c_int64() for _ in range(5)]
     E._chk(E.L.wdem_domain_stats(E.h, *[C.byref(x) for x in v]))
@@ -179,7 +183,7 @@ class DistributedEngine:
             dist.broadcast(t, 0)
         E._chk(L.wdem_comm_init_nccl(E.h, C.c_int(self.rank), C.c_int(self.world), bytes(t.numpy().tobytes())))
         self.cuts = quantile_cuts(S, self.world, axis) if cuts is None else np.asarray(cuts, dtype=np.float64)
-        _set_domain(E, axis, self.cuts, S.global_max_id if hasattr(S, "global_max_id") else _max_id(S))
+        _set_domain(E, axis, self.cuts, getattr(S, "global_max_id", None) or _max_id(S))
         if sel is None:
             sel = np.nonzero(owner_of(S, self.cuts, axis) == self.rank)[0]
         _load_part(E, S, sel)
@@ -189,6 +193,20 @@ class DistributedEngine:
 
     def owned(self):
         return _owned(self.E)
+
+    def num_owned(self):
+        return self.E.L.wdem_num_owned(self.E.h)
+
+    def step_e2e(self, n, ids, pos, vel, angVel, ids_out, pos_out, vel_out, angVel_out):
+        """End-to-end step of this subdomain: host state (by id) -> device, n steps, owned state -> host.  Returns (owned count, Ek, stats);
+        the owned set (and its order) may change when spheres migrate, so outputs carry their ids."""
+        E = self.E
+        _set_owned(E, ids, pos, vel, angVel)
+        st = E.step(n)
+        m = self.num_owned()
+        assert m <= len(ids_out), "output buffers too small for the owned set"
+        E._chk(E.L.wdem_download_owned(E.h, ptr(ids_out), ptr(pos_out), None, ptr(vel_out), ptr(angVel_out), None, None))
+        return m, E.kinetic_energy(), st
 
     def domain_stats(self):
         return _domain_stats(self.E)
