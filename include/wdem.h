@@ -89,6 +89,9 @@ int wdem_upload_materials(wdem_handle h, int n, const int32_t* kind, const doubl
 int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const double* pos, const double* ori, const double* vel,
                         const double* angVel, const double* mass, const double* inertia, const double* radius,
                         const uint32_t* flags, const uint32_t* mask, const int32_t* matId);
+/* DemData.force/torque accumulated by the previous step's ContactLoop (consumed by the next Leapfrog, Leapfrog.cpp:144-160); upload order,
+ * either may be NULL (= zero).  Only right after wdem_upload_spheres. */
+int wdem_upload_forces(wdem_handle h, const double* force, const double* torque);
 /* Walls (dem/Wall.hpp): static; vel may be NULL. */
 int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* pos, const int32_t* axis, const int32_t* sense,
                       const double* vel, const uint32_t* mask, const int32_t* matId);

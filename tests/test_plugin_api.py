@@ -1,0 +1,208 @@
+"""The reference-facing plugin layer (woo_b200.woo: GpuDemLoop + reference-named objects, C++/pybind11 over the C-ABI).
+GPU tests are ports of the reference's own tests for this path (py/tests/test_hertz.py, test_pbc.py, test_core.py) with
+``woo.utils.defaultEngines`` replaced by ``woo.utils.gpuEngines``; CPU tests cover the object model and the loud failure without a GPU."""
+import math
+import numpy as np
+import pytest
+from woo_b200 import woo
+from woo_b200.woo.core import Scene
+from woo_b200.woo.dem import (DemField, Sphere, Wall, Facet, FrictMat, HertzMat, Leapfrog, InsertionSortCollider, ContactLoop, DynDt, GpuDemLoop, Bo1_Wall_Aabb,
+                              Cg2_Sphere_Sphere_L6Geom, Cp2_FrictMat_FrictPhys, Cp2_HertzMat_HertzPhys, Law2_L6Geom_FrictPhys_IdealElPl, Law2_L6Geom_HertzPhys_DMT)
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+# ------------------------------------------------------------------------------------------------ CPU: object model
+def test_reference_defaults():
+    # attribute names and defaults of the reference headers (SURVEY §8b "Attributes to mirror")
+    assert Leapfrog().damping == .2 and Leapfrog().reset is False
+    assert InsertionSortCollider().verletDist == -.05
+    cl = ContactLoop()
+    assert cl.applyForces is True and cl.updatePhys == 0 and cl.dist00 is True and cl.reorderEvery == 1000 and cl.evalStress is False
+    g = Cg2_Sphere_Sphere_L6Geom()
+    assert (g.noRatch, g.iniLensTouch, g.trsfRenorm, g.approxMask) == (False, True, 100, 0)
+    c = Cp2_HertzMat_HertzPhys()
+    assert c.poisson == .2 and math.isnan(c.en)
+    l = Law2_L6Geom_FrictPhys_IdealElPl()
+    assert (l.noSlip, l.noBreak, l.noFrict, l.iniEqlb, l.relRollStiff, l.relTwistStiff, l.rollTanPhi) == (False, False, False, False, 0., 0., 0.)
+    assert Law2_L6Geom_HertzPhys_DMT().noAttraction is True
+    d = DynDt()
+    assert d.stepPeriod == 100 and d.maxRelInc == 1e-4 and d.dryRun is False
+    f = DemField()
+    assert f.loneMask == 2 and f.distFactor == -1 and tuple(f.gravity) == (0, 0, 0)
+    assert DemField.defaultMovableMask == 0b0101 and DemField.defaultBoundaryMask == 0b0011
+    m = woo.utils.defaultMaterial()
+    assert (m.density, m.young, m.ktDivKn) == (1e3, 1e7, .2) and m.tanPhi == math.tan(.5)
+    S = Scene()
+    assert math.isnan(S.dt) and S.dtSafety == .9 and S.step == 0 and S.periodic is False
+    assert woo.utils.spherePWaveDt(1e-3, 2400, 30e9) == 2.8284271247461903e-07      # py/utils.py:80-81
+
+
+def test_particle_container_and_nodes():
+    S = Scene(fields=[DemField()])
+    ids = S.dem.par.add([woo.utils.sphere((0, 0, 0), .05), woo.utils.sphere((0, .2, 0), .05, fixed=True), woo.utils.wall(0, axis=2, sense=1)])
+    assert ids == [0, 1, 2] and len(S.dem.par) == 3
+    p = S.dem.par[0]
+    assert p.mass == pytest.approx(4 / 3 * math.pi * .05 ** 3 * 1e3) and p.inertia[0] == pytest.approx(.4 * p.mass * .05 ** 2)     # Sphere.cpp:26-33
+    assert S.dem.par[1].blocked == "xyzXYZ" and S.dem.par[2].shape.axis == 2 and S.dem.par[2].mask == 3 and p.mask == 5
+    assert len(S.dem.nodes) == 1        # only moving nodes are collected (ParticleContainer.cpp:193-198)
+    with pytest.raises(RuntimeError):
+        S.dem.par.add(p)                # already has an id
+    S.dem.nodes[0].pos += (13, 14, 15)
+    assert tuple(S.dem.par[0].pos) == (13, 14, 15)
+    with pytest.raises(IndexError):
+        S.dem.par[7]
+
+
+def test_cpu_engines_do_not_run_on_their_own():
+    S = Scene(fields=[DemField()])
+    S.dem.par.add(woo.utils.sphere((0, 0, 0), .05))
+    S.dt = 1e-5
+    S.engines = woo.utils.defaultEngines()
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        S.one()
+
+
+def test_unsupported_settings_raise():
+    S = Scene(fields=[DemField()]); S.dem.par.add(woo.utils.sphere((0, 0, 0), .05)); S.dt = 1e-5
+    e = woo.utils.defaultEngines()
+    e[2].updatePhys = 1
+    S.engines = [GpuDemLoop(*e)]
+    with pytest.raises(RuntimeError, match="updatePhys"):
+        S.one()
+    S.engines = [GpuDemLoop(*woo.utils.defaultEngines(cp2=Cp2_FrictMat_FrictPhys(), law=Law2_L6Geom_HertzPhys_DMT()))]
+    with pytest.raises(RuntimeError, match="supported functor pairs"):
+        S.one()
+    S.engines = woo.utils.gpuEngines(); S.trackEnergy = True
+    with pytest.raises(RuntimeError, match="trackEnergy"):
+        S.one()
+    with pytest.raises(RuntimeError, match="degenerate"):
+        S.cell.hSize = [[1, 0, 0], [0, 0, 0], [0, 0, 1]]      # py/tests/test_pbc.py:60-62
+
+
+@pytest.mark.skipif(_has_cuda(), reason="this box has a GPU")
+def test_fails_loudly_without_gpu():
+    S = Scene(fields=[DemField()]); S.dem.par.add(woo.utils.sphere((0, 0, 0), .05)); S.dt = 1e-5
+    S.engines = woo.utils.gpuEngines()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.one()
+
+
+# ------------------------------------------------------------------------------------------------ GPU: ports of reference tests
+@pytest.mark.gpu
+@pytest.mark.parametrize("v0", [1, 1e-2, 1e-4])
+def test_hertz_elastic_collision_time(v0):
+    """py/tests/test_hertz.py:13-47 (the LawTester is replaced by initial velocities and a Python observer engine)."""
+    S = Scene(fields=[DemField()])
+    m = HertzMat(density=1e3, young=1e8, ktDivKn=.2, tanPhi=.5, surfEnergy=0, alpha=0)
+    S.dem.par.add([woo.utils.sphere((0, 0, 0), .05, mat=m, vel=(0, v0 / 2, 0)), woo.utils.sphere((0, .1 + 1e-9, 0), .05, mat=m, vel=(0, -v0 / 2, 0))])
+    S.dtSafety = .4
+    seen = {}
+
+    def observer(S):
+        real = S.dem.con.existsReal(0, 1)
+        if real and "t0" not in seen:
+            seen["t0"] = S.time
+        if not real and "t0" in seen and "t1" not in seen:
+            seen["t1"] = S.time
+    S.engines = woo.utils.gpuEngines(damping=0., cp2=Cp2_HertzMat_HertzPhys(en=0, label='cp2', poisson=.2), law=Law2_L6Geom_HertzPhys_DMT(), dynDtPeriod=10) + [observer]
+    for _ in range(200000):
+        S.one()
+        if "t1" in seen:
+            break
+    E, nu, rho, d = 1e8, .2, 1e3, .1
+    Eeff = (E * E) / (E * (1 - nu ** 2) + E * (1 - nu ** 2))
+    tau = 2.214 * (rho / Eeff) ** (2 / 5.) * (d / v0 ** (1 / 5.))
+    assert abs((seen["t1"] - seen["t0"]) - tau) < .01 * tau + 2 * S.dt
+
+
+def _pbc_scene(spheres):
+    S = Scene(fields=[DemField()])
+    S.periodic = True
+    S.cell.setBox(1., 1., 1.)
+    S.engines = woo.utils.gpuEngines(damping=0.)
+    S.dem.par.add([Sphere.make(c, radius=r) for c, r in spheres])
+    S.dt = 1e-9
+    return S
+
+
+@pytest.mark.gpu
+def test_pbc_collisions():
+    # py/tests/test_pbc.py:130-171
+    S = _pbc_scene([((.3, .5, .5), .4), ((.7, .9, .5), .1)]); S.one()
+    assert tuple(S.dem.con[0, 1].cellDist) == (0, 0, 0)
+    S = _pbc_scene([((.3, .5, .5), .4), ((.7, .9, .5), .1)]); S.dem.nodes[0].pos += (13, 14, 15); S.one()
+    assert tuple(S.dem.con[0, 1].cellDist) == (13, 14, 15)
+    S = _pbc_scene([((.3, .5, .5), .4), ((.8, .9, .5), .2)])
+    with pytest.raises(RuntimeError):
+        S.one()
+    for shift2 in [(0, 0, 0), (1, 2, 3), (6, 8, -4)]:
+        S = _pbc_scene([((.5, .5, .5), .2), ((.8, .6, .5), .2)]); S.dem.nodes[1].pos += shift2; S.one()
+        assert tuple(S.dem.con[0, 1].cellDist) == tuple(-np.array(shift2))
+
+
+@pytest.mark.gpu
+def test_ten_spheres_contact_force_sign():
+    # py/tests/test_core.py:436-453
+    S = Scene(fields=[DemField()])
+    S.dem.par.add([woo.utils.sphere((x * .95, 0, 0), .5) for x in range(10)])
+    S.engines = woo.utils.gpuEngines(damping=0.); S.dt = 1e-5
+    S.one()
+    c = S.dem.con[4, 5]
+    assert c.real and c.phys.force[0] < 0 and c.geom.uN < 0
+    assert S.dem.par[0].f[0] < 0 and S.dem.par[9].f[0] > 0 and abs(S.dem.par[4].f[0]) < 1e-9 * abs(S.dem.par[0].f[0])
+    assert c.phys.kn == pytest.approx(1 / (2 * .5 / (1e7 * math.pi * .5 ** 2)))       # py/models.py:16-19
+
+
+@pytest.mark.gpu
+def test_plugin_matches_array_level_engine_and_run_fast_path():
+    from woo_b200 import scenes as sc
+    from woo_b200.engine import Engine
+    Sp = sc.random_gas(300, box=.4, r=.02, psd_ratio=2.0, seed=41)
+    E = Engine(Sp.params).load(Sp); E.step(120)
+    ref = E.spheres()
+
+    def build():
+        S = Scene(fields=[DemField(gravity=Sp.params.gravity)])
+        m = FrictMat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)
+        S.dem.par.add([woo.utils.sphere(Sp.pos[i], Sp.radius[i], mat=m, vel=Sp.vel[i]) for i in range(Sp.n)])
+        for i in range(Sp.n):
+            S.dem.par[i].angVel = Sp.angVel[i]
+        S.dem.par.add([Wall.make(w["pos"], axis=w["axis"], sense=w["sense"], mat=m) for w in Sp.walls])
+        S.engines = woo.utils.gpuEngines(damping=.2, dynDtPeriod=10)
+        return S
+    S = build()
+    for _ in range(120):
+        S.one()
+    got = np.array([S.dem.par[i].pos for i in range(Sp.n)])
+    assert np.array_equal(got, ref["pos"]) and S.step == 120 and S.dt == E.scalars()["dt"]
+    assert np.array_equal(np.array([S.dem.par[i].f for i in range(Sp.n)]), ref["force"])
+    assert S.engines[0].collider.nFullRuns == E.scalars()["nFullRuns"]
+    S2 = build(); S2.one(); S2.run(119, True)        # first step fixes dt, then one C-ABI call for the rest
+    assert np.array_equal(np.array([S2.dem.par[i].pos for i in range(Sp.n)]), ref["pos"]) and S2.step == 120 and S2.time == pytest.approx(S.time, rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_host_edits_reach_the_device():
+    S = Scene(fields=[DemField(gravity=(0, 0, -10))])
+    S.dem.par.add([woo.utils.sphere((0, 0, 1), .1), woo.utils.wall(0, axis=2, sense=1)])
+    S.engines = woo.utils.gpuEngines(damping=0.); S.dt = 1e-4
+    S.run(10, True)
+    z = S.dem.par[0].pos[2]
+    assert z < 1
+    S.dem.par[0].vel = (0, 0, 5.)
+    S.one()
+    assert S.dem.par[0].pos[2] > z and S.dem.par[0].vel[2] == pytest.approx(5. - 10 * 1e-4)
+    n = len(S.dem.par); z, vz, step = S.dem.par[0].pos[2], S.dem.par[0].vel[2], S.step
+    S.dem.par.add(woo.utils.sphere((1, 0, 1), .1))          # topology change -> re-upload from the latest device state, forces included
+    S.one(); S.one()
+    assert len(S.dem.par) == n + 1 and S.step == step + 2
+    assert S.dem.par[0].vel[2] == pytest.approx(vz - 2 * 10 * 1e-4) and S.dem.par[0].pos[2] > z
+    # the new sphere saw zero force in its first Leapfrog, gravity from the second on
+    assert S.dem.par[n].vel[2] == pytest.approx(-10 * 1e-4) and S.dem.par[n].pos[2] < 1

@@ -937,6 +937,17 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
   });
 }
 
+int wdem_upload_forces(wdem_handle h, const double* force, const double* torque) {
+  return guarded(h, [&] {
+    if (!h->conDirty || h->cur != 0 || h->comm) throw EngErr{"wdem_upload_forces: call right after wdem_upload_spheres (single-domain runs)", WDEM_ERR_INVALID};
+    const size_t n = (size_t)h->n; if (!n) return;
+    std::vector<double> soa(6 * n, 0.);
+    for (size_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { if (force) soa[k * n + i] = force[3 * i + k]; if (torque) soa[(3 + k) * n + i] = torque[3 * i + k]; }
+    for (int k = 0; k < 6; k++) CK(cudaMemcpyAsync(h->sph[0].f[k].p, soa.data() + k * n, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  });
+}
+
 int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* pos, const int32_t* axis, const int32_t* sense, const double* vel, const uint32_t* mask,
                       const int32_t* matId) {
   return guarded(h, [&] {

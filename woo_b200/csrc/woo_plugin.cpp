@@ -1,0 +1,511 @@
+// woo_plugin.cpp — host side of the drop-in boundary, C++/pybind11 like the reference's own host code.
+//
+// * GpuDemLoop: one Engine that takes the slot of [Leapfrog, InsertionSortCollider, ContactLoop(, DynDt)] in Scene.engines
+//   (reference: py/utils.py:122-129, core/Engine.hpp:19-104, Scene::doOneStep core/Scene.cpp:366-432).  It reads the attributes of the
+//   reference's engine/functor objects it is constructed from, uploads the DemField through the C-ABI of include/wdem.h and steps on the
+//   GPU.  C-ABI errors become std::runtime_error, which is what the reference's engines throw out of run().
+// * A minimal object model with the reference's class and attribute names (Scene, Cell, DemField, Particle, Node, DemData, Sphere, Wall,
+//   Facet, FrictMat, HertzMat, Contact, L6Geom, FrictPhys and the attribute-carrying engine/functor classes), enough for the reference's
+//   scripts/tests of this path to run by renaming the import.  Inside real Woo the same GpuDemLoop body is registered with
+//   WOO_PLUGIN(dem,(GpuDemLoop)) against Woo's own classes instead.
+// There is no CPU implementation behind any of these classes: running Leapfrog/InsertionSortCollider/ContactLoop/DynDt on their own throws.
+#include <pybind11/pybind11.h>
+#include <pybind11/numpy.h>
+#include <pybind11/stl.h>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/wdem.h"
+
+namespace py = pybind11;
+using std::shared_ptr; using std::make_shared; using std::string; using std::vector;
+typedef std::array<double, 3> V3; typedef std::array<int, 3> V3i; typedef std::array<double, 4> Q4; typedef std::array<double, 9> M3;
+static const double NaN = std::numeric_limits<double>::quiet_NaN();
+
+static py::array_t<double> np3(const V3& v) { py::array_t<double> a(3); std::memcpy(a.mutable_data(), v.data(), 24); return a; }
+static py::array_t<double> np4(const Q4& v) { py::array_t<double> a(4); std::memcpy(a.mutable_data(), v.data(), 32); return a; }
+static py::array_t<double> np33(const M3& m) { py::array_t<double> a({3, 3}); std::memcpy(a.mutable_data(), m.data(), 72); return a; }
+static py::array_t<int> np3i(const V3i& v) { py::array_t<int> a(3); std::memcpy(a.mutable_data(), v.data(), 12); return a; }
+template <size_t N> static std::array<double, N> seqN(const py::object& o, const char* what) {
+  py::array_t<double, py::array::c_style | py::array::forcecast> a = py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(o);
+  if (!a || (size_t)a.size() != N) throw std::invalid_argument(string(what) + ": expected " + std::to_string(N) + " numbers");
+  std::array<double, N> r; std::memcpy(r.data(), a.data(), N * 8); return r;
+}
+
+struct DemField; struct Scene;
+
+// ---- materials (dem/FrictMat.hpp:20-31, dem/Hertz.hpp:9-16)
+struct Material { double density = 1e3; int id = -1; virtual ~Material() {} virtual int kind() const { return -1; } };
+struct ElastMat : Material { double young = 1e9; };
+struct FrictMat : ElastMat { double tanPhi = .5, ktDivKn = .2; int kind() const override { return WDEM_MAT_FRICT; } };
+struct HertzMat : FrictMat { double surfEnergy = 0., alpha = 0.; int kind() const override { return WDEM_MAT_HERTZ; } };
+
+// ---- nodes and particles (core/Field.hpp:102-103, dem/Particle.hpp:91-97,198-292)
+enum { DOF_ALL = 63, GRAVITY_SKIP = 512, DAMPING_SKIP = 2048 };
+struct DemData {
+  V3 vel{{0, 0, 0}}, angVel{{0, 0, 0}}, force{{0, 0, 0}}, torque{{0, 0, 0}}, inertia{{0, 0, 0}}; double mass = 0; unsigned flags = 0;
+  DemField* field = nullptr;
+  string blockedGet() const { string r; const char* n = "xyzXYZ"; for (int i = 0; i < 6; i++) if (flags & (1u << i)) r += n[i]; return r; }
+  void blockedSet(const string& s) { flags &= ~63u; for (char c : s) { const char* n = "xyzXYZ"; const char* p = strchr(n, c); if (!p) throw std::invalid_argument("blocked: only xyzXYZ allowed"); flags |= 1u << (p - n); } }
+};
+struct Node { V3 pos{{0, 0, 0}}; Q4 ori{{0, 0, 0, 1}}; shared_ptr<DemData> dem; };
+struct Shape { vector<shared_ptr<Node>> nodes; virtual ~Shape() {} virtual int numNodes() const = 0; };
+struct Sphere : Shape { double radius = NaN; int numNodes() const override { return 1; } };
+struct Wall : Shape { int sense = 0, axis = 0; int numNodes() const override { return 1; } };
+struct Facet : Shape { V3 fakeVel{{0, 0, 0}}; double halfThick = 0.; V3 n21lim{{NaN, NaN, NaN}}; int numNodes() const override { return 3; } };
+struct Particle { int id = -1; unsigned mask = 1; shared_ptr<Shape> shape; shared_ptr<Material> material; DemField* field = nullptr; };
+
+// ---- contacts (dem/Contact.hpp:21-106, dem/L6Geom.hpp:16-21, dem/FrictMat.hpp:33-35)
+struct CGeomNode { V3 pos; };
+struct L6Geom { double uN = NaN; M3 trsf; CGeomNode node; };
+struct FrictPhys { V3 force, torque; double kn = NaN, kt = NaN, tanPhi = NaN; };
+struct Contact { int id1 = -1, id2 = -1; V3i cellDist{{0, 0, 0}}; int stepCreated = -1; shared_ptr<L6Geom> geom; shared_ptr<FrictPhys> phys; bool isReal() const { return geom && phys; } };
+
+struct GpuDemLoop;
+struct ParticleContainer { DemField* dem = nullptr; vector<shared_ptr<Particle>> v; };
+struct ContactContainer { DemField* dem = nullptr; vector<shared_ptr<Contact>> v; std::map<std::pair<int, int>, size_t> ix; };
+
+// ---- the field (dem/Particle.hpp:339-361)
+struct DemField {
+  ParticleContainer par; ContactContainer con; vector<shared_ptr<Node>> nodes;
+  V3 gravity{{0, 0, 0}}; unsigned loneMask = 2; double distFactor = -1.;
+  // coherence with the device copy (SURVEY §7 "Host<->device coherence"): upload once, download lazily
+  GpuDemLoop* owner = nullptr; bool topoDirty = true, stateDirty = false, deviceNewer = false, contactsStale = true;
+  DemField() { par.dem = this; con.dem = this; }
+  void pull(); void pullContacts();
+  void touchState() { stateDirty = true; }
+};
+
+// ---- periodic cell (core/Cell.hpp)
+struct Cell { M3 hSize{{1, 0, 0, 0, 1, 0, 0, 0, 1}}, gradV{{0, 0, 0, 0, 0, 0, 0, 0, 0}}, nextGradV{{0, 0, 0, 0, 0, 0, 0, 0, 0}}; int homoDeform = WDEM_HOMO_GRADV2; bool dirty = true; };
+
+// ---- engines (core/Engine.hpp:19-104)
+struct Engine {
+  bool dead = false; string label; Scene* scene = nullptr; shared_ptr<DemField> field;
+  virtual ~Engine() {}
+  virtual void run() { throw std::runtime_error(string(cls()) + ".run(): woo_b200 has no CPU implementation of this engine; put it into GpuDemLoop(leapfrog, collider, contactLoop, dynDt)"); }
+  virtual double critDt() { return std::numeric_limits<double>::infinity(); }
+  virtual const char* cls() const { return "Engine"; }
+};
+struct Leapfrog : Engine { double damping = .2; bool reset = false, kinSplit = false, dontCollect = false; const char* cls() const override { return "Leapfrog"; } };
+struct BoundFunctor { virtual ~BoundFunctor() {} };
+struct Bo1_Sphere_Aabb : BoundFunctor {}; struct Bo1_Facet_Aabb : BoundFunctor {}; struct Bo1_Wall_Aabb : BoundFunctor { double halfThick = 0.; };
+struct InsertionSortCollider : Engine { vector<shared_ptr<BoundFunctor>> boundDispatcher; double verletDist = -.05; long nFullRuns = 0; const char* cls() const override { return "InsertionSortCollider"; } };
+struct CGeomFunctor { bool noRatch = false, iniLensTouch = true; int trsfRenorm = 100, approxMask = 0; virtual ~CGeomFunctor() {} };
+struct Cg2_Sphere_Sphere_L6Geom : CGeomFunctor {}; struct Cg2_Wall_Sphere_L6Geom : CGeomFunctor {}; struct Cg2_Facet_Sphere_L6Geom : CGeomFunctor {};
+struct CPhysFunctor { string label; virtual ~CPhysFunctor() {} };
+struct Cp2_FrictMat_FrictPhys : CPhysFunctor { py::object tanPhi = py::none(); };
+struct Cp2_HertzMat_HertzPhys : CPhysFunctor { double poisson = .2, en = NaN; };
+struct LawFunctor { string label; virtual ~LawFunctor() {} };
+struct Law2_L6Geom_FrictPhys_IdealElPl : LawFunctor { bool noSlip = false, noBreak = false, noFrict = false, iniEqlb = false; double relRollStiff = 0., relTwistStiff = 0., rollTanPhi = 0.; };
+struct Law2_L6Geom_HertzPhys_DMT : LawFunctor { bool noAttraction = true; };
+struct ContactLoop : Engine {
+  vector<shared_ptr<CGeomFunctor>> geoDisp; vector<shared_ptr<CPhysFunctor>> phyDisp; vector<shared_ptr<LawFunctor>> lawDisp;
+  bool applyForces = true, evalStress = false, dist00 = true; int updatePhys = 0, reorderEvery = 1000; py::object hook = py::none();
+  const char* cls() const override { return "ContactLoop"; }
+};
+struct DynDt : Engine { int stepPeriod = 100; double maxRelInc = 1e-4; bool dryRun = false; const char* cls() const override { return "DynDt"; } };
+
+// ---- Scene (core/Scene.hpp:191-205, Scene.cpp:366-432)
+struct Scene {
+  double dt = NaN, nextDt = NaN, dtSafety = .9, time = 0; long step = 0; bool periodic = false, trackEnergy = false, deterministic = false;
+  shared_ptr<Cell> cell = make_shared<Cell>(); vector<py::object> engines; vector<shared_ptr<DemField>> fields;
+  shared_ptr<DemField> dem() const { if (fields.empty()) throw std::runtime_error("Scene has no DemField"); return fields[0]; }
+  void one(); void run(long n);
+};
+
+// ---- the B200 engine group
+static void chk(wdem_handle h, int rc) { if (rc != WDEM_OK) throw std::runtime_error(string("GpuDemLoop: ") + wdem_last_error(h)); }
+
+struct GpuDemLoop : Engine {
+  shared_ptr<Leapfrog> leapfrog; shared_ptr<InsertionSortCollider> collider; shared_ptr<ContactLoop> contactLoop; shared_ptr<DynDt> dynDt;
+  int device = 0; wdem_handle h = nullptr; wdem_config cfg; bool haveCfg = false; long nSpheres = 0; wdem_stats last;
+  vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf;
+  const char* cls() const override { return "GpuDemLoop"; }
+  ~GpuDemLoop() override { release(); }
+  void release() { if (h) { wdem_destroy(h); h = nullptr; } if (field && field->owner == this) field->owner = nullptr; }
+
+  // attributes of the wrapped engines -> wdem_config (the reference engines re-read theirs at every run())
+  wdem_config makeConfig() {
+    if (!leapfrog || !collider || !contactLoop) throw std::runtime_error("GpuDemLoop needs leapfrog, collider and contactLoop");
+    if (!scene || !field) throw std::runtime_error("GpuDemLoop is not attached to a Scene with a DemField");
+    wdem_config c; wdem_default_config(&c);
+    c.device = device; c.dt = scene->dt; c.dtSafety = scene->dtSafety; c.periodic = scene->periodic ? 1 : 0;
+    for (int k = 0; k < 3; k++) c.gravity[k] = field->gravity[k];
+    c.loneMask = field->loneMask; c.distFactor = field->distFactor;
+    c.damping = leapfrog->damping; c.reset = leapfrog->reset ? 1 : 0;
+    c.verletDist = collider->verletDist;
+    for (auto& b : collider->boundDispatcher) if (auto w = dynamic_cast<Bo1_Wall_Aabb*>(b.get())) c.wallHalfThick = w->halfThick;
+    if (contactLoop->geoDisp.empty() || contactLoop->phyDisp.size() != 1 || contactLoop->lawDisp.size() != 1) throw std::runtime_error("GpuDemLoop: ContactLoop needs Cg2 functors, exactly one Cp2 and one Law2 functor");
+    const CGeomFunctor& g0 = *contactLoop->geoDisp[0];
+    for (auto& g : contactLoop->geoDisp) {
+      if (g->approxMask != 0) throw std::runtime_error("GpuDemLoop: Cg2_*.approxMask!=0 is not supported");
+      if (g->noRatch != g0.noRatch || g->iniLensTouch != g0.iniLensTouch || g->trsfRenorm != g0.trsfRenorm) throw std::runtime_error("GpuDemLoop: all Cg2 functors must share noRatch/iniLensTouch/trsfRenorm");
+    }
+    c.noRatch = g0.noRatch; c.iniLensTouch = g0.iniLensTouch; c.trsfRenorm = g0.trsfRenorm;
+    c.applyForces = contactLoop->applyForces;
+    if (contactLoop->updatePhys != 0) throw std::runtime_error("GpuDemLoop: ContactLoop.updatePhys is not supported");
+    if (contactLoop->evalStress) throw std::runtime_error("GpuDemLoop: ContactLoop.evalStress is not supported");
+    if (!contactLoop->hook.is_none()) throw std::runtime_error("GpuDemLoop: ContactLoop.hook is not supported");
+    if (scene->trackEnergy) throw std::runtime_error("GpuDemLoop: Scene.trackEnergy is not supported");
+    auto* lin = dynamic_cast<Law2_L6Geom_FrictPhys_IdealElPl*>(contactLoop->lawDisp[0].get());
+    auto* dmt = dynamic_cast<Law2_L6Geom_HertzPhys_DMT*>(contactLoop->lawDisp[0].get());
+    auto* cpF = dynamic_cast<Cp2_FrictMat_FrictPhys*>(contactLoop->phyDisp[0].get());
+    auto* cpH = dynamic_cast<Cp2_HertzMat_HertzPhys*>(contactLoop->phyDisp[0].get());
+    if (lin && cpF) {
+      if (!cpF->tanPhi.is_none()) throw std::runtime_error("GpuDemLoop: Cp2_FrictMat_FrictPhys.tanPhi (MatchMaker) is not supported");
+      if (lin->iniEqlb) throw std::runtime_error("GpuDemLoop: Law2_L6Geom_FrictPhys_IdealElPl.iniEqlb is not supported");
+      c.law = WDEM_LAW_IDEALELPL; c.noSlip = lin->noSlip; c.noBreak = lin->noBreak; c.noFrict = lin->noFrict;
+      c.relRollStiff = lin->relRollStiff; c.relTwistStiff = lin->relTwistStiff; c.rollTanPhi = lin->rollTanPhi;
+    } else if (dmt && cpH) {
+      c.law = WDEM_LAW_HERTZ_DMT; c.noAttraction = dmt->noAttraction; c.poisson = cpH->poisson; c.en = cpH->en;
+    } else throw std::runtime_error("GpuDemLoop: supported functor pairs are Cp2_FrictMat_FrictPhys+Law2_L6Geom_FrictPhys_IdealElPl and Cp2_HertzMat_HertzPhys+Law2_L6Geom_HertzPhys_DMT (FUNCTOR2D dispatch of the reference, Hertz.hpp:54,77)");
+    if (dynDt && !dynDt->dead) { if (dynDt->dryRun) throw std::runtime_error("GpuDemLoop: DynDt.dryRun is not supported"); c.dynDtPeriod = dynDt->stepPeriod; c.maxRelInc = dynDt->maxRelInc; }
+    else c.dynDtPeriod = 0;
+    return c;
+  }
+  static bool sameCfg(const wdem_config& a, const wdem_config& b) {
+    if (std::memcmp(&a, &b, sizeof(wdem_config)) == 0) return true;
+    wdem_config x = a, y = b; if (std::isnan(x.dt) && std::isnan(y.dt)) x.dt = y.dt = 0; if (std::isnan(x.en) && std::isnan(y.en)) x.en = y.en = 0;
+    return std::memcmp(&x, &y, sizeof(wdem_config)) == 0;
+  }
+
+  // DemField -> device (SoA host staging; ids are Particle.id)
+  void upload() {
+    DemField& F = *field;
+    if (F.owner && F.owner != this) throw std::runtime_error("GpuDemLoop: the DemField is already attached to another GpuDemLoop");
+    if (h && F.owner == this && F.deviceNewer) F.pull();   // a re-upload (particles added, masses changed, ...) starts from the latest device state
+    wdem_config c = makeConfig();
+    if (h && c.law != cfg.law) { wdem_destroy(h); h = nullptr; }
+    if (!h) { int rc = wdem_create(&c, &h); if (rc != WDEM_OK) { h = nullptr; throw std::runtime_error(string("GpuDemLoop: ") + wdem_last_error(nullptr)); } }
+    else chk(h, wdem_set_config(h, &c));
+    cfg = c; haveCfg = true;
+    // materials, de-duplicated by object identity
+    vector<Material*> mats; std::map<Material*, int> matIx;
+    auto matOf = [&](const shared_ptr<Particle>& p) { Material* m = p->material.get(); if (!m) throw std::runtime_error("particle #" + std::to_string(p->id) + " has no material"); auto it = matIx.find(m); if (it != matIx.end()) return it->second; int k = (int)mats.size(); mats.push_back(m); matIx[m] = k; return k; };
+    vector<int32_t> sid, smat, wid, waxis, wsense, wmat, fid, fmat; vector<uint32_t> sflags, smask, wmask, fmask;
+    vector<double> spos, sori, svel, sang, smass, sin, srad, sfrc, strq, wpos, wvel, fv, fvv, ffk, fht, fnl;
+    sphereIds.clear(); sphereOf.clear();
+    for (auto& p : F.par.v) {
+      if (!p) continue;
+      if (!p->shape) throw std::runtime_error("particle #" + std::to_string(p->id) + " has no shape");
+      const int m = matOf(p);
+      if (auto* s = dynamic_cast<Sphere*>(p->shape.get())) {
+        const Node& n = *s->nodes.at(0); const DemData& d = *n.dem;
+        if (!(d.inertia[0] == d.inertia[1] && d.inertia[1] == d.inertia[2])) throw std::runtime_error("GpuDemLoop: aspherical inertia is not supported (particle #" + std::to_string(p->id) + ")");
+        sid.push_back(p->id); smat.push_back(m); sflags.push_back(d.flags); smask.push_back(p->mask);
+        for (int k = 0; k < 3; k++) { spos.push_back(n.pos[k]); svel.push_back(d.vel[k]); sang.push_back(d.angVel[k]); sfrc.push_back(d.force[k]); strq.push_back(d.torque[k]); }
+        for (int k = 0; k < 4; k++) sori.push_back(n.ori[k]);
+        smass.push_back(d.mass); sin.push_back(d.inertia[0]); srad.push_back(s->radius);
+        sphereIds.push_back(p->id); sphereOf.push_back(p);
+      } else if (auto* w = dynamic_cast<Wall*>(p->shape.get())) {
+        const Node& n = *w->nodes.at(0);
+        if (n.dem->angVel[0] != 0 || n.dem->angVel[1] != 0 || n.dem->angVel[2] != 0) throw std::runtime_error("GpuDemLoop: rotating walls are not supported");
+        wid.push_back(p->id); waxis.push_back(w->axis); wsense.push_back(w->sense); wmat.push_back(m); wmask.push_back(p->mask);
+        for (int k = 0; k < 3; k++) { wpos.push_back(n.pos[k]); wvel.push_back(n.dem->vel[k]); }
+      } else if (auto* f = dynamic_cast<Facet*>(p->shape.get())) {
+        fid.push_back(p->id); fmat.push_back(m); fmask.push_back(p->mask); fht.push_back(f->halfThick);
+        for (int v = 0; v < 3; v++) { const Node& n = *f->nodes.at(v); for (int k = 0; k < 3; k++) { fv.push_back(n.pos[k]); fvv.push_back(n.dem->vel[k]); } }
+        for (int k = 0; k < 3; k++) { ffk.push_back(f->fakeVel[k]); fnl.push_back(f->n21lim[k]); }
+      } else throw std::runtime_error("GpuDemLoop: particle #" + std::to_string(p->id) + ": only Sphere, Wall and Facet shapes are supported");
+    }
+    if (mats.empty()) throw std::runtime_error("GpuDemLoop: no particles");
+    vector<int32_t> mk; vector<double> md, my, mkt, mtp, mse, mal;
+    for (Material* m : mats) {
+      auto* fm = dynamic_cast<FrictMat*>(m);
+      if (!fm) throw std::runtime_error("GpuDemLoop: materials must be FrictMat or HertzMat");
+      auto* hm = dynamic_cast<HertzMat*>(m);
+      mk.push_back(m->kind()); md.push_back(m->density); my.push_back(fm->young); mkt.push_back(fm->ktDivKn); mtp.push_back(fm->tanPhi); mse.push_back(hm ? hm->surfEnergy : 0.); mal.push_back(hm ? hm->alpha : 0.);
+    }
+    chk(h, wdem_upload_materials(h, (int)mats.size(), mk.data(), md.data(), my.data(), mkt.data(), mtp.data(), mse.data(), mal.data()));
+    chk(h, wdem_upload_spheres(h, (int64_t)sid.size(), sid.data(), spos.data(), sori.data(), svel.data(), sang.data(), smass.data(), sin.data(), srad.data(), sflags.data(), smask.data(), smat.data()));
+    chk(h, wdem_upload_forces(h, sfrc.data(), strq.data()));
+    chk(h, wdem_upload_walls(h, (int)wid.size(), wid.data(), wpos.data(), waxis.data(), wsense.data(), wvel.data(), wmask.data(), wmat.data()));
+    chk(h, wdem_upload_facets(h, (int)fid.size(), fid.data(), fv.data(), fvv.data(), ffk.data(), fht.data(), fnl.data(), fmask.data(), fmat.data()));
+    if (scene->periodic) { Cell& C = *scene->cell; chk(h, wdem_set_cell(h, C.hSize.data(), C.gradV.data(), C.nextGradV.data(), C.homoDeform)); C.dirty = false; }
+    nSpheres = (long)sid.size();
+    F.owner = this; F.topoDirty = false; F.stateDirty = false; F.deviceNewer = false; F.contactsStale = true;
+  }
+  void pushState() {   // host edits of pos/vel/angVel since the last run
+    DemField& F = *field; const size_t n = sphereOf.size();
+    vector<double> pos(3 * n), vel(3 * n), ang(3 * n);
+    for (size_t i = 0; i < n; i++) { const Node& nd = *sphereOf[i]->shape->nodes[0]; for (int k = 0; k < 3; k++) { pos[3 * i + k] = nd.pos[k]; vel[3 * i + k] = nd.dem->vel[k]; ang[3 * i + k] = nd.dem->angVel[k]; } }
+    if (n) chk(h, wdem_set_state(h, 0, (int64_t)n, pos.data(), vel.data(), ang.data()));
+    F.stateDirty = false;
+  }
+  void prepare() {
+    if (!field) throw std::runtime_error("GpuDemLoop: no DemField");
+    DemField& F = *field;
+    if (!h || F.topoDirty || F.owner != this) upload();
+    else {
+      wdem_config c = makeConfig();
+      if (!sameCfg(c, cfg)) { chk(h, wdem_set_config(h, &c)); cfg = c; }
+      if (F.stateDirty) { if (F.deviceNewer) throw std::runtime_error("GpuDemLoop: host state edited before the device state was read back"); pushState(); }
+      if (scene->periodic && scene->cell->dirty) { Cell& C = *scene->cell; chk(h, wdem_set_next_gradv(h, C.nextGradV.data())); C.dirty = false; }
+    }
+  }
+  double critDt() override { prepare(); double d; chk(h, wdem_crit_dt(h, &d)); return d; }   // DemField::critDt -> pWaveDt (Funcs.cpp:151-175)
+  void step(long n) {
+    prepare();
+    std::memset(&last, 0, sizeof(last));
+    { py::gil_scoped_release nogil; chk(h, wdem_step(h, n, &last)); }
+    DemField& F = *field; F.deviceNewer = true; F.contactsStale = true;
+    int64_t nf = 0; double libDt = NaN;
+    chk(h, wdem_get_scalars(h, &libDt, nullptr, nullptr, nullptr, &nf));
+    collider->nFullRuns = (long)nf;
+    if (scene->periodic) chk(h, wdem_get_cell(h, scene->cell->hSize.data()));
+    cfg.dt = libDt;                        // what the library will use next; Scene.dt follows through nextDt in the epilogue
+    if (libDt != scene->dt) scene->nextDt = libDt;
+  }
+  void run() override { step(1); }
+};
+
+void DemField::pull() {
+  if (!deviceNewer || !owner || !owner->h) return;
+  const size_t n = owner->sphereOf.size();
+  vector<double> pos(3 * n), ori(4 * n), vel(3 * n), ang(3 * n), f(3 * n), t(3 * n);
+  if (n) { chk(owner->h, wdem_download_state(owner->h, pos.data(), ori.data(), vel.data(), ang.data())); chk(owner->h, wdem_download_forces(owner->h, f.data(), t.data())); }
+  for (size_t i = 0; i < n; i++) {
+    Node& nd = *owner->sphereOf[i]->shape->nodes[0]; DemData& d = *nd.dem;
+    for (int k = 0; k < 3; k++) { nd.pos[k] = pos[3 * i + k]; d.vel[k] = vel[3 * i + k]; d.angVel[k] = ang[3 * i + k]; d.force[k] = f[3 * i + k]; d.torque[k] = t[3 * i + k]; }
+    for (int k = 0; k < 4; k++) nd.ori[k] = ori[4 * i + k];
+  }
+  deviceNewer = false;
+}
+void DemField::pullContacts() {
+  if (!contactsStale || !owner || !owner->h) return;
+  wdem_handle h = owner->h;
+  int64_t n = wdem_download_contacts(h, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (n < 0) chk(h, 1);
+  vector<int32_t> ids(2 * n), cd(3 * n), real(n), sc(n); vector<double> uN(n), f(3 * n), t(3 * n), trsf(9 * n), cp(3 * n), ph(3 * n);
+  if (n) { int64_t m = wdem_download_contacts(h, 0, n, ids.data(), cd.data(), real.data(), uN.data(), f.data(), t.data(), trsf.data(), cp.data(), ph.data(), sc.data()); if (m < 0) chk(h, 1); }
+  con.v.clear(); con.ix.clear();
+  for (int64_t i = 0; i < n; i++) {
+    auto C = make_shared<Contact>(); C->id1 = ids[2 * i]; C->id2 = ids[2 * i + 1]; C->stepCreated = sc[i];
+    for (int k = 0; k < 3; k++) C->cellDist[k] = cd[3 * i + k];
+    if (real[i]) {
+      C->geom = make_shared<L6Geom>(); C->phys = make_shared<FrictPhys>(); C->geom->uN = uN[i];
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C->geom->trsf[3 * r + c] = trsf[9 * i + 3 * c + r];   // column-major on the wire
+      for (int k = 0; k < 3; k++) { C->geom->node.pos[k] = cp[3 * i + k]; C->phys->force[k] = f[3 * i + k]; C->phys->torque[k] = t[3 * i + k]; }
+      C->phys->kn = ph[3 * i]; C->phys->kt = ph[3 * i + 1]; C->phys->tanPhi = ph[3 * i + 2];
+    }
+    con.ix[{std::min(C->id1, C->id2), std::max(C->id1, C->id2)}] = con.v.size(); con.v.push_back(C);
+  }
+  contactsStale = false;
+}
+
+// Scene::doOneStep (Scene.cpp:366-432) for an engine list whose DEM group is a GpuDemLoop; other entries may be Python callables f(scene)
+void Scene::one() {
+  GpuDemLoop* gpu = nullptr;
+  for (auto& o : engines) {
+    if (py::isinstance<Engine>(o)) { Engine& e = o.cast<Engine&>(); e.scene = this; if (!e.field && !fields.empty()) e.field = fields[0]; if (auto g = dynamic_cast<GpuDemLoop*>(&e)) gpu = g; }
+  }
+  if (std::isnan(dt) || std::isinf(dt) || dt < 0) {   // Scene.cpp:380-398
+    double crit = std::numeric_limits<double>::infinity();
+    for (auto& o : engines) if (py::isinstance<Engine>(o)) { Engine& e = o.cast<Engine&>(); if (!e.dead) crit = std::min(crit, e.critDt()); }
+    if (std::isinf(crit)) throw std::runtime_error("Failed to obtain meaningful dt from engines and fields automatically");
+    dt = dtSafety * crit;
+  }
+  for (auto& o : engines) {
+    if (py::isinstance<Engine>(o)) { Engine& e = o.cast<Engine&>(); if (!e.dead) e.run(); }
+    else o(py::cast(this, py::return_value_policy::reference));
+  }
+  (void)gpu;
+  step++; time += dt;
+  if (!std::isnan(nextDt)) { dt = nextDt; nextDt = NaN; }
+}
+void Scene::run(long n) {
+  // fast path: the GPU group is the only engine -> one C-ABI call for all n steps (no per-step host round trip)
+  if (n > 1 && engines.size() == 1 && py::isinstance<GpuDemLoop>(engines[0]) && !(std::isnan(dt) || std::isinf(dt) || dt < 0)) {
+    GpuDemLoop& g = engines[0].cast<GpuDemLoop&>();
+    if (!g.dead) {
+      g.scene = this; if (!g.field && !fields.empty()) g.field = fields[0];
+      g.step(n);
+      double libDt, libTime; int64_t libStep; chk(g.h, wdem_get_scalars(g.h, &libDt, &libTime, &libStep, nullptr, nullptr));
+      step += n; time = libTime; dt = libDt; nextDt = NaN;
+      return;
+    }
+  }
+  for (long i = 0; i < n; i++) one();
+}
+
+// ---- factories (Particle::make dem/Particle.cpp:51-69; Sphere::lumpMassInertia dem/Sphere.cpp:26-33)
+static shared_ptr<Material> defaultMaterial() { auto m = make_shared<FrictMat>(); m->density = 1e3; m->young = 1e7; m->ktDivKn = .2; m->tanPhi = std::tan(.5); return m; }
+static shared_ptr<Particle> makeParticle(const shared_ptr<Shape>& sh, shared_ptr<Material> mat, bool fixed, unsigned mask) {
+  auto p = make_shared<Particle>(); p->shape = sh; p->material = mat ? mat : defaultMaterial(); p->mask = mask;
+  sh->nodes.resize(sh->numNodes());
+  for (auto& n : sh->nodes) { if (!n) n = make_shared<Node>(); if (!n->dem) n->dem = make_shared<DemData>(); if (fixed) n->dem->flags |= DOF_ALL; }
+  if (auto* s = dynamic_cast<Sphere*>(sh.get())) {
+    DemData& d = *sh->nodes[0]->dem; const double r = s->radius;
+    d.mass = (4 / 3.) * M_PI * (r * r * r) * p->material->density; const double I = (2. / 5.) * d.mass * (r * r); d.inertia = {{I, I, I}};
+  }
+  return p;
+}
+
+template <class T, class... Bases> static py::class_<T, Bases..., shared_ptr<T>> kwclass(py::module_& m, const char* name) {
+  // keyword constructor like the reference's Object(**kw) (lib/object/Object.hpp:353-367): T(attr=value, ...)
+  py::class_<T, Bases..., shared_ptr<T>> c(m, name);
+  c.def(py::init([](py::kwargs kw) { auto o = make_shared<T>(); py::object po = py::cast(o); for (auto it : kw) py::setattr(po, it.first, it.second); return o; }));
+  return c;
+}
+#define RW(cls, a) .def_readwrite(#a, &cls::a)
+
+PYBIND11_MODULE(_woo, m) {
+  m.doc() = "woo_b200: reference-named host objects + GpuDemLoop over the wdem C-ABI";
+  // ---- materials
+  kwclass<Material>(m, "Material") RW(Material, density) RW(Material, id);
+  kwclass<ElastMat, Material>(m, "ElastMat") RW(ElastMat, young);
+  kwclass<FrictMat, ElastMat>(m, "FrictMat") RW(FrictMat, tanPhi) RW(FrictMat, ktDivKn);
+  kwclass<HertzMat, FrictMat>(m, "HertzMat") RW(HertzMat, surfEnergy) RW(HertzMat, alpha);
+  // ---- nodes
+#define V3P(cls, pyname, expr, PULL, TOUCH) .def_property(pyname, [](cls& s) { PULL; return np3(expr); }, [](cls& s, py::object o) { PULL; expr = seqN<3>(o, pyname); TOUCH; })
+  kwclass<DemData>(m, "DemData")
+      V3P(DemData, "vel", s.vel, if (s.field) s.field->pull(), if (s.field) s.field->touchState())
+      V3P(DemData, "angVel", s.angVel, if (s.field) s.field->pull(), if (s.field) s.field->touchState())
+      V3P(DemData, "force", s.force, if (s.field) s.field->pull(), if (s.field) s.field->topoDirty = true)
+      V3P(DemData, "torque", s.torque, if (s.field) s.field->pull(), if (s.field) s.field->topoDirty = true)
+      V3P(DemData, "inertia", s.inertia, (void)0, if (s.field) s.field->topoDirty = true)
+      .def_property("mass", [](DemData& s) { return s.mass; }, [](DemData& s, double v) { s.mass = v; if (s.field) s.field->topoDirty = true; })
+      .def_property("flags", [](DemData& s) { return s.flags; }, [](DemData& s, unsigned v) { s.flags = v; if (s.field) s.field->topoDirty = true; })
+      .def_property("blocked", &DemData::blockedGet, [](DemData& s, const string& v) { s.blockedSet(v); if (s.field) s.field->topoDirty = true; })
+      .def_property("gravitySkip", [](DemData& s) { return bool(s.flags & GRAVITY_SKIP); }, [](DemData& s, bool b) { s.flags = b ? (s.flags | GRAVITY_SKIP) : (s.flags & ~GRAVITY_SKIP); if (s.field) s.field->topoDirty = true; })
+      .def_property("dampingSkip", [](DemData& s) { return bool(s.flags & DAMPING_SKIP); }, [](DemData& s, bool b) { s.flags = b ? (s.flags | DAMPING_SKIP) : (s.flags & ~DAMPING_SKIP); if (s.field) s.field->topoDirty = true; });
+  kwclass<Node>(m, "Node")
+      V3P(Node, "pos", s.pos, if (s.dem && s.dem->field) s.dem->field->pull(), if (s.dem && s.dem->field) s.dem->field->touchState())
+      .def_property("ori", [](Node& s) { if (s.dem && s.dem->field) s.dem->field->pull(); return np4(s.ori); }, [](Node& s, py::object o) { s.ori = seqN<4>(o, "ori"); if (s.dem && s.dem->field) s.dem->field->topoDirty = true; })
+      .def_readwrite("dem", &Node::dem);
+  // ---- shapes and particles
+  py::class_<Shape, shared_ptr<Shape>>(m, "Shape").def_readwrite("nodes", &Shape::nodes);
+  kwclass<Sphere, Shape>(m, "Sphere") RW(Sphere, radius)
+      .def_static("make", [](py::object center, double radius, shared_ptr<Material> mat, unsigned mask, bool fixed) {
+        auto s = make_shared<Sphere>(); s->radius = radius; auto p = makeParticle(s, mat, fixed, mask); s->nodes[0]->pos = seqN<3>(center, "center"); return p; },
+        py::arg("center"), py::arg("radius"), py::arg("mat") = py::none(), py::arg("mask") = 5u, py::arg("fixed") = false);
+  kwclass<Wall, Shape>(m, "Wall") RW(Wall, sense) RW(Wall, axis)
+      .def_static("make", [](py::object position, int axis, int sense, shared_ptr<Material> mat, unsigned mask, bool fixed) {
+        auto w = make_shared<Wall>(); w->axis = axis; w->sense = sense; auto p = makeParticle(w, mat, fixed, mask);
+        if (py::isinstance<py::float_>(position) || py::isinstance<py::int_>(position)) { V3 x{{0, 0, 0}}; x[axis] = position.cast<double>(); w->nodes[0]->pos = x; }
+        else w->nodes[0]->pos = seqN<3>(position, "position");
+        return p; },
+        py::arg("position"), py::arg("axis"), py::arg("sense") = 0, py::arg("mat") = py::none(), py::arg("mask") = 3u, py::arg("fixed") = true);
+  kwclass<Facet, Shape>(m, "Facet") RW(Facet, halfThick)
+      .def_property("fakeVel", [](Facet& f) { return np3(f.fakeVel); }, [](Facet& f, py::object o) { f.fakeVel = seqN<3>(o, "fakeVel"); })
+      .def_property("n21lim", [](Facet& f) { return np3(f.n21lim); }, [](Facet& f, py::object o) { f.n21lim = seqN<3>(o, "n21lim"); })
+      .def_static("make", [](py::object vertices, shared_ptr<Material> mat, double halfThick, py::object fakeVel, unsigned mask, bool fixed) {
+        auto f = make_shared<Facet>(); f->halfThick = halfThick; if (!fakeVel.is_none()) f->fakeVel = seqN<3>(fakeVel, "fakeVel");
+        auto p = makeParticle(f, mat, fixed, mask); auto vv = seqN<9>(vertices, "vertices");
+        for (int v = 0; v < 3; v++) f->nodes[v]->pos = {{vv[3 * v], vv[3 * v + 1], vv[3 * v + 2]}};
+        return p; },
+        py::arg("vertices"), py::arg("mat") = py::none(), py::arg("halfThick") = 0., py::arg("fakeVel") = py::none(), py::arg("mask") = 3u, py::arg("fixed") = true);
+#define NODE0(p) (*(p).shape->nodes.at(0))
+  kwclass<Particle>(m, "Particle") RW(Particle, id) RW(Particle, mask) RW(Particle, shape) RW(Particle, material)
+      .def_property("mat", [](Particle& p) { return p.material; }, [](Particle& p, shared_ptr<Material> mm) { p.material = mm; if (p.field) p.field->topoDirty = true; })
+      V3P(Particle, "pos", NODE0(s).pos, if (s.field) s.field->pull(), if (s.field) s.field->touchState())
+      V3P(Particle, "vel", NODE0(s).dem->vel, if (s.field) s.field->pull(), if (s.field) s.field->touchState())
+      V3P(Particle, "angVel", NODE0(s).dem->angVel, if (s.field) s.field->pull(), if (s.field) s.field->touchState())
+      .def_property_readonly("ori", [](Particle& p) { if (p.field) p.field->pull(); return np4(NODE0(p).ori); })
+      .def_property_readonly("f", [](Particle& p) { if (p.field) p.field->pull(); return np3(NODE0(p).dem->force); })
+      .def_property_readonly("t", [](Particle& p) { if (p.field) p.field->pull(); return np3(NODE0(p).dem->torque); })
+      .def_property_readonly("mass", [](Particle& p) { return NODE0(p).dem->mass; })
+      .def_property_readonly("inertia", [](Particle& p) { return np3(NODE0(p).dem->inertia); })
+      .def_property("blocked", [](Particle& p) { return NODE0(p).dem->blockedGet(); }, [](Particle& p, const string& b) { NODE0(p).dem->blockedSet(b); if (p.field) p.field->topoDirty = true; })
+      .def_property_readonly("Ek", [](Particle& p) {   // DemData::getEk_any, aperiodic (Particle.cpp:247-265)
+        if (p.field) p.field->pull(); const DemData& d = *NODE0(p).dem; double e = .5 * d.mass * (d.vel[0] * d.vel[0] + d.vel[1] * d.vel[1] + d.vel[2] * d.vel[2]);
+        for (int k = 0; k < 3; k++) e += .5 * d.inertia[k] * d.angVel[k] * d.angVel[k]; return e; })
+      .def_static("make", [](shared_ptr<Shape> sh, shared_ptr<Material> mat, bool fixed) { return makeParticle(sh, mat, fixed, 1u); }, py::arg("shape"), py::arg("mat"), py::arg("fixed") = false);
+  // ---- contacts
+  py::class_<CGeomNode>(m, "CGeomNode").def_property_readonly("pos", [](CGeomNode& n) { return np3(n.pos); });
+  py::class_<L6Geom, shared_ptr<L6Geom>>(m, "L6Geom").def_readonly("uN", &L6Geom::uN).def_property_readonly("trsf", [](L6Geom& g) { return np33(g.trsf); }).def_readonly("node", &L6Geom::node);
+  py::class_<FrictPhys, shared_ptr<FrictPhys>>(m, "FrictPhys").def_property_readonly("force", [](FrictPhys& p) { return np3(p.force); }).def_property_readonly("torque", [](FrictPhys& p) { return np3(p.torque); })
+      .def_readonly("kn", &FrictPhys::kn).def_readonly("kt", &FrictPhys::kt).def_readonly("tanPhi", &FrictPhys::tanPhi);
+  py::class_<Contact, shared_ptr<Contact>>(m, "Contact").def_readonly("id1", &Contact::id1).def_readonly("id2", &Contact::id2).def_readonly("stepCreated", &Contact::stepCreated)
+      .def_readonly("geom", &Contact::geom).def_readonly("phys", &Contact::phys).def_property_readonly("real", &Contact::isReal)
+      .def_property_readonly("cellDist", [](Contact& c) { return np3i(c.cellDist); });
+  py::class_<ContactContainer>(m, "ContactContainer")
+      .def("__len__", [](ContactContainer& c) { c.dem->pullContacts(); return c.v.size(); })
+      .def("__getitem__", [](ContactContainer& c, std::pair<int, int> ij) { c.dem->pullContacts(); auto it = c.ix.find({std::min(ij.first, ij.second), std::max(ij.first, ij.second)}); if (it == c.ix.end()) throw py::index_error("No such contact ##" + std::to_string(ij.first) + "+" + std::to_string(ij.second)); return c.v[it->second]; })
+      .def("__getitem__", [](ContactContainer& c, long i) { c.dem->pullContacts(); if (i < 0) i += (long)c.v.size(); if (i < 0 || i >= (long)c.v.size()) throw py::index_error(); return c.v[i]; })
+      .def("existsReal", [](ContactContainer& c, int a, int b) { c.dem->pullContacts(); auto it = c.ix.find({std::min(a, b), std::max(a, b)}); return it != c.ix.end() && c.v[it->second]->isReal(); })
+      .def("countReal", [](ContactContainer& c) { c.dem->pullContacts(); size_t n = 0; for (auto& x : c.v) n += x->isReal(); return n; })
+      .def("__iter__", [](ContactContainer& c) { c.dem->pullContacts(); return py::make_iterator(c.v.begin(), c.v.end()); }, py::keep_alive<0, 1>());
+  py::class_<ParticleContainer>(m, "ParticleContainer")
+      .def("__len__", [](ParticleContainer& c) { return c.v.size(); })
+      .def("__getitem__", [](ParticleContainer& c, long i) { if (i < 0) i += (long)c.v.size(); if (i < 0 || i >= (long)c.v.size() || !c.v[i]) throw py::index_error("No such particle: #" + std::to_string(i)); return c.v[i]; })
+      .def("__iter__", [](ParticleContainer& c) { return py::make_iterator(c.v.begin(), c.v.end()); }, py::keep_alive<0, 1>())
+      .def("add", [](ParticleContainer& c, py::object o) -> py::object {   // ParticleContainer::add + pyAppend, nodes=-1 (ParticleContainer.cpp:23-73,193-198)
+        auto addOne = [&](shared_ptr<Particle> p) {
+          if (p->id >= 0) throw std::runtime_error("Particle already has id " + std::to_string(p->id) + " set; appending such particle (for the second time) is not allowed.");
+          p->id = (int)c.v.size(); p->field = c.dem; c.v.push_back(p);
+          for (auto& n : p->shape->nodes) {
+            n->dem->field = c.dem; const DemData& d = *n->dem;
+            const bool moving = (d.mass != 0 && (d.flags & DOF_ALL) != DOF_ALL) || d.vel[0] != 0 || d.vel[1] != 0 || d.vel[2] != 0 || d.angVel[0] != 0 || d.angVel[1] != 0 || d.angVel[2] != 0;   // DemData::guessMoving
+            if (moving) c.dem->nodes.push_back(n);
+          }
+          c.dem->topoDirty = true; return p->id; };
+        if (py::isinstance<Particle>(o)) return py::int_(addOne(o.cast<shared_ptr<Particle>>()));
+        py::list ids; for (auto it : o) ids.append(addOne(it.cast<shared_ptr<Particle>>())); return ids; });
+  kwclass<DemField>(m, "DemField")
+      .def_property_readonly("par", [](DemField& f) -> ParticleContainer& { return f.par; }, py::return_value_policy::reference_internal)
+      .def_property_readonly("con", [](DemField& f) -> ContactContainer& { return f.con; }, py::return_value_policy::reference_internal)
+      .def_readonly("nodes", &DemField::nodes)
+      .def_property("gravity", [](DemField& f) { return np3(f.gravity); }, [](DemField& f, py::object o) { f.gravity = seqN<3>(o, "gravity"); })
+      RW(DemField, loneMask) RW(DemField, distFactor)
+      .def_property_readonly_static("defaultMovableMask", [](py::object) { return 5u; }).def_property_readonly_static("defaultBoundaryMask", [](py::object) { return 3u; })
+      .def_property_readonly_static("defaultLoneMask", [](py::object) { return 2u; });
+  // ---- cell
+  py::class_<Cell, shared_ptr<Cell>>(m, "Cell")
+      .def_property("hSize", [](Cell& c) { return np33(c.hSize); }, [](Cell& c, py::object o) {
+        M3 h = seqN<9>(py::module_::import("numpy").attr("asarray")(o, "float64").attr("reshape")(9), "hSize");
+        const double det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) + h[2] * (h[3] * h[7] - h[4] * h[6]);
+        if (det == 0) throw std::runtime_error("Cell is degenerate (zero volume).");   // Cell.cpp:99
+        c.hSize = h; c.dirty = true; })
+      .def("setBox", [](Cell& c, double x, double y, double z) { c.hSize = {{x, 0, 0, 0, y, 0, 0, 0, z}}; c.dirty = true; })
+      .def_property("gradV", [](Cell& c) { return np33(c.gradV); }, [](Cell& c, py::object o) { c.gradV = seqN<9>(py::module_::import("numpy").attr("asarray")(o, "float64").attr("reshape")(9), "gradV"); c.dirty = true; })
+      .def_property("nextGradV", [](Cell& c) { return np33(c.nextGradV); }, [](Cell& c, py::object o) { c.nextGradV = seqN<9>(py::module_::import("numpy").attr("asarray")(o, "float64").attr("reshape")(9), "nextGradV"); c.dirty = true; })
+      .def_property("homoDeform", [](Cell& c) { return c.homoDeform; }, [](Cell& c, py::object o) {
+        if (py::isinstance<py::str>(o)) { static const std::map<string, int> nm{{"none", 0}, {"pos", 1}, {"vel", 2}, {"vel2", 3}, {"gradV2", 4}}; auto it = nm.find(o.cast<string>()); if (it == nm.end()) throw std::invalid_argument("Cell.homoDeform: unknown name"); c.homoDeform = it->second; }
+        else c.homoDeform = o.cast<int>();
+        c.dirty = true; });
+  // ---- engines and functors (attribute carriers; names and defaults from the reference headers cited in include/wdem.h)
+  kwclass<Engine>(m, "Engine") RW(Engine, dead) RW(Engine, label) RW(Engine, field).def("__call__", [](Engine& e, Scene& s) { e.scene = &s; if (!e.field && !s.fields.empty()) e.field = s.fields[0]; e.run(); });
+  kwclass<Leapfrog, Engine>(m, "Leapfrog") RW(Leapfrog, damping) RW(Leapfrog, reset) RW(Leapfrog, kinSplit) RW(Leapfrog, dontCollect);
+  py::class_<BoundFunctor, shared_ptr<BoundFunctor>>(m, "BoundFunctor");
+  kwclass<Bo1_Sphere_Aabb, BoundFunctor>(m, "Bo1_Sphere_Aabb"); kwclass<Bo1_Facet_Aabb, BoundFunctor>(m, "Bo1_Facet_Aabb"); kwclass<Bo1_Wall_Aabb, BoundFunctor>(m, "Bo1_Wall_Aabb") RW(Bo1_Wall_Aabb, halfThick);
+  py::class_<InsertionSortCollider, Engine, shared_ptr<InsertionSortCollider>>(m, "InsertionSortCollider")
+      .def(py::init([](vector<shared_ptr<BoundFunctor>> bo, py::kwargs kw) { auto o = make_shared<InsertionSortCollider>(); o->boundDispatcher = bo; py::object po = py::cast(o); for (auto it : kw) py::setattr(po, it.first, it.second); return o; }), py::arg("boundDispatcher") = vector<shared_ptr<BoundFunctor>>())
+      RW(InsertionSortCollider, boundDispatcher) RW(InsertionSortCollider, verletDist).def_readonly("nFullRuns", &InsertionSortCollider::nFullRuns);
+  py::class_<CGeomFunctor, shared_ptr<CGeomFunctor>>(m, "CGeomFunctor") RW(CGeomFunctor, noRatch) RW(CGeomFunctor, iniLensTouch) RW(CGeomFunctor, trsfRenorm) RW(CGeomFunctor, approxMask);
+  kwclass<Cg2_Sphere_Sphere_L6Geom, CGeomFunctor>(m, "Cg2_Sphere_Sphere_L6Geom"); kwclass<Cg2_Wall_Sphere_L6Geom, CGeomFunctor>(m, "Cg2_Wall_Sphere_L6Geom"); kwclass<Cg2_Facet_Sphere_L6Geom, CGeomFunctor>(m, "Cg2_Facet_Sphere_L6Geom");
+  py::class_<CPhysFunctor, shared_ptr<CPhysFunctor>>(m, "CPhysFunctor") RW(CPhysFunctor, label);
+  kwclass<Cp2_FrictMat_FrictPhys, CPhysFunctor>(m, "Cp2_FrictMat_FrictPhys") RW(Cp2_FrictMat_FrictPhys, tanPhi);
+  kwclass<Cp2_HertzMat_HertzPhys, CPhysFunctor>(m, "Cp2_HertzMat_HertzPhys") RW(Cp2_HertzMat_HertzPhys, poisson) RW(Cp2_HertzMat_HertzPhys, en);
+  py::class_<LawFunctor, shared_ptr<LawFunctor>>(m, "LawFunctor") RW(LawFunctor, label);
+  kwclass<Law2_L6Geom_FrictPhys_IdealElPl, LawFunctor>(m, "Law2_L6Geom_FrictPhys_IdealElPl") RW(Law2_L6Geom_FrictPhys_IdealElPl, noSlip) RW(Law2_L6Geom_FrictPhys_IdealElPl, noBreak) RW(Law2_L6Geom_FrictPhys_IdealElPl, noFrict)
+      RW(Law2_L6Geom_FrictPhys_IdealElPl, iniEqlb) RW(Law2_L6Geom_FrictPhys_IdealElPl, relRollStiff) RW(Law2_L6Geom_FrictPhys_IdealElPl, relTwistStiff) RW(Law2_L6Geom_FrictPhys_IdealElPl, rollTanPhi);
+  kwclass<Law2_L6Geom_HertzPhys_DMT, LawFunctor>(m, "Law2_L6Geom_HertzPhys_DMT") RW(Law2_L6Geom_HertzPhys_DMT, noAttraction);
+  py::class_<ContactLoop, Engine, shared_ptr<ContactLoop>>(m, "ContactLoop")
+      .def(py::init([](vector<shared_ptr<CGeomFunctor>> g, vector<shared_ptr<CPhysFunctor>> p, vector<shared_ptr<LawFunctor>> l, py::kwargs kw) {
+        auto o = make_shared<ContactLoop>(); o->geoDisp = g; o->phyDisp = p; o->lawDisp = l; py::object po = py::cast(o); for (auto it : kw) py::setattr(po, it.first, it.second); return o; }),
+        py::arg("geoDisp") = vector<shared_ptr<CGeomFunctor>>(), py::arg("phyDisp") = vector<shared_ptr<CPhysFunctor>>(), py::arg("lawDisp") = vector<shared_ptr<LawFunctor>>())
+      RW(ContactLoop, geoDisp) RW(ContactLoop, phyDisp) RW(ContactLoop, lawDisp) RW(ContactLoop, applyForces) RW(ContactLoop, evalStress) RW(ContactLoop, dist00) RW(ContactLoop, updatePhys) RW(ContactLoop, reorderEvery) RW(ContactLoop, hook);
+  kwclass<DynDt, Engine>(m, "DynDt") RW(DynDt, stepPeriod) RW(DynDt, maxRelInc) RW(DynDt, dryRun);
+  py::class_<GpuDemLoop, Engine, shared_ptr<GpuDemLoop>>(m, "GpuDemLoop")
+      .def(py::init([](shared_ptr<Leapfrog> lf, shared_ptr<InsertionSortCollider> co, shared_ptr<ContactLoop> cl, shared_ptr<DynDt> dd, int device, py::kwargs kw) {
+        auto o = make_shared<GpuDemLoop>(); o->leapfrog = lf; o->collider = co; o->contactLoop = cl; o->dynDt = dd; o->device = device; py::object po = py::cast(o); for (auto it : kw) py::setattr(po, it.first, it.second); return o; }),
+        py::arg("leapfrog"), py::arg("collider"), py::arg("contactLoop"), py::arg("dynDt") = py::none(), py::arg("device") = 0)
+      RW(GpuDemLoop, leapfrog) RW(GpuDemLoop, collider) RW(GpuDemLoop, contactLoop) RW(GpuDemLoop, dynDt) RW(GpuDemLoop, device)
+      .def("sync", [](GpuDemLoop& g) { if (g.field) { g.field->pull(); g.field->pullContacts(); } }, "Download particle state and contacts into the host objects now (otherwise done lazily on first access).")
+      .def("release", &GpuDemLoop::release)
+      .def_property_readonly("stats", [](GpuDemLoop& g) { py::dict d; d["n_spheres"] = g.last.n_spheres; d["n_contacts"] = g.last.n_contacts; d["n_real"] = g.last.n_real; d["n_rebuilds"] = g.last.n_rebuilds; d["n_launches"] = g.last.n_launches; d["device_ms"] = g.last.device_ms; return d; });
+  // ---- scene
+  py::class_<Scene, shared_ptr<Scene>>(m, "Scene")
+      .def(py::init([](vector<shared_ptr<DemField>> fields, py::kwargs kw) { auto s = make_shared<Scene>(); s->fields = fields; py::object po = py::cast(s); for (auto it : kw) py::setattr(po, it.first, it.second); return s; }), py::arg("fields") = vector<shared_ptr<DemField>>())
+      RW(Scene, dt) RW(Scene, nextDt) RW(Scene, dtSafety) RW(Scene, time) RW(Scene, step) RW(Scene, periodic) RW(Scene, trackEnergy) RW(Scene, deterministic) RW(Scene, engines) RW(Scene, fields)
+      .def_readonly("cell", &Scene::cell).def_property_readonly("dem", &Scene::dem)
+      .def("one", &Scene::one).def("run", [](Scene& s, long n, bool) { s.run(n); }, py::arg("steps") = 1, py::arg("wait") = true).def("wait", [](Scene&) {});
+}

@@ -87,8 +87,9 @@ class SceneSpec:
 
     def mass_inertia(self):
         dens = np.array([m[1] for m in self.mats], dtype=np.float64)[self.mat]
-        m = (4 / 3.) * math.pi * self.radius ** 3 * dens
-        I = (2. / 5.) * m * self.radius ** 2
+        r = self.radius
+        m = (4 / 3.) * math.pi * (r * r * r) * dens     # pow3(x)=x*x*x (Math.hpp:162), not pow()
+        I = (2. / 5.) * m * (r * r)
         return m, I
 
     def sphere_ids(self):
