@@ -160,7 +160,7 @@ struct wdem_engine {
   CsrStore csr[2]; int curR = 0;
   // scratch
   DBuf<uint32_t> keys, keysAlt; DBuf<int> idx, idxAlt, cellStart, counts, offsets; DBuf<unsigned char> cubTemp; DBuf<double> blk;
-  DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt;
+  DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt; DBuf<int> realFlag, realPos; DBuf<int32_t> tmpCd[3];
   Counters* dCnt = nullptr; Counters* hCnt = nullptr;
   // scene scalars
   double dt = NAN, time = 0, nextDt = NAN, verletDist = NAN; long long step = 0, nFullRuns = 0; bool conDirty = true;
@@ -557,16 +557,27 @@ void rebuild(wdem_engine* E) {
     Nst.ensure((size_t)std::max<long long>(nC0, 1), tot, hertz, rolling, c.periodic);
     Contacts N = Nst.view(), O = Ost.view();
     E->srcOld.ensure((size_t)std::max<long long>(nC0, 1), tot);
-    if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, N, O, oc, perm, nullptr, E->srcOld.p);
-    else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, pg, pu, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, N, oc, perm, nullptr, E->srcOld.p, E->dCnt);
+    // the fill kernels write (pair, kind, cellDist) in emission order into scratch planes; k_carry moves them to their final place
+    const size_t nT = (size_t)std::max<long long>(nC0, 1);
+    E->ckeys.ensure(nT, tot); E->cvals.ensure(nT, tot); E->realFlag.ensure(nT + 1, tot); E->realPos.ensure(nT + 1, tot);
+    Contacts T = N; T.pair = reinterpret_cast<int2*>(E->ckeys.p); T.flags = E->cvals.p;
+    if (c.periodic) { for (auto& b : E->tmpCd) b.ensure(nT, tot); T.cdx = E->tmpCd[0].p; T.cdy = E->tmpCd[1].p; T.cdz = E->tmpCd[2].p; }
+    if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, T, O, oc, perm, nullptr, E->srcOld.p);
+    else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, pg, pu, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
     E->launches++;
     if (nWalls) {
-      if (!c.periodic) k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, N, O, oc, perm, nullptr, E->srcOld.p);
-      else k_pairs_ws_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, N, oc, perm, nullptr, E->srcOld.p, E->dCnt);
+      if (!c.periodic) k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, T, O, oc, perm, nullptr, E->srcOld.p);
+      else k_pairs_ws_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
       E->launches++;
     }
-    if (nFacets) { k_pairs_fs<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, nullptr, E->offsets.p + 2 * n, N, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
-    if (nC0 > 0) { k_carry<<<nblk(nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, c.law, rolling, c.periodic, E->step); E->launches++; }
+    if (nFacets) { k_pairs_fs<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, nullptr, E->offsets.p + 2 * n, T, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
+    if (nC0 > 0) {
+      // real-first order inside the sphere-sphere segment (the reference reorders its contacts for the same reason, ContactLoop.cpp:75-91):
+      // warps of k_contact_ss then see either all-real or all-potential contacts instead of paying the long path for half-empty warps
+      k_was_real<<<nblk(nSS + 1, 256), 256, 0, st>>>(E->srcOld.p, O.flags, nSS, E->realFlag.p);
+      exclusiveSum(E, E->realFlag.p, E->realPos.p, (int)nSS + 1);
+      k_carry<<<nblk(nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, T, E->realPos.p, nSS, c.law, rolling, c.periodic, E->step); E->launches += 4;
+    }
     // 6b. orphans: real contacts of the previous table that no candidate claimed (AABBs separated while real)
     long long nOrph = 0;
     if (oc.valid && E->nC > 0) {
@@ -596,7 +607,10 @@ void rebuild(wdem_engine* E) {
     if (nC > 0) {
       CK(cudaMemsetAsync(E->rowCount.p, 0, ((size_t)n + 1) * sizeof(int), st));   // reused as the per-row cursor
       k_csr_fill<<<nblk(nC, 256), 256, 0, st>>>(N, nC, E->S().id, E->dWalls.p, E->dFacets.p, Ncsr.rowStart.p, E->rowCount.p, Ncsr.rowEntry.p, Ncsr.rowOther.p); E->launches++;
-      k_row_sort<<<nb128, 128, 0, st>>>(n, Ncsr.rowStart.p, Ncsr.rowEntry.p, Ncsr.rowOther.p); E->launches++;
+      E->idx.ensure((size_t)n + 1, tot);   // the cell-sort scratch is free again: queue of long rows + its counter
+      CK(cudaMemsetAsync(E->idx.p + n, 0, sizeof(int), st));
+      k_row_sort<<<nb128, 128, 0, st>>>(n, Ncsr.rowStart.p, Ncsr.rowEntry.p, Ncsr.rowOther.p, E->idx.p, E->idx.p + n);
+      k_row_sort_long<<<148 * 8, 128, 0, st>>>(E->idx.p, E->idx.p + n, Ncsr.rowStart.p, Ncsr.rowEntry.p, Ncsr.rowOther.p); E->launches += 2;
     }
     Ncsr.valid = true;
   }
@@ -838,6 +852,7 @@ int wdem_create(const wdem_config* cfg, wdem_handle* out) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) throw CudaErr{std::string("device '") + prop.name + "' is not sm_100 (this library carries sm_100a code only)", WDEM_ERR_CUDA};
     E = new wdem_engine(); E->cfg = *cfg; E->dt = cfg->dt;
+    if (const char* g = getenv("WDEM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob: 32/64/128
     CK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&E->ev0)); CK(cudaEventCreate(&E->ev1));
     for (auto& e : E->evp) CK(cudaEventCreate(&e));
@@ -855,7 +870,7 @@ int wdem_destroy(wdem_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release();
   h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
-  h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release();
+  h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
   h->dom.release(); delete h->comm; h->comm = nullptr;
   if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt);
   if (h->ev0) cudaEventDestroy(h->ev0); if (h->ev1) cudaEventDestroy(h->ev1); for (auto& e : h->evp) if (e) cudaEventDestroy(e);

@@ -162,13 +162,26 @@ __global__ void __launch_bounds__(256) k_leapfrog(Spheres S, int n, StepU u, Cou
 // Shared tail of the three Cg2 functors: Cg2_Any_Any_L6Geom__Base::handleSpheresLikeContact
 // (src/dem/L6Geom.cpp:49-216, approxMask==0) -> Cp2 (once) -> Law2 -> global force output.
 // ------------------------------------------------------------------------------------------------
-struct MatPair { double young1, young2, ktDivKn1, ktDivKn2, tanPhi1, tanPhi2, surf1, surf2, alpha1, alpha2; int kind1, kind2; };
+// who to name in a device error report; ids are looked up only on the (cold) error path
+struct ErrCtx { const int32_t* sid; int slotA; int idA; int slotB; };
+__device__ __noinline__ void report_error(Counters* cnt, int code, const ErrCtx& ec) {
+  cnt->error = code; cnt->errA = ec.slotA >= 0 ? ec.sid[ec.slotA] : ec.idA; cnt->errB = ec.sid[ec.slotB];
+}
+// persistent state of a real contact, loaded up front so that all of a thread's loads are in flight together
+struct Hist { d3 t0, t1; double4 cp; double ft0, ft1, ph0, ph1, ph2, ph3, ph4; };
+template <int LAW>
+__device__ __forceinline__ void load_hist(const Contacts& C, long long c, Hist& H) {
+  H.t0 = mk3(C.t0x[c], C.t0y[c], C.t0z[c]); H.t1 = mk3(C.t1x[c], C.t1y[c], C.t1z[c]);
+  H.cp = C.cp[c]; H.ft0 = C.ft0[c]; H.ft1 = C.ft1[c];
+  H.ph0 = C.ph[0][c]; H.ph1 = C.ph[1][c]; H.ph2 = C.ph[2][c];
+  if (LAW == 1) { H.ph3 = C.ph[3][c]; H.ph4 = C.ph[4][c]; }
+}
 
 template <int LAW>
 __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uint32_t fl, const StepU& u, d3 pos1, d3 vel1, d3 w1, d3 pos2,
                                              d3 vel2, d3 w2, d3 shiftVel2, d3 normal, d3 contPt, double uN, double r1, double r2,
-                                             const Material* mats, int matA, int matB, double massA, double massB, Counters* cnt,
-                                             int idA, int idB, unsigned& nRealOut) {
+                                             const Material* mats, const int32_t* matArr, double massA, double massB, Counters* cnt,
+                                             const ErrCtx& ec, int matBoundary, const Hist& H, unsigned& nRealOut) {
   const bool wasReal = fl & CF_REAL;
   d3 c0, c1, c2, gvel = mk3(0, 0, 0), gang = mk3(0, 0, 0);
   double kn, kt, tanPhi, p3 = 0, p4 = 0, ftA = 0, ftB = 0, tq0 = 0, tq1 = 0, tq2 = 0;
@@ -185,21 +198,21 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
     double rr = (r1 > 0 && r2 > 0) ? fmin(r1, r2) : (r1 > 0 ? r1 : r2);
     double A = M_PI * (rr * rr);
     // ---- Cp2 (ContactLoop.cpp:179-181)
-    const Material m1 = mats[matA], m2 = mats[matB];
+    const Material m1 = mats[ec.slotA >= 0 ? matArr[ec.slotA] : matBoundary], m2 = mats[matArr[ec.slotB]];
     if (LAW == 0) {  // Cp2_FrictMat_FrictPhys::updateFrictPhys (FrictMat.cpp:20-44)
       kn = 1 / (1 / (m1.young * A / l0) + 1 / (m2.young * A / l1));
       kt = .5 * (m1.ktDivKn + m2.ktDivKn) * kn;
       tanPhi = fmin(m1.tanPhi, m2.tanPhi);
       C.ph[0][c] = kn; C.ph[1][c] = kt; C.ph[2][c] = tanPhi;
     } else {         // Cp2_HertzMat_HertzPhys::go (Hertz.cpp:34-77)
-      if (m1.kind != 1 || m2.kind != 1) { cnt->error = ERR_NO_PHYS; cnt->errA = idA; cnt->errB = idB; return; }
+      if (m1.kind != 1 || m2.kind != 1) { report_error(cnt, ERR_NO_PHYS, ec); return; }
       const double nu1 = u.poisson, nu2 = u.poisson, E1 = m1.young, E2 = m2.young;
       double K = (4 / 3.) * 1. / ((1 - nu1 * nu1) / E1 + (1 - nu2 * nu2) / E2);
       double R = 1. / (1. / l0 + 1. / l1);
       double kn0 = K * sqrt(R);
       double gamma = fmin(m1.surfEnergy, m2.surfEnergy);
       double alpha = .5 * (m1.alpha + m2.alpha);
-      if (!(alpha == 0. || gamma == 0.)) { cnt->error = ERR_SCHWARZ; cnt->errA = idA; cnt->errB = idB; return; }
+      if (!(alpha == 0. || gamma == 0.)) { report_error(cnt, ERR_SCHWARZ, ec); return; }
       double G1 = E1 / (2 * (1 + nu1)), G2 = E2 / (2 * (1 + nu2));
       double G = .5 * (G1 + G2);
       double nu = .5 * (nu1 + nu2);
@@ -219,10 +232,9 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
     atomicAdd(&cnt->nCreated, 1ull);
   } else {
     // ---- update geometry (L6Geom.cpp:72-216)
-    const d3 prevN = mk3(C.t0x[c], C.t0y[c], C.t0z[c]);
-    const d3 prev1 = mk3(C.t1x[c], C.t1y[c], C.t1z[c]);
-    const double4 pcp = C.cp[c];
-    const d3 prevContPt = xyz(pcp);
+    const d3 prevN = H.t0;
+    const d3 prev1 = H.t1;
+    const d3 prevContPt = xyz(H.cp);
     const double dt = u.dt;
     d3 normRotVec = cross(prevN, normal);
     d3 midN = .5 * (prevN + normal);
@@ -250,9 +262,9 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
     d3 relVel = (v2s + cross(w2, c2x)) - (vel1 + cross(w1, c1x));
     gvel = mk3(dot(midN, relVel), dot(mid1, relVel), dot(mid2, relVel));
     if (u.rolling) { d3 dw = w2 - w1; gang = mk3(dot(midN, dw), dot(mid1, dw), dot(mid2, dw)); }
-    kn = C.ph[0][c]; kt = C.ph[1][c]; tanPhi = C.ph[2][c];
-    if (LAW == 1) { p3 = C.ph[3][c]; p4 = C.ph[4][c]; }
-    ftA = C.ft0[c]; ftB = C.ft1[c];
+    kn = H.ph0; kt = H.ph1; tanPhi = H.ph2;
+    if (LAW == 1) { p3 = H.ph3; p4 = H.ph4; }
+    ftA = H.ft0; ftB = H.ft1;
     // CPhys.torque is zeroed at the top of the law every step (IdealElPl.cpp:43), so it carries no history
   }
   // ---- Law2
@@ -272,7 +284,7 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
           if (FtNorm == 0.) ratio = 0.;
           ftA *= ratio; ftB *= ratio;
         }
-        if (!(Fn == Fn) || !(ftA == ftA) || !(ftB == ftB)) { cnt->error = ERR_NAN_FORCE; cnt->errA = idA; cnt->errB = idB; }
+        if (!(Fn == Fn) || !(ftA == ftA) || !(ftB == ftB)) report_error(cnt, ERR_NAN_FORCE, ec);
       }
       if (u.rolling) {                                                     // IdealElPl.cpp:94-123
         double charLen = fabs(r1) + fabs(r2);
@@ -306,7 +318,7 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
       double sq = ftA * ftA + ftB * ftB;
       if (sq > maxFt * maxFt) { double FtNorm = sqrt(sq); double ratio = maxFt / FtNorm; ftA *= ratio; ftB *= ratio; }
       else { ftA += eta * gvel.y; ftB += eta * gvel.z; }
-      if (!(Fn == Fn) || !(ftA == ftA) || !(ftB == ftB)) { cnt->error = ERR_NAN_FORCE; cnt->errA = idA; cnt->errB = idB; }
+      if (!(Fn == Fn) || !(ftA == ftA) || !(ftB == ftB)) report_error(cnt, ERR_NAN_FORCE, ec);
     }
   }
   if (!keep) {
@@ -346,9 +358,12 @@ __device__ __forceinline__ void block_count(unsigned isReal, unsigned evald, Cou
 // (src/dem/Sphere.cpp:92-117) fused with Cp2 and Law2.  One thread per candidate pair.
 // ------------------------------------------------------------------------------------------------
 template <int LAW>
-__device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint32_t fl, const Spheres& S, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
-  const int2 pr = C.pair[c];
+__device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
+  const bool real = fl & CF_REAL;
+  // every load of a real contact is issued here, before the first use: two dependent round trips (flags+pair, then everything) instead of four
   const double4 pa = S.posr[pr.x], pb = S.posr[pr.y];
+  double4 va = make_double4(0, 0, 0, 0), vb = va, wa = va, wb = va; Hist H;
+  if (real) { va = S.velm[pr.x]; vb = S.velm[pr.y]; wa = S.angi[pr.x]; wb = S.angi[pr.y]; load_hist<LAW>(C, c, H); }
   d3 shift2 = mk3(0, 0, 0), shiftVel2 = mk3(0, 0, 0);
   if (u.periodic) {
     d3 cd = mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]);
@@ -360,28 +375,24 @@ __device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint3
   double d2 = sqn(relPos);
   double rs = u.absDistFactor * (r1 + r2);
   double unDistSq = d2 - rs * rs;
-  if (unDistSq > 0 && !(fl & CF_REAL)) return;
+  if (unDistSq > 0 && !real) return;
   double dist = sqrt(d2);
   double uN = dist - (r1 + r2);
   d3 normal = relPos / dist;
   d3 contPt = p1 + (r1 + 0.5 * uN) * normal;
-  d3 v1 = mk3(0, 0, 0), v2 = v1, w1 = v1, w2 = v1; double mA = 0, mB = 0;
-  if (fl & CF_REAL) {
-    double4 a = S.velm[pr.x], b = S.velm[pr.y]; v1 = xyz(a); v2 = xyz(b);
-    a = S.angi[pr.x]; b = S.angi[pr.y]; w1 = xyz(a); w2 = xyz(b);
-  } else if (LAW == 1) { mA = S.velm[pr.x].w; mB = S.velm[pr.y].w; }
-  int matA = 0, matB = 0;
-  if (!(fl & CF_REAL)) { matA = S.mat[pr.x]; matB = S.mat[pr.y]; }
-  contact_tail<LAW>(C, c, fl, u, p1, v1, w1, p2, v2, w2, shiftVel2, normal, contPt, uN, r1, r2, mats, matA, matB, mA, mB, cnt, S.id[pr.x], S.id[pr.y], isReal);
+  double mA = 0, mB = 0;
+  if (!real && LAW == 1) { mA = S.velm[pr.x].w; mB = S.velm[pr.y].w; }
+  const ErrCtx ec{S.id, pr.x, 0, pr.y};
+  contact_tail<LAW>(C, c, fl, u, p1, xyz(va), xyz(wa), p2, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, r1, r2, mats, S.mat, mA, mB, cnt, ec, 0, H, isReal);
 }
 
 template <int LAW>
-__global__ void __launch_bounds__(128) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt) {
+__global__ void __launch_bounds__(128, 4) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt) {
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
   if (c < first + n) {
-    const uint32_t fl = C.flags[c];
-    if (!(fl & CF_DEAD)) { evald = 1; contact_ss<LAW>(C, c, fl, S, mats, u, cnt, isReal); }
+    const uint32_t fl = C.flags[c]; const int2 pr = C.pair[c];
+    if (!(fl & CF_DEAD)) { evald = 1; contact_ss<LAW>(C, c, fl, pr, S, mats, u, cnt, isReal); }
   }
   block_count(isReal, evald, cnt);
 }
@@ -390,10 +401,12 @@ __global__ void __launch_bounds__(128) k_contact_ss(Contacts C, long long first,
 // Wall+Sphere: Cg2_Wall_Sphere_L6Geom::go (src/dem/Wall.cpp:50-84)
 // ------------------------------------------------------------------------------------------------
 template <int LAW>
-__device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint32_t fl, const Spheres& S, const Wall* walls, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
-  const int2 pr = C.pair[c];
+__device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Wall* walls, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
+  const bool real = fl & CF_REAL;
   const Wall W = walls[pr.x];
   const double4 pb = S.posr[pr.y];
+  double4 vb = make_double4(0, 0, 0, 0), wb = vb; Hist H;
+  if (real) { vb = S.velm[pr.y]; wb = S.angi[pr.y]; load_hist<LAW>(C, c, H); }
   d3 shift2 = mk3(0, 0, 0), shiftVel2 = mk3(0, 0, 0);
   if (u.periodic) {
     d3 cd = mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]);
@@ -403,22 +416,21 @@ __device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint3
   const d3 spherePos = xyz(pb) + shift2;
   const double radius = pb.w; const int ax = W.axis;
   double dist = comp(spherePos, ax) - comp(wallPos, ax);
-  if (!(fl & CF_REAL) && fabs(dist) > radius) return;
+  if (!real && fabs(dist) > radius) return;
   d3 contPt = spherePos; setc(contPt, ax, comp(wallPos, ax));
   d3 normal = mk3(0, 0, 0);
   double nax;
   if (W.sense == 0) {
-    if (!(fl & CF_REAL)) nax = dist > 0 ? 1. : -1.;
-    else nax = (ax == 0 ? C.t0x[c] : (ax == 1 ? C.t0y[c] : C.t0z[c]));
+    if (!real) nax = dist > 0 ? 1. : -1.;
+    else nax = comp(H.t0, ax);
   } else nax = (W.sense == 1 ? 1. : -1.);
   setc(normal, ax, nax);
   double uN = nax * dist - radius;
-  d3 v2 = mk3(0, 0, 0), w2 = v2; double mB = 0;
-  if (fl & CF_REAL) { double4 b = S.velm[pr.y]; v2 = xyz(b); b = S.angi[pr.y]; w2 = xyz(b); }
-  else if (LAW == 1) mB = S.velm[pr.y].w;
-  int matB = (fl & CF_REAL) ? 0 : S.mat[pr.y];
-  contact_tail<LAW>(C, c, fl, u, wallPos, mk3(W.vel[0], W.vel[1], W.vel[2]), mk3(0, 0, 0), spherePos, v2, w2, shiftVel2, normal, contPt, uN, -radius, radius,
-                    mats, W.mat, matB, 0., mB, cnt, W.id, S.id[pr.y], isReal);
+  double mB = 0;
+  if (!real && LAW == 1) mB = S.velm[pr.y].w;
+  const ErrCtx ec{S.id, -1, W.id, pr.y};
+  contact_tail<LAW>(C, c, fl, u, wallPos, mk3(W.vel[0], W.vel[1], W.vel[2]), mk3(0, 0, 0), spherePos, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, -radius, radius,
+                    mats, S.mat, 0., mB, cnt, ec, W.mat, H, isReal);
 }
 
 template <int LAW>
@@ -426,8 +438,8 @@ __global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first,
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
   if (c < first + n) {
-    const uint32_t fl = C.flags[c];
-    if (!(fl & CF_DEAD)) { evald = 1; contact_ws<LAW>(C, c, fl, S, walls, mats, u, cnt, isReal); }
+    const uint32_t fl = C.flags[c]; const int2 pr = C.pair[c];
+    if (!(fl & CF_DEAD)) { evald = 1; contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal); }
   }
   block_count(isReal, evald, cnt);
 }
@@ -465,10 +477,11 @@ __device__ __forceinline__ void facetAdjustImpl(d3 fN, d3 edgePt, d3 unitOutVec,
 }
 
 template <int LAW>
-__device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint32_t fl, const Spheres& S, const Facet* facets, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
-  const int2 pr = C.pair[c];
+__device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Facet* facets, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
   const Facet* F = facets + pr.x;
   const double4 pb = S.posr[pr.y];
+  double4 vb = make_double4(0, 0, 0, 0), wb = vb; Hist H;
+  if (fl & CF_REAL) { vb = S.velm[pr.y]; wb = S.angi[pr.y]; load_hist<LAW>(C, c, H); }
   d3 shift2 = mk3(0, 0, 0), shiftVel2 = mk3(0, 0, 0);
   if (u.periodic) {
     d3 cd = mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]);
@@ -495,14 +508,14 @@ __device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint3
     case 3: contPt = v1; break;
     case 5: contPt = v0; break;
     case 6: contPt = v2; break;
-    default: cnt->error = ERR_FACET_IMPOSSIBLE; cnt->errA = F->id; cnt->errB = S.id[pr.y]; return;
+    default: { const ErrCtx ec{S.id, -1, F->id, pr.y}; report_error(cnt, ERR_FACET_IMPOSSIBLE, ec); return; }
   }
   d3 normal = sC - contPt;
   if (sqn(normal) > (radius + ht) * (radius + ht) && !real) return;
   double dist = nrm(normal);
   if (dist != 0) normal = normal / dist;
   else {
-    if (real) { d3 c0 = mk3(C.t0x[c], C.t0y[c], C.t0z[c]), c1 = mk3(C.t1x[c], C.t1y[c], C.t1z[c]); normal = quatRotate(quatFromCols(c0, c1, cross(c0, c1)), mk3(1, 0, 0)); }
+    if (real) normal = quatRotate(quatFromCols(H.t0, H.t1, cross(H.t0, H.t1)), mk3(1, 0, 0));
     else normal = mk3(1, 0, 0);
   }
   if (w > 0) {  // Facet::adjustBoundaryContactGeom (Facet.cpp:220-237); edgeNums (Facet.cpp:374)
@@ -537,11 +550,10 @@ __device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint3
     if (!(fk.x != fk.x)) linVel = linVel + fk;
     else linVel = dot(linVel, fNormal) * fNormal;
   }
-  d3 vs = mk3(0, 0, 0), ws = vs; double mB = 0;
-  if (real) { double4 b = S.velm[pr.y]; vs = xyz(b); b = S.angi[pr.y]; ws = xyz(b); }
-  else if (LAW == 1) mB = S.velm[pr.y].w;
-  int matB = real ? 0 : S.mat[pr.y];
-  contact_tail<LAW>(C, c, fl, u, contPt, linVel, angVel, sC, vs, ws, shiftVel2, normal, contPt, uN, fmax(ht, radius), radius, mats, F->mat, matB, 0., mB, cnt, F->id, S.id[pr.y], isReal);
+  double mB = 0;
+  if (!real && LAW == 1) mB = S.velm[pr.y].w;
+  const ErrCtx ec{S.id, -1, F->id, pr.y};
+  contact_tail<LAW>(C, c, fl, u, contPt, linVel, angVel, sC, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, fmax(ht, radius), radius, mats, S.mat, 0., mB, cnt, ec, F->mat, H, isReal);
 }
 
 template <int LAW>
@@ -549,8 +561,8 @@ __global__ void __launch_bounds__(128) k_contact_fs(Contacts C, long long first,
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
   if (c < first + n) {
-    const uint32_t fl = C.flags[c];
-    if (!(fl & CF_DEAD)) { evald = 1; contact_fs<LAW>(C, c, fl, S, facets, mats, u, cnt, isReal); }
+    const uint32_t fl = C.flags[c]; const int2 pr = C.pair[c];
+    if (!(fl & CF_DEAD)) { evald = 1; contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal); }
   }
   block_count(isReal, evald, cnt);
 }
@@ -562,13 +574,13 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
   if (c < first + n) {
-    const uint32_t fl = C.flags[c];
+    const uint32_t fl = C.flags[c]; const int2 pr = C.pair[c];
     if (!(fl & CF_DEAD)) {
       evald = 1;
       const int kind = cf_kind(fl);
-      if (kind == KIND_SS) contact_ss<LAW>(C, c, fl, S, mats, u, cnt, isReal);
-      else if (kind == KIND_WS) contact_ws<LAW>(C, c, fl, S, walls, mats, u, cnt, isReal);
-      else contact_fs<LAW>(C, c, fl, S, facets, mats, u, cnt, isReal);
+      if (kind == KIND_SS) contact_ss<LAW>(C, c, fl, pr, S, mats, u, cnt, isReal);
+      else if (kind == KIND_WS) contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal);
+      else contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal);
     }
   }
   block_count(isReal, evald, cnt);
@@ -579,11 +591,15 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
 // (ContactLoop.cpp:270-276, Contact.cpp:24-35, Particle.hpp:249) as a deterministic segmented reduction over the
 // particle's incidence row (ascending id of the other particle), fused with Leapfrog's force reset (Leapfrog.cpp:240-245).
 // ------------------------------------------------------------------------------------------------
+// One thread per sphere walks its row in order; the loads of RB entries (entry word, global force, contact point) are issued together before the
+// sequential adds, so a row costs ~3 dependent round trips per RB entries instead of 3 per entry.
+#define RB 4
 __global__ void __launch_bounds__(256) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t fl = S.flags[i];
   if (fl & F_GHOST) return;   // forces are reduced by the owner only
+  const int e0 = rowStart[i], e1 = rowStart[i + 1];
   const double4 pr = S.posr[i];
   const d3 pos = xyz(pr);
   d3 F, T;
@@ -591,23 +607,29 @@ __global__ void __launch_bounds__(256) k_reduce(Spheres S, int n, Contacts C, co
     F = (u.hasGravity && !(fl & F_GRAVITY_SKIP)) ? (S.velm[i].w * u.gravity) : mk3(0, 0, 0);
     T = mk3(0, 0, 0);
   } else { F = mk3(S.fx[i], S.fy[i], S.fz[i]); T = mk3(S.tx[i], S.ty[i], S.tz[i]); }
-  const int e0 = rowStart[i], e1 = rowStart[i + 1];
-  for (int e = e0; e < e1; e++) {
-    const uint32_t ent = rowEntry[e];
-    const uint32_t c = ent >> 1;
-    const double4 fg = C.Fg[c];
-    if (fg.w == 0.) continue;
-    const double4 cp = C.cp[c];
-    d3 Fc = xyz(fg), xc;
-    if (ent & 1u) {  // this particle is pB: sign=-1, branch from pos+shift2
-      Fc = Fc * (-1.);
-      d3 p = pos;
-      if (u.periodic) p = pos + mulMV(u.hSize, mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]));
-      xc = xyz(cp) - p;
-    } else xc = xyz(cp) - pos;
-    d3 Tc = cross(xc, Fc);
-    if (u.rolling) { double4 tg = C.Tg[c]; d3 tt = xyz(tg); if (ent & 1u) tt = tt * (-1.); Tc = Tc + tt; }
-    F = F + Fc; T = T + Tc;
+  for (int e = e0; e < e1; e += RB) {
+    uint32_t ent[RB]; double4 fg[RB], cp[RB];
+#pragma unroll
+    for (int k = 0; k < RB; k++) ent[k] = (e + k < e1) ? rowEntry[e + k] : 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < RB; k++) fg[k] = (ent[k] != 0xffffffffu) ? C.Fg[ent[k] >> 1] : make_double4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < RB; k++) cp[k] = (fg[k].w != 0.) ? C.cp[ent[k] >> 1] : make_double4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < RB; k++) {
+      if (fg[k].w == 0.) continue;
+      const uint32_t c = ent[k] >> 1;
+      d3 Fc = xyz(fg[k]), xc;
+      if (ent[k] & 1u) {  // this particle is pB: sign=-1, branch from pos+shift2
+        Fc = Fc * (-1.);
+        d3 p = pos;
+        if (u.periodic) p = pos + mulMV(u.hSize, mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]));
+        xc = xyz(cp[k]) - p;
+      } else xc = xyz(cp[k]) - pos;
+      d3 Tc = cross(xc, Fc);
+      if (u.rolling) { double4 tg = C.Tg[c]; d3 tt = xyz(tg); if (ent[k] & 1u) tt = tt * (-1.); Tc = Tc + tt; }
+      F = F + Fc; T = T + Tc;
+    }
   }
   S.fx[i] = F.x; S.fy[i] = F.y; S.fz[i] = F.z;
   S.tx[i] = T.x; S.ty[i] = T.y; S.tz[i] = T.z;
@@ -767,7 +789,12 @@ __device__ __forceinline__ void copy_history(const Contacts& N, long long cn, co
 // find the previous contact between the sphere in (old) slot `oslot` and the particle with id `otherId`
 __device__ __forceinline__ long long find_old(const OldCsr& oc, int oslot, int otherId) {
   if (!oc.valid || oslot < 0) return -1;
-  for (int e = oc.rowStart[oslot]; e < oc.rowStart[oslot + 1]; e++) if (oc.rowOther[e] == otherId) return (long long)(oc.rowEntry[e] >> 1);
+  int lo = oc.rowStart[oslot], hi = oc.rowStart[oslot + 1] - 1;   // rows are sorted by the partner's id (k_row_sort)
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1; const int v = oc.rowOther[mid];
+    if (v == otherId) return (long long)(oc.rowEntry[mid] >> 1);
+    if (v < otherId) lo = mid + 1; else hi = mid - 1;
+  }
   return -1;
 }
 // same, falling back to the rows that migrated in when one of the two spheres arrived in this full run
@@ -1060,23 +1087,39 @@ __global__ void __launch_bounds__(128) k_pairs_ws_peri(Spheres S, int n, const W
   if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
 }
 
-// carry L6Geom/FrictPhys history of contacts that were real into the new table: one thread per NEW contact (coalesced writes)
-__global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Contacts O, const int* __restrict__ srcOld, int law, int rolling, int periodic, long long stepNow) {
+// carry L6Geom/FrictPhys history of contacts that were real into the new table: one thread per NEW contact.  T holds (pair, kind, cellDist) in
+// emission order; sphere-sphere contacts are placed real-first (stable): dst = realPos[c] for carried-real ones, nReal + (c - realPos[c]) otherwise.
+__global__ void __launch_bounds__(256) k_was_real(const int* __restrict__ srcOld, const uint32_t* __restrict__ oflags, long long nSS, int* flag) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nSS) return;
+  int f = 0;
+  if (c < nSS) { const int co = srcOld[c]; f = (co >= 0 && (oflags[co] & CF_REAL)) ? 1 : 0; }
+  flag[c] = f;
+}
+__global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Contacts O, const int* __restrict__ srcOld, Contacts T, const int* __restrict__ realPos, long long nSS,
+                                              int law, int rolling, int periodic, long long stepNow) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nNew) return;
   const int co = srcOld[c];
-  if (co >= 0 && (O.flags[co] & CF_REAL)) {
-    copy_history(N, c, O, co, law, rolling, periodic);
-    N.Fg[c] = O.Fg[co];
-    N.flags[c] |= CF_REAL;
+  const bool carried = co >= 0 && (O.flags[co] & CF_REAL);
+  long long d = c;
+  if (c < nSS) { const long long rp = realPos[c]; d = carried ? rp : (long long)realPos[nSS] + (c - rp); }
+  N.pair[d] = T.pair[c];
+  uint32_t fl = T.flags[c];
+  if (periodic) { N.cdx[d] = T.cdx[c]; N.cdy[d] = T.cdy[c]; N.cdz[d] = T.cdz[c]; }
+  if (carried) {
+    copy_history(N, d, O, co, law, rolling, periodic);
+    N.Fg[d] = O.Fg[co];
+    fl |= CF_REAL;
     O.flags[co] |= CF_CLAIMED;
   } else {
     // a potential contact that survives a full run keeps the cellDist it was created with (handleBoundInversionPeri only creates
     // when !hasInter, InsertionSortCollider.cpp:844-893)
-    if (periodic && co >= 0) { N.cdx[c] = O.cdx[co]; N.cdy[c] = O.cdy[co]; N.cdz[c] = O.cdz[co]; }
-    N.stepCreated[c] = (int)stepNow;
-    N.Fg[c] = make_double4(0, 0, 0, 0);
+    if (periodic && co >= 0) { N.cdx[d] = O.cdx[co]; N.cdy[d] = O.cdy[co]; N.cdz[d] = O.cdz[co]; }
+    N.stepCreated[d] = (int)stepNow;
+    N.Fg[d] = make_double4(0, 0, 0, 0);
   }
+  N.flags[d] = fl;
 }
 
 // old real contacts nobody claimed = orphans: count (and add their incidences to the row counts), then append behind the grid candidates
@@ -1122,15 +1165,52 @@ __global__ void __launch_bounds__(256) k_csr_fill(Contacts C, long long nTot, co
   const int p = rowStart[pr.y] + atomicAdd(&cursor[pr.y], 1);
   rowEntry[p] = (uint32_t)(c << 1) | 1u; rowOther[p] = idA;
 }
-__global__ void __launch_bounds__(128) k_row_sort(int n, const int* __restrict__ rowStart, uint32_t* __restrict__ rowEntry, int32_t* __restrict__ rowOther) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int b = rowStart[i], e = rowStart[i + 1];
-  for (int a = b + 1; a < e; a++) {  // insertion sort (rows hold ~8 entries)
+// Short rows (most of them) are insertion-sorted by one thread; long rows (large spheres of a wide size distribution) are queued and
+// sorted by one warp each (bitonic network in shared memory), so that a few long rows do not serialise whole warps.
+#define ROW_SHORT 16
+#define ROW_WARP_MAX 512
+__device__ __forceinline__ void row_insertion_sort(int b, int e, uint32_t* __restrict__ rowEntry, int32_t* __restrict__ rowOther) {
+  for (int a = b + 1; a < e; a++) {
     const int32_t ko = rowOther[a]; const uint32_t ke = rowEntry[a];
     int q = a - 1;
     while (q >= b && rowOther[q] > ko) { rowOther[q + 1] = rowOther[q]; rowEntry[q + 1] = rowEntry[q]; q--; }
     rowOther[q + 1] = ko; rowEntry[q + 1] = ke;
+  }
+}
+__global__ void __launch_bounds__(128) k_row_sort(int n, const int* __restrict__ rowStart, uint32_t* __restrict__ rowEntry, int32_t* __restrict__ rowOther, int* __restrict__ longRows,
+                                                 int* __restrict__ nLong) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = rowStart[i], e = rowStart[i + 1];
+  if (e - b > ROW_SHORT) { longRows[atomicAdd(nLong, 1)] = i; return; }
+  row_insertion_sort(b, e, rowEntry, rowOther);
+}
+__global__ void __launch_bounds__(128) k_row_sort_long(const int* __restrict__ longRows, const int* __restrict__ nLong, const int* __restrict__ rowStart, uint32_t* __restrict__ rowEntry,
+                                                      int32_t* __restrict__ rowOther) {
+  __shared__ int32_t sK[4][ROW_WARP_MAX]; __shared__ uint32_t sV[4][ROW_WARP_MAX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nl = *nLong;
+  for (int q = blockIdx.x * 4 + w; q < nl; q += gridDim.x * 4) {
+    const int i = longRows[q];
+    const int b = rowStart[i], len = rowStart[i + 1] - b;
+    if (len > ROW_WARP_MAX) { if (lane == 0) row_insertion_sort(b, b + len, rowEntry, rowOther); __syncwarp(); continue; }
+    int P = 32; while (P < len) P <<= 1;
+    for (int k = lane; k < P; k += 32) { sK[w][k] = k < len ? rowOther[b + k] : 0x7fffffff; sV[w][k] = k < len ? rowEntry[b + k] : 0u; }
+    __syncwarp();
+    for (int k = 2; k <= P; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < P; t += 32) {
+          const int x = t ^ j;
+          if (x > t) {
+            const bool up = (t & k) == 0;
+            const int32_t a = sK[w][t], c = sK[w][x];
+            if ((a > c) == up) { sK[w][t] = c; sK[w][x] = a; const uint32_t v = sV[w][t]; sV[w][t] = sV[w][x]; sV[w][x] = v; }
+          }
+        }
+        __syncwarp();
+      }
+    for (int k = lane; k < len; k += 32) { rowOther[b + k] = sK[w][k]; rowEntry[b + k] = sV[w][k]; }
+    __syncwarp();
   }
 }
 
