@@ -252,3 +252,85 @@ def periodic_gas(n, *, cell=(.5, .5, .5), r=.02, psd_ratio=1.0, seed=0, vmax=1.0
     S.params = Params(gravity=(0, 0, 0), damping=.1, law=law, verletDist=-.05, dynDtPeriod=10, en=en, periodic=1)
     S.cell = dict(hSize=H, gradV=g, nextGradV=g, homoDeform=homoDeform)
     return S.finalize()
+
+
+def hertz_deposition(n, *, r=1e-3, seed=3, aspect=(8, 1, 1), en=.5, young=1e8, density=2500., spacing_factor=2.2, vz0=0.0, vfluct=0.0):
+    """cfg3 of BASELINE.json in small: monodisperse Hertz/DMT deposition (HertzMat, poisson .2, en .5, noAttraction, damping 0) in a box of
+    5 walls with aspect 8:1:1, the long axis x being the slab axis of the multi-GPU runs."""
+    rng = np.random.default_rng(seed)
+    sp = spacing_factor * r
+    k = (n / (aspect[0] * aspect[1] * aspect[2])) ** (1 / 3.)
+    nx, ny, nz = (max(1, int(round(k * a))) for a in aspect)
+    while nx * ny * nz < n:
+        nx += 1
+    p = lattice(nx, ny, nz, sp, (0, 0, 0), 0.05 * r, rng)
+    p = p[rng.permutation(len(p))][:n]
+    S = SceneSpec()
+    S.mats = [hertz_mat(density=density, young=young, tanPhi=.5, surfEnergy=0., alpha=0.)]
+    S.pos, S.radius = p, np.full(n, r)
+    if vz0 or vfluct:
+        S.vel = np.tile([0., 0., -vz0], (n, 1)) * rng.uniform(.5, 1.5, (n, 1)) + rng.uniform(-vfluct, vfluct, (n, 3))
+    S.walls = box_walls((0, 0, 0), (nx * sp, ny * sp, nz * sp), mat=0)
+    S.params = Params(gravity=(0, 0, -9.81), damping=0., law=LAW_HERTZ_DMT, verletDist=-.05, dtSafety=.9, dynDtPeriod=100, en=en, poisson=.2, noAttraction=1)
+    return S.finalize()
+
+
+def periodic_shear(n, *, r=1e-3, seed=4, solid=.55, rate=1.0, vfluct=0.0, young=1e7, density=2500.):
+    """cfg4 of BASELINE.json in small: monodisperse spheres at solid fraction ``solid`` in a cubic periodic cell under simple shear
+    gradV = [[0,rate,0],[0,0,0],[0,0,0]] (homoDeform gradV2), linear law, no gravity; velocities start on the mean field gradV·x."""
+    rng = np.random.default_rng(seed)
+    L = (n * (4 / 3.) * math.pi * r ** 3 / solid) ** (1 / 3.)
+    m = int(math.ceil(n ** (1 / 3.)))
+    sp = L / m
+    g = np.stack(np.meshgrid(np.arange(m), np.arange(m), np.arange(m), indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    p = (g + .5) * sp + rng.uniform(-.05 * r, .05 * r, g.shape)
+    p = p[rng.permutation(len(p))][:n]
+    G = np.array([[0, rate, 0], [0, 0, 0], [0, 0, 0]], dtype=np.float64)
+    S = SceneSpec()
+    S.mats = [frict_mat(density=density, young=young, ktDivKn=.2, tanPhi=.5)]
+    S.pos, S.radius = p, np.full(n, r)
+    S.vel = p @ G.T + rng.uniform(-vfluct, vfluct, p.shape)
+    S.params = Params(gravity=(0, 0, 0), damping=.2, law=LAW_IDEALELPL, verletDist=-.05, dtSafety=.9, dynDtPeriod=100, periodic=1)
+    S.cell = dict(hSize=np.eye(3) * L, gradV=G, nextGradV=G, homoDeform=HOMO_GRADV2)
+    return S.finalize()
+
+
+def drum(n, *, r=2e-3, seed=5, R=None, length=None, div=32, axial=8, omega=5.0, young=1e7, density=2500., fill=.35, vz0=0.0, vfluct=0.0):
+    """cfg5 of BASELINE.json in small: spheres in a horizontal cylinder (axis x) made of static facets whose ``fakeVel = -R*omega*n x ax`` mimics the
+    rotation (py/triangulated.py:56-58), closed by two Walls; linear law.  Spheres start on a jittered lattice in the lower part."""
+    rng = np.random.default_rng(seed)
+    sp = 2.2 * r
+    vol = n * sp ** 3 / fill
+    if R is None:
+        R = (vol / (math.pi * 4)) ** (1 / 3.)          # length = 4 R
+    if length is None:
+        length = 4 * R
+    ax = np.array([1., 0, 0])
+    F = []
+    th = np.linspace(0, 2 * math.pi, div + 1)
+    xs = np.linspace(0, length, axial + 1)
+    for i in range(axial):
+        for j in range(div):
+            a = np.array([xs[i], R * math.cos(th[j]), R * math.sin(th[j])]); b = np.array([xs[i + 1], R * math.cos(th[j]), R * math.sin(th[j])])
+            c = np.array([xs[i + 1], R * math.cos(th[j + 1]), R * math.sin(th[j + 1])]); d = np.array([xs[i], R * math.cos(th[j + 1]), R * math.sin(th[j + 1])])
+            for tri in ((a, b, c), (a, c, d)):
+                nn = np.cross(tri[1] - tri[0], tri[2] - tri[0]); nn /= np.linalg.norm(nn)
+                F.append(dict(v=np.array(tri), halfThick=0., fakeVel=tuple(-R * omega * np.cross(nn, ax)), mat=0, mask=MASK_BOUNDARY))
+    # lattice points inside the cylinder, lowest first
+    m = int(math.ceil(2 * R / sp)); mx = int(length / sp) - 1
+    g = np.stack(np.meshgrid(np.arange(mx), np.arange(m), np.arange(m), indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    p = np.array([sp, -R, -R]) + (g + .5) * sp
+    p = p[np.hypot(p[:, 1], p[:, 2]) < R - 1.5 * r]
+    p = p[np.argsort(p[:, 2], kind="stable")][:n]
+    if len(p) < n:
+        raise ValueError("drum too small for %d spheres" % n)
+    p = p + rng.uniform(-.05 * r, .05 * r, p.shape)
+    S = SceneSpec()
+    S.mats = [frict_mat(density=density, young=young, ktDivKn=.2, tanPhi=.5)]
+    S.pos, S.radius = p[rng.permutation(n)], np.full(n, r)
+    if vz0 or vfluct:
+        S.vel = np.tile([0., 0., -vz0], (n, 1)) * rng.uniform(.5, 1.5, (n, 1)) + rng.uniform(-vfluct, vfluct, (n, 3))
+    S.facets = F
+    S.walls = [dict(pos=(0, 0, 0), axis=0, sense=1, mat=0, mask=MASK_BOUNDARY), dict(pos=(length, 0, 0), axis=0, sense=-1, mat=0, mask=MASK_BOUNDARY)]
+    S.params = Params(gravity=(0, 0, -9.81), damping=.2, law=LAW_IDEALELPL, verletDist=-.05, dtSafety=.9, dynDtPeriod=100)
+    return S.finalize()
