@@ -456,8 +456,8 @@ void rebuild(wdem_engine* E) {
   OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = Ocsr.valid ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
   if (E->comm && E->dom.nImm > 0) { oc.immKeys = E->dom.immKeysAlt.p; oc.immVals = E->dom.immValsAlt.p; oc.nImm = E->dom.nImm; }
   const int* perm = nullptr;
-  Grid g; memset(&g, 0, sizeof(g));
-  PeriU pu; memset(&pu, 0, sizeof(pu)); PGrid pg; memset(&pg, 0, sizeof(pg));
+  HGrid g; memset(&g, 0, sizeof(g));
+  PeriU pu; memset(&pu, 0, sizeof(pu));
   if (c.periodic) {
     if (nFacets) throw EngErr{"Facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     if (!E->hWalls.empty() && E->cell.hasShear) throw EngErr{"Walls not supported in skewed periodic boundary conditions.", WDEM_ERR_RUNTIME};  // Wall.cpp:30
@@ -477,26 +477,51 @@ void rebuild(wdem_engine* E) {
       double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
       for (int b = 0; b < nb; b++) for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], hb[7 * b + k]); hi[k] = std::max(hi[k], hb[7 * b + 3 + k]); }
       for (int k = 0; k < 3; k++) if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) throw EngErr{"non-finite particle position at collider run", WDEM_ERR_RUNTIME};
-      // 2. grid: cell edge ~ smallest enlarged AABB, but no more than ~8 cells per sphere
-      double cell = 2 * (E->minRadius + vd);
-      double vol = std::max(hi[0] - lo[0], cell) * std::max(hi[1] - lo[1], cell) * std::max(hi[2] - lo[2], cell);
-      cell = std::max(cell, std::cbrt(vol / (8.0 * n)));
-      g.cell = cell; g.inv = 1. / cell; g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
-      g.nx = std::max(1, (int)std::floor((hi[0] - lo[0]) * g.inv) + 1); g.ny = std::max(1, (int)std::floor((hi[1] - lo[1]) * g.inv) + 1); g.nz = std::max(1, (int)std::floor((hi[2] - lo[2]) * g.inv) + 1);
-      ncells = (long long)g.nx * g.ny * g.nz;
-      if (ncells > (1ll << 31) - 2) throw EngErr{"collider grid too large", WDEM_ERR_RUNTIME};
+      // 2. size-class grids (HGrid): level L = radii [rmin 2^L, rmin 2^(L+1)), cell edge = largest enlarged box of the level, at most ~8 cells per sphere
+      const double rmin = E->minRadius, rmax = std::max(E->dom.rmaxGlobal, rmin);
+      int nL = 1; while (nL < WD_MAX_LEVELS && rmin * (double)(1 << nL) <= rmax) nL++;
+      g.nL = nL; g.periodic = 0; g.rmin = rmin; g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+      double ext[3]; for (int k = 0; k < 3; k++) ext[k] = hi[k] - lo[k];
+      for (int L = 0; L < nL; L++) {
+        const double rL = (L == nL - 1) ? rmax : std::min(rmax, rmin * (double)(2 << L));
+        const double reach = rL + vd;
+        double cell = 2 * reach * (1 + 1e-9) + 1e-300;
+        const double vol = std::max(ext[0], cell) * std::max(ext[1], cell) * std::max(ext[2], cell);
+        cell = std::max(cell, std::cbrt(vol / (8.0 * n)));
+        g.base[L] = (int)ncells;
+        for (int k = 0; k < 3; k++) { g.inv[L][k] = 1. / cell; g.n[L][k] = std::max(1, (int)std::floor(ext[k] / cell) + 1); g.reach[L][k] = reach; }
+        ncells += (long long)g.n[L][0] * g.n[L][1] * g.n[L][2];
+        if (ncells > (1ll << 31) - 2) throw EngErr{"collider grid too large", WDEM_ERR_RUNTIME};
+      }
+      g.base[nL] = (int)ncells;
       // 3. cell keys
       k_cellkeys<<<nb, 256, 0, st>>>(E->S().posr, n, g, E->keys.p, E->idx.p); E->launches++;
     } else {
-      // periodic: nc[k] cells along each (unsheared) cell axis; the hash wraps, positions do not
+      // periodic: per level nc[k] cells along each (unsheared) cell axis; the hash wraps, positions do not
       const d3 sz = E->cell.size;
-      double cell = 2 * (E->minRadius + vd);
-      cell = std::max(cell, std::cbrt((sz.x * sz.y * sz.z) / (8.0 * n)));
-      auto nc = [&](double s) { return (int)std::min(1024., std::max(1., std::floor(s / cell))); };
-      pg.nx = nc(sz.x); pg.ny = nc(sz.y); pg.nz = nc(sz.z);
-      pg.invx = pg.nx / sz.x; pg.invy = pg.ny / sz.y; pg.invz = pg.nz / sz.z;
-      ncells = (long long)pg.nx * pg.ny * pg.nz;
-      k_cellkeys_peri<<<nb, 256, 0, st>>>(E->S().posr, n, pg, pu, E->keys.p, E->idx.p); E->launches++;
+      const double rmin = E->minRadius, rmax = std::max(E->dom.rmaxGlobal, rmin);
+      int nL = 1; while (nL < WD_MAX_LEVELS && rmin * (double)(1 << nL) <= rmax) nL++;
+      g.nL = nL; g.periodic = 1; g.rmin = rmin;
+      double fac[3] = {1, 1, 1};   // Cell::shearAlignedExtents of a unit extent (Cell.cpp:68-79)
+      if (E->cell.hasShear) {
+        const d3 cv = E->cell.cosv; double hx = 1, hy = 1, hz = 1;
+        hy += .5 * (1 / cv.x - 1); hz += .5 * (1 / cv.x - 1); hz += .5 * (1 / cv.y - 1); hx += .5 * (1 / cv.y - 1); hx += .5 * (1 / cv.z - 1); hy += .5 * (1 / cv.z - 1);
+        fac[0] = hx; fac[1] = hy; fac[2] = hz;
+      }
+      const double szk[3] = {sz.x, sz.y, sz.z};
+      const double capCell = std::cbrt((sz.x * sz.y * sz.z) / (8.0 * n));
+      for (int L = 0; L < nL; L++) {
+        const double rL = (L == nL - 1) ? rmax : std::min(rmax, rmin * (double)(2 << L));
+        g.base[L] = (int)ncells;
+        for (int k = 0; k < 3; k++) {
+          const double reach = (fac[k] * rL) * (1 + 1e-9) + vd;
+          const double cell = std::max(2 * reach * (1 + 1e-9), capCell);
+          g.reach[L][k] = reach; g.n[L][k] = (int)std::min(1024., std::max(1., std::floor(szk[k] / cell))); g.inv[L][k] = g.n[L][k] / szk[k];
+        }
+        ncells += (long long)g.n[L][0] * g.n[L][1] * g.n[L][2];
+      }
+      g.base[nL] = (int)ncells;
+      k_cellkeys_peri<<<nb, 256, 0, st>>>(E->S().posr, n, g, pu, E->keys.p, E->idx.p); E->launches++;
     }
     // radix sort by cell, reorder all sphere arrays into cell order
     int keyBits = 1; while ((1ll << keyBits) < ncells) keyBits++;
@@ -530,7 +555,7 @@ void rebuild(wdem_engine* E) {
     E->rowCount.ensure((size_t)n + 1, tot);
     CK(cudaMemsetAsync(E->rowCount.p, 0, ((size_t)n + 1) * sizeof(int), st));
     if (!c.periodic) k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr);
-    else k_pairs_ss_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, pg, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
+    else k_pairs_ss_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
     E->launches++;
     if (nWalls) {
       if (!c.periodic) k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr);
@@ -563,7 +588,7 @@ void rebuild(wdem_engine* E) {
     Contacts T = N; T.pair = reinterpret_cast<int2*>(E->ckeys.p); T.flags = E->cvals.p;
     if (c.periodic) { for (auto& b : E->tmpCd) b.ensure(nT, tot); T.cdx = E->tmpCd[0].p; T.cdy = E->tmpCd[1].p; T.cdz = E->tmpCd[2].p; }
     if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, T, O, oc, perm, nullptr, E->srcOld.p);
-    else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, pg, pu, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
+    else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
     E->launches++;
     if (nWalls) {
       if (!c.periodic) k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, T, O, oc, perm, nullptr, E->srcOld.p);

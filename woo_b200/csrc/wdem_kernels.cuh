@@ -705,7 +705,25 @@ __global__ void __launch_bounds__(256) k_ekin(Spheres S, int n, StepU u, double*
 // potential contacts is rebuilt as { (i,j) : enlarged AABBs overlap (closed intervals, spatialOverlap :67-73) and
 // Collider::mayCollide (Collision.cpp:21-43) } from a uniform grid over radix-sorted cell keys.
 // ================================================================================================
-struct Grid { double ox, oy, oz, inv; int nx, ny, nz; double cell; };
+// Size-class grids: level L holds the spheres with radius in [rmin*2^L, rmin*2^(L+1)); its cells are as large as the largest enlarged box of the
+// level, so a sphere finds every partner of its own or a coarser level within 3x3x3 cells of that level's grid.  The SMALLER sphere (lower level;
+// same level: lower slot) emits the pair, which keeps the work per thread bounded (<= 27 cells per level) for wide size distributions where a single
+// grid sized for the smallest sphere makes the largest ones scan hundreds of cells.  Cells of all levels share one key space / cellStart array.
+#define WD_MAX_LEVELS 8
+struct HGrid {
+  int nL, periodic;
+  double rmin;
+  double ox, oy, oz;                    // aperiodic: origin (lower corner of the bounding box of the centres)
+  double inv[WD_MAX_LEVELS][3];         // cells per unit length
+  int n[WD_MAX_LEVELS][3];              // cells per axis
+  int base[WD_MAX_LEVELS + 1];          // first key of the level
+  double reach[WD_MAX_LEVELS][3];       // largest half-extent of an enlarged box of the level, per axis (periodic: shear-aligned)
+};
+__host__ __device__ __forceinline__ int levelOf(const HGrid& g, double r) {
+  int L = 0;
+  while (L + 1 < g.nL && r >= g.rmin * (double)(2 << L)) L++;
+  return L;
+}
 
 __global__ void __launch_bounds__(256) k_bounds(const double4* __restrict__ posr, int n, double* blk /*7 per block*/) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -729,12 +747,13 @@ __device__ __forceinline__ int cellCoord(double x, double o, double inv, int n) 
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
-__global__ void __launch_bounds__(256) k_cellkeys(const double4* __restrict__ posr, int n, Grid g, uint32_t* keys, int* idx) {
+__global__ void __launch_bounds__(256) k_cellkeys(const double4* __restrict__ posr, int n, HGrid g, uint32_t* keys, int* idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double4 p = posr[i];
-  int ix = cellCoord(p.x, g.ox, g.inv, g.nx), iy = cellCoord(p.y, g.oy, g.inv, g.ny), iz = cellCoord(p.z, g.oz, g.inv, g.nz);
-  keys[i] = (uint32_t)((iz * g.ny + iy) * g.nx + ix);
+  const int L = levelOf(g, p.w);
+  int ix = cellCoord(p.x, g.ox, g.inv[L][0], g.n[L][0]), iy = cellCoord(p.y, g.oy, g.inv[L][1], g.n[L][1]), iz = cellCoord(p.z, g.oz, g.inv[L][2], g.n[L][2]);
+  keys[i] = (uint32_t)(g.base[L] + (iz * g.n[L][1] + iy) * g.n[L][0] + ix);
   idx[i] = i;
 }
 
@@ -808,48 +827,50 @@ __device__ __forceinline__ long long find_old2(const OldCsr& oc, int oslot, int 
   return co;
 }
 
-// Sphere+Sphere candidates.  Ownership: the pair is emitted by the sphere with the larger radius (ties: larger slot), whose search
-// box (own AABB grown by its own half-extent) necessarily contains the centre of the other.  FILL=false counts, FILL=true writes
-// pairs (canonical pA = lower id) and carries L6Geom/FrictPhys history of contacts that were real (sorted-row lookup).
+// Sphere+Sphere candidates (see HGrid for the ownership rule).  FILL=false counts, FILL=true writes pairs (canonical pA = lower id) and looks up the
+// previous contact of the pair (history carry-over by k_carry).
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_pairs_ss(Spheres S, int n, Grid g, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
+__global__ void __launch_bounds__(128) k_pairs_ss(Spheres S, int n, HGrid g, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
                                                  const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
                                                  int* __restrict__ rowCount, int* __restrict__ srcOld) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double4 pi = S.posr[i];
-  const double H = 2 * (pi.w + vd) * (1 + 1e-12) + 1e-300;
-  const int x0 = cellCoord(pi.x - H, g.ox, g.inv, g.nx), x1 = cellCoord(pi.x + H, g.ox, g.inv, g.nx);
-  const int y0 = cellCoord(pi.y - H, g.oy, g.inv, g.ny), y1 = cellCoord(pi.y + H, g.oy, g.inv, g.ny);
-  const int z0 = cellCoord(pi.z - H, g.oz, g.inv, g.nz), z1 = cellCoord(pi.z + H, g.oz, g.inv, g.nz);
+  const int Li = levelOf(g, pi.w);
   const uint32_t mi = S.mask[i];
   const uint32_t fi = S.flags[i];
   int cntLocal = 0;
   long long out = FILL ? offsets[i] : 0;
   int idI = 0, oslotI = 0;
   if (FILL) { idI = S.id[i]; oslotI = perm ? perm[i] : i; }
-  for (int iz = z0; iz <= z1; iz++)
-    for (int iy = y0; iy <= y1; iy++) {
-      const int k0 = (iz * g.ny + iy) * g.nx;
-      const int jb = cellStart[k0 + x0], je = cellStart[k0 + x1 + 1];
-      for (int j = jb; j < je; j++) {
-        if (j == i) continue;
-        const double4 pj = S.posr[j];
-        if (!(pj.w < pi.w || (pj.w == pi.w && j < i))) continue;
-        if (!aabbOverlapSS(pi, pj, vd)) continue;
-        if (!mayCollide(mi, S.mask[j], loneMask)) continue;
-        if ((fi & F_GHOST) && (S.flags[j] & F_GHOST)) continue;   // ghost-ghost pairs belong to other subdomains
-        if (FILL) {
-          const int idJ = S.id[j];
-          const long long c = out + cntLocal;
-          const bool iIsA = idI < idJ;
-          N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
-          srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
-          N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
-        } else atomicAdd(&rowCount[j], 1);
-        cntLocal++;
+  for (int L = Li; L < g.nL; L++) {
+    const double H = ((pi.w + vd) + g.reach[L][0]) * (1 + 1e-12) + 1e-300;
+    const int nx = g.n[L][0], ny = g.n[L][1], nz = g.n[L][2];
+    const int x0 = cellCoord(pi.x - H, g.ox, g.inv[L][0], nx), x1 = cellCoord(pi.x + H, g.ox, g.inv[L][0], nx);
+    const int y0 = cellCoord(pi.y - H, g.oy, g.inv[L][1], ny), y1 = cellCoord(pi.y + H, g.oy, g.inv[L][1], ny);
+    const int z0 = cellCoord(pi.z - H, g.oz, g.inv[L][2], nz), z1 = cellCoord(pi.z + H, g.oz, g.inv[L][2], nz);
+    for (int iz = z0; iz <= z1; iz++)
+      for (int iy = y0; iy <= y1; iy++) {
+        const int k0 = g.base[L] + (iz * ny + iy) * nx;
+        int jb = cellStart[k0 + x0]; const int je = cellStart[k0 + x1 + 1];
+        if (L == Li && jb <= i) jb = i + 1;   // same level: the lower slot emits (slots of a level are contiguous and ascending along the row)
+        for (int j = jb; j < je; j++) {
+          const double4 pj = S.posr[j];
+          if (!aabbOverlapSS(pi, pj, vd)) continue;
+          if (!mayCollide(mi, S.mask[j], loneMask)) continue;
+          if ((fi & F_GHOST) && (S.flags[j] & F_GHOST)) continue;   // ghost-ghost pairs belong to other subdomains
+          if (FILL) {
+            const int idJ = S.id[j];
+            const long long c = out + cntLocal;
+            const bool iIsA = idI < idJ;
+            N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
+            srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
+            N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
+          } else atomicAdd(&rowCount[j], 1);
+          cntLocal++;
+        }
       }
-    }
+  }
   if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
 }
 
@@ -937,7 +958,6 @@ __global__ void __launch_bounds__(128) k_pairs_fs(Spheres S, int n, const Facet*
 // the integer cellDist.  Positions are never wrapped (InsertionSortCollider.hpp:28-29); only the grid hash wraps.
 // ================================================================================================
 struct PeriU { m33 unshear; d3 size; d3 cosv; int hasShear; };   // Cell::unshearPt, getSize, getCos, hasShear (Cell.hpp:82-97)
-struct PGrid { double invx, invy, invz; int nx, ny, nz; };       // nc[k] cells of size[k]/nc[k] along each cell axis
 
 __device__ __forceinline__ void periAabb(const PeriU& pu, double4 p, double vd, d3& mn, d3& mx) {
   d3 half = mk3(p.w, p.w, p.w);
@@ -976,72 +996,78 @@ __device__ __forceinline__ int overlapPeri(d3 mn1, d3 mx1, d3 mn2, d3 mx2, d3 si
 __device__ __forceinline__ int imod(int a, int n) { int m = a % n; return m < 0 ? m + n : m; }
 __device__ __forceinline__ double wrap01(double u, double size) { double xn = u / size; xn -= floor(xn); return xn * size; }
 
-__global__ void __launch_bounds__(256) k_cellkeys_peri(const double4* __restrict__ posr, int n, PGrid g, PeriU pu, uint32_t* keys, int* idx) {
+__global__ void __launch_bounds__(256) k_cellkeys_peri(const double4* __restrict__ posr, int n, HGrid g, PeriU pu, uint32_t* keys, int* idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const d3 u = mulMV(pu.unshear, xyz(posr[i]));
-  int ix = min(g.nx - 1, max(0, (int)floor(wrap01(u.x, pu.size.x) * g.invx)));
-  int iy = min(g.ny - 1, max(0, (int)floor(wrap01(u.y, pu.size.y) * g.invy)));
-  int iz = min(g.nz - 1, max(0, (int)floor(wrap01(u.z, pu.size.z) * g.invz)));
-  keys[i] = (uint32_t)((iz * g.ny + iy) * g.nx + ix);
+  const double4 p = posr[i];
+  const int L = levelOf(g, p.w);
+  const d3 u = mulMV(pu.unshear, xyz(p));
+  int ix = min(g.n[L][0] - 1, max(0, (int)floor(wrap01(u.x, pu.size.x) * g.inv[L][0])));
+  int iy = min(g.n[L][1] - 1, max(0, (int)floor(wrap01(u.y, pu.size.y) * g.inv[L][1])));
+  int iz = min(g.n[L][2] - 1, max(0, (int)floor(wrap01(u.z, pu.size.z) * g.inv[L][2])));
+  keys[i] = (uint32_t)(g.base[L] + (iz * g.n[L][1] + iy) * g.n[L][0] + ix);
   idx[i] = i;
 }
 
-// Sphere+Sphere candidates in a periodic cell; same ownership rule as k_pairs_ss (the larger sphere searches), cells wrap.
+// Sphere+Sphere candidates in a periodic cell; same ownership rule as k_pairs_ss, cells wrap (positions do not).
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_pairs_ss_peri(Spheres S, int n, PGrid g, PeriU pu, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
+__global__ void __launch_bounds__(128) k_pairs_ss_peri(Spheres S, int n, HGrid g, PeriU pu, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
                                                       const int* __restrict__ offsets, Contacts N, OldCsr oc, const int* __restrict__ perm,
                                                       int* __restrict__ rowCount, int* __restrict__ srcOld, Counters* cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double4 pi = S.posr[i];
+  const int Li = levelOf(g, pi.w);
   d3 mnI, mxI; periAabb(pu, pi, vd, mnI, mxI);
   const d3 ui = mulMV(pu.unshear, xyz(pi));
   const double cx = wrap01(ui.x, pu.size.x), cy = wrap01(ui.y, pu.size.y), cz = wrap01(ui.z, pu.size.z);
-  // |Δcentre| <= half_i + half_j <= 2*half_i = extent of the own box (radius_j <= radius_i); small relative + absolute slack
-  const double Hx = (mxI.x - mnI.x) * (1 + 1e-9) + 1e-9 / g.invx, Hy = (mxI.y - mnI.y) * (1 + 1e-9) + 1e-9 / g.invy, Hz = (mxI.z - mnI.z) * (1 + 1e-9) + 1e-9 / g.invz;
-  int x0 = (int)floor((cx - Hx) * g.invx), x1 = (int)floor((cx + Hx) * g.invx); if (x1 - x0 + 1 >= g.nx) { x0 = 0; x1 = g.nx - 1; }
-  int y0 = (int)floor((cy - Hy) * g.invy), y1 = (int)floor((cy + Hy) * g.invy); if (y1 - y0 + 1 >= g.ny) { y0 = 0; y1 = g.ny - 1; }
-  int z0 = (int)floor((cz - Hz) * g.invz), z1 = (int)floor((cz + Hz) * g.invz); if (z1 - z0 + 1 >= g.nz) { z0 = 0; z1 = g.nz - 1; }
-  // the x range wraps into at most two runs of consecutive cells
-  const int wx0 = imod(x0, g.nx), wx1 = imod(x1, g.nx);
-  const int nseg = (wx0 <= wx1) ? 1 : 2;
   const uint32_t mi = S.mask[i];
   const uint32_t fi = S.flags[i];
   const int idI = S.id[i];
   const int oslotI = FILL ? (perm ? perm[i] : i) : 0;
   int cntLocal = 0;
   long long out = FILL ? offsets[i] : 0;
-  for (int iz = z0; iz <= z1; iz++)
-    for (int iy = y0; iy <= y1; iy++) {
-      const int k0 = (imod(iz, g.nz) * g.ny + imod(iy, g.ny)) * g.nx;
-      for (int seg = 0; seg < nseg; seg++) {
-        const int sa = (nseg == 1) ? wx0 : (seg == 0 ? wx0 : 0), sb = (nseg == 1) ? wx1 : (seg == 0 ? g.nx - 1 : wx1);
-        const int jb = cellStart[k0 + sa], je = cellStart[k0 + sb + 1];
-        for (int j = jb; j < je; j++) {
-          if (j == i) continue;
-          const double4 pj = S.posr[j];
-          if (!(pj.w < pi.w || (pj.w == pi.w && j < i))) continue;
-          if (!mayCollide(mi, S.mask[j], loneMask)) continue;
-          if ((fi & F_GHOST) && (S.flags[j] & F_GHOST)) continue;
-          d3 mnJ, mxJ; periAabb(pu, pj, vd, mnJ, mxJ);
-          const int idJ = S.id[j];
-          const bool iIsA = idI < idJ;
-          int per[3];
-          const int ov = iIsA ? overlapPeri(mnI, mxI, mnJ, mxJ, pu.size, per) : overlapPeri(mnJ, mxJ, mnI, mxI, pu.size, per);
-          if (ov < 0) { cnt->error = ERR_AMBIGUOUS_PERI; cnt->errA = iIsA ? idI : idJ; cnt->errB = iIsA ? idJ : idI; continue; }
-          if (!ov) continue;
-          if (FILL) {
-            const long long c = out + cntLocal;
-            N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
-            N.cdx[c] = per[0]; N.cdy[c] = per[1]; N.cdz[c] = per[2];
-            srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
-            N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
-          } else atomicAdd(&rowCount[j], 1);
-          cntLocal++;
+  for (int L = Li; L < g.nL; L++) {
+    const int nx = g.n[L][0], ny = g.n[L][1], nz = g.n[L][2];
+    // |Δcentre| <= half_i + half_j <= half_i + reach of the level; small relative + absolute slack
+    const double Hx = (.5 * (mxI.x - mnI.x) + g.reach[L][0]) * (1 + 1e-9) + 1e-9 / g.inv[L][0], Hy = (.5 * (mxI.y - mnI.y) + g.reach[L][1]) * (1 + 1e-9) + 1e-9 / g.inv[L][1],
+                 Hz = (.5 * (mxI.z - mnI.z) + g.reach[L][2]) * (1 + 1e-9) + 1e-9 / g.inv[L][2];
+    int x0 = (int)floor((cx - Hx) * g.inv[L][0]), x1 = (int)floor((cx + Hx) * g.inv[L][0]); if (x1 - x0 + 1 >= nx) { x0 = 0; x1 = nx - 1; }
+    int y0 = (int)floor((cy - Hy) * g.inv[L][1]), y1 = (int)floor((cy + Hy) * g.inv[L][1]); if (y1 - y0 + 1 >= ny) { y0 = 0; y1 = ny - 1; }
+    int z0 = (int)floor((cz - Hz) * g.inv[L][2]), z1 = (int)floor((cz + Hz) * g.inv[L][2]); if (z1 - z0 + 1 >= nz) { z0 = 0; z1 = nz - 1; }
+    // the x range wraps into at most two runs of consecutive cells
+    const int wx0 = imod(x0, nx), wx1 = imod(x1, nx);
+    const int nseg = (wx0 <= wx1) ? 1 : 2;
+    for (int iz = z0; iz <= z1; iz++)
+      for (int iy = y0; iy <= y1; iy++) {
+        const int k0 = g.base[L] + (imod(iz, nz) * ny + imod(iy, ny)) * nx;
+        for (int seg = 0; seg < nseg; seg++) {
+          const int sa = (nseg == 1) ? wx0 : (seg == 0 ? wx0 : 0), sb = (nseg == 1) ? wx1 : (seg == 0 ? nx - 1 : wx1);
+          const int jb = cellStart[k0 + sa], je = cellStart[k0 + sb + 1];
+          for (int j = jb; j < je; j++) {
+            if (L == Li && j <= i) continue;   // same level: the lower slot emits
+            const double4 pj = S.posr[j];
+            if (!mayCollide(mi, S.mask[j], loneMask)) continue;
+            if ((fi & F_GHOST) && (S.flags[j] & F_GHOST)) continue;
+            d3 mnJ, mxJ; periAabb(pu, pj, vd, mnJ, mxJ);
+            const int idJ = S.id[j];
+            const bool iIsA = idI < idJ;
+            int per[3];
+            const int ov = iIsA ? overlapPeri(mnI, mxI, mnJ, mxJ, pu.size, per) : overlapPeri(mnJ, mxJ, mnI, mxI, pu.size, per);
+            if (ov < 0) { cnt->error = ERR_AMBIGUOUS_PERI; cnt->errA = iIsA ? idI : idJ; cnt->errB = iIsA ? idJ : idI; continue; }
+            if (!ov) continue;
+            if (FILL) {
+              const long long c = out + cntLocal;
+              N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
+              N.cdx[c] = per[0]; N.cdy[c] = per[1]; N.cdz[c] = per[2];
+              srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
+              N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
+            } else atomicAdd(&rowCount[j], 1);
+            cntLocal++;
+          }
         }
       }
-    }
+  }
   if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
 }
 
