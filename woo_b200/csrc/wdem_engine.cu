@@ -144,7 +144,10 @@ struct wdem_engine {
   wdem_config cfg;
   Transport* comm = nullptr; DomainState dom;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t stream2 = nullptr;       // boundary (wall/facet/orphan) contact kernels run beside the sphere-sphere kernel
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFlag = nullptr, evFork = nullptr, evJoin = nullptr;
+  static const int NEVSET = 4;          // per-phase events are harvested a few steps later, so profiling does not stall the pipeline
+  cudaEvent_t evr[NEVSET][6] = {}; bool evPending[NEVSET] = {false, false, false, false}; double phaseAcc[5] = {0, 0, 0, 0, 0};
   std::string err;
   int64_t bytes = 0;
   bool profiling = false;
@@ -729,21 +732,81 @@ double dynDtCritGlobal(wdem_engine* E) {
 }
 double pown(double x, unsigned n) { unsigned d = n >> 1, r = n & 1; double a = d == 0 ? 1 : pown(x * x, d); double b = r == 0 ? 1 : x; return a * b; }  // Math.hpp:161-176
 
-void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
+void harvestPhases(wdem_engine* E, int set) {
+  if (!E->evPending[set]) return;
+  CK(cudaEventSynchronize(E->evr[set][5]));
+  float ms;
+  for (int k = 0; k < 5; k++) { CK(cudaEventElapsedTime(&ms, E->evr[set][k], E->evr[set][k + 1])); E->phaseAcc[k] += ms; }
+  E->evPending[set] = false;
+}
+
+// ContactLoop + force reduction of one step.  `guard` points at the device-side Verlet-dirty flag: kernels launched before the host knows whether a
+// collider full run is due return immediately when it is set (they are launched again after the full run).
+void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, cudaEvent_t* ev) {
+  const wdem_config& c = E->cfg; cudaStream_t st = E->stream, st2 = E->stream2;
+  Contacts C = E->con[E->curC].view();
+  static const bool sideOff = getenv("WDEM_NO_SIDE_STREAM") != nullptr;
+  const bool side = !sideOff && (E->nWS + E->nFS + E->nOrph) > 0 && E->nSS > 0;   // boundary kernels are small and latency-bound: overlap them with the big one
+  cudaStream_t sb = side ? st2 : st;
+  if (ev) CK(cudaEventRecord(ev[2], st));
+  if (side) { CK(cudaEventRecord(E->evFork, st)); CK(cudaStreamWaitEvent(st2, E->evFork, 0)); }
+  if (E->nWS > 0) {
+    if (c.law == 0) k_contact_ws<0><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard);
+    else k_contact_ws<1><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard);
+    E->launches++;
+  }
+  if (E->nFS > 0) {
+    if (c.law == 0) k_contact_fs<0><<<nblk(E->nFS, 128), 128, 0, sb>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt, guard);
+    else k_contact_fs<1><<<nblk(E->nFS, 128), 128, 0, sb>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt, guard);
+    E->launches++;
+  }
+  if (E->nOrph > 0) {
+    const long long f0 = E->nSS + E->nWS + E->nFS;
+    if (c.law == 0) k_contact_orphans<0><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard);
+    else k_contact_orphans<1><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard);
+    E->launches++;
+  }
+  // the big kernel goes last so that the small boundary kernels already occupy their share of the SMs
+  if (E->nSS > 0) {
+    if (c.law == 0) k_contact_ss<0><<<nblk(E->nSS, 128), 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard);
+    else k_contact_ss<1><<<nblk(E->nSS, 128), 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard);
+    E->launches++;
+  }
+  if (side) { CK(cudaEventRecord(E->evJoin, st2)); CK(cudaStreamWaitEvent(st, E->evJoin, 0)); }
+  if (ev) CK(cudaEventRecord(ev[3], st));
+  const int nNow = E->n;   // a full run of a decomposed scene changes the local sphere count (migration, ghosts)
+  if (nNow > 0 && c.applyForces) {
+    CsrStore& R = E->csr[E->curR];
+    k_reduce<<<nblk(nNow, 256), 256, 0, st>>>(E->S(), nNow, C, R.rowStart.p, R.rowEntry.p, u, guard); E->launches++;
+  }
+  if (ev) CK(cudaEventRecord(ev[4], st));
+}
+
+void oneStep(wdem_engine* E, wdem_stats* stats) {
   const wdem_config& c = E->cfg;
   cudaStream_t st = E->stream;
   ensureVerletAndDt(E);
   if (c.periodic) E->cell.integrateAndUpdate(E->dt);
   StepU u = makeUniforms(E);
   const int n = E->n;
-  const bool prof = E->profiling;
-  if (prof) CK(cudaEventRecord(E->evp[0], st));
+  cudaEvent_t* ev = nullptr;
+  if (E->profiling) { const int set = (int)(E->step % wdem_engine::NEVSET); harvestPhases(E, set); ev = E->evr[set]; }
+  if (ev) CK(cudaEventRecord(ev[0], st));
   if (n > 0) { k_leapfrog<<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt); E->launches++; }
-  if (prof) CK(cudaEventRecord(E->evp[1], st));
-  // collider: full run if contacts are dirty / verletDist==0 / any sphere moved farther than verletDist
+  if (ev) CK(cudaEventRecord(ev[1], st));
+  // collider: full run if contacts are dirty / verletDist==0 / any sphere moved farther than verletDist (flag raised by k_leapfrog)
   bool full = E->conDirty || E->verletDist == 0;
   if (E->comm) E->comm->allreduceMaxInt(&E->dCnt->dirty, 2, st);   // (dirty, error): every subdomain rebuilds / fails in the same step
-  fetchCounters(E);
+  CK(cudaMemcpyAsync(E->hCnt, E->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(E->evFlag, st));
+  // Speculate that no full run is due (the common case): enqueue the rest of the step behind the flag copy, guarded on the device by the flag,
+  // so the GPU keeps running while the host waits for the flag.
+  const bool speculate = !full;
+  if (speculate) {
+    if (E->comm) haloExchange(E);
+    launchContactsAndReduce(E, u, &E->dCnt->dirty, ev);
+  }
+  CK(cudaEventSynchronize(E->evFlag));
   checkDeviceError(E);
   if (E->hCnt->dirty) full = true;
   if (full) {
@@ -751,37 +814,8 @@ void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
     E->conDirty = false;
     CK(cudaMemsetAsync(&E->dCnt->dirty, 0, sizeof(int), st));
     if (stats) stats->n_rebuilds++;
-  } else if (E->comm) haloExchange(E);
-  if (prof) CK(cudaEventRecord(E->evp[2], st));
-  Contacts C = E->con[E->curC].view();
-  if (E->nSS > 0) {
-    if (c.law == 0) k_contact_ss<0><<<nblk(E->nSS, 128), 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt);
-    else k_contact_ss<1><<<nblk(E->nSS, 128), 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt);
-    E->launches++;
+    launchContactsAndReduce(E, u, &E->dCnt->dirty, ev);
   }
-  if (E->nWS > 0) {
-    if (c.law == 0) k_contact_ws<0><<<nblk(E->nWS, 128), 128, 0, st>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt);
-    else k_contact_ws<1><<<nblk(E->nWS, 128), 128, 0, st>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt);
-    E->launches++;
-  }
-  if (E->nFS > 0) {
-    if (c.law == 0) k_contact_fs<0><<<nblk(E->nFS, 128), 128, 0, st>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt);
-    else k_contact_fs<1><<<nblk(E->nFS, 128), 128, 0, st>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt);
-    E->launches++;
-  }
-  if (E->nOrph > 0) {
-    const long long f0 = E->nSS + E->nWS + E->nFS;
-    if (c.law == 0) k_contact_orphans<0><<<nblk(E->nOrph, 128), 128, 0, st>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt);
-    else k_contact_orphans<1><<<nblk(E->nOrph, 128), 128, 0, st>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt);
-    E->launches++;
-  }
-  if (prof) CK(cudaEventRecord(E->evp[3], st));
-  const int nNow = E->n;   // a full run of a decomposed scene changes the local sphere count (migration, ghosts)
-  if (nNow > 0 && c.applyForces) {
-    CsrStore& R = E->csr[E->curR];
-    k_reduce<<<nblk(nNow, 256), 256, 0, st>>>(E->S(), nNow, C, R.rowStart.p, R.rowEntry.p, u); E->launches++;
-  }
-  if (prof) CK(cudaEventRecord(E->evp[4], st));
   // DynDt (PeriodicEngine::isActivated, Engine.cpp:170-195 with stepModulo/initRun defaults; DynDt::run DynDt.cpp:90-113)
   if (c.dynDtPeriod > 0) {
     bool initNow = E->dynStepLast < 0;
@@ -797,11 +831,7 @@ void oneStep(wdem_engine* E, wdem_stats* stats, float* phaseMs) {
       }
     }
   }
-  if (prof) {
-    CK(cudaEventRecord(E->evp[5], st)); CK(cudaEventSynchronize(E->evp[5]));
-    float ms;
-    for (int k = 0; k < 5; k++) { CK(cudaEventElapsedTime(&ms, E->evp[k], E->evp[k + 1])); phaseMs[k] += ms; }
-  }
+  if (ev) { CK(cudaEventRecord(ev[5], st)); E->evPending[E->step % wdem_engine::NEVSET] = true; }
   // epilogue (Scene.cpp:428-432)
   if (c.periodic) E->cell.setNextGradV();
   E->step++; E->time += E->dt;
@@ -879,8 +909,10 @@ int wdem_create(const wdem_config* cfg, wdem_handle* out) {
     E = new wdem_engine(); E->cfg = *cfg; E->dt = cfg->dt;
     if (const char* g = getenv("WDEM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob: 32/64/128
     CK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&E->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreate(&E->ev0)); CK(cudaEventCreate(&E->ev1));
-    for (auto& e : E->evp) CK(cudaEventCreate(&e));
+    CK(cudaEventCreateWithFlags(&E->evFlag, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&E->evFork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&E->evJoin, cudaEventDisableTiming));
+    for (auto& set : E->evr) for (auto& e : set) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&E->dCnt, sizeof(Counters))); CK(cudaMemset(E->dCnt, 0, sizeof(Counters)));
     CK(cudaMallocHost(&E->hCnt, sizeof(Counters))); memset(E->hCnt, 0, sizeof(Counters));
     *out = E;
@@ -898,7 +930,9 @@ int wdem_destroy(wdem_handle h) {
   h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
   h->dom.release(); delete h->comm; h->comm = nullptr;
   if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt);
-  if (h->ev0) cudaEventDestroy(h->ev0); if (h->ev1) cudaEventDestroy(h->ev1); for (auto& e : h->evp) if (e) cudaEventDestroy(e);
+  if (h->ev0) cudaEventDestroy(h->ev0); if (h->ev1) cudaEventDestroy(h->ev1); for (auto& set : h->evr) for (auto& e : set) if (e) cudaEventDestroy(e);
+  if (h->evFlag) cudaEventDestroy(h->evFlag); if (h->evFork) cudaEventDestroy(h->evFork); if (h->evJoin) cudaEventDestroy(h->evJoin);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return WDEM_OK;
@@ -1049,16 +1083,18 @@ int wdem_get_cell(wdem_handle h, double* hSize) { return guarded(h, [&] { for (i
 int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats) {
   return guarded(h, [&] {
     wdem_stats local; memset(&local, 0, sizeof(local));
-    float phase[5] = {0, 0, 0, 0, 0};
+    for (double& p : h->phaseAcc) p = 0.;
     long long l0 = h->launches;
     CK(cudaMemsetAsync(h->dCnt, 0, 4 * sizeof(unsigned long long), h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
-    for (int64_t s = 0; s < nsteps; s++) oneStep(h, &local, phase);
+    for (int64_t s = 0; s < nsteps; s++) oneStep(h, &local);
     CK(cudaEventRecord(h->ev1, h->stream));
     if (h->comm) h->comm->allreduceMaxInt(&h->dCnt->dirty, 2, h->stream);
     fetchCounters(h);
     CK(cudaEventSynchronize(h->ev1));
+    for (int k = 0; k < wdem_engine::NEVSET; k++) harvestPhases(h, k);
     checkDeviceError(h);
+    const double* phase = h->phaseAcc;
     float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     if (stats) {
       local.device_ms = ms; local.n_spheres = h->comm ? h->dom.nOwn : h->n; local.n_full_runs_total = h->nFullRuns; local.n_launches = h->launches - l0; local.step = h->step; local.dt = h->dt; local.time = h->time;

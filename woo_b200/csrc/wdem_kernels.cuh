@@ -74,7 +74,7 @@ __device__ __forceinline__ double signd(double f) { return f < 0 ? -1. : (f > 0 
 // Verlet-distance dirtiness test of AabbCollider::aabbIsDirty (src/dem/Collision.cpp:80-123).
 // Streaming kernel: one thread per sphere.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_leapfrog(Spheres S, int n, StepU u, Counters* cnt) {
+__global__ void __launch_bounds__(256, 4) k_leapfrog(Spheres S, int n, StepU u, Counters* cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t fl = S.flags[i];
@@ -387,11 +387,14 @@ __device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint3
 }
 
 template <int LAW>
-__global__ void __launch_bounds__(128, 4) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt) {
+__global__ void __launch_bounds__(128, 4) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
-  if (c < first + n) {
-    const uint32_t fl = C.flags[c]; const int2 pr = C.pair[c];
+  const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
+  uint32_t fl = CF_DEAD; int2 pr = make_int2(0, 0);
+  if (c < first + n) { fl = C.flags[c]; pr = C.pair[c]; }
+  if (stale) return;          // uniform over the grid
+  {
     if (!(fl & CF_DEAD)) { evald = 1; contact_ss<LAW>(C, c, fl, pr, S, mats, u, cnt, isReal); }
   }
   block_count(isReal, evald, cnt);
@@ -434,11 +437,14 @@ __device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint3
 }
 
 template <int LAW>
-__global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Material* mats, StepU u, Counters* cnt) {
+__global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
-  if (c < first + n) {
-    const uint32_t fl = C.flags[c]; const int2 pr = C.pair[c];
+  const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
+  uint32_t fl = CF_DEAD; int2 pr = make_int2(0, 0);
+  if (c < first + n) { fl = C.flags[c]; pr = C.pair[c]; }
+  if (stale) return;          // uniform over the grid
+  {
     if (!(fl & CF_DEAD)) { evald = 1; contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal); }
   }
   block_count(isReal, evald, cnt);
@@ -557,11 +563,14 @@ __device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint3
 }
 
 template <int LAW>
-__global__ void __launch_bounds__(128) k_contact_fs(Contacts C, long long first, long long n, Spheres S, const Facet* facets, const Material* mats, StepU u, Counters* cnt) {
+__global__ void __launch_bounds__(128) k_contact_fs(Contacts C, long long first, long long n, Spheres S, const Facet* facets, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
-  if (c < first + n) {
-    const uint32_t fl = C.flags[c]; const int2 pr = C.pair[c];
+  const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
+  uint32_t fl = CF_DEAD; int2 pr = make_int2(0, 0);
+  if (c < first + n) { fl = C.flags[c]; pr = C.pair[c]; }
+  if (stale) return;          // uniform over the grid
+  {
     if (!(fl & CF_DEAD)) { evald = 1; contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal); }
   }
   block_count(isReal, evald, cnt);
@@ -570,11 +579,14 @@ __global__ void __launch_bounds__(128) k_contact_fs(Contacts C, long long first,
 // Orphans: contacts that are real although their AABBs no longer overlap (the collider never removes a real contact,
 // InsertionSortCollider.cpp:78-113); rare, kept in a mixed-kind tail segment.
 template <int LAW>
-__global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Facet* facets, const Material* mats, StepU u, Counters* cnt) {
+__global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Facet* facets, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
-  if (c < first + n) {
-    const uint32_t fl = C.flags[c]; const int2 pr = C.pair[c];
+  const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
+  uint32_t fl = CF_DEAD; int2 pr = make_int2(0, 0);
+  if (c < first + n) { fl = C.flags[c]; pr = C.pair[c]; }
+  if (stale) return;          // uniform over the grid
+  {
     if (!(fl & CF_DEAD)) {
       evald = 1;
       const int kind = cf_kind(fl);
@@ -594,7 +606,9 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
 // One thread per sphere walks its row in order; the loads of RB entries (entry word, global force, contact point) are issued together before the
 // sequential adds, so a row costs ~3 dependent round trips per RB entries instead of 3 per entry.
 #define RB 4
-__global__ void __launch_bounds__(256) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u) {
+__global__ void __launch_bounds__(256) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u,
+                                               const int* __restrict__ guard) {
+  if (guard && *guard) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t fl = S.flags[i];
@@ -1203,13 +1217,33 @@ __device__ __forceinline__ void row_insertion_sort(int b, int e, uint32_t* __res
     rowOther[q + 1] = ko; rowEntry[q + 1] = ke;
   }
 }
+// short rows: all entries are loaded up front (independent loads), sorted in registers by an odd-even transposition network, written back
+template <int M>
+__device__ __forceinline__ void row_sort_regs(int b, int len, uint32_t* __restrict__ rowEntry, int32_t* __restrict__ rowOther) {
+  int32_t ko[M]; uint32_t ke[M];
+#pragma unroll
+  for (int k = 0; k < M; k++) { ko[k] = k < len ? rowOther[b + k] : 0x7fffffff; ke[k] = k < len ? rowEntry[b + k] : 0u; }
+#pragma unroll
+  for (int r = 0; r < M; r++) {
+#pragma unroll
+    for (int k = (r & 1); k + 1 < M; k += 2) {
+      const bool sw = ko[k] > ko[k + 1];
+      const int32_t a = sw ? ko[k + 1] : ko[k], c = sw ? ko[k] : ko[k + 1]; ko[k] = a; ko[k + 1] = c;
+      const uint32_t x = sw ? ke[k + 1] : ke[k], y = sw ? ke[k] : ke[k + 1]; ke[k] = x; ke[k + 1] = y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < M; k++) if (k < len) { rowOther[b + k] = ko[k]; rowEntry[b + k] = ke[k]; }
+}
 __global__ void __launch_bounds__(128) k_row_sort(int n, const int* __restrict__ rowStart, uint32_t* __restrict__ rowEntry, int32_t* __restrict__ rowOther, int* __restrict__ longRows,
                                                  int* __restrict__ nLong) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int b = rowStart[i], e = rowStart[i + 1];
-  if (e - b > ROW_SHORT) { longRows[atomicAdd(nLong, 1)] = i; return; }
-  row_insertion_sort(b, e, rowEntry, rowOther);
+  const int b = rowStart[i], len = rowStart[i + 1] - b;
+  if (len > ROW_SHORT) { longRows[atomicAdd(nLong, 1)] = i; return; }
+  if (len <= 1) return;
+  if (len <= 8) row_sort_regs<8>(b, len, rowEntry, rowOther);
+  else row_sort_regs<ROW_SHORT>(b, len, rowEntry, rowOther);
 }
 __global__ void __launch_bounds__(128) k_row_sort_long(const int* __restrict__ longRows, const int* __restrict__ nLong, const int* __restrict__ rowStart, uint32_t* __restrict__ rowEntry,
                                                       int32_t* __restrict__ rowOther) {
