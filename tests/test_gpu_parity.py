@@ -200,3 +200,33 @@ def test_decomposed_periodic_shear(world):
     compare_potential(O, E)
     S = sc.periodic_gas(300, cell=(.45, .45, .45), r=.02, psd_ratio=3.0, seed=17, gradV=[[-1.0, .5, 0], [0, -1.0, 0], [.3, 0, -1.0]], shear0=.3)
     compare(S, 100, check_every=25, label="decomposed periodic skew", make=cluster(world, axis=1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# end-to-end path (host buffers in, host buffers out): the chunk-pipelined wdem_step_e2e must give the resident path's bits
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [37, 3000])
+def test_step_e2e_pipelined_matches_resident_and_oracle(n, monkeypatch):
+    S = sc.random_gas(n, box=.3 if n < 100 else .9, r=.02, psd_ratio=2.0, seed=21)
+    O = Oracle(S); A = engine_for(S); B = engine_for(S)
+    A.step(30); B.step(30); O.step(30)                      # rebuilds have reordered the slots: upload order != slot order
+    s = B.spheres()
+    pos, vel, w = s["pos"].copy(), s["vel"].copy(), s["angVel"].copy()
+    po, vo = np.empty_like(pos), np.empty_like(vel)
+    for k in range(40):
+        ek, st = B.step_e2e(1, pos, vel, w, po, vo)
+        A.step(1); O.step(1)
+        sa = A.spheres()
+        assert np.array_equal(po, sa["pos"]) and np.array_equal(vo, sa["vel"]), f"e2e outputs differ from the resident path at step {k}"
+        assert abs(ek - A.kinetic_energy()) <= 1e-13 * abs(ek)    # block sums run over slots; a collider run inside the step reorders them
+        assert st.n_real == len(A.contacts(True)["ids"])
+        pos, po = po, pos; vel, vo = vo, vel
+        w = B.spheres()["angVel"].copy()                    # angVel is an input of the call only; read it back for the next one
+    so, sb = O.spheres(), B.spheres()
+    for k_ in ("pos", "vel", "angVel", "force", "torque"):
+        assert np.array_equal(so[k_], sb[k_]), k_
+    assert A.scalars() == B.scalars()
+    # the sequential fallback gives the same bits
+    monkeypatch.setenv("WDEM_E2E_SEQUENTIAL", "1")
+    ek2, _ = B.step_e2e(1, pos, vel, w, po, vo); A.step(1)
+    assert np.array_equal(po, A.spheres()["pos"]) and abs(ek2 - A.kinetic_energy()) <= 1e-13 * abs(ek2)

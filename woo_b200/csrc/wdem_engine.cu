@@ -169,7 +169,12 @@ struct wdem_engine {
   double dt = NAN, time = 0, nextDt = NAN, verletDist = NAN; long long step = 0, nFullRuns = 0; bool conDirty = true;
   long long dynStepLast = -1, dynStepPrev = -1;
   HostCell cell;
-  long long launches = 0;
+  long long launches = 0; int numSMs = 148;
+  // end-to-end pipeline (wdem_step_e2e): host<->device copies of the state overlap with the integrator chunk by chunk
+  static const int NCHUNK = 16; int nChunk = 8;   // NCHUNK = capacity, nChunk = pieces in use (WDEM_E2E_CHUNKS)
+  struct E2E { bool active = false; const double *pos = nullptr, *vel = nullptr, *angVel = nullptr; double *posOut = nullptr, *velOut = nullptr; } e2e;
+  cudaStream_t sH2D = nullptr, sD2H = nullptr; cudaEvent_t evUp[NCHUNK] = {}, evLf[NCHUNK] = {}, evEk = nullptr;
+  DBuf<double> ioIn, ioOut; double* hEk = nullptr; size_t hEkCap = 0; int ekBlocks = 0;
   Spheres S() { return sph[cur].view(); }
 };
 
@@ -768,8 +773,9 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   }
   // the big kernel goes last so that the small boundary kernels already occupy their share of the SMs
   if (E->nSS > 0) {
-    if (c.law == 0) k_contact_ss<0><<<nblk(E->nSS, 128), 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard);
-    else k_contact_ss<1><<<nblk(E->nSS, 128), 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard);
+    const int gridSS = std::min(nblk(E->nSS, 128), E->numSMs * WD_CONTACT_CTAS_PER_SM);   // persistent: one CTA per resident slot
+    if (c.law == 0) k_contact_ss<0><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard);
+    else k_contact_ss<1><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard);
     E->launches++;
   }
   if (side) { CK(cudaEventRecord(E->evJoin, st2)); CK(cudaStreamWaitEvent(st, E->evJoin, 0)); }
@@ -782,6 +788,44 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   if (ev) CK(cudaEventRecord(ev[4], st));
 }
 
+// Leapfrog of the end-to-end path: the host state arrives in NCHUNK pieces on a copy stream; each piece is integrated as soon as it has landed
+// (k_leapfrog_io, upload order) and its new pos/vel start their way back on a second copy stream while later pieces are still being uploaded
+// and, after the last piece, while the contact kernels run.  PCIe is full duplex, so the step costs about max(H2D, D2H) + contacts.
+void leapfrogPipelined(wdem_engine* E, const StepU& u) {
+  const long long n = E->n; cudaStream_t st = E->stream;
+  const wdem_engine::E2E& io = E->e2e;
+  double* in = E->ioIn.p; double* out = E->ioOut.p;
+  LeapIO lio{in, in + 3 * n, in + 6 * n, out, out + 3 * n};
+  const int NCH = E->nChunk;
+  const long long per = (n + NCH - 1) / NCH;
+  // the staging buffers are free: the previous call waited for its copies; order the copy streams behind whatever the main stream did before
+  CK(cudaEventRecord(E->evFork, st)); CK(cudaStreamWaitEvent(E->sH2D, E->evFork, 0));
+  for (int c = 0; c < NCH; c++) {
+    const long long first = c * per, cnt = std::min(per, n - first);
+    if (cnt <= 0) break;
+    CK(cudaMemcpyAsync(in + 3 * first, io.pos + 3 * first, cnt * 24, cudaMemcpyHostToDevice, E->sH2D));
+    CK(cudaMemcpyAsync(in + 3 * n + 3 * first, io.vel + 3 * first, cnt * 24, cudaMemcpyHostToDevice, E->sH2D));
+    CK(cudaMemcpyAsync(in + 6 * n + 3 * first, io.angVel + 3 * first, cnt * 24, cudaMemcpyHostToDevice, E->sH2D));
+    CK(cudaEventRecord(E->evUp[c], E->sH2D));
+  }
+  for (int c = 0; c < NCH; c++) {
+    const long long first = c * per, cnt = std::min(per, n - first);
+    if (cnt <= 0) break;
+    CK(cudaStreamWaitEvent(st, E->evUp[c], 0));
+    k_leapfrog_io<<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->up2slot.p, first, cnt, lio); E->launches++;
+    CK(cudaEventRecord(E->evLf[c], st));
+    CK(cudaStreamWaitEvent(E->sD2H, E->evLf[c], 0));
+    if (io.posOut) CK(cudaMemcpyAsync(io.posOut + 3 * first, out + 3 * first, cnt * 24, cudaMemcpyDeviceToHost, E->sD2H));
+    if (io.velOut) CK(cudaMemcpyAsync(io.velOut + 3 * first, out + 3 * n + 3 * first, cnt * 24, cudaMemcpyDeviceToHost, E->sD2H));
+  }
+  // kinetic energy of the new state (velocities are final after Leapfrog): block sums, summed by the host in a fixed order
+  const int nb = nblk(n, 256); E->blk.ensure((size_t)nb * 7, E->bytes); E->ekBlocks = nb;
+  if ((size_t)nb > E->hEkCap) { if (E->hEk) cudaFreeHost(E->hEk); CK(cudaMallocHost(&E->hEk, (size_t)nb * sizeof(double))); E->hEkCap = nb; }
+  k_ekin<<<nb, 256, 0, st>>>(E->S(), (int)n, u, E->blk.p); E->launches++;
+  CK(cudaEventRecord(E->evEk, st)); CK(cudaStreamWaitEvent(E->sD2H, E->evEk, 0));
+  CK(cudaMemcpyAsync(E->hEk, E->blk.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, E->sD2H));
+}
+
 void oneStep(wdem_engine* E, wdem_stats* stats) {
   const wdem_config& c = E->cfg;
   cudaStream_t st = E->stream;
@@ -792,7 +836,8 @@ void oneStep(wdem_engine* E, wdem_stats* stats) {
   cudaEvent_t* ev = nullptr;
   if (E->profiling) { const int set = (int)(E->step % wdem_engine::NEVSET); harvestPhases(E, set); ev = E->evr[set]; }
   if (ev) CK(cudaEventRecord(ev[0], st));
-  if (n > 0) { k_leapfrog<<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt); E->launches++; }
+  if (n > 0 && E->e2e.active) leapfrogPipelined(E, u);
+  else if (n > 0) { k_leapfrog<<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt); E->launches++; }
   if (ev) CK(cudaEventRecord(ev[1], st));
   // collider: full run if contacts are dirty / verletDist==0 / any sphere moved farther than verletDist (flag raised by k_leapfrog)
   bool full = E->conDirty || E->verletDist == 0;
@@ -906,10 +951,16 @@ int wdem_create(const wdem_config* cfg, wdem_handle* out) {
     CK(cudaSetDevice(cfg->device));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) throw CudaErr{std::string("device '") + prop.name + "' is not sm_100 (this library carries sm_100a code only)", WDEM_ERR_CUDA};
-    E = new wdem_engine(); E->cfg = *cfg; E->dt = cfg->dt;
+    E = new wdem_engine(); E->cfg = *cfg; E->dt = cfg->dt; E->numSMs = prop.multiProcessorCount;
+    if (const char* g = getenv("WDEM_E2E_CHUNKS")) E->nChunk = std::max(1, std::min((int)wdem_engine::NCHUNK, atoi(g)));
     if (const char* g = getenv("WDEM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob: 32/64/128
     CK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&E->stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&E->sH2D, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&E->sD2H, cudaStreamNonBlocking));
+    const unsigned evf = getenv("WDEM_E2E_TRACE") ? cudaEventDefault : cudaEventDisableTiming;
+    for (auto& e : E->evUp) CK(cudaEventCreateWithFlags(&e, evf));
+    for (auto& e : E->evLf) CK(cudaEventCreateWithFlags(&e, evf));
+    CK(cudaEventCreateWithFlags(&E->evEk, evf));
     CK(cudaEventCreate(&E->ev0)); CK(cudaEventCreate(&E->ev1));
     CK(cudaEventCreateWithFlags(&E->evFlag, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&E->evFork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&E->evJoin, cudaEventDisableTiming));
     for (auto& set : E->evr) for (auto& e : set) CK(cudaEventCreate(&e));
@@ -933,6 +984,9 @@ int wdem_destroy(wdem_handle h) {
   if (h->ev0) cudaEventDestroy(h->ev0); if (h->ev1) cudaEventDestroy(h->ev1); for (auto& set : h->evr) for (auto& e : set) if (e) cudaEventDestroy(e);
   if (h->evFlag) cudaEventDestroy(h->evFlag); if (h->evFork) cudaEventDestroy(h->evFork); if (h->evJoin) cudaEventDestroy(h->evJoin);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  for (cudaStream_t cs : {h->sH2D, h->sD2H}) if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
+  for (auto& e : h->evUp) if (e) cudaEventDestroy(e); for (auto& e : h->evLf) if (e) cudaEventDestroy(e); if (h->evEk) cudaEventDestroy(h->evEk);
+  h->ioIn.release(); h->ioOut.release(); if (h->hEk) cudaFreeHost(h->hEk);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return WDEM_OK;
@@ -1080,8 +1134,8 @@ int wdem_set_cell(wdem_handle h, const double* hSize, const double* gradV, const
 int wdem_set_next_gradv(wdem_handle h, const double* g) { return guarded(h, [&] { for (int i = 0; i < 9; i++) h->cell.nextGradV.m[i] = g[i]; }); }
 int wdem_get_cell(wdem_handle h, double* hSize) { return guarded(h, [&] { for (int i = 0; i < 9; i++) hSize[i] = h->cell.hSize.m[i]; }); }
 
-int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats) {
-  return guarded(h, [&] {
+static void stepN(wdem_handle h, int64_t nsteps, wdem_stats* stats, bool cheapStats) {
+  {
     wdem_stats local; memset(&local, 0, sizeof(local));
     for (double& p : h->phaseAcc) p = 0.;
     long long l0 = h->launches;
@@ -1099,12 +1153,17 @@ int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats) {
     if (stats) {
       local.device_ms = ms; local.n_spheres = h->comm ? h->dom.nOwn : h->n; local.n_full_runs_total = h->nFullRuns; local.n_launches = h->launches - l0; local.step = h->step; local.dt = h->dt; local.time = h->time;
       local.ms_integrate = phase[0]; local.ms_rebuild = phase[1]; local.ms_contact = phase[2]; local.ms_reduce = phase[3]; local.ms_dyndt = phase[4];
-      long long nr, na; countContacts(h, nr, na); local.n_contacts = na; local.n_real = nr;
+      // cheapStats (end-to-end path, one step per call): no extra counting kernel + sync; the step's own counters give the real contacts exactly
+      // and the table size stands in for the number of live candidates
+      long long nr, na;
+      if (cheapStats) { nr = (long long)h->hCnt->nReal; na = h->nC; } else countContacts(h, nr, na);
+      local.n_contacts = na; local.n_real = nr;
       local.sum_real = (int64_t)h->hCnt->nReal; local.sum_potential_evaluated = (int64_t)h->hCnt->nPotEval - (int64_t)h->hCnt->nReal; local.sum_contacts = (int64_t)h->hCnt->nPotEval;
       *stats = local;
     }
-  });
+  }
 }
+int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats) { return guarded(h, [&] { stepN(h, nsteps, stats, false); }); }
 
 int wdem_set_state(wdem_handle h, int64_t first, int64_t cnt, const double* pos, const double* vel, const double* angVel) {
   return guarded(h, [&] {
@@ -1152,6 +1211,26 @@ int wdem_kinetic_energy(wdem_handle h, double* ek) {
 
 int wdem_step_e2e(wdem_handle h, int64_t nsteps, const double* pos_in, const double* vel_in, const double* angVel_in, double* pos_out, double* vel_out, double* ek_out,
                   wdem_stats* stats) {
+  if (h && !h->comm && nsteps == 1 && h->n > 0 && pos_in && vel_in && angVel_in && !getenv("WDEM_E2E_SEQUENTIAL")) {
+    // pipelined: copies overlap with the integrator chunk by chunk (leapfrogPipelined); same results as the sequential path below
+    return guarded(h, [&] {
+      const size_t n = (size_t)h->n;
+      ensureUp2Slot(h);
+      h->ioIn.ensure(9 * n, h->bytes); h->ioOut.ensure(6 * n, h->bytes);
+      h->e2e.active = true; h->e2e.pos = pos_in; h->e2e.vel = vel_in; h->e2e.angVel = angVel_in; h->e2e.posOut = pos_out; h->e2e.velOut = vel_out;
+      try { stepN(h, 1, stats, true); } catch (...) { h->e2e.active = false; cudaStreamSynchronize(h->sH2D); cudaStreamSynchronize(h->sD2H); throw; }
+      h->e2e.active = false;
+      CK(cudaEventRecord(h->evEk, h->sD2H));
+      CK(cudaStreamSynchronize(h->sD2H));
+      if (getenv("WDEM_E2E_TRACE")) {   // device timeline of the call relative to its start (ms): upload / integrate per chunk, end of step, last byte on the host
+        float a, b; std::string ln = "e2e trace:";
+        for (int c = 0; c < h->nChunk; c++) { cudaEventElapsedTime(&a, h->ev0, h->evUp[c]); cudaEventElapsedTime(&b, h->ev0, h->evLf[c]); char t[64]; snprintf(t, sizeof(t), " [%.2f %.2f]", a, b); ln += t; }
+        cudaEventElapsedTime(&a, h->ev0, h->ev1); cudaEventElapsedTime(&b, h->ev0, h->evEk);
+        fprintf(stderr, "%s step_end %.2f d2h_end %.2f\n", ln.c_str(), a, b);
+      }
+      if (ek_out) { double e = 0; for (int b = 0; b < h->ekBlocks; b++) e += h->hEk[b]; *ek_out = e; }
+    });
+  }
   int rc = wdem_set_state(h, 0, h ? h->n : 0, pos_in, vel_in, angVel_in);
   if (rc) return rc;
   rc = wdem_step(h, nsteps, stats);

@@ -74,12 +74,18 @@ __device__ __forceinline__ double signd(double f) { return f < 0 ? -1. : (f > 0 
 // Verlet-distance dirtiness test of AabbCollider::aabbIsDirty (src/dem/Collision.cpp:80-123).
 // Streaming kernel: one thread per sphere.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4) k_leapfrog(Spheres S, int n, StepU u, Counters* cnt) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// host-state staging of the end-to-end path (wdem_step_e2e): pos/vel/angVel come from / go to buffers in upload order
+struct LeapIO { const double* pos; const double* vel; const double* angVel; double* posOut; double* velOut; };
+template <bool EXT>
+__device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const StepU& u, Counters* cnt, const LeapIO& io, long long ut) {
   const uint32_t fl = S.flags[i];
   if (fl & F_GHOST) return;   // integrated by its owner; refreshed by the halo exchange
   double4 pr = S.posr[i], vm = S.velm[i], ai = S.angi[i], qo = S.ori[i];
+  if (EXT) {
+    pr.x = io.pos[3 * ut]; pr.y = io.pos[3 * ut + 1]; pr.z = io.pos[3 * ut + 2];
+    vm.x = io.vel[3 * ut]; vm.y = io.vel[3 * ut + 1]; vm.z = io.vel[3 * ut + 2];
+    ai.x = io.angVel[3 * ut]; ai.y = io.angVel[3 * ut + 1]; ai.z = io.angVel[3 * ut + 2];
+  }
   d3 f = mk3(S.fx[i], S.fy[i], S.fz[i]);
   d3 t = mk3(S.tx[i], S.ty[i], S.tz[i]);
   d3 pos = xyz(pr), vel = xyz(vm), w = xyz(ai);
@@ -156,6 +162,22 @@ __global__ void __launch_bounds__(256, 4) k_leapfrog(Spheres S, int n, StepU u, 
   double d2 = fmax(0., sqn(dl));
   if (d2 > u.maxD2) cnt->dirty = 1;
   if (!(d2 == d2)) { cnt->dirty = 1; cnt->error = ERR_NAN_POS; cnt->errA = S.id[i]; }
+  if (EXT) {
+    io.posOut[3 * ut] = pos.x; io.posOut[3 * ut + 1] = pos.y; io.posOut[3 * ut + 2] = pos.z;
+    io.velOut[3 * ut] = vel.x; io.velOut[3 * ut + 1] = vel.y; io.velOut[3 * ut + 2] = vel.z;
+  }
+}
+__global__ void __launch_bounds__(256, 4) k_leapfrog(Spheres S, int n, StepU u, Counters* cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  leapfrog_body<false>(S, i, u, cnt, LeapIO{}, 0);
+}
+// the same integrator over a chunk [first, first+cnt) of the UPLOAD order: inputs are read from, and the new pos/vel written to, staging
+// buffers (coalesced), the rest of the state is gathered by slot.  Lets host<->device copies of other chunks overlap with the integration.
+__global__ void __launch_bounds__(256, 4) k_leapfrog_io(Spheres S, StepU u, Counters* cnt, const int* __restrict__ up2slot, long long first, long long cnt_, LeapIO io) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt_) return;
+  leapfrog_body<true>(S, up2slot[first + t], u, cnt, io, first + t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -386,16 +408,43 @@ __device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint3
   contact_tail<LAW>(C, c, fl, u, p1, xyz(va), xyz(wa), p2, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, r1, r2, mats, S.mat, mA, mB, cnt, ec, 0, H, isReal);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// L2 prefetch of everything contact_ss<LAW> will load for contact c (its table entry is already in registers)
 template <int LAW>
-__global__ void __launch_bounds__(128, 4) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
-  long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned isReal = 0, evald = 0;
+__device__ __forceinline__ void prefetch_contact_ss(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S) {
+  if (fl & CF_DEAD) return;
+  prefetch_l2(S.posr + pr.x); prefetch_l2(S.posr + pr.y);
+  if (!(fl & CF_REAL)) return;
+  prefetch_l2(S.velm + pr.x); prefetch_l2(S.velm + pr.y); prefetch_l2(S.angi + pr.x); prefetch_l2(S.angi + pr.y);
+  prefetch_l2(C.t0x + c); prefetch_l2(C.t0y + c); prefetch_l2(C.t0z + c); prefetch_l2(C.t1x + c); prefetch_l2(C.t1y + c); prefetch_l2(C.t1z + c);
+  prefetch_l2(C.cp + c); prefetch_l2(C.ft0 + c); prefetch_l2(C.ft1 + c);
+  prefetch_l2(C.ph[0] + c); prefetch_l2(C.ph[1] + c); prefetch_l2(C.ph[2] + c);
+  if (LAW == 1) { prefetch_l2(C.ph[3] + c); prefetch_l2(C.ph[4] + c); }
+}
+
+// Persistent software-pipelined grid (one CTA per resident slot, tiles of 128 candidates, stride gridDim): while tile k is computed, the table
+// entries (flags, pair) of tile k+2 are in flight into registers and the sphere/history lines of tile k+1 are being pulled into L2, so the
+// dependent chain flags+pair -> gathers -> math of a tile only ever waits for L2, not for HBM.  Real-first order (k_carry) + round-robin tiles
+// balance the long (real) and short (potential) tiles over the CTAs.
+#define WD_CONTACT_CTAS_PER_SM 4
+template <int LAW>
+__global__ void __launch_bounds__(128, WD_CONTACT_CTAS_PER_SM) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
   const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
-  uint32_t fl = CF_DEAD; int2 pr = make_int2(0, 0);
-  if (c < first + n) { fl = C.flags[c]; pr = C.pair[c]; }
+  const long long end = first + n, stride = (long long)gridDim.x * blockDim.x;
+  long long c0 = first + (long long)blockIdx.x * blockDim.x + threadIdx.x, c1 = c0 + stride;
+  uint32_t fl0 = CF_DEAD, fl1 = CF_DEAD; int2 pr0 = make_int2(0, 0), pr1 = pr0;
+  if (c0 < end) { fl0 = C.flags[c0]; pr0 = C.pair[c0]; }
+  if (c1 < end) { fl1 = C.flags[c1]; pr1 = C.pair[c1]; }
   if (stale) return;          // uniform over the grid
-  {
-    if (!(fl & CF_DEAD)) { evald = 1; contact_ss<LAW>(C, c, fl, pr, S, mats, u, cnt, isReal); }
+  unsigned isReal = 0, evald = 0;
+  // whole tiles: the loop condition is uniform over the CTA (tile base), lanes beyond the end carry CF_DEAD
+  for (long long base = first + (long long)blockIdx.x * blockDim.x; base < end; base += stride) {
+    const long long c2 = c1 + stride;
+    uint32_t fl2 = CF_DEAD; int2 pr2 = make_int2(0, 0);
+    if (c2 < end) { fl2 = C.flags[c2]; pr2 = C.pair[c2]; }
+    prefetch_contact_ss<LAW>(C, c1, fl1, pr1, S);
+    if (!(fl0 & CF_DEAD)) { evald++; unsigned r = 0; contact_ss<LAW>(C, c0, fl0, pr0, S, mats, u, cnt, r); isReal += r; }
+    c0 = c1; fl0 = fl1; pr0 = pr1; c1 = c2; fl1 = fl2; pr1 = pr2;
   }
   block_count(isReal, evald, cnt);
 }
