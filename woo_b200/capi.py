@@ -46,7 +46,7 @@ def load(build=True):
             _build.build()
         if not os.path.exists(_build.LIB):
             raise RuntimeError("libwdem.so is missing: build it with `python -m woo_b200.build` (no CPU fallback exists)")
-        L = C.CDLL(_build.LIB)
+        L = C.CDLL(os.environ.get("WDEM_LIB_VARIANT") or _build.LIB)   # WDEM_LIB_VARIANT: kernel-tuning experiments only
         L.wdem_last_error.restype = C.c_char_p
         L.wdem_last_error.argtypes = [C.c_void_p]
         L.wdem_num_contacts.restype = C.c_int64

@@ -426,7 +426,9 @@ __device__ __forceinline__ void prefetch_contact_ss(const Contacts& C, long long
 // entries (flags, pair) of tile k+2 are in flight into registers and the sphere/history lines of tile k+1 are being pulled into L2, so the
 // dependent chain flags+pair -> gathers -> math of a tile only ever waits for L2, not for HBM.  Real-first order (k_carry) + round-robin tiles
 // balance the long (real) and short (potential) tiles over the CTAs.
+#ifndef WD_CONTACT_CTAS_PER_SM
 #define WD_CONTACT_CTAS_PER_SM 4
+#endif
 template <int LAW>
 __global__ void __launch_bounds__(128, WD_CONTACT_CTAS_PER_SM) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
   const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
