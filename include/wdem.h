@@ -117,10 +117,22 @@ int wdem_set_state(wdem_handle h, int64_t first, int64_t n, const double* pos, c
 int64_t wdem_num_contacts(wdem_handle h, int realOnly);
 /* Contacts sorted by canonical key (id1,id2): boundary first, sphere-sphere lower id first. Returns the count (<0: error).
  * ids 2/contact, cellDist 3, real 1, uN 1, forceLocal 3, torqueLocal 3, trsf 9 (column-major), contPt 3, phys 3 (kn,kt,tanPhi),
- * stepCreated 1. */
+ * stepCreated 1, physRaw 5 (the stored constants, see wdem_upload_contacts). Any pointer may be NULL. */
 int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t* ids, int32_t* cellDist, int32_t* real, double* uN,
                                double* forceLocal, double* torqueLocal, double* trsf, double* contPt, double* phys,
-                               int32_t* stepCreated);
+                               int32_t* stepCreated, double* physRaw);
+/* Import the persistent state of existing REAL contacts (resume from a saved Scene, or keep the contact history when the particle set is
+ * re-uploaded): Contact{cellDist,stepCreated} (Contact.hpp:95-106), L6Geom{trsf,uN}+CGeom.node.pos (L6Geom.hpp:16-21, Contact.hpp:21),
+ * FrictPhys{force,torque,kn,kt,tanPhi} (Contact.hpp:32-33, FrictMat.hpp:33-35) / HertzPhys (Hertz.hpp:20-26).  Same layout and canonical order
+ * as wdem_download_contacts (boundary particle first; sphere-sphere: id1<id2); physRaw is 5 doubles per contact exactly as downloaded
+ * (linear law: kn,kt,tanPhi,0,0; Hertz: K*sqrt(R), kt0, tanPhi, alpha_sqrtMK, 4*pi*R*gamma).  Call after the particles are uploaded and before
+ * the first wdem_step; the rows are matched to the candidate pairs of the first collider run by (id1,id2) — a real contact whose boxes no
+ * longer overlap is kept, as the reference's collider never deletes a real contact (InsertionSortCollider.cpp:78-113).  cellDist, stepCreated and
+ * torqueLocal may be NULL. */
+int wdem_upload_contacts(wdem_handle h, int64_t n, const int32_t* ids, const int32_t* cellDist, const int32_t* stepCreated, const double* uN,
+                         const double* forceLocal, const double* torqueLocal, const double* trsf, const double* contPt, const double* physRaw);
+/* Scene.step / Scene.time (Scene.hpp:191-205) of a resumed scene: trsfRenorm and DynDt's period count scene steps. */
+int wdem_set_scene(wdem_handle h, int64_t step, double time);
 /* DemField::critDt -> DemFuncs::pWaveDt (Funcs.cpp:151-175). */
 int wdem_crit_dt(wdem_handle h, double* dt);
 /* Σ ½ m v² + ½ ω·I·ω  (DemData::getEk_any, Particle.cpp:247-265), device reduction. */

@@ -230,3 +230,66 @@ def test_step_e2e_pipelined_matches_resident_and_oracle(n, monkeypatch):
     monkeypatch.setenv("WDEM_E2E_SEQUENTIAL", "1")
     ek2, _ = B.step_e2e(1, pos, vel, w, po, vo); A.step(1)
     assert np.array_equal(po, A.spheres()["pos"]) and abs(ek2 - A.kinetic_energy()) <= 1e-13 * abs(ek2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# wdem_upload_contacts / wdem_set_scene: a run resumed from downloaded state + contact history continues bit for bit.
+# The candidate set of the resumed engine differs (its collider runs at other steps), which must not matter: real contacts, their history and the
+# per-particle summation order do not depend on it.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["gas-linear-rolling", "gas-hertz", "facets", "periodic"])
+def test_resume_from_uploaded_contacts(kind):
+    from woo_b200.engine import Engine
+    if kind == "gas-linear-rolling":
+        S = sc.random_gas(400, box=.5, r=.02, psd_ratio=3.0, seed=31); S.params.relRollStiff = .3; S.params.relTwistStiff = .2; S.params.rollTanPhi = .4
+    elif kind == "gas-hertz":
+        S = sc.random_gas(400, box=.5, r=.02, psd_ratio=2.0, seed=32, law=sc.LAW_HERTZ_DMT, en=.7)
+    elif kind == "facets":
+        S = sc.facet_box_scene(300, seed=33)
+    else:
+        S = sc.periodic_gas(300, seed=34, gradV=[[0, 1., 0], [0, 0, 0], [0, 0, 0]], shear0=.1)
+    S.params.dynDtPeriod = 0        # PeriodicEngine's own counters are not part of the exchanged state
+    O = Oracle(S); A = engine_for(S)
+    A.step(150); O.step(150)
+    s, c, sca = A.spheres(), A.contacts(True), A.scalars()
+    assert len(c["ids"]) > 10
+    B = Engine(S.params)
+    B.spec = S
+    B.upload_materials(S.mats)
+    m, I = S.mass_inertia()
+    B.upload_spheres(S.sphere_ids(), s["pos"], S.radius, m, I, S.mat, S.mask, S.flags, s["vel"], s["angVel"], ori=s["ori"])
+    B._chk(B.L.wdem_upload_forces(B.h, s["force"].ctypes.data_as(__import__("ctypes").c_void_p), s["torque"].ctypes.data_as(__import__("ctypes").c_void_p)))
+    B.upload_walls(S.wall_ids(), S.walls); B.upload_facets(S.facet_ids(), S.facets)
+    if S.cell is not None:
+        B.set_cell(A.cell_hsize(), S.cell.get("gradV"), S.cell.get("nextGradV"), S.cell.get("homoDeform", 4))
+    B.set_scene(sca["step"], sca["time"])
+    B.upload_contacts(c)
+    for k in range(4):
+        A.step(40); B.step(40); O.step(40)
+        sa, sb, so = A.spheres(), B.spheres(), O.spheres()
+        for k_ in ("pos", "vel", "angVel", "force", "torque"):
+            assert np.array_equal(sa[k_], sb[k_]), f"{kind}: {k_} of the resumed run differs after {40 * (k + 1)} steps"
+            assert np.array_equal(so[k_], sb[k_]), f"{kind}: {k_} differs from the oracle"
+        ca, cb = A.contacts(True), B.contacts(True)
+        assert [tuple(x) for x in ca["ids"]] == [tuple(x) for x in cb["ids"]]
+        for k_ in ("uN", "force", "torque", "trsf", "contPt", "physRaw", "stepCreated", "cellDist"):
+            assert np.array_equal(ca[k_], cb[k_]), f"{kind}: contact {k_} of the resumed run differs"
+    assert A.scalars()["step"] == B.scalars()["step"] and A.scalars()["time"] == B.scalars()["time"]
+
+
+def test_upload_contacts_rejects_bad_input():
+    from woo_b200.engine import Engine, WdemError
+    S = sc.random_gas(50, box=.3, r=.02, seed=35)
+    A = engine_for(S); A.step(30); c = A.contacts(True)
+    with pytest.raises(WdemError):
+        A.upload_contacts(c)                                   # after the first step
+    B = engine_for(S)
+    bad = {k: v.copy() for k, v in c.items()}
+    ss = np.nonzero(bad["ids"][:, 0] >= len(S.walls))[0] if S.boundaries_first else np.nonzero(bad["ids"][:, 0] < S.n)[0]
+    if len(ss):
+        bad["ids"][ss[0]] = bad["ids"][ss[0]][::-1]            # id1 > id2
+        with pytest.raises(WdemError):
+            B.upload_contacts(bad)
+    bad = {k: v.copy() for k, v in c.items()}; bad["ids"][0, 1] = 10 ** 6
+    with pytest.raises(WdemError):
+        B.upload_contacts(bad)

@@ -206,3 +206,35 @@ def test_host_edits_reach_the_device():
     assert S.dem.par[0].vel[2] == pytest.approx(vz - 2 * 10 * 1e-4) and S.dem.par[0].pos[2] > z
     # the new sphere saw zero force in its first Leapfrog, gravity from the second on
     assert S.dem.par[n].vel[2] == pytest.approx(-10 * 1e-4) and S.dem.par[n].pos[2] < 1
+
+
+@pytest.mark.gpu
+def test_contact_history_survives_adding_particles():
+    """ParticleContainer.add in mid-run re-uploads the particle set; the real contacts (L6Geom frame, shear force, stepCreated) must survive it like
+    the reference's ContactContainer does: the run with a bystander sphere added at step 150 equals the run that had it from the start."""
+    from woo_b200 import scenes as sc
+    Sp = sc.random_gas(250, box=.4, r=.02, psd_ratio=2.0, seed=43)
+
+    def build(with_bystander):
+        S = Scene(fields=[DemField(gravity=Sp.params.gravity)])
+        m = FrictMat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)
+        S.dem.par.add([woo.utils.sphere(Sp.pos[i], Sp.radius[i], mat=m, vel=Sp.vel[i]) for i in range(Sp.n)])
+        S.dem.par.add([Wall.make(w["pos"], axis=w["axis"], sense=w["sense"], mat=m) for w in Sp.walls])
+        if with_bystander:
+            S.dem.par.add(woo.utils.sphere((5., 5., 5.), .02, mat=m, fixed=True))
+        S.engines = woo.utils.gpuEngines(damping=.2, dynDtPeriod=0); S.dt = 2e-5
+        return S, m
+    A, _ = build(True); A.run(300, True)
+    B, m = build(False); B.run(150, True)
+    nreal = sum(1 for c in B.dem.con if c.real)
+    created = {(c.id1, c.id2): c.stepCreated for c in B.dem.con if c.real}
+    B.dem.par.add(woo.utils.sphere((5., 5., 5.), .02, mat=m, fixed=True))
+    B.run(150, True)
+    assert nreal > 20 and B.step == A.step == 300
+    for i in range(Sp.n):
+        assert tuple(A.dem.par[i].pos) == tuple(B.dem.par[i].pos) and tuple(A.dem.par[i].f) == tuple(B.dem.par[i].f), i
+    kept = [(c.id1, c.id2) for c in B.dem.con if c.real and (c.id1, c.id2) in created and c.stepCreated == created[(c.id1, c.id2)]]
+    assert len(kept) > 10
+    ca = {(c.id1, c.id2): tuple(c.phys.force) for c in A.dem.con if c.real}
+    cb = {(c.id1, c.id2): tuple(c.phys.force) for c in B.dem.con if c.real}
+    assert ca == cb

@@ -59,7 +59,7 @@ struct GRec {   // a ghost: what the contact functors read
   double4 posr, velm, angi; uint32_t flags, mask; int32_t mat, id;
 };
 struct CRec {   // history row of a real contact keyed by particle ids
-  int32_t idA, idB; uint32_t flags; int32_t stepCreated; int32_t cd[3]; int32_t pad;
+  int32_t idA, idB; uint32_t flags; int32_t stepCreated; int32_t cd[3]; int32_t pad; int32_t pairY, pad2;
   double t[6]; double4 cp; double fl[3]; double ph[5]; double tq[3]; double4 Fg;
 };
 
@@ -132,13 +132,15 @@ __global__ void __launch_bounds__(128) k_dom_pack_rows(const int* __restrict__ s
 }
 // received rows are appended behind the previous table (so that k_carry can index them) and keyed for the lookup
 __global__ void __launch_bounds__(256) k_dom_unpack_rows(Contacts O, long long base, int cnt, const CRec* __restrict__ in, int law, int rolling, int periodic,
-                                                        unsigned long long* keys, int* vals) {
+                                                        unsigned long long* keys, int* vals, int uploaded) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= cnt) return;
   const CRec r = in[k];
   const long long co = base + k;
-  O.pair[co] = make_int2(r.pad, -1);
-  O.flags[co] = (r.flags & (CF_KIND_MASK | CF_REAL)) | CF_CLAIMED;   // never an orphan candidate: the sender keeps or drops it by its own rules
+  // migrated rows are never orphan candidates (the sender keeps or drops them by its own rules); rows imported by wdem_upload_contacts carry the
+  // slots of their particles in the current generation and become orphans if no candidate claims them (real although the AABBs are apart)
+  O.pair[co] = uploaded ? make_int2(r.pad, r.pairY) : make_int2(r.pad, -1);
+  O.flags[co] = (r.flags & (CF_KIND_MASK | CF_REAL)) | (uploaded ? 0u : (uint32_t)CF_CLAIMED);
   O.stepCreated[co] = r.stepCreated;
   if (periodic) { O.cdx[co] = r.cd[0]; O.cdy[co] = r.cd[1]; O.cdz[co] = r.cd[2]; }
   O.t0x[co] = r.t[0]; O.t0y[co] = r.t[1]; O.t0z[co] = r.t[2]; O.t1x[co] = r.t[3]; O.t1y[co] = r.t[4]; O.t1z[co] = r.t[5];

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include "../../include/wdem.h"
+#include <unordered_map>
 #include "wdem_kernels.cuh"
 #include "wdem_domain.cuh"
 #include "wdem_comm.h"
@@ -158,6 +159,8 @@ struct wdem_engine {
   std::vector<Facet> hFacets; DBuf<Facet> dFacets; DBuf<int> fgCellStart, fgCellFacet; FacetGrid fgrid; bool fgridValid = false;
   double minRadius = INFINITY, pwaveDt = INFINITY;
   std::vector<double> hRadius; std::vector<int32_t> hMatOfSphere;
+  std::vector<int32_t> hIds;                // Particle.id of the spheres in upload order
+  std::vector<CRec> pendingRows;            // contact history imported by wdem_upload_contacts, consumed by the next collider full run
   // contacts
   ContactStore con[2]; int curC = 0; long long nSS = 0, nWS = 0, nFS = 0, nOrph = 0, nC = 0;
   CsrStore csr[2]; int curR = 0;
@@ -370,7 +373,7 @@ void domainExchange(wdem_engine* E) {
   if (nImmR > 0) {
     Ost.ensure((size_t)(E->nC + nImmR), tot, hertz, rolling, c.periodic, /*keep*/ true, st);
     M.immKeys.ensure(nImmR, tot); M.immKeysAlt.ensure(nImmR, tot); M.immVals.ensure(nImmR, tot); M.immValsAlt.ensure(nImmR, tot);
-    k_dom_unpack_rows<<<nblk(nImmR, 256), 256, 0, st>>>(Ost.view(), E->nC, (int)nImmR, as<CRec>(M.recvBuf, recvRowsBase), c.law, rolling, c.periodic, M.immKeys.p, M.immVals.p);
+    k_dom_unpack_rows<<<nblk(nImmR, 256), 256, 0, st>>>(Ost.view(), E->nC, (int)nImmR, as<CRec>(M.recvBuf, recvRowsBase), c.law, rolling, c.periodic, M.immKeys.p, M.immVals.p, 0);
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, M.immKeys.p, M.immKeysAlt.p, M.immVals.p, M.immValsAlt.p, (int)nImmR, 0, 64, st);
     E->cubTemp.ensure(tb, tot);
@@ -463,6 +466,23 @@ void rebuild(wdem_engine* E) {
   CsrStore& Ncsr = E->csr[1 - E->curR];
   OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = Ocsr.valid ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
   if (E->comm && E->dom.nImm > 0) { oc.immKeys = E->dom.immKeysAlt.p; oc.immVals = E->dom.immValsAlt.p; oc.nImm = E->dom.nImm; }
+  bool imported = false;
+  if (!E->pendingRows.empty()) {
+    // wdem_upload_contacts: append the imported history rows behind the previous table and key them by (idA,idB), like rows that migrate in
+    DomainState& M = E->dom; const size_t nR = E->pendingRows.size();
+    Ost.ensure((size_t)(E->nC + nR), tot, hertz, rolling, c.periodic, /*keep*/ true, st);
+    M.recvBuf.ensure(nR * sizeof(CRec) + 64, tot);
+    CK(cudaMemcpyAsync(M.recvBuf.p, E->pendingRows.data(), nR * sizeof(CRec), cudaMemcpyHostToDevice, st));
+    M.immKeys.ensure(nR, tot); M.immKeysAlt.ensure(nR, tot); M.immVals.ensure(nR, tot); M.immValsAlt.ensure(nR, tot);
+    k_dom_unpack_rows<<<nblk(nR, 256), 256, 0, st>>>(Ost.view(), E->nC, (int)nR, as<CRec>(M.recvBuf), c.law, rolling, c.periodic, M.immKeys.p, M.immVals.p, 1);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, M.immKeys.p, M.immKeysAlt.p, M.immVals.p, M.immValsAlt.p, (int)nR, 0, 64, st);
+    E->cubTemp.ensure(tb, tot);
+    cub::DeviceRadixSort::SortPairs(E->cubTemp.p, tb, M.immKeys.p, M.immKeysAlt.p, M.immVals.p, M.immValsAlt.p, (int)nR, 0, 64, st);
+    CK(cudaStreamSynchronize(st));   // pendingRows is pageable host memory
+    oc.immKeys = M.immKeysAlt.p; oc.immVals = M.immValsAlt.p; oc.nImm = (int)nR; oc.immAll = 1;
+    E->nC += (long long)nR; E->pendingRows.clear(); E->pendingRows.shrink_to_fit(); imported = true; E->launches += 4;
+  }
   const int* perm = nullptr;
   HGrid g; memset(&g, 0, sizeof(g));
   PeriU pu; memset(&pu, 0, sizeof(pu));
@@ -613,7 +633,7 @@ void rebuild(wdem_engine* E) {
     }
     // 6b. orphans: real contacts of the previous table that no candidate claimed (AABBs separated while real)
     long long nOrph = 0;
-    if (oc.valid && E->nC > 0) {
+    if ((oc.valid || imported) && E->nC > 0) {
       E->orphCnt.ensure(1, tot);
       CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
       const int32_t* oldSid = E->comm ? E->dom.oldIds.p : E->sph[1 - E->cur].id.p;
@@ -1045,6 +1065,7 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
       pw = std::min(pw, radius[i] / (1. * std::sqrt(m.young / m.density)));  // DemFuncs::pWaveDt (Funcs.cpp:151-175)
     }
     h->n = (int)n; h->minRadius = minR; h->pwaveDt = pw; h->maxId = maxId;
+    h->hIds.assign(id.begin(), id.end()); h->pendingRows.clear();
     h->cur = 0;
     SphereStore& s = h->sph[0];
     s.ensure(std::max<int64_t>(n, 1), h->bytes);
@@ -1249,7 +1270,7 @@ int64_t wdem_num_contacts(wdem_handle h, int realOnly) {
 }
 
 int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t* ids, int32_t* cellDist, int32_t* real, double* uN, double* forceLocal, double* torqueLocal,
-                               double* trsf, double* contPt, double* phys, int32_t* stepCreated) {
+                               double* trsf, double* contPt, double* phys, int32_t* stepCreated, double* physRaw) {
   int64_t nOut = 0;
   int rc = guarded(h, [&] {
     const long long nC = h->nC; if (nC == 0) return;
@@ -1299,9 +1320,51 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
         else { double u_ = cp[c].w; phys[3 * i] = (3 / 2.) * ph[0][c] * std::sqrt(-u_); phys[3 * i + 1] = ph[1][c] * std::sqrt(u_ < 0 ? -u_ : 0); phys[3 * i + 2] = ph[2][c]; }
       }
       if (stepCreated) stepCreated[i] = sc[c];
+      if (physRaw) for (int k = 0; k < 5; k++) physRaw[5 * i + k] = (isReal && k < (hertz ? 5 : 3)) ? ph[k][c] : 0.;
     }
   });
   return rc ? -1 : nOut;
+}
+
+int wdem_upload_contacts(wdem_handle h, int64_t n, const int32_t* ids, const int32_t* cellDist, const int32_t* stepCreated, const double* uN, const double* forceLocal,
+                         const double* torqueLocal, const double* trsf, const double* contPt, const double* physRaw) {
+  return guarded(h, [&] {
+    if (n < 0 || (n > 0 && (!ids || !uN || !forceLocal || !trsf || !contPt || !physRaw))) throw EngErr{"wdem_upload_contacts: bad arguments", WDEM_ERR_INVALID};
+    if (h->comm) throw EngErr{"wdem_upload_contacts: not available in decomposed runs", WDEM_ERR_UNSUPPORTED};
+    if (!h->conDirty || h->cur != 0 || h->nC != 0) throw EngErr{"wdem_upload_contacts: call after wdem_upload_spheres/walls/facets and before the first step", WDEM_ERR_INVALID};
+    const bool hertz = h->cfg.law == WDEM_LAW_HERTZ_DMT, rolling = (h->cfg.relRollStiff > 0. && h->cfg.rollTanPhi > 0.);
+    std::unordered_map<int32_t, int> sph, wal, fac;
+    for (size_t i = 0; i < h->hIds.size(); i++) sph[h->hIds[i]] = (int)i;
+    for (size_t i = 0; i < h->hWalls.size(); i++) wal[h->hWalls[i].id] = (int)i;
+    for (size_t i = 0; i < h->hFacets.size(); i++) fac[h->hFacets[i].id] = (int)i;
+    std::vector<CRec> rows((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+      CRec r; memset(&r, 0, sizeof(r));
+      const int32_t a = ids[2 * i], b = ids[2 * i + 1];
+      auto sb = sph.find(b);
+      if (sb == sph.end()) throw EngErr{"wdem_upload_contacts: contact ##" + std::to_string(a) + "+" + std::to_string(b) + ": id2 must be a sphere (canonical order: boundary first, lower sphere id first)", WDEM_ERR_INVALID};
+      int kind, ia;
+      auto sa = sph.find(a);
+      if (sa != sph.end()) { if (!(a < b)) throw EngErr{"wdem_upload_contacts: sphere-sphere contacts must have id1<id2 (##" + std::to_string(a) + "+" + std::to_string(b) + ")", WDEM_ERR_INVALID}; kind = KIND_SS; ia = sa->second; }
+      else if (wal.count(a)) { kind = KIND_WS; ia = wal[a]; }
+      else if (fac.count(a)) { kind = KIND_FS; ia = fac[a]; }
+      else throw EngErr{"wdem_upload_contacts: unknown particle id " + std::to_string(a), WDEM_ERR_INVALID};
+      r.idA = a; r.idB = b; r.flags = CF_REAL | ((uint32_t)kind << CF_KIND_SHIFT); r.stepCreated = stepCreated ? stepCreated[i] : 0;
+      for (int k = 0; k < 3; k++) r.cd[k] = cellDist ? cellDist[3 * i + k] : 0;
+      r.pad = ia; r.pairY = sb->second;
+      for (int k = 0; k < 6; k++) r.t[k] = trsf[9 * i + k];                       // columns 0 and 1 (column-major on the wire); column 2 = c0 x c1
+      r.cp = make_double4(contPt[3 * i], contPt[3 * i + 1], contPt[3 * i + 2], uN[i]);
+      for (int k = 0; k < 3; k++) { r.fl[k] = forceLocal[3 * i + k]; r.tq[k] = (torqueLocal && rolling) ? torqueLocal[3 * i + k] : 0.; }
+      for (int k = 0; k < (hertz ? 5 : 3); k++) r.ph[k] = physRaw[5 * i + k];
+      r.Fg = make_double4(0, 0, 0, 0);                                            // rewritten by the contact kernel before anybody reads it
+      rows[(size_t)i] = r;
+    }
+    h->pendingRows.swap(rows);
+  });
+}
+
+int wdem_set_scene(wdem_handle h, int64_t step, double time) {
+  return guarded(h, [&] { if (step < 0) throw EngErr{"wdem_set_scene: negative step", WDEM_ERR_INVALID}; h->step = step; h->time = time; h->dynStepLast = h->dynStepPrev = -1; });
 }
 
 int wdem_crit_dt(wdem_handle h, double* dt) { return guarded(h, [&] { *dt = h->pwaveDt; }); }

@@ -856,6 +856,7 @@ struct OldCsr {  // incidence rows of the previous contact table (for history ca
   const int* rowStart; const uint32_t* rowEntry; const int32_t* rowOther; int valid;
   // history rows that arrived with spheres migrating in from another subdomain (sorted by key (idA<<32|idB)); see wdem_domain.cuh
   const unsigned long long* immKeys; const int* immVals; int nImm;
+  int immAll;   // rows imported by wdem_upload_contacts: consult them for every pair, not only for spheres that just arrived
 };
 
 __device__ __forceinline__ void copy_history(const Contacts& N, long long cn, const Contacts& O, long long co, int law, int rolling, int periodic) {
@@ -884,7 +885,7 @@ __device__ __forceinline__ long long find_old(const OldCsr& oc, int oslot, int o
 // same, falling back to the rows that migrated in when one of the two spheres arrived in this full run
 __device__ __forceinline__ long long find_old2(const OldCsr& oc, int oslot, int otherId, uint32_t arrivedBits, int idA, int idB) {
   long long co = find_old(oc, oslot, otherId);
-  if (co < 0 && oc.nImm > 0 && (arrivedBits & F_ARRIVED)) {
+  if (co < 0 && oc.nImm > 0 && (oc.immAll || (arrivedBits & F_ARRIVED))) {
     const unsigned long long key = ((unsigned long long)(uint32_t)idA << 32) | (uint32_t)idB;
     int lo = 0, hi = oc.nImm - 1;
     while (lo <= hi) { const int mid = (lo + hi) >> 1; const unsigned long long k = oc.immKeys[mid]; if (k == key) return oc.immVals[mid]; if (k < key) lo = mid + 1; else hi = mid - 1; }

@@ -64,7 +64,7 @@ struct Particle { int id = -1; unsigned mask = 1; shared_ptr<Shape> shape; share
 // ---- contacts (dem/Contact.hpp:21-106, dem/L6Geom.hpp:16-21, dem/FrictMat.hpp:33-35)
 struct CGeomNode { V3 pos; };
 struct L6Geom { double uN = NaN; M3 trsf; CGeomNode node; };
-struct FrictPhys { V3 force, torque; double kn = NaN, kt = NaN, tanPhi = NaN; };
+struct FrictPhys { V3 force, torque; double kn = NaN, kt = NaN, tanPhi = NaN; double raw[5] = {0, 0, 0, 0, 0}; /* the constants as the device stores them (wdem.h: physRaw) */ };
 struct Contact { int id1 = -1, id2 = -1; V3i cellDist{{0, 0, 0}}; int stepCreated = -1; shared_ptr<L6Geom> geom; shared_ptr<FrictPhys> phys; bool isReal() const { return geom && phys; } };
 
 struct GpuDemLoop;
@@ -78,7 +78,7 @@ struct DemField {
   // coherence with the device copy (SURVEY §7 "Host<->device coherence"): upload once, download lazily
   GpuDemLoop* owner = nullptr; bool topoDirty = true, stateDirty = false, deviceNewer = false, contactsStale = true;
   DemField() { par.dem = this; con.dem = this; }
-  void pull(); void pullContacts();
+  void pull(); void pullContacts(); void pushContacts(wdem_handle h);
   void touchState() { stateDirty = true; }
 };
 
@@ -181,8 +181,11 @@ struct GpuDemLoop : Engine {
     DemField& F = *field;
     if (F.owner && F.owner != this) throw std::runtime_error("GpuDemLoop: the DemField is already attached to another GpuDemLoop");
     if (h && F.owner == this && F.deviceNewer) F.pull();   // a re-upload (particles added, masses changed, ...) starts from the latest device state
+    // ... and keeps the contact history: the reference's containers survive ParticleContainer::add/remove (ParticleContainer.cpp:23-73,121-157),
+    // so the real contacts are read back and imported again behind the new particle set (contacts of removed particles are dropped)
+    if (h && F.owner == this) F.pullContacts();
     wdem_config c = makeConfig();
-    if (h && c.law != cfg.law) { wdem_destroy(h); h = nullptr; }
+    if (h && c.law != cfg.law) { wdem_destroy(h); h = nullptr; F.con.v.clear(); F.con.ix.clear(); }   // another law: the stored phys constants mean nothing to it
     if (!h) { int rc = wdem_create(&c, &h); if (rc != WDEM_OK) { h = nullptr; throw std::runtime_error(string("GpuDemLoop: ") + wdem_last_error(nullptr)); } }
     else chk(h, wdem_set_config(h, &c));
     cfg = c; haveCfg = true;
@@ -229,6 +232,8 @@ struct GpuDemLoop : Engine {
     chk(h, wdem_upload_walls(h, (int)wid.size(), wid.data(), wpos.data(), waxis.data(), wsense.data(), wvel.data(), wmask.data(), wmat.data()));
     chk(h, wdem_upload_facets(h, (int)fid.size(), fid.data(), fv.data(), fvv.data(), ffk.data(), fht.data(), fnl.data(), fmask.data(), fmat.data()));
     if (scene->periodic) { Cell& C = *scene->cell; chk(h, wdem_set_cell(h, C.hSize.data(), C.gradV.data(), C.nextGradV.data(), C.homoDeform)); C.dirty = false; }
+    chk(h, wdem_set_scene(h, (int64_t)scene->step, scene->time));
+    F.pushContacts(h);
     nSpheres = (long)sid.size();
     F.owner = this; F.topoDirty = false; F.stateDirty = false; F.deviceNewer = false; F.contactsStale = true;
   }
@@ -281,10 +286,10 @@ void DemField::pull() {
 void DemField::pullContacts() {
   if (!contactsStale || !owner || !owner->h) return;
   wdem_handle h = owner->h;
-  int64_t n = wdem_download_contacts(h, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  int64_t n = wdem_download_contacts(h, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   if (n < 0) chk(h, 1);
-  vector<int32_t> ids(2 * n), cd(3 * n), real(n), sc(n); vector<double> uN(n), f(3 * n), t(3 * n), trsf(9 * n), cp(3 * n), ph(3 * n);
-  if (n) { int64_t m = wdem_download_contacts(h, 0, n, ids.data(), cd.data(), real.data(), uN.data(), f.data(), t.data(), trsf.data(), cp.data(), ph.data(), sc.data()); if (m < 0) chk(h, 1); }
+  vector<int32_t> ids(2 * n), cd(3 * n), real(n), sc(n); vector<double> uN(n), f(3 * n), t(3 * n), trsf(9 * n), cp(3 * n), ph(3 * n), raw(5 * n);
+  if (n) { int64_t m = wdem_download_contacts(h, 0, n, ids.data(), cd.data(), real.data(), uN.data(), f.data(), t.data(), trsf.data(), cp.data(), ph.data(), sc.data(), raw.data()); if (m < 0) chk(h, 1); }
   con.v.clear(); con.ix.clear();
   for (int64_t i = 0; i < n; i++) {
     auto C = make_shared<Contact>(); C->id1 = ids[2 * i]; C->id2 = ids[2 * i + 1]; C->stepCreated = sc[i];
@@ -294,10 +299,27 @@ void DemField::pullContacts() {
       for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C->geom->trsf[3 * r + c] = trsf[9 * i + 3 * c + r];   // column-major on the wire
       for (int k = 0; k < 3; k++) { C->geom->node.pos[k] = cp[3 * i + k]; C->phys->force[k] = f[3 * i + k]; C->phys->torque[k] = t[3 * i + k]; }
       C->phys->kn = ph[3 * i]; C->phys->kt = ph[3 * i + 1]; C->phys->tanPhi = ph[3 * i + 2];
+      for (int k = 0; k < 5; k++) C->phys->raw[k] = raw[5 * i + k];
     }
     con.ix[{std::min(C->id1, C->id2), std::max(C->id1, C->id2)}] = con.v.size(); con.v.push_back(C);
   }
   contactsStale = false;
+}
+
+// real contacts of the host container -> device (after a re-upload of the particle set); contacts whose particles no longer exist are dropped,
+// as ParticleContainer::remove deletes the contacts of a removed particle (ParticleContainer.cpp:121-157)
+void DemField::pushContacts(wdem_handle h) {
+  vector<int32_t> ids, cd, sc; vector<double> uN, f, t, trsf, cp, raw;
+  auto alive = [&](int id) { return id >= 0 && (size_t)id < par.v.size() && par.v[id]; };
+  for (auto& C : con.v) {
+    if (!C || !C->isReal() || !alive(C->id1) || !alive(C->id2)) continue;
+    ids.push_back(C->id1); ids.push_back(C->id2); sc.push_back(C->stepCreated); uN.push_back(C->geom->uN);
+    for (int k = 0; k < 3; k++) { cd.push_back(C->cellDist[k]); f.push_back(C->phys->force[k]); t.push_back(C->phys->torque[k]); cp.push_back(C->geom->node.pos[k]); }
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) trsf.push_back(C->geom->trsf[3 * r + c]);   // column-major on the wire
+    for (int k = 0; k < 5; k++) raw.push_back(C->phys->raw[k]);
+  }
+  if (!sc.empty()) chk(h, wdem_upload_contacts(h, (int64_t)sc.size(), ids.data(), cd.data(), sc.data(), uN.data(), f.data(), t.data(), trsf.data(), cp.data(), raw.data()));
+  contactsStale = true;
 }
 
 // Scene::doOneStep (Scene.cpp:366-432) for an engine list whose DEM group is a GpuDemLoop; other entries may be Python callables f(scene)

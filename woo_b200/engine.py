@@ -148,19 +148,30 @@ class Engine:
         return n
 
     def contacts(self, real_only=False):
-        n = self.L.wdem_download_contacts(self.h, C.c_int(int(real_only)), C.c_int64(0), *([None] * 10))
+        n = self.L.wdem_download_contacts(self.h, C.c_int(int(real_only)), C.c_int64(0), *([None] * 11))
         if n < 0:
             self._chk(1)
         o = dict(ids=np.zeros((n, 2), np.int32), cellDist=np.zeros((n, 3), np.int32), real=np.zeros(n, np.int32), uN=np.zeros(n),
                  force=np.zeros((n, 3)), torque=np.zeros((n, 3)), trsf=np.zeros((n, 9)), contPt=np.zeros((n, 3)), phys=np.zeros((n, 3)),
-                 stepCreated=np.zeros(n, np.int32))
+                 stepCreated=np.zeros(n, np.int32), physRaw=np.zeros((n, 5)))
         if n:
             m = self.L.wdem_download_contacts(self.h, C.c_int(int(real_only)), C.c_int64(n), ptr(o["ids"]), ptr(o["cellDist"]), ptr(o["real"]),
                                               ptr(o["uN"]), ptr(o["force"]), ptr(o["torque"]), ptr(o["trsf"]), ptr(o["contPt"]), ptr(o["phys"]),
-                                              ptr(o["stepCreated"]))
+                                              ptr(o["stepCreated"]), ptr(o["physRaw"]))
             if m < 0:
                 self._chk(1)
         return o
+
+    def upload_contacts(self, c):
+        """Import the history of real contacts as returned by contacts(True) (resume / re-upload); before the first step."""
+        m = np.asarray(c["real"]).astype(bool) if "real" in c else np.ones(len(c["ids"]), bool)
+        g = lambda k, dt: np.ascontiguousarray(np.asarray(c[k])[m], dtype=dt)
+        ids, cd, sc = g("ids", np.int32), g("cellDist", np.int32), g("stepCreated", np.int32)
+        uN, f, t, tr, cp, ph = (g(k, np.float64) for k in ("uN", "force", "torque", "trsf", "contPt", "physRaw"))
+        self._chk(self.L.wdem_upload_contacts(self.h, C.c_int64(len(ids)), ptr(ids), ptr(cd), ptr(sc), ptr(uN), ptr(f), ptr(t), ptr(tr), ptr(cp), ptr(ph)))
+
+    def set_scene(self, step, time):
+        self._chk(self.L.wdem_set_scene(self.h, C.c_int64(int(step)), C.c_double(float(time))))
 
     def kinetic_energy(self):
         e = C.c_double()
