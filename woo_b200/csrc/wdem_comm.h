@@ -21,6 +21,7 @@ struct Transport {
   int rank = 0, world = 1;
   virtual ~Transport() {}
   virtual void abort() {}   // wake subdomains blocked in a collective after a local failure (in-process transport only)
+  virtual bool multiProcess() const { return false; }   // one process per GPU: device buffers of the peers can be mapped with CUDA IPC
   // in-place max over ranks of n ints in device memory, ordered on the stream
   virtual void allreduceMaxInt(int* dptr, int n, cudaStream_t st) = 0;
   // every rank contributes n host int64 and receives world*n (rank-major); blocks the host
@@ -53,6 +54,7 @@ struct NcclTransport : Transport {
     if (dStage) cudaFree(dStage);
     if (hStage) cudaFreeHost(hStage);
   }
+  bool multiProcess() const override { return true; }
   void allreduceMaxInt(int* dptr, int n, cudaStream_t st) override { WD_NCCL(ncclAllReduce(dptr, dptr, n, ncclInt32, ncclMax, comm, st)); }
   void allgather64(const int64_t* mine, int n, int64_t* all, cudaStream_t st) override {
     const size_t need = (size_t)n * (world + 1);

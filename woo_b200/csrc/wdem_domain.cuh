@@ -235,6 +235,67 @@ __global__ void __launch_bounds__(256) k_halo_unpack(Spheres S, const int* __res
   S.posr[i] = p; S.velm[i] = v; S.angi[i] = w;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// Per-step exchange over NVLink peer memory (one process per GPU; mailboxes mapped with CUDA IPC): instead of ncclAllReduce + ncclSend/ncclRecv
+// every owner stores the pos/vel/angVel of its exported spheres straight into the neighbours' halo buffers and then publishes ONE 64-bit word
+// per peer, (step stamp | device error | Verlet-dirty), with release semantics at system scope; the receiver spins on the words of all ranks
+// (acquire), which gives it the global dirty/error maximum and the guarantee that the halo payload written before the word has landed.
+// Buffers and words are double-buffered by step parity: a rank can run at most one step ahead of a peer (it needs the peer's word of step k to
+// finish step k), so the slot of step k+2 is never written before the peer has consumed step k.
+// ------------------------------------------------------------------------------------------------------------------------------------
+struct PeerU {
+  int rank, world;
+  unsigned long long* words[WDEM_MAX_RANKS];   // peer r's word array [2][WDEM_MAX_RANKS] (mine included)
+  double* halo[WDEM_MAX_RANKS];                // peer r's halo buffers: 2 x haloCap doubles
+  long long haloCap;                           // doubles per parity buffer
+  int sendBase[WDEM_MAX_RANKS + 1];            // my export list: entries [sendBase[r], sendBase[r+1]) go to rank r
+  long long dstOff[WDEM_MAX_RANKS];            // where my segment starts in rank r's halo buffer (in spheres)
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+
+__global__ void __launch_bounds__(256) k_halo_push(Spheres S, const int* __restrict__ slots, int n, PeerU P, int parity) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int r = 0;
+  while (k >= P.sendBase[r + 1]) r++;
+  const int i = slots[k];
+  const double4 p = S.posr[i], v = S.velm[i], w = S.angi[i];
+  double* o = P.halo[r] + (long long)parity * P.haloCap + 9ll * (P.dstOff[r] + (k - P.sendBase[r]));
+  o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = v.x; o[4] = v.y; o[5] = v.z; o[6] = w.x; o[7] = w.y; o[8] = w.z;
+}
+// one CTA, one thread per rank: publish my word to every peer (after the halo payload: previous kernel on the stream + system fence), then wait for
+// theirs.  cnt->dirty / cnt->error become the maxima over all ranks.  A peer that never answers (it failed on the host) ends the wait after
+// `timeoutCycles` with ERR_PEER_TIMEOUT instead of hanging the GPU.
+__global__ void k_peer_sync(PeerU P, Counters* cnt, unsigned long long stamp, int parity, long long timeoutCycles) {
+  __shared__ int sDirty[WDEM_MAX_RANKS], sErr[WDEM_MAX_RANKS];
+  const int r = threadIdx.x;
+  const unsigned long long mine = (stamp << 16) | ((unsigned long long)(cnt->error & 0x7fff) << 1) | (unsigned long long)(cnt->dirty ? 1 : 0);
+  int d = 0, e = 0;
+  if (r < P.world) {
+    __threadfence_system();
+    st_release_sys(P.words[r] + parity * WDEM_MAX_RANKS + P.rank, mine);
+    const unsigned long long* w = P.words[P.rank] + parity * WDEM_MAX_RANKS + r;
+    const long long t0 = clock64();
+    unsigned long long v = ld_acquire_sys(w);
+    while ((v >> 16) != stamp) {
+      if (clock64() - t0 > timeoutCycles) { v = (stamp << 16) | ((unsigned long long)ERR_PEER_TIMEOUT << 1) | 1ull; break; }
+      __nanosleep(100);
+      v = ld_acquire_sys(w);
+    }
+    d = (int)(v & 1ull); e = (int)((v >> 1) & 0x7fff);
+  }
+  sDirty[r] = d; sErr[r] = e;
+  __syncthreads();
+  if (r == 0) {
+    int dm = 0, em = 0;
+    for (int q = 0; q < P.world; q++) { dm = max(dm, sDirty[q]); em = max(em, sErr[q]); }
+    cnt->dirty = dm;
+    if (em && !cnt->error) { cnt->error = em; cnt->errA = -1; cnt->errB = -1; }
+    __threadfence();
+  }
+}
+
 // contacts counted once over all ranks: by the owner of the sphere that is pA (sphere-sphere) / of the sphere (boundary contacts)
 __global__ void __launch_bounds__(256) k_count_contacts_owned(Contacts C, long long n, const uint32_t* __restrict__ sflags, unsigned long long* out) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -134,6 +134,8 @@ struct DomainState {
   DBuf<uint32_t> dkeys, dkeysAlt, emask; DBuf<int> dslots, dslotsAlt, dstart, origSlot, perm2, rowCnt, rowOff, perRank, flag, off;
   DBuf<char> sendBuf, recvBuf; DBuf<unsigned long long> immKeys, immKeysAlt; DBuf<int> immVals, immValsAlt; int nImm = 0;
   long long migratedOut = 0, migratedIn = 0, rowsIn = 0;
+  // per-step exchange over peer memory (k_halo_push / k_peer_sync): my mailbox (words + 2 halo buffers), the peers' mailboxes mapped with CUDA IPC
+  struct Peer { bool active = false, disabled = false; char* box = nullptr; long long haloCap = 0; void* base[WDEM_MAX_RANKS] = {}; std::vector<long long> dstOff; long long maxRecvTot = 0; } peer;
   void release() {
     sendSlot.release(); recvSlot.release(); exportId.release(); importId.release(); oldIds.release(); haloSend.release(); haloRecv.release(); dkeys.release(); dkeysAlt.release();
     emask.release(); dslots.release(); dslotsAlt.release(); dstart.release(); origSlot.release(); perm2.release(); rowCnt.release(); rowOff.release(); perRank.release();
@@ -233,6 +235,7 @@ void checkDeviceError(wdem_engine* E) {
     case ERR_NAN_POS: throw EngErr{"NaN position of particle #" + std::to_string(h.errA), WDEM_ERR_RUNTIME};
     case ERR_NO_PHYS: throw EngErr{"ContactLoop: " + pr + ": no Contact.phys created (Cp2_HertzMat_HertzPhys needs HertzMat on both particles; ContactLoop.cpp:181)", WDEM_ERR_RUNTIME};
     case ERR_SCHWARZ: throw EngErr{"Law2_L6Geom_HertzPhys_DMT: Schwarz model (alpha!=0 and gamma!=0) is out of scope " + pr, WDEM_ERR_UNSUPPORTED};
+    case ERR_PEER_TIMEOUT: throw EngErr{"slab decomposition: a neighbouring subdomain did not publish its step flags in time (it failed or stalled)", WDEM_ERR_RUNTIME};
     case ERR_AMBIGUOUS_PERI: throw EngErr{"InsertionSortCollider: ambiguous periodic contact " + pr + " (particle too large for the cell; InsertionSortCollider.cpp:979-981)", WDEM_ERR_RUNTIME};
     case ERR_FACET_IMPOSSIBLE: throw EngErr{"Cg2_Facet_Sphere_L6Geom: impossible sphere-facet intersection " + pr + " (Facet.cpp:358)", WDEM_ERR_RUNTIME};
     default: throw EngErr{"device error " + std::to_string(h.error) + " " + pr, WDEM_ERR_RUNTIME};
@@ -400,6 +403,12 @@ void domainExchange(wdem_engine* E) {
     rOffG[r] = accG * sizeof(GRec); rBytG[r] = M.recvCnt[r] * sizeof(GRec); accG += M.recvCnt[r];
   }
   M.nSendTot = accS; M.nRecvTot = accG;
+  M.peer.dstOff.assign(W, 0); M.peer.maxRecvTot = 0;
+  for (int r = 0; r < W; r++) {   // where my segment starts in rank r's receive layout (segments ordered by source rank), and the largest halo of any rank
+    long long off = 0, totR = 0;
+    for (int q = 0; q < W; q++) { if (q < R) off += ga[(size_t)q * W + r]; totR += ga[(size_t)q * W + r]; }
+    M.peer.dstOff[r] = off; M.peer.maxRecvTot = std::max(M.peer.maxRecvTot, totR);
+  }
   M.sendBuf.ensure(accS * sizeof(GRec) + 64, tot); M.recvBuf.ensure(accG * sizeof(GRec) + 64, tot);
   M.exportId.ensure(std::max<size_t>(accS, 1), tot); M.importId.ensure(std::max<size_t>(accG, 1), tot);
   if (accS > 0) {
@@ -426,6 +435,77 @@ void domainExchange(wdem_engine* E) {
   M.migratedOut += nE; M.migratedIn += (long long)nImmP; M.rowsIn += (long long)nImmR;
 }
 
+static const size_t PEER_WORDS_BYTES = 2 * WDEM_MAX_RANKS * sizeof(unsigned long long);
+void peerTeardown(wdem_engine* E, bool collective) {
+  DomainState::Peer& P = E->dom.peer; Transport* T = E->comm;
+  if (!P.box) return;
+  cudaStreamSynchronize(E->stream);
+  for (int r = 0; r < WDEM_MAX_RANKS; r++) if (P.base[r] && T && r != T->rank) { cudaIpcCloseMemHandle(P.base[r]); P.base[r] = nullptr; }
+  if (collective && T) { int64_t z = 0; std::vector<int64_t> all(T->world); T->allgather64(&z, 1, all.data(), E->stream); }   // nobody maps my box any more
+  cudaFree(P.box); P.box = nullptr; P.active = false;
+}
+// (re)create the mailboxes; collective (called by all ranks from the same collider run).  Any failure disables the peer path on ALL ranks (NCCL stays).
+void peerSetup(wdem_engine* E) {
+  DomainState::Peer& P = E->dom.peer; Transport* T = E->comm; const int W = T->world, R = T->rank; cudaStream_t st = E->stream;
+  static const bool off = getenv("WDEM_NO_PEER") != nullptr;
+  if (off || P.disabled || !T->multiProcess() || W < 2) return;
+  const long long need = 9 * P.maxRecvTot;
+  if (P.active && need <= P.haloCap) return;      // same decision on every rank: maxRecvTot is a global maximum
+  peerTeardown(E, true);
+  P.haloCap = std::max<long long>(2 * need, 1 << 17);
+  const size_t bytes = PEER_WORDS_BYTES + 2 * (size_t)P.haloCap * sizeof(double);
+  int64_t ok = 1; cudaIpcMemHandle_t hd; memset(&hd, 0, sizeof(hd));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  if (cudaMalloc(&P.box, bytes) != cudaSuccess) { P.box = nullptr; ok = 0; cudaGetLastError(); }
+  if (ok) { CK(cudaMemsetAsync(P.box, 0, bytes, st)); CK(cudaStreamSynchronize(st)); if (cudaIpcGetMemHandle(&hd, P.box) != cudaSuccess) { ok = 0; cudaGetLastError(); } }
+  std::vector<int64_t> mine(9, 0), all((size_t)9 * W, 0);
+  memcpy(mine.data(), &hd, 64); mine[8] = ok;
+  T->allgather64(mine.data(), 9, all.data(), st);
+  for (int r = 0; r < W; r++) if (!all[(size_t)9 * r + 8]) ok = 0;
+  if (ok) {
+    for (int r = 0; r < W && ok; r++) {
+      if (r == R) { P.base[r] = P.box; continue; }
+      cudaIpcMemHandle_t hr; memcpy(&hr, &all[(size_t)9 * r], 64);
+      if (cudaIpcOpenMemHandle(&P.base[r], hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { P.base[r] = nullptr; ok = 0; cudaGetLastError(); }
+    }
+  }
+  int64_t ok2 = ok; std::vector<int64_t> all2(W, 0);
+  T->allgather64(&ok2, 1, all2.data(), st);
+  for (int r = 0; r < W; r++) if (!all2[r]) ok = 0;
+  if (!ok) {   // some rank could not allocate / export / map: everybody falls back to NCCL for good
+    for (int r = 0; r < W; r++) if (P.base[r] && r != R) { cudaIpcCloseMemHandle(P.base[r]); } 
+    for (auto& b : P.base) b = nullptr;
+    std::vector<int64_t> all3(W, 0); int64_t z = 0; T->allgather64(&z, 1, all3.data(), st);
+    if (P.box) { cudaFree(P.box); P.box = nullptr; }
+    P.disabled = true; P.active = false; return;
+  }
+  P.active = true;
+}
+PeerU makePeerU(wdem_engine* E) {
+  DomainState& M = E->dom; Transport* T = E->comm; PeerU u; memset(&u, 0, sizeof(u));
+  u.rank = T->rank; u.world = T->world; u.haloCap = M.peer.haloCap;
+  int acc = 0;
+  for (int r = 0; r < T->world; r++) {
+    u.words[r] = reinterpret_cast<unsigned long long*>(M.peer.base[r]);
+    u.halo[r] = reinterpret_cast<double*>(static_cast<char*>(M.peer.base[r]) + PEER_WORDS_BYTES);
+    u.sendBase[r] = acc; acc += (int)M.sendCnt[r]; u.dstOff[r] = M.peer.dstOff[r];
+  }
+  for (int r = T->world; r <= WDEM_MAX_RANKS; r++) u.sendBase[r] = acc;
+  return u;
+}
+// per step, after Leapfrog: push my exported spheres into the neighbours' halo buffers, publish (stamp|error|dirty), wait for everybody's word
+void peerExchange(wdem_engine* E) {
+  DomainState& M = E->dom; cudaStream_t st = E->stream;
+  const PeerU u = makePeerU(E); const int parity = (int)(E->step & 1);
+  if (M.nSendTot && !E->conDirty) { k_halo_push<<<nblk(M.nSendTot, 256), 256, 0, st>>>(E->S(), M.sendSlot.p, (int)M.nSendTot, u, parity); E->launches++; }
+  k_peer_sync<<<1, WDEM_MAX_RANKS, 0, st>>>(u, E->dCnt, (unsigned long long)(E->step + 1), parity, 20000000000ll); E->launches++;
+}
+void peerUnpack(wdem_engine* E) {
+  DomainState& M = E->dom; const int parity = (int)(E->step & 1);
+  const double* buf = reinterpret_cast<const double*>(M.peer.box + PEER_WORDS_BYTES) + (long long)parity * M.peer.haloCap;
+  if (M.nRecvTot) { k_halo_unpack<<<nblk(M.nRecvTot, 256), 256, 0, E->stream>>>(E->S(), M.recvSlot.p, (int)M.nRecvTot, buf); E->launches++; }
+}
+
 // after the full run: exported / imported ids -> slots of the sorted generation
 void domainFinishRebuild(wdem_engine* E) {
   DomainState& M = E->dom; cudaStream_t st = E->stream;
@@ -433,6 +513,7 @@ void domainFinishRebuild(wdem_engine* E) {
   if (M.nSendTot) { k_dom_ids_to_slots<<<nblk(M.nSendTot, 256), 256, 0, st>>>(M.exportId.p, (int)M.nSendTot, E->id2slot.p, M.sendSlot.p); E->launches++; }
   if (M.nRecvTot) { k_dom_ids_to_slots<<<nblk(M.nRecvTot, 256), 256, 0, st>>>(M.importId.p, (int)M.nRecvTot, E->id2slot.p, M.recvSlot.p); E->launches++; }
   M.haloSend.ensure(std::max<size_t>(M.nSendTot * 9, 1), E->bytes); M.haloRecv.ensure(std::max<size_t>(M.nRecvTot * 9, 1), E->bytes);
+  peerSetup(E);
 }
 
 // per step (no full run): owners send pos, vel, angVel of the spheres they exported; 72 B per ghost
@@ -861,14 +942,18 @@ void oneStep(wdem_engine* E, wdem_stats* stats) {
   if (ev) CK(cudaEventRecord(ev[1], st));
   // collider: full run if contacts are dirty / verletDist==0 / any sphere moved farther than verletDist (flag raised by k_leapfrog)
   bool full = E->conDirty || E->verletDist == 0;
-  if (E->comm) E->comm->allreduceMaxInt(&E->dCnt->dirty, 2, st);   // (dirty, error): every subdomain rebuilds / fails in the same step
+  // (dirty, error): every subdomain rebuilds / fails in the same step; over peer memory together with the halo payload, else NCCL
+  const bool peer = E->comm && E->dom.peer.active;
+  if (peer) peerExchange(E);
+  else if (E->comm) E->comm->allreduceMaxInt(&E->dCnt->dirty, 2, st);
   CK(cudaMemcpyAsync(E->hCnt, E->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(E->evFlag, st));
   // Speculate that no full run is due (the common case): enqueue the rest of the step behind the flag copy, guarded on the device by the flag,
   // so the GPU keeps running while the host waits for the flag.
   const bool speculate = !full;
   if (speculate) {
-    if (E->comm) haloExchange(E);
+    if (peer) peerUnpack(E);
+    else if (E->comm) haloExchange(E);
     launchContactsAndReduce(E, u, &E->dCnt->dirty, ev);
   }
   CK(cudaEventSynchronize(E->evFlag));
@@ -999,6 +1084,7 @@ int wdem_destroy(wdem_handle h) {
   for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release();
   h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
   h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
+  peerTeardown(h, false);
   h->dom.release(); delete h->comm; h->comm = nullptr;
   if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt);
   if (h->ev0) cudaEventDestroy(h->ev0); if (h->ev1) cudaEventDestroy(h->ev1); for (auto& set : h->evr) for (auto& e : set) if (e) cudaEventDestroy(e);

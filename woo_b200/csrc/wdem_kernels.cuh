@@ -65,7 +65,7 @@ struct StepU {            // per-step uniforms
 };
 
 struct Counters { unsigned long long nReal, nPotEval, nCreated, nBroken; int dirty; int error; int errA, errB; };
-enum { ERR_NONE = 0, ERR_NAN_FORCE = 1, ERR_NAN_POS = 2, ERR_NO_PHYS = 3, ERR_SCHWARZ = 4, ERR_FACET_IMPOSSIBLE = 5, ERR_AMBIGUOUS_PERI = 6 };
+enum { ERR_NONE = 0, ERR_NAN_FORCE = 1, ERR_NAN_POS = 2, ERR_NO_PHYS = 3, ERR_SCHWARZ = 4, ERR_FACET_IMPOSSIBLE = 5, ERR_AMBIGUOUS_PERI = 6, ERR_PEER_TIMEOUT = 7 };
 
 __device__ __forceinline__ double signd(double f) { return f < 0 ? -1. : (f > 0 ? 1. : 0.); }  // Mathr::Sign (Math.hpp:145)
 
