@@ -133,6 +133,16 @@ int wdem_upload_contacts(wdem_handle h, int64_t n, const int32_t* ids, const int
                          const double* forceLocal, const double* torqueLocal, const double* trsf, const double* contPt, const double* physRaw);
 /* Scene.step / Scene.time (Scene.hpp:191-205) of a resumed scene: trsfRenorm and DynDt's period count scene steps. */
 int wdem_set_scene(wdem_handle h, int64_t step, double time);
+/* Walls after the last step, in upload order (any pointer may be NULL): position (a wall uploaded with a nonzero velocity is in DemField.nodes and is
+ * translated by Leapfrog, pos += vel*dt — Leapfrog.cpp:195-199,275-278, Particle.cpp:638-640) and the force / torque the LAST step's contacts put on the wall
+ * (ContactLoop::applyForceUninodal, ContactLoop.cpp:270-276; summed in ascending id of the sphere).  This is DemData.force of a moving wall, which Leapfrog
+ * resets every step; for a wall at rest the reference never resets and keeps accumulating — take the per-step value times the steps instead.
+ * Decomposed runs: the share of this subdomain's spheres. */
+int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torque);
+/* ContactLoop.stress with evalStress=True (ContactLoop.hpp:117, ContactLoop.cpp:116,123,218-231,243-244): sum over real contacts of F (x) dPos / cell volume,
+ * row-major 3x3, periodic scenes only; evaluated on demand from the state the last step left (decomposed runs: this subdomain's share — add the
+ * results of all subdomains).  Contacts with facets fail like the reference (multi-nodal particles). */
+int wdem_get_stress(wdem_handle h, double* stress9);
 /* DemField::critDt -> DemFuncs::pWaveDt (Funcs.cpp:151-175). */
 int wdem_crit_dt(wdem_handle h, double* dt);
 /* Σ ½ m v² + ½ ω·I·ω  (DemData::getEk_any, Particle.cpp:247-265), device reduction. */

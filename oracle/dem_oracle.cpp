@@ -188,6 +188,8 @@ struct Sphere {
 };
 struct Wall {
   int id; V3 pos; int axis, sense; V3 vel, angVel; unsigned mask; int mat; V3 force, torque; Aabb bb; V3 lastPos;
+  bool moving = false;   // Particle::guessMoving at ParticleContainer::add (ParticleContainer.cpp:193-198, Particle.cpp:638-640): a node with nonzero velocity
+                         // enters DemField.nodes and is integrated by Leapfrog; a fixed wall at rest never is
 };
 struct Facet {
   int id; V3 v[3]; V3 vvel[3]; V3 fakeVel; Real halfThick; Real n21lim[3]; unsigned mask; int mat; Aabb bb; V3 lastPos[3];
@@ -1027,6 +1029,14 @@ struct Scene {
         s.torque = V3();
       }
     }
+    // boundary nodes that are in DemField.nodes (walls added with a velocity): mass 0 and all DOFs blocked => Leapfrog's "fixed particle" branch
+    // (Leapfrog.cpp:195-199): no acceleration, leapfrogTranslate pos += vel*dt (:275-278), force/torque reset to mass*gravity = 0 (:240-245)
+    for (Wall& w : walls) {
+      if (!w.moving) continue;
+      if (P.periodic) throw std::runtime_error("moving walls in a periodic cell are not supported");
+      w.pos += w.vel * dt;
+      if (P.reset) { w.force = V3(); w.torque = V3(); }
+    }
   }
 
   // ------------------------------------------------------------------------------------------
@@ -1169,6 +1179,7 @@ int orc_add_spheres(void* h, int n, const double* pos, const double* radius, con
 int orc_add_wall(void* h, const double* pos, int axis, int sense, int mat, unsigned mask, const double* vel) {
   Scene* S = (Scene*)h; Wall w; w.id = (int)S->par.size(); w.pos = V3(pos[0], pos[1], pos[2]); w.axis = axis; w.sense = sense; w.mat = mat; w.mask = mask;
   if (vel) w.vel = V3(vel[0], vel[1], vel[2]);
+  w.moving = (w.vel != V3(0, 0, 0));
   S->par.push_back(PRef{SHAPE_WALL, (int)S->walls.size()}); S->walls.push_back(w); S->conDirty = true; return w.id;
 }
 int orc_add_facet(void* h, const double* v /*9*/, double halfThick, const double* fakeVel, const double* n21lim, const double* vvel /*9 or NULL*/, int mat, unsigned mask) {
@@ -1207,6 +1218,10 @@ void orc_set_sphere_state(void* h, int idx, const double* pos, const double* vel
   Sphere& s = ((Scene*)h)->sph[idx];
   if (pos) s.pos = V3(pos[0], pos[1], pos[2]); if (vel) s.vel = V3(vel[0], vel[1], vel[2]); if (angVel) s.angVel = V3(angVel[0], angVel[1], angVel[2]);
 }
+void orc_get_walls(void* h, double* pos, double* force, double* torque) {
+  Scene* S = (Scene*)h;
+  for (size_t i = 0; i < S->walls.size(); i++) for (int k = 0; k < 3; k++) { if (pos) pos[3 * i + k] = S->walls[i].pos[k]; if (force) force[3 * i + k] = S->walls[i].force[k]; if (torque) torque[3 * i + k] = S->walls[i].torque[k]; }
+}
 void orc_get_wall_forces(void* h, double* force) { Scene* S = (Scene*)h; for (size_t i = 0; i < S->walls.size(); i++) for (int k = 0; k < 3; k++) force[3 * i + k] = S->walls[i].force[k]; }
 long orc_num_contacts(void* h, int realOnly) { Scene* S = (Scene*)h; long n = 0; for (auto& kv : S->con) if (!realOnly || kv.second.isReal()) n++; return n; }
 // contacts in canonical key order. Arrays may be NULL. Returns count written.
@@ -1226,6 +1241,30 @@ long orc_get_contacts(void* h, int realOnly, int* ids /*2n*/, int* cellDist /*3n
     n++;
   }
   return n;
+}
+// ContactLoop.stress (ContactLoop.cpp:116,218-231,243-244) as the last step left it: sum over real contacts of F (x) branch / V with F = node.ori * phys.force
+// (global force as applied to pA), branch = Contact::dPos (Contact.cpp:54-59), V = Cell::getVolume (Cell.hpp:121).  The reference adds the terms in
+// its (thread-dependent) loop order; here: canonical contact order.  Row-major 3x3.  Only defined in periodic scenes (doStress, ContactLoop.cpp:123).
+int orc_get_stress(void* h, double* out9) {
+  Scene* S = (Scene*)h;
+  ORC_TRY(h)
+  if (!S->P.periodic) throw std::runtime_error("ContactLoop.evalStress needs a periodic scene");
+  M3 st; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) st(i, j) = 0;
+  for (auto& kv : S->con) {
+    const Contact& C = kv.second; if (!C.isReal()) continue;
+    const PRef& a = S->par[C.idA]; const PRef& b = S->par[C.idB];
+    if (a.kind == SHAPE_FACET || b.kind == SHAPE_FACET) throw std::runtime_error("ContactLoop.trackWork not allowed with multi-nodal particles in contact");
+    const V3& pa = a.kind == SHAPE_SPHERE ? S->sph[a.idx].pos : S->walls[a.idx].pos;
+    const V3& pb = b.kind == SHAPE_SPHERE ? S->sph[b.idx].pos : S->walls[b.idx].pos;
+    V3 branch = pb - pa;
+    if (C.cellDist[0] != 0 || C.cellDist[1] != 0 || C.cellDist[2] != 0) branch = branch + S->cell.intrShiftPos(C.cellDist);
+    const V3 F = quatRotate(C.ori, C.force);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) st(i, j) += F[i] * branch[j];
+  }
+  const M3& H = S->cell.hSize;
+  const Real vol = H(0, 0) * (H(1, 1) * H(2, 2) - H(1, 2) * H(2, 1)) - H(0, 1) * (H(1, 0) * H(2, 2) - H(1, 2) * H(2, 0)) + H(0, 2) * (H(1, 0) * H(2, 1) - H(1, 1) * H(2, 0));
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out9[3 * i + j] = st(i, j) / vol;
+  ORC_CATCH(h)
 }
 int orc_num_threads() {
 #ifdef _OPENMP

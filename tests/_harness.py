@@ -120,6 +120,18 @@ class Oracle:
     def pWaveDt(self): return self.L.orc_pwave_dt(self.h)
     def kineticEnergy(self): return self.L.orc_kinetic_energy(self.h)
 
+    def walls(self):
+        n = len(self.spec.walls)
+        o = {k: np.zeros((n, 3)) for k in ("pos", "force", "torque")}
+        if n:
+            self.L.orc_get_walls(self.h, _p(o["pos"], C.c_double), _p(o["force"], C.c_double), _p(o["torque"], C.c_double))
+        return o
+
+    def stress(self):
+        o = np.zeros((3, 3))
+        self._chk(self.L.orc_get_stress(self.h, _p(o, C.c_double)))
+        return o
+
     def cell_hsize(self):
         h = np.zeros((3, 3))
         self.L.orc_get_cell(self.h, _p(h, C.c_double))

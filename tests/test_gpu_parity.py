@@ -293,3 +293,55 @@ def test_upload_contacts_rejects_bad_input():
     bad = {k: v.copy() for k, v in c.items()}; bad["ids"][0, 1] = 10 ** 6
     with pytest.raises(WdemError):
         B.upload_contacts(bad)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ContactLoop.evalStress: stress = sum F (x) dPos / V over real contacts, periodic scenes
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [1, 2])
+def test_periodic_stress_matches_oracle(world):
+    S = sc.periodic_gas(500, seed=51, gradV=[[0, .5, 0], [0, 0, 0], [0, 0, -.3]], shear0=.15, psd_ratio=2.0)
+    O = Oracle(S)
+    if world == 1:
+        E = engine_for(S); stress = E.stress
+    else:
+        from woo_b200.domain import LocalCluster
+        E = LocalCluster(S, world, axis=0); stress = lambda: sum(e.stress() for e in E.E)
+    for k in range(3):
+        O.step(60); E.step(60)
+        so, sg = O.stress(), stress()
+        scale = np.abs(so).max()
+        assert scale > 0
+        # the sum over contacts runs in table order on the device and in canonical order in the oracle: 1e-10 relative (north_star tolerance)
+        assert np.allclose(sg, so, rtol=1e-10, atol=1e-10 * scale), f"stress differs after {60 * (k + 1)} steps:\n{sg}\n{so}"
+    with pytest.raises(Exception):
+        engine_for(sc.random_gas(50, box=.3, r=.02, seed=52)).stress()      # aperiodic: not defined (ContactLoop.cpp:123)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# moving walls (piston): a wall uploaded with a velocity is in DemField.nodes and is translated by Leapfrog (Particle.cpp:638-640, Leapfrog.cpp:195-199,275-278);
+# its force is the sum over the step's contacts
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("law", [sc.LAW_IDEALELPL, sc.LAW_HERTZ_DMT])
+def test_moving_wall_piston(law):
+    S = sc.random_gas(300, box=.4, r=.02, psd_ratio=2.0, seed=61, law=law, en=.6 if law else float("nan"))
+    top = [w for w in S.walls if w["axis"] == 2 and w["sense"] == -1]
+    assert len(top) == 1
+    top[0]["vel"] = (0., 0., -.8)                                  # the lid comes down and compresses the gas
+    S.walls[0]["vel"] = (.05, 0., 0.) if S.walls[0]["axis"] != 0 else (0., .05, 0.)    # a wall sliding in its own plane: only the contact kinematics see it
+    O = Oracle(S); E = engine_for(S)
+    z0 = E.walls()["pos"][S.walls.index(top[0]), 2]
+    for k in range(5):
+        O.step(60); E.step(60)
+        wo, wg = O.walls(), E.walls()
+        assert np.array_equal(wo["pos"], wg["pos"]), "wall positions differ"
+        so, sg = O.spheres(), E.spheres()
+        for k_ in ("pos", "vel", "angVel", "force", "torque"):
+            assert np.array_equal(so[k_], sg[k_]), f"{k_} differs after {60 * (k + 1)} steps"
+        co, cg = O.contacts(True), E.contacts(True)
+        assert [tuple(x) for x in co["ids"]] == [tuple(x) for x in cg["ids"]]
+        assert O.nFullRuns == E.scalars()["nFullRuns"]
+        mv = [i for i, w in enumerate(S.walls) if any(w.get("vel", (0, 0, 0)))]
+        assert np.array_equal(wo["force"][mv], wg["force"][mv]) and np.array_equal(wo["torque"][mv], wg["torque"][mv]), "force on the moving walls differs"
+    zi = S.walls.index(top[0])
+    assert E.walls()["pos"][zi, 2] < z0 - .8 * 299 * E.scalars()["dt"] * .5 and np.abs(E.walls()["force"][zi]).max() > 0

@@ -159,3 +159,21 @@ def test_dyndt_rate_limit():
     S = two_spheres(sc.LAW_IDEALELPL, gap=-1e-4, mat=sc.frict_mat(young=1e7)); S.params.dt = 1e-8; S.params.dynDtPeriod = 10
     O = Oracle(S); O.step(11)
     assert O.dt == pytest.approx(1e-8 * (1 + 1e-4) ** 10, rel=1e-12)
+
+
+def test_stress_two_spheres_across_the_cell_boundary():
+    """ContactLoop.evalStress (ContactLoop.cpp:218-231,243-244): one contact across the periodic boundary, normal along x: stress_xx = Fn*|dPos_x|/V with
+    the branch taken through the boundary (Contact::dPos adds hSize*cellDist, Contact.cpp:54-59); everything else is zero."""
+    S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+    S.pos = np.array([(.05, .5, .5), (.96, .5, .5)]); S.radius = np.array([.05, .05])      # overlap 0.01 through x=0/1
+    S.params = sc.Params(dt=1e-7, periodic=1, damping=0., dynDtPeriod=0)
+    S.cell = dict(hSize=np.diag([1., 2., .5]), homoDeform=sc.HOMO_GRADV2)
+    O = Oracle(S.finalize()); O.step(2)
+    c = O.contacts(True)
+    assert len(c["ids"]) == 1 and tuple(c["cellDist"][0]) == (-1, 0, 0)
+    st = O.stress()
+    fn = c["force"][0][0]; assert fn < 0                                  # compressive normal force in the local frame
+    # F on pA is along the normal (pA -> pB = -x through the boundary): F_x = fn * n_x = -fn; branch_x = -0.09
+    assert st[0, 0] == pytest.approx((-fn) * (-.09) / 1.0, rel=1e-6)
+    st[0, 0] = 0
+    assert np.abs(st).max() < 1e-12 * abs(fn)

@@ -157,7 +157,7 @@ struct wdem_engine {
   // particles
   int n = 0; SphereStore sph[2]; int cur = 0; DBuf<int> id2slot, up2slot; int maxId = -1; bool up2slotValid = false;
   std::vector<Material> hMats; DBuf<Material> dMats;
-  std::vector<Wall> hWalls; DBuf<Wall> dWalls;
+  std::vector<Wall> hWalls; DBuf<Wall> dWalls; bool anyMovingWall = false;
   std::vector<Facet> hFacets; DBuf<Facet> dFacets; DBuf<int> fgCellStart, fgCellFacet; FacetGrid fgrid; bool fgridValid = false;
   double minRadius = INFINITY, pwaveDt = INFINITY;
   std::vector<double> hRadius; std::vector<int32_t> hMatOfSphere;
@@ -748,6 +748,7 @@ void rebuild(wdem_engine* E) {
     }
     Ncsr.valid = true;
   }
+  if (E->anyMovingWall) { k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), makeUniforms(E), E->dCnt, 1); E->launches++; }   // Aabb::nodeLastPos (Collision.cpp:138-141)
   E->nSS = nSS; E->nWS = nWS; E->nFS = nFS; E->nOrph = nOrphOut; E->nC = nSS + nWS + nFS + nOrphOut;
   E->curC = 1 - E->curC; E->curR = 1 - E->curR;
   E->nFullRuns++;
@@ -939,6 +940,10 @@ void oneStep(wdem_engine* E, wdem_stats* stats) {
   if (ev) CK(cudaEventRecord(ev[0], st));
   if (n > 0 && E->e2e.active) leapfrogPipelined(E, u);
   else if (n > 0) { k_leapfrog<<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt); E->launches++; }
+  if (E->anyMovingWall) {
+    if (c.periodic) throw EngErr{"moving walls in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), u, E->dCnt, 0); E->launches++;
+  }
   if (ev) CK(cudaEventRecord(ev[1], st));
   // collider: full run if contacts are dirty / verletDist==0 / any sphere moved farther than verletDist (flag raised by k_leapfrog)
   bool full = E->conDirty || E->verletDist == 0;
@@ -1192,10 +1197,13 @@ int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* po
       Wall w; memset(&w, 0, sizeof(w));
       for (int k = 0; k < 3; k++) { w.pos[k] = pos[3 * i + k]; w.vel[k] = vel ? vel[3 * i + k] : 0.; }
       w.axis = axis[i]; w.sense = sense[i]; w.mask = mask ? mask[i] : 3u; w.mat = matId ? matId[i] : 0; w.id = ids[i];
+      w.moving = (w.vel[0] != 0. || w.vel[1] != 0. || w.vel[2] != 0.) ? 1 : 0;
+      for (int k = 0; k < 3; k++) w.lastPos[k] = w.pos[k];
       if (w.axis < 0 || w.axis > 2 || w.sense < -1 || w.sense > 1) throw EngErr{"Wall.axis must be 0..2 and Wall.sense -1,0,1", WDEM_ERR_INVALID};
       if (w.mat < 0 || w.mat >= (int)h->hMats.size()) throw EngErr{"wall material index out of range", WDEM_ERR_INVALID};
       h->hWalls[i] = w;
     }
+    h->anyMovingWall = false; for (auto& w : h->hWalls) if (w.moving) h->anyMovingWall = true;
     h->dWalls.ensure(std::max(n, 1), h->bytes);
     if (n) CK(cudaMemcpyAsync(h->dWalls.p, h->hWalls.data(), n * sizeof(Wall), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1313,6 +1321,61 @@ int wdem_kinetic_energy(wdem_handle h, double* ek) {
       for (double v : hb) e += v;
     }
     *ek = e;
+  });
+}
+
+int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torque) {
+  return guarded(h, [&] {
+    const size_t nW = h->hWalls.size(); if (!nW) return;
+    cudaStream_t st = h->stream;
+    auto W = d2h(h->dWalls.p, nW, st);
+    for (size_t w = 0; w < nW; w++) for (int k = 0; k < 3; k++) { if (pos) pos[3 * w + k] = W[w].pos[k]; if (force) force[3 * w + k] = 0.; if (torque) torque[3 * w + k] = 0.; }
+    if ((!force && !torque) || h->nC == 0) return;
+    // wall-sphere contacts live in [nSS, nSS+nWS) and among the orphans; forces are added per wall in ascending id of the sphere, the order of
+    // the per-particle contact map the reference walks (Particle.hpp:36)
+    const long long nC = h->nC; ContactStore& cs = h->con[h->curC];
+    auto flags = d2h(cs.flags.p, nC, st); auto pair = d2h(cs.pair.p, nC, st); auto Fg = d2h(cs.Fg.p, nC, st); auto cp = d2h(cs.cp.p, nC, st);
+    auto sid = d2h(h->S().id, h->n, st); auto sfl = d2h(h->S().flags, h->n, st);
+    const bool rolling = (h->cfg.relRollStiff > 0. && h->cfg.rollTanPhi > 0.);
+    std::vector<double4> Tg; if (rolling) Tg = d2h(cs.Tg.p, nC, st);
+    struct Row { int wall, sid; long long c; };
+    std::vector<Row> rows;
+    for (long long c = 0; c < nC; c++) {
+      if (!(flags[c] & CF_REAL) || (flags[c] & CF_DEAD) || cf_kind(flags[c]) != KIND_WS || Fg[c].w == 0.) continue;
+      if (sfl[pair[c].y] & F_GHOST) continue;
+      rows.push_back(Row{pair[c].x, sid[pair[c].y], c});
+    }
+    std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.wall != b.wall ? a.wall < b.wall : a.sid < b.sid; });
+    std::vector<d3> F(nW, mk3(0, 0, 0)), T(nW, mk3(0, 0, 0));
+    for (const Row& r : rows) {
+      const d3 Fc = xyz(Fg[r.c]);                                     // wall = pA: sign +1 (Contact.cpp:28-31)
+      const d3 xc = xyz(cp[r.c]) - mk3(W[r.wall].pos[0], W[r.wall].pos[1], W[r.wall].pos[2]);
+      d3 Tc = cross(xc, Fc);
+      if (rolling) Tc = Tc + xyz(Tg[r.c]);
+      F[r.wall] = F[r.wall] + Fc; T[r.wall] = T[r.wall] + Tc;
+    }
+    for (size_t w = 0; w < nW; w++) { if (force) { force[3 * w] = F[w].x; force[3 * w + 1] = F[w].y; force[3 * w + 2] = F[w].z; } if (torque) { torque[3 * w] = T[w].x; torque[3 * w + 1] = T[w].y; torque[3 * w + 2] = T[w].z; } }
+  });
+}
+
+int wdem_get_stress(wdem_handle h, double* stress9) {
+  return guarded(h, [&] {
+    if (!stress9) throw EngErr{"wdem_get_stress: null output", WDEM_ERR_INVALID};
+    if (!h->cfg.periodic) throw EngErr{"ContactLoop.evalStress needs a periodic scene (ContactLoop.cpp:123)", WDEM_ERR_INVALID};
+    for (int k = 0; k < 9; k++) stress9[k] = 0.;
+    const long long nC = h->nC;
+    if (nC > 0) {
+      const int nb = nblk(nC, 256); h->blk.ensure((size_t)nb * 9 + 1, h->bytes);
+      int* flag = reinterpret_cast<int*>(h->blk.p + (size_t)nb * 9);
+      CK(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+      k_stress<<<nb, 256, 0, h->stream>>>(h->con[h->curC].view(), nC, h->S(), h->dWalls.p, makeUniforms(h), h->blk.p, flag);
+      auto hb = d2h(h->blk.p, (size_t)nb * 9 + 1, h->stream);
+      int hf; memcpy(&hf, &hb[(size_t)nb * 9], sizeof(int));
+      if (hf) throw EngErr{"ContactLoop.trackWork not allowed with multi-nodal particles in contact (facets; ContactLoop.cpp:220)", WDEM_ERR_UNSUPPORTED};
+      for (int b = 0; b < nb; b++) for (int k = 0; k < 9; k++) stress9[k] += hb[9 * (size_t)b + k];
+    }
+    const double vol = mDet(h->cell.hSize);
+    for (int k = 0; k < 9; k++) stress9[k] /= vol;
   });
 }
 

@@ -33,7 +33,8 @@ struct Spheres {          // one slot per sphere; slots are re-ordered by grid c
   int32_t* up;            // upload index (for downloads)
 };
 
-struct Wall { double pos[3]; double vel[3]; int32_t axis, sense; uint32_t mask; int32_t mat; int32_t id; int32_t pad; };
+// moving: the wall's node is in DemField.nodes (added with a nonzero velocity: Particle::guessMoving, Particle.cpp:638-640) and is translated by Leapfrog
+struct Wall { double pos[3]; double vel[3]; double lastPos[3]; int32_t axis, sense; uint32_t mask; int32_t mat; int32_t id; int32_t moving; };
 struct Facet { double v[9]; double vvel[9]; double fakeVel[3]; double halfThick; double n21lim[3]; double bmin[3], bmax[3]; uint32_t mask; int32_t mat; int32_t id; int32_t pad; };
 struct FacetGrid { double ox, oy, oz, inv; int nx, ny, nz; const int* cellStart; const int* cellFacet; };
 struct Material { int32_t kind; int32_t pad; double density, young, ktDivKn, tanPhi, surfEnergy, alpha; };
@@ -178,6 +179,21 @@ __global__ void __launch_bounds__(256, 4) k_leapfrog_io(Spheres S, StepU u, Coun
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cnt_) return;
   leapfrog_body<true>(S, up2slot[first + t], u, cnt, io, first + t);
+}
+
+// Leapfrog for boundary nodes that are in DemField.nodes (moving walls: mass 0, all DOFs blocked => the "fixed particle" branch, Leapfrog.cpp:195-199):
+// leapfrogTranslate only (:275-278), plus the Verlet test of their Aabb (Collision.cpp:113-121).  setLast: record Aabb::nodeLastPos at a full run.
+__global__ void k_walls_step(Wall* walls, int n, StepU u, Counters* cnt, int setLast) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  Wall W = walls[w];
+  if (setLast) { for (int k = 0; k < 3; k++) walls[w].lastPos[k] = W.pos[k]; return; }
+  if (!W.moving) return;
+  d3 pos = mk3(W.pos[0], W.pos[1], W.pos[2]) + mk3(W.vel[0], W.vel[1], W.vel[2]) * u.dt;
+  walls[w].pos[0] = pos.x; walls[w].pos[1] = pos.y; walls[w].pos[2] = pos.z;
+  const d3 dl = mk3(W.lastPos[0], W.lastPos[1], W.lastPos[2]) - pos;
+  const double d2 = fmax(0., sqn(dl));
+  if (d2 > u.maxD2 || !(d2 == d2)) cnt->dirty = 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -763,6 +779,38 @@ __global__ void __launch_bounds__(256) k_ekin(Spheres S, int n, StepU u, double*
   sm[threadIdx.x] = e; __syncthreads();
   for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s]; __syncthreads(); }
   if (threadIdx.x == 0) blockSum[blockIdx.x] = sm[0];
+}
+
+// ContactLoop.stress (ContactLoop.cpp:116,218-231): sum over real contacts of F (x) branch, F = global force on pA (C.Fg), branch = Contact::dPos
+// (Contact.cpp:54-59).  Evaluated on demand from the state the last step left; per-block partial sums in a fixed tree order, summed by the host in
+// block order (the reference's own order depends on its thread schedule).  Facets are multi-nodal: the reference throws (ContactLoop.cpp:220).
+__global__ void __launch_bounds__(256) k_stress(Contacts C, long long n, Spheres S, const Wall* __restrict__ walls, StepU u, double* blockSum /*9 per block*/, int* hasFacet) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < n) {
+    const uint32_t fl = C.flags[c];
+    if ((fl & CF_REAL) && !(fl & CF_DEAD)) {
+      const int kind = cf_kind(fl); const int2 pr = C.pair[c];
+      if (kind == KIND_FS) *hasFacet = 1;
+      else if (!(S.flags[pr.y] & F_GHOST) || (kind == KIND_SS && !(S.flags[pr.x] & F_GHOST))) {
+        // decomposed runs: a cross-slab pair lives on both sides; the side owning pA (sphere-sphere) / the sphere (wall) reports it
+        const bool mineToReport = kind == KIND_SS ? !(S.flags[pr.x] & F_GHOST) : !(S.flags[pr.y] & F_GHOST);
+        if (mineToReport) {
+          const double4 F = C.Fg[c];
+          const d3 pb = xyz(S.posr[pr.y]);
+          const d3 pa = kind == KIND_SS ? xyz(S.posr[pr.x]) : mk3(walls[pr.x].pos[0], walls[pr.x].pos[1], walls[pr.x].pos[2]);
+          d3 br = pb - pa;
+          if (u.periodic) { const int cx = C.cdx[c], cy = C.cdy[c], cz = C.cdz[c]; if (cx != 0 || cy != 0 || cz != 0) br = br + mulMV(u.hSize, mk3((double)cx, (double)cy, (double)cz)); }
+          v[0] = F.x * br.x; v[1] = F.x * br.y; v[2] = F.x * br.z; v[3] = F.y * br.x; v[4] = F.y * br.y; v[5] = F.y * br.z; v[6] = F.z * br.x; v[7] = F.z * br.y; v[8] = F.z * br.z;
+        }
+      }
+    }
+  }
+  __shared__ double sm[9][256];
+  for (int k = 0; k < 9; k++) sm[k][threadIdx.x] = v[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) for (int k = 0; k < 9; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0) for (int k = 0; k < 9; k++) blockSum[9ll * blockIdx.x + k] = sm[k][0];
 }
 
 // ================================================================================================

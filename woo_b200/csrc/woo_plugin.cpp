@@ -108,6 +108,7 @@ struct Law2_L6Geom_HertzPhys_DMT : LawFunctor { bool noAttraction = true; };
 struct ContactLoop : Engine {
   vector<shared_ptr<CGeomFunctor>> geoDisp; vector<shared_ptr<CPhysFunctor>> phyDisp; vector<shared_ptr<LawFunctor>> lawDisp;
   bool applyForces = true, evalStress = false, dist00 = true; int updatePhys = 0, reorderEvery = 1000; py::object hook = py::none();
+  M3 stress{{0, 0, 0, 0, 0, 0, 0, 0, 0}};   // ContactLoop.hpp:116-127: filled after every step when evalStress and the scene is periodic
   const char* cls() const override { return "ContactLoop"; }
 };
 struct DynDt : Engine { int stepPeriod = 100; double maxRelInc = 1e-4; bool dryRun = false; const char* cls() const override { return "DynDt"; } };
@@ -126,7 +127,7 @@ static void chk(wdem_handle h, int rc) { if (rc != WDEM_OK) throw std::runtime_e
 struct GpuDemLoop : Engine {
   shared_ptr<Leapfrog> leapfrog; shared_ptr<InsertionSortCollider> collider; shared_ptr<ContactLoop> contactLoop; shared_ptr<DynDt> dynDt;
   int device = 0; wdem_handle h = nullptr; wdem_config cfg; bool haveCfg = false; long nSpheres = 0; wdem_stats last;
-  vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf;
+  vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf, wallOf;
   const char* cls() const override { return "GpuDemLoop"; }
   ~GpuDemLoop() override { release(); }
   void release() { if (h) { wdem_destroy(h); h = nullptr; } if (field && field->owner == this) field->owner = nullptr; }
@@ -151,7 +152,6 @@ struct GpuDemLoop : Engine {
     c.noRatch = g0.noRatch; c.iniLensTouch = g0.iniLensTouch; c.trsfRenorm = g0.trsfRenorm;
     c.applyForces = contactLoop->applyForces;
     if (contactLoop->updatePhys != 0) throw std::runtime_error("GpuDemLoop: ContactLoop.updatePhys is not supported");
-    if (contactLoop->evalStress) throw std::runtime_error("GpuDemLoop: ContactLoop.evalStress is not supported");
     if (!contactLoop->hook.is_none()) throw std::runtime_error("GpuDemLoop: ContactLoop.hook is not supported");
     if (scene->trackEnergy) throw std::runtime_error("GpuDemLoop: Scene.trackEnergy is not supported");
     auto* lin = dynamic_cast<Law2_L6Geom_FrictPhys_IdealElPl*>(contactLoop->lawDisp[0].get());
@@ -194,7 +194,7 @@ struct GpuDemLoop : Engine {
     auto matOf = [&](const shared_ptr<Particle>& p) { Material* m = p->material.get(); if (!m) throw std::runtime_error("particle #" + std::to_string(p->id) + " has no material"); auto it = matIx.find(m); if (it != matIx.end()) return it->second; int k = (int)mats.size(); mats.push_back(m); matIx[m] = k; return k; };
     vector<int32_t> sid, smat, wid, waxis, wsense, wmat, fid, fmat; vector<uint32_t> sflags, smask, wmask, fmask;
     vector<double> spos, sori, svel, sang, smass, sin, srad, sfrc, strq, wpos, wvel, fv, fvv, ffk, fht, fnl;
-    sphereIds.clear(); sphereOf.clear();
+    sphereIds.clear(); sphereOf.clear(); wallOf.clear();
     for (auto& p : F.par.v) {
       if (!p) continue;
       if (!p->shape) throw std::runtime_error("particle #" + std::to_string(p->id) + " has no shape");
@@ -212,6 +212,7 @@ struct GpuDemLoop : Engine {
         if (n.dem->angVel[0] != 0 || n.dem->angVel[1] != 0 || n.dem->angVel[2] != 0) throw std::runtime_error("GpuDemLoop: rotating walls are not supported");
         wid.push_back(p->id); waxis.push_back(w->axis); wsense.push_back(w->sense); wmat.push_back(m); wmask.push_back(p->mask);
         for (int k = 0; k < 3; k++) { wpos.push_back(n.pos[k]); wvel.push_back(n.dem->vel[k]); }
+        wallOf.push_back(p);
       } else if (auto* f = dynamic_cast<Facet*>(p->shape.get())) {
         fid.push_back(p->id); fmat.push_back(m); fmask.push_back(p->mask); fht.push_back(f->halfThick);
         for (int v = 0; v < 3; v++) { const Node& n = *f->nodes.at(v); for (int k = 0; k < 3; k++) { fv.push_back(n.pos[k]); fvv.push_back(n.dem->vel[k]); } }
@@ -265,6 +266,8 @@ struct GpuDemLoop : Engine {
     chk(h, wdem_get_scalars(h, &libDt, nullptr, nullptr, nullptr, &nf));
     collider->nFullRuns = (long)nf;
     if (scene->periodic) chk(h, wdem_get_cell(h, scene->cell->hSize.data()));
+    if (contactLoop->evalStress && scene->periodic) chk(h, wdem_get_stress(h, contactLoop->stress.data()));   // doStress (ContactLoop.cpp:123)
+    else contactLoop->stress.fill(0.);
     cfg.dt = libDt;                        // what the library will use next; Scene.dt follows through nextDt in the epilogue
     if (libDt != scene->dt) scene->nextDt = libDt;
   }
@@ -280,6 +283,13 @@ void DemField::pull() {
     Node& nd = *owner->sphereOf[i]->shape->nodes[0]; DemData& d = *nd.dem;
     for (int k = 0; k < 3; k++) { nd.pos[k] = pos[3 * i + k]; d.vel[k] = vel[3 * i + k]; d.angVel[k] = ang[3 * i + k]; d.force[k] = f[3 * i + k]; d.torque[k] = t[3 * i + k]; }
     for (int k = 0; k < 4; k++) nd.ori[k] = ori[4 * i + k];
+  }
+  // walls: position (a wall added with a velocity is moved by Leapfrog) and the force/torque of the last step's contacts (wdem.h: wdem_download_walls)
+  const size_t nw = owner->wallOf.size();
+  if (nw) {
+    vector<double> wp(3 * nw), wf(3 * nw), wt(3 * nw);
+    chk(owner->h, wdem_download_walls(owner->h, wp.data(), wf.data(), wt.data()));
+    for (size_t i = 0; i < nw; i++) { Node& nd = *owner->wallOf[i]->shape->nodes[0]; for (int k = 0; k < 3; k++) { nd.pos[k] = wp[3 * i + k]; nd.dem->force[k] = wf[3 * i + k]; nd.dem->torque[k] = wt[3 * i + k]; } }
   }
   deviceNewer = false;
 }
@@ -514,7 +524,7 @@ PYBIND11_MODULE(_woo, m) {
       .def(py::init([](vector<shared_ptr<CGeomFunctor>> g, vector<shared_ptr<CPhysFunctor>> p, vector<shared_ptr<LawFunctor>> l, py::kwargs kw) {
         auto o = make_shared<ContactLoop>(); o->geoDisp = g; o->phyDisp = p; o->lawDisp = l; py::object po = py::cast(o); for (auto it : kw) py::setattr(po, it.first, it.second); return o; }),
         py::arg("geoDisp") = vector<shared_ptr<CGeomFunctor>>(), py::arg("phyDisp") = vector<shared_ptr<CPhysFunctor>>(), py::arg("lawDisp") = vector<shared_ptr<LawFunctor>>())
-      RW(ContactLoop, geoDisp) RW(ContactLoop, phyDisp) RW(ContactLoop, lawDisp) RW(ContactLoop, applyForces) RW(ContactLoop, evalStress) RW(ContactLoop, dist00) RW(ContactLoop, updatePhys) RW(ContactLoop, reorderEvery) RW(ContactLoop, hook);
+      RW(ContactLoop, geoDisp) RW(ContactLoop, phyDisp) RW(ContactLoop, lawDisp) RW(ContactLoop, applyForces) RW(ContactLoop, evalStress).def_property_readonly("stress", [](ContactLoop& c) { return np33(c.stress); }) RW(ContactLoop, dist00) RW(ContactLoop, updatePhys) RW(ContactLoop, reorderEvery) RW(ContactLoop, hook);
   kwclass<DynDt, Engine>(m, "DynDt") RW(DynDt, stepPeriod) RW(DynDt, maxRelInc) RW(DynDt, dryRun);
   py::class_<GpuDemLoop, Engine, shared_ptr<GpuDemLoop>>(m, "GpuDemLoop")
       .def(py::init([](shared_ptr<Leapfrog> lf, shared_ptr<InsertionSortCollider> co, shared_ptr<ContactLoop> cl, shared_ptr<DynDt> dd, int device, py::kwargs kw) {

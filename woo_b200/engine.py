@@ -173,6 +173,20 @@ class Engine:
     def set_scene(self, step, time):
         self._chk(self.L.wdem_set_scene(self.h, C.c_int64(int(step)), C.c_double(float(time))))
 
+    def walls(self):
+        """pos / force / torque of the walls after the last step (force: the last step's contacts)."""
+        n = len(self.spec.walls) if getattr(self, "spec", None) is not None else 0
+        o = {k: np.zeros((n, 3)) for k in ("pos", "force", "torque")}
+        if n:
+            self._chk(self.L.wdem_download_walls(self.h, ptr(o["pos"]), ptr(o["force"]), ptr(o["torque"])))
+        return o
+
+    def stress(self):
+        """ContactLoop.stress (evalStress) of the current state, 3x3."""
+        o = np.zeros((3, 3))
+        self._chk(self.L.wdem_get_stress(self.h, ptr(o)))
+        return o
+
     def kinetic_energy(self):
         e = C.c_double()
         self._chk(self.L.wdem_kinetic_energy(self.h, C.byref(e)))
