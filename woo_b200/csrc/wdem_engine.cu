@@ -885,7 +885,7 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   const int nNow = E->n;   // a full run of a decomposed scene changes the local sphere count (migration, ghosts)
   if (nNow > 0 && c.applyForces) {
     CsrStore& R = E->csr[E->curR];
-    k_reduce<<<nblk(nNow, 256), 256, 0, st>>>(E->S(), nNow, C, R.rowStart.p, R.rowEntry.p, u, guard); E->launches++;
+    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, R.rowStart.p, R.rowEntry.p, u, guard); E->launches++;
   }
   if (ev) CK(cudaEventRecord(ev[4], st));
 }

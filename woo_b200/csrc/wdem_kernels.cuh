@@ -672,8 +672,18 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
 // ------------------------------------------------------------------------------------------------
 // One thread per sphere walks its row in order; the loads of RB entries (entry word, global force, contact point) are issued together before the
 // sequential adds, so a row costs ~3 dependent round trips per RB entries instead of 3 per entry.
-#define RB 4
-__global__ void __launch_bounds__(256) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u,
+#ifndef WD_REDUCE_RB
+#define WD_REDUCE_RB 4
+#endif
+// 128 threads x 6 CTAs/SM (80 registers): measured best of {256x2 (94 regs) 0.149 ms, 128x5 0.145, 256x3 0.131, 128x6 0.127, 128x7 0.136, 128x8 0.162 (spills)}
+#ifndef WD_REDUCE_BLOCK
+#define WD_REDUCE_BLOCK 128
+#endif
+#ifndef WD_REDUCE_MINB
+#define WD_REDUCE_MINB 6
+#endif
+#define RB WD_REDUCE_RB
+__global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u,
                                                const int* __restrict__ guard) {
   if (guard && *guard) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
