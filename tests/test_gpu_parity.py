@@ -345,3 +345,9 @@ def test_moving_wall_piston(law):
         assert np.array_equal(wo["force"][mv], wg["force"][mv]) and np.array_equal(wo["torque"][mv], wg["torque"][mv]), "force on the moving walls differs"
     zi = S.walls.index(top[0])
     assert E.walls()["pos"][zi, 2] < z0 - .8 * 299 * E.scalars()["dt"] * .5 and np.abs(E.walls()["force"][zi]).max() > 0
+
+
+def test_gpu_matches_reference_python_models():
+    """The CUDA path against golden vectors made by the reference's own py/models.py (tests/golden/ref_models.json)."""
+    from test_oracle_kat import check_against_ref_models
+    check_against_ref_models(engine_for, lambda E: E.contacts(True))

@@ -177,3 +177,41 @@ def test_stress_two_spheres_across_the_cell_boundary():
     assert st[0, 0] == pytest.approx((-fn) * (-.09) / 1.0, rel=1e-6)
     st[0, 0] = 0
     assert np.abs(st).max() < 1e-12 * abs(fn)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors produced by the reference's own Python contact models (py/models.py CundallModel/HertzModel, scripts/make_golden_models.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _ref_model_rows():
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_models.json")))["rows"]
+
+
+def ref_model_scene(row, law):
+    """Two spheres of the golden row at rest, overlapping by delta."""
+    S = sc.SceneSpec()
+    mk = sc.frict_mat if law == sc.LAW_IDEALELPL else sc.hertz_mat
+    S.mats = [mk(density=1e3, young=row["E1"], ktDivKn=.2, tanPhi=.5), mk(density=1e3, young=row["E2"], ktDivKn=.2, tanPhi=.5)]
+    S.pos = np.array([[0, 0, 0], [0, 0, row["r1"] + row["r2"] - row["delta"]]], dtype=float)
+    S.radius = np.array([row["r1"], row["r2"]]); S.mat = np.array([0, 1], dtype=np.int32)
+    S.params = sc.Params(law=law, damping=0., dt=1e-9, dynDtPeriod=0, poisson=row["nu"], en=float("nan"))
+    return S.finalize()
+
+
+def check_against_ref_models(make_engine, contacts_of):
+    for row in _ref_model_rows():
+        E = make_engine(ref_model_scene(row, sc.LAW_IDEALELPL)); E.step(1)
+        c = contacts_of(E)
+        assert len(c["uN"]) == 1
+        # the reference's CundallModel.kn = 1/(r1/(E1 A)+r2/(E2 A)) vs Cp2_FrictMat_FrictPhys' 1/(1/(E1 A/l0)+1/(E2 A/l1)): same value up to rounding
+        assert c["phys"][0, 0] == pytest.approx(row["cundall_kn"], rel=1e-13)
+        assert c["force"][0, 0] == pytest.approx(-row["cundall_kn"] * row["delta"], rel=1e-9)
+        E = make_engine(ref_model_scene(row, sc.LAW_HERTZ_DMT)); E.step(1)
+        c = contacts_of(E)
+        assert len(c["uN"]) == 1
+        assert c["force"][0, 0] == pytest.approx(-row["hertz_F"], rel=1e-9)                         # F = K sqrt(R) delta^(3/2)
+        assert c["phys"][0, 0] == pytest.approx(1.5 * row["hertz_K"] * math.sqrt(row["hertz_R"]) * math.sqrt(row["delta"]), rel=1e-9)   # tangent stiffness dF/d(delta)
+
+
+def test_oracle_matches_reference_python_models():
+    check_against_ref_models(lambda S: Oracle(S), lambda O: O.contacts(True))
