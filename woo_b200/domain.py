@@ -200,13 +200,23 @@ class DistributedEngine:
     def step_e2e(self, n, ids, pos, vel, angVel, ids_out, pos_out, vel_out, angVel_out):
         """End-to-end step of this subdomain: host state (by id) -> device, n steps, owned state -> host.  Returns (owned count, Ek, stats);
         the owned set (and its order) may change when spheres migrate, so outputs carry their ids."""
+        import os, time
         E = self.E
+        t0 = time.perf_counter()
         _set_owned(E, ids, pos, vel, angVel)
+        t1 = time.perf_counter()
         st = E.step(n)
+        t2 = time.perf_counter()
         m = self.num_owned()
         assert m <= len(ids_out), "output buffers too small for the owned set"
         E._chk(E.L.wdem_download_owned(E.h, ptr(ids_out), ptr(pos_out), None, ptr(vel_out), ptr(angVel_out), None, None))
-        return m, E.kinetic_energy(), st
+        t3 = time.perf_counter()
+        ek = E.kinetic_energy()
+        if os.environ.get("WDEM_E2E_TRACE"):
+            import sys
+            print("rank %d e2e: set_owned %.2f ms, step %.2f ms (device %.2f, rebuilds %d), download %.2f ms, ek %.2f ms" % (
+                self.rank, (t1 - t0) * 1e3, (t2 - t1) * 1e3, st.device_ms, st.n_rebuilds, (t3 - t2) * 1e3, (time.perf_counter() - t3) * 1e3), file=sys.stderr, flush=True)
+        return m, ek, st
 
     def domain_stats(self):
         return _domain_stats(self.E)
