@@ -82,8 +82,13 @@ def ncu_traffic():
         return None
 
 
+LAW = "linear"     # --law hertz: the same bed under Cp2_HertzMat_HertzPhys + Law2_L6Geom_HertzPhys_DMT with cfg3's material (extra data point, not the default line)
+
+
 def workload(n, seed):
     from woo_b200 import scenes as sc
+    if LAW == "hertz":   # BASELINE.json configs[2] material and law: HertzMat(rho=2500, E=1e8, tanPhi=.5), poisson=.2, en=.5, noAttraction, damping 0
+        return sc.deposition(n, r=1e-3, psd_ratio=4.0, seed=seed, law=sc.LAW_HERTZ_DMT, layers=LAYERS, damping=0., young=1e8, density=2500., en=.5)
     return sc.deposition(n, r=1e-3, psd_ratio=4.0, seed=seed, law=sc.LAW_IDEALELPL, layers=LAYERS, damping=.2, young=1e7, density=2500.)
 
 
@@ -108,7 +113,7 @@ def workload_tiled(n, tiles_x=None):
     S.mat = S.mask = S.flags = None
     lo = d["lo"]; hi = np.array([lo[0] + tx * L[0], lo[1] + ty * L[1], d["hi"][2]])
     S.walls = sc.box_walls(tuple(lo), tuple(hi), mat=0)
-    S.params.dt = float(d["dt"])
+    S.params.dt = float(d["dt"]) if LAW == "linear" else float("nan")    # another law: start from dtSafety * pWaveDt, DynDt takes over
     return S.finalize(), dict(tiles=tiles, tiles_x=tx, tiles_y=ty)
 
 
@@ -130,7 +135,7 @@ def workload_slab(n, rank, world):
     S.mat = S.mask = S.flags = None
     lo = d["lo"]; hi = np.array([lo[0] + world * tx * L[0], lo[1] + ty * L[1], d["hi"][2]])
     S.walls = sc.box_walls(tuple(lo), tuple(hi), mat=0)
-    S.params.dt = float(d["dt"])
+    S.params.dt = float(d["dt"]) if LAW == "linear" else float("nan")
     nloc = m * tiles; nb = len(S.walls)
     S.boundaries_first = True
     S.ids = (nb + rank * nloc + np.arange(nloc)).astype(np.int32)
@@ -260,11 +265,12 @@ def run_gpu(args):
     out = {
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: 1M polydisperse spheres (PSD 1:4) settled under gravity, Leapfrog+collider+ContactLoop(Cg2_Sphere_Sphere/Wall_Sphere_L6Geom, Cp2_FrictMat_FrictPhys, Law2_L6Geom_FrictPhys_IdealElPl)+DynDt",
+        "config": {"workload": "cfg2: 1M polydisperse spheres (PSD 1:4) settled under gravity, Leapfrog+collider+ContactLoop(Cg2_Sphere_Sphere/Wall_Sphere_L6Geom, Cp2_FrictMat_FrictPhys, Law2_L6Geom_FrictPhys_IdealElPl)+DynDt" if LAW == "linear" else
+                   "cfg2 bed under cfg3's law and material: 1M polydisperse spheres (PSD 1:4), HertzMat(E=1e8), Cp2_HertzMat_HertzPhys(poisson=.2, en=.5)+Law2_L6Geom_HertzPhys_DMT, damping 0, DynDt",
                    "n_spheres_per_gpu": n, "initial_state": ("tiled pre-settled 20k bed (tests/golden/cfg2_sample_20k.npz) %dx%d, re-settled" % (tiling["tiles_x"], tiling["tiles_y"])) if tiling else "jittered lattice", "settle_steps": args.settle, "real_contacts": n_real, "candidate_contacts": n_con, "rebuilds_in_timed_region": n_reb,
                    "l2_policy": "inputs larger than L2 (per-step working set %.0f MB > 126 MB)" % (step_bytes / 1e6), "parallelism": ("%d x-slabs of one box, 1 per GPU; ghosts refreshed per step and spheres migrated at collider runs over NCCL" % world) if world > 1 else "single GPU",
                    "settle_wall_s": round(settle_s, 1)},
-        "roofline": {"bound": "hbm", "kernel": "k_contact_ss<IdealElPl>", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_source": (ncu_traffic() or {}).get("source"),
+        "roofline": {"bound": "hbm", "kernel": "k_contact_ss<IdealElPl>" if LAW == "linear" else "k_contact_ss<HertzDMT>", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_source": (ncu_traffic() or {}).get("source"),
                      "algorithmic_bytes_per_launch": bytes_contact, "ms_per_launch": ms_contact,
                      "step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9, "frac": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9 / peak},
                      "phase_ms_per_step": {k: stats[k] / K for k in ("ms_integrate", "ms_rebuild", "ms_contact", "ms_reduce", "ms_dyndt")}},
@@ -335,8 +341,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--law", default="linear", choices=["linear", "hertz"], help="hertz: extra data point with cfg3's law and material on the same bed")
     ap.add_argument("--ncu-range", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
+    global LAW
+    LAW = args.law
     if args.impl == "reference":
         run_reference(args)
     else:
