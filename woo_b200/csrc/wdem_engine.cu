@@ -59,7 +59,7 @@ struct SphereStore {
 };
 
 struct ContactStore {
-  DBuf<int2> pair; DBuf<uint32_t> flags; DBuf<int32_t> stepCreated, cd[3]; DBuf<double> t[6], fl[3], ph[5], tq[3]; DBuf<double4> cp, Fg, Tg;
+  DBuf<int2> pair; DBuf<uint32_t> flags, realBits; DBuf<int32_t> stepCreated, cd[3]; DBuf<double> t[6], fl[3], ph[5], tq[3]; DBuf<double4> cp, Fg, Tg;
   size_t cap = 0;
   void ensure(size_t n, int64_t& tot, bool hertz, bool rolling, bool periodic, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return;
@@ -69,13 +69,13 @@ struct ContactStore {
     for (auto& b : t) b.ensure(n, tot, keep, st); for (auto& b : fl) b.ensure(n, tot, keep, st);
     for (int k = 0; k < (hertz ? 5 : 3); k++) ph[k].ensure(n, tot, keep, st);
     if (rolling) { for (auto& b : tq) b.ensure(n, tot, keep, st); Tg.ensure(n, tot, keep, st); }
-    cp.ensure(n, tot, keep, st); Fg.ensure(n, tot, keep, st);
+    cp.ensure(n, tot, keep, st); Fg.ensure(n, tot, keep, st); realBits.ensure(n / 32 + 2, tot, keep, st);
     cap = n;
   }
   Contacts view() { Contacts C; C.pair = pair.p; C.flags = flags.p; C.stepCreated = stepCreated.p; C.cdx = cd[0].p; C.cdy = cd[1].p; C.cdz = cd[2].p;
     C.t0x = t[0].p; C.t0y = t[1].p; C.t0z = t[2].p; C.t1x = t[3].p; C.t1y = t[4].p; C.t1z = t[5].p; C.cp = cp.p; C.fn = fl[0].p; C.ft0 = fl[1].p; C.ft1 = fl[2].p;
-    for (int k = 0; k < 5; k++) C.ph[k] = ph[k].p; C.tq0 = tq[0].p; C.tq1 = tq[1].p; C.tq2 = tq[2].p; C.Fg = Fg.p; C.Tg = Tg.p; return C; }
-  void release() { pair.release(); flags.release(); stepCreated.release(); for (auto& b : cd) b.release(); for (auto& b : t) b.release(); for (auto& b : fl) b.release(); for (auto& b : ph) b.release(); for (auto& b : tq) b.release(); cp.release(); Fg.release(); Tg.release(); cap = 0; }
+    for (int k = 0; k < 5; k++) C.ph[k] = ph[k].p; C.tq0 = tq[0].p; C.tq1 = tq[1].p; C.tq2 = tq[2].p; C.Fg = Fg.p; C.Tg = Tg.p; C.realBits = realBits.p; return C; }
+  void release() { pair.release(); flags.release(); stepCreated.release(); for (auto& b : cd) b.release(); for (auto& b : t) b.release(); for (auto& b : fl) b.release(); for (auto& b : ph) b.release(); for (auto& b : tq) b.release(); cp.release(); Fg.release(); Tg.release(); realBits.release(); cap = 0; }
 };
 
 struct CsrStore { DBuf<int> rowStart; DBuf<uint32_t> rowEntry; DBuf<int32_t> rowOther; bool valid = false; void release() { rowStart.release(); rowEntry.release(); rowOther.release(); } };
@@ -731,6 +731,7 @@ void rebuild(wdem_engine* E) {
     }
     const long long nC = nC0 + nOrph;
     nOrphOut = nOrph;
+    if (nC > 0) { k_realbits<<<nblk(nC, 256), 256, 0, st>>>(N.flags, nC, N.realBits); E->launches++; }
     // 7. per-particle incidence rows sorted by the other particle's id: scan of row counts, cursor fill, per-row sort
     const long long nK = 2 * nC;
     Ncsr.rowStart.ensure((size_t)n + 2, tot); Ncsr.rowEntry.ensure((size_t)std::max<long long>(nK, 1), tot); Ncsr.rowOther.ensure((size_t)std::max<long long>(nK, 1), tot);

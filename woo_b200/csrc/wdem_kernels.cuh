@@ -51,6 +51,8 @@ struct Contacts {         // SoA planes, one entry per candidate pair (real or p
   double *tq0, *tq1, *tq2;  // CPhys.torque (only with rolling/twisting resistance)
   double4* Fg;            // global force on pA (xyz), w = 1 if the contact is real in this step else 0
   double4* Tg;            // global contact torque on pA (rolling resistance only)
+  uint32_t* realBits;     // 1 bit per contact: real (CF_REAL and not dead); set at full runs (k_realbits), flipped by the contact kernels when a contact is
+                          // created / broken.  Half a megabyte for 4 M candidates, i.e. L2-resident: the force reduction tests it instead of gathering Fg.
 };
 
 struct StepU {            // per-step uniforms
@@ -365,7 +367,7 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
     uint32_t nf = (fl & ~CF_REAL) | ((fl & CF_ORPHAN) ? CF_DEAD : 0);
     C.flags[c] = nf;
     C.Fg[c] = make_double4(0, 0, 0, 0);
-    if (wasReal) atomicAdd(&cnt->nBroken, 1ull);
+    if (wasReal) { atomicAnd(&C.realBits[c >> 5], ~(1u << (c & 31))); atomicAdd(&cnt->nBroken, 1ull); }
     return;
   }
   // ---- store state
@@ -373,7 +375,7 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
   C.t1x[c] = c1.x; C.t1y[c] = c1.y; C.t1z[c] = c1.z;
   C.cp[c] = make_double4(contPt.x, contPt.y, contPt.z, uN);
   C.fn[c] = Fn; C.ft0[c] = ftA; C.ft1[c] = ftB;
-  if (!wasReal) C.flags[c] = fl | CF_REAL;
+  if (!wasReal) { C.flags[c] = fl | CF_REAL; atomicOr(&C.realBits[c >> 5], 1u << (c & 31)); }
   // ---- Contact::getForceTorqueBranch (Contact.cpp:24-35): F = ori * phys.force, ori = Quaternionr(trsf)
   q4 q = quatFromCols(c0, c1, c2);
   d3 Fglob = quatRotate(q, mk3(Fn, ftA, ftB));
@@ -702,13 +704,19 @@ __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Sphe
     uint32_t ent[RB]; double4 fg[RB], cp[RB];
 #pragma unroll
     for (int k = 0; k < RB; k++) ent[k] = (e + k < e1) ? rowEntry[e + k] : 0xffffffffu;
+    // real? one L2-resident bit per contact decides, so the force and the contact point of a real contact are gathered together (one round trip)
+    // and potential contacts (half of the candidates of a dense bed) cost no gather at all
+    bool real[RB];
 #pragma unroll
-    for (int k = 0; k < RB; k++) fg[k] = (ent[k] != 0xffffffffu) ? C.Fg[ent[k] >> 1] : make_double4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < RB; k++) cp[k] = (fg[k].w != 0.) ? C.cp[ent[k] >> 1] : make_double4(0, 0, 0, 0);
+    for (int k = 0; k < RB; k++) { const uint32_t c = ent[k] >> 1; real[k] = (ent[k] != 0xffffffffu) && ((C.realBits[c >> 5] >> (c & 31)) & 1u); }
 #pragma unroll
     for (int k = 0; k < RB; k++) {
-      if (fg[k].w == 0.) continue;
+      fg[k] = real[k] ? C.Fg[ent[k] >> 1] : make_double4(0, 0, 0, 0);
+      cp[k] = real[k] ? C.cp[ent[k] >> 1] : make_double4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < RB; k++) {
+      if (!real[k]) continue;
       const uint32_t c = ent[k] >> 1;
       d3 Fc = xyz(fg[k]), xc;
       if (ent[k] & 1u) {  // this particle is pB: sign=-1, branch from pos+shift2
@@ -953,8 +961,11 @@ __device__ __forceinline__ long long find_old2(const OldCsr& oc, int oslot, int 
 
 // Sphere+Sphere candidates (see HGrid for the ownership rule).  FILL=false counts, FILL=true writes pairs (canonical pA = lower id) and looks up the
 // previous contact of the pair (history carry-over by k_carry).
+#ifndef WD_PAIRS_MINB
+#define WD_PAIRS_MINB 1
+#endif
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_pairs_ss(Spheres S, int n, HGrid g, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
+__global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int n, HGrid g, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
                                                  const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
                                                  int* __restrict__ rowCount, int* __restrict__ srcOld) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1408,6 +1419,14 @@ __global__ void __launch_bounds__(256) k_scatter_state(Spheres S, int n, const i
 __global__ void __launch_bounds__(256) k_up2slot(const int32_t* __restrict__ up, int n, int* up2slot) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) up2slot[up[i]] = i;
+}
+// realBits of a freshly built table: one thread per contact, one word per warp (tables start warp-aligned)
+__global__ void __launch_bounds__(256) k_realbits(const uint32_t* __restrict__ flags, long long n, uint32_t* __restrict__ bits) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t f = 0;
+  if (c < n) f = flags[c];
+  const unsigned m = __ballot_sync(0xffffffffu, (f & CF_REAL) && !(f & CF_DEAD));
+  if ((threadIdx.x & 31) == 0 && c < n + 31) bits[c >> 5] = m;
 }
 __global__ void __launch_bounds__(256) k_count_flags(const uint32_t* __restrict__ flags, long long n, unsigned long long* out /*[0]=real,[1]=alive*/) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
