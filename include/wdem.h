@@ -139,6 +139,13 @@ int wdem_set_scene(wdem_handle h, int64_t step, double time);
  * resets every step; for a wall at rest the reference never resets and keeps accumulating — take the per-step value times the steps instead.
  * Decomposed runs: the share of this subdomain's spheres. */
 int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torque);
+/* Scene.trackEnergy (Scene.hpp:191-205, core/EnergyTracker.hpp): on = the step kernels also accumulate the EnergyTracker entries of this path, 8 doubles in the order
+ * kinetic, grav, nonviscDamp (Leapfrog.cpp:53-98), elast, plast, broken (IdealElPl.cpp:28-40,64-75,85-92), viscN, viscT (Hertz.cpp:181,193,199,203-207; Hertz's
+ * sliding and elastic terms go to plast / elast).  "kinetic" and "elast" are resettable: they hold the last step's value (Scene.cpp:416), the others accumulate from
+ * the moment tracking was switched on.  Sums are formed with atomics: equal to the reference's to rounding, not bitwise.  The gradV work of periodic scenes
+ * (ContactLoop.cpp:243-250) is not tracked. */
+int wdem_track_energy(wdem_handle h, int on);
+int wdem_get_energy(wdem_handle h, double* out8);
 /* ContactLoop.stress with evalStress=True (ContactLoop.hpp:117, ContactLoop.cpp:116,123,218-231,243-244): sum over real contacts of F (x) dPos / cell volume,
  * row-major 3x3, periodic scenes only; evaluated on demand from the state the last step left (decomposed runs: this subdomain's share — add the
  * results of all subdomains).  Contacts with facets fail like the reference (multi-nodal particles). */

@@ -313,6 +313,14 @@ struct Bound {
 };
 
 struct Scene {
+  // Scene.trackEnergy / EnergyTracker (core/EnergyTracker.hpp:30-60): named accumulators; "kinetic" and "elast" are resettable (zeroed in the step prologue, Scene.cpp:416)
+  enum { EN_KINETIC = 0, EN_GRAV, EN_DAMP, EN_ELAST, EN_PLAST, EN_BROKEN, EN_VISCN, EN_VISCT, EN_COUNT };
+  bool trackEnergy = false; double energy[EN_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void eadd(int ix, Real v) {  // EnergyTracker::add (EnergyTracker.cpp:26-34): NaN is ignored; callable from parallel sections
+    if (std::isnan(v)) return;
+    #pragma omp atomic
+    energy[ix] += v;
+  }
   Params P; Cell cell;
   std::vector<Material> mats; std::vector<Sphere> sph; std::vector<Wall> walls; std::vector<Facet> facets; std::vector<PRef> par;
   std::map<uint64_t, Contact> con;          // ordered by canonical key
@@ -807,7 +815,13 @@ struct Scene {
   // ------------------------------------------------------------------------------------------
   bool lawIdealElPl(Contact& C) {  // Law2_L6Geom_FrictPhys_IdealElPl::go (IdealElPl.cpp:15-125); iniEqlb, trackEnergy not restated
     Real uN = C.uN;
-    if (uN > 0 && !P.noBreak) return false;
+    if (uN > 0 && !P.noBreak) {
+      if (P.noSlip && trackEnergy) {   // IdealElPl.cpp:28-40: the elastic potential of the breaking contact is lost
+        const Real Fn = C.kn * uN; const Real t0 = C.force[1] + (P.dt * C.kt) * C.gvel[1], t1 = C.force[2] + (P.dt * C.kt) * C.gvel[2];
+        eadd(EN_BROKEN, .5 * (pow2(Fn) / C.kn + (t0 * t0 + t1 * t1) / C.kt));
+      }
+      return false;
+    }
     C.torque = V3();
     C.force[0] = C.kn * uN;
     Real& Ft0 = C.force[1]; Real& Ft1 = C.force[2];
@@ -821,9 +835,15 @@ struct Scene {
         Real FtNorm = std::sqrt(FtSq);
         Real ratio = maxFt / FtNorm;
         if (FtNorm == 0.) ratio = 0.;
+        if (trackEnergy) eadd(EN_PLAST, C.kt != 0. ? (maxFt) * (FtNorm - maxFt) / C.kt : 0.);   // IdealElPl.cpp:64-75
         Ft0 *= ratio; Ft1 *= ratio;
       }
       if (std::isnan(C.force[0]) || std::isnan(Ft0) || std::isnan(Ft1)) throw std::runtime_error("NaN force in contact ##" + std::to_string(C.idA) + "+" + std::to_string(C.idB));
+    }
+    if (trackEnergy) {   // IdealElPl.cpp:85-92
+      Real elast = 0.5 * (pow2(C.force[0]) / C.kn + (C.kt != 0. ? (Ft0 * Ft0 + Ft1 * Ft1) / C.kt : 0.));
+      if (std::isnan(elast)) elast = 0.;
+      eadd(EN_ELAST, elast);
     }
     if (P.relRollStiff > 0. && P.rollTanPhi > 0.) {
       Real charLen = C.lens[0] + C.lens[1];
@@ -859,12 +879,23 @@ struct Scene {
     Real Fnv = eta * velN;
     if (C.alpha == 0. && P.noAttraction && Fne + Fnv > 0) Fnv = -Fne;
     Fn = Fne + Fna + Fnv;
+    if (trackEnergy) eadd(EN_VISCN, Fnv * velN * dt);   // Hertz.cpp:181
     C.kt = C.kt0 * std::sqrt(C.uN < 0 ? -C.uN : 0);
     Ft0 += (dt * C.kt) * vT0; Ft1 += (dt * C.kt) * vT1;
     Real maxFt = std::abs(std::min(0., Fn) * C.tanPhi);
     Real FtSq = Ft0 * Ft0 + Ft1 * Ft1;
-    if (FtSq > pow2(maxFt)) { Real FtNorm = std::sqrt(FtSq); Real ratio = maxFt / FtNorm; Ft0 *= ratio; Ft1 *= ratio; }
-    else { Ft0 += eta * vT0; Ft1 += eta * vT1; }
+    if (FtSq > pow2(maxFt)) {
+      Real FtNorm = std::sqrt(FtSq); Real ratio = maxFt / FtNorm;
+      if (trackEnergy) eadd(EN_PLAST, (.5 * (FtNorm - maxFt) + maxFt) * (FtNorm - maxFt) / C.kt);   // Hertz.cpp:193
+      Ft0 *= ratio; Ft1 *= ratio;
+    } else {
+      Ft0 += eta * vT0; Ft1 += eta * vT1;
+      if (trackEnergy) eadd(EN_VISCT, eta * (vT0 * vT0 + vT1 * vT1) * dt);   // Hertz.cpp:199
+    }
+    if (trackEnergy && C.uN < 0) {   // Hertz.cpp:203-207; normalElasticEnergy = kn0*(2/5)*pown(sqrt(delta),5) (Hertz.hpp:70,76)
+      const Real sq = std::sqrt(-C.uN);
+      eadd(EN_ELAST, kn0 * (2 / 5.) * (((sq * sq) * (sq * sq)) * sq) + 0.5 * (Ft0 * Ft0 + Ft1 * Ft1) / C.kt);
+    }
     return true;
   }
 
@@ -978,6 +1009,10 @@ struct Scene {
     const V3 g(P.gravity[0], P.gravity[1], P.gravity[2]);
     const bool hasGravity = (g != V3(0, 0, 0));
     const long n = (long)sph.size();
+    // Leapfrog.cpp:130-132: no energy in the first step of a periodic scene with a velocity gradient (the mean-field velocity is not applied yet)
+    bool gradVIsIdentity = true;
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) if (cell.gradV(a, b) != (a == b ? 1. : 0.)) gradVIsIdentity = false;
+    const bool reallyTrackEnergy = trackEnergy && (!P.periodic || step > 0 || gradVIsIdentity);
     #pragma omp parallel for schedule(guided)
     for (long i = 0; i < n; i++) {
       Sphere& s = sph[i];
@@ -985,6 +1020,20 @@ struct Scene {
       const bool blockedAll = (fl & DOF_ALL) == DOF_ALL, blockedNone = (fl & DOF_ALL) == 0;
       const bool damp = (damping != 0. && !(fl & DAMPING_SKIP));
       V3& f = s.force; V3& t = s.torque;
+      if (reallyTrackEnergy) {
+        // Leapfrog::doDampingDissipation (Leapfrog.cpp:53-65) and doGravityWork (:67-74), with the values at the start of the step
+        if (damp && !(fl & ENERGY_SKIP)) {
+          const V3 av(std::abs(s.vel.x), std::abs(s.vel.y), std::abs(s.vel.z)), af(std::abs(f.x), std::abs(f.y), std::abs(f.z));
+          const V3 aw(std::abs(s.angVel.x), std::abs(s.angVel.y), std::abs(s.angVel.z)), at(std::abs(t.x), std::abs(t.y), std::abs(t.z));
+          eadd(EN_DAMP, dot(av, af) * damping * dt + dot(aw, at) * damping * dt);
+        }
+        if (hasGravity && !(fl & GRAVITY_SKIP)) {
+          Real gr = 0;
+          if (blockedNone) gr = -dot(g, s.vel) * s.mass * dt;
+          else { for (int k = 0; k < 3; k++) if (!(fl & (1u << k))) gr -= g[k] * s.vel[k] * s.mass * dt; }
+          eadd(EN_GRAV, gr);
+        }
+      }
       V3 pprevFluctVel, pprevFluctAngVel, linAccel, angAccel;
       if (!blockedAll) {
         // computeAccel (Leapfrog.cpp:37-42)
@@ -1012,6 +1061,14 @@ struct Scene {
           if (homoDeform == HOMO_VEL_2ND) s.vel += mulMV(midGradV, s.vel - (dt / 2.) * linAccel) * dt;
           s.vel += mulMV(dGradV, s.pos);
         } else if (homoDeform == HOMO_POS) s.pos += mulMV(cell.nextGradV, s.pos) * dt;
+      }
+      if (reallyTrackEnergy && !(fl & ENERGY_SKIP)) {
+        // Leapfrog::doKineticEnergy (Leapfrog.cpp:76-98): on-step value from the mid-step fluctuation velocities; a fully blocked node passes zeros (:198)
+        const V3 cfv = pprevFluctVel + (.5 * dt) * linAccel, cfw = pprevFluctAngVel + (.5 * dt) * angAccel;
+        const Real Etrans = .5 * s.mass * sqNorm(cfv);
+        Real Erot = 0.5 * dot(cfw, V3(s.inertia * cfw.x, s.inertia * cfw.y, s.inertia * cfw.z));
+        if (std::isnan(Erot) || std::isinf(s.inertia)) Erot = 0;
+        eadd(EN_KINETIC, Etrans + Erot);
       }
       s.pos += s.vel * dt;  // leapfrogTranslate (Leapfrog.cpp:275-278)
       // leapfrogSphericalRotate (Leapfrog.cpp:280-297)
@@ -1105,6 +1162,7 @@ struct Scene {
       P.dt = P.dtSafety * crDt;
     }
     if (P.periodic) cell.integrateAndUpdate(P.dt);
+    if (trackEnergy) { energy[EN_KINETIC] = 0; energy[EN_ELAST] = 0; }   // energy->resetResettables() (Scene.cpp:416)
     leapfrogRun();
     colliderRun();
     contactLoopRun();
@@ -1266,6 +1324,9 @@ int orc_get_stress(void* h, double* out9) {
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out9[3 * i + j] = st(i, j) / vol;
   ORC_CATCH(h)
 }
+void orc_set_track_energy(void* h, int on) { ((Scene*)h)->trackEnergy = on != 0; }
+// kinetic, grav, nonviscDamp, elast, plast, broken, viscN, viscT
+void orc_get_energy(void* h, double* out8) { for (int k = 0; k < Scene::EN_COUNT; k++) out8[k] = ((Scene*)h)->energy[k]; }
 int orc_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

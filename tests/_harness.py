@@ -127,6 +127,14 @@ class Oracle:
             self.L.orc_get_walls(self.h, _p(o["pos"], C.c_double), _p(o["force"], C.c_double), _p(o["torque"], C.c_double))
         return o
 
+    def track_energy(self, on=True):
+        self.L.orc_set_track_energy(self.h, C.c_int(int(on)))
+
+    def energy(self):
+        o = np.zeros(8)
+        self.L.orc_get_energy(self.h, _p(o, C.c_double))
+        return dict(zip(("kinetic", "grav", "nonviscDamp", "elast", "plast", "broken", "viscN", "viscT"), o.tolist()))
+
     def stress(self):
         o = np.zeros((3, 3))
         self._chk(self.L.orc_get_stress(self.h, _p(o, C.c_double)))

@@ -351,3 +351,44 @@ def test_gpu_matches_reference_python_models():
     """The CUDA path against golden vectors made by the reference's own py/models.py (tests/golden/ref_models.json)."""
     from test_oracle_kat import check_against_ref_models
     check_against_ref_models(engine_for, lambda E: E.contacts(True))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Scene.trackEnergy (SURVEY §8f-3): EnergyTracker entries, device vs oracle.  Sums run over thousands of terms in different orders (atomics): 1e-9 relative.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["linear", "linear-noslip", "hertz", "periodic", "decomposed"])
+def test_track_energy_matches_oracle(kind):
+    if kind == "linear":
+        S = sc.random_gas(400, box=.5, r=.02, psd_ratio=3.0, seed=71)
+        S.flags[::9] = sc.DOF_ALL; S.flags[1::9] = 256; S.flags[2::9] = sc.GRAVITY_SKIP; S.flags[3::9] = sc.DAMPING_SKIP; S.flags[4::9] = 1 | 16
+    elif kind == "linear-noslip":
+        S = sc.random_gas(400, box=.5, r=.02, psd_ratio=2.0, seed=72); S.params.noSlip = 1
+    elif kind == "hertz":
+        S = sc.random_gas(400, box=.5, r=.02, psd_ratio=2.0, seed=73, law=sc.LAW_HERTZ_DMT, en=.6)
+    elif kind == "periodic":
+        S = sc.periodic_gas(400, seed=74, gradV=[[0, 1., 0], [0, 0, 0], [0, 0, 0]], shear0=.1, psd_ratio=2.0)
+    else:
+        S = sc.random_gas(500, box=.5, r=.02, psd_ratio=3.0, seed=75)
+    O = Oracle(S); O.track_energy(True)
+    if kind == "decomposed":
+        from woo_b200.domain import LocalCluster
+        E = LocalCluster(S, 2, axis=0)
+        for e in E.E:
+            e.track_energy(True)
+        energy = lambda: {k: sum(e.energy()[k] for e in E.E) for k in E.E[0].energy()}
+    else:
+        E = engine_for(S); E.track_energy(True); energy = E.energy
+    seen = set()
+    for k in range(4):
+        O.step(80); E.step(80)
+        eo, eg = O.energy(), energy()
+        scale = max(abs(v) for v in eo.values())
+        for name in eo:
+            assert eg[name] == pytest.approx(eo[name], rel=1e-9, abs=1e-12 * scale), f"{kind}: energy[{name}] after {80 * (k + 1)} steps: {eg[name]} vs {eo[name]}"
+            if eo[name] != 0:
+                seen.add(name)
+        # tracking does not touch the trajectory
+        assert np.array_equal(O.spheres()["pos"], E.spheres()["pos"])
+    want = {"linear": {"kinetic", "grav", "nonviscDamp", "elast", "plast"}, "linear-noslip": {"kinetic", "elast", "broken"}, "hertz": {"kinetic", "elast", "viscN", "viscT", "plast"},
+            "periodic": {"kinetic", "elast"}, "decomposed": {"kinetic", "elast", "plast"}}[kind]
+    assert want <= seen, f"{kind}: entries never became non-zero: {want - seen}"

@@ -215,3 +215,41 @@ def check_against_ref_models(make_engine, contacts_of):
 
 def test_oracle_matches_reference_python_models():
     check_against_ref_models(lambda S: Oracle(S), lambda O: O.contacts(True))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Scene.trackEnergy: the EnergyTracker entries of this path
+# ---------------------------------------------------------------------------------------------------------------
+def test_energy_conservation_elastic_collision():
+    """Two spheres collide head-on, linear law, no friction/damping/gravity: kinetic + elast stays at the initial kinetic energy (leapfrog: to O(dt^2))."""
+    S = two_spheres(sc.LAW_IDEALELPL, v0=1., gap=1e-4, mat=sc.frict_mat(density=1e3, young=1e7, ktDivKn=.2, tanPhi=0.)); S.params.dynDtPeriod = 0; S.params.dt = 2e-6
+    O = Oracle(S); O.track_energy(True)
+    m = S.mass_inertia()[0][0]; e0 = 2 * .5 * m * .5 ** 2
+    seen_elast = 0.
+    for _ in range(60):
+        O.step(50)
+        e = O.energy(); seen_elast = max(seen_elast, e["elast"])
+        assert e["kinetic"] + e["elast"] == pytest.approx(e0, rel=5e-3)       # kinetic is the on-step estimate, elast belongs to the end of the step
+        assert e["plast"] == 0 and e["nonviscDamp"] == 0 and e["grav"] == 0
+    assert seen_elast > .5 * e0 and O.num_contacts(True) == 0       # they did touch and separate again
+
+
+def test_energy_free_fall_and_damping_like_the_reference_test():
+    """py/tests/test_energy.py:69-90 (TestLeapfrog): a wall, a sphere, gravity, damping .4.  grav + kinetic + elast + nonviscDamp (+plast) add up to ~0 (start at
+    rest with zero potential); gravitySkip leaves no 'grav', dampingSkip no 'nonviscDamp'."""
+    def scene(flags=0):
+        S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+        S.pos = np.array([[0, 0, .9]]); S.radius = np.array([.8]); S.flags = np.array([flags], dtype=np.uint32)
+        S.walls = [dict(pos=(0, 0, 0), axis=2, sense=1, mat=0, mask=sc.MASK_BOUNDARY)]
+        S.params = sc.Params(gravity=(0, 0, -10), damping=.4, dtSafety=.9, dynDtPeriod=100)
+        return S.finalize()
+    O = Oracle(scene()); O.track_energy(True); O.step(400)
+    e = O.energy()
+    assert e["grav"] != 0 and e["nonviscDamp"] > 0 and e["kinetic"] >= 0
+    tot = sum(e.values()); sabs = sum(abs(v) for v in e.values())
+    assert abs(tot) < 2e-2 * sabs, e                                   # EnergyTracker.relErr (EnergyTracker.cpp:41-43) stays small
+    S = scene(flags=sc.GRAVITY_SKIP); S.vel[0] = (0, 0, -1)
+    O = Oracle(S); O.track_energy(True); O.step(400)
+    assert O.energy()["grav"] == 0 and O.energy()["nonviscDamp"] != 0
+    O = Oracle(scene(flags=sc.DAMPING_SKIP)); O.track_energy(True); O.step(400)
+    assert O.energy()["grav"] != 0 and O.energy()["nonviscDamp"] == 0

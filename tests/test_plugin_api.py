@@ -79,9 +79,10 @@ def test_unsupported_settings_raise():
     S.engines = [GpuDemLoop(*woo.utils.defaultEngines(cp2=Cp2_FrictMat_FrictPhys(), law=Law2_L6Geom_HertzPhys_DMT()))]
     with pytest.raises(RuntimeError, match="supported functor pairs"):
         S.one()
-    S.engines = woo.utils.gpuEngines(); S.trackEnergy = True
-    with pytest.raises(RuntimeError, match="trackEnergy"):
+    S.engines = woo.utils.gpuEngines(); S.trackEnergy = True; S.periodic = True; S.engines[0].contactLoop.evalStress = True
+    with pytest.raises(RuntimeError, match="trackEnergy"):          # the gradV work needs the stress every step: not supported
         S.one()
+    S.periodic = False; S.trackEnergy = False; S.engines[0].contactLoop.evalStress = False
     with pytest.raises(RuntimeError, match="degenerate"):
         S.cell.hSize = [[1, 0, 0], [0, 0, 0], [0, 0, 1]]      # py/tests/test_pbc.py:60-62
 
@@ -238,3 +239,26 @@ def test_contact_history_survives_adding_particles():
     ca = {(c.id1, c.id2): tuple(c.phys.force) for c in A.dem.con if c.real}
     cb = {(c.id1, c.id2): tuple(c.phys.force) for c in B.dem.con if c.real}
     assert ca == cb
+
+
+@pytest.mark.gpu
+def test_energy_tracking_like_the_reference_test():
+    """py/tests/test_energy.py:69-90 (TestLeapfrog) with the GPU engine group: Scene(trackEnergy=True), a wall and a sphere under gravity with damping .4."""
+    def scene():
+        S = Scene(fields=[DemField(gravity=(0, 0, -10))]); S.dtSafety = .9; S.trackEnergy = True
+        m = woo.utils.defaultMaterial()
+        S.dem.par.add([Wall.make(0, axis=2, sense=1, mat=m), Sphere.make((0, 0, .9), radius=.8, mat=m)])
+        S.engines = woo.utils.gpuEngines(damping=.4)
+        return S
+    S = scene()
+    for n in S.dem.nodes:
+        n.dem.gravitySkip = True
+    S.dem.par[1].vel = (0, 0, -1)
+    S.run(400, True)
+    assert "grav" not in S.energy and S.energy["nonviscDamp"] != 0.
+    S = scene()
+    for n in S.dem.nodes:
+        n.dem.dampingSkip = True
+    S.run(400, True)
+    assert S.energy["grav"] != 0. and "nonviscDamp" not in S.energy
+    assert "kinetic" in S.energy and "elast" in S.energy

@@ -175,6 +175,7 @@ struct wdem_engine {
   long long dynStepLast = -1, dynStepPrev = -1;
   HostCell cell;
   long long launches = 0; int numSMs = 148;
+  bool trackEnergy = false; DBuf<double> dEnergy;   // Scene.trackEnergy: EN_* accumulators on the device
   // end-to-end pipeline (wdem_step_e2e): host<->device copies of the state overlap with the integrator chunk by chunk
   static const int NCHUNK = 16; int nChunk = 8;   // NCHUNK = capacity, nChunk = pieces in use (WDEM_E2E_CHUNKS)
   struct E2E { bool active = false; const double *pos = nullptr, *vel = nullptr, *angVel = nullptr; double *posOut = nullptr, *velOut = nullptr; } e2e;
@@ -221,6 +222,11 @@ StepU makeUniforms(wdem_engine* E) {
   u.law = c.law; u.noSlip = c.noSlip; u.noBreak = c.noBreak; u.noFrict = c.noFrict; u.noAttraction = c.noAttraction;
   u.rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.); u.relRollStiff = c.relRollStiff; u.relTwistStiff = c.relTwistStiff; u.rollTanPhi = c.rollTanPhi;
   u.poisson = c.poisson; u.en = c.en;
+  u.energy = E->trackEnergy ? E->dEnergy.p : nullptr;
+  {   // Leapfrog.cpp:130-132
+    bool ident = true; for (int k = 0; k < 9; k++) if (E->cell.gradV.m[k] != ((k % 4 == 0) ? 1. : 0.)) ident = false;
+    u.trackLeapfrog = (E->trackEnergy && (!c.periodic || E->step > 0 || ident)) ? 1 : 0;
+  }
   u.viscAlpha = (c.en > 0 && c.en < 1.) ? (-std::sqrt(5.) * std::log(c.en) / (std::sqrt(std::log(c.en) * std::log(c.en) + M_PI * M_PI))) : 0.;
   return u;
 }
@@ -859,26 +865,42 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   if (ev) CK(cudaEventRecord(ev[2], st));
   if (side) { CK(cudaEventRecord(E->evFork, st)); CK(cudaStreamWaitEvent(st2, E->evFork, 0)); }
   if (E->nWS > 0) {
-    if (c.law == 0) k_contact_ws<0><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard);
-    else k_contact_ws<1><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard);
+    switch (c.law + (u.energy ? 2 : 0)) {
+      case 0: k_contact_ws<0><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 1: k_contact_ws<1><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 2: k_contact_ws<2><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 3: k_contact_ws<3><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard); break;
+    }
     E->launches++;
   }
   if (E->nFS > 0) {
-    if (c.law == 0) k_contact_fs<0><<<nblk(E->nFS, 128), 128, 0, sb>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt, guard);
-    else k_contact_fs<1><<<nblk(E->nFS, 128), 128, 0, sb>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt, guard);
+    switch (c.law + (u.energy ? 2 : 0)) {
+      case 0: k_contact_fs<0><<<nblk(E->nFS, 128), 128, 0, sb>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 1: k_contact_fs<1><<<nblk(E->nFS, 128), 128, 0, sb>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 2: k_contact_fs<2><<<nblk(E->nFS, 128), 128, 0, sb>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 3: k_contact_fs<3><<<nblk(E->nFS, 128), 128, 0, sb>>>(C, E->nSS + E->nWS, E->nFS, E->S(), E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
+    }
     E->launches++;
   }
   if (E->nOrph > 0) {
     const long long f0 = E->nSS + E->nWS + E->nFS;
-    if (c.law == 0) k_contact_orphans<0><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard);
-    else k_contact_orphans<1><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard);
+    switch (c.law + (u.energy ? 2 : 0)) {
+      case 0: k_contact_orphans<0><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 1: k_contact_orphans<1><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 2: k_contact_orphans<2><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 3: k_contact_orphans<3><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
+    }
     E->launches++;
   }
   // the big kernel goes last so that the small boundary kernels already occupy their share of the SMs
   if (E->nSS > 0) {
     const int gridSS = std::min(nblk(E->nSS, 128), E->numSMs * WD_CONTACT_CTAS_PER_SM);   // persistent: one CTA per resident slot
-    if (c.law == 0) k_contact_ss<0><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard);
-    else k_contact_ss<1><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard);
+    switch (c.law + (u.energy ? 2 : 0)) {
+      case 0: k_contact_ss<0><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 1: k_contact_ss<1><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 2: k_contact_ss<2><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 3: k_contact_ss<3><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+    }
     E->launches++;
   }
   if (side) { CK(cudaEventRecord(E->evJoin, st2)); CK(cudaStreamWaitEvent(st, E->evJoin, 0)); }
@@ -915,7 +937,9 @@ void leapfrogPipelined(wdem_engine* E, const StepU& u) {
     const long long first = c * per, cnt = std::min(per, n - first);
     if (cnt <= 0) break;
     CK(cudaStreamWaitEvent(st, E->evUp[c], 0));
-    k_leapfrog_io<<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->up2slot.p, first, cnt, lio); E->launches++;
+    if (u.energy) k_leapfrog_io<true><<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->up2slot.p, first, cnt, lio);
+    else k_leapfrog_io<false><<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->up2slot.p, first, cnt, lio);
+    E->launches++;
     CK(cudaEventRecord(E->evLf[c], st));
     CK(cudaStreamWaitEvent(E->sD2H, E->evLf[c], 0));
     if (io.posOut) CK(cudaMemcpyAsync(io.posOut + 3 * first, out + 3 * first, cnt * 24, cudaMemcpyDeviceToHost, E->sD2H));
@@ -935,12 +959,19 @@ void oneStep(wdem_engine* E, wdem_stats* stats) {
   ensureVerletAndDt(E);
   if (c.periodic) E->cell.integrateAndUpdate(E->dt);
   StepU u = makeUniforms(E);
+  if (u.energy) {   // energy->resetResettables() (Scene.cpp:416): "kinetic" and "elast" restart from zero every step
+    CK(cudaMemsetAsync(u.energy + EN_KINETIC, 0, sizeof(double), E->stream)); CK(cudaMemsetAsync(u.energy + EN_ELAST, 0, sizeof(double), E->stream));
+  }
   const int n = E->n;
   cudaEvent_t* ev = nullptr;
   if (E->profiling) { const int set = (int)(E->step % wdem_engine::NEVSET); harvestPhases(E, set); ev = E->evr[set]; }
   if (ev) CK(cudaEventRecord(ev[0], st));
   if (n > 0 && E->e2e.active) leapfrogPipelined(E, u);
-  else if (n > 0) { k_leapfrog<<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt); E->launches++; }
+  else if (n > 0) {
+    if (u.energy) k_leapfrog<true><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
+    else k_leapfrog<false><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
+    E->launches++;
+  }
   if (E->anyMovingWall) {
     if (c.periodic) throw EngErr{"moving walls in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), u, E->dCnt, 0); E->launches++;
@@ -1098,7 +1129,7 @@ int wdem_destroy(wdem_handle h) {
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   for (cudaStream_t cs : {h->sH2D, h->sD2H}) if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
   for (auto& e : h->evUp) if (e) cudaEventDestroy(e); for (auto& e : h->evLf) if (e) cudaEventDestroy(e); if (h->evEk) cudaEventDestroy(h->evEk);
-  h->ioIn.release(); h->ioOut.release(); if (h->hEk) cudaFreeHost(h->hEk);
+  h->dEnergy.release(); h->ioIn.release(); h->ioOut.release(); if (h->hEk) cudaFreeHost(h->hEk);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return WDEM_OK;
@@ -1356,6 +1387,22 @@ int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torqu
       F[r.wall] = F[r.wall] + Fc; T[r.wall] = T[r.wall] + Tc;
     }
     for (size_t w = 0; w < nW; w++) { if (force) { force[3 * w] = F[w].x; force[3 * w + 1] = F[w].y; force[3 * w + 2] = F[w].z; } if (torque) { torque[3 * w] = T[w].x; torque[3 * w + 1] = T[w].y; torque[3 * w + 2] = T[w].z; } }
+  });
+}
+
+int wdem_track_energy(wdem_handle h, int on) {
+  return guarded(h, [&] {
+    if (on && !h->trackEnergy) { h->dEnergy.ensure(EN_COUNT, h->bytes); CK(cudaMemsetAsync(h->dEnergy.p, 0, EN_COUNT * sizeof(double), h->stream)); CK(cudaStreamSynchronize(h->stream)); }
+    h->trackEnergy = on != 0;
+  });
+}
+int wdem_get_energy(wdem_handle h, double* out8) {
+  return guarded(h, [&] {
+    if (!out8) throw EngErr{"wdem_get_energy: null output", WDEM_ERR_INVALID};
+    for (int k = 0; k < EN_COUNT; k++) out8[k] = 0.;
+    if (!h->trackEnergy) throw EngErr{"Scene.trackEnergy is off (wdem_track_energy)", WDEM_ERR_INVALID};
+    auto v = d2h(h->dEnergy.p, EN_COUNT, h->stream);
+    for (int k = 0; k < EN_COUNT; k++) out8[k] = v[k];
   });
 }
 

@@ -7,7 +7,7 @@
 namespace wd {
 
 // DemData flags (src/dem/Particle.hpp:198-203)
-enum { F_DOF_ALL = 63, F_GRAVITY_SKIP = 512, F_DAMPING_SKIP = 2048 };
+enum { F_DOF_ALL = 63, F_ENERGY_SKIP = 256, F_GRAVITY_SKIP = 512, F_DAMPING_SKIP = 2048 };
 // engine-internal bits kept in the same word (DemData.flags uses bits 0..11): ghost copy of a sphere owned by another subdomain;
 // sphere that migrated into this subdomain at the current collider full run
 enum : uint32_t { F_GHOST = 1u << 30, F_ARRIVED = 1u << 29 };
@@ -65,7 +65,24 @@ struct StepU {            // per-step uniforms
   double absDistFactor;
   int law; int noSlip, noBreak, noFrict, noAttraction; int rolling; double relRollStiff, relTwistStiff, rollTanPhi;
   double poisson, en, viscAlpha;  // viscAlpha = -sqrt(5) ln(en)/sqrt(ln(en)^2+pi^2), host-computed (Hertz.cpp:69)
+  double* energy;                 // Scene.trackEnergy: device accumulators (EN_*), else nullptr; only the TRACK kernel variants look at it
+  int trackLeapfrog;              // Leapfrog.cpp:130-132: reallyTrackEnergy (off in step 0 of a periodic scene with a velocity gradient)
 };
+// EnergyTracker entries of this path (core/EnergyTracker.hpp): "kinetic" and "elast" are resettable (zeroed in the step prologue, Scene.cpp:416)
+enum { EN_KINETIC = 0, EN_GRAV, EN_DAMP, EN_ELAST, EN_PLAST, EN_BROKEN, EN_VISCN, EN_VISCT, EN_COUNT };
+// EnergyTracker::add from a (possibly divergent) warp: the lowest active lane adds up the values of the active lanes in lane order and issues one atomic
+__device__ __forceinline__ void energy_add(double* en, int ix, double v) {
+  if (v != v) v = 0.;                          // NaN is ignored (EnergyTracker.cpp:30)
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  double sum = 0.;
+  for (int src = 0; src < 32; src++) {
+    if (!((m >> src) & 1u)) continue;            // uniform over the active lanes
+    const double o = __shfl_sync(m, v, src);
+    sum += o;
+  }
+  if (lane == leader && sum != 0.) atomicAdd(en + ix, sum);
+}
 
 struct Counters { unsigned long long nReal, nPotEval, nCreated, nBroken; int dirty; int error; int errA, errB; };
 enum { ERR_NONE = 0, ERR_NAN_FORCE = 1, ERR_NAN_POS = 2, ERR_NO_PHYS = 3, ERR_SCHWARZ = 4, ERR_FACET_IMPOSSIBLE = 5, ERR_AMBIGUOUS_PERI = 6, ERR_PEER_TIMEOUT = 7 };
@@ -79,7 +96,7 @@ __device__ __forceinline__ double signd(double f) { return f < 0 ? -1. : (f > 0 
 // ------------------------------------------------------------------------------------------------
 // host-state staging of the end-to-end path (wdem_step_e2e): pos/vel/angVel come from / go to buffers in upload order
 struct LeapIO { const double* pos; const double* vel; const double* angVel; double* posOut; double* velOut; };
-template <bool EXT>
+template <bool EXT, bool TRACK>
 __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const StepU& u, Counters* cnt, const LeapIO& io, long long ut) {
   const uint32_t fl = S.flags[i];
   if (fl & F_GHOST) return;   // integrated by its owner; refreshed by the halo exchange
@@ -96,6 +113,23 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
   const bool blockedAll = (fl & F_DOF_ALL) == F_DOF_ALL, blockedNone = (fl & F_DOF_ALL) == 0;
   const bool damp = (u.damping != 0. && !(fl & F_DAMPING_SKIP));
   d3 linAccel = mk3(0, 0, 0), angAccel = mk3(0, 0, 0);
+  d3 trkV = mk3(0, 0, 0), trkW = mk3(0, 0, 0);                             // pprevFluctVel / pprevFluctAngVel for doKineticEnergy (zero for a fully blocked node, :198)
+  if (TRACK && u.trackLeapfrog) {
+    // Leapfrog::doDampingDissipation (:53-65) and doGravityWork (:67-74), with the values at the start of the step
+    if (damp && !(fl & F_ENERGY_SKIP))
+      energy_add(u.energy, EN_DAMP, dot(mk3(fabs(vel.x), fabs(vel.y), fabs(vel.z)), mk3(fabs(f.x), fabs(f.y), fabs(f.z))) * u.damping * dt +
+                                        dot(mk3(fabs(w.x), fabs(w.y), fabs(w.z)), mk3(fabs(t.x), fabs(t.y), fabs(t.z))) * u.damping * dt);
+    if (u.hasGravity && !(fl & F_GRAVITY_SKIP)) {
+      double gr = 0;
+      if (blockedNone) gr = -dot(u.gravity, vel) * mass * dt;
+      else {
+        if (!(fl & 1u)) gr -= u.gravity.x * vel.x * mass * dt;
+        if (!(fl & 2u)) gr -= u.gravity.y * vel.y * mass * dt;
+        if (!(fl & 4u)) gr -= u.gravity.z * vel.z * mass * dt;
+      }
+      energy_add(u.energy, EN_GRAV, gr);
+    }
+  }
   if (!blockedAll) {
     if (blockedNone) linAccel = f / mass;                                  // computeAccel :37-42
     else {
@@ -110,6 +144,7 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
       else pfv = vel;
       pfw = (u.homoDeform == 4) ? w - u.spinVec : w;
     } else { pfv = vel; pfw = w; }
+    if (TRACK) { trkV = pfv; trkW = pfw; }
     if (damp) {                                                            // nonviscDamp2nd :33-35
       linAccel.x *= 1 - u.damping * signd(f.x * (pfv.x + 0.5 * dt * linAccel.x));
       linAccel.y *= 1 - u.damping * signd(f.y * (pfv.y + 0.5 * dt * linAccel.y));
@@ -138,6 +173,13 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
       if (u.homoDeform == 3) vel = vel + mulMV(u.midGradV, vel - (dt / 2.) * linAccel) * dt;
       vel = vel + mulMV(u.dGradV, pos);
     } else if (u.homoDeform == 1) pos = pos + mulMV(u.nextGradV, pos) * dt;
+  }
+  if (TRACK && u.trackLeapfrog && !(fl & F_ENERGY_SKIP)) {                  // doKineticEnergy :76-98
+    const d3 cfv = trkV + (.5 * dt) * linAccel, cfw = trkW + (.5 * dt) * angAccel;
+    const double Etrans = .5 * mass * sqn(cfv);
+    double Erot = 0.5 * dot(cfw, mk3(inertia * cfw.x, inertia * cfw.y, inertia * cfw.z));
+    if (!(Erot == Erot) || isinf(inertia)) Erot = 0;
+    energy_add(u.energy, EN_KINETIC, Etrans + Erot);
   }
   pos = pos + vel * dt;                                                    // leapfrogTranslate :275-278
   // leapfrogSphericalRotate :280-297 (orientation of a sphere feeds no contact functor: tolerance-level parity)
@@ -170,17 +212,19 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
     io.velOut[3 * ut] = vel.x; io.velOut[3 * ut + 1] = vel.y; io.velOut[3 * ut + 2] = vel.z;
   }
 }
+template <bool TRACK>
 __global__ void __launch_bounds__(256, 4) k_leapfrog(Spheres S, int n, StepU u, Counters* cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  leapfrog_body<false>(S, i, u, cnt, LeapIO{}, 0);
+  leapfrog_body<false, TRACK>(S, i, u, cnt, LeapIO{}, 0);
 }
 // the same integrator over a chunk [first, first+cnt) of the UPLOAD order: inputs are read from, and the new pos/vel written to, staging
 // buffers (coalesced), the rest of the state is gathered by slot.  Lets host<->device copies of other chunks overlap with the integration.
+template <bool TRACK>
 __global__ void __launch_bounds__(256, 4) k_leapfrog_io(Spheres S, StepU u, Counters* cnt, const int* __restrict__ up2slot, long long first, long long cnt_, LeapIO io) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cnt_) return;
-  leapfrog_body<true>(S, up2slot[first + t], u, cnt, io, first + t);
+  leapfrog_body<true, TRACK>(S, up2slot[first + t], u, cnt, io, first + t);
 }
 
 // Leapfrog for boundary nodes that are in DemField.nodes (moving walls: mass 0, all DOFs blocked => the "fixed particle" branch, Leapfrog.cpp:195-199):
@@ -214,14 +258,15 @@ __device__ __forceinline__ void load_hist(const Contacts& C, long long c, Hist& 
   H.t0 = mk3(C.t0x[c], C.t0y[c], C.t0z[c]); H.t1 = mk3(C.t1x[c], C.t1y[c], C.t1z[c]);
   H.cp = C.cp[c]; H.ft0 = C.ft0[c]; H.ft1 = C.ft1[c];
   H.ph0 = C.ph[0][c]; H.ph1 = C.ph[1][c]; H.ph2 = C.ph[2][c];
-  if (LAW == 1) { H.ph3 = C.ph[3][c]; H.ph4 = C.ph[4][c]; }
+  if ((LAW & 1) == 1) { H.ph3 = C.ph[3][c]; H.ph4 = C.ph[4][c]; }
 }
 
 template <int LAW>
 __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uint32_t fl, const StepU& u, d3 pos1, d3 vel1, d3 w1, d3 pos2,
                                              d3 vel2, d3 w2, d3 shiftVel2, d3 normal, d3 contPt, double uN, double r1, double r2,
                                              const Material* mats, const int32_t* matArr, double massA, double massB, Counters* cnt,
-                                             const ErrCtx& ec, int matBoundary, const Hist& H, unsigned& nRealOut) {
+                                             const ErrCtx& ec, int matBoundary, const Hist& H, unsigned& nRealOut, const bool mine = true) {
+  // mine (energy tracking in decomposed runs): a cross-slab pair is evaluated on both sides; the side owning pA books its energy
   const bool wasReal = fl & CF_REAL;
   d3 c0, c1, c2, gvel = mk3(0, 0, 0), gang = mk3(0, 0, 0);
   double kn, kt, tanPhi, p3 = 0, p4 = 0, ftA = 0, ftB = 0, tq0 = 0, tq1 = 0, tq2 = 0;
@@ -239,7 +284,7 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
     double A = M_PI * (rr * rr);
     // ---- Cp2 (ContactLoop.cpp:179-181)
     const Material m1 = mats[ec.slotA >= 0 ? matArr[ec.slotA] : matBoundary], m2 = mats[matArr[ec.slotB]];
-    if (LAW == 0) {  // Cp2_FrictMat_FrictPhys::updateFrictPhys (FrictMat.cpp:20-44)
+    if ((LAW & 1) == 0) {  // Cp2_FrictMat_FrictPhys::updateFrictPhys (FrictMat.cpp:20-44)
       kn = 1 / (1 / (m1.young * A / l0) + 1 / (m2.young * A / l1));
       kt = .5 * (m1.ktDivKn + m2.ktDivKn) * kn;
       tanPhi = fmin(m1.tanPhi, m2.tanPhi);
@@ -303,15 +348,20 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
     gvel = mk3(dot(midN, relVel), dot(mid1, relVel), dot(mid2, relVel));
     if (u.rolling) { d3 dw = w2 - w1; gang = mk3(dot(midN, dw), dot(mid1, dw), dot(mid2, dw)); }
     kn = H.ph0; kt = H.ph1; tanPhi = H.ph2;
-    if (LAW == 1) { p3 = H.ph3; p4 = H.ph4; }
+    if ((LAW & 1) == 1) { p3 = H.ph3; p4 = H.ph4; }
     ftA = H.ft0; ftB = H.ft1;
     // CPhys.torque is zeroed at the top of the law every step (IdealElPl.cpp:43), so it carries no history
   }
   // ---- Law2
   double Fn; bool keep = true;
-  if (LAW == 0) {  // Law2_L6Geom_FrictPhys_IdealElPl::go (IdealElPl.cpp:15-125), iniEqlb/trackEnergy unsupported
-    if (uN > 0 && !u.noBreak) keep = false;
-    else {
+  if ((LAW & 1) == 0) {  // Law2_L6Geom_FrictPhys_IdealElPl::go (IdealElPl.cpp:15-125), iniEqlb/trackEnergy unsupported
+    if (uN > 0 && !u.noBreak) {
+      keep = false;
+      if (LAW >= 2 && mine && u.noSlip) {   // IdealElPl.cpp:28-40: the elastic potential of the breaking contact is lost
+        const double FnB = kn * uN, t0 = ftA + (u.dt * kt) * gvel.y, t1 = ftB + (u.dt * kt) * gvel.z;
+        energy_add(u.energy, EN_BROKEN, .5 * ((FnB * FnB) / kn + (t0 * t0 + t1 * t1) / kt));
+      }
+    } else {
       Fn = kn * uN;
       if (u.noFrict || tanPhi == 0.) { ftA = 0; ftB = 0; }
       else {
@@ -322,9 +372,14 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
           double FtNorm = sqrt(sq);
           double ratio = maxFt / FtNorm;
           if (FtNorm == 0.) ratio = 0.;
+          if (LAW >= 2 && mine) energy_add(u.energy, EN_PLAST, kt != 0. ? (maxFt) * (FtNorm - maxFt) / kt : 0.);   // IdealElPl.cpp:64-75
           ftA *= ratio; ftB *= ratio;
         }
         if (!(Fn == Fn) || !(ftA == ftA) || !(ftB == ftB)) report_error(cnt, ERR_NAN_FORCE, ec);
+      }
+      if (LAW >= 2 && mine) {                                              // IdealElPl.cpp:85-92
+        double elast = 0.5 * ((Fn * Fn) / kn + (kt != 0. ? (ftA * ftA + ftB * ftB) / kt : 0.));
+        energy_add(u.energy, EN_ELAST, elast);
       }
       if (u.rolling) {                                                     // IdealElPl.cpp:94-123
         double charLen = fabs(r1) + fabs(r2);
@@ -352,12 +407,23 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
       double Fnv = eta * gvel.x;
       if (alphaZero && u.noAttraction && Fne + Fnv > 0) Fnv = -Fne;
       Fn = Fne + Fna + Fnv;
+      if (LAW >= 2 && mine) energy_add(u.energy, EN_VISCN, Fnv * gvel.x * u.dt);                      // Hertz.cpp:181
       double ktc = kt0 * sqrt(uN < 0 ? -uN : 0);
       ftA += (u.dt * ktc) * gvel.y; ftB += (u.dt * ktc) * gvel.z;
       double maxFt = fabs(fmin(0., Fn) * tanPhi);
       double sq = ftA * ftA + ftB * ftB;
-      if (sq > maxFt * maxFt) { double FtNorm = sqrt(sq); double ratio = maxFt / FtNorm; ftA *= ratio; ftB *= ratio; }
-      else { ftA += eta * gvel.y; ftB += eta * gvel.z; }
+      if (sq > maxFt * maxFt) {
+        double FtNorm = sqrt(sq); double ratio = maxFt / FtNorm;
+        if (LAW >= 2 && mine) energy_add(u.energy, EN_PLAST, (.5 * (FtNorm - maxFt) + maxFt) * (FtNorm - maxFt) / ktc);   // Hertz.cpp:193
+        ftA *= ratio; ftB *= ratio;
+      } else {
+        ftA += eta * gvel.y; ftB += eta * gvel.z;
+        if (LAW >= 2 && mine) energy_add(u.energy, EN_VISCT, eta * (gvel.y * gvel.y + gvel.z * gvel.z) * u.dt);           // Hertz.cpp:199
+      }
+      if (LAW >= 2 && mine && uN < 0) {                                                               // Hertz.cpp:203-207, Hertz.hpp:70,76
+        const double sq5 = sqrt(-uN);
+        energy_add(u.energy, EN_ELAST, kn0 * (2 / 5.) * (((sq5 * sq5) * (sq5 * sq5)) * sq5) + 0.5 * (ftA * ftA + ftB * ftB) / ktc);
+      }
       if (!(Fn == Fn) || !(ftA == ftA) || !(ftB == ftB)) report_error(cnt, ERR_NAN_FORCE, ec);
     }
   }
@@ -421,9 +487,10 @@ __device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint3
   d3 normal = relPos / dist;
   d3 contPt = p1 + (r1 + 0.5 * uN) * normal;
   double mA = 0, mB = 0;
-  if (!real && LAW == 1) { mA = S.velm[pr.x].w; mB = S.velm[pr.y].w; }
+  if (!real && (LAW & 1) == 1) { mA = S.velm[pr.x].w; mB = S.velm[pr.y].w; }
   const ErrCtx ec{S.id, pr.x, 0, pr.y};
-  contact_tail<LAW>(C, c, fl, u, p1, xyz(va), xyz(wa), p2, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, r1, r2, mats, S.mat, mA, mB, cnt, ec, 0, H, isReal);
+  const bool mine = (LAW >= 2) ? !(S.flags[pr.x] & F_GHOST) : true;
+  contact_tail<LAW>(C, c, fl, u, p1, xyz(va), xyz(wa), p2, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, r1, r2, mats, S.mat, mA, mB, cnt, ec, 0, H, isReal, mine);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -437,7 +504,7 @@ __device__ __forceinline__ void prefetch_contact_ss(const Contacts& C, long long
   prefetch_l2(C.t0x + c); prefetch_l2(C.t0y + c); prefetch_l2(C.t0z + c); prefetch_l2(C.t1x + c); prefetch_l2(C.t1y + c); prefetch_l2(C.t1z + c);
   prefetch_l2(C.cp + c); prefetch_l2(C.ft0 + c); prefetch_l2(C.ft1 + c);
   prefetch_l2(C.ph[0] + c); prefetch_l2(C.ph[1] + c); prefetch_l2(C.ph[2] + c);
-  if (LAW == 1) { prefetch_l2(C.ph[3] + c); prefetch_l2(C.ph[4] + c); }
+  if ((LAW & 1) == 1) { prefetch_l2(C.ph[3] + c); prefetch_l2(C.ph[4] + c); }
 }
 
 // Persistent software-pipelined grid (one CTA per resident slot, tiles of 128 candidates, stride gridDim): while tile k is computed, the table
@@ -499,7 +566,7 @@ __device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint3
   setc(normal, ax, nax);
   double uN = nax * dist - radius;
   double mB = 0;
-  if (!real && LAW == 1) mB = S.velm[pr.y].w;
+  if (!real && (LAW & 1) == 1) mB = S.velm[pr.y].w;
   const ErrCtx ec{S.id, -1, W.id, pr.y};
   contact_tail<LAW>(C, c, fl, u, wallPos, mk3(W.vel[0], W.vel[1], W.vel[2]), mk3(0, 0, 0), spherePos, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, -radius, radius,
                     mats, S.mat, 0., mB, cnt, ec, W.mat, H, isReal);
@@ -626,7 +693,7 @@ __device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint3
     else linVel = dot(linVel, fNormal) * fNormal;
   }
   double mB = 0;
-  if (!real && LAW == 1) mB = S.velm[pr.y].w;
+  if (!real && (LAW & 1) == 1) mB = S.velm[pr.y].w;
   const ErrCtx ec{S.id, -1, F->id, pr.y};
   contact_tail<LAW>(C, c, fl, u, contPt, linVel, angVel, sC, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, fmax(ht, radius), radius, mats, S.mat, 0., mB, cnt, ec, F->mat, H, isReal);
 }

@@ -117,6 +117,7 @@ struct DynDt : Engine { int stepPeriod = 100; double maxRelInc = 1e-4; bool dryR
 struct Scene {
   double dt = NaN, nextDt = NaN, dtSafety = .9, time = 0; long step = 0; bool periodic = false, trackEnergy = false, deterministic = false;
   shared_ptr<Cell> cell = make_shared<Cell>(); vector<py::object> engines; vector<shared_ptr<DemField>> fields;
+  std::map<string, double> energy;   // Scene.energy (core/EnergyTracker.hpp) as far as this path feeds it; filled after every step when trackEnergy
   shared_ptr<DemField> dem() const { if (fields.empty()) throw std::runtime_error("Scene has no DemField"); return fields[0]; }
   void one(); void run(long n);
 };
@@ -127,7 +128,7 @@ static void chk(wdem_handle h, int rc) { if (rc != WDEM_OK) throw std::runtime_e
 struct GpuDemLoop : Engine {
   shared_ptr<Leapfrog> leapfrog; shared_ptr<InsertionSortCollider> collider; shared_ptr<ContactLoop> contactLoop; shared_ptr<DynDt> dynDt;
   int device = 0; wdem_handle h = nullptr; wdem_config cfg; bool haveCfg = false; long nSpheres = 0; wdem_stats last;
-  vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf, wallOf;
+  vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf, wallOf; bool trackingOn = false;
   const char* cls() const override { return "GpuDemLoop"; }
   ~GpuDemLoop() override { release(); }
   void release() { if (h) { wdem_destroy(h); h = nullptr; } if (field && field->owner == this) field->owner = nullptr; }
@@ -153,7 +154,7 @@ struct GpuDemLoop : Engine {
     c.applyForces = contactLoop->applyForces;
     if (contactLoop->updatePhys != 0) throw std::runtime_error("GpuDemLoop: ContactLoop.updatePhys is not supported");
     if (!contactLoop->hook.is_none()) throw std::runtime_error("GpuDemLoop: ContactLoop.hook is not supported");
-    if (scene->trackEnergy) throw std::runtime_error("GpuDemLoop: Scene.trackEnergy is not supported");
+    if (scene->trackEnergy && contactLoop->evalStress && scene->periodic) throw std::runtime_error("GpuDemLoop: Scene.trackEnergy together with ContactLoop.evalStress (gradV work) is not supported");
     auto* lin = dynamic_cast<Law2_L6Geom_FrictPhys_IdealElPl*>(contactLoop->lawDisp[0].get());
     auto* dmt = dynamic_cast<Law2_L6Geom_HertzPhys_DMT*>(contactLoop->lawDisp[0].get());
     auto* cpF = dynamic_cast<Cp2_FrictMat_FrictPhys*>(contactLoop->phyDisp[0].get());
@@ -259,6 +260,7 @@ struct GpuDemLoop : Engine {
   double critDt() override { prepare(); double d; chk(h, wdem_crit_dt(h, &d)); return d; }   // DemField::critDt -> pWaveDt (Funcs.cpp:151-175)
   void step(long n) {
     prepare();
+    if (scene->trackEnergy && !trackingOn) { chk(h, wdem_track_energy(h, 1)); trackingOn = true; }
     std::memset(&last, 0, sizeof(last));
     { py::gil_scoped_release nogil; chk(h, wdem_step(h, n, &last)); }
     DemField& F = *field; F.deviceNewer = true; F.contactsStale = true;
@@ -266,6 +268,14 @@ struct GpuDemLoop : Engine {
     chk(h, wdem_get_scalars(h, &libDt, nullptr, nullptr, nullptr, &nf));
     collider->nFullRuns = (long)nf;
     if (scene->periodic) chk(h, wdem_get_cell(h, scene->cell->hSize.data()));
+    chk(h, wdem_track_energy(h, scene->trackEnergy ? 1 : 0));   // takes effect from the next step on, like flipping Scene.trackEnergy between steps
+    if (scene->trackEnergy && trackingOn) {
+      double e[8]; chk(h, wdem_get_energy(h, e));
+      static const char* names[8] = {"kinetic", "grav", "nonviscDamp", "elast", "plast", "broken", "viscN", "viscT"};
+      // EnergyTracker semantics: "grav" appears as soon as gravity acts, the ZeroDontCreate entries only once they are non-zero (EnergyTracker.cpp:26-34)
+      for (int k = 0; k < 8; k++) { const bool always = (k == 0 || k == 3); if (always || e[k] != 0. || scene->energy.count(names[k])) scene->energy[names[k]] = e[k]; }
+    }
+    trackingOn = scene->trackEnergy;
     if (contactLoop->evalStress && scene->periodic) chk(h, wdem_get_stress(h, contactLoop->stress.data()));   // doStress (ContactLoop.cpp:123)
     else contactLoop->stress.fill(0.);
     cfg.dt = libDt;                        // what the library will use next; Scene.dt follows through nextDt in the epilogue
@@ -537,7 +547,7 @@ PYBIND11_MODULE(_woo, m) {
   // ---- scene
   py::class_<Scene, shared_ptr<Scene>>(m, "Scene")
       .def(py::init([](vector<shared_ptr<DemField>> fields, py::kwargs kw) { auto s = make_shared<Scene>(); s->fields = fields; py::object po = py::cast(s); for (auto it : kw) py::setattr(po, it.first, it.second); return s; }), py::arg("fields") = vector<shared_ptr<DemField>>())
-      RW(Scene, dt) RW(Scene, nextDt) RW(Scene, dtSafety) RW(Scene, time) RW(Scene, step) RW(Scene, periodic) RW(Scene, trackEnergy) RW(Scene, deterministic) RW(Scene, engines) RW(Scene, fields)
+      RW(Scene, dt) RW(Scene, nextDt) RW(Scene, dtSafety) RW(Scene, time) RW(Scene, step) RW(Scene, periodic) RW(Scene, trackEnergy).def_property_readonly("energy", [](Scene& S) { py::dict d; for (auto& kv : S.energy) d[py::str(kv.first)] = kv.second; return d; }) RW(Scene, deterministic) RW(Scene, engines) RW(Scene, fields)
       .def_readonly("cell", &Scene::cell).def_property_readonly("dem", &Scene::dem)
       .def("one", &Scene::one).def("run", [](Scene& s, long n, bool) { s.run(n); }, py::arg("steps") = 1, py::arg("wait") = true).def("wait", [](Scene&) {});
 }

@@ -181,6 +181,17 @@ class Engine:
             self._chk(self.L.wdem_download_walls(self.h, ptr(o["pos"]), ptr(o["force"]), ptr(o["torque"])))
         return o
 
+    ENERGY_NAMES = ("kinetic", "grav", "nonviscDamp", "elast", "plast", "broken", "viscN", "viscT")
+
+    def track_energy(self, on=True):
+        self._chk(self.L.wdem_track_energy(self.h, C.c_int(int(on))))
+
+    def energy(self):
+        """Scene.energy entries of this path as a dict (wdem.h: wdem_get_energy)."""
+        o = np.zeros(8)
+        self._chk(self.L.wdem_get_energy(self.h, ptr(o)))
+        return dict(zip(self.ENERGY_NAMES, o.tolist()))
+
     def stress(self):
         """ContactLoop.stress (evalStress) of the current state, 3x3."""
         o = np.zeros((3, 3))
