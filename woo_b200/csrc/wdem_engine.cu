@@ -168,7 +168,7 @@ struct wdem_engine {
   CsrStore csr[2]; int curR = 0;
   // scratch
   DBuf<uint32_t> keys, keysAlt; DBuf<int> idx, idxAlt, cellStart, counts, offsets; DBuf<unsigned char> cubTemp; DBuf<double> blk;
-  DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt; DBuf<int> realFlag, realPos; DBuf<int32_t> tmpCd[3];
+  DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld, candBuf; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt; DBuf<int> realFlag, realPos; DBuf<int32_t> tmpCd[3];
   Counters* dCnt = nullptr; Counters* hCnt = nullptr;
   // scene scalars
   double dt = NAN, time = 0, nextDt = NAN, verletDist = NAN; long long step = 0, nFullRuns = 0; bool conDirty = true;
@@ -669,7 +669,10 @@ void rebuild(wdem_engine* E) {
     const int nb128 = nblk(n, 128);
     E->rowCount.ensure((size_t)n + 1, tot);
     CK(cudaMemsetAsync(E->rowCount.p, 0, ((size_t)n + 1) * sizeof(int), st));
-    if (!c.periodic) k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr);
+    static const bool noCand = getenv("WDEM_NO_CAND_CACHE") != nullptr;
+    int* cand = nullptr;
+    if (!c.periodic && !noCand) { E->candBuf.ensure((size_t)WD_CAND_CAP * n, tot); cand = E->candBuf.p; }
+    if (!c.periodic) k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr, cand);
     else k_pairs_ss_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
     E->launches++;
     if (nWalls) {
@@ -702,7 +705,7 @@ void rebuild(wdem_engine* E) {
     E->ckeys.ensure(nT, tot); E->cvals.ensure(nT, tot); E->realFlag.ensure(nT + 1, tot); E->realPos.ensure(nT + 1, tot);
     Contacts T = N; T.pair = reinterpret_cast<int2*>(E->ckeys.p); T.flags = E->cvals.p;
     if (c.periodic) { for (auto& b : E->tmpCd) b.ensure(nT, tot); T.cdx = E->tmpCd[0].p; T.cdy = E->tmpCd[1].p; T.cdz = E->tmpCd[2].p; }
-    if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, T, O, oc, perm, nullptr, E->srcOld.p);
+    if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, E->offsets.p, T, O, oc, perm, nullptr, E->srcOld.p, cand);
     else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
     E->launches++;
     if (nWalls) {
@@ -1120,7 +1123,7 @@ int wdem_destroy(wdem_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release();
   h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
-  h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
+  h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->candBuf.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
   peerTeardown(h, false);
   h->dom.release(); delete h->comm; h->comm = nullptr;
   if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt);

@@ -1028,23 +1028,43 @@ __device__ __forceinline__ long long find_old2(const OldCsr& oc, int oslot, int 
 
 // Sphere+Sphere candidates (see HGrid for the ownership rule).  FILL=false counts, FILL=true writes pairs (canonical pA = lower id) and looks up the
 // previous contact of the pair (history carry-over by k_carry).
+#ifndef WD_CAND_CAP
+#define WD_CAND_CAP 16
+#endif
 #ifndef WD_PAIRS_MINB
 #define WD_PAIRS_MINB 12   // 40 registers, 75 % occupancy: measured 0.173 ms/step of collider work vs 0.178 (64 registers) and 0.176 (48 or 32 registers)
 #endif
 template <bool FILL>
 __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int n, HGrid g, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
                                                  const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
-                                                 int* __restrict__ rowCount, int* __restrict__ srcOld) {
+                                                 int* __restrict__ rowCount, int* __restrict__ srcOld, int* __restrict__ cand) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double4 pi = S.posr[i];
-  const int Li = levelOf(g, pi.w);
-  const uint32_t mi = S.mask[i];
   const uint32_t fi = S.flags[i];
   int cntLocal = 0;
   long long out = FILL ? offsets[i] : 0;
   int idI = 0, oslotI = 0;
   if (FILL) { idI = S.id[i]; oslotI = perm ? perm[i] : i; }
+  // the counting pass leaves the partners it found (up to WD_CAND_CAP per sphere, in discovery order) in `cand`; the filling pass then only has to look up
+  // the previous contact and write the pair, without walking the cells again.  Spheres with more partners than the cache holds repeat the search.
+  if (FILL && cand) {
+    const int cnt = counts[i];
+    if (cnt <= WD_CAND_CAP) {
+      for (int k = 0; k < cnt; k++) {
+        const int j = cand[(long long)k * n + i];
+        const int idJ = S.id[j];
+        const long long c = out + k;
+        const bool iIsA = idI < idJ;
+        N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
+        srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
+        N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
+      }
+      return;
+    }
+  }
+  const double4 pi = S.posr[i];
+  const int Li = levelOf(g, pi.w);
+  const uint32_t mi = S.mask[i];
   for (int L = Li; L < g.nL; L++) {
     const double H = ((pi.w + vd) + g.reach[L][0]) * (1 + 1e-12) + 1e-300;
     const int nx = g.n[L][0], ny = g.n[L][1], nz = g.n[L][2];
@@ -1068,7 +1088,7 @@ __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int 
             N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
             srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
             N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
-          } else atomicAdd(&rowCount[j], 1);
+          } else { atomicAdd(&rowCount[j], 1); if (cand && cntLocal < WD_CAND_CAP) cand[(long long)cntLocal * n + i] = j; }
           cntLocal++;
         }
       }
