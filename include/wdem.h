@@ -99,6 +99,16 @@ int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* po
 int wdem_upload_facets(wdem_handle h, int n, const int32_t* ids, const double* verts, const double* vvel, const double* fakeVel,
                        const double* halfThick, const double* n21lim, const uint32_t* mask, const int32_t* matId);
 /* Periodic cell (core/Cell.hpp): Cell.setHSize + gradV/nextGradV/homoDeform. */
+/* Kinematic groups of facets: a clump of boundary particles whose massless, fully blocked master node carries a prescribed velocity and angular velocity
+ * (ParticleContainer::addClumped + ClumpData, Clump.cpp:187-261; examples/mill.py:38-42: a rotating drum).  Every step the master node is moved by Leapfrog's
+ * fixed-particle branch (Leapfrog.cpp:195-199,275-297) and its members follow rigidly (ClumpData::applyToMembers, Clump.cpp:293-307): node position
+ * pos + ori*relPos, node velocity vel + angVel x (p - pos); the facets' Aabbs take part in the Verlet test and the collider run like any other particle.
+ * groupOfFacet: per uploaded facet the group index or -1 (static); pos 3, ori 4 (x,y,z,w), vel 3, angVel 3 per group; at most 8 groups, aperiodic scenes.
+ * Call after wdem_upload_facets, before the first step.  Forces on the members are not fed back (all DOFs of the master are blocked). */
+int wdem_upload_facet_groups(wdem_handle h, int nGroups, const int32_t* groupOfFacet, const double* pos, const double* ori, const double* vel,
+                             const double* angVel);
+/* Facet node positions (9 per facet, upload order) and the groups' master nodes after the last step; any pointer may be NULL. */
+int wdem_download_facets(wdem_handle h, double* verts, double* groupPos, double* groupOri);
 int wdem_set_cell(wdem_handle h, const double* hSize, const double* gradV, const double* nextGradV, int homoDeform);
 int wdem_set_next_gradv(wdem_handle h, const double* nextGradV);
 int wdem_get_cell(wdem_handle h, double* hSize);

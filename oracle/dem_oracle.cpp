@@ -194,6 +194,9 @@ struct Wall {
 struct Facet {
   int id; V3 v[3]; V3 vvel[3]; V3 fakeVel; Real halfThick; Real n21lim[3]; unsigned mask; int mat; Aabb bb; V3 lastPos[3];
 };
+// Master node of a clump of boundary particles that moves them rigidly (ParticleContainer::addClumped -> ClumpData::makeClump, Clump.cpp:187-261): a massless,
+// fully blocked node with prescribed vel/angVel (examples/mill.py:38-42) whose members are facets.  relPos are the members' node positions in the clump's frame.
+struct FacetGroup { V3 pos; Quat ori; V3 vel, angVel; std::vector<int> facets; std::vector<V3> relPos; };
 struct PRef { int kind, idx; };
 
 struct Contact {
@@ -322,7 +325,7 @@ struct Scene {
     energy[ix] += v;
   }
   Params P; Cell cell;
-  std::vector<Material> mats; std::vector<Sphere> sph; std::vector<Wall> walls; std::vector<Facet> facets; std::vector<PRef> par;
+  std::vector<Material> mats; std::vector<Sphere> sph; std::vector<Wall> walls; std::vector<Facet> facets; std::vector<FacetGroup> groups; std::vector<PRef> par;
   std::map<uint64_t, Contact> con;          // ordered by canonical key
   std::vector<Contact*> lin; bool linDirty = true;
   std::vector<uint64_t> pending;            // ContactContainer::requestRemoval queue
@@ -1088,6 +1091,28 @@ struct Scene {
     }
     // boundary nodes that are in DemField.nodes (walls added with a velocity): mass 0 and all DOFs blocked => Leapfrog's "fixed particle" branch
     // (Leapfrog.cpp:195-199): no acceleration, leapfrogTranslate pos += vel*dt (:275-278), force/torque reset to mass*gravity = 0 (:240-245)
+    // clump master nodes of kinematic facet groups: all DOFs blocked => Leapfrog's fixed-particle branch: leapfrogTranslate + leapfrogSphericalRotate with the
+    // prescribed velocities (Leapfrog.cpp:195-199,275-297), then ClumpData::applyToMembers (Clump.cpp:293-307, called from Leapfrog.cpp:252)
+    for (FacetGroup& G : groups) {
+      if (P.periodic) throw std::runtime_error("moving facets in a periodic cell are not supported");
+      G.pos += G.vel * dt;
+      V3 axis = G.angVel;
+      if (axis != V3(0, 0, 0)) {
+        Real angle = norm(axis); axis = axis / angle;
+        Real ha = 0.5 * (angle * dt);
+        Real sn = std::sin(ha);
+        Quat q(std::cos(ha), sn * axis.x, sn * axis.y, sn * axis.z);
+        G.ori = quatMul(q, G.ori);
+      }
+      quatNormalize(G.ori);
+      for (size_t k = 0; k < G.facets.size(); k++) {
+        Facet& f = facets[G.facets[k]];
+        for (int i = 0; i < 3; i++) {
+          f.v[i] = G.pos + quatRotate(G.ori, G.relPos[3 * k + i]);
+          f.vvel[i] = G.vel + cross(G.angVel, f.v[i] - G.pos);
+        }
+      }
+    }
     for (Wall& w : walls) {
       if (!w.moving) continue;
       if (P.periodic) throw std::runtime_error("moving walls in a periodic cell are not supported");
@@ -1245,6 +1270,26 @@ int orc_add_facet(void* h, const double* v /*9*/, double halfThick, const double
   for (int i = 0; i < 3; i++) { f.v[i] = V3(v[3 * i], v[3 * i + 1], v[3 * i + 2]); if (vvel) f.vvel[i] = V3(vvel[3 * i], vvel[3 * i + 1], vvel[3 * i + 2]); f.n21lim[i] = n21lim ? n21lim[i] : NaN; }
   f.halfThick = halfThick; if (fakeVel) f.fakeVel = V3(fakeVel[0], fakeVel[1], fakeVel[2]); f.mat = mat; f.mask = mask;
   S->par.push_back(PRef{SHAPE_FACET, (int)S->facets.size()}); S->facets.push_back(f); S->conDirty = true; return f.id;
+}
+// facetIdx: indices into the facets in the order they were added
+int orc_add_facet_group(void* h, const double* pos, const double* ori /*x,y,z,w*/, const double* vel, const double* angVel, int n, const int* facetIdx) {
+  Scene* S = (Scene*)h;
+  ORC_TRY(h)
+  FacetGroup G; G.pos = V3(pos[0], pos[1], pos[2]); G.ori = Quat(ori[3], ori[0], ori[1], ori[2]); G.vel = V3(vel[0], vel[1], vel[2]); G.angVel = V3(angVel[0], angVel[1], angVel[2]);
+  const Quat qc(G.ori.w, -G.ori.x, -G.ori.y, -G.ori.z);   // conjugate
+  for (int k = 0; k < n; k++) {
+    if (facetIdx[k] < 0 || facetIdx[k] >= (int)S->facets.size()) throw std::runtime_error("facet group: bad facet index");
+    G.facets.push_back(facetIdx[k]);
+    for (int i = 0; i < 3; i++) G.relPos.push_back(quatRotate(qc, S->facets[facetIdx[k]].v[i] - G.pos));   // Clump.cpp:252
+  }
+  // members follow the master from the start (ClumpData::applyToMembers runs in every Leapfrog): positions as given, velocities from the master
+  for (size_t k = 0; k < G.facets.size(); k++) { Facet& f = S->facets[G.facets[k]]; for (int i = 0; i < 3; i++) f.vvel[i] = G.vel + cross(G.angVel, f.v[i] - G.pos); }
+  S->groups.push_back(G);
+  ORC_CATCH(h)
+}
+void orc_get_facets(void* h, double* verts /*9 per facet*/) {
+  Scene* S = (Scene*)h;
+  for (size_t f = 0; f < S->facets.size(); f++) for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) verts[9 * f + 3 * i + k] = S->facets[f].v[i][k];
 }
 void orc_set_cell(void* h, const double* hSize /*row-major 9*/, const double* gradV, const double* nextGradV, int homoDeform) {
   Scene* S = (Scene*)h; Cell& c = S->cell;

@@ -16,6 +16,7 @@ def golden_scenes():
         "gas_hertz": (lambda: sc.random_gas(300, box=.45, r=.02, psd_ratio=2.0, seed=102, law=sc.LAW_HERTZ_DMT, en=.7), 250),
         "deposition": (lambda: sc.deposition(1500, seed=103), 2500),
         "facet_box": (lambda: sc.facet_box_scene(250, seed=104, halfThick=.003), 600),
+        "rotating_drum": (lambda: sc.drum(400, div=12, axial=3, vz0=.8, vfluct=.4, omega=7., rotate=True), 4000),
         "periodic_shear": (lambda: sc.periodic_gas(300, seed=105, gradV=[[0, 1., 0], [0, 0, 0], [0, 0, 0]], shear0=.1, psd_ratio=2.0), 500),
     }
 

@@ -78,6 +78,11 @@ class Oracle:
                 vv = np.ascontiguousarray(f.get("vvel", np.zeros(9)), dtype=np.float64).reshape(9)
                 L.orc_add_facet(h, _p(v, C.c_double), C.c_double(f.get("halfThick", 0.)), _p(fv, C.c_double), _p(nl, C.c_double),
                                 _p(vv, C.c_double), C.c_int(f.get("mat", 0)), C.c_uint(f.get("mask", 3)))
+            for g in getattr(S, "facet_groups", []):
+                a = lambda k: np.ascontiguousarray(g[k], dtype=np.float64)
+                ix = np.ascontiguousarray(g["facets"], dtype=np.int32)
+                self._chk(L.orc_add_facet_group(h, _p(a("pos"), C.c_double), _p(a("ori"), C.c_double), _p(a("vel"), C.c_double), _p(a("angVel"), C.c_double),
+                                                C.c_int(len(ix)), _p(ix, C.c_int)))
 
         def add_spheres():
             if S.n:
@@ -125,6 +130,12 @@ class Oracle:
         o = {k: np.zeros((n, 3)) for k in ("pos", "force", "torque")}
         if n:
             self.L.orc_get_walls(self.h, _p(o["pos"], C.c_double), _p(o["force"], C.c_double), _p(o["torque"], C.c_double))
+        return o
+
+    def facets(self):
+        o = np.zeros((len(self.spec.facets), 3, 3))
+        if len(o):
+            self.L.orc_get_facets(self.h, _p(o, C.c_double))
         return o
 
     def track_energy(self, on=True):

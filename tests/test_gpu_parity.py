@@ -392,3 +392,24 @@ def test_track_energy_matches_oracle(kind):
     want = {"linear": {"kinetic", "grav", "nonviscDamp", "elast", "plast"}, "linear-noslip": {"kinetic", "elast", "broken"}, "hertz": {"kinetic", "elast", "viscN", "viscT", "plast"},
             "periodic": {"kinetic", "elast"}, "decomposed": {"kinetic", "elast", "plast"}}[kind]
     assert want <= seen, f"{kind}: entries never became non-zero: {want - seen}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kinematic facet groups: a clump of facets whose blocked master node carries an angular velocity — a drum that really rotates
+# (examples/mill.py:38-42; Clump.cpp:293-307, Leapfrog.cpp:195-199,275-297)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [1, 2])
+def test_rotating_drum_facet_group(world):
+    S = sc.drum(600, div=16, axial=4, vz0=1., vfluct=.5, omega=8., rotate=True)
+    S.facet_groups[0]["vel"] = (.02, 0., 0.)                     # and creeps along its axis
+    f0 = np.array([f["v"] for f in S.facets])
+    O, E = compare(S, 8000, check_every=2000, label=f"rotating drum world={world}", make=cluster(world) if world > 1 else None)
+    fo = O.facets()
+    fg = E.facets() if world == 1 else E.E[0].facets()
+    assert np.array_equal(fo, fg), "facet node positions differ from the oracle"
+    assert np.abs(fo - f0).max() > .05 * np.abs(f0).max(), "the drum did not move"
+    ids = O.contacts(True)["ids"]
+    assert (ids[:, 0] >= S.n + len(S.walls)).sum() > 30, "no facet contacts formed"
+    # the turning wall drags the bed along: the spheres' mean angular momentum about the axis has the sign of the rotation
+    s = O.spheres(); ybar, zbar = s["pos"][:, 1].mean(), s["pos"][:, 2].mean()
+    assert ((s["pos"][:, 1] - ybar) * s["vel"][:, 2] - (s["pos"][:, 2] - zbar) * s["vel"][:, 1]).mean() > 0

@@ -262,3 +262,30 @@ def test_energy_tracking_like_the_reference_test():
     S.run(400, True)
     assert S.energy["grav"] != 0. and "nonviscDamp" not in S.energy
     assert "kinetic" in S.energy and "elast" in S.energy
+
+
+@pytest.mark.gpu
+def test_rotating_drum_with_add_clumped():
+    """examples/mill.py:38-42 in small: facets clumped to a central node that carries the angular velocity; the drum turns, carries the grains along, and the
+    result equals the array-level engine driven through wdem_upload_facet_groups."""
+    from woo_b200 import scenes as sc
+    from woo_b200.engine import Engine
+    from woo_b200.woo.core import Node
+    Sp = sc.drum(300, div=12, axial=3, vz0=.5, vfluct=.3, omega=6., rotate=True)
+    E = Engine(Sp.params).load(Sp); E.step(400)
+    S = Scene(fields=[DemField(gravity=Sp.params.gravity)])
+    m = FrictMat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)
+    S.dem.par.add([woo.utils.sphere(Sp.pos[i], Sp.radius[i], mat=m, vel=Sp.vel[i]) for i in range(Sp.n)])
+    S.dem.par.add([Wall.make(w["pos"], axis=w["axis"], sense=w["sense"], mat=m) for w in Sp.walls])
+    facets = [Facet.make([tuple(v) for v in f["v"]], mat=m) for f in Sp.facets]
+    g = Sp.facet_groups[0]
+    central = Node(pos=g["pos"])
+    S.dem.par.addClumped(facets, centralNode=central)
+    central.dem.angVel = g["angVel"]
+    S.engines = woo.utils.gpuEngines(damping=.2, dynDtPeriod=100)
+    v0 = np.array(facets[0].shape.nodes[0].pos)
+    S.run(400, True)
+    assert np.array_equal(np.array([S.dem.par[i].pos for i in range(Sp.n)]), E.spheres()["pos"])
+    v1 = np.array(facets[0].shape.nodes[0].pos)
+    assert np.array_equal(v1, E.facets()[0, 0]) and np.linalg.norm(v1 - v0) > 1e-3
+    assert abs(np.linalg.norm(np.array(central.ori)) - 1) < 1e-12 and abs(central.ori[3]) < 1.      # the master node has turned

@@ -158,7 +158,9 @@ struct wdem_engine {
   int n = 0; SphereStore sph[2]; int cur = 0; DBuf<int> id2slot, up2slot; int maxId = -1; bool up2slotValid = false;
   std::vector<Material> hMats; DBuf<Material> dMats;
   std::vector<Wall> hWalls; DBuf<Wall> dWalls; bool anyMovingWall = false;
-  std::vector<Facet> hFacets; DBuf<Facet> dFacets; DBuf<int> fgCellStart, fgCellFacet; FacetGrid fgrid; bool fgridValid = false;
+  std::vector<Facet> hFacets; DBuf<Facet> dFacets; DBuf<int> fgCellStart, fgCellFacet, fgCursor; FacetGrid fgrid; bool fgridValid = false;
+  GroupsU groups{};                      // kinematic facet groups (wdem_upload_facet_groups): master nodes integrated on the host, members on the device
+  std::vector<double> groupRadius;       // largest distance of a member node from its master node (bounding sphere of the sweep of a rotating group)
   double minRadius = INFINITY, pwaveDt = INFINITY;
   std::vector<double> hRadius; std::vector<int32_t> hMatOfSphere;
   std::vector<int32_t> hIds;                // Particle.id of the spheres in upload order
@@ -249,6 +251,7 @@ void checkDeviceError(wdem_engine* E) {
 }
 
 void buildFacetGrid(wdem_engine* E);
+void rebinFacets(wdem_engine* E);
 
 // -------------------------------------------------------------------------------------------------
 // Slab decomposition: host orchestration of migration, ghost export and the per-step ghost refresh.
@@ -546,6 +549,7 @@ void rebuild(wdem_engine* E) {
   int64_t& tot = E->bytes;
   long long nSS = 0, nWS = 0, nFS = 0, nOrphOut = 0;
   if (!E->fgridValid) buildFacetGrid(E);
+  if (E->groups.n > 0 && !E->hFacets.empty()) rebinFacets(E);
   const int nFacets = (int)E->hFacets.size();
   ContactStore& Nst = E->con[1 - E->curC];
   ContactStore& Ost = E->con[E->curC];
@@ -774,6 +778,12 @@ void buildFacetGrid(wdem_engine* E) {
   double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   std::vector<double> ext; ext.reserve(nf);
   for (auto& f : E->hFacets) { double e = 0; for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], f.bmin[k] - vd); hi[k] = std::max(hi[k], f.bmax[k] + vd); e = std::max(e, f.bmax[k] - f.bmin[k]); } ext.push_back(e); }
+  // a rotating group sweeps its bounding sphere: size the (fixed) grid for it; a group that translates out of the grid is still binned correctly (clamped
+  // cell coordinates on both sides of the lookup), only less efficiently
+  for (int gi = 0; gi < E->groups.n; gi++) {
+    const d3 c = E->groups.g[gi].pos; const double R = E->groupRadius[gi] + vd; const double cc3[3] = {c.x, c.y, c.z};
+    for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], cc3[k] - R); hi[k] = std::max(hi[k], cc3[k] + R); }
+  }
   std::nth_element(ext.begin(), ext.begin() + nf / 2, ext.end());
   double cell = std::max(ext[nf / 2] + 2 * vd, 1e-300);
   double vol = std::max(hi[0] - lo[0], cell) * std::max(hi[1] - lo[1], cell) * std::max(hi[2] - lo[2], cell);
@@ -804,6 +814,22 @@ void buildFacetGrid(wdem_engine* E) {
   }
   g.cellStart = E->fgCellStart.p; g.cellFacet = E->fgCellFacet.p;
   E->fgridValid = true;
+}
+
+// full run with moving facets: refresh their boxes and re-bin them on the device into the grid laid out by buildFacetGrid (same geometry, new lists)
+void rebinFacets(wdem_engine* E) {
+  const int nf = (int)E->hFacets.size(); cudaStream_t st = E->stream; FacetGrid& g = E->fgrid;
+  const size_t ncell = (size_t)g.nx * g.ny * g.nz;
+  k_facets_step<<<nblk(nf, 128), 128, 0, st>>>(E->dFacets.p, nf, E->groups, makeUniforms(E), E->dCnt, 1);
+  CK(cudaMemsetAsync(E->fgCellStart.p, 0, (ncell + 1) * sizeof(int), st));
+  k_fgrid_bin<<<nblk(nf, 128), 128, 0, st>>>(E->dFacets.p, nf, g, E->verletDist, E->fgCellStart.p, nullptr, nullptr, 0);
+  exclusiveSum(E, E->fgCellStart.p, E->fgCellStart.p, (int)ncell + 1);
+  int total = 0; CK(cudaMemcpyAsync(&total, E->fgCellStart.p + ncell, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  E->fgCellFacet.ensure((size_t)std::max(total, 1), E->bytes); E->fgCursor.ensure(ncell + 1, E->bytes);
+  g.cellStart = E->fgCellStart.p; g.cellFacet = E->fgCellFacet.p;
+  CK(cudaMemsetAsync(E->fgCursor.p, 0, (ncell + 1) * sizeof(int), st));
+  k_fgrid_bin<<<nblk(nf, 128), 128, 0, st>>>(E->dFacets.p, nf, g, E->verletDist, nullptr, E->fgCursor.p, E->fgCellFacet.p, 1);
+  E->launches += 5;
 }
 
 void ensureVerletAndDt(wdem_engine* E) {
@@ -975,6 +1001,26 @@ void oneStep(wdem_engine* E, wdem_stats* stats) {
     else k_leapfrog<false><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
     E->launches++;
   }
+  if (E->groups.n > 0 && !E->hFacets.empty()) {
+    if (c.periodic) throw EngErr{"moving facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    // master nodes: all DOFs blocked => Leapfrog's fixed-particle branch with the prescribed velocities: leapfrogTranslate + leapfrogSphericalRotate
+    // (Leapfrog.cpp:195-199,275-297) on the host (a handful of nodes; libm sin/cos), members on the device (ClumpData::applyToMembers, Clump.cpp:293-307)
+    for (int gi = 0; gi < E->groups.n; gi++) {
+      GroupU& G = E->groups.g[gi]; const double dt = E->dt;
+      G.pos = G.pos + G.vel * dt;
+      d3 axis = G.angVel;
+      if (axis.x != 0. || axis.y != 0. || axis.z != 0.) {
+        const double angle = nrm(axis); axis = axis / angle;
+        const double ha = 0.5 * (angle * dt), sn = std::sin(ha), qw = std::cos(ha), qx = sn * axis.x, qy = sn * axis.y, qz = sn * axis.z;
+        const q4 o = G.ori;
+        G.ori.w = qw * o.w - qx * o.x - qy * o.y - qz * o.z; G.ori.x = qw * o.x + qx * o.w + qy * o.z - qz * o.y;
+        G.ori.y = qw * o.y + qy * o.w + qz * o.x - qx * o.z; G.ori.z = qw * o.z + qz * o.w + qx * o.y - qy * o.x;
+      }
+      const double nn = std::sqrt(((G.ori.x * G.ori.x + G.ori.y * G.ori.y) + G.ori.z * G.ori.z) + G.ori.w * G.ori.w);
+      G.ori.w /= nn; G.ori.x /= nn; G.ori.y /= nn; G.ori.z /= nn;
+    }
+    k_facets_step<<<nblk((long long)E->hFacets.size(), 128), 128, 0, st>>>(E->dFacets.p, (int)E->hFacets.size(), E->groups, u, E->dCnt, 0); E->launches++;
+  }
   if (E->anyMovingWall) {
     if (c.periodic) throw EngErr{"moving walls in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), u, E->dCnt, 0); E->launches++;
@@ -1122,7 +1168,7 @@ int wdem_destroy(wdem_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release();
-  h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
+  h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->fgCursor.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
   h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->candBuf.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
   peerTeardown(h, false);
   h->dom.release(); delete h->comm; h->comm = nullptr;
@@ -1267,7 +1313,53 @@ int wdem_upload_facets(wdem_handle h, int n, const int32_t* ids, const double* v
     h->dFacets.ensure(std::max(n, 1), h->bytes);
     if (n) CK(cudaMemcpyAsync(h->dFacets.p, h->hFacets.data(), n * sizeof(Facet), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->conDirty = true; h->fgridValid = false;
+    h->conDirty = true; h->fgridValid = false; h->groups.n = 0; h->groupRadius.clear();
+  });
+}
+
+int wdem_upload_facet_groups(wdem_handle h, int nGroups, const int32_t* groupOfFacet, const double* pos, const double* ori, const double* vel, const double* angVel) {
+  return guarded(h, [&] {
+    const int nf = (int)h->hFacets.size();
+    if (nGroups < 0 || nGroups > WD_MAX_GROUPS) throw EngErr{"wdem_upload_facet_groups: at most " + std::to_string(WD_MAX_GROUPS) + " groups", WDEM_ERR_UNSUPPORTED};
+    if (nGroups > 0 && (!groupOfFacet || !pos || !ori || !vel || !angVel)) throw EngErr{"wdem_upload_facet_groups: bad arguments", WDEM_ERR_INVALID};
+    if (!h->conDirty || h->nC != 0) throw EngErr{"wdem_upload_facet_groups: call after wdem_upload_facets and before the first step", WDEM_ERR_INVALID};
+    h->groups.n = nGroups; h->groupRadius.assign(nGroups, 0.);
+    for (int g = 0; g < nGroups; g++) {
+      GroupU& G = h->groups.g[g];
+      G.pos = mk3(pos[3 * g], pos[3 * g + 1], pos[3 * g + 2]); G.ori.x = ori[4 * g]; G.ori.y = ori[4 * g + 1]; G.ori.z = ori[4 * g + 2]; G.ori.w = ori[4 * g + 3];
+      G.vel = mk3(vel[3 * g], vel[3 * g + 1], vel[3 * g + 2]); G.angVel = mk3(angVel[3 * g], angVel[3 * g + 1], angVel[3 * g + 2]);
+    }
+    for (int f = 0; f < nf; f++) {
+      Facet& F = h->hFacets[f];
+      const int g = groupOfFacet[f];
+      if (g >= nGroups) throw EngErr{"wdem_upload_facet_groups: group index out of range", WDEM_ERR_INVALID};
+      F.group1 = g < 0 ? 0 : g + 1;
+      for (int k = 0; k < 9; k++) F.lastv[k] = F.v[k];
+      if (g < 0) continue;
+      const GroupU& G = h->groups.g[g]; q4 qc = G.ori; qc.x = -qc.x; qc.y = -qc.y; qc.z = -qc.z;      // conjugate
+      for (int i = 0; i < 3; i++) {
+        const d3 d = mk3(F.v[3 * i], F.v[3 * i + 1], F.v[3 * i + 2]) - G.pos;
+        const d3 r = quatRotate(qc, d);                                                               // ClumpData.relPos (Clump.cpp:252)
+        F.rel[3 * i] = r.x; F.rel[3 * i + 1] = r.y; F.rel[3 * i + 2] = r.z;
+        const d3 vv = G.vel + cross(G.angVel, d);
+        F.vvel[3 * i] = vv.x; F.vvel[3 * i + 1] = vv.y; F.vvel[3 * i + 2] = vv.z;
+        h->groupRadius[g] = std::max(h->groupRadius[g], nrm(d));
+      }
+    }
+    if (nf) CK(cudaMemcpyAsync(h->dFacets.p, h->hFacets.data(), nf * sizeof(Facet), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->fgridValid = false;
+  });
+}
+int wdem_download_facets(wdem_handle h, double* verts, double* groupPos, double* groupOri) {
+  return guarded(h, [&] {
+    const size_t nf = h->hFacets.size();
+    if (verts && nf) { auto F = d2h(h->dFacets.p, nf, h->stream); for (size_t f = 0; f < nf; f++) for (int k = 0; k < 9; k++) verts[9 * f + k] = F[f].v[k]; }
+    for (int g = 0; g < h->groups.n; g++) {
+      const GroupU& G = h->groups.g[g];
+      if (groupPos) { groupPos[3 * g] = G.pos.x; groupPos[3 * g + 1] = G.pos.y; groupPos[3 * g + 2] = G.pos.z; }
+      if (groupOri) { groupOri[4 * g] = G.ori.x; groupOri[4 * g + 1] = G.ori.y; groupOri[4 * g + 2] = G.ori.z; groupOri[4 * g + 3] = G.ori.w; }
+    }
   });
 }
 

@@ -35,7 +35,13 @@ struct Spheres {          // one slot per sphere; slots are re-ordered by grid c
 
 // moving: the wall's node is in DemField.nodes (added with a nonzero velocity: Particle::guessMoving, Particle.cpp:638-640) and is translated by Leapfrog
 struct Wall { double pos[3]; double vel[3]; double lastPos[3]; int32_t axis, sense; uint32_t mask; int32_t mat; int32_t id; int32_t moving; };
-struct Facet { double v[9]; double vvel[9]; double fakeVel[3]; double halfThick; double n21lim[3]; double bmin[3], bmax[3]; uint32_t mask; int32_t mat; int32_t id; int32_t pad; };
+// group1: 1 + index of the kinematic group (clump of boundary particles with a prescribed rigid motion) the facet belongs to, 0 = static;
+// rel: node positions in the group's frame (ClumpData.relPos, Clump.cpp:252); lastv: Aabb::nodeLastPos
+struct Facet { double v[9]; double vvel[9]; double fakeVel[3]; double halfThick; double n21lim[3]; double bmin[3], bmax[3]; uint32_t mask; int32_t mat; int32_t id; int32_t group1;
+               double rel[9]; double lastv[9]; };
+#define WD_MAX_GROUPS 8
+struct GroupU { d3 pos; q4 ori; d3 vel, angVel; };
+struct GroupsU { int n; GroupU g[WD_MAX_GROUPS]; };
 struct FacetGrid { double ox, oy, oz, inv; int nx, ny, nz; const int* cellStart; const int* cellFacet; };
 struct Material { int32_t kind; int32_t pad; double density, young, ktDivKn, tanPhi, surfEnergy, alpha; };
 
@@ -227,6 +233,37 @@ __global__ void __launch_bounds__(256, 4) k_leapfrog_io(Spheres S, StepU u, Coun
   leapfrog_body<true, TRACK>(S, up2slot[first + t], u, cnt, io, first + t);
 }
 
+// ClumpData::applyToMembers (Clump.cpp:293-307) for facets of kinematic groups, after the host has integrated the groups' master nodes: node position
+// = clumpPos + clumpOri*relPos, node velocity = clump.vel + clump.angVel x (pos - clumpPos); plus the Verlet test of the facet's Aabb (every node,
+// Collision.cpp:113-121; rotation is ignored for facets: maxRot=-1, Facet.cpp:277).  mode 1 (at a full run): refresh Aabb (Bo1_Facet_Aabb::go, Facet.cpp:275-298)
+// and Aabb::nodeLastPos of ALL facets.
+__global__ void __launch_bounds__(128) k_facets_step(Facet* facets, int n, GroupsU G, StepU u, Counters* cnt, int mode) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  Facet* F = facets + f;
+  if (mode == 1) {
+    const double ht = F->halfThick;
+    for (int k = 0; k < 3; k++) {
+      double mn = F->v[k] - ht, mx = F->v[k] + ht;
+      for (int j = 1; j < 3; j++) { mn = fmin(mn, F->v[3 * j + k] - ht); mx = fmax(mx, F->v[3 * j + k] + ht); }
+      F->bmin[k] = mn; F->bmax[k] = mx;
+    }
+    for (int k = 0; k < 9; k++) F->lastv[k] = F->v[k];
+    return;
+  }
+  const int gi = F->group1 - 1;
+  if (gi < 0) return;
+  const GroupU g = G.g[gi];
+  double d2 = 0;
+  for (int i = 0; i < 3; i++) {
+    const d3 p = g.pos + quatRotate(g.ori, mk3(F->rel[3 * i], F->rel[3 * i + 1], F->rel[3 * i + 2]));
+    const d3 vv = g.vel + cross(g.angVel, p - g.pos);
+    F->v[3 * i] = p.x; F->v[3 * i + 1] = p.y; F->v[3 * i + 2] = p.z;
+    F->vvel[3 * i] = vv.x; F->vvel[3 * i + 1] = vv.y; F->vvel[3 * i + 2] = vv.z;
+    d2 = fmax(d2, sqn(mk3(F->lastv[3 * i], F->lastv[3 * i + 1], F->lastv[3 * i + 2]) - p));
+  }
+  if (d2 > u.maxD2 || !(d2 == d2)) cnt->dirty = 1;
+}
 // Leapfrog for boundary nodes that are in DemField.nodes (moving walls: mass 0, all DOFs blocked => the "fixed particle" branch, Leapfrog.cpp:195-199):
 // leapfrogTranslate only (:275-278), plus the Verlet test of their Aabb (Collision.cpp:113-121).  setLast: record Aabb::nodeLastPos at a full run.
 __global__ void k_walls_step(Wall* walls, int n, StepU u, Counters* cnt, int setLast) {
@@ -1127,6 +1164,22 @@ __global__ void __launch_bounds__(128) k_pairs_ws(Spheres S, int n, const Wall* 
     cntLocal++;
   }
   if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
+}
+
+// device-side binning of the facets into the (fixed) facet grid at a full run: count per cell, scan (host: cub), fill through per-cell cursors
+__global__ void __launch_bounds__(128) k_fgrid_bin(const Facet* __restrict__ facets, int n, FacetGrid fg, double vd, int* __restrict__ cellCount /*+1 shifted*/, int* __restrict__ cursor,
+                                                  int* __restrict__ cellFacet, int fill) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const Facet* F = facets + f;
+  const int x0 = cellCoord(F->bmin[0] - vd, fg.ox, fg.inv, fg.nx), x1 = cellCoord(F->bmax[0] + vd, fg.ox, fg.inv, fg.nx);
+  const int y0 = cellCoord(F->bmin[1] - vd, fg.oy, fg.inv, fg.ny), y1 = cellCoord(F->bmax[1] + vd, fg.oy, fg.inv, fg.ny);
+  const int z0 = cellCoord(F->bmin[2] - vd, fg.oz, fg.inv, fg.nz), z1 = cellCoord(F->bmax[2] + vd, fg.oz, fg.inv, fg.nz);
+  for (int iz = z0; iz <= z1; iz++) for (int iy = y0; iy <= y1; iy++) for (int ix = x0; ix <= x1; ix++) {
+    const int k = (iz * fg.ny + iy) * fg.nx + ix;
+    if (!fill) atomicAdd(&cellCount[k], 1);
+    else cellFacet[fg.cellStart[k] + atomicAdd(&cursor[k], 1)] = f;
+  }
 }
 
 // Facet+Sphere candidates: Bo1_Facet_Aabb (Facet.cpp:275-298): vertex min/max ± halfThick, then ± verletDist.  Facets are static and are

@@ -69,11 +69,13 @@ struct Contact { int id1 = -1, id2 = -1; V3i cellDist{{0, 0, 0}}; int stepCreate
 
 struct GpuDemLoop;
 struct ParticleContainer { DemField* dem = nullptr; vector<shared_ptr<Particle>> v; };
+// clump of boundary particles moved rigidly by its master node (ParticleContainer::addClumped -> ClumpData::makeClump, Clump.cpp:187-261)
+struct ClumpGroup { shared_ptr<Node> master; vector<int> members; /* Particle ids */ };
 struct ContactContainer { DemField* dem = nullptr; vector<shared_ptr<Contact>> v; std::map<std::pair<int, int>, size_t> ix; };
 
 // ---- the field (dem/Particle.hpp:339-361)
 struct DemField {
-  ParticleContainer par; ContactContainer con; vector<shared_ptr<Node>> nodes;
+  ParticleContainer par; ContactContainer con; vector<shared_ptr<Node>> nodes; vector<ClumpGroup> clumps;
   V3 gravity{{0, 0, 0}}; unsigned loneMask = 2; double distFactor = -1.;
   // coherence with the device copy (SURVEY §7 "Host<->device coherence"): upload once, download lazily
   GpuDemLoop* owner = nullptr; bool topoDirty = true, stateDirty = false, deviceNewer = false, contactsStale = true;
@@ -128,7 +130,7 @@ static void chk(wdem_handle h, int rc) { if (rc != WDEM_OK) throw std::runtime_e
 struct GpuDemLoop : Engine {
   shared_ptr<Leapfrog> leapfrog; shared_ptr<InsertionSortCollider> collider; shared_ptr<ContactLoop> contactLoop; shared_ptr<DynDt> dynDt;
   int device = 0; wdem_handle h = nullptr; wdem_config cfg; bool haveCfg = false; long nSpheres = 0; wdem_stats last;
-  vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf, wallOf; bool trackingOn = false;
+  vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf, wallOf, facetOf; bool trackingOn = false;
   const char* cls() const override { return "GpuDemLoop"; }
   ~GpuDemLoop() override { release(); }
   void release() { if (h) { wdem_destroy(h); h = nullptr; } if (field && field->owner == this) field->owner = nullptr; }
@@ -195,7 +197,7 @@ struct GpuDemLoop : Engine {
     auto matOf = [&](const shared_ptr<Particle>& p) { Material* m = p->material.get(); if (!m) throw std::runtime_error("particle #" + std::to_string(p->id) + " has no material"); auto it = matIx.find(m); if (it != matIx.end()) return it->second; int k = (int)mats.size(); mats.push_back(m); matIx[m] = k; return k; };
     vector<int32_t> sid, smat, wid, waxis, wsense, wmat, fid, fmat; vector<uint32_t> sflags, smask, wmask, fmask;
     vector<double> spos, sori, svel, sang, smass, sin, srad, sfrc, strq, wpos, wvel, fv, fvv, ffk, fht, fnl;
-    sphereIds.clear(); sphereOf.clear(); wallOf.clear();
+    sphereIds.clear(); sphereOf.clear(); wallOf.clear(); facetOf.clear();
     for (auto& p : F.par.v) {
       if (!p) continue;
       if (!p->shape) throw std::runtime_error("particle #" + std::to_string(p->id) + " has no shape");
@@ -218,6 +220,7 @@ struct GpuDemLoop : Engine {
         fid.push_back(p->id); fmat.push_back(m); fmask.push_back(p->mask); fht.push_back(f->halfThick);
         for (int v = 0; v < 3; v++) { const Node& n = *f->nodes.at(v); for (int k = 0; k < 3; k++) { fv.push_back(n.pos[k]); fvv.push_back(n.dem->vel[k]); } }
         for (int k = 0; k < 3; k++) { ffk.push_back(f->fakeVel[k]); fnl.push_back(f->n21lim[k]); }
+        facetOf.push_back(p);
       } else throw std::runtime_error("GpuDemLoop: particle #" + std::to_string(p->id) + ": only Sphere, Wall and Facet shapes are supported");
     }
     if (mats.empty()) throw std::runtime_error("GpuDemLoop: no particles");
@@ -233,6 +236,18 @@ struct GpuDemLoop : Engine {
     chk(h, wdem_upload_forces(h, sfrc.data(), strq.data()));
     chk(h, wdem_upload_walls(h, (int)wid.size(), wid.data(), wpos.data(), waxis.data(), wsense.data(), wvel.data(), wmask.data(), wmat.data()));
     chk(h, wdem_upload_facets(h, (int)fid.size(), fid.data(), fv.data(), fvv.data(), ffk.data(), fht.data(), fnl.data(), fmask.data(), fmat.data()));
+    if (!F.clumps.empty()) {   // kinematic groups of facets: master node pos/ori/vel/angVel, members follow on the device
+      std::map<int, int> facetIx; for (size_t i = 0; i < facetOf.size(); i++) facetIx[facetOf[i]->id] = (int)i;
+      vector<int32_t> of(facetOf.size(), -1); vector<double> gp, go, gv, gw;
+      for (size_t g = 0; g < F.clumps.size(); g++) {
+        const Node& M = *F.clumps[g].master;
+        if ((M.dem->flags & DOF_ALL) != DOF_ALL) throw std::runtime_error("GpuDemLoop: the master node of a clump of boundary particles must have all DOFs blocked (its motion is prescribed)");
+        for (int id : F.clumps[g].members) { auto it = facetIx.find(id); if (it == facetIx.end()) throw std::runtime_error("GpuDemLoop: only Facets can be members of a kinematic clump (particle #" + std::to_string(id) + ")"); of[it->second] = (int32_t)g; }
+        for (int k = 0; k < 3; k++) { gp.push_back(M.pos[k]); gv.push_back(M.dem->vel[k]); gw.push_back(M.dem->angVel[k]); }
+        for (int k = 0; k < 4; k++) go.push_back(M.ori[k]);
+      }
+      chk(h, wdem_upload_facet_groups(h, (int)F.clumps.size(), of.data(), gp.data(), go.data(), gv.data(), gw.data()));
+    }
     if (scene->periodic) { Cell& C = *scene->cell; chk(h, wdem_set_cell(h, C.hSize.data(), C.gradV.data(), C.nextGradV.data(), C.homoDeform)); C.dirty = false; }
     chk(h, wdem_set_scene(h, (int64_t)scene->step, scene->time));
     F.pushContacts(h);
@@ -249,6 +264,7 @@ struct GpuDemLoop : Engine {
   void prepare() {
     if (!field) throw std::runtime_error("GpuDemLoop: no DemField");
     DemField& F = *field;
+    if (F.stateDirty && !F.clumps.empty()) F.topoDirty = true;   // the edit may concern a clump's master node (its vel/angVel): take the full path
     if (!h || F.topoDirty || F.owner != this) upload();
     else {
       wdem_config c = makeConfig();
@@ -300,6 +316,12 @@ void DemField::pull() {
     vector<double> wp(3 * nw), wf(3 * nw), wt(3 * nw);
     chk(owner->h, wdem_download_walls(owner->h, wp.data(), wf.data(), wt.data()));
     for (size_t i = 0; i < nw; i++) { Node& nd = *owner->wallOf[i]->shape->nodes[0]; for (int k = 0; k < 3; k++) { nd.pos[k] = wp[3 * i + k]; nd.dem->force[k] = wf[3 * i + k]; nd.dem->torque[k] = wt[3 * i + k]; } }
+  }
+  if (!clumps.empty() && !owner->facetOf.empty()) {
+    const size_t nf = owner->facetOf.size(); vector<double> fv(9 * nf), gp(3 * clumps.size()), go(4 * clumps.size());
+    chk(owner->h, wdem_download_facets(owner->h, fv.data(), gp.data(), go.data()));
+    for (size_t i = 0; i < nf; i++) for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) owner->facetOf[i]->shape->nodes[v]->pos[k] = fv[9 * i + 3 * v + k];
+    for (size_t g = 0; g < clumps.size(); g++) { Node& M = *clumps[g].master; for (int k = 0; k < 3; k++) M.pos[k] = gp[3 * g + k]; for (int k = 0; k < 4; k++) M.ori[k] = go[4 * g + k]; }
   }
   deviceNewer = false;
 }
@@ -491,6 +513,17 @@ PYBIND11_MODULE(_woo, m) {
           c.dem->topoDirty = true; return p->id; };
         if (py::isinstance<Particle>(o)) return py::int_(addOne(o.cast<shared_ptr<Particle>>()));
         py::list ids; for (auto it : o) ids.append(addOne(it.cast<shared_ptr<Particle>>())); return ids; });
+  m.attr("ParticleContainer").attr("addClumped") = py::cpp_function([](ParticleContainer& c, py::object pars, shared_ptr<Node> centralNode) -> shared_ptr<Node> {
+        // ParticleContainer::addClumped (ParticleContainer.cpp) for boundary particles with a user-given master node: the members keep their positions, the master's
+        // vel/angVel (all DOFs blocked) move them rigidly from now on (examples/mill.py:38-42)
+        if (!centralNode) throw std::runtime_error("addClumped: centralNode is required (members without mass; Clump.cpp:239)");
+        if (!centralNode->dem) { centralNode->dem = make_shared<DemData>(); centralNode->dem->flags |= DOF_ALL; }
+        centralNode->dem->field = c.dem;
+        ClumpGroup G; G.master = centralNode;
+        py::object add = py::cast(&c, py::return_value_policy::reference).attr("add");
+        for (auto it : pars) { auto p = it.cast<shared_ptr<Particle>>(); if (p->id < 0) add(p); G.members.push_back(p->id); }
+        c.dem->clumps.push_back(G); c.dem->nodes.push_back(centralNode); c.dem->topoDirty = true;
+        return centralNode; }, py::is_method(m.attr("ParticleContainer")), py::arg("pars"), py::arg("centralNode"));
   kwclass<DemField>(m, "DemField")
       .def_property_readonly("par", [](DemField& f) -> ParticleContainer& { return f.par; }, py::return_value_policy::reference_internal)
       .def_property_readonly("con", [](DemField& f) -> ContactContainer& { return f.con; }, py::return_value_policy::reference_internal)

@@ -45,6 +45,7 @@ def _load_part(E, S, sel):
     E.upload_spheres(ids[sel], S.pos[sel], S.radius[sel], m[sel], I[sel], S.mat[sel], S.mask[sel], S.flags[sel], S.vel[sel], S.angVel[sel])
     E.upload_walls(S.wall_ids(), S.walls)
     E.upload_facets(S.facet_ids(), S.facets)
+    E.upload_facet_groups(len(S.facets), getattr(S, "facet_groups", []))
     if S.cell is not None:
         E.set_cell(S.cell["hSize"], S.cell.get("gradV"), S.cell.get("nextGradV"), S.cell.get("homoDeform", 4))
 

@@ -99,6 +99,24 @@ class Engine:
         mask = np.array([f.get("mask", 3) for f in facets], dtype=np.uint32); mat = np.array([f.get("mat", 0) for f in facets], dtype=np.int32)
         self._chk(self.L.wdem_upload_facets(self.h, C.c_int(n), ptr(ids), ptr(v), ptr(vv), ptr(fk), ptr(ht), ptr(nl), ptr(mask), ptr(mat)))
 
+    def upload_facet_groups(self, n_facets, groups):
+        """Kinematic groups of facets (wdem.h: wdem_upload_facet_groups): dicts with pos, ori (x,y,z,w), vel, angVel, facets (indices)."""
+        if not groups:
+            return
+        of = np.full(n_facets, -1, np.int32)
+        for gi, g in enumerate(groups):
+            of[np.asarray(g["facets"], dtype=np.int64)] = gi
+        arr = lambda k, w: f64([g[k] for g in groups], (len(groups), w))
+        self._chk(self.L.wdem_upload_facet_groups(self.h, C.c_int(len(groups)), ptr(of), ptr(arr("pos", 3)), ptr(arr("ori", 4)), ptr(arr("vel", 3)), ptr(arr("angVel", 3))))
+
+    def facets(self):
+        """Facet node positions after the last step, (n,3,3)."""
+        n = len(self.spec.facets) if getattr(self, "spec", None) is not None else 0
+        o = np.zeros((n, 3, 3))
+        if n:
+            self._chk(self.L.wdem_download_facets(self.h, ptr(o), None, None))
+        return o
+
     def set_cell(self, hSize, gradV=None, nextGradV=None, homoDeform=4):
         self._chk(self.L.wdem_set_cell(self.h, ptr(f64(hSize)), ptr(f64(gradV)), ptr(f64(nextGradV)), C.c_int(homoDeform)))
 
@@ -110,6 +128,7 @@ class Engine:
         self.upload_spheres(S.sphere_ids(), S.pos, S.radius, m, I, S.mat, S.mask, S.flags, S.vel, S.angVel)
         self.upload_walls(S.wall_ids(), S.walls)
         self.upload_facets(S.facet_ids(), S.facets)
+        self.upload_facet_groups(len(S.facets), getattr(S, "facet_groups", []))
         if S.cell is not None:
             self.set_cell(S.cell["hSize"], S.cell.get("gradV"), S.cell.get("nextGradV"), S.cell.get("homoDeform", 4))
         return self

@@ -64,6 +64,7 @@ class SceneSpec:
     flags: np.ndarray = None
     walls: list = field(default_factory=list)  # dict(pos, axis, sense, mat, mask, vel)
     facets: list = field(default_factory=list)  # dict(v(3,3), halfThick, fakeVel, n21lim, vvel, mat, mask)
+    facet_groups: list = field(default_factory=list)  # kinematic groups: dict(pos, ori (x,y,z,w), vel, angVel, facets=[indices into ``facets``])
     params: Params = field(default_factory=Params)
     cell: dict = None                           # dict(hSize(3,3), gradV, nextGradV, homoDeform)
     boundaries_first: bool = False              # ids: walls+facets first, then spheres
@@ -295,7 +296,7 @@ def periodic_shear(n, *, r=1e-3, seed=4, solid=.55, rate=1.0, vfluct=0.0, young=
     return S.finalize()
 
 
-def drum(n, *, r=2e-3, seed=5, R=None, length=None, div=32, axial=8, omega=5.0, young=1e7, density=2500., fill=.35, vz0=0.0, vfluct=0.0):
+def drum(n, *, r=2e-3, seed=5, R=None, length=None, div=32, axial=8, omega=5.0, young=1e7, density=2500., fill=.35, vz0=0.0, vfluct=0.0, rotate=False):
     """cfg5 of BASELINE.json in small: spheres in a horizontal cylinder (axis x) made of static facets whose ``fakeVel = -R*omega*n x ax`` mimics the
     rotation (py/triangulated.py:56-58), closed by two Walls; linear law.  Spheres start on a jittered lattice in the lower part."""
     rng = np.random.default_rng(seed)
@@ -331,6 +332,10 @@ def drum(n, *, r=2e-3, seed=5, R=None, length=None, div=32, axial=8, omega=5.0, 
     if vz0 or vfluct:
         S.vel = np.tile([0., 0., -vz0], (n, 1)) * rng.uniform(.5, 1.5, (n, 1)) + rng.uniform(-vfluct, vfluct, (n, 3))
     S.facets = F
+    if rotate:   # the drum really turns: the facets are clumped to a master node on the axis that carries the angular velocity (examples/mill.py:38-42)
+        for f in F:
+            f["fakeVel"] = (0., 0., 0.)
+        S.facet_groups = [dict(pos=(.5 * length, 0., 0.), ori=(0., 0., 0., 1.), vel=(0., 0., 0.), angVel=(omega, 0., 0.), facets=list(range(len(F))))]
     S.walls = [dict(pos=(0, 0, 0), axis=0, sense=1, mat=0, mask=MASK_BOUNDARY), dict(pos=(length, 0, 0), axis=0, sense=-1, mat=0, mask=MASK_BOUNDARY)]
     S.params = Params(gravity=(0, 0, -9.81), damping=.2, law=LAW_IDEALELPL, verletDist=-.05, dtSafety=.9, dynDtPeriod=100)
     return S.finalize()
