@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include "../../include/wdem.h"
+#include <chrono>
 #include <unordered_map>
 #include "wdem_kernels.cuh"
 #include "wdem_domain.cuh"
@@ -312,6 +313,9 @@ void exclusiveSum(wdem_engine* E, const int* in, int* out, int n) {
 //   2. ghosts of the previous generation are dropped; every owned sphere whose enlarged AABB can reach a box owned by rank r is exported to r.
 // Leaves the new generation (owned first, then ghosts; unsorted) in the current sphere store.
 void domainExchange(wdem_engine* E) {
+  static const bool tr = getenv("WDEM_REBUILD_TRACE") != nullptr;
+  static double tacc[10] = {0}; static int tcnt = 0; std::chrono::steady_clock::time_point tp[10];
+  auto TM = [&](int k) { if (tr) { cudaStreamSynchronize(E->stream); tp[k] = std::chrono::steady_clock::now(); } };
   Transport* T = E->comm; DomainState& M = E->dom;
   const int W = T->world, R = T->rank; cudaStream_t st = E->stream; int64_t& tot = E->bytes;
   const wdem_config& c = E->cfg;
@@ -322,6 +326,7 @@ void domainExchange(wdem_engine* E) {
   Spheres A = Ast.view();
   ContactStore& Ost = E->con[E->curC]; CsrStore& Ocsr = E->csr[E->curR];
   OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = (Ocsr.valid && E->nC > 0) ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
+  TM(0);
   // ---- 1. classify and group by destination
   std::vector<int> start(W + 3, 0);
   const size_t nn = std::max(n, 1);
@@ -338,6 +343,7 @@ void domainExchange(wdem_engine* E) {
     E->launches += 7;
   }
   const int nKeep = start[1] - start[0], nE = start[W + 1] - start[1];
+  TM(1);
   // ---- 2. emigrants: particle records and history rows
   std::vector<int> hRowOff(nE + 1, 0);
   if (nE > 0) {
@@ -348,12 +354,14 @@ void domainExchange(wdem_engine* E) {
     CK(cudaMemcpyAsync(hRowOff.data(), M.rowOff.p, (nE + 1) * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
     E->launches += 3;
   }
+  TM(2);
   std::vector<int64_t> mine(2 * W, 0), all((size_t)2 * W * W, 0);
   for (int r = 0; r < W; r++) {
     const int a = start[1 + r] - start[1], b = start[2 + r] - start[1];
     mine[2 * r] = b - a; mine[2 * r + 1] = hRowOff[b] - hRowOff[a];
   }
   T->allgather64(mine.data(), 2 * W, all.data(), st);
+  TM(3);
   std::vector<size_t> sOffP(W, 0), sBytP(W, 0), rOffP(W, 0), rBytP(W, 0), sOffR(W, 0), sBytR(W, 0), rOffR(W, 0), rBytR(W, 0);
   size_t nImmP = 0, nImmR = 0, accP = 0, accR = 0;
   for (int r = 0; r < W; r++) {
@@ -374,6 +382,7 @@ void domainExchange(wdem_engine* E) {
   }
   T->alltoallv(M.sendBuf.p, sOffP.data(), sBytP.data(), M.recvBuf.p, rOffP.data(), rBytP.data(), st);
   T->alltoallv(M.sendBuf.p + sendRowsBase, sOffR.data(), sBytR.data(), M.recvBuf.p + recvRowsBase, rOffR.data(), rBytR.data(), st);
+  TM(4);
   // ---- 3. new owned set = kept + immigrants
   const int nOwn = nKeep + (int)nImmP;
   Bst.ensure((size_t)std::max(nOwn + (int)M.nRecvTot + 1024, 1), tot);
@@ -392,6 +401,7 @@ void domainExchange(wdem_engine* E) {
     cub::DeviceRadixSort::SortPairs(E->cubTemp.p, tb, M.immKeys.p, M.immKeysAlt.p, M.immVals.p, M.immValsAlt.p, (int)nImmR, 0, 64, st);
     E->launches += 4;
   }
+  TM(5);
   // ---- 5. ghost export
   M.perRank.ensure(WDEM_MAX_RANKS, tot); M.emask.ensure((size_t)std::max(nOwn, 1), tot);
   CK(cudaMemsetAsync(M.perRank.p, 0, WDEM_MAX_RANKS * sizeof(int), st));
@@ -400,9 +410,11 @@ void domainExchange(wdem_engine* E) {
     k_dom_export_mask<<<nblk(nOwn, 256), 256, 0, st>>>(B, nOwn, D, M.emask.p, M.perRank.p); E->launches++;
     CK(cudaMemcpyAsync(hPer.data(), M.perRank.p, WDEM_MAX_RANKS * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
   }
+  TM(6);
   std::vector<int64_t> gm(W, 0), ga((size_t)W * W, 0);
   for (int r = 0; r < W; r++) gm[r] = hPer[r];
   T->allgather64(gm.data(), W, ga.data(), st);
+  TM(7);
   M.sendCnt.assign(W, 0); M.recvCnt.assign(W, 0);
   std::vector<size_t> sOffG(W, 0), sBytG(W, 0), rOffG(W, 0), rBytG(W, 0);
   size_t accS = 0, accG = 0;
@@ -435,6 +447,7 @@ void domainExchange(wdem_engine* E) {
   const int nNew = nOwn + (int)accG;
   Bst.ensure((size_t)std::max(nNew, 1), tot, /*keep*/ true, st); B = Bst.view();
   if (accG > 0) { k_dom_unpack_ghosts<<<nblk(accG, 256), 256, 0, st>>>(B, nOwn, (int)accG, as<GRec>(M.recvBuf), M.importId.p); E->launches++; }
+  TM(8);
   // ---- 6. bookkeeping for the history lookup of the full run that follows
   M.oldIds.ensure(nn, tot); M.origSlot.ensure((size_t)std::max(nNew, 1), tot);
   if (n > 0) CK(cudaMemcpyAsync(M.oldIds.p, A.id, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
@@ -442,6 +455,11 @@ void domainExchange(wdem_engine* E) {
   if (n > 0) { k_dom_clear_id2slot<<<nblk(n, 256), 256, 0, st>>>(A.id, n, E->id2slot.p); E->launches++; }
   E->n = nNew; E->cur = 1 - E->cur; M.nOwn = nOwn; E->up2slotValid = false;
   M.migratedOut += nE; M.migratedIn += (long long)nImmP; M.rowsIn += (long long)nImmR;
+  if (tr) {
+    TM(9); for (int k = 0; k < 9; k++) tacc[k] += std::chrono::duration<double, std::milli>(tp[k + 1] - tp[k]).count();
+    if (++tcnt % 50 == 0 && R == 0) { fprintf(stderr, "domainExchange trace (rank %d, mean of %d, ms): classify %.3f rows %.3f allgather1 %.3f sizes %.3f pack+a2a %.3f gather/unpack %.3f mask %.3f allgather2 %.3f ghosts %.3f | nE %d nImm %zu\n",
+                                    R, tcnt, tacc[0] / tcnt, tacc[1] / tcnt, tacc[2] / tcnt, tacc[3] / tcnt, tacc[4] / tcnt, tacc[5] / tcnt, tacc[6] / tcnt, tacc[7] / tcnt, tacc[8] / tcnt, nE, nImmP); }
+  }
 }
 
 static const size_t PEER_WORDS_BYTES = 2 * WDEM_MAX_RANKS * sizeof(unsigned long long);
@@ -542,7 +560,11 @@ void haloExchange(wdem_engine* E) {
 void rebuild(wdem_engine* E) {
   const wdem_config& c = E->cfg;
   cudaStream_t st = E->stream;
+  static const bool traceReb = getenv("WDEM_REBUILD_TRACE") != nullptr;
+  auto now = [&] { if (traceReb) cudaStreamSynchronize(E->stream); return std::chrono::steady_clock::now(); };
+  auto t0 = now();
   if (E->comm) domainExchange(E);   // migration + ghosts; leaves the new (unsorted) generation in the current store
+  auto t1 = now();
   const int n = E->n;
   const bool hertz = c.law == WDEM_LAW_HERTZ_DMT, rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.);
   const double vd = E->verletDist;
@@ -766,7 +788,13 @@ void rebuild(wdem_engine* E) {
   E->nSS = nSS; E->nWS = nWS; E->nFS = nFS; E->nOrph = nOrphOut; E->nC = nSS + nWS + nFS + nOrphOut;
   E->curC = 1 - E->curC; E->curR = 1 - E->curR;
   E->nFullRuns++;
+  auto t2 = now();
   if (E->comm) domainFinishRebuild(E);
+  if (traceReb) {
+    auto t3 = now(); auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    static double acc[3] = {0, 0, 0}; static int cnt = 0; acc[0] += ms(t0, t1); acc[1] += ms(t1, t2); acc[2] += ms(t2, t3); cnt++;
+    if (cnt % 50 == 0) fprintf(stderr, "rebuild trace (rank %d, mean of %d): domainExchange %.3f ms, collider run %.3f ms, finish %.3f ms\n", E->comm ? E->comm->rank : 0, cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt);
+  }
 }
 
 // Static facets are binned once on the host (they never move in this engine: Impose/clump motion is out of scope).
