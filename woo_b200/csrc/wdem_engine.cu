@@ -951,12 +951,12 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   }
   // the big kernel goes last so that the small boundary kernels already occupy their share of the SMs
   if (E->nSS > 0) {
-    const int gridSS = std::min(nblk(E->nSS, 128), E->numSMs * WD_CONTACT_CTAS_PER_SM);   // persistent: one CTA per resident slot
+    const int gridSS = std::min(nblk(E->nSS, WD_CONTACT_BLOCK), E->numSMs * WD_CONTACT_CTAS_PER_SM);   // persistent: one CTA per resident slot
     switch (c.law + (u.energy ? 2 : 0)) {
-      case 0: k_contact_ss<0><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 1: k_contact_ss<1><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 2: k_contact_ss<2><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 3: k_contact_ss<3><<<gridSS, 128, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 0: k_contact_ss<0><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 1: k_contact_ss<1><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 2: k_contact_ss<2><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 3: k_contact_ss<3><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
     }
     E->launches++;
   }

@@ -551,8 +551,11 @@ __device__ __forceinline__ void prefetch_contact_ss(const Contacts& C, long long
 #ifndef WD_CONTACT_CTAS_PER_SM
 #define WD_CONTACT_CTAS_PER_SM 4
 #endif
+#ifndef WD_CONTACT_BLOCK
+#define WD_CONTACT_BLOCK 128
+#endif
 template <int LAW>
-__global__ void __launch_bounds__(128, WD_CONTACT_CTAS_PER_SM) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
+__global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
   const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
   const long long end = first + n, stride = (long long)gridDim.x * blockDim.x;
   long long c0 = first + (long long)blockIdx.x * blockDim.x + threadIdx.x, c1 = c0 + stride;
