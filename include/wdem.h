@@ -91,6 +91,13 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
                         const uint32_t* flags, const uint32_t* mask, const int32_t* matId);
 /* DemData.force/torque accumulated by the previous step's ContactLoop (consumed by the next Leapfrog, Leapfrog.cpp:144-160); upload order,
  * either may be NULL (= zero).  Only right after wdem_upload_spheres. */
+/* ParticleContainer::add in mid-run (ParticleContainer.cpp:23-73; what Inlets do, Inlet.cpp): append spheres to the device state without re-uploading
+ * the scene.  Same arrays as wdem_upload_spheres; ids are required and must be unused.  Existing spheres, their forces and the whole contact history stay;
+ * the new spheres start with zero force and the collider re-initialises at the next step (contacts dirty).  Upload order continues:
+ * the new spheres follow the old ones in wdem_download_state / wdem_set_state.  Single-domain runs only. */
+int wdem_add_spheres(wdem_handle h, int64_t n, const int32_t* ids, const double* pos, const double* ori, const double* vel, const double* angVel,
+                     const double* mass, const double* inertia, const double* radius, const uint32_t* flags, const uint32_t* mask,
+                     const int32_t* matId);
 int wdem_upload_forces(wdem_handle h, const double* force, const double* torque);
 /* Walls (dem/Wall.hpp): static; vel may be NULL. */
 int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* pos, const int32_t* axis, const int32_t* sense,

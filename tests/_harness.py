@@ -132,6 +132,14 @@ class Oracle:
             self.L.orc_get_walls(self.h, _p(o["pos"], C.c_double), _p(o["force"], C.c_double), _p(o["torque"], C.c_double))
         return o
 
+    def add_spheres(self, pos, radius, mass, inertia, mat, mask=None, flags=None, vel=None, angVel=None):
+        """ParticleContainer.add in mid-run; returns the id of the first new particle (ids continue after everything added so far)."""
+        a = lambda x, dt: None if x is None else np.ascontiguousarray(x, dtype=dt)
+        pos, radius, mass, inertia, vel, angVel = (a(x, np.float64) for x in (pos, radius, mass, inertia, vel, angVel))
+        mat = a(mat, np.int32); mask = a(mask, np.uint32); flags = a(flags, np.uint32)
+        return self.L.orc_add_spheres(self.h, C.c_int(len(radius)), _p(pos, C.c_double), _p(radius, C.c_double), _p(mass, C.c_double), _p(inertia, C.c_double),
+                                      _p(mat, C.c_int), _p(mask, C.c_uint), _p(flags, C.c_uint), _p(vel, C.c_double), _p(angVel, C.c_double), None)
+
     def facets(self):
         o = np.zeros((len(self.spec.facets), 3, 3))
         if len(o):

@@ -413,3 +413,39 @@ def test_rotating_drum_facet_group(world):
     # the turning wall drags the bed along: the spheres' mean angular momentum about the axis has the sign of the rotation
     s = O.spheres(); ybar, zbar = s["pos"][:, 1].mean(), s["pos"][:, 2].mean()
     assert ((s["pos"][:, 1] - ybar) * s["vel"][:, 2] - (s["pos"][:, 2] - zbar) * s["vel"][:, 1]).mean() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# wdem_add_spheres (the insertion half of Inlets): ParticleContainer.add in mid-run without re-uploading the scene
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("law", [sc.LAW_IDEALELPL, sc.LAW_HERTZ_DMT])
+def test_add_spheres_mid_run(law):
+    import math
+    S = sc.random_gas(300, box=.5, r=.02, psd_ratio=2.0, seed=81, law=law, en=.6 if law else float("nan"))
+    O = Oracle(S); E = engine_for(S)
+    rng = np.random.default_rng(82)
+    dens = S.mats[0][1]
+    for batch in range(3):
+        O.step(70); E.step(70)
+        m = 40
+        pos = rng.uniform(.05, .45, (m, 3)); rad = .02 * np.exp(rng.uniform(math.log(.4), math.log(2.5), m))      # also smaller and larger than anything so far
+        vel = rng.uniform(-1, 1, (m, 3)); ang = rng.uniform(-5, 5, (m, 3))
+        mass = dens * (4 / 3.) * math.pi * rad ** 3; inertia = .4 * mass * rad ** 2
+        first = O.add_spheres(pos, rad, mass, inertia, np.zeros(m, np.int32), vel=vel, angVel=ang)
+        ids = np.arange(first, first + m, dtype=np.int32)
+        E.add_spheres(ids, pos, rad, mass, inertia, vel=vel, angVel=ang)
+        for k in range(3):
+            O.step(40); E.step(40)
+            # the oracle lists spheres in the order they were added, and so does the engine (upload order continues)
+            so = O.spheres(); no = len(so["pos"])
+            sg = E.spheres()
+            assert len(sg["pos"]) == no == S.n + (batch + 1) * m
+            for k_ in ("pos", "vel", "angVel", "force", "torque"):
+                assert np.array_equal(so[k_], sg[k_]), f"{k_} differs after batch {batch}, check {k}"
+            co, cg = O.contacts(True), E.contacts(True)
+            assert [tuple(x) for x in co["ids"]] == [tuple(x) for x in cg["ids"]] and np.array_equal(co["force"], cg["force"]) and np.array_equal(co["trsf"], cg["trsf"])
+            assert O.nFullRuns == E.scalars()["nFullRuns"] and O.dt == E.scalars()["dt"]
+    assert np.array_equal(co["stepCreated"], cg["stepCreated"])
+    from woo_b200.engine import WdemError
+    with pytest.raises(WdemError):
+        E.add_spheres(ids[:1], pos[:1], rad[:1], mass[:1], inertia[:1])          # id already in use

@@ -289,3 +289,37 @@ def test_rotating_drum_with_add_clumped():
     v1 = np.array(facets[0].shape.nodes[0].pos)
     assert np.array_equal(v1, E.facets()[0, 0]) and np.linalg.norm(v1 - v0) > 1e-3
     assert abs(np.linalg.norm(np.array(central.ori)) - 1) < 1e-12 and abs(central.ori[3]) < 1.      # the master node has turned
+
+
+@pytest.mark.gpu
+def test_inlet_like_additions_use_the_device_append_path():
+    """Spheres added batch by batch while the scene runs (what an Inlet does): the plugin appends them on the device (wdem_add_spheres); the result equals the
+    array-level engine fed the same batches, and a batch with a new material falls back to the full re-upload with the contact history kept."""
+    from woo_b200 import scenes as sc
+    from woo_b200.engine import Engine
+    Sp = sc.random_gas(200, box=.4, r=.02, psd_ratio=2.0, seed=91)
+    E = Engine(Sp.params).load(Sp)
+    S = Scene(fields=[DemField(gravity=Sp.params.gravity)])
+    m = FrictMat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)
+    S.dem.par.add([Wall.make(w["pos"], axis=w["axis"], sense=w["sense"], mat=m) for w in Sp.walls])          # boundaries first: ids 0..5
+    S.dem.par.add([woo.utils.sphere(Sp.pos[i], Sp.radius[i], mat=m, vel=Sp.vel[i]) for i in range(Sp.n)])
+    for i in range(Sp.n):
+        S.dem.par[len(Sp.walls) + i].angVel = Sp.angVel[i]
+    S.engines = woo.utils.gpuEngines(damping=.2, dynDtPeriod=0); S.dt = 2e-5
+    Sp.boundaries_first = True; Sp.params.dynDtPeriod = 0; Sp.params.dt = 2e-5
+    E = Engine(Sp.params).load(Sp)
+    rng = np.random.default_rng(92)
+    nxt = len(Sp.walls) + Sp.n
+    for batch in range(3):
+        S.run(60, True); E.step(60)
+        k = 25
+        pos = rng.uniform(.05, .35, (k, 3)); rad = rng.uniform(.012, .03, k); vel = rng.uniform(-1, 1, (k, 3))
+        mat = m if batch < 2 else FrictMat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)                    # last batch: another material object
+        ids = S.dem.par.add([woo.utils.sphere(pos[i], rad[i], mat=mat, vel=vel[i]) for i in range(k)])
+        assert ids == list(range(nxt, nxt + k)); nxt += k
+        mass = (4 / 3.) * math.pi * (rad * rad * rad) * 2500.          # Sphere::lumpMassInertia's expression (Sphere.cpp:26-33), as scenes.mass_inertia
+        E.add_spheres(np.array(ids, np.int32), pos, rad, mass, (2. / 5.) * mass * (rad * rad), vel=vel)
+    S.run(60, True); E.step(60)
+    got = np.array([S.dem.par[i].pos for i in range(len(Sp.walls), nxt)])
+    assert np.array_equal(got, E.spheres()["pos"])
+    assert np.array_equal(np.array([S.dem.par[i].f for i in range(len(Sp.walls), nxt)]), E.spheres()["force"])

@@ -15,6 +15,7 @@
 #include "../../include/wdem.h"
 #include <chrono>
 #include <unordered_map>
+#include <unordered_set>
 #include "wdem_kernels.cuh"
 #include "wdem_domain.cuh"
 #include "wdem_comm.h"
@@ -79,7 +80,7 @@ struct ContactStore {
   void release() { pair.release(); flags.release(); stepCreated.release(); for (auto& b : cd) b.release(); for (auto& b : t) b.release(); for (auto& b : fl) b.release(); for (auto& b : ph) b.release(); for (auto& b : tq) b.release(); cp.release(); Fg.release(); Tg.release(); realBits.release(); cap = 0; }
 };
 
-struct CsrStore { DBuf<int> rowStart; DBuf<uint32_t> rowEntry; DBuf<int32_t> rowOther; bool valid = false; void release() { rowStart.release(); rowEntry.release(); rowOther.release(); } };
+struct CsrStore { DBuf<int> rowStart; DBuf<uint32_t> rowEntry; DBuf<int32_t> rowOther; bool valid = false; int nRows = 0; void release() { rowStart.release(); rowEntry.release(); rowOther.release(); } };
 
 // ---- host-side 3x3 helpers for the periodic cell (src/core/Cell.cpp:81-120), row-major m33
 m33 mIdent() { m33 r; for (int i = 0; i < 9; i++) r.m[i] = (i % 4 == 0) ? 1. : 0.; return r; }
@@ -325,7 +326,7 @@ void domainExchange(wdem_engine* E) {
   SphereStore& Ast = E->sph[E->cur]; SphereStore& Bst = E->sph[1 - E->cur];
   Spheres A = Ast.view();
   ContactStore& Ost = E->con[E->curC]; CsrStore& Ocsr = E->csr[E->curR];
-  OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = (Ocsr.valid && E->nC > 0) ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
+  OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = (Ocsr.valid && E->nC > 0) ? 1 : 0; oc.nRows = Ocsr.nRows; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
   TM(0);
   // ---- 1. classify and group by destination
   std::vector<int> start(W + 3, 0);
@@ -577,7 +578,7 @@ void rebuild(wdem_engine* E) {
   ContactStore& Ost = E->con[E->curC];
   CsrStore& Ocsr = E->csr[E->curR];
   CsrStore& Ncsr = E->csr[1 - E->curR];
-  OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = Ocsr.valid ? 1 : 0; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
+  OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = Ocsr.valid ? 1 : 0; oc.nRows = Ocsr.nRows; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
   if (E->comm && E->dom.nImm > 0) { oc.immKeys = E->dom.immKeysAlt.p; oc.immVals = E->dom.immValsAlt.p; oc.nImm = E->dom.nImm; }
   bool imported = false;
   if (!E->pendingRows.empty()) {
@@ -782,7 +783,7 @@ void rebuild(wdem_engine* E) {
       k_row_sort<<<nb128, 128, 0, st>>>(n, Ncsr.rowStart.p, Ncsr.rowEntry.p, Ncsr.rowOther.p, E->idx.p, E->idx.p + n);
       k_row_sort_long<<<148 * 8, 128, 0, st>>>(E->idx.p, E->idx.p + n, Ncsr.rowStart.p, Ncsr.rowEntry.p, Ncsr.rowOther.p); E->launches += 2;
     }
-    Ncsr.valid = true;
+    Ncsr.valid = true; Ncsr.nRows = n;
   }
   if (E->anyMovingWall) { k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), makeUniforms(E), E->dCnt, 1); E->launches++; }   // Aabb::nodeLastPos (Collision.cpp:138-141)
   E->nSS = nSS; E->nWS = nWS; E->nFS = nFS; E->nOrph = nOrphOut; E->nC = nSS + nWS + nFS + nOrphOut;
@@ -1294,6 +1295,56 @@ int wdem_upload_forces(wdem_handle h, const double* force, const double* torque)
     for (size_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { if (force) soa[k * n + i] = force[3 * i + k]; if (torque) soa[(3 + k) * n + i] = torque[3 * i + k]; }
     for (int k = 0; k < 6; k++) CK(cudaMemcpyAsync(h->sph[0].f[k].p, soa.data() + k * n, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int wdem_add_spheres(wdem_handle h, int64_t m, const int32_t* ids, const double* pos, const double* ori, const double* vel, const double* angVel, const double* mass,
+                     const double* inertia, const double* radius, const uint32_t* flags, const uint32_t* mask, const int32_t* matId) {
+  return guarded(h, [&] {
+    if (m < 0 || (m > 0 && (!ids || !pos || !mass || !inertia || !radius))) throw EngErr{"wdem_add_spheres: bad arguments", WDEM_ERR_INVALID};
+    if (h->comm) throw EngErr{"wdem_add_spheres: not available in decomposed runs", WDEM_ERR_UNSUPPORTED};
+    if (h->hMats.empty() || h->hIds.size() != (size_t)h->n) throw EngErr{"wdem_add_spheres: upload materials and spheres first", WDEM_ERR_INVALID};
+    if (m == 0) return;
+    const int64_t n0 = h->n, n1 = n0 + m;
+    if (n1 > (1ll << 30)) throw EngErr{"too many spheres", WDEM_ERR_INVALID};
+    std::unordered_set<int32_t> used(h->hIds.begin(), h->hIds.end());
+    for (auto& w : h->hWalls) used.insert(w.id);
+    for (auto& f : h->hFacets) used.insert(f.id);
+    std::vector<double4> posr(m), velm(m), angi(m), q(m); std::vector<uint32_t> fl(m), mk(m); std::vector<int32_t> mt(m), id(m), up(m);
+    int maxId = h->maxId; double minR = h->minRadius, pw = h->pwaveDt, rmax = h->dom.rmaxGlobal;
+    for (int64_t i = 0; i < m; i++) {
+      id[i] = ids[i]; up[i] = (int32_t)(n0 + i);
+      if (id[i] < 0 || !used.insert(id[i]).second) throw EngErr{"wdem_add_spheres: particle id " + std::to_string(id[i]) + " is negative or already in use", WDEM_ERR_INVALID};
+      maxId = std::max(maxId, id[i]);
+      fl[i] = flags ? flags[i] : 0u; mk[i] = mask ? mask[i] : 5u; mt[i] = matId ? matId[i] : 0;
+      if (mt[i] < 0 || mt[i] >= (int)h->hMats.size()) throw EngErr{"sphere material index out of range", WDEM_ERR_INVALID};
+      if (fl[i] & (64u | 128u)) throw EngErr{"clumps are not supported by the GPU engine (DemData.flags has CLUMP bits)", WDEM_ERR_UNSUPPORTED};
+      if (!(radius[i] > 0)) throw EngErr{"sphere #" + std::to_string(id[i]) + ": radius must be positive", WDEM_ERR_INVALID};
+      if ((fl[i] & 7u) != 7u && !(mass[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive mass with free translational DOFs", WDEM_ERR_INVALID};
+      if ((fl[i] & 56u) != 56u && !(inertia[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive inertia with free rotational DOFs", WDEM_ERR_INVALID};
+      posr[i] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], radius[i]);
+      velm[i] = make_double4(vel ? vel[3 * i] : 0, vel ? vel[3 * i + 1] : 0, vel ? vel[3 * i + 2] : 0, mass[i]);
+      angi[i] = make_double4(angVel ? angVel[3 * i] : 0, angVel ? angVel[3 * i + 1] : 0, angVel ? angVel[3 * i + 2] : 0, inertia[i]);
+      q[i] = ori ? make_double4(ori[4 * i], ori[4 * i + 1], ori[4 * i + 2], ori[4 * i + 3]) : make_double4(0, 0, 0, 1);
+      minR = std::min(minR, radius[i]); rmax = std::max(rmax, radius[i]);
+      const Material& mm = h->hMats[mt[i]];
+      pw = std::min(pw, radius[i] / (1. * std::sqrt(mm.young / mm.density)));
+    }
+    cudaStream_t st = h->stream;
+    SphereStore& s = h->sph[h->cur];
+    s.ensure((size_t)n1, h->bytes, /*keep*/ true, st);
+    auto H2D = [&](void* d, const void* src, size_t b) { CK(cudaMemcpyAsync(d, src, b, cudaMemcpyHostToDevice, st)); };
+    H2D(s.posr.p + n0, posr.data(), m * sizeof(double4)); H2D(s.velm.p + n0, velm.data(), m * sizeof(double4)); H2D(s.angi.p + n0, angi.data(), m * sizeof(double4)); H2D(s.ori.p + n0, q.data(), m * sizeof(double4));
+    for (auto& b : s.f) CK(cudaMemsetAsync(b.p + n0, 0, m * sizeof(double), st));     // a new particle sees zero force in its first Leapfrog
+    for (auto& b : s.l) CK(cudaMemsetAsync(b.p + n0, 0, m * sizeof(double), st));
+    H2D(s.flags.p + n0, fl.data(), m * 4); H2D(s.mask.p + n0, mk.data(), m * 4); H2D(s.mat.p + n0, mt.data(), m * 4); H2D(s.id.p + n0, id.data(), m * 4); H2D(s.up.p + n0, up.data(), m * 4);
+    const size_t oldCap = h->id2slot.cap;
+    h->id2slot.ensure((size_t)maxId + 2, h->bytes, /*keep*/ true, st);
+    if (h->id2slot.cap > oldCap) CK(cudaMemsetAsync(h->id2slot.p + oldCap, 0xFF, (h->id2slot.cap - oldCap) * sizeof(int), st));
+    CK(cudaStreamSynchronize(st));
+    h->n = (int)n1; h->minRadius = minR; h->pwaveDt = pw; h->maxId = maxId; h->dom.rmaxGlobal = rmax; h->dom.nOwn = (int)n1;
+    h->hIds.insert(h->hIds.end(), id.begin(), id.end());
+    h->conDirty = true; h->up2slotValid = false;     // ParticleContainer::add marks the contacts dirty: the collider re-initialises at the next step (ParticleContainer.cpp:23-73)
   });
 }
 

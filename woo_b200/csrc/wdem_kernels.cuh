@@ -1027,6 +1027,7 @@ __device__ __forceinline__ bool mayCollide(uint32_t mA, uint32_t mB, uint32_t lo
 
 struct OldCsr {  // incidence rows of the previous contact table (for history carry-over)
   const int* rowStart; const uint32_t* rowEntry; const int32_t* rowOther; int valid;
+  int nRows;   // spheres the rows were built for; slots beyond (spheres appended since, wdem_add_spheres) have no previous contacts
   // history rows that arrived with spheres migrating in from another subdomain (sorted by key (idA<<32|idB)); see wdem_domain.cuh
   const unsigned long long* immKeys; const int* immVals; int nImm;
   int immAll;   // rows imported by wdem_upload_contacts: consult them for every pair, not only for spheres that just arrived
@@ -1046,7 +1047,7 @@ __device__ __forceinline__ void copy_history(const Contacts& N, long long cn, co
 
 // find the previous contact between the sphere in (old) slot `oslot` and the particle with id `otherId`
 __device__ __forceinline__ long long find_old(const OldCsr& oc, int oslot, int otherId) {
-  if (!oc.valid || oslot < 0) return -1;
+  if (!oc.valid || oslot < 0 || oslot >= oc.nRows) return -1;
   int lo = oc.rowStart[oslot], hi = oc.rowStart[oslot + 1] - 1;   // rows are sorted by the partner's id (k_row_sort)
   while (lo <= hi) {
     const int mid = (lo + hi) >> 1; const int v = oc.rowOther[mid];

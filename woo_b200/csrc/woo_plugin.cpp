@@ -76,6 +76,7 @@ struct ContactContainer { DemField* dem = nullptr; vector<shared_ptr<Contact>> v
 // ---- the field (dem/Particle.hpp:339-361)
 struct DemField {
   ParticleContainer par; ContactContainer con; vector<shared_ptr<Node>> nodes; vector<ClumpGroup> clumps;
+  vector<shared_ptr<Particle>> pendingAdds;   // spheres added while the scene lives on the device: appended there (wdem_add_spheres) instead of re-uploading everything
   V3 gravity{{0, 0, 0}}; unsigned loneMask = 2; double distFactor = -1.;
   // coherence with the device copy (SURVEY §7 "Host<->device coherence"): upload once, download lazily
   GpuDemLoop* owner = nullptr; bool topoDirty = true, stateDirty = false, deviceNewer = false, contactsStale = true;
@@ -131,6 +132,7 @@ struct GpuDemLoop : Engine {
   shared_ptr<Leapfrog> leapfrog; shared_ptr<InsertionSortCollider> collider; shared_ptr<ContactLoop> contactLoop; shared_ptr<DynDt> dynDt;
   int device = 0; wdem_handle h = nullptr; wdem_config cfg; bool haveCfg = false; long nSpheres = 0; wdem_stats last;
   vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf, wallOf, facetOf; bool trackingOn = false;
+  std::map<Material*, int> matIndex;   // materials as uploaded (by object identity)
   const char* cls() const override { return "GpuDemLoop"; }
   ~GpuDemLoop() override { release(); }
   void release() { if (h) { wdem_destroy(h); h = nullptr; } if (field && field->owner == this) field->owner = nullptr; }
@@ -251,8 +253,28 @@ struct GpuDemLoop : Engine {
     if (scene->periodic) { Cell& C = *scene->cell; chk(h, wdem_set_cell(h, C.hSize.data(), C.gradV.data(), C.nextGradV.data(), C.homoDeform)); C.dirty = false; }
     chk(h, wdem_set_scene(h, (int64_t)scene->step, scene->time));
     F.pushContacts(h);
-    nSpheres = (long)sid.size();
-    F.owner = this; F.topoDirty = false; F.stateDirty = false; F.deviceNewer = false; F.contactsStale = true;
+    nSpheres = (long)sid.size(); matIndex = matIx;
+    F.owner = this; F.topoDirty = false; F.stateDirty = false; F.deviceNewer = false; F.contactsStale = true; F.pendingAdds.clear();
+  }
+  // spheres added since the upload: append them on the device (ParticleContainer::add in mid-run; the contact history and everything else stays where it is)
+  bool appendSpheres() {
+    DemField& F = *field;
+    vector<int32_t> sid, smat; vector<uint32_t> sflags, smask; vector<double> spos, sori, svel, sang, smass, sin, srad;
+    for (auto& p : F.pendingAdds) {
+      auto* s = dynamic_cast<Sphere*>(p->shape.get()); auto it = matIndex.find(p->material.get());
+      if (!s || it == matIndex.end()) return false;                                 // a new material (or not a sphere): take the full path
+      const Node& n = *s->nodes.at(0); const DemData& d = *n.dem;
+      if (!(d.inertia[0] == d.inertia[1] && d.inertia[1] == d.inertia[2])) return false;
+      sid.push_back(p->id); smat.push_back(it->second); sflags.push_back(d.flags); smask.push_back(p->mask);
+      for (int k = 0; k < 3; k++) { spos.push_back(n.pos[k]); svel.push_back(d.vel[k]); sang.push_back(d.angVel[k]); }
+      for (int k = 0; k < 4; k++) sori.push_back(n.ori[k]);
+      smass.push_back(d.mass); sin.push_back(d.inertia[0]); srad.push_back(s->radius);
+    }
+    if (F.stateDirty) { if (F.deviceNewer) throw std::runtime_error("GpuDemLoop: host state edited before the device state was read back"); pushState(); }
+    chk(h, wdem_add_spheres(h, (int64_t)sid.size(), sid.data(), spos.data(), sori.data(), svel.data(), sang.data(), smass.data(), sin.data(), srad.data(), sflags.data(), smask.data(), smat.data()));
+    for (auto& p : F.pendingAdds) { sphereIds.push_back(p->id); sphereOf.push_back(p); }
+    nSpheres = (long)sphereOf.size(); F.pendingAdds.clear(); F.contactsStale = true;
+    return true;
   }
   void pushState() {   // host edits of pos/vel/angVel since the last run
     DemField& F = *field; const size_t n = sphereOf.size();
@@ -265,6 +287,7 @@ struct GpuDemLoop : Engine {
     if (!field) throw std::runtime_error("GpuDemLoop: no DemField");
     DemField& F = *field;
     if (F.stateDirty && !F.clumps.empty()) F.topoDirty = true;   // the edit may concern a clump's master node (its vel/angVel): take the full path
+    if (h && !F.topoDirty && F.owner == this && !F.pendingAdds.empty() && !appendSpheres()) F.topoDirty = true;
     if (!h || F.topoDirty || F.owner != this) upload();
     else {
       wdem_config c = makeConfig();
@@ -510,7 +533,9 @@ PYBIND11_MODULE(_woo, m) {
             const bool moving = (d.mass != 0 && (d.flags & DOF_ALL) != DOF_ALL) || d.vel[0] != 0 || d.vel[1] != 0 || d.vel[2] != 0 || d.angVel[0] != 0 || d.angVel[1] != 0 || d.angVel[2] != 0;   // DemData::guessMoving
             if (moving) c.dem->nodes.push_back(n);
           }
-          c.dem->topoDirty = true; return p->id; };
+          if (c.dem->owner && !c.dem->topoDirty && dynamic_cast<Sphere*>(p->shape.get())) c.dem->pendingAdds.push_back(p);
+          else c.dem->topoDirty = true;
+          return p->id; };
         if (py::isinstance<Particle>(o)) return py::int_(addOne(o.cast<shared_ptr<Particle>>()));
         py::list ids; for (auto it : o) ids.append(addOne(it.cast<shared_ptr<Particle>>())); return ids; });
   m.attr("ParticleContainer").attr("addClumped") = py::cpp_function([](ParticleContainer& c, py::object pars, shared_ptr<Node> centralNode) -> shared_ptr<Node> {

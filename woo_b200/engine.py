@@ -78,6 +78,17 @@ class Engine:
         args = [f64(pos), f64(ori), f64(vel), f64(angVel), f64(mass), f64(inertia), f64(radius)]
         self._chk(self.L.wdem_upload_spheres(self.h, C.c_int64(n), ptr(ids), *[ptr(a) for a in args], ptr(flags), ptr(mask), ptr(mat)))
 
+    def add_spheres(self, ids, pos, radius, mass, inertia, mat=None, mask=None, flags=None, vel=None, angVel=None, ori=None):
+        """Append spheres in mid-run (wdem.h: wdem_add_spheres)."""
+        m = len(radius)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        mat = None if mat is None else np.ascontiguousarray(mat, dtype=np.int32)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+        flags = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint32)
+        args = [f64(pos), f64(ori), f64(vel), f64(angVel), f64(mass), f64(inertia), f64(radius)]
+        self._chk(self.L.wdem_add_spheres(self.h, C.c_int64(m), ptr(ids), *[ptr(a) for a in args], ptr(flags), ptr(mask), ptr(mat)))
+        self.n += m
+
     def upload_walls(self, ids, walls):
         n = len(walls)
         if n == 0:
