@@ -98,6 +98,10 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
 int wdem_add_spheres(wdem_handle h, int64_t n, const int32_t* ids, const double* pos, const double* ori, const double* vel, const double* angVel,
                      const double* mass, const double* inertia, const double* radius, const uint32_t* flags, const uint32_t* mask,
                      const int32_t* matId);
+/* ParticleContainer::remove in mid-run (ParticleContainer.cpp:121-157; what Outlets do): the spheres with these ids leave the device state, the remaining ones keep
+ * their state, their forces and their contact history; contacts of the removed spheres are dropped and the collider re-initialises at the next step.  The upload
+ * order closes up (remaining spheres keep their relative order).  Single-domain runs only. */
+int wdem_remove_spheres(wdem_handle h, int64_t n, const int32_t* ids);
 int wdem_upload_forces(wdem_handle h, const double* force, const double* torque);
 /* Walls (dem/Wall.hpp): static; vel may be NULL. */
 int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* pos, const int32_t* axis, const int32_t* sense,

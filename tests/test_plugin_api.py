@@ -323,3 +323,33 @@ def test_inlet_like_additions_use_the_device_append_path():
     got = np.array([S.dem.par[i].pos for i in range(len(Sp.walls), nxt)])
     assert np.array_equal(got, E.spheres()["pos"])
     assert np.array_equal(np.array([S.dem.par[i].f for i in range(len(Sp.walls), nxt)]), E.spheres()["force"])
+
+
+@pytest.mark.gpu
+def test_outlet_like_removals_use_the_device_path():
+    """ParticleContainer.remove in mid-run (what an Outlet does) drops the spheres on the device (wdem_remove_spheres); equals the array-level engine."""
+    from woo_b200 import scenes as sc
+    from woo_b200.engine import Engine
+    Sp = sc.random_gas(250, box=.4, r=.02, psd_ratio=2.0, seed=93); Sp.boundaries_first = True; Sp.params.dynDtPeriod = 0; Sp.params.dt = 2e-5
+    E = Engine(Sp.params).load(Sp)
+    S = Scene(fields=[DemField(gravity=Sp.params.gravity)])
+    m = FrictMat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)
+    nb = len(Sp.walls)
+    S.dem.par.add([Wall.make(w["pos"], axis=w["axis"], sense=w["sense"], mat=m) for w in Sp.walls])
+    S.dem.par.add([woo.utils.sphere(Sp.pos[i], Sp.radius[i], mat=m, vel=Sp.vel[i]) for i in range(Sp.n)])
+    for i in range(Sp.n):
+        S.dem.par[nb + i].angVel = Sp.angVel[i]
+    S.engines = woo.utils.gpuEngines(damping=.2, dynDtPeriod=0); S.dt = 2e-5
+    S.run(100, True); E.step(100)
+    rng = np.random.default_rng(94)
+    gone = sorted(int(x) for x in rng.choice(np.arange(nb, nb + Sp.n), 40, replace=False))
+    for i in gone:
+        S.dem.par.remove(i)
+    E.remove_spheres(np.array(gone, np.int32))
+    with pytest.raises(IndexError):
+        S.dem.par[gone[0]]
+    S.run(120, True); E.step(120)
+    left = [i for i in range(nb, nb + Sp.n) if i not in set(gone)]
+    assert np.array_equal(np.array([S.dem.par[i].pos for i in left]), E.spheres()["pos"])
+    assert np.array_equal(np.array([S.dem.par[i].f for i in left]), E.spheres()["force"])
+    assert all(c.id1 not in gone and c.id2 not in gone for c in S.dem.con)

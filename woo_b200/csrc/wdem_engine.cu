@@ -179,6 +179,7 @@ struct wdem_engine {
   long long dynStepLast = -1, dynStepPrev = -1;
   HostCell cell;
   long long launches = 0; int numSMs = 148;
+  bool compactPending = false;   // spheres were removed since the last full run: the current generation is not the one the incidence rows were built for
   bool trackEnergy = false; DBuf<double> dEnergy;   // Scene.trackEnergy: EN_* accumulators on the device
   // end-to-end pipeline (wdem_step_e2e): host<->device copies of the state overlap with the integrator chunk by chunk
   static const int NCHUNK = 16; int nChunk = 8;   // NCHUNK = capacity, nChunk = pieces in use (WDEM_E2E_CHUNKS)
@@ -676,7 +677,7 @@ void rebuild(wdem_engine* E) {
     k_reorder<<<nb, 256, 0, st>>>(dst.view(), E->S(), E->idxAlt.p, n, E->id2slot.p); E->launches++;
     E->cur = 1 - E->cur; E->up2slotValid = false;
     perm = E->idxAlt.p;
-    if (E->comm) {   // slots of the previous table's generation: through the pre-sort generation built by domainExchange
+    if (E->comm || E->compactPending) {   // slots of the previous table's generation: through the pre-sort generation built by domainExchange / wdem_remove_spheres
       E->dom.perm2.ensure(n, tot);
       k_dom_compose<<<nb, 256, 0, st>>>(E->dom.origSlot.p, E->idxAlt.p, n, E->dom.perm2.p); E->launches++;
       perm = E->dom.perm2.p;
@@ -753,7 +754,7 @@ void rebuild(wdem_engine* E) {
     if ((oc.valid || imported) && E->nC > 0) {
       E->orphCnt.ensure(1, tot);
       CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
-      const int32_t* oldSid = E->comm ? E->dom.oldIds.p : E->sph[1 - E->cur].id.p;
+      const int32_t* oldSid = (E->comm || E->compactPending) ? E->dom.oldIds.p : E->sph[1 - E->cur].id.p;
       const uint32_t* sfl = E->comm ? E->S().flags : nullptr;
       k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, sfl, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 0); E->launches++;
       int hN = 0; CK(cudaMemcpyAsync(&hN, E->orphCnt.p, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
@@ -788,7 +789,7 @@ void rebuild(wdem_engine* E) {
   if (E->anyMovingWall) { k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), makeUniforms(E), E->dCnt, 1); E->launches++; }   // Aabb::nodeLastPos (Collision.cpp:138-141)
   E->nSS = nSS; E->nWS = nWS; E->nFS = nFS; E->nOrph = nOrphOut; E->nC = nSS + nWS + nFS + nOrphOut;
   E->curC = 1 - E->curC; E->curR = 1 - E->curR;
-  E->nFullRuns++;
+  E->nFullRuns++; E->compactPending = false;
   auto t2 = now();
   if (E->comm) domainFinishRebuild(E);
   if (traceReb) {
@@ -1266,7 +1267,7 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
       pw = std::min(pw, radius[i] / (1. * std::sqrt(m.young / m.density)));  // DemFuncs::pWaveDt (Funcs.cpp:151-175)
     }
     h->n = (int)n; h->minRadius = minR; h->pwaveDt = pw; h->maxId = maxId;
-    h->hIds.assign(id.begin(), id.end()); h->pendingRows.clear();
+    h->hIds.assign(id.begin(), id.end()); h->pendingRows.clear(); h->compactPending = false;
     h->cur = 0;
     SphereStore& s = h->sph[0];
     s.ensure(std::max<int64_t>(n, 1), h->bytes);
@@ -1342,9 +1343,45 @@ int wdem_add_spheres(wdem_handle h, int64_t m, const int32_t* ids, const double*
     h->id2slot.ensure((size_t)maxId + 2, h->bytes, /*keep*/ true, st);
     if (h->id2slot.cap > oldCap) CK(cudaMemsetAsync(h->id2slot.p + oldCap, 0xFF, (h->id2slot.cap - oldCap) * sizeof(int), st));
     CK(cudaStreamSynchronize(st));
+    if (h->compactPending) {   // the appended slots have no counterpart in the generation the incidence rows were built for
+      h->dom.origSlot.ensure((size_t)n1, h->bytes, /*keep*/ true, st);
+      CK(cudaMemsetAsync(h->dom.origSlot.p + n0, 0xFF, (size_t)m * sizeof(int), st)); CK(cudaStreamSynchronize(st));
+    }
     h->n = (int)n1; h->minRadius = minR; h->pwaveDt = pw; h->maxId = maxId; h->dom.rmaxGlobal = rmax; h->dom.nOwn = (int)n1;
     h->hIds.insert(h->hIds.end(), id.begin(), id.end());
     h->conDirty = true; h->up2slotValid = false;     // ParticleContainer::add marks the contacts dirty: the collider re-initialises at the next step (ParticleContainer.cpp:23-73)
+  });
+}
+
+int wdem_remove_spheres(wdem_handle h, int64_t m, const int32_t* ids) {
+  return guarded(h, [&] {
+    if (m < 0 || (m > 0 && !ids)) throw EngErr{"wdem_remove_spheres: bad arguments", WDEM_ERR_INVALID};
+    if (h->comm) throw EngErr{"wdem_remove_spheres: not available in decomposed runs", WDEM_ERR_UNSUPPORTED};
+    if (m == 0) return;
+    const int n0 = h->n; cudaStream_t st = h->stream; int64_t& tot = h->bytes;
+    if (h->hIds.size() != (size_t)n0) throw EngErr{"wdem_remove_spheres: no spheres uploaded", WDEM_ERR_INVALID};
+    std::unordered_set<int32_t> gone(ids, ids + m);
+    if ((int64_t)gone.size() != m) throw EngErr{"wdem_remove_spheres: duplicate ids", WDEM_ERR_INVALID};
+    std::vector<int> newUpOf(n0); std::vector<int32_t> keptIds; keptIds.reserve(n0); size_t found = 0;
+    for (int u = 0; u < n0; u++) { if (gone.count(h->hIds[u])) { newUpOf[u] = -1; found++; } else { newUpOf[u] = (int)keptIds.size(); keptIds.push_back(h->hIds[u]); } }
+    if (found != (size_t)m) throw EngErr{"wdem_remove_spheres: unknown sphere id", WDEM_ERR_INVALID};
+    const int n1 = n0 - (int)m;
+    SphereStore& A = h->sph[h->cur]; SphereStore& B = h->sph[1 - h->cur];
+    B.ensure((size_t)std::max(n1, 1), tot);
+    h->idx.ensure((size_t)n0 + 1, tot); h->counts.ensure((size_t)n0 + 1, tot); h->offsets.ensure((size_t)n0 + 1, tot); h->dom.origSlot.ensure((size_t)std::max(n1, 1), tot);
+    CK(cudaMemcpyAsync(h->idx.p, newUpOf.data(), (size_t)n0 * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (!h->compactPending && h->csr[h->curR].valid) {   // ids by slot of the generation the rows / the contact table refer to (k_orphans)
+      h->dom.oldIds.ensure((size_t)n0, tot);
+      CK(cudaMemcpyAsync(h->dom.oldIds.p, A.id.p, (size_t)n0 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    k_keep_flag<<<nblk(n0, 256), 256, 0, st>>>(A.up.p, n0, h->idx.p, h->counts.p);
+    exclusiveSum(h, h->counts.p, h->offsets.p, n0);
+    k_compact_spheres<<<nblk(n0, 256), 256, 0, st>>>(B.view(), A.view(), n0, h->counts.p, h->offsets.p, h->idx.p, h->id2slot.p, h->dom.origSlot.p);
+    CK(cudaStreamSynchronize(st));   // newUpOf is pageable host memory
+    h->launches += 4;
+    h->cur = 1 - h->cur; h->n = n1; h->dom.nOwn = n1; h->hIds.swap(keptIds);
+    h->compactPending = h->csr[h->curR].valid;   // before the first full run there is no history to look up
+    h->conDirty = true; h->up2slotValid = false;  // ParticleContainer::remove marks the contacts dirty (ParticleContainer.cpp:121-157)
   });
 }
 
@@ -1537,6 +1574,8 @@ int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torqu
     auto W = d2h(h->dWalls.p, nW, st);
     for (size_t w = 0; w < nW; w++) for (int k = 0; k < 3; k++) { if (pos) pos[3 * w + k] = W[w].pos[k]; if (force) force[3 * w + k] = 0.; if (torque) torque[3 * w + k] = 0.; }
     if ((!force && !torque) || h->nC == 0) return;
+    if (h->compactPending) throw EngErr{"spheres were removed since the last step: step once before reading contacts, wall forces or the stress (the table still refers to the old slots)", WDEM_ERR_INVALID};
+
     // wall-sphere contacts live in [nSS, nSS+nWS) and among the orphans; forces are added per wall in ascending id of the sphere, the order of
     // the per-particle contact map the reference walks (Particle.hpp:36)
     const long long nC = h->nC; ContactStore& cs = h->con[h->curC];
@@ -1586,6 +1625,7 @@ int wdem_get_stress(wdem_handle h, double* stress9) {
     if (!h->cfg.periodic) throw EngErr{"ContactLoop.evalStress needs a periodic scene (ContactLoop.cpp:123)", WDEM_ERR_INVALID};
     for (int k = 0; k < 9; k++) stress9[k] = 0.;
     const long long nC = h->nC;
+    if (h->compactPending) throw EngErr{"spheres were removed since the last step: step once before reading contacts, wall forces or the stress (the table still refers to the old slots)", WDEM_ERR_INVALID};
     if (nC > 0) {
       const int nb = nblk(nC, 256); h->blk.ensure((size_t)nb * 9 + 1, h->bytes);
       int* flag = reinterpret_cast<int*>(h->blk.p + (size_t)nb * 9);
@@ -1645,6 +1685,7 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
   int64_t nOut = 0;
   int rc = guarded(h, [&] {
     const long long nC = h->nC; if (nC == 0) return;
+    if (h->compactPending) throw EngErr{"spheres were removed since the last step: step once before reading contacts, wall forces or the stress (the table still refers to the old slots)", WDEM_ERR_INVALID};
     cudaStream_t st = h->stream; ContactStore& cs = h->con[h->curC];
     auto pair = d2h(cs.pair.p, nC, st); auto flags = d2h(cs.flags.p, nC, st); auto sid = d2h(h->S().id, h->n, st);
     std::vector<uint32_t> sfl; if (h->comm) sfl = d2h(h->S().flags, h->n, st);

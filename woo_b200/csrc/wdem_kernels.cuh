@@ -1560,6 +1560,26 @@ __global__ void __launch_bounds__(256) k_scatter_state(Spheres S, int n, const i
   if (vel) { double4 v = S.velm[i]; v.x = vel[3 * t]; v.y = vel[3 * t + 1]; v.z = vel[3 * t + 2]; S.velm[i] = v; }
   if (angVel) { double4 w = S.angi[i]; w.x = angVel[3 * t]; w.y = angVel[3 * t + 1]; w.z = angVel[3 * t + 2]; S.angi[i] = w; }
 }
+// ParticleContainer::remove (ParticleContainer.cpp:121-157) on the device: the kept spheres move to the front of the other generation in slot order; their upload index is
+// renumbered (newUpOf: old upload index -> new one, -1 = removed), origSlot remembers the slot they had when the incidence rows were built (id2slot still holds
+// it), and the removed ids vanish from id2slot so that their contacts are dropped at the next full run (k_orphans).
+__global__ void __launch_bounds__(256) k_keep_flag(const int32_t* __restrict__ up, int n, const int* __restrict__ newUpOf, int* flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = newUpOf[up[i]] >= 0 ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_compact_spheres(Spheres dst, Spheres src, int n, const int* __restrict__ flag, const int* __restrict__ off, const int* __restrict__ newUpOf,
+                                                        int* __restrict__ id2slot, int* __restrict__ origSlot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int id = src.id[i];
+  if (!flag[i]) { id2slot[id] = -1; return; }
+  const int k = off[i];
+  dst.posr[k] = src.posr[i]; dst.velm[k] = src.velm[i]; dst.angi[k] = src.angi[i]; dst.ori[k] = src.ori[i];
+  dst.fx[k] = src.fx[i]; dst.fy[k] = src.fy[i]; dst.fz[k] = src.fz[i]; dst.tx[k] = src.tx[i]; dst.ty[k] = src.ty[i]; dst.tz[k] = src.tz[i];
+  dst.lx[k] = src.lx[i]; dst.ly[k] = src.ly[i]; dst.lz[k] = src.lz[i];
+  dst.flags[k] = src.flags[i]; dst.mask[k] = src.mask[i]; dst.mat[k] = src.mat[i]; dst.id[k] = id; dst.up[k] = newUpOf[src.up[i]];
+  origSlot[k] = id2slot[id];
+}
 __global__ void __launch_bounds__(256) k_up2slot(const int32_t* __restrict__ up, int n, int* up2slot) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) up2slot[up[i]] = i;

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <set>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -76,6 +77,7 @@ struct ContactContainer { DemField* dem = nullptr; vector<shared_ptr<Contact>> v
 // ---- the field (dem/Particle.hpp:339-361)
 struct DemField {
   ParticleContainer par; ContactContainer con; vector<shared_ptr<Node>> nodes; vector<ClumpGroup> clumps;
+  vector<int> pendingRemoves;                 // ids of spheres removed while the scene lives on the device (wdem_remove_spheres)
   vector<shared_ptr<Particle>> pendingAdds;   // spheres added while the scene lives on the device: appended there (wdem_add_spheres) instead of re-uploading everything
   V3 gravity{{0, 0, 0}}; unsigned loneMask = 2; double distFactor = -1.;
   // coherence with the device copy (SURVEY §7 "Host<->device coherence"): upload once, download lazily
@@ -254,7 +256,19 @@ struct GpuDemLoop : Engine {
     chk(h, wdem_set_scene(h, (int64_t)scene->step, scene->time));
     F.pushContacts(h);
     nSpheres = (long)sid.size(); matIndex = matIx;
-    F.owner = this; F.topoDirty = false; F.stateDirty = false; F.deviceNewer = false; F.contactsStale = true; F.pendingAdds.clear();
+    F.owner = this; F.topoDirty = false; F.stateDirty = false; F.deviceNewer = false; F.contactsStale = true; F.pendingAdds.clear(); F.pendingRemoves.clear();
+  }
+  // spheres removed since the upload (ParticleContainer::remove): drop them on the device; the rest keeps state, forces and contact history
+  void removeSpheres() {
+    DemField& F = *field;
+    if (F.stateDirty) { if (F.deviceNewer) throw std::runtime_error("GpuDemLoop: host state edited before the device state was read back"); pushState(); }
+    if (F.deviceNewer) F.pull();     // the host copies must be current before the arrays they map to close up
+    vector<int32_t> ids(F.pendingRemoves.begin(), F.pendingRemoves.end());
+    chk(h, wdem_remove_spheres(h, (int64_t)ids.size(), ids.data()));
+    std::set<int> gone(ids.begin(), ids.end());
+    vector<int> sid2; vector<shared_ptr<Particle>> sof2;
+    for (size_t i = 0; i < sphereOf.size(); i++) if (!gone.count(sphereIds[i])) { sid2.push_back(sphereIds[i]); sof2.push_back(sphereOf[i]); }
+    sphereIds.swap(sid2); sphereOf.swap(sof2); nSpheres = (long)sphereOf.size(); F.pendingRemoves.clear(); F.contactsStale = true;
   }
   // spheres added since the upload: append them on the device (ParticleContainer::add in mid-run; the contact history and everything else stays where it is)
   bool appendSpheres() {
@@ -287,6 +301,7 @@ struct GpuDemLoop : Engine {
     if (!field) throw std::runtime_error("GpuDemLoop: no DemField");
     DemField& F = *field;
     if (F.stateDirty && !F.clumps.empty()) F.topoDirty = true;   // the edit may concern a clump's master node (its vel/angVel): take the full path
+    if (h && !F.topoDirty && F.owner == this && !F.pendingRemoves.empty()) removeSpheres();
     if (h && !F.topoDirty && F.owner == this && !F.pendingAdds.empty() && !appendSpheres()) F.topoDirty = true;
     if (!h || F.topoDirty || F.owner != this) upload();
     else {
@@ -538,6 +553,20 @@ PYBIND11_MODULE(_woo, m) {
           return p->id; };
         if (py::isinstance<Particle>(o)) return py::int_(addOne(o.cast<shared_ptr<Particle>>()));
         py::list ids; for (auto it : o) ids.append(addOne(it.cast<shared_ptr<Particle>>())); return ids; });
+  m.attr("ParticleContainer").attr("remove") = py::cpp_function([](ParticleContainer& c, int id) {
+        // ParticleContainer::remove (ParticleContainer.cpp:121-157): the particle and its contacts go; ids are not reused here
+        if (id < 0 || (size_t)id >= c.v.size() || !c.v[id]) throw py::index_error("No such particle: #" + std::to_string(id));
+        shared_ptr<Particle> p = c.v[id];
+        DemField& F = *c.dem;
+        const bool sphere = dynamic_cast<Sphere*>(p->shape.get()) != nullptr;
+        auto pa = std::find(F.pendingAdds.begin(), F.pendingAdds.end(), p);
+        if (pa != F.pendingAdds.end()) F.pendingAdds.erase(pa);                       // never reached the device
+        else if (F.owner && !F.topoDirty && sphere) F.pendingRemoves.push_back(id);
+        else F.topoDirty = true;
+        if (F.topoDirty && F.owner) { F.pull(); F.pullContacts(); }                  // the full path re-uploads from the host copies: make them current first
+        for (auto& n : p->shape->nodes) { auto it = std::find(F.nodes.begin(), F.nodes.end(), n); if (it != F.nodes.end()) F.nodes.erase(it); }
+        c.v[id].reset(); p->id = -1; F.contactsStale = true;
+      }, py::is_method(m.attr("ParticleContainer")), py::arg("id"));
   m.attr("ParticleContainer").attr("addClumped") = py::cpp_function([](ParticleContainer& c, py::object pars, shared_ptr<Node> centralNode) -> shared_ptr<Node> {
         // ParticleContainer::addClumped (ParticleContainer.cpp) for boundary particles with a user-given master node: the members keep their positions, the master's
         // vel/angVel (all DOFs blocked) move them rigidly from now on (examples/mill.py:38-42)

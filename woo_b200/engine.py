@@ -89,6 +89,12 @@ class Engine:
         self._chk(self.L.wdem_add_spheres(self.h, C.c_int64(m), ptr(ids), *[ptr(a) for a in args], ptr(flags), ptr(mask), ptr(mat)))
         self.n += m
 
+    def remove_spheres(self, ids):
+        """Remove spheres by Particle.id in mid-run (wdem.h: wdem_remove_spheres)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self._chk(self.L.wdem_remove_spheres(self.h, C.c_int64(len(ids)), ptr(ids)))
+        self.n -= len(ids)
+
     def upload_walls(self, ids, walls):
         n = len(walls)
         if n == 0:
