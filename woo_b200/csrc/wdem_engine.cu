@@ -699,9 +699,9 @@ void rebuild(wdem_engine* E) {
     CK(cudaMemsetAsync(E->rowCount.p, 0, ((size_t)n + 1) * sizeof(int), st));
     static const bool noCand = getenv("WDEM_NO_CAND_CACHE") != nullptr;
     int* cand = nullptr;
-    if (!c.periodic && !noCand) { E->candBuf.ensure((size_t)WD_CAND_CAP * n, tot); cand = E->candBuf.p; }
+    if (!noCand) { E->candBuf.ensure((size_t)WD_CAND_CAP * n * (c.periodic ? 4 : 1), tot); cand = E->candBuf.p; }
     if (!c.periodic) k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr, cand);
-    else k_pairs_ss_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
+    else k_pairs_ss_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt, cand);
     E->launches++;
     if (nWalls) {
       if (!c.periodic) k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr);
@@ -734,7 +734,7 @@ void rebuild(wdem_engine* E) {
     Contacts T = N; T.pair = reinterpret_cast<int2*>(E->ckeys.p); T.flags = E->cvals.p;
     if (c.periodic) { for (auto& b : E->tmpCd) b.ensure(nT, tot); T.cdx = E->tmpCd[0].p; T.cdy = E->tmpCd[1].p; T.cdz = E->tmpCd[2].p; }
     if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, E->offsets.p, T, O, oc, perm, nullptr, E->srcOld.p, cand);
-    else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, nullptr, E->offsets.p, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
+    else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, E->offsets.p, T, oc, perm, nullptr, E->srcOld.p, E->dCnt, cand);
     E->launches++;
     if (nWalls) {
       if (!c.periodic) k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, T, O, oc, perm, nullptr, E->srcOld.p);

@@ -1292,9 +1292,27 @@ __global__ void __launch_bounds__(256) k_cellkeys_peri(const double4* __restrict
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_pairs_ss_peri(Spheres S, int n, HGrid g, PeriU pu, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
                                                       const int* __restrict__ offsets, Contacts N, OldCsr oc, const int* __restrict__ perm,
-                                                      int* __restrict__ rowCount, int* __restrict__ srcOld, Counters* cnt) {
+                                                      int* __restrict__ rowCount, int* __restrict__ srcOld, Counters* cnt, int* __restrict__ cand) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // partner cache as in k_pairs_ss; an entry holds the partner's slot and the three periods (4 ints)
+  if (FILL && cand) {
+    const int cntI = counts[i];
+    if (cntI <= WD_CAND_CAP) {
+      const int idI_ = S.id[i]; const uint32_t fi_ = S.flags[i]; const int oslot_ = perm ? perm[i] : i; const long long out_ = offsets[i];
+      for (int k = 0; k < cntI; k++) {
+        const int j = cand[(4ll * k + 0) * n + i];
+        const int idJ = S.id[j];
+        const long long c = out_ + k;
+        const bool iIsA = idI_ < idJ;
+        N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
+        N.cdx[c] = cand[(4ll * k + 1) * n + i]; N.cdy[c] = cand[(4ll * k + 2) * n + i]; N.cdz[c] = cand[(4ll * k + 3) * n + i];
+        srcOld[c] = (int)find_old2(oc, oslot_, idJ, oc.nImm > 0 ? (fi_ | S.flags[j]) : 0u, iIsA ? idI_ : idJ, iIsA ? idJ : idI_);
+        N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
+      }
+      return;
+    }
+  }
   const double4 pi = S.posr[i];
   const int Li = levelOf(g, pi.w);
   d3 mnI, mxI; periAabb(pu, pi, vd, mnI, mxI);
@@ -1341,7 +1359,12 @@ __global__ void __launch_bounds__(128) k_pairs_ss_peri(Spheres S, int n, HGrid g
               N.cdx[c] = per[0]; N.cdy[c] = per[1]; N.cdz[c] = per[2];
               srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
               N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
-            } else atomicAdd(&rowCount[j], 1);
+            } else {
+              atomicAdd(&rowCount[j], 1);
+              if (cand && cntLocal < WD_CAND_CAP) {
+                cand[(4ll * cntLocal + 0) * n + i] = j; cand[(4ll * cntLocal + 1) * n + i] = per[0]; cand[(4ll * cntLocal + 2) * n + i] = per[1]; cand[(4ll * cntLocal + 3) * n + i] = per[2];
+              }
+            }
             cntLocal++;
           }
         }
