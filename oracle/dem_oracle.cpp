@@ -185,6 +185,7 @@ struct Aabb { V3 mn, mx; bool has = false; };
 struct Sphere {
   int id; V3 pos; Quat ori; V3 vel, angVel, force, torque; Real mass, inertia, radius; unsigned flags, mask; int mat;
   Aabb bb; V3 lastPos;
+  bool dead = false;   // removed by ParticleContainer::remove (the slot stays: ids are not renumbered)
 };
 struct Wall {
   int id; V3 pos; int axis, sense; V3 vel, angVel; unsigned mask; int mat; V3 force, torque; Aabb bb; V3 lastPos;
@@ -1308,13 +1309,35 @@ double orc_get_verlet_dist(void* h) { return ((Scene*)h)->P.verletDist; }
 int orc_get_nfullruns(void* h) { return ((Scene*)h)->nFullRuns; }
 double orc_pwave_dt(void* h) { return ((Scene*)h)->pWaveDt(); }
 double orc_kinetic_energy(void* h) { return ((Scene*)h)->kineticEnergy(); }
-int orc_num_spheres(void* h) { return (int)((Scene*)h)->sph.size(); }
+// ParticleContainer::remove (ParticleContainer.cpp:121-157): the particle's contacts are deleted at once, the particle leaves the container (its id is not
+// handed out again here) and the contacts are marked dirty, so the collider re-initialises at the next step.  The restatement keeps the array slot and takes the
+// particle out of the game: no mask (never a collision candidate again), no motion, no forces; the getters skip it.
+int orc_remove_spheres(void* h, int n, const int* ids) {
+  Scene* S = (Scene*)h;
+  ORC_TRY(h)
+  for (int k = 0; k < n; k++) {
+    if (ids[k] < 0 || ids[k] >= (int)S->par.size() || S->par[ids[k]].kind != SHAPE_SPHERE || S->sph[S->par[ids[k]].idx].dead) throw std::runtime_error("remove: no such sphere #" + std::to_string(ids[k]));
+    Sphere& sp = S->sph[S->par[ids[k]].idx];
+    sp.dead = true; sp.mask = 0; sp.vel = V3(); sp.angVel = V3(); sp.force = V3(); sp.torque = V3(); sp.flags = DOF_ALL | GRAVITY_SKIP | ENERGY_SKIP | DAMPING_SKIP;
+  }
+  for (auto it = S->con.begin(); it != S->con.end();) {
+    const Contact& C = it->second;
+    auto deadId = [&](int id) { const PRef& p = S->par[id]; return p.kind == SHAPE_SPHERE && S->sph[p.idx].dead; };
+    if (deadId(C.idA) || deadId(C.idB)) it = S->con.erase(it); else ++it;
+  }
+  S->linDirty = true; S->conDirty = true;   // queued removal requests of erased contacts are skipped by removePending (key not found)
+  ORC_CATCH(h)
+}
+int orc_num_spheres(void* h) { int n = 0; for (auto& s : ((Scene*)h)->sph) if (!s.dead) n++; return n; }
 void orc_get_spheres(void* h, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque) {
   Scene* S = (Scene*)h;
-  for (size_t i = 0; i < S->sph.size(); i++) {
-    const Sphere& s = S->sph[i];
+  size_t i = 0;
+  for (size_t q = 0; q < S->sph.size(); q++) {
+    const Sphere& s = S->sph[q];
+    if (s.dead) continue;
     for (int k = 0; k < 3; k++) { if (pos) pos[3 * i + k] = s.pos[k]; if (vel) vel[3 * i + k] = s.vel[k]; if (angVel) angVel[3 * i + k] = s.angVel[k]; if (force) force[3 * i + k] = s.force[k]; if (torque) torque[3 * i + k] = s.torque[k]; }
     if (ori) { ori[4 * i] = s.ori.x; ori[4 * i + 1] = s.ori.y; ori[4 * i + 2] = s.ori.z; ori[4 * i + 3] = s.ori.w; }
+    i++;
   }
 }
 void orc_set_sphere_state(void* h, int idx, const double* pos, const double* vel, const double* angVel) {

@@ -140,6 +140,10 @@ class Oracle:
         return self.L.orc_add_spheres(self.h, C.c_int(len(radius)), _p(pos, C.c_double), _p(radius, C.c_double), _p(mass, C.c_double), _p(inertia, C.c_double),
                                       _p(mat, C.c_int), _p(mask, C.c_uint), _p(flags, C.c_uint), _p(vel, C.c_double), _p(angVel, C.c_double), None)
 
+    def remove_spheres(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self._chk(self.L.orc_remove_spheres(self.h, C.c_int(len(ids)), _p(ids, C.c_int)))
+
     def facets(self):
         o = np.zeros((len(self.spec.facets), 3, 3))
         if len(o):

@@ -464,8 +464,8 @@ def test_add_spheres_mid_run(law):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# wdem_remove_spheres (the deletion half: Outlets): ParticleContainer.remove in mid-run.  The oracle keeps its particle arrays dense, so the check goes
-# through the resume path (proven equal to the oracle above): removing spheres in a running engine == a fresh engine started from the same state without them.
+# wdem_remove_spheres (the deletion half: Outlets): ParticleContainer.remove in mid-run.  Checked twice: against the oracle (which takes the removed
+# particle out of the game but keeps its slot) and through the resume path: removing spheres in a running engine == a fresh engine started from the same state without them.
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("law", [sc.LAW_IDEALELPL, sc.LAW_HERTZ_DMT])
 def test_remove_spheres_mid_run(law):
@@ -473,21 +473,23 @@ def test_remove_spheres_mid_run(law):
     from woo_b200.engine import Engine, WdemError
     S = sc.random_gas(400, box=.5, r=.02, psd_ratio=2.5, seed=95, law=law, en=.6 if law else float("nan")); S.params.dynDtPeriod = 0
     X = engine_for(S); X.step(150)
+    O = Oracle(S); O.step(150)
     s, c, sca = X.spheres(), X.contacts(True), X.scalars()
     ids_all = S.sphere_ids()
     rng = np.random.default_rng(96)
     gone = np.sort(rng.choice(ids_all, 60, replace=False)).astype(np.int32)
     assert np.isin(c["ids"], gone).any(), "the removed spheres should have contacts"
     keep = ~np.isin(ids_all, gone)
-    X.remove_spheres(gone)
+    X.remove_spheres(gone); O.remove_spheres(gone)
     with pytest.raises(WdemError):
         X.contacts(True)                                  # the table still refers to the old slots until the next step
     # a sphere added in the same breath (removal + insertion before the next collider run)
     m_, I_ = S.mass_inertia()
-    new_id = int(ids_all.max()) + len(S.walls) + 7
+    new_id = S.n + len(S.walls)                           # the id ParticleContainer.add hands out next (and the oracle does)
     newp = dict(pos=np.array([[.25, .25, .45]]), rad=np.array([.03]), vel=np.array([[0., 0., -2.]]))
     mass_new = S.mats[0][1] * (4 / 3.) * np.pi * newp["rad"] ** 3
     X.add_spheres(np.array([new_id], np.int32), newp["pos"], newp["rad"], mass_new, .4 * mass_new * newp["rad"] ** 2, vel=newp["vel"])
+    assert O.add_spheres(newp["pos"], newp["rad"], mass_new, .4 * mass_new * newp["rad"] ** 2, np.zeros(1, np.int32), vel=newp["vel"]) == new_id
     # the fresh engine: remaining spheres with their state, forces and the contacts among them, plus the new sphere
     pr = copy.copy(S.params); pr.dt = sca["dt"]
     Y = Engine(pr); Y.spec = S
@@ -503,11 +505,13 @@ def test_remove_spheres_mid_run(law):
     alive = ~np.isin(c["ids"], gone).any(axis=1)
     Y.upload_contacts({k: v[alive] for k, v in c.items()})
     for k in range(3):
-        X.step(50); Y.step(50)
-        sx, sy = X.spheres(), Y.spheres()
-        assert len(sx["pos"]) == S.n - len(gone) + 1
+        X.step(50); Y.step(50); O.step(50)
+        sx, sy, so = X.spheres(), Y.spheres(), O.spheres()
+        assert len(sx["pos"]) == S.n - len(gone) + 1 == len(so["pos"])
         for k_ in ("pos", "vel", "angVel", "force", "torque"):
             assert np.array_equal(sx[k_], sy[k_]), f"{k_} differs {50 * (k + 1)} steps after the removal"
+            assert np.array_equal(sx[k_], so[k_]), f"{k_} differs from the oracle {50 * (k + 1)} steps after the removal"
+        assert X.scalars()["nFullRuns"] == O.nFullRuns
         cx, cy = X.contacts(True), Y.contacts(True)
         assert np.array_equal(cx["ids"], cy["ids"]) and not np.isin(cx["ids"], gone).any()
         for k_ in ("uN", "force", "trsf", "stepCreated", "physRaw"):
