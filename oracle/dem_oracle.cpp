@@ -7,8 +7,9 @@
 // (needs Eigen3/Boost/TBB; none installed, no network) and ships no golden data for this path.
 // The oracle is pinned against the reference's own known-answer tests (tests/test_oracle_kat.py:
 // Hertz collision time test_hertz.py:30-47, pWaveDt utils.py:80-81, Cundall kn models.py:16-19,
-// PBC cellDist test_pbc.py:130-171, Wall+sphere Leapfrog test_energy.py:69-90) and otherwise by review
-// against the cited lines.  Eigen's fixed-size reductions are restated as left-to-right sums
+// PBC cellDist test_pbc.py:130-171, Wall+sphere Leapfrog and EnergyTracker entries test_energy.py:69-90), against golden vectors produced by the reference's own
+// Python contact models (py/models.py CundallModel / HertzModel, imported from /root/reference by scripts/make_golden_models.py -> tests/golden/ref_models.json)
+// and otherwise by review against the cited lines.  tests/golden/scene_*.npz pin the oracle's own output against drift between rounds.  Eigen's fixed-size reductions are restated as left-to-right sums
 // ((c0+c1)+c2); see DESIGN.md "Eigen semantics".
 //
 // Every function cites the reference file:line (relative to /root/reference) it follows.
