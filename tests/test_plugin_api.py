@@ -353,3 +353,29 @@ def test_outlet_like_removals_use_the_device_path():
     assert np.array_equal(np.array([S.dem.par[i].pos for i in left]), E.spheres()["pos"])
     assert np.array_equal(np.array([S.dem.par[i].f for i in left]), E.spheres()["force"])
     assert all(c.id1 not in gone and c.id2 not in gone for c in S.dem.con)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: object model of the later additions
+def test_object_model_clumps_removal_energy_stress_cpu():
+    from woo_b200.woo.core import Node
+    S = Scene(fields=[DemField()])
+    m = woo.utils.defaultMaterial()
+    ids = S.dem.par.add([woo.utils.sphere((0, 0, i * .2), .05, mat=m) for i in range(4)])
+    assert ids == [0, 1, 2, 3] and len(S.dem.nodes) == 4
+    S.dem.par.remove(2)
+    with pytest.raises(IndexError):
+        S.dem.par[2]
+    with pytest.raises(IndexError):
+        S.dem.par.remove(2)
+    assert len(S.dem.nodes) == 3 and S.dem.par.add(woo.utils.sphere((1, 1, 1), .05, mat=m)) == 4      # ids are not handed out again
+    facets = [Facet.make([(0, 0, 0), (1, 0, 0), (0, 1, 0)], mat=m), Facet.make([(1, 0, 0), (1, 1, 0), (0, 1, 0)], mat=m)]
+    central = Node(pos=(.5, .5, 0))
+    assert S.dem.par.addClumped(facets, centralNode=central) is central
+    assert [f.id for f in facets] == [5, 6] and central.dem.blocked == "xyzXYZ" and central in S.dem.nodes
+    central.dem.angVel = (0, 0, 3.)
+    assert tuple(central.dem.angVel) == (0, 0, 3.)
+    with pytest.raises(RuntimeError):
+        S.dem.par.addClumped(facets, centralNode=None)
+    assert S.energy == {} and S.trackEnergy is False
+    cl = ContactLoop()
+    assert cl.evalStress is False and np.array_equal(cl.stress, np.zeros((3, 3)))
