@@ -172,7 +172,7 @@ struct wdem_engine {
   CsrStore csr[2]; int curR = 0;
   // scratch
   DBuf<uint32_t> keys, keysAlt; DBuf<int> idx, idxAlt, cellStart, counts, offsets; DBuf<unsigned char> cubTemp; DBuf<double> blk;
-  DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld, candBuf; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt; DBuf<int> realFlag, realPos; DBuf<int32_t> tmpCd[3];
+  DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld, candBuf; DBuf<uint32_t> wallBits; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt; DBuf<int> realFlag, realPos; DBuf<int32_t> tmpCd[3];
   Counters* dCnt = nullptr; Counters* hCnt = nullptr;
   // scene scalars
   double dt = NAN, time = 0, nextDt = NAN, verletDist = NAN; long long step = 0, nFullRuns = 0; bool conDirty = true;
@@ -700,15 +700,19 @@ void rebuild(wdem_engine* E) {
     static const bool noCand = getenv("WDEM_NO_CAND_CACHE") != nullptr;
     int* cand = nullptr;
     if (!noCand) { E->candBuf.ensure((size_t)WD_CAND_CAP * n * (c.periodic ? 4 : 1), tot); cand = E->candBuf.p; }
-    if (!c.periodic) k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr, cand);
+    static const bool noWallMerge = getenv("WDEM_NO_WALL_MERGE") != nullptr;
+    WallPass wp; memset(&wp, 0, sizeof(wp));
+    const bool mergeWalls = !c.periodic && nWalls > 0 && nWalls <= 32 && !noWallMerge;
+    if (mergeWalls) { E->wallBits.ensure((size_t)n, tot); wp.walls = E->dWalls.p; wp.nWalls = nWalls; wp.halfThick = c.wallHalfThick; wp.bits = E->wallBits.p; }
+    if (!c.periodic) k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr, cand, wp);
     else k_pairs_ss_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt, cand);
     E->launches++;
-    if (nWalls) {
+    if (nWalls && !mergeWalls) {
       if (!c.periodic) k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr);
       else k_pairs_ws_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
       E->launches++;
     }
-    else CK(cudaMemsetAsync(E->counts.p + n, 0, (size_t)n * sizeof(int), st));
+    else if (!nWalls) CK(cudaMemsetAsync(E->counts.p + n, 0, (size_t)n * sizeof(int), st));
     if (nFacets) { k_pairs_fs<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, E->counts.p + 2 * n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++; }
     else CK(cudaMemsetAsync(E->counts.p + 2 * n, 0, (size_t)n * sizeof(int), st));
     CK(cudaMemsetAsync(E->counts.p + 3 * n, 0, sizeof(int), st));
@@ -733,10 +737,10 @@ void rebuild(wdem_engine* E) {
     E->ckeys.ensure(nT, tot); E->cvals.ensure(nT, tot); E->realFlag.ensure(nT + 1, tot); E->realPos.ensure(nT + 1, tot);
     Contacts T = N; T.pair = reinterpret_cast<int2*>(E->ckeys.p); T.flags = E->cvals.p;
     if (c.periodic) { for (auto& b : E->tmpCd) b.ensure(nT, tot); T.cdx = E->tmpCd[0].p; T.cdy = E->tmpCd[1].p; T.cdz = E->tmpCd[2].p; }
-    if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, E->offsets.p, T, O, oc, perm, nullptr, E->srcOld.p, cand);
+    if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, E->offsets.p, T, O, oc, perm, nullptr, E->srcOld.p, cand, wp);
     else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, E->offsets.p, T, oc, perm, nullptr, E->srcOld.p, E->dCnt, cand);
     E->launches++;
-    if (nWalls) {
+    if (nWalls && !mergeWalls) {
       if (!c.periodic) k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, T, O, oc, perm, nullptr, E->srcOld.p);
       else k_pairs_ws_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
       E->launches++;
@@ -1199,7 +1203,7 @@ int wdem_destroy(wdem_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release();
   h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->fgCursor.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
-  h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->candBuf.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
+  h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->candBuf.release(); h->wallBits.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
   peerTeardown(h, false);
   h->dom.release(); delete h->comm; h->comm = nullptr;
   if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt);

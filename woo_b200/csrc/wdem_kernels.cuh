@@ -1069,6 +1069,9 @@ __device__ __forceinline__ long long find_old2(const OldCsr& oc, int oslot, int 
 
 // Sphere+Sphere candidates (see HGrid for the ownership rule).  FILL=false counts, FILL=true writes pairs (canonical pA = lower id) and looks up the
 // previous contact of the pair (history carry-over by k_carry).
+// wall candidates found in the same pass as the sphere candidates (aperiodic scenes with at most 32 walls): the counting pass leaves the walls whose boxes overlap
+// the sphere's as a bit mask, the filling pass writes those pairs without touching the sphere's position again.  walls == nullptr: separate k_pairs_ws launches.
+struct WallPass { const Wall* walls; int nWalls; double halfThick; uint32_t* bits; };
 #ifndef WD_CAND_CAP
 #define WD_CAND_CAP 16
 #endif
@@ -1078,7 +1081,7 @@ __device__ __forceinline__ long long find_old2(const OldCsr& oc, int oslot, int 
 template <bool FILL>
 __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int n, HGrid g, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
                                                  const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
-                                                 int* __restrict__ rowCount, int* __restrict__ srcOld, int* __restrict__ cand) {
+                                                 int* __restrict__ rowCount, int* __restrict__ srcOld, int* __restrict__ cand, WallPass wp) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t fi = S.flags[i];
@@ -1086,6 +1089,17 @@ __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int 
   long long out = FILL ? offsets[i] : 0;
   int idI = 0, oslotI = 0;
   if (FILL) { idI = S.id[i]; oslotI = perm ? perm[i] : i; }
+  if (FILL && wp.walls && !(fi & F_GHOST)) {   // wall pairs of this sphere (segment [nSS, nSS+nWS) of the table: offsets of the second counts block)
+    uint32_t m = wp.bits[i]; long long c = offsets[n + i];
+    while (m) {
+      const int w = __ffs(m) - 1; m &= m - 1;
+      const int wid = wp.walls[w].id;
+      N.pair[c] = make_int2(w, i);
+      srcOld[c] = (int)find_old2(oc, oslotI, wid, fi, wid, idI);
+      N.flags[c] = (KIND_WS << CF_KIND_SHIFT);
+      c++;
+    }
+  }
   // the counting pass leaves the partners it found (up to WD_CAND_CAP per sphere, in discovery order) in `cand`; the filling pass then only has to look up
   // the previous contact and write the pair, without walking the cells again.  Spheres with more partners than the cache holds repeat the search.
   if (FILL && cand) {
@@ -1134,7 +1148,26 @@ __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int 
         }
       }
   }
-  if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
+  if (!FILL) {
+    int wcnt = 0;
+    if (wp.walls) {   // Bo1_Wall_Aabb (Wall.cpp:25-38), the test of k_pairs_ws
+      uint32_t m = 0;
+      if (!(fi & F_GHOST)) {
+        for (int w = 0; w < wp.nWalls; w++) {
+          const Wall W = wp.walls[w];
+          const double pc = comp(xyz(pi), W.axis);
+          double wmin = W.pos[W.axis], wmax = wmin;
+          if (wp.halfThick > 0) { wmin -= wp.halfThick; wmax += wp.halfThick; }
+          wmin = wmin - vd; wmax = wmax + vd;
+          if (!(((pc - pi.w) - vd <= wmax) && ((pc + pi.w) + vd >= wmin))) continue;
+          if (!mayCollide(mi, W.mask, loneMask)) continue;
+          m |= 1u << w; wcnt++;
+        }
+      }
+      wp.bits[i] = m; counts[n + i] = wcnt;
+    }
+    counts[i] = cntLocal; if (cntLocal + wcnt) atomicAdd(&rowCount[i], cntLocal + wcnt);
+  }
 }
 
 // Wall+Sphere candidates: Bo1_Wall_Aabb (Wall.cpp:25-38): the wall box is the plane coordinate (± halfThick) ± verletDist on its axis, infinite elsewhere.
