@@ -551,8 +551,8 @@ struct Scene {
     // grid
     Real maxExt = 0;
     for (long id = 0; id < nPar; id++) for (int k = 0; k < 3; k++) { Real e = maxima[3 * id + k] - minima[3 * id + k]; if (!std::isinf(e)) maxExt = std::max(maxExt, e); }
-    int nc[3]; Real cs[3];
-    for (int k = 0; k < 3; k++) { nc[k] = std::max(1, (int)std::floor(cell.size[k] / std::max(maxExt, 1e-300))); nc[k] = std::min(nc[k], 256); cs[k] = cell.size[k] / nc[k]; }
+    int nc[3];
+    for (int k = 0; k < 3; k++) { nc[k] = std::max(1, (int)std::floor(cell.size[k] / std::max(maxExt, 1e-300))); nc[k] = std::min(nc[k], 256); }
     auto cidx = [&](int ix, int iy, int iz) { return ((long)iz * nc[1] + iy) * nc[0] + ix; };
     std::vector<std::vector<int>> cells((size_t)nc[0] * nc[1] * nc[2]);
     std::vector<int> infIds;
