@@ -40,3 +40,13 @@ def test_create_fails_loudly_without_a_gpu():
     rc = L.wdem_create(C.byref(cfg), C.byref(h))
     assert rc != 0 and not h.value
     assert b"no CPU fallback" in L.wdem_last_error(None)
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/wdem.h must compile as C99 (no C++ or torch types in the signatures)."""
+    import shutil, subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", os.path.join(ROOT, "include", "wdem.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
