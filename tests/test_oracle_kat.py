@@ -253,3 +253,49 @@ def test_energy_free_fall_and_damping_like_the_reference_test():
     assert O.energy()["grav"] == 0 and O.energy()["nonviscDamp"] != 0
     O = Oracle(scene(flags=sc.DAMPING_SKIP)); O.track_energy(True); O.step(400)
     assert O.energy()["grav"] != 0 and O.energy()["nonviscDamp"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# py/tests/test_pbc.py TestPBC (:16-128): cell integration and the homoDeform modes of Leapfrog.  The reference runs [Leapfrog] alone; the oracle runs the whole
+# loop, which makes no difference within the single step these tests look at (contact forces act from the next step on).
+# ---------------------------------------------------------------------------------------------------------------
+def _pbc_two_spheres(homo, dt):
+    S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+    init_pos = np.array([1., 1. + .999999999999999999, 1. + 10 * 3.]); init_vel = np.array([0., 0., 5.])
+    S.pos = np.array([[1., 1., 1.], init_pos]); S.radius = np.array([.5, .5]); S.vel = np.array([[0., 0., 0.], init_vel])
+    S.params = sc.Params(dt=dt, periodic=1, damping=0., dynDtPeriod=0)
+    S.cell = dict(hSize=np.diag([2.5, 2.5, 3.]), gradV=np.zeros((3, 3)), nextGradV=np.diag([0., 0., -1.]), homoDeform=homo)
+    return S.finalize(), init_pos, init_vel
+
+
+def test_pbc_velgrad_changes_hsize():
+    # testVelGrad (:33-49): hSize += dt*gradV*hSize per step (gradV is still zero in the first step: nextGradV takes effect in the epilogue), homoDeform='vel2'
+    S, _, _ = _pbc_two_spheres(sc.HOMO_VEL_2ND, 1e-3)
+    O = Oracle(S)
+    h = np.diag([2.5, 2.5, 3.]); g = np.zeros((3, 3))
+    for i in range(10):
+        h = h + 1e-3 * g @ h
+        O.step(1)
+        g = np.diag([0., 0., -1.])
+    assert np.allclose(O.cell_hsize(), h, rtol=0, atol=5e-8)         # assertAlmostEqual: 7 places
+
+
+def test_pbc_homothetic_resize_vel_and_pos():
+    # testHomotheticResizeVel (:67-77): homoDeform='vel': v_z = v0_z + z0*gradV_zz after one step
+    S, p0, v0 = _pbc_two_spheres(sc.HOMO_VEL, 1e-5)
+    O = Oracle(S); O.step(1)
+    assert O.spheres()["vel"][1, 2] == pytest.approx(v0[2] + p0[2] * -1., abs=5e-8)
+    # testHomotheticResizePos (:78-85): homoDeform='pos' with dt=0: velocity untouched, position moved by z0*gradV_zz*dt (= 0)
+    S, p0, v0 = _pbc_two_spheres(sc.HOMO_POS, 0.)
+    O = Oracle(S); O.step(1)
+    s = O.spheres()
+    assert s["vel"][1, 2] == pytest.approx(v0[2], abs=5e-8) and s["pos"][1, 2] == pytest.approx(p0[2] + p0[2] * -1. * 0., abs=5e-8)
+
+
+@pytest.mark.parametrize("homo", [sc.HOMO_VEL_2ND, sc.HOMO_POS])
+def test_pbc_kinetic_energy_is_of_the_fluctuation_velocity(homo):
+    # testKineticEnergy / testKineticEnergy_homoPos (:104-121): Ek counts the fluctuation velocity only, not the velocity gradient
+    S, p0, v0 = _pbc_two_spheres(homo, 0.)
+    O = Oracle(S); O.step(1)
+    m = S.mass_inertia()[0][1]
+    assert O.kineticEnergy() == pytest.approx(.5 * m * float(v0 @ v0), rel=1e-7)
