@@ -379,3 +379,13 @@ def test_object_model_clumps_removal_energy_stress_cpu():
     assert S.energy == {} and S.trackEnergy is False
     cl = ContactLoop()
     assert cl.evalStress is False and np.array_equal(cl.stress, np.zeros((3, 3)))
+
+
+def test_guess_moving():
+    """py/tests/test_demfield.py:11-22"""
+    from woo_b200.woo.dem import DemData
+    assert DemData(blocked='', mass=0).guessMoving() is False           # zero mass, don't move
+    assert DemData(blocked='xyz', mass=0).guessMoving() is False
+    assert DemData(blocked='xyzXY', mass=1).guessMoving() is True       # something not blocked, move
+    assert DemData(blocked='xyzXYZ', mass=1).guessMoving() is False     # everything blocked, not move
+    assert DemData(blocked='xyzXYZ', vel=(1, 1, 1), mass=1).guessMoving() is True      # velocity assigned, move

@@ -52,6 +52,8 @@ enum { DOF_ALL = 63, GRAVITY_SKIP = 512, DAMPING_SKIP = 2048 };
 struct DemData {
   V3 vel{{0, 0, 0}}, angVel{{0, 0, 0}}, force{{0, 0, 0}}, torque{{0, 0, 0}}, inertia{{0, 0, 0}}; double mass = 0; unsigned flags = 0;
   DemField* field = nullptr;
+  // DemData::guessMoving (Particle.cpp:638-640): does the node need motion integration?
+  bool guessMoving() const { return (mass != 0 && (flags & 63u) != 63u) || vel[0] != 0 || vel[1] != 0 || vel[2] != 0 || angVel[0] != 0 || angVel[1] != 0 || angVel[2] != 0; }
   string blockedGet() const { string r; const char* n = "xyzXYZ"; for (int i = 0; i < 6; i++) if (flags & (1u << i)) r += n[i]; return r; }
   void blockedSet(const string& s) { flags &= ~63u; for (char c : s) { const char* n = "xyzXYZ"; const char* p = strchr(n, c); if (!p) throw std::invalid_argument("blocked: only xyzXYZ allowed"); flags |= 1u << (p - n); } }
 };
@@ -477,6 +479,7 @@ PYBIND11_MODULE(_woo, m) {
       .def_property("flags", [](DemData& s) { return s.flags; }, [](DemData& s, unsigned v) { s.flags = v; if (s.field) s.field->topoDirty = true; })
       .def_property("blocked", &DemData::blockedGet, [](DemData& s, const string& v) { s.blockedSet(v); if (s.field) s.field->topoDirty = true; })
       .def_property("gravitySkip", [](DemData& s) { return bool(s.flags & GRAVITY_SKIP); }, [](DemData& s, bool b) { s.flags = b ? (s.flags | GRAVITY_SKIP) : (s.flags & ~GRAVITY_SKIP); if (s.field) s.field->topoDirty = true; })
+      .def("guessMoving", &DemData::guessMoving)
       .def_property("dampingSkip", [](DemData& s) { return bool(s.flags & DAMPING_SKIP); }, [](DemData& s, bool b) { s.flags = b ? (s.flags | DAMPING_SKIP) : (s.flags & ~DAMPING_SKIP); if (s.field) s.field->topoDirty = true; });
   kwclass<Node>(m, "Node")
       V3P(Node, "pos", s.pos, if (s.dem && s.dem->field) s.dem->field->pull(), if (s.dem && s.dem->field) s.dem->field->touchState())
@@ -545,7 +548,7 @@ PYBIND11_MODULE(_woo, m) {
           p->id = (int)c.v.size(); p->field = c.dem; c.v.push_back(p);
           for (auto& n : p->shape->nodes) {
             n->dem->field = c.dem; const DemData& d = *n->dem;
-            const bool moving = (d.mass != 0 && (d.flags & DOF_ALL) != DOF_ALL) || d.vel[0] != 0 || d.vel[1] != 0 || d.vel[2] != 0 || d.angVel[0] != 0 || d.angVel[1] != 0 || d.angVel[2] != 0;   // DemData::guessMoving
+            const bool moving = d.guessMoving();
             if (moving) c.dem->nodes.push_back(n);
           }
           if (c.dem->owner && !c.dem->topoDirty && dynamic_cast<Sphere*>(p->shape.get())) c.dem->pendingAdds.push_back(p);
