@@ -299,3 +299,20 @@ def test_pbc_kinetic_energy_is_of_the_fluctuation_velocity(homo):
     O = Oracle(S); O.step(1)
     m = S.mass_inertia()[0][1]
     assert O.kineticEnergy() == pytest.approx(.5 * m * float(v0 @ v0), rel=1e-7)
+
+
+def test_dyndt_two_sphere_analytic():
+    """DynDt::nodalCritDtSq (DynDt.cpp:16-58) for two equal spheres in contact along y with kt = .2 kn: translational stiffness (kt, kn, kt), rotational
+    r^2 kt (1,0,1) => the normal DOF is critical: critDt = sqrt(2 m / kn); DynDt::run (:90-113) then sets nextDt = dtSafety*critDt when the rate limit does not bind."""
+    S = two_spheres(sc.LAW_IDEALELPL, gap=-1e-4, mat=sc.frict_mat(density=1e3, young=1e7, ktDivKn=.2, tanPhi=.5))
+    S.params.dt = 1e-7; S.params.dynDtPeriod = 1; S.params.maxRelInc = 1e6; S.params.dtSafety = .9
+    O = Oracle(S); O.step(2)            # step 0 starts the period count, step 1 computes nextDt, which is Scene.dt from step 2 on
+    kn = O.contacts(True)["phys"][0, 0]; m = S.mass_inertia()[0][0]
+    assert O.dt == pytest.approx(.9 * math.sqrt(2 * m / kn), rel=1e-12)
+    # with stiffer tangential springs the rotational DOF takes over: I/(r^2 kt) = .4 m/kt < m/kn for kt > .4 kn
+    S = two_spheres(sc.LAW_IDEALELPL, gap=-1e-4, mat=sc.frict_mat(density=1e3, young=1e7, ktDivKn=.8, tanPhi=.5))
+    S.params.dt = 1e-7; S.params.dynDtPeriod = 1; S.params.maxRelInc = 1e6; S.params.dtSafety = .9
+    O = Oracle(S); O.step(2)            # step 0 starts the period count, step 1 computes nextDt, which is Scene.dt from step 2 on
+    c = O.contacts(True); kn, kt = c["phys"][0, 0], c["phys"][0, 1]
+    assert kt == pytest.approx(.8 * kn, rel=1e-14)
+    assert O.dt == pytest.approx(.9 * math.sqrt(2 * .4 * m / kt), rel=1e-12)
