@@ -316,3 +316,20 @@ def test_dyndt_two_sphere_analytic():
     c = O.contacts(True); kn, kt = c["phys"][0, 0], c["phys"][0, 1]
     assert kt == pytest.approx(.8 * kn, rel=1e-14)
     assert O.dt == pytest.approx(.9 * math.sqrt(2 * .4 * m / kt), rel=1e-12)
+
+
+def test_leapfrog_damping_gravity_analytic():
+    """Leapfrog (Leapfrog.cpp:33-48,104-255) on one free sphere: the first step sees zero force (forces are those of the previous step); from then on
+    f = m g and Cundall's non-viscous damping scales the acceleration by (1 - damping*sign(f*(v + dt/2 a))) = 1 - damping for a sphere accelerating with the force."""
+    def run(flags):
+        S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+        S.pos = np.array([[0., 0., 1.]]); S.radius = np.array([.1]); S.flags = np.array([flags], dtype=np.uint32)
+        S.params = sc.Params(gravity=(0, 0, -10.), damping=.4, dt=1e-4, dynDtPeriod=0)
+        O = Oracle(S.finalize()); O.step(11)
+        return O.spheres()
+    s = run(0)
+    assert s["vel"][0, 2] == pytest.approx(10 * -10. * (1 - .4) * 1e-4, rel=1e-12)
+    assert s["pos"][0, 2] == pytest.approx(1. + sum(k * -10. * .6 * 1e-4 for k in range(1, 11)) * 1e-4, rel=1e-14)
+    assert run(sc.DAMPING_SKIP)["vel"][0, 2] == pytest.approx(10 * -10. * 1e-4, rel=1e-12)
+    assert run(sc.GRAVITY_SKIP)["vel"][0, 2] == 0.
+    assert run(4)["vel"][0, 2] == 0. and run(4)["pos"][0, 2] == 1.          # z translation blocked (DemData flag DOF_Z)
