@@ -333,3 +333,23 @@ def test_leapfrog_damping_gravity_analytic():
     assert run(sc.DAMPING_SKIP)["vel"][0, 2] == pytest.approx(10 * -10. * 1e-4, rel=1e-12)
     assert run(sc.GRAVITY_SKIP)["vel"][0, 2] == 0.
     assert run(4)["vel"][0, 2] == 0. and run(4)["pos"][0, 2] == 1.          # z translation blocked (DemData flag DOF_Z)
+
+
+def test_coulomb_limit_and_noslip():
+    """Law2_L6Geom_FrictPhys_IdealElPl (IdealElPl.cpp:49-77): the shear force grows by kt*velT*dt per step until |Ft| reaches |Fn|*tanPhi and stays on the cone;
+    with noSlip it keeps growing.  Two spheres with all DOFs blocked, one sliding past the other at constant velocity."""
+    def run(noSlip, steps):
+        S = two_spheres(sc.LAW_IDEALELPL, gap=-1e-4, mat=sc.frict_mat(density=1e3, young=1e7, ktDivKn=.2, tanPhi=.5))
+        S.flags[:] = sc.DOF_ALL; S.vel[1] = (1., 0., 0.)
+        S.params.dt = 1e-6; S.params.dynDtPeriod = 0; S.params.noSlip = noSlip
+        O = Oracle(S); O.step(steps)
+        return O.contacts(True)
+    c = run(0, 600)
+    fn, ft = c["force"][0, 0], math.hypot(c["force"][0, 1], c["force"][0, 2])
+    assert fn < 0 and ft == pytest.approx(abs(fn) * .5, rel=1e-12)
+    c2 = run(1, 600)
+    ft2 = math.hypot(c2["force"][0, 1], c2["force"][0, 2])
+    kt = c2["phys"][0, 1]
+    assert ft2 > ft and ft2 == pytest.approx(kt * 1. * 599 * 1e-6, rel=2e-2)      # kt * |velT| * t (the frame turns a little as the sphere slides past)
+    early = run(0, 50)
+    assert math.hypot(early["force"][0, 1], early["force"][0, 2]) == pytest.approx(early["phys"][0, 1] * 1. * 49 * 1e-6, rel=1e-3)   # below the cone: elastic
