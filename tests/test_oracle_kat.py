@@ -353,3 +353,21 @@ def test_coulomb_limit_and_noslip():
     assert ft2 > ft and ft2 == pytest.approx(kt * 1. * 599 * 1e-6, rel=2e-2)      # kt * |velT| * t (the frame turns a little as the sphere slides past)
     early = run(0, 50)
     assert math.hypot(early["force"][0, 1], early["force"][0, 2]) == pytest.approx(early["phys"][0, 1] * 1. * 49 * 1e-6, rel=1e-3)   # below the cone: elastic
+
+
+def test_sphere_resting_on_wall_equilibrium():
+    """A sphere settling on a Wall under gravity with non-viscous damping comes to rest where kn*|uN| = m*g, with the Wall-Sphere stiffness kn = E*pi*r/2
+    (Cg2_Wall_Sphere_L6Geom passes radii (-r, r), L6Geom.lens = (r, r), contA = pi r^2: Wall.cpp:82, L6Geom.cpp:61, FrictMat.cpp:20-44)."""
+    r, E, rho, g = .1, 1e7, 1e3, 10.
+    S = sc.SceneSpec(); S.mats = [sc.frict_mat(density=rho, young=E)]
+    S.pos = np.array([[0., 0., r + 1e-4]]); S.radius = np.array([r])
+    S.walls = [dict(pos=(0, 0, 0), axis=2, sense=1, mat=0, mask=sc.MASK_BOUNDARY)]
+    S.params = sc.Params(gravity=(0, 0, -g), damping=.4, dtSafety=.5, dynDtPeriod=100)
+    O = Oracle(S.finalize()); O.step(60000)
+    c = O.contacts(True)
+    assert len(c["uN"]) == 1
+    kn = c["phys"][0, 0]; m = S.mass_inertia()[0][0]
+    assert kn == pytest.approx(E * math.pi * r / 2, rel=1e-13)
+    assert abs(O.spheres()["vel"][0, 2]) < 1e-9
+    assert -c["uN"][0] == pytest.approx(m * g / kn, rel=1e-6)
+    assert O.spheres()["force"][0, 2] == pytest.approx(0., abs=1e-6 * m * g)
