@@ -371,3 +371,22 @@ def test_sphere_resting_on_wall_equilibrium():
     assert abs(O.spheres()["vel"][0, 2]) < 1e-9
     assert -c["uN"][0] == pytest.approx(m * g / kn, rel=1e-6)
     assert O.spheres()["force"][0, 2] == pytest.approx(0., abs=1e-6 * m * g)
+
+
+@pytest.mark.parametrize("centre,cp,region", [((.25, .25, .19), (.25, .25, 0.), "face"), ((.5, -.1, .1), (.5, 0., 0.), "edge"), ((1.1, -.1, .05), (1., 0., 0.), "vertex")])
+def test_facet_sphere_closest_point(centre, cp, region):
+    """Cg2_Facet_Sphere_L6Geom::go (Facet.cpp:333-391): the contact point is the point of the triangle closest to the sphere centre (face / edge / vertex regions),
+    the normal points from it to the centre and uN = distance - radius (halfThick = 0)."""
+    r = .2
+    S = sc.SceneSpec(); S.mats = [sc.frict_mat()]
+    S.pos = np.array([centre], dtype=float); S.radius = np.array([r])
+    S.facets = [dict(v=np.array([(0., 0., 0.), (1., 0., 0.), (0., 1., 0.)]), halfThick=0., mat=0, mask=sc.MASK_BOUNDARY)]
+    S.params = sc.Params(dt=1e-9, damping=0., dynDtPeriod=0)
+    O = Oracle(S.finalize()); O.step(1)
+    c = O.contacts(True)
+    assert len(c["uN"]) == 1, region
+    d = np.array(centre) - np.array(cp); dist = np.linalg.norm(d)
+    assert np.allclose(c["contPt"][0], cp, rtol=0, atol=1e-12)
+    assert c["uN"][0] == pytest.approx(dist - r, rel=1e-9)
+    assert np.allclose(c["trsf"][0][:3], d / dist, rtol=0, atol=1e-9)         # first column of trsf = contact normal
+    assert c["force"][0, 0] == pytest.approx(c["phys"][0, 0] * c["uN"][0], rel=1e-12)
