@@ -390,3 +390,27 @@ def test_facet_sphere_closest_point(centre, cp, region):
     assert c["uN"][0] == pytest.approx(dist - r, rel=1e-9)
     assert np.allclose(c["trsf"][0][:3], d / dist, rtol=0, atol=1e-9)         # first column of trsf = contact normal
     assert c["force"][0, 0] == pytest.approx(c["phys"][0, 0] * c["uN"][0], rel=1e-12)
+
+
+@pytest.mark.parametrize("en", [.3, .5, .8])
+def test_hertz_restitution_coefficient(en):
+    """Cp2_HertzMat_HertzPhys.en -> alpha_sqrtMK (Hertz.cpp:63-75, Antypov & Elliott 2012): the viscous term is built so that a head-on collision of two spheres
+    loses velocity by the factor en, independently of the impact speed — with Law2_L6Geom_HertzPhys_DMT.noAttraction=False.  The default noAttraction=True clips the
+    viscous force where it would pull the spheres together at the end of the collision (Hertz.cpp:177), so less is dissipated and the rebound is faster."""
+    def rebound(v0, noAttraction):
+        S = two_spheres(sc.LAW_HERTZ_DMT, v0=v0, gap=1e-9, en=en); S.params.noAttraction = noAttraction
+        O = Oracle(S)
+        touched = False
+        for _ in range(400000):
+            O.step(20)
+            real = O.num_contacts(True)
+            touched = touched or real
+            if touched and not real:
+                break
+        s = O.spheres()
+        assert touched
+        return (s["vel"][1, 1] - s["vel"][0, 1]) / v0
+    for v0 in (1., 1e-2):
+        free = rebound(v0, 0)
+        assert free == pytest.approx(en, rel=3e-2), (en, v0)
+        assert rebound(v0, 1) >= free * (1 - 1e-9)
