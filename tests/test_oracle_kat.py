@@ -414,3 +414,13 @@ def test_hertz_restitution_coefficient(en):
         free = rebound(v0, 0)
         assert free == pytest.approx(en, rel=3e-2), (en, v0)
         assert rebound(v0, 1) >= free * (1 - 1e-9)
+
+
+@pytest.mark.parametrize("ma,mb,collide", [(0b01, 0b10, False), (0b10, 0b10, False), (0b0101, 0b0011, True), (0b0110, 0b0010, False), (0b0111, 0b0011, False), (0b0101, 0b0111, True)])
+def test_collision_masks(ma, mb, collide):
+    """Collider::mayCollide (Collision.cpp:21-43; masks Particle.hpp:339-349): two particles may collide iff their masks share a bit and none of the shared
+    bits lies in DemField.loneMask (0b0010 by default: boundary particles, which all carry it, do not collide with each other)."""
+    S = two_spheres(sc.LAW_IDEALELPL, gap=-1e-3, mat=sc.frict_mat())
+    S.mask[:] = (ma, mb); S.params.dt = 1e-7; S.params.dynDtPeriod = 0
+    O = Oracle(S); O.step(2)
+    assert (O.num_contacts(False) == 1) == collide and (O.num_contacts(True) == 1) == collide
