@@ -35,7 +35,9 @@ CASES = [(K.test_pwave_dt, ()), (K.test_cundall_kn_and_hertz_force, ()), (K.test
          (K.test_stress_two_spheres_across_the_cell_boundary, ()), (K.test_pbc_velgrad_changes_hsize, ()), (K.test_pbc_homothetic_resize_vel_and_pos, ()),
          (K.test_pbc_kinetic_energy_is_of_the_fluctuation_velocity, (K.sc.HOMO_VEL_2ND,)), (K.test_pbc_kinetic_energy_is_of_the_fluctuation_velocity, (K.sc.HOMO_POS,)),
          (K.test_facet_sphere_closest_point, ((.25, .25, .19), (.25, .25, 0.), "face")), (K.test_facet_sphere_closest_point, ((.5, -.1, .1), (.5, 0., 0.), "edge")),
-         (K.test_facet_sphere_closest_point, ((1.1, -.1, .05), (1., 0., 0.), "vertex")), (K.test_hertz_collision_time, (1e-2,))]
+         (K.test_facet_sphere_closest_point, ((1.1, -.1, .05), (1., 0., 0.), "vertex")), (K.test_hertz_collision_time, (1e-2,)),
+         (K.test_hertz_restitution_coefficient, (.5,)), (K.test_collision_masks, (0b01, 0b10, False)), (K.test_collision_masks, (0b10, 0b10, False)),
+         (K.test_collision_masks, (0b0101, 0b0011, True)), (K.test_collision_masks, (0b0111, 0b0011, False)), (K.test_collision_masks, (0b0101, 0b0111, True))]
 
 
 @pytest.mark.parametrize("kat,args", CASES, ids=[f"{f.__name__}{list(a) if a else ''}" for f, a in CASES])
