@@ -9,8 +9,9 @@
 // Hertz collision time test_hertz.py:30-47, pWaveDt utils.py:80-81, Cundall kn models.py:16-19,
 // PBC cellDist test_pbc.py:130-171, Wall+sphere Leapfrog and EnergyTracker entries test_energy.py:69-90), against golden vectors produced by the reference's own
 // Python contact models (py/models.py CundallModel / HertzModel, imported from /root/reference by scripts/make_golden_models.py -> tests/golden/ref_models.json)
-// and otherwise by review against the cited lines.  tests/golden/scene_*.npz pin the oracle's own output against drift between rounds.  Eigen's fixed-size reductions are restated as left-to-right sums
-// ((c0+c1)+c2); see DESIGN.md "Eigen semantics".
+// and otherwise by review against the cited lines.  tests/golden/scene_*.npz pin the oracle's own output against drift between rounds.  The order of Eigen's fixed-size 3-term reductions is restated from
+// the Eigen sources and switchable (WD_SUM3_ORDER / WD_TRACE_ORDER / WD_MATPROD_ORDER below); tests/test_order_sensitivity.py shows that the
+// real-contact set and the 1e-10 force tolerance do not depend on it.  scripts/replay_in_woo.py replays tests/golden/ in a real Woo build.
 //
 // Every function cites the reference file:line (relative to /root/reference) it follows.
 // Build: g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC (oracle/Makefile).
@@ -55,7 +56,40 @@ static inline V3& operator+=(V3& a, const V3& b) { a.x += b.x; a.y += b.y; a.z +
 static inline V3& operator-=(V3& a, const V3& b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; return a; }
 static inline bool operator==(const V3& a, const V3& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 static inline bool operator!=(const V3& a, const V3& b) { return !(a == b); }
-static inline Real sum3(Real a, Real b, Real c) { return (a + b) + c; }
+// Order of Eigen's 3-term reductions: the same three switches (names, meaning, defaults) as woo_b200/csrc/wdem_math.cuh; analysis in
+// DESIGN.md section 2.  oracle/Makefile also builds libdem_oracle_alt.so with every order flipped (tests/test_order_sensitivity.py).
+#ifndef WD_SUM3_ORDER
+#define WD_SUM3_ORDER 0      // dot/squaredNorm/norm, Transpose<Matrix3>*Vector3: 0 = (c0+c1)+c2 (Eigen>=3.3 SSE2 Packet2d + tail), 1 = c0+(c1+c2) (novec halves)
+#endif
+#ifndef WD_TRACE_ORDER
+#define WD_TRACE_ORDER 1     // Matrix3::trace() in Quaternion(Matrix3): 1 = c0+(c1+c2) (strided diagonal: novec halves), 0 = (c0+c1)+c2
+#endif
+#ifndef WD_MATPROD_ORDER
+#define WD_MATPROD_ORDER 1   // Matrix3*Vector3, Matrix3*Matrix3: 1 = rows 0,1 (c0+c1)+c2 + row 2 c0+(c1+c2); 0 = all (c0+c1)+c2; 2 = all c0+(c1+c2)
+#endif
+static inline Real sum3(Real a, Real b, Real c) {
+#if WD_SUM3_ORDER == 0
+  return (a + b) + c;
+#else
+  return a + (b + c);
+#endif
+}
+static inline Real trace3(Real a, Real b, Real c) {
+#if WD_TRACE_ORDER == 0
+  return (a + b) + c;
+#else
+  return a + (b + c);
+#endif
+}
+static inline Real rowsum3(int row, Real a, Real b, Real c) {
+#if WD_MATPROD_ORDER == 0
+  (void)row; return (a + b) + c;
+#elif WD_MATPROD_ORDER == 1
+  return row < 2 ? (a + b) + c : a + (b + c);
+#else
+  (void)row; return a + (b + c);
+#endif
+}
 static inline Real dot(const V3& a, const V3& b) { return sum3(a.x * b.x, a.y * b.y, a.z * b.z); }
 static inline Real sqNorm(const V3& a) { return dot(a, a); }
 static inline Real norm(const V3& a) { return std::sqrt(sqNorm(a)); }
@@ -74,8 +108,8 @@ struct M3 {  // column-major: c[j] is column j
   static M3 Identity() { M3 m; m.c[0].x = m.c[1].y = m.c[2].z = 1; return m; }
 };
 static inline V3 mulMV(const M3& m, const V3& v) {  // m*v, row-wise dot
-  return V3(sum3(m(0, 0) * v.x, m(0, 1) * v.y, m(0, 2) * v.z), sum3(m(1, 0) * v.x, m(1, 1) * v.y, m(1, 2) * v.z),
-            sum3(m(2, 0) * v.x, m(2, 1) * v.y, m(2, 2) * v.z));
+  return V3(rowsum3(0, m(0, 0) * v.x, m(0, 1) * v.y, m(0, 2) * v.z), rowsum3(1, m(1, 0) * v.x, m(1, 1) * v.y, m(1, 2) * v.z),
+            rowsum3(2, m(2, 0) * v.x, m(2, 1) * v.y, m(2, 2) * v.z));
 }
 static inline V3 mulMtV(const M3& m, const V3& v) {  // m^T*v = (col_j . v)
   return V3(dot(m.c[0], v), dot(m.c[1], v), dot(m.c[2], v));
@@ -119,7 +153,7 @@ struct Quat {
 // Eigen Quaternion(Matrix3) — quaternionbase_assign_impl<Other,3,3>; used at L6Geom.cpp:68,215
 static inline Quat quatFromMat(const M3& m) {
   Quat q;
-  Real t = (m(0, 0) + m(1, 1)) + m(2, 2);
+  Real t = trace3(m(0, 0), m(1, 1), m(2, 2));
   if (t > 0) {
     t = std::sqrt(t + 1.0);
     q.w = 0.5 * t;

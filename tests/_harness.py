@@ -9,11 +9,12 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "libdem_oracle.so")
 
 
-def build_oracle():
+def build_oracle(variant=""):
     src = os.path.join(ORACLE_DIR, "dem_oracle.cpp")
-    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+    so = os.path.join(ORACLE_DIR, "libdem_oracle%s.so" % ("_" + variant if variant else ""))
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
-    return ORACLE_SO
+    return so
 
 
 class OrcParams(C.Structure):
@@ -28,26 +29,26 @@ def _p(a, t):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(build_oracle())
+def lib(variant=""):
+    """variant "alt": the oracle built with every 3-term reduction order flipped (oracle/Makefile), for tests/test_order_sensitivity.py."""
+    if variant not in _libs:
+        L = C.CDLL(build_oracle(variant))
         L.orc_create.restype = C.c_void_p
         L.orc_last_error.restype = C.c_char_p
         for f in ("orc_get_dt", "orc_get_time", "orc_get_verlet_dist", "orc_pwave_dt", "orc_kinetic_energy"):
             getattr(L, f).restype = C.c_double
         for f in ("orc_get_step", "orc_num_contacts", "orc_get_contacts"):
             getattr(L, f).restype = C.c_long
-        _lib = L
-    return _lib
+        _libs[variant] = L
+    return _libs[variant]
 
 
 class Oracle:
-    def __init__(self, spec=None):
-        self.L = lib()
+    def __init__(self, spec=None, variant=""):
+        self.L = lib(variant)
         self.h = C.c_void_p(self.L.orc_create())
         if spec is not None:
             self.load(spec)

@@ -32,25 +32,37 @@ def nvcc():
     return p
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+# variant "alt": every 3-term reduction order flipped (wdem_math.cuh switches) -> libwdem_alt.so, loaded only by tests/test_order_sensitivity.py
+VARIANTS = {"": [], "alt": ["-DWD_SUM3_ORDER=1", "-DWD_TRACE_ORDER=0", "-DWD_MATPROD_ORDER=2"]}
+
+
+def lib_path(variant=""):
+    return LIB if not variant else os.path.join(HERE, "libwdem_%s.so" % variant)
+
+
+def needs_build(variant=""):
+    lib = lib_path(variant)
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not needs_build():
-        return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + nccl_flags()
+def build(force=False, verbose=False, extra=(), variant=""):
+    lib = lib_path(variant)
+    if not force and not needs_build(variant):
+        return lib
+    cmd = [nvcc()] + NVCC_FLAGS + VARIANTS[variant] + list(extra) + ["-o", lib] + [os.path.join(CSRC, s) for s in SOURCES] + nccl_flags()
     env = dict(os.environ)
     env.pop("CXX", None); env.pop("CC", None)
     cmd += ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd, env=env)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     build(force="-f" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "-v" in sys.argv else [])
+    if "--all" in sys.argv:
+        build(force="-f" in sys.argv, verbose=True, variant="alt")

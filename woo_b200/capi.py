@@ -5,7 +5,7 @@ import os
 import numpy as np
 from . import build as _build
 
-_LIB = None
+_LIBS = {}
 
 
 class WdemConfig(C.Structure):
@@ -35,26 +35,27 @@ EXPORTS = ["wdem_default_config", "wdem_create", "wdem_destroy", "wdem_last_erro
            "wdem_comm_init_local", "wdem_set_domain", "wdem_num_owned", "wdem_download_owned", "wdem_set_owned", "wdem_domain_stats"]
 
 
-def lib_path():
-    return _build.LIB
+def lib_path(variant=""):
+    return _build.lib_path(variant)
 
 
-def load(build=True):
-    global _LIB
-    if _LIB is None:
+def load(build=True, variant=""):
+    """variant "alt": libwdem_alt.so (flipped reduction orders, woo_b200/build.py), used only by the order-sensitivity test."""
+    if variant not in _LIBS:
+        path = _build.lib_path(variant)
         if build:
-            _build.build()
-        if not os.path.exists(_build.LIB):
-            raise RuntimeError("libwdem.so is missing: build it with `python -m woo_b200.build` (no CPU fallback exists)")
-        L = C.CDLL(os.environ.get("WDEM_LIB_VARIANT") or _build.LIB)   # WDEM_LIB_VARIANT: kernel-tuning experiments only
+            _build.build(variant=variant)
+        if not os.path.exists(path):
+            raise RuntimeError("%s is missing: build it with `python -m woo_b200.build --all` (no CPU fallback exists)" % os.path.basename(path))
+        L = C.CDLL((os.environ.get("WDEM_LIB_VARIANT") if not variant else None) or path)   # WDEM_LIB_VARIANT: kernel-tuning experiments only
         L.wdem_last_error.restype = C.c_char_p
         L.wdem_last_error.argtypes = [C.c_void_p]
         L.wdem_num_contacts.restype = C.c_int64
         L.wdem_download_contacts.restype = C.c_int64
         L.wdem_num_owned.restype = C.c_int64
         L.wdem_local_group_create.restype = C.c_void_p
-        _LIB = L
-    return _LIB
+        _LIBS[variant] = L
+    return _LIBS[variant]
 
 
 def ptr(a, t=None):

@@ -89,7 +89,11 @@ m33 mAdd(const m33& a, const m33& b) { m33 r; for (int i = 0; i < 9; i++) r.m[i]
 m33 mSub(const m33& a, const m33& b) { m33 r; for (int i = 0; i < 9; i++) r.m[i] = a.m[i] - b.m[i]; return r; }
 m33 mScale(const m33& a, double s) { m33 r; for (int i = 0; i < 9; i++) r.m[i] = a.m[i] * s; return r; }
 m33 mT(const m33& a) { m33 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[3 * i + j] = a.m[3 * j + i]; return r; }
-m33 mMul(const m33& a, const m33& b) { m33 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[3 * i + j] = (a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j]) + a.m[3 * i + 2] * b.m[6 + j]; return r; }
+m33 mMul(const m33& a, const m33& b) {   // Matrix3*Matrix3: column j of the result = a * (column j of b), row order per WD_MATPROD_ORDER
+  m33 r;
+  for (int j = 0; j < 3; j++) { const d3 c = mulMV(a, mk3(b.m[j], b.m[3 + j], b.m[6 + j])); r.m[j] = c.x; r.m[3 + j] = c.y; r.m[6 + j] = c.z; }
+  return r;
+}
 double mDet(const m33& a) { const double* m = a.m; return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]); }
 m33 mInv(const m33& a) {
   const double* m = a.m; double id = 1. / mDet(a); m33 r;

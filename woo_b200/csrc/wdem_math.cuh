@@ -1,11 +1,60 @@
 // wdem_math.cuh — float64 3-vector / quaternion helpers for the sm_100a DEM kernels.
-// Operation order is part of the contract: the translation unit is compiled with --fmad=false and every
-// reduction is left-to-right ((c0+c1)+c2), see DESIGN.md "Eigen semantics".  IEEE div/sqrt (fp64 default).
+// Operation order is part of the contract: the translation unit is compiled with --fmad=false and the order of
+// every 3-term reduction is fixed by the three switches below (the same names and defaults are used by
+// oracle/dem_oracle.cpp; DESIGN.md section 2 "Eigen semantics" has the analysis).  IEEE div/sqrt (fp64 default).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
 
+// The reference evaluates its 3-vector algebra with Eigen; Eigen is not available here, so the order in which Eigen adds the three
+// products of dot()/squaredNorm(), of Matrix3*Vector3 / Matrix3*Matrix3 and of Matrix3::trace() is restated from its sources.
+//   WD_SUM3_ORDER    dot / squaredNorm / norm of 3-vectors, Transpose<Matrix3>*Vector3:
+//                    0 = (c0+c1)+c2  [default: Eigen >= 3.3 on x86-64/SSE2, redux LinearVectorizedTraversal: one Packet2d + scalar tail]
+//                    1 = c0+(c1+c2)  [Eigen without vectorisation / Eigen 3.2: redux_novec_unroller splits by halves]
+//   WD_TRACE_ORDER   Matrix3::trace() inside Quaternion(Matrix3) (strided diagonal: never vectorised):
+//                    1 = c0+(c1+c2)  [default: redux_novec_unroller by halves]     0 = (c0+c1)+c2
+//   WD_MATPROD_ORDER rows of Matrix3*Vector3 and Matrix3*Matrix3 (coefficient-based lazy product):
+//                    1 = rows 0,1 (c0+c1)+c2 (Packet2d pmul/pmadd chain), row 2 c0+(c1+c2) (scalar tail through a strided row: novec redux)  [default]
+//                    0 = every row (c0+c1)+c2        2 = every row c0+(c1+c2) [no vectorisation]
+// tests/test_order_sensitivity.py runs the parity scenes under the flipped orders (libwdem_alt.so / libdem_oracle_alt.so) and shows
+// that the real-contact set is unchanged and forces move by < 1e-10 relative, i.e. that parity does not hinge on this choice.
+#ifndef WD_SUM3_ORDER
+#define WD_SUM3_ORDER 0
+#endif
+#ifndef WD_TRACE_ORDER
+#define WD_TRACE_ORDER 1
+#endif
+#ifndef WD_MATPROD_ORDER
+#define WD_MATPROD_ORDER 1
+#endif
+
 namespace wd {
+
+__host__ __device__ __forceinline__ double sum3(double a, double b, double c) {
+#if WD_SUM3_ORDER == 0
+  return (a + b) + c;
+#else
+  return a + (b + c);
+#endif
+}
+__host__ __device__ __forceinline__ double trace3(double a, double b, double c) {
+#if WD_TRACE_ORDER == 0
+  return (a + b) + c;
+#else
+  return a + (b + c);
+#endif
+}
+// row `ROW` of a coefficient-based 3x3 product
+template <int ROW>
+__host__ __device__ __forceinline__ double rowsum3(double a, double b, double c) {
+#if WD_MATPROD_ORDER == 0
+  return (a + b) + c;
+#elif WD_MATPROD_ORDER == 1
+  return ROW < 2 ? (a + b) + c : a + (b + c);
+#else
+  return a + (b + c);
+#endif
+}
 
 struct d3 {
   double x, y, z;
@@ -17,7 +66,7 @@ __host__ __device__ __forceinline__ d3 operator-(d3 a) { return mk3(-a.x, -a.y, 
 __host__ __device__ __forceinline__ d3 operator*(d3 a, double s) { return mk3(a.x * s, a.y * s, a.z * s); }
 __host__ __device__ __forceinline__ d3 operator*(double s, d3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
 __host__ __device__ __forceinline__ d3 operator/(d3 a, double s) { return mk3(a.x / s, a.y / s, a.z / s); }
-__host__ __device__ __forceinline__ double dot(d3 a, d3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__host__ __device__ __forceinline__ double dot(d3 a, d3 b) { return sum3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __host__ __device__ __forceinline__ double sqn(d3 a) { return dot(a, a); }
 __host__ __device__ __forceinline__ double nrm(d3 a) { return sqrt(sqn(a)); }
 __host__ __device__ __forceinline__ d3 cross(d3 a, d3 b) {
@@ -34,7 +83,7 @@ __host__ __device__ __forceinline__ q4 quatFromCols(d3 c0, d3 c1, d3 c2) {
   // m(i,j) = cj[i]
   const double m00 = c0.x, m10 = c0.y, m20 = c0.z, m01 = c1.x, m11 = c1.y, m21 = c1.z, m02 = c2.x, m12 = c2.y, m22 = c2.z;
   q4 q;
-  double t = (m00 + m11) + m22;
+  double t = trace3(m00, m11, m22);
   if (t > 0) {
     t = sqrt(t + 1.0);
     q.w = 0.5 * t;
@@ -72,8 +121,8 @@ __host__ __device__ __forceinline__ d3 quatRotate(q4 q, d3 v) {
 
 struct m33 { double m[9]; };  // row-major, host-prepared uniforms
 __host__ __device__ __forceinline__ d3 mulMV(const m33& M, d3 v) {
-  return mk3((M.m[0] * v.x + M.m[1] * v.y) + M.m[2] * v.z, (M.m[3] * v.x + M.m[4] * v.y) + M.m[5] * v.z,
-             (M.m[6] * v.x + M.m[7] * v.y) + M.m[8] * v.z);
+  return mk3(rowsum3<0>(M.m[0] * v.x, M.m[1] * v.y, M.m[2] * v.z), rowsum3<1>(M.m[3] * v.x, M.m[4] * v.y, M.m[5] * v.z),
+             rowsum3<2>(M.m[6] * v.x, M.m[7] * v.y, M.m[8] * v.z));
 }
 
 }  // namespace wd

@@ -13,8 +13,8 @@ class WdemError(RuntimeError):
 class Engine:
     """One DemField on one GPU.  Mirrors the C-ABI 1:1; arrays in, arrays out."""
 
-    def __init__(self, params=None, device=0, **kw):
-        self.L = capi.load()
+    def __init__(self, params=None, device=0, variant="", **kw):
+        self.L = capi.load(variant=variant)
         self.cfg = WdemConfig()
         self.L.wdem_default_config(C.byref(self.cfg))
         self.cfg.device = device
