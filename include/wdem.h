@@ -197,6 +197,9 @@ int wdem_download_owned(wdem_handle h, int32_t* ids, double* pos, double* ori, d
 /* Overwrite pos/vel/angVel (any may be NULL) of owned spheres addressed by Particle.id; fails if an id is not owned here. */
 int wdem_set_owned(wdem_handle h, int64_t n, const int32_t* ids, const double* pos, const double* vel, const double* angVel);
 int wdem_domain_stats(wdem_handle h, int64_t* nOwned, int64_t* nGhosts, int64_t* migratedOut, int64_t* migratedIn, int64_t* rowsIn);
+/* 1 if the per-step halo / dirty-flag exchange of this subdomain runs over NVLink peer memory (CUDA-IPC mailboxes), 0 if it uses the NCCL calls
+   (single-process transport, WDEM_NO_PEER, or a peer that could not be mapped); -1 on a bad handle. */
+int wdem_peer_active(wdem_handle h);
 
 /* Device-level info for bench.py: bytes allocated, stream pointer (cudaStream_t) */
 int wdem_device_info(wdem_handle h, int64_t* bytes_allocated, void** stream);

@@ -368,6 +368,7 @@ struct Scene {
   long step = 0; Real time = 0; Real nextDt = NaN;
   // collider state
   std::vector<Bound> BB[3]; std::vector<Real> minima, maxima; int nFullRuns = 0; bool conDirty = false; bool verletSet = false;
+  std::vector<int> freeIds; std::vector<int> lastAdded;   // ParticleContainer::freeIds (ParticleContainer.cpp:23-36,125); ids handed out by the last orc_add_spheres
   long dynDtStepLast = -1, dynDtStepPrev = -1;
   std::string err;
 
@@ -1284,14 +1285,23 @@ int orc_add_material(void* h, int kind, double density, double young, double ktD
 // bulk add; ids are assigned sequentially in call order (like S.dem.par.add). vel/angVel/ori may be NULL.
 int orc_add_spheres(void* h, int n, const double* pos, const double* radius, const double* mass, const double* inertia, const int* mat,
                     const unsigned* mask, const unsigned* flags, const double* vel, const double* angVel, const double* ori /*xyzw*/) {
-  Scene* S = (Scene*)h; int first = (int)S->par.size();
+  Scene* S = (Scene*)h; int first = -1; S->lastAdded.clear();
   for (int i = 0; i < n; i++) {
-    Sphere s; s.id = (int)S->par.size(); s.pos = V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]); s.radius = radius[i]; s.mass = mass[i]; s.inertia = inertia[i];
+    // ParticleContainer::findFreeId (ParticleContainer.cpp:23-36): ids freed by remove() are handed out again, oldest first; ids beyond the (shrunk, :152-155)
+    // container are dropped.  The restatement never shrinks its arrays, so the container size is 1 + the largest id still alive.
+    int size = 0;
+    for (int q = (int)S->par.size() - 1; q >= 0; q--) { const PRef& pr = S->par[q]; if (pr.kind != SHAPE_SPHERE || !S->sph[pr.idx].dead) { size = q + 1; break; } }
+    int id = size;
+    while (!S->freeIds.empty()) { const int f = S->freeIds.front(); S->freeIds.erase(S->freeIds.begin()); if (f <= size) { id = f; break; } }
+    if (first < 0) first = id;
+    S->lastAdded.push_back(id);
+    Sphere s; s.id = id; s.pos = V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]); s.radius = radius[i]; s.mass = mass[i]; s.inertia = inertia[i];
     s.mat = mat[i]; s.mask = mask ? mask[i] : 5u; s.flags = flags ? flags[i] : 0u;
     if (vel) s.vel = V3(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
     if (angVel) s.angVel = V3(angVel[3 * i], angVel[3 * i + 1], angVel[3 * i + 2]);
     if (ori) s.ori = Quat(ori[4 * i + 3], ori[4 * i], ori[4 * i + 1], ori[4 * i + 2]);
-    S->par.push_back(PRef{SHAPE_SPHERE, (int)S->sph.size()}); S->sph.push_back(s);
+    if (id < (int)S->par.size()) S->sph[S->par[id].idx] = s;      // a removed particle's id: the slot is taken over (nothing of the old particle survives)
+    else { S->par.push_back(PRef{SHAPE_SPHERE, (int)S->sph.size()}); S->sph.push_back(s); }
   }
   S->conDirty = true; return first;
 }
@@ -1344,8 +1354,8 @@ double orc_get_verlet_dist(void* h) { return ((Scene*)h)->P.verletDist; }
 int orc_get_nfullruns(void* h) { return ((Scene*)h)->nFullRuns; }
 double orc_pwave_dt(void* h) { return ((Scene*)h)->pWaveDt(); }
 double orc_kinetic_energy(void* h) { return ((Scene*)h)->kineticEnergy(); }
-// ParticleContainer::remove (ParticleContainer.cpp:121-157): the particle's contacts are deleted at once, the particle leaves the container (its id is not
-// handed out again here) and the contacts are marked dirty, so the collider re-initialises at the next step.  The restatement keeps the array slot and takes the
+// ParticleContainer::remove (ParticleContainer.cpp:121-157): the particle's contacts are deleted at once, the particle leaves the container (its id goes to
+// freeIds and is handed out again by the next add) and the contacts are marked dirty, so the collider re-initialises at the next step.  The restatement keeps the array slot and takes the
 // particle out of the game: no mask (never a collision candidate again), no motion, no forces; the getters skip it.
 int orc_remove_spheres(void* h, int n, const int* ids) {
   Scene* S = (Scene*)h;
@@ -1353,6 +1363,7 @@ int orc_remove_spheres(void* h, int n, const int* ids) {
   for (int k = 0; k < n; k++) {
     if (ids[k] < 0 || ids[k] >= (int)S->par.size() || S->par[ids[k]].kind != SHAPE_SPHERE || S->sph[S->par[ids[k]].idx].dead) throw std::runtime_error("remove: no such sphere #" + std::to_string(ids[k]));
     Sphere& sp = S->sph[S->par[ids[k]].idx];
+    S->freeIds.push_back(ids[k]);
     sp.dead = true; sp.mask = 0; sp.vel = V3(); sp.angVel = V3(); sp.force = V3(); sp.torque = V3(); sp.flags = DOF_ALL | GRAVITY_SKIP | ENERGY_SKIP | DAMPING_SKIP;
   }
   for (auto it = S->con.begin(); it != S->con.end();) {
@@ -1363,6 +1374,9 @@ int orc_remove_spheres(void* h, int n, const int* ids) {
   S->linDirty = true; S->conDirty = true;   // queued removal requests of erased contacts are skipped by removePending (key not found)
   ORC_CATCH(h)
 }
+// ids handed out by the last orc_add_spheres / ids of the live spheres in the order of orc_get_spheres
+int orc_last_added_ids(void* h, int* out) { Scene* S = (Scene*)h; for (size_t i = 0; i < S->lastAdded.size(); i++) out[i] = S->lastAdded[i]; return (int)S->lastAdded.size(); }
+void orc_get_sphere_ids(void* h, int* out) { Scene* S = (Scene*)h; size_t i = 0; for (auto& s : S->sph) if (!s.dead) out[i++] = s.id; }
 int orc_num_spheres(void* h) { int n = 0; for (auto& s : ((Scene*)h)->sph) if (!s.dead) n++; return n; }
 void orc_get_spheres(void* h, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque) {
   Scene* S = (Scene*)h;

@@ -141,6 +141,17 @@ class Oracle:
         return self.L.orc_add_spheres(self.h, C.c_int(len(radius)), _p(pos, C.c_double), _p(radius, C.c_double), _p(mass, C.c_double), _p(inertia, C.c_double),
                                       _p(mat, C.c_int), _p(mask, C.c_uint), _p(flags, C.c_uint), _p(vel, C.c_double), _p(angVel, C.c_double), None)
 
+    def last_added_ids(self, n):
+        """Ids ParticleContainer.add handed out in the last add_spheres (freed ids are reused oldest-first, ParticleContainer.cpp:23-36)."""
+        o = np.zeros(n, np.int32)
+        assert self.L.orc_last_added_ids(self.h, _p(o, C.c_int)) == n
+        return o
+
+    def sphere_ids(self):
+        o = np.zeros(self.L.orc_num_spheres(self.h), np.int32)
+        self.L.orc_get_sphere_ids(self.h, _p(o, C.c_int))
+        return o
+
     def remove_spheres(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         self._chk(self.L.orc_remove_spheres(self.h, C.c_int(len(ids)), _p(ids, C.c_int)))

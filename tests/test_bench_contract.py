@@ -21,7 +21,8 @@ def test_reference_arm_json_line():
 
 @pytest.mark.gpu
 def test_gpu_arm_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "40", "--warmup", "3", "--settle", "200", "--e2e-steps", "5", "--cpu-steps", "5", "--n", "200000"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "40", "--warmup", "3", "--settle", "200", "--e2e-steps", "5", "--cpu-steps", "5", "--n", "200000",
+                        "--cfg3-n", "200000", "--cfg4-n", "100000", "--cfg5-n", "100000", "--cfg-settle", "300", "--cfg1-cpu-steps", "100"],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
@@ -31,3 +32,8 @@ def test_gpu_arm_json_line():
     assert d["value"] > 0 and d["gpu_launches"] > 0 and d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.2 and d["roofline"]["peak"] > 1000
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and d["cpu_baseline"]["kind"] == "port"
+    assert "200000" in d["config"]["workload"] and d["config"]["n_spheres_total"] == 200000          # the label follows --n
+    assert set(d["configs"]) == {"cfg1_deposition_10k", "cfg3_hertz_4M", "cfg4_periodic_shear", "cfg5_drum_2M"}
+    for c in d["configs"].values():
+        assert c["value"] > 0 and c["n_spheres"] > 0 and "workload" in c
+    assert d["configs"]["cfg1_deposition_10k"]["same_window"]["cpu_port_value"] > 0

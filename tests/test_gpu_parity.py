@@ -67,7 +67,7 @@ def test_blocked_dofs_and_skips():
 
 
 def test_law_flags():
-    for kw in (dict(noSlip=1), dict(noFrict=1), dict(noRatch=1), dict(trsfRenorm=7), dict(damping=0.), dict(relRollStiff=.3, relTwistStiff=.2, rollTanPhi=.4)):
+    for kw in (dict(noSlip=1), dict(noFrict=1), dict(noRatch=1), dict(trsfRenorm=7), dict(damping=0.), dict(relRollStiff=.3, relTwistStiff=.2, rollTanPhi=.4), dict(applyForces=0)):
         S = sc.random_gas(200, box=.4, r=.02, seed=7)
         for k, v in kw.items():
             setattr(S.params, k, v)
@@ -485,7 +485,7 @@ def test_remove_spheres_mid_run(law):
         X.contacts(True)                                  # the table still refers to the old slots until the next step
     # a sphere added in the same breath (removal + insertion before the next collider run)
     m_, I_ = S.mass_inertia()
-    new_id = S.n + len(S.walls)                           # the id ParticleContainer.add hands out next (and the oracle does)
+    new_id = int(gone[0])                                 # the id ParticleContainer.add hands out next: the oldest freed one (findFreeId, ParticleContainer.cpp:23-36)
     newp = dict(pos=np.array([[.25, .25, .45]]), rad=np.array([.03]), vel=np.array([[0., 0., -2.]]))
     mass_new = S.mats[0][1] * (4 / 3.) * np.pi * newp["rad"] ** 3
     X.add_spheres(np.array([new_id], np.int32), newp["pos"], newp["rad"], mass_new, .4 * mass_new * newp["rad"] ** 2, vel=newp["vel"])
@@ -508,9 +508,11 @@ def test_remove_spheres_mid_run(law):
         X.step(50); Y.step(50); O.step(50)
         sx, sy, so = X.spheres(), Y.spheres(), O.spheres()
         assert len(sx["pos"]) == S.n - len(gone) + 1 == len(so["pos"])
+        # the engine lists spheres in upload order (the new one last), the oracle by container slot (the new one took over a freed slot): compare by id
+        ox, oo = np.argsort(cat(ids_all[keep], [new_id])), np.argsort(O.sphere_ids())
         for k_ in ("pos", "vel", "angVel", "force", "torque"):
             assert np.array_equal(sx[k_], sy[k_]), f"{k_} differs {50 * (k + 1)} steps after the removal"
-            assert np.array_equal(sx[k_], so[k_]), f"{k_} differs from the oracle {50 * (k + 1)} steps after the removal"
+            assert np.array_equal(sx[k_][ox], so[k_][oo]), f"{k_} differs from the oracle {50 * (k + 1)} steps after the removal"
         assert X.scalars()["nFullRuns"] == O.nFullRuns
         cx, cy = X.contacts(True), Y.contacts(True)
         assert np.array_equal(cx["ids"], cy["ids"]) and not np.isin(cx["ids"], gone).any()
@@ -518,3 +520,42 @@ def test_remove_spheres_mid_run(law):
             assert np.array_equal(cx[k_], cy[k_]), k_
     with pytest.raises(WdemError):
         X.remove_spheres(gone[:1])                        # already gone
+
+
+# A freed id is handed out again (ParticleContainer::findFreeId): the newcomer must not inherit anything from the removed particle's contacts, even when it lands
+# right where the old one was and touches the same partners before the next collider run (round-1 advisor finding).
+@pytest.mark.parametrize("law", [sc.LAW_IDEALELPL, sc.LAW_HERTZ_DMT])
+def test_id_reuse_after_remove_starts_with_fresh_contacts(law):
+    import math
+    S = sc.random_gas(300, box=.45, r=.02, psd_ratio=2.0, seed=131, law=law, en=.6 if law else float("nan")); S.params.dynDtPeriod = 0
+    O = Oracle(S); E = engine_for(S)
+    O.step(120); E.step(120)
+    c = E.contacts(True); s = E.spheres()
+    ss = c["ids"][(c["ids"][:, 0] < S.n) & (np.abs(c["force"][:, 1:]).max(axis=1) > 0)]          # sphere-sphere contacts that carry shear history
+    cnt = np.bincount(ss.reshape(-1), minlength=S.n)
+    g = int(np.argmax(cnt)); assert cnt[g] >= 2, "need a sphere with several sheared contacts"
+    partners = set(int(x) for x in ss[(ss == g).any(axis=1)].reshape(-1)) - {g}
+    E.remove_spheres(np.array([g], np.int32)); O.remove_spheres(np.array([g], np.int32))
+    pos = s["pos"][g:g + 1].copy(); rad = S.radius[g:g + 1] * .97; vel = np.array([[.3, -.2, .1]]); ang = np.array([[5., 0., -3.]])
+    mass = S.mats[0][1] * (4 / 3.) * math.pi * rad ** 3; inertia = .4 * mass * rad ** 2
+    assert O.add_spheres(pos, rad, mass, inertia, np.zeros(1, np.int32), vel=vel, angVel=ang) == g          # the same id again
+    E.add_spheres(np.array([g], np.int32), pos, rad, mass, inertia, vel=vel, angVel=ang)
+    step0 = E.scalars()["step"]
+    ids_e = np.concatenate([np.delete(S.sphere_ids(), g), [g]])
+    for k in range(1, 4):
+        n = 1 if k == 1 else 30
+        O.step(n); E.step(n)
+        so, sg = O.spheres(), E.spheres()
+        oo, oe = np.argsort(O.sphere_ids()), np.argsort(ids_e)
+        for k_ in ("pos", "vel", "angVel", "force", "torque"):
+            assert np.array_equal(so[k_][oo], sg[k_][oe]), f"{k_} differs from the oracle after id reuse (check {k})"
+        co, cg = O.contacts(True), E.contacts(True)
+        assert [tuple(x) for x in co["ids"]] == [tuple(x) for x in cg["ids"]]
+        for k_ in ("uN", "force", "trsf", "stepCreated"):
+            assert np.array_equal(co[k_], cg[k_]), f"contact {k_} differs from the oracle after id reuse"
+        if k == 1:
+            mine = (cg["ids"] == g).any(axis=1)
+            touched = set(int(x) for x in cg["ids"][mine].reshape(-1)) - {g}
+            assert touched & partners, "the newcomer should touch partners of the removed sphere"
+            assert (cg["stepCreated"][mine] == step0).all() and np.all(cg["force"][mine][:, 1:] == 0.), "contacts of the newcomer must be fresh: created now, no shear history"
+    assert O.nFullRuns == E.scalars()["nFullRuns"]

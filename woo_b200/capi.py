@@ -32,7 +32,7 @@ EXPORTS = ["wdem_default_config", "wdem_create", "wdem_destroy", "wdem_last_erro
            "wdem_set_next_gradv", "wdem_get_cell", "wdem_step", "wdem_step_e2e", "wdem_download_state", "wdem_download_forces",
            "wdem_set_state", "wdem_num_contacts", "wdem_download_contacts", "wdem_upload_contacts", "wdem_set_scene", "wdem_get_stress", "wdem_download_walls", "wdem_track_energy", "wdem_get_energy", "wdem_upload_facet_groups", "wdem_download_facets", "wdem_crit_dt", "wdem_kinetic_energy", "wdem_get_scalars",
            "wdem_device_info", "wdem_comm_unique_id", "wdem_comm_init_nccl", "wdem_local_group_create", "wdem_local_group_destroy",
-           "wdem_comm_init_local", "wdem_set_domain", "wdem_num_owned", "wdem_download_owned", "wdem_set_owned", "wdem_domain_stats"]
+           "wdem_comm_init_local", "wdem_set_domain", "wdem_num_owned", "wdem_download_owned", "wdem_set_owned", "wdem_domain_stats", "wdem_peer_active"]
 
 
 def lib_path(variant=""):

@@ -105,12 +105,14 @@ __global__ void __launch_bounds__(128) k_dom_count_rows(const int* __restrict__ 
 __device__ __forceinline__ void crec_from(const Contacts& O, long long co, int idA, int idB, int law, int rolling, int periodic, CRec& r) {
   r.idA = idA; r.idB = idB; r.flags = O.flags[co]; r.stepCreated = O.stepCreated[co]; r.pad = 0;
   r.cd[0] = periodic ? O.cdx[co] : 0; r.cd[1] = periodic ? O.cdy[co] : 0; r.cd[2] = periodic ? O.cdz[co] : 0;
-  r.t[0] = O.t0x[co]; r.t[1] = O.t0y[co]; r.t[2] = O.t0z[co]; r.t[3] = O.t1x[co]; r.t[4] = O.t1y[co]; r.t[5] = O.t1z[co];
-  r.cp = O.cp[co]; r.fl[0] = O.fn[co]; r.fl[1] = O.ft0[co]; r.fl[2] = O.ft1[co];
-  for (int k = 0; k < 3; k++) r.ph[k] = O.ph[k][co];
-  r.ph[3] = law == 1 ? O.ph[3][co] : 0.; r.ph[4] = law == 1 ? O.ph[4][co] : 0.;
-  r.tq[0] = rolling ? O.tq0[co] : 0.; r.tq[1] = rolling ? O.tq1[co] : 0.; r.tq[2] = rolling ? O.tq2[co] : 0.;
-  r.Fg = O.Fg[co];
+  const double4 r0 = O.rec[4 * co], r1 = O.rec[4 * co + 1], r3 = O.rec[4 * co + 3], p = O.ph[co];
+  r.t[0] = r0.x; r.t[1] = r0.y; r.t[2] = r0.z; r.t[3] = r1.x; r.t[4] = r1.y; r.t[5] = r1.z;
+  r.cp = O.rec[4 * co + 2]; r.fl[0] = r3.w; r.fl[1] = r0.w; r.fl[2] = r1.w;
+  r.ph[0] = p.x; r.ph[1] = p.y; r.ph[2] = p.z;
+  r.ph[3] = law == 1 ? p.w : 0.; r.ph[4] = law == 1 ? O.ph4[co] : 0.;
+  double4 tq = make_double4(0, 0, 0, 0); if (rolling) tq = O.tq[co];
+  r.tq[0] = tq.x; r.tq[1] = tq.y; r.tq[2] = tq.z;
+  r.Fg = make_double4(r3.x, r3.y, r3.z, 0.);
 }
 __global__ void __launch_bounds__(128) k_dom_pack_rows(const int* __restrict__ slots, int first, int cnt, OldCsr oc, Contacts O, const int32_t* __restrict__ sid,
                                                       const Wall* __restrict__ walls, const Facet* __restrict__ facets, const int* __restrict__ rowOff, int law, int rolling,
@@ -143,12 +145,11 @@ __global__ void __launch_bounds__(256) k_dom_unpack_rows(Contacts O, long long b
   O.flags[co] = (r.flags & (CF_KIND_MASK | CF_REAL)) | (uploaded ? 0u : (uint32_t)CF_CLAIMED);
   O.stepCreated[co] = r.stepCreated;
   if (periodic) { O.cdx[co] = r.cd[0]; O.cdy[co] = r.cd[1]; O.cdz[co] = r.cd[2]; }
-  O.t0x[co] = r.t[0]; O.t0y[co] = r.t[1]; O.t0z[co] = r.t[2]; O.t1x[co] = r.t[3]; O.t1y[co] = r.t[4]; O.t1z[co] = r.t[5];
-  O.cp[co] = r.cp; O.fn[co] = r.fl[0]; O.ft0[co] = r.fl[1]; O.ft1[co] = r.fl[2];
-  for (int q = 0; q < 3; q++) O.ph[q][co] = r.ph[q];
-  if (law == 1) { O.ph[3][co] = r.ph[3]; O.ph[4][co] = r.ph[4]; }
-  if (rolling) { O.tq0[co] = r.tq[0]; O.tq1[co] = r.tq[1]; O.tq2[co] = r.tq[2]; }
-  O.Fg[co] = r.Fg;
+  O.rec[4 * co] = make_double4(r.t[0], r.t[1], r.t[2], r.fl[1]); O.rec[4 * co + 1] = make_double4(r.t[3], r.t[4], r.t[5], r.fl[2]);
+  O.rec[4 * co + 2] = r.cp; O.rec[4 * co + 3] = make_double4(r.Fg.x, r.Fg.y, r.Fg.z, r.fl[0]);
+  O.ph[co] = make_double4(r.ph[0], r.ph[1], r.ph[2], law == 1 ? r.ph[3] : 0.);
+  if (law == 1) O.ph4[co] = r.ph[4];
+  if (rolling) O.tq[co] = make_double4(r.tq[0], r.tq[1], r.tq[2], 0.);
   keys[k] = ((unsigned long long)(uint32_t)r.idA << 32) | (uint32_t)r.idB;
   vals[k] = (int)co;
 }

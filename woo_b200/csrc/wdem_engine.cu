@@ -61,23 +61,22 @@ struct SphereStore {
 };
 
 struct ContactStore {
-  DBuf<int2> pair; DBuf<uint32_t> flags, realBits; DBuf<int32_t> stepCreated, cd[3]; DBuf<double> t[6], fl[3], ph[5], tq[3]; DBuf<double4> cp, Fg, Tg;
+  DBuf<int2> pair; DBuf<uint32_t> flags, realBits; DBuf<int32_t> stepCreated, cd[3]; DBuf<double4> rec, ph, tq, Tg; DBuf<double> ph4;
   size_t cap = 0;
   void ensure(size_t n, int64_t& tot, bool hertz, bool rolling, bool periodic, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return;
     n = std::max(n, cap + cap / 2);
     pair.ensure(n, tot, keep, st); flags.ensure(n, tot, keep, st); stepCreated.ensure(n, tot, keep, st);
     if (periodic) for (auto& b : cd) b.ensure(n, tot, keep, st);
-    for (auto& b : t) b.ensure(n, tot, keep, st); for (auto& b : fl) b.ensure(n, tot, keep, st);
-    for (int k = 0; k < (hertz ? 5 : 3); k++) ph[k].ensure(n, tot, keep, st);
-    if (rolling) { for (auto& b : tq) b.ensure(n, tot, keep, st); Tg.ensure(n, tot, keep, st); }
-    cp.ensure(n, tot, keep, st); Fg.ensure(n, tot, keep, st); realBits.ensure(n / 32 + 2, tot, keep, st);
+    rec.ensure(4 * n, tot, keep, st); ph.ensure(n, tot, keep, st);
+    if (hertz) ph4.ensure(n, tot, keep, st);
+    if (rolling) { tq.ensure(n, tot, keep, st); Tg.ensure(n, tot, keep, st); }
+    realBits.ensure(n / 32 + 2, tot, keep, st);
     cap = n;
   }
   Contacts view() { Contacts C; C.pair = pair.p; C.flags = flags.p; C.stepCreated = stepCreated.p; C.cdx = cd[0].p; C.cdy = cd[1].p; C.cdz = cd[2].p;
-    C.t0x = t[0].p; C.t0y = t[1].p; C.t0z = t[2].p; C.t1x = t[3].p; C.t1y = t[4].p; C.t1z = t[5].p; C.cp = cp.p; C.fn = fl[0].p; C.ft0 = fl[1].p; C.ft1 = fl[2].p;
-    for (int k = 0; k < 5; k++) C.ph[k] = ph[k].p; C.tq0 = tq[0].p; C.tq1 = tq[1].p; C.tq2 = tq[2].p; C.Fg = Fg.p; C.Tg = Tg.p; C.realBits = realBits.p; return C; }
-  void release() { pair.release(); flags.release(); stepCreated.release(); for (auto& b : cd) b.release(); for (auto& b : t) b.release(); for (auto& b : fl) b.release(); for (auto& b : ph) b.release(); for (auto& b : tq) b.release(); cp.release(); Fg.release(); Tg.release(); realBits.release(); cap = 0; }
+    C.rec = rec.p; C.ph = ph.p; C.ph4 = ph4.p; C.tq = tq.p; C.Tg = Tg.p; C.realBits = realBits.p; return C; }
+  void release() { pair.release(); flags.release(); stepCreated.release(); for (auto& b : cd) b.release(); rec.release(); ph.release(); ph4.release(); tq.release(); Tg.release(); realBits.release(); cap = 0; }
 };
 
 struct CsrStore { DBuf<int> rowStart; DBuf<uint32_t> rowEntry; DBuf<int32_t> rowOther; bool valid = false; int nRows = 0; void release() { rowStart.release(); rowEntry.release(); rowOther.release(); } };
@@ -973,9 +972,10 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   if (side) { CK(cudaEventRecord(E->evJoin, st2)); CK(cudaStreamWaitEvent(st, E->evJoin, 0)); }
   if (ev) CK(cudaEventRecord(ev[3], st));
   const int nNow = E->n;   // a full run of a decomposed scene changes the local sphere count (migration, ghosts)
-  if (nNow > 0 && c.applyForces) {
+  if (nNow > 0 && (c.applyForces || c.reset)) {
+    // ContactLoop.applyForces=False: no contact force is applied, but Leapfrog.reset still sets force = gravity*mass, torque = 0 (Leapfrog.cpp:240-245): null rows
     CsrStore& R = E->csr[E->curR];
-    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, R.rowStart.p, R.rowEntry.p, u, guard); E->launches++;
+    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard); E->launches++;
   }
   if (ev) CK(cudaEventRecord(ev[4], st));
 }
@@ -1274,6 +1274,13 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
       const Material& m = h->hMats[mt[i]];
       pw = std::min(pw, radius[i] / (1. * std::sqrt(m.young / m.density)));  // DemFuncs::pWaveDt (Funcs.cpp:151-175)
     }
+    {   // Particle.id is the key of id2slot and of the contact history: duplicates would silently corrupt both
+      std::vector<int32_t> srt(id); std::sort(srt.begin(), srt.end());
+      auto dup = std::adjacent_find(srt.begin(), srt.end());
+      if (dup != srt.end()) throw EngErr{"wdem_upload_spheres: duplicate particle id " + std::to_string(*dup), WDEM_ERR_INVALID};
+      for (auto& w : h->hWalls) if (std::binary_search(srt.begin(), srt.end(), w.id)) throw EngErr{"wdem_upload_spheres: particle id " + std::to_string(w.id) + " is already used by a wall", WDEM_ERR_INVALID};
+      for (auto& f : h->hFacets) if (std::binary_search(srt.begin(), srt.end(), f.id)) throw EngErr{"wdem_upload_spheres: particle id " + std::to_string(f.id) + " is already used by a facet", WDEM_ERR_INVALID};
+    }
     h->n = (int)n; h->minRadius = minR; h->pwaveDt = pw; h->maxId = maxId;
     h->hIds.assign(id.begin(), id.end()); h->pendingRows.clear(); h->compactPending = false;
     h->cur = 0;
@@ -1383,6 +1390,10 @@ int wdem_remove_spheres(wdem_handle h, int64_t m, const int32_t* ids) {
       CK(cudaMemcpyAsync(h->dom.oldIds.p, A.id.p, (size_t)n0 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     }
     k_keep_flag<<<nblk(n0, 256), 256, 0, st>>>(A.up.p, n0, h->idx.p, h->counts.p);
+    if (h->csr[h->curR].valid && h->nC > 0) {   // the removed particles' contacts go with them (before id2slot forgets where their rows are)
+      CsrStore& R = h->csr[h->curR]; ContactStore& cs = h->con[h->curC];
+      k_kill_rows<<<nblk(n0, 256), 256, 0, st>>>(A.id.p, n0, h->counts.p, h->id2slot.p, R.rowStart.p, R.rowEntry.p, R.nRows, cs.flags.p, cs.realBits.p); h->launches++;
+    }
     exclusiveSum(h, h->counts.p, h->offsets.p, n0);
     k_compact_spheres<<<nblk(n0, 256), 256, 0, st>>>(B.view(), A.view(), n0, h->counts.p, h->offsets.p, h->idx.p, h->id2slot.p, h->dom.origSlot.p);
     CK(cudaStreamSynchronize(st));   // newUpOf is pageable host memory
@@ -1587,22 +1598,23 @@ int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torqu
     // wall-sphere contacts live in [nSS, nSS+nWS) and among the orphans; forces are added per wall in ascending id of the sphere, the order of
     // the per-particle contact map the reference walks (Particle.hpp:36)
     const long long nC = h->nC; ContactStore& cs = h->con[h->curC];
-    auto flags = d2h(cs.flags.p, nC, st); auto pair = d2h(cs.pair.p, nC, st); auto Fg = d2h(cs.Fg.p, nC, st); auto cp = d2h(cs.cp.p, nC, st);
+    auto flags = d2h(cs.flags.p, nC, st); auto pair = d2h(cs.pair.p, nC, st); auto rec = d2h(cs.rec.p, 4 * (size_t)nC, st);
+    auto Fg = [&](long long c) { return rec[4 * c + 3]; }; auto cp = [&](long long c) { return rec[4 * c + 2]; };
     auto sid = d2h(h->S().id, h->n, st); auto sfl = d2h(h->S().flags, h->n, st);
     const bool rolling = (h->cfg.relRollStiff > 0. && h->cfg.rollTanPhi > 0.);
     std::vector<double4> Tg; if (rolling) Tg = d2h(cs.Tg.p, nC, st);
     struct Row { int wall, sid; long long c; };
     std::vector<Row> rows;
     for (long long c = 0; c < nC; c++) {
-      if (!(flags[c] & CF_REAL) || (flags[c] & CF_DEAD) || cf_kind(flags[c]) != KIND_WS || Fg[c].w == 0.) continue;
+      if (!(flags[c] & CF_REAL) || (flags[c] & CF_DEAD) || cf_kind(flags[c]) != KIND_WS) continue;
       if (sfl[pair[c].y] & F_GHOST) continue;
       rows.push_back(Row{pair[c].x, sid[pair[c].y], c});
     }
     std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.wall != b.wall ? a.wall < b.wall : a.sid < b.sid; });
     std::vector<d3> F(nW, mk3(0, 0, 0)), T(nW, mk3(0, 0, 0));
     for (const Row& r : rows) {
-      const d3 Fc = xyz(Fg[r.c]);                                     // wall = pA: sign +1 (Contact.cpp:28-31)
-      const d3 xc = xyz(cp[r.c]) - mk3(W[r.wall].pos[0], W[r.wall].pos[1], W[r.wall].pos[2]);
+      const d3 Fc = xyz(Fg(r.c));                                     // wall = pA: sign +1 (Contact.cpp:28-31)
+      const d3 xc = xyz(cp(r.c)) - mk3(W[r.wall].pos[0], W[r.wall].pos[1], W[r.wall].pos[2]);
       d3 Tc = cross(xc, Fc);
       if (rolling) Tc = Tc + xyz(Tg[r.c]);
       F[r.wall] = F[r.wall] + Fc; T[r.wall] = T[r.wall] + Tc;
@@ -1697,13 +1709,17 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
     cudaStream_t st = h->stream; ContactStore& cs = h->con[h->curC];
     auto pair = d2h(cs.pair.p, nC, st); auto flags = d2h(cs.flags.p, nC, st); auto sid = d2h(h->S().id, h->n, st);
     std::vector<uint32_t> sfl; if (h->comm) sfl = d2h(h->S().flags, h->n, st);
-    std::vector<std::vector<double>> t(6), f(3), ph(5), tq(3);
-    for (int k = 0; k < 6; k++) t[k] = d2h(cs.t[k].p, nC, st);
-    for (int k = 0; k < 3; k++) f[k] = d2h(cs.fl[k].p, nC, st);
     const bool hertz = h->cfg.law == WDEM_LAW_HERTZ_DMT, rolling = (h->cfg.relRollStiff > 0. && h->cfg.rollTanPhi > 0.);
-    for (int k = 0; k < (hertz ? 5 : 3); k++) ph[k] = d2h(cs.ph[k].p, nC, st);
-    if (rolling) for (int k = 0; k < 3; k++) tq[k] = d2h(cs.tq[k].p, nC, st);
-    auto cp = d2h(cs.cp.p, nC, st); auto sc = d2h(cs.stepCreated.p, nC, st);
+    auto rec = d2h(cs.rec.p, 4 * (size_t)nC, st); auto php = d2h(cs.ph.p, nC, st);
+    std::vector<double> ph4v; if (hertz) ph4v = d2h(cs.ph4.p, nC, st);
+    std::vector<double4> tqv; if (rolling) tqv = d2h(cs.tq.p, nC, st);
+    auto sc = d2h(cs.stepCreated.p, nC, st);
+    // views of the 128-byte record (wdem_kernels.cuh: struct Contacts)
+    auto tcol = [&](int k, long long c) { const double4& v = rec[4 * c + (k / 3)]; return (k % 3) == 0 ? v.x : ((k % 3) == 1 ? v.y : v.z); };
+    auto fl = [&](int k, long long c) { return k == 0 ? rec[4 * c + 3].w : (k == 1 ? rec[4 * c].w : rec[4 * c + 1].w); };
+    auto phk = [&](int k, long long c) { const double4& v = php[c]; return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : (k == 3 ? v.w : ph4v[c]))); };
+    auto tqk = [&](int k, long long c) { const double4& v = tqv[c]; return k == 0 ? v.x : (k == 1 ? v.y : v.z); };
+    auto cp = [&](long long c) { return rec[4 * c + 2]; };
     std::vector<int32_t> cdv[3];
     if (h->cfg.periodic) for (int k = 0; k < 3; k++) cdv[k] = d2h(cs.cd[k].p, nC, st);
     struct Row { uint64_t key; long long c; };
@@ -1724,23 +1740,23 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
       if (ids) { ids[2 * i] = (int32_t)(rows[i].key >> 32); ids[2 * i + 1] = (int32_t)(rows[i].key & 0xFFFFFFFFu); }
       if (cellDist) for (int k = 0; k < 3; k++) cellDist[3 * i + k] = h->cfg.periodic ? cdv[k][c] : 0;
       if (real) real[i] = isReal;
-      if (uN) uN[i] = isReal ? cp[c].w : NAN;
-      if (forceLocal) for (int k = 0; k < 3; k++) forceLocal[3 * i + k] = isReal ? f[k][c] : 0.;
-      if (torqueLocal) for (int k = 0; k < 3; k++) torqueLocal[3 * i + k] = (isReal && rolling) ? tq[k][c] : 0.;
+      if (uN) uN[i] = isReal ? cp(c).w : NAN;
+      if (forceLocal) for (int k = 0; k < 3; k++) forceLocal[3 * i + k] = isReal ? fl(k, c) : 0.;
+      if (torqueLocal) for (int k = 0; k < 3; k++) torqueLocal[3 * i + k] = (isReal && rolling) ? tqk(k, c) : 0.;
       if (trsf) {
-        d3 c0 = mk3(t[0][c], t[1][c], t[2][c]), c1 = mk3(t[3][c], t[4][c], t[5][c]); d3 c2 = cross(c0, c1);
+        d3 c0 = mk3(tcol(0, c), tcol(1, c), tcol(2, c)), c1 = mk3(tcol(3, c), tcol(4, c), tcol(5, c)); d3 c2 = cross(c0, c1);
         double* o = trsf + 9 * i;
         if (isReal) { o[0] = c0.x; o[1] = c0.y; o[2] = c0.z; o[3] = c1.x; o[4] = c1.y; o[5] = c1.z; o[6] = c2.x; o[7] = c2.y; o[8] = c2.z; }
         else for (int k = 0; k < 9; k++) o[k] = (k % 4 == 0) ? 1. : 0.;
       }
-      if (contPt) { contPt[3 * i] = isReal ? cp[c].x : NAN; contPt[3 * i + 1] = isReal ? cp[c].y : NAN; contPt[3 * i + 2] = isReal ? cp[c].z : NAN; }
+      if (contPt) { contPt[3 * i] = isReal ? cp(c).x : NAN; contPt[3 * i + 1] = isReal ? cp(c).y : NAN; contPt[3 * i + 2] = isReal ? cp(c).z : NAN; }
       if (phys) {
         if (!isReal) { phys[3 * i] = phys[3 * i + 1] = phys[3 * i + 2] = NAN; }
-        else if (!hertz) { phys[3 * i] = ph[0][c]; phys[3 * i + 1] = ph[1][c]; phys[3 * i + 2] = ph[2][c]; }
-        else { double u_ = cp[c].w; phys[3 * i] = (3 / 2.) * ph[0][c] * std::sqrt(-u_); phys[3 * i + 1] = ph[1][c] * std::sqrt(u_ < 0 ? -u_ : 0); phys[3 * i + 2] = ph[2][c]; }
+        else if (!hertz) { phys[3 * i] = phk(0, c); phys[3 * i + 1] = phk(1, c); phys[3 * i + 2] = phk(2, c); }
+        else { double u_ = cp(c).w; phys[3 * i] = (3 / 2.) * phk(0, c) * std::sqrt(-u_); phys[3 * i + 1] = phk(1, c) * std::sqrt(u_ < 0 ? -u_ : 0); phys[3 * i + 2] = phk(2, c); }
       }
       if (stepCreated) stepCreated[i] = sc[c];
-      if (physRaw) for (int k = 0; k < 5; k++) physRaw[5 * i + k] = (isReal && k < (hertz ? 5 : 3)) ? ph[k][c] : 0.;
+      if (physRaw) for (int k = 0; k < 5; k++) physRaw[5 * i + k] = (isReal && k < (hertz ? 5 : 3)) ? phk(k, c) : 0.;
     }
   });
   return rc ? -1 : nOut;
@@ -1869,6 +1885,8 @@ int wdem_domain_stats(wdem_handle h, int64_t* nOwned, int64_t* nGhosts, int64_t*
     if (migratedOut) *migratedOut = h->dom.migratedOut; if (migratedIn) *migratedIn = h->dom.migratedIn; if (rowsIn) *rowsIn = h->dom.rowsIn;
   });
 }
+
+int wdem_peer_active(wdem_handle h) { return h ? ((h->comm && h->dom.peer.active) ? 1 : 0) : -1; }
 
 int wdem_device_info(wdem_handle h, int64_t* bytes, void** stream) { return guarded(h, [&] { if (bytes) *bytes = h->bytes; if (stream) *stream = (void*)h->stream; }); }
 

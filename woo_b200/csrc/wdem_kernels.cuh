@@ -45,17 +45,20 @@ struct GroupsU { int n; GroupU g[WD_MAX_GROUPS]; };
 struct FacetGrid { double ox, oy, oz, inv; int nx, ny, nz; const int* cellStart; const int* cellFacet; };
 struct Material { int32_t kind; int32_t pad; double density, young, ktDivKn, tanPhi, surfEnergy, alpha; };
 
-struct Contacts {         // SoA planes, one entry per candidate pair (real or potential)
+struct Contacts {         // one entry per candidate pair (real or potential)
   int2* pair;             // SS: (slotA, slotB) with id[slotA] < id[slotB]; WS: (wall index, slot); FS: (facet index, slot)
   uint32_t* flags;
   int32_t* stepCreated;
   int32_t *cdx, *cdy, *cdz;            // Contact.cellDist (periodic only)
-  double *t0x, *t0y, *t0z, *t1x, *t1y, *t1z;  // L6Geom.trsf columns 0 and 1 (column 2 = c0 x c1, recomputed bit-identically)
-  double4* cp;            // contact point xyz (CGeom.node.pos), w = uN
-  double *fn, *ft0, *ft1; // CPhys.force in the local frame
-  double* ph[5];          // linear: kn, kt, tanPhi ; Hertz: kn0=K*sqrt(R), kt0, tanPhi, alpha_sqrtMK, Fna=4*pi*R*gamma
-  double *tq0, *tq1, *tq2;  // CPhys.torque (only with rolling/twisting resistance)
-  double4* Fg;            // global force on pA (xyz), w = 1 if the contact is real in this step else 0
+  // The persistent state of a contact is ONE 128-byte record = one cache line (4 x double4), rec[4c+k]:
+  //   k=0: L6Geom.trsf column 0 (xyz), w = CPhys.force[1] (ft0)        k=1: trsf column 1 (xyz), w = CPhys.force[2] (ft1)
+  //   k=2: contact point CGeom.node.pos (xyz), w = uN                   k=3: global force on pA (xyz), w = CPhys.force[0] (fn)
+  // (trsf column 2 = c0 x c1 is recomputed bit-identically.)  The contact kernel reads k=0..2 and writes the whole line; the force reduction gathers the second
+  // half (k=2,3: one 64-byte fetch per incidence instead of two sectors in two planes); the history carry-over of a full run copies one line per contact.
+  double4* rec;
+  double4* ph;            // Cp2 constants, written once at creation: linear (kn, kt, tanPhi, -); Hertz (kn0=K*sqrt(R), kt0, tanPhi, alpha_sqrtMK)
+  double* ph4;            // Hertz only: Fna=4*pi*R*gamma (or -1: alpha!=0)
+  double4* tq;            // CPhys.torque xyz (only with rolling/twisting resistance)
   double4* Tg;            // global contact torque on pA (rolling resistance only)
   uint32_t* realBits;     // 1 bit per contact: real (CF_REAL and not dead); set at full runs (k_realbits), flipped by the contact kernels when a contact is
                           // created / broken.  Half a megabyte for 4 M candidates, i.e. L2-resident: the force reduction tests it instead of gathering Fg.
@@ -292,10 +295,11 @@ __device__ __noinline__ void report_error(Counters* cnt, int code, const ErrCtx&
 struct Hist { d3 t0, t1; double4 cp; double ft0, ft1, ph0, ph1, ph2, ph3, ph4; };
 template <int LAW>
 __device__ __forceinline__ void load_hist(const Contacts& C, long long c, Hist& H) {
-  H.t0 = mk3(C.t0x[c], C.t0y[c], C.t0z[c]); H.t1 = mk3(C.t1x[c], C.t1y[c], C.t1z[c]);
-  H.cp = C.cp[c]; H.ft0 = C.ft0[c]; H.ft1 = C.ft1[c];
-  H.ph0 = C.ph[0][c]; H.ph1 = C.ph[1][c]; H.ph2 = C.ph[2][c];
-  if ((LAW & 1) == 1) { H.ph3 = C.ph[3][c]; H.ph4 = C.ph[4][c]; }
+  const double4 a = C.rec[4 * c], b = C.rec[4 * c + 1], p = C.ph[c];
+  H.cp = C.rec[4 * c + 2];
+  H.t0 = xyz(a); H.ft0 = a.w; H.t1 = xyz(b); H.ft1 = b.w;
+  H.ph0 = p.x; H.ph1 = p.y; H.ph2 = p.z;
+  if ((LAW & 1) == 1) { H.ph3 = p.w; H.ph4 = C.ph4[c]; }
 }
 
 template <int LAW>
@@ -325,7 +329,7 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
       kn = 1 / (1 / (m1.young * A / l0) + 1 / (m2.young * A / l1));
       kt = .5 * (m1.ktDivKn + m2.ktDivKn) * kn;
       tanPhi = fmin(m1.tanPhi, m2.tanPhi);
-      C.ph[0][c] = kn; C.ph[1][c] = kt; C.ph[2][c] = tanPhi;
+      C.ph[c] = make_double4(kn, kt, tanPhi, 0.);
     } else {         // Cp2_HertzMat_HertzPhys::go (Hertz.cpp:34-77)
       if (m1.kind != 1 || m2.kind != 1) { report_error(cnt, ERR_NO_PHYS, ec); return; }
       const double nu1 = u.poisson, nu2 = u.poisson, E1 = m1.young, E2 = m2.young;
@@ -348,7 +352,7 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
       // ph[4] = Fna = 4*pi*R*gamma (Hertz.cpp:113) when alpha==0; alpha!=0 implies gamma==0 here (Fna=0) and is flagged by -1:
       // the noAttraction clamp applies only when alpha==0 (Hertz.cpp:177)
       kn = kn0; kt = kt0; p3 = asmk; p4 = (alpha == 0.) ? (4 * M_PI * R * gamma) : -1.0;
-      C.ph[0][c] = kn0; C.ph[1][c] = kt0; C.ph[2][c] = tanPhi; C.ph[3][c] = asmk; C.ph[4][c] = p4;
+      C.ph[c] = make_double4(kn0, kt0, tanPhi, asmk); C.ph4[c] = p4;
     }
     C.stepCreated[c] = (int)u.step;
     atomicAdd(&cnt->nCreated, 1ull);
@@ -469,22 +473,21 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
     // contact while its (frozen) AABBs overlap, i.e. unless it is an orphan (InsertionSortCollider.hpp:213-218)
     uint32_t nf = (fl & ~CF_REAL) | ((fl & CF_ORPHAN) ? CF_DEAD : 0);
     C.flags[c] = nf;
-    C.Fg[c] = make_double4(0, 0, 0, 0);
+    C.rec[4 * c + 3] = make_double4(0, 0, 0, 0);
     if (wasReal) { atomicAnd(&C.realBits[c >> 5], ~(1u << (c & 31))); atomicAdd(&cnt->nBroken, 1ull); }
     return;
   }
   // ---- store state
-  C.t0x[c] = c0.x; C.t0y[c] = c0.y; C.t0z[c] = c0.z;
-  C.t1x[c] = c1.x; C.t1y[c] = c1.y; C.t1z[c] = c1.z;
-  C.cp[c] = make_double4(contPt.x, contPt.y, contPt.z, uN);
-  C.fn[c] = Fn; C.ft0[c] = ftA; C.ft1[c] = ftB;
+  C.rec[4 * c] = make_double4(c0.x, c0.y, c0.z, ftA);
+  C.rec[4 * c + 1] = make_double4(c1.x, c1.y, c1.z, ftB);
+  C.rec[4 * c + 2] = make_double4(contPt.x, contPt.y, contPt.z, uN);
   if (!wasReal) { C.flags[c] = fl | CF_REAL; atomicOr(&C.realBits[c >> 5], 1u << (c & 31)); }
   // ---- Contact::getForceTorqueBranch (Contact.cpp:24-35): F = ori * phys.force, ori = Quaternionr(trsf)
   q4 q = quatFromCols(c0, c1, c2);
   d3 Fglob = quatRotate(q, mk3(Fn, ftA, ftB));
-  C.Fg[c] = make_double4(Fglob.x, Fglob.y, Fglob.z, 1.0);
+  C.rec[4 * c + 3] = make_double4(Fglob.x, Fglob.y, Fglob.z, Fn);
   if (u.rolling) {
-    C.tq0[c] = tq0; C.tq1[c] = tq1; C.tq2[c] = tq2;
+    C.tq[c] = make_double4(tq0, tq1, tq2, 0.);
     d3 Tg = (tq0 == 0. && tq1 == 0. && tq2 == 0.) ? mk3(0, 0, 0) : quatRotate(q, mk3(tq0, tq1, tq2));
     C.Tg[c] = make_double4(Tg.x, Tg.y, Tg.z, 0);
   }
@@ -538,10 +541,8 @@ __device__ __forceinline__ void prefetch_contact_ss(const Contacts& C, long long
   prefetch_l2(S.posr + pr.x); prefetch_l2(S.posr + pr.y);
   if (!(fl & CF_REAL)) return;
   prefetch_l2(S.velm + pr.x); prefetch_l2(S.velm + pr.y); prefetch_l2(S.angi + pr.x); prefetch_l2(S.angi + pr.y);
-  prefetch_l2(C.t0x + c); prefetch_l2(C.t0y + c); prefetch_l2(C.t0z + c); prefetch_l2(C.t1x + c); prefetch_l2(C.t1y + c); prefetch_l2(C.t1z + c);
-  prefetch_l2(C.cp + c); prefetch_l2(C.ft0 + c); prefetch_l2(C.ft1 + c);
-  prefetch_l2(C.ph[0] + c); prefetch_l2(C.ph[1] + c); prefetch_l2(C.ph[2] + c);
-  if ((LAW & 1) == 1) { prefetch_l2(C.ph[3] + c); prefetch_l2(C.ph[4] + c); }
+  prefetch_l2(C.rec + 4 * c); prefetch_l2(C.rec + 4 * c + 2); prefetch_l2(C.ph + c);
+  if ((LAW & 1) == 1) prefetch_l2(C.ph4 + c);
 }
 
 // Persistent software-pipelined grid (one CTA per resident slot, tiles of 128 candidates, stride gridDim): while tile k is computed, the table
@@ -799,7 +800,7 @@ __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Sphe
   if (i >= n) return;
   const uint32_t fl = S.flags[i];
   if (fl & F_GHOST) return;   // forces are reduced by the owner only
-  const int e0 = rowStart[i], e1 = rowStart[i + 1];
+  const int e0 = rowStart ? rowStart[i] : 0, e1 = rowStart ? rowStart[i + 1] : 0;   // no rows: ContactLoop.applyForces=False, only Leapfrog's reset
   const double4 pr = S.posr[i];
   const d3 pos = xyz(pr);
   d3 F, T;
@@ -818,8 +819,8 @@ __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Sphe
     for (int k = 0; k < RB; k++) { const uint32_t c = ent[k] >> 1; real[k] = (ent[k] != 0xffffffffu) && ((C.realBits[c >> 5] >> (c & 31)) & 1u); }
 #pragma unroll
     for (int k = 0; k < RB; k++) {
-      fg[k] = real[k] ? C.Fg[ent[k] >> 1] : make_double4(0, 0, 0, 0);
-      cp[k] = real[k] ? C.cp[ent[k] >> 1] : make_double4(0, 0, 0, 0);
+      fg[k] = real[k] ? C.rec[4ll * (ent[k] >> 1) + 3] : make_double4(0, 0, 0, 0);
+      cp[k] = real[k] ? C.rec[4ll * (ent[k] >> 1) + 2] : make_double4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int k = 0; k < RB; k++) {
@@ -857,13 +858,14 @@ __global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, con
         const uint32_t ent = rowEntry[e]; const uint32_t c = ent >> 1;
         const uint32_t cfl = C.flags[c];
         if (!(cfl & CF_REAL)) continue;
-        d3 c0 = mk3(C.t0x[c], C.t0y[c], C.t0z[c]), c1 = mk3(C.t1x[c], C.t1y[c], C.t1z[c]);
+        d3 c0 = xyz(C.rec[4ll * c]), c1 = xyz(C.rec[4ll * c + 1]);
         d3 c2 = cross(c0, c1);
         d3 nrmv = quatRotate(quatFromCols(c0, c1, c2), mk3(1, 0, 0));
         d3 n2 = mk3(nrmv.x * nrmv.x, nrmv.y * nrmv.y, nrmv.z * nrmv.z);
         double kn, kt;
-        if (law == 0) { kn = C.ph[0][c]; kt = C.ph[1][c]; }
-        else { double uN = C.cp[c].w; kn = (3 / 2.) * C.ph[0][c] * sqrt(-uN); kt = C.ph[1][c] * sqrt(uN < 0 ? -uN : 0); }
+        const double4 php = C.ph[c];
+        if (law == 0) { kn = php.x; kt = php.y; }
+        else { double uN = C.rec[4ll * c + 2].w; kn = (3 / 2.) * php.x * sqrt(-uN); kt = php.y * sqrt(uN < 0 ? -uN : 0); }
         // lens[ix] (iniLensTouch): SS: own radius; WS/FS: the sphere's radius on both sides (L6Geom.cpp:61, Wall.cpp:82)
         double len = myR;
         if (cf_kind(cfl) == KIND_SS) { int2 pr = C.pair[c]; len = (ent & 1u) ? S.posr[pr.y].w : S.posr[pr.x].w; }
@@ -921,7 +923,7 @@ __global__ void __launch_bounds__(256) k_stress(Contacts C, long long n, Spheres
         // decomposed runs: a cross-slab pair lives on both sides; the side owning pA (sphere-sphere) / the sphere (wall) reports it
         const bool mineToReport = kind == KIND_SS ? !(S.flags[pr.x] & F_GHOST) : !(S.flags[pr.y] & F_GHOST);
         if (mineToReport) {
-          const double4 F = C.Fg[c];
+          const double4 F = C.rec[4 * c + 3];
           const d3 pb = xyz(S.posr[pr.y]);
           const d3 pa = kind == KIND_SS ? xyz(S.posr[pr.x]) : mk3(walls[pr.x].pos[0], walls[pr.x].pos[1], walls[pr.x].pos[2]);
           d3 br = pb - pa;
@@ -1034,13 +1036,11 @@ struct OldCsr {  // incidence rows of the previous contact table (for history ca
 };
 
 __device__ __forceinline__ void copy_history(const Contacts& N, long long cn, const Contacts& O, long long co, int law, int rolling, int periodic) {
-  N.t0x[cn] = O.t0x[co]; N.t0y[cn] = O.t0y[co]; N.t0z[cn] = O.t0z[co];
-  N.t1x[cn] = O.t1x[co]; N.t1y[cn] = O.t1y[co]; N.t1z[cn] = O.t1z[co];
-  N.cp[cn] = O.cp[co];
-  N.fn[cn] = O.fn[co]; N.ft0[cn] = O.ft0[co]; N.ft1[cn] = O.ft1[co];
-  N.ph[0][cn] = O.ph[0][co]; N.ph[1][cn] = O.ph[1][co]; N.ph[2][cn] = O.ph[2][co];
-  if (law == 1) { N.ph[3][cn] = O.ph[3][co]; N.ph[4][cn] = O.ph[4][co]; }
-  if (rolling) { N.tq0[cn] = O.tq0[co]; N.tq1[cn] = O.tq1[co]; N.tq2[cn] = O.tq2[co]; }
+  // the whole 128-byte record (frame, shear force, contact point, uN, global force) + the Cp2 constants
+  const double4 r0 = O.rec[4 * co], r1 = O.rec[4 * co + 1], r2 = O.rec[4 * co + 2], r3 = O.rec[4 * co + 3], p = O.ph[co];
+  N.rec[4 * cn] = r0; N.rec[4 * cn + 1] = r1; N.rec[4 * cn + 2] = r2; N.rec[4 * cn + 3] = r3; N.ph[cn] = p;
+  if (law == 1) N.ph4[cn] = O.ph4[co];
+  if (rolling) N.tq[cn] = O.tq[co];
   N.stepCreated[cn] = O.stepCreated[co];
   if (periodic) { N.cdx[cn] = O.cdx[co]; N.cdy[cn] = O.cdy[co]; N.cdz[cn] = O.cdz[co]; }
 }
@@ -1470,15 +1470,14 @@ __global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Conta
   if (periodic) { N.cdx[d] = T.cdx[c]; N.cdy[d] = T.cdy[c]; N.cdz[d] = T.cdz[c]; }
   if (carried) {
     copy_history(N, d, O, co, law, rolling, periodic);
-    N.Fg[d] = O.Fg[co];
     fl |= CF_REAL;
     O.flags[co] |= CF_CLAIMED;
   } else {
     // a potential contact that survives a full run keeps the cellDist it was created with (handleBoundInversionPeri only creates
     // when !hasInter, InsertionSortCollider.cpp:844-893)
-    if (periodic && co >= 0) { N.cdx[d] = O.cdx[co]; N.cdy[d] = O.cdy[co]; N.cdz[d] = O.cdz[co]; }
+    if (periodic && co >= 0 && !(O.flags[co] & CF_DEAD)) { N.cdx[d] = O.cdx[co]; N.cdy[d] = O.cdy[co]; N.cdz[d] = O.cdz[co]; }
     N.stepCreated[d] = (int)stepNow;
-    N.Fg[d] = make_double4(0, 0, 0, 0);
+    N.rec[4 * d + 3] = make_double4(0, 0, 0, 0);
   }
   N.flags[d] = fl;
 }
@@ -1505,7 +1504,6 @@ __global__ void __launch_bounds__(256) k_orphans(Contacts O, long long nOld, Con
   const long long c = nNewBase + k;
   N.pair[c] = pr;
   copy_history(N, c, O, co, law, rolling, periodic);
-  N.Fg[c] = O.Fg[co];
   N.flags[c] = CF_REAL | CF_ORPHAN | (fl & CF_KIND_MASK);
 }
 
@@ -1622,6 +1620,21 @@ __global__ void __launch_bounds__(256) k_scatter_state(Spheres S, int n, const i
 __global__ void __launch_bounds__(256) k_keep_flag(const int32_t* __restrict__ up, int n, const int* __restrict__ newUpOf, int* flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flag[i] = newUpOf[up[i]] >= 0 ? 1 : 0;
+}
+// the contacts of a removed particle are deleted with it (ParticleContainer::remove -> ContactContainer::remove, ParticleContainer.cpp:121-157): every entry of
+// its incidence row dies here, so that neither the history carry-over nor the orphan pass of the next full run can hand its frame / shear force to a NEW particle that
+// reuses the id (ParticleContainer::findFreeId hands freed ids out again).  rows are addressed by the slot the sphere had when they were built (id2slot).
+__global__ void __launch_bounds__(256) k_kill_rows(const int32_t* __restrict__ sid, int n, const int* __restrict__ keepFlag, const int* __restrict__ id2slot, const int* __restrict__ rowStart,
+                                                  const uint32_t* __restrict__ rowEntry, int nRows, uint32_t* cflags, uint32_t* realBits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || keepFlag[i]) return;
+  const int rs = id2slot[sid[i]];
+  if (rs < 0 || rs >= nRows) return;
+  for (int e = rowStart[rs]; e < rowStart[rs + 1]; e++) {
+    const uint32_t c = rowEntry[e] >> 1;
+    cflags[c] = (cflags[c] & ~(uint32_t)CF_REAL) | CF_DEAD | CF_CLAIMED;
+    atomicAnd(&realBits[c >> 5], ~(1u << (c & 31)));
+  }
 }
 __global__ void __launch_bounds__(256) k_compact_spheres(Spheres dst, Spheres src, int n, const int* __restrict__ flag, const int* __restrict__ off, const int* __restrict__ newUpOf,
                                                         int* __restrict__ id2slot, int* __restrict__ origSlot) {
