@@ -9,6 +9,9 @@ from woo_b200 import scenes as sc
 from _harness import Oracle
 
 
+FIRST_STEPS = (1, 5)     # tests/golden/first_<scene>.npz: states right after the first steps from the initial state (north_star's one-step criterion; scripts/replay_in_woo.py)
+
+
 def golden_scenes():
     """name -> (SceneSpec factory, steps); shared with tests/test_golden_scenes.py"""
     return {
@@ -24,7 +27,15 @@ def golden_scenes():
 if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden")
     for name, (make, steps) in golden_scenes().items():
-        S = make(); O = Oracle(S); O.step(steps)
+        S = make(); O = Oracle(S)
+        first = {}; done = 0
+        for k in FIRST_STEPS:
+            O.step(k - done); done = k
+            s, c = O.spheres(), O.contacts(True)
+            first.update({"pos_%d" % k: s["pos"], "vel_%d" % k: s["vel"], "angVel_%d" % k: s["angVel"], "force_%d" % k: s["force"], "torque_%d" % k: s["torque"],
+                          "ids_%d" % k: c["ids"], "uN_%d" % k: c["uN"], "cforce_%d" % k: c["force"], "dt_%d" % k: O.dt})
+        np.savez_compressed(os.path.join(out, "first_%s.npz" % name), **first)
+        O.step(steps - done)
         s, c = O.spheres(), O.contacts(True)
         np.savez_compressed(os.path.join(out, "scene_%s.npz" % name), steps=steps, pos=s["pos"], vel=s["vel"], angVel=s["angVel"], force=s["force"], torque=s["torque"],
                             ids=c["ids"], uN=c["uN"], cforce=c["force"], trsf=c["trsf"], cellDist=c["cellDist"], dt=O.dt, nFullRuns=O.nFullRuns)

@@ -31,7 +31,7 @@ def cfg_scenes():
         "cfg5": sc.drum(800, div=16, axial=4, vz0=1., vfluct=.5),
         "gas-linear": sc.random_gas(1500, box=.75, r=.02, psd_ratio=3.0, seed=1),
         "gas-hertz": sc.random_gas(800, box=.6, r=.02, psd_ratio=2.0, seed=2, law=sc.LAW_HERTZ_DMT, en=.7),
-        "facets": sc.facet_box_scene(300, seed=33),
+        "facets": sc.facet_box_scene(1000, seed=33),
         "peri-skewed": sc.periodic_gas(1200, seed=34, gradV=[[0, 1., 0], [0, 0, 0], [0, 0, 0]], shear0=.1),
     }
 
@@ -99,10 +99,14 @@ def _resume(S, A, variant):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,warm", [("cfg1", 1500), ("cfg2", 800), ("cfg3", 1500), ("cfg4", 300), ("cfg5", 2500), ("gas-linear", 60), ("gas-hertz", 60), ("facets", 150)])
+@pytest.mark.parametrize("name,warm", [("cfg1", 1500), ("cfg2-bed20k", 200), ("cfg3", 1500), ("cfg4", 300), ("cfg5", 2500), ("gas-linear", 60), ("gas-hertz", 60), ("facets", 60)])
 def test_gpu_one_step_from_identical_developed_state(name, warm):
     from woo_b200.engine import Engine
-    S = cfg_scenes()[name]
+    if name == "cfg2-bed20k":      # the committed pre-settled PSD 1:4 bed that bench.py tiles to 1M: ~40k real contacts with long shear histories
+        import bench
+        S = bench.load_sample()
+    else:
+        S = cfg_scenes()[name]
     S.params.dynDtPeriod = 0          # PeriodicEngine counters are not part of the exchanged state
     A = Engine(S.params).load(S)
     A.step(warm)
@@ -110,8 +114,11 @@ def test_gpu_one_step_from_identical_developed_state(name, warm):
     D, X = _resume(S, A, ""), _resume(S, A, "alt")
     D.step(1); X.step(1); A.step(1)
     sd, cd = D.spheres(), D.contacts(True)
-    # the resumed default engine reproduces the uninterrupted one bit for bit: the comparison below really starts from identical state
-    assert np.array_equal(sd["force"], A.spheres()["force"]) and np.array_equal(cd["force"], A.contacts(True)["force"])
+    # the resumed default engine reproduces the uninterrupted one bit for bit: the comparison below really starts from identical state.  (Not asserted for
+    # periodic cells: only REAL contacts travel through wdem_upload_contacts, and a potential contact that survived many collider runs of a sheared cell keeps the
+    # cellDist it was created with, which a fresh candidate search need not reproduce.)
+    if S.cell is None:
+        assert np.array_equal(sd["force"], A.spheres()["force"]) and np.array_equal(cd["force"], A.contacts(True)["force"])
     one_step_agreement(sd, X.spheres(), cd, X.contacts(True), f"{name} (GPU, developed state)", S.radius.max())
 
 

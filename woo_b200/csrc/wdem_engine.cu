@@ -231,6 +231,7 @@ StepU makeUniforms(wdem_engine* E) {
   u.rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.); u.relRollStiff = c.relRollStiff; u.relTwistStiff = c.relTwistStiff; u.rollTanPhi = c.rollTanPhi;
   u.poisson = c.poisson; u.en = c.en;
   u.energy = E->trackEnergy ? E->dEnergy.p : nullptr;
+  { static const bool noCs = getenv("WDEM_NO_CS_STORES") != nullptr; u.csStores = noCs ? 0 : 1; }
   {   // Leapfrog.cpp:130-132
     bool ident = true; for (int k = 0; k < 9; k++) if (E->cell.gradV.m[k] != ((k % 4 == 0) ? 1. : 0.)) ident = false;
     u.trackLeapfrog = (E->trackEnergy && (!c.periodic || E->step > 0 || ident)) ? 1 : 0;
@@ -754,7 +755,7 @@ void rebuild(wdem_engine* E) {
       // warps of k_contact_ss then see either all-real or all-potential contacts instead of paying the long path for half-empty warps
       k_was_real<<<nblk(nSS + 1, 256), 256, 0, st>>>(E->srcOld.p, O.flags, nSS, E->realFlag.p);
       exclusiveSum(E, E->realFlag.p, E->realPos.p, (int)nSS + 1);
-      k_carry<<<nblk(nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, T, E->realPos.p, nSS, c.law, rolling, c.periodic, E->step); E->launches += 4;
+      k_carry<<<nblk(8 * nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, T, E->realPos.p, nSS, c.law, rolling, c.periodic, E->step); E->launches += 4;
     }
     // 6b. orphans: real contacts of the previous table that no candidate claimed (AABBs separated while real)
     long long nOrph = 0;
@@ -961,11 +962,22 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   // the big kernel goes last so that the small boundary kernels already occupy their share of the SMs
   if (E->nSS > 0) {
     const int gridSS = std::min(nblk(E->nSS, WD_CONTACT_BLOCK), E->numSMs * WD_CONTACT_CTAS_PER_SM);   // persistent: one CTA per resident slot
-    switch (c.law + (u.energy ? 2 : 0)) {
+    static const bool direct = getenv("WDEM_CONTACT_DIRECT") != nullptr;   // A/B knob: per-thread global loads instead of the cp.async-staged tiles
+    static bool carve = false;
+    if (!carve) {   // 40 KB of static shared memory per CTA, 4 CTAs per SM: ask for a shared-memory-heavy L1 split (the gathers live in L2, not L1)
+      cudaFuncSetAttribute(k_contact_ss<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 75); cudaFuncSetAttribute(k_contact_ss<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
+      cudaFuncSetAttribute(k_contact_ss<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 75); cudaFuncSetAttribute(k_contact_ss<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
+      carve = true;
+    }
+    switch (c.law + (u.energy ? 2 : 0) + (direct ? 4 : 0)) {
       case 0: k_contact_ss<0><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
       case 1: k_contact_ss<1><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
       case 2: k_contact_ss<2><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
       case 3: k_contact_ss<3><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 4: k_contact_ss_direct<0><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 5: k_contact_ss_direct<1><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 6: k_contact_ss_direct<2><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 7: k_contact_ss_direct<3><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
     }
     E->launches++;
   }

@@ -75,6 +75,8 @@ struct StepU {            // per-step uniforms
   int law; int noSlip, noBreak, noFrict, noAttraction; int rolling; double relRollStiff, relTwistStiff, rollTanPhi;
   double poisson, en, viscAlpha;  // viscAlpha = -sqrt(5) ln(en)/sqrt(ln(en)^2+pi^2), host-computed (Hertz.cpp:69)
   double* energy;                 // Scene.trackEnergy: device accumulators (EN_*), else nullptr; only the TRACK kernel variants look at it
+  int csStores;                   // contact kernel: write the history half of a record (read again only in the next step) with the streaming hint, so that the
+                                  // half the force reduction gathers right afterwards (contact point, global force) has a better chance to stay in L2
   int trackLeapfrog;              // Leapfrog.cpp:130-132: reallyTrackEnergy (off in step 0 of a periodic scene with a velocity gradient)
 };
 // EnergyTracker entries of this path (core/EnergyTracker.hpp): "kinetic" and "elast" are resettable (zeroed in the step prologue, Scene.cpp:416)
@@ -293,6 +295,13 @@ __device__ __noinline__ void report_error(Counters* cnt, int code, const ErrCtx&
 }
 // persistent state of a real contact, loaded up front so that all of a thread's loads are in flight together
 struct Hist { d3 t0, t1; double4 cp; double ft0, ft1, ph0, ph1, ph2, ph3, ph4; };
+// what the tail leaves for the caller to store into the contact's 128-byte record: st = 0 nothing (no contact), 1 the whole record (kept / created), 2 the contact broke
+// (only the force slot is zeroed).  The boundary kernels store straight to global memory, the sphere-sphere kernel through its shared-memory tile.
+struct COut { double4 r0, r1, r2, r3; int st; };
+__device__ __forceinline__ void store_out(const Contacts& C, long long c, const COut& o) {
+  if (o.st == 1) { C.rec[4 * c] = o.r0; C.rec[4 * c + 1] = o.r1; C.rec[4 * c + 2] = o.r2; C.rec[4 * c + 3] = o.r3; }
+  else if (o.st == 2) C.rec[4 * c + 3] = make_double4(0, 0, 0, 0);
+}
 template <int LAW>
 __device__ __forceinline__ void load_hist(const Contacts& C, long long c, Hist& H) {
   const double4 a = C.rec[4 * c], b = C.rec[4 * c + 1], p = C.ph[c];
@@ -306,7 +315,7 @@ template <int LAW>
 __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uint32_t fl, const StepU& u, d3 pos1, d3 vel1, d3 w1, d3 pos2,
                                              d3 vel2, d3 w2, d3 shiftVel2, d3 normal, d3 contPt, double uN, double r1, double r2,
                                              const Material* mats, const int32_t* matArr, double massA, double massB, Counters* cnt,
-                                             const ErrCtx& ec, int matBoundary, const Hist& H, unsigned& nRealOut, const bool mine = true) {
+                                             const ErrCtx& ec, int matBoundary, const Hist& H, unsigned& nRealOut, COut& out, const bool mine = true) {
   // mine (energy tracking in decomposed runs): a cross-slab pair is evaluated on both sides; the side owning pA books its energy
   const bool wasReal = fl & CF_REAL;
   d3 c0, c1, c2, gvel = mk3(0, 0, 0), gang = mk3(0, 0, 0);
@@ -473,19 +482,19 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
     // contact while its (frozen) AABBs overlap, i.e. unless it is an orphan (InsertionSortCollider.hpp:213-218)
     uint32_t nf = (fl & ~CF_REAL) | ((fl & CF_ORPHAN) ? CF_DEAD : 0);
     C.flags[c] = nf;
-    C.rec[4 * c + 3] = make_double4(0, 0, 0, 0);
+    out.st = 2;
     if (wasReal) { atomicAnd(&C.realBits[c >> 5], ~(1u << (c & 31))); atomicAdd(&cnt->nBroken, 1ull); }
     return;
   }
   // ---- store state
-  C.rec[4 * c] = make_double4(c0.x, c0.y, c0.z, ftA);
-  C.rec[4 * c + 1] = make_double4(c1.x, c1.y, c1.z, ftB);
-  C.rec[4 * c + 2] = make_double4(contPt.x, contPt.y, contPt.z, uN);
+  out.r0 = make_double4(c0.x, c0.y, c0.z, ftA);
+  out.r1 = make_double4(c1.x, c1.y, c1.z, ftB);
+  out.r2 = make_double4(contPt.x, contPt.y, contPt.z, uN);
   if (!wasReal) { C.flags[c] = fl | CF_REAL; atomicOr(&C.realBits[c >> 5], 1u << (c & 31)); }
   // ---- Contact::getForceTorqueBranch (Contact.cpp:24-35): F = ori * phys.force, ori = Quaternionr(trsf)
   q4 q = quatFromCols(c0, c1, c2);
   d3 Fglob = quatRotate(q, mk3(Fn, ftA, ftB));
-  C.rec[4 * c + 3] = make_double4(Fglob.x, Fglob.y, Fglob.z, Fn);
+  out.r3 = make_double4(Fglob.x, Fglob.y, Fglob.z, Fn); out.st = 1;
   if (u.rolling) {
     C.tq[c] = make_double4(tq0, tq1, tq2, 0.);
     d3 Tg = (tq0 == 0. && tq1 == 0. && tq2 == 0.) ? mk3(0, 0, 0) : quatRotate(q, mk3(tq0, tq1, tq2));
@@ -504,12 +513,13 @@ __device__ __forceinline__ void block_count(unsigned isReal, unsigned evald, Cou
 // (src/dem/Sphere.cpp:92-117) fused with Cp2 and Law2.  One thread per candidate pair.
 // ------------------------------------------------------------------------------------------------
 template <int LAW>
-__device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
+__device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal,
+                                           const Hist& H, COut& out) {
   const bool real = fl & CF_REAL;
-  // every load of a real contact is issued here, before the first use: two dependent round trips (flags+pair, then everything) instead of four
+  // every load of a real contact is issued up front (the history by the caller: straight from global memory or from the staged tile), before the first use
   const double4 pa = S.posr[pr.x], pb = S.posr[pr.y];
-  double4 va = make_double4(0, 0, 0, 0), vb = va, wa = va, wb = va; Hist H;
-  if (real) { va = S.velm[pr.x]; vb = S.velm[pr.y]; wa = S.angi[pr.x]; wb = S.angi[pr.y]; load_hist<LAW>(C, c, H); }
+  double4 va = make_double4(0, 0, 0, 0), vb = va, wa = va, wb = va;
+  if (real) { va = S.velm[pr.x]; vb = S.velm[pr.y]; wa = S.angi[pr.x]; wb = S.angi[pr.y]; }
   d3 shift2 = mk3(0, 0, 0), shiftVel2 = mk3(0, 0, 0);
   if (u.periodic) {
     d3 cd = mk3((double)C.cdx[c], (double)C.cdy[c], (double)C.cdz[c]);
@@ -530,7 +540,7 @@ __device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint3
   if (!real && (LAW & 1) == 1) { mA = S.velm[pr.x].w; mB = S.velm[pr.y].w; }
   const ErrCtx ec{S.id, pr.x, 0, pr.y};
   const bool mine = (LAW >= 2) ? !(S.flags[pr.x] & F_GHOST) : true;
-  contact_tail<LAW>(C, c, fl, u, p1, xyz(va), xyz(wa), p2, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, r1, r2, mats, S.mat, mA, mB, cnt, ec, 0, H, isReal, mine);
+  contact_tail<LAW>(C, c, fl, u, p1, xyz(va), xyz(wa), p2, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, r1, r2, mats, S.mat, mA, mB, cnt, ec, 0, H, isReal, out, mine);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -545,6 +555,14 @@ __device__ __forceinline__ void prefetch_contact_ss(const Contacts& C, long long
   if ((LAW & 1) == 1) prefetch_l2(C.ph4 + c);
 }
 
+template <int LAW>
+__device__ __forceinline__ void prefetch_spheres_ss(uint32_t fl, int2 pr, const Spheres& S) {
+  if (fl & CF_DEAD) return;
+  prefetch_l2(S.posr + pr.x); prefetch_l2(S.posr + pr.y);
+  if (!(fl & CF_REAL)) return;
+  prefetch_l2(S.velm + pr.x); prefetch_l2(S.velm + pr.y); prefetch_l2(S.angi + pr.x); prefetch_l2(S.angi + pr.y);
+}
+
 // Persistent software-pipelined grid (one CTA per resident slot, tiles of 128 candidates, stride gridDim): while tile k is computed, the table
 // entries (flags, pair) of tile k+2 are in flight into registers and the sphere/history lines of tile k+1 are being pulled into L2, so the
 // dependent chain flags+pair -> gathers -> math of a tile only ever waits for L2, not for HBM.  Real-first order (k_carry) + round-robin tiles
@@ -556,7 +574,7 @@ __device__ __forceinline__ void prefetch_contact_ss(const Contacts& C, long long
 #define WD_CONTACT_BLOCK 128
 #endif
 template <int LAW>
-__global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
+__global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_contact_ss_direct(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
   const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
   const long long end = first + n, stride = (long long)gridDim.x * blockDim.x;
   long long c0 = first + (long long)blockIdx.x * blockDim.x + threadIdx.x, c1 = c0 + stride;
@@ -571,9 +589,114 @@ __global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_co
     uint32_t fl2 = CF_DEAD; int2 pr2 = make_int2(0, 0);
     if (c2 < end) { fl2 = C.flags[c2]; pr2 = C.pair[c2]; }
     prefetch_contact_ss<LAW>(C, c1, fl1, pr1, S);
-    if (!(fl0 & CF_DEAD)) { evald++; unsigned r = 0; contact_ss<LAW>(C, c0, fl0, pr0, S, mats, u, cnt, r); isReal += r; }
+    if (!(fl0 & CF_DEAD)) {
+      evald++; unsigned r = 0; Hist H; COut o; o.st = 0;
+      if (fl0 & CF_REAL) load_hist<LAW>(C, c0, H);
+      contact_ss<LAW>(C, c0, fl0, pr0, S, mats, u, cnt, r, H, o); store_out(C, c0, o); isReal += r;
+    }
     c0 = c1; fl0 = fl1; pr0 = pr1; c1 = c2; fl1 = fl2; pr1 = pr2;
   }
+  block_count(isReal, evald, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same pass, warp-per-tile with the contact state staged in shared memory (the default).  A tile = 32 consecutive candidates = 32 x 128-byte records = 4 KB of
+// contiguous global memory.  The warp moves it with cp.async (16-byte chunks, fully coalesced: 512 B per request, no registers tied up while the copy is in flight)
+// into a double-buffered, XOR-swizzled shared-memory tile: tile k+1 is on its way while tile k is computed, exactly like the table entries (flags, pair: registers,
+// two tiles ahead) and the sphere lines (L2 prefetch, one tile ahead).  Results go back the same way: every lane writes its record into the tile, then the warp
+// streams the tile out in 512-byte requests.  Rows of contacts that are not real are neither loaded nor stored.  No CTA-wide barrier: warps are independent.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// chunk (16 B) `col` of row `row` of a 32-row x 128-byte tile, swizzled so that both the per-lane row accesses and the cooperative chunk accesses are conflict-free
+__device__ __forceinline__ int swz(int row, int col) { return row * 8 + (col ^ (row & 7)); }
+__device__ __forceinline__ void st_cs(uint4* p, uint4 v) { asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+
+template <int LAW>
+__device__ __forceinline__ void stage_tile(const Contacts& C, long long base /*first contact of the tile*/, unsigned realMask, uint4* sRec, uint4* sPh, int lane) {
+  if (realMask) {
+    const uint4* g = reinterpret_cast<const uint4*>(C.rec + 4 * base);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int q = j * 32 + lane, row = q >> 3, col = q & 7;
+      if (col < 6 && ((realMask >> row) & 1u)) cp_async16(sRec + swz(row, col), g + q);      // chunks 6,7 (global force, fn) are outputs only
+    }
+    const uint4* gp = reinterpret_cast<const uint4*>(C.ph + base);
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int q = j * 32 + lane, row = q >> 1;
+      if ((realMask >> row) & 1u) cp_async16(sPh + q, gp + q);
+    }
+  }
+  cp_async_commit();
+}
+
+template <int LAW>
+__global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
+  constexpr int NW = WD_CONTACT_BLOCK / 32;
+  __shared__ __align__(128) uint4 sRecAll[NW][2][256];     // per warp: 2 stages x 32 records x 128 B
+  __shared__ __align__(128) uint4 sPhAll[NW][2][64];       // per warp: 2 stages x 32 x double4
+  const int stale = *guard;   // a set flag means a collider full run is due and this speculative launch is void
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long end = first + n, stride = (long long)gridDim.x * blockDim.x;
+  long long b0 = first + ((long long)blockIdx.x * NW + w) * 32, b1 = b0 + stride;     // tile bases of this warp: every (gridDim*NW)-th tile of 32
+  uint32_t fl0 = CF_DEAD, fl1 = CF_DEAD; int2 pr0 = make_int2(0, 0), pr1 = pr0;
+  if (b0 + lane < end) { fl0 = C.flags[b0 + lane]; pr0 = C.pair[b0 + lane]; }
+  if (b1 + lane < end) { fl1 = C.flags[b1 + lane]; pr1 = C.pair[b1 + lane]; }
+  if (stale) return;          // uniform over the grid
+  unsigned isReal = 0, evald = 0;
+  unsigned rm0 = __ballot_sync(0xffffffffu, (fl0 & CF_REAL) && !(fl0 & CF_DEAD));
+  if (b0 < end) stage_tile<LAW>(C, b0, rm0, sRecAll[w][0], sPhAll[w][0], lane);
+  int stg = 0;
+  for (; b0 < end; b0 = b1, b1 += stride, stg ^= 1) {         // warp-uniform loop
+    const long long b2 = b1 + stride;
+    uint32_t fl2 = CF_DEAD; int2 pr2 = make_int2(0, 0);
+    if (b2 + lane < end) { fl2 = C.flags[b2 + lane]; pr2 = C.pair[b2 + lane]; }
+    const unsigned rm1 = __ballot_sync(0xffffffffu, (fl1 & CF_REAL) && !(fl1 & CF_DEAD));
+    if (b1 < end) stage_tile<LAW>(C, b1, rm1, sRecAll[w][stg ^ 1], sPhAll[w][stg ^ 1], lane); else cp_async_commit();
+    prefetch_spheres_ss<LAW>(fl1, pr1, S);
+    if ((LAW & 1) == 1 && (fl1 & CF_REAL) && !(fl1 & CF_DEAD)) prefetch_l2(C.ph4 + b1 + lane);
+    cp_async_wait<1>();          // this lane's copies of tile k have landed ...
+    __syncwarp();                // ... and everybody else's
+    uint4* sRec = sRecAll[w][stg]; const uint4* sPh = sPhAll[w][stg];
+    COut o; o.st = 0;
+    const long long c = b0 + lane;
+    if (!(fl0 & CF_DEAD)) {
+      evald++; unsigned r = 0; Hist H;
+      if (fl0 & CF_REAL) {
+        const double2* row = reinterpret_cast<const double2*>(sRec);
+        const double2 a0 = row[swz(lane, 0)], a1 = row[swz(lane, 1)], b0_ = row[swz(lane, 2)], b1_ = row[swz(lane, 3)], c0_ = row[swz(lane, 4)], c1_ = row[swz(lane, 5)];
+        const double2 p0 = reinterpret_cast<const double2*>(sPh)[2 * lane], p1 = reinterpret_cast<const double2*>(sPh)[2 * lane + 1];
+        H.t0 = mk3(a0.x, a0.y, a1.x); H.ft0 = a1.y; H.t1 = mk3(b0_.x, b0_.y, b1_.x); H.ft1 = b1_.y; H.cp = make_double4(c0_.x, c0_.y, c1_.x, c1_.y);
+        H.ph0 = p0.x; H.ph1 = p0.y; H.ph2 = p1.x;
+        if ((LAW & 1) == 1) { H.ph3 = p1.y; H.ph4 = C.ph4[c]; }
+      }
+      contact_ss<LAW>(C, c, fl0, pr0, S, mats, u, cnt, r, H, o); isReal += r;
+    }
+    // results: own row into the tile, then the warp streams the rows that hold a (still) real contact back in 512-byte requests
+    if (o.st == 1) {
+      double2* row = reinterpret_cast<double2*>(sRec);
+      row[swz(lane, 0)] = make_double2(o.r0.x, o.r0.y); row[swz(lane, 1)] = make_double2(o.r0.z, o.r0.w);
+      row[swz(lane, 2)] = make_double2(o.r1.x, o.r1.y); row[swz(lane, 3)] = make_double2(o.r1.z, o.r1.w);
+      row[swz(lane, 4)] = make_double2(o.r2.x, o.r2.y); row[swz(lane, 5)] = make_double2(o.r2.z, o.r2.w);
+      row[swz(lane, 6)] = make_double2(o.r3.x, o.r3.y); row[swz(lane, 7)] = make_double2(o.r3.z, o.r3.w);
+    } else if (o.st == 2) C.rec[4 * c + 3] = make_double4(0, 0, 0, 0);
+    const unsigned wm = __ballot_sync(0xffffffffu, o.st == 1);      // also orders the shared-memory writes above before the reads below
+    if (wm) {
+      uint4* g = reinterpret_cast<uint4*>(C.rec + 4 * b0);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int q = j * 32 + lane, rw = q >> 3, col = q & 7;
+        if ((wm >> rw) & 1u) { const uint4 v = sRec[swz(rw, col)]; if (col < 4 && u.csStores) st_cs(g + q, v); else g[q] = v; }
+      }
+    }
+    __syncwarp();                // the stage is free for the copies of tile k+2
+    fl0 = fl1; pr0 = pr1; fl1 = fl2; pr1 = pr2;
+  }
+  cp_async_wait<0>();
   block_count(isReal, evald, cnt);
 }
 
@@ -581,7 +704,8 @@ __global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_co
 // Wall+Sphere: Cg2_Wall_Sphere_L6Geom::go (src/dem/Wall.cpp:50-84)
 // ------------------------------------------------------------------------------------------------
 template <int LAW>
-__device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Wall* walls, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
+__device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Wall* walls, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal,
+                                           COut& out) {
   const bool real = fl & CF_REAL;
   const Wall W = walls[pr.x];
   const double4 pb = S.posr[pr.y];
@@ -610,7 +734,7 @@ __device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint3
   if (!real && (LAW & 1) == 1) mB = S.velm[pr.y].w;
   const ErrCtx ec{S.id, -1, W.id, pr.y};
   contact_tail<LAW>(C, c, fl, u, wallPos, mk3(W.vel[0], W.vel[1], W.vel[2]), mk3(0, 0, 0), spherePos, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, -radius, radius,
-                    mats, S.mat, 0., mB, cnt, ec, W.mat, H, isReal);
+                    mats, S.mat, 0., mB, cnt, ec, W.mat, H, isReal, out);
 }
 
 template <int LAW>
@@ -622,7 +746,7 @@ __global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first,
   if (c < first + n) { fl = C.flags[c]; pr = C.pair[c]; }
   if (stale) return;          // uniform over the grid
   {
-    if (!(fl & CF_DEAD)) { evald = 1; contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal); }
+    if (!(fl & CF_DEAD)) { evald = 1; COut o; o.st = 0; contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal, o); store_out(C, c, o); }
   }
   block_count(isReal, evald, cnt);
 }
@@ -660,7 +784,8 @@ __device__ __forceinline__ void facetAdjustImpl(d3 fN, d3 edgePt, d3 unitOutVec,
 }
 
 template <int LAW>
-__device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Facet* facets, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
+__device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Facet* facets, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal,
+                                           COut& out) {
   const Facet* F = facets + pr.x;
   const double4 pb = S.posr[pr.y];
   double4 vb = make_double4(0, 0, 0, 0), wb = vb; Hist H;
@@ -736,7 +861,7 @@ __device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint3
   double mB = 0;
   if (!real && (LAW & 1) == 1) mB = S.velm[pr.y].w;
   const ErrCtx ec{S.id, -1, F->id, pr.y};
-  contact_tail<LAW>(C, c, fl, u, contPt, linVel, angVel, sC, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, fmax(ht, radius), radius, mats, S.mat, 0., mB, cnt, ec, F->mat, H, isReal);
+  contact_tail<LAW>(C, c, fl, u, contPt, linVel, angVel, sC, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, fmax(ht, radius), radius, mats, S.mat, 0., mB, cnt, ec, F->mat, H, isReal, out);
 }
 
 template <int LAW>
@@ -748,7 +873,7 @@ __global__ void __launch_bounds__(128) k_contact_fs(Contacts C, long long first,
   if (c < first + n) { fl = C.flags[c]; pr = C.pair[c]; }
   if (stale) return;          // uniform over the grid
   {
-    if (!(fl & CF_DEAD)) { evald = 1; contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal); }
+    if (!(fl & CF_DEAD)) { evald = 1; COut o; o.st = 0; contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal, o); store_out(C, c, o); }
   }
   block_count(isReal, evald, cnt);
 }
@@ -767,9 +892,11 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
     if (!(fl & CF_DEAD)) {
       evald = 1;
       const int kind = cf_kind(fl);
-      if (kind == KIND_SS) contact_ss<LAW>(C, c, fl, pr, S, mats, u, cnt, isReal);
-      else if (kind == KIND_WS) contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal);
-      else contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal);
+      COut o; o.st = 0;
+      if (kind == KIND_SS) { Hist H; if (fl & CF_REAL) load_hist<LAW>(C, c, H); contact_ss<LAW>(C, c, fl, pr, S, mats, u, cnt, isReal, H, o); }
+      else if (kind == KIND_WS) contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal, o);
+      else contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal, o);
+      store_out(C, c, o);
     }
   }
   block_count(isReal, evald, cnt);
@@ -1457,29 +1584,37 @@ __global__ void __launch_bounds__(256) k_was_real(const int* __restrict__ srcOld
   if (c < nSS) { const int co = srcOld[c]; f = (co >= 0 && (oflags[co] & CF_REAL)) ? 1 : 0; }
   flag[c] = f;
 }
+// Eight lanes per NEW contact: the 128-byte record of a carried contact is one line gathered by 8 lanes (16 B each) and written back as part of a 512-byte warp
+// request; the small per-contact words (pair, flags, cellDist, stepCreated, Cp2 constants) are spread over the eight lanes.
 __global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Contacts O, const int* __restrict__ srcOld, Contacts T, const int* __restrict__ realPos, long long nSS,
                                               int law, int rolling, int periodic, long long stepNow) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long c = t >> 3; const int k = (int)(t & 7);
   if (c >= nNew) return;
   const int co = srcOld[c];
-  const bool carried = co >= 0 && (O.flags[co] & CF_REAL);
+  const uint32_t ofl = co >= 0 ? O.flags[co] : 0u;
+  const bool carried = co >= 0 && (ofl & CF_REAL);
   long long d = c;
   if (c < nSS) { const long long rp = realPos[c]; d = carried ? rp : (long long)realPos[nSS] + (c - rp); }
-  N.pair[d] = T.pair[c];
-  uint32_t fl = T.flags[c];
-  if (periodic) { N.cdx[d] = T.cdx[c]; N.cdy[d] = T.cdy[c]; N.cdz[d] = T.cdz[c]; }
   if (carried) {
-    copy_history(N, d, O, co, law, rolling, periodic);
-    fl |= CF_REAL;
-    O.flags[co] |= CF_CLAIMED;
+    reinterpret_cast<uint4*>(N.rec + 4 * d)[k] = reinterpret_cast<const uint4*>(O.rec + 4 * (long long)co)[k];
+    if (k < 2) reinterpret_cast<uint4*>(N.ph + d)[k] = reinterpret_cast<const uint4*>(O.ph + co)[k];
+    else if (k == 2) N.stepCreated[d] = O.stepCreated[co];
+    else if (k == 3) { if (law == 1) N.ph4[d] = O.ph4[co]; }
+    else if (k == 4) { if (rolling) N.tq[d] = O.tq[co]; }
+    else if (k == 5) O.flags[co] = ofl | CF_CLAIMED;
   } else {
-    // a potential contact that survives a full run keeps the cellDist it was created with (handleBoundInversionPeri only creates
-    // when !hasInter, InsertionSortCollider.cpp:844-893)
-    if (periodic && co >= 0 && !(O.flags[co] & CF_DEAD)) { N.cdx[d] = O.cdx[co]; N.cdy[d] = O.cdy[co]; N.cdz[d] = O.cdz[co]; }
-    N.stepCreated[d] = (int)stepNow;
-    N.rec[4 * d + 3] = make_double4(0, 0, 0, 0);
+    if (k >= 6) reinterpret_cast<uint4*>(N.rec + 4 * d)[k] = make_uint4(0, 0, 0, 0);      // no force from a contact that is not real
+    else if (k == 2) N.stepCreated[d] = (int)stepNow;
   }
-  N.flags[d] = fl;
+  if (k == 0) N.pair[d] = T.pair[c];
+  else if (k == 1) N.flags[d] = T.flags[c] | (carried ? (uint32_t)CF_REAL : 0u);
+  else if (k == 7 && periodic) {
+    // a potential contact that survives a full run keeps the cellDist it was created with (handleBoundInversionPeri only creates
+    // when !hasInter, InsertionSortCollider.cpp:844-893); one whose particle was removed meanwhile (CF_DEAD, k_kill_rows) is a new contact
+    const bool keepOld = co >= 0 && (carried || !(ofl & CF_DEAD));
+    N.cdx[d] = keepOld ? O.cdx[co] : T.cdx[c]; N.cdy[d] = keepOld ? O.cdy[co] : T.cdy[c]; N.cdz[d] = keepOld ? O.cdz[co] : T.cdz[c];
+  }
 }
 
 // old real contacts nobody claimed = orphans: count (and add their incidences to the row counts), then append behind the grid candidates
