@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(128) k_dom_count_rows(const int* __restrict__ 
 __device__ __forceinline__ void crec_from(const Contacts& O, long long co, int idA, int idB, int law, int rolling, int periodic, CRec& r) {
   r.idA = idA; r.idB = idB; r.flags = O.flags[co]; r.stepCreated = O.stepCreated[co]; r.pad = 0;
   r.cd[0] = periodic ? O.cdx[co] : 0; r.cd[1] = periodic ? O.cdy[co] : 0; r.cd[2] = periodic ? O.cdz[co] : 0;
-  const double4 r0 = O.rec[4 * co], r1 = O.rec[4 * co + 1], r3 = O.rec[4 * co + 3], p = O.ph[co];
+  const double4 r0 = O.rA[co], r1 = O.rB[co], r3 = O.rD[co], p = O.ph[co];
   r.t[0] = r0.x; r.t[1] = r0.y; r.t[2] = r0.z; r.t[3] = r1.x; r.t[4] = r1.y; r.t[5] = r1.z;
-  r.cp = O.rec[4 * co + 2]; r.fl[0] = r3.w; r.fl[1] = r0.w; r.fl[2] = r1.w;
+  r.cp = O.rC[co]; r.fl[0] = r3.w; r.fl[1] = r0.w; r.fl[2] = r1.w;
   r.ph[0] = p.x; r.ph[1] = p.y; r.ph[2] = p.z;
   r.ph[3] = law == 1 ? p.w : 0.; r.ph[4] = law == 1 ? O.ph4[co] : 0.;
   double4 tq = make_double4(0, 0, 0, 0); if (rolling) tq = O.tq[co];
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(256) k_dom_unpack_rows(Contacts O, long long b
   O.flags[co] = (r.flags & (CF_KIND_MASK | CF_REAL)) | (uploaded ? 0u : (uint32_t)CF_CLAIMED);
   O.stepCreated[co] = r.stepCreated;
   if (periodic) { O.cdx[co] = r.cd[0]; O.cdy[co] = r.cd[1]; O.cdz[co] = r.cd[2]; }
-  O.rec[4 * co] = make_double4(r.t[0], r.t[1], r.t[2], r.fl[1]); O.rec[4 * co + 1] = make_double4(r.t[3], r.t[4], r.t[5], r.fl[2]);
-  O.rec[4 * co + 2] = r.cp; O.rec[4 * co + 3] = make_double4(r.Fg.x, r.Fg.y, r.Fg.z, r.fl[0]);
+  O.rA[co] = make_double4(r.t[0], r.t[1], r.t[2], r.fl[1]); O.rB[co] = make_double4(r.t[3], r.t[4], r.t[5], r.fl[2]);
+  O.rC[co] = r.cp; O.rD[co] = make_double4(r.Fg.x, r.Fg.y, r.Fg.z, r.fl[0]);
   O.ph[co] = make_double4(r.ph[0], r.ph[1], r.ph[2], law == 1 ? r.ph[3] : 0.);
   if (law == 1) O.ph4[co] = r.ph[4];
   if (rolling) O.tq[co] = make_double4(r.tq[0], r.tq[1], r.tq[2], 0.);
@@ -268,10 +268,10 @@ __global__ void __launch_bounds__(256) k_halo_push(Spheres S, const int* __restr
 // one CTA, one thread per rank: publish my word to every peer (after the halo payload: previous kernel on the stream + system fence), then wait for
 // theirs.  cnt->dirty / cnt->error become the maxima over all ranks.  A peer that never answers (it failed on the host) ends the wait after
 // `timeoutCycles` with ERR_PEER_TIMEOUT instead of hanging the GPU.
-__global__ void k_peer_sync(PeerU P, Counters* cnt, unsigned long long stamp, int parity, long long timeoutCycles) {
+__global__ void k_peer_sync(PeerU P, Counters* cnt, int* flag /*this step's Verlet-dirty slot*/, unsigned long long stamp, int parity, long long timeoutCycles) {
   __shared__ int sDirty[WDEM_MAX_RANKS], sErr[WDEM_MAX_RANKS];
   const int r = threadIdx.x;
-  const unsigned long long mine = (stamp << 16) | ((unsigned long long)(cnt->error & 0x7fff) << 1) | (unsigned long long)(cnt->dirty ? 1 : 0);
+  const unsigned long long mine = (stamp << 16) | ((unsigned long long)(cnt->error & 0x7fff) << 1) | (unsigned long long)(*flag ? 1 : 0);
   int d = 0, e = 0;
   if (r < P.world) {
     __threadfence_system();
@@ -291,7 +291,7 @@ __global__ void k_peer_sync(PeerU P, Counters* cnt, unsigned long long stamp, in
   if (r == 0) {
     int dm = 0, em = 0;
     for (int q = 0; q < P.world; q++) { dm = max(dm, sDirty[q]); em = max(em, sErr[q]); }
-    cnt->dirty = dm;
+    *flag = dm;
     if (em && !cnt->error) { cnt->error = em; cnt->errA = -1; cnt->errB = -1; }
     __threadfence();
   }

@@ -61,22 +61,22 @@ struct SphereStore {
 };
 
 struct ContactStore {
-  DBuf<int2> pair; DBuf<uint32_t> flags, realBits; DBuf<int32_t> stepCreated, cd[3]; DBuf<double4> rec, ph, tq, Tg; DBuf<double> ph4;
+  DBuf<int2> pair; DBuf<uint32_t> flags, realBits; DBuf<int32_t> stepCreated, cd[3]; DBuf<double4> r[4], ph, tq, Tg; DBuf<double> ph4;
   size_t cap = 0;
   void ensure(size_t n, int64_t& tot, bool hertz, bool rolling, bool periodic, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return;
     n = std::max(n, cap + cap / 2);
     pair.ensure(n, tot, keep, st); flags.ensure(n, tot, keep, st); stepCreated.ensure(n, tot, keep, st);
     if (periodic) for (auto& b : cd) b.ensure(n, tot, keep, st);
-    rec.ensure(4 * n, tot, keep, st); ph.ensure(n, tot, keep, st);
+    for (auto& b : r) b.ensure(n, tot, keep, st); ph.ensure(n, tot, keep, st);
     if (hertz) ph4.ensure(n, tot, keep, st);
     if (rolling) { tq.ensure(n, tot, keep, st); Tg.ensure(n, tot, keep, st); }
     realBits.ensure(n / 32 + 2, tot, keep, st);
     cap = n;
   }
   Contacts view() { Contacts C; C.pair = pair.p; C.flags = flags.p; C.stepCreated = stepCreated.p; C.cdx = cd[0].p; C.cdy = cd[1].p; C.cdz = cd[2].p;
-    C.rec = rec.p; C.ph = ph.p; C.ph4 = ph4.p; C.tq = tq.p; C.Tg = Tg.p; C.realBits = realBits.p; return C; }
-  void release() { pair.release(); flags.release(); stepCreated.release(); for (auto& b : cd) b.release(); rec.release(); ph.release(); ph4.release(); tq.release(); Tg.release(); realBits.release(); cap = 0; }
+    C.rA = r[0].p; C.rB = r[1].p; C.rC = r[2].p; C.rD = r[3].p; C.ph = ph.p; C.ph4 = ph4.p; C.tq = tq.p; C.Tg = Tg.p; C.realBits = realBits.p; return C; }
+  void release() { pair.release(); flags.release(); stepCreated.release(); for (auto& b : cd) b.release(); for (auto& b : r) b.release(); ph.release(); ph4.release(); tq.release(); Tg.release(); realBits.release(); cap = 0; }
 };
 
 struct CsrStore { DBuf<int> rowStart; DBuf<uint32_t> rowEntry; DBuf<int32_t> rowOther; bool valid = false; int nRows = 0; void release() { rowStart.release(); rowEntry.release(); rowOther.release(); } };
@@ -140,7 +140,7 @@ struct DomainState {
   DBuf<char> sendBuf, recvBuf; DBuf<unsigned long long> immKeys, immKeysAlt; DBuf<int> immVals, immValsAlt; int nImm = 0;
   long long migratedOut = 0, migratedIn = 0, rowsIn = 0;
   // per-step exchange over peer memory (k_halo_push / k_peer_sync): my mailbox (words + 2 halo buffers), the peers' mailboxes mapped with CUDA IPC
-  struct Peer { bool active = false, disabled = false; char* box = nullptr; long long haloCap = 0; void* base[WDEM_MAX_RANKS] = {}; std::vector<long long> dstOff; long long maxRecvTot = 0; } peer;
+  struct Peer { bool active = false, disabled = false; unsigned long long syncSeq = 0; char* box = nullptr; long long haloCap = 0; void* base[WDEM_MAX_RANKS] = {}; std::vector<long long> dstOff; long long maxRecvTot = 0; } peer;
   void release() {
     sendSlot.release(); recvSlot.release(); exportId.release(); importId.release(); oldIds.release(); haloSend.release(); haloRecv.release(); dkeys.release(); dkeysAlt.release();
     emask.release(); dslots.release(); dslotsAlt.release(); dstart.release(); origSlot.release(); perm2.release(); rowCnt.release(); rowOff.release(); perRank.release();
@@ -153,7 +153,9 @@ struct wdem_engine {
   Transport* comm = nullptr; DomainState dom;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;       // boundary (wall/facet/orphan) contact kernels run beside the sphere-sphere kernel
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFlag = nullptr, evFork = nullptr, evJoin = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFlag = nullptr, evFork = nullptr, evJoin = nullptr, evOrph = nullptr;
+  // steps are enqueued in batches of up to batchK without a host wait (Counters::gflag); batchK adapts to the number of steps between collider full runs
+  int batchMax = 16, batchK = 1; long long stepsSinceFullRun = 0;
   static const int NEVSET = 4;          // per-phase events are harvested a few steps later, so profiling does not stall the pipeline
   cudaEvent_t evr[NEVSET][6] = {}; bool evPending[NEVSET] = {false, false, false, false}; double phaseAcc[5] = {0, 0, 0, 0, 0};
   std::string err;
@@ -171,12 +173,13 @@ struct wdem_engine {
   std::vector<int32_t> hIds;                // Particle.id of the spheres in upload order
   std::vector<CRec> pendingRows;            // contact history imported by wdem_upload_contacts, consumed by the next collider full run
   // contacts
-  ContactStore con[2]; int curC = 0; long long nSS = 0, nWS = 0, nFS = 0, nOrph = 0, nC = 0;
+  ContactStore con[2]; int curC = 0; long long nSS = 0, nSSa = 0, nWS = 0, nFS = 0, nOrph = 0, nC = 0;   // table: [SS active (nSSa) | SS dormant | WS | FS | orphans]
   CsrStore csr[2]; int curR = 0;
   // scratch
   DBuf<uint32_t> keys, keysAlt; DBuf<int> idx, idxAlt, cellStart, counts, offsets; DBuf<unsigned char> cubTemp; DBuf<double> blk;
   DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld, candBuf; DBuf<uint32_t> wallBits; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt; DBuf<int> realFlag, realPos; DBuf<int32_t> tmpCd[3];
-  Counters* dCnt = nullptr; Counters* hCnt = nullptr;
+  double* hBounds = nullptr; bool boundsValid = false;   // pinned, 2 x 8: bounding box of the sphere centres at the last two full runs
+  Counters* dCnt = nullptr; Counters* hCnt = nullptr; int* hScratch = nullptr;   // pinned: per-step counters, small read-backs of the full run
   // scene scalars
   double dt = NAN, time = 0, nextDt = NAN, verletDist = NAN; long long step = 0, nFullRuns = 0; bool conDirty = true;
   long long dynStepLast = -1, dynStepPrev = -1;
@@ -225,13 +228,13 @@ StepU makeUniforms(wdem_engine* E) {
       u.deltaSpinVec = (-.5) * a + .5 * b;
     }
   }
+  u.gIn = E->dCnt->gflag; u.gOut = E->dCnt->gflag + 1;
   u.step = E->step; u.renormNow = (c.trsfRenorm > 0 && (E->step % c.trsfRenorm) == 0); u.noRatch = c.noRatch;
   u.absDistFactor = std::abs(c.distFactor);
   u.law = c.law; u.noSlip = c.noSlip; u.noBreak = c.noBreak; u.noFrict = c.noFrict; u.noAttraction = c.noAttraction;
   u.rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.); u.relRollStiff = c.relRollStiff; u.relTwistStiff = c.relTwistStiff; u.rollTanPhi = c.rollTanPhi;
   u.poisson = c.poisson; u.en = c.en;
   u.energy = E->trackEnergy ? E->dEnergy.p : nullptr;
-  { static const bool noCs = getenv("WDEM_NO_CS_STORES") != nullptr; u.csStores = noCs ? 0 : 1; }
   {   // Leapfrog.cpp:130-132
     bool ident = true; for (int k = 0; k < 9; k++) if (E->cell.gradV.m[k] != ((k % 4 == 0) ? 1. : 0.)) ident = false;
     u.trackLeapfrog = (E->trackEnergy && (!c.periodic || E->step > 0 || ident)) ? 1 : 0;
@@ -527,14 +530,16 @@ PeerU makePeerU(wdem_engine* E) {
   return u;
 }
 // per step, after Leapfrog: push my exported spheres into the neighbours' halo buffers, publish (stamp|error|dirty), wait for everybody's word
-void peerExchange(wdem_engine* E) {
+// The exchanges are numbered (syncSeq), not the steps: steps of a batch that turned out void are enqueued again after the full run, and a stamp must never repeat.
+// Every rank enqueues the same sequence of exchanges (same batch sizes, same global flags), so the numbers agree.
+void peerExchange(wdem_engine* E, int* flag) {
   DomainState& M = E->dom; cudaStream_t st = E->stream;
-  const PeerU u = makePeerU(E); const int parity = (int)(E->step & 1);
+  const PeerU u = makePeerU(E); const unsigned long long seq = ++M.peer.syncSeq; const int parity = (int)(seq & 1);
   if (M.nSendTot && !E->conDirty) { k_halo_push<<<nblk(M.nSendTot, 256), 256, 0, st>>>(E->S(), M.sendSlot.p, (int)M.nSendTot, u, parity); E->launches++; }
-  k_peer_sync<<<1, WDEM_MAX_RANKS, 0, st>>>(u, E->dCnt, (unsigned long long)(E->step + 1), parity, 20000000000ll); E->launches++;
+  k_peer_sync<<<1, WDEM_MAX_RANKS, 0, st>>>(u, E->dCnt, flag, seq, parity, 20000000000ll); E->launches++;
 }
 void peerUnpack(wdem_engine* E) {
-  DomainState& M = E->dom; const int parity = (int)(E->step & 1);
+  DomainState& M = E->dom; const int parity = (int)(M.peer.syncSeq & 1);
   const double* buf = reinterpret_cast<const double*>(M.peer.box + PEER_WORDS_BYTES) + (long long)parity * M.peer.haloCap;
   if (M.nRecvTot) { k_halo_unpack<<<nblk(M.nRecvTot, 256), 256, 0, E->stream>>>(E->S(), M.recvSlot.p, (int)M.nRecvTot, buf); E->launches++; }
 }
@@ -575,7 +580,7 @@ void rebuild(wdem_engine* E) {
   const bool hertz = c.law == WDEM_LAW_HERTZ_DMT, rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.);
   const double vd = E->verletDist;
   int64_t& tot = E->bytes;
-  long long nSS = 0, nWS = 0, nFS = 0, nOrphOut = 0;
+  long long nSS = 0, nSSa = 0, nWS = 0, nFS = 0, nOrphOut = 0;   // nSSa: active sphere-sphere contacts (the first nSSa of the nSS); the rest is dormant
   if (!E->fgridValid) buildFacetGrid(E);
   if (E->groups.n > 0 && !E->hFacets.empty()) rebinFacets(E);
   const int nFacets = (int)E->hFacets.size();
@@ -616,13 +621,19 @@ void rebuild(wdem_engine* E) {
     E->keys.ensure(n, tot); E->keysAlt.ensure(n, tot); E->idx.ensure(n, tot); E->idxAlt.ensure(n, tot);
     if (!c.periodic) {
       // 1. bounds of sphere centres
-      E->blk.ensure((size_t)nb * 7, tot);
-      k_bounds<<<nb, 256, 0, st>>>(E->S().posr, n, E->blk.p); E->launches++;
-      std::vector<double> hb((size_t)nb * 7);
-      CK(cudaMemcpyAsync(hb.data(), E->blk.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-      for (int b = 0; b < nb; b++) for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], hb[7 * b + k]); hi[k] = std::max(hi[k], hb[7 * b + 3 + k]); }
+      // The grid only has to COVER the spheres for speed, not for correctness (cell coordinates are clamped on both sides of every lookup), so the box measured at
+      // the previous full run (read back without waiting, pinned memory) lays out this run's grid; only the first run after an upload waits for its own.
+      E->blk.ensure((size_t)nb * 7 + 8, tot);
+      double* dB = E->blk.p + (size_t)nb * 7;
+      k_bounds<<<nb, 256, 0, st>>>(E->S().posr, n, E->blk.p);
+      k_bounds_final<<<1, 256, 0, st>>>(E->blk.p, nb, dB); E->launches += 2;
+      const int slot = (int)(E->nFullRuns & 1);
+      CK(cudaMemcpyAsync(E->hBounds + 8 * slot, dB, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      const double* hb = E->hBounds + 8 * (1 - slot);
+      if (!E->boundsValid) { CK(cudaStreamSynchronize(st)); hb = E->hBounds + 8 * slot; }
+      E->boundsValid = true;
+      double lo[3], hi[3];
+      for (int k = 0; k < 3; k++) { lo[k] = hb[k] - 2 * vd; hi[k] = hb[3 + k] + 2 * vd; }
       for (int k = 0; k < 3; k++) if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) throw EngErr{"non-finite particle position at collider run", WDEM_ERR_RUNTIME};
       // 2. size-class grids (HGrid): level L = radii [rmin 2^L, rmin 2^(L+1)), cell edge = largest enlarged box of the level, at most ~8 cells per sphere
       const double rmin = E->minRadius, rmax = std::max(E->dom.rmaxGlobal, rmin);
@@ -694,9 +705,11 @@ void rebuild(wdem_engine* E) {
     cub::DeviceScan::InclusiveScan(nullptr, tb, E->cellStart.p, E->cellStart.p, cub::Max(), (int)(ncells + 1), st);
     E->cubTemp.ensure(tb, tot);
     cub::DeviceScan::InclusiveScan(E->cubTemp.p, tb, E->cellStart.p, E->cellStart.p, cub::Max(), (int)(ncells + 1), st); E->launches += 2;
-    // 5. count candidates: [SS by sphere | WS by sphere]
+    // 5. count candidates: [active SS by sphere | dormant SS by sphere | WS by sphere | FS by sphere]
     const int nWalls = (int)E->hWalls.size();
-    E->counts.ensure((size_t)3 * n + 1, tot); E->offsets.ensure((size_t)3 * n + 1, tot);
+    E->counts.ensure((size_t)4 * n + 1, tot); E->offsets.ensure((size_t)4 * n + 1, tot);
+    static const bool noDormant = getenv("WDEM_NO_DORMANT") != nullptr;
+    const double adf = std::abs(c.distFactor), dormOn = (!noDormant && !c.periodic && !c.noBreak && vd > 0.) ? 1. : -1.;
     Contacts dummy; memset(&dummy, 0, sizeof(dummy));
     const int nb128 = nblk(n, 128);
     E->rowCount.ensure((size_t)n + 1, tot);
@@ -708,29 +721,30 @@ void rebuild(wdem_engine* E) {
     WallPass wp; memset(&wp, 0, sizeof(wp));
     const bool mergeWalls = !c.periodic && nWalls > 0 && nWalls <= 32 && !noWallMerge;
     if (mergeWalls) { E->wallBits.ensure((size_t)n, tot); wp.walls = E->dWalls.p; wp.nWalls = nWalls; wp.halfThick = c.wallHalfThick; wp.bits = E->wallBits.p; }
-    if (!c.periodic) k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr, cand, wp);
-    else k_pairs_ss_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt, cand);
+    if (!c.periodic) k_pairs_ss<false><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr, cand, wp, adf, dormOn);
+    else {
+      k_pairs_ss_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt, cand);
+      CK(cudaMemsetAsync(E->counts.p + n, 0, (size_t)n * sizeof(int), st));    // no dormant contacts in a periodic cell
+    }
     E->launches++;
     if (nWalls && !mergeWalls) {
-      if (!c.periodic) k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr);
-      else k_pairs_ws_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, E->counts.p + n, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
+      if (!c.periodic) k_pairs_ws<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, E->counts.p + 2 * n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr);
+      else k_pairs_ws_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, E->counts.p + 2 * n, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
       E->launches++;
     }
-    else if (!nWalls) CK(cudaMemsetAsync(E->counts.p + n, 0, (size_t)n * sizeof(int), st));
-    if (nFacets) { k_pairs_fs<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, E->counts.p + 2 * n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++; }
-    else CK(cudaMemsetAsync(E->counts.p + 2 * n, 0, (size_t)n * sizeof(int), st));
-    CK(cudaMemsetAsync(E->counts.p + 3 * n, 0, sizeof(int), st));
+    else if (!nWalls) CK(cudaMemsetAsync(E->counts.p + 2 * n, 0, (size_t)n * sizeof(int), st));
+    if (nFacets) { k_pairs_fs<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, E->counts.p + 3 * n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++; }
+    else CK(cudaMemsetAsync(E->counts.p + 3 * n, 0, (size_t)n * sizeof(int), st));
+    CK(cudaMemsetAsync(E->counts.p + 4 * n, 0, sizeof(int), st));
     tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, E->counts.p, E->offsets.p, 3 * n + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, E->counts.p, E->offsets.p, 4 * n + 1, st);
     E->cubTemp.ensure(tb, tot);
-    cub::DeviceScan::ExclusiveSum(E->cubTemp.p, tb, E->counts.p, E->offsets.p, 3 * n + 1, st); E->launches += 2;
-    int hOff[3];
-    CK(cudaMemcpyAsync(&hOff[0], E->offsets.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&hOff[1], E->offsets.p + 2 * n, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&hOff[2], E->offsets.p + 3 * n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    cub::DeviceScan::ExclusiveSum(E->cubTemp.p, tb, E->counts.p, E->offsets.p, 4 * n + 1, st); E->launches += 2;
+    int* hOff = E->hScratch;   // pinned
+    for (int k = 0; k < 4; k++) CK(cudaMemcpyAsync(&hOff[k], E->offsets.p + (size_t)(k + 1) * n, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    nSS = hOff[0]; nWS = hOff[1] - hOff[0]; nFS = hOff[2] - hOff[1];
-    if (hOff[2] < 0 || (long long)hOff[2] >= (1ll << 30)) throw EngErr{"too many potential contacts for one device", WDEM_ERR_RUNTIME};
+    nSSa = hOff[0]; nSS = hOff[1]; nWS = hOff[2] - hOff[1]; nFS = hOff[3] - hOff[2];
+    if (hOff[3] < 0 || (long long)hOff[3] >= (1ll << 30)) throw EngErr{"too many potential contacts for one device", WDEM_ERR_RUNTIME};
     // 6. fill pairs + carry history
     const long long nC0 = nSS + nWS + nFS;
     Nst.ensure((size_t)std::max<long long>(nC0, 1), tot, hertz, rolling, c.periodic);
@@ -741,52 +755,64 @@ void rebuild(wdem_engine* E) {
     E->ckeys.ensure(nT, tot); E->cvals.ensure(nT, tot); E->realFlag.ensure(nT + 1, tot); E->realPos.ensure(nT + 1, tot);
     Contacts T = N; T.pair = reinterpret_cast<int2*>(E->ckeys.p); T.flags = E->cvals.p;
     if (c.periodic) { for (auto& b : E->tmpCd) b.ensure(nT, tot); T.cdx = E->tmpCd[0].p; T.cdy = E->tmpCd[1].p; T.cdz = E->tmpCd[2].p; }
-    if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, E->offsets.p, T, O, oc, perm, nullptr, E->srcOld.p, cand, wp);
+    if (!c.periodic) k_pairs_ss<true><<<nb128, 128, 0, st>>>(E->S(), n, g, E->cellStart.p, vd, c.loneMask, E->counts.p, E->offsets.p, T, O, oc, perm, nullptr, E->srcOld.p, cand, wp, adf, dormOn);
     else k_pairs_ss_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, g, pu, E->cellStart.p, vd, c.loneMask, E->counts.p, E->offsets.p, T, oc, perm, nullptr, E->srcOld.p, E->dCnt, cand);
     E->launches++;
     if (nWalls && !mergeWalls) {
-      if (!c.periodic) k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, T, O, oc, perm, nullptr, E->srcOld.p);
-      else k_pairs_ws_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + n, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
+      if (!c.periodic) k_pairs_ws<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + 2 * n, T, O, oc, perm, nullptr, E->srcOld.p);
+      else k_pairs_ws_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + 2 * n, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
       E->launches++;
     }
-    if (nFacets) { k_pairs_fs<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, nullptr, E->offsets.p + 2 * n, T, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
+    if (nFacets) { k_pairs_fs<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, nullptr, E->offsets.p + 3 * n, T, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
     if (nC0 > 0) {
       // real-first order inside the sphere-sphere segment (the reference reorders its contacts for the same reason, ContactLoop.cpp:75-91):
       // warps of k_contact_ss then see either all-real or all-potential contacts instead of paying the long path for half-empty warps
-      k_was_real<<<nblk(nSS + 1, 256), 256, 0, st>>>(E->srcOld.p, O.flags, nSS, E->realFlag.p);
-      exclusiveSum(E, E->realFlag.p, E->realPos.p, (int)nSS + 1);
-      k_carry<<<nblk(8 * nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, T, E->realPos.p, nSS, c.law, rolling, c.periodic, E->step); E->launches += 4;
+      k_was_real<<<nblk(nSSa + 1, 256), 256, 0, st>>>(E->srcOld.p, O.flags, nSSa, E->realFlag.p);
+      exclusiveSum(E, E->realFlag.p, E->realPos.p, (int)nSSa + 1);
+      k_carry<<<nblk(8 * nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, T, E->realPos.p, nSSa, c.law, rolling, c.periodic, E->step); E->launches += 4;
     }
-    // 6b. orphans: real contacts of the previous table that no candidate claimed (AABBs separated while real)
+    // 6b. orphans: real contacts of the previous table that no candidate claimed (AABBs separated while real).  The counting pass adds their incidences to the row
+    // counts; how many there are travels to the host while the GPU goes on with the rows of the grid candidates, so the wait costs no idle time.
     long long nOrph = 0;
-    if ((oc.valid || imported) && E->nC > 0) {
+    const bool orphPass = (oc.valid || imported) && E->nC > 0;
+    const int32_t* oldSid = (E->comm || E->compactPending) ? E->dom.oldIds.p : E->sph[1 - E->cur].id.p;
+    const uint32_t* sfl = E->comm ? E->S().flags : nullptr;
+    int* hOrph = E->hScratch + 8; *hOrph = 0;
+    if (orphPass) {
       E->orphCnt.ensure(1, tot);
       CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
-      const int32_t* oldSid = (E->comm || E->compactPending) ? E->dom.oldIds.p : E->sph[1 - E->cur].id.p;
-      const uint32_t* sfl = E->comm ? E->S().flags : nullptr;
       k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, sfl, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 0); E->launches++;
-      int hN = 0; CK(cudaMemcpyAsync(&hN, E->orphCnt.p, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-      if (hN > 0) {
-        nOrph = hN;
-        Nst.ensure((size_t)(nC0 + nOrph), tot, hertz, rolling, c.periodic, /*keep*/ true, st);
-        N = Nst.view();
-        CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
-        k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, sfl, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 1); E->launches++;
-      }
+      CK(cudaMemcpyAsync(hOrph, E->orphCnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(E->evOrph, st));
     }
-    const long long nC = nC0 + nOrph;
-    nOrphOut = nOrph;
-    if (nC > 0) { k_realbits<<<nblk(nC, 256), 256, 0, st>>>(N.flags, nC, N.realBits); E->launches++; }
+    if (nC0 > 0) { k_realbits<<<nblk(nC0, 256), 256, 0, st>>>(N.flags, 0, nC0, N.realBits); E->launches++; }
     // 7. per-particle incidence rows sorted by the other particle's id: scan of row counts, cursor fill, per-row sort
-    const long long nK = 2 * nC;
-    Ncsr.rowStart.ensure((size_t)n + 2, tot); Ncsr.rowEntry.ensure((size_t)std::max<long long>(nK, 1), tot); Ncsr.rowOther.ensure((size_t)std::max<long long>(nK, 1), tot);
+    const long long slack = 4096;
+    Ncsr.rowStart.ensure((size_t)n + 2, tot); Ncsr.rowEntry.ensure((size_t)(2 * (nC0 + slack)), tot); Ncsr.rowOther.ensure((size_t)(2 * (nC0 + slack)), tot);
     tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, E->rowCount.p, Ncsr.rowStart.p, n + 1, st);
     E->cubTemp.ensure(tb, tot);
     cub::DeviceScan::ExclusiveSum(E->cubTemp.p, tb, E->rowCount.p, Ncsr.rowStart.p, n + 1, st); E->launches += 2;
+    CK(cudaMemsetAsync(E->rowCount.p, 0, ((size_t)n + 1) * sizeof(int), st));   // reused as the per-row cursor
+    if (nC0 > 0) { k_csr_fill<<<nblk(nC0, 256), 256, 0, st>>>(N, 0, nC0, E->S().id, E->dWalls.p, E->dFacets.p, Ncsr.rowStart.p, E->rowCount.p, Ncsr.rowEntry.p, Ncsr.rowOther.p); E->launches++; }
+    if (orphPass) {
+      CK(cudaEventSynchronize(E->evOrph));
+      if (*hOrph > 0) {
+        nOrph = *hOrph;
+        Nst.ensure((size_t)(nC0 + nOrph), tot, hertz, rolling, c.periodic, /*keep*/ true, st);
+        N = Nst.view();
+        Ncsr.rowEntry.ensure((size_t)(2 * (nC0 + nOrph)), tot, /*keep*/ true, st); Ncsr.rowOther.ensure((size_t)(2 * (nC0 + nOrph)), tot, /*keep*/ true, st);
+        CK(cudaMemsetAsync(E->orphCnt.p, 0, sizeof(int), st));
+        k_orphans<<<nblk(E->nC, 256), 256, 0, st>>>(O, E->nC, N, nC0, oldSid, E->id2slot.p, sfl, c.law, rolling, c.periodic, E->orphCnt.p, E->rowCount.p, 1);
+        const long long w0 = nC0 & ~31ll;
+        k_realbits<<<nblk(nC0 + nOrph - w0, 256), 256, 0, st>>>(N.flags, w0, nC0 + nOrph, N.realBits);
+        k_csr_fill<<<nblk(nOrph, 256), 256, 0, st>>>(N, nC0, nC0 + nOrph, E->S().id, E->dWalls.p, E->dFacets.p, Ncsr.rowStart.p, E->rowCount.p, Ncsr.rowEntry.p, Ncsr.rowOther.p);
+        E->launches += 3;
+      }
+    }
+    const long long nC = nC0 + nOrph;
+    nOrphOut = nOrph;
     if (nC > 0) {
-      CK(cudaMemsetAsync(E->rowCount.p, 0, ((size_t)n + 1) * sizeof(int), st));   // reused as the per-row cursor
-      k_csr_fill<<<nblk(nC, 256), 256, 0, st>>>(N, nC, E->S().id, E->dWalls.p, E->dFacets.p, Ncsr.rowStart.p, E->rowCount.p, Ncsr.rowEntry.p, Ncsr.rowOther.p); E->launches++;
       E->idx.ensure((size_t)n + 1, tot);   // the cell-sort scratch is free again: queue of long rows + its counter
       CK(cudaMemsetAsync(E->idx.p + n, 0, sizeof(int), st));
       k_row_sort<<<nb128, 128, 0, st>>>(n, Ncsr.rowStart.p, Ncsr.rowEntry.p, Ncsr.rowOther.p, E->idx.p, E->idx.p + n);
@@ -795,7 +821,7 @@ void rebuild(wdem_engine* E) {
     Ncsr.valid = true; Ncsr.nRows = n;
   }
   if (E->anyMovingWall) { k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), makeUniforms(E), E->dCnt, 1); E->launches++; }   // Aabb::nodeLastPos (Collision.cpp:138-141)
-  E->nSS = nSS; E->nWS = nWS; E->nFS = nFS; E->nOrph = nOrphOut; E->nC = nSS + nWS + nFS + nOrphOut;
+  E->nSS = nSS; E->nSSa = nSSa; E->nWS = nWS; E->nFS = nFS; E->nOrph = nOrphOut; E->nC = nSS + nWS + nFS + nOrphOut;
   E->curC = 1 - E->curC; E->curR = 1 - E->curR;
   E->nFullRuns++; E->compactPending = false;
   auto t2 = now();
@@ -927,7 +953,7 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   const wdem_config& c = E->cfg; cudaStream_t st = E->stream, st2 = E->stream2;
   Contacts C = E->con[E->curC].view();
   static const bool sideOff = getenv("WDEM_NO_SIDE_STREAM") != nullptr;
-  const bool side = !sideOff && (E->nWS + E->nFS + E->nOrph) > 0 && E->nSS > 0;   // boundary kernels are small and latency-bound: overlap them with the big one
+  const bool side = !sideOff && (E->nWS + E->nFS + E->nOrph) > 0 && E->nSSa > 0;   // boundary kernels are small and latency-bound: overlap them with the big one
   cudaStream_t sb = side ? st2 : st;
   if (ev) CK(cudaEventRecord(ev[2], st));
   if (side) { CK(cudaEventRecord(E->evFork, st)); CK(cudaStreamWaitEvent(st2, E->evFork, 0)); }
@@ -960,24 +986,13 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
     E->launches++;
   }
   // the big kernel goes last so that the small boundary kernels already occupy their share of the SMs
-  if (E->nSS > 0) {
-    const int gridSS = std::min(nblk(E->nSS, WD_CONTACT_BLOCK), E->numSMs * WD_CONTACT_CTAS_PER_SM);   // persistent: one CTA per resident slot
-    static const bool direct = getenv("WDEM_CONTACT_DIRECT") != nullptr;   // A/B knob: per-thread global loads instead of the cp.async-staged tiles
-    static bool carve = false;
-    if (!carve) {   // 40 KB of static shared memory per CTA, 4 CTAs per SM: ask for a shared-memory-heavy L1 split (the gathers live in L2, not L1)
-      cudaFuncSetAttribute(k_contact_ss<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 75); cudaFuncSetAttribute(k_contact_ss<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
-      cudaFuncSetAttribute(k_contact_ss<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 75); cudaFuncSetAttribute(k_contact_ss<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
-      carve = true;
-    }
-    switch (c.law + (u.energy ? 2 : 0) + (direct ? 4 : 0)) {
-      case 0: k_contact_ss<0><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 1: k_contact_ss<1><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 2: k_contact_ss<2><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 3: k_contact_ss<3><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 4: k_contact_ss_direct<0><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 5: k_contact_ss_direct<1><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 6: k_contact_ss_direct<2><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
-      case 7: k_contact_ss_direct<3><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSS, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+  if (E->nSSa > 0) {
+    const int gridSS = std::min(nblk(E->nSSa, WD_CONTACT_BLOCK), E->numSMs * WD_CONTACT_CTAS_PER_SM);   // persistent: one CTA per resident slot
+    switch (c.law + (u.energy ? 2 : 0)) {
+      case 0: k_contact_ss<0><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSSa, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 1: k_contact_ss<1><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSSa, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 2: k_contact_ss<2><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSSa, E->S(), E->dMats.p, u, E->dCnt, guard); break;
+      case 3: k_contact_ss<3><<<gridSS, WD_CONTACT_BLOCK, 0, st>>>(C, 0, E->nSSa, E->S(), E->dMats.p, u, E->dCnt, guard); break;
     }
     E->launches++;
   }
@@ -1032,24 +1047,17 @@ void leapfrogPipelined(wdem_engine* E, const StepU& u) {
   CK(cudaMemcpyAsync(E->hEk, E->blk.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, E->sD2H));
 }
 
-void oneStep(wdem_engine* E, wdem_stats* stats) {
+// ---- one step in pieces, so that several steps can be enqueued before the host looks at the Verlet flags (Counters::gflag) ----
+struct StepSnap { HostCell cell; GroupsU groups; long long step; double time; StepU u; };
+
+// host prologue (Scene::doOneStep up to the engines, Scene.cpp:414-419): cell integration, per-step uniforms, master nodes of kinematic facet groups
+StepU stepPrologue(wdem_engine* E, int k) {
   const wdem_config& c = E->cfg;
-  cudaStream_t st = E->stream;
-  ensureVerletAndDt(E);
   if (c.periodic) E->cell.integrateAndUpdate(E->dt);
   StepU u = makeUniforms(E);
+  u.gIn = E->dCnt->gflag + k; u.gOut = E->dCnt->gflag + k + 1;
   if (u.energy) {   // energy->resetResettables() (Scene.cpp:416): "kinetic" and "elast" restart from zero every step
     CK(cudaMemsetAsync(u.energy + EN_KINETIC, 0, sizeof(double), E->stream)); CK(cudaMemsetAsync(u.energy + EN_ELAST, 0, sizeof(double), E->stream));
-  }
-  const int n = E->n;
-  cudaEvent_t* ev = nullptr;
-  if (E->profiling) { const int set = (int)(E->step % wdem_engine::NEVSET); harvestPhases(E, set); ev = E->evr[set]; }
-  if (ev) CK(cudaEventRecord(ev[0], st));
-  if (n > 0 && E->e2e.active) leapfrogPipelined(E, u);
-  else if (n > 0) {
-    if (u.energy) k_leapfrog<true><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
-    else k_leapfrog<false><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
-    E->launches++;
   }
   if (E->groups.n > 0 && !E->hFacets.empty()) {
     if (c.periodic) throw EngErr{"moving facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
@@ -1069,59 +1077,121 @@ void oneStep(wdem_engine* E, wdem_stats* stats) {
       const double nn = std::sqrt(((G.ori.x * G.ori.x + G.ori.y * G.ori.y) + G.ori.z * G.ori.z) + G.ori.w * G.ori.w);
       G.ori.w /= nn; G.ori.x /= nn; G.ori.y /= nn; G.ori.z /= nn;
     }
-    k_facets_step<<<nblk((long long)E->hFacets.size(), 128), 128, 0, st>>>(E->dFacets.p, (int)E->hFacets.size(), E->groups, u, E->dCnt, 0); E->launches++;
   }
+  return u;
+}
+
+// Leapfrog (+ boundary nodes) and, in decomposed runs, the exchange of (dirty, error) and of the halo payload
+void enqueueIntegrate(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
+  const wdem_config& c = E->cfg; cudaStream_t st = E->stream; const int n = E->n;
+  if (ev) CK(cudaEventRecord(ev[0], st));
+  if (n > 0 && E->e2e.active) leapfrogPipelined(E, u);
+  else if (n > 0) {
+    if (u.energy) k_leapfrog<true><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
+    else k_leapfrog<false><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
+    E->launches++;
+  }
+  if (E->groups.n > 0 && !E->hFacets.empty()) { k_facets_step<<<nblk((long long)E->hFacets.size(), 128), 128, 0, st>>>(E->dFacets.p, (int)E->hFacets.size(), E->groups, u, E->dCnt, 0); E->launches++; }
   if (E->anyMovingWall) {
     if (c.periodic) throw EngErr{"moving walls in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), u, E->dCnt, 0); E->launches++;
   }
   if (ev) CK(cudaEventRecord(ev[1], st));
-  // collider: full run if contacts are dirty / verletDist==0 / any sphere moved farther than verletDist (flag raised by k_leapfrog)
-  bool full = E->conDirty || E->verletDist == 0;
   // (dirty, error): every subdomain rebuilds / fails in the same step; over peer memory together with the halo payload, else NCCL
-  const bool peer = E->comm && E->dom.peer.active;
-  if (peer) peerExchange(E);
-  else if (E->comm) E->comm->allreduceMaxInt(&E->dCnt->dirty, 2, st);
-  CK(cudaMemcpyAsync(E->hCnt, E->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(E->evFlag, st));
-  // Speculate that no full run is due (the common case): enqueue the rest of the step behind the flag copy, guarded on the device by the flag,
-  // so the GPU keeps running while the host waits for the flag.
-  const bool speculate = !full;
-  if (speculate) {
-    if (peer) peerUnpack(E);
-    else if (E->comm) haloExchange(E);
-    launchContactsAndReduce(E, u, &E->dCnt->dirty, ev);
-  }
-  CK(cudaEventSynchronize(E->evFlag));
-  checkDeviceError(E);
-  if (E->hCnt->dirty) full = true;
-  if (full) {
-    rebuild(E);
-    E->conDirty = false;
-    CK(cudaMemsetAsync(&E->dCnt->dirty, 0, sizeof(int), st));
-    if (stats) stats->n_rebuilds++;
-    launchContactsAndReduce(E, u, &E->dCnt->dirty, ev);
-  }
-  // DynDt (PeriodicEngine::isActivated, Engine.cpp:170-195 with stepModulo/initRun defaults; DynDt::run DynDt.cpp:90-113)
-  if (c.dynDtPeriod > 0) {
-    bool initNow = E->dynStepLast < 0;
-    if (initNow) E->dynStepLast = E->step;
-    if ((E->step - E->dynStepLast >= c.dynDtPeriod) || (E->step % c.dynDtPeriod == 0)) {
-      E->dynStepPrev = E->dynStepLast; E->dynStepLast = E->step;
-      double crDt = dynDtCritGlobal(E);
-      if (!std::isinf(crDt)) {
-        int nSteps = (int)(E->step - E->dynStepPrev);
-        double maxNewDt = E->dt * pown(1. + c.maxRelInc, (unsigned)nSteps);
-        double nDt = std::min(crDt * c.dtSafety, maxNewDt);
-        if (nDt != E->dt) E->nextDt = nDt;
-      }
+  if (E->comm && E->dom.peer.active) peerExchange(E, u.gOut);
+  else if (E->comm) E->comm->allreduceMaxInt(&E->dCnt->error, WD_KMAX + 2, st);
+}
+// ghosts refreshed, then ContactLoop + force reduction, all void on the device if this step's flag is up
+void enqueueContacts(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
+  if (E->comm && E->dom.peer.active) peerUnpack(E);
+  else if (E->comm) haloExchange(E);
+  launchContactsAndReduce(E, u, u.gOut, ev);
+}
+// Scene::doOneStep's tail (Scene.cpp:428-432)
+void stepEpilogue(wdem_engine* E) {
+  if (E->cfg.periodic) E->cell.setNextGradV();
+  E->step++; E->time += E->dt; E->stepsSinceFullRun++;
+  if (!std::isnan(E->nextDt)) { E->dt = E->nextDt; E->nextDt = NAN; }
+}
+// DynDt (PeriodicEngine::isActivated, Engine.cpp:170-195 with stepModulo/initRun defaults; DynDt::run DynDt.cpp:90-113)
+bool dynDtDue(const wdem_engine* E, long long step) {
+  const int P = E->cfg.dynDtPeriod;
+  if (P <= 0) return false;
+  const long long last = E->dynStepLast < 0 ? E->step : E->dynStepLast;     // the first check initialises the counter with the current step
+  return (step - last >= P) || (step % P == 0);
+}
+void dynDtIfDue(wdem_engine* E) {
+  const wdem_config& c = E->cfg;
+  if (c.dynDtPeriod <= 0) return;
+  if (E->dynStepLast < 0) E->dynStepLast = E->step;
+  if ((E->step - E->dynStepLast >= c.dynDtPeriod) || (E->step % c.dynDtPeriod == 0)) {
+    E->dynStepPrev = E->dynStepLast; E->dynStepLast = E->step;
+    double crDt = dynDtCritGlobal(E);
+    if (!std::isinf(crDt)) {
+      int nSteps = (int)(E->step - E->dynStepPrev);
+      double maxNewDt = E->dt * pown(1. + c.maxRelInc, (unsigned)nSteps);
+      double nDt = std::min(crDt * c.dtSafety, maxNewDt);
+      if (nDt != E->dt) E->nextDt = nDt;
     }
   }
-  if (ev) { CK(cudaEventRecord(ev[5], st)); E->evPending[E->step % wdem_engine::NEVSET] = true; }
-  // epilogue (Scene.cpp:428-432)
-  if (c.periodic) E->cell.setNextGradV();
-  E->step++; E->time += E->dt;
-  if (!std::isnan(E->nextDt)) { E->dt = E->nextDt; E->nextDt = NAN; }
+}
+
+// `nsteps` steps of Scene::doOneStep.  Steps are enqueued in batches of K without a host wait in between; on the device every kernel of a batch is guarded by the
+// Verlet flags of the steps before it (Counters::gflag), so the first step that needs a collider full run stops everything behind it.  The host then rolls its own
+// per-step state (cell, facet-group masters, step counter) back to that step, does the full run, repeats the contact pass of that step and carries on.  K follows
+// the observed number of steps between full runs (1 while every step triggers one, e.g. in free fall); it is 1 for the end-to-end path, with Scene.trackEnergy
+// (resettable energies are zeroed per step) and always ends at a step in which DynDt is due.
+void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
+  cudaStream_t st = E->stream;
+  std::vector<StepSnap> snaps;
+  int64_t done = 0;
+  while (done < nsteps) {
+    ensureVerletAndDt(E);
+    const bool full0 = E->conDirty || E->verletDist == 0;     // a full run is certain: do not enqueue the contact pass speculatively
+    if (E->cfg.dynDtPeriod > 0 && E->dynStepLast < 0) E->dynStepLast = E->step;      // PeriodicEngine's first activation check
+    const long long since0 = E->stepsSinceFullRun;
+    int K = 1;
+    if (!full0 && !E->e2e.active && !E->trackEnergy && E->n > 0) {
+      K = (int)std::min<int64_t>(std::min(E->batchK, E->batchMax), nsteps - done);
+      for (int k = 0; k < K; k++) if (dynDtDue(E, E->step + k)) { K = k + 1; break; }
+    }
+    snaps.resize(K);
+    for (int k = 0; k < K; k++) {
+      const StepU u = stepPrologue(E, k);
+      snaps[k] = StepSnap{E->cell, E->groups, E->step, E->time, u};
+      cudaEvent_t* ev = nullptr;
+      if (E->profiling) { const int set = (int)(E->step % wdem_engine::NEVSET); harvestPhases(E, set); ev = E->evr[set]; }
+      enqueueIntegrate(E, u, ev);
+      if (!full0) enqueueContacts(E, u, ev);
+      if (ev) { CK(cudaEventRecord(ev[5], st)); E->evPending[E->step % wdem_engine::NEVSET] = true; }
+      if (k < K - 1) stepEpilogue(E);
+    }
+    CK(cudaMemcpyAsync(E->hCnt, E->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(E->evFlag, st));
+    CK(cudaEventSynchronize(E->evFlag));
+    checkDeviceError(E);
+    int kd = full0 ? 0 : -1;
+    if (!full0) for (int k = 0; k < K; k++) if (E->hCnt->gflag[k + 1]) { kd = k; break; }
+    int executed = K;
+    if (kd >= 0) {
+      // back to step kd, after its prologue and its Leapfrog
+      E->cell = snaps[kd].cell; E->groups = snaps[kd].groups; E->step = snaps[kd].step; E->time = snaps[kd].time;
+      const long long interval = since0 + kd + 1;
+      rebuild(E);
+      E->conDirty = false; E->stepsSinceFullRun = -1;      // the epilogue below counts this step
+      E->batchK = (int)std::max<long long>(1, std::min<long long>(E->batchMax, interval / 2));
+      CK(cudaMemsetAsync(E->dCnt->gflag, 0, sizeof(int) * (WD_KMAX + 1), st));
+      if (stats) stats->n_rebuilds++;
+      StepU u = snaps[kd].u; u.gIn = E->dCnt->gflag; u.gOut = E->dCnt->gflag;      // slot 0 is always 0: the repeated pass is not speculative
+      cudaEvent_t* ev = E->profiling ? E->evr[E->step % wdem_engine::NEVSET] : nullptr;
+      launchContactsAndReduce(E, u, u.gOut, ev);
+      if (ev) CK(cudaEventRecord(ev[5], st));
+      executed = kd + 1;
+    } else if (E->stepsSinceFullRun + K > 2 * (long long)E->batchK) E->batchK = std::min(E->batchMax, E->batchK + 1);      // long quiet stretch: larger batches
+    dynDtIfDue(E);
+    stepEpilogue(E);
+    done += executed;
+  }
 }
 
 template <class F>
@@ -1207,6 +1277,10 @@ int wdem_create(const wdem_config* cfg, wdem_handle* out) {
     for (auto& set : E->evr) for (auto& e : set) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&E->dCnt, sizeof(Counters))); CK(cudaMemset(E->dCnt, 0, sizeof(Counters)));
     CK(cudaMallocHost(&E->hCnt, sizeof(Counters))); memset(E->hCnt, 0, sizeof(Counters));
+    CK(cudaMallocHost(&E->hScratch, 256 * sizeof(int))); memset(E->hScratch, 0, 256 * sizeof(int));
+    CK(cudaMallocHost(&E->hBounds, 16 * sizeof(double))); memset(E->hBounds, 0, 16 * sizeof(double));
+    CK(cudaEventCreateWithFlags(&E->evOrph, cudaEventDisableTiming));
+    if (const char* g = getenv("WDEM_BATCH")) E->batchMax = std::max(1, std::min(WD_KMAX, atoi(g)));
     *out = E;
     return WDEM_OK;
   } catch (CudaErr& e) { g_createError = e.msg; delete E; return e.code; }
@@ -1222,7 +1296,7 @@ int wdem_destroy(wdem_handle h) {
   h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->candBuf.release(); h->wallBits.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
   peerTeardown(h, false);
   h->dom.release(); delete h->comm; h->comm = nullptr;
-  if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt);
+  if (h->dCnt) cudaFree(h->dCnt); if (h->hCnt) cudaFreeHost(h->hCnt); if (h->hScratch) cudaFreeHost(h->hScratch); if (h->hBounds) cudaFreeHost(h->hBounds); if (h->evOrph) cudaEventDestroy(h->evOrph);
   if (h->ev0) cudaEventDestroy(h->ev0); if (h->ev1) cudaEventDestroy(h->ev1); for (auto& set : h->evr) for (auto& e : set) if (e) cudaEventDestroy(e);
   if (h->evFlag) cudaEventDestroy(h->evFlag); if (h->evFork) cudaEventDestroy(h->evFork); if (h->evJoin) cudaEventDestroy(h->evJoin);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
@@ -1310,8 +1384,8 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
     h->dom.nOwn = (int)n; h->dom.globalsValid = false; h->dom.rmaxGlobal = 0; for (int64_t i = 0; i < n; i++) h->dom.rmaxGlobal = std::max(h->dom.rmaxGlobal, radius[i]);
     h->dom.nSendTot = h->dom.nRecvTot = 0; h->dom.nImm = 0;
     CK(cudaStreamSynchronize(st));
-    h->conDirty = true; h->nC = h->nSS = h->nWS = h->nFS = 0; h->csr[0].valid = h->csr[1].valid = false; h->up2slotValid = false;
-    h->verletDist = NAN; h->fgridValid = false;
+    h->conDirty = true; h->nC = h->nSS = h->nSSa = h->nWS = h->nFS = h->nOrph = 0; h->csr[0].valid = h->csr[1].valid = false; h->up2slotValid = false;
+    h->verletDist = NAN; h->fgridValid = false; h->boundsValid = false; h->batchK = 1;
   });
 }
 
@@ -1530,9 +1604,9 @@ static void stepN(wdem_handle h, int64_t nsteps, wdem_stats* stats, bool cheapSt
     long long l0 = h->launches;
     CK(cudaMemsetAsync(h->dCnt, 0, 4 * sizeof(unsigned long long), h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
-    for (int64_t s = 0; s < nsteps; s++) oneStep(h, &local);
+    runSteps(h, nsteps, &local);
     CK(cudaEventRecord(h->ev1, h->stream));
-    if (h->comm) h->comm->allreduceMaxInt(&h->dCnt->dirty, 2, h->stream);
+    if (h->comm) h->comm->allreduceMaxInt(&h->dCnt->error, 1, h->stream);
     fetchCounters(h);
     CK(cudaEventSynchronize(h->ev1));
     for (int k = 0; k < wdem_engine::NEVSET; k++) harvestPhases(h, k);
@@ -1610,8 +1684,8 @@ int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torqu
     // wall-sphere contacts live in [nSS, nSS+nWS) and among the orphans; forces are added per wall in ascending id of the sphere, the order of
     // the per-particle contact map the reference walks (Particle.hpp:36)
     const long long nC = h->nC; ContactStore& cs = h->con[h->curC];
-    auto flags = d2h(cs.flags.p, nC, st); auto pair = d2h(cs.pair.p, nC, st); auto rec = d2h(cs.rec.p, 4 * (size_t)nC, st);
-    auto Fg = [&](long long c) { return rec[4 * c + 3]; }; auto cp = [&](long long c) { return rec[4 * c + 2]; };
+    auto flags = d2h(cs.flags.p, nC, st); auto pair = d2h(cs.pair.p, nC, st); auto rCv = d2h(cs.r[2].p, nC, st), rDv = d2h(cs.r[3].p, nC, st);
+    auto Fg = [&](long long c) { return rDv[c]; }; auto cp = [&](long long c) { return rCv[c]; };
     auto sid = d2h(h->S().id, h->n, st); auto sfl = d2h(h->S().flags, h->n, st);
     const bool rolling = (h->cfg.relRollStiff > 0. && h->cfg.rollTanPhi > 0.);
     std::vector<double4> Tg; if (rolling) Tg = d2h(cs.Tg.p, nC, st);
@@ -1722,16 +1796,17 @@ int64_t wdem_download_contacts(wdem_handle h, int realOnly, int64_t cap, int32_t
     auto pair = d2h(cs.pair.p, nC, st); auto flags = d2h(cs.flags.p, nC, st); auto sid = d2h(h->S().id, h->n, st);
     std::vector<uint32_t> sfl; if (h->comm) sfl = d2h(h->S().flags, h->n, st);
     const bool hertz = h->cfg.law == WDEM_LAW_HERTZ_DMT, rolling = (h->cfg.relRollStiff > 0. && h->cfg.rollTanPhi > 0.);
-    auto rec = d2h(cs.rec.p, 4 * (size_t)nC, st); auto php = d2h(cs.ph.p, nC, st);
+    std::vector<double4> rv[4]; for (int k = 0; k < 4; k++) rv[k] = d2h(cs.r[k].p, nC, st);
+    auto php = d2h(cs.ph.p, nC, st);
     std::vector<double> ph4v; if (hertz) ph4v = d2h(cs.ph4.p, nC, st);
     std::vector<double4> tqv; if (rolling) tqv = d2h(cs.tq.p, nC, st);
     auto sc = d2h(cs.stepCreated.p, nC, st);
-    // views of the 128-byte record (wdem_kernels.cuh: struct Contacts)
-    auto tcol = [&](int k, long long c) { const double4& v = rec[4 * c + (k / 3)]; return (k % 3) == 0 ? v.x : ((k % 3) == 1 ? v.y : v.z); };
-    auto fl = [&](int k, long long c) { return k == 0 ? rec[4 * c + 3].w : (k == 1 ? rec[4 * c].w : rec[4 * c + 1].w); };
+    // views of the four state planes (wdem_kernels.cuh: struct Contacts)
+    auto tcol = [&](int k, long long c) { const double4& v = rv[k / 3][c]; return (k % 3) == 0 ? v.x : ((k % 3) == 1 ? v.y : v.z); };
+    auto fl = [&](int k, long long c) { return k == 0 ? rv[3][c].w : (k == 1 ? rv[0][c].w : rv[1][c].w); };
     auto phk = [&](int k, long long c) { const double4& v = php[c]; return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : (k == 3 ? v.w : ph4v[c]))); };
     auto tqk = [&](int k, long long c) { const double4& v = tqv[c]; return k == 0 ? v.x : (k == 1 ? v.y : v.z); };
-    auto cp = [&](long long c) { return rec[4 * c + 2]; };
+    auto cp = [&](long long c) { return rv[2][c]; };
     std::vector<int32_t> cdv[3];
     if (h->cfg.periodic) for (int k = 0; k < 3; k++) cdv[k] = d2h(cs.cd[k].p, nC, st);
     struct Row { uint64_t key; long long c; };

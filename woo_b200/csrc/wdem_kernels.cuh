@@ -12,7 +12,7 @@ enum { F_DOF_ALL = 63, F_ENERGY_SKIP = 256, F_GRAVITY_SKIP = 512, F_DAMPING_SKIP
 // sphere that migrated into this subdomain at the current collider full run
 enum : uint32_t { F_GHOST = 1u << 30, F_ARRIVED = 1u << 29 };
 // contact flags
-enum { CF_REAL = 1, CF_ORPHAN = 2, CF_DEAD = 4, CF_CLAIMED = 8, CF_KIND_SHIFT = 4, CF_KIND_MASK = 3u << 4 };
+enum { CF_REAL = 1, CF_ORPHAN = 2, CF_DEAD = 4, CF_CLAIMED = 8, CF_KIND_SHIFT = 4, CF_KIND_MASK = 3u << 4, CF_DORMANT = 64 };
 __host__ __device__ __forceinline__ int cf_kind(uint32_t f) { return (int)((f >> 4) & 3u); }
 enum { KIND_SS = 0, KIND_WS = 1, KIND_FS = 2 };
 
@@ -50,12 +50,13 @@ struct Contacts {         // one entry per candidate pair (real or potential)
   uint32_t* flags;
   int32_t* stepCreated;
   int32_t *cdx, *cdy, *cdz;            // Contact.cellDist (periodic only)
-  // The persistent state of a contact is ONE 128-byte record = one cache line (4 x double4), rec[4c+k]:
-  //   k=0: L6Geom.trsf column 0 (xyz), w = CPhys.force[1] (ft0)        k=1: trsf column 1 (xyz), w = CPhys.force[2] (ft1)
-  //   k=2: contact point CGeom.node.pos (xyz), w = uN                   k=3: global force on pA (xyz), w = CPhys.force[0] (fn)
-  // (trsf column 2 = c0 x c1 is recomputed bit-identically.)  The contact kernel reads k=0..2 and writes the whole line; the force reduction gathers the second
-  // half (k=2,3: one 64-byte fetch per incidence instead of two sectors in two planes); the history carry-over of a full run copies one line per contact.
-  double4* rec;
+  // The persistent state of a contact lives in four double4 planes (every per-thread access of a warp is one fully used 32-byte sector per lane, 1 KB contiguous per
+  // warp; the force reduction gathers rC and rD; the history carry-over of a full run copies 4 sectors per contact instead of the 14 scalar planes of round 1):
+  //   rA: L6Geom.trsf column 0 (xyz), w = CPhys.force[1] (ft0)        rB: trsf column 1 (xyz), w = CPhys.force[2] (ft1)
+  //   rC: contact point CGeom.node.pos (xyz), w = uN                   rD: global force on pA (xyz), w = CPhys.force[0] (fn)
+  // (trsf column 2 = c0 x c1 is recomputed bit-identically.)  An array-of-records layout (one 128-byte line per contact, staged through shared memory with cp.async)
+  // was measured and is slower: 0.299 ms vs 0.227 ms for the contact kernel at 1M spheres — strided per-lane accesses cost 4x the L1 wavefronts.
+  double4 *rA, *rB, *rC, *rD;
   double4* ph;            // Cp2 constants, written once at creation: linear (kn, kt, tanPhi, -); Hertz (kn0=K*sqrt(R), kt0, tanPhi, alpha_sqrtMK)
   double* ph4;            // Hertz only: Fna=4*pi*R*gamma (or -1: alpha!=0)
   double4* tq;            // CPhys.torque xyz (only with rolling/twisting resistance)
@@ -71,12 +72,11 @@ struct StepU {            // per-step uniforms
   m33 shiftVelM;          // gradV*pprevHsize (GRADV2) or gradV*hSize (VEL, VEL_2ND) or 0  (Cell::intrShiftVel)
   m33 gradV, nextGradV, dGradV, midGradV, ImLL4hInv, IpLL4h, LmL; d3 spinVec, deltaSpinVec;
   long long step; int renormNow; int noRatch;
+  const int* gIn; int* gOut;      // this step's slots of Counters::gflag
   double absDistFactor;
   int law; int noSlip, noBreak, noFrict, noAttraction; int rolling; double relRollStiff, relTwistStiff, rollTanPhi;
   double poisson, en, viscAlpha;  // viscAlpha = -sqrt(5) ln(en)/sqrt(ln(en)^2+pi^2), host-computed (Hertz.cpp:69)
   double* energy;                 // Scene.trackEnergy: device accumulators (EN_*), else nullptr; only the TRACK kernel variants look at it
-  int csStores;                   // contact kernel: write the history half of a record (read again only in the next step) with the streaming hint, so that the
-                                  // half the force reduction gathers right afterwards (contact point, global force) has a better chance to stay in L2
   int trackLeapfrog;              // Leapfrog.cpp:130-132: reallyTrackEnergy (off in step 0 of a periodic scene with a velocity gradient)
 };
 // EnergyTracker entries of this path (core/EnergyTracker.hpp): "kinetic" and "elast" are resettable (zeroed in the step prologue, Scene.cpp:416)
@@ -95,7 +95,12 @@ __device__ __forceinline__ void energy_add(double* en, int ix, double v) {
   if (lane == leader && sum != 0.) atomicAdd(en + ix, sum);
 }
 
-struct Counters { unsigned long long nReal, nPotEval, nCreated, nBroken; int dirty; int error; int errA, errB; };
+// gflag: the Verlet-dirty flags of a BATCH of steps enqueued without a host wait in between.  Step k of a batch reads gflag[k] ("a full run was already due when I
+// started: I am void, pass it on") and raises gflag[k+1] ("a sphere moved farther than verletDist in this step": contacts and force reduction of this step and every
+// kernel of the later steps return at once).  gflag[0] is always 0.  The host reads the array once per batch, does the collider full run for the first raised step
+// and goes on from there.  [error, gflag...] is one block of ints so that decomposed runs can max-reduce it in one call.
+#define WD_KMAX 32
+struct Counters { unsigned long long nReal, nPotEval, nCreated, nBroken; int error; int gflag[WD_KMAX + 1]; int errA, errB; };
 enum { ERR_NONE = 0, ERR_NAN_FORCE = 1, ERR_NAN_POS = 2, ERR_NO_PHYS = 3, ERR_SCHWARZ = 4, ERR_FACET_IMPOSSIBLE = 5, ERR_AMBIGUOUS_PERI = 6, ERR_PEER_TIMEOUT = 7 };
 
 __device__ __forceinline__ double signd(double f) { return f < 0 ? -1. : (f > 0 ? 1. : 0.); }  // Mathr::Sign (Math.hpp:145)
@@ -216,8 +221,8 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
   // Verlet test (Collision.cpp:113-121): d2 > maxD2 strictly
   d3 dl = mk3(S.lx[i], S.ly[i], S.lz[i]) - pos;
   double d2 = fmax(0., sqn(dl));
-  if (d2 > u.maxD2) cnt->dirty = 1;
-  if (!(d2 == d2)) { cnt->dirty = 1; cnt->error = ERR_NAN_POS; cnt->errA = S.id[i]; }
+  if (d2 > u.maxD2) *u.gOut = 1;
+  if (!(d2 == d2)) { *u.gOut = 1; cnt->error = ERR_NAN_POS; cnt->errA = S.id[i]; }
   if (EXT) {
     io.posOut[3 * ut] = pos.x; io.posOut[3 * ut + 1] = pos.y; io.posOut[3 * ut + 2] = pos.z;
     io.velOut[3 * ut] = vel.x; io.velOut[3 * ut + 1] = vel.y; io.velOut[3 * ut + 2] = vel.z;
@@ -226,6 +231,7 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
 template <bool TRACK>
 __global__ void __launch_bounds__(256, 4) k_leapfrog(Spheres S, int n, StepU u, Counters* cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (*u.gIn) { if (i == 0) *u.gOut = 1; return; }      // an earlier step of this batch is waiting for its collider full run: void, and say so to the next step
   if (i >= n) return;
   leapfrog_body<false, TRACK>(S, i, u, cnt, LeapIO{}, 0);
 }
@@ -234,6 +240,7 @@ __global__ void __launch_bounds__(256, 4) k_leapfrog(Spheres S, int n, StepU u, 
 template <bool TRACK>
 __global__ void __launch_bounds__(256, 4) k_leapfrog_io(Spheres S, StepU u, Counters* cnt, const int* __restrict__ up2slot, long long first, long long cnt_, LeapIO io) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (*u.gIn) { if (first + t == 0) *u.gOut = 1; return; }
   if (t >= cnt_) return;
   leapfrog_body<true, TRACK>(S, up2slot[first + t], u, cnt, io, first + t);
 }
@@ -256,6 +263,7 @@ __global__ void __launch_bounds__(128) k_facets_step(Facet* facets, int n, Group
     for (int k = 0; k < 9; k++) F->lastv[k] = F->v[k];
     return;
   }
+  if (*u.gIn) return;
   const int gi = F->group1 - 1;
   if (gi < 0) return;
   const GroupU g = G.g[gi];
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(128) k_facets_step(Facet* facets, int n, Group
     F->vvel[3 * i] = vv.x; F->vvel[3 * i + 1] = vv.y; F->vvel[3 * i + 2] = vv.z;
     d2 = fmax(d2, sqn(mk3(F->lastv[3 * i], F->lastv[3 * i + 1], F->lastv[3 * i + 2]) - p));
   }
-  if (d2 > u.maxD2 || !(d2 == d2)) cnt->dirty = 1;
+  if (d2 > u.maxD2 || !(d2 == d2)) *u.gOut = 1;
 }
 // Leapfrog for boundary nodes that are in DemField.nodes (moving walls: mass 0, all DOFs blocked => the "fixed particle" branch, Leapfrog.cpp:195-199):
 // leapfrogTranslate only (:275-278), plus the Verlet test of their Aabb (Collision.cpp:113-121).  setLast: record Aabb::nodeLastPos at a full run.
@@ -276,12 +284,12 @@ __global__ void k_walls_step(Wall* walls, int n, StepU u, Counters* cnt, int set
   if (w >= n) return;
   Wall W = walls[w];
   if (setLast) { for (int k = 0; k < 3; k++) walls[w].lastPos[k] = W.pos[k]; return; }
-  if (!W.moving) return;
+  if (!W.moving || *u.gIn) return;
   d3 pos = mk3(W.pos[0], W.pos[1], W.pos[2]) + mk3(W.vel[0], W.vel[1], W.vel[2]) * u.dt;
   walls[w].pos[0] = pos.x; walls[w].pos[1] = pos.y; walls[w].pos[2] = pos.z;
   const d3 dl = mk3(W.lastPos[0], W.lastPos[1], W.lastPos[2]) - pos;
   const double d2 = fmax(0., sqn(dl));
-  if (d2 > u.maxD2 || !(d2 == d2)) cnt->dirty = 1;
+  if (d2 > u.maxD2 || !(d2 == d2)) *u.gOut = 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -295,17 +303,10 @@ __device__ __noinline__ void report_error(Counters* cnt, int code, const ErrCtx&
 }
 // persistent state of a real contact, loaded up front so that all of a thread's loads are in flight together
 struct Hist { d3 t0, t1; double4 cp; double ft0, ft1, ph0, ph1, ph2, ph3, ph4; };
-// what the tail leaves for the caller to store into the contact's 128-byte record: st = 0 nothing (no contact), 1 the whole record (kept / created), 2 the contact broke
-// (only the force slot is zeroed).  The boundary kernels store straight to global memory, the sphere-sphere kernel through its shared-memory tile.
-struct COut { double4 r0, r1, r2, r3; int st; };
-__device__ __forceinline__ void store_out(const Contacts& C, long long c, const COut& o) {
-  if (o.st == 1) { C.rec[4 * c] = o.r0; C.rec[4 * c + 1] = o.r1; C.rec[4 * c + 2] = o.r2; C.rec[4 * c + 3] = o.r3; }
-  else if (o.st == 2) C.rec[4 * c + 3] = make_double4(0, 0, 0, 0);
-}
 template <int LAW>
 __device__ __forceinline__ void load_hist(const Contacts& C, long long c, Hist& H) {
-  const double4 a = C.rec[4 * c], b = C.rec[4 * c + 1], p = C.ph[c];
-  H.cp = C.rec[4 * c + 2];
+  const double4 a = C.rA[c], b = C.rB[c], p = C.ph[c];
+  H.cp = C.rC[c];
   H.t0 = xyz(a); H.ft0 = a.w; H.t1 = xyz(b); H.ft1 = b.w;
   H.ph0 = p.x; H.ph1 = p.y; H.ph2 = p.z;
   if ((LAW & 1) == 1) { H.ph3 = p.w; H.ph4 = C.ph4[c]; }
@@ -315,7 +316,7 @@ template <int LAW>
 __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uint32_t fl, const StepU& u, d3 pos1, d3 vel1, d3 w1, d3 pos2,
                                              d3 vel2, d3 w2, d3 shiftVel2, d3 normal, d3 contPt, double uN, double r1, double r2,
                                              const Material* mats, const int32_t* matArr, double massA, double massB, Counters* cnt,
-                                             const ErrCtx& ec, int matBoundary, const Hist& H, unsigned& nRealOut, COut& out, const bool mine = true) {
+                                             const ErrCtx& ec, int matBoundary, const Hist& H, unsigned& nRealOut, const bool mine = true) {
   // mine (energy tracking in decomposed runs): a cross-slab pair is evaluated on both sides; the side owning pA books its energy
   const bool wasReal = fl & CF_REAL;
   d3 c0, c1, c2, gvel = mk3(0, 0, 0), gang = mk3(0, 0, 0);
@@ -482,19 +483,19 @@ __device__ __forceinline__ void contact_tail(const Contacts& C, long long c, uin
     // contact while its (frozen) AABBs overlap, i.e. unless it is an orphan (InsertionSortCollider.hpp:213-218)
     uint32_t nf = (fl & ~CF_REAL) | ((fl & CF_ORPHAN) ? CF_DEAD : 0);
     C.flags[c] = nf;
-    out.st = 2;
+    C.rD[c] = make_double4(0, 0, 0, 0);
     if (wasReal) { atomicAnd(&C.realBits[c >> 5], ~(1u << (c & 31))); atomicAdd(&cnt->nBroken, 1ull); }
     return;
   }
   // ---- store state
-  out.r0 = make_double4(c0.x, c0.y, c0.z, ftA);
-  out.r1 = make_double4(c1.x, c1.y, c1.z, ftB);
-  out.r2 = make_double4(contPt.x, contPt.y, contPt.z, uN);
+  C.rA[c] = make_double4(c0.x, c0.y, c0.z, ftA);
+  C.rB[c] = make_double4(c1.x, c1.y, c1.z, ftB);
+  C.rC[c] = make_double4(contPt.x, contPt.y, contPt.z, uN);
   if (!wasReal) { C.flags[c] = fl | CF_REAL; atomicOr(&C.realBits[c >> 5], 1u << (c & 31)); }
   // ---- Contact::getForceTorqueBranch (Contact.cpp:24-35): F = ori * phys.force, ori = Quaternionr(trsf)
   q4 q = quatFromCols(c0, c1, c2);
   d3 Fglob = quatRotate(q, mk3(Fn, ftA, ftB));
-  out.r3 = make_double4(Fglob.x, Fglob.y, Fglob.z, Fn); out.st = 1;
+  C.rD[c] = make_double4(Fglob.x, Fglob.y, Fglob.z, Fn);
   if (u.rolling) {
     C.tq[c] = make_double4(tq0, tq1, tq2, 0.);
     d3 Tg = (tq0 == 0. && tq1 == 0. && tq2 == 0.) ? mk3(0, 0, 0) : quatRotate(q, mk3(tq0, tq1, tq2));
@@ -514,7 +515,7 @@ __device__ __forceinline__ void block_count(unsigned isReal, unsigned evald, Cou
 // ------------------------------------------------------------------------------------------------
 template <int LAW>
 __device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal,
-                                           const Hist& H, COut& out) {
+                                           const Hist& H) {
   const bool real = fl & CF_REAL;
   // every load of a real contact is issued up front (the history by the caller: straight from global memory or from the staged tile), before the first use
   const double4 pa = S.posr[pr.x], pb = S.posr[pr.y];
@@ -540,7 +541,7 @@ __device__ __forceinline__ void contact_ss(const Contacts& C, long long c, uint3
   if (!real && (LAW & 1) == 1) { mA = S.velm[pr.x].w; mB = S.velm[pr.y].w; }
   const ErrCtx ec{S.id, pr.x, 0, pr.y};
   const bool mine = (LAW >= 2) ? !(S.flags[pr.x] & F_GHOST) : true;
-  contact_tail<LAW>(C, c, fl, u, p1, xyz(va), xyz(wa), p2, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, r1, r2, mats, S.mat, mA, mB, cnt, ec, 0, H, isReal, out, mine);
+  contact_tail<LAW>(C, c, fl, u, p1, xyz(va), xyz(wa), p2, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, r1, r2, mats, S.mat, mA, mB, cnt, ec, 0, H, isReal, mine);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -551,7 +552,7 @@ __device__ __forceinline__ void prefetch_contact_ss(const Contacts& C, long long
   prefetch_l2(S.posr + pr.x); prefetch_l2(S.posr + pr.y);
   if (!(fl & CF_REAL)) return;
   prefetch_l2(S.velm + pr.x); prefetch_l2(S.velm + pr.y); prefetch_l2(S.angi + pr.x); prefetch_l2(S.angi + pr.y);
-  prefetch_l2(C.rec + 4 * c); prefetch_l2(C.rec + 4 * c + 2); prefetch_l2(C.ph + c);
+  prefetch_l2(C.rA + c); prefetch_l2(C.rB + c); prefetch_l2(C.rC + c); prefetch_l2(C.ph + c);
   if ((LAW & 1) == 1) prefetch_l2(C.ph4 + c);
 }
 
@@ -574,7 +575,7 @@ __device__ __forceinline__ void prefetch_spheres_ss(uint32_t fl, int2 pr, const 
 #define WD_CONTACT_BLOCK 128
 #endif
 template <int LAW>
-__global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_contact_ss_direct(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
+__global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
   const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
   const long long end = first + n, stride = (long long)gridDim.x * blockDim.x;
   long long c0 = first + (long long)blockIdx.x * blockDim.x + threadIdx.x, c1 = c0 + stride;
@@ -590,9 +591,9 @@ __global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_co
     if (c2 < end) { fl2 = C.flags[c2]; pr2 = C.pair[c2]; }
     prefetch_contact_ss<LAW>(C, c1, fl1, pr1, S);
     if (!(fl0 & CF_DEAD)) {
-      evald++; unsigned r = 0; Hist H; COut o; o.st = 0;
+      evald++; unsigned r = 0; Hist H;
       if (fl0 & CF_REAL) load_hist<LAW>(C, c0, H);
-      contact_ss<LAW>(C, c0, fl0, pr0, S, mats, u, cnt, r, H, o); store_out(C, c0, o); isReal += r;
+      contact_ss<LAW>(C, c0, fl0, pr0, S, mats, u, cnt, r, H); isReal += r;
     }
     c0 = c1; fl0 = fl1; pr0 = pr1; c1 = c2; fl1 = fl2; pr1 = pr2;
   }
@@ -600,112 +601,10 @@ __global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_co
 }
 
 // ------------------------------------------------------------------------------------------------
-// The same pass, warp-per-tile with the contact state staged in shared memory (the default).  A tile = 32 consecutive candidates = 32 x 128-byte records = 4 KB of
-// contiguous global memory.  The warp moves it with cp.async (16-byte chunks, fully coalesced: 512 B per request, no registers tied up while the copy is in flight)
-// into a double-buffered, XOR-swizzled shared-memory tile: tile k+1 is on its way while tile k is computed, exactly like the table entries (flags, pair: registers,
-// two tiles ahead) and the sphere lines (L2 prefetch, one tile ahead).  Results go back the same way: every lane writes its record into the tile, then the warp
-// streams the tile out in 512-byte requests.  Rows of contacts that are not real are neither loaded nor stored.  No CTA-wide barrier: warps are independent.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// chunk (16 B) `col` of row `row` of a 32-row x 128-byte tile, swizzled so that both the per-lane row accesses and the cooperative chunk accesses are conflict-free
-__device__ __forceinline__ int swz(int row, int col) { return row * 8 + (col ^ (row & 7)); }
-__device__ __forceinline__ void st_cs(uint4* p, uint4 v) { asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
-
-template <int LAW>
-__device__ __forceinline__ void stage_tile(const Contacts& C, long long base /*first contact of the tile*/, unsigned realMask, uint4* sRec, uint4* sPh, int lane) {
-  if (realMask) {
-    const uint4* g = reinterpret_cast<const uint4*>(C.rec + 4 * base);
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int q = j * 32 + lane, row = q >> 3, col = q & 7;
-      if (col < 6 && ((realMask >> row) & 1u)) cp_async16(sRec + swz(row, col), g + q);      // chunks 6,7 (global force, fn) are outputs only
-    }
-    const uint4* gp = reinterpret_cast<const uint4*>(C.ph + base);
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const int q = j * 32 + lane, row = q >> 1;
-      if ((realMask >> row) & 1u) cp_async16(sPh + q, gp + q);
-    }
-  }
-  cp_async_commit();
-}
-
-template <int LAW>
-__global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_contact_ss(Contacts C, long long first, long long n, Spheres S, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
-  constexpr int NW = WD_CONTACT_BLOCK / 32;
-  __shared__ __align__(128) uint4 sRecAll[NW][2][256];     // per warp: 2 stages x 32 records x 128 B
-  __shared__ __align__(128) uint4 sPhAll[NW][2][64];       // per warp: 2 stages x 32 x double4
-  const int stale = *guard;   // a set flag means a collider full run is due and this speculative launch is void
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long end = first + n, stride = (long long)gridDim.x * blockDim.x;
-  long long b0 = first + ((long long)blockIdx.x * NW + w) * 32, b1 = b0 + stride;     // tile bases of this warp: every (gridDim*NW)-th tile of 32
-  uint32_t fl0 = CF_DEAD, fl1 = CF_DEAD; int2 pr0 = make_int2(0, 0), pr1 = pr0;
-  if (b0 + lane < end) { fl0 = C.flags[b0 + lane]; pr0 = C.pair[b0 + lane]; }
-  if (b1 + lane < end) { fl1 = C.flags[b1 + lane]; pr1 = C.pair[b1 + lane]; }
-  if (stale) return;          // uniform over the grid
-  unsigned isReal = 0, evald = 0;
-  unsigned rm0 = __ballot_sync(0xffffffffu, (fl0 & CF_REAL) && !(fl0 & CF_DEAD));
-  if (b0 < end) stage_tile<LAW>(C, b0, rm0, sRecAll[w][0], sPhAll[w][0], lane);
-  int stg = 0;
-  for (; b0 < end; b0 = b1, b1 += stride, stg ^= 1) {         // warp-uniform loop
-    const long long b2 = b1 + stride;
-    uint32_t fl2 = CF_DEAD; int2 pr2 = make_int2(0, 0);
-    if (b2 + lane < end) { fl2 = C.flags[b2 + lane]; pr2 = C.pair[b2 + lane]; }
-    const unsigned rm1 = __ballot_sync(0xffffffffu, (fl1 & CF_REAL) && !(fl1 & CF_DEAD));
-    if (b1 < end) stage_tile<LAW>(C, b1, rm1, sRecAll[w][stg ^ 1], sPhAll[w][stg ^ 1], lane); else cp_async_commit();
-    prefetch_spheres_ss<LAW>(fl1, pr1, S);
-    if ((LAW & 1) == 1 && (fl1 & CF_REAL) && !(fl1 & CF_DEAD)) prefetch_l2(C.ph4 + b1 + lane);
-    cp_async_wait<1>();          // this lane's copies of tile k have landed ...
-    __syncwarp();                // ... and everybody else's
-    uint4* sRec = sRecAll[w][stg]; const uint4* sPh = sPhAll[w][stg];
-    COut o; o.st = 0;
-    const long long c = b0 + lane;
-    if (!(fl0 & CF_DEAD)) {
-      evald++; unsigned r = 0; Hist H;
-      if (fl0 & CF_REAL) {
-        const double2* row = reinterpret_cast<const double2*>(sRec);
-        const double2 a0 = row[swz(lane, 0)], a1 = row[swz(lane, 1)], b0_ = row[swz(lane, 2)], b1_ = row[swz(lane, 3)], c0_ = row[swz(lane, 4)], c1_ = row[swz(lane, 5)];
-        const double2 p0 = reinterpret_cast<const double2*>(sPh)[2 * lane], p1 = reinterpret_cast<const double2*>(sPh)[2 * lane + 1];
-        H.t0 = mk3(a0.x, a0.y, a1.x); H.ft0 = a1.y; H.t1 = mk3(b0_.x, b0_.y, b1_.x); H.ft1 = b1_.y; H.cp = make_double4(c0_.x, c0_.y, c1_.x, c1_.y);
-        H.ph0 = p0.x; H.ph1 = p0.y; H.ph2 = p1.x;
-        if ((LAW & 1) == 1) { H.ph3 = p1.y; H.ph4 = C.ph4[c]; }
-      }
-      contact_ss<LAW>(C, c, fl0, pr0, S, mats, u, cnt, r, H, o); isReal += r;
-    }
-    // results: own row into the tile, then the warp streams the rows that hold a (still) real contact back in 512-byte requests
-    if (o.st == 1) {
-      double2* row = reinterpret_cast<double2*>(sRec);
-      row[swz(lane, 0)] = make_double2(o.r0.x, o.r0.y); row[swz(lane, 1)] = make_double2(o.r0.z, o.r0.w);
-      row[swz(lane, 2)] = make_double2(o.r1.x, o.r1.y); row[swz(lane, 3)] = make_double2(o.r1.z, o.r1.w);
-      row[swz(lane, 4)] = make_double2(o.r2.x, o.r2.y); row[swz(lane, 5)] = make_double2(o.r2.z, o.r2.w);
-      row[swz(lane, 6)] = make_double2(o.r3.x, o.r3.y); row[swz(lane, 7)] = make_double2(o.r3.z, o.r3.w);
-    } else if (o.st == 2) C.rec[4 * c + 3] = make_double4(0, 0, 0, 0);
-    const unsigned wm = __ballot_sync(0xffffffffu, o.st == 1);      // also orders the shared-memory writes above before the reads below
-    if (wm) {
-      uint4* g = reinterpret_cast<uint4*>(C.rec + 4 * b0);
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int q = j * 32 + lane, rw = q >> 3, col = q & 7;
-        if ((wm >> rw) & 1u) { const uint4 v = sRec[swz(rw, col)]; if (col < 4 && u.csStores) st_cs(g + q, v); else g[q] = v; }
-      }
-    }
-    __syncwarp();                // the stage is free for the copies of tile k+2
-    fl0 = fl1; pr0 = pr1; fl1 = fl2; pr1 = pr2;
-  }
-  cp_async_wait<0>();
-  block_count(isReal, evald, cnt);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Wall+Sphere: Cg2_Wall_Sphere_L6Geom::go (src/dem/Wall.cpp:50-84)
 // ------------------------------------------------------------------------------------------------
 template <int LAW>
-__device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Wall* walls, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal,
-                                           COut& out) {
+__device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Wall* walls, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
   const bool real = fl & CF_REAL;
   const Wall W = walls[pr.x];
   const double4 pb = S.posr[pr.y];
@@ -734,7 +633,7 @@ __device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint3
   if (!real && (LAW & 1) == 1) mB = S.velm[pr.y].w;
   const ErrCtx ec{S.id, -1, W.id, pr.y};
   contact_tail<LAW>(C, c, fl, u, wallPos, mk3(W.vel[0], W.vel[1], W.vel[2]), mk3(0, 0, 0), spherePos, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, -radius, radius,
-                    mats, S.mat, 0., mB, cnt, ec, W.mat, H, isReal, out);
+                    mats, S.mat, 0., mB, cnt, ec, W.mat, H, isReal);
 }
 
 template <int LAW>
@@ -746,7 +645,7 @@ __global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first,
   if (c < first + n) { fl = C.flags[c]; pr = C.pair[c]; }
   if (stale) return;          // uniform over the grid
   {
-    if (!(fl & CF_DEAD)) { evald = 1; COut o; o.st = 0; contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal, o); store_out(C, c, o); }
+    if (!(fl & CF_DEAD)) { evald = 1; contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal); }
   }
   block_count(isReal, evald, cnt);
 }
@@ -784,8 +683,7 @@ __device__ __forceinline__ void facetAdjustImpl(d3 fN, d3 edgePt, d3 unitOutVec,
 }
 
 template <int LAW>
-__device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Facet* facets, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal,
-                                           COut& out) {
+__device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint32_t fl, int2 pr, const Spheres& S, const Facet* facets, const Material* mats, const StepU& u, Counters* cnt, unsigned& isReal) {
   const Facet* F = facets + pr.x;
   const double4 pb = S.posr[pr.y];
   double4 vb = make_double4(0, 0, 0, 0), wb = vb; Hist H;
@@ -861,7 +759,7 @@ __device__ __forceinline__ void contact_fs(const Contacts& C, long long c, uint3
   double mB = 0;
   if (!real && (LAW & 1) == 1) mB = S.velm[pr.y].w;
   const ErrCtx ec{S.id, -1, F->id, pr.y};
-  contact_tail<LAW>(C, c, fl, u, contPt, linVel, angVel, sC, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, fmax(ht, radius), radius, mats, S.mat, 0., mB, cnt, ec, F->mat, H, isReal, out);
+  contact_tail<LAW>(C, c, fl, u, contPt, linVel, angVel, sC, xyz(vb), xyz(wb), shiftVel2, normal, contPt, uN, fmax(ht, radius), radius, mats, S.mat, 0., mB, cnt, ec, F->mat, H, isReal);
 }
 
 template <int LAW>
@@ -873,7 +771,7 @@ __global__ void __launch_bounds__(128) k_contact_fs(Contacts C, long long first,
   if (c < first + n) { fl = C.flags[c]; pr = C.pair[c]; }
   if (stale) return;          // uniform over the grid
   {
-    if (!(fl & CF_DEAD)) { evald = 1; COut o; o.st = 0; contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal, o); store_out(C, c, o); }
+    if (!(fl & CF_DEAD)) { evald = 1; contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal); }
   }
   block_count(isReal, evald, cnt);
 }
@@ -892,11 +790,9 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
     if (!(fl & CF_DEAD)) {
       evald = 1;
       const int kind = cf_kind(fl);
-      COut o; o.st = 0;
-      if (kind == KIND_SS) { Hist H; if (fl & CF_REAL) load_hist<LAW>(C, c, H); contact_ss<LAW>(C, c, fl, pr, S, mats, u, cnt, isReal, H, o); }
-      else if (kind == KIND_WS) contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal, o);
-      else contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal, o);
-      store_out(C, c, o);
+      if (kind == KIND_SS) { Hist H; if (fl & CF_REAL) load_hist<LAW>(C, c, H); contact_ss<LAW>(C, c, fl, pr, S, mats, u, cnt, isReal, H); }
+      else if (kind == KIND_WS) contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal);
+      else contact_fs<LAW>(C, c, fl, pr, S, facets, mats, u, cnt, isReal);
     }
   }
   block_count(isReal, evald, cnt);
@@ -946,8 +842,8 @@ __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Sphe
     for (int k = 0; k < RB; k++) { const uint32_t c = ent[k] >> 1; real[k] = (ent[k] != 0xffffffffu) && ((C.realBits[c >> 5] >> (c & 31)) & 1u); }
 #pragma unroll
     for (int k = 0; k < RB; k++) {
-      fg[k] = real[k] ? C.rec[4ll * (ent[k] >> 1) + 3] : make_double4(0, 0, 0, 0);
-      cp[k] = real[k] ? C.rec[4ll * (ent[k] >> 1) + 2] : make_double4(0, 0, 0, 0);
+      fg[k] = real[k] ? C.rD[ent[k] >> 1] : make_double4(0, 0, 0, 0);
+      cp[k] = real[k] ? C.rC[ent[k] >> 1] : make_double4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int k = 0; k < RB; k++) {
@@ -985,14 +881,14 @@ __global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, con
         const uint32_t ent = rowEntry[e]; const uint32_t c = ent >> 1;
         const uint32_t cfl = C.flags[c];
         if (!(cfl & CF_REAL)) continue;
-        d3 c0 = xyz(C.rec[4ll * c]), c1 = xyz(C.rec[4ll * c + 1]);
+        d3 c0 = xyz(C.rA[c]), c1 = xyz(C.rB[c]);
         d3 c2 = cross(c0, c1);
         d3 nrmv = quatRotate(quatFromCols(c0, c1, c2), mk3(1, 0, 0));
         d3 n2 = mk3(nrmv.x * nrmv.x, nrmv.y * nrmv.y, nrmv.z * nrmv.z);
         double kn, kt;
         const double4 php = C.ph[c];
         if (law == 0) { kn = php.x; kt = php.y; }
-        else { double uN = C.rec[4ll * c + 2].w; kn = (3 / 2.) * php.x * sqrt(-uN); kt = php.y * sqrt(uN < 0 ? -uN : 0); }
+        else { double uN = C.rC[c].w; kn = (3 / 2.) * php.x * sqrt(-uN); kt = php.y * sqrt(uN < 0 ? -uN : 0); }
         // lens[ix] (iniLensTouch): SS: own radius; WS/FS: the sphere's radius on both sides (L6Geom.cpp:61, Wall.cpp:82)
         double len = myR;
         if (cf_kind(cfl) == KIND_SS) { int2 pr = C.pair[c]; len = (ent & 1u) ? S.posr[pr.y].w : S.posr[pr.x].w; }
@@ -1050,7 +946,7 @@ __global__ void __launch_bounds__(256) k_stress(Contacts C, long long n, Spheres
         // decomposed runs: a cross-slab pair lives on both sides; the side owning pA (sphere-sphere) / the sphere (wall) reports it
         const bool mineToReport = kind == KIND_SS ? !(S.flags[pr.x] & F_GHOST) : !(S.flags[pr.y] & F_GHOST);
         if (mineToReport) {
-          const double4 F = C.rec[4 * c + 3];
+          const double4 F = C.rD[c];
           const d3 pb = xyz(S.posr[pr.y]);
           const d3 pa = kind == KIND_SS ? xyz(S.posr[pr.x]) : mk3(walls[pr.x].pos[0], walls[pr.x].pos[1], walls[pr.x].pos[2]);
           d3 br = pb - pa;
@@ -1109,6 +1005,26 @@ __global__ void __launch_bounds__(256) k_bounds(const double4* __restrict__ posr
   if (threadIdx.x == 0) for (int k = 0; k < 7; k++) blk[7 * blockIdx.x + k] = sm[k][0];
 }
 
+// second stage: the block results -> 7 numbers (min xyz, max xyz, max radius)
+__global__ void __launch_bounds__(256) k_bounds_final(const double* __restrict__ blk, int nb, double* out) {
+  double v[7] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0};
+  for (int b = threadIdx.x; b < nb; b += 256) {
+    for (int k = 0; k < 3; k++) v[k] = fmin(v[k], blk[7 * b + k]);
+    for (int k = 3; k < 7; k++) v[k] = fmax(v[k], blk[7 * b + k]);
+  }
+  __shared__ double sm[7][256];
+  for (int k = 0; k < 7; k++) sm[k][threadIdx.x] = v[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      for (int k = 0; k < 3; k++) sm[k][threadIdx.x] = fmin(sm[k][threadIdx.x], sm[k][threadIdx.x + s]);
+      for (int k = 3; k < 7; k++) sm[k][threadIdx.x] = fmax(sm[k][threadIdx.x], sm[k][threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) for (int k = 0; k < 7; k++) out[k] = sm[k][0];
+}
+
 __device__ __forceinline__ int cellCoord(double x, double o, double inv, int n) {
   int c = (int)floor((x - o) * inv);
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
@@ -1164,8 +1080,8 @@ struct OldCsr {  // incidence rows of the previous contact table (for history ca
 
 __device__ __forceinline__ void copy_history(const Contacts& N, long long cn, const Contacts& O, long long co, int law, int rolling, int periodic) {
   // the whole 128-byte record (frame, shear force, contact point, uN, global force) + the Cp2 constants
-  const double4 r0 = O.rec[4 * co], r1 = O.rec[4 * co + 1], r2 = O.rec[4 * co + 2], r3 = O.rec[4 * co + 3], p = O.ph[co];
-  N.rec[4 * cn] = r0; N.rec[4 * cn + 1] = r1; N.rec[4 * cn + 2] = r2; N.rec[4 * cn + 3] = r3; N.ph[cn] = p;
+  const double4 r0 = O.rA[co], r1 = O.rB[co], r2 = O.rC[co], r3 = O.rD[co], p = O.ph[co];
+  N.rA[cn] = r0; N.rB[cn] = r1; N.rC[cn] = r2; N.rD[cn] = r3; N.ph[cn] = p;
   if (law == 1) N.ph4[cn] = O.ph4[co];
   if (rolling) N.tq[cn] = O.tq[co];
   N.stepCreated[cn] = O.stepCreated[co];
@@ -1205,19 +1121,33 @@ struct WallPass { const Wall* walls; int nWalls; double halfThick; uint32_t* bit
 #ifndef WD_PAIRS_MINB
 #define WD_PAIRS_MINB 12   // 40 registers, 75 % occupancy: measured 0.173 ms/step of collider work vs 0.178 (64 registers) and 0.176 (48 or 32 registers)
 #endif
+// DORMANT potential contacts.  Between two collider full runs no sphere is farther than verletDist from where it was at the last one (the Verlet test runs in every
+// step, before the contacts, and triggers the full run in the same step: Collision.cpp:113-121), so a candidate pair whose centres were farther apart than
+// |distFactor|(r1+r2) + 2 verletDist at the full run cannot touch before the next one: Cg2_Sphere_Sphere_L6Geom::go would return false in every step in between
+// (Sphere.cpp:101-104) and leave no trace.  In a dense bed that is ~80 % of the potential contacts (the enlarged boxes overlap long before the spheres can touch).
+// Such pairs stay in the table (the candidate set is the reference's), flagged CF_DORMANT in a segment of their own behind the active sphere-sphere contacts,
+// but the contact kernel does not visit them and they take no place in the incidence rows.  dormMargin2 < 0 switches this off (periodic cells: the shift
+// hSize*cellDist moves with the cell; Law2.noBreak: a real contact may live at any distance).
+__device__ __forceinline__ bool isDormant(double4 a, double4 b, double adf, double vd2x, double on) {
+  if (!(on > 0.)) return false;
+  const double rs = adf * (a.w + b.w) + vd2x;                 // |distFactor|(r1+r2) + 2 verletDist
+  const d3 dl = xyz(b) - xyz(a);
+  return sqn(dl) > (rs * rs) * (1. + 1e-9);
+}
 template <bool FILL>
 __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int n, HGrid g, const int* __restrict__ cellStart, double vd, uint32_t loneMask, int* counts,
                                                  const int* __restrict__ offsets, Contacts N, Contacts O, OldCsr oc, const int* __restrict__ perm,
-                                                 int* __restrict__ rowCount, int* __restrict__ srcOld, int* __restrict__ cand, WallPass wp) {
+                                                 int* __restrict__ rowCount, int* __restrict__ srcOld, int* __restrict__ cand, WallPass wp, double adf, double dormOn) {
+  // counts / offsets blocks: [0,n) active sphere-sphere pairs by emitting sphere, [n,2n) dormant ones, [2n,3n) wall pairs, [3n,4n) facet pairs
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t fi = S.flags[i];
-  int cntLocal = 0;
-  long long out = FILL ? offsets[i] : 0;
+  int cntLocal = 0, dormLocal = 0;
+  long long out = FILL ? offsets[i] : 0, outD = FILL ? offsets[n + i] : 0;
   int idI = 0, oslotI = 0;
   if (FILL) { idI = S.id[i]; oslotI = perm ? perm[i] : i; }
-  if (FILL && wp.walls && !(fi & F_GHOST)) {   // wall pairs of this sphere (segment [nSS, nSS+nWS) of the table: offsets of the second counts block)
-    uint32_t m = wp.bits[i]; long long c = offsets[n + i];
+  if (FILL && wp.walls && !(fi & F_GHOST)) {   // wall pairs of this sphere (segment [nSS, nSS+nWS) of the table: offsets of the third counts block)
+    uint32_t m = wp.bits[i]; long long c = offsets[2 * n + i];
     while (m) {
       const int w = __ffs(m) - 1; m &= m - 1;
       const int wid = wp.walls[w].id;
@@ -1227,19 +1157,21 @@ __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int 
       c++;
     }
   }
-  // the counting pass leaves the partners it found (up to WD_CAND_CAP per sphere, in discovery order) in `cand`; the filling pass then only has to look up
-  // the previous contact and write the pair, without walking the cells again.  Spheres with more partners than the cache holds repeat the search.
+  // the counting pass leaves the partners it found (up to WD_CAND_CAP per sphere, in discovery order; bit 31: dormant) in `cand`; the filling pass then only has to
+  // look up the previous contact and write the pair, without walking the cells again.  Spheres with more partners than the cache holds repeat the search.
   if (FILL && cand) {
-    const int cnt = counts[i];
+    const int cnt = counts[i] + counts[n + i];
     if (cnt <= WD_CAND_CAP) {
+      int ka = 0, kd = 0;
       for (int k = 0; k < cnt; k++) {
-        const int j = cand[(long long)k * n + i];
+        const int je = cand[(long long)k * n + i];
+        const int j = je & 0x7fffffff; const bool dorm = je < 0;
         const int idJ = S.id[j];
-        const long long c = out + k;
         const bool iIsA = idI < idJ;
+        const long long c = dorm ? outD + (kd++) : out + (ka++);
         N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
-        srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
-        N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
+        srcOld[c] = dorm ? -1 : (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
+        N.flags[c] = (KIND_SS << CF_KIND_SHIFT) | (dorm ? (uint32_t)CF_DORMANT : 0u);
       }
       return;
     }
@@ -1263,15 +1195,19 @@ __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int 
           if (!aabbOverlapSS(pi, pj, vd)) continue;
           if (!mayCollide(mi, S.mask[j], loneMask)) continue;
           if ((fi & F_GHOST) && (S.flags[j] & F_GHOST)) continue;   // ghost-ghost pairs belong to other subdomains
+          const bool dorm = isDormant(pi, pj, adf, 2. * vd, dormOn);
           if (FILL) {
             const int idJ = S.id[j];
-            const long long c = out + cntLocal;
+            const long long c = dorm ? outD + dormLocal : out + cntLocal;
             const bool iIsA = idI < idJ;
             N.pair[c] = iIsA ? make_int2(i, j) : make_int2(j, i);
-            srcOld[c] = (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
-            N.flags[c] = (KIND_SS << CF_KIND_SHIFT);
-          } else { atomicAdd(&rowCount[j], 1); if (cand && cntLocal < WD_CAND_CAP) cand[(long long)cntLocal * n + i] = j; }
-          cntLocal++;
+            srcOld[c] = dorm ? -1 : (int)find_old2(oc, oslotI, idJ, oc.nImm > 0 ? (fi | S.flags[j]) : 0u, iIsA ? idI : idJ, iIsA ? idJ : idI);
+            N.flags[c] = (KIND_SS << CF_KIND_SHIFT) | (dorm ? (uint32_t)CF_DORMANT : 0u);
+          } else {
+            if (!dorm) atomicAdd(&rowCount[j], 1);
+            if (cand && cntLocal + dormLocal < WD_CAND_CAP) cand[(long long)(cntLocal + dormLocal) * n + i] = dorm ? (j | (int)0x80000000) : j;
+          }
+          if (dorm) dormLocal++; else cntLocal++;
         }
       }
   }
@@ -1291,9 +1227,9 @@ __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int 
           m |= 1u << w; wcnt++;
         }
       }
-      wp.bits[i] = m; counts[n + i] = wcnt;
+      wp.bits[i] = m; counts[2 * n + i] = wcnt;
     }
-    counts[i] = cntLocal; if (cntLocal + wcnt) atomicAdd(&rowCount[i], cntLocal + wcnt);
+    counts[i] = cntLocal; counts[n + i] = dormLocal; if (cntLocal + wcnt) atomicAdd(&rowCount[i], cntLocal + wcnt);
   }
 }
 
@@ -1584,8 +1520,8 @@ __global__ void __launch_bounds__(256) k_was_real(const int* __restrict__ srcOld
   if (c < nSS) { const int co = srcOld[c]; f = (co >= 0 && (oflags[co] & CF_REAL)) ? 1 : 0; }
   flag[c] = f;
 }
-// Eight lanes per NEW contact: the 128-byte record of a carried contact is one line gathered by 8 lanes (16 B each) and written back as part of a 512-byte warp
-// request; the small per-contact words (pair, flags, cellDist, stepCreated, Cp2 constants) are spread over the eight lanes.
+// Eight lanes per NEW contact: the four 32-byte sectors of a carried contact's state are gathered by lane pairs (16 B each) and written as part of 128-byte warp
+// requests per plane; the small per-contact words (pair, flags, cellDist, stepCreated, Cp2 constants) are spread over the eight lanes.
 __global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Contacts O, const int* __restrict__ srcOld, Contacts T, const int* __restrict__ realPos, long long nSS,
                                               int law, int rolling, int periodic, long long stepNow) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1597,14 +1533,15 @@ __global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Conta
   long long d = c;
   if (c < nSS) { const long long rp = realPos[c]; d = carried ? rp : (long long)realPos[nSS] + (c - rp); }
   if (carried) {
-    reinterpret_cast<uint4*>(N.rec + 4 * d)[k] = reinterpret_cast<const uint4*>(O.rec + 4 * (long long)co)[k];
+    const double4* src = (k >> 1) == 0 ? O.rA : ((k >> 1) == 1 ? O.rB : ((k >> 1) == 2 ? O.rC : O.rD)); double4* dst = (k >> 1) == 0 ? N.rA : ((k >> 1) == 1 ? N.rB : ((k >> 1) == 2 ? N.rC : N.rD));
+    reinterpret_cast<uint4*>(dst + d)[k & 1] = reinterpret_cast<const uint4*>(src + co)[k & 1];
     if (k < 2) reinterpret_cast<uint4*>(N.ph + d)[k] = reinterpret_cast<const uint4*>(O.ph + co)[k];
     else if (k == 2) N.stepCreated[d] = O.stepCreated[co];
     else if (k == 3) { if (law == 1) N.ph4[d] = O.ph4[co]; }
     else if (k == 4) { if (rolling) N.tq[d] = O.tq[co]; }
     else if (k == 5) O.flags[co] = ofl | CF_CLAIMED;
   } else {
-    if (k >= 6) reinterpret_cast<uint4*>(N.rec + 4 * d)[k] = make_uint4(0, 0, 0, 0);      // no force from a contact that is not real
+    if (k >= 6) reinterpret_cast<uint4*>(N.rD + d)[k & 1] = make_uint4(0, 0, 0, 0);      // no force from a contact that is not real
     else if (k == 2) N.stepCreated[d] = (int)stepNow;
   }
   if (k == 0) N.pair[d] = T.pair[c];
@@ -1644,12 +1581,14 @@ __global__ void __launch_bounds__(256) k_orphans(Contacts O, long long nOld, Con
 
 // per-particle incidence rows: rowStart = exclusive scan of rowCount (host: cub), then fill through per-row cursors and sort each row by the
 // other particle's id (the canonical summation order).  Replaces a global 64-bit radix sort.
-__global__ void __launch_bounds__(256) k_csr_fill(Contacts C, long long nTot, const int32_t* __restrict__ sid, const Wall* __restrict__ walls, const Facet* __restrict__ facets,
+__global__ void __launch_bounds__(256) k_csr_fill(Contacts C, long long first, long long nTot, const int32_t* __restrict__ sid, const Wall* __restrict__ walls, const Facet* __restrict__ facets,
                                                  const int* __restrict__ rowStart, int* __restrict__ cursor, uint32_t* __restrict__ rowEntry, int32_t* __restrict__ rowOther) {
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nTot) return;
   const int2 pr = C.pair[c];
-  const int kind = cf_kind(C.flags[c]);
+  const uint32_t cfl = C.flags[c];
+  if (cfl & CF_DORMANT) return;     // dormant potential contacts take no place in the incidence rows (see isDormant)
+  const int kind = cf_kind(cfl);
   int idA;
   if (kind == KIND_SS) {
     idA = sid[pr.x];
@@ -1789,8 +1728,8 @@ __global__ void __launch_bounds__(256) k_up2slot(const int32_t* __restrict__ up,
   if (i < n) up2slot[up[i]] = i;
 }
 // realBits of a freshly built table: one thread per contact, one word per warp (tables start warp-aligned)
-__global__ void __launch_bounds__(256) k_realbits(const uint32_t* __restrict__ flags, long long n, uint32_t* __restrict__ bits) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_realbits(const uint32_t* __restrict__ flags, long long first /*multiple of 32*/, long long n, uint32_t* __restrict__ bits) {
+  const long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t f = 0;
   if (c < n) f = flags[c];
   const unsigned m = __ballot_sync(0xffffffffu, (f & CF_REAL) && !(f & CF_DEAD));
