@@ -155,10 +155,11 @@ int wdem_upload_contacts(wdem_handle h, int64_t n, const int32_t* ids, const int
 /* Scene.step / Scene.time (Scene.hpp:191-205) of a resumed scene: trsfRenorm and DynDt's period count scene steps. */
 int wdem_set_scene(wdem_handle h, int64_t step, double time);
 /* Walls after the last step, in upload order (any pointer may be NULL): position (a wall uploaded with a nonzero velocity is in DemField.nodes and is
- * translated by Leapfrog, pos += vel*dt — Leapfrog.cpp:195-199,275-278, Particle.cpp:638-640) and the force / torque the LAST step's contacts put on the wall
- * (ContactLoop::applyForceUninodal, ContactLoop.cpp:270-276; summed in ascending id of the sphere).  This is DemData.force of a moving wall, which Leapfrog
- * resets every step; for a wall at rest the reference never resets and keeps accumulating — take the per-step value times the steps instead.
- * Decomposed runs: the share of this subdomain's spheres. */
+ * translated by Leapfrog, pos += vel*dt — Leapfrog.cpp:195-199,275-278, Particle.cpp:638-640) and DemData.force / torque as the reference's scripts see them
+ * (ContactLoop::applyForceUninodal, ContactLoop.cpp:270-276): for a MOVING wall the last step's contacts (Leapfrog resets its force every step; summed in ascending id
+ * of the sphere, bit-identical to the oracle); for a wall AT REST the value accumulated over all steps since wdem_upload_walls — the reference never resets it
+ * (the node is not in DemField.nodes); accumulated on the device per step, equal to the reference to rounding (its own order of additions is that of
+ * its contact loop).  Decomposed runs: the share of this subdomain's spheres. */
 int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torque);
 /* Scene.trackEnergy (Scene.hpp:191-205, core/EnergyTracker.hpp): on = the step kernels also accumulate the EnergyTracker entries of this path, 8 doubles in the order
  * kinetic, grav, nonviscDamp (Leapfrog.cpp:53-98), elast, plast, broken (IdealElPl.cpp:28-40,64-75,85-92), viscN, viscT (Hertz.cpp:181,193,199,203-207; Hertz's

@@ -164,7 +164,8 @@ struct wdem_engine {
   // particles
   int n = 0; SphereStore sph[2]; int cur = 0; DBuf<int> id2slot, up2slot; int maxId = -1; bool up2slotValid = false;
   std::vector<Material> hMats; DBuf<Material> dMats;
-  std::vector<Wall> hWalls; DBuf<Wall> dWalls; bool anyMovingWall = false;
+  std::vector<Wall> hWalls; DBuf<Wall> dWalls; bool anyMovingWall = false, anyStaticWall = false;
+  DBuf<double> wallAcc, wallPartial;     // accumulated force/torque on walls at rest (never reset in the reference: ContactLoop.cpp:270-276), per-step block partials
   std::vector<Facet> hFacets; DBuf<Facet> dFacets; DBuf<int> fgCellStart, fgCellFacet, fgCursor; FacetGrid fgrid; bool fgridValid = false;
   GroupsU groups{};                      // kinematic facet groups (wdem_upload_facet_groups): master nodes integrated on the host, members on the device
   std::vector<double> groupRadius;       // largest distance of a member node from its master node (bounding sphere of the sweep of a rotating group)
@@ -769,7 +770,7 @@ void rebuild(wdem_engine* E) {
       // warps of k_contact_ss then see either all-real or all-potential contacts instead of paying the long path for half-empty warps
       k_was_real<<<nblk(nSSa + 1, 256), 256, 0, st>>>(E->srcOld.p, O.flags, nSSa, E->realFlag.p);
       exclusiveSum(E, E->realFlag.p, E->realPos.p, (int)nSSa + 1);
-      k_carry<<<nblk(8 * nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, T, E->realPos.p, nSSa, c.law, rolling, c.periodic, E->step); E->launches += 4;
+      k_carry<<<nblk(nC0, 256), 256, 0, st>>>(N, nC0, O, E->srcOld.p, T, E->realPos.p, nSSa, c.law, rolling, c.periodic, E->step); E->launches += 4;
     }
     // 6b. orphans: real contacts of the previous table that no candidate claimed (AABBs separated while real).  The counting pass adds their incidences to the row
     // counts; how many there are travels to the host while the GPU goes on with the rows of the grid candidates, so the wait costs no idle time.
@@ -985,6 +986,11 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
     }
     E->launches++;
   }
+  if (E->anyStaticWall && c.applyForces && (E->nWS + E->nOrph) > 0) {
+    const int nW = (int)E->hWalls.size();
+    k_wall_sum<<<dim3(WD_WALL_PARTS, nW), 256, 0, sb>>>(C, E->nSS, E->nWS, E->nSS + E->nWS + E->nFS, E->nOrph, E->dWalls.p, E->S(), u, guard, E->wallPartial.p);
+    k_wall_acc<<<nblk(nW * 6, 64), 64, 0, sb>>>(E->wallPartial.p, nW, guard, E->wallAcc.p); E->launches += 2;
+  }
   // the big kernel goes last so that the small boundary kernels already occupy their share of the SMs
   if (E->nSSa > 0) {
     const int gridSS = std::min(nblk(E->nSSa, WD_CONTACT_BLOCK), E->numSMs * WD_CONTACT_CTAS_PER_SM);   // persistent: one CTA per resident slot
@@ -1145,7 +1151,11 @@ void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
   cudaStream_t st = E->stream;
   std::vector<StepSnap> snaps;
   int64_t done = 0;
+  static const bool trace = getenv("WDEM_STEP_TRACE") != nullptr;      // host-side timers of the stepping loop (diagnostics)
+  double tEnq = 0, tWait = 0, tReb = 0; long nBatch = 0, nVoid = 0, nReb = 0; auto clk = [] { return std::chrono::steady_clock::now(); };
+  auto msSince = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(clk() - a).count(); };
   while (done < nsteps) {
+    auto t0 = clk();
     ensureVerletAndDt(E);
     const bool full0 = E->conDirty || E->verletDist == 0;     // a full run is certain: do not enqueue the contact pass speculatively
     if (E->cfg.dynDtPeriod > 0 && E->dynStepLast < 0) E->dynStepLast = E->step;      // PeriodicEngine's first activation check
@@ -1168,7 +1178,9 @@ void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
     }
     CK(cudaMemcpyAsync(E->hCnt, E->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(E->evFlag, st));
+    if (trace) { tEnq += msSince(t0); t0 = clk(); }
     CK(cudaEventSynchronize(E->evFlag));
+    if (trace) { tWait += msSince(t0); t0 = clk(); nBatch++; }
     checkDeviceError(E);
     int kd = full0 ? 0 : -1;
     if (!full0) for (int k = 0; k < K; k++) if (E->hCnt->gflag[k + 1]) { kd = k; break; }
@@ -1187,11 +1199,14 @@ void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
       launchContactsAndReduce(E, u, u.gOut, ev);
       if (ev) CK(cudaEventRecord(ev[5], st));
       executed = kd + 1;
+      if (trace) { CK(cudaStreamSynchronize(st)); tReb += msSince(t0); nReb++; nVoid += K - executed; }
     } else if (E->stepsSinceFullRun + K > 2 * (long long)E->batchK) E->batchK = std::min(E->batchMax, E->batchK + 1);      // long quiet stretch: larger batches
     dynDtIfDue(E);
     stepEpilogue(E);
     done += executed;
   }
+  if (trace && nsteps > 1) fprintf(stderr, "runSteps trace: %lld steps in %ld batches (batchK now %d), %ld full runs, %ld void steps | host ms: enqueue %.2f, wait %.2f, full runs + repeated pass %.2f\n",
+                                   (long long)nsteps, nBatch, E->batchK, nReb, nVoid, tEnq, tWait, tReb);
 }
 
 template <class F>
@@ -1505,7 +1520,9 @@ int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* po
       if (w.mat < 0 || w.mat >= (int)h->hMats.size()) throw EngErr{"wall material index out of range", WDEM_ERR_INVALID};
       h->hWalls[i] = w;
     }
-    h->anyMovingWall = false; for (auto& w : h->hWalls) if (w.moving) h->anyMovingWall = true;
+    h->anyMovingWall = h->anyStaticWall = false; for (auto& w : h->hWalls) { if (w.moving) h->anyMovingWall = true; else h->anyStaticWall = true; }
+    h->wallAcc.ensure((size_t)std::max(n, 1) * 6, h->bytes); h->wallPartial.ensure((size_t)std::max(n, 1) * 6 * WD_WALL_PARTS, h->bytes);
+    CK(cudaMemsetAsync(h->wallAcc.p, 0, (size_t)std::max(n, 1) * 6 * sizeof(double), h->stream));
     h->dWalls.ensure(std::max(n, 1), h->bytes);
     if (n) CK(cudaMemcpyAsync(h->dWalls.p, h->hWalls.data(), n * sizeof(Wall), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1678,7 +1695,12 @@ int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torqu
     cudaStream_t st = h->stream;
     auto W = d2h(h->dWalls.p, nW, st);
     for (size_t w = 0; w < nW; w++) for (int k = 0; k < 3; k++) { if (pos) pos[3 * w + k] = W[w].pos[k]; if (force) force[3 * w + k] = 0.; if (torque) torque[3 * w + k] = 0.; }
-    if ((!force && !torque) || h->nC == 0) return;
+    if (!force && !torque) return;
+    if (h->nC == 0 || (!h->anyMovingWall && !h->compactPending)) {   // no wall in DemField.nodes: only the accumulated values of the walls at rest
+      auto acc = d2h(h->wallAcc.p, nW * 6, st);
+      for (size_t w = 0; w < nW; w++) for (int k = 0; k < 3; k++) { if (force) force[3 * w + k] = acc[6 * w + k]; if (torque) torque[3 * w + k] = acc[6 * w + 3 + k]; }
+      return;
+    }
     if (h->compactPending) throw EngErr{"spheres were removed since the last step: step once before reading contacts, wall forces or the stress (the table still refers to the old slots)", WDEM_ERR_INVALID};
 
     // wall-sphere contacts live in [nSS, nSS+nWS) and among the orphans; forces are added per wall in ascending id of the sphere, the order of
@@ -1705,7 +1727,13 @@ int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torqu
       if (rolling) Tc = Tc + xyz(Tg[r.c]);
       F[r.wall] = F[r.wall] + Fc; T[r.wall] = T[r.wall] + Tc;
     }
-    for (size_t w = 0; w < nW; w++) { if (force) { force[3 * w] = F[w].x; force[3 * w + 1] = F[w].y; force[3 * w + 2] = F[w].z; } if (torque) { torque[3 * w] = T[w].x; torque[3 * w + 1] = T[w].y; torque[3 * w + 2] = T[w].z; } }
+    // walls at rest: the value accumulated since the upload (k_wall_sum / k_wall_acc); moving walls (reset by Leapfrog every step): this step's contacts
+    auto acc = d2h(h->wallAcc.p, nW * 6, st);
+    for (size_t w = 0; w < nW; w++) {
+      const bool mv = W[w].moving != 0;
+      if (force) for (int k = 0; k < 3; k++) force[3 * w + k] = mv ? comp(F[w], k) : acc[6 * w + k];
+      if (torque) for (int k = 0; k < 3; k++) torque[3 * w + k] = mv ? comp(T[w], k) : acc[6 * w + 3 + k];
+    }
   });
 }
 

@@ -866,6 +866,48 @@ __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Sphe
 }
 
 // ------------------------------------------------------------------------------------------------
+// Force / torque on walls that are NOT in DemField.nodes (at rest when added: ParticleContainer.cpp:193-198).  Leapfrog never visits them, so nothing ever resets
+// their DemData.force: ContactLoop::applyForceUninodal keeps adding, step after step (ContactLoop.cpp:270-276) — scripts read wall.f as an accumulated
+// value.  Per step: block partial sums over the wall+sphere contacts (fixed tree order), then one add per wall into the accumulator.  The reference's own order of
+// these additions is its contact-loop order; agreement is to rounding (tests: 1e-9), the walls do not move, so nothing feeds back into the dynamics.
+// ------------------------------------------------------------------------------------------------
+#define WD_WALL_PARTS 16
+__global__ void __launch_bounds__(256) k_wall_sum(Contacts C, long long first, long long n, long long firstOrph, long long nOrph, const Wall* __restrict__ walls, Spheres S, StepU u,
+                                                 const int* __restrict__ guard, double* __restrict__ partial /*[nWalls][WD_WALL_PARTS][6]*/) {
+  if (*guard) return;
+  const int w = blockIdx.y, p = blockIdx.x;
+  const Wall W = walls[w];
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  auto visit = [&](long long c) {
+    const uint32_t fl = C.flags[c];
+    if (!(fl & CF_REAL) || (fl & CF_DEAD) || cf_kind(fl) != KIND_WS) return;
+    const int2 pr = C.pair[c];
+    if (pr.x != w || (S.flags[pr.y] & F_GHOST)) return;
+    const d3 F = xyz(C.rD[c]), xc = xyz(C.rC[c]) - mk3(W.pos[0], W.pos[1], W.pos[2]);      // wall = pA: sign +1 (Contact.cpp:28-31)
+    d3 T = cross(xc, F);
+    if (u.rolling) T = T + xyz(C.Tg[c]);
+    v[0] += F.x; v[1] += F.y; v[2] += F.z; v[3] += T.x; v[4] += T.y; v[5] += T.z;
+  };
+  const long long chunk = (n + WD_WALL_PARTS - 1) / WD_WALL_PARTS, b = first + p * chunk, e = min(first + n, b + chunk);
+  for (long long c = b + threadIdx.x; c < e; c += 256) visit(c);
+  if (p == 0) for (long long c = firstOrph + threadIdx.x; c < firstOrph + nOrph; c += 256) visit(c);
+  __shared__ double sm[6][256];
+  for (int k = 0; k < 6; k++) sm[k][threadIdx.x] = v[k];
+  __syncthreads();
+  for (int s_ = 128; s_ > 0; s_ >>= 1) { if ((int)threadIdx.x < s_) for (int k = 0; k < 6; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + s_]; __syncthreads(); }
+  if (threadIdx.x < 6) partial[((long long)w * WD_WALL_PARTS + p) * 6 + threadIdx.x] = sm[threadIdx.x][0];
+}
+__global__ void k_wall_acc(const double* __restrict__ partial, int nWalls, const int* __restrict__ guard, double* __restrict__ acc /*[nWalls][6]*/) {
+  if (*guard) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nWalls * 6) return;
+  const int w = t / 6, k = t % 6;
+  double sum = 0;
+  for (int p = 0; p < WD_WALL_PARTS; p++) sum += partial[((long long)w * WD_WALL_PARTS + p) * 6 + k];
+  acc[t] += sum;
+}
+
+// ------------------------------------------------------------------------------------------------
 // DynDt::nodalCritDtSq (src/dem/DynDt.cpp:16-58): per-sphere stiffness sums over real contacts -> min of 2*m/k.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, int law,
@@ -1119,7 +1161,7 @@ struct WallPass { const Wall* walls; int nWalls; double halfThick; uint32_t* bit
 #define WD_CAND_CAP 16
 #endif
 #ifndef WD_PAIRS_MINB
-#define WD_PAIRS_MINB 12   // 40 registers, 75 % occupancy: measured 0.173 ms/step of collider work vs 0.178 (64 registers) and 0.176 (48 or 32 registers)
+#define WD_PAIRS_MINB 10   // 48 registers (round 1 measured 40/48/64 registers within 3 %; the dormant test needs a few more than 40)
 #endif
 // DORMANT potential contacts.  Between two collider full runs no sphere is farther than verletDist from where it was at the last one (the Verlet test runs in every
 // step, before the contacts, and triggers the full run in the same step: Collision.cpp:113-121), so a candidate pair whose centres were farther apart than
@@ -1520,38 +1562,30 @@ __global__ void __launch_bounds__(256) k_was_real(const int* __restrict__ srcOld
   if (c < nSS) { const int co = srcOld[c]; f = (co >= 0 && (oflags[co] & CF_REAL)) ? 1 : 0; }
   flag[c] = f;
 }
-// Eight lanes per NEW contact: the four 32-byte sectors of a carried contact's state are gathered by lane pairs (16 B each) and written as part of 128-byte warp
-// requests per plane; the small per-contact words (pair, flags, cellDist, stepCreated, Cp2 constants) are spread over the eight lanes.
 __global__ void __launch_bounds__(256) k_carry(Contacts N, long long nNew, Contacts O, const int* __restrict__ srcOld, Contacts T, const int* __restrict__ realPos, long long nSS,
                                               int law, int rolling, int periodic, long long stepNow) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long c = t >> 3; const int k = (int)(t & 7);
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nNew) return;
   const int co = srcOld[c];
   const uint32_t ofl = co >= 0 ? O.flags[co] : 0u;
   const bool carried = co >= 0 && (ofl & CF_REAL);
   long long d = c;
   if (c < nSS) { const long long rp = realPos[c]; d = carried ? rp : (long long)realPos[nSS] + (c - rp); }
+  N.pair[d] = T.pair[c];
+  uint32_t fl = T.flags[c];
+  if (periodic) { N.cdx[d] = T.cdx[c]; N.cdy[d] = T.cdy[c]; N.cdz[d] = T.cdz[c]; }
   if (carried) {
-    const double4* src = (k >> 1) == 0 ? O.rA : ((k >> 1) == 1 ? O.rB : ((k >> 1) == 2 ? O.rC : O.rD)); double4* dst = (k >> 1) == 0 ? N.rA : ((k >> 1) == 1 ? N.rB : ((k >> 1) == 2 ? N.rC : N.rD));
-    reinterpret_cast<uint4*>(dst + d)[k & 1] = reinterpret_cast<const uint4*>(src + co)[k & 1];
-    if (k < 2) reinterpret_cast<uint4*>(N.ph + d)[k] = reinterpret_cast<const uint4*>(O.ph + co)[k];
-    else if (k == 2) N.stepCreated[d] = O.stepCreated[co];
-    else if (k == 3) { if (law == 1) N.ph4[d] = O.ph4[co]; }
-    else if (k == 4) { if (rolling) N.tq[d] = O.tq[co]; }
-    else if (k == 5) O.flags[co] = ofl | CF_CLAIMED;
+    copy_history(N, d, O, co, law, rolling, periodic);      // four 32-byte sectors + the Cp2 constants (round 1: 14 scalar planes, one sector each)
+    fl |= CF_REAL;
+    O.flags[co] = ofl | CF_CLAIMED;
   } else {
-    if (k >= 6) reinterpret_cast<uint4*>(N.rD + d)[k & 1] = make_uint4(0, 0, 0, 0);      // no force from a contact that is not real
-    else if (k == 2) N.stepCreated[d] = (int)stepNow;
-  }
-  if (k == 0) N.pair[d] = T.pair[c];
-  else if (k == 1) N.flags[d] = T.flags[c] | (carried ? (uint32_t)CF_REAL : 0u);
-  else if (k == 7 && periodic) {
     // a potential contact that survives a full run keeps the cellDist it was created with (handleBoundInversionPeri only creates
     // when !hasInter, InsertionSortCollider.cpp:844-893); one whose particle was removed meanwhile (CF_DEAD, k_kill_rows) is a new contact
-    const bool keepOld = co >= 0 && (carried || !(ofl & CF_DEAD));
-    N.cdx[d] = keepOld ? O.cdx[co] : T.cdx[c]; N.cdy[d] = keepOld ? O.cdy[co] : T.cdy[c]; N.cdz[d] = keepOld ? O.cdz[co] : T.cdz[c];
+    if (periodic && co >= 0 && !(ofl & CF_DEAD)) { N.cdx[d] = O.cdx[co]; N.cdy[d] = O.cdy[co]; N.cdz[d] = O.cdz[co]; }
+    N.stepCreated[d] = (int)stepNow;
+    N.rD[d] = make_double4(0, 0, 0, 0);
   }
+  N.flags[d] = fl;
 }
 
 // old real contacts nobody claimed = orphans: count (and add their incidences to the row counts), then append behind the grid candidates
