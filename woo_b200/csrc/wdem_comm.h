@@ -26,6 +26,8 @@ struct Transport {
   virtual void allreduceMaxInt(int* dptr, int n, cudaStream_t st) = 0;
   // every rank contributes n host int64 and receives world*n (rank-major); blocks the host
   virtual void allgather64(const int64_t* mine, int n, int64_t* all, cudaStream_t st) = 0;
+  // every rank contributes `bytes` of DEVICE memory and receives world*bytes (rank-major) in device memory; ordered on the stream, no host wait
+  virtual void allgatherDev(const void* dSend, void* dRecv, size_t bytes, cudaStream_t st) = 0;
   // device payload exchange, sizes known on both sides; segment r of send goes to rank r, segment r of recv comes from rank r
   virtual void alltoallv(const char* sendBase, const size_t* sendOff, const size_t* sendBytes, char* recvBase, const size_t* recvOff,
                          const size_t* recvBytes, cudaStream_t st) = 0;
@@ -72,6 +74,7 @@ struct NcclTransport : Transport {
     WD_CUDA(cudaStreamSynchronize(st));
     memcpy(all, hStage + n, (size_t)n * world * sizeof(int64_t));
   }
+  void allgatherDev(const void* dSend, void* dRecv, size_t bytes, cudaStream_t st) override { WD_NCCL(ncclAllGather(dSend, dRecv, bytes, ncclChar, comm, st)); }
   void alltoallv(const char* sendBase, const size_t* sendOff, const size_t* sendBytes, char* recvBase, const size_t* recvOff, const size_t* recvBytes,
                  cudaStream_t st) override {
     WD_NCCL(ncclGroupStart());
@@ -89,8 +92,8 @@ struct LocalGroup {
   int world;
   std::mutex m; std::condition_variable cv; int waiting = 0; long gen = 0; bool broken = false;
   std::vector<const char*> sendBase; std::vector<const size_t*> sendOff;
-  std::vector<std::vector<int64_t>> slots;
-  explicit LocalGroup(int w) : world(w), sendBase(w, nullptr), sendOff(w, nullptr), slots(w) {}
+  std::vector<std::vector<int64_t>> slots; std::vector<std::vector<char>> blobs;
+  explicit LocalGroup(int w) : world(w), sendBase(w, nullptr), sendOff(w, nullptr), slots(w), blobs(w) {}
   void barrier() {
     std::unique_lock<std::mutex> lk(m);
     if (broken) throw CommErr{"local group: another subdomain failed"};
@@ -114,6 +117,18 @@ struct LocalTransport : Transport {
     G->barrier();
     for (int r = 0; r < world; r++) memcpy(all + (size_t)r * n, G->slots[r].data(), n * sizeof(int64_t));
     G->barrier();
+  }
+  void allgatherDev(const void* dSend, void* dRecv, size_t bytes, cudaStream_t st) override {
+    std::vector<char> mine(bytes);
+    WD_CUDA(cudaMemcpyAsync(mine.data(), dSend, bytes, cudaMemcpyDeviceToHost, st));
+    WD_CUDA(cudaStreamSynchronize(st));
+    G->blobs[rank] = mine;
+    G->barrier();
+    std::vector<char> all(bytes * world);
+    for (int r = 0; r < world; r++) memcpy(all.data() + (size_t)r * bytes, G->blobs[r].data(), bytes);
+    G->barrier();
+    WD_CUDA(cudaMemcpyAsync(dRecv, all.data(), all.size(), cudaMemcpyHostToDevice, st));
+    WD_CUDA(cudaStreamSynchronize(st));
   }
   void allreduceMaxInt(int* dptr, int n, cudaStream_t st) override {
     std::vector<int> h(n);

@@ -102,6 +102,26 @@ __global__ void __launch_bounds__(128) k_dom_count_rows(const int* __restrict__ 
   if (oc.valid) { const int s = slots[first + k]; for (int e = oc.rowStart[s]; e < oc.rowStart[s + 1]; e++) { const uint32_t f = oflags[oc.rowEntry[e] >> 1]; if ((f & CF_REAL) && !(f & CF_DEAD)) c++; } }
   rowCnt[k] = c;
 }
+// the same for ALL spheres in destination order (sorted keys): 0 for everything that does not emigrate, so that an exclusive scan over the whole array gives the
+// row offsets of the emigrants without the host having to know how many there are
+__global__ void __launch_bounds__(128) k_dom_count_rows_all(const uint32_t* __restrict__ keys, const int* __restrict__ slots, int n, int world, OldCsr oc, const uint32_t* __restrict__ oflags, int* rowCnt) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n) return;
+  int c = 0;
+  if (k < n && oc.valid) {
+    const uint32_t key = keys[k];
+    if (key >= 1u && key <= (uint32_t)world) { const int s = slots[k]; for (int e = oc.rowStart[s]; e < oc.rowStart[s + 1]; e++) { const uint32_t f = oflags[oc.rowEntry[e] >> 1]; if ((f & CF_REAL) && !(f & CF_DEAD)) c++; } }
+  }
+  rowCnt[k] = c;
+}
+// one thread: first index of every destination key (empty keys inherit the next one's), and what goes to every rank: (spheres, history rows)
+__global__ void k_dom_send_counts(int* start /*[world+3], pre-filled with n by k_dom_starts*/, int n, int world, const int* __restrict__ rowOff, int* perDest /*[2*world]*/) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  start[world + 2] = n;
+  for (int k = world + 1; k >= 0; k--) if (start[k] == n) start[k] = start[k + 1];
+  for (int r = 0; r < world; r++) { const int a = start[1 + r], b = start[2 + r]; perDest[2 * r] = b - a; perDest[2 * r + 1] = rowOff[b] - rowOff[a]; }
+}
+
 __device__ __forceinline__ void crec_from(const Contacts& O, long long co, int idA, int idB, int law, int rolling, int periodic, CRec& r) {
   r.idA = idA; r.idB = idB; r.flags = O.flags[co]; r.stepCreated = O.stepCreated[co]; r.pad = 0;
   r.cd[0] = periodic ? O.cdx[co] : 0; r.cd[1] = periodic ? O.cdy[co] : 0; r.cd[2] = periodic ? O.cdz[co] : 0;
@@ -188,6 +208,21 @@ __global__ void __launch_bounds__(256) k_dom_pack_ghosts(Spheres S, int nOwn, co
   if (i >= nOwn || !((mask[i] >> r) & 1u)) return;
   GRec g; g.posr = S.posr[i]; g.velm = S.velm[i]; g.angi = S.angi[i]; g.flags = (S.flags[i] & ~F_ARRIVED) | F_GHOST; g.mask = S.mask[i]; g.mat = S.mat[i]; g.id = S.id[i];
   out[off[i]] = g; exportId[off[i]] = g.id;
+}
+// all destinations in one pass: a sphere exported to rank r takes the next free place of r's segment (atomic cursor).  The order inside a segment is arbitrary
+// but the SAME on both sides: exportId here, importId on the receiver are filled from the same records.
+struct GhostSeg { int base[WDEM_MAX_RANKS]; };
+__global__ void __launch_bounds__(256) k_dom_pack_ghosts_all(Spheres S, int nOwn, const uint32_t* __restrict__ mask, int world, GhostSeg seg, int* __restrict__ cursor, GRec* out, int32_t* exportId) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nOwn) return;
+  uint32_t m = mask[i];
+  if (!m) return;
+  GRec g; g.posr = S.posr[i]; g.velm = S.velm[i]; g.angi = S.angi[i]; g.flags = (S.flags[i] & ~F_ARRIVED) | F_GHOST; g.mask = S.mask[i]; g.mat = S.mat[i]; g.id = S.id[i];
+  while (m) {
+    const int r = __ffs(m) - 1; m &= m - 1;
+    const int pos = seg.base[r] + atomicAdd(&cursor[r], 1);
+    out[pos] = g; exportId[pos] = g.id;
+  }
 }
 __global__ void __launch_bounds__(256) k_dom_unpack_ghosts(Spheres S, int first, int cnt, const GRec* __restrict__ in, int32_t* importId) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;

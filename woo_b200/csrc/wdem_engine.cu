@@ -337,57 +337,50 @@ void domainExchange(wdem_engine* E) {
   ContactStore& Ost = E->con[E->curC]; CsrStore& Ocsr = E->csr[E->curR];
   OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = (Ocsr.valid && E->nC > 0) ? 1 : 0; oc.nRows = Ocsr.nRows; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
   TM(0);
-  // ---- 1. classify and group by destination
+  // ---- 1. classify and group by destination; 2. what every rank sends to every other: counted on the device, exchanged from device memory (one host wait)
   std::vector<int> start(W + 3, 0);
   const size_t nn = std::max(n, 1);
   M.dkeys.ensure(nn, tot); M.dkeysAlt.ensure(nn, tot); M.dslots.ensure(nn, tot); M.dslotsAlt.ensure(nn, tot); M.dstart.ensure(W + 3, tot);
+  M.rowCnt.ensure(nn + 1, tot); M.rowOff.ensure(nn + 1, tot); M.perRank.ensure((size_t)2 * WDEM_MAX_RANKS * (W + 1), tot);
+  int* dMine = M.perRank.p; int* dAll = M.perRank.p + 2 * WDEM_MAX_RANKS;      // (spheres, rows) per destination: mine, then everybody's
+  std::vector<int> all((size_t)2 * W * W, 0);
   if (n > 0) {
     k_dom_classify<<<nblk(n, 256), 256, 0, st>>>(A, n, D, M.dkeys.p, M.dslots.p);
     int bits = 1; while ((1 << bits) < W + 2) bits++;
     sortPairs32(E, M.dkeys.p, M.dkeysAlt.p, M.dslots.p, M.dslotsAlt.p, n, bits);
     k_fill_int<<<1, 64, 0, st>>>(M.dstart.p, W + 3, n);
     k_dom_starts<<<nblk(n, 256), 256, 0, st>>>(M.dkeysAlt.p, n, M.dstart.p);
-    CK(cudaMemcpyAsync(start.data(), M.dstart.p, (W + 3) * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-    start[W + 2] = n;
-    for (int k = W + 1; k >= 0; k--) if (start[k] == n) start[k] = start[k + 1];
-    E->launches += 7;
-  }
+    k_dom_count_rows_all<<<nblk(n + 1, 128), 128, 0, st>>>(M.dkeysAlt.p, M.dslotsAlt.p, n, W, oc, Ost.flags.p, M.rowCnt.p);
+    exclusiveSum(E, M.rowCnt.p, M.rowOff.p, n + 1);
+    k_dom_send_counts<<<1, 32, 0, st>>>(M.dstart.p, n, W, M.rowOff.p, dMine);
+    E->launches += 11;
+  } else { CK(cudaMemsetAsync(dMine, 0, 2 * W * sizeof(int), st)); CK(cudaMemsetAsync(M.dstart.p, 0, (W + 3) * sizeof(int), st)); }
+  T->allgatherDev(dMine, dAll, (size_t)2 * W * sizeof(int), st);
+  int* hTab = E->hScratch + 16;      // pinned: [W+3 starts | W*2W table]  (WDEM_MAX_RANKS = 16: 19 + 512 ints < 256?  no -> table goes through a vector below)
+  CK(cudaMemcpyAsync(hTab, M.dstart.p, (W + 3) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(all.data(), dAll, all.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int k = 0; k < W + 3; k++) start[k] = hTab[k];
+  if (n == 0) for (int k = 0; k < W + 3; k++) start[k] = 0;
   const int nKeep = start[1] - start[0], nE = start[W + 1] - start[1];
-  TM(1);
-  // ---- 2. emigrants: particle records and history rows
-  std::vector<int> hRowOff(nE + 1, 0);
-  if (nE > 0) {
-    M.rowCnt.ensure(nE + 1, tot); M.rowOff.ensure(nE + 1, tot);
-    k_dom_count_rows<<<nblk(nE, 128), 128, 0, st>>>(M.dslotsAlt.p, start[1], nE, oc, Ost.flags.p, M.rowCnt.p);
-    CK(cudaMemsetAsync(M.rowCnt.p + nE, 0, sizeof(int), st));
-    exclusiveSum(E, M.rowCnt.p, M.rowOff.p, nE + 1);
-    CK(cudaMemcpyAsync(hRowOff.data(), M.rowOff.p, (nE + 1) * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-    E->launches += 3;
-  }
-  TM(2);
-  std::vector<int64_t> mine(2 * W, 0), all((size_t)2 * W * W, 0);
-  for (int r = 0; r < W; r++) {
-    const int a = start[1 + r] - start[1], b = start[2 + r] - start[1];
-    mine[2 * r] = b - a; mine[2 * r + 1] = hRowOff[b] - hRowOff[a];
-  }
-  T->allgather64(mine.data(), 2 * W, all.data(), st);
-  TM(3);
+  TM(1); TM(2); TM(3);
   std::vector<size_t> sOffP(W, 0), sBytP(W, 0), rOffP(W, 0), rBytP(W, 0), sOffR(W, 0), sBytR(W, 0), rOffR(W, 0), rBytR(W, 0);
-  size_t nImmP = 0, nImmR = 0, accP = 0, accR = 0;
+  size_t nImmP = 0, nImmR = 0, accP = 0, accR = 0, accSR = 0;
   for (int r = 0; r < W; r++) {
-    sOffP[r] = (size_t)(start[1 + r] - start[1]) * sizeof(PRec); sBytP[r] = (size_t)mine[2 * r] * sizeof(PRec);
-    sOffR[r] = (size_t)hRowOff[start[1 + r] - start[1]] * sizeof(CRec); sBytR[r] = (size_t)mine[2 * r + 1] * sizeof(CRec);
+    const size_t mp = (size_t)all[(size_t)R * 2 * W + 2 * r], mr = (size_t)all[(size_t)R * 2 * W + 2 * r + 1];
+    sOffP[r] = (size_t)(start[1 + r] - start[1]) * sizeof(PRec); sBytP[r] = mp * sizeof(PRec);
+    sOffR[r] = accSR * sizeof(CRec); sBytR[r] = mr * sizeof(CRec); accSR += mr;
     const size_t np = (size_t)all[(size_t)r * 2 * W + 2 * R], nr = (size_t)all[(size_t)r * 2 * W + 2 * R + 1];
     rOffP[r] = accP * sizeof(PRec); rBytP[r] = np * sizeof(PRec); accP += np;
     rOffR[r] = accR * sizeof(CRec); rBytR[r] = nr * sizeof(CRec); accR += nr;
   }
   nImmP = accP; nImmR = accR;
   const size_t sendRowsBase = (size_t)nE * sizeof(PRec), recvRowsBase = nImmP * sizeof(PRec);
-  M.sendBuf.ensure(sendRowsBase + (size_t)hRowOff[nE] * sizeof(CRec) + 64, tot); M.recvBuf.ensure(recvRowsBase + nImmR * sizeof(CRec) + 64, tot);
+  M.sendBuf.ensure(sendRowsBase + accSR * sizeof(CRec) + 64, tot); M.recvBuf.ensure(recvRowsBase + nImmR * sizeof(CRec) + 64, tot);
   if (nE > 0) {
     k_dom_pack_particles<<<nblk(nE, 256), 256, 0, st>>>(A, M.dslotsAlt.p, start[1], nE, as<PRec>(M.sendBuf));
-    if (hRowOff[nE] > 0)
-      k_dom_pack_rows<<<nblk(nE, 128), 128, 0, st>>>(M.dslotsAlt.p, start[1], nE, oc, Ost.view(), A.id, E->dWalls.p, E->dFacets.p, M.rowOff.p, c.law, rolling, c.periodic, as<CRec>(M.sendBuf, sendRowsBase));
+    if (accSR > 0)      // rowOff is an exclusive scan over ALL spheres in destination order; the kept ones (key 0, in front) have no rows, so the emigrants' offsets start at 0
+      k_dom_pack_rows<<<nblk(nE, 128), 128, 0, st>>>(M.dslotsAlt.p, start[1], nE, oc, Ost.view(), A.id, E->dWalls.p, E->dFacets.p, M.rowOff.p + start[1], c.law, rolling, c.periodic, as<CRec>(M.sendBuf, sendRowsBase));
     E->launches += 2;
   }
   T->alltoallv(M.sendBuf.p, sOffP.data(), sBytP.data(), M.recvBuf.p, rOffP.data(), rBytP.data(), st);
@@ -412,24 +405,23 @@ void domainExchange(wdem_engine* E) {
     E->launches += 4;
   }
   TM(5);
-  // ---- 5. ghost export
-  M.perRank.ensure(WDEM_MAX_RANKS, tot); M.emask.ensure((size_t)std::max(nOwn, 1), tot);
-  CK(cudaMemsetAsync(M.perRank.p, 0, WDEM_MAX_RANKS * sizeof(int), st));
-  std::vector<int> hPer(WDEM_MAX_RANKS, 0);
-  if (nOwn > 0) {
-    k_dom_export_mask<<<nblk(nOwn, 256), 256, 0, st>>>(B, nOwn, D, M.emask.p, M.perRank.p); E->launches++;
-    CK(cudaMemcpyAsync(hPer.data(), M.perRank.p, WDEM_MAX_RANKS * sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-  }
-  TM(6);
-  std::vector<int64_t> gm(W, 0), ga((size_t)W * W, 0);
-  for (int r = 0; r < W; r++) gm[r] = hPer[r];
-  T->allgather64(gm.data(), W, ga.data(), st);
-  TM(7);
+  // ---- 5. ghost export: per-destination counts on the device, exchanged from device memory (the second and last host wait), one packing pass for all destinations
+  M.emask.ensure((size_t)std::max(nOwn, 1), tot);
+  int* dPer = M.perRank.p; int* dPerAll = M.perRank.p + WDEM_MAX_RANKS;
+  CK(cudaMemsetAsync(dPer, 0, WDEM_MAX_RANKS * sizeof(int), st));
+  if (nOwn > 0) { k_dom_export_mask<<<nblk(nOwn, 256), 256, 0, st>>>(B, nOwn, D, M.emask.p, dPer); E->launches++; }
+  T->allgatherDev(dPer, dPerAll, WDEM_MAX_RANKS * sizeof(int), st);
+  std::vector<int> ga((size_t)W * WDEM_MAX_RANKS, 0);
+  CK(cudaMemcpyAsync(ga.data(), dPerAll, ga.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  TM(6); TM(7);
   M.sendCnt.assign(W, 0); M.recvCnt.assign(W, 0);
   std::vector<size_t> sOffG(W, 0), sBytG(W, 0), rOffG(W, 0), rBytG(W, 0);
   size_t accS = 0, accG = 0;
+  GhostSeg seg; memset(&seg, 0, sizeof(seg));
   for (int r = 0; r < W; r++) {
-    M.sendCnt[r] = (size_t)gm[r]; M.recvCnt[r] = (size_t)ga[(size_t)r * W + R];
+    M.sendCnt[r] = (size_t)ga[(size_t)R * WDEM_MAX_RANKS + r]; M.recvCnt[r] = (size_t)ga[(size_t)r * WDEM_MAX_RANKS + R];
+    seg.base[r] = (int)accS;
     sOffG[r] = accS * sizeof(GRec); sBytG[r] = M.sendCnt[r] * sizeof(GRec); accS += M.sendCnt[r];
     rOffG[r] = accG * sizeof(GRec); rBytG[r] = M.recvCnt[r] * sizeof(GRec); accG += M.recvCnt[r];
   }
@@ -437,21 +429,14 @@ void domainExchange(wdem_engine* E) {
   M.peer.dstOff.assign(W, 0); M.peer.maxRecvTot = 0;
   for (int r = 0; r < W; r++) {   // where my segment starts in rank r's receive layout (segments ordered by source rank), and the largest halo of any rank
     long long off = 0, totR = 0;
-    for (int q = 0; q < W; q++) { if (q < R) off += ga[(size_t)q * W + r]; totR += ga[(size_t)q * W + r]; }
+    for (int q = 0; q < W; q++) { if (q < R) off += ga[(size_t)q * WDEM_MAX_RANKS + r]; totR += ga[(size_t)q * WDEM_MAX_RANKS + r]; }
     M.peer.dstOff[r] = off; M.peer.maxRecvTot = std::max(M.peer.maxRecvTot, totR);
   }
   M.sendBuf.ensure(accS * sizeof(GRec) + 64, tot); M.recvBuf.ensure(accG * sizeof(GRec) + 64, tot);
   M.exportId.ensure(std::max<size_t>(accS, 1), tot); M.importId.ensure(std::max<size_t>(accG, 1), tot);
   if (accS > 0) {
-    M.flag.ensure((size_t)nOwn + 1, tot); M.off.ensure((size_t)nOwn + 1, tot);
-    size_t base = 0;
-    for (int r = 0; r < W; r++) {
-      if (!M.sendCnt[r]) continue;
-      k_dom_export_flag<<<nblk(nOwn, 256), 256, 0, st>>>(M.emask.p, nOwn, r, M.flag.p);
-      exclusiveSum(E, M.flag.p, M.off.p, nOwn);
-      k_dom_pack_ghosts<<<nblk(nOwn, 256), 256, 0, st>>>(B, nOwn, M.emask.p, r, M.off.p, as<GRec>(M.sendBuf) + base, M.exportId.p + base);
-      base += M.sendCnt[r]; E->launches += 4;
-    }
+    CK(cudaMemsetAsync(dPer, 0, WDEM_MAX_RANKS * sizeof(int), st));      // reused as the per-destination cursors
+    k_dom_pack_ghosts_all<<<nblk(nOwn, 256), 256, 0, st>>>(B, nOwn, M.emask.p, W, seg, dPer, as<GRec>(M.sendBuf), M.exportId.p); E->launches++;
   }
   T->alltoallv(M.sendBuf.p, sOffG.data(), sBytG.data(), M.recvBuf.p, rOffG.data(), rBytG.data(), st);
   const int nNew = nOwn + (int)accG;
@@ -954,7 +939,7 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   const wdem_config& c = E->cfg; cudaStream_t st = E->stream, st2 = E->stream2;
   Contacts C = E->con[E->curC].view();
   static const bool sideOff = getenv("WDEM_NO_SIDE_STREAM") != nullptr;
-  const bool side = !sideOff && (E->nWS + E->nFS + E->nOrph) > 0 && E->nSSa > 0;   // boundary kernels are small and latency-bound: overlap them with the big one
+  const bool side = !sideOff && (E->nWS + E->nFS + E->nOrph) > 0 && E->nSSa > 200000;   // small scenes: the fork/join costs more host time than the overlap wins   // boundary kernels are small and latency-bound: overlap them with the big one
   cudaStream_t sb = side ? st2 : st;
   if (ev) CK(cudaEventRecord(ev[2], st));
   if (side) { CK(cudaEventRecord(E->evFork, st)); CK(cudaStreamWaitEvent(st2, E->evFork, 0)); }
@@ -986,11 +971,6 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
     }
     E->launches++;
   }
-  if (E->anyStaticWall && c.applyForces && (E->nWS + E->nOrph) > 0) {
-    const int nW = (int)E->hWalls.size();
-    k_wall_sum<<<dim3(WD_WALL_PARTS, nW), 256, 0, sb>>>(C, E->nSS, E->nWS, E->nSS + E->nWS + E->nFS, E->nOrph, E->dWalls.p, E->S(), u, guard, E->wallPartial.p);
-    k_wall_acc<<<nblk(nW * 6, 64), 64, 0, sb>>>(E->wallPartial.p, nW, guard, E->wallAcc.p); E->launches += 2;
-  }
   // the big kernel goes last so that the small boundary kernels already occupy their share of the SMs
   if (E->nSSa > 0) {
     const int gridSS = std::min(nblk(E->nSSa, WD_CONTACT_BLOCK), E->numSMs * WD_CONTACT_CTAS_PER_SM);   // persistent: one CTA per resident slot
@@ -1008,7 +988,12 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   if (nNow > 0 && (c.applyForces || c.reset)) {
     // ContactLoop.applyForces=False: no contact force is applied, but Leapfrog.reset still sets force = gravity*mass, torque = 0 (Leapfrog.cpp:240-245): null rows
     CsrStore& R = E->csr[E->curR];
-    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard); E->launches++;
+    WallSum ws; memset(&ws, 0, sizeof(ws));
+    if (E->anyStaticWall && c.applyForces && (E->nWS + E->nOrph) > 0) {      // forces on walls at rest accumulate (never reset in the reference): extra blocks of the same launch
+      ws.walls = E->dWalls.p; ws.nWalls = (int)E->hWalls.size(); ws.first = E->nSS; ws.n = E->nWS; ws.firstOrph = E->nSS + E->nWS + E->nFS; ws.nOrph = E->nOrph;
+      ws.partial = E->wallPartial.p; ws.acc = E->wallAcc.p; ws.ticket = reinterpret_cast<unsigned*>(E->wallAcc.p + (size_t)ws.nWalls * 6);
+    }
+    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK) + ws.nWalls * WD_WALL_PARTS, WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard, ws); E->launches++;
   }
   if (ev) CK(cudaEventRecord(ev[4], st));
 }
@@ -1521,8 +1506,8 @@ int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* po
       h->hWalls[i] = w;
     }
     h->anyMovingWall = h->anyStaticWall = false; for (auto& w : h->hWalls) { if (w.moving) h->anyMovingWall = true; else h->anyStaticWall = true; }
-    h->wallAcc.ensure((size_t)std::max(n, 1) * 6, h->bytes); h->wallPartial.ensure((size_t)std::max(n, 1) * 6 * WD_WALL_PARTS, h->bytes);
-    CK(cudaMemsetAsync(h->wallAcc.p, 0, (size_t)std::max(n, 1) * 6 * sizeof(double), h->stream));
+    h->wallAcc.ensure((size_t)std::max(n, 1) * 6 + 1, h->bytes); h->wallPartial.ensure((size_t)std::max(n, 1) * 6 * WD_WALL_PARTS, h->bytes);      // + the ticket word
+    CK(cudaMemsetAsync(h->wallAcc.p, 0, ((size_t)std::max(n, 1) * 6 + 1) * sizeof(double), h->stream));
     h->dWalls.ensure(std::max(n, 1), h->bytes);
     if (n) CK(cudaMemcpyAsync(h->dWalls.p, h->hWalls.data(), n * sizeof(Wall), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));

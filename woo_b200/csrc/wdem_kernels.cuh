@@ -803,6 +803,61 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
 // (ContactLoop.cpp:270-276, Contact.cpp:24-35, Particle.hpp:249) as a deterministic segmented reduction over the
 // particle's incidence row (ascending id of the other particle), fused with Leapfrog's force reset (Leapfrog.cpp:240-245).
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Force / torque on walls that are NOT in DemField.nodes (at rest when added: ParticleContainer.cpp:193-198).  Leapfrog never visits them, so nothing ever resets
+// their DemData.force: ContactLoop::applyForceUninodal keeps adding, step after step (ContactLoop.cpp:270-276, SURVEY A.6) — scripts read wall.f as an accumulated
+// value.  Per step: block partial sums over the wall+sphere contacts (fixed tree order), then one add per wall into the accumulator.  The reference's own order of
+// these additions is its contact-loop order; agreement is to rounding (tests: 1e-9), the walls do not move, so nothing feeds back into the dynamics.
+// The work rides on the force-reduction launch (extra blocks behind the sphere blocks of k_reduce): no launch of its own, and it runs when the contact kernels are done.
+// ------------------------------------------------------------------------------------------------
+#ifndef WD_REDUCE_BLOCK
+#define WD_REDUCE_BLOCK 128     // 128 threads x 6 CTAs/SM (80 registers): measured best of {256x2 (94 regs) 0.149 ms, 128x5 0.145, 256x3 0.131, 128x6 0.127, 128x7 0.136, 128x8 0.162 (spills)}
+#endif
+#define WD_WALL_PARTS 32
+struct WallSum {   // nWalls == 0: nothing to do
+  const Wall* walls; int nWalls; long long first, n, firstOrph, nOrph;      // wall+sphere segment and orphan segment of the contact table
+  double* partial /*[nWalls][WD_WALL_PARTS][6]*/; double* acc /*[nWalls][6]*/; unsigned* ticket;
+};
+// block (w, p) = wall w, part p of the wall+sphere segment; the last block to finish adds the parts up in part order and books them
+__device__ __forceinline__ void wall_sum_block(const Contacts& C, const Spheres& S, const StepU& u, const WallSum& ws, int wb) {
+  const int w = wb / WD_WALL_PARTS, p = wb % WD_WALL_PARTS, nt = blockDim.x;
+  const Wall W = ws.walls[w];
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  auto visit = [&](long long c) {
+    const uint32_t fl = C.flags[c];
+    if (!(fl & CF_REAL) || (fl & CF_DEAD) || cf_kind(fl) != KIND_WS) return;
+    const int2 pr = C.pair[c];
+    if (pr.x != w || (S.flags[pr.y] & F_GHOST)) return;
+    const d3 F = xyz(C.rD[c]), xc = xyz(C.rC[c]) - mk3(W.pos[0], W.pos[1], W.pos[2]);      // wall = pA: sign +1 (Contact.cpp:28-31)
+    d3 T = cross(xc, F);
+    if (u.rolling) T = T + xyz(C.Tg[c]);
+    v[0] += F.x; v[1] += F.y; v[2] += F.z; v[3] += T.x; v[4] += T.y; v[5] += T.z;
+  };
+  if (!W.moving) {      // a moving wall is in DemField.nodes: Leapfrog resets its force every step, wdem_download_walls reports the last step's contacts
+    const long long chunk = (ws.n + WD_WALL_PARTS - 1) / WD_WALL_PARTS, b = ws.first + p * chunk, e = min(ws.first + ws.n, b + chunk);
+    for (long long c = b + threadIdx.x; c < e; c += nt) visit(c);
+    if (p == 0) for (long long c = ws.firstOrph + threadIdx.x; c < ws.firstOrph + ws.nOrph; c += nt) visit(c);
+  }
+  __shared__ double sm[6][WD_REDUCE_BLOCK];
+  __shared__ unsigned last;
+  for (int k = 0; k < 6; k++) sm[k][threadIdx.x] = v[k];
+  __syncthreads();
+  for (int s_ = nt / 2; s_ > 0; s_ >>= 1) { if ((int)threadIdx.x < s_) for (int k = 0; k < 6; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + s_]; __syncthreads(); }
+  if (threadIdx.x < 6) ws.partial[(long long)wb * 6 + threadIdx.x] = sm[threadIdx.x][0];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ws.ticket, 1u);
+  __syncthreads();
+  if (last != (unsigned)(ws.nWalls * WD_WALL_PARTS - 1)) return;
+  __threadfence();
+  for (int t = threadIdx.x; t < ws.nWalls * 6; t += nt) {
+    const int w2 = t / 6, k = t % 6;
+    double sum = 0;
+    for (int q = 0; q < WD_WALL_PARTS; q++) sum += ws.partial[((long long)w2 * WD_WALL_PARTS + q) * 6 + k];
+    ws.acc[t] += sum;
+  }
+  if (threadIdx.x == 0) *ws.ticket = 0;
+}
 // One thread per sphere walks its row in order; the loads of RB entries (entry word, global force, contact point) are issued together before the
 // sequential adds, so a row costs ~3 dependent round trips per RB entries instead of 3 per entry.
 #ifndef WD_REDUCE_RB
@@ -817,8 +872,10 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
 #endif
 #define RB WD_REDUCE_RB
 __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u,
-                                               const int* __restrict__ guard) {
+                                               const int* __restrict__ guard, WallSum ws) {
   if (guard && *guard) return;
+  const int nbS = (n + WD_REDUCE_BLOCK - 1) / WD_REDUCE_BLOCK;
+  if ((int)blockIdx.x >= nbS) { wall_sum_block(C, S, u, ws, (int)blockIdx.x - nbS); return; }      // blocks behind the spheres: walls at rest
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t fl = S.flags[i];
@@ -863,48 +920,6 @@ __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Sphe
   }
   S.fx[i] = F.x; S.fy[i] = F.y; S.fz[i] = F.z;
   S.tx[i] = T.x; S.ty[i] = T.y; S.tz[i] = T.z;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Force / torque on walls that are NOT in DemField.nodes (at rest when added: ParticleContainer.cpp:193-198).  Leapfrog never visits them, so nothing ever resets
-// their DemData.force: ContactLoop::applyForceUninodal keeps adding, step after step (ContactLoop.cpp:270-276, SURVEY A.6) — scripts read wall.f as an accumulated
-// value.  Per step: block partial sums over the wall+sphere contacts (fixed tree order), then one add per wall into the accumulator.  The reference's own order of
-// these additions is its contact-loop order; agreement is to rounding (tests: 1e-9), the walls do not move, so nothing feeds back into the dynamics.
-// ------------------------------------------------------------------------------------------------
-#define WD_WALL_PARTS 16
-__global__ void __launch_bounds__(256) k_wall_sum(Contacts C, long long first, long long n, long long firstOrph, long long nOrph, const Wall* __restrict__ walls, Spheres S, StepU u,
-                                                 const int* __restrict__ guard, double* __restrict__ partial /*[nWalls][WD_WALL_PARTS][6]*/) {
-  if (*guard) return;
-  const int w = blockIdx.y, p = blockIdx.x;
-  const Wall W = walls[w];
-  double v[6] = {0, 0, 0, 0, 0, 0};
-  auto visit = [&](long long c) {
-    const uint32_t fl = C.flags[c];
-    if (!(fl & CF_REAL) || (fl & CF_DEAD) || cf_kind(fl) != KIND_WS) return;
-    const int2 pr = C.pair[c];
-    if (pr.x != w || (S.flags[pr.y] & F_GHOST)) return;
-    const d3 F = xyz(C.rD[c]), xc = xyz(C.rC[c]) - mk3(W.pos[0], W.pos[1], W.pos[2]);      // wall = pA: sign +1 (Contact.cpp:28-31)
-    d3 T = cross(xc, F);
-    if (u.rolling) T = T + xyz(C.Tg[c]);
-    v[0] += F.x; v[1] += F.y; v[2] += F.z; v[3] += T.x; v[4] += T.y; v[5] += T.z;
-  };
-  const long long chunk = (n + WD_WALL_PARTS - 1) / WD_WALL_PARTS, b = first + p * chunk, e = min(first + n, b + chunk);
-  for (long long c = b + threadIdx.x; c < e; c += 256) visit(c);
-  if (p == 0) for (long long c = firstOrph + threadIdx.x; c < firstOrph + nOrph; c += 256) visit(c);
-  __shared__ double sm[6][256];
-  for (int k = 0; k < 6; k++) sm[k][threadIdx.x] = v[k];
-  __syncthreads();
-  for (int s_ = 128; s_ > 0; s_ >>= 1) { if ((int)threadIdx.x < s_) for (int k = 0; k < 6; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + s_]; __syncthreads(); }
-  if (threadIdx.x < 6) partial[((long long)w * WD_WALL_PARTS + p) * 6 + threadIdx.x] = sm[threadIdx.x][0];
-}
-__global__ void k_wall_acc(const double* __restrict__ partial, int nWalls, const int* __restrict__ guard, double* __restrict__ acc /*[nWalls][6]*/) {
-  if (*guard) return;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nWalls * 6) return;
-  const int w = t / 6, k = t % 6;
-  double sum = 0;
-  for (int p = 0; p < WD_WALL_PARTS; p++) sum += partial[((long long)w * WD_WALL_PARTS + p) * 6 + k];
-  acc[t] += sum;
 }
 
 // ------------------------------------------------------------------------------------------------
