@@ -179,7 +179,7 @@ struct wdem_engine {
   // scratch
   DBuf<uint32_t> keys, keysAlt; DBuf<int> idx, idxAlt, cellStart, counts, offsets; DBuf<unsigned char> cubTemp; DBuf<double> blk;
   DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld, candBuf; DBuf<uint32_t> wallBits; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt; DBuf<int> realFlag, realPos; DBuf<int32_t> tmpCd[3];
-  double* hBounds = nullptr; bool boundsValid = false;   // pinned, 2 x 8: bounding box of the sphere centres at the last two full runs
+  double* hBounds = nullptr; bool boundsValid = false; DBuf<double> boundsBuf;   // pinned, 2 x 8: bounding box of the sphere centres at the last two full runs
   Counters* dCnt = nullptr; Counters* hCnt = nullptr; int* hScratch = nullptr;   // pinned: per-step counters, small read-backs of the full run
   // scene scalars
   double dt = NAN, time = 0, nextDt = NAN, verletDist = NAN; long long step = 0, nFullRuns = 0; bool conDirty = true;
@@ -609,10 +609,10 @@ void rebuild(wdem_engine* E) {
       // 1. bounds of sphere centres
       // The grid only has to COVER the spheres for speed, not for correctness (cell coordinates are clamped on both sides of every lookup), so the box measured at
       // the previous full run (read back without waiting, pinned memory) lays out this run's grid; only the first run after an upload waits for its own.
-      E->blk.ensure((size_t)nb * 7 + 8, tot);
-      double* dB = E->blk.p + (size_t)nb * 7;
-      k_bounds<<<nb, 256, 0, st>>>(E->S().posr, n, E->blk.p);
-      k_bounds_final<<<1, 256, 0, st>>>(E->blk.p, nb, dB); E->launches += 2;
+      E->blk.ensure((size_t)nb * 7, tot);
+      if (!E->boundsBuf.p) { E->boundsBuf.ensure(16, tot); CK(cudaMemsetAsync(E->boundsBuf.p, 0, 16 * sizeof(double), st)); }      // 7 results + the ticket word (the kernel leaves it at 0)
+      double* dB = E->boundsBuf.p; unsigned* tick = reinterpret_cast<unsigned*>(dB + 8);
+      k_bounds<<<nb, 256, 0, st>>>(E->S().posr, n, E->blk.p, dB, tick); E->launches++;
       const int slot = (int)(E->nFullRuns & 1);
       CK(cudaMemcpyAsync(E->hBounds + 8 * slot, dB, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
       const double* hb = E->hBounds + 8 * (1 - slot);
@@ -1302,7 +1302,7 @@ int wdem_destroy(wdem_handle h) {
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   for (cudaStream_t cs : {h->sH2D, h->sD2H}) if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
   for (auto& e : h->evUp) if (e) cudaEventDestroy(e); for (auto& e : h->evLf) if (e) cudaEventDestroy(e); if (h->evEk) cudaEventDestroy(h->evEk);
-  h->dEnergy.release(); h->ioIn.release(); h->ioOut.release(); if (h->hEk) cudaFreeHost(h->hEk);
+  h->boundsBuf.release(); h->wallAcc.release(); h->wallPartial.release(); h->dEnergy.release(); h->ioIn.release(); h->ioOut.release(); if (h->hEk) cudaFreeHost(h->hEk);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return WDEM_OK;

@@ -808,12 +808,12 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
 // their DemData.force: ContactLoop::applyForceUninodal keeps adding, step after step (ContactLoop.cpp:270-276) — scripts read wall.f as an accumulated
 // value.  Per step: block partial sums over the wall+sphere contacts (fixed tree order), then one add per wall into the accumulator.  The reference's own order of
 // these additions is its contact-loop order; agreement is to rounding (tests: 1e-9), the walls do not move, so nothing feeds back into the dynamics.
-// The work rides on the force-reduction launch (extra blocks behind the sphere blocks of k_reduce): no launch of its own, and it runs when the contact kernels are done.
+// The work rides on the force-reduction launch (extra blocks in front of the sphere blocks of k_reduce): no launch of its own, and it runs when the contact kernels are done.
 // ------------------------------------------------------------------------------------------------
 #ifndef WD_REDUCE_BLOCK
 #define WD_REDUCE_BLOCK 128     // 128 threads x 6 CTAs/SM (80 registers): measured best of {256x2 (94 regs) 0.149 ms, 128x5 0.145, 256x3 0.131, 128x6 0.127, 128x7 0.136, 128x8 0.162 (spills)}
 #endif
-#define WD_WALL_PARTS 32
+#define WD_WALL_PARTS 128
 struct WallSum {   // nWalls == 0: nothing to do
   const Wall* walls; int nWalls; long long first, n, firstOrph, nOrph;      // wall+sphere segment and orphan segment of the contact table
   double* partial /*[nWalls][WD_WALL_PARTS][6]*/; double* acc /*[nWalls][6]*/; unsigned* ticket;
@@ -874,9 +874,9 @@ __device__ __forceinline__ void wall_sum_block(const Contacts& C, const Spheres&
 __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u,
                                                const int* __restrict__ guard, WallSum ws) {
   if (guard && *guard) return;
-  const int nbS = (n + WD_REDUCE_BLOCK - 1) / WD_REDUCE_BLOCK;
-  if ((int)blockIdx.x >= nbS) { wall_sum_block(C, S, u, ws, (int)blockIdx.x - nbS); return; }      // blocks behind the spheres: walls at rest
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nbW = ws.nWalls * WD_WALL_PARTS;
+  if ((int)blockIdx.x < nbW) { wall_sum_block(C, S, u, ws, (int)blockIdx.x); return; }      // the first blocks: walls at rest (short gather loops, overlapped by the sphere blocks)
+  int i = (blockIdx.x - nbW) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t fl = S.flags[i];
   if (fl & F_GHOST) return;   // forces are reduced by the owner only
@@ -1045,7 +1045,7 @@ __host__ __device__ __forceinline__ int levelOf(const HGrid& g, double r) {
   return L;
 }
 
-__global__ void __launch_bounds__(256) k_bounds(const double4* __restrict__ posr, int n, double* blk /*7 per block*/) {
+__global__ void __launch_bounds__(256) k_bounds(const double4* __restrict__ posr, int n, double* blk /*7 per block*/, double* out /*7: min xyz, max xyz, max radius*/, unsigned* ticket) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[7] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0};
   if (i < n) { double4 p = posr[i]; v[0] = v[3] = p.x; v[1] = v[4] = p.y; v[2] = v[5] = p.z; v[6] = p.w; }
@@ -1060,9 +1060,33 @@ __global__ void __launch_bounds__(256) k_bounds(const double4* __restrict__ posr
     __syncthreads();
   }
   if (threadIdx.x == 0) for (int k = 0; k < 7; k++) blk[7 * blockIdx.x + k] = sm[k][0];
+  // the last block to finish folds the block results into the 7 numbers
+  __shared__ unsigned last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (last != gridDim.x - 1) return;
+  __threadfence();
+  double w[7] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0};
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) {
+    for (int k = 0; k < 3; k++) w[k] = fmin(w[k], blk[7 * b + k]);
+    for (int k = 3; k < 7; k++) w[k] = fmax(w[k], blk[7 * b + k]);
+  }
+  __syncthreads();
+  for (int k = 0; k < 7; k++) sm[k][threadIdx.x] = w[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      for (int k = 0; k < 3; k++) sm[k][threadIdx.x] = fmin(sm[k][threadIdx.x], sm[k][threadIdx.x + s]);
+      for (int k = 3; k < 7; k++) sm[k][threadIdx.x] = fmax(sm[k][threadIdx.x], sm[k][threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { for (int k = 0; k < 7; k++) out[k] = sm[k][0]; *ticket = 0; }
 }
 
-// second stage: the block results -> 7 numbers (min xyz, max xyz, max radius)
+// (kept for reference / tools) second stage as a kernel of its own: the block results -> 7 numbers (min xyz, max xyz, max radius)
 __global__ void __launch_bounds__(256) k_bounds_final(const double* __restrict__ blk, int nb, double* out) {
   double v[7] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0};
   for (int b = threadIdx.x; b < nb; b += 256) {
