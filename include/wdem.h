@@ -58,7 +58,9 @@ typedef struct wdem_config {
   int32_t dynDtPeriod;
   int32_t periodic;
   int32_t device;      /* CUDA device ordinal */
-  int32_t reserved[7];
+  int32_t evalStress;  /* ContactLoop.evalStress (ContactLoop.hpp:117): with Scene.trackEnergy in a periodic scene the stress is evaluated every step and the work of the
+                        * velocity gradient is booked as the "gradV" energy (ContactLoop.cpp:243-250); the stress itself is available on demand either way (wdem_get_stress) */
+  int32_t reserved[6];
 } wdem_config;
 
 /* Counters of the last wdem_step call (cumulative ones say so). */
@@ -165,9 +167,12 @@ int wdem_download_walls(wdem_handle h, double* pos, double* force, double* torqu
  * kinetic, grav, nonviscDamp (Leapfrog.cpp:53-98), elast, plast, broken (IdealElPl.cpp:28-40,64-75,85-92), viscN, viscT (Hertz.cpp:181,193,199,203-207; Hertz's
  * sliding and elastic terms go to plast / elast).  "kinetic" and "elast" are resettable: they hold the last step's value (Scene.cpp:416), the others accumulate from
  * the moment tracking was switched on.  Sums are formed with atomics: equal to the reference's to rounding, not bitwise.  The gradV work of periodic scenes
- * (ContactLoop.cpp:243-250) is not tracked. */
+ * (ContactLoop.cpp:243-250) is a separate entry: wdem_get_gradv_work. */
 int wdem_track_energy(wdem_handle h, int on);
 int wdem_get_energy(wdem_handle h, double* out8);
+/* EnergyTracker entry "gradV" (ContactLoop.cpp:243-250): -tr(gradV . midStress) dt midVol accumulated over the steps taken with trackEnergy and evalStress in a
+ * periodic scene (midStress / midVol: means of this and the previous step's stress / cell volume).  Decomposed runs: this subdomain's share. */
+int wdem_get_gradv_work(wdem_handle h, double* work);
 /* ContactLoop.stress with evalStress=True (ContactLoop.hpp:117, ContactLoop.cpp:116,123,218-231,243-244): sum over real contacts of F (x) dPos / cell volume,
  * row-major 3x3, periodic scenes only; evaluated on demand from the state the last step left (decomposed runs: this subdomain's share — add the
  * results of all subdomains).  Contacts with facets fail like the reference (multi-nodal particles). */

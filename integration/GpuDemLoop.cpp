@@ -49,7 +49,7 @@ wdem_config GpuDemLoop::makeConfig(){
 	c.applyForces=contactLoop->applyForces;
 	if(contactLoop->updatePhys!=ContactLoop::UPDATE_PHYS_NEVER) throw std::runtime_error("GpuDemLoop: ContactLoop.updatePhys is not supported");
 	if(contactLoop->hook) throw std::runtime_error("GpuDemLoop: ContactLoop.hook is not supported");
-	if(scene->trackEnergy && contactLoop->evalStress && scene->isPeriodic) throw std::runtime_error("GpuDemLoop: Scene.trackEnergy together with ContactLoop.evalStress (gradV work) is not supported");
+	c.evalStress=(contactLoop->evalStress && scene->isPeriodic)?1:0;          // with Scene.trackEnergy: the "gradV" energy (ContactLoop.cpp:243-250)
 	auto lin=dynamic_pointer_cast<Law2_L6Geom_FrictPhys_IdealElPl>(ll[0]); auto dmt=dynamic_pointer_cast<Law2_L6Geom_HertzPhys_DMT>(ll[0]);
 	auto cpF=dynamic_pointer_cast<Cp2_FrictMat_FrictPhys>(pp[0]); auto cpH=dynamic_pointer_cast<Cp2_HertzMat_HertzPhys>(pp[0]);
 	if(lin && cpF){
@@ -242,6 +242,7 @@ void GpuDemLoop::run(){
 		double e[8]; chk(h,wdem_get_energy(h,e));
 		static const char* names[8]={"kinetic","grav","nonviscDamp","elast","plast","broken","viscN","viscT"};
 		for(int k=0;k<8;k++){ int ix=-1; const bool reset=(k==0||k==3); scene->energy->add(e[k]-(reset?0.:scene->energy->getValue(names[k],0.)),names[k],ix,reset?EnergyTracker::IsResettable:EnergyTracker::ZeroDontCreate); }
+		if(cfg.evalStress){ double w=0; chk(h,wdem_get_gradv_work(h,&w)); int ix=-1; scene->energy->add(w-scene->energy->getValue("gradV",0.),"gradV",ix,EnergyTracker::IsIncrement|EnergyTracker::ZeroDontCreate); }
 	}
 	if(contactLoop->evalStress && scene->isPeriodic){ double s9[9]; chk(h,wdem_get_stress(h,s9)); for(int i:{0,1,2}) for(int j:{0,1,2}) contactLoop->stress(i,j)=s9[3*i+j]; }
 	// the library has already applied DynDt's result to its own dt; Scene.dt follows through nextDt in Scene::doOneStep's epilogue (Scene.cpp:432)

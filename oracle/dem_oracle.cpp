@@ -355,6 +355,8 @@ struct Scene {
   // Scene.trackEnergy / EnergyTracker (core/EnergyTracker.hpp:30-60): named accumulators; "kinetic" and "elast" are resettable (zeroed in the step prologue, Scene.cpp:416)
   enum { EN_KINETIC = 0, EN_GRAV, EN_DAMP, EN_ELAST, EN_PLAST, EN_BROKEN, EN_VISCN, EN_VISCT, EN_COUNT };
   bool trackEnergy = false; double energy[EN_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // ContactLoop.evalStress + the "gradV" energy (ContactLoop.cpp:116,218-231,243-254)
+  bool evalStress = false; M3 prevStress; Real prevVol = NaN; double gradVWork = 0;
   void eadd(int ix, Real v) {  // EnergyTracker::add (EnergyTracker.cpp:26-34): NaN is ignored; callable from parallel sections
     if (std::isnan(v)) return;
     #pragma omp atomic
@@ -1228,10 +1230,41 @@ struct Scene {
     leapfrogRun();
     colliderRun();
     contactLoopRun();
+    if (P.periodic && evalStress) {   // ContactLoop.cpp:243-254 (after the contact loop, before the deterministic force application: same state)
+      const M3 st = stressNow(); const Real vol = detM(cell.hSize);
+      if (trackEnergy) {
+        const M3 mid = scaleM(addMM(st, prevStress), .5);
+        const Real midVol = !std::isnan(prevVol) ? .5 * (prevVol + vol) : vol;
+        const M3 gs = mulMM(cell.gradV, mid);
+        gradVWork += -trace3(gs(0, 0), gs(1, 1), gs(2, 2)) * P.dt * midVol;
+      }
+      prevVol = vol; prevStress = st;
+    }
     dynDtRun();
     if (P.periodic) cell.setNextGradV();
     step++; time += P.dt;
     if (!std::isnan(nextDt)) { P.dt = nextDt; nextDt = NaN; }
+  }
+
+  // ContactLoop.stress (ContactLoop.cpp:116,218-231,243-244): sum over real contacts of F (x) branch / V with F = node.ori * phys.force (global force as applied to
+  // pA), branch = Contact::dPos (Contact.cpp:54-59), V = Cell::getVolume (Cell.hpp:121).  The reference adds the terms in its (thread-dependent) loop order; here:
+  // canonical contact order.
+  M3 stressNow() const {
+    M3 st; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) st(i, j) = 0;
+    for (auto& kv : con) {
+      const Contact& C = kv.second; if (!C.isReal()) continue;
+      const PRef& a = par[C.idA]; const PRef& b = par[C.idB];
+      if (a.kind == SHAPE_FACET || b.kind == SHAPE_FACET) throw std::runtime_error("ContactLoop.trackWork not allowed with multi-nodal particles in contact");
+      const V3& pa = a.kind == SHAPE_SPHERE ? sph[a.idx].pos : walls[a.idx].pos;
+      const V3& pb = b.kind == SHAPE_SPHERE ? sph[b.idx].pos : walls[b.idx].pos;
+      V3 branch = pb - pa;
+      if (C.cellDist[0] != 0 || C.cellDist[1] != 0 || C.cellDist[2] != 0) branch = branch + cell.intrShiftPos(C.cellDist);
+      const V3 F = quatRotate(C.ori, C.force);
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) st(i, j) += F[i] * branch[j];
+    }
+    const Real vol = detM(cell.hSize);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) st(i, j) = st(i, j) / vol;
+    return st;
   }
 
   // observables (Particle.cpp:247-265, Funcs.cpp:84-113)
@@ -1417,30 +1450,17 @@ long orc_get_contacts(void* h, int realOnly, int* ids /*2n*/, int* cellDist /*3n
   }
   return n;
 }
-// ContactLoop.stress (ContactLoop.cpp:116,218-231,243-244) as the last step left it: sum over real contacts of F (x) branch / V with F = node.ori * phys.force
-// (global force as applied to pA), branch = Contact::dPos (Contact.cpp:54-59), V = Cell::getVolume (Cell.hpp:121).  The reference adds the terms in
-// its (thread-dependent) loop order; here: canonical contact order.  Row-major 3x3.  Only defined in periodic scenes (doStress, ContactLoop.cpp:123).
+// ContactLoop.stress as the last step left it (Scene::stressNow), row-major 3x3.  Only defined in periodic scenes (doStress, ContactLoop.cpp:123).
 int orc_get_stress(void* h, double* out9) {
   Scene* S = (Scene*)h;
   ORC_TRY(h)
   if (!S->P.periodic) throw std::runtime_error("ContactLoop.evalStress needs a periodic scene");
-  M3 st; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) st(i, j) = 0;
-  for (auto& kv : S->con) {
-    const Contact& C = kv.second; if (!C.isReal()) continue;
-    const PRef& a = S->par[C.idA]; const PRef& b = S->par[C.idB];
-    if (a.kind == SHAPE_FACET || b.kind == SHAPE_FACET) throw std::runtime_error("ContactLoop.trackWork not allowed with multi-nodal particles in contact");
-    const V3& pa = a.kind == SHAPE_SPHERE ? S->sph[a.idx].pos : S->walls[a.idx].pos;
-    const V3& pb = b.kind == SHAPE_SPHERE ? S->sph[b.idx].pos : S->walls[b.idx].pos;
-    V3 branch = pb - pa;
-    if (C.cellDist[0] != 0 || C.cellDist[1] != 0 || C.cellDist[2] != 0) branch = branch + S->cell.intrShiftPos(C.cellDist);
-    const V3 F = quatRotate(C.ori, C.force);
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) st(i, j) += F[i] * branch[j];
-  }
-  const M3& H = S->cell.hSize;
-  const Real vol = H(0, 0) * (H(1, 1) * H(2, 2) - H(1, 2) * H(2, 1)) - H(0, 1) * (H(1, 0) * H(2, 2) - H(1, 2) * H(2, 0)) + H(0, 2) * (H(1, 0) * H(2, 1) - H(1, 1) * H(2, 0));
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out9[3 * i + j] = st(i, j) / vol;
+  const M3 st = S->stressNow();
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out9[3 * i + j] = st(i, j);
   ORC_CATCH(h)
 }
+void orc_set_eval_stress(void* h, int on) { ((Scene*)h)->evalStress = on != 0; }
+double orc_get_gradv_work(void* h) { return ((Scene*)h)->gradVWork; }
 void orc_set_track_energy(void* h, int on) { ((Scene*)h)->trackEnergy = on != 0; }
 // kinetic, grav, nonviscDamp, elast, plast, broken, viscN, viscT
 void orc_get_energy(void* h, double* out8) { for (int k = 0; k < Scene::EN_COUNT; k++) out8[k] = ((Scene*)h)->energy[k]; }

@@ -38,7 +38,7 @@ def lib(variant=""):
         L = C.CDLL(build_oracle(variant))
         L.orc_create.restype = C.c_void_p
         L.orc_last_error.restype = C.c_char_p
-        for f in ("orc_get_dt", "orc_get_time", "orc_get_verlet_dist", "orc_pwave_dt", "orc_kinetic_energy"):
+        for f in ("orc_get_dt", "orc_get_time", "orc_get_verlet_dist", "orc_pwave_dt", "orc_kinetic_energy", "orc_get_gradv_work"):
             getattr(L, f).restype = C.c_double
         for f in ("orc_get_step", "orc_num_contacts", "orc_get_contacts"):
             getattr(L, f).restype = C.c_long
@@ -169,6 +169,13 @@ class Oracle:
         o = np.zeros(8)
         self.L.orc_get_energy(self.h, _p(o, C.c_double))
         return dict(zip(("kinetic", "grav", "nonviscDamp", "elast", "plast", "broken", "viscN", "viscT"), o.tolist()))
+
+    def eval_stress(self, on=True):
+        """ContactLoop.evalStress: with track_energy in a periodic scene the gradV work is booked every step (ContactLoop.cpp:243-254)."""
+        self.L.orc_set_eval_stress(self.h, C.c_int(int(on)))
+
+    def gradv_work(self):
+        return self.L.orc_get_gradv_work(self.h)
 
     def stress(self):
         o = np.zeros((3, 3))

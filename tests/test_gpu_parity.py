@@ -318,6 +318,23 @@ def test_periodic_stress_matches_oracle(world):
         engine_for(sc.random_gas(50, box=.3, r=.02, seed=52)).stress()      # aperiodic: not defined (ContactLoop.cpp:123)
 
 
+# Scene.trackEnergy + ContactLoop.evalStress in a periodic scene: the work of the velocity gradient, -tr(gradV.midStress) dt midVol per step, is the "gradV" energy
+# (ContactLoop.cpp:243-254)
+def test_gradv_work_matches_oracle():
+    S = sc.periodic_gas(500, seed=53, gradV=[[-.8, .5, 0], [0, -.6, 0], [0, 0, -.7]], shear0=.1, psd_ratio=2.0)      # a cell being compressed and sheared
+    O = Oracle(S); O.track_energy(True); O.eval_stress(True)
+    from woo_b200.engine import Engine
+    E = Engine(S.params, evalStress=1).load(S); E.track_energy(True)
+    for k in range(3):
+        O.step(80); E.step(80)
+        wo, wg = O.gradv_work(), E.gradv_work()
+        assert wo != 0 and wg == pytest.approx(wo, rel=1e-9), f"gradV work {wg} vs {wo} after {80 * (k + 1)} steps"
+        eo, eg = O.energy(), E.energy()
+        for name in eo:
+            assert eg[name] == pytest.approx(eo[name], rel=1e-9, abs=1e-12 * max(abs(v) for v in eo.values()))
+    assert np.array_equal(O.spheres()["pos"], E.spheres()["pos"])          # bookkeeping only: the trajectory is untouched
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # moving walls (piston): a wall uploaded with a velocity is in DemField.nodes and is translated by Leapfrog (Particle.cpp:638-640, Leapfrog.cpp:195-199,275-278);
 # its force is the sum over the step's contacts

@@ -424,3 +424,29 @@ def test_collision_masks(ma, mb, collide):
     S.mask[:] = (ma, mb); S.params.dt = 1e-7; S.params.dynDtPeriod = 0
     O = Oracle(S); O.step(2)
     assert (O.num_contacts(False) == 1) == collide and (O.num_contacts(True) == 1) == collide
+
+
+def test_gradv_work_two_spheres_compressed_across_the_cell():
+    """ContactLoop.cpp:243-254: with trackEnergy and evalStress the work of the velocity gradient on the contact stress is booked as "gradV".  Two blocked spheres
+    in a cell shrinking along x at a constant rate, positions following the cell (homoDeform "pos"): the contact force is kn*uN along x, so
+    dW = -gradV_xx * (F_x * branch_x / V) * dt * V summed over the steps = minus the elastic energy stored in the contact: the entry closes the energy balance
+    (elast + gradV = const for this frictionless, motionless pair)."""
+    import math
+    S = sc.SceneSpec()
+    S.mats = [sc.frict_mat(density=1000., young=1e6, tanPhi=0.)]
+    L, r = 1.0, .199
+    S.pos = np.array([[.2, .5, .5], [.8, .5, .5]]); S.radius = np.array([r, r])      # apart by .6 inside the cell, by .4 across its x boundary
+    S.flags = np.array([sc.DOF_ALL, sc.DOF_ALL], dtype=np.uint32)
+    rate = -.2
+    G = np.diag([rate, 0., 0.])
+    S.params = sc.Params(periodic=1, damping=0., dynDtPeriod=0, dt=1e-3, verletDist=.05)
+    S.cell = dict(hSize=np.eye(3) * L, gradV=G, nextGradV=G, homoDeform=sc.HOMO_POS)      # positions follow the cell affinely (the formula assumes an affine branch)
+    O = Oracle(S.finalize()); O.track_energy(True); O.eval_stress(True)
+    O.step(400)
+    c = O.contacts(True)
+    assert len(c["ids"]) >= 1 and (c["uN"] < 0).all()
+    kn = c["phys"][0, 0]
+    elastic = sum(.5 * kn * u * u for u in c["uN"])
+    assert O.energy()["elast"] == pytest.approx(elastic, rel=1e-12)
+    # the step-wise trapezoid sum lags the spring energy by about one step's increment
+    assert O.gradv_work() == pytest.approx(-elastic, rel=2e-2)

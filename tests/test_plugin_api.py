@@ -79,10 +79,7 @@ def test_unsupported_settings_raise():
     S.engines = [GpuDemLoop(*woo.utils.defaultEngines(cp2=Cp2_FrictMat_FrictPhys(), law=Law2_L6Geom_HertzPhys_DMT()))]
     with pytest.raises(RuntimeError, match="supported functor pairs"):
         S.one()
-    S.engines = woo.utils.gpuEngines(); S.trackEnergy = True; S.periodic = True; S.engines[0].contactLoop.evalStress = True
-    with pytest.raises(RuntimeError, match="trackEnergy"):          # the gradV work needs the stress every step: not supported
-        S.one()
-    S.periodic = False; S.trackEnergy = False; S.engines[0].contactLoop.evalStress = False
+    S.engines = woo.utils.gpuEngines(); S.periodic = False
     with pytest.raises(RuntimeError, match="degenerate"):
         S.cell.hSize = [[1, 0, 0], [0, 0, 0], [0, 0, 1]]      # py/tests/test_pbc.py:60-62
 

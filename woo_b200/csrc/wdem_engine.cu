@@ -187,6 +187,7 @@ struct wdem_engine {
   HostCell cell;
   long long launches = 0; int numSMs = 148;
   bool compactPending = false;   // spheres were removed since the last full run: the current generation is not the one the incidence rows were built for
+  double gradVWork = 0, prevVol = NAN, prevStress[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // EnergyTracker "gradV" (ContactLoop.cpp:243-254)
   bool trackEnergy = false; DBuf<double> dEnergy;   // Scene.trackEnergy: EN_* accumulators on the device
   // end-to-end pipeline (wdem_step_e2e): host<->device copies of the state overlap with the integrator chunk by chunk
   static const int NCHUNK = 16; int nChunk = 8;   // NCHUNK = capacity, nChunk = pieces in use (WDEM_E2E_CHUNKS)
@@ -1038,6 +1039,39 @@ void leapfrogPipelined(wdem_engine* E, const StepU& u) {
   CK(cudaMemcpyAsync(E->hEk, E->blk.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, E->sD2H));
 }
 
+template <class T> std::vector<T> d2h(const T* p, size_t n, cudaStream_t st);
+// ContactLoop.stress (ContactLoop.cpp:116,218-231,243-244) of the state the last contact pass left: block partial sums on the device, added up in block order
+void computeStress(wdem_engine* h, double* stress9) {
+  if (!h->cfg.periodic) throw EngErr{"ContactLoop.evalStress needs a periodic scene (ContactLoop.cpp:123)", WDEM_ERR_INVALID};
+  for (int k = 0; k < 9; k++) stress9[k] = 0.;
+  const long long nC = h->nC;
+  if (h->compactPending) throw EngErr{"spheres were removed since the last step: step once before reading contacts, wall forces or the stress (the table still refers to the old slots)", WDEM_ERR_INVALID};
+  if (nC > 0) {
+    const int nb = nblk(nC, 256); h->blk.ensure((size_t)nb * 9 + 1, h->bytes);
+    int* flag = reinterpret_cast<int*>(h->blk.p + (size_t)nb * 9);
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+    k_stress<<<nb, 256, 0, h->stream>>>(h->con[h->curC].view(), nC, h->S(), h->dWalls.p, makeUniforms(h), h->blk.p, flag);
+    auto hb = d2h(h->blk.p, (size_t)nb * 9 + 1, h->stream);
+    int hf; memcpy(&hf, &hb[(size_t)nb * 9], sizeof(int));
+    if (hf) throw EngErr{"ContactLoop.trackWork not allowed with multi-nodal particles in contact (facets; ContactLoop.cpp:220)", WDEM_ERR_UNSUPPORTED};
+    for (int b = 0; b < nb; b++) for (int k = 0; k < 9; k++) stress9[k] += hb[9 * (size_t)b + k];
+  }
+  const double vol = mDet(h->cell.hSize);
+  for (int k = 0; k < 9; k++) stress9[k] /= vol;
+}
+// gradV work (ContactLoop.cpp:243-254), once per step after the contact pass when Scene.trackEnergy and ContactLoop.evalStress are both on
+void gradVWorkStep(wdem_engine* E) {
+  if (!(E->cfg.periodic && E->cfg.evalStress)) return;
+  if (!E->trackEnergy) { E->prevVol = NAN; return; }      // doStress without trackEnergy: the reference still updates prevStress/prevVol; restarting the mean is the same to O(dt)
+  double s9[9]; computeStress(E, s9);
+  const double vol = mDet(E->cell.hSize);
+  const double midVol = !std::isnan(E->prevVol) ? .5 * (E->prevVol + vol) : vol;
+  m33 mid; for (int k = 0; k < 9; k++) mid.m[k] = .5 * (s9[k] + E->prevStress[k]);
+  const m33 gs = mMul(E->cell.gradV, mid);
+  E->gradVWork += -((gs.m[0] + gs.m[4]) + gs.m[8]) * E->dt * midVol;
+  E->prevVol = vol; for (int k = 0; k < 9; k++) E->prevStress[k] = s9[k];
+}
+
 // ---- one step in pieces, so that several steps can be enqueued before the host looks at the Verlet flags (Counters::gflag) ----
 struct StepSnap { HostCell cell; GroupsU groups; long long step; double time; StepU u; };
 
@@ -1186,6 +1220,7 @@ void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
       executed = kd + 1;
       if (trace) { CK(cudaStreamSynchronize(st)); tReb += msSince(t0); nReb++; nVoid += K - executed; }
     } else if (E->stepsSinceFullRun + K > 2 * (long long)E->batchK) E->batchK = std::min(E->batchMax, E->batchK + 1);      // long quiet stretch: larger batches
+    gradVWorkStep(E);
     dynDtIfDue(E);
     stepEpilogue(E);
     done += executed;
@@ -1741,24 +1776,10 @@ int wdem_get_energy(wdem_handle h, double* out8) {
 int wdem_get_stress(wdem_handle h, double* stress9) {
   return guarded(h, [&] {
     if (!stress9) throw EngErr{"wdem_get_stress: null output", WDEM_ERR_INVALID};
-    if (!h->cfg.periodic) throw EngErr{"ContactLoop.evalStress needs a periodic scene (ContactLoop.cpp:123)", WDEM_ERR_INVALID};
-    for (int k = 0; k < 9; k++) stress9[k] = 0.;
-    const long long nC = h->nC;
-    if (h->compactPending) throw EngErr{"spheres were removed since the last step: step once before reading contacts, wall forces or the stress (the table still refers to the old slots)", WDEM_ERR_INVALID};
-    if (nC > 0) {
-      const int nb = nblk(nC, 256); h->blk.ensure((size_t)nb * 9 + 1, h->bytes);
-      int* flag = reinterpret_cast<int*>(h->blk.p + (size_t)nb * 9);
-      CK(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
-      k_stress<<<nb, 256, 0, h->stream>>>(h->con[h->curC].view(), nC, h->S(), h->dWalls.p, makeUniforms(h), h->blk.p, flag);
-      auto hb = d2h(h->blk.p, (size_t)nb * 9 + 1, h->stream);
-      int hf; memcpy(&hf, &hb[(size_t)nb * 9], sizeof(int));
-      if (hf) throw EngErr{"ContactLoop.trackWork not allowed with multi-nodal particles in contact (facets; ContactLoop.cpp:220)", WDEM_ERR_UNSUPPORTED};
-      for (int b = 0; b < nb; b++) for (int k = 0; k < 9; k++) stress9[k] += hb[9 * (size_t)b + k];
-    }
-    const double vol = mDet(h->cell.hSize);
-    for (int k = 0; k < 9; k++) stress9[k] /= vol;
+    computeStress(h, stress9);
   });
 }
+int wdem_get_gradv_work(wdem_handle h, double* work) { return guarded(h, [&] { if (!work) throw EngErr{"wdem_get_gradv_work: null output", WDEM_ERR_INVALID}; *work = h->gradVWork; }); }
 
 int wdem_step_e2e(wdem_handle h, int64_t nsteps, const double* pos_in, const double* vel_in, const double* angVel_in, double* pos_out, double* vel_out, double* ek_out,
                   wdem_stats* stats) {

@@ -162,7 +162,7 @@ struct GpuDemLoop : Engine {
     c.applyForces = contactLoop->applyForces;
     if (contactLoop->updatePhys != 0) throw std::runtime_error("GpuDemLoop: ContactLoop.updatePhys is not supported");
     if (!contactLoop->hook.is_none()) throw std::runtime_error("GpuDemLoop: ContactLoop.hook is not supported");
-    if (scene->trackEnergy && contactLoop->evalStress && scene->periodic) throw std::runtime_error("GpuDemLoop: Scene.trackEnergy together with ContactLoop.evalStress (gradV work) is not supported");
+    c.evalStress = (contactLoop->evalStress && scene->periodic) ? 1 : 0;      // with Scene.trackEnergy: the "gradV" energy (ContactLoop.cpp:243-250)
     auto* lin = dynamic_cast<Law2_L6Geom_FrictPhys_IdealElPl*>(contactLoop->lawDisp[0].get());
     auto* dmt = dynamic_cast<Law2_L6Geom_HertzPhys_DMT*>(contactLoop->lawDisp[0].get());
     auto* cpF = dynamic_cast<Cp2_FrictMat_FrictPhys*>(contactLoop->phyDisp[0].get());
@@ -330,6 +330,7 @@ struct GpuDemLoop : Engine {
       static const char* names[8] = {"kinetic", "grav", "nonviscDamp", "elast", "plast", "broken", "viscN", "viscT"};
       // EnergyTracker semantics: "grav" appears as soon as gravity acts, the ZeroDontCreate entries only once they are non-zero (EnergyTracker.cpp:26-34)
       for (int k = 0; k < 8; k++) { const bool always = (k == 0 || k == 3); if (always || e[k] != 0. || scene->energy.count(names[k])) scene->energy[names[k]] = e[k]; }
+      if (cfg.evalStress) { double w = 0; chk(h, wdem_get_gradv_work(h, &w)); if (w != 0. || scene->energy.count("gradV")) scene->energy["gradV"] = w; }      // IsIncrement | ZeroDontCreate
     }
     trackingOn = scene->trackEnergy;
     if (contactLoop->evalStress && scene->periodic) chk(h, wdem_get_stress(h, contactLoop->stress.data()));   // doStress (ContactLoop.cpp:123)

@@ -228,6 +228,12 @@ class Engine:
         self._chk(self.L.wdem_get_energy(self.h, ptr(o)))
         return dict(zip(self.ENERGY_NAMES, o.tolist()))
 
+    def gradv_work(self):
+        """EnergyTracker entry "gradV" (wdem.h: wdem_get_gradv_work)."""
+        w = C.c_double()
+        self._chk(self.L.wdem_get_gradv_work(self.h, C.byref(w)))
+        return w.value
+
     def stress(self):
         """ContactLoop.stress (evalStress) of the current state, 3x3."""
         o = np.zeros((3, 3))
