@@ -944,12 +944,20 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   cudaStream_t sb = side ? st2 : st;
   if (ev) CK(cudaEventRecord(ev[2], st));
   if (side) { CK(cudaEventRecord(E->evFork, st)); CK(cudaStreamWaitEvent(st2, E->evFork, 0)); }
+  // forces on walls at rest accumulate (never reset in the reference): summed by the wall-contact kernels themselves (wall_acc_block)
+  WallAcc wa; memset(&wa, 0, sizeof(wa)); WallAcc wo = wa;
+  if (E->anyStaticWall && c.applyForces && (E->nWS + E->nOrph) > 0) {
+    const int nW = std::min((int)E->hWalls.size(), WD_ACC_WALLS), nbW = nblk(E->nWS, 128), nbO = nblk(E->nOrph, 128);
+    E->wallPartial.ensure((size_t)(nbW + nbO + 1) * nW * 6, E->bytes);
+    wa.nWalls = nW; wa.nBlocksTotal = nbW + nbO; wa.blockBase = 0; wa.partial = E->wallPartial.p; wa.acc = E->wallAcc.p; wa.ticket = reinterpret_cast<unsigned*>(E->wallAcc.p + E->hWalls.size() * 6);
+    wo = wa; wo.blockBase = nbW;
+  }
   if (E->nWS > 0) {
     switch (c.law + (u.energy ? 2 : 0)) {
-      case 0: k_contact_ws<0><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard); break;
-      case 1: k_contact_ws<1><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard); break;
-      case 2: k_contact_ws<2><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard); break;
-      case 3: k_contact_ws<3><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 0: k_contact_ws<0><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard, wa); break;
+      case 1: k_contact_ws<1><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard, wa); break;
+      case 2: k_contact_ws<2><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard, wa); break;
+      case 3: k_contact_ws<3><<<nblk(E->nWS, 128), 128, 0, sb>>>(C, E->nSS, E->nWS, E->S(), E->dWalls.p, E->dMats.p, u, E->dCnt, guard, wa); break;
     }
     E->launches++;
   }
@@ -965,10 +973,10 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   if (E->nOrph > 0) {
     const long long f0 = E->nSS + E->nWS + E->nFS;
     switch (c.law + (u.energy ? 2 : 0)) {
-      case 0: k_contact_orphans<0><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
-      case 1: k_contact_orphans<1><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
-      case 2: k_contact_orphans<2><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
-      case 3: k_contact_orphans<3><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard); break;
+      case 0: k_contact_orphans<0><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard, wo); break;
+      case 1: k_contact_orphans<1><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard, wo); break;
+      case 2: k_contact_orphans<2><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard, wo); break;
+      case 3: k_contact_orphans<3><<<nblk(E->nOrph, 128), 128, 0, sb>>>(C, f0, E->nOrph, E->S(), E->dWalls.p, E->dFacets.p, E->dMats.p, u, E->dCnt, guard, wo); break;
     }
     E->launches++;
   }
@@ -989,12 +997,7 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   if (nNow > 0 && (c.applyForces || c.reset)) {
     // ContactLoop.applyForces=False: no contact force is applied, but Leapfrog.reset still sets force = gravity*mass, torque = 0 (Leapfrog.cpp:240-245): null rows
     CsrStore& R = E->csr[E->curR];
-    WallSum ws; memset(&ws, 0, sizeof(ws));
-    if (E->anyStaticWall && c.applyForces && (E->nWS + E->nOrph) > 0) {      // forces on walls at rest accumulate (never reset in the reference): extra blocks of the same launch
-      ws.walls = E->dWalls.p; ws.nWalls = (int)E->hWalls.size(); ws.first = E->nSS; ws.n = E->nWS; ws.firstOrph = E->nSS + E->nWS + E->nFS; ws.nOrph = E->nOrph;
-      ws.partial = E->wallPartial.p; ws.acc = E->wallAcc.p; ws.ticket = reinterpret_cast<unsigned*>(E->wallAcc.p + (size_t)ws.nWalls * 6);
-    }
-    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK) + ws.nWalls * WD_WALL_PARTS, WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard, ws); E->launches++;
+    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard); E->launches++;
   }
   if (ev) CK(cudaEventRecord(ev[4], st));
 }
@@ -1541,7 +1544,7 @@ int wdem_upload_walls(wdem_handle h, int n, const int32_t* ids, const double* po
       h->hWalls[i] = w;
     }
     h->anyMovingWall = h->anyStaticWall = false; for (auto& w : h->hWalls) { if (w.moving) h->anyMovingWall = true; else h->anyStaticWall = true; }
-    h->wallAcc.ensure((size_t)std::max(n, 1) * 6 + 1, h->bytes); h->wallPartial.ensure((size_t)std::max(n, 1) * 6 * WD_WALL_PARTS, h->bytes);      // + the ticket word
+    h->wallAcc.ensure((size_t)std::max(n, 1) * 6 + 1, h->bytes);      // + the ticket word
     CK(cudaMemsetAsync(h->wallAcc.p, 0, ((size_t)std::max(n, 1) * 6 + 1) * sizeof(double), h->stream));
     h->dWalls.ensure(std::max(n, 1), h->bytes);
     if (n) CK(cudaMemcpyAsync(h->dWalls.p, h->hWalls.data(), n * sizeof(Wall), cudaMemcpyHostToDevice, h->stream));

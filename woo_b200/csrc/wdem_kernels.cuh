@@ -603,6 +603,91 @@ __global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Force / torque on walls that are NOT in DemField.nodes (at rest when added: ParticleContainer.cpp:193-198).  Leapfrog never visits them, so nothing ever resets
+// their DemData.force: ContactLoop::applyForceUninodal keeps adding, step after step (ContactLoop.cpp:270-276, SURVEY A.6) — scripts read wall.f as an accumulated
+// value.  The wall+sphere kernels (k_contact_ws, k_contact_orphans) do it on the fly: every warp adds up the contacts of each wall it holds (butterfly shuffle,
+// fixed order), the block leaves one partial sum per wall, and the last block to finish (ticket) adds the partials in block order into the accumulator.  The
+// reference's own order of these additions is its contact-loop order; agreement is to rounding (tests: 1e-9); the walls do not move, so nothing feeds back.
+// At most WD_ACC_WALLS walls take part (the rest report the last step's contacts like a moving wall).
+// ------------------------------------------------------------------------------------------------
+#define WD_ACC_WALLS 32
+struct WallAcc {   // nWalls == 0: off
+  int nWalls; int nBlocksTotal;      // blocks of all wall-contact launches of this step (the ticket counts them)
+  int blockBase;                     // first partial row of this launch
+  double* partial /*[nBlocksTotal][nWalls][6]*/; double* acc /*[nWalls][6]*/; unsigned* ticket;
+};
+// called by ALL threads of a 128-thread block; (w, F, xc x F + T) of this thread's contact if it is a real contact on a wall at rest, w < 0 otherwise
+__device__ __forceinline__ void wall_acc_block(const WallAcc& wa, int w, d3 F, d3 T) {
+  __shared__ double sW[4][WD_ACC_WALLS][6];
+  __shared__ unsigned last;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int q = lane; q < wa.nWalls * 6; q += 32) sW[wp][q / 6][q % 6] = 0.;
+  __syncwarp();
+  unsigned todo = __ballot_sync(0xffffffffu, w >= 0);
+  while (todo) {      // one round per wall present in this warp
+    const int cur = __shfl_sync(0xffffffffu, w, __ffs(todo) - 1);
+    const bool mine = (w == cur);
+    double v[6] = {mine ? F.x : 0., mine ? F.y : 0., mine ? F.z : 0., mine ? T.x : 0., mine ? T.y : 0., mine ? T.z : 0.};
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    if (lane == 0) for (int k = 0; k < 6; k++) sW[wp][cur][k] = v[k];
+    todo &= ~__ballot_sync(0xffffffffu, mine);
+  }
+  __syncthreads();
+  double* row = wa.partial + (long long)(wa.blockBase + blockIdx.x) * wa.nWalls * 6;
+  for (int q = threadIdx.x; q < wa.nWalls * 6; q += blockDim.x) row[q] = ((sW[0][q / 6][q % 6] + sW[1][q / 6][q % 6]) + sW[2][q / 6][q % 6]) + sW[3][q / 6][q % 6];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(wa.ticket, 1u);
+  __syncthreads();
+  if (last != (unsigned)(wa.nBlocksTotal - 1)) return;
+  __threadfence();
+  // the last block: G groups of threads share the block range of every value, partial sums combined in group order (fixed order, a few hundred blocks)
+  __shared__ double red[128];
+  const int nv = wa.nWalls * 6, G = max(1, (int)blockDim.x / nv), nB = wa.nBlocksTotal, per = (nB + G - 1) / G;
+  for (int q0 = 0; q0 < nv; q0 += blockDim.x) {      // one pass unless there are more than 21 walls
+    const int q = q0 + (int)threadIdx.x % min(nv, (int)blockDim.x), g = (int)threadIdx.x / min(nv, (int)blockDim.x);
+    double sum = 0;
+    if (g < G && q < nv) {
+      const int b0 = g * per, b1 = min(nB, b0 + per);
+      int b = b0;
+      for (; b + 4 <= b1; b += 4) {
+        const double a0 = wa.partial[(long long)b * nv + q], a1 = wa.partial[(long long)(b + 1) * nv + q], a2 = wa.partial[(long long)(b + 2) * nv + q], a3 = wa.partial[(long long)(b + 3) * nv + q];
+        sum = (((sum + a0) + a1) + a2) + a3;
+      }
+      for (; b < b1; b++) sum += wa.partial[(long long)b * nv + q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) red[threadIdx.x] = sum;
+    __syncthreads();
+    if (g == 0 && q < nv) {
+      double tot = 0;
+      for (int k = 0; k < G; k++) tot += red[k * min(nv, (int)blockDim.x) + (q - q0)];
+      wa.acc[q] += tot;
+    }
+  }
+  if (threadIdx.x == 0) *wa.ticket = 0;
+}
+// this thread's contribution after its wall+sphere contact was evaluated (reads back what the tail just stored)
+__device__ __forceinline__ void wall_acc_contact(const WallAcc& wa, const Contacts& C, long long c, bool valid, int2 pr, const Wall* walls, const Spheres& S, const StepU& u, int kindIsWS) {
+  int w = -1; d3 F = mk3(0, 0, 0), T = F;
+  if (valid && kindIsWS && pr.x < wa.nWalls) {
+    const uint32_t fl = C.flags[c];
+    if ((fl & CF_REAL) && !(fl & CF_DEAD) && !walls[pr.x].moving && !(S.flags[pr.y] & F_GHOST)) {
+      w = pr.x;
+      F = xyz(C.rD[c]);                                                                 // wall = pA: sign +1 (Contact.cpp:28-31)
+      const d3 xc = xyz(C.rC[c]) - mk3(walls[w].pos[0], walls[w].pos[1], walls[w].pos[2]);
+      T = cross(xc, F);
+      if (u.rolling) T = T + xyz(C.Tg[c]);
+    }
+  }
+  wall_acc_block(wa, w, F, T);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Wall+Sphere: Cg2_Wall_Sphere_L6Geom::go (src/dem/Wall.cpp:50-84)
 // ------------------------------------------------------------------------------------------------
 template <int LAW>
@@ -639,7 +724,7 @@ __device__ __forceinline__ void contact_ws(const Contacts& C, long long c, uint3
 }
 
 template <int LAW>
-__global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
+__global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard, WallAcc wa) {
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
   const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
@@ -650,6 +735,7 @@ __global__ void __launch_bounds__(128) k_contact_ws(Contacts C, long long first,
     if (!(fl & CF_DEAD)) { evald = 1; contact_ws<LAW>(C, c, fl, pr, S, walls, mats, u, cnt, isReal); }
   }
   block_count(isReal, evald, cnt);
+  if (wa.nWalls) wall_acc_contact(wa, C, c, isReal != 0, pr, walls, S, u, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -781,7 +867,7 @@ __global__ void __launch_bounds__(128) k_contact_fs(Contacts C, long long first,
 // Orphans: contacts that are real although their AABBs no longer overlap (the collider never removes a real contact,
 // InsertionSortCollider.cpp:78-113); rare, kept in a mixed-kind tail segment.
 template <int LAW>
-__global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Facet* facets, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard) {
+__global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long first, long long n, Spheres S, const Wall* walls, const Facet* facets, const Material* mats, StepU u, Counters* cnt, const int* __restrict__ guard, WallAcc wa) {
   long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned isReal = 0, evald = 0;
   const int stale = *guard;   // issued together with the loads below; a set flag means a collider full run is due and this speculative launch is void
@@ -798,6 +884,7 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
     }
   }
   block_count(isReal, evald, cnt);
+  if (wa.nWalls) wall_acc_contact(wa, C, c, isReal != 0, pr, walls, S, u, cf_kind(fl) == KIND_WS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -805,61 +892,6 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
 // (ContactLoop.cpp:270-276, Contact.cpp:24-35, Particle.hpp:249) as a deterministic segmented reduction over the
 // particle's incidence row (ascending id of the other particle), fused with Leapfrog's force reset (Leapfrog.cpp:240-245).
 // ------------------------------------------------------------------------------------------------
-// ------------------------------------------------------------------------------------------------
-// Force / torque on walls that are NOT in DemField.nodes (at rest when added: ParticleContainer.cpp:193-198).  Leapfrog never visits them, so nothing ever resets
-// their DemData.force: ContactLoop::applyForceUninodal keeps adding, step after step (ContactLoop.cpp:270-276, SURVEY A.6) — scripts read wall.f as an accumulated
-// value.  Per step: block partial sums over the wall+sphere contacts (fixed tree order), then one add per wall into the accumulator.  The reference's own order of
-// these additions is its contact-loop order; agreement is to rounding (tests: 1e-9), the walls do not move, so nothing feeds back into the dynamics.
-// The work rides on the force-reduction launch (extra blocks in front of the sphere blocks of k_reduce): no launch of its own, and it runs when the contact kernels are done.
-// ------------------------------------------------------------------------------------------------
-#ifndef WD_REDUCE_BLOCK
-#define WD_REDUCE_BLOCK 128     // 128 threads x 6 CTAs/SM (80 registers): measured best of {256x2 (94 regs) 0.149 ms, 128x5 0.145, 256x3 0.131, 128x6 0.127, 128x7 0.136, 128x8 0.162 (spills)}
-#endif
-#define WD_WALL_PARTS 128
-struct WallSum {   // nWalls == 0: nothing to do
-  const Wall* walls; int nWalls; long long first, n, firstOrph, nOrph;      // wall+sphere segment and orphan segment of the contact table
-  double* partial /*[nWalls][WD_WALL_PARTS][6]*/; double* acc /*[nWalls][6]*/; unsigned* ticket;
-};
-// block (w, p) = wall w, part p of the wall+sphere segment; the last block to finish adds the parts up in part order and books them
-__device__ __forceinline__ void wall_sum_block(const Contacts& C, const Spheres& S, const StepU& u, const WallSum& ws, int wb) {
-  const int w = wb / WD_WALL_PARTS, p = wb % WD_WALL_PARTS, nt = blockDim.x;
-  const Wall W = ws.walls[w];
-  double v[6] = {0, 0, 0, 0, 0, 0};
-  auto visit = [&](long long c) {
-    const uint32_t fl = C.flags[c];
-    if (!(fl & CF_REAL) || (fl & CF_DEAD) || cf_kind(fl) != KIND_WS) return;
-    const int2 pr = C.pair[c];
-    if (pr.x != w || (S.flags[pr.y] & F_GHOST)) return;
-    const d3 F = xyz(C.rD[c]), xc = xyz(C.rC[c]) - mk3(W.pos[0], W.pos[1], W.pos[2]);      // wall = pA: sign +1 (Contact.cpp:28-31)
-    d3 T = cross(xc, F);
-    if (u.rolling) T = T + xyz(C.Tg[c]);
-    v[0] += F.x; v[1] += F.y; v[2] += F.z; v[3] += T.x; v[4] += T.y; v[5] += T.z;
-  };
-  if (!W.moving) {      // a moving wall is in DemField.nodes: Leapfrog resets its force every step, wdem_download_walls reports the last step's contacts
-    const long long chunk = (ws.n + WD_WALL_PARTS - 1) / WD_WALL_PARTS, b = ws.first + p * chunk, e = min(ws.first + ws.n, b + chunk);
-    for (long long c = b + threadIdx.x; c < e; c += nt) visit(c);
-    if (p == 0) for (long long c = ws.firstOrph + threadIdx.x; c < ws.firstOrph + ws.nOrph; c += nt) visit(c);
-  }
-  __shared__ double sm[6][WD_REDUCE_BLOCK];
-  __shared__ unsigned last;
-  for (int k = 0; k < 6; k++) sm[k][threadIdx.x] = v[k];
-  __syncthreads();
-  for (int s_ = nt / 2; s_ > 0; s_ >>= 1) { if ((int)threadIdx.x < s_) for (int k = 0; k < 6; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + s_]; __syncthreads(); }
-  if (threadIdx.x < 6) ws.partial[(long long)wb * 6 + threadIdx.x] = sm[threadIdx.x][0];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(ws.ticket, 1u);
-  __syncthreads();
-  if (last != (unsigned)(ws.nWalls * WD_WALL_PARTS - 1)) return;
-  __threadfence();
-  for (int t = threadIdx.x; t < ws.nWalls * 6; t += nt) {
-    const int w2 = t / 6, k = t % 6;
-    double sum = 0;
-    for (int q = 0; q < WD_WALL_PARTS; q++) sum += ws.partial[((long long)w2 * WD_WALL_PARTS + q) * 6 + k];
-    ws.acc[t] += sum;
-  }
-  if (threadIdx.x == 0) *ws.ticket = 0;
-}
 // One thread per sphere walks its row in order; the loads of RB entries (entry word, global force, contact point) are issued together before the
 // sequential adds, so a row costs ~3 dependent round trips per RB entries instead of 3 per entry.
 #ifndef WD_REDUCE_RB
@@ -874,18 +906,9 @@ __device__ __forceinline__ void wall_sum_block(const Contacts& C, const Spheres&
 #endif
 #define RB WD_REDUCE_RB
 __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u,
-                                               const int* __restrict__ guard, WallSum ws) {
+                                               const int* __restrict__ guard) {
   if (guard && *guard) return;
-  // walls at rest: their (short, gather-bound) blocks are spread evenly among the sphere blocks, every `stride`-th block, so that they neither form a tail
-  // nor hold all SMs at the start
-  const int nbW = ws.nWalls * WD_WALL_PARTS;
-  int sb = blockIdx.x;
-  if (nbW > 0) {
-    const int stride = (int)gridDim.x / nbW, b = blockIdx.x;
-    if (b % stride == 0 && b / stride < nbW) { wall_sum_block(C, S, u, ws, b / stride); return; }
-    sb = b - min(nbW, (b + stride - 1) / stride);
-  }
-  int i = sb * blockDim.x + threadIdx.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t fl = S.flags[i];
   if (fl & F_GHOST) return;   // forces are reduced by the owner only
