@@ -949,7 +949,7 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   if (E->anyStaticWall && c.applyForces && (E->nWS + E->nOrph) > 0) {
     const int nW = std::min((int)E->hWalls.size(), WD_ACC_WALLS), nbW = nblk(E->nWS, 128), nbO = nblk(E->nOrph, 128);
     E->wallPartial.ensure((size_t)(nbW + nbO + 1) * nW * 6, E->bytes);
-    wa.nWalls = nW; wa.nBlocksTotal = nbW + nbO; wa.blockBase = 0; wa.partial = E->wallPartial.p; wa.acc = E->wallAcc.p; wa.ticket = reinterpret_cast<unsigned*>(E->wallAcc.p + E->hWalls.size() * 6);
+    wa.nWalls = nW; wa.nBlocksTotal = nbW + nbO; wa.blockBase = 0; wa.foldInKernel = (nbW + nbO) <= 96 ? 1 : 0; wa.partial = E->wallPartial.p; wa.acc = E->wallAcc.p; wa.ticket = reinterpret_cast<unsigned*>(E->wallAcc.p + E->hWalls.size() * 6);
     wo = wa; wo.blockBase = nbW;
   }
   if (E->nWS > 0) {
@@ -999,6 +999,7 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
     CsrStore& R = E->csr[E->curR];
     k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard); E->launches++;
   }
+  if (wa.nWalls && !wa.foldInKernel) { k_wall_fold<<<wa.nWalls * 6, 256, 0, st>>>(wa.partial, wa.nBlocksTotal, wa.nWalls * 6, wa.acc, guard); E->launches++; }
   if (ev) CK(cudaEventRecord(ev[4], st));
 }
 

@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(WD_CONTACT_BLOCK, WD_CONTACT_CTAS_PER_SM) k_co
 struct WallAcc {   // nWalls == 0: off
   int nWalls; int nBlocksTotal;      // blocks of all wall-contact launches of this step (the ticket counts them)
   int blockBase;                     // first partial row of this launch
+  int foldInKernel;                  // few blocks: the last one to finish books the partial sums; many blocks: k_wall_fold does it after the force reduction
   double* partial /*[nBlocksTotal][nWalls][6]*/; double* acc /*[nWalls][6]*/; unsigned* ticket;
 };
 // called by ALL threads of a 128-thread block; (w, F, xc x F + T) of this thread's contact if it is a real contact on a wall at rest, w < 0 otherwise
@@ -639,6 +640,7 @@ __device__ __forceinline__ void wall_acc_block(const WallAcc& wa, int w, d3 F, d
   __syncthreads();
   double* row = wa.partial + (long long)(wa.blockBase + blockIdx.x) * wa.nWalls * 6;
   for (int q = threadIdx.x; q < wa.nWalls * 6; q += blockDim.x) row[q] = ((sW[0][q / 6][q % 6] + sW[1][q / 6][q % 6]) + sW[2][q / 6][q % 6]) + sW[3][q / 6][q % 6];
+  if (!wa.foldInKernel) return;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(wa.ticket, 1u);
@@ -670,6 +672,17 @@ __device__ __forceinline__ void wall_acc_block(const WallAcc& wa, int w, d3 F, d
     }
   }
   if (threadIdx.x == 0) *wa.ticket = 0;
+}
+// many partial rows (large scenes): one block per value adds its column up with a fixed tree and books it
+__global__ void __launch_bounds__(256) k_wall_fold(const double* __restrict__ partial, int nB, int nv, double* acc, const int* __restrict__ guard) {
+  if (*guard) return;
+  const int q = blockIdx.x;
+  double sum = 0;
+  for (int b = threadIdx.x; b < nB; b += 256) sum += partial[(long long)b * nv + q];
+  __shared__ double sm[256];
+  sm[threadIdx.x] = sum; __syncthreads();
+  for (int s_ = 128; s_ > 0; s_ >>= 1) { if ((int)threadIdx.x < s_) sm[threadIdx.x] += sm[threadIdx.x + s_]; __syncthreads(); }
+  if (threadIdx.x == 0) acc[q] += sm[0];
 }
 // this thread's contribution after its wall+sphere contact was evaluated (reads back what the tail just stored)
 __device__ __forceinline__ void wall_acc_contact(const WallAcc& wa, const Contacts& C, long long c, bool valid, int2 pr, const Wall* walls, const Spheres& S, const StepU& u, int kindIsWS) {
