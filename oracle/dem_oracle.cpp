@@ -192,6 +192,15 @@ static inline void quatNormalize(Quat& q) {
   Real n = std::sqrt(((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
   q.w /= n; q.x /= n; q.y /= n; q.z /= n;
 }
+// Leapfrog::DotQ (Leapfrog.cpp:324-331)
+static inline Quat dotQ(const V3& w, const Quat& Q) {
+  Quat d;
+  d.w = (-Q.x * w.x - Q.y * w.y - Q.z * w.z) / 2;
+  d.x = (Q.w * w.x - Q.z * w.y + Q.y * w.z) / 2;
+  d.y = (Q.z * w.x + Q.w * w.y - Q.x * w.z) / 2;
+  d.z = (-Q.y * w.x + Q.x * w.y + Q.w * w.z) / 2;
+  return d;
+}
 static inline M3 quatToMat(const Quat& q) {  // Eigen toRotationMatrix
   M3 r;
   Real tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
@@ -221,6 +230,7 @@ struct Sphere {
   int id; V3 pos; Quat ori; V3 vel, angVel, force, torque; Real mass, inertia, radius; unsigned flags, mask; int mat;
   Aabb bb; V3 lastPos;
   bool dead = false;   // removed by ParticleContainer::remove (the slot stays: ids are not renumbered)
+  int clump = -1;      // index of the clump this sphere is a member of (DemData::isClumped), -1: free
 };
 struct Wall {
   int id; V3 pos; int axis, sense; V3 vel, angVel; unsigned mask; int mat; V3 force, torque; Aabb bb; V3 lastPos;
@@ -233,6 +243,12 @@ struct Facet {
 // Master node of a clump of boundary particles that moves them rigidly (ParticleContainer::addClumped -> ClumpData::makeClump, Clump.cpp:187-261): a massless,
 // fully blocked node with prescribed vel/angVel (examples/mill.py:38-42) whose members are facets.  relPos are the members' node positions in the clump's frame.
 struct FacetGroup { V3 pos; Quat ori; V3 vel, angVel; std::vector<int> facets; std::vector<V3> relPos; };
+// Clump of spheres with mass (ClumpData, Clump.hpp:38-60): the master node carries mass / principal inertia and is integrated by Leapfrog (aspherical rotation when
+// the inertia components differ); member nodes are slaves (DemData::isClumped): positions, orientations and velocities follow, forces are collected from them.
+struct Clump {
+  V3 pos; Quat ori; V3 vel, angVel, angMom = V3(NaN, NaN, NaN); Real mass = 0; V3 inertia; V3 force, torque; unsigned flags = 0;
+  std::vector<int> members /*sphere indices*/; std::vector<V3> relPos; std::vector<Quat> relOri;
+};
 struct PRef { int kind, idx; };
 
 struct Contact {
@@ -363,7 +379,7 @@ struct Scene {
     energy[ix] += v;
   }
   Params P; Cell cell;
-  std::vector<Material> mats; std::vector<Sphere> sph; std::vector<Wall> walls; std::vector<Facet> facets; std::vector<FacetGroup> groups; std::vector<PRef> par;
+  std::vector<Material> mats; std::vector<Sphere> sph; std::vector<Wall> walls; std::vector<Facet> facets; std::vector<FacetGroup> groups; std::vector<Clump> clumps; std::vector<PRef> par;
   std::map<uint64_t, Contact> con;          // ordered by canonical key
   std::vector<Contact*> lin; bool linDirty = true;
   std::vector<uint64_t> pending;            // ContactContainer::requestRemoval queue
@@ -387,6 +403,8 @@ struct Scene {
     unsigned mA = maskOf(a), mB = maskOf(b);
     if (!(mA & mB)) return false;
     if ((mA & mB & P.loneMask) != 0) return false;
+    // particles inside the same clump (Collision.cpp:31-40)
+    if (par[a].kind == SHAPE_SPHERE && par[b].kind == SHAPE_SPHERE) { const int ca = sph[par[a].idx].clump, cb = sph[par[b].idx].clump; if (ca >= 0 && ca == cb) return false; }
     // only sphere-sphere, wall-sphere, facet-sphere have functors on this path (ContactLoop.cpp:149 "if(!cgf) continue")
     return true;
   }
@@ -1058,6 +1076,7 @@ struct Scene {
     #pragma omp parallel for schedule(guided)
     for (long i = 0; i < n; i++) {
       Sphere& s = sph[i];
+      if (s.clump >= 0) continue;      // integrated via the clump's master node (Leapfrog.cpp:150)
       const unsigned fl = s.flags;
       const bool blockedAll = (fl & DOF_ALL) == DOF_ALL, blockedNone = (fl & DOF_ALL) == 0;
       const bool damp = (damping != 0. && !(fl & DAMPING_SKIP));
@@ -1128,6 +1147,80 @@ struct Scene {
         s.torque = V3();
       }
     }
+    // clump master nodes (Leapfrog.cpp:148-255 with isClump): forces from the members, spherical or aspherical rotation, then the members follow
+    if (!clumps.empty()) {
+      if (P.periodic) throw std::runtime_error("clumps in a periodic cell are not supported");
+      if (trackEnergy) throw std::runtime_error("Scene.trackEnergy with clumps is not supported");
+      #pragma omp parallel for schedule(guided)
+      for (long ci = 0; ci < (long)clumps.size(); ci++) {
+        Clump& c = clumps[ci];
+        const unsigned fl = c.flags;
+        const bool blockedAll = (fl & DOF_ALL) == DOF_ALL, blockedNone = (fl & DOF_ALL) == 0, blockedAllRot = (fl & 56u) == 56u;
+        const bool damp = (damping != 0. && !(fl & DAMPING_SKIP));
+        if (!blockedAll) {      // ClumpData::forceTorqueFromMembers (Clump.cpp:272-280): accumulates to the node's own force/torque (gravity from the last reset)
+          for (int m : c.members) { const Sphere& ms = sph[m]; c.force += ms.force; c.torque += ms.torque + cross(ms.pos - c.pos, ms.force); }
+        }
+        V3& f = c.force; V3& t = c.torque;
+        const bool aspherical = !(c.inertia.x == c.inertia.y && c.inertia.y == c.inertia.z), useAspherical = aspherical && !blockedAllRot;      // Particle.hpp:275-277
+        V3 linAccel, angAccel;
+        if (!blockedAll) {
+          if (blockedNone) linAccel = f / c.mass;
+          else { for (int k = 0; k < 3; k++) if (!(fl & (1u << k))) linAccel[k] += f[k] / c.mass; }
+          if (damp) for (int k = 0; k < 3; k++) linAccel[k] *= 1 - damping * Sign(f[k] * (c.vel[k] + 0.5 * dt * linAccel[k]));
+          c.vel += dt * linAccel;
+          if (c.inertia != V3(0, 0, 0)) {
+            if (!useAspherical) {
+              if (blockedNone) angAccel = V3(t.x / c.inertia.x, t.y / c.inertia.y, t.z / c.inertia.z);
+              else { for (int k = 0; k < 3; k++) if (!(fl & (1u << (k + 3)))) angAccel[k] += t[k] / c.inertia[k]; }
+              if (damp) for (int k = 0; k < 3; k++) angAccel[k] *= 1 - damping * Sign(t[k] * (c.angVel[k] + 0.5 * dt * angAccel[k]));
+              c.angVel += dt * angAccel;
+            } else {
+              for (int k = 0; k < 3; k++) if (fl & (1u << (k + 3))) t[k] = 0;                                    // block DOFs here (Leapfrog.cpp:188)
+              if (damp) for (int k = 0; k < 3; k++) t[k] *= 1 - damping * Sign(t[k] * c.angVel[k]);              // nonviscDamp1st (Leapfrog.cpp:28-30)
+            }
+          }
+        }
+        c.pos += c.vel * dt;
+        if (!useAspherical) {      // leapfrogSphericalRotate (Leapfrog.cpp:280-297)
+          V3 axis = c.angVel;
+          if (axis != V3(0, 0, 0)) {
+            Real angle = norm(axis); axis = axis / angle;
+            Real ha = 0.5 * (angle * dt); Real sn = std::sin(ha);
+            c.ori = quatMul(Quat(std::cos(ha), sn * axis.x, sn * axis.y, sn * axis.z), c.ori);
+          }
+          quatNormalize(c.ori);
+        } else {      // leapfrogAsphericalRotate (Leapfrog.cpp:299-321)
+          if (c.inertia == V3(0, 0, 0)) throw std::runtime_error("Leapfrog::run: inertia==(0,0,0), but the node wants to use aspherical integrator");
+          const Quat qc(c.ori.w, -c.ori.x, -c.ori.y, -c.ori.z);
+          if (std::isnan(std::min(c.angMom.x, std::min(c.angMom.y, c.angMom.z))) || c.angMom.x != c.angMom.x || c.angMom.y != c.angMom.y || c.angMom.z != c.angMom.z) {
+            const V3 wl = quatRotate(qc, c.angVel); c.angMom = V3(c.inertia.x * wl.x, c.inertia.y * wl.y, c.inertia.z * wl.z);
+          }
+          const M3 A = quatToMat(qc);                                             // rotation matrix from global to local r.f.
+          const V3 l_n = c.angMom + dt / 2 * t;
+          const V3 l_b_n = mulMV(A, l_n);
+          const V3 w_b_n(l_b_n.x / c.inertia.x, l_b_n.y / c.inertia.y, l_b_n.z / c.inertia.z);
+          const Quat dotQ_n = dotQ(w_b_n, c.ori);
+          const Quat Q_half(c.ori.w + dt / 2 * dotQ_n.w, c.ori.x + dt / 2 * dotQ_n.x, c.ori.y + dt / 2 * dotQ_n.y, c.ori.z + dt / 2 * dotQ_n.z);
+          c.angMom += dt * t;
+          const V3 l_b_half = mulMV(A, c.angMom);
+          const V3 w_b_half(l_b_half.x / c.inertia.x, l_b_half.y / c.inertia.y, l_b_half.z / c.inertia.z);
+          const Quat dotQ_half = dotQ(w_b_half, Q_half);
+          c.ori = Quat(c.ori.w + dt * dotQ_half.w, c.ori.x + dt * dotQ_half.x, c.ori.y + dt * dotQ_half.y, c.ori.z + dt * dotQ_half.z);
+          c.angVel = quatRotate(c.ori, w_b_half);
+          quatNormalize(c.ori);
+        }
+        if (P.reset) { c.force = (hasGravity && !(fl & GRAVITY_SKIP)) ? (c.mass * g) : V3(); c.torque = V3(); }      // gravity on the clump itself, not on the members
+        // ClumpData::applyToMembers (Clump.cpp:293-307)
+        for (size_t k = 0; k < c.members.size(); k++) {
+          Sphere& ms = sph[c.members[k]];
+          ms.pos = c.pos + quatRotate(c.ori, c.relPos[k]);
+          ms.ori = quatMul(c.ori, c.relOri[k]);
+          ms.vel = c.vel + cross(c.angVel, ms.pos - c.pos);
+          ms.angVel = c.angVel;
+          if (P.reset) { ms.force = V3(); ms.torque = V3(); }
+        }
+      }
+    }
     // boundary nodes that are in DemField.nodes (walls added with a velocity): mass 0 and all DOFs blocked => Leapfrog's "fixed particle" branch
     // (Leapfrog.cpp:195-199): no acceleration, leapfrogTranslate pos += vel*dt (:275-278), force/torque reset to mass*gravity = 0 (:240-245)
     // clump master nodes of kinematic facet groups: all DOFs blocked => Leapfrog's fixed-particle branch: leapfrogTranslate + leapfrogSphericalRotate with the
@@ -1173,8 +1266,9 @@ struct Scene {
       const PRef& p = par[id];
       if (p.kind != SHAPE_SPHERE) continue;  // walls/facets are not in dem.nodes
       const Sphere& s = sph[p.idx];
-      if ((s.flags & DOF_ALL) == DOF_ALL) continue;
       std::sort(inc[id].begin(), inc[id].end(), [](const Inc& a, const Inc& b) { return a.other < b.other; });
+      if (s.clump >= 0) continue;      // a clumped node is not in DemField.nodes: its contacts count for the clump's master node (below)
+      if ((s.flags & DOF_ALL) == DOF_ALL) continue;
       V3 ktrans, krot;
       for (const Inc& e : inc[id]) {
         const Contact& C = *e.C;
@@ -1186,6 +1280,24 @@ struct Scene {
       Real r = Inf;
       for (int k = 0; k < 3; k++) if (ktrans[k] != 0 && s.mass > 0. && !(s.flags & (1u << k))) r = std::min(r, s.mass / std::abs(ktrans[k]));
       for (int k = 0; k < 3; k++) if (krot[k] != 0 && s.inertia > 0. && !(s.flags & (1u << (k + 3)))) r = std::min(r, s.inertia / std::abs(krot[k]));
+      ret = std::min(ret, 2 * r);
+    }
+    // clump master nodes: stiffnesses of the contacts of all member particles, member by member (DynDt.cpp:48-52), against the clump's mass and principal inertia
+    for (const Clump& c : clumps) {
+      if ((c.flags & DOF_ALL) == DOF_ALL) continue;
+      V3 ktrans, krot;
+      for (int m : c.members) {
+        for (const Inc& e : inc[sph[m].id]) {
+          const Contact& C = *e.C;
+          V3 n = quatRotate(C.ori, V3(1, 0, 0));
+          V3 n2(n.x * n.x, n.y * n.y, n.z * n.z);
+          ktrans += n2 * (C.kn - C.kt) + V3(C.kt, C.kt, C.kt);
+          krot += pow2(C.lens[e.side]) * C.kt * V3(n2[1] + n2[2], n2[2] + n2[0], n2[0] + n2[1]);
+        }
+      }
+      Real r = Inf;
+      for (int k = 0; k < 3; k++) if (ktrans[k] != 0 && c.mass > 0. && !(c.flags & (1u << k))) r = std::min(r, c.mass / std::abs(ktrans[k]));
+      for (int k = 0; k < 3; k++) if (krot[k] != 0 && c.inertia[k] > 0. && !(c.flags & (1u << (k + 3)))) r = std::min(r, c.inertia[k] / std::abs(krot[k]));
       ret = std::min(ret, 2 * r);
     }
     return std::sqrt(ret);
@@ -1365,6 +1477,38 @@ int orc_add_facet_group(void* h, const double* pos, const double* ori /*x,y,z,w*
   for (size_t k = 0; k < G.facets.size(); k++) { Facet& f = S->facets[G.facets[k]]; for (int i = 0; i < 3; i++) f.vvel[i] = G.vel + cross(G.angVel, f.v[i] - G.pos); }
   S->groups.push_back(G);
   ORC_CATCH(h)
+}
+// ParticleContainer.addClumped(spheres) with the clump's mass properties given by the caller (ClumpData::makeClump computes them from the members: Clump.cpp:187-261;
+// here they are inputs, so that oracle and engine start from the same numbers): members become slaves (DemData::setClumped), relPos / relOri in the clump's frame
+int orc_add_clump(void* h, int n, const int* sphereIds, const double* pos, const double* ori /*x,y,z,w*/, const double* vel, const double* angVel, double mass, const double* inertia,
+                  unsigned flags) {
+  Scene* S = (Scene*)h;
+  ORC_TRY(h)
+  Clump c; c.pos = V3(pos[0], pos[1], pos[2]); c.ori = Quat(ori[3], ori[0], ori[1], ori[2]); c.vel = V3(vel[0], vel[1], vel[2]); c.angVel = V3(angVel[0], angVel[1], angVel[2]);
+  c.mass = mass; c.inertia = V3(inertia[0], inertia[1], inertia[2]); c.flags = flags;
+  const Quat qc(c.ori.w, -c.ori.x, -c.ori.y, -c.ori.z);
+  for (int k = 0; k < n; k++) {
+    const int id = sphereIds[k];
+    if (id < 0 || id >= (int)S->par.size() || S->par[id].kind != SHAPE_SPHERE) throw std::runtime_error("clump: member #" + std::to_string(id) + " is not a sphere");
+    Sphere& ms = S->sph[S->par[id].idx];
+    if (ms.clump >= 0) throw std::runtime_error("Node of particle #" + std::to_string(id) + ": already clumped.");
+    ms.clump = (int)S->clumps.size();
+    c.members.push_back(S->par[id].idx);
+    c.relPos.push_back(quatRotate(qc, ms.pos - c.pos));      // Clump.cpp:252-253
+    c.relOri.push_back(quatMul(qc, ms.ori));
+  }
+  // the members follow the master from the start
+  for (size_t k = 0; k < c.members.size(); k++) { Sphere& ms = S->sph[c.members[k]]; ms.vel = c.vel + cross(c.angVel, ms.pos - c.pos); ms.angVel = c.angVel; }
+  S->clumps.push_back(c); S->conDirty = true;
+  ORC_CATCH(h)
+}
+void orc_get_clumps(void* h, double* pos, double* ori, double* vel, double* angVel) {
+  Scene* S = (Scene*)h;
+  for (size_t i = 0; i < S->clumps.size(); i++) {
+    const Clump& c = S->clumps[i];
+    for (int k = 0; k < 3; k++) { pos[3 * i + k] = c.pos[k]; vel[3 * i + k] = c.vel[k]; angVel[3 * i + k] = c.angVel[k]; }
+    ori[4 * i] = c.ori.x; ori[4 * i + 1] = c.ori.y; ori[4 * i + 2] = c.ori.z; ori[4 * i + 3] = c.ori.w;
+  }
 }
 void orc_get_facets(void* h, double* verts /*9 per facet*/) {
   Scene* S = (Scene*)h;

@@ -94,6 +94,12 @@ class Oracle:
             add_boundaries(); add_spheres()
         else:
             add_spheres(); add_boundaries()
+        ids = S.sphere_ids()
+        for c in getattr(S, "clumps", []):
+            a = lambda k: np.ascontiguousarray(c[k], dtype=np.float64)
+            mem = np.ascontiguousarray(ids[np.asarray(c["members"], dtype=np.int64)], dtype=np.int32)
+            self._chk(L.orc_add_clump(h, C.c_int(len(mem)), _p(mem, C.c_int), _p(a("pos"), C.c_double), _p(a("ori"), C.c_double), _p(a("vel"), C.c_double), _p(a("angVel"), C.c_double),
+                                      C.c_double(c["mass"]), _p(a("inertia"), C.c_double), C.c_uint(int(c.get("flags", 0)))))
         P = OrcParams(); L.orc_default_params(C.byref(P))
         for k, v in vars(S.params).items():
             if k == "gravity":
@@ -155,6 +161,13 @@ class Oracle:
     def remove_spheres(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         self._chk(self.L.orc_remove_spheres(self.h, C.c_int(len(ids)), _p(ids, C.c_int)))
+
+    def clumps(self):
+        n = len(getattr(self.spec, "clumps", []))
+        o = dict(pos=np.zeros((n, 3)), ori=np.zeros((n, 4)), vel=np.zeros((n, 3)), angVel=np.zeros((n, 3)))
+        if n:
+            self.L.orc_get_clumps(self.h, _p(o["pos"], C.c_double), _p(o["ori"], C.c_double), _p(o["vel"], C.c_double), _p(o["angVel"], C.c_double))
+        return o
 
     def facets(self):
         o = np.zeros((len(self.spec.facets), 3, 3))

@@ -450,3 +450,63 @@ def test_gradv_work_two_spheres_compressed_across_the_cell():
     assert O.energy()["elast"] == pytest.approx(elastic, rel=1e-12)
     # the step-wise trapezoid sum lags the spring energy by about one step's increment
     assert O.gradv_work() == pytest.approx(-elastic, rel=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clumps of spheres with mass: ClumpData::forceTorqueFromMembers / applyToMembers (Clump.cpp:272-307), Leapfrog's aspherical integrator
+# (Leapfrog.cpp:299-331)
+# ---------------------------------------------------------------------------------------------------------------
+def _dumbbells(n=1, omega=(0., 0., 0.), vel=(0., 0., 0.), gravity=(0., 0., 0.), damping=0., r=.05, sep=.1, asym=False):
+    S = sc.SceneSpec()
+    S.mats = [sc.frict_mat(density=1000., young=1e6, tanPhi=.4)]
+    pos, rad, groups = [], [], []
+    for i in range(n):
+        c = np.array([.5 * i, 0., 1.])
+        if asym:      # three unequal spheres in an L: three different principal moments
+            pts, rr = [c, c + [sep, 0, 0], c + [0, 1.3 * sep, .2 * sep]], [r, .8 * r, .6 * r]
+        else:
+            pts, rr = [c - [sep / 2, 0, 0], c + [sep / 2, 0, 0]], [r, r]
+        groups.append(list(range(len(pos), len(pos) + len(pts)))); pos += pts; rad += rr
+    S.pos, S.radius = np.array(pos), np.array(rad)
+    S.params = sc.Params(gravity=gravity, damping=damping, dynDtPeriod=0, dt=1e-4)
+    S.finalize()
+    return sc.make_clumps(S, groups, vel=[vel] * n, angVel=[omega] * n)
+
+
+def test_clump_free_rotation_conserves_angular_momentum_and_shape():
+    S = _dumbbells(asym=True, omega=(3., -2., 5.), vel=(.1, .2, -.3))
+    c0 = S.clumps[0]
+    O = Oracle(S)
+
+    def L_global(cl, k=0):
+        q = cl["ori"][k]; x, y, z, w = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        return R @ (c0["inertia"] * (R.T @ cl["angVel"][k]))
+    # Leapfrog.cpp:303-305 initialises DemData.angMom as the LOCAL I*(ori^-1*angVel) and lines 308-309 then use it as the GLOBAL angular momentum:
+    # what the reference conserves from the first step on is that vector (it equals the true R*I*R^T*angVel only when ori is the identity).  The oracle restates the code, not the intent.
+    x, y, z, w = c0["ori"]
+    R0 = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    L0 = c0["inertia"] * (R0.T @ c0["angVel"])
+    d0 = np.linalg.norm(S.pos[1] - S.pos[0])
+    O.step(5000)
+    cl, s = O.clumps(), O.spheres()
+    assert np.allclose(L_global(cl), L0, rtol=0, atol=1e-3 * np.abs(L0).max())               # torque-free: the angular momentum stands still (ori is at n+1, angVel at n+1/2: O(dt*|w|) apart)
+    assert np.linalg.norm(s["pos"][1] - s["pos"][0]) == pytest.approx(d0, rel=1e-12)         # rigid
+    assert np.allclose(cl["pos"][0], c0["pos"] + 5000 * 1e-4 * np.array([.1, .2, -.3]), rtol=1e-12)
+    assert not np.allclose(cl["angVel"][0], c0["angVel"], rtol=1e-3)                          # an asymmetric top: the angular velocity itself wanders
+    assert np.allclose(s["vel"][2], cl["vel"][0] + np.cross(cl["angVel"][0], s["pos"][2] - cl["pos"][0]), rtol=1e-12, atol=1e-14)
+
+
+def test_clump_falls_like_a_point_mass_and_lands_on_a_wall():
+    S = _dumbbells(gravity=(0, 0, -9.81), damping=0.)
+    S.walls = [dict(pos=(0, 0, .9), axis=2, sense=1, mat=0, mask=sc.MASK_BOUNDARY)]
+    S.params.damping = .3
+    O = Oracle(S)
+    O.step(100)       # still in the air: z = z0 - g t^2/2 (leapfrog: first step without gravity, force reset after the integration)
+    t = 100 * 1e-4
+    assert O.clumps()["pos"][0, 2] == pytest.approx(1. - .5 * 9.81 * t * (t - 1e-4) * (1 - .3), rel=1e-9)      # Cundall damping acts against the motion: factor (1 - damping) while accelerating
+    O.step(40000)
+    cl, c = O.clumps(), O.contacts(True)
+    assert len(c["ids"]) == 2 and abs(cl["vel"][0, 2]) < 1e-3                                    # both spheres rest on the wall
+    fz = c["force"][:, 0].sum()                                                                   # normal forces carry the clump's weight
+    assert abs(fz) == pytest.approx(S.clumps[0]["mass"] * 9.81, rel=1e-2)

@@ -64,6 +64,7 @@ class SceneSpec:
     flags: np.ndarray = None
     walls: list = field(default_factory=list)  # dict(pos, axis, sense, mat, mask, vel)
     facets: list = field(default_factory=list)  # dict(v(3,3), halfThick, fakeVel, n21lim, vvel, mat, mask)
+    clumps: list = field(default_factory=list)  # rigid aggregates of spheres with mass: dict(members=[sphere indices], pos, ori (x,y,z,w), vel, angVel, mass, inertia(3), flags); see make_clumps
     facet_groups: list = field(default_factory=list)  # kinematic groups: dict(pos, ori (x,y,z,w), vel, angVel, facets=[indices into ``facets``])
     params: Params = field(default_factory=Params)
     cell: dict = None                           # dict(hSize(3,3), gradV, nextGradV, homoDeform)
@@ -116,6 +117,40 @@ def frict_mat(density=1e3, young=1e7, ktDivKn=.2, tanPhi=math.tan(.5)):
 
 def hertz_mat(density=1e3, young=1e8, ktDivKn=.2, tanPhi=.5, surfEnergy=0.0, alpha=0.0):
     return (MAT_HERTZ, density, young, ktDivKn, tanPhi, surfEnergy, alpha)
+
+
+CLUMP_CLUMPED = 64      # DemData flag of a member node (src/dem/Particle.hpp:200)
+
+
+def make_clumps(S, groups, vel=None, angVel=None):
+    """Turn groups of (non-overlapping) spheres of a finalized SceneSpec into rigid clumps: mass, centroid, principal inertia and orientation as
+    ClumpData::makeClump derives them (Clump.cpp:187-261; numpy's eigh stands in for Woo's computePrincipalAxes — the numbers are inputs to both the oracle and the engine).
+    Members get the CLUMPED flag, the clump's velocity field and are listed in S.clumps."""
+    m, I = S.mass_inertia()
+    for gi, g in enumerate(groups):
+        g = np.asarray(g, dtype=np.int64)
+        M = m[g].sum(); c = (m[g, None] * S.pos[g]).sum(axis=0) / M
+        T = np.zeros((3, 3))
+        for k in g:
+            d = S.pos[k] - c
+            T += I[k] * np.eye(3) + m[k] * (d @ d * np.eye(3) - np.outer(d, d))
+        w, V = np.linalg.eigh(T)
+        if np.linalg.det(V) < 0:
+            V[:, 2] = -V[:, 2]
+        # Eigen Quaternion(Matrix3) of the rotation whose columns are the principal axes
+        tr = V[0, 0] + V[1, 1] + V[2, 2]
+        if tr > 0:
+            s4 = math.sqrt(tr + 1.) * 2; q = np.array([(V[2, 1] - V[1, 2]) / s4, (V[0, 2] - V[2, 0]) / s4, (V[1, 0] - V[0, 1]) / s4, .25 * s4])
+        else:
+            i = int(np.argmax([V[0, 0], V[1, 1], V[2, 2]])); j, k2 = (i + 1) % 3, (i + 2) % 3
+            s4 = math.sqrt(V[i, i] - V[j, j] - V[k2, k2] + 1.) * 2
+            q = np.zeros(4); q[i] = .25 * s4; q[j] = (V[j, i] + V[i, j]) / s4; q[k2] = (V[k2, i] + V[i, k2]) / s4; q[3] = (V[k2, j] - V[j, k2]) / s4
+        q /= np.linalg.norm(q)
+        cv = np.zeros(3) if vel is None else np.asarray(vel[gi], dtype=np.float64); cw = np.zeros(3) if angVel is None else np.asarray(angVel[gi], dtype=np.float64)
+        S.clumps.append(dict(members=[int(k) for k in g], pos=c, ori=q, vel=cv, angVel=cw, mass=float(M), inertia=w.copy(), flags=0))
+        S.flags[g] |= CLUMP_CLUMPED
+        S.vel[g] = cv + np.cross(cw, S.pos[g] - c); S.angVel[g] = cw
+    return S
 
 
 def box_walls(lo, hi, mat=0, top=False):
