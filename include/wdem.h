@@ -120,6 +120,24 @@ int wdem_upload_facets(wdem_handle h, int n, const int32_t* ids, const double* v
  * Call after wdem_upload_facets, before the first step.  Forces on the members are not fed back (all DOFs of the master are blocked). */
 int wdem_upload_facet_groups(wdem_handle h, int nGroups, const int32_t* groupOfFacet, const double* pos, const double* ori, const double* vel,
                              const double* angVel);
+/* Clumps of spheres with mass (ClumpData, src/dem/Clump.hpp; ParticleContainer::addClumped, S.dem.par.addClumped): rigid aggregates whose master node carries
+ * the mass and the principal inertia.  Replaces, for sphere members, what Leapfrog::run does with a clump node (Leapfrog.cpp:148-255): every step
+ * ClumpData::forceTorqueFromMembers (Clump.cpp:272-280), the spherical or — when the principal inertias differ — the aspherical integrator
+ * (leapfrogAsphericalRotate, Leapfrog.cpp:299-321), the reset (gravity acts on the master node only) and ClumpData::applyToMembers (Clump.cpp:293-307).
+ * Members of one clump never collide (Collider::mayCollide, Collision.cpp:34-39); DynDt weighs the members' contact stiffnesses against the clump's mass
+ * and inertia (DynDt.cpp:48-52).
+ * memberStart: nClumps+1 offsets into memberIds (particle ids of spheres uploaded with the CLUMPED flag, DemData.flags bit 64, in ClumpData.nodes order);
+ * pos 3, ori 4 (x,y,z,w), vel 3, angVel 3, angMom 3 (NULL or NaN: initialised by the first step, Leapfrog.cpp:303-305), mass 1, inertia 3 (principal), flags
+ * (DemData.flags of the master node: blocked DOFs, *_SKIP bits) per clump; relPos 3 / relOri 4 per member (ClumpData.relPos/relOri; NULL: derived from the
+ * uploaded member state as ClumpData::makeClump does, Clump.cpp:252-253).  Call right after wdem_upload_spheres; every sphere with the CLUMPED flag must be a
+ * member of exactly one clump.  Aperiodic, single-device scenes without Scene.trackEnergy; wdem_add_spheres / wdem_remove_spheres are refused while clumps exist. */
+int wdem_upload_clumps(wdem_handle h, int32_t nClumps, const int32_t* memberStart, const int32_t* memberIds, const double* pos, const double* ori,
+                       const double* vel, const double* angVel, const double* angMom, const double* mass, const double* inertia, const uint32_t* flags,
+                       const double* relPos, const double* relOri);
+/* State of the clump master nodes in upload order: 3 doubles per clump (ori: 4, x,y,z,w); any pointer may be NULL.  force/torque are what the next step's
+ * forceTorqueFromMembers adds to (mass*gravity after Leapfrog's reset). */
+int wdem_download_clumps(wdem_handle h, double* pos, double* ori, double* vel, double* angVel, double* angMom, double* force, double* torque);
+int64_t wdem_num_clumps(wdem_handle h);
 /* Facet node positions (9 per facet, upload order) and the groups' master nodes after the last step; any pointer may be NULL. */
 int wdem_download_facets(wdem_handle h, double* verts, double* groupPos, double* groupOri);
 int wdem_set_cell(wdem_handle h, const double* hSize, const double* gradV, const double* nextGradV, int homoDeform);

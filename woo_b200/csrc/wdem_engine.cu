@@ -56,7 +56,7 @@ struct SphereStore {
     flags.ensure(n, tot, keep, st); mask.ensure(n, tot, keep, st); mat.ensure(n, tot, keep, st); id.ensure(n, tot, keep, st); up.ensure(n, tot, keep, st);
   }
   Spheres view() { Spheres S; S.posr = posr.p; S.velm = velm.p; S.angi = angi.p; S.ori = ori.p; S.fx = f[0].p; S.fy = f[1].p; S.fz = f[2].p; S.tx = f[3].p; S.ty = f[4].p; S.tz = f[5].p;
-    S.lx = l[0].p; S.ly = l[1].p; S.lz = l[2].p; S.flags = flags.p; S.mask = mask.p; S.mat = mat.p; S.id = id.p; S.up = up.p; return S; }
+    S.lx = l[0].p; S.ly = l[1].p; S.lz = l[2].p; S.flags = flags.p; S.mask = mask.p; S.mat = mat.p; S.id = id.p; S.up = up.p; S.clumpOfId = nullptr; return S; }
   void release() { posr.release(); velm.release(); angi.release(); ori.release(); for (auto& b : f) b.release(); for (auto& b : l) b.release(); flags.release(); mask.release(); mat.release(); id.release(); up.release(); }
 };
 
@@ -77,6 +77,15 @@ struct ContactStore {
   Contacts view() { Contacts C; C.pair = pair.p; C.flags = flags.p; C.stepCreated = stepCreated.p; C.cdx = cd[0].p; C.cdy = cd[1].p; C.cdz = cd[2].p;
     C.rA = r[0].p; C.rB = r[1].p; C.rC = r[2].p; C.rD = r[3].p; C.ph = ph.p; C.ph4 = ph4.p; C.tq = tq.p; C.Tg = Tg.p; C.realBits = realBits.p; return C; }
   void release() { pair.release(); flags.release(); stepCreated.release(); for (auto& b : cd) b.release(); for (auto& b : r) b.release(); ph.release(); ph4.release(); tq.release(); Tg.release(); realBits.release(); cap = 0; }
+};
+
+// clumps of spheres with mass (wdem_upload_clumps): master nodes integrated by k_clumps_step
+struct ClumpStore {
+  int n = 0, nMem = 0;
+  DBuf<double4> pos, ori, vel, angVel, angMom, force, torque, inertia, relPos, relOri; DBuf<uint32_t> flags; DBuf<int> memStart; DBuf<int32_t> memId, clumpOfId;
+  Clumps view() { Clumps K; K.n = n; K.pos = pos.p; K.ori = ori.p; K.vel = vel.p; K.angVel = angVel.p; K.angMom = angMom.p; K.force = force.p; K.torque = torque.p; K.inertia = inertia.p; K.flags = flags.p;
+    K.memStart = memStart.p; K.memId = memId.p; K.relPos = relPos.p; K.relOri = relOri.p; return K; }
+  void release() { for (auto* b : {&pos, &ori, &vel, &angVel, &angMom, &force, &torque, &inertia, &relPos, &relOri}) b->release(); flags.release(); memStart.release(); memId.release(); clumpOfId.release(); n = nMem = 0; }
 };
 
 struct CsrStore { DBuf<int> rowStart; DBuf<uint32_t> rowEntry; DBuf<int32_t> rowOther; bool valid = false; int nRows = 0; void release() { rowStart.release(); rowEntry.release(); rowOther.release(); } };
@@ -167,8 +176,10 @@ struct wdem_engine {
   std::vector<Wall> hWalls; DBuf<Wall> dWalls; bool anyMovingWall = false, anyStaticWall = false;
   DBuf<double> wallAcc, wallPartial;     // accumulated force/torque on walls at rest (never reset in the reference: ContactLoop.cpp:270-276), per-step block partials
   std::vector<Facet> hFacets; DBuf<Facet> dFacets; DBuf<int> fgCellStart, fgCellFacet, fgCursor; FacetGrid fgrid; bool fgridValid = false;
+  ClumpStore clumps;                     // clumps of spheres with mass (wdem_upload_clumps)
   GroupsU groups{};                      // kinematic facet groups (wdem_upload_facet_groups): master nodes integrated on the host, members on the device
   std::vector<double> groupRadius;       // largest distance of a member node from its master node (bounding sphere of the sweep of a rotating group)
+  int nClumpedUploaded = 0;             // spheres uploaded with the CLUMPED flag that no clump has claimed yet
   double minRadius = INFINITY, pwaveDt = INFINITY;
   std::vector<double> hRadius; std::vector<int32_t> hMatOfSphere;
   std::vector<int32_t> hIds;                // Particle.id of the spheres in upload order
@@ -194,7 +205,7 @@ struct wdem_engine {
   struct E2E { bool active = false; const double *pos = nullptr, *vel = nullptr, *angVel = nullptr; double *posOut = nullptr, *velOut = nullptr; } e2e;
   cudaStream_t sH2D = nullptr, sD2H = nullptr; cudaEvent_t evUp[NCHUNK] = {}, evLf[NCHUNK] = {}, evEk = nullptr;
   DBuf<double> ioIn, ioOut; double* hEk = nullptr; size_t hEkCap = 0; int ekBlocks = 0;
-  Spheres S() { return sph[cur].view(); }
+  Spheres S() { Spheres v = sph[cur].view(); v.clumpOfId = clumps.n ? clumps.clumpOfId.p : nullptr; return v; }
 };
 
 namespace {
@@ -253,6 +264,7 @@ void checkDeviceError(wdem_engine* E) {
   switch (h.error) {
     case ERR_NAN_FORCE: throw EngErr{"NaN force in contact " + pr + " (IdealElPl.cpp:79-83)", WDEM_ERR_RUNTIME};
     case ERR_NAN_POS: throw EngErr{"NaN position of particle #" + std::to_string(h.errA), WDEM_ERR_RUNTIME};
+    case ERR_CLUMP_INERTIA: throw EngErr{"Leapfrog::run: inertia==(0,0,0), but the node wants to use aspherical integrator (clump " + std::to_string(h.errA) + "; Leapfrog.cpp:225)", WDEM_ERR_RUNTIME};
     case ERR_NO_PHYS: throw EngErr{"ContactLoop: " + pr + ": no Contact.phys created (Cp2_HertzMat_HertzPhys needs HertzMat on both particles; ContactLoop.cpp:181)", WDEM_ERR_RUNTIME};
     case ERR_SCHWARZ: throw EngErr{"Law2_L6Geom_HertzPhys_DMT: Schwarz model (alpha!=0 and gamma!=0) is out of scope " + pr, WDEM_ERR_UNSUPPORTED};
     case ERR_PEER_TIMEOUT: throw EngErr{"slab decomposition: a neighbouring subdomain did not publish its step flags in time (it failed or stalled)", WDEM_ERR_RUNTIME};
@@ -906,10 +918,11 @@ void fetchCounters(wdem_engine* E) {
 
 double dynDtCrit(wdem_engine* E) {
   const int n = E->n; if (n == 0) return INFINITY;
-  const int nb = nblk(n, 256);
+  const int nbS = nblk(n, 256), nbK = nblk(E->clumps.n, 256), nb = nbS + nbK;
   E->blk.ensure((size_t)std::max(nb, 1) * 7, E->bytes);
   CsrStore& R = E->csr[E->curR];
-  k_dyndt<<<nb, 256, 0, E->stream>>>(E->S(), n, E->con[E->curC].view(), R.rowStart.p, R.rowEntry.p, E->cfg.law, E->blk.p); E->launches++;
+  k_dyndt<<<nbS, 256, 0, E->stream>>>(E->S(), n, E->con[E->curC].view(), R.rowStart.p, R.rowEntry.p, E->cfg.law, E->blk.p); E->launches++;
+  if (nbK) { k_clumps_dyndt<<<nbK, 256, 0, E->stream>>>(E->clumps.view(), E->S(), E->id2slot.p, E->con[E->curC].view(), R.rowStart.p, R.rowEntry.p, E->cfg.law, E->blk.p + nbS); E->launches++; }
   std::vector<double> hb(nb);
   CK(cudaMemcpyAsync(hb.data(), E->blk.p, nb * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CK(cudaStreamSynchronize(E->stream));
@@ -1119,6 +1132,11 @@ void enqueueIntegrate(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
     if (u.energy) k_leapfrog<true><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
     else k_leapfrog<false><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
     E->launches++;
+  }
+  if (E->nClumpedUploaded > 0) throw EngErr{std::to_string(E->nClumpedUploaded) + " spheres carry the CLUMPED flag but no clump was uploaded (wdem_upload_clumps)", WDEM_ERR_INVALID};
+  if (E->clumps.n > 0) {
+    if (c.periodic || E->comm || E->e2e.active || E->trackEnergy) throw EngErr{"clumps of spheres: periodic cells, decomposed runs, wdem_step_e2e and Scene.trackEnergy are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    k_clumps_step<<<nblk(E->clumps.n, 128), 128, 0, st>>>(E->clumps.view(), E->S(), E->id2slot.p, u, E->dCnt); E->launches++;
   }
   if (E->groups.n > 0 && !E->hFacets.empty()) { k_facets_step<<<nblk((long long)E->hFacets.size(), 128), 128, 0, st>>>(E->dFacets.p, (int)E->hFacets.size(), E->groups, u, E->dCnt, 0); E->launches++; }
   if (E->anyMovingWall) {
@@ -1330,7 +1348,7 @@ int wdem_destroy(wdem_handle h) {
   if (!h) return WDEM_ERR_INVALID;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release();
+  for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release(); h->clumps.release();
   h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->fgCursor.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
   h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->candBuf.release(); h->wallBits.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
   peerTeardown(h, false);
@@ -1387,7 +1405,7 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
       maxId = std::max(maxId, id[i]);
       fl[i] = flags ? flags[i] : 0u; mk[i] = mask ? mask[i] : 5u; mt[i] = matId ? matId[i] : 0;
       if (mt[i] < 0 || mt[i] >= (int)h->hMats.size()) throw EngErr{"sphere material index out of range", WDEM_ERR_INVALID};
-      if (fl[i] & (64u | 128u)) throw EngErr{"clumps are not supported by the GPU engine (DemData.flags has CLUMP bits)", WDEM_ERR_UNSUPPORTED};
+      if (fl[i] & 128u) throw EngErr{"sphere #" + std::to_string(id[i]) + ": DemData.flags has the CLUMP bit (a master node is not a particle: wdem_upload_clumps)", WDEM_ERR_INVALID};
       if (!(radius[i] > 0)) throw EngErr{"sphere #" + std::to_string(id[i]) + ": radius must be positive", WDEM_ERR_INVALID};
       if ((fl[i] & 7u) != 7u && !(mass[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive mass with free translational DOFs", WDEM_ERR_INVALID};
       if ((fl[i] & 56u) != 56u && !(inertia[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive inertia with free rotational DOFs", WDEM_ERR_INVALID};
@@ -1425,8 +1443,82 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
     CK(cudaStreamSynchronize(st));
     h->conDirty = true; h->nC = h->nSS = h->nSSa = h->nWS = h->nFS = h->nOrph = 0; h->csr[0].valid = h->csr[1].valid = false; h->up2slotValid = false;
     h->verletDist = NAN; h->fgridValid = false; h->boundsValid = false; h->batchK = 1;
+    h->clumps.release(); h->nClumpedUploaded = 0; for (int64_t i = 0; i < n; i++) if (fl[i] & 64u) h->nClumpedUploaded++;
   });
 }
+
+// ClumpData of the scene's clumps of spheres (Clump.hpp).  relPos/relOri NULL: derived from the members' uploaded state as ClumpData::makeClump does
+// (Clump.cpp:252-253).  angMom NULL or NaN: initialised by the first step (Leapfrog.cpp:303-305).
+int wdem_upload_clumps(wdem_handle h, int32_t nClumps, const int32_t* memberStart, const int32_t* memberIds, const double* pos, const double* ori, const double* vel, const double* angVel,
+                       const double* angMom, const double* mass, const double* inertia, const uint32_t* flags, const double* relPos, const double* relOri) {
+  return guarded(h, [&] {
+    if (nClumps < 0 || (nClumps > 0 && (!memberStart || !memberIds || !pos || !ori || !mass || !inertia))) throw EngErr{"wdem_upload_clumps: bad arguments", WDEM_ERR_INVALID};
+    if (!h->conDirty || h->cur != 0 || h->nC != 0) throw EngErr{"wdem_upload_clumps: call right after wdem_upload_spheres", WDEM_ERR_INVALID};
+    if (h->comm) throw EngErr{"wdem_upload_clumps: not available in decomposed runs", WDEM_ERR_UNSUPPORTED};
+    if (h->cfg.periodic) throw EngErr{"wdem_upload_clumps: clumps in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    ClumpStore& K = h->clumps; K.release();
+    if (nClumps == 0) return;
+    const int n = h->n, nMem = memberStart[nClumps];
+    if (memberStart[0] != 0 || nMem < 0) throw EngErr{"wdem_upload_clumps: memberStart must start at 0 and ascend", WDEM_ERR_INVALID};
+    cudaStream_t st = h->stream;
+    // the members' uploaded state (upload order: no collider run has re-ordered the slots yet)
+    std::vector<double4> sp(n), so(n); std::vector<uint32_t> sfl(n);
+    SphereStore& s = h->sph[0];
+    CK(cudaMemcpyAsync(sp.data(), s.posr.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(so.data(), s.ori.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sfl.data(), s.flags.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    std::unordered_map<int32_t, int> upOf; upOf.reserve(n * 2); for (int i = 0; i < n; i++) upOf[h->hIds[i]] = i;
+    std::vector<int32_t> clumpOfId((size_t)std::max(h->maxId, 0) + 2, -1);
+    std::vector<double4> cp(nClumps), co(nClumps), cv(nClumps), cw(nClumps), cl(nClumps), cf(nClumps), ct(nClumps), cI(nClumps), rp(nMem), rq(nMem); std::vector<uint32_t> cfl(nClumps); std::vector<int> ms(memberStart, memberStart + nClumps + 1);
+    int nClumped = 0;
+    for (int c = 0; c < nClumps; c++) {
+      if (ms[c + 1] <= ms[c]) throw EngErr{"ClumpData::makeClump: 0 nodes.", WDEM_ERR_INVALID};
+      cfl[c] = flags ? flags[c] : 0u;
+      if ((cfl[c] & 7u) != 7u && !(mass[c] > 0)) throw EngErr{"DemField.selfTest: clump " + std::to_string(c) + " has non-positive mass with free translational DOFs", WDEM_ERR_INVALID};
+      cp[c] = make_double4(pos[3 * c], pos[3 * c + 1], pos[3 * c + 2], mass[c]); co[c] = make_double4(ori[4 * c], ori[4 * c + 1], ori[4 * c + 2], ori[4 * c + 3]);
+      cv[c] = vel ? make_double4(vel[3 * c], vel[3 * c + 1], vel[3 * c + 2], 0) : make_double4(0, 0, 0, 0); cw[c] = angVel ? make_double4(angVel[3 * c], angVel[3 * c + 1], angVel[3 * c + 2], 0) : make_double4(0, 0, 0, 0);
+      cl[c] = angMom ? make_double4(angMom[3 * c], angMom[3 * c + 1], angMom[3 * c + 2], 0) : make_double4(NAN, NAN, NAN, 0);
+      cf[c] = ct[c] = make_double4(0, 0, 0, 0); cI[c] = make_double4(inertia[3 * c], inertia[3 * c + 1], inertia[3 * c + 2], 0);
+      q4 q; q.x = co[c].x; q.y = co[c].y; q.z = co[c].z; q.w = co[c].w; const q4 qc = quatConj(q);
+      for (int m = ms[c]; m < ms[c + 1]; m++) {
+        auto it = upOf.find(memberIds[m]);
+        if (it == upOf.end()) throw EngErr{"clump: member #" + std::to_string(memberIds[m]) + " is not a sphere", WDEM_ERR_INVALID};
+        const int i = it->second;
+        if (clumpOfId[memberIds[m]] >= 0) throw EngErr{"Node of particle #" + std::to_string(memberIds[m]) + ": already clumped.", WDEM_ERR_INVALID};
+        if (!(sfl[i] & 64u)) throw EngErr{"clump member #" + std::to_string(memberIds[m]) + ": DemData.flags lacks the CLUMPED bit", WDEM_ERR_INVALID};
+        clumpOfId[memberIds[m]] = c; nClumped++;
+        if (relPos) rp[m] = make_double4(relPos[3 * m], relPos[3 * m + 1], relPos[3 * m + 2], 0);
+        else { const d3 r = quatRotate(qc, xyz(sp[i]) - xyz(cp[c])); rp[m] = make_double4(r.x, r.y, r.z, 0); }
+        if (relOri) rq[m] = make_double4(relOri[4 * m], relOri[4 * m + 1], relOri[4 * m + 2], relOri[4 * m + 3]);
+        else { q4 mo; mo.x = so[i].x; mo.y = so[i].y; mo.z = so[i].z; mo.w = so[i].w; const q4 r = quatMul(qc, mo); rq[m] = make_double4(r.x, r.y, r.z, r.w); }
+      }
+    }
+    if (nClumped != h->nClumpedUploaded) throw EngErr{"wdem_upload_clumps: " + std::to_string(h->nClumpedUploaded) + " spheres carry the CLUMPED flag but " + std::to_string(nClumped) + " are members of the uploaded clumps", WDEM_ERR_INVALID};
+    K.n = nClumps; K.nMem = nMem;
+    auto up4 = [&](DBuf<double4>& b, const std::vector<double4>& v) { b.ensure(v.size(), h->bytes); CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(double4), cudaMemcpyHostToDevice, st)); };
+    up4(K.pos, cp); up4(K.ori, co); up4(K.vel, cv); up4(K.angVel, cw); up4(K.angMom, cl); up4(K.force, cf); up4(K.torque, ct); up4(K.inertia, cI); up4(K.relPos, rp); up4(K.relOri, rq);
+    K.flags.ensure(nClumps, h->bytes); CK(cudaMemcpyAsync(K.flags.p, cfl.data(), nClumps * 4, cudaMemcpyHostToDevice, st));
+    K.memStart.ensure(nClumps + 1, h->bytes); CK(cudaMemcpyAsync(K.memStart.p, ms.data(), (nClumps + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    K.memId.ensure(nMem, h->bytes); CK(cudaMemcpyAsync(K.memId.p, memberIds, nMem * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    K.clumpOfId.ensure(clumpOfId.size(), h->bytes); CK(cudaMemcpyAsync(K.clumpOfId.p, clumpOfId.data(), clumpOfId.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // Leapfrog precedes the first collider run: the members must be addressable by id from the first step on
+    k_id2slot_fill<<<nblk(n, 256), 256, 0, st>>>(s.id.p, n, h->id2slot.p); h->launches++;
+    CK(cudaStreamSynchronize(st));
+    h->nClumpedUploaded = 0;      // all claimed
+  });
+}
+int wdem_download_clumps(wdem_handle h, double* pos, double* ori, double* vel, double* angVel, double* angMom, double* force, double* torque) {
+  return guarded(h, [&] {
+    ClumpStore& K = h->clumps; const int n = K.n; if (n == 0) return;
+    std::vector<double4> b(n);
+    auto get = [&](DBuf<double4>& src, double* dst, int w) {
+      if (!dst) return;
+      CK(cudaMemcpyAsync(b.data(), src.p, n * sizeof(double4), cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+      for (int i = 0; i < n; i++) { dst[w * i] = b[i].x; dst[w * i + 1] = b[i].y; dst[w * i + 2] = b[i].z; if (w == 4) dst[w * i + 3] = b[i].w; }
+    };
+    get(K.pos, pos, 3); get(K.ori, ori, 4); get(K.vel, vel, 3); get(K.angVel, angVel, 3); get(K.angMom, angMom, 3); get(K.force, force, 3); get(K.torque, torque, 3);
+  });
+}
+int64_t wdem_num_clumps(wdem_handle h) { return h ? h->clumps.n : 0; }
 
 int wdem_upload_forces(wdem_handle h, const double* force, const double* torque) {
   return guarded(h, [&] {
@@ -1459,7 +1551,7 @@ int wdem_add_spheres(wdem_handle h, int64_t m, const int32_t* ids, const double*
       maxId = std::max(maxId, id[i]);
       fl[i] = flags ? flags[i] : 0u; mk[i] = mask ? mask[i] : 5u; mt[i] = matId ? matId[i] : 0;
       if (mt[i] < 0 || mt[i] >= (int)h->hMats.size()) throw EngErr{"sphere material index out of range", WDEM_ERR_INVALID};
-      if (fl[i] & (64u | 128u)) throw EngErr{"clumps are not supported by the GPU engine (DemData.flags has CLUMP bits)", WDEM_ERR_UNSUPPORTED};
+      if (fl[i] & (64u | 128u)) throw EngErr{"wdem_add_spheres: clump members cannot be added to a running scene", WDEM_ERR_UNSUPPORTED};
       if (!(radius[i] > 0)) throw EngErr{"sphere #" + std::to_string(id[i]) + ": radius must be positive", WDEM_ERR_INVALID};
       if ((fl[i] & 7u) != 7u && !(mass[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive mass with free translational DOFs", WDEM_ERR_INVALID};
       if ((fl[i] & 56u) != 56u && !(inertia[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive inertia with free rotational DOFs", WDEM_ERR_INVALID};
@@ -1497,6 +1589,7 @@ int wdem_remove_spheres(wdem_handle h, int64_t m, const int32_t* ids) {
   return guarded(h, [&] {
     if (m < 0 || (m > 0 && !ids)) throw EngErr{"wdem_remove_spheres: bad arguments", WDEM_ERR_INVALID};
     if (h->comm) throw EngErr{"wdem_remove_spheres: not available in decomposed runs", WDEM_ERR_UNSUPPORTED};
+    if (h->clumps.n) throw EngErr{"wdem_remove_spheres: not available in scenes with clumps", WDEM_ERR_UNSUPPORTED};
     if (m == 0) return;
     const int n0 = h->n; cudaStream_t st = h->stream; int64_t& tot = h->bytes;
     if (h->hIds.size() != (size_t)n0) throw EngErr{"wdem_remove_spheres: no spheres uploaded", WDEM_ERR_INVALID};

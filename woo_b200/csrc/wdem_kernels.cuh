@@ -7,7 +7,7 @@
 namespace wd {
 
 // DemData flags (src/dem/Particle.hpp:198-203)
-enum { F_DOF_ALL = 63, F_ENERGY_SKIP = 256, F_GRAVITY_SKIP = 512, F_DAMPING_SKIP = 2048 };
+enum { F_DOF_ALL = 63, F_CLUMPED = 64, F_CLUMP = 128, F_ENERGY_SKIP = 256, F_GRAVITY_SKIP = 512, F_DAMPING_SKIP = 2048 };
 // engine-internal bits kept in the same word (DemData.flags uses bits 0..11): ghost copy of a sphere owned by another subdomain;
 // sphere that migrated into this subdomain at the current collider full run
 enum : uint32_t { F_GHOST = 1u << 30, F_ARRIVED = 1u << 29 };
@@ -31,6 +31,14 @@ struct Spheres {          // one slot per sphere; slots are re-ordered by grid c
   int32_t* mat;           // material index
   int32_t* id;            // Particle.id
   int32_t* up;            // upload index (for downloads)
+  const int32_t* clumpOfId;   // by Particle.id: index of the clump the sphere is a member of, -1 free; NULL when the scene has no clumps
+};
+// Clumps of spheres with mass (ClumpData, src/dem/Clump.hpp): one entry per master node; members are addressed by particle id (their slots move at collider full runs)
+struct Clumps {
+  int n;
+  double4 *pos /*x,y,z,mass*/, *ori /*x,y,z,w*/, *vel, *angVel, *angMom, *force, *torque;
+  const double4* inertia; const uint32_t* flags;
+  const int* memStart; const int32_t* memId; const double4* relPos; const double4* relOri;
 };
 
 // moving: the wall's node is in DemField.nodes (added with a nonzero velocity: Particle::guessMoving, Particle.cpp:638-640) and is translated by Leapfrog
@@ -101,7 +109,7 @@ __device__ __forceinline__ void energy_add(double* en, int ix, double v) {
 // and goes on from there.  [error, gflag...] is one block of ints so that decomposed runs can max-reduce it in one call.
 #define WD_KMAX 32
 struct Counters { unsigned long long nReal, nPotEval, nCreated, nBroken; int error; int gflag[WD_KMAX + 1]; int errA, errB; };
-enum { ERR_NONE = 0, ERR_NAN_FORCE = 1, ERR_NAN_POS = 2, ERR_NO_PHYS = 3, ERR_SCHWARZ = 4, ERR_FACET_IMPOSSIBLE = 5, ERR_AMBIGUOUS_PERI = 6, ERR_PEER_TIMEOUT = 7 };
+enum { ERR_NONE = 0, ERR_NAN_FORCE = 1, ERR_NAN_POS = 2, ERR_NO_PHYS = 3, ERR_SCHWARZ = 4, ERR_FACET_IMPOSSIBLE = 5, ERR_AMBIGUOUS_PERI = 6, ERR_PEER_TIMEOUT = 7, ERR_CLUMP_INERTIA = 8 };
 
 __device__ __forceinline__ double signd(double f) { return f < 0 ? -1. : (f > 0 ? 1. : 0.); }  // Mathr::Sign (Math.hpp:145)
 
@@ -115,7 +123,7 @@ struct LeapIO { const double* pos; const double* vel; const double* angVel; doub
 template <bool EXT, bool TRACK>
 __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const StepU& u, Counters* cnt, const LeapIO& io, long long ut) {
   const uint32_t fl = S.flags[i];
-  if (fl & F_GHOST) return;   // integrated by its owner; refreshed by the halo exchange
+  if (fl & (F_GHOST | F_CLUMPED)) return;   // ghost: integrated by its owner, refreshed by the halo exchange; clumped: follows its master node (k_clumps_step; Leapfrog.cpp:153)
   double4 pr = S.posr[i], vm = S.velm[i], ai = S.angi[i], qo = S.ori[i];
   if (EXT) {
     pr.x = io.pos[3 * ut]; pr.y = io.pos[3 * ut + 1]; pr.z = io.pos[3 * ut + 2];
@@ -228,6 +236,130 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
     io.velOut[3 * ut] = vel.x; io.velOut[3 * ut + 1] = vel.y; io.velOut[3 * ut + 2] = vel.z;
   }
 }
+// Leapfrog::run for clump master nodes (Leapfrog.cpp:148-255 with isClump): ClumpData::forceTorqueFromMembers (Clump.cpp:272-280), spherical or aspherical
+// integration (leapfrogAsphericalRotate, Leapfrog.cpp:299-331), reset, ClumpData::applyToMembers (Clump.cpp:293-307), and the members' Verlet test.
+// One thread per clump: members are few, and their forces must be summed in member order.
+__device__ __forceinline__ q4 dotQ(d3 w, q4 Q) {   // Leapfrog::DotQ (Leapfrog.cpp:324-331)
+  q4 d;
+  d.w = (-Q.x * w.x - Q.y * w.y - Q.z * w.z) / 2;
+  d.x = (Q.w * w.x - Q.z * w.y + Q.y * w.z) / 2;
+  d.y = (Q.z * w.x + Q.w * w.y - Q.x * w.z) / 2;
+  d.z = (-Q.y * w.x + Q.x * w.y + Q.w * w.z) / 2;
+  return d;
+}
+__global__ void __launch_bounds__(128) k_clumps_step(Clumps K, Spheres S, const int* __restrict__ id2slot, StepU u, Counters* cnt) {
+  if (*u.gIn) return;      // void step (k_leapfrog passes the flag on)
+  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= K.n) return;
+  const uint32_t fl = K.flags[ci];
+  const double4 p4 = K.pos[ci], o4 = K.ori[ci], in4 = K.inertia[ci];
+  d3 pos = xyz(p4), vel = xyz(K.vel[ci]), w = xyz(K.angVel[ci]), f = xyz(K.force[ci]), t = xyz(K.torque[ci]), angMom = xyz(K.angMom[ci]);
+  const d3 inertia = xyz(in4); const double mass = p4.w, dt = u.dt;
+  q4 ori; ori.x = o4.x; ori.y = o4.y; ori.z = o4.z; ori.w = o4.w;
+  const int m0 = K.memStart[ci], m1 = K.memStart[ci + 1];
+  const bool blockedAll = (fl & F_DOF_ALL) == F_DOF_ALL, blockedNone = (fl & F_DOF_ALL) == 0, blockedAllRot = (fl & 56u) == 56u;
+  const bool damp = (u.damping != 0. && !(fl & F_DAMPING_SKIP));
+  if (!blockedAll) {
+    for (int m = m0; m < m1; m++) {
+      const int s = id2slot[K.memId[m]];
+      const d3 mf = mk3(S.fx[s], S.fy[s], S.fz[s]), mt = mk3(S.tx[s], S.ty[s], S.tz[s]);
+      f = f + mf; t = t + (mt + cross(xyz(S.posr[s]) - pos, mf));
+    }
+  }
+  const bool aspherical = !(inertia.x == inertia.y && inertia.y == inertia.z), useAspherical = aspherical && !blockedAllRot;      // Particle.hpp:275-277
+  const bool hasInertia = !(inertia.x == 0. && inertia.y == 0. && inertia.z == 0.);
+  d3 linAccel = mk3(0, 0, 0), angAccel = mk3(0, 0, 0);
+  if (!blockedAll) {
+    if (blockedNone) linAccel = f / mass;
+    else {
+      if (!(fl & 1u)) linAccel.x += f.x / mass;
+      if (!(fl & 2u)) linAccel.y += f.y / mass;
+      if (!(fl & 4u)) linAccel.z += f.z / mass;
+    }
+    if (damp) {
+      linAccel.x *= 1 - u.damping * signd(f.x * (vel.x + 0.5 * dt * linAccel.x));
+      linAccel.y *= 1 - u.damping * signd(f.y * (vel.y + 0.5 * dt * linAccel.y));
+      linAccel.z *= 1 - u.damping * signd(f.z * (vel.z + 0.5 * dt * linAccel.z));
+    }
+    vel = vel + dt * linAccel;
+    if (hasInertia) {
+      if (!useAspherical) {
+        if (blockedNone) angAccel = mk3(t.x / inertia.x, t.y / inertia.y, t.z / inertia.z);
+        else {
+          if (!(fl & 8u)) angAccel.x += t.x / inertia.x;
+          if (!(fl & 16u)) angAccel.y += t.y / inertia.y;
+          if (!(fl & 32u)) angAccel.z += t.z / inertia.z;
+        }
+        if (damp) {
+          angAccel.x *= 1 - u.damping * signd(t.x * (w.x + 0.5 * dt * angAccel.x));
+          angAccel.y *= 1 - u.damping * signd(t.y * (w.y + 0.5 * dt * angAccel.y));
+          angAccel.z *= 1 - u.damping * signd(t.z * (w.z + 0.5 * dt * angAccel.z));
+        }
+        w = w + dt * angAccel;
+      } else {
+        if (fl & 8u) t.x = 0; if (fl & 16u) t.y = 0; if (fl & 32u) t.z = 0;      // Leapfrog.cpp:188
+        if (damp) {                                                           // nonviscDamp1st (Leapfrog.cpp:28-30)
+          t.x *= 1 - u.damping * signd(t.x * w.x); t.y *= 1 - u.damping * signd(t.y * w.y); t.z *= 1 - u.damping * signd(t.z * w.z);
+        }
+      }
+    }
+  }
+  pos = pos + vel * dt;
+  if (!useAspherical) {      // leapfrogSphericalRotate (Leapfrog.cpp:280-297)
+    if (w.x != 0. || w.y != 0. || w.z != 0.) {
+      const double angle = nrm(w); const d3 ax = w / angle;
+      double ha = 0.5 * (angle * dt), sn, cs;
+      sincos(ha, &sn, &cs);
+      q4 q; q.w = cs; q.x = sn * ax.x; q.y = sn * ax.y; q.z = sn * ax.z;
+      ori = quatMul(q, ori);
+    }
+    ori = quatNormalized(ori);
+  } else {                   // leapfrogAsphericalRotate (Leapfrog.cpp:299-321)
+    if (!hasInertia) { cnt->error = ERR_CLUMP_INERTIA; cnt->errA = ci; return; }
+    const q4 qc = quatConj(ori);
+    if (!(angMom.x == angMom.x) || !(angMom.y == angMom.y) || !(angMom.z == angMom.z)) {
+      const d3 wl = quatRotate(qc, w); angMom = mk3(inertia.x * wl.x, inertia.y * wl.y, inertia.z * wl.z);
+    }
+    const m33 A = quatToMat(qc);
+    const d3 l_n = angMom + (dt / 2) * t;
+    const d3 l_b_n = mulMV(A, l_n);
+    const d3 w_b_n = mk3(l_b_n.x / inertia.x, l_b_n.y / inertia.y, l_b_n.z / inertia.z);
+    const q4 dq_n = dotQ(w_b_n, ori);
+    q4 Qh; Qh.w = ori.w + (dt / 2) * dq_n.w; Qh.x = ori.x + (dt / 2) * dq_n.x; Qh.y = ori.y + (dt / 2) * dq_n.y; Qh.z = ori.z + (dt / 2) * dq_n.z;
+    angMom = angMom + dt * t;
+    const d3 l_b_h = mulMV(A, angMom);
+    const d3 w_b_h = mk3(l_b_h.x / inertia.x, l_b_h.y / inertia.y, l_b_h.z / inertia.z);
+    const q4 dq_h = dotQ(w_b_h, Qh);
+    ori.w = ori.w + dt * dq_h.w; ori.x = ori.x + dt * dq_h.x; ori.y = ori.y + dt * dq_h.y; ori.z = ori.z + dt * dq_h.z;
+    w = quatRotate(ori, w_b_h);
+    ori = quatNormalized(ori);
+  }
+  if (u.reset) { f = (u.hasGravity && !(fl & F_GRAVITY_SKIP)) ? (mass * u.gravity) : mk3(0, 0, 0); t = mk3(0, 0, 0); }      // gravity acts on the master node, not on the members
+  K.pos[ci] = make_double4(pos.x, pos.y, pos.z, mass); K.ori[ci] = make_double4(ori.x, ori.y, ori.z, ori.w);
+  K.vel[ci] = make_double4(vel.x, vel.y, vel.z, 0); K.angVel[ci] = make_double4(w.x, w.y, w.z, 0); K.angMom[ci] = make_double4(angMom.x, angMom.y, angMom.z, 0);
+  K.force[ci] = make_double4(f.x, f.y, f.z, 0); K.torque[ci] = make_double4(t.x, t.y, t.z, 0);
+  bool dirty = false, nan = false;
+  for (int m = m0; m < m1; m++) {
+    const int s = id2slot[K.memId[m]];
+    const double4 rp = K.relPos[m], ro = K.relOri[m];
+    const d3 mp = pos + quatRotate(ori, xyz(rp));
+    q4 rq; rq.x = ro.x; rq.y = ro.y; rq.z = ro.z; rq.w = ro.w;
+    const q4 mo = quatMul(ori, rq);
+    const d3 mv = vel + cross(w, mp - pos);
+    S.posr[s] = make_double4(mp.x, mp.y, mp.z, S.posr[s].w);
+    S.velm[s] = make_double4(mv.x, mv.y, mv.z, S.velm[s].w);
+    S.angi[s] = make_double4(w.x, w.y, w.z, S.angi[s].w);
+    S.ori[s] = make_double4(mo.x, mo.y, mo.z, mo.w);
+    if (u.reset) { S.fx[s] = 0; S.fy[s] = 0; S.fz[s] = 0; S.tx[s] = 0; S.ty[s] = 0; S.tz[s] = 0; }
+    const d3 dl = mk3(S.lx[s], S.ly[s], S.lz[s]) - mp;      // Verlet test (Collision.cpp:113-121)
+    const double d2 = fmax(0., sqn(dl));
+    if (d2 > u.maxD2) dirty = true;
+    if (!(d2 == d2)) nan = true;
+  }
+  if (dirty || nan) *u.gOut = 1;
+  if (nan) { cnt->error = ERR_NAN_POS; cnt->errA = K.memId[m0]; }
+}
+
 template <bool TRACK>
 __global__ void __launch_bounds__(256, 4) k_leapfrog(Spheres S, int n, StepU u, Counters* cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -930,7 +1062,7 @@ __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Sphe
   const d3 pos = xyz(pr);
   d3 F, T;
   if (u.reset) {
-    F = (u.hasGravity && !(fl & F_GRAVITY_SKIP)) ? (S.velm[i].w * u.gravity) : mk3(0, 0, 0);
+    F = (u.hasGravity && !(fl & (F_GRAVITY_SKIP | F_CLUMPED))) ? (S.velm[i].w * u.gravity) : mk3(0, 0, 0);      // clumped: gravity acts on the master node (Leapfrog.cpp:240-252)
     T = mk3(0, 0, 0);
   } else { F = mk3(S.fx[i], S.fy[i], S.fz[i]); T = mk3(S.tx[i], S.ty[i], S.tz[i]); }
   for (int e = e0; e < e1; e += RB) {
@@ -970,14 +1102,8 @@ __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Sphe
 // ------------------------------------------------------------------------------------------------
 // DynDt::nodalCritDtSq (src/dem/DynDt.cpp:16-58): per-sphere stiffness sums over real contacts -> min of 2*m/k.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, int law,
-                                              double* blockMin) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double ret = INFINITY;
-  if (i < n) {
-    const uint32_t fl = S.flags[i];
-    if ((fl & F_DOF_ALL) != F_DOF_ALL && !(fl & F_GHOST)) {
-      d3 ktr = mk3(0, 0, 0), krot = mk3(0, 0, 0);
+// DynDt::nodalStiffAdd (DynDt.cpp:16-36) for the sphere in slot i: its real contacts in the order of its incidence row
+__device__ __forceinline__ void nodal_stiff_add(const Spheres& S, const Contacts& C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, int law, int i, d3& ktr, d3& krot) {
       const double myR = S.posr[i].w;
       for (int e = rowStart[i]; e < rowStart[i + 1]; e++) {
         const uint32_t ent = rowEntry[e]; const uint32_t c = ent >> 1;
@@ -997,6 +1123,22 @@ __global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, con
         ktr = ktr + (n2 * (kn - kt) + mk3(kt, kt, kt));
         krot = krot + (len * len) * kt * mk3(n2.y + n2.z, n2.z + n2.x, n2.x + n2.y);
       }
+}
+__device__ __forceinline__ void block_min_store(double ret, double* blockMin) {
+  __shared__ double sm[256];
+  sm[threadIdx.x] = ret; __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sm[threadIdx.x] = fmin(sm[threadIdx.x], sm[threadIdx.x + s]); __syncthreads(); }
+  if (threadIdx.x == 0) blockMin[blockIdx.x] = sm[0];
+}
+__global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, int law,
+                                              double* blockMin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double ret = INFINITY;
+  if (i < n) {
+    const uint32_t fl = S.flags[i];
+    if ((fl & F_DOF_ALL) != F_DOF_ALL && !(fl & (F_GHOST | F_CLUMPED))) {      // a clumped node is not in DemField.nodes: its contacts count for the master node (k_clumps_dyndt)
+      d3 ktr = mk3(0, 0, 0), krot = mk3(0, 0, 0);
+      nodal_stiff_add(S, C, rowStart, rowEntry, law, i, ktr, krot);
       const double mass = S.velm[i].w, inertia = S.angi[i].w;
       if (ktr.x != 0 && mass > 0. && !(fl & 1u)) ret = fmin(ret, mass / fabs(ktr.x));
       if (ktr.y != 0 && mass > 0. && !(fl & 2u)) ret = fmin(ret, mass / fabs(ktr.y));
@@ -1007,10 +1149,33 @@ __global__ void __launch_bounds__(256) k_dyndt(Spheres S, int n, Contacts C, con
       ret = 2 * ret;
     }
   }
-  __shared__ double sm[256];
-  sm[threadIdx.x] = ret; __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sm[threadIdx.x] = fmin(sm[threadIdx.x], sm[threadIdx.x + s]); __syncthreads(); }
-  if (threadIdx.x == 0) blockMin[blockIdx.x] = sm[0];
+  block_min_store(ret, blockMin);
+}
+// DynDt::nodalCritDtSq for clump master nodes (DynDt.cpp:48-52): contacts of all members, member by member, against the clump's mass and principal inertia
+__global__ void __launch_bounds__(256) k_clumps_dyndt(Clumps K, Spheres S, const int* __restrict__ id2slot, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry,
+                                                     int law, double* blockMin) {
+  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  double ret = INFINITY;
+  if (ci < K.n) {
+    const uint32_t fl = K.flags[ci];
+    if ((fl & F_DOF_ALL) != F_DOF_ALL) {
+      d3 ktr = mk3(0, 0, 0), krot = mk3(0, 0, 0);
+      for (int m = K.memStart[ci]; m < K.memStart[ci + 1]; m++) nodal_stiff_add(S, C, rowStart, rowEntry, law, id2slot[K.memId[m]], ktr, krot);
+      const double mass = K.pos[ci].w; const d3 inertia = xyz(K.inertia[ci]);
+      if (ktr.x != 0 && mass > 0. && !(fl & 1u)) ret = fmin(ret, mass / fabs(ktr.x));
+      if (ktr.y != 0 && mass > 0. && !(fl & 2u)) ret = fmin(ret, mass / fabs(ktr.y));
+      if (ktr.z != 0 && mass > 0. && !(fl & 4u)) ret = fmin(ret, mass / fabs(ktr.z));
+      if (krot.x != 0 && inertia.x > 0. && !(fl & 8u)) ret = fmin(ret, inertia.x / fabs(krot.x));
+      if (krot.y != 0 && inertia.y > 0. && !(fl & 16u)) ret = fmin(ret, inertia.y / fabs(krot.y));
+      if (krot.z != 0 && inertia.z > 0. && !(fl & 32u)) ret = fmin(ret, inertia.z / fabs(krot.z));
+      ret = 2 * ret;
+    }
+  }
+  block_min_store(ret, blockMin);
+}
+__global__ void __launch_bounds__(256) k_id2slot_fill(const int32_t* __restrict__ id, int n, int* id2slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) id2slot[id[i]] = i;
 }
 
 // kinetic energy Σ ½ m v·v + ½ I ω·ω (aperiodic: DemData::getEk_any, Particle.cpp:247-265); per-block partial sums, fixed order
@@ -1321,6 +1486,7 @@ __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int 
           if (!aabbOverlapSS(pi, pj, vd)) continue;
           if (!mayCollide(mi, S.mask[j], loneMask)) continue;
           if ((fi & F_GHOST) && (S.flags[j] & F_GHOST)) continue;   // ghost-ghost pairs belong to other subdomains
+          if ((fi & F_CLUMPED) && S.clumpOfId && (S.flags[j] & F_CLUMPED) && S.clumpOfId[S.id[i]] == S.clumpOfId[S.id[j]]) continue;   // members of one clump (Collision.cpp:34-39)
           const bool dorm = isDormant(pi, pj, adf, 2. * vd, dormOn);
           if (FILL) {
             const int idJ = S.id[j];

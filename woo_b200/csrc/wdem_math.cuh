@@ -119,7 +119,30 @@ __host__ __device__ __forceinline__ d3 quatRotate(q4 q, d3 v) {
   return (v + q.w * uv) + cross(qv, uv);
 }
 
+// Eigen quaternion product a*b
+__host__ __device__ __forceinline__ q4 quatMul(q4 a, q4 b) {
+  q4 r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z; r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z; r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  return r;
+}
+__host__ __device__ __forceinline__ q4 quatConj(q4 q) { q4 r; r.w = q.w; r.x = -q.x; r.y = -q.y; r.z = -q.z; return r; }
+__host__ __device__ __forceinline__ q4 quatNormalized(q4 q) {
+  const double n = sqrt(((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
+  q4 r; r.w = q.w / n; r.x = q.x / n; r.y = q.y / n; r.z = q.z / n; return r;
+}
+
 struct m33 { double m[9]; };  // row-major, host-prepared uniforms
+// Eigen QuaternionBase::toRotationMatrix
+__host__ __device__ __forceinline__ m33 quatToMat(q4 q) {
+  m33 r;
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  r.m[0] = 1 - (tyy + tzz); r.m[1] = txy - twz; r.m[2] = txz + twy;
+  r.m[3] = txy + twz; r.m[4] = 1 - (txx + tzz); r.m[5] = tyz - twx;
+  r.m[6] = txz - twy; r.m[7] = tyz + twx; r.m[8] = 1 - (txx + tyy);
+  return r;
+}
 __host__ __device__ __forceinline__ d3 mulMV(const m33& M, d3 v) {
   return mk3(rowsum3<0>(M.m[0] * v.x, M.m[1] * v.y, M.m[2] * v.z), rowsum3<1>(M.m[3] * v.x, M.m[4] * v.y, M.m[5] * v.z),
              rowsum3<2>(M.m[6] * v.x, M.m[7] * v.y, M.m[8] * v.z));

@@ -126,6 +126,30 @@ class Engine:
         arr = lambda k, w: f64([g[k] for g in groups], (len(groups), w))
         self._chk(self.L.wdem_upload_facet_groups(self.h, C.c_int(len(groups)), ptr(of), ptr(arr("pos", 3)), ptr(arr("ori", 4)), ptr(arr("vel", 3)), ptr(arr("angVel", 3))))
 
+    def upload_clumps(self, sphere_ids, clumps):
+        """Clumps of spheres with mass (wdem.h: wdem_upload_clumps): dicts with members (indices into the uploaded spheres), pos, ori (x,y,z,w), vel, angVel, mass,
+        inertia (3), flags and optionally angMom, relPos, relOri."""
+        if not clumps:
+            return
+        ids = np.asarray(sphere_ids, dtype=np.int64)
+        start = np.zeros(len(clumps) + 1, np.int32); start[1:] = np.cumsum([len(c["members"]) for c in clumps])
+        mem = np.ascontiguousarray(np.concatenate([ids[np.asarray(c["members"], dtype=np.int64)] for c in clumps]), dtype=np.int32)
+        arr = lambda k, w: f64([c[k] for c in clumps], (len(clumps), w))
+        opt = lambda k, w: arr(k, w) if all(k in c for c in clumps) else None
+        cat = lambda k, w: f64(np.concatenate([np.asarray(c[k], dtype=np.float64).reshape(-1, w) for c in clumps])) if all(k in c for c in clumps) else None
+        fl = np.array([int(c.get("flags", 0)) for c in clumps], dtype=np.uint32)
+        self.n_clumps = len(clumps)
+        self._chk(self.L.wdem_upload_clumps(self.h, C.c_int32(len(clumps)), ptr(start), ptr(mem), ptr(arr("pos", 3)), ptr(arr("ori", 4)), ptr(arr("vel", 3)), ptr(arr("angVel", 3)),
+                                            ptr(opt("angMom", 3)), ptr(f64([c["mass"] for c in clumps])), ptr(arr("inertia", 3)), ptr(fl), ptr(cat("relPos", 3)), ptr(cat("relOri", 4))))
+
+    def clumps(self):
+        """State of the clump master nodes (wdem.h: wdem_download_clumps)."""
+        n = int(self.L.wdem_num_clumps(self.h))
+        o = dict(pos=np.zeros((n, 3)), ori=np.zeros((n, 4)), vel=np.zeros((n, 3)), angVel=np.zeros((n, 3)), angMom=np.zeros((n, 3)), force=np.zeros((n, 3)), torque=np.zeros((n, 3)))
+        if n:
+            self._chk(self.L.wdem_download_clumps(self.h, *[ptr(o[k]) for k in ("pos", "ori", "vel", "angVel", "angMom", "force", "torque")]))
+        return o
+
     def facets(self):
         """Facet node positions after the last step, (n,3,3)."""
         n = len(self.spec.facets) if getattr(self, "spec", None) is not None else 0
@@ -145,6 +169,7 @@ class Engine:
         self.upload_spheres(S.sphere_ids(), S.pos, S.radius, m, I, S.mat, S.mask, S.flags, S.vel, S.angVel)
         self.upload_walls(S.wall_ids(), S.walls)
         self.upload_facets(S.facet_ids(), S.facets)
+        self.upload_clumps(S.sphere_ids(), getattr(S, "clumps", []))
         self.upload_facet_groups(len(S.facets), getattr(S, "facet_groups", []))
         if S.cell is not None:
             self.set_cell(S.cell["hSize"], S.cell.get("gradV"), S.cell.get("nextGradV"), S.cell.get("homoDeform", 4))

@@ -204,6 +204,38 @@ def deposition(n, *, r=5e-3, psd_ratio=1.0, seed=1, law=LAW_IDEALELPL, layers=No
     return S.finalize()
 
 
+def clump_deposition(n_clumps, n_free=0, *, r=5e-3, seed=11, law=LAW_IDEALELPL, damping=.2, dynDtPeriod=100, spin=5.0):
+    """Gravity deposition of rigid aggregates (dumbbells, L-shaped trimers of unequal spheres, 4-sphere chains; random orientation and spin) mixed with free
+    spheres in an open-top box of 5 Walls.  The members of a clump touch or overlap slightly (they never collide with each other)."""
+    rng = np.random.default_rng(seed)
+    n_sites = n_clumps + n_free
+    nz = max(1, round(n_sites ** (1 / 3.))); nx = max(1, int(math.ceil(math.sqrt(n_sites / nz)))); ny = max(1, int(math.ceil(n_sites / (nx * nz))))
+    sp = 5.2 * r       # every aggregate fits a ball of radius 2.5 r
+    sites = lattice(nx, ny, nz, sp, (0, 0, 0), 0.05 * r, rng)
+    sites = sites[rng.permutation(len(sites))][:n_sites]
+    pos, rad, groups = [], [], []
+    for i in range(n_clumps):
+        kind = i % 3
+        if kind == 0: loc, rr = np.array([[-.9, 0, 0], [.9, 0, 0]]) * r, [r, r]
+        elif kind == 1: loc, rr = np.array([[0, 0, 0], [1.7, 0, 0], [0, 1.4, .3]]) * r, [r, .8 * r, .6 * r]
+        else: loc, rr = np.array([[-1.5, 0, 0], [-.5, 0, .2], [.5, 0, -.2], [1.5, 0, 0]]) * r, [.7 * r, .8 * r, .8 * r, .7 * r]
+        loc = loc - loc.mean(axis=0)
+        q = rng.normal(size=4); q /= np.linalg.norm(q); x, y, z, w = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        groups.append(list(range(len(pos), len(pos) + len(rr))))
+        pos += list(sites[i] + loc @ R.T); rad += rr
+    for i in range(n_free):
+        pos.append(sites[n_clumps + i]); rad.append(r * rng.uniform(.7, 1.))
+    S = SceneSpec()
+    S.mats = [frict_mat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)] if law == LAW_IDEALELPL else [hertz_mat(density=2500., young=1e8, tanPhi=.5)]
+    S.pos, S.radius = np.array(pos), np.array(rad)
+    S.walls = box_walls((0, 0, 0), (nx * sp, ny * sp, nz * sp), mat=0)
+    S.params = Params(gravity=(0, 0, -9.81), damping=damping, law=law, verletDist=-.05, dtSafety=.9, dynDtPeriod=dynDtPeriod)
+    S.finalize()
+    S.vel[len(S.pos) - n_free:] = rng.uniform(-.05, .05, (n_free, 3))
+    return make_clumps(S, groups, vel=rng.uniform(-.05, .05, (n_clumps, 3)), angVel=rng.uniform(-spin, spin, (n_clumps, 3)))
+
+
 def random_gas(n, *, box=1.0, r=0.02, psd_ratio=1.0, seed=0, vmax=1.0, law=LAW_IDEALELPL, overlap=True, walls=True,
                angvel=1.0, en=float("nan")):
     """Dense random cloud with overlaps and random velocities: exercises creation, update, breakage and sliding
