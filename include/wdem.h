@@ -138,6 +138,9 @@ int wdem_upload_clumps(wdem_handle h, int32_t nClumps, const int32_t* memberStar
  * forceTorqueFromMembers adds to (mass*gravity after Leapfrog's reset). */
 int wdem_download_clumps(wdem_handle h, double* pos, double* ori, double* vel, double* angVel, double* angMom, double* force, double* torque);
 int64_t wdem_num_clumps(wdem_handle h);
+/* DemData.force / torque of the master nodes at upload time (3 per clump; either may be NULL = zero): what a scene that has already run carries there
+ * (mass*gravity after Leapfrog's reset).  Only right after wdem_upload_clumps. */
+int wdem_upload_clump_forces(wdem_handle h, const double* force, const double* torque);
 /* Facet node positions (9 per facet, upload order) and the groups' master nodes after the last step; any pointer may be NULL. */
 int wdem_download_facets(wdem_handle h, double* verts, double* groupPos, double* groupOri);
 int wdem_set_cell(wdem_handle h, const double* hSize, const double* gradV, const double* nextGradV, int homoDeform);

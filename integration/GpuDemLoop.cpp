@@ -89,7 +89,7 @@ void GpuDemLoop::upload(){
 		const int m=matOf(p);
 		if(auto* s=dynamic_cast<Sphere*>(p->shape.get())){
 			const Node& n=*s->nodes[0]; const DemData& d=n.getData<DemData>();
-			if(d.isClumped() || d.isClump()) throw std::runtime_error("GpuDemLoop: clumps of spheres are not supported (particle #"+to_string(p->id)+")");
+			if(d.isClump()) throw std::runtime_error("GpuDemLoop: particle #"+to_string(p->id)+": a clump's master node cannot be the node of a particle");      // members (isClumped) are fine: wdem_upload_clumps below
 			if(d.impose) throw std::runtime_error("GpuDemLoop: DemData.impose is not supported (particle #"+to_string(p->id)+")");
 			if(!(d.inertia[0]==d.inertia[1] && d.inertia[1]==d.inertia[2])) throw std::runtime_error("GpuDemLoop: aspherical inertia is not supported (particle #"+to_string(p->id)+")");
 			sid.push_back(p->id); smat.push_back(m); sflags.push_back(d.flags); smask.push_back(p->mask);
@@ -122,13 +122,31 @@ void GpuDemLoop::upload(){
 	chk(h,wdem_upload_forces(h,sfrc.data(),strq.data()));
 	chk(h,wdem_upload_walls(h,(int)wid.size(),wid.data(),wpos.data(),waxis.data(),wsense.data(),wvel.data(),wmask.data(),wmat.data()));
 	chk(h,wdem_upload_facets(h,(int)fid.size(),fid.data(),fv.data(),fvv.data(),ffk.data(),fht.data(),fnl.data(),fmask.data(),fmat.data()));
-	// kinematic clumps of facets: nodes in DemField.nodes that carry ClumpData with all DOFs blocked (examples/mill.py:38-42, Clump.cpp:187-261)
+	// clumps: nodes in DemField.nodes that carry ClumpData (Clump.cpp:187-261).  Members that are spheres: a clump with mass, integrated on the device
+	// (wdem_upload_clumps); members that are facets: a kinematic group whose master has all DOFs blocked (examples/mill.py:38-42)
+	clumpOf.clear();
 	{
 		std::map<const Node*,int> facetOfNode; for(size_t i=0;i<facetOf.size();i++) for(const auto& n: facetOf[i]->shape->nodes) facetOfNode[n.get()]=(int)i;
+		std::map<const Node*,int> idOfSphereNode; for(const auto& p: sphereOf) idOfSphereNode[p->shape->nodes[0].get()]=p->id;
 		vector<int32_t> of(facetOf.size(),-1); vector<double> gp,go,gv,gw; int ng=0;
+		vector<int32_t> cStart{0},cMem; vector<uint32_t> cFl; vector<double> cp,co,cv,cw,cl,cm,cI,cf,ct,crp,cro;
 		for(const auto& n: dem.nodes){
 			if(!n->hasData<DemData>() || !n->getData<DemData>().isClump()) continue;
 			const ClumpData& cd=n->getData<DemData>().cast<ClumpData>();
+			if(!cd.nodes.empty() && idOfSphereNode.count(cd.nodes[0].get())){
+				if(cd.impose) throw std::runtime_error("GpuDemLoop: DemData.impose on a clump is not supported");
+				for(size_t i=0;i<cd.nodes.size();i++){
+					auto it=idOfSphereNode.find(cd.nodes[i].get()); if(it==idOfSphereNode.end()) throw std::runtime_error("GpuDemLoop: a clump must consist of Spheres only, or of Facets only");
+					cMem.push_back(it->second);
+					for(int k:{0,1,2}) crp.push_back(cd.relPos[i][k]);
+					cro.push_back(cd.relOri[i].x()); cro.push_back(cd.relOri[i].y()); cro.push_back(cd.relOri[i].z()); cro.push_back(cd.relOri[i].w());
+				}
+				cStart.push_back((int32_t)cMem.size()); cFl.push_back(cd.flags); cm.push_back(cd.mass);
+				for(int k:{0,1,2}){ cp.push_back(n->pos[k]); cv.push_back(cd.vel[k]); cw.push_back(cd.angVel[k]); cl.push_back(cd.angMom[k]); cI.push_back(cd.inertia[k]); cf.push_back(cd.force[k]); ct.push_back(cd.torque[k]); }
+				co.push_back(n->ori.x()); co.push_back(n->ori.y()); co.push_back(n->ori.z()); co.push_back(n->ori.w());
+				clumpOf.push_back(n);
+				continue;
+			}
 			if(!cd.isBlockedAll()) throw std::runtime_error("GpuDemLoop: the master node of a clump of boundary particles must have all DOFs blocked (its motion is prescribed)");
 			for(const auto& mn: cd.nodes){ auto it=facetOfNode.find(mn.get()); if(it==facetOfNode.end()) throw std::runtime_error("GpuDemLoop: only Facets can be members of a kinematic clump"); of[it->second]=ng; }
 			for(int k:{0,1,2}){ gp.push_back(n->pos[k]); gv.push_back(cd.vel[k]); gw.push_back(cd.angVel[k]); }
@@ -136,6 +154,10 @@ void GpuDemLoop::upload(){
 			ng++;
 		}
 		if(ng>0) chk(h,wdem_upload_facet_groups(h,ng,of.data(),gp.data(),go.data(),gv.data(),gw.data()));
+		if(!clumpOf.empty()){
+			chk(h,wdem_upload_clumps(h,(int32_t)clumpOf.size(),cStart.data(),cMem.data(),cp.data(),co.data(),cv.data(),cw.data(),cl.data(),cm.data(),cI.data(),cFl.data(),crp.data(),cro.data()));
+			chk(h,wdem_upload_clump_forces(h,cf.data(),ct.data()));
+		}
 	}
 	if(scene->isPeriodic){
 		const Cell& C=*scene->cell; double H[9],G[9],N[9];
@@ -180,6 +202,16 @@ void GpuDemLoop::pull(){
 		const size_t nw=wallOf.size(); vector<double> wp(3*nw),wf(3*nw),wt(3*nw);
 		chk(h,wdem_download_walls(h,wp.data(),wf.data(),wt.data()));
 		for(size_t i=0;i<nw;i++){ Node& nd=*wallOf[i]->shape->nodes[0]; DemData& d=nd.getData<DemData>(); nd.pos=Vector3r(wp[3*i],wp[3*i+1],wp[3*i+2]); d.force=Vector3r(wf[3*i],wf[3*i+1],wf[3*i+2]); d.torque=Vector3r(wt[3*i],wt[3*i+1],wt[3*i+2]); }
+	}
+	if(!clumpOf.empty()){
+		const size_t nc=clumpOf.size(); vector<double> p(3*nc),o(4*nc),v(3*nc),w(3*nc),l(3*nc),f(3*nc),t(3*nc);
+		chk(h,wdem_download_clumps(h,p.data(),o.data(),v.data(),w.data(),l.data(),f.data(),t.data()));
+		for(size_t i=0;i<nc;i++){
+			Node& nd=*clumpOf[i]; ClumpData& d=nd.getData<DemData>().cast<ClumpData>();
+			nd.pos=Vector3r(p[3*i],p[3*i+1],p[3*i+2]); nd.ori=Quaternionr(o[4*i+3],o[4*i],o[4*i+1],o[4*i+2]);
+			d.vel=Vector3r(v[3*i],v[3*i+1],v[3*i+2]); d.angVel=Vector3r(w[3*i],w[3*i+1],w[3*i+2]); d.angMom=Vector3r(l[3*i],l[3*i+1],l[3*i+2]);
+			d.force=Vector3r(f[3*i],f[3*i+1],f[3*i+2]); d.torque=Vector3r(t[3*i],t[3*i+1],t[3*i+2]);
+		}
 	}
 	if(!facetOf.empty()){
 		const size_t nf=facetOf.size(); vector<double> v(9*nf);

@@ -32,7 +32,7 @@ struct GpuDemLoop: public Engine{
 	// host <-> device
 	void release();
 	wdem_config makeConfig();            // attributes of the wrapped engines / functors -> wdem_config (re-read every step, as the reference engines do)
-	void upload();                       // DemField -> device: materials, spheres, walls, facets, kinematic clumps of facets, cell, contact history
+	void upload();                       // DemField -> device: materials, spheres, clumps of spheres, walls, facets, kinematic clumps of facets, cell, contact history
 	void prepare();                      // before a step: (re-)upload if particles changed, else push attribute / state edits
 	void pull();                         // device -> Node.pos/ori, DemData.vel/angVel/force/torque (lazily: only when `sync` or somebody asks)
 	void pullContacts();                 // device -> DemField.contacts as real Contact/L6Geom/FrictPhys|HertzPhys objects (S.save(), S.dem.con[i,j], VtkExport keep working)
@@ -41,6 +41,7 @@ struct GpuDemLoop: public Engine{
 	// not attributes: device handle and the host-side bookkeeping of what lives there
 	wdem_handle h=nullptr; wdem_config cfg; bool haveCfg=false;
 	vector<shared_ptr<Particle>> sphereOf, wallOf, facetOf;      // particles in upload order
+	vector<shared_ptr<Node>> clumpOf;                            // master nodes of the clumps of spheres, in upload order
 	size_t nParticlesUploaded=0; long stepUploaded=-1; bool trackingOn=false;
 	#define woo_dem_GpuDemLoop__CLASS_BASE_DOC_ATTRS \
 		GpuDemLoop,Engine,"Leapfrog + InsertionSortCollider + ContactLoop (+ DynDt) for spheres, walls and facets as one engine running on a CUDA device (B200, sm_100a; no CPU fallback). Attributes of the wrapped engines keep their meaning and are re-read every step; settings the device path does not implement raise in :obj:`selfTest`.", \

@@ -386,3 +386,92 @@ def test_guess_moving():
     assert DemData(blocked='xyzXY', mass=1).guessMoving() is True       # something not blocked, move
     assert DemData(blocked='xyzXYZ', mass=1).guessMoving() is False     # everything blocked, not move
     assert DemData(blocked='xyzXYZ', vel=(1, 1, 1), mass=1).guessMoving() is True      # velocity assigned, move
+
+
+# ---- clumps of spheres with mass: py/tests/test_clump.py TestSimpleClump, against the plugin -----------------------------------------------------------------
+def _simple_clump():
+    S = Scene(fields=[DemField()])
+    S.dem.par.addClumped([woo.utils.sphere((0, 0, 0), 1), woo.utils.sphere((0, 0, 3), .5)])
+    for n in (S.dem.par[0].shape.nodes[0], S.dem.par[1].shape.nodes[0]):
+        S.dem.nodesAppend(n)
+    return (S,) + tuple(S.dem.nodes)
+
+
+def test_clump_consistency_and_static_properties():
+    """test_clump.py:30-64 (testConsistency, testStaticProperties)"""
+    S, bC, b1, b2 = _simple_clump()
+    assert b1 in bC.dem.nodes and b2 in bC.dem.nodes
+    assert bC.dem.clump and b1.dem.clumped and b2.dem.clumped
+    assert b1.dem.master == bC and b2.dem.master == bC
+    assert bC.dem.mass == b1.dem.mass + b2.dem.mass
+    c = (b1.dem.mass * np.array(b1.pos) + b2.dem.mass * np.array(b2.pos)) / bC.dem.mass
+    assert np.array_equal(np.array(bC.pos), c)
+    i1, i2 = [(8. / 15) * math.pi * S.dem.par[i].mat.density * S.dem.par[i].shape.radius ** 5 for i in (0, 1)]
+    iMax = i1 + i2 + b1.dem.mass * np.linalg.norm(np.array(b1.pos) - c) ** 2 + b2.dem.mass * np.linalg.norm(np.array(b2.pos) - c) ** 2
+    iC = sorted(bC.dem.inertia)
+    assert iC[0] == pytest.approx(i1 + i2, rel=1e-7) and iC[1] == pytest.approx(iMax, rel=1e-7) and iC[2] == pytest.approx(iMax, rel=1e-7)
+    # the orientation matches the order of the inertia: the axis of the smallest moment is the line of centres
+    x, y, z, w = bC.ori
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    assert abs(abs(R[:, int(np.argmin(bC.dem.inertia))] @ np.array([0, 0, 1.])) - 1) < 1e-12
+    assert np.allclose(np.array(bC.pos) + R @ np.array(bC.dem.relPos[1]), b2.pos, atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_clump_member_velocities_assigned_by_leapfrog():
+    """test_clump.py:65-81 (testVelocity): dt=0, one step updates the members' velocities from the master node"""
+    S, bC, b1, b2 = _simple_clump()
+    S.dt = 0
+    bC.dem.vel = (1., .2, .4); bC.dem.angVel = (0, .4, .1)
+    S.engines = woo.utils.gpuEngines(damping=0., dynDtPeriod=0)
+    S.one()
+    for b in (b1, b2):
+        assert np.array_equal(np.array(b.dem.vel), np.array(bC.dem.vel) + np.cross(np.array(bC.dem.angVel), np.array(b.pos) - np.array(bC.pos)))
+        assert np.array_equal(np.array(b.dem.angVel), np.array(bC.dem.angVel))
+
+
+@pytest.mark.gpu
+def test_clump_members_do_not_collide():
+    """test_clump.py:82-91 (testNoCollide)"""
+    S = Scene(fields=[DemField()])
+    S.dem.par.addClumped([woo.utils.sphere(c, r) for c, r in [((1, 0, 0), 1), ((0, 1, 0), 1), ((0, 0, 1), 1)]])
+    S.engines = woo.utils.gpuEngines(damping=0., dynDtPeriod=0); S.dt = 1e-5
+    S.one()
+    assert len(S.dem.con) == 0
+
+
+@pytest.mark.gpu
+def test_clumps_through_the_plugin_equal_the_array_level_engine():
+    from woo_b200 import scenes as sc
+    from woo_b200.engine import Engine
+    Sp = sc.clump_deposition(20, 15)
+    S = Scene(fields=[DemField(gravity=Sp.params.gravity)])
+    m = FrictMat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)
+    pars = [woo.utils.sphere(Sp.pos[i], Sp.radius[i], mat=m) for i in range(Sp.n)]
+    member = set(i for c in Sp.clumps for i in c["members"])
+    masters = []
+    # ids in the order of the array-level scene: spheres first (clump members get theirs inside addClumped)
+    k = 0
+    for c in Sp.clumps:
+        assert c["members"][0] == k; k += len(c["members"])
+        masters.append(S.dem.par.addClumped([pars[i] for i in c["members"]]))
+    S.dem.par.add([pars[i] for i in range(Sp.n) if i not in member])
+    S.dem.par.add([Wall.make(w["pos"], axis=w["axis"], sense=w["sense"], mat=m) for w in Sp.walls])
+    for i in range(Sp.n):
+        if i not in member:
+            pars[i].vel = Sp.vel[i]
+    # the plugin derives centroid / principal axes itself (Jacobi instead of the scene helper's eigh): feed ITS numbers to the array-level engine
+    for c, M in zip(Sp.clumps, masters):
+        M.dem.vel = c["vel"]; M.dem.angVel = c["angVel"]
+        assert np.allclose(sorted(M.dem.inertia), sorted(c["inertia"]), rtol=1e-10) and np.allclose(M.pos, c["pos"], rtol=1e-13)
+        c.update(pos=np.array(M.pos), ori=np.array(M.ori), inertia=np.array(M.dem.inertia), mass=M.dem.mass, relPos=np.array(M.dem.relPos), relOri=np.array(M.dem.relOri))
+    E = Engine(Sp.params).load(Sp)
+    S.engines = woo.utils.gpuEngines(damping=.2, dynDtPeriod=100); S.dtSafety = Sp.params.dtSafety
+    E.step(3000); S.run(3000, True)
+    assert np.array_equal(np.array([p.pos for p in pars]), E.spheres()["pos"])
+    kc = E.clumps()
+    assert np.array_equal(np.array([M.pos for M in masters]), kc["pos"]) and np.array_equal(np.array([M.dem.angVel for M in masters]), kc["angVel"])
+    assert np.array_equal(np.array([M.dem.angMom for M in masters]), kc["angMom"])
+    # reading the state back (lazy pull of spheres and master nodes) does not disturb the run
+    E.step(500); S.run(500, True)
+    assert np.array_equal(np.array([p.pos for p in pars]), E.spheres()["pos"])

@@ -1519,6 +1519,18 @@ int wdem_download_clumps(wdem_handle h, double* pos, double* ori, double* vel, d
   });
 }
 int64_t wdem_num_clumps(wdem_handle h) { return h ? h->clumps.n : 0; }
+int wdem_upload_clump_forces(wdem_handle h, const double* force, const double* torque) {
+  return guarded(h, [&] {
+    ClumpStore& K = h->clumps; const int n = K.n;
+    if (!h->conDirty || h->cur != 0 || h->nC != 0) throw EngErr{"wdem_upload_clump_forces: call right after wdem_upload_clumps", WDEM_ERR_INVALID};
+    std::vector<double4> b(n);
+    for (int w = 0; w < 2; w++) {
+      const double* src = w ? torque : force; if (!src || n == 0) continue;
+      for (int i = 0; i < n; i++) b[i] = make_double4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0);
+      CK(cudaMemcpyAsync((w ? K.torque : K.force).p, b.data(), n * sizeof(double4), cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream));
+    }
+  });
+}
 
 int wdem_upload_forces(wdem_handle h, const double* force, const double* torque) {
   return guarded(h, [&] {

@@ -49,7 +49,10 @@ struct HertzMat : FrictMat { double surfEnergy = 0., alpha = 0.; int kind() cons
 
 // ---- nodes and particles (core/Field.hpp:102-103, dem/Particle.hpp:91-97,198-292)
 enum { DOF_ALL = 63, GRAVITY_SKIP = 512, DAMPING_SKIP = 2048 };
+struct Node;
 struct DemData {
+  virtual ~DemData() {}
+  std::weak_ptr<Node> master;      // the clump's master node of a clumped node (DemData::master, Particle.hpp:233)
   V3 vel{{0, 0, 0}}, angVel{{0, 0, 0}}, force{{0, 0, 0}}, torque{{0, 0, 0}}, inertia{{0, 0, 0}}; double mass = 0; unsigned flags = 0;
   DemField* field = nullptr;
   // DemData::guessMoving (Particle.cpp:638-640): does the node need motion integration?
@@ -58,6 +61,9 @@ struct DemData {
   void blockedSet(const string& s) { flags &= ~63u; for (char c : s) { const char* n = "xyzXYZ"; const char* p = strchr(n, c); if (!p) throw std::invalid_argument("blocked: only xyzXYZ allowed"); flags |= 1u << (p - n); } }
 };
 struct Node { V3 pos{{0, 0, 0}}; Q4 ori{{0, 0, 0, 1}}; shared_ptr<DemData> dem; };
+// master node data of a clump of spheres with mass (dem/Clump.hpp:60-100)
+enum { CLUMP_CLUMPED = 64, CLUMP_CLUMP = 128 };
+struct ClumpData : DemData { vector<shared_ptr<Node>> nodes; vector<V3> relPos; vector<Q4> relOri; V3 angMom{{NaN, NaN, NaN}}; double equivRad = NaN; };
 struct Shape { vector<shared_ptr<Node>> nodes; virtual ~Shape() {} virtual int numNodes() const = 0; };
 struct Sphere : Shape { double radius = NaN; int numNodes() const override { return 1; } };
 struct Wall : Shape { int sense = 0, axis = 0; int numNodes() const override { return 1; } };
@@ -79,6 +85,7 @@ struct ContactContainer { DemField* dem = nullptr; vector<shared_ptr<Contact>> v
 // ---- the field (dem/Particle.hpp:339-361)
 struct DemField {
   ParticleContainer par; ContactContainer con; vector<shared_ptr<Node>> nodes; vector<ClumpGroup> clumps;
+  vector<shared_ptr<Node>> sphereClumps;      // master nodes carrying ClumpData (clumps of spheres with mass, integrated on the device)
   vector<int> pendingRemoves;                 // ids of spheres removed while the scene lives on the device (wdem_remove_spheres)
   vector<shared_ptr<Particle>> pendingAdds;   // spheres added while the scene lives on the device: appended there (wdem_add_spheres) instead of re-uploading everything
   V3 gravity{{0, 0, 0}}; unsigned loneMask = 2; double distFactor = -1.;
@@ -254,6 +261,24 @@ struct GpuDemLoop : Engine {
       }
       chk(h, wdem_upload_facet_groups(h, (int)F.clumps.size(), of.data(), gp.data(), go.data(), gv.data(), gw.data()));
     }
+    if (!F.sphereClumps.empty()) {   // clumps of spheres with mass (ClumpData): wdem_upload_clumps
+      std::map<const Node*, int> idOfNode; for (auto& p : sphereOf) idOfNode[p->shape->nodes[0].get()] = p->id;
+      vector<int32_t> cStart{0}, cMem; vector<uint32_t> cFl; vector<double> cp, co, cv, cw, cl, cm, cI, cf, ct, crp, cro;
+      for (auto& n : F.sphereClumps) {
+        const ClumpData& cd = static_cast<const ClumpData&>(*n->dem);
+        for (size_t i = 0; i < cd.nodes.size(); i++) {
+          auto it = idOfNode.find(cd.nodes[i].get()); if (it == idOfNode.end()) throw std::runtime_error("GpuDemLoop: a member of a clump is not (or no longer) a Sphere of this DemField");
+          cMem.push_back(it->second);
+          for (int k = 0; k < 3; k++) crp.push_back(cd.relPos[i][k]);
+          for (int k = 0; k < 4; k++) cro.push_back(cd.relOri[i][k]);
+        }
+        cStart.push_back((int32_t)cMem.size()); cFl.push_back(cd.flags & ~(unsigned)CLUMP_CLUMP); cm.push_back(cd.mass);
+        for (int k = 0; k < 3; k++) { cp.push_back(n->pos[k]); cv.push_back(cd.vel[k]); cw.push_back(cd.angVel[k]); cl.push_back(cd.angMom[k]); cI.push_back(cd.inertia[k]); cf.push_back(cd.force[k]); ct.push_back(cd.torque[k]); }
+        for (int k = 0; k < 4; k++) co.push_back(n->ori[k]);
+      }
+      chk(h, wdem_upload_clumps(h, (int32_t)F.sphereClumps.size(), cStart.data(), cMem.data(), cp.data(), co.data(), cv.data(), cw.data(), cl.data(), cm.data(), cI.data(), cFl.data(), crp.data(), cro.data()));
+      chk(h, wdem_upload_clump_forces(h, cf.data(), ct.data()));
+    }
     if (scene->periodic) { Cell& C = *scene->cell; chk(h, wdem_set_cell(h, C.hSize.data(), C.gradV.data(), C.nextGradV.data(), C.homoDeform)); C.dirty = false; }
     chk(h, wdem_set_scene(h, (int64_t)scene->step, scene->time));
     F.pushContacts(h);
@@ -302,7 +327,8 @@ struct GpuDemLoop : Engine {
   void prepare() {
     if (!field) throw std::runtime_error("GpuDemLoop: no DemField");
     DemField& F = *field;
-    if (F.stateDirty && !F.clumps.empty()) F.topoDirty = true;   // the edit may concern a clump's master node (its vel/angVel): take the full path
+    if (F.stateDirty && (!F.clumps.empty() || !F.sphereClumps.empty())) F.topoDirty = true;   // the edit may concern a clump's master node (its vel/angVel): take the full path
+    if (!F.sphereClumps.empty() && (!F.pendingAdds.empty() || !F.pendingRemoves.empty())) F.topoDirty = true;   // no incremental add/remove beside clumps (wdem.h)
     if (h && !F.topoDirty && F.owner == this && !F.pendingRemoves.empty()) removeSpheres();
     if (h && !F.topoDirty && F.owner == this && !F.pendingAdds.empty() && !appendSpheres()) F.topoDirty = true;
     if (!h || F.topoDirty || F.owner != this) upload();
@@ -357,6 +383,15 @@ void DemField::pull() {
     vector<double> wp(3 * nw), wf(3 * nw), wt(3 * nw);
     chk(owner->h, wdem_download_walls(owner->h, wp.data(), wf.data(), wt.data()));
     for (size_t i = 0; i < nw; i++) { Node& nd = *owner->wallOf[i]->shape->nodes[0]; for (int k = 0; k < 3; k++) { nd.pos[k] = wp[3 * i + k]; nd.dem->force[k] = wf[3 * i + k]; nd.dem->torque[k] = wt[3 * i + k]; } }
+  }
+  if (!sphereClumps.empty()) {
+    const size_t nc = sphereClumps.size(); vector<double> p(3 * nc), o(4 * nc), v(3 * nc), w(3 * nc), l(3 * nc), cf(3 * nc), ct(3 * nc);
+    chk(owner->h, wdem_download_clumps(owner->h, p.data(), o.data(), v.data(), w.data(), l.data(), cf.data(), ct.data()));
+    for (size_t i = 0; i < nc; i++) {
+      Node& nd = *sphereClumps[i]; ClumpData& d = static_cast<ClumpData&>(*nd.dem);
+      for (int k = 0; k < 3; k++) { nd.pos[k] = p[3 * i + k]; d.vel[k] = v[3 * i + k]; d.angVel[k] = w[3 * i + k]; d.angMom[k] = l[3 * i + k]; d.force[k] = cf[3 * i + k]; d.torque[k] = ct[3 * i + k]; }
+      for (int k = 0; k < 4; k++) nd.ori[k] = o[4 * i + k];
+    }
   }
   if (!clumps.empty() && !owner->facetOf.empty()) {
     const size_t nf = owner->facetOf.size(); vector<double> fv(9 * nf), gp(3 * clumps.size()), go(4 * clumps.size());
@@ -481,7 +516,14 @@ PYBIND11_MODULE(_woo, m) {
       .def_property("blocked", &DemData::blockedGet, [](DemData& s, const string& v) { s.blockedSet(v); if (s.field) s.field->topoDirty = true; })
       .def_property("gravitySkip", [](DemData& s) { return bool(s.flags & GRAVITY_SKIP); }, [](DemData& s, bool b) { s.flags = b ? (s.flags | GRAVITY_SKIP) : (s.flags & ~GRAVITY_SKIP); if (s.field) s.field->topoDirty = true; })
       .def("guessMoving", &DemData::guessMoving)
+      .def_property_readonly("clump", [](DemData& s) { return bool(s.flags & CLUMP_CLUMP); }).def_property_readonly("clumped", [](DemData& s) { return bool(s.flags & CLUMP_CLUMPED); })
+      .def_property_readonly("master", [](DemData& s) { return s.master.lock(); })
       .def_property("dampingSkip", [](DemData& s) { return bool(s.flags & DAMPING_SKIP); }, [](DemData& s, bool b) { s.flags = b ? (s.flags | DAMPING_SKIP) : (s.flags & ~DAMPING_SKIP); if (s.field) s.field->topoDirty = true; });
+  py::class_<ClumpData, DemData, shared_ptr<ClumpData>>(m, "ClumpData")
+      .def_readonly("nodes", &ClumpData::nodes).def_readonly("equivRad", &ClumpData::equivRad)
+      .def_property_readonly("relPos", [](ClumpData& s) { py::list l; for (auto& v : s.relPos) l.append(np3(v)); return l; })
+      .def_property_readonly("relOri", [](ClumpData& s) { py::list l; for (auto& v : s.relOri) l.append(np4(v)); return l; })
+      V3P(ClumpData, "angMom", s.angMom, if (s.field) s.field->pull(), if (s.field) s.field->topoDirty = true);
   kwclass<Node>(m, "Node")
       V3P(Node, "pos", s.pos, if (s.dem && s.dem->field) s.dem->field->pull(), if (s.dem && s.dem->field) s.dem->field->touchState())
       .def_property("ori", [](Node& s) { if (s.dem && s.dem->field) s.dem->field->pull(); return np4(s.ori); }, [](Node& s, py::object o) { s.ori = seqN<4>(o, "ori"); if (s.dem && s.dem->field) s.dem->field->topoDirty = true; })
@@ -574,18 +616,95 @@ PYBIND11_MODULE(_woo, m) {
   m.attr("ParticleContainer").attr("addClumped") = py::cpp_function([](ParticleContainer& c, py::object pars, shared_ptr<Node> centralNode) -> shared_ptr<Node> {
         // ParticleContainer::addClumped (ParticleContainer.cpp) for boundary particles with a user-given master node: the members keep their positions, the master's
         // vel/angVel (all DOFs blocked) move them rigidly from now on (examples/mill.py:38-42)
-        if (!centralNode) throw std::runtime_error("addClumped: centralNode is required (members without mass; Clump.cpp:239)");
+        if (!centralNode) {
+          // ClumpData::makeClump for particles with mass (Clump.cpp:187-261): centroid, principal axes and inertia from the members (spheres only on this path)
+          vector<shared_ptr<Particle>> pp; for (auto it : pars) pp.push_back(it.cast<shared_ptr<Particle>>());
+          if (pp.empty()) throw std::runtime_error("ClumpData::makeClump: 0 nodes.");
+          py::object add = py::cast(&c, py::return_value_policy::reference).attr("add");
+          auto cd = make_shared<ClumpData>(); cd->flags |= CLUMP_CLUMP; cd->field = c.dem;
+          auto cNode = make_shared<Node>(); cNode->dem = cd;
+          double M = 0; V3 Sg{{0, 0, 0}}; double Ig[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+          for (auto& p : pp) {
+            if (!dynamic_cast<Sphere*>(p->shape.get())) throw std::runtime_error("addClumped: without centralNode only Spheres can be clumped on this path");
+            Node& n = *p->shape->nodes[0]; DemData& d = *n.dem;
+            if (d.flags & CLUMP_CLUMPED) throw std::runtime_error("Node of particle #" + std::to_string(p->id) + ": already clumped.");
+            M += d.mass;
+            for (int k = 0; k < 3; k++) Sg[k] += d.mass * n.pos[k];
+            // inertiaTensorTranslate(diag(inertia) [a sphere: rotation changes nothing], mass, -pos) (Volumetric.cpp:194-197)
+            const double oo = n.pos[0] * n.pos[0] + n.pos[1] * n.pos[1] + n.pos[2] * n.pos[2];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Ig[i][j] += (i == j ? d.inertia[i] : 0.) + d.mass * ((i == j ? oo : 0.) - n.pos[i] * n.pos[j]);
+          }
+          if (!(M > 0)) throw std::runtime_error("ClumpData::makeClump: no nodes with mass, therefore centralNode must be given, of which position will be used instead");
+          if (pp.size() == 1) {   // Clump.cpp:204-217
+            Node& n0 = *pp[0]->shape->nodes[0]; cNode->pos = n0.pos; cNode->ori = n0.ori; cd->mass = n0.dem->mass; cd->inertia = n0.dem->inertia;
+          } else {
+            // Volumetric::computePrincipalAxes (Volumetric.cpp:173-191): centroid, inertia about it, eigen-decomposition.  Jacobi rotations stand in for Eigen's
+            // SelfAdjointEigenSolver (eigenvalues ascending as there); the eigenvector matrix is made a proper rotation before it becomes the orientation
+            for (int k = 0; k < 3; k++) cNode->pos[k] = Sg[k] / M;
+            const V3& P = cNode->pos; const double pp2 = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+            double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) A[i][j] = Ig[i][j] - M * ((i == j ? pp2 : 0.) - P[i] * P[j]);
+            for (int sweep = 0; sweep < 60; sweep++) {
+              const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+              if (off <= 1e-60 * (A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2])) break;
+              for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+                if (A[p][q] == 0.) continue;
+                const double th = (A[q][q] - A[p][p]) / (2 * A[p][q]), t = (th >= 0 ? 1. : -1.) / (std::abs(th) + std::sqrt(th * th + 1)), cs = 1 / std::sqrt(t * t + 1), sn = t * cs;
+                for (int k = 0; k < 3; k++) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = cs * akp - sn * akq; A[k][q] = sn * akp + cs * akq; }
+                for (int k = 0; k < 3; k++) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = cs * apk - sn * aqk; A[q][k] = sn * apk + cs * aqk; }
+                for (int k = 0; k < 3; k++) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = cs * vkp - sn * vkq; V[k][q] = sn * vkp + cs * vkq; }
+              }
+            }
+            int ord[3] = {0, 1, 2}; std::sort(ord, ord + 3, [&](int a, int b) { return A[a][a] < A[b][b]; });
+            double R[3][3]; for (int j = 0; j < 3; j++) { cd->inertia[j] = A[ord[j]][ord[j]]; for (int i = 0; i < 3; i++) R[i][j] = V[i][ord[j]]; }
+            const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) + R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+            if (det < 0) for (int i = 0; i < 3; i++) R[i][2] = -R[i][2];
+            // Eigen Quaternion(Matrix3), then normalize
+            double qw, qx, qy, qz; const double tr = R[0][0] + R[1][1] + R[2][2];
+            if (tr > 0) { double t = std::sqrt(tr + 1.0); qw = 0.5 * t; t = 0.5 / t; qx = (R[2][1] - R[1][2]) * t; qy = (R[0][2] - R[2][0]) * t; qz = (R[1][0] - R[0][1]) * t; }
+            else {
+              int i = 0; if (R[1][1] > R[0][0]) i = 1; if (R[2][2] > R[i][i]) i = 2; const int j = (i + 1) % 3, k = (j + 1) % 3;
+              double t = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0); double qv[3]; qv[i] = 0.5 * t; t = 0.5 / t; qw = (R[k][j] - R[j][k]) * t; qv[j] = (R[j][i] + R[i][j]) * t; qv[k] = (R[k][i] + R[i][k]) * t;
+              qx = qv[0]; qy = qv[1]; qz = qv[2];
+            }
+            const double qn = std::sqrt(qx * qx + qy * qy + qz * qz + qw * qw); cNode->ori = {{qx / qn, qy / qn, qz / qn, qw / qn}};
+            cd->mass = M;
+          }
+          cd->equivRad = (std::sqrt(cd->inertia[0] / cd->mass) + std::sqrt(cd->inertia[1] / cd->mass) + std::sqrt(cd->inertia[2] / cd->mass)) / 3;
+          // relPos = ori^-1 * (pos - clumpPos), relOri = ori^-1 * ori_member (Clump.cpp:252-253)
+          const Q4& Q = cNode->ori; const double cw = Q[3], cx = -Q[0], cy = -Q[1], cz = -Q[2];
+          for (auto& p : pp) {
+            if (p->id < 0) add(p);
+            Node& n = *p->shape->nodes[0]; DemData& d = *n.dem;
+            const double v[3] = {n.pos[0] - cNode->pos[0], n.pos[1] - cNode->pos[1], n.pos[2] - cNode->pos[2]};
+            double uv[3] = {cy * v[2] - cz * v[1], cz * v[0] - cx * v[2], cx * v[1] - cy * v[0]}; for (double& u : uv) u += u;      // Eigen _transformVector
+            const double c2[3] = {cy * uv[2] - cz * uv[1], cz * uv[0] - cx * uv[2], cx * uv[1] - cy * uv[0]};
+            cd->relPos.push_back(V3{{(v[0] + cw * uv[0]) + c2[0], (v[1] + cw * uv[1]) + c2[1], (v[2] + cw * uv[2]) + c2[2]}});
+            const double bx = n.ori[0], by = n.ori[1], bz = n.ori[2], bw = n.ori[3];
+            cd->relOri.push_back(Q4{{cw * bx + cx * bw + cy * bz - cz * by, cw * by + cy * bw + cz * bx - cx * bz, cw * bz + cz * bw + cx * by - cy * bx, cw * bw - cx * bx - cy * by - cz * bz}});
+            cd->nodes.push_back(p->shape->nodes[0]);
+            d.flags |= CLUMP_CLUMPED; d.master = cNode;
+            // pyAppendClumped adds the particles without their nodes: only the clump node goes to DemField.nodes (ParticleContainer.cpp:213)
+            auto itn = std::find(c.dem->nodes.begin(), c.dem->nodes.end(), p->shape->nodes[0]); if (itn != c.dem->nodes.end()) c.dem->nodes.erase(itn);
+          }
+          c.dem->sphereClumps.push_back(cNode); c.dem->nodes.push_back(cNode); c.dem->topoDirty = true;
+          return cNode;
+        }
         if (!centralNode->dem) { centralNode->dem = make_shared<DemData>(); centralNode->dem->flags |= DOF_ALL; }
         centralNode->dem->field = c.dem;
         ClumpGroup G; G.master = centralNode;
         py::object add = py::cast(&c, py::return_value_policy::reference).attr("add");
         for (auto it : pars) { auto p = it.cast<shared_ptr<Particle>>(); if (p->id < 0) add(p); G.members.push_back(p->id); }
         c.dem->clumps.push_back(G); c.dem->nodes.push_back(centralNode); c.dem->topoDirty = true;
-        return centralNode; }, py::is_method(m.attr("ParticleContainer")), py::arg("pars"), py::arg("centralNode"));
+        return centralNode; }, py::is_method(m.attr("ParticleContainer")), py::arg("pars"), py::arg("centralNode") = shared_ptr<Node>());
   kwclass<DemField>(m, "DemField")
       .def_property_readonly("par", [](DemField& f) -> ParticleContainer& { return f.par; }, py::return_value_policy::reference_internal)
       .def_property_readonly("con", [](DemField& f) -> ContactContainer& { return f.con; }, py::return_value_policy::reference_internal)
       .def_readonly("nodes", &DemField::nodes)
+      .def("nodesAppend", [](DemField& f, shared_ptr<Node> n) {   // DemField::pyNodesAppend (Particle.cpp): a clumped node in DemField.nodes is skipped by Leapfrog (Leapfrog.cpp:153) — harmless
+        if (!n || !n->dem) throw std::runtime_error("DemField.nodesAppend: Node.dem is None");
+        if (std::find(f.nodes.begin(), f.nodes.end(), n) != f.nodes.end()) throw std::runtime_error("DemField.nodesAppend: the node is already in DemField.nodes");
+        f.nodes.push_back(n); })
       .def_property("gravity", [](DemField& f) { return np3(f.gravity); }, [](DemField& f, py::object o) { f.gravity = seqN<3>(o, "gravity"); })
       RW(DemField, loneMask) RW(DemField, distFactor)
       .def_property_readonly_static("defaultMovableMask", [](py::object) { return 5u; }).def_property_readonly_static("defaultBoundaryMask", [](py::object) { return 3u; })
