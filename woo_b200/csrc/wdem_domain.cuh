@@ -175,6 +175,45 @@ __global__ void __launch_bounds__(256) k_dom_unpack_rows(Contacts O, long long b
 }
 
 // ghost export: bit r of mask[i] set if the enlarged box of owned sphere i can overlap the enlarged box of a sphere owned by rank r
+// Full run without migration (the usual case in a bed at rest), one pass over the current generation IN PLACE: counts the owned spheres that left the slab
+// (out[0]; any rank > 0 => everybody takes the regrouping path) and, for the owned spheres, the ghost-export mask and per-destination counts (out[1+r]).
+// Ghosts of the previous generation get mask 0.
+__global__ void __launch_bounds__(256) k_dom_fast_scan(Spheres S, int n, DomainU D, uint32_t* mask, int* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t m = 0, emig = 0;
+  if (i < n) {
+    if (!(S.flags[i] & F_GHOST)) {
+      const double4 p = S.posr[i];
+      const double x = slabCoord(D, p), h = slabHalf(D, p) + D.reach;
+      emig = ownerOf(D, x) != D.rank;
+      for (int r = 0; r < D.world; r++) {
+        if (r == D.rank) continue;
+        const double lo = D.bounds[r], hi = D.bounds[r + 1];
+        bool hit;
+        if (!D.periodic) hit = (x + h >= lo) && (x - h <= hi);
+        else {
+          if (x >= lo && x < hi) hit = true;
+          else { const double d1 = wrap01(lo - x, D.dim), d2 = wrap01(x - hi, D.dim); hit = fmin(d1, d2) <= h; }
+        }
+        if (hit) m |= 1u << r;
+      }
+    }
+    mask[i] = m;
+  }
+  const unsigned e = __reduce_add_sync(0xffffffffu, emig);
+  if ((threadIdx.x & 31) == 0 && e) atomicAdd(&out[0], (int)e);
+  for (int r = 0; r < D.world; r++) {
+    const unsigned c = __reduce_add_sync(0xffffffffu, (m >> r) & 1u);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&out[1 + r], (int)c);
+  }
+}
+// the ghosts of the previous generation leave in place: their slots are cut off by the full run that follows
+__global__ void __launch_bounds__(256) k_dom_mark_dead(uint32_t* flags, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t f = flags[i];
+  flags[i] = (f & F_GHOST) ? (f | F_DEADSLOT) : (f & ~F_ARRIVED);
+}
 __global__ void __launch_bounds__(256) k_dom_export_mask(Spheres S, int nOwn, DomainU D, uint32_t* mask, int* perRank) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t m = 0;
@@ -212,7 +251,8 @@ __global__ void __launch_bounds__(256) k_dom_pack_ghosts(Spheres S, int nOwn, co
 // all destinations in one pass: a sphere exported to rank r takes the next free place of r's segment (atomic cursor).  The order inside a segment is arbitrary
 // but the SAME on both sides: exportId here, importId on the receiver are filled from the same records.
 struct GhostSeg { int base[WDEM_MAX_RANKS]; };
-__global__ void __launch_bounds__(256) k_dom_pack_ghosts_all(Spheres S, int nOwn, const uint32_t* __restrict__ mask, int world, GhostSeg seg, int* __restrict__ cursor, GRec* out, int32_t* exportId) {
+struct GhostDst { GRec* out[WDEM_MAX_RANKS]; };   // where destination r's records go: a segment of my send buffer (NCCL path) or of r's own staging area (peer memory)
+__global__ void __launch_bounds__(256) k_dom_pack_ghosts_all(Spheres S, int nOwn, const uint32_t* __restrict__ mask, int world, GhostSeg seg, int* __restrict__ cursor, GhostDst dst, int32_t* exportId) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nOwn) return;
   uint32_t m = mask[i];
@@ -220,8 +260,8 @@ __global__ void __launch_bounds__(256) k_dom_pack_ghosts_all(Spheres S, int nOwn
   GRec g; g.posr = S.posr[i]; g.velm = S.velm[i]; g.angi = S.angi[i]; g.flags = (S.flags[i] & ~F_ARRIVED) | F_GHOST; g.mask = S.mask[i]; g.mat = S.mat[i]; g.id = S.id[i];
   while (m) {
     const int r = __ffs(m) - 1; m &= m - 1;
-    const int pos = seg.base[r] + atomicAdd(&cursor[r], 1);
-    out[pos] = g; exportId[pos] = g.id;
+    const int k = atomicAdd(&cursor[r], 1);
+    dst.out[r][k] = g; exportId[seg.base[r] + k] = g.id;
   }
 }
 __global__ void __launch_bounds__(256) k_dom_unpack_ghosts(Spheres S, int first, int cnt, const GRec* __restrict__ in, int32_t* importId) {

@@ -145,15 +145,16 @@ struct DomainState {
   int nOwn = 0; int globalMaxId = -1; bool globalsValid = false; double rmaxGlobal = 0;
   std::vector<size_t> sendCnt, recvCnt; size_t nSendTot = 0, nRecvTot = 0;   // ghosts exported to / imported from every rank
   DBuf<int> sendSlot, recvSlot; DBuf<int32_t> exportId, importId, oldIds; DBuf<double> haloSend, haloRecv;
-  DBuf<uint32_t> dkeys, dkeysAlt, emask; DBuf<int> dslots, dslotsAlt, dstart, origSlot, perm2, rowCnt, rowOff, perRank, flag, off;
+  DBuf<uint32_t> dkeys, dkeysAlt, emask; DBuf<int> dslots, dslotsAlt, dstart, origSlot, perm2, rowCnt, rowOff, perRank, flag, off, syncFlag;
   DBuf<char> sendBuf, recvBuf; DBuf<unsigned long long> immKeys, immKeysAlt; DBuf<int> immVals, immValsAlt; int nImm = 0;
   long long migratedOut = 0, migratedIn = 0, rowsIn = 0;
   // per-step exchange over peer memory (k_halo_push / k_peer_sync): my mailbox (words + 2 halo buffers), the peers' mailboxes mapped with CUDA IPC
+  int deadSlots = 0;      // slots of the current generation flagged F_DEADSLOT (domainExchange's in-place path), cut off by the collider run that follows
   struct Peer { bool active = false, disabled = false; unsigned long long syncSeq = 0; char* box = nullptr; long long haloCap = 0; void* base[WDEM_MAX_RANKS] = {}; std::vector<long long> dstOff; long long maxRecvTot = 0; } peer;
   void release() {
     sendSlot.release(); recvSlot.release(); exportId.release(); importId.release(); oldIds.release(); haloSend.release(); haloRecv.release(); dkeys.release(); dkeysAlt.release();
     emask.release(); dslots.release(); dslotsAlt.release(); dstart.release(); origSlot.release(); perm2.release(); rowCnt.release(); rowOff.release(); perRank.release();
-    flag.release(); off.release(); sendBuf.release(); recvBuf.release(); immKeys.release(); immKeysAlt.release(); immVals.release(); immValsAlt.release();
+    flag.release(); off.release(); syncFlag.release(); sendBuf.release(); recvBuf.release(); immKeys.release(); immKeysAlt.release(); immVals.release(); immValsAlt.release();
   }
 };
 
@@ -335,9 +336,11 @@ void exclusiveSum(wdem_engine* E, const int* in, int* out, int n) {
 //   1. owned spheres whose slab coordinate left the slab migrate (full state + the history rows of their real contacts);
 //   2. ghosts of the previous generation are dropped; every owned sphere whose enlarged AABB can reach a box owned by rank r is exported to r.
 // Leaves the new generation (owned first, then ghosts; unsorted) in the current sphere store.
+static const size_t PEER_WORDS_BYTES = 2 * WDEM_MAX_RANKS * sizeof(unsigned long long);
+PeerU makePeerU(wdem_engine* E);
 void domainExchange(wdem_engine* E) {
   static const bool tr = getenv("WDEM_REBUILD_TRACE") != nullptr;
-  static double tacc[10] = {0}; static int tcnt = 0; std::chrono::steady_clock::time_point tp[10];
+  static double tacc[12] = {0}; static int tcnt = 0; std::chrono::steady_clock::time_point tp[12];
   auto TM = [&](int k) { if (tr) { cudaStreamSynchronize(E->stream); tp[k] = std::chrono::steady_clock::now(); } };
   Transport* T = E->comm; DomainState& M = E->dom;
   const int W = T->world, R = T->rank; cudaStream_t st = E->stream; int64_t& tot = E->bytes;
@@ -350,6 +353,70 @@ void domainExchange(wdem_engine* E) {
   ContactStore& Ost = E->con[E->curC]; CsrStore& Ocsr = E->csr[E->curR];
   OldCsr oc; memset(&oc, 0, sizeof(oc)); oc.valid = (Ocsr.valid && E->nC > 0) ? 1 : 0; oc.nRows = Ocsr.nRows; oc.rowStart = Ocsr.rowStart.p; oc.rowEntry = Ocsr.rowEntry.p; oc.rowOther = Ocsr.rowOther.p;
   TM(0);
+  // ---- 0. nothing migrates anywhere (the usual case in a bed at rest): the owned spheres stay where they are, the ghosts of the previous generation are flagged
+  //         dead in place and the new ones appended behind them — no regrouping sort, no copy of the sphere arrays, one host wait
+  static const bool noFast = getenv("WDEM_NO_FAST_EXCHANGE") != nullptr;
+  M.deadSlots = 0;
+  if (!noFast) {
+    M.emask.ensure((size_t)std::max(n, 1), tot); M.perRank.ensure((size_t)2 * WDEM_MAX_RANKS * (W + 1), tot);
+    int* dMineF = M.perRank.p; int* dAllF = M.perRank.p + 2 * WDEM_MAX_RANKS;      // [emigrants + (no owned sphere), ghosts per destination...] : mine, then everybody's
+    CK(cudaMemsetAsync(dMineF, 0, 2 * WDEM_MAX_RANKS * sizeof(int), st));
+    if (n > 0) { k_dom_fast_scan<<<nblk(n, 256), 256, 0, st>>>(A, n, D, M.emask.p, dMineF); E->launches++; }
+    if (!(M.nOwn > 0 && n == M.nOwn + (int)M.nRecvTot)) { k_fill_int<<<1, 1, 0, st>>>(dMineF + 1 + W, 1, 1); E->launches++; }      // my veto (e.g. nothing owned here)
+    T->allgatherDev(dMineF, dAllF, (size_t)2 * WDEM_MAX_RANKS * sizeof(int), st);
+    std::vector<int> fa((size_t)W * 2 * WDEM_MAX_RANKS, 0);
+    CK(cudaMemcpyAsync(fa.data(), dAllF, fa.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // every rank reaches the same verdict: nobody emigrates anywhere, and every rank's arrays are [owned + ghosts of the last full run] with at least one owned sphere
+    long long vetoAll = 0;
+    for (int r = 0; r < W; r++) vetoAll += (long long)fa[(size_t)r * 2 * WDEM_MAX_RANKS] + fa[(size_t)r * 2 * WDEM_MAX_RANKS + 1 + W];
+    if (vetoAll == 0) {
+      TM(1);
+      const int nGhostOld = (int)M.nRecvTot;
+      M.sendCnt.assign(W, 0); M.recvCnt.assign(W, 0);
+      size_t accS = 0, accG = 0; GhostSeg seg; memset(&seg, 0, sizeof(seg));
+      auto cnt = [&](int src, int dst) { return (size_t)fa[(size_t)src * 2 * WDEM_MAX_RANKS + 1 + dst]; };
+      for (int r = 0; r < W; r++) { M.sendCnt[r] = cnt(R, r); M.recvCnt[r] = cnt(r, R); seg.base[r] = (int)accS; accS += M.sendCnt[r]; accG += M.recvCnt[r]; }
+      std::vector<size_t> sOffG(W, 0), sBytG(W, 0), rOffG(W, 0), rBytG(W, 0);
+      { size_t a = 0, b = 0; for (int r = 0; r < W; r++) { sOffG[r] = a * sizeof(GRec); sBytG[r] = M.sendCnt[r] * sizeof(GRec); a += M.sendCnt[r]; rOffG[r] = b * sizeof(GRec); rBytG[r] = M.recvCnt[r] * sizeof(GRec); b += M.recvCnt[r]; } }
+      M.nSendTot = accS; M.nRecvTot = accG;
+      M.peer.dstOff.assign(W, 0); M.peer.maxRecvTot = 0;
+      for (int r = 0; r < W; r++) {
+        long long off = 0, totR = 0;
+        for (int q = 0; q < W; q++) { if (q < R) off += (long long)cnt(q, r); totR += (long long)cnt(q, r); }
+        M.peer.dstOff[r] = off; M.peer.maxRecvTot = std::max(M.peer.maxRecvTot, totR);
+      }
+      M.sendBuf.ensure(accS * sizeof(GRec) + 64, tot); M.recvBuf.ensure(accG * sizeof(GRec) + 64, tot);
+      M.exportId.ensure(std::max<size_t>(accS, 1), tot); M.importId.ensure(std::max<size_t>(accG, 1), tot);
+      DomainState::Peer& P = M.peer;
+      const bool viaPeer = P.active && 9 * P.maxRecvTot <= P.haloCap;
+      const size_t stageOff = PEER_WORDS_BYTES + 2 * (size_t)P.haloCap * sizeof(double);
+      GhostDst gd; memset(&gd, 0, sizeof(gd));
+      for (int r = 0; r < W; r++) gd.out[r] = viaPeer ? reinterpret_cast<GRec*>(static_cast<char*>(P.base[r]) + stageOff) + P.dstOff[r] : as<GRec>(M.sendBuf) + seg.base[r];
+      int* dCur = M.perRank.p;      // per-destination cursors
+      CK(cudaMemsetAsync(dCur, 0, WDEM_MAX_RANKS * sizeof(int), st));
+      if (accS > 0) { k_dom_pack_ghosts_all<<<nblk(n, 256), 256, 0, st>>>(A, n, M.emask.p, W, seg, dCur, gd, M.exportId.p); E->launches++; }
+      const GRec* ghostsIn = as<GRec>(M.recvBuf);
+      if (viaPeer) {
+        M.syncFlag.ensure(4, tot); CK(cudaMemsetAsync(M.syncFlag.p, 0, 4 * sizeof(int), st));
+        const PeerU u = makePeerU(E); const unsigned long long seq = ++P.syncSeq;
+        k_peer_sync<<<1, WDEM_MAX_RANKS, 0, st>>>(u, E->dCnt, M.syncFlag.p, seq, (int)(seq & 1), 20000000000ll); E->launches++;
+        ghostsIn = reinterpret_cast<const GRec*>(P.box + stageOff);
+      } else T->alltoallv(M.sendBuf.p, sOffG.data(), sBytG.data(), M.recvBuf.p, rOffG.data(), rBytG.data(), st);
+      const int nNew = n + (int)accG;
+      Ast.ensure((size_t)std::max(nNew + 1024, 1), tot, /*keep*/ true, st); A = Ast.view();
+      if (n > 0) { k_dom_mark_dead<<<nblk(n, 256), 256, 0, st>>>(A.flags, n); E->launches++; }
+      if (accG > 0) { k_dom_unpack_ghosts<<<nblk(accG, 256), 256, 0, st>>>(A, n, (int)accG, ghostsIn, M.importId.p); E->launches++; }
+      M.oldIds.ensure((size_t)std::max(n, 1), tot); M.origSlot.ensure((size_t)std::max(nNew, 1), tot);
+      if (n > 0) CK(cudaMemcpyAsync(M.oldIds.p, A.id, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+      if (nNew > 0) { k_dom_orig_slot<<<nblk(nNew, 256), 256, 0, st>>>(A.id, nNew, E->id2slot.p, M.origSlot.p); E->launches++; }
+      if (n > 0) { k_dom_clear_id2slot<<<nblk(n, 256), 256, 0, st>>>(A.id, n, E->id2slot.p); E->launches++; }
+      E->n = nNew; M.deadSlots = nGhostOld; M.nImm = 0; E->up2slotValid = false;
+      if (tr) { TM(2); tacc[8] += std::chrono::duration<double, std::milli>(tp[1] - tp[0]).count(); tacc[9] += std::chrono::duration<double, std::milli>(tp[2] - tp[1]).count();
+        static int fcnt = 0; if (++fcnt % 25 == 0) { fprintf(stderr, "domainExchange trace (rank %d, last 25 of %d in-place calls): scan+counts %.3f ms, ghosts+bookkeeping %.3f ms\n", R, fcnt, tacc[8] / 25, tacc[9] / 25); tacc[8] = tacc[9] = 0; } }
+      return;
+    }
+  }
   // ---- 1. classify and group by destination; 2. what every rank sends to every other: counted on the device, exchanged from device memory (one host wait)
   std::vector<int> start(W + 3, 0);
   const size_t nn = std::max(n, 1);
@@ -376,7 +443,7 @@ void domainExchange(wdem_engine* E) {
   for (int k = 0; k < W + 3; k++) start[k] = hTab[k];
   if (n == 0) for (int k = 0; k < W + 3; k++) start[k] = 0;
   const int nKeep = start[1] - start[0], nE = start[W + 1] - start[1];
-  TM(1); TM(2); TM(3);
+  TM(1);
   std::vector<size_t> sOffP(W, 0), sBytP(W, 0), rOffP(W, 0), rBytP(W, 0), sOffR(W, 0), sBytR(W, 0), rOffR(W, 0), rBytR(W, 0);
   size_t nImmP = 0, nImmR = 0, accP = 0, accR = 0, accSR = 0;
   for (int r = 0; r < W; r++) {
@@ -398,7 +465,7 @@ void domainExchange(wdem_engine* E) {
   }
   T->alltoallv(M.sendBuf.p, sOffP.data(), sBytP.data(), M.recvBuf.p, rOffP.data(), rBytP.data(), st);
   T->alltoallv(M.sendBuf.p + sendRowsBase, sOffR.data(), sBytR.data(), M.recvBuf.p + recvRowsBase, rOffR.data(), rBytR.data(), st);
-  TM(4);
+  TM(2);
   // ---- 3. new owned set = kept + immigrants
   const int nOwn = nKeep + (int)nImmP;
   Bst.ensure((size_t)std::max(nOwn + (int)M.nRecvTot + 1024, 1), tot);
@@ -417,7 +484,7 @@ void domainExchange(wdem_engine* E) {
     cub::DeviceRadixSort::SortPairs(E->cubTemp.p, tb, M.immKeys.p, M.immKeysAlt.p, M.immVals.p, M.immValsAlt.p, (int)nImmR, 0, 64, st);
     E->launches += 4;
   }
-  TM(5);
+  TM(3);
   // ---- 5. ghost export: per-destination counts on the device, exchanged from device memory (the second and last host wait), one packing pass for all destinations
   M.emask.ensure((size_t)std::max(nOwn, 1), tot);
   int* dPer = M.perRank.p; int* dPerAll = M.perRank.p + WDEM_MAX_RANKS;
@@ -427,7 +494,7 @@ void domainExchange(wdem_engine* E) {
   std::vector<int> ga((size_t)W * WDEM_MAX_RANKS, 0);
   CK(cudaMemcpyAsync(ga.data(), dPerAll, ga.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  TM(6); TM(7);
+  TM(4);
   M.sendCnt.assign(W, 0); M.recvCnt.assign(W, 0);
   std::vector<size_t> sOffG(W, 0), sBytG(W, 0), rOffG(W, 0), rBytG(W, 0);
   size_t accS = 0, accG = 0;
@@ -447,15 +514,29 @@ void domainExchange(wdem_engine* E) {
   }
   M.sendBuf.ensure(accS * sizeof(GRec) + 64, tot); M.recvBuf.ensure(accG * sizeof(GRec) + 64, tot);
   M.exportId.ensure(std::max<size_t>(accS, 1), tot); M.importId.ensure(std::max<size_t>(accG, 1), tot);
-  if (accS > 0) {
-    CK(cudaMemsetAsync(dPer, 0, WDEM_MAX_RANKS * sizeof(int), st));      // reused as the per-destination cursors
-    k_dom_pack_ghosts_all<<<nblk(nOwn, 256), 256, 0, st>>>(B, nOwn, M.emask.p, W, seg, dPer, as<GRec>(M.sendBuf), M.exportId.p); E->launches++;
-  }
-  T->alltoallv(M.sendBuf.p, sOffG.data(), sBytG.data(), M.recvBuf.p, rOffG.data(), rBytG.data(), st);
+  if (accS > 0) CK(cudaMemsetAsync(dPer, 0, WDEM_MAX_RANKS * sizeof(int), st));      // reused as the per-destination cursors
+  // ghost records travel like the per-step halo when the mailboxes are up and large enough (the same decision on every rank: maxRecvTot is a global maximum; it is
+  // also peerSetup's criterion, so the mailboxes used here are not re-created by this full run): stored straight into the receiver's staging area over NVLink, then one
+  // release/acquire word per peer.  Otherwise (first full run, NCCL-only transports) ncclSend/ncclRecv — measured 0.4-2.5 ms per exchange for < 1 MB on the B200 boxes.
+  DomainState::Peer& P = M.peer;
+  const bool viaPeer = P.active && 9 * P.maxRecvTot <= P.haloCap;
+  const size_t stageOff = PEER_WORDS_BYTES + 2 * (size_t)P.haloCap * sizeof(double);
+  GhostDst gd; memset(&gd, 0, sizeof(gd));
+  for (int r = 0; r < W; r++) gd.out[r] = viaPeer ? reinterpret_cast<GRec*>(static_cast<char*>(P.base[r]) + stageOff) + P.dstOff[r] : as<GRec>(M.sendBuf) + seg.base[r];
+  if (accS > 0) { k_dom_pack_ghosts_all<<<nblk(nOwn, 256), 256, 0, st>>>(B, nOwn, M.emask.p, W, seg, dPer, gd, M.exportId.p); E->launches++; }
+  TM(5);
+  const GRec* ghostsIn = as<GRec>(M.recvBuf);
+  if (viaPeer) {
+    M.syncFlag.ensure(4, tot); CK(cudaMemsetAsync(M.syncFlag.p, 0, 4 * sizeof(int), st));
+    const PeerU u = makePeerU(E); const unsigned long long seq = ++P.syncSeq;
+    k_peer_sync<<<1, WDEM_MAX_RANKS, 0, st>>>(u, E->dCnt, M.syncFlag.p, seq, (int)(seq & 1), 20000000000ll); E->launches++;
+    ghostsIn = reinterpret_cast<const GRec*>(P.box + stageOff);
+  } else T->alltoallv(M.sendBuf.p, sOffG.data(), sBytG.data(), M.recvBuf.p, rOffG.data(), rBytG.data(), st);
+  TM(6);
   const int nNew = nOwn + (int)accG;
   Bst.ensure((size_t)std::max(nNew, 1), tot, /*keep*/ true, st); B = Bst.view();
-  if (accG > 0) { k_dom_unpack_ghosts<<<nblk(accG, 256), 256, 0, st>>>(B, nOwn, (int)accG, as<GRec>(M.recvBuf), M.importId.p); E->launches++; }
-  TM(8);
+  if (accG > 0) { k_dom_unpack_ghosts<<<nblk(accG, 256), 256, 0, st>>>(B, nOwn, (int)accG, ghostsIn, M.importId.p); E->launches++; }
+  TM(7);
   // ---- 6. bookkeeping for the history lookup of the full run that follows
   M.oldIds.ensure(nn, tot); M.origSlot.ensure((size_t)std::max(nNew, 1), tot);
   if (n > 0) CK(cudaMemcpyAsync(M.oldIds.p, A.id, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
@@ -464,13 +545,12 @@ void domainExchange(wdem_engine* E) {
   E->n = nNew; E->cur = 1 - E->cur; M.nOwn = nOwn; E->up2slotValid = false;
   M.migratedOut += nE; M.migratedIn += (long long)nImmP; M.rowsIn += (long long)nImmR;
   if (tr) {
-    TM(9); for (int k = 0; k < 9; k++) tacc[k] += std::chrono::duration<double, std::milli>(tp[k + 1] - tp[k]).count();
-    if (++tcnt % 50 == 0 && R == 0) { fprintf(stderr, "domainExchange trace (rank %d, mean of %d, ms): classify %.3f rows %.3f allgather1 %.3f sizes %.3f pack+a2a %.3f gather/unpack %.3f mask %.3f allgather2 %.3f ghosts %.3f | nE %d nImm %zu\n",
-                                    R, tcnt, tacc[0] / tcnt, tacc[1] / tcnt, tacc[2] / tcnt, tacc[3] / tcnt, tacc[4] / tcnt, tacc[5] / tcnt, tacc[6] / tcnt, tacc[7] / tcnt, tacc[8] / tcnt, nE, nImmP); }
+    TM(8); for (int k = 0; k < 8; k++) tacc[k] += std::chrono::duration<double, std::milli>(tp[k + 1] - tp[k]).count();
+    if (++tcnt % 50 == 0) { fprintf(stderr, "domainExchange trace (rank %d, mean of %d, ms): classify+counts %.3f | pack+a2a(migrants) %.3f | kept+unpack %.3f | mask+counts %.3f | ghost pack %.3f | ghost a2a %.3f | ghost unpack %.3f | bookkeeping %.3f | nE %d nImm %zu nGhostOut %zu\n",
+                                    R, tcnt, tacc[0] / tcnt, tacc[1] / tcnt, tacc[2] / tcnt, tacc[3] / tcnt, tacc[4] / tcnt, tacc[5] / tcnt, tacc[6] / tcnt, tacc[7] / tcnt, nE, nImmP, accS); }
   }
 }
 
-static const size_t PEER_WORDS_BYTES = 2 * WDEM_MAX_RANKS * sizeof(unsigned long long);
 void peerTeardown(wdem_engine* E, bool collective) {
   DomainState::Peer& P = E->dom.peer; Transport* T = E->comm;
   if (!P.box) return;
@@ -488,7 +568,7 @@ void peerSetup(wdem_engine* E) {
   if (P.active && need <= P.haloCap) return;      // same decision on every rank: maxRecvTot is a global maximum
   peerTeardown(E, true);
   P.haloCap = std::max<long long>(2 * need, 1 << 17);
-  const size_t bytes = PEER_WORDS_BYTES + 2 * (size_t)P.haloCap * sizeof(double);
+  const size_t bytes = PEER_WORDS_BYTES + 2 * (size_t)P.haloCap * sizeof(double) + (size_t)(P.haloCap / 9 + 1) * sizeof(GRec);      // words | halo x2 | ghost staging area (full runs)
   int64_t ok = 1; cudaIpcMemHandle_t hd; memset(&hd, 0, sizeof(hd));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
   if (cudaMalloc(&P.box, bytes) != cudaSuccess) { P.box = nullptr; ok = 0; cudaGetLastError(); }
@@ -569,13 +649,14 @@ void haloExchange(wdem_engine* E) {
 // -------------------------------------------------------------------------------------------------
 void rebuild(wdem_engine* E) {
   const wdem_config& c = E->cfg;
+  if (!E->comm) E->dom.deadSlots = 0;
   cudaStream_t st = E->stream;
   static const bool traceReb = getenv("WDEM_REBUILD_TRACE") != nullptr;
   auto now = [&] { if (traceReb) cudaStreamSynchronize(E->stream); return std::chrono::steady_clock::now(); };
   auto t0 = now();
   if (E->comm) domainExchange(E);   // migration + ghosts; leaves the new (unsorted) generation in the current store
   auto t1 = now();
-  const int n = E->n;
+  int n = E->n;
   const bool hertz = c.law == WDEM_LAW_HERTZ_DMT, rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.);
   const double vd = E->verletDist;
   int64_t& tot = E->bytes;
@@ -615,8 +696,9 @@ void rebuild(wdem_engine* E) {
     pu.unshear = E->cell.unshearTrsf; pu.size = E->cell.size; pu.cosv = E->cell.cosv; pu.hasShear = E->cell.hasShear ? 1 : 0;
   }
   if (n > 0) {
-    const int nb = nblk(n, 256);
+    int nb = nblk(n, 256);
     long long ncells = 0;
+    const int nDead = E->dom.deadSlots; E->dom.deadSlots = 0;      // slots flagged F_DEADSLOT: they get the key behind the last cell and are cut off after the sort
     E->keys.ensure(n, tot); E->keysAlt.ensure(n, tot); E->idx.ensure(n, tot); E->idxAlt.ensure(n, tot);
     if (!c.periodic) {
       // 1. bounds of sphere centres
@@ -652,7 +734,7 @@ void rebuild(wdem_engine* E) {
       }
       g.base[nL] = (int)ncells;
       // 3. cell keys
-      k_cellkeys<<<nb, 256, 0, st>>>(E->S().posr, n, g, E->keys.p, E->idx.p); E->launches++;
+      k_cellkeys<<<nb, 256, 0, st>>>(E->S().posr, n, g, E->keys.p, E->idx.p, nDead ? E->S().flags : nullptr, (uint32_t)ncells); E->launches++;
     } else {
       // periodic: per level nc[k] cells along each (unsheared) cell axis; the hash wraps, positions do not
       const d3 sz = E->cell.size;
@@ -678,14 +760,15 @@ void rebuild(wdem_engine* E) {
         ncells += (long long)g.n[L][0] * g.n[L][1] * g.n[L][2];
       }
       g.base[nL] = (int)ncells;
-      k_cellkeys_peri<<<nb, 256, 0, st>>>(E->S().posr, n, g, pu, E->keys.p, E->idx.p); E->launches++;
+      k_cellkeys_peri<<<nb, 256, 0, st>>>(E->S().posr, n, g, pu, E->keys.p, E->idx.p, nDead ? E->S().flags : nullptr, (uint32_t)ncells); E->launches++;
     }
     // radix sort by cell, reorder all sphere arrays into cell order
-    int keyBits = 1; while ((1ll << keyBits) < ncells) keyBits++;
+    int keyBits = 1; while ((1ll << keyBits) < ncells + (nDead ? 1 : 0)) keyBits++;
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, E->keys.p, E->keysAlt.p, E->idx.p, E->idxAlt.p, n, 0, keyBits, st);
     E->cubTemp.ensure(tb, tot);
     cub::DeviceRadixSort::SortPairs(E->cubTemp.p, tb, E->keys.p, E->keysAlt.p, E->idx.p, E->idxAlt.p, n, 0, keyBits, st); E->launches += 4;
+    if (nDead) { n -= nDead; E->n = n; nb = nblk(n, 256); }      // the dead slots sorted to the end: gone
     SphereStore& dst = E->sph[1 - E->cur];
     dst.ensure(n, tot);
     k_reorder<<<nb, 256, 0, st>>>(dst.view(), E->S(), E->idxAlt.p, n, E->id2slot.p); E->launches++;
@@ -828,7 +911,7 @@ void rebuild(wdem_engine* E) {
   if (traceReb) {
     auto t3 = now(); auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     static double acc[3] = {0, 0, 0}; static int cnt = 0; acc[0] += ms(t0, t1); acc[1] += ms(t1, t2); acc[2] += ms(t2, t3); cnt++;
-    if (cnt % 50 == 0) fprintf(stderr, "rebuild trace (rank %d, mean of %d): domainExchange %.3f ms, collider run %.3f ms, finish %.3f ms\n", E->comm ? E->comm->rank : 0, cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt);
+    if (cnt % 25 == 0) { fprintf(stderr, "rebuild trace (rank %d, mean of the last 25 of %d): domainExchange %.3f ms, collider run %.3f ms, finish %.3f ms\n", E->comm ? E->comm->rank : 0, cnt, acc[0] / 25, acc[1] / 25, acc[2] / 25); acc[0] = acc[1] = acc[2] = 0; }
   }
 }
 

@@ -10,7 +10,8 @@ namespace wd {
 enum { F_DOF_ALL = 63, F_CLUMPED = 64, F_CLUMP = 128, F_ENERGY_SKIP = 256, F_GRAVITY_SKIP = 512, F_DAMPING_SKIP = 2048 };
 // engine-internal bits kept in the same word (DemData.flags uses bits 0..11): ghost copy of a sphere owned by another subdomain;
 // sphere that migrated into this subdomain at the current collider full run
-enum : uint32_t { F_GHOST = 1u << 30, F_ARRIVED = 1u << 29 };
+// slot whose sphere left the arrays in place (a ghost of the previous generation): sorted behind the last cell and cut off by the collider full run
+enum : uint32_t { F_GHOST = 1u << 30, F_ARRIVED = 1u << 29, F_DEADSLOT = 1u << 28 };
 // contact flags
 enum { CF_REAL = 1, CF_ORPHAN = 2, CF_DEAD = 4, CF_CLAIMED = 8, CF_KIND_SHIFT = 4, CF_KIND_MASK = 3u << 4, CF_DORMANT = 64 };
 __host__ __device__ __forceinline__ int cf_kind(uint32_t f) { return (int)((f >> 4) & 3u); }
@@ -1321,9 +1322,10 @@ __device__ __forceinline__ int cellCoord(double x, double o, double inv, int n) 
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
-__global__ void __launch_bounds__(256) k_cellkeys(const double4* __restrict__ posr, int n, HGrid g, uint32_t* keys, int* idx) {
+__global__ void __launch_bounds__(256) k_cellkeys(const double4* __restrict__ posr, int n, HGrid g, uint32_t* keys, int* idx, const uint32_t* __restrict__ deadFlags, uint32_t deadKey) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (deadFlags && (deadFlags[i] & F_DEADSLOT)) { keys[i] = deadKey; idx[i] = i; return; }
   double4 p = posr[i];
   const int L = levelOf(g, p.w);
   int ix = cellCoord(p.x, g.ox, g.inv[L][0], g.n[L][0]), iy = cellCoord(p.y, g.oy, g.inv[L][1], g.n[L][1]), iz = cellCoord(p.z, g.oz, g.inv[L][2], g.n[L][2]);
@@ -1663,9 +1665,10 @@ __device__ __forceinline__ int overlapPeri(d3 mn1, d3 mx1, d3 mn2, d3 mx2, d3 si
 __device__ __forceinline__ int imod(int a, int n) { int m = a % n; return m < 0 ? m + n : m; }
 __device__ __forceinline__ double wrap01(double u, double size) { double xn = u / size; xn -= floor(xn); return xn * size; }
 
-__global__ void __launch_bounds__(256) k_cellkeys_peri(const double4* __restrict__ posr, int n, HGrid g, PeriU pu, uint32_t* keys, int* idx) {
+__global__ void __launch_bounds__(256) k_cellkeys_peri(const double4* __restrict__ posr, int n, HGrid g, PeriU pu, uint32_t* keys, int* idx, const uint32_t* __restrict__ deadFlags, uint32_t deadKey) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (deadFlags && (deadFlags[i] & F_DEADSLOT)) { keys[i] = deadKey; idx[i] = i; return; }
   const double4 p = posr[i];
   const int L = levelOf(g, p.w);
   const d3 u = mulMV(pu.unshear, xyz(p));
