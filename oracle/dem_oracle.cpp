@@ -231,9 +231,10 @@ struct Sphere {
   Aabb bb; V3 lastPos;
   bool dead = false;   // removed by ParticleContainer::remove (the slot stays: ids are not renumbered)
   int clump = -1;      // index of the clump this sphere is a member of (DemData::isClumped), -1: free
+  int impose = -1;     // index of the set of impositions on the node (DemData.impose), -1: none
 };
 struct Wall {
-  int id; V3 pos; int axis, sense; V3 vel, angVel; unsigned mask; int mat; V3 force, torque; Aabb bb; V3 lastPos;
+  int id; V3 pos; int axis, sense; V3 vel, angVel; unsigned mask; int mat; V3 force, torque; Aabb bb; V3 lastPos; int impose = -1;
   bool moving = false;   // Particle::guessMoving at ParticleContainer::add (ParticleContainer.cpp:193-198, Particle.cpp:638-640): a node with nonzero velocity
                          // enters DemField.nodes and is integrated by Leapfrog; a fixed wall at rest never is
 };
@@ -242,7 +243,41 @@ struct Facet {
 };
 // Master node of a clump of boundary particles that moves them rigidly (ParticleContainer::addClumped -> ClumpData::makeClump, Clump.cpp:187-261): a massless,
 // fully blocked node with prescribed vel/angVel (examples/mill.py:38-42) whose members are facets.  relPos are the members' node positions in the clump's frame.
-struct FacetGroup { V3 pos; Quat ori; V3 vel, angVel; std::vector<int> facets; std::vector<V3> relPos; };
+struct FacetGroup { V3 pos; Quat ori; V3 vel, angVel; std::vector<int> facets; std::vector<V3> relPos; int impose = -1; };
+// Impose (Particle.hpp:130-160, Impose.hpp, Impose.cpp): hooks called by Leapfrog on a node — velocity after the accelerations are applied and again at the end of
+// the node's step, force at the reset, readForce before the reset.  One descriptor per Impose object; a node refers to a SET of them (CombinedImpose, Impose.cpp:283-300).
+enum { IMP_HARMONIC = 1, IMP_ALIGNED_HARMONIC = 2, IMP_CONSTANT_FORCE = 3, IMP_RADIAL_FORCE = 4, IMP_LOCAL6 = 5, IMP_VEL_READ_FORCE = 6, IMP_READ_FORCE = 7, IMP_VARIABLE_VEL3D = 8,
+       IMP_VARIABLE_ALIGNED_ROTATION = 9 };
+enum { IMPW_VELOCITY = 1, IMPW_FORCE = 2, IMPW_READ_FORCE = 8 };
+struct ImposeDesc {
+  int kind = 0, flags = 0; double v[16] = {0}; Quat ori; std::vector<double> times, vals, vals2;
+  size_t ipos = 0, ipos2 = 0;                 // linearInterpolate's lookup cookies
+  double sumF = 0, dist = 0; V3 F, T;         // VelocityAndReadForce.sumF/.dist, ReadForce.F/.T
+  int nNodes = 0;                             // nodes carrying it
+  int what() const {
+    switch (kind) {
+      case IMP_HARMONIC: case IMP_ALIGNED_HARMONIC: case IMP_VARIABLE_VEL3D: case IMP_VARIABLE_ALIGNED_ROTATION: return IMPW_VELOCITY;
+      case IMP_CONSTANT_FORCE: case IMP_RADIAL_FORCE: return IMPW_FORCE;
+      case IMP_LOCAL6: return IMPW_VELOCITY | IMPW_FORCE;
+      case IMP_VEL_READ_FORCE: return IMPW_VELOCITY | IMPW_READ_FORCE;
+      case IMP_READ_FORCE: return IMPW_READ_FORCE;
+    }
+    return 0;
+  }
+};
+// linearInterpolate (supp/smoothing/LinearInterpolate.hpp:13-52) for values of `w` components per time point
+static inline void linInterp(Real t, const std::vector<double>& tt, const std::vector<double>& val, int w, size_t& _pos, double* out) {
+  size_t pos = _pos; const size_t n = tt.size();
+  const double *A, *B; Real rel;
+  if (t <= tt[0]) { _pos = 0; A = &val[0]; B = &val[(n > 1 ? 1 : 0) * w]; rel = 0.; }
+  else if (t >= tt[n - 1]) { _pos = n - 2; A = n > 1 ? &val[pos * w] : &val[(n - 1) * w]; B = &val[(n - 1) * w]; rel = 1.; }
+  else {
+    pos = std::min(pos, n - 2);
+    while ((tt[pos] > t) || (tt[pos + 1] < t)) { if (tt[pos] > t) pos--; else pos++; }
+    _pos = pos; A = &val[pos * w]; B = &val[(pos + 1) * w]; rel = (t - tt[pos]) / (tt[pos + 1] - tt[pos]);
+  }
+  for (int k = 0; k < w; k++) out[k] = (rel == 0.) ? A[k] : (rel == 1.) ? B[k] : A[k] + (B[k] - A[k]) * rel;
+}
 // Clump of spheres with mass (ClumpData, Clump.hpp:38-60): the master node carries mass / principal inertia and is integrated by Leapfrog (aspherical rotation when
 // the inertia components differ); member nodes are slaves (DemData::isClumped): positions, orientations and velocities follow, forces are collected from them.
 struct Clump {
@@ -386,6 +421,7 @@ struct Scene {
   long step = 0; Real time = 0; Real nextDt = NaN;
   // collider state
   std::vector<Bound> BB[3]; std::vector<Real> minima, maxima; int nFullRuns = 0; bool conDirty = false; bool verletSet = false;
+  std::vector<ImposeDesc> imposes; std::vector<std::vector<int>> imposeSets;
   std::vector<int> freeIds; std::vector<int> lastAdded;   // ParticleContainer::freeIds (ParticleContainer.cpp:23-36,125); ids handed out by the last orc_add_spheres
   long dynDtStepLast = -1, dynDtStepPrev = -1;
   std::string err;
@@ -1053,8 +1089,120 @@ struct Scene {
   // Leapfrog::run, spherical branch (Leapfrog.cpp:104-255,33-48,258-297)
   // ------------------------------------------------------------------------------------------
   static Real Sign(Real f) { if (f < 0) return -1; if (f > 0) return 1; return 0; }  // Math.hpp:145
+  // ---- Impose hooks; time-dependent values are evaluated once per step (they depend on Scene.time and Scene.dt only)
+  struct ImpStep { double vMag = 0; double vImp[3] = {0, 0, 0}, wImp[3] = {0, 0, 0}; };
+  std::vector<ImpStep> impStep;
+  void imposePrepareStep() {
+    impStep.assign(imposes.size(), ImpStep());
+    for (size_t i = 0; i < imposes.size(); i++) {
+      ImposeDesc& d = imposes[i]; ImpStep& r = impStep[i];
+      switch (d.kind) {
+        case IMP_HARMONIC: { const Real omega = 2 * M_PI * d.v[0]; r.vMag = d.v[1] * omega * std::cos(omega * (time - d.v[5])); break; }      // Impose.hpp:8-9
+        case IMP_ALIGNED_HARMONIC: for (int ax = 0; ax < 3; ax++) { if (std::isnan(d.v[ax]) || std::isnan(d.v[3 + ax])) { r.vImp[ax] = NaN; continue; } const Real omega = 2 * M_PI * d.v[ax]; r.vImp[ax] = d.v[3 + ax] * omega * std::cos(omega * time); } break;      // Impose.hpp:53-57
+        case IMP_VARIABLE_VEL3D: {      // Impose.cpp:196-205,216
+          if (d.times.empty()) throw std::runtime_error("VariableVelocity3d: times must not be empty.");
+          Real t = time + .5 * P.dt - d.v[0];
+          if ((d.flags & 2) && (t < 0 || t > d.times.back())) { const Real norm = t / d.times.back(); t = (norm - std::floor(norm)) * d.times.back(); }
+          linInterp(t, d.times, d.vals, 3, d.ipos, r.vImp);
+          if (!d.vals2.empty()) linInterp(t, d.times, d.vals2, 3, d.ipos2, r.wImp);
+          break;
+        }
+        case IMP_VARIABLE_ALIGNED_ROTATION: {      // Impose.cpp:95-100
+          Real t = time; if ((d.flags & 1) && t > d.times.back()) t = std::fmod(t, d.times.back());
+          linInterp(t, d.times, d.vals, 1, d.ipos, &r.vMag); break;
+        }
+        case IMP_VEL_READ_FORCE: if (d.nNodes > 0) { d.sumF = 0; d.dist += d.v[3] * P.dt; } break;      // the first node of the step resets (Impose.cpp:166-173)
+        case IMP_READ_FORCE: if (d.nNodes > 0) { d.F = V3(); d.T = V3(); } break;
+        default: break;
+      }
+    }
+  }
+  void imposeVelocity(int set, V3& vel, V3& angVel) {
+    for (int ix : imposeSets[set]) {
+      const ImposeDesc& d = imposes[ix]; const ImpStep& r = impStep[ix];
+      switch (d.kind) {
+        case IMP_HARMONIC: case IMP_VEL_READ_FORCE: {
+          const V3 dir(d.v[d.kind == IMP_HARMONIC ? 2 : 0], d.v[d.kind == IMP_HARMONIC ? 3 : 1], d.v[d.kind == IMP_HARMONIC ? 4 : 2]);
+          const Real mag = d.kind == IMP_HARMONIC ? r.vMag : d.v[3];
+          const bool lat = d.kind == IMP_HARMONIC ? !(d.flags & 1) : (d.flags & 1);      // HarmonicOscillation.perpFree (inverted) / VelocityAndReadForce.latBlock
+          if (lat) vel = dir * mag;
+          else { const V3 vLat = vel - dir * dot(vel, dir); vel = vLat + dir * mag; }      // Impose.hpp:11-12, Impose.cpp:158-161
+          break;
+        }
+        case IMP_ALIGNED_HARMONIC: for (int ax = 0; ax < 3; ax++) if (!std::isnan(r.vImp[ax])) vel[ax] = r.vImp[ax]; break;
+        case IMP_VARIABLE_VEL3D: {      // Impose.cpp:193-226
+          const bool rot = !(d.ori.w == 1 && d.ori.x == 0 && d.ori.y == 0 && d.ori.z == 0), diff = d.flags & 1;
+          const Quat qc(d.ori.w, -d.ori.x, -d.ori.y, -d.ori.z);
+          V3 v = rot ? quatRotate(qc, vel) : vel;
+          for (int ax = 0; ax < 3; ax++) v[ax] = (diff ? v[ax] : 0) + (std::isnan(r.vImp[ax]) ? (diff ? 0 : v[ax]) : r.vImp[ax]);
+          vel = rot ? quatRotate(d.ori, v) : v;
+          if (!d.vals2.empty()) {
+            V3 av = rot ? quatRotate(qc, angVel) : angVel;
+            for (int ax = 0; ax < 3; ax++) av[ax] = (diff ? av[ax] : 0) + (std::isnan(r.wImp[ax]) ? (diff ? 0 : av[ax]) : r.wImp[ax]);
+            angVel = rot ? quatRotate(d.ori, av) : av;
+          }
+          break;
+        }
+        case IMP_VARIABLE_ALIGNED_ROTATION: angVel[(int)d.v[0]] = r.vMag; break;
+        case IMP_LOCAL6: {      // Impose.cpp:72-82 (note: ori takes global to local here)
+          const Quat qc(d.ori.w, -d.ori.x, -d.ori.y, -d.ori.z);
+          for (int i = 0; i < 6; i++) {
+            if (!((int)d.v[6 + i] & IMPW_VELOCITY)) continue;
+            if (i < 3) { V3 loc = quatRotate(d.ori, vel); loc[i] = d.v[i]; vel = quatRotate(qc, loc); }
+            else { V3 loc = quatRotate(d.ori, angVel); loc[i % 3] = d.v[i]; angVel = quatRotate(qc, loc); }
+          }
+          break;
+        }
+        default: break;
+      }
+    }
+  }
+  void imposeForce(int set, const V3& pos, V3& force, V3& torque) {
+    for (int ix : imposeSets[set]) {
+      const ImposeDesc& d = imposes[ix];
+      switch (d.kind) {
+        case IMP_CONSTANT_FORCE: force += V3(d.v[0], d.v[1], d.v[2]); break;
+        case IMP_RADIAL_FORCE: {      // Impose.cpp:49-58
+          const V3 A(d.v[0], d.v[1], d.v[2]), B(d.v[3], d.v[4], d.v[5]);
+          const V3 ab = B - A; const V3 axis = ab / norm(ab);
+          const V3 C = A + axis * dot(pos - A, axis);
+          const V3 towards = C - pos;
+          if (sqNorm(towards) == 0) break;
+          force -= (towards / norm(towards)) * d.v[6];
+          break;
+        }
+        case IMP_LOCAL6: {      // Impose.cpp:83-87: the value replaces whatever was there (gravity included)
+          const Quat qc(d.ori.w, -d.ori.x, -d.ori.y, -d.ori.z);
+          for (int i = 0; i < 6; i++) {
+            if (!((int)d.v[6 + i] & IMPW_FORCE)) continue;
+            V3 u; u[i % 3] = 1;
+            if (i < 3) force = quatRotate(qc, d.v[i] * u); else torque = quatRotate(qc, d.v[i] * u);
+          }
+          break;
+        }
+        default: break;
+      }
+    }
+  }
+  void imposeReadForce(int set, const V3& pos, const V3& force, const V3& torque) {
+    for (int ix : imposeSets[set]) {
+      ImposeDesc& d = imposes[ix];
+      if (d.kind == IMP_VEL_READ_FORCE) {      // Impose.cpp:175-177
+        const Real f = dot(force, V3(d.v[0], d.v[1], d.v[2]));
+        #pragma omp critical(impose_read)
+        d.sumF += ((d.flags & 2) ? -1 : 1) * f;
+      } else if (d.kind == IMP_READ_FORCE) {   // Impose.cpp:144-155
+        #pragma omp critical(impose_read)
+        {
+          if (!(d.flags & 1)) { d.F += force; d.T += torque; }
+          else { const Quat qc(d.ori.w, -d.ori.x, -d.ori.y, -d.ori.z); d.F += quatRotate(qc, force); d.T += quatRotate(qc, torque + cross(pos - V3(d.v[0], d.v[1], d.v[2]), force)); }
+        }
+      }
+    }
+  }
   void leapfrogRun() {
     const Real dt = P.dt; const Real damping = P.damping;
+    imposePrepareStep();
     const int homoDeform = P.periodic ? cell.homoDeform : -1;
     M3 dGradV = subMM(cell.nextGradV, cell.gradV);
     M3 midGradV = scaleM(addMM(cell.gradV, cell.nextGradV), .5);
@@ -1113,6 +1261,7 @@ struct Scene {
           s.angVel += dt * angAccel;
           if (homoDeform == HOMO_GRADV2) s.angVel -= deltaSpinVec;
         }
+        if (s.impose >= 0) imposeVelocity(s.impose, s.vel, s.angVel);      // re-applied to cancel the effect of forces (Leapfrog.cpp:203-205)
       } else {
         if (homoDeform == HOMO_GRADV2) s.vel = mulMV(ImLL4hInv, mulMV(LmL, s.pos) + mulMV(IpLL4h, s.vel));
       }
@@ -1142,10 +1291,13 @@ struct Scene {
         s.ori = quatMul(q, s.ori);
       }
       quatNormalize(s.ori);
+      if (s.impose >= 0) imposeReadForce(s.impose, s.pos, s.force, s.torque);      // Leapfrog.cpp:238
       if (P.reset) {
         s.force = (hasGravity && !(fl & GRAVITY_SKIP)) ? (s.mass * g) : V3();
         s.torque = V3();
+        if (s.impose >= 0) imposeForce(s.impose, s.pos, s.force, s.torque);        // Leapfrog.cpp:244
       }
+      if (s.impose >= 0) imposeVelocity(s.impose, s.vel, s.angVel);                // Leapfrog.cpp:248
     }
     // clump master nodes (Leapfrog.cpp:148-255 with isClump): forces from the members, spherical or aspherical rotation, then the members follow
     if (!clumps.empty()) {
@@ -1237,6 +1389,7 @@ struct Scene {
         G.ori = quatMul(q, G.ori);
       }
       quatNormalize(G.ori);
+      if (G.impose >= 0) imposeVelocity(G.impose, G.vel, G.angVel);      // before applyToMembers (Leapfrog.cpp:248-252)
       for (size_t k = 0; k < G.facets.size(); k++) {
         Facet& f = facets[G.facets[k]];
         for (int i = 0; i < 3; i++) {
@@ -1250,6 +1403,7 @@ struct Scene {
       if (P.periodic) throw std::runtime_error("moving walls in a periodic cell are not supported");
       w.pos += w.vel * dt;
       if (P.reset) { w.force = V3(); w.torque = V3(); }
+      if (w.impose >= 0) { V3 dummyW; imposeVelocity(w.impose, w.vel, dummyW); }      // fully blocked node: only the call at the end of the node's step (Leapfrog.cpp:248)
     }
   }
 
@@ -1501,6 +1655,34 @@ int orc_add_clump(void* h, int n, const int* sphereIds, const double* pos, const
   for (size_t k = 0; k < c.members.size(); k++) { Sphere& ms = S->sph[c.members[k]]; ms.vel = c.vel + cross(c.angVel, ms.pos - c.pos); ms.angVel = c.angVel; }
   S->clumps.push_back(c); S->conDirty = true;
   ORC_CATCH(h)
+}
+// Impose: descriptors, sets of descriptors (CombinedImpose), attachment to nodes.  v[16]: HARMONIC freq, amp, dir(3, normalized), t0 [flags&1: perpFree] |
+// ALIGNED_HARMONIC freqs(3), amps(3) | CONSTANT_FORCE F(3) | RADIAL_FORCE A(3), B(3), F | LOCAL6 values(6), whats(6) + ori | VEL_READ_FORCE dir(3), vel [flags&1 latBlock, &2 invF] |
+// READ_FORCE node pos(3) + ori [flags&1: has node] | VARIABLE_VEL3D t0 + ori + times/vals(/vals2 = angVels) [flags&1 diff, &2 wrap] | VARIABLE_ALIGNED_ROTATION axis + times/vals(1 per time) [flags&1 wrap]
+int orc_add_impose(void* h, int kind, int flags, const double* v, const double* ori /*x,y,z,w or NULL*/, int nTimes, const double* times, const double* vals, const double* vals2) {
+  Scene* S = (Scene*)h;
+  ImposeDesc d; d.kind = kind; d.flags = flags; for (int k = 0; k < 16; k++) d.v[k] = v ? v[k] : 0.;
+  if (ori) d.ori = Quat(ori[3], ori[0], ori[1], ori[2]);
+  const int w = kind == IMP_VARIABLE_ALIGNED_ROTATION ? 1 : 3;
+  if (nTimes > 0) { d.times.assign(times, times + nTimes); d.vals.assign(vals, vals + (size_t)w * nTimes); if (vals2) d.vals2.assign(vals2, vals2 + (size_t)w * nTimes); }
+  S->imposes.push_back(d);
+  return (int)S->imposes.size() - 1;
+}
+int orc_add_impose_set(void* h, int n, const int* ops) { Scene* S = (Scene*)h; S->imposeSets.push_back(std::vector<int>(ops, ops + n)); return (int)S->imposeSets.size() - 1; }
+// kind of node: 0 sphere (particle id), 1 wall (particle id), 2 facet group (index)
+int orc_attach_impose(void* h, int nodeKind, int which, int set) {
+  Scene* S = (Scene*)h;
+  ORC_TRY(h)
+  if (set < 0 || set >= (int)S->imposeSets.size()) throw std::runtime_error("impose set out of range");
+  bool readF = false; for (int ix : S->imposeSets[set]) { S->imposes[ix].nNodes++; if (S->imposes[ix].what() & IMPW_READ_FORCE) readF = true; }
+  if (nodeKind == 0) { if (which < 0 || which >= (int)S->par.size() || S->par[which].kind != SHAPE_SPHERE) throw std::runtime_error("impose: not a sphere"); S->sph[S->par[which].idx].impose = set; }
+  else if (nodeKind == 1) { if (which < 0 || which >= (int)S->par.size() || S->par[which].kind != SHAPE_WALL) throw std::runtime_error("impose: not a wall"); if (readF) throw std::runtime_error("readForce on walls is not part of this path"); Wall& w = S->walls[S->par[which].idx]; w.impose = set; w.moving = true; /* DemData::guessMoving: || impose (Particle.cpp:639) */ }
+  else { if (which < 0 || which >= (int)S->groups.size()) throw std::runtime_error("impose: no such facet group"); if (readF) throw std::runtime_error("readForce on facet groups is not part of this path"); S->groups[which].impose = set; }
+  ORC_CATCH(h)
+}
+void orc_get_impose_state(void* h, int ix, double* out /*sumF, dist, F(3), T(3)*/) {
+  const ImposeDesc& d = ((Scene*)h)->imposes[ix];
+  out[0] = d.sumF; out[1] = d.dist; for (int k = 0; k < 3; k++) { out[2 + k] = d.F[k]; out[5 + k] = d.T[k]; }
 }
 void orc_get_clumps(void* h, double* pos, double* ori, double* vel, double* angVel) {
   Scene* S = (Scene*)h;

@@ -95,6 +95,19 @@ class Oracle:
         else:
             add_spheres(); add_boundaries()
         ids = S.sphere_ids()
+        for d in getattr(S, "imposes", []):
+            nt = len(d["times"])
+            L.orc_add_impose(h, C.c_int(d["kind"]), C.c_int(d["flags"]), _p(np.ascontiguousarray(d["v"]), C.c_double), _p(np.ascontiguousarray(d["ori"]), C.c_double), C.c_int(nt),
+                             _p(np.ascontiguousarray(d["times"]), C.c_double) if nt else None, _p(np.ascontiguousarray(d["vals"]), C.c_double) if nt else None,
+                             _p(np.ascontiguousarray(d["vals2"]), C.c_double) if len(d["vals2"]) else None)
+        for st in getattr(S, "impose_sets", []):
+            a = np.ascontiguousarray(st, dtype=np.int32); L.orc_add_impose_set(h, C.c_int(len(a)), _p(a, C.c_int))
+        for kind, arr, idof in ((0, getattr(S, "sphere_impose", None), lambda i: int(ids[i])), (1, getattr(S, "wall_impose", None), lambda i: int(S.wall_ids()[i])), (2, getattr(S, "group_impose", None), lambda i: i)):
+            if arr is None:
+                continue
+            for i, k in enumerate(arr):
+                if k >= 0:
+                    self._chk(L.orc_attach_impose(h, C.c_int(kind), C.c_int(idof(i)), C.c_int(int(k))))
         for c in getattr(S, "clumps", []):
             a = lambda k: np.ascontiguousarray(c[k], dtype=np.float64)
             mem = np.ascontiguousarray(ids[np.asarray(c["members"], dtype=np.int64)], dtype=np.int32)
@@ -161,6 +174,11 @@ class Oracle:
     def remove_spheres(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         self._chk(self.L.orc_remove_spheres(self.h, C.c_int(len(ids)), _p(ids, C.c_int)))
+
+    def impose_state(self, ix):
+        """sumF, dist (VelocityAndReadForce), F, T (ReadForce) of impose descriptor ix"""
+        o = np.zeros(8); self.L.orc_get_impose_state(self.h, C.c_int(ix), _p(o, C.c_double))
+        return dict(sumF=o[0], dist=o[1], F=o[2:5].copy(), T=o[5:8].copy())
 
     def clumps(self):
         n = len(getattr(self.spec, "clumps", []))

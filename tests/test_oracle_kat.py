@@ -510,3 +510,77 @@ def test_clump_falls_like_a_point_mass_and_lands_on_a_wall():
     assert len(c["ids"]) == 2 and abs(cl["vel"][0, 2]) < 1e-3                                    # both spheres rest on the wall
     fz = c["force"][:, 0].sum()                                                                   # normal forces carry the clump's weight
     assert abs(fz) == pytest.approx(S.clumps[0]["mass"] * 9.81, rel=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Impose (Particle.hpp:130-160, Impose.hpp, Impose.cpp; hooks in Leapfrog.cpp:203-205,238,244,248)
+# ---------------------------------------------------------------------------------------------------------------
+def _free_spheres(n=1, gravity=(0, 0, 0), damping=0., dt=1e-4, r=.05):
+    S = sc.SceneSpec()
+    S.mats = [sc.frict_mat(density=1000., young=1e6, tanPhi=.4)]
+    S.pos = np.array([[.5 * i, 0., 1.] for i in range(n)]); S.radius = np.full(n, r)
+    S.params = sc.Params(gravity=gravity, damping=damping, dynDtPeriod=0, dt=dt)
+    return S.finalize()
+
+
+def test_impose_harmonic_oscillation_follows_a_sine():
+    S = _free_spheres(2, gravity=(0, 0, -9.81))
+    f, A = 5., .02
+    sc.attach_impose(S, [sc.imp_harmonic(f, A, dir=(1, 0, 0))], spheres=[0])                    # all other velocity components zeroed: gravity has no effect
+    sc.attach_impose(S, [sc.imp_harmonic(f, A, dir=(0, 3, 0), perpFree=True)], spheres=[1])      # only the y component is prescribed: the sphere falls freely in z
+    O = Oracle(S)
+    N = 1000; O.step(N); t = N * 1e-4
+    s = O.spheres()
+    assert s["pos"][0, 0] == pytest.approx(A * math.sin(2 * math.pi * f * t), abs=2e-4) and s["pos"][0, 2] == 1. and s["pos"][0, 1] == 0.
+    assert s["vel"][0, 0] == pytest.approx(A * 2 * math.pi * f * math.cos(2 * math.pi * f * (t - 1e-4)), rel=1e-12)     # evaluated with the time of the last step
+    assert s["pos"][1, 1] == pytest.approx(A * math.sin(2 * math.pi * f * t), abs=2e-4)
+    assert s["pos"][1, 2] == pytest.approx(1. - .5 * 9.81 * t * (t - 1e-4), rel=1e-9)
+
+
+def test_impose_forces_constant_radial_local6():
+    S = _free_spheres(3)
+    m = S.mass_inertia()[0]
+    sc.attach_impose(S, [sc.imp_constant_force((0, 2., 0))], spheres=[0])
+    S.pos[1] = (.5, .3, 1.)
+    sc.attach_impose(S, [sc.imp_radial_force((.5, 0, 0), (.5, 0, 5), -1.5)], spheres=[1])        # negative: towards the axis x=.5,y=0
+    sc.attach_impose(S, [sc.imp_local6((0, 0, 3., 0, 0, 0), (0, 0, 2, 0, 0, 0)), sc.imp_constant_force((1., 0, 0))], spheres=[2])       # CombinedImpose: later ones see the earlier ones' result
+    O = Oracle(S)
+    O.step(1)
+    f = O.spheres()["force"]
+    assert np.array_equal(f[0], [0, 2., 0])
+    assert np.allclose(f[1], [0, -1.5, 0], atol=1e-15)
+    assert np.array_equal(f[2], [1., 0, 3.])
+    O.step(100); t = 100 * 1e-4
+    assert O.spheres()["vel"][0, 1] == pytest.approx(2. / m[0] * t, rel=1e-9)
+
+
+def test_impose_velocity_and_read_force_on_a_pushed_sphere():
+    """A sphere driven against a fixed one at constant velocity: sumF is the contact force along dir (of the previous step), dist the path."""
+    S = _free_spheres(2)
+    S.pos[1] = (.1 + 1e-6, 0, 1.); S.flags[1] = 63
+    k = sc.attach_impose(S, [sc.imp_velocity_and_read_force((2, 0, 0), .05, invF=True), sc.imp_read_force()], spheres=[0])
+    O = Oracle(S)
+    O.step(200)
+    st, st2 = O.impose_state(S.impose_sets[k][0]), O.impose_state(S.impose_sets[k][1])
+    s, c = O.spheres(), O.contacts(True)
+    assert st["dist"] == pytest.approx(200 * 1e-4 * .05, rel=1e-12) and s["pos"][0, 0] == pytest.approx(st["dist"], rel=1e-9)      # a free node: the velocity is imposed before the first translation
+    assert len(c["ids"]) == 1 and st["sumF"] > 0
+    O.step(1)
+    # what step 201 read is the force left by step 200's contact loop
+    assert O.impose_state(S.impose_sets[k][0])["sumF"] == pytest.approx(-s["force"][0, 0], rel=1e-12)
+    assert np.allclose(O.impose_state(S.impose_sets[k][1])["F"], s["force"][0], rtol=1e-12)
+    assert st2["F"][0] == pytest.approx(-st["sumF"], rel=1e-12)
+
+
+def test_impose_variable_velocity_on_a_wall_and_table_semantics():
+    S = _free_spheres(1, gravity=(0, 0, -9.81))
+    S.walls = [dict(pos=(0, 0, .9), axis=2, sense=1, mat=0, mask=sc.MASK_BOUNDARY)]
+    S.finalize()
+    nan = float("nan")
+    sc.attach_impose(S, [sc.imp_variable_velocity3d([0., .01, .02], [(0, 0, 0), (nan, 0, .5), (nan, 0, .5)])], walls=[0])
+    O = Oracle(S)
+    O.step(300)       # t = .03: ramp 0 -> .5 over [0,.01], then constant
+    w = O.walls()
+    z_expected = .9 + (.5 * .5 * .01 + .5 * .02)
+    assert w["pos"][0, 2] == pytest.approx(z_expected, abs=2 * .5 * 1e-4)
+    assert O.nFullRuns > 1

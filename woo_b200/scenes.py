@@ -64,6 +64,12 @@ class SceneSpec:
     flags: np.ndarray = None
     walls: list = field(default_factory=list)  # dict(pos, axis, sense, mat, mask, vel)
     facets: list = field(default_factory=list)  # dict(v(3,3), halfThick, fakeVel, n21lim, vvel, mat, mask)
+    # Impose (Particle.hpp:130-160, Impose.hpp): descriptors (imp_* helpers below), sets of descriptor indices (CombinedImpose), and per node the index of its set (-1: none)
+    imposes: list = field(default_factory=list)
+    impose_sets: list = field(default_factory=list)
+    sphere_impose: object = None        # int array per sphere (index into impose_sets), or None
+    wall_impose: object = None          # int array per wall
+    group_impose: object = None         # int array per facet group
     clumps: list = field(default_factory=list)  # rigid aggregates of spheres with mass: dict(members=[sphere indices], pos, ori (x,y,z,w), vel, angVel, mass, inertia(3), flags); see make_clumps
     facet_groups: list = field(default_factory=list)  # kinematic groups: dict(pos, ori (x,y,z,w), vel, angVel, facets=[indices into ``facets``])
     params: Params = field(default_factory=Params)
@@ -117,6 +123,78 @@ def frict_mat(density=1e3, young=1e7, ktDivKn=.2, tanPhi=math.tan(.5)):
 
 def hertz_mat(density=1e3, young=1e8, ktDivKn=.2, tanPhi=.5, surfEnergy=0.0, alpha=0.0):
     return (MAT_HERTZ, density, young, ktDivKn, tanPhi, surfEnergy, alpha)
+
+
+# ---- Impose descriptors (wdem.h: wdem_impose; kinds and the meaning of v[16] follow include/wdem.h)
+IMP_HARMONIC, IMP_ALIGNED_HARMONIC, IMP_CONSTANT_FORCE, IMP_RADIAL_FORCE, IMP_LOCAL6, IMP_VEL_READ_FORCE, IMP_READ_FORCE, IMP_VARIABLE_VEL3D, IMP_VARIABLE_ALIGNED_ROTATION = range(1, 10)
+
+
+def _imp(kind, flags=0, v=(), ori=(0, 0, 0, 1), times=(), vals=(), vals2=()):
+    vv = np.zeros(16); vv[:len(v)] = v
+    return dict(kind=kind, flags=int(flags), v=vv, ori=np.asarray(ori, dtype=np.float64), times=np.asarray(times, dtype=np.float64),
+                vals=np.asarray(vals, dtype=np.float64).reshape(-1), vals2=np.asarray(vals2, dtype=np.float64).reshape(-1))
+
+
+def _unit(d):
+    d = np.asarray(d, dtype=np.float64); return d / math.sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])       # Eigen normalize()
+
+
+def imp_harmonic(freq, amp, dir=(1, 0, 0), t0=0., perpFree=False):
+    """HarmonicOscillation (Impose.hpp:5-25)"""
+    return _imp(IMP_HARMONIC, 1 if perpFree else 0, [freq, amp, *_unit(dir), t0])
+
+
+def imp_aligned_harmonic(freqs, amps):
+    """AlignedHarmonicOscillations (Impose.hpp:49-65); NaN frequency: axis untouched"""
+    return _imp(IMP_ALIGNED_HARMONIC, 0, [*freqs, *amps])
+
+
+def imp_constant_force(F):
+    return _imp(IMP_CONSTANT_FORCE, 0, F)
+
+
+def imp_radial_force(A, B, F):
+    return _imp(IMP_RADIAL_FORCE, 0, [*A, *B, F])
+
+
+def imp_local6(values, whats, ori=(0, 0, 0, 1)):
+    """Local6Dofs (Impose.hpp:90-110): whats 0 nothing, 1 velocity, 2 force per local DoF"""
+    return _imp(IMP_LOCAL6, 0, [*values, *whats], ori)
+
+
+def imp_velocity_and_read_force(dir, vel, latBlock=True, invF=False):
+    return _imp(IMP_VEL_READ_FORCE, (1 if latBlock else 0) | (2 if invF else 0), [*_unit(dir), vel])
+
+
+def imp_read_force(node_pos=None, node_ori=(0, 0, 0, 1)):
+    return _imp(IMP_READ_FORCE, 0 if node_pos is None else 1, (0, 0, 0) if node_pos is None else node_pos, node_ori)
+
+
+def imp_variable_velocity3d(times, vels, angVels=(), ori=(0, 0, 0, 1), diff=False, wrap=False, t0=0.):
+    return _imp(IMP_VARIABLE_VEL3D, (1 if diff else 0) | (2 if wrap else 0), [t0], ori, times, vels, angVels)
+
+
+def imp_variable_aligned_rotation(axis, timeAngVel, wrap=False):
+    ta = np.asarray(timeAngVel, dtype=np.float64).reshape(-1, 2)
+    return _imp(IMP_VARIABLE_ALIGNED_ROTATION, 1 if wrap else 0, [axis], (0, 0, 0, 1), ta[:, 0], ta[:, 1])
+
+
+def attach_impose(S, ops, spheres=(), walls=(), groups=()):
+    """Put the impositions `ops` (descriptor dicts; several = CombinedImpose) on the given sphere / wall / facet-group indices."""
+    ix = []
+    for o in ops:
+        S.imposes.append(o); ix.append(len(S.imposes) - 1)
+    S.impose_sets.append(ix); k = len(S.impose_sets) - 1
+    if len(spheres):
+        if S.sphere_impose is None: S.sphere_impose = np.full(len(S.pos), -1, np.int32)
+        S.sphere_impose[np.asarray(spheres, dtype=np.int64)] = k
+    if len(walls):
+        if S.wall_impose is None: S.wall_impose = np.full(len(S.walls), -1, np.int32)
+        S.wall_impose[np.asarray(walls, dtype=np.int64)] = k
+    if len(groups):
+        if S.group_impose is None: S.group_impose = np.full(len(S.facet_groups), -1, np.int32)
+        S.group_impose[np.asarray(groups, dtype=np.int64)] = k
+    return k
 
 
 CLUMP_CLUMPED = 64      # DemData flag of a member node (src/dem/Particle.hpp:200)
