@@ -76,6 +76,27 @@ typedef struct wdem_stats {
   int64_t sum_contacts, sum_real, sum_potential_evaluated;           /* summed over the steps of this call (roofline accounting) */
 } wdem_stats;
 
+/* One Impose object (src/dem/Particle.hpp:130-160, src/dem/Impose.hpp, Impose.cpp): the hooks Leapfrog calls on a node that carries DemData.impose — velocity
+ * after the accelerations were applied and again at the end of the node's step (Leapfrog.cpp:203-205,248), force at the reset (:244), readForce before the reset (:238).
+ * kind and the meaning of v[16] / flags:
+ *  1 HarmonicOscillation          v = freq, amp, dir(3, normalized), t0; flags&1 perpFree
+ *  2 AlignedHarmonicOscillations  v = freqs(3), amps(3); NaN: axis untouched
+ *  3 ConstantForce                v = F(3)
+ *  4 RadialForce                  v = nodeA.pos(3), nodeB.pos(3), F
+ *  5 Local6Dofs                   v = values(6), whats(6; 0 nothing, 1 velocity, 2 force); ori
+ *  6 VelocityAndReadForce         v = dir(3, normalized), vel, dist (its value at upload); flags&1 latBlock, &2 invF (energyName is not supported)
+ *  7 ReadForce                    flags&1: node given, v = node.pos(3), ori = node.ori
+ *  8 VariableVelocity3d           v = t0; ori; times[nTimes], vals = vels (3 per time), vals2 = angVels (3 per time) or NULL; flags&1 diff, &2 wrap (hooks are not supported)
+ *  9 VariableAlignedRotation      v = axis; times/vals = timeAngVel columns (1 value per time); flags&1 wrap
+ * Not on this path: CircularOrbit, StableCircularOrbit, InterpolatedMotion. */
+typedef struct wdem_impose {
+  int32_t kind, flags;
+  double v[16];
+  double ori[4];                 /* x,y,z,w */
+  int32_t nTimes; int32_t pad;
+  const double* times; const double* vals; const double* vals2;
+} wdem_impose;
+
 int wdem_default_config(wdem_config* cfg);
 int wdem_create(const wdem_config* cfg, wdem_handle* out);
 int wdem_destroy(wdem_handle h);
@@ -141,6 +162,18 @@ int64_t wdem_num_clumps(wdem_handle h);
 /* DemData.force / torque of the master nodes at upload time (3 per clump; either may be NULL = zero): what a scene that has already run carries there
  * (mass*gravity after Leapfrog's reset).  Only right after wdem_upload_clumps. */
 int wdem_upload_clump_forces(wdem_handle h, const double* force, const double* torque);
+/* DemData.impose of the scene's nodes.  imp[nImp]: the Impose objects; a node refers to a SET of them (CombinedImpose, Impose.cpp:283-300: applied in order):
+ * set s = setOps[setStart[s] .. setStart[s+1]).  Spheres: sphereSet[k] is the set of the sphere with particle id sphereIds[k]; wallSet / groupSet: per uploaded wall /
+ * per facet group, -1 none, NULL = none at all.  A wall that carries an imposition is integrated like one added with a velocity (DemData::guessMoving, Particle.cpp:638-640).
+ * Walls and facet-group master nodes (all DOFs blocked) take velocity impositions only; the read-force kinds work on spheres, single-device runs.
+ * Time-dependent factors are evaluated by the host with libm once per step (they depend on Scene.time and Scene.dt only).  Call after the particles are uploaded, before
+ * the first step; at most 16 Impose objects.  Not with wdem_step_e2e. */
+int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int32_t nSets, const int32_t* setStart, const int32_t* setOps, int64_t nSphereIds,
+                        const int32_t* sphereIds, const int32_t* sphereSet, const int32_t* wallSet, const int32_t* groupSet);
+/* Velocities of the boundary nodes an imposition may have changed: 3 per uploaded wall, 3 + 3 per facet group; any pointer may be NULL. */
+int wdem_download_boundary_velocities(wdem_handle h, double* wallVel, double* groupVel, double* groupAngVel);
+/* out[8]: VelocityAndReadForce.sumF, .dist; ReadForce.F(3), .T(3) of Impose object ix after the last step (sums of what the last step's Leapfrog read). */
+int wdem_get_impose_state(wdem_handle h, int32_t ix, double* out);
 /* Facet node positions (9 per facet, upload order) and the groups' master nodes after the last step; any pointer may be NULL. */
 int wdem_download_facets(wdem_handle h, double* verts, double* groupPos, double* groupOri);
 int wdem_set_cell(wdem_handle h, const double* hSize, const double* gradV, const double* nextGradV, int homoDeform);

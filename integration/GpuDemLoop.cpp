@@ -6,6 +6,7 @@
 #include"Wall.hpp"
 #include"Facet.hpp"
 #include"Clump.hpp"
+#include"Impose.hpp"
 #include"FrictMat.hpp"
 #include"Hertz.hpp"
 #include"IdealElPl.hpp"
@@ -82,6 +83,7 @@ void GpuDemLoop::upload(){
 	};
 	vector<int32_t> sid,smat,wid,waxis,wsense,wmat,fid,fmat; vector<uint32_t> sflags,smask,wmask,fmask;
 	vector<double> spos,sori,svel,sang,smass,sin,srad,sfrc,strq,wpos,wvel,fv,fvv,ffk,fht,fnl;
+	vector<shared_ptr<Impose>> sphImpose; vector<int32_t> sphImposeId;
 	sphereOf.clear(); wallOf.clear(); facetOf.clear();
 	for(const auto& p: *dem.particles){
 		if(!p) continue;
@@ -90,7 +92,7 @@ void GpuDemLoop::upload(){
 		if(auto* s=dynamic_cast<Sphere*>(p->shape.get())){
 			const Node& n=*s->nodes[0]; const DemData& d=n.getData<DemData>();
 			if(d.isClump()) throw std::runtime_error("GpuDemLoop: particle #"+to_string(p->id)+": a clump's master node cannot be the node of a particle");      // members (isClumped) are fine: wdem_upload_clumps below
-			if(d.impose) throw std::runtime_error("GpuDemLoop: DemData.impose is not supported (particle #"+to_string(p->id)+")");
+			if(d.impose){ sphImpose.push_back(d.impose); sphImposeId.push_back(p->id); }
 			if(!(d.inertia[0]==d.inertia[1] && d.inertia[1]==d.inertia[2])) throw std::runtime_error("GpuDemLoop: aspherical inertia is not supported (particle #"+to_string(p->id)+")");
 			sid.push_back(p->id); smat.push_back(m); sflags.push_back(d.flags); smask.push_back(p->mask);
 			for(int k:{0,1,2}){ spos.push_back(n.pos[k]); svel.push_back(d.vel[k]); sang.push_back(d.angVel[k]); sfrc.push_back(d.force[k]); strq.push_back(d.torque[k]); }
@@ -159,6 +161,7 @@ void GpuDemLoop::upload(){
 			chk(h,wdem_upload_clump_forces(h,cf.data(),ct.data()));
 		}
 	}
+	uploadImposes(sphImpose,sphImposeId);
 	if(scene->isPeriodic){
 		const Cell& C=*scene->cell; double H[9],G[9],N[9];
 		for(int i:{0,1,2}) for(int j:{0,1,2}){ H[3*i+j]=C.hSize(i,j); G[3*i+j]=C.gradV(i,j); N[3*i+j]=C.nextGradV(i,j); }
@@ -167,6 +170,59 @@ void GpuDemLoop::upload(){
 	chk(h,wdem_set_scene(h,(int64_t)scene->step,scene->time));
 	pushContacts();
 	nParticlesUploaded=dem.particles->size(); stepUploaded=scene->step;
+}
+
+// DemData.impose -> wdem_upload_imposes: one wdem_impose per distinct Impose object, one set per distinct DemData.impose (a CombinedImpose is a set of several)
+void GpuDemLoop::uploadImposes(const vector<shared_ptr<Impose>>& sphImpose, const vector<int32_t>& sphImposeId){
+	DemField& dem=field->cast<DemField>();
+	imposeOf.clear();
+	vector<wdem_impose> imps; vector<vector<double>> keep; std::map<Impose*,int> ixOf; std::map<Impose*,int> setOf; vector<int32_t> setStart{0},setOps;
+	auto q4=[](double* o, const Quaternionr& q){ o[0]=q.x(); o[1]=q.y(); o[2]=q.z(); o[3]=q.w(); };
+	std::function<int(const shared_ptr<Impose>&)> one=[&](const shared_ptr<Impose>& I)->int{
+		auto it=ixOf.find(I.get()); if(it!=ixOf.end()) return it->second;
+		wdem_impose w; memset(&w,0,sizeof(w)); w.ori[3]=1;
+		if(auto* h=dynamic_cast<HarmonicOscillation*>(I.get())){ w.kind=1; w.flags=h->perpFree?1:0; w.v[0]=h->freq; w.v[1]=h->amp; for(int k:{0,1,2}) w.v[2+k]=h->dir[k]; w.v[5]=h->t0; }
+		else if(auto* a=dynamic_cast<AlignedHarmonicOscillations*>(I.get())){ w.kind=2; for(int k:{0,1,2}){ w.v[k]=a->freqs[k]; w.v[3+k]=a->amps[k]; } }
+		else if(auto* c=dynamic_cast<ConstantForce*>(I.get())){ w.kind=3; for(int k:{0,1,2}) w.v[k]=c->F[k]; }
+		else if(auto* r=dynamic_cast<RadialForce*>(I.get())){ if(!r->nodeA||!r->nodeB) throw std::runtime_error("RadialForce: nodeA and nodeB must not be None."); w.kind=4; for(int k:{0,1,2}){ w.v[k]=r->nodeA->pos[k]; w.v[3+k]=r->nodeB->pos[k]; } w.v[6]=r->F; }
+		else if(auto* l=dynamic_cast<Local6Dofs*>(I.get())){ w.kind=5; for(int k=0;k<6;k++){ w.v[k]=l->values[k]; w.v[6+k]=l->whats[k]; } q4(w.ori,l->ori); }
+		else if(auto* v=dynamic_cast<VelocityAndReadForce*>(I.get())){ if(!v->energyName.empty()) throw std::runtime_error("GpuDemLoop: VelocityAndReadForce.energyName is not supported"); w.kind=6; w.flags=(v->latBlock?1:0)|(v->invF?2:0); for(int k:{0,1,2}) w.v[k]=v->dir[k]; w.v[3]=v->vel; }
+		else if(auto* f=dynamic_cast<ReadForce*>(I.get())){ w.kind=7; if(f->node){ w.flags=1; for(int k:{0,1,2}) w.v[k]=f->node->pos[k]; q4(w.ori,f->node->ori); } }
+		else if(auto* vv=dynamic_cast<VariableVelocity3d*>(I.get())){
+			for(const auto& hk: vv->hooks) if(!hk.empty()) throw std::runtime_error("GpuDemLoop: VariableVelocity3d.hooks are not supported");
+			w.kind=8; w.flags=(vv->diff?1:0)|(vv->wrap?2:0); w.v[0]=vv->t0; q4(w.ori,vv->ori); w.nTimes=(int)vv->times.size();
+			keep.push_back(vv->times); w.times=keep.back().data();
+			keep.emplace_back(); for(const auto& x: vv->vels) for(int k:{0,1,2}) keep.back().push_back(x[k]); w.vals=keep.back().data();
+			if(!vv->angVels.empty()){ keep.emplace_back(); for(const auto& x: vv->angVels) for(int k:{0,1,2}) keep.back().push_back(x[k]); w.vals2=keep.back().data(); }
+		}
+		else if(auto* va=dynamic_cast<VariableAlignedRotation*>(I.get())){
+			w.kind=9; w.flags=va->wrap?1:0; w.v[0]=va->axis; w.nTimes=(int)va->timeAngVel.size();
+			keep.emplace_back(); for(const auto& x: va->timeAngVel) keep.back().push_back(x[0]); w.times=keep.back().data();
+			keep.emplace_back(); for(const auto& x: va->timeAngVel) keep.back().push_back(x[1]); w.vals=keep.back().data();
+		}
+		else throw std::runtime_error("GpuDemLoop: "+I->pyStr()+" is not supported (CircularOrbit, StableCircularOrbit, InterpolatedMotion are not on the device path)");
+		imps.push_back(w); imposeOf.push_back(I); return ixOf[I.get()]=(int)imps.size()-1;
+	};
+	auto setFor=[&](const shared_ptr<Impose>& I)->int{
+		auto it=setOf.find(I.get()); if(it!=setOf.end()) return it->second;
+		if(auto* c=dynamic_cast<CombinedImpose*>(I.get())){ for(const auto& i: c->imps) setOps.push_back(one(i)); } else setOps.push_back(one(I));
+		setStart.push_back((int32_t)setOps.size()); return setOf[I.get()]=(int)setStart.size()-2;
+	};
+	// NB: vector<double> in `keep` must not reallocate after its data() was taken: reserve generously
+	keep.reserve(64);
+	vector<int32_t> sphSet; for(const auto& I: sphImpose) sphSet.push_back(setFor(I));
+	vector<int32_t> wallSet(wallOf.size(),-1); bool anyWall=false;
+	for(size_t i=0;i<wallOf.size();i++){ const auto& imp=wallOf[i]->shape->nodes[0]->getData<DemData>().impose; if(imp){ wallSet[i]=setFor(imp); anyWall=true; } }
+	vector<int32_t> groupSet; bool anyGroup=false;
+	for(const auto& n: dem.nodes){
+		if(!n->hasData<DemData>() || !n->getData<DemData>().isClump()) continue;
+		const ClumpData& cd=n->getData<DemData>().cast<ClumpData>();
+		const bool sphereClump=std::find(clumpOf.begin(),clumpOf.end(),n)!=clumpOf.end();
+		if(sphereClump){ if(cd.impose) throw std::runtime_error("GpuDemLoop: DemData.impose on a clump of spheres is not supported"); continue; }
+		groupSet.push_back(cd.impose?setFor(cd.impose):-1); if(cd.impose) anyGroup=true;
+	}
+	if(imps.empty()) return;
+	chk(h,wdem_upload_imposes(h,(int32_t)imps.size(),imps.data(),(int32_t)setStart.size()-1,setStart.data(),setOps.data(),(int64_t)sphImposeId.size(),sphImposeId.data(),sphSet.data(),anyWall?wallSet.data():nullptr,anyGroup?groupSet.data():nullptr));
 }
 
 void GpuDemLoop::pushContacts(){
@@ -202,6 +258,15 @@ void GpuDemLoop::pull(){
 		const size_t nw=wallOf.size(); vector<double> wp(3*nw),wf(3*nw),wt(3*nw);
 		chk(h,wdem_download_walls(h,wp.data(),wf.data(),wt.data()));
 		for(size_t i=0;i<nw;i++){ Node& nd=*wallOf[i]->shape->nodes[0]; DemData& d=nd.getData<DemData>(); nd.pos=Vector3r(wp[3*i],wp[3*i+1],wp[3*i+2]); d.force=Vector3r(wf[3*i],wf[3*i+1],wf[3*i+2]); d.torque=Vector3r(wt[3*i],wt[3*i+1],wt[3*i+2]); }
+	}
+	if(!imposeOf.empty() && !wallOf.empty()){      // walls whose velocity an imposition changes
+		vector<double> wv(3*wallOf.size()); chk(h,wdem_download_boundary_velocities(h,wv.data(),nullptr,nullptr));
+		for(size_t i=0;i<wallOf.size();i++) wallOf[i]->shape->nodes[0]->getData<DemData>().vel=Vector3r(wv[3*i],wv[3*i+1],wv[3*i+2]);
+	}
+	for(size_t i=0;i<imposeOf.size();i++){      // what the last step's Leapfrog read / accumulated (wdem_get_impose_state)
+		double o[8]; chk(h,wdem_get_impose_state(h,(int32_t)i,o));
+		if(auto* v=dynamic_cast<VelocityAndReadForce*>(imposeOf[i].get())){ v->sumF.set(o[0]); v->dist=o[1]; }
+		else if(auto* f=dynamic_cast<ReadForce*>(imposeOf[i].get())){ f->F.set(Vector3r(o[2],o[3],o[4])); f->T.set(Vector3r(o[5],o[6],o[7])); }
 	}
 	if(!clumpOf.empty()){
 		const size_t nc=clumpOf.size(); vector<double> p(3*nc),o(4*nc),v(3*nc),w(3*nc),l(3*nc),f(3*nc),t(3*nc);

@@ -36,11 +36,13 @@ struct GpuDemLoop: public Engine{
 	void prepare();                      // before a step: (re-)upload if particles changed, else push attribute / state edits
 	void pull();                         // device -> Node.pos/ori, DemData.vel/angVel/force/torque (lazily: only when `sync` or somebody asks)
 	void pullContacts();                 // device -> DemField.contacts as real Contact/L6Geom/FrictPhys|HertzPhys objects (S.save(), S.dem.con[i,j], VtkExport keep working)
+	void uploadImposes(const vector<shared_ptr<Impose>>& sphImpose, const vector<int32_t>& sphImposeId);   // DemData.impose of spheres, walls and facet-clump masters -> wdem_upload_imposes
 	void pushContacts();                 // real contacts of DemField.contacts -> wdem_upload_contacts (resume from a loaded Scene)
 	WOO_DECL_LOGGER;
 	// not attributes: device handle and the host-side bookkeeping of what lives there
 	wdem_handle h=nullptr; wdem_config cfg; bool haveCfg=false;
 	vector<shared_ptr<Particle>> sphereOf, wallOf, facetOf;      // particles in upload order
+	vector<shared_ptr<Impose>> imposeOf;                         // Impose objects in upload order (their sumF / dist / F / T are read back in pull())
 	vector<shared_ptr<Node>> clumpOf;                            // master nodes of the clumps of spheres, in upload order
 	size_t nParticlesUploaded=0; long stepUploaded=-1; bool trackingOn=false;
 	#define woo_dem_GpuDemLoop__CLASS_BASE_DOC_ATTRS \

@@ -1663,6 +1663,7 @@ int orc_add_impose(void* h, int kind, int flags, const double* v, const double* 
   Scene* S = (Scene*)h;
   ImposeDesc d; d.kind = kind; d.flags = flags; for (int k = 0; k < 16; k++) d.v[k] = v ? v[k] : 0.;
   if (ori) d.ori = Quat(ori[3], ori[0], ori[1], ori[2]);
+  if (kind == IMP_VEL_READ_FORCE) d.dist = d.v[4];      // VelocityAndReadForce.dist is an attribute: a scene may start with a value
   const int w = kind == IMP_VARIABLE_ALIGNED_ROTATION ? 1 : 3;
   if (nTimes > 0) { d.times.assign(times, times + nTimes); d.vals.assign(vals, vals + (size_t)w * nTimes); if (vals2) d.vals2.assign(vals2, vals2 + (size_t)w * nTimes); }
   S->imposes.push_back(d);

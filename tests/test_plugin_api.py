@@ -475,3 +475,62 @@ def test_clumps_through_the_plugin_equal_the_array_level_engine():
     # reading the state back (lazy pull of spheres and master nodes) does not disturb the run
     E.step(500); S.run(500, True)
     assert np.array_equal(np.array([p.pos for p in pars]), E.spheres()["pos"])
+
+
+# ---- Impose through the plugin -----------------------------------------------------------------------------------------------------------------------------
+def test_impose_object_model_cpu():
+    from woo_b200.woo.dem import (HarmonicOscillation, AlignedHarmonicOscillations, ConstantForce, RadialForce, Local6Dofs, VelocityAndReadForce, ReadForce, VariableVelocity3d,
+                                  VariableAlignedRotation, CombinedImpose, DemData)
+    from woo_b200.woo.core import Node
+    a, b = HarmonicOscillation(freq=10., amp=.1, dir=(0, 0, 2)), ConstantForce(F=(0, 0, 1))
+    c = a + b
+    assert isinstance(c, CombinedImpose) and len(c.imps) == 2 and len((c + ReadForce()).imps) == 3      # Impose.__add__ (Impose.cpp:302-312)
+    assert DemData(blocked='xyzXYZ', mass=1, impose=a).guessMoving() is True                             # DemData::guessMoving: ... || impose (Particle.cpp:638-640)
+    with pytest.raises(RuntimeError):
+        Local6Dofs(whats=(0, 3, 0, 0, 0, 0))
+    with pytest.raises(ValueError):
+        VariableAlignedRotation(timeAngVel=[(0, 0), (2, 1), (1, 2)])
+    p = woo.utils.sphere((0, 0, 0), .1); p.impose = a
+    assert p.shape.nodes[0].dem.impose is a
+    v = VelocityAndReadForce(dir=(1, 0, 0), vel=.5)
+    assert v.latBlock is True and v.invF is False and v.dist == 0 and v.sumF == 0                        # Impose.hpp:160-168 defaults
+    assert VariableVelocity3d(times=[0, 1], vels=[(0, 0, 0), (1, 0, 0)]).diff is False and RadialForce(nodeA=Node(pos=(0, 0, 0)), nodeB=Node(pos=(0, 0, 1)), F=2.).F == 2.
+
+
+@pytest.mark.gpu
+def test_impose_through_the_plugin_equals_the_array_level_engine():
+    from woo_b200 import scenes as sc
+    from woo_b200.engine import Engine
+    from woo_b200.woo.dem import HarmonicOscillation, ConstantForce, VelocityAndReadForce, ReadForce, VariableVelocity3d
+    Sp = sc.random_gas(150, box=.4, r=.02, psd_ratio=1.5, seed=12)
+    nan = float("nan")
+    k1 = sc.attach_impose(Sp, [sc.imp_harmonic(20., .01, dir=(1, 1, 0), perpFree=True), sc.imp_constant_force((0, 0, .03))], spheres=range(0, 10))
+    k2 = sc.attach_impose(Sp, [sc.imp_velocity_and_read_force((0, 0, 3), -.1, latBlock=False), sc.imp_read_force()], spheres=range(10, 30))
+    k3 = sc.attach_impose(Sp, [sc.imp_variable_velocity3d([0, .005, .01], [(nan, nan, 0), (nan, nan, .2), (nan, nan, -.2)], wrap=True)], walls=[4])
+    E = Engine(Sp.params).load(Sp)
+    S = Scene(fields=[DemField(gravity=Sp.params.gravity)])
+    m = FrictMat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)
+    walls = [Wall.make(w["pos"], axis=w["axis"], sense=w["sense"], mat=m) for w in Sp.walls]
+    wimp = VariableVelocity3d(times=[0, .005, .01], vels=[(nan, nan, 0), (nan, nan, .2), (nan, nan, -.2)], wrap=True)
+    walls[4].impose = wimp
+    S.dem.par.add(walls)                                                                                   # boundaries first in this scene: ids 0..5
+    pars = [woo.utils.sphere(Sp.pos[i], Sp.radius[i], mat=m, vel=Sp.vel[i]) for i in range(Sp.n)]
+    i1 = HarmonicOscillation(freq=20., amp=.01, dir=(1, 1, 0), perpFree=True) + ConstantForce(F=(0, 0, .03))
+    vr, rf = VelocityAndReadForce(dir=(0, 0, 3), vel=-.1, latBlock=False), ReadForce()
+    i2 = vr + rf
+    for i in range(0, 10): pars[i].impose = i1
+    for i in range(10, 30): pars[i].impose = i2
+    S.dem.par.add(pars)
+    for i in range(Sp.n):
+        pars[i].angVel = Sp.angVel[i]
+    assert walls[4].shape.nodes[0] in S.dem.nodes                                                          # an imposition makes the wall's node move (guessMoving)
+    S.engines = woo.utils.gpuEngines(damping=Sp.params.damping, dynDtPeriod=Sp.params.dynDtPeriod); S.dt = Sp.params.dt; S.dtSafety = Sp.params.dtSafety
+    E.step(600); S.run(600, True)
+    assert np.array_equal(np.array([p.pos for p in pars]), E.spheres()["pos"]) and np.array_equal(np.array([p.vel for p in pars]), E.spheres()["vel"])
+    assert np.array_equal(np.array(walls[4].pos), E.walls()["pos"][4])
+    st = E.impose_state(Sp.impose_sets[k2][0]); st2 = E.impose_state(Sp.impose_sets[k2][1])
+    assert vr.dist == st["dist"] and vr.sumF == pytest.approx(st["sumF"], rel=1e-9, abs=1e-12) and np.allclose(rf.F, st2["F"], rtol=1e-9, atol=1e-12)
+    # changing an attribute of an Impose in mid-run takes the full re-upload path (state and contact history kept)
+    vr.vel = .05
+    S.run(50, True)
+    assert vr.dist == pytest.approx(st["dist"] + 50 * S.dt * .05, rel=1e-9)

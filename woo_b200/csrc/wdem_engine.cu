@@ -56,7 +56,7 @@ struct SphereStore {
     flags.ensure(n, tot, keep, st); mask.ensure(n, tot, keep, st); mat.ensure(n, tot, keep, st); id.ensure(n, tot, keep, st); up.ensure(n, tot, keep, st);
   }
   Spheres view() { Spheres S; S.posr = posr.p; S.velm = velm.p; S.angi = angi.p; S.ori = ori.p; S.fx = f[0].p; S.fy = f[1].p; S.fz = f[2].p; S.tx = f[3].p; S.ty = f[4].p; S.tz = f[5].p;
-    S.lx = l[0].p; S.ly = l[1].p; S.lz = l[2].p; S.flags = flags.p; S.mask = mask.p; S.mat = mat.p; S.id = id.p; S.up = up.p; S.clumpOfId = nullptr; return S; }
+    S.lx = l[0].p; S.ly = l[1].p; S.lz = l[2].p; S.flags = flags.p; S.mask = mask.p; S.mat = mat.p; S.id = id.p; S.up = up.p; S.clumpOfId = nullptr; S.impOfId = nullptr; return S; }
   void release() { posr.release(); velm.release(); angi.release(); ori.release(); for (auto& b : f) b.release(); for (auto& b : l) b.release(); flags.release(); mask.release(); mat.release(); id.release(); up.release(); }
 };
 
@@ -178,6 +178,11 @@ struct wdem_engine {
   DBuf<double> wallAcc, wallPartial;     // accumulated force/torque on walls at rest (never reset in the reference: ContactLoop.cpp:270-276), per-step block partials
   std::vector<Facet> hFacets; DBuf<Facet> dFacets; DBuf<int> fgCellStart, fgCellFacet, fgCursor; FacetGrid fgrid; bool fgridValid = false;
   ClumpStore clumps;                     // clumps of spheres with mass (wdem_upload_clumps)
+  // Impose (wdem_upload_imposes): descriptors and their host state, sets, node attachments, and the per-step ring of resolved impositions
+  struct ImposeHost { int kind = 0, flags = 0; double v[16] = {0}; double ori[4] = {0, 0, 0, 1}; std::vector<double> times, vals, vals2; size_t ipos = 0, ipos2 = 0; double dist = 0; int nNodes = 0; };
+  std::vector<ImposeHost> imposes; std::vector<int> impSetStart, impSetOps, wallImpSet, groupImpSet; std::vector<double> impWallVel;
+  DBuf<int> dImpSetStart, dImpSetOps; DBuf<int32_t> dImpOfId; bool impSpheres = false, impRead = false; ImpSlot* hImpRing = nullptr; DBuf<ImpSlot> dImpRing; int lastImpSlot = 0;
+  ImposeDev impDev(int slot) { ImposeDev I; I.slot = dImpRing.p ? dImpRing.p + slot : nullptr; I.setStart = dImpSetStart.p; I.setOps = dImpSetOps.p; return I; }
   GroupsU groups{};                      // kinematic facet groups (wdem_upload_facet_groups): master nodes integrated on the host, members on the device
   std::vector<double> groupRadius;       // largest distance of a member node from its master node (bounding sphere of the sweep of a rotating group)
   int nClumpedUploaded = 0;             // spheres uploaded with the CLUMPED flag that no clump has claimed yet
@@ -206,7 +211,7 @@ struct wdem_engine {
   struct E2E { bool active = false; const double *pos = nullptr, *vel = nullptr, *angVel = nullptr; double *posOut = nullptr, *velOut = nullptr; } e2e;
   cudaStream_t sH2D = nullptr, sD2H = nullptr; cudaEvent_t evUp[NCHUNK] = {}, evLf[NCHUNK] = {}, evEk = nullptr;
   DBuf<double> ioIn, ioOut; double* hEk = nullptr; size_t hEkCap = 0; int ekBlocks = 0;
-  Spheres S() { Spheres v = sph[cur].view(); v.clumpOfId = clumps.n ? clumps.clumpOfId.p : nullptr; return v; }
+  Spheres S() { Spheres v = sph[cur].view(); v.clumpOfId = clumps.n ? clumps.clumpOfId.p : nullptr; v.impOfId = impSpheres ? dImpOfId.p : nullptr; return v; }
 };
 
 namespace {
@@ -902,7 +907,7 @@ void rebuild(wdem_engine* E) {
     }
     Ncsr.valid = true; Ncsr.nRows = n;
   }
-  if (E->anyMovingWall) { k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), makeUniforms(E), E->dCnt, 1); E->launches++; }   // Aabb::nodeLastPos (Collision.cpp:138-141)
+  if (E->anyMovingWall) { k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), makeUniforms(E), E->dCnt, 1, nullptr); E->launches++; }   // Aabb::nodeLastPos (Collision.cpp:138-141)
   E->nSS = nSS; E->nSSa = nSSa; E->nWS = nWS; E->nFS = nFS; E->nOrph = nOrphOut; E->nC = nSS + nWS + nFS + nOrphOut;
   E->curC = 1 - E->curC; E->curR = 1 - E->curR;
   E->nFullRuns++; E->compactPending = false;
@@ -1093,7 +1098,7 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   if (nNow > 0 && (c.applyForces || c.reset)) {
     // ContactLoop.applyForces=False: no contact force is applied, but Leapfrog.reset still sets force = gravity*mass, torque = 0 (Leapfrog.cpp:240-245): null rows
     CsrStore& R = E->csr[E->curR];
-    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard); E->launches++;
+    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard, E->impDev(u.impSlot)); E->launches++;
   }
   if (wa.nWalls && !wa.foldInKernel) { k_wall_fold<<<wa.nWalls * 6, 256, 0, st>>>(wa.partial, wa.nBlocksTotal, wa.nWalls * 6, wa.acc, guard); E->launches++; }
   if (ev) CK(cudaEventRecord(ev[4], st));
@@ -1173,14 +1178,70 @@ void gradVWorkStep(wdem_engine* E) {
 }
 
 // ---- one step in pieces, so that several steps can be enqueued before the host looks at the Verlet flags (Counters::gflag) ----
-struct StepSnap { HostCell cell; GroupsU groups; long long step; double time; StepU u; };
+struct StepSnap { HostCell cell; GroupsU groups; long long step; double time; StepU u; std::vector<double> wallVel; };
+
+// linearInterpolate (supp/smoothing/LinearInterpolate.hpp:13-52), `w` values per time point
+void linInterp(double t, const std::vector<double>& tt, const std::vector<double>& val, int w, size_t& _pos, double* out) {
+  size_t pos = _pos; const size_t n = tt.size();
+  const double *A, *B; double rel;
+  if (t <= tt[0]) { _pos = 0; A = &val[0]; B = &val[(n > 1 ? 1 : 0) * w]; rel = 0.; }
+  else if (t >= tt[n - 1]) { _pos = n - 2; A = n > 1 ? &val[pos * w] : &val[(n - 1) * w]; B = &val[(n - 1) * w]; rel = 1.; }
+  else {
+    pos = std::min(pos, n - 2);
+    while ((tt[pos] > t) || (tt[pos + 1] < t)) { if (tt[pos] > t) pos--; else pos++; }
+    _pos = pos; A = &val[pos * w]; B = &val[(pos + 1) * w]; rel = (t - tt[pos]) / (tt[pos + 1] - tt[pos]);
+  }
+  for (int k = 0; k < w; k++) out[k] = (rel == 0.) ? A[k] : (rel == 1.) ? B[k] : A[k] + (B[k] - A[k]) * rel;
+}
+// the impositions of the coming step: everything that depends on Scene.time / Scene.dt is evaluated here (libm), walls and facet-group masters are moved on
+void imposePrepareStep(wdem_engine* E, int slot) {
+  ImpSlot& H = E->hImpRing[slot]; memset(&H, 0, offsetof(ImpSlot, acc));
+  const double time = E->time, dt = E->dt; const double NaNv = std::numeric_limits<double>::quiet_NaN();
+  for (size_t i = 0; i < E->imposes.size(); i++) {
+    wdem_engine::ImposeHost& d = E->imposes[i]; ImpOp& o = H.op[i];
+    for (int k = 0; k < 4; k++) o.ori[k] = d.ori[k];
+    switch (d.kind) {
+      case 1: { const double omega = 2 * M_PI * d.v[0]; o.kind = IOP_DIR; o.flags = (d.flags & 1) ? 0 : 1; o.a[0] = d.v[2]; o.a[1] = d.v[3]; o.a[2] = d.v[4]; o.a[3] = d.v[1] * omega * std::cos(omega * (time - d.v[5])); break; }
+      case 2: o.kind = IOP_AXES_SET; for (int ax = 0; ax < 3; ax++) { if (std::isnan(d.v[ax]) || std::isnan(d.v[3 + ax])) { o.a[ax] = NaNv; continue; } const double omega = 2 * M_PI * d.v[ax]; o.a[ax] = d.v[3 + ax] * omega * std::cos(omega * time); } break;
+      case 3: o.kind = IOP_FADD; for (int k = 0; k < 3; k++) o.a[k] = d.v[k]; break;
+      case 4: { o.kind = IOP_FRADIAL; const d3 A = mk3(d.v[0], d.v[1], d.v[2]), B = mk3(d.v[3], d.v[4], d.v[5]); const d3 ab = B - A; const d3 ax = ab / nrm(ab);
+                o.a[0] = A.x; o.a[1] = A.y; o.a[2] = A.z; o.a[3] = ax.x; o.a[4] = ax.y; o.a[5] = ax.z; o.a[6] = d.v[6]; break; }
+      case 5: o.kind = IOP_LOCAL6; for (int k = 0; k < 6; k++) { o.a[k] = d.v[k]; o.m[k] = (int)d.v[6 + k]; } break;
+      case 6: o.kind = IOP_DIR; o.flags = ((d.flags & 1) ? 1 : 0) | 2 | ((d.flags & 2) ? 4 : 0); for (int k = 0; k < 4; k++) o.a[k] = d.v[k]; break;
+      case 7: o.kind = IOP_READFT; o.flags = d.flags & 1; for (int k = 0; k < 3; k++) o.a[k] = d.v[k]; break;
+      case 8: {
+        double t = time + .5 * dt - d.v[0];
+        if ((d.flags & 2) && (t < 0 || t > d.times.back())) { const double norm = t / d.times.back(); t = (norm - std::floor(norm)) * d.times.back(); }
+        o.kind = IOP_VAR3D; const bool rot = !(d.ori[3] == 1 && d.ori[0] == 0 && d.ori[1] == 0 && d.ori[2] == 0);
+        o.flags = (d.flags & 1) | (rot ? 2 : 0) | (d.vals2.empty() ? 0 : 4);
+        linInterp(t, d.times, d.vals, 3, d.ipos, o.a);
+        if (!d.vals2.empty()) linInterp(t, d.times, d.vals2, 3, d.ipos2, o.a + 3);
+        break;
+      }
+      case 9: { double t = time; if ((d.flags & 1) && t > d.times.back()) t = std::fmod(t, d.times.back()); o.kind = IOP_ANGAXIS; o.m[0] = (int)d.v[0]; linInterp(t, d.times, d.vals, 1, d.ipos, o.a); break; }
+      default: break;
+    }
+  }
+  // walls: all DOFs blocked, so only the imposition changes their velocity: the host follows it (Impose::velocity at the end of the node's step, Leapfrog.cpp:248)
+  ImposeDev I; I.slot = &H; I.setStart = E->impSetStart.data(); I.setOps = E->impSetOps.data();
+  for (size_t w = 0; w < E->wallImpSet.size() && w < 32; w++) {
+    if (E->wallImpSet[w] < 0) continue;
+    d3 v = mk3(E->impWallVel[3 * w], E->impWallVel[3 * w + 1], E->impWallVel[3 * w + 2]), dummy = mk3(0, 0, 0);
+    impose_velocity(I, E->wallImpSet[w], v, dummy);
+    E->impWallVel[3 * w] = v.x; E->impWallVel[3 * w + 1] = v.y; E->impWallVel[3 * w + 2] = v.z;
+    H.wallHas[w] = 1; H.wallVel[3 * w] = v.x; H.wallVel[3 * w + 1] = v.y; H.wallVel[3 * w + 2] = v.z;
+  }
+  CK(cudaMemsetAsync(E->dImpRing.p[slot].acc, 0, sizeof(H.acc), E->stream));
+  CK(cudaMemcpyAsync(E->dImpRing.p + slot, &H, offsetof(ImpSlot, acc), cudaMemcpyHostToDevice, E->stream));
+}
 
 // host prologue (Scene::doOneStep up to the engines, Scene.cpp:414-419): cell integration, per-step uniforms, master nodes of kinematic facet groups
 StepU stepPrologue(wdem_engine* E, int k) {
   const wdem_config& c = E->cfg;
   if (c.periodic) E->cell.integrateAndUpdate(E->dt);
   StepU u = makeUniforms(E);
-  u.gIn = E->dCnt->gflag + k; u.gOut = E->dCnt->gflag + k + 1;
+  u.gIn = E->dCnt->gflag + k; u.gOut = E->dCnt->gflag + k + 1; u.impSlot = k;
+  if (!E->imposes.empty()) imposePrepareStep(E, k);
   if (u.energy) {   // energy->resetResettables() (Scene.cpp:416): "kinetic" and "elast" restart from zero every step
     CK(cudaMemsetAsync(u.energy + EN_KINETIC, 0, sizeof(double), E->stream)); CK(cudaMemsetAsync(u.energy + EN_ELAST, 0, sizeof(double), E->stream));
   }
@@ -1201,6 +1262,10 @@ StepU stepPrologue(wdem_engine* E, int k) {
       }
       const double nn = std::sqrt(((G.ori.x * G.ori.x + G.ori.y * G.ori.y) + G.ori.z * G.ori.z) + G.ori.w * G.ori.w);
       G.ori.w /= nn; G.ori.x /= nn; G.ori.y /= nn; G.ori.z /= nn;
+      if (gi < (int)E->groupImpSet.size() && E->groupImpSet[gi] >= 0) {      // Impose::velocity before applyToMembers (Leapfrog.cpp:248-252)
+        ImposeDev I; I.slot = &E->hImpRing[k]; I.setStart = E->impSetStart.data(); I.setOps = E->impSetOps.data();
+        impose_velocity(I, E->groupImpSet[gi], G.vel, G.angVel);
+      }
     }
   }
   return u;
@@ -1212,10 +1277,16 @@ void enqueueIntegrate(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
   if (ev) CK(cudaEventRecord(ev[0], st));
   if (n > 0 && E->e2e.active) leapfrogPipelined(E, u);
   else if (n > 0) {
-    if (u.energy) k_leapfrog<true><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
+    if (E->impSpheres) {
+      if (E->comm && E->impRead) throw EngErr{"Impose: the read-force kinds (VelocityAndReadForce, ReadForce) are not available in decomposed runs", WDEM_ERR_UNSUPPORTED};
+      if (u.energy) k_leapfrog_imp<true><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt, E->impDev(u.impSlot));
+      else k_leapfrog_imp<false><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt, E->impDev(u.impSlot));
+    }
+    else if (u.energy) k_leapfrog<true><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
     else k_leapfrog<false><<<nblk(n, 256), 256, 0, st>>>(E->S(), n, u, E->dCnt);
     E->launches++;
   }
+  if (!E->imposes.empty() && E->e2e.active) throw EngErr{"Impose is not available with wdem_step_e2e", WDEM_ERR_UNSUPPORTED};
   if (E->nClumpedUploaded > 0) throw EngErr{std::to_string(E->nClumpedUploaded) + " spheres carry the CLUMPED flag but no clump was uploaded (wdem_upload_clumps)", WDEM_ERR_INVALID};
   if (E->clumps.n > 0) {
     if (c.periodic || E->comm || E->e2e.active || E->trackEnergy) throw EngErr{"clumps of spheres: periodic cells, decomposed runs, wdem_step_e2e and Scene.trackEnergy are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
@@ -1224,7 +1295,7 @@ void enqueueIntegrate(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
   if (E->groups.n > 0 && !E->hFacets.empty()) { k_facets_step<<<nblk((long long)E->hFacets.size(), 128), 128, 0, st>>>(E->dFacets.p, (int)E->hFacets.size(), E->groups, u, E->dCnt, 0); E->launches++; }
   if (E->anyMovingWall) {
     if (c.periodic) throw EngErr{"moving walls in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
-    k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), u, E->dCnt, 0); E->launches++;
+    k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), u, E->dCnt, 0, E->wallImpSet.empty() ? nullptr : E->dImpRing.p + u.impSlot); E->launches++;
   }
   if (ev) CK(cudaEventRecord(ev[1], st));
   // (dirty, error): every subdomain rebuilds / fails in the same step; over peer memory together with the halo payload, else NCCL
@@ -1292,7 +1363,7 @@ void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
     snaps.resize(K);
     for (int k = 0; k < K; k++) {
       const StepU u = stepPrologue(E, k);
-      snaps[k] = StepSnap{E->cell, E->groups, E->step, E->time, u};
+      snaps[k] = StepSnap{E->cell, E->groups, E->step, E->time, u, E->impWallVel};
       cudaEvent_t* ev = nullptr;
       if (E->profiling) { const int set = (int)(E->step % wdem_engine::NEVSET); harvestPhases(E, set); ev = E->evr[set]; }
       enqueueIntegrate(E, u, ev);
@@ -1311,7 +1382,7 @@ void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
     int executed = K;
     if (kd >= 0) {
       // back to step kd, after its prologue and its Leapfrog
-      E->cell = snaps[kd].cell; E->groups = snaps[kd].groups; E->step = snaps[kd].step; E->time = snaps[kd].time;
+      E->cell = snaps[kd].cell; E->groups = snaps[kd].groups; E->step = snaps[kd].step; E->time = snaps[kd].time; E->impWallVel = snaps[kd].wallVel;
       const long long interval = since0 + kd + 1;
       rebuild(E);
       E->conDirty = false; E->stepsSinceFullRun = -1;      // the epilogue below counts this step
@@ -1325,6 +1396,10 @@ void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
       executed = kd + 1;
       if (trace) { CK(cudaStreamSynchronize(st)); tReb += msSince(t0); nReb++; nVoid += K - executed; }
     } else if (E->stepsSinceFullRun + K > 2 * (long long)E->batchK) E->batchK = std::min(E->batchMax, E->batchK + 1);      // long quiet stretch: larger batches
+    if (!E->imposes.empty()) {      // VelocityAndReadForce.dist: += vel*dt in every executed step in which some node carried it (Impose.cpp:166-173)
+      for (auto& d : E->imposes) if (d.kind == 6 && d.nNodes > 0) for (int k = 0; k < executed; k++) d.dist += d.v[3] * snaps[k].u.dt;
+      E->lastImpSlot = executed - 1;
+    }
     gradVWorkStep(E);
     dynDtIfDue(E);
     stepEpilogue(E);
@@ -1432,6 +1507,7 @@ int wdem_destroy(wdem_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release(); h->clumps.release();
+  h->dImpSetStart.release(); h->dImpSetOps.release(); h->dImpOfId.release(); h->dImpRing.release(); if (h->hImpRing) cudaFreeHost(h->hImpRing);
   h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->fgCursor.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
   h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->candBuf.release(); h->wallBits.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
   peerTeardown(h, false);
@@ -1526,6 +1602,7 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
     CK(cudaStreamSynchronize(st));
     h->conDirty = true; h->nC = h->nSS = h->nSSa = h->nWS = h->nFS = h->nOrph = 0; h->csr[0].valid = h->csr[1].valid = false; h->up2slotValid = false;
     h->verletDist = NAN; h->fgridValid = false; h->boundsValid = false; h->batchK = 1;
+    h->imposes.clear(); h->impSetStart.clear(); h->impSetOps.clear(); h->wallImpSet.clear(); h->groupImpSet.clear(); h->impSpheres = false; h->impRead = false;
     h->clumps.release(); h->nClumpedUploaded = 0; for (int64_t i = 0; i < n; i++) if (fl[i] & 64u) h->nClumpedUploaded++;
   });
 }
@@ -1602,6 +1679,90 @@ int wdem_download_clumps(wdem_handle h, double* pos, double* ori, double* vel, d
   });
 }
 int64_t wdem_num_clumps(wdem_handle h) { return h ? h->clumps.n : 0; }
+
+int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int32_t nSets, const int32_t* setStart, const int32_t* setOps, int64_t nSphereIds,
+                        const int32_t* sphereIds, const int32_t* sphereSet, const int32_t* wallSet, const int32_t* groupSet) {
+  return guarded(h, [&] {
+    if (nImp < 0 || nImp > WD_MAX_IMPOSE) throw EngErr{"wdem_upload_imposes: at most " + std::to_string(WD_MAX_IMPOSE) + " Impose objects", WDEM_ERR_UNSUPPORTED};
+    if (nImp > 0 && (!imp || nSets <= 0 || !setStart || !setOps)) throw EngErr{"wdem_upload_imposes: bad arguments", WDEM_ERR_INVALID};
+    if (!h->conDirty || h->nC != 0 || h->cur != 0) throw EngErr{"wdem_upload_imposes: call after the particles are uploaded and before the first step", WDEM_ERR_INVALID};
+    if (h->cfg.periodic && (wallSet || groupSet)) throw EngErr{"wdem_upload_imposes: moving walls / facet groups in a periodic cell are not supported", WDEM_ERR_UNSUPPORTED};
+    h->imposes.clear(); h->impSetStart.clear(); h->impSetOps.clear(); h->wallImpSet.clear(); h->groupImpSet.clear(); h->impSpheres = false; h->impRead = false;
+    if (nImp == 0) return;
+    cudaStream_t st = h->stream;
+    for (int i = 0; i < nImp; i++) {
+      const wdem_impose& s = imp[i]; wdem_engine::ImposeHost d;
+      if (s.kind < 1 || s.kind > 9) throw EngErr{"wdem_upload_imposes: unknown kind " + std::to_string(s.kind) + " (CircularOrbit, StableCircularOrbit, InterpolatedMotion are not on this path)", WDEM_ERR_UNSUPPORTED};
+      d.kind = s.kind; d.flags = s.flags; memcpy(d.v, s.v, sizeof(d.v)); memcpy(d.ori, s.ori, sizeof(d.ori));
+      if (s.kind == 8 || s.kind == 9) {
+        if (s.nTimes <= 0 || !s.times || !s.vals) throw EngErr{s.kind == 8 ? "VariableVelocity3d: times must not be empty." : "VariableAlignedRotation: timeAngVel must not be empty.", WDEM_ERR_INVALID};
+        const int w = s.kind == 8 ? 3 : 1;
+        d.times.assign(s.times, s.times + s.nTimes); d.vals.assign(s.vals, s.vals + (size_t)w * s.nTimes); if (s.vals2) d.vals2.assign(s.vals2, s.vals2 + (size_t)w * s.nTimes);
+        for (int k = 0; k + 1 < s.nTimes; k++) if (!(d.times[k + 1] >= d.times[k])) throw EngErr{"Impose: time values must be non-decreasing", WDEM_ERR_INVALID};
+      }
+      if (s.kind == 5) for (int k = 0; k < 6; k++) { const int w = (int)s.v[6 + k]; if (w != 0 && w != 1 && w != 2) throw EngErr{"Local6Dofs.whats components must be 0, 2 or 1", WDEM_ERR_INVALID}; }
+      if (s.kind == 6) d.dist = s.v[4];
+      if (s.kind == 6 || s.kind == 7) h->impRead = true;
+      h->imposes.push_back(d);
+    }
+    h->impSetStart.assign(setStart, setStart + nSets + 1); h->impSetOps.assign(setOps, setOps + setStart[nSets]);
+    for (int v : h->impSetOps) if (v < 0 || v >= nImp) throw EngErr{"wdem_upload_imposes: set refers to an unknown Impose object", WDEM_ERR_INVALID};
+    auto setKinds = [&](int set, bool& vel, bool& other) { for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) { const int k = h->imposes[h->impSetOps[e]].kind; if (k == 1 || k == 2 || k == 8 || k == 9) vel = true; else if (k == 5) { vel = true; for (int q = 0; q < 6; q++) if ((int)h->imposes[h->impSetOps[e]].v[6 + q] == 2) other = true; } else if (k == 6) { vel = true; other = true; } else other = true; } };
+    auto touch = [&](int set) { if (set < 0) return; if (set >= nSets) throw EngErr{"wdem_upload_imposes: set index out of range", WDEM_ERR_INVALID}; for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) h->imposes[h->impSetOps[e]].nNodes++; };
+    // spheres: table by particle id
+    std::vector<int32_t> ofId((size_t)std::max(h->maxId, 0) + 2, -1);
+    std::unordered_set<int32_t> known(h->hIds.begin(), h->hIds.end());
+    for (int64_t k = 0; k < nSphereIds; k++) {
+      if (sphereSet[k] < 0) continue;
+      if (!known.count(sphereIds[k])) throw EngErr{"wdem_upload_imposes: particle #" + std::to_string(sphereIds[k]) + " is not an uploaded sphere", WDEM_ERR_INVALID};
+      touch(sphereSet[k]); ofId[sphereIds[k]] = sphereSet[k]; h->impSpheres = true;
+    }
+    h->dImpOfId.ensure(ofId.size(), h->bytes); CK(cudaMemcpyAsync(h->dImpOfId.p, ofId.data(), ofId.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (wallSet) {
+      if (h->hWalls.size() > 32) throw EngErr{"wdem_upload_imposes: impositions on walls need at most 32 walls", WDEM_ERR_UNSUPPORTED};
+      h->wallImpSet.assign(wallSet, wallSet + h->hWalls.size()); h->impWallVel.assign(3 * h->hWalls.size(), 0.);
+      bool any = false;
+      for (size_t w = 0; w < h->hWalls.size(); w++) {
+        for (int k = 0; k < 3; k++) h->impWallVel[3 * w + k] = h->hWalls[w].vel[k];
+        if (wallSet[w] < 0) continue;
+        bool vel = false, other = false; setKinds(wallSet[w], vel, other);
+        if (other) throw EngErr{"wdem_upload_imposes: walls (all DOFs blocked) take velocity impositions only", WDEM_ERR_UNSUPPORTED};
+        touch(wallSet[w]); h->hWalls[w].moving = 1; any = true;      // DemData::guessMoving: ... || impose (Particle.cpp:638-640)
+      }
+      if (any) { h->anyMovingWall = true; h->anyStaticWall = false; for (auto& w : h->hWalls) if (!w.moving) h->anyStaticWall = true; CK(cudaMemcpyAsync(h->dWalls.p, h->hWalls.data(), h->hWalls.size() * sizeof(Wall), cudaMemcpyHostToDevice, st)); }
+      else h->wallImpSet.clear();
+    }
+    if (groupSet) {
+      h->groupImpSet.assign(groupSet, groupSet + h->groups.n);
+      for (int g = 0; g < h->groups.n; g++) { if (groupSet[g] < 0) continue; bool vel = false, other = false; setKinds(groupSet[g], vel, other); if (other) throw EngErr{"wdem_upload_imposes: facet groups (all DOFs blocked) take velocity impositions only", WDEM_ERR_UNSUPPORTED}; touch(groupSet[g]); }
+    }
+    h->dImpSetStart.ensure(h->impSetStart.size(), h->bytes); CK(cudaMemcpyAsync(h->dImpSetStart.p, h->impSetStart.data(), h->impSetStart.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    h->dImpSetOps.ensure(std::max<size_t>(h->impSetOps.size(), 1), h->bytes); if (!h->impSetOps.empty()) CK(cudaMemcpyAsync(h->dImpSetOps.p, h->impSetOps.data(), h->impSetOps.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    h->dImpRing.ensure(WD_KMAX + 1, h->bytes); CK(cudaMemsetAsync(h->dImpRing.p, 0, (WD_KMAX + 1) * sizeof(ImpSlot), st));
+    if (!h->hImpRing) CK(cudaMallocHost(&h->hImpRing, (WD_KMAX + 1) * sizeof(ImpSlot)));
+    h->lastImpSlot = 0;
+    CK(cudaStreamSynchronize(st));
+  });
+}
+int wdem_download_boundary_velocities(wdem_handle h, double* wallVel, double* groupVel, double* groupAngVel) {
+  return guarded(h, [&] {
+    if (wallVel) for (size_t w = 0; w < h->hWalls.size(); w++) for (int k = 0; k < 3; k++)
+      wallVel[3 * w + k] = (w < h->wallImpSet.size() && h->wallImpSet[w] >= 0) ? h->impWallVel[3 * w + k] : h->hWalls[w].vel[k];
+    for (int g = 0; g < h->groups.n; g++) {
+      const GroupU& G = h->groups.g[g];
+      if (groupVel) { groupVel[3 * g] = G.vel.x; groupVel[3 * g + 1] = G.vel.y; groupVel[3 * g + 2] = G.vel.z; }
+      if (groupAngVel) { groupAngVel[3 * g] = G.angVel.x; groupAngVel[3 * g + 1] = G.angVel.y; groupAngVel[3 * g + 2] = G.angVel.z; }
+    }
+  });
+}
+int wdem_get_impose_state(wdem_handle h, int32_t ix, double* out) {
+  return guarded(h, [&] {
+    if (ix < 0 || ix >= (int)h->imposes.size() || !out) throw EngErr{"wdem_get_impose_state: bad arguments", WDEM_ERR_INVALID};
+    double acc[8];
+    CK(cudaMemcpyAsync(acc, h->dImpRing.p[h->lastImpSlot].acc + 8 * ix, sizeof(acc), cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+    out[0] = acc[0]; out[1] = h->imposes[ix].dist; for (int k = 0; k < 6; k++) out[2 + k] = acc[1 + k];
+  });
+}
 int wdem_upload_clump_forces(wdem_handle h, const double* force, const double* torque) {
   return guarded(h, [&] {
     ClumpStore& K = h->clumps; const int n = K.n;

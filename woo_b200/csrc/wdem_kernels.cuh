@@ -33,7 +33,114 @@ struct Spheres {          // one slot per sphere; slots are re-ordered by grid c
   int32_t* id;            // Particle.id
   int32_t* up;            // upload index (for downloads)
   const int32_t* clumpOfId;   // by Particle.id: index of the clump the sphere is a member of, -1 free; NULL when the scene has no clumps
+  const int32_t* impOfId;     // by Particle.id: index of the node's set of impositions (DemData.impose), -1 none; NULL when no sphere carries one
 };
+// Impose (Particle.hpp:130-160, Impose.hpp, Impose.cpp): one resolved imposition.  Everything that depends on Scene.time / Scene.dt only (harmonic
+// factors, interpolated tables) is evaluated by the host once per step with libm, so host, device and oracle see the same numbers.
+#define WD_MAX_IMPOSE 16
+enum { IOP_DIR = 1, IOP_AXES_SET = 2, IOP_VAR3D = 3, IOP_ANGAXIS = 4, IOP_LOCAL6 = 5, IOP_FADD = 6, IOP_FRADIAL = 7, IOP_READFT = 8 };
+struct ImpOp {
+  int kind, flags;      // DIR: flags&1 zero the lateral velocity, &2 read force (VelocityAndReadForce), &4 invF | VAR3D: &1 diff, &2 rotated frame, &4 angular velocity too | READFT: &1 node frame
+  double ori[4];        // x,y,z,w
+  double a[7];          // DIR dir(3), magnitude | AXES_SET values(3; NaN: untouched) | VAR3D vImp(3), wImp(3) | ANGAXIS value | LOCAL6 values(6) | FADD F(3) | FRADIAL A(3), unit axis(3), F | READFT node pos(3)
+  int m[6];             // ANGAXIS m[0] = axis | LOCAL6 whats(6)
+};
+struct ImpSlot {        // what one step of a batch needs (ring indexed by the step's position in the batch, like Counters::gflag)
+  ImpOp op[WD_MAX_IMPOSE];
+  double wallVel[32 * 3]; int wallHas[32];      // new velocity of walls that carry a velocity imposition (computed by the host: all DOFs blocked, nothing else changes it)
+  double acc[WD_MAX_IMPOSE * 8];                // per op: sumF | F(3), T(3) of the read-force kinds; zeroed when the batch is enqueued
+};
+struct ImposeDev { ImpSlot* slot; const int* setStart; const int* setOps; };
+__host__ __device__ __forceinline__ q4 impOri(const ImpOp& o) { q4 q; q.x = o.ori[0]; q.y = o.ori[1]; q.z = o.ori[2]; q.w = o.ori[3]; return q; }
+// Impose::velocity of every imposition of the set, in order (CombinedImpose::velocity, Impose.cpp:288-292)
+__host__ __device__ __forceinline__ void impose_velocity(const ImposeDev& I, int set, d3& vel, d3& w) {
+  for (int e = I.setStart[set]; e < I.setStart[set + 1]; e++) {
+    const ImpOp& o = I.slot->op[I.setOps[e]];
+    switch (o.kind) {
+      case IOP_DIR: {      // HarmonicOscillation (Impose.hpp:6-13), VelocityAndReadForce (Impose.cpp:156-162)
+        const d3 dir = mk3(o.a[0], o.a[1], o.a[2]);
+        if (o.flags & 1) vel = dir * o.a[3];
+        else { const d3 vLat = vel - dir * dot(vel, dir); vel = vLat + dir * o.a[3]; }
+        break;
+      }
+      case IOP_AXES_SET:   // AlignedHarmonicOscillations (Impose.hpp:50-58)
+        if (o.a[0] == o.a[0]) vel.x = o.a[0];
+        if (o.a[1] == o.a[1]) vel.y = o.a[1];
+        if (o.a[2] == o.a[2]) vel.z = o.a[2];
+        break;
+      case IOP_VAR3D: {    // VariableVelocity3d (Impose.cpp:193-226)
+        const bool diff = o.flags & 1, rot = o.flags & 2;
+        const q4 q = impOri(o), qc = quatConj(q);
+        d3 v = rot ? quatRotate(qc, vel) : vel;
+        v.x = (diff ? v.x : 0) + (!(o.a[0] == o.a[0]) ? (diff ? 0 : v.x) : o.a[0]);
+        v.y = (diff ? v.y : 0) + (!(o.a[1] == o.a[1]) ? (diff ? 0 : v.y) : o.a[1]);
+        v.z = (diff ? v.z : 0) + (!(o.a[2] == o.a[2]) ? (diff ? 0 : v.z) : o.a[2]);
+        vel = rot ? quatRotate(q, v) : v;
+        if (o.flags & 4) {
+          d3 av = rot ? quatRotate(qc, w) : w;
+          av.x = (diff ? av.x : 0) + (!(o.a[3] == o.a[3]) ? (diff ? 0 : av.x) : o.a[3]);
+          av.y = (diff ? av.y : 0) + (!(o.a[4] == o.a[4]) ? (diff ? 0 : av.y) : o.a[4]);
+          av.z = (diff ? av.z : 0) + (!(o.a[5] == o.a[5]) ? (diff ? 0 : av.z) : o.a[5]);
+          w = rot ? quatRotate(q, av) : av;
+        }
+        break;
+      }
+      case IOP_ANGAXIS: setc(w, o.m[0], o.a[0]); break;      // VariableAlignedRotation (Impose.cpp:95-100)
+      case IOP_LOCAL6: {   // Local6Dofs (Impose.cpp:72-82): ori takes global to local
+        const q4 q = impOri(o), qc = quatConj(q);
+        for (int i = 0; i < 6; i++) {
+          if (!(o.m[i] & 1)) continue;
+          if (i < 3) { d3 loc = quatRotate(q, vel); setc(loc, i, o.a[i]); vel = quatRotate(qc, loc); }
+          else { d3 loc = quatRotate(q, w); setc(loc, i - 3, o.a[i]); w = quatRotate(qc, loc); }
+        }
+        break;
+      }
+      default: break;
+    }
+  }
+}
+// Impose::force at Leapfrog's reset (Leapfrog.cpp:244): on top of mass*gravity, before the contact forces of the step are added
+__host__ __device__ __forceinline__ void impose_force(const ImposeDev& I, int set, d3 pos, d3& F, d3& T) {
+  for (int e = I.setStart[set]; e < I.setStart[set + 1]; e++) {
+    const ImpOp& o = I.slot->op[I.setOps[e]];
+    switch (o.kind) {
+      case IOP_FADD: F = F + mk3(o.a[0], o.a[1], o.a[2]); break;      // ConstantForce (Impose.cpp:45-47)
+      case IOP_FRADIAL: {                                             // RadialForce (Impose.cpp:49-58)
+        const d3 A = mk3(o.a[0], o.a[1], o.a[2]), axis = mk3(o.a[3], o.a[4], o.a[5]);
+        const d3 C = A + axis * dot(pos - A, axis);
+        const d3 towards = C - pos;
+        if (sqn(towards) == 0) break;
+        F = F - (towards / nrm(towards)) * o.a[6];
+        break;
+      }
+      case IOP_LOCAL6: {                                              // Impose.cpp:83-87: replaces what was there
+        const q4 qc = quatConj(impOri(o));
+        for (int i = 0; i < 6; i++) {
+          if (!(o.m[i] & 2)) continue;
+          d3 u = mk3(0, 0, 0); setc(u, i % 3, 1.);
+          if (i < 3) F = quatRotate(qc, o.a[i] * u); else T = quatRotate(qc, o.a[i] * u);
+        }
+        break;
+      }
+      default: break;
+    }
+  }
+}
+#ifdef __CUDACC__
+// Impose::readForce before the reset (Leapfrog.cpp:238); sums over the nodes of an imposition (OpenMPAccumulator in the reference: unordered there as well)
+__device__ __forceinline__ void impose_read_force(const ImposeDev& I, int set, d3 pos, d3 F, d3 T) {
+  for (int e = I.setStart[set]; e < I.setStart[set + 1]; e++) {
+    const int ix = I.setOps[e]; const ImpOp& o = I.slot->op[ix]; double* acc = I.slot->acc + 8 * ix;
+    if (o.kind == IOP_DIR && (o.flags & 2)) { const double f = dot(F, mk3(o.a[0], o.a[1], o.a[2])); atomicAdd(acc, ((o.flags & 4) ? -1. : 1.) * f); }      // Impose.cpp:175-177
+    else if (o.kind == IOP_READFT) {                                                                                                                      // Impose.cpp:144-155
+      d3 f = F, t = T;
+      if (o.flags & 1) { const q4 qc = quatConj(impOri(o)); f = quatRotate(qc, F); t = quatRotate(qc, T + cross(pos - mk3(o.a[0], o.a[1], o.a[2]), F)); }
+      atomicAdd(acc + 1, f.x); atomicAdd(acc + 2, f.y); atomicAdd(acc + 3, f.z); atomicAdd(acc + 4, t.x); atomicAdd(acc + 5, t.y); atomicAdd(acc + 6, t.z);
+    }
+  }
+}
+#endif
+
 // Clumps of spheres with mass (ClumpData, src/dem/Clump.hpp): one entry per master node; members are addressed by particle id (their slots move at collider full runs)
 struct Clumps {
   int n;
@@ -81,7 +188,8 @@ struct StepU {            // per-step uniforms
   m33 shiftVelM;          // gradV*pprevHsize (GRADV2) or gradV*hSize (VEL, VEL_2ND) or 0  (Cell::intrShiftVel)
   m33 gradV, nextGradV, dGradV, midGradV, ImLL4hInv, IpLL4h, LmL; d3 spinVec, deltaSpinVec;
   long long step; int renormNow; int noRatch;
-  const int* gIn; int* gOut;      // this step's slots of Counters::gflag
+  const int* gIn; int* gOut;
+  int impSlot;      // position of this step in the ring of Impose slots (ImpSlot)      // this step's slots of Counters::gflag
   double absDistFactor;
   int law; int noSlip, noBreak, noFrict, noAttraction; int rolling; double relRollStiff, relTwistStiff, rollTanPhi;
   double poisson, en, viscAlpha;  // viscAlpha = -sqrt(5) ln(en)/sqrt(ln(en)^2+pi^2), host-computed (Hertz.cpp:69)
@@ -121,9 +229,11 @@ __device__ __forceinline__ double signd(double f) { return f < 0 ? -1. : (f > 0 
 // ------------------------------------------------------------------------------------------------
 // host-state staging of the end-to-end path (wdem_step_e2e): pos/vel/angVel come from / go to buffers in upload order
 struct LeapIO { const double* pos; const double* vel; const double* angVel; double* posOut; double* velOut; };
-template <bool EXT, bool TRACK>
-__device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const StepU& u, Counters* cnt, const LeapIO& io, long long ut) {
+template <bool EXT, bool TRACK, bool IMP = false>
+__device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const StepU& u, Counters* cnt, const LeapIO& io, long long ut, const ImposeDev* I = nullptr) {
   const uint32_t fl = S.flags[i];
+  int impSet = -1;
+  if (IMP) impSet = S.impOfId[S.id[i]];
   if (fl & (F_GHOST | F_CLUMPED)) return;   // ghost: integrated by its owner, refreshed by the halo exchange; clumped: follows its master node (k_clumps_step; Leapfrog.cpp:153)
   double4 pr = S.posr[i], vm = S.velm[i], ai = S.angi[i], qo = S.ori[i];
   if (EXT) {
@@ -192,6 +302,7 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
       w = w + dt * angAccel;
       if (u.periodic && u.homoDeform == 4) w = w - u.deltaSpinVec;
     }
+    if (IMP && impSet >= 0) impose_velocity(*I, impSet, vel, w);      // re-applied so that forces do not alter what is prescribed (Leapfrog.cpp:203-205)
   } else if (u.periodic && u.homoDeform == 4) vel = mulMV(u.ImLL4hInv, mulMV(u.LmL, pos) + mulMV(u.IpLL4h, vel));
   if (u.periodic && u.homoDeform != 4) {                                   // applyPeriodicCorrections :258-273
     if (u.homoDeform == 2 || u.homoDeform == 3) {
@@ -222,6 +333,10 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
   {
     double nn = sqrt(((qo.x * qo.x + qo.y * qo.y) + qo.z * qo.z) + qo.w * qo.w);
     qo.x /= nn; qo.y /= nn; qo.z /= nn; qo.w /= nn;
+  }
+  if (IMP && impSet >= 0) {
+    impose_read_force(*I, impSet, pos, f, t);      // the forces of the previous step, before they are reset (Leapfrog.cpp:238); the force impositions act in k_reduce
+    impose_velocity(*I, impSet, vel, w);           // Leapfrog.cpp:248
   }
   S.posr[i] = make_double4(pos.x, pos.y, pos.z, pr.w);
   S.velm[i] = make_double4(vel.x, vel.y, vel.z, mass);
@@ -368,6 +483,14 @@ __global__ void __launch_bounds__(256, 4) k_leapfrog(Spheres S, int n, StepU u, 
   if (i >= n) return;
   leapfrog_body<false, TRACK>(S, i, u, cnt, LeapIO{}, 0);
 }
+// the same with the Impose hooks (scenes in which some sphere carries an imposition)
+template <bool TRACK>
+__global__ void __launch_bounds__(256, 4) k_leapfrog_imp(Spheres S, int n, StepU u, Counters* cnt, ImposeDev I) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (*u.gIn) { if (i == 0) *u.gOut = 1; return; }
+  if (i >= n) return;
+  leapfrog_body<false, TRACK, true>(S, i, u, cnt, LeapIO{}, 0, &I);
+}
 // the same integrator over a chunk [first, first+cnt) of the UPLOAD order: inputs are read from, and the new pos/vel written to, staging
 // buffers (coalesced), the rest of the state is gathered by slot.  Lets host<->device copies of other chunks overlap with the integration.
 template <bool TRACK>
@@ -412,7 +535,7 @@ __global__ void __launch_bounds__(128) k_facets_step(Facet* facets, int n, Group
 }
 // Leapfrog for boundary nodes that are in DemField.nodes (moving walls: mass 0, all DOFs blocked => the "fixed particle" branch, Leapfrog.cpp:195-199):
 // leapfrogTranslate only (:275-278), plus the Verlet test of their Aabb (Collision.cpp:113-121).  setLast: record Aabb::nodeLastPos at a full run.
-__global__ void k_walls_step(Wall* walls, int n, StepU u, Counters* cnt, int setLast) {
+__global__ void k_walls_step(Wall* walls, int n, StepU u, Counters* cnt, int setLast, const ImpSlot* imp) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n) return;
   Wall W = walls[w];
@@ -420,6 +543,7 @@ __global__ void k_walls_step(Wall* walls, int n, StepU u, Counters* cnt, int set
   if (!W.moving || *u.gIn) return;
   d3 pos = mk3(W.pos[0], W.pos[1], W.pos[2]) + mk3(W.vel[0], W.vel[1], W.vel[2]) * u.dt;
   walls[w].pos[0] = pos.x; walls[w].pos[1] = pos.y; walls[w].pos[2] = pos.z;
+  if (imp && w < 32 && imp->wallHas[w]) for (int k = 0; k < 3; k++) walls[w].vel[k] = imp->wallVel[3 * w + k];      // Impose::velocity at the end of the node's step (Leapfrog.cpp:248)
   const d3 dl = mk3(W.lastPos[0], W.lastPos[1], W.lastPos[2]) - pos;
   const double d2 = fmax(0., sqn(dl));
   if (d2 > u.maxD2 || !(d2 == d2)) *u.gOut = 1;
@@ -1052,7 +1176,7 @@ __global__ void __launch_bounds__(128) k_contact_orphans(Contacts C, long long f
 #endif
 #define RB WD_REDUCE_RB
 __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Spheres S, int n, Contacts C, const int* __restrict__ rowStart, const uint32_t* __restrict__ rowEntry, StepU u,
-                                               const int* __restrict__ guard) {
+                                               const int* __restrict__ guard, ImposeDev I) {
   if (guard && *guard) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1065,6 +1189,7 @@ __global__ void __launch_bounds__(WD_REDUCE_BLOCK, WD_REDUCE_MINB) k_reduce(Sphe
   if (u.reset) {
     F = (u.hasGravity && !(fl & (F_GRAVITY_SKIP | F_CLUMPED))) ? (S.velm[i].w * u.gravity) : mk3(0, 0, 0);      // clumped: gravity acts on the master node (Leapfrog.cpp:240-252)
     T = mk3(0, 0, 0);
+    if (S.impOfId) { const int set = S.impOfId[S.id[i]]; if (set >= 0) impose_force(I, set, pos, F, T); }      // Impose::force at the reset (Leapfrog.cpp:244)
   } else { F = mk3(S.fx[i], S.fy[i], S.fz[i]); T = mk3(S.tx[i], S.ty[i], S.tz[i]); }
   for (int e = e0; e < e1; e += RB) {
     uint32_t ent[RB]; double4 fg[RB], cp[RB];

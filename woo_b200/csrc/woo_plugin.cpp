@@ -50,13 +50,31 @@ struct HertzMat : FrictMat { double surfEnergy = 0., alpha = 0.; int kind() cons
 // ---- nodes and particles (core/Field.hpp:102-103, dem/Particle.hpp:91-97,198-292)
 enum { DOF_ALL = 63, GRAVITY_SKIP = 512, DAMPING_SKIP = 2048 };
 struct Node;
+// ---- Impose (dem/Particle.hpp:130-160, dem/Impose.hpp): attribute carriers; the device evaluates them (wdem_upload_imposes).  kind() = wdem_impose.kind
+struct Impose : std::enable_shared_from_this<Impose> {
+  virtual ~Impose() {} virtual int kind() const { return 0; }
+  DemField* field = nullptr;                       // set when uploaded: attribute changes after that force a re-upload
+  double sumF = 0, dist = 0; V3 F{{0, 0, 0}}, T{{0, 0, 0}};      // results read back by DemField::pull (VelocityAndReadForce.sumF/.dist, ReadForce.F/.T)
+  void touch();
+};
+struct HarmonicOscillation : Impose { double freq = NaN, amp = NaN, t0 = 0; V3 dir{{1, 0, 0}}; bool perpFree = false; int kind() const override { return 1; } };
+struct AlignedHarmonicOscillations : Impose { V3 freqs{{NaN, NaN, NaN}}, amps{{0, 0, 0}}; int kind() const override { return 2; } };
+struct ConstantForce : Impose { V3 Fc{{0, 0, 0}}; int kind() const override { return 3; } };
+struct RadialForce : Impose { shared_ptr<Node> nodeA, nodeB; double Fmag = 0; int kind() const override { return 4; } };
+struct Local6Dofs : Impose { Q4 ori{{0, 0, 0, 1}}; std::array<double, 6> values{{0, 0, 0, 0, 0, 0}}; std::array<int, 6> whats{{0, 0, 0, 0, 0, 0}}; int kind() const override { return 5; } };
+struct VelocityAndReadForce : Impose { V3 dir{{1, 0, 0}}; double vel = 0; bool latBlock = true, invF = false; string energyName; int kind() const override { return 6; } };
+struct ReadForce : Impose { shared_ptr<Node> node; int kind() const override { return 7; } };
+struct VariableVelocity3d : Impose { vector<double> times; vector<V3> vels, angVels; Q4 ori{{0, 0, 0, 1}}; vector<string> hooks; bool diff = false, wrap = false; double t0 = 0; int kind() const override { return 8; } };
+struct VariableAlignedRotation : Impose { int axis = 0; vector<std::array<double, 2>> timeAngVel; bool wrap = false; int kind() const override { return 9; } };
+struct CombinedImpose : Impose { vector<shared_ptr<Impose>> imps; };
 struct DemData {
   virtual ~DemData() {}
+  shared_ptr<Impose> impose;
   std::weak_ptr<Node> master;      // the clump's master node of a clumped node (DemData::master, Particle.hpp:233)
   V3 vel{{0, 0, 0}}, angVel{{0, 0, 0}}, force{{0, 0, 0}}, torque{{0, 0, 0}}, inertia{{0, 0, 0}}; double mass = 0; unsigned flags = 0;
   DemField* field = nullptr;
   // DemData::guessMoving (Particle.cpp:638-640): does the node need motion integration?
-  bool guessMoving() const { return (mass != 0 && (flags & 63u) != 63u) || vel[0] != 0 || vel[1] != 0 || vel[2] != 0 || angVel[0] != 0 || angVel[1] != 0 || angVel[2] != 0; }
+  bool guessMoving() const { return (mass != 0 && (flags & 63u) != 63u) || vel[0] != 0 || vel[1] != 0 || vel[2] != 0 || angVel[0] != 0 || angVel[1] != 0 || angVel[2] != 0 || bool(impose); }
   string blockedGet() const { string r; const char* n = "xyzXYZ"; for (int i = 0; i < 6; i++) if (flags & (1u << i)) r += n[i]; return r; }
   void blockedSet(const string& s) { flags &= ~63u; for (char c : s) { const char* n = "xyzXYZ"; const char* p = strchr(n, c); if (!p) throw std::invalid_argument("blocked: only xyzXYZ allowed"); flags |= 1u << (p - n); } }
 };
@@ -92,6 +110,7 @@ struct DemField {
   // coherence with the device copy (SURVEY §7 "Host<->device coherence"): upload once, download lazily
   GpuDemLoop* owner = nullptr; bool topoDirty = true, stateDirty = false, deviceNewer = false, contactsStale = true;
   DemField() { par.dem = this; con.dem = this; }
+  vector<shared_ptr<Impose>> imposeOf;        // Impose objects in upload order
   void pull(); void pullContacts(); void pushContacts(wdem_handle h);
   void touchState() { stateDirty = true; }
 };
@@ -192,6 +211,51 @@ struct GpuDemLoop : Engine {
     return std::memcmp(&x, &y, sizeof(wdem_config)) == 0;
   }
 
+  // DemData.impose -> wdem_upload_imposes: one wdem_impose per distinct Impose object, one set per distinct DemData.impose (CombinedImpose = a set of several)
+  void uploadImposes() {
+    DemField& F = *field; F.imposeOf.clear();
+    vector<wdem_impose> imps; vector<vector<double>> keep; keep.reserve(64); std::map<Impose*, int> ixOf, setOf; vector<int32_t> setStart{0}, setOps;
+    auto unit = [](const V3& d, double* o) { const double n = std::sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]); for (int k = 0; k < 3; k++) o[k] = d[k] / n; };      // postLoad: dir.normalize()
+    std::function<int(const shared_ptr<Impose>&)> one = [&](const shared_ptr<Impose>& I) -> int {
+      auto it = ixOf.find(I.get()); if (it != ixOf.end()) return it->second;
+      wdem_impose w; std::memset(&w, 0, sizeof(w)); w.ori[3] = 1; w.kind = I->kind();
+      if (auto* p = dynamic_cast<HarmonicOscillation*>(I.get())) { w.flags = p->perpFree ? 1 : 0; w.v[0] = p->freq; w.v[1] = p->amp; unit(p->dir, w.v + 2); w.v[5] = p->t0; }
+      else if (auto* p = dynamic_cast<AlignedHarmonicOscillations*>(I.get())) { for (int k = 0; k < 3; k++) { w.v[k] = p->freqs[k]; w.v[3 + k] = p->amps[k]; } }
+      else if (auto* p = dynamic_cast<ConstantForce*>(I.get())) { for (int k = 0; k < 3; k++) w.v[k] = p->Fc[k]; }
+      else if (auto* p = dynamic_cast<RadialForce*>(I.get())) { if (!p->nodeA || !p->nodeB) throw std::runtime_error("RadialForce: nodeA and nodeB must not be None."); for (int k = 0; k < 3; k++) { w.v[k] = p->nodeA->pos[k]; w.v[3 + k] = p->nodeB->pos[k]; } w.v[6] = p->Fmag; }
+      else if (auto* p = dynamic_cast<Local6Dofs*>(I.get())) { for (int k = 0; k < 6; k++) { w.v[k] = p->values[k]; w.v[6 + k] = p->whats[k]; } for (int k = 0; k < 4; k++) w.ori[k] = p->ori[k]; }
+      else if (auto* p = dynamic_cast<VelocityAndReadForce*>(I.get())) { if (!p->energyName.empty()) throw std::runtime_error("GpuDemLoop: VelocityAndReadForce.energyName is not supported"); w.flags = (p->latBlock ? 1 : 0) | (p->invF ? 2 : 0); unit(p->dir, w.v); w.v[3] = p->vel; w.v[4] = p->dist; }
+      else if (auto* p = dynamic_cast<ReadForce*>(I.get())) { if (p->node) { w.flags = 1; for (int k = 0; k < 3; k++) w.v[k] = p->node->pos[k]; for (int k = 0; k < 4; k++) w.ori[k] = p->node->ori[k]; } }
+      else if (auto* p = dynamic_cast<VariableVelocity3d*>(I.get())) {
+        for (auto& hk : p->hooks) if (!hk.empty()) throw std::runtime_error("GpuDemLoop: VariableVelocity3d.hooks are not supported");
+        if (p->times.size() != p->vels.size()) throw std::runtime_error("VariableVelocity3d: times and vels must have the same length (not " + std::to_string(p->times.size()) + ", " + std::to_string(p->vels.size()) + ").");
+        if (!p->angVels.empty() && p->angVels.size() != p->times.size()) throw std::runtime_error("VariableVelocity3d.angVels: if not empty, it length (" + std::to_string(p->angVels.size()) + " must be equal to the length of times (" + std::to_string(p->times.size()) + ").");
+        w.flags = (p->diff ? 1 : 0) | (p->wrap ? 2 : 0); w.v[0] = p->t0; for (int k = 0; k < 4; k++) w.ori[k] = p->ori[k]; w.nTimes = (int)p->times.size();
+        keep.push_back(p->times); w.times = keep.back().data();
+        keep.emplace_back(); for (auto& x : p->vels) for (int k = 0; k < 3; k++) keep.back().push_back(x[k]); w.vals = keep.back().data();
+        if (!p->angVels.empty()) { keep.emplace_back(); for (auto& x : p->angVels) for (int k = 0; k < 3; k++) keep.back().push_back(x[k]); w.vals2 = keep.back().data(); }
+      }
+      else if (auto* p = dynamic_cast<VariableAlignedRotation*>(I.get())) {
+        w.flags = p->wrap ? 1 : 0; w.v[0] = p->axis; w.nTimes = (int)p->timeAngVel.size();
+        keep.emplace_back(); for (auto& x : p->timeAngVel) keep.back().push_back(x[0]); w.times = keep.back().data();
+        keep.emplace_back(); for (auto& x : p->timeAngVel) keep.back().push_back(x[1]); w.vals = keep.back().data();
+      }
+      else throw std::runtime_error("GpuDemLoop: this Impose class is not supported on the device path");
+      I->field = field.get(); imps.push_back(w); F.imposeOf.push_back(I); return ixOf[I.get()] = (int)imps.size() - 1;
+    };
+    auto setFor = [&](const shared_ptr<Impose>& I) -> int {
+      auto it = setOf.find(I.get()); if (it != setOf.end()) return it->second;
+      if (auto* c = dynamic_cast<CombinedImpose*>(I.get())) { for (auto& i : c->imps) setOps.push_back(one(i)); I->field = field.get(); } else setOps.push_back(one(I));
+      setStart.push_back((int32_t)setOps.size()); return setOf[I.get()] = (int)setStart.size() - 2;
+    };
+    vector<int32_t> sid, sset, wset(wallOf.size(), -1), gset(F.clumps.size(), -1); bool anyWall = false, anyGroup = false;
+    for (auto& p : sphereOf) { auto& imp = p->shape->nodes[0]->dem->impose; if (imp) { sid.push_back(p->id); sset.push_back(setFor(imp)); } }
+    for (size_t i = 0; i < wallOf.size(); i++) { auto& imp = wallOf[i]->shape->nodes[0]->dem->impose; if (imp) { wset[i] = setFor(imp); anyWall = true; } }
+    for (size_t g = 0; g < F.clumps.size(); g++) { auto& imp = F.clumps[g].master->dem->impose; if (imp) { gset[g] = setFor(imp); anyGroup = true; } }
+    for (auto& n : F.sphereClumps) if (n->dem->impose) throw std::runtime_error("GpuDemLoop: DemData.impose on a clump of spheres is not supported");
+    if (imps.empty()) return;
+    chk(h, wdem_upload_imposes(h, (int32_t)imps.size(), imps.data(), (int32_t)setStart.size() - 1, setStart.data(), setOps.data(), (int64_t)sid.size(), sid.data(), sset.data(), anyWall ? wset.data() : nullptr, anyGroup ? gset.data() : nullptr));
+  }
   // DemField -> device (SoA host staging; ids are Particle.id)
   void upload() {
     DemField& F = *field;
@@ -279,6 +343,7 @@ struct GpuDemLoop : Engine {
       chk(h, wdem_upload_clumps(h, (int32_t)F.sphereClumps.size(), cStart.data(), cMem.data(), cp.data(), co.data(), cv.data(), cw.data(), cl.data(), cm.data(), cI.data(), cFl.data(), crp.data(), cro.data()));
       chk(h, wdem_upload_clump_forces(h, cf.data(), ct.data()));
     }
+    uploadImposes();
     if (scene->periodic) { Cell& C = *scene->cell; chk(h, wdem_set_cell(h, C.hSize.data(), C.gradV.data(), C.nextGradV.data(), C.homoDeform)); C.dirty = false; }
     chk(h, wdem_set_scene(h, (int64_t)scene->step, scene->time));
     F.pushContacts(h);
@@ -367,6 +432,7 @@ struct GpuDemLoop : Engine {
   void run() override { step(1); }
 };
 
+void Impose::touch() { if (field) field->topoDirty = true; }
 void DemField::pull() {
   if (!deviceNewer || !owner || !owner->h) return;
   const size_t n = owner->sphereOf.size();
@@ -383,6 +449,16 @@ void DemField::pull() {
     vector<double> wp(3 * nw), wf(3 * nw), wt(3 * nw);
     chk(owner->h, wdem_download_walls(owner->h, wp.data(), wf.data(), wt.data()));
     for (size_t i = 0; i < nw; i++) { Node& nd = *owner->wallOf[i]->shape->nodes[0]; for (int k = 0; k < 3; k++) { nd.pos[k] = wp[3 * i + k]; nd.dem->force[k] = wf[3 * i + k]; nd.dem->torque[k] = wt[3 * i + k]; } }
+  }
+  if (!imposeOf.empty()) {      // boundary nodes whose velocity an imposition changes
+    const size_t nwl = owner->wallOf.size(), ng = clumps.size(); vector<double> wv(3 * nwl + 3), gv(3 * ng + 3), gw(3 * ng + 3);
+    chk(owner->h, wdem_download_boundary_velocities(owner->h, wv.data(), owner->facetOf.empty() ? nullptr : gv.data(), owner->facetOf.empty() ? nullptr : gw.data()));
+    for (size_t i = 0; i < nwl; i++) for (int k = 0; k < 3; k++) owner->wallOf[i]->shape->nodes[0]->dem->vel[k] = wv[3 * i + k];
+    if (!owner->facetOf.empty()) for (size_t g = 0; g < ng; g++) for (int k = 0; k < 3; k++) { clumps[g].master->dem->vel[k] = gv[3 * g + k]; clumps[g].master->dem->angVel[k] = gw[3 * g + k]; }
+  }
+  for (size_t i = 0; i < imposeOf.size(); i++) {      // what the last step's Leapfrog read / accumulated
+    double o[8]; chk(owner->h, wdem_get_impose_state(owner->h, (int32_t)i, o));
+    Impose& I = *imposeOf[i]; I.sumF = o[0]; I.dist = o[1]; for (int k = 0; k < 3; k++) { I.F[k] = o[2 + k]; I.T[k] = o[5 + k]; }
   }
   if (!sphereClumps.empty()) {
     const size_t nc = sphereClumps.size(); vector<double> p(3 * nc), o(4 * nc), v(3 * nc), w(3 * nc), l(3 * nc), cf(3 * nc), ct(3 * nc);
@@ -516,9 +592,44 @@ PYBIND11_MODULE(_woo, m) {
       .def_property("blocked", &DemData::blockedGet, [](DemData& s, const string& v) { s.blockedSet(v); if (s.field) s.field->topoDirty = true; })
       .def_property("gravitySkip", [](DemData& s) { return bool(s.flags & GRAVITY_SKIP); }, [](DemData& s, bool b) { s.flags = b ? (s.flags | GRAVITY_SKIP) : (s.flags & ~GRAVITY_SKIP); if (s.field) s.field->topoDirty = true; })
       .def("guessMoving", &DemData::guessMoving)
+      .def_property("impose", [](DemData& s) { return s.impose; }, [](DemData& s, shared_ptr<Impose> i) { s.impose = i; if (s.field) s.field->topoDirty = true; })
       .def_property_readonly("clump", [](DemData& s) { return bool(s.flags & CLUMP_CLUMP); }).def_property_readonly("clumped", [](DemData& s) { return bool(s.flags & CLUMP_CLUMPED); })
       .def_property_readonly("master", [](DemData& s) { return s.master.lock(); })
       .def_property("dampingSkip", [](DemData& s) { return bool(s.flags & DAMPING_SKIP); }, [](DemData& s, bool b) { s.flags = b ? (s.flags | DAMPING_SKIP) : (s.flags & ~DAMPING_SKIP); if (s.field) s.field->topoDirty = true; });
+  // ---- Impose classes (dem/Impose.hpp); attribute changes after the upload trigger a re-upload (which keeps particle state and contact history)
+#define RWI(cls, a) .def_property(#a, [](cls& s) { return s.a; }, [](cls& s, decltype(cls::a) v) { s.a = v; s.touch(); })
+#define V3I(cls, pyname, mem) .def_property(pyname, [](cls& s) { return np3(s.mem); }, [](cls& s, py::object o) { s.mem = seqN<3>(o, pyname); s.touch(); })
+  py::class_<Impose, shared_ptr<Impose>>(m, "Impose")
+      .def("__add__", [](shared_ptr<Impose> a, shared_ptr<Impose> b) {      // Impose::pyAdd (Impose.cpp:302-312)
+        auto c = make_shared<CombinedImpose>();
+        if (auto* ca = dynamic_cast<CombinedImpose*>(a.get())) c->imps = ca->imps; else c->imps.push_back(a);
+        if (auto* cb = dynamic_cast<CombinedImpose*>(b.get())) c->imps.insert(c->imps.end(), cb->imps.begin(), cb->imps.end()); else c->imps.push_back(b);
+        return c; });
+  kwclass<HarmonicOscillation, Impose>(m, "HarmonicOscillation") RWI(HarmonicOscillation, freq) RWI(HarmonicOscillation, amp) RWI(HarmonicOscillation, t0) RWI(HarmonicOscillation, perpFree) V3I(HarmonicOscillation, "dir", dir);
+  kwclass<AlignedHarmonicOscillations, Impose>(m, "AlignedHarmonicOscillations") V3I(AlignedHarmonicOscillations, "freqs", freqs) V3I(AlignedHarmonicOscillations, "amps", amps);
+  kwclass<ConstantForce, Impose>(m, "ConstantForce") V3I(ConstantForce, "F", Fc);
+  kwclass<RadialForce, Impose>(m, "RadialForce") RWI(RadialForce, nodeA) RWI(RadialForce, nodeB).def_property("F", [](RadialForce& s) { return s.Fmag; }, [](RadialForce& s, double v) { s.Fmag = v; s.touch(); });
+  kwclass<Local6Dofs, Impose>(m, "Local6Dofs")
+      .def_property("ori", [](Local6Dofs& s) { return np4(s.ori); }, [](Local6Dofs& s, py::object o) { s.ori = seqN<4>(o, "ori"); s.touch(); })
+      .def_property("values", [](Local6Dofs& s) { return s.values; }, [](Local6Dofs& s, py::object o) { s.values = seqN<6>(o, "values"); s.touch(); })
+      .def_property("whats", [](Local6Dofs& s) { return s.whats; }, [](Local6Dofs& s, std::array<int, 6> w) {
+        for (int i = 0; i < 6; i++) if (w[i] != 0 && w[i] != 1 && w[i] != 2) throw std::runtime_error("Local6Dofs.whats components must be 0, 2 or 1 (whats[" + std::to_string(i) + "] invalid)");      // Impose.hpp:96-103
+        s.whats = w; s.touch(); });
+  kwclass<VelocityAndReadForce, Impose>(m, "VelocityAndReadForce") V3I(VelocityAndReadForce, "dir", dir) RWI(VelocityAndReadForce, vel) RWI(VelocityAndReadForce, latBlock) RWI(VelocityAndReadForce, invF) RWI(VelocityAndReadForce, energyName)
+      .def_property("dist", [](VelocityAndReadForce& s) { if (s.field) s.field->pull(); return s.dist; }, [](VelocityAndReadForce& s, double v) { if (s.field) s.field->pull(); s.dist = v; s.touch(); })
+      .def_property_readonly("sumF", [](VelocityAndReadForce& s) { if (s.field) s.field->pull(); return s.sumF; });
+  kwclass<ReadForce, Impose>(m, "ReadForce") RWI(ReadForce, node)
+      .def_property_readonly("F", [](ReadForce& s) { if (s.field) s.field->pull(); return np3(s.F); }).def_property_readonly("T", [](ReadForce& s) { if (s.field) s.field->pull(); return np3(s.T); });
+  kwclass<VariableVelocity3d, Impose>(m, "VariableVelocity3d") RWI(VariableVelocity3d, times) RWI(VariableVelocity3d, hooks) RWI(VariableVelocity3d, diff) RWI(VariableVelocity3d, wrap) RWI(VariableVelocity3d, t0)
+      .def_property("ori", [](VariableVelocity3d& s) { return np4(s.ori); }, [](VariableVelocity3d& s, py::object o) { s.ori = seqN<4>(o, "ori"); s.touch(); })
+      .def_property("vels", [](VariableVelocity3d& s) { py::list l; for (auto& v : s.vels) l.append(np3(v)); return l; }, [](VariableVelocity3d& s, py::iterable o) { s.vels.clear(); for (auto it : o) s.vels.push_back(seqN<3>(py::reinterpret_borrow<py::object>(it), "vels")); s.touch(); })
+      .def_property("angVels", [](VariableVelocity3d& s) { py::list l; for (auto& v : s.angVels) l.append(np3(v)); return l; }, [](VariableVelocity3d& s, py::iterable o) { s.angVels.clear(); for (auto it : o) s.angVels.push_back(seqN<3>(py::reinterpret_borrow<py::object>(it), "angVels")); s.touch(); });
+  kwclass<VariableAlignedRotation, Impose>(m, "VariableAlignedRotation") RWI(VariableAlignedRotation, axis) RWI(VariableAlignedRotation, wrap)
+      .def_property("timeAngVel", [](VariableAlignedRotation& s) { return s.timeAngVel; }, [](VariableAlignedRotation& s, py::iterable o) {
+        s.timeAngVel.clear(); for (auto it : o) s.timeAngVel.push_back(seqN<2>(py::reinterpret_borrow<py::object>(it), "timeAngVel"));
+        for (size_t i = 0; i + 1 < s.timeAngVel.size(); i++) if (!(s.timeAngVel[i + 1][0] >= s.timeAngVel[i][0])) throw py::value_error("VariableAlignedRotation.timeAngVel: time values must be non-decreasing");      // Impose.cpp:89-93
+        s.touch(); });
+  py::class_<CombinedImpose, Impose, shared_ptr<CombinedImpose>>(m, "CombinedImpose").def_readonly("imps", &CombinedImpose::imps);
   py::class_<ClumpData, DemData, shared_ptr<ClumpData>>(m, "ClumpData")
       .def_readonly("nodes", &ClumpData::nodes).def_readonly("equivRad", &ClumpData::equivRad)
       .def_property_readonly("relPos", [](ClumpData& s) { py::list l; for (auto& v : s.relPos) l.append(np3(v)); return l; })
@@ -552,6 +663,7 @@ PYBIND11_MODULE(_woo, m) {
         py::arg("vertices"), py::arg("mat") = py::none(), py::arg("halfThick") = 0., py::arg("fakeVel") = py::none(), py::arg("mask") = 3u, py::arg("fixed") = true);
 #define NODE0(p) (*(p).shape->nodes.at(0))
   kwclass<Particle>(m, "Particle") RW(Particle, id) RW(Particle, mask) RW(Particle, shape) RW(Particle, material)
+      .def_property("impose", [](Particle& p) { return NODE0(p).dem->impose; }, [](Particle& p, shared_ptr<Impose> i) { for (auto& n : p.shape->nodes) n->dem->impose = i; if (p.field) p.field->topoDirty = true; })      // Particle::setImpose (Particle.cpp)
       .def_property("mat", [](Particle& p) { return p.material; }, [](Particle& p, shared_ptr<Material> mm) { p.material = mm; if (p.field) p.field->topoDirty = true; })
       V3P(Particle, "pos", NODE0(s).pos, if (s.field) s.field->pull(), if (s.field) s.field->touchState())
       V3P(Particle, "vel", NODE0(s).dem->vel, if (s.field) s.field->pull(), if (s.field) s.field->touchState())

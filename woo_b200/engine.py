@@ -126,6 +126,36 @@ class Engine:
         arr = lambda k, w: f64([g[k] for g in groups], (len(groups), w))
         self._chk(self.L.wdem_upload_facet_groups(self.h, C.c_int(len(groups)), ptr(of), ptr(arr("pos", 3)), ptr(arr("ori", 4)), ptr(arr("vel", 3)), ptr(arr("angVel", 3))))
 
+    def upload_imposes(self, S):
+        """DemData.impose of spheres, walls and facet groups of a SceneSpec (wdem.h: wdem_upload_imposes)."""
+        from .capi import WdemImpose
+        imps = getattr(S, "imposes", [])
+        if not imps:
+            return
+        keep = []      # arrays referenced by pointer from the descriptors
+        arr = (WdemImpose * len(imps))()
+        for a, d in zip(arr, imps):
+            a.kind, a.flags = int(d["kind"]), int(d["flags"])
+            a.v[:] = [float(x) for x in d["v"]]; a.ori[:] = [float(x) for x in d["ori"]]
+            a.nTimes = len(d["times"])
+            for name in ("times", "vals", "vals2"):
+                if len(d[name]):
+                    b = np.ascontiguousarray(d[name], dtype=np.float64); keep.append(b); setattr(a, name, b.ctypes.data)
+        start = np.zeros(len(S.impose_sets) + 1, np.int32); start[1:] = np.cumsum([len(s) for s in S.impose_sets])
+        ops = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int32) for s in S.impose_sets]), dtype=np.int32)
+        sid = np.ascontiguousarray(S.sphere_ids(), dtype=np.int32)
+        sset = None if S.sphere_impose is None else np.ascontiguousarray(S.sphere_impose, dtype=np.int32)
+        wset = None if S.wall_impose is None else np.ascontiguousarray(S.wall_impose, dtype=np.int32)
+        gset = None if S.group_impose is None else np.ascontiguousarray(S.group_impose, dtype=np.int32)
+        self._chk(self.L.wdem_upload_imposes(self.h, C.c_int32(len(imps)), arr, C.c_int32(len(S.impose_sets)), ptr(start), ptr(ops), C.c_int64(len(sid) if sset is not None else 0),
+                                             ptr(sid), ptr(sset), ptr(wset), ptr(gset)))
+
+    def impose_state(self, ix):
+        """sumF, dist (VelocityAndReadForce), F, T (ReadForce) of Impose object ix (wdem.h: wdem_get_impose_state)."""
+        o = np.zeros(8)
+        self._chk(self.L.wdem_get_impose_state(self.h, C.c_int32(ix), ptr(o)))
+        return dict(sumF=o[0], dist=o[1], F=o[2:5].copy(), T=o[5:8].copy())
+
     def upload_clumps(self, sphere_ids, clumps):
         """Clumps of spheres with mass (wdem.h: wdem_upload_clumps): dicts with members (indices into the uploaded spheres), pos, ori (x,y,z,w), vel, angVel, mass,
         inertia (3), flags and optionally angMom, relPos, relOri."""
@@ -173,6 +203,7 @@ class Engine:
         self.upload_facet_groups(len(S.facets), getattr(S, "facet_groups", []))
         if S.cell is not None:
             self.set_cell(S.cell["hSize"], S.cell.get("gradV"), S.cell.get("nextGradV"), S.cell.get("homoDeform", 4))
+        self.upload_imposes(S)
         return self
 
     # ---- stepping
