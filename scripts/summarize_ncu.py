@@ -1,6 +1,6 @@
 """Summarise ncu outputs brought back in gpurun_out/ into small tracked files under profiles/.
   python scripts/summarize_ncu.py launches gpurun_out/launches_X.csv profiles/rNN_launches.md
-  python scripts/summarize_ncu.py full gpurun_out/prof_X.ncu-rep profiles/rNN_full.md
+  python scripts/summarize_ncu.py full gpurun_out/prof_X.ncu-rep|X_raw.csv profiles/rNN_full.md
 """
 import collections, csv, subprocess, sys
 
@@ -28,7 +28,8 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # src: an .ncu-rep, or the CSV that `ncu -i X.ncu-rep --page raw --csv` printed on the GPU box (scripts/gpu_profile.sh)
+    out = open(src).read() if src.endswith(".csv") else subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
