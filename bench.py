@@ -383,12 +383,14 @@ def run_gpu(args):
         s = E.spheres()
         tp, tv, tw = pin(s["pos"]), pin(s["vel"]), pin(s["angVel"])
         po, vo = torch.empty_like(tp).pin_memory(), torch.empty_like(tv).pin_memory()
+        # stats=False: each call returns when that step's pos/vel/kinetic energy are in the host buffers; the contact pass preparing the next step's forces
+        # overlaps the next call's upload (include/wdem.h).  The closing barrier() synchronises the device, so the last step's contact pass is inside the timed region.
         for _ in range(3):
-            E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy()); tp, po = po, tp; tv, vo = vo, tv
+            E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy(), stats=False); tp, po = po, tp; tv, vo = vo, tv
         barrier()
         e0 = time.time()
         for _ in range(ke):
-            ek, _st = E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy())
+            ek, _st = E.step_e2e(1, tp.numpy(), tv.numpy(), tw.numpy(), po.numpy(), vo.numpy(), stats=False)
             tp, po = po, tp; tv, vo = vo, tv     # the step's output buffers are the next step's host-side input (no host copy)
         barrier()
         e1 = time.time()
@@ -422,11 +424,12 @@ def run_gpu(args):
     E.close()
     # ---- reduce over ranks (max of times)
     t = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([stats["sum_real"], stats["sum_potential_evaluated"], stats["n_rebuilds"], stats["n_launches"], stats["n_real"], stats["n_contacts"]], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([stats["sum_real"], stats["sum_potential_evaluated"], stats["n_rebuilds"], stats["n_launches"], stats["n_real"], stats["n_contacts"], h2d, d2h], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, e2e_ms, wall_ms = [float(x) for x in t.cpu()]
-    sum_real, sum_pot, n_reb, n_launch, n_real, n_con = [float(x) for x in cnt.cpu()]
+    sum_real, sum_pot, n_reb, n_launch, n_real, n_con, h2d, d2h = [float(x) for x in cnt.cpu()]
+    h2d, d2h = int(h2d), int(d2h)      # whole job: summed over the ranks, like `value`
     configs = None
     if not args.no_configs:
         configs = bench_configs(args, rank, world, local)
@@ -451,7 +454,7 @@ def run_gpu(args):
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg2: %d polydisperse spheres (PSD 1:4) per GPU settled under gravity, %s" % (n, law_s),
                    "n_spheres_per_gpu": n, "n_spheres_total": ntot, "law": LAW,
-                   "initial_state": ("tiled pre-settled 20k bed (tests/golden/cfg2_sample_20k.npz) %dx%d, re-settled" % (tiling["tiles_x"], tiling["tiles_y"])) if tiling else "jittered lattice", "settle_steps": args.settle, "real_contacts": n_real, "candidate_contacts": n_con, "rebuilds_in_timed_region": n_reb,
+                   "initial_state": ("tiled pre-settled 20k bed (tests/golden/cfg2_sample_20k.npz) %dx%d, re-settled" % (tiling["tiles_x"], tiling["tiles_y"])) if tiling else "jittered lattice", "settle_steps": args.settle, "real_contacts": n_real, "candidate_contacts": n_con, "rebuilds_in_timed_region": n_reb / world,      # every subdomain does its full runs in the same steps
                    "l2_policy": "inputs larger than L2 (per-step working set %.0f MB > 126 MB)" % (step_bytes / 1e6), "parallelism": ("%d x-slabs of one box, 1 per GPU; ghosts refreshed per step over NVLink peer memory, spheres migrated at collider runs over NCCL" % world) if world > 1 else "single GPU",
                    "settle_wall_s": round(settle_s, 1), "cpu_affinity": affinity},
         "roofline": {"bound": "hbm", "kernel": "k_contact_ss<IdealElPl>" if LAW == "linear" else "k_contact_ss<HertzDMT>", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
@@ -460,7 +463,7 @@ def run_gpu(args):
                      "step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9, "frac": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9 / peak},
                      "phase_ms_per_step": {k: stats[k] / K for k in ("ms_integrate", "ms_rebuild", "ms_contact", "ms_reduce", "ms_dyndt")}},
         "e2e": {"value": ntot * ke / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
-                "api": "wdem_step_e2e (C-ABI, pinned host buffers)" if D is None else "wdem_set_owned + wdem_step + wdem_download_owned per rank (C-ABI, pinned host buffers)"},
+                "api": "wdem_step_e2e (C-ABI, pinned host buffers, stats=NULL: a step's contact pass overlaps the next step's upload)" if D is None else "wdem_set_owned + wdem_step + wdem_download_owned per rank (C-ABI, pinned host buffers)"},
         "gpu_launches": int(n_launch), "clocks": ck, "wall_ms_per_step": wall_ms / K,
     }
     if parity is not None:

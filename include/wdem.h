@@ -117,13 +117,17 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
 /* ParticleContainer::add in mid-run (ParticleContainer.cpp:23-73; what Inlets do, Inlet.cpp): append spheres to the device state without re-uploading
  * the scene.  Same arrays as wdem_upload_spheres; ids are required and must be unused.  Existing spheres, their forces and the whole contact history stay;
  * the new spheres start with zero force and the collider re-initialises at the next step (contacts dirty).  Upload order continues:
- * the new spheres follow the old ones in wdem_download_state / wdem_set_state.  Single-domain runs only. */
+ * the new spheres follow the old ones in wdem_download_state / wdem_set_state.
+ * Decomposed runs: call on EVERY rank with the SAME arguments (collective in spirit, no communication inside).  Each rank keeps the spheres whose centre lies in
+ * its slab (periodic cells: every world-th sphere of the list) and the full run that follows sends every sphere home and exports its ghosts.  The id check then
+ * covers what the subdomain holds (owned spheres, ghost copies, boundaries); global uniqueness is the caller's business. */
 int wdem_add_spheres(wdem_handle h, int64_t n, const int32_t* ids, const double* pos, const double* ori, const double* vel, const double* angVel,
                      const double* mass, const double* inertia, const double* radius, const uint32_t* flags, const uint32_t* mask,
                      const int32_t* matId);
 /* ParticleContainer::remove in mid-run (ParticleContainer.cpp:121-157; what Outlets do): the spheres with these ids leave the device state, the remaining ones keep
  * their state, their forces and their contact history; contacts of the removed spheres are dropped and the collider re-initialises at the next step.  The upload
- * order closes up (remaining spheres keep their relative order).  Single-domain runs only. */
+ * order closes up (remaining spheres keep their relative order).
+ * Decomposed runs: call on EVERY rank with the SAME list; each rank lets go of what it holds of it (owned spheres and ghost copies) and ignores the ids it does not hold. */
 int wdem_remove_spheres(wdem_handle h, int64_t n, const int32_t* ids);
 int wdem_upload_forces(wdem_handle h, const double* force, const double* torque);
 /* Walls (dem/Wall.hpp): static; vel may be NULL. */
@@ -183,7 +187,11 @@ int wdem_get_cell(wdem_handle h, double* hSize);
 /* nsteps times Scene::doOneStep restricted to this engine group (Scene.cpp:366-432): cell.integrateAndUpdate,
  * Leapfrog, collider, ContactLoop, DynDt, epilogue (step++, time+=dt, dt=nextDt). stats may be NULL. */
 int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats);
-/* End-to-end variant for the public API benchmark: uploads pos/vel/angVel (host, upload order), steps, downloads pos/vel. */
+/* End-to-end variant (host buffers in and out; what a host program that owns the particle state calls every step, cf. Scene::doOneStep with the state in
+ * DemField.nodes): uploads pos/vel/angVel (host, upload order), steps, downloads pos/vel (+ kinetic energy).  The copies overlap with the integrator chunk by chunk.
+ * With stats == NULL (and nsteps == 1) the call returns as soon as the step's positions and velocities are on the host: the contact pass that prepares the forces
+ * of the NEXT step is still running and overlaps the next call's upload.  Every other entry point waits for it as usual; an error raised by that contact pass
+ * (NaN force, ...) is reported by the next call.  With stats != NULL the call waits for the whole step (the counters are part of the statistics). */
 int wdem_step_e2e(wdem_handle h, int64_t nsteps, const double* pos_in, const double* vel_in, const double* angVel_in,
                   double* pos_out, double* vel_out, double* ek_out, wdem_stats* stats);
 
@@ -210,6 +218,11 @@ int wdem_upload_contacts(wdem_handle h, int64_t n, const int32_t* ids, const int
                          const double* forceLocal, const double* torqueLocal, const double* trsf, const double* contPt, const double* physRaw);
 /* Scene.step / Scene.time (Scene.hpp:191-205) of a resumed scene: trsfRenorm and DynDt's period count scene steps. */
 int wdem_set_scene(wdem_handle h, int64_t step, double time);
+/* PeriodicEngine.stepLast / .stepPrev of DynDt (Engine.hpp:156-157, Engine.cpp:170-195): the step of DynDt's last activation and of the one before, -1 = never ran.
+ * wdem_set_scene resets both to -1 (a fresh engine); set them after it to resume a run exactly where a saved scene left it — otherwise DynDt's period restarts at the
+ * resumed step.  Either output pointer may be NULL. */
+int wdem_set_periodic_state(wdem_handle h, int64_t dynDtStepLast, int64_t dynDtStepPrev);
+int wdem_get_periodic_state(wdem_handle h, int64_t* dynDtStepLast, int64_t* dynDtStepPrev);
 /* Walls after the last step, in upload order (any pointer may be NULL): position (a wall uploaded with a nonzero velocity is in DemField.nodes and is
  * translated by Leapfrog, pos += vel*dt — Leapfrog.cpp:195-199,275-278, Particle.cpp:638-640) and DemData.force / torque as the reference's scripts see them
  * (ContactLoop::applyForceUninodal, ContactLoop.cpp:270-276): for a MOVING wall the last step's contacts (Leapfrog resets its force every step; summed in ascending id
@@ -251,6 +264,13 @@ int wdem_local_group_destroy(void* group);
 int wdem_comm_init_local(wdem_handle h, void* group, int rank);
 /* cuts: world-1 ascending slab boundaries along axis (absolute coordinates; periodic: fractions of the cell size). globalMaxId: largest Particle.id of the scene. */
 int wdem_set_domain(wdem_handle h, int axis, int ncuts, const double* cuts, int64_t globalMaxId);
+/* Re-balancing at collider full runs (quantile cuts at rebuild time).  When, at a full run, the largest subdomain owns more than (1+tolerance) times the
+ * mean number of spheres — and at least minFullRuns full runs have passed since the last re-balancing — the cuts move to the k/world quantiles of the slab coordinate
+ * of all spheres (a 2048-bin histogram over the global extent, summed over the ranks) and the spheres migrate accordingly in the same full run.  Results do not depend on
+ * the cuts (N subdomains are bit-identical to one).  tolerance 0 switches it off (the default).  Collective: call with the same values on every rank.
+ * wdem_get_domain: the current cuts (world-1 values) and how many times they were moved; either pointer may be NULL. */
+int wdem_set_rebalance(wdem_handle h, double tolerance, int minFullRuns);
+int wdem_get_domain(wdem_handle h, double* cuts, int64_t* nRebalances);
 int64_t wdem_num_owned(wdem_handle h);
 /* Owned spheres in subdomain order with their ids (any pointer but ids may be NULL); arrays sized by wdem_num_owned. */
 int wdem_download_owned(wdem_handle h, int32_t* ids, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque);

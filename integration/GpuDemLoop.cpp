@@ -168,6 +168,7 @@ void GpuDemLoop::upload(){
 		chk(h,wdem_set_cell(h,H,G,N,C.homoDeform));
 	}
 	chk(h,wdem_set_scene(h,(int64_t)scene->step,scene->time));
+	if(dynDt && !dynDt->dead) chk(h,wdem_set_periodic_state(h,dynDt->stepLast,dynDt->stepPrev));   // a re-upload in mid-run does not restart DynDt's period
 	pushContacts();
 	nParticlesUploaded=dem.particles->size(); stepUploaded=scene->step;
 }
@@ -334,6 +335,7 @@ void GpuDemLoop::run(){
 	int64_t nf=0; double libDt=NaN;
 	chk(h,wdem_get_scalars(h,&libDt,nullptr,nullptr,nullptr,&nf));
 	collider->nFullRuns=(int)nf;
+	if(dynDt && !dynDt->dead){ int64_t a=-1,b=-1; chk(h,wdem_get_periodic_state(h,&a,&b)); dynDt->stepLast=(long)a; dynDt->stepPrev=(long)b; }
 	if(scene->isPeriodic){ double H[9]; chk(h,wdem_get_cell(h,H)); Matrix3r m; for(int i:{0,1,2}) for(int j:{0,1,2}) m(i,j)=H[3*i+j]; scene->cell->setHSize(m); }
 	if(scene->trackEnergy){
 		double e[8]; chk(h,wdem_get_energy(h,e));

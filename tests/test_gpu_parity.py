@@ -181,6 +181,82 @@ def test_decomposed_scrambled_start_and_axes():
         compare(S, 120, check_every=30, label=f"decomposed scrambled axis={axis}", make=cluster(3, axis=axis, scramble=True))
 
 
+@pytest.mark.parametrize("kind", ["gas", "periodic"])
+def test_decomposed_rebalance_moves_cuts_and_keeps_bits(kind):
+    """wdem_set_rebalance: lopsided cuts (one subdomain owns most of the scene) move to the quantiles at a full run; the result stays bit-identical to the oracle."""
+    from woo_b200.domain import LocalCluster
+    if kind == "gas":
+        S = sc.random_gas(600, box=.5, r=.02, psd_ratio=3.0, seed=41); lo, hi = S.pos[:, 0].min(), S.pos[:, 0].max()
+        cuts = [lo + .1 * (hi - lo), lo + .2 * (hi - lo)]
+    else:
+        S = sc.periodic_gas(500, cell=(.6, .4, .45), r=.02, psd_ratio=2.0, seed=43, gradV=[[0, 2.0, 0], [0, 0, 0], [0, 0, 0]]); cuts = [.1, .2]
+
+    def make(S_):
+        E = LocalCluster(S_, 3, axis=0, cuts=cuts); E.set_rebalance(.10, 2); return E
+    O, E = compare(S, 200, check_every=25, label="rebalance " + kind, make=make)
+    if kind == "periodic": compare_potential(O, E)
+    new_cuts, nreb = E.domain()
+    own = [d["owned"] for d in E.domain_stats()]
+    assert nreb >= 1 and not np.allclose(new_cuts, cuts), (new_cuts, nreb)
+    assert max(own) <= 1.25 * np.mean(own), "still unbalanced after re-balancing: %r" % own
+    assert sum(own) == S.n
+
+
+@pytest.mark.parametrize("kind", ["gas-hertz", "periodic"])
+def test_decomposed_add_and_remove_spheres(kind):
+    """wdem_add_spheres / wdem_remove_spheres in decomposed runs (the same call on every subdomain): insertion, removal, and a freed id handed out again, all
+    bit-identical to the oracle — i.e. to the single-domain engine."""
+    import math
+    from woo_b200.domain import LocalCluster
+    if kind == "gas-hertz":
+        S = sc.random_gas(400, box=.5, r=.02, psd_ratio=2.0, seed=181, law=sc.LAW_HERTZ_DMT, en=.6); lo, hi = .05, .45
+    else:
+        S = sc.periodic_gas(400, cell=(.6, .4, .45), r=.02, psd_ratio=2.0, seed=183, gradV=[[0, 1.5, 0], [0, 0, 0], [0, 0, 0]]); lo, hi = .0, .4
+    O = Oracle(S); E = LocalCluster(S, 3, axis=0)
+    rng = np.random.default_rng(182)
+    dens = S.mats[0][1]
+
+    def check(label):
+        so, sg = O.spheres(), E.spheres()
+        oo = np.argsort(O.sphere_ids())
+        assert len(sg["pos"]) == len(so["pos"]), label
+        for k_ in ("pos", "vel", "angVel", "force", "torque"):
+            assert np.array_equal(so[k_][oo], sg[k_]), f"{label}: {k_} differs"
+        co, cg = O.contacts(True), E.contacts(True)
+        assert [tuple(x) for x in co["ids"]] == [tuple(x) for x in cg["ids"]], label
+        for k_ in ("uN", "force", "trsf", "stepCreated"):
+            assert np.array_equal(co[k_], cg[k_]), f"{label}: contact {k_} differs"
+        assert O.nFullRuns == E.scalars()["nFullRuns"] and O.dt == E.scalars()["dt"], label
+
+    O.step(60); E.step(60); check("before")
+    for batch in range(2):
+        m = 30
+        pos = rng.uniform(lo, hi, (m, 3)); rad = .02 * np.exp(rng.uniform(math.log(.5), math.log(2.), m))
+        vel = rng.uniform(-1, 1, (m, 3)); ang = rng.uniform(-5, 5, (m, 3))
+        mass = dens * (4 / 3.) * math.pi * rad ** 3; inertia = .4 * mass * rad ** 2
+        first = O.add_spheres(pos, rad, mass, inertia, np.zeros(m, np.int32), vel=vel, angVel=ang)
+        ids = np.arange(first, first + m, dtype=np.int32)
+        E.add_spheres(ids, pos, rad, mass, inertia, vel=vel, angVel=ang)
+        for k in range(2):
+            O.step(40); E.step(40); check(f"after insertion {batch}.{k}")
+    live = np.sort(O.sphere_ids())
+    gone = np.sort(rng.choice(live, 50, replace=False)).astype(np.int32)
+    assert np.isin(O.contacts(True)["ids"], gone).any(), "the removed spheres should have contacts"
+    O.remove_spheres(gone); E.remove_spheres(gone)
+    # a newcomer takes over the oldest freed id in the same breath (ParticleContainer::findFreeId)
+    rad = np.array([.025]); mass = dens * (4 / 3.) * math.pi * rad ** 3; pos = np.array([[.5 * (lo + hi)] * 3]); vel = np.array([[.2, -.1, .3]])
+    new_id = O.add_spheres(pos, rad, mass, .4 * mass * rad ** 2, np.zeros(1, np.int32), vel=vel)
+    assert new_id == int(gone[0])
+    E.add_spheres(np.array([new_id], np.int32), pos, rad, mass, .4 * mass * rad ** 2, vel=vel)
+    for k in range(3):
+        O.step(40); E.step(40); check(f"after removal {k}")
+    st = E.domain_stats()
+    assert sum(d["owned"] for d in st) == len(O.sphere_ids())
+    from woo_b200.engine import WdemError
+    with pytest.raises(WdemError):
+        E.add_spheres(np.array([new_id], np.int32), pos, rad, mass, .4 * mass * rad ** 2)      # id in use
+
+
 def test_decomposed_deposition():
     S = sc.deposition(2000, seed=1)
     compare(S, 400, check_every=100, label="decomposed deposition", make=cluster(4))
@@ -205,8 +281,8 @@ def test_decomposed_periodic_shear(world):
 # ---------------------------------------------------------------------------------------------------------------
 # end-to-end path (host buffers in, host buffers out): the chunk-pipelined wdem_step_e2e must give the resident path's bits
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [37, 3000])
-def test_step_e2e_pipelined_matches_resident_and_oracle(n, monkeypatch):
+@pytest.mark.parametrize("n,stats", [(37, True), (3000, True), (3000, False)])
+def test_step_e2e_pipelined_matches_resident_and_oracle(n, stats, monkeypatch):
     S = sc.random_gas(n, box=.3 if n < 100 else .9, r=.02, psd_ratio=2.0, seed=21)
     O = Oracle(S); A = engine_for(S); B = engine_for(S)
     A.step(30); B.step(30); O.step(30)                      # rebuilds have reordered the slots: upload order != slot order
@@ -214,12 +290,12 @@ def test_step_e2e_pipelined_matches_resident_and_oracle(n, monkeypatch):
     pos, vel, w = s["pos"].copy(), s["vel"].copy(), s["angVel"].copy()
     po, vo = np.empty_like(pos), np.empty_like(vel)
     for k in range(40):
-        ek, st = B.step_e2e(1, pos, vel, w, po, vo)
+        ek, st = B.step_e2e(1, pos, vel, w, po, vo, stats=stats)      # stats=False: returns while the step's contact pass is still running
         A.step(1); O.step(1)
         sa = A.spheres()
         assert np.array_equal(po, sa["pos"]) and np.array_equal(vo, sa["vel"]), f"e2e outputs differ from the resident path at step {k}"
         assert abs(ek - A.kinetic_energy()) <= 1e-13 * abs(ek)    # block sums run over slots; a collider run inside the step reorders them
-        assert st.n_real == len(A.contacts(True)["ids"])
+        if stats: assert st.n_real == len(A.contacts(True)["ids"])
         pos, po = po, pos; vel, vo = vo, vel
         w = B.spheres()["angVel"].copy()                    # angVel is an input of the call only; read it back for the next one
     so, sb = O.spheres(), B.spheres()
@@ -237,10 +313,13 @@ def test_step_e2e_pipelined_matches_resident_and_oracle(n, monkeypatch):
 # The candidate set of the resumed engine differs (its collider runs at other steps), which must not matter: real contacts, their history and the
 # per-particle summation order do not depend on it.
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind", ["gas-linear-rolling", "gas-hertz", "facets", "periodic"])
+@pytest.mark.parametrize("kind", ["gas-linear-rolling", "gas-hertz", "facets", "periodic", "gas-dyndt"])
 def test_resume_from_uploaded_contacts(kind):
     from woo_b200.engine import Engine
-    if kind == "gas-linear-rolling":
+    import copy
+    if kind == "gas-dyndt":      # DynDt keeps firing across the resume: its PeriodicEngine counters travel through wdem_set_periodic_state, dt through the config
+        S = sc.random_gas(400, box=.5, r=.02, psd_ratio=3.0, seed=36)
+    elif kind == "gas-linear-rolling":
         S = sc.random_gas(400, box=.5, r=.02, psd_ratio=3.0, seed=31); S.params.relRollStiff = .3; S.params.relTwistStiff = .2; S.params.rollTanPhi = .4
     elif kind == "gas-hertz":
         S = sc.random_gas(400, box=.5, r=.02, psd_ratio=2.0, seed=32, law=sc.LAW_HERTZ_DMT, en=.7)
@@ -248,12 +327,13 @@ def test_resume_from_uploaded_contacts(kind):
         S = sc.facet_box_scene(300, seed=33)
     else:
         S = sc.periodic_gas(300, seed=34, gradV=[[0, 1., 0], [0, 0, 0], [0, 0, 0]], shear0=.1)
-    S.params.dynDtPeriod = 0        # PeriodicEngine's own counters are not part of the exchanged state
+    S.params.dynDtPeriod = 40 if kind == "gas-dyndt" else 0
     O = Oracle(S); A = engine_for(S)
     A.step(150); O.step(150)
     s, c, sca = A.spheres(), A.contacts(True), A.scalars()
     assert len(c["ids"]) > 10
-    B = Engine(S.params)
+    P = copy.copy(S.params); P.dt = sca["dt"]
+    B = Engine(P)
     B.spec = S
     B.upload_materials(S.mats)
     m, I = S.mass_inertia()
@@ -263,9 +343,13 @@ def test_resume_from_uploaded_contacts(kind):
     if S.cell is not None:
         B.set_cell(A.cell_hsize(), S.cell.get("gradV"), S.cell.get("nextGradV"), S.cell.get("homoDeform", 4))
     B.set_scene(sca["step"], sca["time"])
+    if kind == "gas-dyndt":
+        assert A.periodic_state() == (120, 80)
+        B.set_periodic_state(*A.periodic_state())
     B.upload_contacts(c)
     for k in range(4):
         A.step(40); B.step(40); O.step(40)
+        assert A.scalars()["dt"] == B.scalars()["dt"]
         sa, sb, so = A.spheres(), B.spheres(), O.spheres()
         for k_ in ("pos", "vel", "angVel", "force", "torque"):
             assert np.array_equal(sa[k_], sb[k_]), f"{kind}: {k_} of the resumed run differs after {40 * (k + 1)} steps"

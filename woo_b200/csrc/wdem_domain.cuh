@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) k_dom_count_rows_all(const uint32_t* __re
   int c = 0;
   if (k < n && oc.valid) {
     const uint32_t key = keys[k];
-    if (key >= 1u && key <= (uint32_t)world) { const int s = slots[k]; for (int e = oc.rowStart[s]; e < oc.rowStart[s + 1]; e++) { const uint32_t f = oflags[oc.rowEntry[e] >> 1]; if ((f & CF_REAL) && !(f & CF_DEAD)) c++; } }
+    if (key >= 1u && key <= (uint32_t)world && slots[k] < oc.nRows) { const int s = slots[k]; for (int e = oc.rowStart[s]; e < oc.rowStart[s + 1]; e++) { const uint32_t f = oflags[oc.rowEntry[e] >> 1]; if ((f & CF_REAL) && !(f & CF_DEAD)) c++; } }
   }
   rowCnt[k] = c;
 }
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(128) k_dom_pack_rows(const int* __restrict__ s
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= cnt || !oc.valid) return;
   const int s = slots[first + k];
+  if (s >= oc.nRows) return;      // appended since the rows were built (wdem_add_spheres): no history
   int w = rowOff[k];
   for (int e = oc.rowStart[s]; e < oc.rowStart[s + 1]; e++) {
     const long long co = oc.rowEntry[e] >> 1;
@@ -206,6 +207,50 @@ __global__ void __launch_bounds__(256) k_dom_fast_scan(Spheres S, int n, DomainU
     const unsigned c = __reduce_add_sync(0xffffffffu, (m >> r) & 1u);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&out[1 + r], (int)c);
   }
+}
+// re-balancing of the cuts at a full run: histogram of the slab coordinate of the owned spheres over [lo, lo + nb/inv) (coordinates outside fall into the end bins)
+#define WD_REBAL_BINS 2048
+__global__ void __launch_bounds__(256) k_dom_coord_hist(Spheres S, int n, DomainU D, double lo, double inv, int* hist /*[WD_REBAL_BINS]*/) {
+  __shared__ int sh[WD_REBAL_BINS];
+  for (int k = threadIdx.x; k < WD_REBAL_BINS; k += blockDim.x) sh[k] = 0;
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(S.flags[i] & F_GHOST)) {
+    const double x = (slabCoord(D, S.posr[i]) - lo) * inv;
+    const int b = x < 0. ? 0 : (x >= (double)(WD_REBAL_BINS - 1) ? WD_REBAL_BINS - 1 : (int)x);
+    atomicAdd(&sh[b], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < WD_REBAL_BINS; k += blockDim.x) if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+// wdem_add_spheres / wdem_remove_spheres in decomposed runs (every rank gets the same list).
+// is any of these ids held here (owned sphere or ghost copy)?
+__global__ void __launch_bounds__(256) k_dom_ids_in_use(const int32_t* __restrict__ ids, int m, const int* __restrict__ id2slot, long long cap, int n, int* flag) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int id = ids[k];
+  if (id >= 0 && id < cap) { const int s = id2slot[id]; if (s >= 0 && s < n) atomicMax(flag, id + 1); }
+}
+// removal: whatever this subdomain holds of the listed spheres stops being owned (the next full run drops it like a ghost of the previous generation); keep[slot]=0 for k_kill_rows
+__global__ void __launch_bounds__(256) k_dom_mark_removed(const int32_t* __restrict__ ids, int m, const int* __restrict__ id2slot, long long cap, int n, uint32_t* flags, int* keep, int* nOwnedGone) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int id = ids[k];
+  if (id < 0 || id >= cap) return;
+  const int s = id2slot[id];
+  if (s < 0 || s >= n) return;
+  keep[s] = 0;
+  if (!(flags[s] & F_GHOST)) atomicAdd(nOwnedGone, 1);
+  flags[s] |= F_GHOST;
+}
+// appended spheres are addressable by id at once (a later add / remove in the same breath must see them)
+__global__ void __launch_bounds__(256) k_dom_map_appended(const int32_t* __restrict__ sid, int first, int cnt, int* id2slot) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < cnt) id2slot[sid[first + k]] = first + k;
+}
+__global__ void __launch_bounds__(256) k_dom_forget_ids(const int32_t* __restrict__ ids, int m, int* id2slot, long long cap) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < m && ids[k] >= 0 && ids[k] < cap) id2slot[ids[k]] = -1;
 }
 // the ghosts of the previous generation leave in place: their slots are cut off by the full run that follows
 __global__ void __launch_bounds__(256) k_dom_mark_dead(uint32_t* flags, int n) {

@@ -149,6 +149,8 @@ struct DomainState {
   DBuf<char> sendBuf, recvBuf; DBuf<unsigned long long> immKeys, immKeysAlt; DBuf<int> immVals, immValsAlt; int nImm = 0;
   long long migratedOut = 0, migratedIn = 0, rowsIn = 0;
   // per-step exchange over peer memory (k_halo_push / k_peer_sync): my mailbox (words + 2 halo buffers), the peers' mailboxes mapped with CUDA IPC
+  // re-balancing (wdem_set_rebalance): when the largest subdomain owns more than (1+rebalTol) x the mean at a full run, the cuts move to the quantiles of the slab coordinate
+  double rebalTol = 0.; int rebalMinRuns = 1; long long lastRebalRun = -1, nRebalances = 0; DBuf<int> hist;
   int deadSlots = 0;      // slots of the current generation flagged F_DEADSLOT (domainExchange's in-place path), cut off by the collider run that follows
   struct Peer { bool active = false, disabled = false; unsigned long long syncSeq = 0; char* box = nullptr; long long haloCap = 0; void* base[WDEM_MAX_RANKS] = {}; std::vector<long long> dstOff; long long maxRecvTot = 0; } peer;
   void release() {
@@ -208,8 +210,9 @@ struct wdem_engine {
   bool trackEnergy = false; DBuf<double> dEnergy;   // Scene.trackEnergy: EN_* accumulators on the device
   // end-to-end pipeline (wdem_step_e2e): host<->device copies of the state overlap with the integrator chunk by chunk
   static const int NCHUNK = 16; int nChunk = 8;   // NCHUNK = capacity, nChunk = pieces in use (WDEM_E2E_CHUNKS)
-  struct E2E { bool active = false; const double *pos = nullptr, *vel = nullptr, *angVel = nullptr; double *posOut = nullptr, *velOut = nullptr; } e2e;
+  struct E2E { bool active = false; bool defer = false; bool ioBusy = false; const double *pos = nullptr, *vel = nullptr, *angVel = nullptr; double *posOut = nullptr, *velOut = nullptr; } e2e;
   cudaStream_t sH2D = nullptr, sD2H = nullptr; cudaEvent_t evUp[NCHUNK] = {}, evLf[NCHUNK] = {}, evEk = nullptr;
+  int lastLfChunk = 0;
   DBuf<double> ioIn, ioOut; double* hEk = nullptr; size_t hEkCap = 0; int ekBlocks = 0;
   Spheres S() { Spheres v = sph[cur].view(); v.clumpOfId = clumps.n ? clumps.clumpOfId.p : nullptr; v.impOfId = impSpheres ? dImpOfId.p : nullptr; return v; }
 };
@@ -343,6 +346,46 @@ void exclusiveSum(wdem_engine* E, const int* in, int* out, int n) {
 // Leaves the new generation (owned first, then ghosts; unsorted) in the current sphere store.
 static const size_t PEER_WORDS_BYTES = 2 * WDEM_MAX_RANKS * sizeof(unsigned long long);
 PeerU makePeerU(wdem_engine* E);
+// New cuts = the k/W quantiles of the slab coordinate of all owned spheres ("quantile cuts at rebuild time"), from a histogram that every rank
+// builds of its own spheres over the global extent; all ranks add up the same table in the same order, so they arrive at the same cuts.  Collective.
+void rebalanceCuts(wdem_engine* E) {
+  Transport* T = E->comm; DomainState& M = E->dom; const int W = T->world; cudaStream_t st = E->stream;
+  const DomainU D = makeDomainU(E);
+  double lo = 0., hi = D.dim;
+  if (!E->cfg.periodic) {      // global extent along the axis: the boxes measured at the last full run (a superset is fine; what lies outside falls into the end bins)
+    const double* hb = E->hBounds + 8 * (int)((E->nFullRuns + 1) & 1);
+    double mine[2] = {hb[M.axis], hb[3 + M.axis]}; int64_t mi[2], all[2 * WDEM_MAX_RANKS];
+    memcpy(mi, mine, sizeof(mine));
+    T->allgather64(mi, 2, all, st);
+    lo = INFINITY; hi = -INFINITY;
+    for (int r = 0; r < W; r++) { double v[2]; memcpy(v, all + 2 * r, sizeof(v)); if (v[0] <= v[1]) { lo = std::min(lo, v[0]); hi = std::max(hi, v[1]); } }
+    if (!(lo < hi) || !std::isfinite(lo) || !std::isfinite(hi)) return;
+  }
+  const double inv = WD_REBAL_BINS / (hi - lo);
+  M.hist.ensure(WD_REBAL_BINS, E->bytes);
+  CK(cudaMemsetAsync(M.hist.p, 0, WD_REBAL_BINS * sizeof(int), st));
+  if (E->n > 0) { k_dom_coord_hist<<<nblk(E->n, 256), 256, 0, st>>>(E->S(), E->n, D, lo, inv, M.hist.p); E->launches++; }
+  std::vector<int> h(WD_REBAL_BINS);
+  CK(cudaMemcpyAsync(h.data(), M.hist.p, WD_REBAL_BINS * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<int64_t> mine(WD_REBAL_BINS), all((size_t)WD_REBAL_BINS * W);
+  for (int k = 0; k < WD_REBAL_BINS; k++) mine[k] = h[k];
+  T->allgather64(mine.data(), WD_REBAL_BINS, all.data(), st);
+  std::vector<long long> tot(WD_REBAL_BINS, 0); long long N = 0;
+  for (int k = 0; k < WD_REBAL_BINS; k++) { for (int r = 0; r < W; r++) tot[k] += all[(size_t)r * WD_REBAL_BINS + k]; N += tot[k]; }
+  if (N <= 0) return;
+  std::vector<double> cuts(W - 1);
+  long long acc = 0; int k = 0;
+  for (int c = 1; c < W; c++) {
+    const double target = (double)N * c / W;
+    while (k < WD_REBAL_BINS - 1 && (double)(acc + tot[k]) < target) { acc += tot[k]; k++; }
+    const double frac = tot[k] > 0 ? std::min(1., std::max(0., (target - (double)acc) / (double)tot[k])) : 0.;
+    double x = lo + ((double)k + frac) / inv;
+    if (c > 1) x = std::max(x, E->cfg.periodic ? cuts[c - 2] * D.dim : cuts[c - 2]);
+    cuts[c - 1] = E->cfg.periodic ? x / D.dim : x;
+  }
+  M.cuts = cuts; M.nRebalances++; M.lastRebalRun = E->nFullRuns;
+}
 void domainExchange(wdem_engine* E) {
   static const bool tr = getenv("WDEM_REBUILD_TRACE") != nullptr;
   static double tacc[12] = {0}; static int tcnt = 0; std::chrono::steady_clock::time_point tp[12];
@@ -352,7 +395,7 @@ void domainExchange(wdem_engine* E) {
   const wdem_config& c = E->cfg;
   const bool hertz = c.law == WDEM_LAW_HERTZ_DMT, rolling = (c.relRollStiff > 0. && c.rollTanPhi > 0.);
   const int n = E->n;
-  const DomainU D = makeDomainU(E);
+  DomainU D = makeDomainU(E);
   SphereStore& Ast = E->sph[E->cur]; SphereStore& Bst = E->sph[1 - E->cur];
   Spheres A = Ast.view();
   ContactStore& Ost = E->con[E->curC]; CsrStore& Ocsr = E->csr[E->curR];
@@ -368,6 +411,8 @@ void domainExchange(wdem_engine* E) {
     CK(cudaMemsetAsync(dMineF, 0, 2 * WDEM_MAX_RANKS * sizeof(int), st));
     if (n > 0) { k_dom_fast_scan<<<nblk(n, 256), 256, 0, st>>>(A, n, D, M.emask.p, dMineF); E->launches++; }
     if (!(M.nOwn > 0 && n == M.nOwn + (int)M.nRecvTot)) { k_fill_int<<<1, 1, 0, st>>>(dMineF + 1 + W, 1, 1); E->launches++; }      // my veto (e.g. nothing owned here)
+    const bool rebalDue = M.rebalTol > 0. && (c.periodic || E->boundsValid) && (E->nFullRuns - M.lastRebalRun) >= M.rebalMinRuns;
+    if (rebalDue) { k_fill_int<<<1, 1, 0, st>>>(dMineF + 2 + W, 1, M.nOwn); E->launches++; }      // how many spheres I own: everybody sees the imbalance in the same table
     T->allgatherDev(dMineF, dAllF, (size_t)2 * WDEM_MAX_RANKS * sizeof(int), st);
     std::vector<int> fa((size_t)W * 2 * WDEM_MAX_RANKS, 0);
     CK(cudaMemcpyAsync(fa.data(), dAllF, fa.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -375,6 +420,11 @@ void domainExchange(wdem_engine* E) {
     // every rank reaches the same verdict: nobody emigrates anywhere, and every rank's arrays are [owned + ghosts of the last full run] with at least one owned sphere
     long long vetoAll = 0;
     for (int r = 0; r < W; r++) vetoAll += (long long)fa[(size_t)r * 2 * WDEM_MAX_RANKS] + fa[(size_t)r * 2 * WDEM_MAX_RANKS + 1 + W];
+    if (rebalDue) {      // the same table on every rank => the same decision
+      long long totOwn = 0, maxOwn = 0;
+      for (int r = 0; r < W; r++) { const long long o = fa[(size_t)r * 2 * WDEM_MAX_RANKS + 2 + W]; totOwn += o; maxOwn = std::max(maxOwn, o); }
+      if (totOwn > 0 && (double)maxOwn * W > (1. + M.rebalTol) * (double)totOwn) { rebalanceCuts(E); D = makeDomainU(E); vetoAll = 1; }
+    }
     if (vetoAll == 0) {
       TM(1);
       const int nGhostOld = (int)M.nRecvTot;
@@ -1098,7 +1148,8 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
   if (nNow > 0 && (c.applyForces || c.reset)) {
     // ContactLoop.applyForces=False: no contact force is applied, but Leapfrog.reset still sets force = gravity*mass, torque = 0 (Leapfrog.cpp:240-245): null rows
     CsrStore& R = E->csr[E->curR];
-    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard, E->impDev(u.impSlot)); E->launches++;
+    k_reduce<<<nblk(nNow, WD_REDUCE_BLOCK), WD_REDUCE_BLOCK, 0, st>>>(E->S(), nNow, C, c.applyForces ? R.rowStart.p : nullptr, R.rowEntry.p, u, guard, E->impDev(u.impSlot));
+    E->launches++;
   }
   if (wa.nWalls && !wa.foldInKernel) { k_wall_fold<<<wa.nWalls * 6, 256, 0, st>>>(wa.partial, wa.nBlocksTotal, wa.nWalls * 6, wa.acc, guard); E->launches++; }
   if (ev) CK(cudaEventRecord(ev[4], st));
@@ -1115,7 +1166,10 @@ void leapfrogPipelined(wdem_engine* E, const StepU& u) {
   const int NCH = E->nChunk;
   const long long per = (n + NCH - 1) / NCH;
   // the staging buffers are free: the previous call waited for its copies; order the copy streams behind whatever the main stream did before
-  CK(cudaEventRecord(E->evFork, st)); CK(cudaStreamWaitEvent(E->sH2D, E->evFork, 0));
+  // Deferred tail (wdem_step_e2e without stats): the previous call returned while its contact pass was still running; the staging buffer was last read by that call's
+  // k_leapfrog_io launches (evLf), so this step's upload only waits for those and overlaps the contact pass of the previous step.
+  if (io.defer && io.ioBusy) CK(cudaStreamWaitEvent(E->sH2D, E->evLf[E->lastLfChunk], 0));
+  else { CK(cudaEventRecord(E->evFork, st)); CK(cudaStreamWaitEvent(E->sH2D, E->evFork, 0)); }
   for (int c = 0; c < NCH; c++) {
     const long long first = c * per, cnt = std::min(per, n - first);
     if (cnt <= 0) break;
@@ -1131,7 +1185,7 @@ void leapfrogPipelined(wdem_engine* E, const StepU& u) {
     if (u.energy) k_leapfrog_io<true><<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->up2slot.p, first, cnt, lio);
     else k_leapfrog_io<false><<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->up2slot.p, first, cnt, lio);
     E->launches++;
-    CK(cudaEventRecord(E->evLf[c], st));
+    CK(cudaEventRecord(E->evLf[c], st)); E->lastLfChunk = c; E->e2e.ioBusy = true;
     CK(cudaStreamWaitEvent(E->sD2H, E->evLf[c], 0));
     if (io.posOut) CK(cudaMemcpyAsync(io.posOut + 3 * first, out + 3 * first, cnt * 24, cudaMemcpyDeviceToHost, E->sD2H));
     if (io.velOut) CK(cudaMemcpyAsync(io.velOut + 3 * first, out + 3 * n + 3 * first, cnt * 24, cudaMemcpyDeviceToHost, E->sD2H));
@@ -1367,12 +1421,18 @@ void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
       cudaEvent_t* ev = nullptr;
       if (E->profiling) { const int set = (int)(E->step % wdem_engine::NEVSET); harvestPhases(E, set); ev = E->evr[set]; }
       enqueueIntegrate(E, u, ev);
+      if (E->e2e.active && E->e2e.defer) {      // the verdict of this step's Verlet test travels before the contact pass is enqueued: the host does not wait for the contacts
+        CK(cudaMemcpyAsync(E->hCnt, E->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(E->evFlag, st));
+      }
       if (!full0) enqueueContacts(E, u, ev);
       if (ev) { CK(cudaEventRecord(ev[5], st)); E->evPending[E->step % wdem_engine::NEVSET] = true; }
       if (k < K - 1) stepEpilogue(E);
     }
-    CK(cudaMemcpyAsync(E->hCnt, E->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(E->evFlag, st));
+    if (!(E->e2e.active && E->e2e.defer)) {
+      CK(cudaMemcpyAsync(E->hCnt, E->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(E->evFlag, st));
+    }
     if (trace) { tEnq += msSince(t0); t0 = clk(); }
     CK(cudaEventSynchronize(E->evFlag));
     if (trace) { tWait += msSince(t0); t0 = clk(); nBatch++; }
@@ -1791,52 +1851,79 @@ int wdem_add_spheres(wdem_handle h, int64_t m, const int32_t* ids, const double*
                      const double* inertia, const double* radius, const uint32_t* flags, const uint32_t* mask, const int32_t* matId) {
   return guarded(h, [&] {
     if (m < 0 || (m > 0 && (!ids || !pos || !mass || !inertia || !radius))) throw EngErr{"wdem_add_spheres: bad arguments", WDEM_ERR_INVALID};
-    if (h->comm) throw EngErr{"wdem_add_spheres: not available in decomposed runs", WDEM_ERR_UNSUPPORTED};
-    if (h->hMats.empty() || h->hIds.size() != (size_t)h->n) throw EngErr{"wdem_add_spheres: upload materials and spheres first", WDEM_ERR_INVALID};
+    // Decomposed runs: every rank is called with the SAME list and keeps the spheres it is responsible for — the slab of the centre, or simply every world-th sphere in a
+    // periodic cell; the collider full run that the insertion triggers sends each one home (migration) and exports the ghosts.  The id check covers what this subdomain
+    // holds (owned spheres and ghost copies) plus the boundaries; global uniqueness of the ids is the caller's business, as in ParticleContainer::insertAt.
+    const bool dec = h->comm != nullptr;
+    if (h->hMats.empty() || (!dec && h->hIds.size() != (size_t)h->n)) throw EngErr{"wdem_add_spheres: upload materials and spheres first", WDEM_ERR_INVALID};
+    if (dec && h->clumps.n) throw EngErr{"wdem_add_spheres: clumps are not supported in decomposed runs", WDEM_ERR_UNSUPPORTED};
     if (m == 0) return;
-    const int64_t n0 = h->n, n1 = n0 + m;
-    if (n1 > (1ll << 30)) throw EngErr{"too many spheres", WDEM_ERR_INVALID};
-    std::unordered_set<int32_t> used(h->hIds.begin(), h->hIds.end());
+    const int64_t n0 = h->n;
+    if (n0 + m > (1ll << 30)) throw EngErr{"too many spheres", WDEM_ERR_INVALID};
+    cudaStream_t st = h->stream;
+    std::unordered_set<int32_t> used;
+    if (!dec) used.insert(h->hIds.begin(), h->hIds.end());
     for (auto& w : h->hWalls) used.insert(w.id);
     for (auto& f : h->hFacets) used.insert(f.id);
-    std::vector<double4> posr(m), velm(m), angi(m), q(m); std::vector<uint32_t> fl(m), mk(m); std::vector<int32_t> mt(m), id(m), up(m);
-    int maxId = h->maxId; double minR = h->minRadius, pw = h->pwaveDt, rmax = h->dom.rmaxGlobal;
-    for (int64_t i = 0; i < m; i++) {
-      id[i] = ids[i]; up[i] = (int32_t)(n0 + i);
-      if (id[i] < 0 || !used.insert(id[i]).second) throw EngErr{"wdem_add_spheres: particle id " + std::to_string(id[i]) + " is negative or already in use", WDEM_ERR_INVALID};
-      maxId = std::max(maxId, id[i]);
-      fl[i] = flags ? flags[i] : 0u; mk[i] = mask ? mask[i] : 5u; mt[i] = matId ? matId[i] : 0;
-      if (mt[i] < 0 || mt[i] >= (int)h->hMats.size()) throw EngErr{"sphere material index out of range", WDEM_ERR_INVALID};
-      if (fl[i] & (64u | 128u)) throw EngErr{"wdem_add_spheres: clump members cannot be added to a running scene", WDEM_ERR_UNSUPPORTED};
-      if (!(radius[i] > 0)) throw EngErr{"sphere #" + std::to_string(id[i]) + ": radius must be positive", WDEM_ERR_INVALID};
-      if ((fl[i] & 7u) != 7u && !(mass[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive mass with free translational DOFs", WDEM_ERR_INVALID};
-      if ((fl[i] & 56u) != 56u && !(inertia[i] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(id[i]) + " has non-positive inertia with free rotational DOFs", WDEM_ERR_INVALID};
-      posr[i] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], radius[i]);
-      velm[i] = make_double4(vel ? vel[3 * i] : 0, vel ? vel[3 * i + 1] : 0, vel ? vel[3 * i + 2] : 0, mass[i]);
-      angi[i] = make_double4(angVel ? angVel[3 * i] : 0, angVel ? angVel[3 * i + 1] : 0, angVel ? angVel[3 * i + 2] : 0, inertia[i]);
-      q[i] = ori ? make_double4(ori[4 * i], ori[4 * i + 1], ori[4 * i + 2], ori[4 * i + 3]) : make_double4(0, 0, 0, 1);
-      minR = std::min(minR, radius[i]); rmax = std::max(rmax, radius[i]);
-      const Material& mm = h->hMats[mt[i]];
-      pw = std::min(pw, radius[i] / (1. * std::sqrt(mm.young / mm.density)));
+    std::vector<char> take(m, 1);
+    if (dec) {
+      const int W = h->comm->world, R = h->comm->rank; const DomainState& M = h->dom;
+      for (int64_t i = 0; i < m; i++) {
+        int r = (int)(i % W);
+        if (!h->cfg.periodic) { const double x = pos[3 * i + M.axis]; r = 0; while (r + 1 < W && x >= M.cuts[r]) r++; }
+        take[i] = (r == R);
+      }
+      if (h->id2slot.p && h->n > 0) {      // ids held here
+        h->idx.ensure((size_t)m + 1, h->bytes);
+        CK(cudaMemcpyAsync(h->idx.p, ids, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st)); CK(cudaMemsetAsync(h->idx.p + m, 0, sizeof(int), st));
+        k_dom_ids_in_use<<<nblk(m, 256), 256, 0, st>>>(h->idx.p, (int)m, h->id2slot.p, (long long)h->id2slot.cap, h->n, h->idx.p + m); h->launches++;
+        int inUse = 0; CK(cudaMemcpyAsync(&inUse, h->idx.p + m, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        if (inUse) throw EngErr{"wdem_add_spheres: particle id " + std::to_string(inUse - 1) + " is negative or already in use", WDEM_ERR_INVALID};
+      }
     }
-    cudaStream_t st = h->stream;
+    std::vector<double4> posr, velm, angi, q; std::vector<uint32_t> fl, mk; std::vector<int32_t> mt, id, up;
+    int maxId = std::max(h->maxId, dec ? h->dom.globalMaxId : -1); double minR = h->minRadius, pw = h->pwaveDt, rmax = h->dom.rmaxGlobal;
+    for (int64_t i0 = 0; i0 < m; i0++) {
+      const int32_t idNew = ids[i0];
+      if (idNew < 0 || !used.insert(idNew).second) throw EngErr{"wdem_add_spheres: particle id " + std::to_string(idNew) + " is negative or already in use", WDEM_ERR_INVALID};
+      maxId = std::max(maxId, idNew);
+      const uint32_t f_ = flags ? flags[i0] : 0u; const int32_t mt_ = matId ? matId[i0] : 0;
+      if (mt_ < 0 || mt_ >= (int)h->hMats.size()) throw EngErr{"sphere material index out of range", WDEM_ERR_INVALID};
+      if (f_ & (64u | 128u)) throw EngErr{"wdem_add_spheres: clump members cannot be added to a running scene", WDEM_ERR_UNSUPPORTED};
+      if (!(radius[i0] > 0)) throw EngErr{"sphere #" + std::to_string(idNew) + ": radius must be positive", WDEM_ERR_INVALID};
+      if ((f_ & 7u) != 7u && !(mass[i0] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(idNew) + " has non-positive mass with free translational DOFs", WDEM_ERR_INVALID};
+      if ((f_ & 56u) != 56u && !(inertia[i0] > 0)) throw EngErr{"DemField.selfTest: particle #" + std::to_string(idNew) + " has non-positive inertia with free rotational DOFs", WDEM_ERR_INVALID};
+      // scene-wide quantities follow the whole list on every rank (they stay consistent without another exchange)
+      minR = std::min(minR, radius[i0]); rmax = std::max(rmax, radius[i0]);
+      const Material& mm = h->hMats[mt_];
+      pw = std::min(pw, radius[i0] / (1. * std::sqrt(mm.young / mm.density)));
+      if (!take[i0]) continue;
+      id.push_back(idNew); up.push_back((int32_t)(n0 + (int64_t)up.size())); fl.push_back(f_); mk.push_back(mask ? mask[i0] : 5u); mt.push_back(mt_);
+      posr.push_back(make_double4(pos[3 * i0], pos[3 * i0 + 1], pos[3 * i0 + 2], radius[i0]));
+      velm.push_back(make_double4(vel ? vel[3 * i0] : 0, vel ? vel[3 * i0 + 1] : 0, vel ? vel[3 * i0 + 2] : 0, mass[i0]));
+      angi.push_back(make_double4(angVel ? angVel[3 * i0] : 0, angVel ? angVel[3 * i0 + 1] : 0, angVel ? angVel[3 * i0 + 2] : 0, inertia[i0]));
+      q.push_back(ori ? make_double4(ori[4 * i0], ori[4 * i0 + 1], ori[4 * i0 + 2], ori[4 * i0 + 3]) : make_double4(0, 0, 0, 1));
+    }
+    const int64_t k = (int64_t)id.size(), n1 = n0 + k;
     SphereStore& s = h->sph[h->cur];
-    s.ensure((size_t)n1, h->bytes, /*keep*/ true, st);
-    auto H2D = [&](void* d, const void* src, size_t b) { CK(cudaMemcpyAsync(d, src, b, cudaMemcpyHostToDevice, st)); };
-    H2D(s.posr.p + n0, posr.data(), m * sizeof(double4)); H2D(s.velm.p + n0, velm.data(), m * sizeof(double4)); H2D(s.angi.p + n0, angi.data(), m * sizeof(double4)); H2D(s.ori.p + n0, q.data(), m * sizeof(double4));
-    for (auto& b : s.f) CK(cudaMemsetAsync(b.p + n0, 0, m * sizeof(double), st));     // a new particle sees zero force in its first Leapfrog
-    for (auto& b : s.l) CK(cudaMemsetAsync(b.p + n0, 0, m * sizeof(double), st));
-    H2D(s.flags.p + n0, fl.data(), m * 4); H2D(s.mask.p + n0, mk.data(), m * 4); H2D(s.mat.p + n0, mt.data(), m * 4); H2D(s.id.p + n0, id.data(), m * 4); H2D(s.up.p + n0, up.data(), m * 4);
+    s.ensure((size_t)std::max<int64_t>(n1, 1), h->bytes, /*keep*/ true, st);
+    auto H2D = [&](void* d, const void* src, size_t b) { if (b) CK(cudaMemcpyAsync(d, src, b, cudaMemcpyHostToDevice, st)); };
+    H2D(s.posr.p + n0, posr.data(), k * sizeof(double4)); H2D(s.velm.p + n0, velm.data(), k * sizeof(double4)); H2D(s.angi.p + n0, angi.data(), k * sizeof(double4)); H2D(s.ori.p + n0, q.data(), k * sizeof(double4));
+    if (k) for (auto& b : s.f) CK(cudaMemsetAsync(b.p + n0, 0, k * sizeof(double), st));     // a new particle sees zero force in its first Leapfrog
+    if (k) for (auto& b : s.l) CK(cudaMemsetAsync(b.p + n0, 0, k * sizeof(double), st));
+    H2D(s.flags.p + n0, fl.data(), k * 4); H2D(s.mask.p + n0, mk.data(), k * 4); H2D(s.mat.p + n0, mt.data(), k * 4); H2D(s.id.p + n0, id.data(), k * 4); H2D(s.up.p + n0, up.data(), k * 4);
     const size_t oldCap = h->id2slot.cap;
     h->id2slot.ensure((size_t)maxId + 2, h->bytes, /*keep*/ true, st);
     if (h->id2slot.cap > oldCap) CK(cudaMemsetAsync(h->id2slot.p + oldCap, 0xFF, (h->id2slot.cap - oldCap) * sizeof(int), st));
+    if (dec && k) { k_dom_map_appended<<<nblk(k, 256), 256, 0, st>>>(s.id.p, (int)n0, (int)k, h->id2slot.p); h->launches++; }
     CK(cudaStreamSynchronize(st));
-    if (h->compactPending) {   // the appended slots have no counterpart in the generation the incidence rows were built for
+    if (h->compactPending && k) {   // the appended slots have no counterpart in the generation the incidence rows were built for
       h->dom.origSlot.ensure((size_t)n1, h->bytes, /*keep*/ true, st);
-      CK(cudaMemsetAsync(h->dom.origSlot.p + n0, 0xFF, (size_t)m * sizeof(int), st)); CK(cudaStreamSynchronize(st));
+      CK(cudaMemsetAsync(h->dom.origSlot.p + n0, 0xFF, (size_t)k * sizeof(int), st)); CK(cudaStreamSynchronize(st));
     }
-    h->n = (int)n1; h->minRadius = minR; h->pwaveDt = pw; h->maxId = maxId; h->dom.rmaxGlobal = rmax; h->dom.nOwn = (int)n1;
-    h->hIds.insert(h->hIds.end(), id.begin(), id.end());
+    h->n = (int)n1; h->minRadius = minR; h->pwaveDt = pw; h->maxId = maxId; h->dom.rmaxGlobal = rmax;
+    if (dec) { h->dom.nOwn += (int)k; h->dom.globalMaxId = std::max(h->dom.globalMaxId, maxId); }
+    else { h->dom.nOwn = (int)n1; h->hIds.insert(h->hIds.end(), id.begin(), id.end()); }
     h->conDirty = true; h->up2slotValid = false;     // ParticleContainer::add marks the contacts dirty: the collider re-initialises at the next step (ParticleContainer.cpp:23-73)
   });
 }
@@ -1844,10 +1931,32 @@ int wdem_add_spheres(wdem_handle h, int64_t m, const int32_t* ids, const double*
 int wdem_remove_spheres(wdem_handle h, int64_t m, const int32_t* ids) {
   return guarded(h, [&] {
     if (m < 0 || (m > 0 && !ids)) throw EngErr{"wdem_remove_spheres: bad arguments", WDEM_ERR_INVALID};
-    if (h->comm) throw EngErr{"wdem_remove_spheres: not available in decomposed runs", WDEM_ERR_UNSUPPORTED};
     if (h->clumps.n) throw EngErr{"wdem_remove_spheres: not available in scenes with clumps", WDEM_ERR_UNSUPPORTED};
     if (m == 0) return;
     const int n0 = h->n; cudaStream_t st = h->stream; int64_t& tot = h->bytes;
+    if (h->comm) {
+      // Decomposed runs: every rank is called with the SAME list and lets go of whatever it holds of it: an owned sphere stops being owned (flagged like a ghost of
+      // the previous generation, which the full run that follows drops), a ghost copy is dropped anyway; in both cases the sphere's contacts go with it and its id
+      // is free again.  Ids this subdomain does not hold are some other subdomain's business (no global "unknown id" check).
+      std::unordered_set<int32_t> gone(ids, ids + m);
+      if ((int64_t)gone.size() != m) throw EngErr{"wdem_remove_spheres: duplicate ids", WDEM_ERR_INVALID};
+      if (n0 == 0 || !h->id2slot.p) return;
+      h->idx.ensure((size_t)m + 1, tot); h->counts.ensure((size_t)n0 + 1, tot);
+      CK(cudaMemcpyAsync(h->idx.p, ids, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st)); CK(cudaMemsetAsync(h->idx.p + m, 0, sizeof(int), st));
+      k_fill_int<<<nblk(n0, 256), 256, 0, st>>>(h->counts.p, n0, 1);
+      SphereStore& A = h->sph[h->cur];
+      k_dom_mark_removed<<<nblk(m, 256), 256, 0, st>>>(h->idx.p, (int)m, h->id2slot.p, (long long)h->id2slot.cap, n0, A.flags.p, h->counts.p, h->idx.p + m);
+      if (h->csr[h->curR].valid && h->nC > 0) {
+        CsrStore& R = h->csr[h->curR]; ContactStore& cs = h->con[h->curC];
+        k_kill_rows<<<nblk(n0, 256), 256, 0, st>>>(A.id.p, n0, h->counts.p, h->id2slot.p, R.rowStart.p, R.rowEntry.p, R.nRows, cs.flags.p, cs.realBits.p); h->launches++;
+      }
+      k_dom_forget_ids<<<nblk(m, 256), 256, 0, st>>>(h->idx.p, (int)m, h->id2slot.p, (long long)h->id2slot.cap);
+      int nOwnedGone = 0; CK(cudaMemcpyAsync(&nOwnedGone, h->idx.p + m, sizeof(int), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+      h->launches += 3;
+      h->dom.nOwn -= nOwnedGone;
+      h->conDirty = true; h->up2slotValid = false;
+      return;
+    }
     if (h->hIds.size() != (size_t)n0) throw EngErr{"wdem_remove_spheres: no spheres uploaded", WDEM_ERR_INVALID};
     std::unordered_set<int32_t> gone(ids, ids + m);
     if ((int64_t)gone.size() != m) throw EngErr{"wdem_remove_spheres: duplicate ids", WDEM_ERR_INVALID};
@@ -1996,6 +2105,7 @@ static void stepN(wdem_handle h, int64_t nsteps, wdem_stats* stats, bool cheapSt
     CK(cudaEventRecord(h->ev0, h->stream));
     runSteps(h, nsteps, &local);
     CK(cudaEventRecord(h->ev1, h->stream));
+    if (h->e2e.active && h->e2e.defer) return;      // deferred tail: the contact pass is still running; its errors (sticky on the device) surface with the next call
     if (h->comm) h->comm->allreduceMaxInt(&h->dCnt->error, 1, h->stream);
     fetchCounters(h);
     CK(cudaEventSynchronize(h->ev1));
@@ -2142,12 +2252,13 @@ int wdem_step_e2e(wdem_handle h, int64_t nsteps, const double* pos_in, const dou
       const size_t n = (size_t)h->n;
       ensureUp2Slot(h);
       h->ioIn.ensure(9 * n, h->bytes); h->ioOut.ensure(6 * n, h->bytes);
+      h->e2e.defer = !stats && !h->profiling && !getenv("WDEM_E2E_NO_DEFER");
       h->e2e.active = true; h->e2e.pos = pos_in; h->e2e.vel = vel_in; h->e2e.angVel = angVel_in; h->e2e.posOut = pos_out; h->e2e.velOut = vel_out;
       try { stepN(h, 1, stats, true); } catch (...) { h->e2e.active = false; cudaStreamSynchronize(h->sH2D); cudaStreamSynchronize(h->sD2H); throw; }
       h->e2e.active = false;
       CK(cudaEventRecord(h->evEk, h->sD2H));
       CK(cudaStreamSynchronize(h->sD2H));
-      if (getenv("WDEM_E2E_TRACE")) {   // device timeline of the call relative to its start (ms): upload / integrate per chunk, end of step, last byte on the host
+      if (getenv("WDEM_E2E_TRACE") && !h->e2e.defer) {   // device timeline of the call relative to its start (ms): upload / integrate per chunk, end of step, last byte on the host
         float a, b; std::string ln = "e2e trace:";
         for (int c = 0; c < h->nChunk; c++) { cudaEventElapsedTime(&a, h->ev0, h->evUp[c]); cudaEventElapsedTime(&b, h->ev0, h->evLf[c]); char t[64]; snprintf(t, sizeof(t), " [%.2f %.2f]", a, b); ln += t; }
         cudaEventElapsedTime(&a, h->ev0, h->ev1); cudaEventElapsedTime(&b, h->ev0, h->evEk);
@@ -2278,6 +2389,12 @@ int wdem_set_scene(wdem_handle h, int64_t step, double time) {
 }
 
 int wdem_crit_dt(wdem_handle h, double* dt) { return guarded(h, [&] { *dt = h->pwaveDt; }); }
+int wdem_set_periodic_state(wdem_handle h, int64_t dynDtStepLast, int64_t dynDtStepPrev) {
+  return guarded(h, [&] { if (dynDtStepLast < -1 || dynDtStepPrev < -1) throw EngErr{"wdem_set_periodic_state: bad step", WDEM_ERR_INVALID}; h->dynStepLast = dynDtStepLast; h->dynStepPrev = dynDtStepPrev; });
+}
+int wdem_get_periodic_state(wdem_handle h, int64_t* dynDtStepLast, int64_t* dynDtStepPrev) {
+  return guarded(h, [&] { if (dynDtStepLast) *dynDtStepLast = h->dynStepLast; if (dynDtStepPrev) *dynDtStepPrev = h->dynStepPrev; });
+}
 int wdem_get_scalars(wdem_handle h, double* dt, double* time, int64_t* step, double* verletDist, int64_t* nFullRuns) {
   return guarded(h, [&] { if (dt) *dt = h->dt; if (time) *time = h->time; if (step) *step = h->step; if (verletDist) *verletDist = h->verletDist; if (nFullRuns) *nFullRuns = h->nFullRuns; });
 }
@@ -2316,6 +2433,20 @@ int wdem_set_domain(wdem_handle h, int axis, int ncuts, const double* cuts, int6
   });
 }
 int64_t wdem_num_owned(wdem_handle h) { return h ? (h->comm ? h->dom.nOwn : h->n) : -1; }
+int wdem_set_rebalance(wdem_handle h, double tolerance, int minFullRuns) {
+  return guarded(h, [&] {
+    if (!h->comm) throw EngErr{"wdem_set_rebalance: initialise the communicator first", WDEM_ERR_INVALID};
+    if (!(tolerance >= 0.) || minFullRuns < 1) throw EngErr{"wdem_set_rebalance: tolerance >= 0 (0 = off), minFullRuns >= 1", WDEM_ERR_INVALID};
+    h->dom.rebalTol = tolerance; h->dom.rebalMinRuns = minFullRuns;
+  });
+}
+int wdem_get_domain(wdem_handle h, double* cuts, int64_t* nRebalances) {
+  return guarded(h, [&] {
+    if (!h->comm) throw EngErr{"wdem_get_domain: not a decomposed run", WDEM_ERR_INVALID};
+    if (cuts) for (size_t k = 0; k < h->dom.cuts.size(); k++) cuts[k] = h->dom.cuts[k];
+    if (nRebalances) *nRebalances = h->dom.nRebalances;
+  });
+}
 int wdem_download_owned(wdem_handle h, int32_t* ids, double* pos, double* ori, double* vel, double* angVel, double* force, double* torque) {
   return guarded(h, [&] {
     const int n = h->n; if (n == 0 || !ids) return;

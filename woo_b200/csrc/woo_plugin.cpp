@@ -144,7 +144,8 @@ struct ContactLoop : Engine {
   M3 stress{{0, 0, 0, 0, 0, 0, 0, 0, 0}};   // ContactLoop.hpp:116-127: filled after every step when evalStress and the scene is periodic
   const char* cls() const override { return "ContactLoop"; }
 };
-struct DynDt : Engine { int stepPeriod = 100; double maxRelInc = 1e-4; bool dryRun = false; const char* cls() const override { return "DynDt"; } };
+struct DynDt : Engine { int stepPeriod = 100; double maxRelInc = 1e-4; bool dryRun = false; long stepLast = -1, stepPrev = -1;   // PeriodicEngine counters (Engine.hpp:156-157)
+  const char* cls() const override { return "DynDt"; } };
 
 // ---- Scene (core/Scene.hpp:191-205, Scene.cpp:366-432)
 struct Scene {
@@ -346,6 +347,7 @@ struct GpuDemLoop : Engine {
     uploadImposes();
     if (scene->periodic) { Cell& C = *scene->cell; chk(h, wdem_set_cell(h, C.hSize.data(), C.gradV.data(), C.nextGradV.data(), C.homoDeform)); C.dirty = false; }
     chk(h, wdem_set_scene(h, (int64_t)scene->step, scene->time));
+    if (dynDt && !dynDt->dead) chk(h, wdem_set_periodic_state(h, dynDt->stepLast, dynDt->stepPrev));      // a re-upload in mid-run does not restart DynDt's period
     F.pushContacts(h);
     nSpheres = (long)sid.size(); matIndex = matIx;
     F.owner = this; F.topoDirty = false; F.stateDirty = false; F.deviceNewer = false; F.contactsStale = true; F.pendingAdds.clear(); F.pendingRemoves.clear();
@@ -414,6 +416,7 @@ struct GpuDemLoop : Engine {
     int64_t nf = 0; double libDt = NaN;
     chk(h, wdem_get_scalars(h, &libDt, nullptr, nullptr, nullptr, &nf));
     collider->nFullRuns = (long)nf;
+    if (dynDt && !dynDt->dead) { int64_t a = -1, b = -1; chk(h, wdem_get_periodic_state(h, &a, &b)); dynDt->stepLast = (long)a; dynDt->stepPrev = (long)b; }
     if (scene->periodic) chk(h, wdem_get_cell(h, scene->cell->hSize.data()));
     chk(h, wdem_track_energy(h, scene->trackEnergy ? 1 : 0));   // takes effect from the next step on, like flipping Scene.trackEnergy between steps
     if (scene->trackEnergy && trackingOn) {
@@ -857,7 +860,7 @@ PYBIND11_MODULE(_woo, m) {
         auto o = make_shared<ContactLoop>(); o->geoDisp = g; o->phyDisp = p; o->lawDisp = l; py::object po = py::cast(o); for (auto it : kw) py::setattr(po, it.first, it.second); return o; }),
         py::arg("geoDisp") = vector<shared_ptr<CGeomFunctor>>(), py::arg("phyDisp") = vector<shared_ptr<CPhysFunctor>>(), py::arg("lawDisp") = vector<shared_ptr<LawFunctor>>())
       RW(ContactLoop, geoDisp) RW(ContactLoop, phyDisp) RW(ContactLoop, lawDisp) RW(ContactLoop, applyForces) RW(ContactLoop, evalStress).def_property_readonly("stress", [](ContactLoop& c) { return np33(c.stress); }) RW(ContactLoop, dist00) RW(ContactLoop, updatePhys) RW(ContactLoop, reorderEvery) RW(ContactLoop, hook);
-  kwclass<DynDt, Engine>(m, "DynDt") RW(DynDt, stepPeriod) RW(DynDt, maxRelInc) RW(DynDt, dryRun);
+  kwclass<DynDt, Engine>(m, "DynDt") RW(DynDt, stepPeriod) RW(DynDt, maxRelInc) RW(DynDt, dryRun) RW(DynDt, stepLast) RW(DynDt, stepPrev);
   py::class_<GpuDemLoop, Engine, shared_ptr<GpuDemLoop>>(m, "GpuDemLoop")
       .def(py::init([](shared_ptr<Leapfrog> lf, shared_ptr<InsertionSortCollider> co, shared_ptr<ContactLoop> cl, shared_ptr<DynDt> dd, int device, py::kwargs kw) {
         auto o = make_shared<GpuDemLoop>(); o->leapfrog = lf; o->collider = co; o->contactLoop = cl; o->dynDt = dd; o->device = device; py::object po = py::cast(o); for (auto it : kw) py::setattr(po, it.first, it.second); return o; }),

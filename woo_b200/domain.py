@@ -73,6 +73,16 @@ def _domain_stats(E):
     return dict(zip(("owned", "ghosts", "migrated_out", "migrated_in", "rows_in"), [x.value for x in v]))
 
 
+def _set_rebalance(E, tolerance, min_full_runs=1):
+    E._chk(E.L.wdem_set_rebalance(E.h, C.c_double(float(tolerance)), C.c_int(int(min_full_runs))))
+
+
+def _get_domain(E, world):
+    cuts = np.zeros(max(world - 1, 1)); nr = C.c_int64()
+    E._chk(E.L.wdem_get_domain(E.h, ptr(cuts), C.byref(nr)))
+    return cuts[:world - 1], nr.value
+
+
 def _max_id(S):
     return S.n + len(S.walls) + len(S.facets) - 1
 
@@ -89,6 +99,7 @@ class LocalCluster:
         if scramble:      # deliberately wrong initial placement: the first collider run must migrate everything home
             own = (own + 1 + np.arange(S.n) % max(world - 1, 1)) % world
         devices = devices or [0] * world
+        self.ids = np.sort(np.asarray(S.sphere_ids(), dtype=np.int32))      # live particle ids (add_spheres / remove_spheres keep it current)
         self.E = []
         for r in range(world):
             E = Engine(S.params, device=devices[r])
@@ -131,6 +142,26 @@ class LocalCluster:
                 raise e
         return out
 
+    def add_spheres(self, ids, pos, radius, mass, inertia, **kw):
+        """wdem_add_spheres on every subdomain with the same list (each keeps what falls into its slab)."""
+        for E in self.E:
+            E.add_spheres(ids, pos, radius, mass, inertia, **kw)
+        self.ids = np.sort(np.concatenate([self.ids, np.asarray(ids, dtype=np.int32)]))
+
+    def remove_spheres(self, ids):
+        """wdem_remove_spheres on every subdomain with the same list."""
+        for E in self.E:
+            E.remove_spheres(ids)
+        self.ids = self.ids[~np.isin(self.ids, ids)]
+
+    def set_rebalance(self, tolerance, min_full_runs=1):
+        """Move the cuts to the quantiles of the slab coordinate at a full run whenever the largest subdomain exceeds (1+tolerance) x the mean (wdem_set_rebalance)."""
+        for E in self.E:
+            _set_rebalance(E, tolerance, min_full_runs)
+
+    def domain(self):
+        return _get_domain(self.E[0], self.world)
+
     def step(self, n=1):
         self.stats = self._all(lambda E: E.step(n))
         return self.stats
@@ -139,7 +170,7 @@ class LocalCluster:
         parts = [_owned(E) for E in self.E]
         ids = np.concatenate([p["ids"] for p in parts])
         order = np.argsort(ids, kind="stable")
-        assert len(ids) == self.S.n and np.array_equal(ids[order], self.S.sphere_ids()), "spheres lost or duplicated across subdomains"
+        assert len(ids) == len(self.ids) and np.array_equal(ids[order], self.ids), "spheres lost or duplicated across subdomains"
         return {k: np.concatenate([p[k] for p in parts])[order] for k in parts[0] if k != "ids"}
 
     def contacts(self, real_only=False):
@@ -188,6 +219,20 @@ class DistributedEngine:
         if sel is None:
             sel = np.nonzero(owner_of(S, self.cuts, axis) == self.rank)[0]
         _load_part(E, S, sel)
+
+    def add_spheres(self, ids, pos, radius, mass, inertia, **kw):
+        """Collective: the same list on every rank (wdem_add_spheres)."""
+        self.E.add_spheres(ids, pos, radius, mass, inertia, **kw)
+
+    def remove_spheres(self, ids):
+        """Collective: the same list on every rank (wdem_remove_spheres)."""
+        self.E.remove_spheres(ids)
+
+    def set_rebalance(self, tolerance, min_full_runs=1):
+        _set_rebalance(self.E, tolerance, min_full_runs)
+
+    def domain(self):
+        return _get_domain(self.E, self.world)
 
     def step(self, n=1):
         return self.E.step(n)

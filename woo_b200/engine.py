@@ -213,9 +213,11 @@ class Engine:
         self.stats = st
         return st
 
-    def step_e2e(self, n, pos, vel, angVel, pos_out, vel_out):
-        st = WdemStats(); ek = C.c_double()
-        self._chk(self.L.wdem_step_e2e(self.h, C.c_int64(n), ptr(pos), ptr(vel), ptr(angVel), ptr(pos_out), ptr(vel_out), C.byref(ek), C.byref(st)))
+    def step_e2e(self, n, pos, vel, angVel, pos_out, vel_out, stats=True):
+        """stats=False: wdem_step_e2e with stats == NULL, i.e. the call returns when the outputs are on the host while the contact pass
+        for the next step is still running (include/wdem.h)."""
+        st = WdemStats() if stats else None; ek = C.c_double()
+        self._chk(self.L.wdem_step_e2e(self.h, C.c_int64(n), ptr(pos), ptr(vel), ptr(angVel), ptr(pos_out), ptr(vel_out), C.byref(ek), C.byref(st) if stats else None))
         self.stats = st
         return ek.value, st
 
@@ -264,6 +266,15 @@ class Engine:
 
     def set_scene(self, step, time):
         self._chk(self.L.wdem_set_scene(self.h, C.c_int64(int(step)), C.c_double(float(time))))
+
+    def periodic_state(self):
+        """(stepLast, stepPrev) of DynDt's PeriodicEngine counters."""
+        a, b = C.c_int64(), C.c_int64()
+        self._chk(self.L.wdem_get_periodic_state(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_periodic_state(self, step_last, step_prev):
+        self._chk(self.L.wdem_set_periodic_state(self.h, C.c_int64(int(step_last)), C.c_int64(int(step_prev))))
 
     def walls(self):
         """pos / force / torque of the walls after the last step (force: the last step's contacts)."""
