@@ -88,7 +88,11 @@ typedef struct wdem_stats {
  *  7 ReadForce                    flags&1: node given, v = node.pos(3), ori = node.ori
  *  8 VariableVelocity3d           v = t0; ori; times[nTimes], vals = vels (3 per time), vals2 = angVels (3 per time) or NULL; flags&1 diff, &2 wrap (hooks are not supported)
  *  9 VariableAlignedRotation      v = axis; times/vals = timeAngVel columns (1 value per time); flags&1 wrap
- * Not on this path: CircularOrbit, StableCircularOrbit, InterpolatedMotion. */
+ * 10 CircularOrbit                v = node.pos(3), omega, -, angle (its value at upload); ori = node.ori; flags&1 rotate      (Impose.cpp:22-37)
+ * 11 StableCircularOrbit          v = node.pos(3), omega, radius, angle; ori = node.ori; flags&1 rotate   (Impose.cpp:38-48; py/triangulated.py:59-64: a cylinder that really rotates)
+ *    The two orbit kinds act on spheres and on facet nodes (wdem_upload_facet_imposes).  They take atan2 / sin / cos of the node's position on the device, so nodes that
+ *    carry them follow the reference to rounding (1e-12 relative), not bit for bit like everything else.
+ * Not on this path: InterpolatedMotion. */
 typedef struct wdem_impose {
   int32_t kind, flags;
   double v[16];
@@ -174,9 +178,13 @@ int wdem_upload_clump_forces(wdem_handle h, const double* force, const double* t
  * the first step; at most 16 Impose objects.  Not with wdem_step_e2e. */
 int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int32_t nSets, const int32_t* setStart, const int32_t* setOps, int64_t nSphereIds,
                         const int32_t* sphereIds, const int32_t* sphereSet, const int32_t* wallSet, const int32_t* groupSet);
+/* DemData.impose of facet NODES: facetSet[f] = the set of impositions all three nodes of uploaded facet f carry, -1 none.  Such nodes are in DemField.nodes
+ * (DemData::guessMoving, Particle.cpp:638-640): Leapfrog's fixed-node branch translates them with their velocity and Impose::velocity at the end of the node's step sets
+ * the velocity of the next one (Leapfrog.cpp:195-199,248).  Velocity impositions only; not for facets of a kinematic group; aperiodic scenes.  Call after wdem_upload_imposes. */
+int wdem_upload_facet_imposes(wdem_handle h, const int32_t* facetSet);
 /* Velocities of the boundary nodes an imposition may have changed: 3 per uploaded wall, 3 + 3 per facet group; any pointer may be NULL. */
 int wdem_download_boundary_velocities(wdem_handle h, double* wallVel, double* groupVel, double* groupAngVel);
-/* out[8]: VelocityAndReadForce.sumF, .dist; ReadForce.F(3), .T(3) of Impose object ix after the last step (sums of what the last step's Leapfrog read). */
+/* out[8]: VelocityAndReadForce.sumF, .dist (CircularOrbit / StableCircularOrbit: .angle in the place of .dist); ReadForce.F(3), .T(3) of Impose object ix after the last step (sums of what the last step's Leapfrog read). */
 int wdem_get_impose_state(wdem_handle h, int32_t ix, double* out);
 /* Facet node positions (9 per facet, upload order) and the groups' master nodes after the last step; any pointer may be NULL. */
 int wdem_download_facets(wdem_handle h, double* verts, double* groupPos, double* groupOri);

@@ -240,6 +240,7 @@ struct Wall {
 };
 struct Facet {
   int id; V3 v[3]; V3 vvel[3]; V3 fakeVel; Real halfThick; Real n21lim[3]; unsigned mask; int mat; Aabb bb; V3 lastPos[3];
+  int impose = -1;     // set of impositions carried by all three nodes (py/triangulated.py:59-64), -1: none
 };
 // Master node of a clump of boundary particles that moves them rigidly (ParticleContainer::addClumped -> ClumpData::makeClump, Clump.cpp:187-261): a massless,
 // fully blocked node with prescribed vel/angVel (examples/mill.py:38-42) whose members are facets.  relPos are the members' node positions in the clump's frame.
@@ -247,7 +248,7 @@ struct FacetGroup { V3 pos; Quat ori; V3 vel, angVel; std::vector<int> facets; s
 // Impose (Particle.hpp:130-160, Impose.hpp, Impose.cpp): hooks called by Leapfrog on a node — velocity after the accelerations are applied and again at the end of
 // the node's step, force at the reset, readForce before the reset.  One descriptor per Impose object; a node refers to a SET of them (CombinedImpose, Impose.cpp:283-300).
 enum { IMP_HARMONIC = 1, IMP_ALIGNED_HARMONIC = 2, IMP_CONSTANT_FORCE = 3, IMP_RADIAL_FORCE = 4, IMP_LOCAL6 = 5, IMP_VEL_READ_FORCE = 6, IMP_READ_FORCE = 7, IMP_VARIABLE_VEL3D = 8,
-       IMP_VARIABLE_ALIGNED_ROTATION = 9 };
+       IMP_VARIABLE_ALIGNED_ROTATION = 9, IMP_CIRCULAR_ORBIT = 10, IMP_STABLE_CIRCULAR_ORBIT = 11 };
 enum { IMPW_VELOCITY = 1, IMPW_FORCE = 2, IMPW_READ_FORCE = 8 };
 struct ImposeDesc {
   int kind = 0, flags = 0; double v[16] = {0}; Quat ori; std::vector<double> times, vals, vals2;
@@ -256,7 +257,7 @@ struct ImposeDesc {
   int nNodes = 0;                             // nodes carrying it
   int what() const {
     switch (kind) {
-      case IMP_HARMONIC: case IMP_ALIGNED_HARMONIC: case IMP_VARIABLE_VEL3D: case IMP_VARIABLE_ALIGNED_ROTATION: return IMPW_VELOCITY;
+      case IMP_HARMONIC: case IMP_ALIGNED_HARMONIC: case IMP_VARIABLE_VEL3D: case IMP_VARIABLE_ALIGNED_ROTATION: case IMP_CIRCULAR_ORBIT: case IMP_STABLE_CIRCULAR_ORBIT: return IMPW_VELOCITY;
       case IMP_CONSTANT_FORCE: case IMP_RADIAL_FORCE: return IMPW_FORCE;
       case IMP_LOCAL6: return IMPW_VELOCITY | IMPW_FORCE;
       case IMP_VEL_READ_FORCE: return IMPW_VELOCITY | IMPW_READ_FORCE;
@@ -1111,16 +1112,37 @@ struct Scene {
           Real t = time; if ((d.flags & 1) && t > d.times.back()) t = std::fmod(t, d.times.back());
           linInterp(t, d.times, d.vals, 1, d.ipos, &r.vMag); break;
         }
-        case IMP_VEL_READ_FORCE: if (d.nNodes > 0) { d.sumF = 0; d.dist += d.v[3] * P.dt; } break;      // the first node of the step resets (Impose.cpp:166-173)
+        case IMP_VEL_READ_FORCE: if (d.nNodes > 0) { d.sumF = 0; d.dist += d.v[3] * P.dt; } break;
+        case IMP_CIRCULAR_ORBIT: case IMP_STABLE_CIRCULAR_ORBIT: if (d.nNodes > 0) d.dist += d.v[3] * P.dt; break;      // .angle += omega*dt, once per step (Impose.cpp:36,47)      // the first node of the step resets (Impose.cpp:166-173)
         case IMP_READ_FORCE: if (d.nNodes > 0) { d.F = V3(); d.T = V3(); } break;
         default: break;
       }
     }
   }
-  void imposeVelocity(int set, V3& vel, V3& angVel) {
+  void imposeVelocity(int set, V3& vel, V3& angVel, const V3& pos) {
     for (int ix : imposeSets[set]) {
       const ImposeDesc& d = imposes[ix]; const ImpStep& r = impStep[ix];
       switch (d.kind) {
+        case IMP_CIRCULAR_ORBIT: {      // Impose.cpp:22-37; v = node.pos(3), omega; ori = node.ori; flags&1 rotate
+          const Quat qc(d.ori.w, -d.ori.x, -d.ori.y, -d.ori.z);
+          const V3 loc = quatRotate(qc, pos - V3(d.v[0], d.v[1], d.v[2]));      // local 2d position (head<2>)
+          const Real theta = std::atan2(loc.y, loc.x), rho = std::sqrt(loc.x * loc.x + loc.y * loc.y);
+          const Real v2t = d.v[3] * rho;
+          const Real ttheta = theta + .5 * v2t * P.dt;      // sic: the tangential velocity, not omega
+          const Quat qz(std::cos(.5 * ttheta), 0., 0., std::sin(.5 * ttheta));      // Quaternionr(AngleAxisr(ttheta, UnitZ))
+          vel = quatRotate(d.ori, quatRotate(qz, V3(0., v2t, 0.)));
+          if (d.flags & 1) angVel = quatRotate(d.ori, V3(0., 0., d.v[3]));
+          break;
+        }
+        case IMP_STABLE_CIRCULAR_ORBIT: {      // Impose.cpp:38-48; v = node.pos(3), omega, radius
+          const Quat qc(d.ori.w, -d.ori.x, -d.ori.y, -d.ori.z); const V3 c(d.v[0], d.v[1], d.v[2]);
+          const V3 loc = quatRotate(qc, pos - c);                                  // Node::glob2loc (Field.hpp:92)
+          const Real th1 = std::atan2(loc.y, loc.x) + d.v[3] * P.dt;              // CompUtils::cart2cyl (CompUtils.cpp:115-117), target angle
+          const V3 pos1 = quatRotate(d.ori, V3(d.v[4] * std::cos(th1), d.v[4] * std::sin(th1), loc.z)) + c;      // cyl2cart (:120-122), loc2glob (Field.hpp:94)
+          vel = (pos1 - pos) / P.dt;
+          if (d.flags & 1) angVel = quatRotate(d.ori, V3(0., 0., d.v[3]));
+          break;
+        }
         case IMP_HARMONIC: case IMP_VEL_READ_FORCE: {
           const V3 dir(d.v[d.kind == IMP_HARMONIC ? 2 : 0], d.v[d.kind == IMP_HARMONIC ? 3 : 1], d.v[d.kind == IMP_HARMONIC ? 4 : 2]);
           const Real mag = d.kind == IMP_HARMONIC ? r.vMag : d.v[3];
@@ -1261,7 +1283,7 @@ struct Scene {
           s.angVel += dt * angAccel;
           if (homoDeform == HOMO_GRADV2) s.angVel -= deltaSpinVec;
         }
-        if (s.impose >= 0) imposeVelocity(s.impose, s.vel, s.angVel);      // re-applied to cancel the effect of forces (Leapfrog.cpp:203-205)
+        if (s.impose >= 0) imposeVelocity(s.impose, s.vel, s.angVel, s.pos);      // re-applied to cancel the effect of forces (Leapfrog.cpp:203-205)
       } else {
         if (homoDeform == HOMO_GRADV2) s.vel = mulMV(ImLL4hInv, mulMV(LmL, s.pos) + mulMV(IpLL4h, s.vel));
       }
@@ -1297,7 +1319,7 @@ struct Scene {
         s.torque = V3();
         if (s.impose >= 0) imposeForce(s.impose, s.pos, s.force, s.torque);        // Leapfrog.cpp:244
       }
-      if (s.impose >= 0) imposeVelocity(s.impose, s.vel, s.angVel);                // Leapfrog.cpp:248
+      if (s.impose >= 0) imposeVelocity(s.impose, s.vel, s.angVel, s.pos);         // Leapfrog.cpp:248
     }
     // clump master nodes (Leapfrog.cpp:148-255 with isClump): forces from the members, spherical or aspherical rotation, then the members follow
     if (!clumps.empty()) {
@@ -1389,7 +1411,7 @@ struct Scene {
         G.ori = quatMul(q, G.ori);
       }
       quatNormalize(G.ori);
-      if (G.impose >= 0) imposeVelocity(G.impose, G.vel, G.angVel);      // before applyToMembers (Leapfrog.cpp:248-252)
+      if (G.impose >= 0) imposeVelocity(G.impose, G.vel, G.angVel, G.pos);      // before applyToMembers (Leapfrog.cpp:248-252)
       for (size_t k = 0; k < G.facets.size(); k++) {
         Facet& f = facets[G.facets[k]];
         for (int i = 0; i < 3; i++) {
@@ -1398,12 +1420,19 @@ struct Scene {
         }
       }
     }
+    // facet nodes that carry an imposition are in DemField.nodes (guessMoving: || impose): fixed-node branch = leapfrogTranslate with the node's velocity, then
+    // Impose::velocity at the end of the node's step sets the velocity of the next one (Leapfrog.cpp:195-199,248)
+    for (Facet& f : facets) {
+      if (f.impose < 0) continue;
+      if (P.periodic) throw std::runtime_error("moving facets in a periodic cell are not supported");
+      for (int i = 0; i < 3; i++) { f.v[i] += f.vvel[i] * dt; V3 dummyW; imposeVelocity(f.impose, f.vvel[i], dummyW, f.v[i]); }
+    }
     for (Wall& w : walls) {
       if (!w.moving) continue;
       if (P.periodic) throw std::runtime_error("moving walls in a periodic cell are not supported");
       w.pos += w.vel * dt;
       if (P.reset) { w.force = V3(); w.torque = V3(); }
-      if (w.impose >= 0) { V3 dummyW; imposeVelocity(w.impose, w.vel, dummyW); }      // fully blocked node: only the call at the end of the node's step (Leapfrog.cpp:248)
+      if (w.impose >= 0) { V3 dummyW; imposeVelocity(w.impose, w.vel, dummyW, w.pos); }      // fully blocked node: only the call at the end of the node's step (Leapfrog.cpp:248)
     }
   }
 
@@ -1670,7 +1699,7 @@ int orc_add_impose(void* h, int kind, int flags, const double* v, const double* 
   return (int)S->imposes.size() - 1;
 }
 int orc_add_impose_set(void* h, int n, const int* ops) { Scene* S = (Scene*)h; S->imposeSets.push_back(std::vector<int>(ops, ops + n)); return (int)S->imposeSets.size() - 1; }
-// kind of node: 0 sphere (particle id), 1 wall (particle id), 2 facet group (index)
+// kind of node: 0 sphere (particle id), 1 wall (particle id), 2 facet group (index), 3 the three nodes of a facet (particle id)
 int orc_attach_impose(void* h, int nodeKind, int which, int set) {
   Scene* S = (Scene*)h;
   ORC_TRY(h)
@@ -1678,6 +1707,7 @@ int orc_attach_impose(void* h, int nodeKind, int which, int set) {
   bool readF = false; for (int ix : S->imposeSets[set]) { S->imposes[ix].nNodes++; if (S->imposes[ix].what() & IMPW_READ_FORCE) readF = true; }
   if (nodeKind == 0) { if (which < 0 || which >= (int)S->par.size() || S->par[which].kind != SHAPE_SPHERE) throw std::runtime_error("impose: not a sphere"); S->sph[S->par[which].idx].impose = set; }
   else if (nodeKind == 1) { if (which < 0 || which >= (int)S->par.size() || S->par[which].kind != SHAPE_WALL) throw std::runtime_error("impose: not a wall"); if (readF) throw std::runtime_error("readForce on walls is not part of this path"); Wall& w = S->walls[S->par[which].idx]; w.impose = set; w.moving = true; /* DemData::guessMoving: || impose (Particle.cpp:639) */ }
+  else if (nodeKind == 3) { if (which < 0 || which >= (int)S->par.size() || S->par[which].kind != SHAPE_FACET) throw std::runtime_error("impose: not a facet"); if (readF) throw std::runtime_error("readForce on facet nodes is not part of this path"); for (int ix : S->imposeSets[set]) S->imposes[ix].nNodes += 2; S->facets[S->par[which].idx].impose = set; }
   else { if (which < 0 || which >= (int)S->groups.size()) throw std::runtime_error("impose: no such facet group"); if (readF) throw std::runtime_error("readForce on facet groups is not part of this path"); S->groups[which].impose = set; }
   ORC_CATCH(h)
 }

@@ -102,7 +102,8 @@ class Oracle:
                              _p(np.ascontiguousarray(d["vals2"]), C.c_double) if len(d["vals2"]) else None)
         for st in getattr(S, "impose_sets", []):
             a = np.ascontiguousarray(st, dtype=np.int32); L.orc_add_impose_set(h, C.c_int(len(a)), _p(a, C.c_int))
-        for kind, arr, idof in ((0, getattr(S, "sphere_impose", None), lambda i: int(ids[i])), (1, getattr(S, "wall_impose", None), lambda i: int(S.wall_ids()[i])), (2, getattr(S, "group_impose", None), lambda i: i)):
+        for kind, arr, idof in ((0, getattr(S, "sphere_impose", None), lambda i: int(ids[i])), (1, getattr(S, "wall_impose", None), lambda i: int(S.wall_ids()[i])), (2, getattr(S, "group_impose", None), lambda i: i),
+                               (3, getattr(S, "facet_impose", None), lambda i: int(S.facet_ids()[i]))):
             if arr is None:
                 continue
             for i, k in enumerate(arr):

@@ -90,6 +90,39 @@ def test_imposition_on_a_facet_group_vibrating_mesh():
     assert not np.array_equal(E.facets(), np.array([f["v"] for f in S.facets]).reshape(-1, 3, 3))
 
 
+def test_orbit_impositions_on_spheres_and_on_the_nodes_of_a_rotating_cylinder():
+    """CircularOrbit / StableCircularOrbit (Impose.cpp:22-48) take atan2 / sin / cos of the node position on the device: nodes that carry them follow the oracle to
+    rounding, and with them — for a while, contacts amplify rounding — the spheres they touch.  A cylinder whose every node carries a StableCircularOrbit is what
+    woo.triangulated.cylinder(angVel=..., realRot=True) builds (py/triangulated.py:59-64)."""
+    om = 5.
+    S = sc.drum(200, div=10, axial=2, vz0=.3, vfluct=.2, omega=om, rotate=False)
+    R = float(np.hypot(S.facets[0]["v"][0][1], S.facets[0]["v"][0][2]))
+    for f in S.facets: f["fakeVel"] = (0., 0., 0.)
+    q = (0., math.sin(math.pi / 4), 0., math.cos(math.pi / 4))      # local z -> the drum's axis x
+    sc.attach_impose(S, [sc.imp_stable_circular_orbit((0., 0., 0.), om, R, node_ori=q)], facets=range(len(S.facets)))
+    sc.attach_impose(S, [sc.imp_circular_orbit((0., 0., 0.), 2., node_ori=q, rotate=True)], spheres=range(0, 5))
+    sc.attach_impose(S, [sc.imp_stable_circular_orbit((0., 0., 0.), -3., .4 * R, node_ori=q)], spheres=range(5, 10))
+    O, E = Oracle(S), engine_for(S)
+    v0 = E.facets().copy()
+    for k in range(4):
+        O.step(100); E.step(100)
+        fo, fg = O.facets(), E.facets()
+        assert np.allclose(fo, fg, rtol=0, atol=1e-12 * R), f"facet nodes differ at step {100 * (k + 1)}: {np.abs(fo - fg).max()}"
+        so, sg = O.spheres(), E.spheres()
+        for key in ("pos", "vel"):
+            # the spheres that carry an orbit are kinematic: rounding only, at every check; the free ones touch them and the cylinder, and contacts amplify rounding
+            # exponentially (2e-7 after 300 steps): tight at the first check, loose afterwards
+            assert np.allclose(so[key][:10], sg[key][:10], rtol=0, atol=1e-11 * max(1., np.abs(so[key]).max())), f"orbiting sphere {key} differs at step {100 * (k + 1)}: {np.abs(so[key][:10] - sg[key][:10]).max()}"
+            assert np.allclose(so[key], sg[key], rtol=0, atol=(1e-8 if k == 0 else 1e-3) * max(1., np.abs(so[key]).max())), f"sphere {key} differs at step {100 * (k + 1)}: {np.abs(so[key] - sg[key]).max()}"
+        assert O.nFullRuns == E.scalars()["nFullRuns"] and O.dt == E.scalars()["dt"]
+        if k == 0:
+            assert [tuple(x) for x in O.contacts(True)["ids"]] == [tuple(x) for x in E.contacts(True)["ids"]]
+        assert O.impose_state(0)["dist"] == E.impose_state(0)["dist"]      # .angle
+    rr = np.hypot(fg[..., 1], fg[..., 2])
+    assert np.allclose(rr, R, rtol=1e-12) and not np.allclose(fg, v0, atol=1e-3 * R), "the cylinder keeps its radius and has turned"
+    assert len(E.contacts(True)["ids"]) > 0 and E.scalars()["nFullRuns"] > 5
+
+
 def test_impose_errors():
     from woo_b200.engine import Engine
     S = _gas(50)
@@ -99,4 +132,8 @@ def test_impose_errors():
     S = _gas(50); S.walls = sc.box_walls((0, 0, 0), (.5, .5, .5)); S.finalize()
     sc.attach_impose(S, [sc.imp_constant_force((0, 0, 1))], walls=[0])
     with pytest.raises(RuntimeError, match="velocity impositions only"):
+        Engine(S.params).load(S)
+    S = _gas(50); S.walls = sc.box_walls((0, 0, 0), (.5, .5, .5)); S.finalize()
+    sc.attach_impose(S, [sc.imp_stable_circular_orbit((0, 0, 0), 1., .1)], walls=[0])
+    with pytest.raises(RuntimeError, match="not on walls"):
         Engine(S.params).load(S)

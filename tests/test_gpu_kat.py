@@ -23,6 +23,10 @@ class GpuAsOracle:
     def kineticEnergy(self): return self.E.kinetic_energy()
     def cell_hsize(self): return self.E.cell_hsize()
     def pWaveDt(self): return self.E.crit_dt()
+    def facets(self): return self.E.facets()
+    def impose_state(self, ix): return self.E.impose_state(ix)
+    @property
+    def nFullRuns(self): return self.E.scalars()["nFullRuns"]
     @property
     def dt(self): return self.E.scalars()["dt"]
     @property
@@ -37,7 +41,8 @@ CASES = [(K.test_pwave_dt, ()), (K.test_cundall_kn_and_hertz_force, ()), (K.test
          (K.test_facet_sphere_closest_point, ((.25, .25, .19), (.25, .25, 0.), "face")), (K.test_facet_sphere_closest_point, ((.5, -.1, .1), (.5, 0., 0.), "edge")),
          (K.test_facet_sphere_closest_point, ((1.1, -.1, .05), (1., 0., 0.), "vertex")), (K.test_hertz_collision_time, (1e-2,)),
          (K.test_hertz_restitution_coefficient, (.5,)), (K.test_collision_masks, (0b01, 0b10, False)), (K.test_collision_masks, (0b10, 0b10, False)),
-         (K.test_collision_masks, (0b0101, 0b0011, True)), (K.test_collision_masks, (0b0111, 0b0011, False)), (K.test_collision_masks, (0b0101, 0b0111, True))]
+         (K.test_collision_masks, (0b0101, 0b0011, True)), (K.test_collision_masks, (0b0111, 0b0011, False)), (K.test_collision_masks, (0b0101, 0b0111, True)),
+         (K.test_impose_circular_orbits_keep_radius_and_turn_by_omega_t, ())]
 
 
 @pytest.mark.parametrize("kat,args", CASES, ids=[f"{f.__name__}{list(a) if a else ''}" for f, a in CASES])

@@ -584,3 +584,38 @@ def test_impose_variable_velocity_on_a_wall_and_table_semantics():
     z_expected = .9 + (.5 * .5 * .01 + .5 * .02)
     assert w["pos"][0, 2] == pytest.approx(z_expected, abs=2 * .5 * 1e-4)
     assert O.nFullRuns > 1
+
+
+def test_impose_circular_orbits_keep_radius_and_turn_by_omega_t():
+    """StableCircularOrbit (Impose.cpp:38-48) keeps the node at `radius` around the local z axis and advances its polar angle by omega*dt per step; CircularOrbit
+    (Impose.cpp:22-37) prescribes the tangential velocity at the approximate mid-step angle (radius not enforced, drifts slowly); a facet whose three nodes carry a
+    StableCircularOrbit turns rigidly (py/triangulated.py:59-64)."""
+    S = _free_spheres(2, gravity=(0, 0, -9.81))
+    q = (0., math.sin(math.pi / 4), 0., math.cos(math.pi / 4))          # local z -> global x (Quaternion.setFromTwoVectors(UnitZ, UnitX))
+    c = np.array([.3, .1, .2]); R, om, dt = .25, 7., 1e-4
+    S.pos[0] = c + (.05, R * math.cos(.4), R * math.sin(.4)); S.pos[1] = c + (-.02, 0., .1)
+    S.facets = [dict(v=np.array([c + (0., R, 0.), c + (.1, R, 0.), c + (0., 0., R)]), halfThick=0., fakeVel=(0., 0., 0.), mat=0, mask=sc.MASK_BOUNDARY)]
+    S.finalize()
+    sc.attach_impose(S, [sc.imp_stable_circular_orbit(c, om, R, node_ori=q, rotate=True)], spheres=[0], facets=[0])
+    sc.attach_impose(S, [sc.imp_circular_orbit(c, om, node_ori=q)], spheres=[1])
+    O = Oracle(S)
+    N = 2000; O.step(N)
+    s = O.spheres()
+    # a free node gets the velocity imposed before it is translated (Leapfrog.cpp:203-205): N steps = N increments of the angle
+    rel = s["pos"][0] - c
+    assert rel[0] == pytest.approx(.05, abs=1e-13) and math.hypot(rel[1], rel[2]) == pytest.approx(R, rel=1e-13)
+    # local frame: x_loc = -z_glob... rotate back with q*: for this q, local (x,y,z) = (-gz, gy, gx)
+    th = math.atan2(rel[1], -rel[2])
+    th0 = math.atan2(R * math.cos(.4), -R * math.sin(.4))
+    assert math.remainder(th - th0 - om * N * dt, 2 * math.pi) == pytest.approx(0., abs=1e-10)
+    assert np.allclose(s["angVel"][0], (om, 0, 0), atol=1e-14)           # rotate: node.ori * (0,0,omega)
+    assert O.impose_state(0)["dist"] == pytest.approx(om * N * dt, rel=1e-12)      # .angle
+    rel1 = s["pos"][1] - c
+    assert rel1[0] == pytest.approx(-.02, abs=1e-13) and math.hypot(rel1[1], rel1[2]) == pytest.approx(.1, rel=1e-3)
+    f = O.facets()[0]
+    for i, r_ in enumerate((R, R, R)):
+        assert math.hypot(f[i][1] - c[1], f[i][2] - c[2]) == pytest.approx(r_, rel=1e-13)
+    assert np.linalg.norm(f[1] - f[0]) == pytest.approx(.1, rel=1e-12)    # rigid: the edge along the axis keeps its length
+    # a fully blocked node is translated first and gets its velocity at the end of the step (Leapfrog.cpp:195-199,248): N steps = N-1 increments
+    assert math.remainder(math.atan2(f[0][1] - c[1], -(f[0][2] - c[2])) - math.atan2(R, 0.) - om * (N - 1) * dt, 2 * math.pi) == pytest.approx(0., abs=1e-10)
+    assert O.nFullRuns > 1

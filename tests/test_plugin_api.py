@@ -289,6 +289,41 @@ def test_rotating_drum_with_add_clumped():
 
 
 @pytest.mark.gpu
+def test_rotating_cylinder_with_stable_circular_orbit_on_every_node():
+    """py/triangulated.py:59-64 (woo.triangulated.cylinder(angVel=..., realRot=True)): one StableCircularOrbit shared by all nodes of the mesh; the plugin sends it to
+    the device as the imposition of the facets' nodes (wdem_upload_facet_imposes) and the result equals the array-level engine (same device code: bit for bit)."""
+    import math
+    from woo_b200 import scenes as sc
+    from woo_b200.engine import Engine
+    from woo_b200.woo.core import Node
+    from woo_b200.woo.dem import StableCircularOrbit
+    om = 6.
+    Sp = sc.drum(300, div=12, axial=3, vz0=.5, vfluct=.3, omega=om, rotate=False)
+    R = float(np.hypot(Sp.facets[0]["v"][0][1], Sp.facets[0]["v"][0][2]))
+    for f in Sp.facets: f["fakeVel"] = (0., 0., 0.)
+    q = (0., math.sin(math.pi / 4), 0., math.cos(math.pi / 4))
+    sc.attach_impose(Sp, [sc.imp_stable_circular_orbit((0., 0., 0.), om, R, node_ori=q)], facets=range(len(Sp.facets)))
+    E = Engine(Sp.params).load(Sp); E.step(400)
+    S = Scene(fields=[DemField(gravity=Sp.params.gravity)])
+    m = FrictMat(density=2500., young=1e7, ktDivKn=.2, tanPhi=.5)
+    S.dem.par.add([woo.utils.sphere(Sp.pos[i], Sp.radius[i], mat=m, vel=Sp.vel[i]) for i in range(Sp.n)])
+    S.dem.par.add([Wall.make(w["pos"], axis=w["axis"], sense=w["sense"], mat=m) for w in Sp.walls])
+    orbit = StableCircularOrbit(node=Node(pos=(0, 0, 0), ori=q), omega=om, radius=R)
+    facets = [Facet.make([tuple(v) for v in f["v"]], mat=m) for f in Sp.facets]
+    for f in facets:
+        for n in f.shape.nodes: n.dem.impose = orbit
+    S.dem.par.add(facets)
+    S.engines = woo.utils.gpuEngines(damping=.2, dynDtPeriod=100)
+    v0 = np.array(facets[0].shape.nodes[0].pos)
+    S.run(400, True)
+    assert np.array_equal(np.array([S.dem.par[i].pos for i in range(Sp.n)]), E.spheres()["pos"])
+    v1 = np.array(facets[0].shape.nodes[0].pos)
+    assert np.array_equal(v1, E.facets()[0, 0]) and np.linalg.norm(v1 - v0) > 1e-3
+    assert math.hypot(v1[1], v1[2]) == pytest.approx(R, rel=1e-12)
+    assert orbit.angle == pytest.approx(om * S.time, rel=1e-9)
+
+
+@pytest.mark.gpu
 def test_inlet_like_additions_use_the_device_append_path():
     """Spheres added batch by batch while the scene runs (what an Inlet does): the plugin appends them on the device (wdem_add_spheres); the result equals the
     array-level engine fed the same batches, and a batch with a new material falls back to the full re-upload with the contact history kept."""

@@ -183,7 +183,7 @@ struct wdem_engine {
   // Impose (wdem_upload_imposes): descriptors and their host state, sets, node attachments, and the per-step ring of resolved impositions
   struct ImposeHost { int kind = 0, flags = 0; double v[16] = {0}; double ori[4] = {0, 0, 0, 1}; std::vector<double> times, vals, vals2; size_t ipos = 0, ipos2 = 0; double dist = 0; int nNodes = 0; };
   std::vector<ImposeHost> imposes; std::vector<int> impSetStart, impSetOps, wallImpSet, groupImpSet; std::vector<double> impWallVel;
-  DBuf<int> dImpSetStart, dImpSetOps; DBuf<int32_t> dImpOfId; bool impSpheres = false, impRead = false; ImpSlot* hImpRing = nullptr; DBuf<ImpSlot> dImpRing; int lastImpSlot = 0;
+  DBuf<int> dImpSetStart, dImpSetOps; DBuf<int32_t> dImpOfId; bool impSpheres = false, impRead = false, impFacetNodes = false; ImpSlot* hImpRing = nullptr; DBuf<ImpSlot> dImpRing; int lastImpSlot = 0;
   ImposeDev impDev(int slot) { ImposeDev I; I.slot = dImpRing.p ? dImpRing.p + slot : nullptr; I.setStart = dImpSetStart.p; I.setOps = dImpSetOps.p; return I; }
   GroupsU groups{};                      // kinematic facet groups (wdem_upload_facet_groups): master nodes integrated on the host, members on the device
   std::vector<double> groupRadius;       // largest distance of a member node from its master node (bounding sphere of the sweep of a rotating group)
@@ -717,7 +717,7 @@ void rebuild(wdem_engine* E) {
   int64_t& tot = E->bytes;
   long long nSS = 0, nSSa = 0, nWS = 0, nFS = 0, nOrphOut = 0;   // nSSa: active sphere-sphere contacts (the first nSSa of the nSS); the rest is dormant
   if (!E->fgridValid) buildFacetGrid(E);
-  if (E->groups.n > 0 && !E->hFacets.empty()) rebinFacets(E);
+  if ((E->groups.n > 0 || E->impFacetNodes) && !E->hFacets.empty()) rebinFacets(E);
   const int nFacets = (int)E->hFacets.size();
   ContactStore& Nst = E->con[1 - E->curC];
   ContactStore& Ost = E->con[E->curC];
@@ -1021,7 +1021,7 @@ void buildFacetGrid(wdem_engine* E) {
 void rebinFacets(wdem_engine* E) {
   const int nf = (int)E->hFacets.size(); cudaStream_t st = E->stream; FacetGrid& g = E->fgrid;
   const size_t ncell = (size_t)g.nx * g.ny * g.nz;
-  k_facets_step<<<nblk(nf, 128), 128, 0, st>>>(E->dFacets.p, nf, E->groups, makeUniforms(E), E->dCnt, 1);
+  k_facets_step<<<nblk(nf, 128), 128, 0, st>>>(E->dFacets.p, nf, E->groups, makeUniforms(E), E->dCnt, 1, E->impDev(0));
   CK(cudaMemsetAsync(E->fgCellStart.p, 0, (ncell + 1) * sizeof(int), st));
   k_fgrid_bin<<<nblk(nf, 128), 128, 0, st>>>(E->dFacets.p, nf, g, E->verletDist, E->fgCellStart.p, nullptr, nullptr, 0);
   exclusiveSum(E, E->fgCellStart.p, E->fgCellStart.p, (int)ncell + 1);
@@ -1272,6 +1272,7 @@ void imposePrepareStep(wdem_engine* E, int slot) {
         if (!d.vals2.empty()) linInterp(t, d.times, d.vals2, 3, d.ipos2, o.a + 3);
         break;
       }
+      case 10: case 11: o.kind = d.kind == 10 ? IOP_ORBIT : IOP_SORBIT; o.flags = d.flags & 1; for (int k = 0; k < 3; k++) o.a[k] = d.v[k]; o.a[3] = d.v[3]; o.a[4] = d.v[4]; o.a[5] = dt; break;
       case 9: { double t = time; if ((d.flags & 1) && t > d.times.back()) t = std::fmod(t, d.times.back()); o.kind = IOP_ANGAXIS; o.m[0] = (int)d.v[0]; linInterp(t, d.times, d.vals, 1, d.ipos, o.a); break; }
       default: break;
     }
@@ -1281,7 +1282,7 @@ void imposePrepareStep(wdem_engine* E, int slot) {
   for (size_t w = 0; w < E->wallImpSet.size() && w < 32; w++) {
     if (E->wallImpSet[w] < 0) continue;
     d3 v = mk3(E->impWallVel[3 * w], E->impWallVel[3 * w + 1], E->impWallVel[3 * w + 2]), dummy = mk3(0, 0, 0);
-    impose_velocity(I, E->wallImpSet[w], v, dummy);
+    impose_velocity(I, E->wallImpSet[w], v, dummy, mk3(0, 0, 0));
     E->impWallVel[3 * w] = v.x; E->impWallVel[3 * w + 1] = v.y; E->impWallVel[3 * w + 2] = v.z;
     H.wallHas[w] = 1; H.wallVel[3 * w] = v.x; H.wallVel[3 * w + 1] = v.y; H.wallVel[3 * w + 2] = v.z;
   }
@@ -1318,7 +1319,7 @@ StepU stepPrologue(wdem_engine* E, int k) {
       G.ori.w /= nn; G.ori.x /= nn; G.ori.y /= nn; G.ori.z /= nn;
       if (gi < (int)E->groupImpSet.size() && E->groupImpSet[gi] >= 0) {      // Impose::velocity before applyToMembers (Leapfrog.cpp:248-252)
         ImposeDev I; I.slot = &E->hImpRing[k]; I.setStart = E->impSetStart.data(); I.setOps = E->impSetOps.data();
-        impose_velocity(I, E->groupImpSet[gi], G.vel, G.angVel);
+        impose_velocity(I, E->groupImpSet[gi], G.vel, G.angVel, G.pos);
       }
     }
   }
@@ -1346,7 +1347,10 @@ void enqueueIntegrate(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
     if (c.periodic || E->comm || E->e2e.active || E->trackEnergy) throw EngErr{"clumps of spheres: periodic cells, decomposed runs, wdem_step_e2e and Scene.trackEnergy are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     k_clumps_step<<<nblk(E->clumps.n, 128), 128, 0, st>>>(E->clumps.view(), E->S(), E->id2slot.p, u, E->dCnt); E->launches++;
   }
-  if (E->groups.n > 0 && !E->hFacets.empty()) { k_facets_step<<<nblk((long long)E->hFacets.size(), 128), 128, 0, st>>>(E->dFacets.p, (int)E->hFacets.size(), E->groups, u, E->dCnt, 0); E->launches++; }
+  if ((E->groups.n > 0 || E->impFacetNodes) && !E->hFacets.empty()) {
+    if (c.periodic) throw EngErr{"moving facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    k_facets_step<<<nblk((long long)E->hFacets.size(), 128), 128, 0, st>>>(E->dFacets.p, (int)E->hFacets.size(), E->groups, u, E->dCnt, 0, E->impDev(u.impSlot)); E->launches++;
+  }
   if (E->anyMovingWall) {
     if (c.periodic) throw EngErr{"moving walls in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     k_walls_step<<<nblk((long long)E->hWalls.size(), 32), 32, 0, st>>>(E->dWalls.p, (int)E->hWalls.size(), u, E->dCnt, 0, E->wallImpSet.empty() ? nullptr : E->dImpRing.p + u.impSlot); E->launches++;
@@ -1458,6 +1462,7 @@ void runSteps(wdem_engine* E, int64_t nsteps, wdem_stats* stats) {
     } else if (E->stepsSinceFullRun + K > 2 * (long long)E->batchK) E->batchK = std::min(E->batchMax, E->batchK + 1);      // long quiet stretch: larger batches
     if (!E->imposes.empty()) {      // VelocityAndReadForce.dist: += vel*dt in every executed step in which some node carried it (Impose.cpp:166-173)
       for (auto& d : E->imposes) if (d.kind == 6 && d.nNodes > 0) for (int k = 0; k < executed; k++) d.dist += d.v[3] * snaps[k].u.dt;
+      for (auto& d : E->imposes) if ((d.kind == 10 || d.kind == 11) && d.nNodes > 0) for (int k = 0; k < executed; k++) d.dist += d.v[3] * snaps[k].u.dt;      // .angle += omega*dt (Impose.cpp:36,47)
       E->lastImpSlot = executed - 1;
     }
     gradVWorkStep(E);
@@ -1662,7 +1667,7 @@ int wdem_upload_spheres(wdem_handle h, int64_t n, const int32_t* ids, const doub
     CK(cudaStreamSynchronize(st));
     h->conDirty = true; h->nC = h->nSS = h->nSSa = h->nWS = h->nFS = h->nOrph = 0; h->csr[0].valid = h->csr[1].valid = false; h->up2slotValid = false;
     h->verletDist = NAN; h->fgridValid = false; h->boundsValid = false; h->batchK = 1;
-    h->imposes.clear(); h->impSetStart.clear(); h->impSetOps.clear(); h->wallImpSet.clear(); h->groupImpSet.clear(); h->impSpheres = false; h->impRead = false;
+    h->imposes.clear(); h->impSetStart.clear(); h->impSetOps.clear(); h->wallImpSet.clear(); h->groupImpSet.clear(); h->impSpheres = false; h->impRead = false; h->impFacetNodes = false;
     h->clumps.release(); h->nClumpedUploaded = 0; for (int64_t i = 0; i < n; i++) if (fl[i] & 64u) h->nClumpedUploaded++;
   });
 }
@@ -1747,12 +1752,14 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
     if (nImp > 0 && (!imp || nSets <= 0 || !setStart || !setOps)) throw EngErr{"wdem_upload_imposes: bad arguments", WDEM_ERR_INVALID};
     if (!h->conDirty || h->nC != 0 || h->cur != 0) throw EngErr{"wdem_upload_imposes: call after the particles are uploaded and before the first step", WDEM_ERR_INVALID};
     if (h->cfg.periodic && (wallSet || groupSet)) throw EngErr{"wdem_upload_imposes: moving walls / facet groups in a periodic cell are not supported", WDEM_ERR_UNSUPPORTED};
-    h->imposes.clear(); h->impSetStart.clear(); h->impSetOps.clear(); h->wallImpSet.clear(); h->groupImpSet.clear(); h->impSpheres = false; h->impRead = false;
+    h->imposes.clear(); h->impSetStart.clear(); h->impSetOps.clear(); h->wallImpSet.clear(); h->groupImpSet.clear(); h->impSpheres = false; h->impRead = false; h->impFacetNodes = false;
     if (nImp == 0) return;
     cudaStream_t st = h->stream;
     for (int i = 0; i < nImp; i++) {
       const wdem_impose& s = imp[i]; wdem_engine::ImposeHost d;
-      if (s.kind < 1 || s.kind > 9) throw EngErr{"wdem_upload_imposes: unknown kind " + std::to_string(s.kind) + " (CircularOrbit, StableCircularOrbit, InterpolatedMotion are not on this path)", WDEM_ERR_UNSUPPORTED};
+      if (s.kind < 1 || s.kind > 11) throw EngErr{"wdem_upload_imposes: unknown kind " + std::to_string(s.kind) + " (InterpolatedMotion is not on this path)", WDEM_ERR_UNSUPPORTED};
+      if ((s.kind == 10 || s.kind == 11) && !(s.v[3] == s.v[3])) throw EngErr{"CircularOrbit / StableCircularOrbit: omega must be given", WDEM_ERR_INVALID};
+      if (s.kind == 11 && !(s.v[4] == s.v[4])) throw EngErr{"StableCircularOrbit: radius must be given", WDEM_ERR_INVALID};
       d.kind = s.kind; d.flags = s.flags; memcpy(d.v, s.v, sizeof(d.v)); memcpy(d.ori, s.ori, sizeof(d.ori));
       if (s.kind == 8 || s.kind == 9) {
         if (s.nTimes <= 0 || !s.times || !s.vals) throw EngErr{s.kind == 8 ? "VariableVelocity3d: times must not be empty." : "VariableAlignedRotation: timeAngVel must not be empty.", WDEM_ERR_INVALID};
@@ -1762,12 +1769,14 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
       }
       if (s.kind == 5) for (int k = 0; k < 6; k++) { const int w = (int)s.v[6 + k]; if (w != 0 && w != 1 && w != 2) throw EngErr{"Local6Dofs.whats components must be 0, 2 or 1", WDEM_ERR_INVALID}; }
       if (s.kind == 6) d.dist = s.v[4];
+      if (s.kind == 10 || s.kind == 11) d.dist = s.v[5];      // .angle at upload
       if (s.kind == 6 || s.kind == 7) h->impRead = true;
       h->imposes.push_back(d);
     }
     h->impSetStart.assign(setStart, setStart + nSets + 1); h->impSetOps.assign(setOps, setOps + setStart[nSets]);
     for (int v : h->impSetOps) if (v < 0 || v >= nImp) throw EngErr{"wdem_upload_imposes: set refers to an unknown Impose object", WDEM_ERR_INVALID};
-    auto setKinds = [&](int set, bool& vel, bool& other) { for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) { const int k = h->imposes[h->impSetOps[e]].kind; if (k == 1 || k == 2 || k == 8 || k == 9) vel = true; else if (k == 5) { vel = true; for (int q = 0; q < 6; q++) if ((int)h->imposes[h->impSetOps[e]].v[6 + q] == 2) other = true; } else if (k == 6) { vel = true; other = true; } else other = true; } };
+    bool orbit = false;
+    auto setKinds = [&](int set, bool& vel, bool& other) { orbit = false; for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) { const int k = h->imposes[h->impSetOps[e]].kind; if (k == 10 || k == 11) orbit = true; if (k == 1 || k == 2 || k == 8 || k == 9 || k == 10 || k == 11) vel = true; else if (k == 5) { vel = true; for (int q = 0; q < 6; q++) if ((int)h->imposes[h->impSetOps[e]].v[6 + q] == 2) other = true; } else if (k == 6) { vel = true; other = true; } else other = true; } };
     auto touch = [&](int set) { if (set < 0) return; if (set >= nSets) throw EngErr{"wdem_upload_imposes: set index out of range", WDEM_ERR_INVALID}; for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) h->imposes[h->impSetOps[e]].nNodes++; };
     // spheres: table by particle id
     std::vector<int32_t> ofId((size_t)std::max(h->maxId, 0) + 2, -1);
@@ -1787,6 +1796,7 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
         if (wallSet[w] < 0) continue;
         bool vel = false, other = false; setKinds(wallSet[w], vel, other);
         if (other) throw EngErr{"wdem_upload_imposes: walls (all DOFs blocked) take velocity impositions only", WDEM_ERR_UNSUPPORTED};
+        if (orbit) throw EngErr{"wdem_upload_imposes: CircularOrbit / StableCircularOrbit act on spheres and on facet nodes (wdem_upload_facet_imposes), not on walls", WDEM_ERR_UNSUPPORTED};
         touch(wallSet[w]); h->hWalls[w].moving = 1; any = true;      // DemData::guessMoving: ... || impose (Particle.cpp:638-640)
       }
       if (any) { h->anyMovingWall = true; h->anyStaticWall = false; for (auto& w : h->hWalls) if (!w.moving) h->anyStaticWall = true; CK(cudaMemcpyAsync(h->dWalls.p, h->hWalls.data(), h->hWalls.size() * sizeof(Wall), cudaMemcpyHostToDevice, st)); }
@@ -1794,7 +1804,7 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
     }
     if (groupSet) {
       h->groupImpSet.assign(groupSet, groupSet + h->groups.n);
-      for (int g = 0; g < h->groups.n; g++) { if (groupSet[g] < 0) continue; bool vel = false, other = false; setKinds(groupSet[g], vel, other); if (other) throw EngErr{"wdem_upload_imposes: facet groups (all DOFs blocked) take velocity impositions only", WDEM_ERR_UNSUPPORTED}; touch(groupSet[g]); }
+      for (int g = 0; g < h->groups.n; g++) { if (groupSet[g] < 0) continue; bool vel = false, other = false; setKinds(groupSet[g], vel, other); if (other) throw EngErr{"wdem_upload_imposes: facet groups (all DOFs blocked) take velocity impositions only", WDEM_ERR_UNSUPPORTED}; if (orbit) throw EngErr{"wdem_upload_imposes: CircularOrbit / StableCircularOrbit act on spheres and on facet nodes (wdem_upload_facet_imposes), not on facet groups", WDEM_ERR_UNSUPPORTED}; touch(groupSet[g]); }
     }
     h->dImpSetStart.ensure(h->impSetStart.size(), h->bytes); CK(cudaMemcpyAsync(h->dImpSetStart.p, h->impSetStart.data(), h->impSetStart.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     h->dImpSetOps.ensure(std::max<size_t>(h->impSetOps.size(), 1), h->bytes); if (!h->impSetOps.empty()) CK(cudaMemcpyAsync(h->dImpSetOps.p, h->impSetOps.data(), h->impSetOps.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1813,6 +1823,30 @@ int wdem_download_boundary_velocities(wdem_handle h, double* wallVel, double* gr
       if (groupVel) { groupVel[3 * g] = G.vel.x; groupVel[3 * g + 1] = G.vel.y; groupVel[3 * g + 2] = G.vel.z; }
       if (groupAngVel) { groupAngVel[3 * g] = G.angVel.x; groupAngVel[3 * g + 1] = G.angVel.y; groupAngVel[3 * g + 2] = G.angVel.z; }
     }
+  });
+}
+int wdem_upload_facet_imposes(wdem_handle h, const int32_t* facetSet) {
+  return guarded(h, [&] {
+    if (h->imposes.empty() || !facetSet) throw EngErr{"wdem_upload_facet_imposes: call after wdem_upload_imposes", WDEM_ERR_INVALID};
+    if (!h->conDirty || h->nC != 0 || h->cur != 0) throw EngErr{"wdem_upload_facet_imposes: call before the first step", WDEM_ERR_INVALID};
+    if (h->cfg.periodic) throw EngErr{"wdem_upload_facet_imposes: moving facets in a periodic cell are not supported", WDEM_ERR_UNSUPPORTED};
+    const int nSets = (int)h->impSetStart.size() - 1; bool any = false;
+    for (size_t f = 0; f < h->hFacets.size(); f++) {
+      const int set = facetSet[f]; h->hFacets[f].nodeImp1 = 0;
+      if (set < 0) continue;
+      if (set >= nSets) throw EngErr{"wdem_upload_facet_imposes: set index out of range", WDEM_ERR_INVALID};
+      if (h->hFacets[f].group1 > 0) throw EngErr{"wdem_upload_facet_imposes: a facet of a kinematic group follows its master node and cannot carry an imposition of its own", WDEM_ERR_INVALID};
+      for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) {
+        wdem_engine::ImposeHost& d = h->imposes[h->impSetOps[e]];
+        const bool velOnly = d.kind == 1 || d.kind == 2 || d.kind == 10 || d.kind == 11 || (d.kind == 8 && d.vals2.empty());
+        if (!velOnly) throw EngErr{"wdem_upload_facet_imposes: facet nodes (all DOFs blocked) take velocity impositions only (HarmonicOscillation, AlignedHarmonicOscillations, VariableVelocity3d without rotation, CircularOrbit, StableCircularOrbit)", WDEM_ERR_UNSUPPORTED};
+        d.nNodes += 3;
+      }
+      h->hFacets[f].nodeImp1 = set + 1; any = true;
+    }
+    h->impFacetNodes = any;
+    if (!h->hFacets.empty()) { CK(cudaMemcpyAsync(h->dFacets.p, h->hFacets.data(), h->hFacets.size() * sizeof(Facet), cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
+    h->fgridValid = false;
   });
 }
 int wdem_get_impose_state(wdem_handle h, int32_t ix, double* out) {

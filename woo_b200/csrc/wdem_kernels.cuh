@@ -38,11 +38,11 @@ struct Spheres {          // one slot per sphere; slots are re-ordered by grid c
 // Impose (Particle.hpp:130-160, Impose.hpp, Impose.cpp): one resolved imposition.  Everything that depends on Scene.time / Scene.dt only (harmonic
 // factors, interpolated tables) is evaluated by the host once per step with libm, so host, device and oracle see the same numbers.
 #define WD_MAX_IMPOSE 16
-enum { IOP_DIR = 1, IOP_AXES_SET = 2, IOP_VAR3D = 3, IOP_ANGAXIS = 4, IOP_LOCAL6 = 5, IOP_FADD = 6, IOP_FRADIAL = 7, IOP_READFT = 8 };
+enum { IOP_DIR = 1, IOP_AXES_SET = 2, IOP_VAR3D = 3, IOP_ANGAXIS = 4, IOP_LOCAL6 = 5, IOP_FADD = 6, IOP_FRADIAL = 7, IOP_READFT = 8, IOP_ORBIT = 9, IOP_SORBIT = 10 };
 struct ImpOp {
   int kind, flags;      // DIR: flags&1 zero the lateral velocity, &2 read force (VelocityAndReadForce), &4 invF | VAR3D: &1 diff, &2 rotated frame, &4 angular velocity too | READFT: &1 node frame
   double ori[4];        // x,y,z,w
-  double a[7];          // DIR dir(3), magnitude | AXES_SET values(3; NaN: untouched) | VAR3D vImp(3), wImp(3) | ANGAXIS value | LOCAL6 values(6) | FADD F(3) | FRADIAL A(3), unit axis(3), F | READFT node pos(3)
+  double a[7];          // ORBIT / SORBIT: node pos(3), omega, radius (SORBIT), dt; ori = node.ori; flags&1 rotate | DIR dir(3), magnitude | AXES_SET values(3; NaN: untouched) | VAR3D vImp(3), wImp(3) | ANGAXIS value | LOCAL6 values(6) | FADD F(3) | FRADIAL A(3), unit axis(3), F | READFT node pos(3)
   int m[6];             // ANGAXIS m[0] = axis | LOCAL6 whats(6)
 };
 struct ImpSlot {        // what one step of a batch needs (ring indexed by the step's position in the batch, like Counters::gflag)
@@ -53,10 +53,32 @@ struct ImpSlot {        // what one step of a batch needs (ring indexed by the s
 struct ImposeDev { ImpSlot* slot; const int* setStart; const int* setOps; };
 __host__ __device__ __forceinline__ q4 impOri(const ImpOp& o) { q4 q; q.x = o.ori[0]; q.y = o.ori[1]; q.z = o.ori[2]; q.w = o.ori[3]; return q; }
 // Impose::velocity of every imposition of the set, in order (CombinedImpose::velocity, Impose.cpp:288-292)
-__host__ __device__ __forceinline__ void impose_velocity(const ImposeDev& I, int set, d3& vel, d3& w) {
+// `pos`: the node's position at the time of the call (only the orbit kinds read it: atan2 / sin / cos of the device's math library there, so nodes that carry them
+// follow the oracle to rounding, not bit for bit).
+__host__ __device__ __forceinline__ void impose_velocity(const ImposeDev& I, int set, d3& vel, d3& w, const d3& pos) {
   for (int e = I.setStart[set]; e < I.setStart[set + 1]; e++) {
     const ImpOp& o = I.slot->op[I.setOps[e]];
     switch (o.kind) {
+      case IOP_ORBIT: {    // CircularOrbit (Impose.cpp:22-37): tangential velocity at the approximate mid-step polar angle, around the local z axis of `node`
+        const q4 q = impOri(o), qc = quatConj(q);
+        const d3 loc = quatRotate(qc, pos - mk3(o.a[0], o.a[1], o.a[2]));
+        const double theta = atan2(loc.y, loc.x), rho = sqrt(loc.x * loc.x + loc.y * loc.y);
+        const double v2t = o.a[3] * rho, tth = theta + .5 * v2t * o.a[5];
+        q4 qz; qz.x = 0.; qz.y = 0.; qz.z = sin(.5 * tth); qz.w = cos(.5 * tth);      // Quaternionr(AngleAxisr(ttheta, UnitZ))
+        vel = quatRotate(q, quatRotate(qz, mk3(0., v2t, 0.)));
+        if (o.flags & 1) w = quatRotate(q, mk3(0., 0., o.a[3]));
+        break;
+      }
+      case IOP_SORBIT: {   // StableCircularOrbit (Impose.cpp:38-48): the velocity that takes the node to (radius, theta + omega dt, z) in one step
+        const q4 q = impOri(o), qc = quatConj(q);
+        const d3 c = mk3(o.a[0], o.a[1], o.a[2]);
+        const d3 loc = quatRotate(qc, pos - c);
+        const double th1 = atan2(loc.y, loc.x) + o.a[3] * o.a[5];
+        const d3 pos1 = quatRotate(q, mk3(o.a[4] * cos(th1), o.a[4] * sin(th1), loc.z)) + c;
+        vel = (pos1 - pos) / o.a[5];
+        if (o.flags & 1) w = quatRotate(q, mk3(0., 0., o.a[3]));
+        break;
+      }
       case IOP_DIR: {      // HarmonicOscillation (Impose.hpp:6-13), VelocityAndReadForce (Impose.cpp:156-162)
         const d3 dir = mk3(o.a[0], o.a[1], o.a[2]);
         if (o.flags & 1) vel = dir * o.a[3];
@@ -154,7 +176,7 @@ struct Wall { double pos[3]; double vel[3]; double lastPos[3]; int32_t axis, sen
 // group1: 1 + index of the kinematic group (clump of boundary particles with a prescribed rigid motion) the facet belongs to, 0 = static;
 // rel: node positions in the group's frame (ClumpData.relPos, Clump.cpp:252); lastv: Aabb::nodeLastPos
 struct Facet { double v[9]; double vvel[9]; double fakeVel[3]; double halfThick; double n21lim[3]; double bmin[3], bmax[3]; uint32_t mask; int32_t mat; int32_t id; int32_t group1;
-               double rel[9]; double lastv[9]; };
+               double rel[9]; double lastv[9]; int32_t nodeImp1, pad1; };      // nodeImp1: 1 + the set of impositions its three nodes carry (0: none)
 #define WD_MAX_GROUPS 8
 struct GroupU { d3 pos; q4 ori; d3 vel, angVel; };
 struct GroupsU { int n; GroupU g[WD_MAX_GROUPS]; };
@@ -302,7 +324,7 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
       w = w + dt * angAccel;
       if (u.periodic && u.homoDeform == 4) w = w - u.deltaSpinVec;
     }
-    if (IMP && impSet >= 0) impose_velocity(*I, impSet, vel, w);      // re-applied so that forces do not alter what is prescribed (Leapfrog.cpp:203-205)
+    if (IMP && impSet >= 0) impose_velocity(*I, impSet, vel, w, pos);      // re-applied so that forces do not alter what is prescribed (Leapfrog.cpp:203-205)
   } else if (u.periodic && u.homoDeform == 4) vel = mulMV(u.ImLL4hInv, mulMV(u.LmL, pos) + mulMV(u.IpLL4h, vel));
   if (u.periodic && u.homoDeform != 4) {                                   // applyPeriodicCorrections :258-273
     if (u.homoDeform == 2 || u.homoDeform == 3) {
@@ -336,7 +358,7 @@ __device__ __forceinline__ void leapfrog_body(const Spheres& S, int i, const Ste
   }
   if (IMP && impSet >= 0) {
     impose_read_force(*I, impSet, pos, f, t);      // the forces of the previous step, before they are reset (Leapfrog.cpp:238); the force impositions act in k_reduce
-    impose_velocity(*I, impSet, vel, w);           // Leapfrog.cpp:248
+    impose_velocity(*I, impSet, vel, w, pos);      // Leapfrog.cpp:248
   }
   S.posr[i] = make_double4(pos.x, pos.y, pos.z, pr.w);
   S.velm[i] = make_double4(vel.x, vel.y, vel.z, mass);
@@ -505,7 +527,7 @@ __global__ void __launch_bounds__(256, 4) k_leapfrog_io(Spheres S, StepU u, Coun
 // = clumpPos + clumpOri*relPos, node velocity = clump.vel + clump.angVel x (pos - clumpPos); plus the Verlet test of the facet's Aabb (every node,
 // Collision.cpp:113-121; rotation is ignored for facets: maxRot=-1, Facet.cpp:277).  mode 1 (at a full run): refresh Aabb (Bo1_Facet_Aabb::go, Facet.cpp:275-298)
 // and Aabb::nodeLastPos of ALL facets.
-__global__ void __launch_bounds__(128) k_facets_step(Facet* facets, int n, GroupsU G, StepU u, Counters* cnt, int mode) {
+__global__ void __launch_bounds__(128) k_facets_step(Facet* facets, int n, GroupsU G, StepU u, Counters* cnt, int mode, ImposeDev I) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= n) return;
   Facet* F = facets + f;
@@ -520,6 +542,21 @@ __global__ void __launch_bounds__(128) k_facets_step(Facet* facets, int n, Group
     return;
   }
   if (*u.gIn) return;
+  if (F->nodeImp1 > 0) {
+    // nodes that carry an imposition are in DemField.nodes: Leapfrog's fixed-node branch translates them with their velocity (leapfrogTranslate, Leapfrog.cpp:195-199)
+    // and Impose::velocity at the end of the node's step (:248) sets the velocity of the next one (py/triangulated.py:59-64: a drum that really rotates)
+    double d2 = 0;
+    for (int i = 0; i < 3; i++) {
+      d3 vv = mk3(F->vvel[3 * i], F->vvel[3 * i + 1], F->vvel[3 * i + 2]), wdum = mk3(0, 0, 0);
+      const d3 p = mk3(F->v[3 * i], F->v[3 * i + 1], F->v[3 * i + 2]) + vv * u.dt;
+      impose_velocity(I, F->nodeImp1 - 1, vv, wdum, p);
+      F->v[3 * i] = p.x; F->v[3 * i + 1] = p.y; F->v[3 * i + 2] = p.z;
+      F->vvel[3 * i] = vv.x; F->vvel[3 * i + 1] = vv.y; F->vvel[3 * i + 2] = vv.z;
+      d2 = fmax(d2, sqn(mk3(F->lastv[3 * i], F->lastv[3 * i + 1], F->lastv[3 * i + 2]) - p));
+    }
+    if (d2 > u.maxD2 || !(d2 == d2)) *u.gOut = 1;
+    return;
+  }
   const int gi = F->group1 - 1;
   if (gi < 0) return;
   const GroupU g = G.g[gi];

@@ -66,6 +66,8 @@ struct VelocityAndReadForce : Impose { V3 dir{{1, 0, 0}}; double vel = 0; bool l
 struct ReadForce : Impose { shared_ptr<Node> node; int kind() const override { return 7; } };
 struct VariableVelocity3d : Impose { vector<double> times; vector<V3> vels, angVels; Q4 ori{{0, 0, 0, 1}}; vector<string> hooks; bool diff = false, wrap = false; double t0 = 0; int kind() const override { return 8; } };
 struct VariableAlignedRotation : Impose { int axis = 0; vector<std::array<double, 2>> timeAngVel; bool wrap = false; int kind() const override { return 9; } };
+struct CircularOrbit : Impose { shared_ptr<Node> node; bool rotate = false; double omega = NaN, angle = 0; int kind() const override { return 10; } };      // Impose.hpp (CircularOrbit)
+struct StableCircularOrbit : CircularOrbit { double radius = NaN; int kind() const override { return 11; } };
 struct CombinedImpose : Impose { vector<shared_ptr<Impose>> imps; };
 struct DemData {
   virtual ~DemData() {}
@@ -162,7 +164,7 @@ static void chk(wdem_handle h, int rc) { if (rc != WDEM_OK) throw std::runtime_e
 struct GpuDemLoop : Engine {
   shared_ptr<Leapfrog> leapfrog; shared_ptr<InsertionSortCollider> collider; shared_ptr<ContactLoop> contactLoop; shared_ptr<DynDt> dynDt;
   int device = 0; wdem_handle h = nullptr; wdem_config cfg; bool haveCfg = false; long nSpheres = 0; wdem_stats last;
-  vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf, wallOf, facetOf; bool trackingOn = false;
+  vector<int> sphereIds; vector<shared_ptr<Particle>> sphereOf, wallOf, facetOf; bool trackingOn = false, facetNodesMove = false;
   std::map<Material*, int> matIndex;   // materials as uploaded (by object identity)
   const char* cls() const override { return "GpuDemLoop"; }
   ~GpuDemLoop() override { release(); }
@@ -241,6 +243,11 @@ struct GpuDemLoop : Engine {
         keep.emplace_back(); for (auto& x : p->timeAngVel) keep.back().push_back(x[0]); w.times = keep.back().data();
         keep.emplace_back(); for (auto& x : p->timeAngVel) keep.back().push_back(x[1]); w.vals = keep.back().data();
       }
+      else if (auto* p = dynamic_cast<CircularOrbit*>(I.get())) {      // also StableCircularOrbit
+        if (!p->node) throw std::runtime_error(string(w.kind == 11 ? "StableCircularOrbit" : "CircularOrbit") + ": node must not be None.");
+        w.flags = p->rotate ? 1 : 0; for (int k = 0; k < 3; k++) w.v[k] = p->node->pos[k]; for (int k = 0; k < 4; k++) w.ori[k] = p->node->ori[k];
+        w.v[3] = p->omega; w.v[5] = p->angle; if (auto* sp = dynamic_cast<StableCircularOrbit*>(p)) w.v[4] = sp->radius;
+      }
       else throw std::runtime_error("GpuDemLoop: this Impose class is not supported on the device path");
       I->field = field.get(); imps.push_back(w); F.imposeOf.push_back(I); return ixOf[I.get()] = (int)imps.size() - 1;
     };
@@ -254,8 +261,17 @@ struct GpuDemLoop : Engine {
     for (size_t i = 0; i < wallOf.size(); i++) { auto& imp = wallOf[i]->shape->nodes[0]->dem->impose; if (imp) { wset[i] = setFor(imp); anyWall = true; } }
     for (size_t g = 0; g < F.clumps.size(); g++) { auto& imp = F.clumps[g].master->dem->impose; if (imp) { gset[g] = setFor(imp); anyGroup = true; } }
     for (auto& n : F.sphereClumps) if (n->dem->impose) throw std::runtime_error("GpuDemLoop: DemData.impose on a clump of spheres is not supported");
+    // facet nodes (py/triangulated.py:59-64: every node of a cylinder carries the same StableCircularOrbit); facets of a kinematic group follow their master node
+    vector<int32_t> fset(facetOf.size(), -1); bool anyFacet = false;
+    for (size_t i = 0; i < facetOf.size(); i++) {
+      auto& nn = facetOf[i]->shape->nodes; auto& imp = nn[0]->dem->impose;
+      if (nn[1]->dem->impose != imp || nn[2]->dem->impose != imp) throw std::runtime_error("GpuDemLoop: the three nodes of facet #" + std::to_string(facetOf[i]->id) + " must carry the same DemData.impose");
+      if (imp) { fset[i] = setFor(imp); anyFacet = true; }
+    }
     if (imps.empty()) return;
     chk(h, wdem_upload_imposes(h, (int32_t)imps.size(), imps.data(), (int32_t)setStart.size() - 1, setStart.data(), setOps.data(), (int64_t)sid.size(), sid.data(), sset.data(), anyWall ? wset.data() : nullptr, anyGroup ? gset.data() : nullptr));
+    if (anyFacet) chk(h, wdem_upload_facet_imposes(h, fset.data()));
+    facetNodesMove = anyFacet;
   }
   // DemField -> device (SoA host staging; ids are Particle.id)
   void upload() {
@@ -462,6 +478,7 @@ void DemField::pull() {
   for (size_t i = 0; i < imposeOf.size(); i++) {      // what the last step's Leapfrog read / accumulated
     double o[8]; chk(owner->h, wdem_get_impose_state(owner->h, (int32_t)i, o));
     Impose& I = *imposeOf[i]; I.sumF = o[0]; I.dist = o[1]; for (int k = 0; k < 3; k++) { I.F[k] = o[2 + k]; I.T[k] = o[5 + k]; }
+    if (auto* co = dynamic_cast<CircularOrbit*>(&I)) co->angle = o[1];
   }
   if (!sphereClumps.empty()) {
     const size_t nc = sphereClumps.size(); vector<double> p(3 * nc), o(4 * nc), v(3 * nc), w(3 * nc), l(3 * nc), cf(3 * nc), ct(3 * nc);
@@ -472,8 +489,8 @@ void DemField::pull() {
       for (int k = 0; k < 4; k++) nd.ori[k] = o[4 * i + k];
     }
   }
-  if (!clumps.empty() && !owner->facetOf.empty()) {
-    const size_t nf = owner->facetOf.size(); vector<double> fv(9 * nf), gp(3 * clumps.size()), go(4 * clumps.size());
+  if ((!clumps.empty() || owner->facetNodesMove) && !owner->facetOf.empty()) {
+    const size_t nf = owner->facetOf.size(); vector<double> fv(9 * nf), gp(3 * clumps.size() + 3), go(4 * clumps.size() + 4);
     chk(owner->h, wdem_download_facets(owner->h, fv.data(), gp.data(), go.data()));
     for (size_t i = 0; i < nf; i++) for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) owner->facetOf[i]->shape->nodes[v]->pos[k] = fv[9 * i + 3 * v + k];
     for (size_t g = 0; g < clumps.size(); g++) { Node& M = *clumps[g].master; for (int k = 0; k < 3; k++) M.pos[k] = gp[3 * g + k]; for (int k = 0; k < 4; k++) M.ori[k] = go[4 * g + k]; }
@@ -627,6 +644,9 @@ PYBIND11_MODULE(_woo, m) {
       .def_property("ori", [](VariableVelocity3d& s) { return np4(s.ori); }, [](VariableVelocity3d& s, py::object o) { s.ori = seqN<4>(o, "ori"); s.touch(); })
       .def_property("vels", [](VariableVelocity3d& s) { py::list l; for (auto& v : s.vels) l.append(np3(v)); return l; }, [](VariableVelocity3d& s, py::iterable o) { s.vels.clear(); for (auto it : o) s.vels.push_back(seqN<3>(py::reinterpret_borrow<py::object>(it), "vels")); s.touch(); })
       .def_property("angVels", [](VariableVelocity3d& s) { py::list l; for (auto& v : s.angVels) l.append(np3(v)); return l; }, [](VariableVelocity3d& s, py::iterable o) { s.angVels.clear(); for (auto it : o) s.angVels.push_back(seqN<3>(py::reinterpret_borrow<py::object>(it), "angVels")); s.touch(); });
+  kwclass<CircularOrbit, Impose>(m, "CircularOrbit") RWI(CircularOrbit, node) RWI(CircularOrbit, rotate) RWI(CircularOrbit, omega)
+      .def_property("angle", [](CircularOrbit& s) { if (s.field) s.field->pull(); return s.angle; }, [](CircularOrbit& s, double v) { if (s.field) s.field->pull(); s.angle = v; s.touch(); });
+  kwclass<StableCircularOrbit, CircularOrbit>(m, "StableCircularOrbit") RWI(StableCircularOrbit, radius);
   kwclass<VariableAlignedRotation, Impose>(m, "VariableAlignedRotation") RWI(VariableAlignedRotation, axis) RWI(VariableAlignedRotation, wrap)
       .def_property("timeAngVel", [](VariableAlignedRotation& s) { return s.timeAngVel; }, [](VariableAlignedRotation& s, py::iterable o) {
         s.timeAngVel.clear(); for (auto it : o) s.timeAngVel.push_back(seqN<2>(py::reinterpret_borrow<py::object>(it), "timeAngVel"));

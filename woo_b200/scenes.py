@@ -70,6 +70,7 @@ class SceneSpec:
     sphere_impose: object = None        # int array per sphere (index into impose_sets), or None
     wall_impose: object = None          # int array per wall
     group_impose: object = None         # int array per facet group
+    facet_impose: object = None         # int array per facet: the set all three nodes of the facet carry
     clumps: list = field(default_factory=list)  # rigid aggregates of spheres with mass: dict(members=[sphere indices], pos, ori (x,y,z,w), vel, angVel, mass, inertia(3), flags); see make_clumps
     facet_groups: list = field(default_factory=list)  # kinematic groups: dict(pos, ori (x,y,z,w), vel, angVel, facets=[indices into ``facets``])
     params: Params = field(default_factory=Params)
@@ -127,6 +128,7 @@ def hertz_mat(density=1e3, young=1e8, ktDivKn=.2, tanPhi=.5, surfEnergy=0.0, alp
 
 # ---- Impose descriptors (wdem.h: wdem_impose; kinds and the meaning of v[16] follow include/wdem.h)
 IMP_HARMONIC, IMP_ALIGNED_HARMONIC, IMP_CONSTANT_FORCE, IMP_RADIAL_FORCE, IMP_LOCAL6, IMP_VEL_READ_FORCE, IMP_READ_FORCE, IMP_VARIABLE_VEL3D, IMP_VARIABLE_ALIGNED_ROTATION = range(1, 10)
+IMP_CIRCULAR_ORBIT, IMP_STABLE_CIRCULAR_ORBIT = 10, 11
 
 
 def _imp(kind, flags=0, v=(), ori=(0, 0, 0, 1), times=(), vals=(), vals2=()):
@@ -179,7 +181,17 @@ def imp_variable_aligned_rotation(axis, timeAngVel, wrap=False):
     return _imp(IMP_VARIABLE_ALIGNED_ROTATION, 1 if wrap else 0, [axis], (0, 0, 0, 1), ta[:, 0], ta[:, 1])
 
 
-def attach_impose(S, ops, spheres=(), walls=(), groups=()):
+def imp_circular_orbit(node_pos, omega, node_ori=(0, 0, 0, 1), rotate=False):
+    """CircularOrbit (Impose.hpp, Impose.cpp:22-37): orbiting around the local z axis of the node (pos, ori)"""
+    return _imp(IMP_CIRCULAR_ORBIT, 1 if rotate else 0, [*node_pos, omega], node_ori)
+
+
+def imp_stable_circular_orbit(node_pos, omega, radius, node_ori=(0, 0, 0, 1), rotate=False):
+    """StableCircularOrbit (Impose.cpp:38-48): as CircularOrbit, with the radius enforced (what woo.triangulated.cylinder(angVel=..., realRot=True) puts on every node)"""
+    return _imp(IMP_STABLE_CIRCULAR_ORBIT, 1 if rotate else 0, [*node_pos, omega, radius], node_ori)
+
+
+def attach_impose(S, ops, spheres=(), walls=(), groups=(), facets=()):
     """Put the impositions `ops` (descriptor dicts; several = CombinedImpose) on the given sphere / wall / facet-group indices."""
     ix = []
     for o in ops:
@@ -194,6 +206,9 @@ def attach_impose(S, ops, spheres=(), walls=(), groups=()):
     if len(groups):
         if S.group_impose is None: S.group_impose = np.full(len(S.facet_groups), -1, np.int32)
         S.group_impose[np.asarray(groups, dtype=np.int64)] = k
+    if len(facets):
+        if S.facet_impose is None: S.facet_impose = np.full(len(S.facets), -1, np.int32)
+        S.facet_impose[np.asarray(facets, dtype=np.int64)] = k
     return k
 
 
