@@ -201,7 +201,17 @@ void GpuDemLoop::uploadImposes(const vector<shared_ptr<Impose>>& sphImpose, cons
 			keep.emplace_back(); for(const auto& x: va->timeAngVel) keep.back().push_back(x[0]); w.times=keep.back().data();
 			keep.emplace_back(); for(const auto& x: va->timeAngVel) keep.back().push_back(x[1]); w.vals=keep.back().data();
 		}
-		else throw std::runtime_error("GpuDemLoop: "+I->pyStr()+" is not supported (CircularOrbit, StableCircularOrbit, InterpolatedMotion are not on the device path)");
+		else if(auto* so=dynamic_cast<StableCircularOrbit*>(I.get())){      // derives from CircularOrbit (Impose.hpp:40): test it first
+			if(!so->node) throw std::runtime_error("StableCircularOrbit: node must not be None.");
+			w.kind=11; w.flags=so->rotate?1:0; for(int k:{0,1,2}) w.v[k]=so->node->pos[k]; w.v[3]=so->omega; w.v[4]=so->radius; w.v[5]=so->angle;
+			w.ori[0]=so->node->ori.x(); w.ori[1]=so->node->ori.y(); w.ori[2]=so->node->ori.z(); w.ori[3]=so->node->ori.w();
+		}
+		else if(auto* co=dynamic_cast<CircularOrbit*>(I.get())){
+			if(!co->node) throw std::runtime_error("CircularOrbit: node must not be None.");
+			w.kind=10; w.flags=co->rotate?1:0; for(int k:{0,1,2}) w.v[k]=co->node->pos[k]; w.v[3]=co->omega; w.v[5]=co->angle;
+			w.ori[0]=co->node->ori.x(); w.ori[1]=co->node->ori.y(); w.ori[2]=co->node->ori.z(); w.ori[3]=co->node->ori.w();
+		}
+		else throw std::runtime_error("GpuDemLoop: "+I->pyStr()+" is not supported (InterpolatedMotion is not on the device path)");
 		imps.push_back(w); imposeOf.push_back(I); return ixOf[I.get()]=(int)imps.size()-1;
 	};
 	auto setFor=[&](const shared_ptr<Impose>& I)->int{
@@ -222,8 +232,16 @@ void GpuDemLoop::uploadImposes(const vector<shared_ptr<Impose>>& sphImpose, cons
 		if(sphereClump){ if(cd.impose) throw std::runtime_error("GpuDemLoop: DemData.impose on a clump of spheres is not supported"); continue; }
 		groupSet.push_back(cd.impose?setFor(cd.impose):-1); if(cd.impose) anyGroup=true;
 	}
+	// facet nodes (py/triangulated.py:59-64: every node of a cylinder carries the same StableCircularOrbit); facets of a kinematic clump follow their master node
+	vector<int32_t> facetSet(facetOf.size(),-1); bool anyFacet=false;
+	for(size_t i=0;i<facetOf.size();i++){
+		const auto& nn=facetOf[i]->shape->nodes; const auto& imp=nn[0]->getData<DemData>().impose;
+		if(nn[1]->getData<DemData>().impose!=imp || nn[2]->getData<DemData>().impose!=imp) throw std::runtime_error("GpuDemLoop: the three nodes of facet #"+to_string(facetOf[i]->id)+" must carry the same DemData.impose");
+		if(imp){ facetSet[i]=setFor(imp); anyFacet=true; }
+	}
 	if(imps.empty()) return;
 	chk(h,wdem_upload_imposes(h,(int32_t)imps.size(),imps.data(),(int32_t)setStart.size()-1,setStart.data(),setOps.data(),(int64_t)sphImposeId.size(),sphImposeId.data(),sphSet.data(),anyWall?wallSet.data():nullptr,anyGroup?groupSet.data():nullptr));
+	if(anyFacet) chk(h,wdem_upload_facet_imposes(h,facetSet.data()));
 }
 
 void GpuDemLoop::pushContacts(){
@@ -268,6 +286,8 @@ void GpuDemLoop::pull(){
 		double o[8]; chk(h,wdem_get_impose_state(h,(int32_t)i,o));
 		if(auto* v=dynamic_cast<VelocityAndReadForce*>(imposeOf[i].get())){ v->sumF.set(o[0]); v->dist=o[1]; }
 		else if(auto* f=dynamic_cast<ReadForce*>(imposeOf[i].get())){ f->F.set(Vector3r(o[2],o[3],o[4])); f->T.set(Vector3r(o[5],o[6],o[7])); }
+		else if(auto* so=dynamic_cast<StableCircularOrbit*>(imposeOf[i].get())) so->angle=o[1];
+		else if(auto* co=dynamic_cast<CircularOrbit*>(imposeOf[i].get())) co->angle=o[1];
 	}
 	if(!clumpOf.empty()){
 		const size_t nc=clumpOf.size(); vector<double> p(3*nc),o(4*nc),v(3*nc),w(3*nc),l(3*nc),f(3*nc),t(3*nc);
