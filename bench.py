@@ -175,21 +175,55 @@ def mgpu_parity(local, steps=200):
         "periodic_shear_4k": lambda: sc.periodic_gas(4000, cell=(1.2, .8, .9), r=.02, psd_ratio=2.0, seed=33, gradV=[[0, 2., 0], [0, 0, 0], [0, 0, 0]]),
         "deposition_20k": lambda: sc.deposition(20000, seed=1),
     }
+    # the same gas with lopsided cuts, re-balancing switched on, and spheres inserted and removed in mid-run (wdem_add_spheres / wdem_remove_spheres on every rank)
+    cases["gas_inlet_outlet_rebalance_4k"] = cases["gas_hertz_4k"]
+
+    def inlet_outlet(S, eng, k):
+        """after 50 steps: 60 new spheres; after 100: 80 spheres leave and a newcomer takes over the oldest freed id (ParticleContainer::findFreeId)"""
+        import math
+        rng = np.random.default_rng(77 + k); dens = S.mats[0][1]
+        if k == 0:
+            m = 60; pos = rng.uniform(.05, .95, (m, 3)); rad = .02 * np.exp(rng.uniform(math.log(.5), math.log(2.), m)); mass = dens * (4 / 3.) * math.pi * rad ** 3
+            eng.add_spheres(np.arange(S.n + len(S.walls), S.n + len(S.walls) + m, dtype=np.int32), pos, rad, mass, .4 * mass * rad ** 2, vel=rng.uniform(-1, 1, (m, 3)))
+        elif k == 1:
+            gone = np.sort(rng.choice(S.sphere_ids(), 80, replace=False)).astype(np.int32)
+            eng.remove_spheres(gone)
+            rad = np.array([.03]); mass = dens * (4 / 3.) * math.pi * rad ** 3
+            eng.add_spheres(gone[:1], np.array([[.5, .5, .5]]), rad, mass, .4 * mass * rad ** 2, vel=np.array([[.3, .2, -.1]]))
+
     for name, make in cases.items():
         S = make()
-        D = DistributedEngine(S, axis=0, device=local)
+        io = name.startswith("gas_inlet")
+        lo, hi = float(S.pos[:, 0].min()), float(S.pos[:, 0].max())
+        D = DistributedEngine(S, axis=0, device=local, cuts=[lo + (hi - lo) * .5 * (c + 1) / world for c in range(world - 1)] if io else None)
+        if io:
+            D.set_rebalance(.1, 2)
         done = 0
         while done < steps:
             k = min(50, steps - done); D.step(k); done += k
+            if io and done in (50, 100):
+                inlet_outlet(S, D, done // 50 - 1)
         o = D.owned(); con = D.E.contacts(True)
         parts = [None] * world
-        dist.all_gather_object(parts, dict(o=o, ids=con["ids"], force=con["force"], stats=D.domain_stats(), peer=bool(D.E.L.wdem_peer_active(D.E.h))))
+        dist.all_gather_object(parts, dict(o=o, ids=con["ids"], force=con["force"], stats=D.domain_stats(), peer=bool(D.E.L.wdem_peer_active(D.E.h)), dom=D.domain() if io else None))
         D.E.close()
         if rank == 0:
-            E = Engine(S.params, device=local).load(S); E.step(steps)
-            ref = E.spheres(); rc = E.contacts(True); E.close()
+            E = Engine(S.params, device=local).load(S)
+            if io:      # the single-domain engine goes through the same insertions and removals; its download is in upload order, the subdomains' by id
+                E.step(50); inlet_outlet(S, E, 0); E.step(50); inlet_outlet(S, E, 1); E.step(steps - 100)
+            else:
+                E.step(steps)
+            ref = E.spheres(); rc = E.contacts(True)
             ids = np.concatenate([p["o"]["ids"] for p in parts]); order = np.argsort(ids)
-            ok = len(ids) == S.n and np.array_equal(ids[order], S.sphere_ids())
+            if io:      # upload order of the single-domain engine: the initial spheres, then the 60 new ones; removal closes the order up; the newcomer comes last
+                rng1 = np.random.default_rng(78); gone = np.sort(rng1.choice(S.sphere_ids(), 80, replace=False)).astype(np.int32)
+                ref_ids = np.concatenate([S.sphere_ids(), np.arange(S.n + len(S.walls), S.n + len(S.walls) + 60)]).astype(np.int32)
+                ref_ids = np.concatenate([ref_ids[~np.isin(ref_ids, gone)], gone[:1]])
+                ro = np.argsort(ref_ids, kind="stable"); ok = len(ids) == len(ref_ids) == len(ref["pos"]) and np.array_equal(ref_ids[ro], ids[order])
+                ref = {k_: v[ro] for k_, v in ref.items()}
+            else:
+                ok = len(ids) == S.n and np.array_equal(ids[order], S.sphere_ids())
+            E.close()
             diff = []
             for k_ in ("pos", "vel", "angVel", "force", "torque"):
                 got = np.concatenate([p["o"][k_] for p in parts])[order]
@@ -201,6 +235,8 @@ def mgpu_parity(local, steps=200):
             out[name] = {"ok": bool(ok and not diff and csame), "bit_identical": not diff, "real_contacts": int(len(rc["ids"])), "contacts_identical": bool(csame),
                          "migrated": int(sum(p["stats"]["migrated_in"] for p in parts)), "ghosts": int(sum(p["stats"]["ghosts"] for p in parts)),
                          "peer_memory_halo": parts[0]["peer"], "steps": steps, "differs": diff}
+            if io:
+                out[name].update({"owned_per_rank": [int(p["stats"]["owned"]) for p in parts], "rebalanced": int(parts[0]["dom"][1]), "inserted": 61, "removed": 80})
     return out
 
 

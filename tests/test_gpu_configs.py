@@ -27,6 +27,18 @@ def test_cfg1_deposition_long_run_observables():
     assert 0.3 < f_o < 0.75
 
 
+def test_cfg1_at_its_named_size_10k_spheres_20k_steps():
+    """BASELINE.json configs[0] as named: 10 000 spheres, 20 000 steps of Leapfrog + collider + ContactLoop(linear) + DynDt — the one configuration the reference itself is
+    timed on (obsolete/perf/inclined.py:16-49).  About a minute of oracle on the box's host cores; the whole trajectory is bit-identical."""
+    S = sc.deposition(10000, seed=1)          # the scene bench.py's configs block times as cfg1
+    assert S.n == 10000
+    O, E = compare(S, 20000, check_every=5000, label="cfg1 10k x 20k")
+    co = O.contacts(True)
+    assert len(co["ids"]) > 2 * S.n and O.nFullRuns > 100
+    so, sg = O.spheres(), E.spheres()
+    assert ob.coord_number(S.sphere_ids(), so["pos"], co["ids"]) == ob.coord_number(S.sphere_ids(), sg["pos"], E.contacts(True)["ids"])
+
+
 @pytest.mark.parametrize("world", [1, 3])
 def test_cfg2_psd_bed(world):
     # the committed pre-settled 20k-sphere PSD 1:4 bed that bench.py tiles to 1M (tests/golden/cfg2_sample_20k.npz): dense, ~4 contacts per sphere

@@ -60,6 +60,23 @@ def test_particle_container_and_nodes():
         S.dem.par[7]
 
 
+def test_particle_container_reuses_freed_ids_like_the_reference():
+    """ParticleContainer::findFreeId / remove (ParticleContainer.cpp:23-36,121-157): freed ids are handed out again oldest first; removing the last particle shrinks the container."""
+    S = Scene(fields=[DemField()])
+    par = S.dem.par
+    ids = par.add([woo.utils.sphere((i, 0, 0), .1) for i in range(6)])
+    assert list(ids) == [0, 1, 2, 3, 4, 5] and len(par) == 6
+    par.remove(1); par.remove(3)
+    assert len(par) == 6
+    assert par.add(woo.utils.sphere((9, 0, 0), .1)) == 1 and par.add(woo.utils.sphere((9, 1, 0), .1)) == 3 and par.add(woo.utils.sphere((9, 2, 0), .1)) == 6
+    par.remove(6); par.remove(5)
+    assert len(par) == 5                                   # shrunk past both
+    with pytest.raises(IndexError):
+        par[5]
+    assert par.add(woo.utils.sphere((9, 3, 0), .1)) == 5   # the stale free id 6 is beyond the size: skipped... 5 <= size: taken
+    assert [p.id for p in par] == [0, 1, 2, 3, 4, 5]
+
+
 def test_cpu_engines_do_not_run_on_their_own():
     S = Scene(fields=[DemField()])
     S.dem.par.add(woo.utils.sphere((0, 0, 0), .05))
@@ -399,7 +416,8 @@ def test_object_model_clumps_removal_energy_stress_cpu():
         S.dem.par[2]
     with pytest.raises(IndexError):
         S.dem.par.remove(2)
-    assert len(S.dem.nodes) == 3 and S.dem.par.add(woo.utils.sphere((1, 1, 1), .05, mat=m)) == 4      # ids are not handed out again
+    assert len(S.dem.nodes) == 3 and S.dem.par.add(woo.utils.sphere((1, 1, 1), .05, mat=m)) == 2      # the freed id is handed out again (findFreeId)
+    assert S.dem.par.add(woo.utils.sphere((1, 1, 2), .05, mat=m)) == 4
     facets = [Facet.make([(0, 0, 0), (1, 0, 0), (0, 1, 0)], mat=m), Facet.make([(1, 0, 0), (1, 1, 0), (0, 1, 0)], mat=m)]
     central = Node(pos=(.5, .5, 0))
     assert S.dem.par.addClumped(facets, centralNode=central) is central

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <list>
 #include <set>
 #include <memory>
 #include <stdexcept>
@@ -97,7 +98,18 @@ struct FrictPhys { V3 force, torque; double kn = NaN, kt = NaN, tanPhi = NaN; do
 struct Contact { int id1 = -1, id2 = -1; V3i cellDist{{0, 0, 0}}; int stepCreated = -1; shared_ptr<L6Geom> geom; shared_ptr<FrictPhys> phys; bool isReal() const { return geom && phys; } };
 
 struct GpuDemLoop;
-struct ParticleContainer { DemField* dem = nullptr; vector<shared_ptr<Particle>> v; };
+struct ParticleContainer {
+  DemField* dem = nullptr; vector<shared_ptr<Particle>> v; std::list<int> freeIds;
+  int findFreeId() {      // ParticleContainer::findFreeId (ParticleContainer.cpp:23-36): freed ids are handed out again, oldest first
+    const long size = (long)v.size();
+    auto it = freeIds.begin();
+    while (!freeIds.empty()) {
+      const int id = *it; it = freeIds.erase(it);
+      if (id <= size) { if (id < size && v[id]) throw std::logic_error("ParticleContainer::findFreeId: freeIds contained " + std::to_string(id) + ", but it is occupied?!"); return id; }
+    }
+    return (int)size;
+  }
+};
 // clump of boundary particles moved rigidly by its master node (ParticleContainer::addClumped -> ClumpData::makeClump, Clump.cpp:187-261)
 struct ClumpGroup { shared_ptr<Node> master; vector<int> members; /* Particle ids */ };
 struct ContactContainer { DemField* dem = nullptr; vector<shared_ptr<Contact>> v; std::map<std::pair<int, int>, size_t> ix; };
@@ -723,7 +735,8 @@ PYBIND11_MODULE(_woo, m) {
       .def("add", [](ParticleContainer& c, py::object o) -> py::object {   // ParticleContainer::add + pyAppend, nodes=-1 (ParticleContainer.cpp:23-73,193-198)
         auto addOne = [&](shared_ptr<Particle> p) {
           if (p->id >= 0) throw std::runtime_error("Particle already has id " + std::to_string(p->id) + " set; appending such particle (for the second time) is not allowed.");
-          p->id = (int)c.v.size(); p->field = c.dem; c.v.push_back(p);
+          const int id = c.findFreeId(); if ((size_t)id >= c.v.size()) c.v.resize(id + 1);      // ParticleContainer::insert -> insertAt (ParticleContainer.cpp:55-73)
+          p->id = id; p->field = c.dem; c.v[id] = p;
           for (auto& n : p->shape->nodes) {
             n->dem->field = c.dem; const DemData& d = *n->dem;
             const bool moving = d.guessMoving();
@@ -735,7 +748,7 @@ PYBIND11_MODULE(_woo, m) {
         if (py::isinstance<Particle>(o)) return py::int_(addOne(o.cast<shared_ptr<Particle>>()));
         py::list ids; for (auto it : o) ids.append(addOne(it.cast<shared_ptr<Particle>>())); return ids; });
   m.attr("ParticleContainer").attr("remove") = py::cpp_function([](ParticleContainer& c, int id) {
-        // ParticleContainer::remove (ParticleContainer.cpp:121-157): the particle and its contacts go; ids are not reused here
+        // ParticleContainer::remove (ParticleContainer.cpp:121-157): the particle and its contacts go, its id joins freeIds; removing the last element shrinks the container
         if (id < 0 || (size_t)id >= c.v.size() || !c.v[id]) throw py::index_error("No such particle: #" + std::to_string(id));
         shared_ptr<Particle> p = c.v[id];
         DemField& F = *c.dem;
@@ -746,7 +759,9 @@ PYBIND11_MODULE(_woo, m) {
         else F.topoDirty = true;
         if (F.topoDirty && F.owner) { F.pull(); F.pullContacts(); }                  // the full path re-uploads from the host copies: make them current first
         for (auto& n : p->shape->nodes) { auto it = std::find(F.nodes.begin(), F.nodes.end(), n); if (it != F.nodes.end()) F.nodes.erase(it); }
+        c.freeIds.push_back(id);
         c.v[id].reset(); p->id = -1; F.contactsStale = true;
+        if ((size_t)(id + 1) == c.v.size()) { int k = id; while (k >= 0 && !c.v[k]) k--; c.v.resize(k + 1); }
       }, py::is_method(m.attr("ParticleContainer")), py::arg("id"));
   m.attr("ParticleContainer").attr("addClumped") = py::cpp_function([](ParticleContainer& c, py::object pars, shared_ptr<Node> centralNode) -> shared_ptr<Node> {
         // ParticleContainer::addClumped (ParticleContainer.cpp) for boundary particles with a user-given master node: the members keep their positions, the master's
