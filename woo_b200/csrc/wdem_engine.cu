@@ -49,15 +49,15 @@ struct DBuf {  // growable device buffer
 };
 
 struct SphereStore {
-  DBuf<double4> posr, velm, angi, ori; DBuf<float4> posf; DBuf<double> f[6], l[3]; DBuf<uint32_t> flags, mask; DBuf<int32_t> mat, id, up;
+  DBuf<double4> posr, velm, angi, ori; DBuf<double> f[6], l[3]; DBuf<uint32_t> flags, mask; DBuf<int32_t> mat, id, up;
   void ensure(size_t n, int64_t& tot, bool keep = false, cudaStream_t st = 0) {
-    posr.ensure(n, tot, keep, st); posf.ensure(n, tot, false, st); velm.ensure(n, tot, keep, st); angi.ensure(n, tot, keep, st); ori.ensure(n, tot, keep, st);
+    posr.ensure(n, tot, keep, st); velm.ensure(n, tot, keep, st); angi.ensure(n, tot, keep, st); ori.ensure(n, tot, keep, st);
     for (auto& b : f) b.ensure(n, tot, keep, st); for (auto& b : l) b.ensure(n, tot, keep, st);
     flags.ensure(n, tot, keep, st); mask.ensure(n, tot, keep, st); mat.ensure(n, tot, keep, st); id.ensure(n, tot, keep, st); up.ensure(n, tot, keep, st);
   }
-  Spheres view() { Spheres S; S.posr = posr.p; S.posf = posf.p; S.velm = velm.p; S.angi = angi.p; S.ori = ori.p; S.fx = f[0].p; S.fy = f[1].p; S.fz = f[2].p; S.tx = f[3].p; S.ty = f[4].p; S.tz = f[5].p;
+  Spheres view() { Spheres S; S.posr = posr.p; S.velm = velm.p; S.angi = angi.p; S.ori = ori.p; S.fx = f[0].p; S.fy = f[1].p; S.fz = f[2].p; S.tx = f[3].p; S.ty = f[4].p; S.tz = f[5].p;
     S.lx = l[0].p; S.ly = l[1].p; S.lz = l[2].p; S.flags = flags.p; S.mask = mask.p; S.mat = mat.p; S.id = id.p; S.up = up.p; S.clumpOfId = nullptr; S.impOfId = nullptr; return S; }
-  void release() { posr.release(); posf.release(); velm.release(); angi.release(); ori.release(); for (auto& b : f) b.release(); for (auto& b : l) b.release(); flags.release(); mask.release(); mat.release(); id.release(); up.release(); }
+  void release() { posr.release(); velm.release(); angi.release(); ori.release(); for (auto& b : f) b.release(); for (auto& b : l) b.release(); flags.release(); mask.release(); mat.release(); id.release(); up.release(); }
 };
 
 struct ContactStore {
@@ -826,7 +826,7 @@ void rebuild(wdem_engine* E) {
     if (nDead) { n -= nDead; E->n = n; nb = nblk(n, 256); }      // the dead slots sorted to the end: gone
     SphereStore& dst = E->sph[1 - E->cur];
     dst.ensure(n, tot);
-    k_reorder<<<nb, 256, 0, st>>>(dst.view(), E->S(), E->idxAlt.p, n, E->id2slot.p, c.periodic ? 0. : g.ox, c.periodic ? 0. : g.oy, c.periodic ? 0. : g.oz); E->launches++;
+    k_reorder<<<nb, 256, 0, st>>>(dst.view(), E->S(), E->idxAlt.p, n, E->id2slot.p); E->launches++;
     E->cur = 1 - E->cur; E->up2slotValid = false;
     perm = E->idxAlt.p;
     if (E->comm || E->compactPending) {   // slots of the previous table's generation: through the pre-sort generation built by domainExchange / wdem_remove_spheres

@@ -22,7 +22,6 @@ enum { KIND_SS = 0, KIND_WS = 1, KIND_FS = 2 };
 // ------------------------------------------------------------------------------------------------
 struct Spheres {          // one slot per sphere; slots are re-ordered by grid cell at every collider full run
   double4* posr;          // x,y,z,radius      (32 B: one sector per gather)
-  float4* posf;           // float copy of posr relative to the collider grid's origin, written at full runs (k_reorder): the candidate search rejects most pairs on it
   double4* velm;          // vx,vy,vz,mass
   double4* angi;          // wx,wy,wz,inertia
   double4* ori;           // quaternion x,y,z,w
@@ -1501,12 +1500,11 @@ __global__ void __launch_bounds__(256) k_cellkeys(const double4* __restrict__ po
 }
 
 // gather all per-sphere arrays into cell order; also refreshes lastPos (Aabb::nodeLastPos, Collision.cpp:138-141)
-__global__ void __launch_bounds__(256) k_reorder(Spheres dst, Spheres src, const int* __restrict__ perm, int n, int* id2slot, double ox, double oy, double oz) {
+__global__ void __launch_bounds__(256) k_reorder(Spheres dst, Spheres src, const int* __restrict__ perm, int n, int* id2slot) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int o = perm[i];
   double4 p = src.posr[o];
-  dst.posf[i] = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), (float)p.w);
   dst.posr[i] = p; dst.velm[i] = src.velm[o]; dst.angi[i] = src.angi[o]; dst.ori[i] = src.ori[o];
   dst.fx[i] = src.fx[o]; dst.fy[i] = src.fy[o]; dst.fz[i] = src.fz[o];
   dst.tx[i] = src.tx[o]; dst.ty[i] = src.ty[o]; dst.tz[i] = src.tz[o];
@@ -1582,6 +1580,8 @@ struct WallPass { const Wall* walls; int nWalls; double halfThick; uint32_t* bit
 #ifndef WD_PAIRS_MINB
 #define WD_PAIRS_MINB 10   // 48 registers (round 1 measured 40/48/64 registers within 3 %; the dormant test needs a few more than 40)
 #endif
+// (Measured and dropped: a single-precision rejection test on a float4 copy of the positions in front of the exact one — half the bytes and a quarter of the fp64
+// work per visited sphere, yet 1.08 ms per full run instead of 1.05: the search waits for dependent loads, and the survivors then pay a second one.)
 // DORMANT potential contacts.  Between two collider full runs no sphere is farther than verletDist from where it was at the last one (the Verlet test runs in every
 // step, before the contacts, and triggers the full run in the same step: Collision.cpp:113-121), so a candidate pair whose centres were farther apart than
 // |distFactor|(r1+r2) + 2 verletDist at the full run cannot touch before the next one: Cg2_Sphere_Sphere_L6Geom::go would return false in every step in between
@@ -1640,8 +1640,6 @@ __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int 
   const double4 pi = S.posr[i];
   const int Li = levelOf(g, pi.w);
   const uint32_t mi = S.mask[i];
-  const float4 qi = S.posf[i];
-  const float wfi = qi.w * 1.000001f + (float)(2. * vd) * 1.000001f + 1e-37f, axi = fabsf(qi.x), ayi = fabsf(qi.y), azi = fabsf(qi.z);
   for (int L = Li; L < g.nL; L++) {
     const double H = ((pi.w + vd) + g.reach[L][0]) * (1 + 1e-12) + 1e-300;
     const int nx = g.n[L][0], ny = g.n[L][1], nz = g.n[L][2];
@@ -1654,14 +1652,6 @@ __global__ void __launch_bounds__(128, WD_PAIRS_MINB) k_pairs_ss(Spheres S, int 
         int jb = cellStart[k0 + x0]; const int je = cellStart[k0 + x1 + 1];
         if (L == Li && jb <= i) jb = i + 1;   // same level: the lower slot emits (slots of a level are contiguous and ascending along the row)
         for (int j = jb; j < je; j++) {
-          // single-precision rejection on the float copy (16 bytes instead of 32, fp32 instead of fp64 for the ~90 % of the visited spheres whose boxes are apart).
-          // Conservative: boxes that overlap in double satisfy |dx| <= r_i + r_j + 2 vd up to a few ulps of the coordinates; the float test allows 1e-6 relative
-          // on the radii and 2.5e-7 relative on the coordinates (float rounding of either: 6e-8), so it only ever rejects pairs the exact test rejects too.
-          const float4 qj = S.posf[j];
-          const float sw = (qj.w + wfi) * 1.000001f;
-          if (fabsf(qj.x - qi.x) > sw + 2.5e-7f * (fabsf(qj.x) + axi)) continue;
-          if (fabsf(qj.y - qi.y) > sw + 2.5e-7f * (fabsf(qj.y) + ayi)) continue;
-          if (fabsf(qj.z - qi.z) > sw + 2.5e-7f * (fabsf(qj.z) + azi)) continue;
           const double4 pj = S.posr[j];
           if (!aabbOverlapSS(pi, pj, vd)) continue;
           if (!mayCollide(mi, S.mask[j], loneMask)) continue;
