@@ -92,7 +92,8 @@ typedef struct wdem_stats {
  * 11 StableCircularOrbit          v = node.pos(3), omega, radius, angle; ori = node.ori; flags&1 rotate   (Impose.cpp:38-48; py/triangulated.py:59-64: a cylinder that really rotates)
  *    The two orbit kinds act on spheres and on facet nodes (wdem_upload_facet_imposes).  They take atan2 / sin / cos of the node's position on the device, so nodes that
  *    carry them follow the reference to rounding (1e-12 relative), not bit for bit like everything else.
- * Not on this path: InterpolatedMotion. */
+ * 12 InterpolatedMotion           v = t0; times[nTimes], vals = poss (3 per time), vals2 = oris (4 per time: x,y,z,w)     (Impose.cpp:120-133)
+ *    on the master nodes of kinematic facet groups only (a mesh that follows a recorded trajectory); evaluated by the host with libm: bit-identical to the oracle. */
 typedef struct wdem_impose {
   int32_t kind, flags;
   double v[16];

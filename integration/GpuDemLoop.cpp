@@ -201,6 +201,12 @@ void GpuDemLoop::uploadImposes(const vector<shared_ptr<Impose>>& sphImpose, cons
 			keep.emplace_back(); for(const auto& x: va->timeAngVel) keep.back().push_back(x[0]); w.times=keep.back().data();
 			keep.emplace_back(); for(const auto& x: va->timeAngVel) keep.back().push_back(x[1]); w.vals=keep.back().data();
 		}
+		else if(auto* im=dynamic_cast<InterpolatedMotion*>(I.get())){      // on master nodes of facet clumps only (libwdem rejects it elsewhere)
+			w.kind=12; w.v[0]=im->t0; w.nTimes=(int)im->times.size();
+			keep.push_back(im->times); w.times=keep.back().data();
+			keep.emplace_back(); for(const auto& x: im->poss) for(int k:{0,1,2}) keep.back().push_back(x[k]); w.vals=keep.back().data();
+			keep.emplace_back(); for(const auto& q: im->oris){ keep.back().push_back(q.x()); keep.back().push_back(q.y()); keep.back().push_back(q.z()); keep.back().push_back(q.w()); } w.vals2=keep.back().data();
+		}
 		else if(auto* so=dynamic_cast<StableCircularOrbit*>(I.get())){      // derives from CircularOrbit (Impose.hpp:40): test it first
 			if(!so->node) throw std::runtime_error("StableCircularOrbit: node must not be None.");
 			w.kind=11; w.flags=so->rotate?1:0; for(int k:{0,1,2}) w.v[k]=so->node->pos[k]; w.v[3]=so->omega; w.v[4]=so->radius; w.v[5]=so->angle;
@@ -211,7 +217,7 @@ void GpuDemLoop::uploadImposes(const vector<shared_ptr<Impose>>& sphImpose, cons
 			w.kind=10; w.flags=co->rotate?1:0; for(int k:{0,1,2}) w.v[k]=co->node->pos[k]; w.v[3]=co->omega; w.v[5]=co->angle;
 			w.ori[0]=co->node->ori.x(); w.ori[1]=co->node->ori.y(); w.ori[2]=co->node->ori.z(); w.ori[3]=co->node->ori.w();
 		}
-		else throw std::runtime_error("GpuDemLoop: "+I->pyStr()+" is not supported (InterpolatedMotion is not on the device path)");
+		else throw std::runtime_error("GpuDemLoop: "+I->pyStr()+" is not supported on the device path");
 		imps.push_back(w); imposeOf.push_back(I); return ixOf[I.get()]=(int)imps.size()-1;
 	};
 	auto setFor=[&](const shared_ptr<Impose>& I)->int{

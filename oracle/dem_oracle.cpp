@@ -248,7 +248,7 @@ struct FacetGroup { V3 pos; Quat ori; V3 vel, angVel; std::vector<int> facets; s
 // Impose (Particle.hpp:130-160, Impose.hpp, Impose.cpp): hooks called by Leapfrog on a node — velocity after the accelerations are applied and again at the end of
 // the node's step, force at the reset, readForce before the reset.  One descriptor per Impose object; a node refers to a SET of them (CombinedImpose, Impose.cpp:283-300).
 enum { IMP_HARMONIC = 1, IMP_ALIGNED_HARMONIC = 2, IMP_CONSTANT_FORCE = 3, IMP_RADIAL_FORCE = 4, IMP_LOCAL6 = 5, IMP_VEL_READ_FORCE = 6, IMP_READ_FORCE = 7, IMP_VARIABLE_VEL3D = 8,
-       IMP_VARIABLE_ALIGNED_ROTATION = 9, IMP_CIRCULAR_ORBIT = 10, IMP_STABLE_CIRCULAR_ORBIT = 11 };
+       IMP_VARIABLE_ALIGNED_ROTATION = 9, IMP_CIRCULAR_ORBIT = 10, IMP_STABLE_CIRCULAR_ORBIT = 11, IMP_INTERPOLATED_MOTION = 12 };
 enum { IMPW_VELOCITY = 1, IMPW_FORCE = 2, IMPW_READ_FORCE = 8 };
 struct ImposeDesc {
   int kind = 0, flags = 0; double v[16] = {0}; Quat ori; std::vector<double> times, vals, vals2;
@@ -257,7 +257,7 @@ struct ImposeDesc {
   int nNodes = 0;                             // nodes carrying it
   int what() const {
     switch (kind) {
-      case IMP_HARMONIC: case IMP_ALIGNED_HARMONIC: case IMP_VARIABLE_VEL3D: case IMP_VARIABLE_ALIGNED_ROTATION: case IMP_CIRCULAR_ORBIT: case IMP_STABLE_CIRCULAR_ORBIT: return IMPW_VELOCITY;
+      case IMP_HARMONIC: case IMP_ALIGNED_HARMONIC: case IMP_VARIABLE_VEL3D: case IMP_VARIABLE_ALIGNED_ROTATION: case IMP_CIRCULAR_ORBIT: case IMP_STABLE_CIRCULAR_ORBIT: case IMP_INTERPOLATED_MOTION: return IMPW_VELOCITY;
       case IMP_CONSTANT_FORCE: case IMP_RADIAL_FORCE: return IMPW_FORCE;
       case IMP_LOCAL6: return IMPW_VELOCITY | IMPW_FORCE;
       case IMP_VEL_READ_FORCE: return IMPW_VELOCITY | IMPW_READ_FORCE;
@@ -1091,7 +1091,7 @@ struct Scene {
   // ------------------------------------------------------------------------------------------
   static Real Sign(Real f) { if (f < 0) return -1; if (f > 0) return 1; return 0; }  // Math.hpp:145
   // ---- Impose hooks; time-dependent values are evaluated once per step (they depend on Scene.time and Scene.dt only)
-  struct ImpStep { double vMag = 0; double vImp[3] = {0, 0, 0}, wImp[3] = {0, 0, 0}; };
+  struct ImpStep { double vMag = 0; double vImp[3] = {0, 0, 0}, wImp[3] = {0, 0, 0}; V3 nextPos; Quat nextOri; };
   std::vector<ImpStep> impStep;
   void imposePrepareStep() {
     impStep.assign(imposes.size(), ImpStep());
@@ -1113,16 +1113,46 @@ struct Scene {
           linInterp(t, d.times, d.vals, 1, d.ipos, &r.vMag); break;
         }
         case IMP_VEL_READ_FORCE: if (d.nNodes > 0) { d.sumF = 0; d.dist += d.v[3] * P.dt; } break;
-        case IMP_CIRCULAR_ORBIT: case IMP_STABLE_CIRCULAR_ORBIT: if (d.nNodes > 0) d.dist += d.v[3] * P.dt; break;      // .angle += omega*dt, once per step (Impose.cpp:36,47)      // the first node of the step resets (Impose.cpp:166-173)
+        case IMP_CIRCULAR_ORBIT: case IMP_STABLE_CIRCULAR_ORBIT: if (d.nNodes > 0) d.dist += d.v[3] * P.dt; break;
+        case IMP_INTERPOLATED_MOTION: {      // Impose.cpp:121-125: v[0] = t0; vals = poss, vals2 = oris (x,y,z,w); ONE cookie for both lookups
+          const Real nextT = time + P.dt - d.v[0];
+          double np[3]; linInterp(nextT, d.times, d.vals, 3, d.ipos, np); r.nextPos = V3(np[0], np[1], np[2]);
+          // linearInterpolateRel (LinearInterpolate.hpp:13-28) on the orientations
+          size_t pos = d.ipos, iA, iB; const size_t n = d.times.size(); Real rel;
+          if (nextT <= d.times[0]) { d.ipos = 0; iA = 0; iB = n > 1 ? 1 : 0; rel = 0; }
+          else if (nextT >= d.times[n - 1]) { d.ipos = n - 2; iA = n > 1 ? pos : n - 1; iB = n - 1; rel = 1; }
+          else { pos = std::min(pos, n - 2); while ((d.times[pos] > nextT) || (d.times[pos + 1] < nextT)) { if (d.times[pos] > nextT) pos--; else pos++; } d.ipos = pos; iA = pos; iB = pos + 1; rel = (nextT - d.times[pos]) / (d.times[pos + 1] - d.times[pos]); }
+          // Quaternionr::slerp (Eigen Geometry/Quaternion.h): dot of the 4 coefficients (x,y,z,w) as Eigen's SSE2 reduction adds them: (xx'+zz') + (yy'+ww')
+          const double* a = &d.vals2[4 * iA]; const double* b = &d.vals2[4 * iB];
+          const Real one = 1. - std::numeric_limits<Real>::epsilon();
+          const Real dd = (a[0] * b[0] + a[2] * b[2]) + (a[1] * b[1] + a[3] * b[3]), absD = std::abs(dd);
+          Real s0, s1;
+          if (absD >= one) { s0 = 1. - rel; s1 = rel; }
+          else { const Real theta = std::acos(absD), sinTheta = std::sin(theta); s0 = std::sin((1. - rel) * theta) / sinTheta; s1 = std::sin(rel * theta) / sinTheta; }
+          if (dd < 0) s1 = -s1;
+          r.nextOri = Quat(s0 * a[3] + s1 * b[3], s0 * a[0] + s1 * b[0], s0 * a[1] + s1 * b[1], s0 * a[2] + s1 * b[2]);
+          break;
+        }      // .angle += omega*dt, once per step (Impose.cpp:36,47)      // the first node of the step resets (Impose.cpp:166-173)
         case IMP_READ_FORCE: if (d.nNodes > 0) { d.F = V3(); d.T = V3(); } break;
         default: break;
       }
     }
   }
-  void imposeVelocity(int set, V3& vel, V3& angVel, const V3& pos) {
+  void imposeVelocity(int set, V3& vel, V3& angVel, const V3& pos, const Quat* nodeOri = nullptr) {
     for (int ix : imposeSets[set]) {
       const ImposeDesc& d = imposes[ix]; const ImpStep& r = impStep[ix];
       switch (d.kind) {
+        case IMP_INTERPOLATED_MOTION: {      // Impose.cpp:120-133 (nextPos / nextOri of the step: imposePrepareStep)
+          vel = (r.nextPos - pos) / P.dt;
+          if (nodeOri) {
+            const Quat rq = quatMul(r.nextOri, Quat(nodeOri->w, -nodeOri->x, -nodeOri->y, -nodeOri->z));      // q+ q0*
+            // AngleAxisr(Quaternionr) of Eigen 3.3/3.4 (Geometry/AngleAxis.h): n = |vec|; angle = 2 atan2(n, |w|); axis = vec / (w < 0 ? -n : n); n == 0: angle 0, axis x
+            Real n = norm(V3(rq.x, rq.y, rq.z)); V3 axis(1, 0, 0); Real angle = 0;
+            if (n != 0) { angle = 2 * std::atan2(n, std::abs(rq.w)); if (rq.w < 0) n = -n; axis = V3(rq.x, rq.y, rq.z) / n; }
+            angVel = (axis * angle) / P.dt;
+          }
+          break;
+        }
         case IMP_CIRCULAR_ORBIT: {      // Impose.cpp:22-37; v = node.pos(3), omega; ori = node.ori; flags&1 rotate
           const Quat qc(d.ori.w, -d.ori.x, -d.ori.y, -d.ori.z);
           const V3 loc = quatRotate(qc, pos - V3(d.v[0], d.v[1], d.v[2]));      // local 2d position (head<2>)
@@ -1411,7 +1441,7 @@ struct Scene {
         G.ori = quatMul(q, G.ori);
       }
       quatNormalize(G.ori);
-      if (G.impose >= 0) imposeVelocity(G.impose, G.vel, G.angVel, G.pos);      // before applyToMembers (Leapfrog.cpp:248-252)
+      if (G.impose >= 0) imposeVelocity(G.impose, G.vel, G.angVel, G.pos, &G.ori);      // before applyToMembers (Leapfrog.cpp:248-252)
       for (size_t k = 0; k < G.facets.size(); k++) {
         Facet& f = facets[G.facets[k]];
         for (int i = 0; i < 3; i++) {
@@ -1694,7 +1724,7 @@ int orc_add_impose(void* h, int kind, int flags, const double* v, const double* 
   if (ori) d.ori = Quat(ori[3], ori[0], ori[1], ori[2]);
   if (kind == IMP_VEL_READ_FORCE) d.dist = d.v[4];      // VelocityAndReadForce.dist is an attribute: a scene may start with a value
   const int w = kind == IMP_VARIABLE_ALIGNED_ROTATION ? 1 : 3;
-  if (nTimes > 0) { d.times.assign(times, times + nTimes); d.vals.assign(vals, vals + (size_t)w * nTimes); if (vals2) d.vals2.assign(vals2, vals2 + (size_t)w * nTimes); }
+  if (nTimes > 0) { d.times.assign(times, times + nTimes); d.vals.assign(vals, vals + (size_t)w * nTimes); if (vals2) d.vals2.assign(vals2, vals2 + (size_t)(kind == IMP_INTERPOLATED_MOTION ? 4 : w) * nTimes); }
   S->imposes.push_back(d);
   return (int)S->imposes.size() - 1;
 }

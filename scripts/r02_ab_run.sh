@@ -1,10 +1,2 @@
-T=${1:-r02s33}
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -m gpu -q -k "not named_size" > gpurun_out/${T}_pytest.log 2>&1; tail -5 gpurun_out/${T}_pytest.log
-python bench.py --no-cpu --e2e-steps 20 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
-python - <<PY
-import json
-for l in open("gpurun_out/${T}_bench.json"):
-    if l.startswith("{"):
-        j=json.loads(l); print("%.4g"%j["value"], "%.4f"%j["ms_per_step"], {k:round(v,4) for k,v in j["roofline"]["phase_ms_per_step"].items()}, "e2e %.4g"%j["e2e"]["value"], "rebuilds", j["config"]["rebuilds_in_timed_region"])
-        for k,v in j.get("configs",{}).items(): print("  ",k,"%.4g"%v["value"],"%.4f"%v["ms_per_step"], v.get("phase_ms_per_step_rank0"))
-PY
+T=${1:-r02s34}
+python -m pytest tests/test_gpu_impose.py tests/test_gpu_kat.py tests/test_plugin_api.py -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; tail -30 gpurun_out/${T}_pytest.log

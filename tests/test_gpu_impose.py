@@ -90,6 +90,27 @@ def test_imposition_on_a_facet_group_vibrating_mesh():
     assert not np.array_equal(E.facets(), np.array([f["v"] for f in S.facets]).reshape(-1, 3, 3))
 
 
+def test_interpolated_motion_of_a_facet_group_bitwise():
+    """InterpolatedMotion (Impose.cpp:111-133) on the master node of a kinematic facet group: the host evaluates it with libm, as the oracle does — bit-identical."""
+    S = sc.drum(200, div=10, axial=2, vz0=.3, vfluct=.2, omega=0., rotate=True)
+    S.facet_groups[0]["angVel"] = (0, 0, 0)
+    c = np.array(S.facet_groups[0]["pos"], dtype=float)
+    qa = lambda a, ax: (*(math.sin(a / 2) * np.asarray(ax, dtype=float) / np.linalg.norm(ax)), math.cos(a / 2))
+    times = [0., .004, .008, .02]
+    poss = [c, c + (1e-3, 0, 0), c + (1e-3, 0, 2e-3), c]
+    oris = [qa(0., (1, 0, 0)), qa(.05, (1, 0, 0)), qa(-.03, (1, 0, .2)), qa(.2, (1, 0, 0))]
+    sc.attach_impose(S, [sc.imp_interpolated_motion(times, poss, oris, t0=5e-4)], groups=[0])
+    O, E = Oracle(S), engine_for(S)
+    for k in range(6):
+        O.step(150); E.step(150)
+        check(O, E, 150 * (k + 1))
+    assert not np.array_equal(E.facets(), np.array([f["v"] for f in S.facets]).reshape(-1, 3, 3))
+    S2 = _gas(50)
+    sc.attach_impose(S2, [sc.imp_interpolated_motion([0, 1], [(0, 0, 0), (1, 0, 0)], [(0, 0, 0, 1), (0, 0, 0, 1)])], spheres=[0])
+    with pytest.raises(RuntimeError, match="facet groups only"):
+        engine_for(S2)
+
+
 def test_orbit_impositions_on_spheres_and_on_the_nodes_of_a_rotating_cylinder():
     """CircularOrbit / StableCircularOrbit (Impose.cpp:22-48) take atan2 / sin / cos of the node position on the device: nodes that carry them follow the oracle to
     rounding, and with them — for a while, contacts amplify rounding — the spheres they touch.  A cylinder whose every node carries a StableCircularOrbit is what

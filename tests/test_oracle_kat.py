@@ -619,3 +619,31 @@ def test_impose_circular_orbits_keep_radius_and_turn_by_omega_t():
     # a fully blocked node is translated first and gets its velocity at the end of the step (Leapfrog.cpp:195-199,248): N steps = N-1 increments
     assert math.remainder(math.atan2(f[0][1] - c[1], -(f[0][2] - c[2])) - math.atan2(R, 0.) - om * (N - 1) * dt, 2 * math.pi) == pytest.approx(0., abs=1e-10)
     assert O.nFullRuns > 1
+
+
+def test_impose_interpolated_motion_reaches_the_given_poses_at_the_given_times():
+    """InterpolatedMotion (Impose.cpp:111-133) on the master node of a facet group: the velocities imposed at the end of a step take the node to the interpolated pose
+    one step later, so at t = times[k] + dt the node is at poss[k], oris[k] (to the rounding of pos += vel*dt and of the rotation by angVel*dt)."""
+    S = _free_spheres(1)
+    c = np.array([.3, .1, .2]); dt = 1e-4
+    S.facets = [dict(v=np.array([c + (0., .1, 0.), c + (.1, .1, 0.), c + (0., 0., .1)]), halfThick=0., fakeVel=(0., 0., 0.), mat=0, mask=sc.MASK_BOUNDARY)]
+    S.facet_groups = [dict(pos=tuple(c), ori=(0., 0., 0., 1.), vel=(0., 0., 0.), angVel=(0., 0., 0.), facets=[0])]
+    S.finalize()
+    qa = lambda a, ax: (*(math.sin(a / 2) * np.asarray(ax, dtype=float) / np.linalg.norm(ax)), math.cos(a / 2))
+    times = [0., .01, .02, .03]
+    poss = [c, c + (.02, 0, 0), c + (.02, .03, 0), c + (.02, .03, -.01)]
+    oris = [qa(0., (1, 0, 0)), qa(.5, (1, 0, 0)), qa(1.2, (1, 1, 0)), qa(1.2, (1, 1, 0))]
+    sc.attach_impose(S, [sc.imp_interpolated_motion(times, poss, oris)], groups=[0])
+    O = Oracle(S)
+    rel = np.array(S.facets[0]["v"]) - c
+
+    def rot(q, v):
+        x, y, z, w = q; u = np.array([x, y, z]); return v + 2 * w * np.cross(u, v) + 2 * np.cross(u, np.cross(u, v))
+    done = 0
+    for k in (1, 2, 3):
+        n = int(round(times[k] / dt)) + 1 - done; O.step(n); done += n      # one step after times[k]
+        f = O.facets()[0]
+        want = np.array([poss[k] + rot(oris[k], r) for r in rel])
+        assert np.allclose(f, want, rtol=0, atol=1e-12), (k, np.abs(f - want).max())
+    O.step(50)                                                              # past the last time point: the pose stays
+    assert np.allclose(O.facets()[0], want, rtol=0, atol=1e-12)

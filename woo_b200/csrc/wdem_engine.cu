@@ -1247,6 +1247,26 @@ void linInterp(double t, const std::vector<double>& tt, const std::vector<double
   }
   for (int k = 0; k < w; k++) out[k] = (rel == 0.) ? A[k] : (rel == 1.) ? B[k] : A[k] + (B[k] - A[k]) * rel;
 }
+// linearInterpolateRel (LinearInterpolate.hpp:13-28): indices of the two end points and the relative position between them; the `A` of the t >= last branch is taken
+// at the cookie's OLD value, as there
+void linRel(double t, const std::vector<double>& tt, size_t& _pos, size_t& iA, size_t& iB, double& rel) {
+  size_t pos = _pos; const size_t n = tt.size();
+  if (t <= tt[0]) { _pos = 0; iA = 0; iB = n > 1 ? 1 : 0; rel = 0.; return; }
+  if (t >= tt[n - 1]) { _pos = n - 2; iA = n > 1 ? pos : n - 1; iB = n - 1; rel = 1.; return; }
+  pos = std::min(pos, n - 2);
+  while ((tt[pos] > t) || (tt[pos + 1] < t)) { if (tt[pos] > t) pos--; else pos++; }
+  _pos = pos; iA = pos; iB = pos + 1; rel = (t - tt[pos]) / (tt[pos + 1] - tt[pos]);
+}
+// Quaternionr::slerp (Eigen/src/Geometry/Quaternion.h); coefficients x,y,z,w; the 4-term dot in the order of Eigen's Packet2d reduction: (xx'+zz') + (yy'+ww')
+void quatSlerp(const double* a, const double* b, double t, double* out) {
+  const double one = 1. - std::numeric_limits<double>::epsilon();
+  const double d = (a[0] * b[0] + a[2] * b[2]) + (a[1] * b[1] + a[3] * b[3]), absD = std::abs(d);
+  double s0, s1;
+  if (absD >= one) { s0 = 1. - t; s1 = t; }
+  else { const double theta = std::acos(absD), sinTheta = std::sin(theta); s0 = std::sin((1. - t) * theta) / sinTheta; s1 = std::sin(t * theta) / sinTheta; }
+  if (d < 0.) s1 = -s1;
+  for (int k = 0; k < 4; k++) out[k] = s0 * a[k] + s1 * b[k];
+}
 // the impositions of the coming step: everything that depends on Scene.time / Scene.dt is evaluated here (libm), walls and facet-group masters are moved on
 void imposePrepareStep(wdem_engine* E, int slot) {
   ImpSlot& H = E->hImpRing[slot]; memset(&H, 0, offsetof(ImpSlot, acc));
@@ -1270,6 +1290,14 @@ void imposePrepareStep(wdem_engine* E, int slot) {
         o.flags = (d.flags & 1) | (rot ? 2 : 0) | (d.vals2.empty() ? 0 : 4);
         linInterp(t, d.times, d.vals, 3, d.ipos, o.a);
         if (!d.vals2.empty()) linInterp(t, d.times, d.vals2, 3, d.ipos2, o.a + 3);
+        break;
+      }
+      case 12: {      // InterpolatedMotion: where the node has to be at the end of this step (Impose.cpp:121-125); one lookup cookie for both tables, as there
+        const double nextT = time + dt - d.v[0];
+        o.kind = IOP_INTERP; o.a[3] = dt;
+        linInterp(nextT, d.times, d.vals, 3, d.ipos, o.a);
+        size_t iA, iB; double rel; linRel(nextT, d.times, d.ipos, iA, iB, rel);
+        quatSlerp(&d.vals2[4 * iA], &d.vals2[4 * iB], rel, o.ori);
         break;
       }
       case 10: case 11: o.kind = d.kind == 10 ? IOP_ORBIT : IOP_SORBIT; o.flags = d.flags & 1; for (int k = 0; k < 3; k++) o.a[k] = d.v[k]; o.a[3] = d.v[3]; o.a[4] = d.v[4]; o.a[5] = dt; break;
@@ -1319,7 +1347,7 @@ StepU stepPrologue(wdem_engine* E, int k) {
       G.ori.w /= nn; G.ori.x /= nn; G.ori.y /= nn; G.ori.z /= nn;
       if (gi < (int)E->groupImpSet.size() && E->groupImpSet[gi] >= 0) {      // Impose::velocity before applyToMembers (Leapfrog.cpp:248-252)
         ImposeDev I; I.slot = &E->hImpRing[k]; I.setStart = E->impSetStart.data(); I.setOps = E->impSetOps.data();
-        impose_velocity(I, E->groupImpSet[gi], G.vel, G.angVel, G.pos);
+        impose_velocity(I, E->groupImpSet[gi], G.vel, G.angVel, G.pos, &G.ori);
       }
     }
   }
@@ -1757,10 +1785,15 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
     cudaStream_t st = h->stream;
     for (int i = 0; i < nImp; i++) {
       const wdem_impose& s = imp[i]; wdem_engine::ImposeHost d;
-      if (s.kind < 1 || s.kind > 11) throw EngErr{"wdem_upload_imposes: unknown kind " + std::to_string(s.kind) + " (InterpolatedMotion is not on this path)", WDEM_ERR_UNSUPPORTED};
+      if (s.kind < 1 || s.kind > 12) throw EngErr{"wdem_upload_imposes: unknown kind " + std::to_string(s.kind), WDEM_ERR_UNSUPPORTED};
       if ((s.kind == 10 || s.kind == 11) && !(s.v[3] == s.v[3])) throw EngErr{"CircularOrbit / StableCircularOrbit: omega must be given", WDEM_ERR_INVALID};
       if (s.kind == 11 && !(s.v[4] == s.v[4])) throw EngErr{"StableCircularOrbit: radius must be given", WDEM_ERR_INVALID};
       d.kind = s.kind; d.flags = s.flags; memcpy(d.v, s.v, sizeof(d.v)); memcpy(d.ori, s.ori, sizeof(d.ori));
+      if (s.kind == 12) {
+        if (s.nTimes <= 0 || !s.times || !s.vals || !s.vals2) throw EngErr{"InterpolatedMotion: poss, oris, times must have the same (non-zero) length", WDEM_ERR_INVALID};
+        d.times.assign(s.times, s.times + s.nTimes); d.vals.assign(s.vals, s.vals + (size_t)3 * s.nTimes); d.vals2.assign(s.vals2, s.vals2 + (size_t)4 * s.nTimes);
+        for (int k = 0; k + 1 < s.nTimes; k++) if (!(d.times[k + 1] > d.times[k])) throw EngErr{"InterpolatedMotion: times must be increasing", WDEM_ERR_INVALID};
+      }
       if (s.kind == 8 || s.kind == 9) {
         if (s.nTimes <= 0 || !s.times || !s.vals) throw EngErr{s.kind == 8 ? "VariableVelocity3d: times must not be empty." : "VariableAlignedRotation: timeAngVel must not be empty.", WDEM_ERR_INVALID};
         const int w = s.kind == 8 ? 3 : 1;
@@ -1775,8 +1808,8 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
     }
     h->impSetStart.assign(setStart, setStart + nSets + 1); h->impSetOps.assign(setOps, setOps + setStart[nSets]);
     for (int v : h->impSetOps) if (v < 0 || v >= nImp) throw EngErr{"wdem_upload_imposes: set refers to an unknown Impose object", WDEM_ERR_INVALID};
-    bool orbit = false;
-    auto setKinds = [&](int set, bool& vel, bool& other) { orbit = false; for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) { const int k = h->imposes[h->impSetOps[e]].kind; if (k == 10 || k == 11) orbit = true; if (k == 1 || k == 2 || k == 8 || k == 9 || k == 10 || k == 11) vel = true; else if (k == 5) { vel = true; for (int q = 0; q < 6; q++) if ((int)h->imposes[h->impSetOps[e]].v[6 + q] == 2) other = true; } else if (k == 6) { vel = true; other = true; } else other = true; } };
+    bool orbit = false, interp = false;
+    auto setKinds = [&](int set, bool& vel, bool& other) { orbit = false; interp = false; for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) { const int k = h->imposes[h->impSetOps[e]].kind; if (k == 10 || k == 11) orbit = true; if (k == 12) interp = true; if (k == 1 || k == 2 || k == 8 || k == 9 || k == 10 || k == 11 || k == 12) vel = true; else if (k == 5) { vel = true; for (int q = 0; q < 6; q++) if ((int)h->imposes[h->impSetOps[e]].v[6 + q] == 2) other = true; } else if (k == 6) { vel = true; other = true; } else other = true; } };
     auto touch = [&](int set) { if (set < 0) return; if (set >= nSets) throw EngErr{"wdem_upload_imposes: set index out of range", WDEM_ERR_INVALID}; for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) h->imposes[h->impSetOps[e]].nNodes++; };
     // spheres: table by particle id
     std::vector<int32_t> ofId((size_t)std::max(h->maxId, 0) + 2, -1);
@@ -1785,6 +1818,7 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
       if (sphereSet[k] < 0) continue;
       if (!known.count(sphereIds[k])) throw EngErr{"wdem_upload_imposes: particle #" + std::to_string(sphereIds[k]) + " is not an uploaded sphere", WDEM_ERR_INVALID};
       touch(sphereSet[k]); ofId[sphereIds[k]] = sphereSet[k]; h->impSpheres = true;
+      { bool v_ = false, o_ = false; setKinds(sphereSet[k], v_, o_); if (interp) throw EngErr{"wdem_upload_imposes: InterpolatedMotion acts on the master nodes of facet groups only", WDEM_ERR_UNSUPPORTED}; }
     }
     h->dImpOfId.ensure(ofId.size(), h->bytes); CK(cudaMemcpyAsync(h->dImpOfId.p, ofId.data(), ofId.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (wallSet) {
@@ -1797,6 +1831,7 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
         bool vel = false, other = false; setKinds(wallSet[w], vel, other);
         if (other) throw EngErr{"wdem_upload_imposes: walls (all DOFs blocked) take velocity impositions only", WDEM_ERR_UNSUPPORTED};
         if (orbit) throw EngErr{"wdem_upload_imposes: CircularOrbit / StableCircularOrbit act on spheres and on facet nodes (wdem_upload_facet_imposes), not on walls", WDEM_ERR_UNSUPPORTED};
+        if (interp) throw EngErr{"wdem_upload_imposes: InterpolatedMotion acts on the master nodes of facet groups only", WDEM_ERR_UNSUPPORTED};
         touch(wallSet[w]); h->hWalls[w].moving = 1; any = true;      // DemData::guessMoving: ... || impose (Particle.cpp:638-640)
       }
       if (any) { h->anyMovingWall = true; h->anyStaticWall = false; for (auto& w : h->hWalls) if (!w.moving) h->anyStaticWall = true; CK(cudaMemcpyAsync(h->dWalls.p, h->hWalls.data(), h->hWalls.size() * sizeof(Wall), cudaMemcpyHostToDevice, st)); }

@@ -38,11 +38,11 @@ struct Spheres {          // one slot per sphere; slots are re-ordered by grid c
 // Impose (Particle.hpp:130-160, Impose.hpp, Impose.cpp): one resolved imposition.  Everything that depends on Scene.time / Scene.dt only (harmonic
 // factors, interpolated tables) is evaluated by the host once per step with libm, so host, device and oracle see the same numbers.
 #define WD_MAX_IMPOSE 16
-enum { IOP_DIR = 1, IOP_AXES_SET = 2, IOP_VAR3D = 3, IOP_ANGAXIS = 4, IOP_LOCAL6 = 5, IOP_FADD = 6, IOP_FRADIAL = 7, IOP_READFT = 8, IOP_ORBIT = 9, IOP_SORBIT = 10 };
+enum { IOP_DIR = 1, IOP_AXES_SET = 2, IOP_VAR3D = 3, IOP_ANGAXIS = 4, IOP_LOCAL6 = 5, IOP_FADD = 6, IOP_FRADIAL = 7, IOP_READFT = 8, IOP_ORBIT = 9, IOP_SORBIT = 10, IOP_INTERP = 11 };
 struct ImpOp {
   int kind, flags;      // DIR: flags&1 zero the lateral velocity, &2 read force (VelocityAndReadForce), &4 invF | VAR3D: &1 diff, &2 rotated frame, &4 angular velocity too | READFT: &1 node frame
   double ori[4];        // x,y,z,w
-  double a[7];          // ORBIT / SORBIT: node pos(3), omega, radius (SORBIT), dt; ori = node.ori; flags&1 rotate | DIR dir(3), magnitude | AXES_SET values(3; NaN: untouched) | VAR3D vImp(3), wImp(3) | ANGAXIS value | LOCAL6 values(6) | FADD F(3) | FRADIAL A(3), unit axis(3), F | READFT node pos(3)
+  double a[7];          // INTERP: position to reach at the end of the coming step (3), dt; ori = orientation to reach | ORBIT / SORBIT: node pos(3), omega, radius (SORBIT), dt; ori = node.ori; flags&1 rotate | DIR dir(3), magnitude | AXES_SET values(3; NaN: untouched) | VAR3D vImp(3), wImp(3) | ANGAXIS value | LOCAL6 values(6) | FADD F(3) | FRADIAL A(3), unit axis(3), F | READFT node pos(3)
   int m[6];             // ANGAXIS m[0] = axis | LOCAL6 whats(6)
 };
 struct ImpSlot {        // what one step of a batch needs (ring indexed by the step's position in the batch, like Counters::gflag)
@@ -55,10 +55,22 @@ __host__ __device__ __forceinline__ q4 impOri(const ImpOp& o) { q4 q; q.x = o.or
 // Impose::velocity of every imposition of the set, in order (CombinedImpose::velocity, Impose.cpp:288-292)
 // `pos`: the node's position at the time of the call (only the orbit kinds read it: atan2 / sin / cos of the device's math library there, so nodes that carry them
 // follow the oracle to rounding, not bit for bit).
-__host__ __device__ __forceinline__ void impose_velocity(const ImposeDev& I, int set, d3& vel, d3& w, const d3& pos) {
+// `nodeOri`: the node's orientation (InterpolatedMotion only: master nodes of facet groups, evaluated by the host with libm; NULL elsewhere).
+__host__ __device__ __forceinline__ void impose_velocity(const ImposeDev& I, int set, d3& vel, d3& w, const d3& pos, const q4* nodeOri = nullptr) {
   for (int e = I.setStart[set]; e < I.setStart[set + 1]; e++) {
     const ImpOp& o = I.slot->op[I.setOps[e]];
     switch (o.kind) {
+      case IOP_INTERP: {   // InterpolatedMotion (Impose.cpp:120-133): the velocities that take the node to (nextPos, nextOri) in one step
+        vel = (mk3(o.a[0], o.a[1], o.a[2]) - pos) / o.a[3];
+        if (nodeOri) {
+          const q4 r = quatMul(impOri(o), quatConj(*nodeOri));      // Leapfrog::leapfrogSphericalRotate does q+ = r q0, so r = q+ q0*
+          // AngleAxisr(r) (Eigen/src/Geometry/AngleAxis.h, operator=(QuaternionBase)): angle = 2 atan2(|vec|, |w|), axis = vec / (+-|vec|)
+          double n = nrm(mk3(r.x, r.y, r.z)); d3 axis = mk3(1., 0., 0.); double angle = 0.;
+          if (n != 0.) { angle = 2. * atan2(n, fabs(r.w)); if (r.w < 0.) n = -n; axis = mk3(r.x, r.y, r.z) / n; }
+          w = (axis * angle) / o.a[3];
+        }
+        break;
+      }
       case IOP_ORBIT: {    // CircularOrbit (Impose.cpp:22-37): tangential velocity at the approximate mid-step polar angle, around the local z axis of `node`
         const q4 q = impOri(o), qc = quatConj(q);
         const d3 loc = quatRotate(qc, pos - mk3(o.a[0], o.a[1], o.a[2]));

@@ -69,6 +69,7 @@ struct VariableVelocity3d : Impose { vector<double> times; vector<V3> vels, angV
 struct VariableAlignedRotation : Impose { int axis = 0; vector<std::array<double, 2>> timeAngVel; bool wrap = false; int kind() const override { return 9; } };
 struct CircularOrbit : Impose { shared_ptr<Node> node; bool rotate = false; double omega = NaN, angle = 0; int kind() const override { return 10; } };      // Impose.hpp (CircularOrbit)
 struct StableCircularOrbit : CircularOrbit { double radius = NaN; int kind() const override { return 11; } };
+struct InterpolatedMotion : Impose { vector<V3> poss; vector<Q4> oris; vector<double> times; double t0 = 0; int kind() const override { return 12; } };
 struct CombinedImpose : Impose { vector<shared_ptr<Impose>> imps; };
 struct DemData {
   virtual ~DemData() {}
@@ -254,6 +255,13 @@ struct GpuDemLoop : Engine {
         w.flags = p->wrap ? 1 : 0; w.v[0] = p->axis; w.nTimes = (int)p->timeAngVel.size();
         keep.emplace_back(); for (auto& x : p->timeAngVel) keep.back().push_back(x[0]); w.times = keep.back().data();
         keep.emplace_back(); for (auto& x : p->timeAngVel) keep.back().push_back(x[1]); w.vals = keep.back().data();
+      }
+      else if (auto* p = dynamic_cast<InterpolatedMotion*>(I.get())) {
+        if (p->poss.size() != p->oris.size() || p->oris.size() != p->times.size()) throw std::runtime_error("InterpolatedMotion: poss, oris, times must have the same length (not " + std::to_string(p->poss.size()) + ", " + std::to_string(p->oris.size()) + ", " + std::to_string(p->times.size()) + ")");      // postLoad (Impose.cpp:115-118)
+        w.v[0] = p->t0; w.nTimes = (int)p->times.size();
+        keep.push_back(p->times); w.times = keep.back().data();
+        keep.emplace_back(); for (auto& x : p->poss) for (int k = 0; k < 3; k++) keep.back().push_back(x[k]); w.vals = keep.back().data();
+        keep.emplace_back(); for (auto& x : p->oris) for (int k = 0; k < 4; k++) keep.back().push_back(x[k]); w.vals2 = keep.back().data();
       }
       else if (auto* p = dynamic_cast<CircularOrbit*>(I.get())) {      // also StableCircularOrbit
         if (!p->node) throw std::runtime_error(string(w.kind == 11 ? "StableCircularOrbit" : "CircularOrbit") + ": node must not be None.");
@@ -656,6 +664,9 @@ PYBIND11_MODULE(_woo, m) {
       .def_property("ori", [](VariableVelocity3d& s) { return np4(s.ori); }, [](VariableVelocity3d& s, py::object o) { s.ori = seqN<4>(o, "ori"); s.touch(); })
       .def_property("vels", [](VariableVelocity3d& s) { py::list l; for (auto& v : s.vels) l.append(np3(v)); return l; }, [](VariableVelocity3d& s, py::iterable o) { s.vels.clear(); for (auto it : o) s.vels.push_back(seqN<3>(py::reinterpret_borrow<py::object>(it), "vels")); s.touch(); })
       .def_property("angVels", [](VariableVelocity3d& s) { py::list l; for (auto& v : s.angVels) l.append(np3(v)); return l; }, [](VariableVelocity3d& s, py::iterable o) { s.angVels.clear(); for (auto it : o) s.angVels.push_back(seqN<3>(py::reinterpret_borrow<py::object>(it), "angVels")); s.touch(); });
+  kwclass<InterpolatedMotion, Impose>(m, "InterpolatedMotion") RWI(InterpolatedMotion, times) RWI(InterpolatedMotion, t0)
+      .def_property("poss", [](InterpolatedMotion& s) { py::list l; for (auto& v : s.poss) l.append(np3(v)); return l; }, [](InterpolatedMotion& s, py::iterable o) { s.poss.clear(); for (auto it : o) s.poss.push_back(seqN<3>(py::reinterpret_borrow<py::object>(it), "poss")); s.touch(); })
+      .def_property("oris", [](InterpolatedMotion& s) { py::list l; for (auto& v : s.oris) l.append(np4(v)); return l; }, [](InterpolatedMotion& s, py::iterable o) { s.oris.clear(); for (auto it : o) s.oris.push_back(seqN<4>(py::reinterpret_borrow<py::object>(it), "oris")); s.touch(); });
   kwclass<CircularOrbit, Impose>(m, "CircularOrbit") RWI(CircularOrbit, node) RWI(CircularOrbit, rotate) RWI(CircularOrbit, omega)
       .def_property("angle", [](CircularOrbit& s) { if (s.field) s.field->pull(); return s.angle; }, [](CircularOrbit& s, double v) { if (s.field) s.field->pull(); s.angle = v; s.touch(); });
   kwclass<StableCircularOrbit, CircularOrbit>(m, "StableCircularOrbit") RWI(StableCircularOrbit, radius);

@@ -128,7 +128,7 @@ def hertz_mat(density=1e3, young=1e8, ktDivKn=.2, tanPhi=.5, surfEnergy=0.0, alp
 
 # ---- Impose descriptors (wdem.h: wdem_impose; kinds and the meaning of v[16] follow include/wdem.h)
 IMP_HARMONIC, IMP_ALIGNED_HARMONIC, IMP_CONSTANT_FORCE, IMP_RADIAL_FORCE, IMP_LOCAL6, IMP_VEL_READ_FORCE, IMP_READ_FORCE, IMP_VARIABLE_VEL3D, IMP_VARIABLE_ALIGNED_ROTATION = range(1, 10)
-IMP_CIRCULAR_ORBIT, IMP_STABLE_CIRCULAR_ORBIT = 10, 11
+IMP_CIRCULAR_ORBIT, IMP_STABLE_CIRCULAR_ORBIT, IMP_INTERPOLATED_MOTION = 10, 11, 12
 
 
 def _imp(kind, flags=0, v=(), ori=(0, 0, 0, 1), times=(), vals=(), vals2=()):
@@ -189,6 +189,11 @@ def imp_circular_orbit(node_pos, omega, node_ori=(0, 0, 0, 1), rotate=False):
 def imp_stable_circular_orbit(node_pos, omega, radius, node_ori=(0, 0, 0, 1), rotate=False):
     """StableCircularOrbit (Impose.cpp:38-48): as CircularOrbit, with the radius enforced (what woo.triangulated.cylinder(angVel=..., realRot=True) puts on every node)"""
     return _imp(IMP_STABLE_CIRCULAR_ORBIT, 1 if rotate else 0, [*node_pos, omega, radius], node_ori)
+
+
+def imp_interpolated_motion(times, poss, oris, t0=0.):
+    """InterpolatedMotion (Impose.hpp, Impose.cpp:111-133): reach poss[k], oris[k] (x,y,z,w) at times[k]+t0; on master nodes of facet groups"""
+    return _imp(IMP_INTERPOLATED_MOTION, 0, [t0], (0, 0, 0, 1), times, poss, oris)
 
 
 def attach_impose(S, ops, spheres=(), walls=(), groups=(), facets=()):

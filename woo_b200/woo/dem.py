@@ -3,4 +3,4 @@ from .._woo import (DemField, DemData, Particle, ParticleContainer, ContactConta
                     Material, ElastMat, FrictMat, HertzMat, Leapfrog, InsertionSortCollider, Bo1_Sphere_Aabb, Bo1_Facet_Aabb, Bo1_Wall_Aabb,
                     ContactLoop, Cg2_Sphere_Sphere_L6Geom, Cg2_Wall_Sphere_L6Geom, Cg2_Facet_Sphere_L6Geom, Cp2_FrictMat_FrictPhys,
                     Cp2_HertzMat_HertzPhys, Law2_L6Geom_FrictPhys_IdealElPl, Law2_L6Geom_HertzPhys_DMT, DynDt, GpuDemLoop, ClumpData, Impose, HarmonicOscillation, AlignedHarmonicOscillations, ConstantForce, RadialForce,
-                    Local6Dofs, VelocityAndReadForce, ReadForce, VariableVelocity3d, VariableAlignedRotation, CombinedImpose, CircularOrbit, StableCircularOrbit)
+                    Local6Dofs, VelocityAndReadForce, ReadForce, VariableVelocity3d, VariableAlignedRotation, CombinedImpose, CircularOrbit, StableCircularOrbit, InterpolatedMotion)
