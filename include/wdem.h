@@ -183,6 +183,10 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
  * (DemData::guessMoving, Particle.cpp:638-640): Leapfrog's fixed-node branch translates them with their velocity and Impose::velocity at the end of the node's step sets
  * the velocity of the next one (Leapfrog.cpp:195-199,248).  Velocity impositions only; not for facets of a kinematic group; aperiodic scenes.  Call after wdem_upload_imposes. */
 int wdem_upload_facet_imposes(wdem_handle h, const int32_t* facetSet);
+/* DemData.impose of the master nodes of clumps of spheres: clumpSet[c] = the set of impositions of uploaded clump c, -1 none.  Leapfrog calls the hooks on the master
+ * node like on any other node (velocity after the accelerations and at the end of the node's step, before ClumpData::applyToMembers; force at the reset;
+ * Leapfrog.cpp:203-205,244,248,252).  All kinds but the read-force ones and InterpolatedMotion.  Call after wdem_upload_clumps and wdem_upload_imposes. */
+int wdem_upload_clump_imposes(wdem_handle h, const int32_t* clumpSet);
 /* Velocities of the boundary nodes an imposition may have changed: 3 per uploaded wall, 3 + 3 per facet group; any pointer may be NULL. */
 int wdem_download_boundary_velocities(wdem_handle h, double* wallVel, double* groupVel, double* groupAngVel);
 /* out[8]: VelocityAndReadForce.sumF, .dist (CircularOrbit / StableCircularOrbit: .angle in the place of .dist); ReadForce.F(3), .T(3) of Impose object ix after the last step (sums of what the last step's Leapfrog read). */

@@ -235,7 +235,7 @@ void GpuDemLoop::uploadImposes(const vector<shared_ptr<Impose>>& sphImpose, cons
 		if(!n->hasData<DemData>() || !n->getData<DemData>().isClump()) continue;
 		const ClumpData& cd=n->getData<DemData>().cast<ClumpData>();
 		const bool sphereClump=std::find(clumpOf.begin(),clumpOf.end(),n)!=clumpOf.end();
-		if(sphereClump){ if(cd.impose) throw std::runtime_error("GpuDemLoop: DemData.impose on a clump of spheres is not supported"); continue; }
+		if(sphereClump) continue;      // clumps of spheres: below, in the order of clumpOf (= the order of wdem_upload_clumps)
 		groupSet.push_back(cd.impose?setFor(cd.impose):-1); if(cd.impose) anyGroup=true;
 	}
 	// facet nodes (py/triangulated.py:59-64: every node of a cylinder carries the same StableCircularOrbit); facets of a kinematic clump follow their master node
@@ -245,8 +245,11 @@ void GpuDemLoop::uploadImposes(const vector<shared_ptr<Impose>>& sphImpose, cons
 		if(nn[1]->getData<DemData>().impose!=imp || nn[2]->getData<DemData>().impose!=imp) throw std::runtime_error("GpuDemLoop: the three nodes of facet #"+to_string(facetOf[i]->id)+" must carry the same DemData.impose");
 		if(imp){ facetSet[i]=setFor(imp); anyFacet=true; }
 	}
+	vector<int32_t> clumpSet(clumpOf.size(),-1); bool anyClump=false;      // master nodes of clumps of spheres
+	for(size_t c=0;c<clumpOf.size();c++){ const auto& imp=clumpOf[c]->getData<DemData>().impose; if(imp){ clumpSet[c]=setFor(imp); anyClump=true; } }
 	if(imps.empty()) return;
 	chk(h,wdem_upload_imposes(h,(int32_t)imps.size(),imps.data(),(int32_t)setStart.size()-1,setStart.data(),setOps.data(),(int64_t)sphImposeId.size(),sphImposeId.data(),sphSet.data(),anyWall?wallSet.data():nullptr,anyGroup?groupSet.data():nullptr));
+	if(anyClump) chk(h,wdem_upload_clump_imposes(h,clumpSet.data()));
 	if(anyFacet) chk(h,wdem_upload_facet_imposes(h,facetSet.data()));
 }
 

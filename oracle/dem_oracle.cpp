@@ -284,6 +284,7 @@ static inline void linInterp(Real t, const std::vector<double>& tt, const std::v
 struct Clump {
   V3 pos; Quat ori; V3 vel, angVel, angMom = V3(NaN, NaN, NaN); Real mass = 0; V3 inertia; V3 force, torque; unsigned flags = 0;
   std::vector<int> members /*sphere indices*/; std::vector<V3> relPos; std::vector<Quat> relOri;
+  int impose = -1;     // set of impositions on the master node
 };
 struct PRef { int kind, idx; };
 
@@ -1383,6 +1384,7 @@ struct Scene {
               if (damp) for (int k = 0; k < 3; k++) t[k] *= 1 - damping * Sign(t[k] * c.angVel[k]);              // nonviscDamp1st (Leapfrog.cpp:28-30)
             }
           }
+          if (c.impose >= 0) imposeVelocity(c.impose, c.vel, c.angVel, c.pos, &c.ori);      // Leapfrog.cpp:203-205
         }
         c.pos += c.vel * dt;
         if (!useAspherical) {      // leapfrogSphericalRotate (Leapfrog.cpp:280-297)
@@ -1413,7 +1415,11 @@ struct Scene {
           c.angVel = quatRotate(c.ori, w_b_half);
           quatNormalize(c.ori);
         }
-        if (P.reset) { c.force = (hasGravity && !(fl & GRAVITY_SKIP)) ? (c.mass * g) : V3(); c.torque = V3(); }      // gravity on the clump itself, not on the members
+        if (P.reset) {      // gravity on the clump itself, not on the members; Impose::force on top (Leapfrog.cpp:240-245)
+          c.force = (hasGravity && !(fl & GRAVITY_SKIP)) ? (c.mass * g) : V3(); c.torque = V3();
+          if (c.impose >= 0) imposeForce(c.impose, c.pos, c.force, c.torque);
+        }
+        if (c.impose >= 0) imposeVelocity(c.impose, c.vel, c.angVel, c.pos, &c.ori);      // Leapfrog.cpp:248, before applyToMembers (:252)
         // ClumpData::applyToMembers (Clump.cpp:293-307)
         for (size_t k = 0; k < c.members.size(); k++) {
           Sphere& ms = sph[c.members[k]];
@@ -1729,7 +1735,7 @@ int orc_add_impose(void* h, int kind, int flags, const double* v, const double* 
   return (int)S->imposes.size() - 1;
 }
 int orc_add_impose_set(void* h, int n, const int* ops) { Scene* S = (Scene*)h; S->imposeSets.push_back(std::vector<int>(ops, ops + n)); return (int)S->imposeSets.size() - 1; }
-// kind of node: 0 sphere (particle id), 1 wall (particle id), 2 facet group (index), 3 the three nodes of a facet (particle id)
+// kind of node: 0 sphere (particle id), 1 wall (particle id), 2 facet group (index), 3 the three nodes of a facet (particle id), 4 master node of a clump of spheres (index)
 int orc_attach_impose(void* h, int nodeKind, int which, int set) {
   Scene* S = (Scene*)h;
   ORC_TRY(h)
@@ -1738,6 +1744,7 @@ int orc_attach_impose(void* h, int nodeKind, int which, int set) {
   if (nodeKind == 0) { if (which < 0 || which >= (int)S->par.size() || S->par[which].kind != SHAPE_SPHERE) throw std::runtime_error("impose: not a sphere"); S->sph[S->par[which].idx].impose = set; }
   else if (nodeKind == 1) { if (which < 0 || which >= (int)S->par.size() || S->par[which].kind != SHAPE_WALL) throw std::runtime_error("impose: not a wall"); if (readF) throw std::runtime_error("readForce on walls is not part of this path"); Wall& w = S->walls[S->par[which].idx]; w.impose = set; w.moving = true; /* DemData::guessMoving: || impose (Particle.cpp:639) */ }
   else if (nodeKind == 3) { if (which < 0 || which >= (int)S->par.size() || S->par[which].kind != SHAPE_FACET) throw std::runtime_error("impose: not a facet"); if (readF) throw std::runtime_error("readForce on facet nodes is not part of this path"); for (int ix : S->imposeSets[set]) S->imposes[ix].nNodes += 2; S->facets[S->par[which].idx].impose = set; }
+  else if (nodeKind == 4) { if (which < 0 || which >= (int)S->clumps.size()) throw std::runtime_error("impose: no such clump"); if (readF) throw std::runtime_error("readForce on clump master nodes is not part of this path"); S->clumps[which].impose = set; }
   else { if (which < 0 || which >= (int)S->groups.size()) throw std::runtime_error("impose: no such facet group"); if (readF) throw std::runtime_error("readForce on facet groups is not part of this path"); S->groups[which].impose = set; }
   ORC_CATCH(h)
 }

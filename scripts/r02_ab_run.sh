@@ -1,2 +1,2 @@
-T=${1:-r02s34}
-python -m pytest tests/test_gpu_impose.py tests/test_gpu_kat.py tests/test_plugin_api.py -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; tail -30 gpurun_out/${T}_pytest.log
+T=${1:-r02s36}
+python -m pytest tests/test_gpu_clumps.py -m gpu -q -k "impositions" > gpurun_out/${T}_pytest.log 2>&1; tail -12 gpurun_out/${T}_pytest.log

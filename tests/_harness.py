@@ -114,6 +114,10 @@ class Oracle:
             mem = np.ascontiguousarray(ids[np.asarray(c["members"], dtype=np.int64)], dtype=np.int32)
             self._chk(L.orc_add_clump(h, C.c_int(len(mem)), _p(mem, C.c_int), _p(a("pos"), C.c_double), _p(a("ori"), C.c_double), _p(a("vel"), C.c_double), _p(a("angVel"), C.c_double),
                                       C.c_double(c["mass"]), _p(a("inertia"), C.c_double), C.c_uint(int(c.get("flags", 0)))))
+        if getattr(S, "clump_impose", None) is not None:      # impositions on clump master nodes: after the clumps exist
+            for i, k in enumerate(S.clump_impose):
+                if k >= 0:
+                    self._chk(L.orc_attach_impose(h, C.c_int(4), C.c_int(i), C.c_int(int(k))))
         P = OrcParams(); L.orc_default_params(C.byref(P))
         for k, v in vars(S.params).items():
             if k == "gravity":

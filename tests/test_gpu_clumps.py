@@ -49,6 +49,30 @@ def test_clump_deposition_bitwise(law):
     assert O.nFullRuns > 100 and len(O.contacts(True)["ids"]) > 100
 
 
+def test_impositions_on_clump_master_nodes_bitwise():
+    """DemData.impose of a clump's master node (Leapfrog.cpp:203-205,244,248 on the clump node, before ClumpData::applyToMembers): a stirrer clump driven harmonically,
+    one pushed by a constant force, one whose rotation about z is prescribed by a table (the members follow rigidly), among free clumps and spheres."""
+    S = sc.clump_deposition(30, 40)
+    nan = float("nan")
+    sc.attach_impose(S, [sc.imp_aligned_harmonic((30., nan, nan), (2e-3, 0, 0))], clumps=[0, 1])
+    sc.attach_impose(S, [sc.imp_constant_force((0, 3e-3, 0)), sc.imp_variable_aligned_rotation(2, [(0, 0), (.01, 20.), (.05, 20.)])], clumps=[2])
+    sc.attach_impose(S, [sc.imp_local6((0, 0, 0, 0, 0, 0), (1, 1, 0, 0, 0, 0))], clumps=[3])      # no lateral motion: falls straight down
+    sc.attach_impose(S, [sc.imp_harmonic(20., 1e-3, dir=(0, 1, 0))], spheres=[len(S.pos) - 1])
+    O, E = Oracle(S), engine_for(S)
+    x3 = E.clumps()["pos"][3].copy()
+    for k in range(16):
+        O.step(500); E.step(500)
+        check(O, E, 500 * (k + 1))
+    c = E.clumps()
+    assert c["pos"][3][0] == x3[0] and c["pos"][3][1] == x3[1] and c["pos"][3][2] < x3[2]
+    assert O.nFullRuns > 50 and len(O.contacts(True)["ids"]) > 30
+    from woo_b200.engine import Engine
+    S2 = sc.clump_deposition(5, 0)
+    sc.attach_impose(S2, [sc.imp_read_force()], clumps=[0])
+    with pytest.raises(RuntimeError, match="read-force kinds"):
+        Engine(S2.params).load(S2)
+
+
 def test_clump_first_steps_and_member_kinematics():
     S = sc.clump_deposition(9, 0, dynDtPeriod=0)
     O, E = Oracle(S), engine_for(S)

@@ -82,10 +82,10 @@ struct ContactStore {
 // clumps of spheres with mass (wdem_upload_clumps): master nodes integrated by k_clumps_step
 struct ClumpStore {
   int n = 0, nMem = 0;
-  DBuf<double4> pos, ori, vel, angVel, angMom, force, torque, inertia, relPos, relOri; DBuf<uint32_t> flags; DBuf<int> memStart; DBuf<int32_t> memId, clumpOfId;
+  DBuf<double4> pos, ori, vel, angVel, angMom, force, torque, inertia, relPos, relOri; DBuf<uint32_t> flags; DBuf<int> memStart, impSet; bool anyImp = false; DBuf<int32_t> memId, clumpOfId;
   Clumps view() { Clumps K; K.n = n; K.pos = pos.p; K.ori = ori.p; K.vel = vel.p; K.angVel = angVel.p; K.angMom = angMom.p; K.force = force.p; K.torque = torque.p; K.inertia = inertia.p; K.flags = flags.p;
-    K.memStart = memStart.p; K.memId = memId.p; K.relPos = relPos.p; K.relOri = relOri.p; return K; }
-  void release() { for (auto* b : {&pos, &ori, &vel, &angVel, &angMom, &force, &torque, &inertia, &relPos, &relOri}) b->release(); flags.release(); memStart.release(); memId.release(); clumpOfId.release(); n = nMem = 0; }
+    K.memStart = memStart.p; K.memId = memId.p; K.relPos = relPos.p; K.relOri = relOri.p; K.impSet = anyImp ? impSet.p : nullptr; return K; }
+  void release() { for (auto* b : {&pos, &ori, &vel, &angVel, &angMom, &force, &torque, &inertia, &relPos, &relOri}) b->release(); flags.release(); memStart.release(); impSet.release(); anyImp = false; memId.release(); clumpOfId.release(); n = nMem = 0; }
 };
 
 struct CsrStore { DBuf<int> rowStart; DBuf<uint32_t> rowEntry; DBuf<int32_t> rowOther; bool valid = false; int nRows = 0; void release() { rowStart.release(); rowEntry.release(); rowOther.release(); } };
@@ -1373,7 +1373,7 @@ void enqueueIntegrate(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
   if (E->nClumpedUploaded > 0) throw EngErr{std::to_string(E->nClumpedUploaded) + " spheres carry the CLUMPED flag but no clump was uploaded (wdem_upload_clumps)", WDEM_ERR_INVALID};
   if (E->clumps.n > 0) {
     if (c.periodic || E->comm || E->e2e.active || E->trackEnergy) throw EngErr{"clumps of spheres: periodic cells, decomposed runs, wdem_step_e2e and Scene.trackEnergy are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
-    k_clumps_step<<<nblk(E->clumps.n, 128), 128, 0, st>>>(E->clumps.view(), E->S(), E->id2slot.p, u, E->dCnt); E->launches++;
+    k_clumps_step<<<nblk(E->clumps.n, 128), 128, 0, st>>>(E->clumps.view(), E->S(), E->id2slot.p, u, E->dCnt, E->impDev(u.impSlot)); E->launches++;
   }
   if ((E->groups.n > 0 || E->impFacetNodes) && !E->hFacets.empty()) {
     if (c.periodic) throw EngErr{"moving facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
@@ -1882,6 +1882,28 @@ int wdem_upload_facet_imposes(wdem_handle h, const int32_t* facetSet) {
     h->impFacetNodes = any;
     if (!h->hFacets.empty()) { CK(cudaMemcpyAsync(h->dFacets.p, h->hFacets.data(), h->hFacets.size() * sizeof(Facet), cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
     h->fgridValid = false;
+  });
+}
+int wdem_upload_clump_imposes(wdem_handle h, const int32_t* clumpSet) {
+  return guarded(h, [&] {
+    if (h->imposes.empty() || !clumpSet || h->clumps.n == 0) throw EngErr{"wdem_upload_clump_imposes: call after wdem_upload_clumps and wdem_upload_imposes", WDEM_ERR_INVALID};
+    if (!h->conDirty || h->nC != 0 || h->cur != 0) throw EngErr{"wdem_upload_clump_imposes: call before the first step", WDEM_ERR_INVALID};
+    const int nSets = (int)h->impSetStart.size() - 1; bool any = false;
+    for (int c = 0; c < h->clumps.n; c++) {
+      const int set = clumpSet[c];
+      if (set < 0) continue;
+      if (set >= nSets) throw EngErr{"wdem_upload_clump_imposes: set index out of range", WDEM_ERR_INVALID};
+      for (int e = h->impSetStart[set]; e < h->impSetStart[set + 1]; e++) {
+        wdem_engine::ImposeHost& d = h->imposes[h->impSetOps[e]];
+        if (d.kind == 6 || d.kind == 7) throw EngErr{"wdem_upload_clump_imposes: the read-force kinds (VelocityAndReadForce, ReadForce) are not available on clump master nodes", WDEM_ERR_UNSUPPORTED};
+        if (d.kind == 12) throw EngErr{"wdem_upload_imposes: InterpolatedMotion acts on the master nodes of facet groups only", WDEM_ERR_UNSUPPORTED};
+        d.nNodes++;
+      }
+      any = true;
+    }
+    h->clumps.impSet.ensure((size_t)h->clumps.n, h->bytes);
+    CK(cudaMemcpyAsync(h->clumps.impSet.p, clumpSet, (size_t)h->clumps.n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream));
+    h->clumps.anyImp = any;
   });
 }
 int wdem_get_impose_state(wdem_handle h, int32_t ix, double* out) {

@@ -181,6 +181,7 @@ struct Clumps {
   double4 *pos /*x,y,z,mass*/, *ori /*x,y,z,w*/, *vel, *angVel, *angMom, *force, *torque;
   const double4* inertia; const uint32_t* flags;
   const int* memStart; const int32_t* memId; const double4* relPos; const double4* relOri;
+  const int* impSet;      // per clump: set of impositions on the master node, -1 none; NULL when no clump carries one
 };
 
 // moving: the wall's node is in DemField.nodes (added with a nonzero velocity: Particle::guessMoving, Particle.cpp:638-640) and is translated by Leapfrog
@@ -397,7 +398,7 @@ __device__ __forceinline__ q4 dotQ(d3 w, q4 Q) {   // Leapfrog::DotQ (Leapfrog.c
   d.z = (-Q.y * w.x + Q.x * w.y + Q.w * w.z) / 2;
   return d;
 }
-__global__ void __launch_bounds__(128) k_clumps_step(Clumps K, Spheres S, const int* __restrict__ id2slot, StepU u, Counters* cnt) {
+__global__ void __launch_bounds__(128) k_clumps_step(Clumps K, Spheres S, const int* __restrict__ id2slot, StepU u, Counters* cnt, ImposeDev I) {
   if (*u.gIn) return;      // void step (k_leapfrog passes the flag on)
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= K.n) return;
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(128) k_clumps_step(Clumps K, Spheres S, const 
   const d3 inertia = xyz(in4); const double mass = p4.w, dt = u.dt;
   q4 ori; ori.x = o4.x; ori.y = o4.y; ori.z = o4.z; ori.w = o4.w;
   const int m0 = K.memStart[ci], m1 = K.memStart[ci + 1];
+  const int impSet = K.impSet ? K.impSet[ci] : -1;      // DemData.impose of the master node
   const bool blockedAll = (fl & F_DOF_ALL) == F_DOF_ALL, blockedNone = (fl & F_DOF_ALL) == 0, blockedAllRot = (fl & 56u) == 56u;
   const bool damp = (u.damping != 0. && !(fl & F_DAMPING_SKIP));
   if (!blockedAll) {
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(128) k_clumps_step(Clumps K, Spheres S, const 
         }
       }
     }
+    if (impSet >= 0) impose_velocity(I, impSet, vel, w, pos, &ori);      // Leapfrog.cpp:203-205
   }
   pos = pos + vel * dt;
   if (!useAspherical) {      // leapfrogSphericalRotate (Leapfrog.cpp:280-297)
@@ -484,7 +487,11 @@ __global__ void __launch_bounds__(128) k_clumps_step(Clumps K, Spheres S, const 
     w = quatRotate(ori, w_b_h);
     ori = quatNormalized(ori);
   }
-  if (u.reset) { f = (u.hasGravity && !(fl & F_GRAVITY_SKIP)) ? (mass * u.gravity) : mk3(0, 0, 0); t = mk3(0, 0, 0); }      // gravity acts on the master node, not on the members
+  if (u.reset) {      // gravity acts on the master node, not on the members; Impose::force on top (Leapfrog.cpp:240-245)
+    f = (u.hasGravity && !(fl & F_GRAVITY_SKIP)) ? (mass * u.gravity) : mk3(0, 0, 0); t = mk3(0, 0, 0);
+    if (impSet >= 0) impose_force(I, impSet, pos, f, t);
+  }
+  if (impSet >= 0) impose_velocity(I, impSet, vel, w, pos, &ori);      // Leapfrog.cpp:248, before applyToMembers (:252)
   K.pos[ci] = make_double4(pos.x, pos.y, pos.z, mass); K.ori[ci] = make_double4(ori.x, ori.y, ori.z, ori.w);
   K.vel[ci] = make_double4(vel.x, vel.y, vel.z, 0); K.angVel[ci] = make_double4(w.x, w.y, w.z, 0); K.angMom[ci] = make_double4(angMom.x, angMom.y, angMom.z, 0);
   K.force[ci] = make_double4(f.x, f.y, f.z, 0); K.torque[ci] = make_double4(t.x, t.y, t.z, 0);

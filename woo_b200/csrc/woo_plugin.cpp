@@ -280,7 +280,8 @@ struct GpuDemLoop : Engine {
     for (auto& p : sphereOf) { auto& imp = p->shape->nodes[0]->dem->impose; if (imp) { sid.push_back(p->id); sset.push_back(setFor(imp)); } }
     for (size_t i = 0; i < wallOf.size(); i++) { auto& imp = wallOf[i]->shape->nodes[0]->dem->impose; if (imp) { wset[i] = setFor(imp); anyWall = true; } }
     for (size_t g = 0; g < F.clumps.size(); g++) { auto& imp = F.clumps[g].master->dem->impose; if (imp) { gset[g] = setFor(imp); anyGroup = true; } }
-    for (auto& n : F.sphereClumps) if (n->dem->impose) throw std::runtime_error("GpuDemLoop: DemData.impose on a clump of spheres is not supported");
+    vector<int32_t> cset(F.sphereClumps.size(), -1); bool anyClump = false;
+    for (size_t c = 0; c < F.sphereClumps.size(); c++) { auto& imp = F.sphereClumps[c]->dem->impose; if (imp) { cset[c] = setFor(imp); anyClump = true; } }
     // facet nodes (py/triangulated.py:59-64: every node of a cylinder carries the same StableCircularOrbit); facets of a kinematic group follow their master node
     vector<int32_t> fset(facetOf.size(), -1); bool anyFacet = false;
     for (size_t i = 0; i < facetOf.size(); i++) {
@@ -290,6 +291,7 @@ struct GpuDemLoop : Engine {
     }
     if (imps.empty()) return;
     chk(h, wdem_upload_imposes(h, (int32_t)imps.size(), imps.data(), (int32_t)setStart.size() - 1, setStart.data(), setOps.data(), (int64_t)sid.size(), sid.data(), sset.data(), anyWall ? wset.data() : nullptr, anyGroup ? gset.data() : nullptr));
+    if (anyClump) chk(h, wdem_upload_clump_imposes(h, cset.data()));
     if (anyFacet) chk(h, wdem_upload_facet_imposes(h, fset.data()));
     facetNodesMove = anyFacet;
   }

@@ -149,6 +149,9 @@ class Engine:
         gset = None if S.group_impose is None else np.ascontiguousarray(S.group_impose, dtype=np.int32)
         self._chk(self.L.wdem_upload_imposes(self.h, C.c_int32(len(imps)), arr, C.c_int32(len(S.impose_sets)), ptr(start), ptr(ops), C.c_int64(len(sid) if sset is not None else 0),
                                              ptr(sid), ptr(sset), ptr(wset), ptr(gset)))
+        cset = getattr(S, "clump_impose", None)
+        if cset is not None:
+            self._chk(self.L.wdem_upload_clump_imposes(self.h, ptr(np.ascontiguousarray(cset, dtype=np.int32))))
         fset = getattr(S, "facet_impose", None)
         if fset is not None:
             self._chk(self.L.wdem_upload_facet_imposes(self.h, ptr(np.ascontiguousarray(fset, dtype=np.int32))))

@@ -71,6 +71,7 @@ class SceneSpec:
     wall_impose: object = None          # int array per wall
     group_impose: object = None         # int array per facet group
     facet_impose: object = None         # int array per facet: the set all three nodes of the facet carry
+    clump_impose: object = None         # int array per clump of spheres: the set on its master node
     clumps: list = field(default_factory=list)  # rigid aggregates of spheres with mass: dict(members=[sphere indices], pos, ori (x,y,z,w), vel, angVel, mass, inertia(3), flags); see make_clumps
     facet_groups: list = field(default_factory=list)  # kinematic groups: dict(pos, ori (x,y,z,w), vel, angVel, facets=[indices into ``facets``])
     params: Params = field(default_factory=Params)
@@ -196,7 +197,7 @@ def imp_interpolated_motion(times, poss, oris, t0=0.):
     return _imp(IMP_INTERPOLATED_MOTION, 0, [t0], (0, 0, 0, 1), times, poss, oris)
 
 
-def attach_impose(S, ops, spheres=(), walls=(), groups=(), facets=()):
+def attach_impose(S, ops, spheres=(), walls=(), groups=(), facets=(), clumps=()):
     """Put the impositions `ops` (descriptor dicts; several = CombinedImpose) on the given sphere / wall / facet-group indices."""
     ix = []
     for o in ops:
@@ -214,6 +215,9 @@ def attach_impose(S, ops, spheres=(), walls=(), groups=(), facets=()):
     if len(facets):
         if S.facet_impose is None: S.facet_impose = np.full(len(S.facets), -1, np.int32)
         S.facet_impose[np.asarray(facets, dtype=np.int64)] = k
+    if len(clumps):
+        if S.clump_impose is None: S.clump_impose = np.full(len(S.clumps), -1, np.int32)
+        S.clump_impose[np.asarray(clumps, dtype=np.int64)] = k
     return k
 
 
