@@ -8,8 +8,8 @@ scripts/make_cpu_sample.py with woo_b200.scenes.deposition seed 2) tiled 10x5 pe
 For N>1 it is ONE box N times as long, cut into N x-slabs (weak scaling): per step every rank refreshes the pos/vel/angVel of its ghosts
 and at collider full runs spheres migrate with their contact history (woo_b200/csrc/wdem_domain.cuh, DESIGN.md "Multi-GPU").
 value  = particle-steps/s with the state resident in HBM (CUDA events on the engine's stream, max over ranks).
-e2e    = same metric through the C-ABI with pinned HOST buffers: per step H2D of pos/vel/angVel, one step, D2H of pos/vel (+ids/angVel
-         when decomposed) and the kinetic energy.
+e2e    = same metric through the C-ABI with pinned HOST buffers: per step H2D of pos/vel/angVel (+ids when decomposed), one step, D2H of pos/vel
+         and the kinetic energy (wdem_step_e2e / wdem_step_e2e_owned).
 configs = the other BASELINE.json configs at their named sizes, a few seconds each, untimed by the headline: cfg1 (10k, with the CPU port on the SAME 10k),
          cfg3 (4M Hertz/DMT, STRONG-scaled over the N GPUs: the north-star target), cfg4 (periodic simple shear, 1M per GPU, ring-closed slabs), cfg5 (2M drum of facets).
 mgpu_parity (N>1) = before anything is timed, the real multi-process path (NCCL migration + CUDA-IPC peer mailboxes) reproduces a single-GPU engine bit for bit
@@ -432,29 +432,31 @@ def run_gpu(args):
         e1 = time.time()
         h2d, d2h = int(n * 72), int(n * 48 + 8)
     else:
-        # decomposed: every rank round-trips the spheres it owns, addressed by id (the owned set changes when spheres migrate)
-        o = D.owned(); m = len(o["ids"]); cap = int(m * 1.05) + 4096
-        buf = lambda w, dt=np.float64: torch.from_numpy(np.zeros((cap, w) if w > 1 else cap, dtype=dt)).pin_memory()
-        ii, pi_, vi, wi = buf(1, np.int32), buf(3), buf(3), buf(3)
-        io, po, vo, wo = buf(1, np.int32), buf(3), buf(3), buf(3)
-        ii.numpy()[:m] = o["ids"]; pi_.numpy()[:m] = o["pos"]; vi.numpy()[:m] = o["vel"]; wi.numpy()[:m] = o["angVel"]
+        # decomposed: every rank round-trips the spheres it owns, addressed by id, through wdem_step_e2e_owned (the chunk pipeline of the single-GPU path per subdomain;
+        # stats=False: the contact pass overlaps the next call's upload).  When spheres migrate the owned set changes and the rank fetches it again (wdem_download_owned).
+        def fresh():
+            o = D.owned(); m_ = len(o["ids"])
+            pinz = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return dict(m=m_, ids=pinz(o["ids"]), pos=pinz(o["pos"]), vel=pinz(o["vel"]), w=pinz(o["angVel"]), po=pinz(np.empty_like(o["pos"])), vo=pinz(np.empty_like(o["vel"])))
+        B = fresh()
 
-        bufs = [[ii, pi_, vi, wi], [io, po, vo, wo]]
-
-        def one(m):
-            a, b = bufs
-            m2, ek, _st = D.step_e2e(1, a[0].numpy()[:m], a[1].numpy()[:m], a[2].numpy()[:m], a[3].numpy()[:m], b[0].numpy(), b[1].numpy(), b[2].numpy(), b[3].numpy())
-            bufs.reverse()          # outputs become the next step's inputs (no host copy)
-            return m2
+        def one():
+            nonlocal B
+            ek, changed, _st = D.step_e2e_owned(B["ids"].numpy(), B["pos"].numpy(), B["vel"].numpy(), B["w"].numpy(), B["po"].numpy(), B["vo"].numpy(), stats=False)
+            if changed:
+                B = fresh()
+            else:
+                B["pos"], B["po"] = B["po"], B["pos"]; B["vel"], B["vo"] = B["vo"], B["vel"]      # outputs become the next step's inputs (no host copy)
         for _ in range(3):
-            m = one(m)
+            one()
         barrier()
         e0 = time.time()
         for _ in range(ke):
-            m = one(m)
+            one()
         barrier()
         e1 = time.time()
-        h2d, d2h = int(m * 76), int(m * 76 + 8)
+        m = B["m"]
+        h2d, d2h = int(m * 76), int(m * 48 + 8)
     e2e_s = e1 - e0
     ck = clocks.stop([(w0, w1), (e0, e1)])
     E.close()
@@ -499,7 +501,7 @@ def run_gpu(args):
                      "step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9, "frac": step_bytes / (stats["device_ms"] / K * 1e-3) / 1e9 / peak},
                      "phase_ms_per_step": {k: stats[k] / K for k in ("ms_integrate", "ms_rebuild", "ms_contact", "ms_reduce", "ms_dyndt")}},
         "e2e": {"value": ntot * ke / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
-                "api": "wdem_step_e2e (C-ABI, pinned host buffers, stats=NULL: a step's contact pass overlaps the next step's upload)" if D is None else "wdem_set_owned + wdem_step + wdem_download_owned per rank (C-ABI, pinned host buffers)"},
+                "api": "wdem_step_e2e (C-ABI, pinned host buffers, stats=NULL: a step's contact pass overlaps the next step's upload)" if D is None else "wdem_step_e2e_owned per rank (C-ABI, pinned host buffers, ids + pos/vel/angVel in, pos/vel out, stats=NULL)"},
         "gpu_launches": int(n_launch), "clocks": ck, "wall_ms_per_step": wall_ms / K,
     }
     if parity is not None:

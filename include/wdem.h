@@ -208,6 +208,12 @@ int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats);
 int wdem_step_e2e(wdem_handle h, int64_t nsteps, const double* pos_in, const double* vel_in, const double* angVel_in,
                   double* pos_out, double* vel_out, double* ek_out, wdem_stats* stats);
 
+/* The same for one subdomain of a decomposed run (also accepted by a single-domain engine): the host sends the state of the m spheres this handle OWNS, addressed by
+ * Particle.id in any order, and receives their new pos / vel in the same order.  m must equal wdem_num_owned.  *owned_changed != 0 (may be NULL): spheres migrated in
+ * this step's collider run; the outputs are still those of the spheres sent, the next call must send the new owned set (wdem_download_owned gives it). */
+int wdem_step_e2e_owned(wdem_handle h, int64_t m, const int32_t* ids, const double* pos_in, const double* vel_in, const double* angVel_in,
+                        double* pos_out, double* vel_out, double* ek_out, int32_t* owned_changed, wdem_stats* stats);
+
 /* Downloads, in upload order; any pointer may be NULL. */
 int wdem_download_state(wdem_handle h, double* pos, double* ori, double* vel, double* angVel);
 int wdem_download_forces(wdem_handle h, double* force, double* torque);

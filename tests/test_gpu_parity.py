@@ -308,6 +308,48 @@ def test_step_e2e_pipelined_matches_resident_and_oracle(n, stats, monkeypatch):
     assert np.array_equal(po, A.spheres()["pos"]) and abs(ek2 - A.kinetic_energy()) <= 1e-13 * abs(ek2)
 
 
+@pytest.mark.parametrize("stats", [True, False])
+def test_step_e2e_owned_matches_resident_decomposed_run(stats):
+    """wdem_step_e2e_owned: every subdomain round-trips the spheres it owns (by id) through host buffers each step; results equal the resident run of the same
+    decomposition — and so the oracle — bit for bit, across collider runs and migrations (the host then fetches the new owned set)."""
+    import threading
+    from woo_b200.domain import LocalCluster, _owned
+    S = sc.random_gas(600, box=.5, r=.02, psd_ratio=3.0, seed=141)
+    O = Oracle(S); A = LocalCluster(S, 2, axis=0)
+    A.step(30); O.step(30)
+    bufs = []
+    for E in A.E:
+        o = _owned(E); bufs.append(dict(ids=o["ids"].copy(), pos=o["pos"].copy(), vel=o["vel"].copy(), w=o["angVel"].copy(), po=np.empty_like(o["pos"]), vo=np.empty_like(o["vel"])))
+    refreshed = 0
+    for k in range(60):
+        res = [None, None]
+
+        def run(r):
+            b = bufs[r]; res[r] = A.E[r].step_e2e_owned(b["ids"], b["pos"], b["vel"], b["w"], b["po"], b["vo"], stats=stats)
+        th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+        [t.start() for t in th]; [t.join() for t in th]
+        O.step(1)
+        so = O.spheres()
+        for r, E in enumerate(A.E):
+            b = bufs[r]
+            assert np.array_equal(b["po"], so["pos"][b["ids"]]) and np.array_equal(b["vo"], so["vel"][b["ids"]]), f"outputs of subdomain {r} differ from the oracle at step {k}"
+            if res[r][1]:      # spheres migrated: fetch the new owned set
+                o = _owned(E); refreshed += 1
+                bufs[r] = dict(ids=o["ids"].copy(), pos=o["pos"].copy(), vel=o["vel"].copy(), w=o["angVel"].copy(), po=np.empty_like(o["pos"]), vo=np.empty_like(o["vel"]))
+            else:
+                b["pos"], b["po"] = b["po"], b["pos"]; b["vel"], b["vo"] = b["vo"], b["vel"]
+                b["w"] = so["angVel"][b["ids"]].copy()          # angVel is an input only
+    assert refreshed > 0, "the test did not see a migration"
+    sg = A.spheres()
+    for k_ in ("pos", "vel", "angVel", "force", "torque"):
+        assert np.array_equal(O.spheres()[k_], sg[k_]), k_
+    assert O.nFullRuns == A.scalars()["nFullRuns"]
+    from woo_b200.engine import WdemError
+    b = bufs[0]
+    with pytest.raises(WdemError):
+        A.E[0].step_e2e_owned(b["ids"][:-1], b["pos"][:-1], b["vel"][:-1], b["w"][:-1], b["po"][:-1], b["vo"][:-1])      # not the whole owned set
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # wdem_upload_contacts / wdem_set_scene (SURVEY §8b, §8f-2): a run resumed from downloaded state + contact history continues bit for bit.
 # The candidate set of the resumed engine differs (its collider runs at other steps), which must not matter: real contacts, their history and the

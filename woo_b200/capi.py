@@ -35,7 +35,7 @@ class WdemStats(C.Structure):
 
 EXPORTS = ["wdem_default_config", "wdem_create", "wdem_destroy", "wdem_last_error", "wdem_set_config", "wdem_set_profiling",
            "wdem_upload_materials", "wdem_upload_spheres", "wdem_add_spheres", "wdem_remove_spheres", "wdem_upload_forces", "wdem_upload_walls", "wdem_upload_facets", "wdem_set_cell",
-           "wdem_set_next_gradv", "wdem_get_cell", "wdem_step", "wdem_step_e2e", "wdem_set_periodic_state", "wdem_get_periodic_state", "wdem_download_state", "wdem_download_forces",
+           "wdem_set_next_gradv", "wdem_get_cell", "wdem_step", "wdem_step_e2e", "wdem_step_e2e_owned", "wdem_set_periodic_state", "wdem_get_periodic_state", "wdem_download_state", "wdem_download_forces",
            "wdem_set_state", "wdem_num_contacts", "wdem_download_contacts", "wdem_upload_contacts", "wdem_set_scene", "wdem_get_stress", "wdem_download_walls", "wdem_track_energy", "wdem_get_energy", "wdem_get_gradv_work", "wdem_upload_facet_groups", "wdem_download_facets", "wdem_upload_clumps", "wdem_download_clumps", "wdem_num_clumps", "wdem_upload_clump_forces", "wdem_upload_imposes", "wdem_upload_facet_imposes", "wdem_upload_clump_imposes", "wdem_get_impose_state", "wdem_download_boundary_velocities", "wdem_crit_dt", "wdem_kinetic_energy", "wdem_get_scalars",
            "wdem_device_info", "wdem_comm_unique_id", "wdem_comm_init_nccl", "wdem_local_group_create", "wdem_local_group_destroy",
            "wdem_comm_init_local", "wdem_set_domain", "wdem_set_rebalance", "wdem_get_domain", "wdem_num_owned", "wdem_download_owned", "wdem_set_owned", "wdem_domain_stats", "wdem_peer_active"]

@@ -243,6 +243,16 @@ __global__ void __launch_bounds__(256) k_dom_mark_removed(const int32_t* __restr
   if (!(flags[s] & F_GHOST)) atomicAdd(nOwnedGone, 1);
   flags[s] |= F_GHOST;
 }
+// wdem_step_e2e_owned: slots of the ids the host sent (its order); an id this subdomain does not own counts as a miss and maps to slot 0 of a ghost-safe no-op
+__global__ void __launch_bounds__(256) k_owned_slots(const int32_t* __restrict__ ids, int m, const int* __restrict__ id2slot, long long cap, int n, const uint32_t* __restrict__ flags,
+                                                     int* __restrict__ slots, int* miss) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int id = ids[k]; int s = -1;
+  if (id >= 0 && id < cap) { s = id2slot[id]; if (s < 0 || s >= n || (flags[s] & F_GHOST)) s = -1; }
+  if (s < 0) atomicAdd(miss, 1);
+  slots[k] = s;
+}
 // appended spheres are addressable by id at once (a later add / remove in the same breath must see them)
 __global__ void __launch_bounds__(256) k_dom_map_appended(const int32_t* __restrict__ sid, int first, int cnt, int* id2slot) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -210,9 +210,9 @@ struct wdem_engine {
   bool trackEnergy = false; DBuf<double> dEnergy;   // Scene.trackEnergy: EN_* accumulators on the device
   // end-to-end pipeline (wdem_step_e2e): host<->device copies of the state overlap with the integrator chunk by chunk
   static const int NCHUNK = 16; int nChunk = 8;   // NCHUNK = capacity, nChunk = pieces in use (WDEM_E2E_CHUNKS)
-  struct E2E { bool active = false; bool defer = false; bool ioBusy = false; const double *pos = nullptr, *vel = nullptr, *angVel = nullptr; double *posOut = nullptr, *velOut = nullptr; } e2e;
+  struct E2E { bool active = false; bool defer = false; bool ioBusy = false; long long count = 0; const int* slotMap = nullptr; const double *pos = nullptr, *vel = nullptr, *angVel = nullptr; double *posOut = nullptr, *velOut = nullptr; } e2e;
   cudaStream_t sH2D = nullptr, sD2H = nullptr; cudaEvent_t evUp[NCHUNK] = {}, evLf[NCHUNK] = {}, evEk = nullptr;
-  int lastLfChunk = 0;
+  int lastLfChunk = 0; DBuf<int> ownedSlot; DBuf<int32_t> ownedIds;      // wdem_step_e2e_owned: slots of the ids the host sent, in its order
   DBuf<double> ioIn, ioOut; double* hEk = nullptr; size_t hEkCap = 0; int ekBlocks = 0;
   Spheres S() { Spheres v = sph[cur].view(); v.clumpOfId = clumps.n ? clumps.clumpOfId.p : nullptr; v.impOfId = impSpheres ? dImpOfId.p : nullptr; return v; }
 };
@@ -1159,7 +1159,7 @@ void launchContactsAndReduce(wdem_engine* E, const StepU& u, const int* guard, c
 // (k_leapfrog_io, upload order) and its new pos/vel start their way back on a second copy stream while later pieces are still being uploaded
 // and, after the last piece, while the contact kernels run.  PCIe is full duplex, so the step costs about max(H2D, D2H) + contacts.
 void leapfrogPipelined(wdem_engine* E, const StepU& u) {
-  const long long n = E->n; cudaStream_t st = E->stream;
+  const long long n = E->e2e.count; cudaStream_t st = E->stream;      // spheres the host sends: all of them, or the subdomain's owned ones (wdem_step_e2e_owned)
   const wdem_engine::E2E& io = E->e2e;
   double* in = E->ioIn.p; double* out = E->ioOut.p;
   LeapIO lio{in, in + 3 * n, in + 6 * n, out, out + 3 * n};
@@ -1182,8 +1182,8 @@ void leapfrogPipelined(wdem_engine* E, const StepU& u) {
     const long long first = c * per, cnt = std::min(per, n - first);
     if (cnt <= 0) break;
     CK(cudaStreamWaitEvent(st, E->evUp[c], 0));
-    if (u.energy) k_leapfrog_io<true><<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->up2slot.p, first, cnt, lio);
-    else k_leapfrog_io<false><<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->up2slot.p, first, cnt, lio);
+    if (u.energy) k_leapfrog_io<true><<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->e2e.slotMap, first, cnt, lio);
+    else k_leapfrog_io<false><<<nblk(cnt, 256), 256, 0, st>>>(E->S(), u, E->dCnt, E->e2e.slotMap, first, cnt, lio);
     E->launches++;
     CK(cudaEventRecord(E->evLf[c], st)); E->lastLfChunk = c; E->e2e.ioBusy = true;
     CK(cudaStreamWaitEvent(E->sD2H, E->evLf[c], 0));
@@ -1191,9 +1191,9 @@ void leapfrogPipelined(wdem_engine* E, const StepU& u) {
     if (io.velOut) CK(cudaMemcpyAsync(io.velOut + 3 * first, out + 3 * n + 3 * first, cnt * 24, cudaMemcpyDeviceToHost, E->sD2H));
   }
   // kinetic energy of the new state (velocities are final after Leapfrog): block sums, summed by the host in a fixed order
-  const int nb = nblk(n, 256); E->blk.ensure((size_t)nb * 7, E->bytes); E->ekBlocks = nb;
+  const int nb = nblk(E->n, 256); E->blk.ensure((size_t)nb * 7, E->bytes); E->ekBlocks = nb;
   if ((size_t)nb > E->hEkCap) { if (E->hEk) cudaFreeHost(E->hEk); CK(cudaMallocHost(&E->hEk, (size_t)nb * sizeof(double))); E->hEkCap = nb; }
-  k_ekin<<<nb, 256, 0, st>>>(E->S(), (int)n, u, E->blk.p); E->launches++;
+  k_ekin<<<nb, 256, 0, st>>>(E->S(), E->n, u, E->blk.p); E->launches++;      // owned spheres only (ghosts are skipped)
   CK(cudaEventRecord(E->evEk, st)); CK(cudaStreamWaitEvent(E->sD2H, E->evEk, 0));
   CK(cudaMemcpyAsync(E->hEk, E->blk.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, E->sD2H));
 }
@@ -2219,6 +2219,41 @@ static void stepN(wdem_handle h, int64_t nsteps, wdem_stats* stats, bool cheapSt
 }
 int wdem_step(wdem_handle h, int64_t nsteps, wdem_stats* stats) { return guarded(h, [&] { stepN(h, nsteps, stats, false); }); }
 
+// End-to-end step of one subdomain (or of a single-domain engine addressed by id): the host sends the state of the spheres it owns BY ID, in any order, and gets the new
+// pos / vel back in the same order.  Same pipeline as wdem_step_e2e (chunked upload -> integrate -> download, contact pass overlapping the download and, with
+// stats == NULL, the next call's upload); the ids are turned into slots on the device first.  *owned_changed != 0: spheres migrated in this step's collider run - the
+// outputs are still those of the spheres sent, but the next call must send the new owned set (wdem_download_owned).
+int wdem_step_e2e_owned(wdem_handle h, int64_t m, const int32_t* ids, const double* pos_in, const double* vel_in, const double* angVel_in, double* pos_out, double* vel_out,
+                        double* ek_out, int32_t* owned_changed, wdem_stats* stats) {
+  return guarded(h, [&] {
+    if (m <= 0 || !ids || !pos_in || !vel_in || !angVel_in) throw EngErr{"wdem_step_e2e_owned: bad arguments", WDEM_ERR_INVALID};
+    if (h->conDirty) throw EngErr{"wdem_step_e2e_owned: step at least once first (ownership is settled by the first collider run)", WDEM_ERR_INVALID};
+    const long long nOwn0 = h->comm ? h->dom.nOwn : h->n;
+    if (m != nOwn0) throw EngErr{"wdem_step_e2e_owned: " + std::to_string(m) + " spheres sent, " + std::to_string(nOwn0) + " owned", WDEM_ERR_INVALID};
+    if (!h->imposes.empty() || h->clumps.n) throw EngErr{"wdem_step_e2e_owned: Impose and clumps are not available on the end-to-end path", WDEM_ERR_UNSUPPORTED};
+    cudaStream_t st = h->stream;
+    const long long mig0 = h->dom.migratedOut + h->dom.migratedIn;
+    h->ownedIds.ensure((size_t)m, h->bytes); h->ownedSlot.ensure((size_t)m, h->bytes); h->orphCnt.ensure(1, h->bytes);
+    h->ioIn.ensure(9 * (size_t)m, h->bytes); h->ioOut.ensure(6 * (size_t)m, h->bytes);
+    // the main stream has to wait for nothing here but its own past; ids -> slots (+ are they all owned?) before the first chunk is integrated
+    CK(cudaMemcpyAsync(h->ownedIds.p, ids, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->orphCnt.p, 0, sizeof(int), st));
+    k_owned_slots<<<nblk(m, 256), 256, 0, st>>>(h->ownedIds.p, (int)m, h->id2slot.p, (long long)h->id2slot.cap, h->n, h->S().flags, h->ownedSlot.p, h->orphCnt.p); h->launches++;
+    int* hMiss = h->hScratch + 12; *hMiss = 0;
+    CK(cudaMemcpyAsync(hMiss, h->orphCnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    h->e2e.defer = !stats && !h->profiling && !getenv("WDEM_E2E_NO_DEFER");
+    h->e2e.count = m; h->e2e.slotMap = h->ownedSlot.p;
+    h->e2e.active = true; h->e2e.pos = pos_in; h->e2e.vel = vel_in; h->e2e.angVel = angVel_in; h->e2e.posOut = pos_out; h->e2e.velOut = vel_out;
+    try { stepN(h, 1, stats, true); } catch (...) { h->e2e.active = false; cudaStreamSynchronize(h->sH2D); cudaStreamSynchronize(h->sD2H); throw; }
+    h->e2e.active = false;
+    CK(cudaEventRecord(h->evEk, h->sD2H));
+    CK(cudaStreamSynchronize(h->sD2H));
+    if (*hMiss) throw EngErr{"wdem_step_e2e_owned: " + std::to_string(*hMiss) + " of the ids sent are not owned by this subdomain (the state is not usable any more)", WDEM_ERR_INVALID};
+    if (ek_out) { double e = 0; for (int b = 0; b < h->ekBlocks; b++) e += h->hEk[b]; *ek_out = e; }
+    if (owned_changed) *owned_changed = (h->dom.migratedOut + h->dom.migratedIn != mig0 || (h->comm ? h->dom.nOwn : h->n) != nOwn0) ? 1 : 0;
+  });
+}
+
 int wdem_set_state(wdem_handle h, int64_t first, int64_t cnt, const double* pos, const double* vel, const double* angVel) {
   return guarded(h, [&] {
     if (h->comm) throw EngErr{"wdem_set_state: not available in decomposed runs (spheres migrate between subdomains)", WDEM_ERR_UNSUPPORTED};
@@ -2344,6 +2379,7 @@ int wdem_step_e2e(wdem_handle h, int64_t nsteps, const double* pos_in, const dou
       ensureUp2Slot(h);
       h->ioIn.ensure(9 * n, h->bytes); h->ioOut.ensure(6 * n, h->bytes);
       h->e2e.defer = !stats && !h->profiling && !getenv("WDEM_E2E_NO_DEFER");
+      h->e2e.count = (long long)n; h->e2e.slotMap = h->up2slot.p;
       h->e2e.active = true; h->e2e.pos = pos_in; h->e2e.vel = vel_in; h->e2e.angVel = angVel_in; h->e2e.posOut = pos_out; h->e2e.velOut = vel_out;
       try { stepN(h, 1, stats, true); } catch (...) { h->e2e.active = false; cudaStreamSynchronize(h->sH2D); cudaStreamSynchronize(h->sD2H); throw; }
       h->e2e.active = false;

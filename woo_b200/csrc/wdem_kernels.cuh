@@ -539,7 +539,9 @@ __global__ void __launch_bounds__(256, 4) k_leapfrog_io(Spheres S, StepU u, Coun
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (*u.gIn) { if (first + t == 0) *u.gOut = 1; return; }
   if (t >= cnt_) return;
-  leapfrog_body<true, TRACK>(S, up2slot[first + t], u, cnt, io, first + t);
+  const int slot = up2slot[first + t];
+  if (slot < 0) return;      // an id the subdomain does not own (wdem_step_e2e_owned counts and reports it)
+  leapfrog_body<true, TRACK>(S, slot, u, cnt, io, first + t);
 }
 
 // ClumpData::applyToMembers (Clump.cpp:293-307) for facets of kinematic groups, after the host has integrated the groups' master nodes: node position

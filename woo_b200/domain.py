@@ -264,5 +264,9 @@ class DistributedEngine:
                 self.rank, (t1 - t0) * 1e3, (t2 - t1) * 1e3, st.device_ms, st.n_rebuilds, (t3 - t2) * 1e3, (time.perf_counter() - t3) * 1e3), file=sys.stderr, flush=True)
         return m, ek, st
 
+    def step_e2e_owned(self, ids, pos, vel, angVel, pos_out, vel_out, stats=False):
+        """The pipelined end-to-end step of this subdomain (wdem_step_e2e_owned): state of the owned spheres by id in, new pos / vel in the same order out."""
+        return self.E.step_e2e_owned(ids, pos, vel, angVel, pos_out, vel_out, stats=stats)
+
     def domain_stats(self):
         return _domain_stats(self.E)

@@ -227,6 +227,13 @@ class Engine:
         self.stats = st
         return ek.value, st
 
+    def step_e2e_owned(self, ids, pos, vel, angVel, pos_out, vel_out, stats=False):
+        """wdem_step_e2e_owned: one end-to-end step of the spheres this handle owns, addressed by id; returns (Ek, owned_changed, stats)."""
+        st = WdemStats() if stats else None; ek = C.c_double(); ch = C.c_int32()
+        self._chk(self.L.wdem_step_e2e_owned(self.h, C.c_int64(len(ids)), ptr(ids), ptr(pos), ptr(vel), ptr(angVel), ptr(pos_out), ptr(vel_out), C.byref(ek), C.byref(ch),
+                                             C.byref(st) if stats else None))
+        return ek.value, bool(ch.value), st
+
     # ---- downloads
     def spheres(self):
         n = self.n
