@@ -355,6 +355,7 @@ void rebalanceCuts(wdem_engine* E) {
   if (!E->cfg.periodic) {      // global extent along the axis: the boxes measured at the last full run (a superset is fine; what lies outside falls into the end bins)
     const double* hb = E->hBounds + 8 * (int)((E->nFullRuns + 1) & 1);
     double mine[2] = {hb[M.axis], hb[3 + M.axis]}; int64_t mi[2], all[2 * WDEM_MAX_RANKS];
+    if (!E->boundsValid) { mine[0] = INFINITY; mine[1] = -INFINITY; }      // no box measured here yet (e.g. nothing owned so far): an empty interval
     memcpy(mi, mine, sizeof(mine));
     T->allgather64(mi, 2, all, st);
     lo = INFINITY; hi = -INFINITY;
@@ -411,7 +412,7 @@ void domainExchange(wdem_engine* E) {
     CK(cudaMemsetAsync(dMineF, 0, 2 * WDEM_MAX_RANKS * sizeof(int), st));
     if (n > 0) { k_dom_fast_scan<<<nblk(n, 256), 256, 0, st>>>(A, n, D, M.emask.p, dMineF); E->launches++; }
     if (!(M.nOwn > 0 && n == M.nOwn + (int)M.nRecvTot)) { k_fill_int<<<1, 1, 0, st>>>(dMineF + 1 + W, 1, 1); E->launches++; }      // my veto (e.g. nothing owned here)
-    const bool rebalDue = M.rebalTol > 0. && (c.periodic || E->boundsValid) && (E->nFullRuns - M.lastRebalRun) >= M.rebalMinRuns;
+    const bool rebalDue = M.rebalTol > 0. && (E->nFullRuns - M.lastRebalRun) >= M.rebalMinRuns;      // the same on every rank (no per-rank state in this condition: what follows is collective)
     if (rebalDue) { k_fill_int<<<1, 1, 0, st>>>(dMineF + 2 + W, 1, M.nOwn); E->launches++; }      // how many spheres I own: everybody sees the imbalance in the same table
     T->allgatherDev(dMineF, dAllF, (size_t)2 * WDEM_MAX_RANKS * sizeof(int), st);
     std::vector<int> fa((size_t)W * 2 * WDEM_MAX_RANKS, 0);
