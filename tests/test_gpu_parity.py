@@ -308,6 +308,30 @@ def test_step_e2e_pipelined_matches_resident_and_oracle(n, stats, monkeypatch):
     assert np.array_equal(po, A.spheres()["pos"]) and abs(ek2 - A.kinetic_energy()) <= 1e-13 * abs(ek2)
 
 
+def test_step_e2e_owned_on_a_single_domain_engine_in_any_id_order():
+    """wdem_step_e2e_owned also serves a single-domain engine: the state travels by Particle.id, here in a scrambled order; outputs come back in that order."""
+    S = sc.random_gas(500, box=.5, r=.02, psd_ratio=2.0, seed=151)
+    A = engine_for(S); B = engine_for(S)
+    A.step(40); B.step(40)
+    ids = S.sphere_ids().astype(np.int32); perm = np.random.default_rng(5).permutation(len(ids)); ids_p = np.ascontiguousarray(ids[perm])
+    s = B.spheres(); pos, vel, w = (np.ascontiguousarray(s[k][perm]) for k in ("pos", "vel", "angVel"))
+    po, vo = np.empty_like(pos), np.empty_like(vel)
+    for k in range(30):
+        ek, changed, _ = B.step_e2e_owned(ids_p, pos, vel, w, po, vo, stats=(k % 2 == 0))
+        A.step(1); sa = A.spheres()
+        assert not changed and np.array_equal(po, sa["pos"][perm]) and np.array_equal(vo, sa["vel"][perm]), f"step {k}"
+        assert abs(ek - A.kinetic_energy()) <= 1e-13 * abs(ek)
+        pos, po = po, pos; vel, vo = vo, vel
+        w = np.ascontiguousarray(sa["angVel"][perm])
+    sb = B.spheres()
+    for k_ in ("pos", "vel", "angVel", "force", "torque"):
+        assert np.array_equal(A.spheres()[k_], sb[k_]), k_
+    from woo_b200.engine import WdemError
+    bad = ids_p.copy(); bad[3] = 10 ** 6
+    with pytest.raises(WdemError):
+        B.step_e2e_owned(bad, pos, vel, w, po, vo)
+
+
 @pytest.mark.parametrize("stats", [True, False])
 def test_step_e2e_owned_matches_resident_decomposed_run(stats):
     """wdem_step_e2e_owned: every subdomain round-trips the spheres it owns (by id) through host buffers each step; results equal the resident run of the same
