@@ -33,19 +33,32 @@ struct CudaErr { std::string msg; int code; };
   } while (0)
 struct EngErr { std::string msg; int code; };
 
+// Growth of the device buffers is stream-ordered (cudaMallocAsync / cudaFreeAsync on the engine's stream, from the device's default pool, whose release threshold
+// wdem_create raises so that freed blocks stay in the pool): while a bed forms, the contact tables of a small scene outgrow their capacity dozens of times, and
+// cudaMalloc + cudaFree (a device-wide synchronisation each) made such a collider run cost 1 ms instead of 0.26 ms (10k spheres).  Everything the engine does with a
+// buffer is ordered on that one stream (side streams are joined before a full run; the end-to-end staging buffers grow only between calls), so freeing in stream order
+// is safe.  Buffers handed to NCCL stay with cudaMalloc (`plain`).
+thread_local cudaStream_t g_allocStream = nullptr;      // the stream of the handle whose entry point is running (guarded())
+static const bool g_noPool = getenv("WDEM_NO_POOL") != nullptr;
 template <class T>
 struct DBuf {  // growable device buffer
-  T* p = nullptr; size_t cap = 0;
+  T* p = nullptr; size_t cap = 0; bool plain = false, pooled = false;
   void ensure(size_t n, int64_t& total, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return;
     size_t ncap = std::max(n, cap + cap / 2);
     T* q = nullptr;
-    CK(cudaMalloc(&q, ncap * sizeof(T)));
-    if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
-    if (p) { CK(cudaStreamSynchronize(st)); CK(cudaFree(p)); total -= (int64_t)(cap * sizeof(T)); }
-    p = q; cap = ncap; total += (int64_t)(ncap * sizeof(T));
+    cudaStream_t s = st ? st : g_allocStream;
+    const bool pool = !plain && !g_noPool && s != nullptr;
+    if (pool) CK(cudaMallocAsync(&q, ncap * sizeof(T), s)); else CK(cudaMalloc(&q, ncap * sizeof(T)));
+    if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s ? s : st));
+    if (p) {
+      if (pooled && s) CK(cudaFreeAsync(p, s));
+      else { CK(cudaStreamSynchronize(s ? s : st)); CK(cudaFree(p)); }
+      total -= (int64_t)(cap * sizeof(T));
+    }
+    p = q; cap = ncap; pooled = pool; total += (int64_t)(ncap * sizeof(T));
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; pooled = false; }
 };
 
 struct SphereStore {
@@ -153,6 +166,7 @@ struct DomainState {
   double rebalTol = 0.; int rebalMinRuns = 1; long long lastRebalRun = -1, nRebalances = 0; DBuf<int> hist;
   int deadSlots = 0;      // slots of the current generation flagged F_DEADSLOT (domainExchange's in-place path), cut off by the collider run that follows
   struct Peer { bool active = false, disabled = false; unsigned long long syncSeq = 0; char* box = nullptr; long long haloCap = 0; void* base[WDEM_MAX_RANKS] = {}; std::vector<long long> dstOff; long long maxRecvTot = 0; } peer;
+  DomainState() { sendBuf.plain = true; recvBuf.plain = true; perRank.plain = true; haloSend.plain = true; haloRecv.plain = true; }      // handed to NCCL / read by peers: plain cudaMalloc
   void release() {
     sendSlot.release(); recvSlot.release(); exportId.release(); importId.release(); oldIds.release(); haloSend.release(); haloRecv.release(); dkeys.release(); dkeysAlt.release();
     emask.release(); dslots.release(); dslotsAlt.release(); dstart.release(); origSlot.release(); perm2.release(); rowCnt.release(); rowOff.release(); perRank.release();
@@ -1508,6 +1522,7 @@ int guarded(wdem_handle h, F&& f) {
   if (!h) return WDEM_ERR_INVALID;
   try {
     if (cudaSetDevice(h->cfg.device) != cudaSuccess) { h->err = "cudaSetDevice failed (no usable CUDA device; this engine has no CPU fallback)"; return WDEM_ERR_CUDA; }
+    g_allocStream = h->stream;
     f();
     return WDEM_OK;
   } catch (CudaErr& e) { h->err = e.msg; if (h->comm) h->comm->abort(); return e.code; }
@@ -1584,6 +1599,9 @@ int wdem_create(const wdem_config* cfg, wdem_handle* out) {
     CK(cudaEventCreate(&E->ev0)); CK(cudaEventCreate(&E->ev1));
     CK(cudaEventCreateWithFlags(&E->evFlag, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&E->evFork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&E->evJoin, cudaEventDisableTiming));
     for (auto& set : E->evr) for (auto& e : set) CK(cudaEventCreate(&e));
+    {   // freed blocks stay in the device's pool instead of going back to the driver at the next synchronisation
+      cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) { unsigned long long keepAll = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keepAll); } else cudaGetLastError();
+    }
     CK(cudaMalloc(&E->dCnt, sizeof(Counters))); CK(cudaMemset(E->dCnt, 0, sizeof(Counters)));
     CK(cudaMallocHost(&E->hCnt, sizeof(Counters))); memset(E->hCnt, 0, sizeof(Counters));
     CK(cudaMallocHost(&E->hScratch, 256 * sizeof(int))); memset(E->hScratch, 0, 256 * sizeof(int));
