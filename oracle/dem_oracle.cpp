@@ -1465,7 +1465,14 @@ struct Scene {
     }
     for (Wall& w : walls) {
       if (!w.moving) continue;
-      if (P.periodic) throw std::runtime_error("moving walls in a periodic cell are not supported");
+      if (P.periodic) {      // a fully blocked node in a deforming cell (Leapfrog.cpp:206-215 fixed branch, applyPeriodicCorrections :258-273), no acceleration
+        if (w.impose >= 0) throw std::runtime_error("impositions on walls in a periodic cell are not supported");
+        if (homoDeform == HOMO_GRADV2) w.vel = mulMV(ImLL4hInv, mulMV(LmL, w.pos) + mulMV(IpLL4h, w.vel));
+        else if (homoDeform == HOMO_VEL || homoDeform == HOMO_VEL_2ND) {
+          if (homoDeform == HOMO_VEL_2ND) w.vel += mulMV(midGradV, w.vel - (dt / 2.) * V3()) * dt;
+          w.vel += mulMV(dGradV, w.pos);
+        } else if (homoDeform == HOMO_POS) w.pos += mulMV(cell.nextGradV, w.pos) * dt;
+      }
       w.pos += w.vel * dt;
       if (P.reset) { w.force = V3(); w.torque = V3(); }
       if (w.impose >= 0) { V3 dummyW; imposeVelocity(w.impose, w.vel, dummyW, w.pos); }      // fully blocked node: only the call at the end of the node's step (Leapfrog.cpp:248)

@@ -1,2 +1,2 @@
-T=${1:-r02s43}
-timeout 500 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 5 python -m pytest tests/test_gpu_parity.py tests/test_gpu_impose.py tests/test_gpu_clumps.py -m gpu -q -x -k "add_and_remove_spheres and gas or rebalance and gas or orbit or e2e_owned_on_a_single or impositions_on_clump or interpolated" > gpurun_out/${T}_sanitizer.log 2>&1; echo "exit $?"; tail -15 gpurun_out/${T}_sanitizer.log | cut -c1-300
+T=${1:-r02s48}
+python -m pytest tests/test_gpu_parity.py -m gpu -q -k "periodic_with or moving_wall" > gpurun_out/${T}_pytest.log 2>&1; tail -30 gpurun_out/${T}_pytest.log | cut -c1-400

@@ -150,6 +150,20 @@ def test_periodic_preskewed_compression():
     compare_potential(O, E)
 
 
+@pytest.mark.parametrize("homo", [sc.HOMO_POS, sc.HOMO_VEL, sc.HOMO_VEL_2ND, sc.HOMO_GRADV2])
+def test_periodic_with_moving_walls_in_a_deforming_cell(homo):
+    """Walls with a velocity are in DemField.nodes; in a periodic cell Leapfrog's fixed-node branch also applies the cell's velocity / position corrections to them
+    (Leapfrog.cpp:206-215,258-273).  A piston closing on a gas in a laterally compressed (non-skewed) cell, every homoDeform mode."""
+    S = sc.periodic_gas(300, cell=(.4, .4, .5), r=.02, psd_ratio=2.0, seed=23, walls=True, gradV=[[-.8, 0, 0], [0, -.5, 0], [0, 0, 0]], homoDeform=homo)
+    S.walls[1]["vel"] = (0., 0., -1.5); S.walls[0]["vel"] = (0., 0., .4)
+    S.finalize()
+    O, E = compare(S, 200, check_every=25, label=f"peri moving walls homoDeform={homo}")
+    compare_potential(O, E)
+    wo, wg = O.walls(), E.walls()
+    assert np.array_equal(wo["pos"], wg["pos"]) and wg["pos"][1, 2] < S.walls[1]["pos"][2] - .01
+    assert (O.contacts(True)["ids"][:, 0] >= S.n).sum() > 3, "no wall contacts"
+
+
 def test_periodic_with_walls():
     S = sc.periodic_gas(300, cell=(.4, .4, .5), r=.02, psd_ratio=2.0, seed=19, walls=True)
     S.params.gravity = (0, 0, -9.81)

@@ -599,7 +599,16 @@ __global__ void k_walls_step(Wall* walls, int n, StepU u, Counters* cnt, int set
   Wall W = walls[w];
   if (setLast) { for (int k = 0; k < 3; k++) walls[w].lastPos[k] = W.pos[k]; return; }
   if (!W.moving || *u.gIn) return;
-  d3 pos = mk3(W.pos[0], W.pos[1], W.pos[2]) + mk3(W.vel[0], W.vel[1], W.vel[2]) * u.dt;
+  d3 pos = mk3(W.pos[0], W.pos[1], W.pos[2]), vel = mk3(W.vel[0], W.vel[1], W.vel[2]);
+  if (u.periodic) {      // a fully blocked node in a deforming cell: Leapfrog's fixed branch corrects its velocity / position like any node's (Leapfrog.cpp:206-215,258-273)
+    if (u.homoDeform == 4) vel = mulMV(u.ImLL4hInv, mulMV(u.LmL, pos) + mulMV(u.IpLL4h, vel));
+    else if (u.homoDeform == 2 || u.homoDeform == 3) {
+      if (u.homoDeform == 3) vel = vel + mulMV(u.midGradV, vel - (u.dt / 2.) * mk3(0, 0, 0)) * u.dt;
+      vel = vel + mulMV(u.dGradV, pos);
+    } else if (u.homoDeform == 1) pos = pos + mulMV(u.nextGradV, pos) * u.dt;
+    walls[w].vel[0] = vel.x; walls[w].vel[1] = vel.y; walls[w].vel[2] = vel.z;
+  }
+  pos = pos + vel * u.dt;
   walls[w].pos[0] = pos.x; walls[w].pos[1] = pos.y; walls[w].pos[2] = pos.z;
   if (imp && w < 32 && imp->wallHas[w]) for (int k = 0; k < 3; k++) walls[w].vel[k] = imp->wallVel[3 * w + k];      // Impose::velocity at the end of the node's step (Leapfrog.cpp:248)
   const d3 dl = mk3(W.lastPos[0], W.lastPos[1], W.lastPos[2]) - pos;
