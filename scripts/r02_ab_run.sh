@@ -1,2 +1,3 @@
-T=${1:-r02s48}
-python -m pytest tests/test_gpu_parity.py -m gpu -q -k "periodic_with or moving_wall" > gpurun_out/${T}_pytest.log 2>&1; tail -30 gpurun_out/${T}_pytest.log | cut -c1-400
+T=${1:-r02s49}
+python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; tail -4 gpurun_out/${T}_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()"

@@ -2252,7 +2252,8 @@ int wdem_step_e2e_owned(wdem_handle h, int64_t m, const int32_t* ids, const doub
     cudaStream_t st = h->stream;
     const long long mig0 = h->dom.migratedOut + h->dom.migratedIn;
     h->ownedIds.ensure((size_t)m, h->bytes); h->ownedSlot.ensure((size_t)m, h->bytes); h->orphCnt.ensure(1, h->bytes);
-    h->ioIn.ensure(9 * (size_t)m, h->bytes); h->ioOut.ensure(6 * (size_t)m, h->bytes);
+    { const double *i0 = h->ioIn.p, *o0 = h->ioOut.p; h->ioIn.ensure(9 * (size_t)m, h->bytes); h->ioOut.ensure(6 * (size_t)m, h->bytes);
+      if (h->ioIn.p != i0 || h->ioOut.p != o0) h->e2e.ioBusy = false; }      // new staging buffers: the copy streams must be ordered behind their (stream-ordered) allocation
     // the main stream has to wait for nothing here but its own past; ids -> slots (+ are they all owned?) before the first chunk is integrated
     CK(cudaMemcpyAsync(h->ownedIds.p, ids, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(h->orphCnt.p, 0, sizeof(int), st));
@@ -2395,7 +2396,8 @@ int wdem_step_e2e(wdem_handle h, int64_t nsteps, const double* pos_in, const dou
     return guarded(h, [&] {
       const size_t n = (size_t)h->n;
       ensureUp2Slot(h);
-      h->ioIn.ensure(9 * n, h->bytes); h->ioOut.ensure(6 * n, h->bytes);
+      { const double *i0 = h->ioIn.p, *o0 = h->ioOut.p; h->ioIn.ensure(9 * n, h->bytes); h->ioOut.ensure(6 * n, h->bytes);
+        if (h->ioIn.p != i0 || h->ioOut.p != o0) h->e2e.ioBusy = false; }      // new staging buffers: the copy streams must be ordered behind their (stream-ordered) allocation
       h->e2e.defer = !stats && !h->profiling && !getenv("WDEM_E2E_NO_DEFER");
       h->e2e.count = (long long)n; h->e2e.slotMap = h->up2slot.p;
       h->e2e.active = true; h->e2e.pos = pos_in; h->e2e.vel = vel_in; h->e2e.angVel = angVel_in; h->e2e.posOut = pos_out; h->e2e.velOut = vel_out;
