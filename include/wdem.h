@@ -160,7 +160,7 @@ int wdem_upload_facet_groups(wdem_handle h, int nGroups, const int32_t* groupOfF
  * pos 3, ori 4 (x,y,z,w), vel 3, angVel 3, angMom 3 (NULL or NaN: initialised by the first step, Leapfrog.cpp:303-305), mass 1, inertia 3 (principal), flags
  * (DemData.flags of the master node: blocked DOFs, *_SKIP bits) per clump; relPos 3 / relOri 4 per member (ClumpData.relPos/relOri; NULL: derived from the
  * uploaded member state as ClumpData::makeClump does, Clump.cpp:252-253).  Call right after wdem_upload_spheres; every sphere with the CLUMPED flag must be a
- * member of exactly one clump.  Aperiodic, single-device scenes without Scene.trackEnergy; wdem_add_spheres / wdem_remove_spheres are refused while clumps exist. */
+ * member of exactly one clump.  Single-device scenes (aperiodic or periodic) without Scene.trackEnergy; wdem_add_spheres / wdem_remove_spheres are refused while clumps exist. */
 int wdem_upload_clumps(wdem_handle h, int32_t nClumps, const int32_t* memberStart, const int32_t* memberIds, const double* pos, const double* ori,
                        const double* vel, const double* angVel, const double* angMom, const double* mass, const double* inertia, const uint32_t* flags,
                        const double* relPos, const double* relOri);

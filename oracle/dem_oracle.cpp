@@ -1354,7 +1354,6 @@ struct Scene {
     }
     // clump master nodes (Leapfrog.cpp:148-255 with isClump): forces from the members, spherical or aspherical rotation, then the members follow
     if (!clumps.empty()) {
-      if (P.periodic) throw std::runtime_error("clumps in a periodic cell are not supported");
       if (trackEnergy) throw std::runtime_error("Scene.trackEnergy with clumps is not supported");
       #pragma omp parallel for schedule(guided)
       for (long ci = 0; ci < (long)clumps.size(); ci++) {
@@ -1371,20 +1370,31 @@ struct Scene {
         if (!blockedAll) {
           if (blockedNone) linAccel = f / c.mass;
           else { for (int k = 0; k < 3; k++) if (!(fl & (1u << k))) linAccel[k] += f[k] / c.mass; }
-          if (damp) for (int k = 0; k < 3; k++) linAccel[k] *= 1 - damping * Sign(f[k] * (c.vel[k] + 0.5 * dt * linAccel[k]));
-          c.vel += dt * linAccel;
+          // fluctuation velocities (Leapfrog.cpp:181-184): the master node of a clump is a node like any other, in a periodic cell too
+          V3 pfv = c.vel, pfw = c.angVel;
+          if (P.periodic) { pfv = cell.pprevFluctVel(c.pos, c.vel, dt); pfw = cell.pprevFluctAngVel(c.angVel); }
+          if (damp) for (int k = 0; k < 3; k++) linAccel[k] *= 1 - damping * Sign(f[k] * (pfv[k] + 0.5 * dt * linAccel[k]));
+          if (homoDeform == HOMO_GRADV2) c.vel = mulMV(ImLL4hInv, (mulMV(LmL, c.pos) + mulMV(IpLL4h, c.vel)) + linAccel * dt);
+          else c.vel += dt * linAccel;
           if (c.inertia != V3(0, 0, 0)) {
             if (!useAspherical) {
               if (blockedNone) angAccel = V3(t.x / c.inertia.x, t.y / c.inertia.y, t.z / c.inertia.z);
               else { for (int k = 0; k < 3; k++) if (!(fl & (1u << (k + 3)))) angAccel[k] += t[k] / c.inertia[k]; }
-              if (damp) for (int k = 0; k < 3; k++) angAccel[k] *= 1 - damping * Sign(t[k] * (c.angVel[k] + 0.5 * dt * angAccel[k]));
+              if (damp) for (int k = 0; k < 3; k++) angAccel[k] *= 1 - damping * Sign(t[k] * (pfw[k] + 0.5 * dt * angAccel[k]));
               c.angVel += dt * angAccel;
+              if (homoDeform == HOMO_GRADV2) c.angVel -= deltaSpinVec;
             } else {
               for (int k = 0; k < 3; k++) if (fl & (1u << (k + 3))) t[k] = 0;                                    // block DOFs here (Leapfrog.cpp:188)
-              if (damp) for (int k = 0; k < 3; k++) t[k] *= 1 - damping * Sign(t[k] * c.angVel[k]);              // nonviscDamp1st (Leapfrog.cpp:28-30)
+              if (damp) for (int k = 0; k < 3; k++) t[k] *= 1 - damping * Sign(t[k] * pfw[k]);                   // nonviscDamp1st (Leapfrog.cpp:28-30)
             }
           }
           if (c.impose >= 0) imposeVelocity(c.impose, c.vel, c.angVel, c.pos, &c.ori);      // Leapfrog.cpp:203-205
+        } else if (homoDeform == HOMO_GRADV2) c.vel = mulMV(ImLL4hInv, mulMV(LmL, c.pos) + mulMV(IpLL4h, c.vel));      // fixed node (Leapfrog.cpp:206-210)
+        if (homoDeform >= 0 && homoDeform != HOMO_GRADV2) {      // applyPeriodicCorrections (Leapfrog.cpp:258-273)
+          if (homoDeform == HOMO_VEL || homoDeform == HOMO_VEL_2ND) {
+            if (homoDeform == HOMO_VEL_2ND) c.vel += mulMV(midGradV, c.vel - (dt / 2.) * linAccel) * dt;
+            c.vel += mulMV(dGradV, c.pos);
+          } else if (homoDeform == HOMO_POS) c.pos += mulMV(cell.nextGradV, c.pos) * dt;
         }
         c.pos += c.vel * dt;
         if (!useAspherical) {      // leapfrogSphericalRotate (Leapfrog.cpp:280-297)

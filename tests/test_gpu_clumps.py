@@ -73,6 +73,29 @@ def test_impositions_on_clump_master_nodes_bitwise():
         Engine(S2.params).load(S2)
 
 
+@pytest.mark.parametrize("homo", [sc.HOMO_POS, sc.HOMO_VEL, sc.HOMO_VEL_2ND, sc.HOMO_GRADV2])
+def test_clumps_in_a_periodic_cell_bitwise(homo):
+    """Rigid aggregates and free spheres in a periodic cell that is compressed and sheared: the clump's master node gets the cell's corrections like any node
+    (fluctuation velocity in the damping, the gradV2 velocity update, applyPeriodicCorrections; Leapfrog.cpp:181-215,258-273), members of one clump never collide,
+    contacts reach across the cell boundary (cellDist)."""
+    S = sc.clump_deposition(40, 60, damping=.1, spin=20.)
+    hi = np.array([max(w["pos"][k] for w in S.walls) for k in range(3)], dtype=float); hi[2] = S.pos[:, 2].max() + 3 * S.radius.max()
+    S.walls = []
+    S.params.periodic = 1; S.params.gravity = (0., 0., 0.); S.params.dynDtPeriod = 20
+    g = np.array([[-12., 6., 0], [0, -12., 0], [0, 0, -12.]])
+    S.cell = dict(hSize=np.diag(hi * 1.01), gradV=g, nextGradV=g, homoDeform=homo)
+    S.vel = S.vel + S.pos @ g.T                                       # the mean field: the particles follow the cell
+    for c in S.clumps: c["vel"] = tuple(np.asarray(c["vel"]) + g @ np.asarray(c["pos"]))
+    S.finalize()
+    O, E = Oracle(S), engine_for(S)
+    for k in range(10):
+        O.step(250); E.step(250)
+        check(O, E, 250 * (k + 1))
+        assert np.array_equal(O.cell_hsize(), E.cell_hsize())
+    co = O.contacts(True)
+    assert len(co["ids"]) > 40 and np.abs(co["cellDist"]).max() > 0, "the test should see contacts across the cell boundary"
+
+
 def test_clump_first_steps_and_member_kinematics():
     S = sc.clump_deposition(9, 0, dynDtPeriod=0)
     O, E = Oracle(S), engine_for(S)
@@ -138,7 +161,7 @@ def test_clump_errors():
     E = Engine(S.params).load(S); E.step(2)
     with pytest.raises(RuntimeError, match="scenes with clumps"):
         E.remove_spheres([int(S.sphere_ids()[-1])])
-    Sp = sc.periodic_gas(50)
-    Sp.flags[:2] |= 64; Sp.clumps = [dict(members=[0, 1], pos=Sp.pos[:2].mean(axis=0), ori=(0, 0, 0, 1), vel=(0, 0, 0), angVel=(0, 0, 0), mass=1., inertia=(1., 2., 3.), flags=0)]
-    with pytest.raises(RuntimeError, match="periodic"):
-        Engine(Sp.params).load(Sp)
+    St = sc.clump_deposition(4, 2)
+    Et = Engine(St.params).load(St); Et.track_energy(True)
+    with pytest.raises(RuntimeError, match="trackEnergy"):
+        Et.step(1)

@@ -1387,7 +1387,7 @@ void enqueueIntegrate(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
   if (!E->imposes.empty() && E->e2e.active) throw EngErr{"Impose is not available with wdem_step_e2e", WDEM_ERR_UNSUPPORTED};
   if (E->nClumpedUploaded > 0) throw EngErr{std::to_string(E->nClumpedUploaded) + " spheres carry the CLUMPED flag but no clump was uploaded (wdem_upload_clumps)", WDEM_ERR_INVALID};
   if (E->clumps.n > 0) {
-    if (c.periodic || E->comm || E->e2e.active || E->trackEnergy) throw EngErr{"clumps of spheres: periodic cells, decomposed runs, wdem_step_e2e and Scene.trackEnergy are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    if (E->comm || E->e2e.active || E->trackEnergy) throw EngErr{"clumps of spheres: decomposed runs, wdem_step_e2e and Scene.trackEnergy are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     k_clumps_step<<<nblk(E->clumps.n, 128), 128, 0, st>>>(E->clumps.view(), E->S(), E->id2slot.p, u, E->dCnt, E->impDev(u.impSlot)); E->launches++;
   }
   if ((E->groups.n > 0 || E->impFacetNodes) && !E->hFacets.empty()) {
@@ -1726,7 +1726,6 @@ int wdem_upload_clumps(wdem_handle h, int32_t nClumps, const int32_t* memberStar
     if (nClumps < 0 || (nClumps > 0 && (!memberStart || !memberIds || !pos || !ori || !mass || !inertia))) throw EngErr{"wdem_upload_clumps: bad arguments", WDEM_ERR_INVALID};
     if (!h->conDirty || h->cur != 0 || h->nC != 0) throw EngErr{"wdem_upload_clumps: call right after wdem_upload_spheres", WDEM_ERR_INVALID};
     if (h->comm) throw EngErr{"wdem_upload_clumps: not available in decomposed runs", WDEM_ERR_UNSUPPORTED};
-    if (h->cfg.periodic) throw EngErr{"wdem_upload_clumps: clumps in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     ClumpStore& K = h->clumps; K.release();
     if (nClumps == 0) return;
     const int n = h->n, nMem = memberStart[nClumps];

@@ -428,12 +428,19 @@ __global__ void __launch_bounds__(128) k_clumps_step(Clumps K, Spheres S, const 
       if (!(fl & 2u)) linAccel.y += f.y / mass;
       if (!(fl & 4u)) linAccel.z += f.z / mass;
     }
-    if (damp) {
-      linAccel.x *= 1 - u.damping * signd(f.x * (vel.x + 0.5 * dt * linAccel.x));
-      linAccel.y *= 1 - u.damping * signd(f.y * (vel.y + 0.5 * dt * linAccel.y));
-      linAccel.z *= 1 - u.damping * signd(f.z * (vel.z + 0.5 * dt * linAccel.z));
+    d3 pfv = vel, pfw = w;      // Cell::pprevFluctVel / pprevFluctAngVel (Cell.cpp:36-57): the clump's master node is a node like any other
+    if (u.periodic) {
+      if (u.homoDeform == 2 || u.homoDeform == 3) pfv = vel - mulMV(u.gradV, pos);
+      else if (u.homoDeform == 4) pfv = vel - mulMV(u.gradV, pos - (dt / 2) * vel);
+      if (u.homoDeform == 4) pfw = w - u.spinVec;
     }
-    vel = vel + dt * linAccel;
+    if (damp) {
+      linAccel.x *= 1 - u.damping * signd(f.x * (pfv.x + 0.5 * dt * linAccel.x));
+      linAccel.y *= 1 - u.damping * signd(f.y * (pfv.y + 0.5 * dt * linAccel.y));
+      linAccel.z *= 1 - u.damping * signd(f.z * (pfv.z + 0.5 * dt * linAccel.z));
+    }
+    if (u.periodic && u.homoDeform == 4) vel = mulMV(u.ImLL4hInv, (mulMV(u.LmL, pos) + mulMV(u.IpLL4h, vel)) + linAccel * dt);
+    else vel = vel + dt * linAccel;
     if (hasInertia) {
       if (!useAspherical) {
         if (blockedNone) angAccel = mk3(t.x / inertia.x, t.y / inertia.y, t.z / inertia.z);
@@ -443,19 +450,26 @@ __global__ void __launch_bounds__(128) k_clumps_step(Clumps K, Spheres S, const 
           if (!(fl & 32u)) angAccel.z += t.z / inertia.z;
         }
         if (damp) {
-          angAccel.x *= 1 - u.damping * signd(t.x * (w.x + 0.5 * dt * angAccel.x));
-          angAccel.y *= 1 - u.damping * signd(t.y * (w.y + 0.5 * dt * angAccel.y));
-          angAccel.z *= 1 - u.damping * signd(t.z * (w.z + 0.5 * dt * angAccel.z));
+          angAccel.x *= 1 - u.damping * signd(t.x * (pfw.x + 0.5 * dt * angAccel.x));
+          angAccel.y *= 1 - u.damping * signd(t.y * (pfw.y + 0.5 * dt * angAccel.y));
+          angAccel.z *= 1 - u.damping * signd(t.z * (pfw.z + 0.5 * dt * angAccel.z));
         }
         w = w + dt * angAccel;
+        if (u.periodic && u.homoDeform == 4) w = w - u.deltaSpinVec;
       } else {
         if (fl & 8u) t.x = 0; if (fl & 16u) t.y = 0; if (fl & 32u) t.z = 0;      // Leapfrog.cpp:188
-        if (damp) {                                                           // nonviscDamp1st (Leapfrog.cpp:28-30)
-          t.x *= 1 - u.damping * signd(t.x * w.x); t.y *= 1 - u.damping * signd(t.y * w.y); t.z *= 1 - u.damping * signd(t.z * w.z);
+        if (damp) {                                                           // nonviscDamp1st (Leapfrog.cpp:28-30) with the fluctuation angular velocity
+          t.x *= 1 - u.damping * signd(t.x * pfw.x); t.y *= 1 - u.damping * signd(t.y * pfw.y); t.z *= 1 - u.damping * signd(t.z * pfw.z);
         }
       }
     }
     if (impSet >= 0) impose_velocity(I, impSet, vel, w, pos, &ori);      // Leapfrog.cpp:203-205
+  } else if (u.periodic && u.homoDeform == 4) vel = mulMV(u.ImLL4hInv, mulMV(u.LmL, pos) + mulMV(u.IpLL4h, vel));      // fixed node, gradV2 (Leapfrog.cpp:206-210)
+  if (u.periodic && u.homoDeform != 4) {      // applyPeriodicCorrections (Leapfrog.cpp:258-273)
+    if (u.homoDeform == 2 || u.homoDeform == 3) {
+      if (u.homoDeform == 3) vel = vel + mulMV(u.midGradV, vel - (dt / 2.) * linAccel) * dt;
+      vel = vel + mulMV(u.dGradV, pos);
+    } else if (u.homoDeform == 1) pos = pos + mulMV(u.nextGradV, pos) * dt;
   }
   pos = pos + vel * dt;
   if (!useAspherical) {      // leapfrogSphericalRotate (Leapfrog.cpp:280-297)
@@ -1935,6 +1949,7 @@ __global__ void __launch_bounds__(128) k_pairs_ss_peri(Spheres S, int n, HGrid g
             const double4 pj = S.posr[j];
             if (!mayCollide(mi, S.mask[j], loneMask)) continue;
             if ((fi & F_GHOST) && (S.flags[j] & F_GHOST)) continue;
+            if ((fi & F_CLUMPED) && S.clumpOfId && (S.flags[j] & F_CLUMPED) && S.clumpOfId[S.id[i]] == S.clumpOfId[S.id[j]]) continue;   // members of one clump (Collision.cpp:34-39)
             d3 mnJ, mxJ; periAabb(pu, pj, vd, mnJ, mxJ);
             const int idJ = S.id[j];
             const bool iIsA = idI < idJ;
