@@ -164,6 +164,23 @@ def test_periodic_with_moving_walls_in_a_deforming_cell(homo):
     assert (O.contacts(True)["ids"][:, 0] >= S.n).sum() > 3, "no wall contacts"
 
 
+@pytest.mark.parametrize("shear0,world", [(0., 1), (.25, 1), (.25, 2)])
+def test_periodic_with_static_facets(shear0, world):
+    """Facets in a periodic cell (Bo1_Facet_Aabb's periodic branch, Facet.cpp:286-297: boxes of the unsheared node positions; Cg2_Facet_Sphere with shift2): a plate in
+    the middle of a sheared cell; one of its triangles sticks out of the cell, so that spheres touch it through the boundary (cellDist != 0)."""
+    S = sc.periodic_gas(400, cell=(.5, .4, .45), r=.02, psd_ratio=2.0, seed=61, gradV=[[0, 1.5, 0], [0, 0, 0], [0, 0, 0]], shear0=shear0)
+    z = .2
+    quad = lambda x0, y0, x1, y1: [np.array([(x0, y0, z), (x1, y0, z), (x1, y1, z)]), np.array([(x0, y0, z), (x1, y1, z), (x0, y1, z)])]
+    tris = quad(.1, .05, .3, .3) + quad(.3, .05, .62, .3) + [np.array([(.05, .3, z), (.25, .55, z + .05), (-.1, .45, z - .03)])]      # the second quad and the last triangle leave the cell
+    S.facets = [dict(v=t, halfThick=.004 * (k % 2), fakeVel=(0., 0., 0.), mat=0, mask=sc.MASK_BOUNDARY) for k, t in enumerate(tris)]
+    S.finalize()
+    O, E = compare(S, 100, check_every=25, label=f"peri facets shear0={shear0} world={world}", make=cluster(world) if world > 1 else None)
+    compare_potential(O, E)
+    co = O.contacts(True)
+    fs = co["ids"][:, 0] >= S.n
+    assert fs.sum() > 5 and np.abs(co["cellDist"][fs]).max() > 0, "the test should see facet contacts through the cell boundary"
+
+
 def test_periodic_with_walls():
     S = sc.periodic_gas(300, cell=(.4, .4, .5), r=.02, psd_ratio=2.0, seed=19, walls=True)
     S.params.gravity = (0, 0, -9.81)

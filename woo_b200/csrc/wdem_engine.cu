@@ -212,6 +212,7 @@ struct wdem_engine {
   // scratch
   DBuf<uint32_t> keys, keysAlt; DBuf<int> idx, idxAlt, cellStart, counts, offsets; DBuf<unsigned char> cubTemp; DBuf<double> blk;
   DBuf<unsigned long long> ckeys, ckeysAlt, cntScratch; DBuf<int> orphCnt, rowCount, srcOld, candBuf; DBuf<uint32_t> wallBits; DBuf<double> ioBuf; DBuf<uint32_t> cvals, cvalsAlt; DBuf<int> realFlag, realPos; DBuf<int32_t> tmpCd[3];
+  DBuf<double> facetBoxes;      // periodic cells: unsheared boxes of the facets at the last full run
   double* hBounds = nullptr; bool boundsValid = false; DBuf<double> boundsBuf;   // pinned, 2 x 8: bounding box of the sphere centres at the last two full runs
   Counters* dCnt = nullptr; Counters* hCnt = nullptr; int* hScratch = nullptr;   // pinned: per-step counters, small read-backs of the full run
   // scene scalars
@@ -761,7 +762,7 @@ void rebuild(wdem_engine* E) {
   HGrid g; memset(&g, 0, sizeof(g));
   PeriU pu; memset(&pu, 0, sizeof(pu));
   if (c.periodic) {
-    if (nFacets) throw EngErr{"Facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    if (nFacets > WD_MAX_PERI_FACETS) throw EngErr{"more than " + std::to_string(WD_MAX_PERI_FACETS) + " facets in a periodic cell are not supported by the GPU engine (every sphere visits every facet there)", WDEM_ERR_UNSUPPORTED};
     if (!E->hWalls.empty() && E->cell.hasShear) throw EngErr{"Walls not supported in skewed periodic boundary conditions.", WDEM_ERR_RUNTIME};  // Wall.cpp:30
     pu.unshear = E->cell.unshearTrsf; pu.size = E->cell.size; pu.cosv = E->cell.cosv; pu.hasShear = E->cell.hasShear ? 1 : 0;
   }
@@ -885,7 +886,13 @@ void rebuild(wdem_engine* E) {
       E->launches++;
     }
     else if (!nWalls) CK(cudaMemsetAsync(E->counts.p + 2 * n, 0, (size_t)n * sizeof(int), st));
-    if (nFacets) { k_pairs_fs<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, E->counts.p + 3 * n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++; }
+    if (nFacets && c.periodic) {      // boxes of the unsheared node positions (they follow the cell's shear), then every sphere against every facet
+      E->facetBoxes.ensure((size_t)6 * nFacets, tot);
+      k_facet_boxes_peri<<<nblk(nFacets, 128), 128, 0, st>>>(E->dFacets.p, nFacets, pu, vd, E->facetBoxes.p);
+      k_pairs_fs_peri<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, nFacets, E->facetBoxes.p, pu, vd, c.loneMask, E->counts.p + 3 * n, nullptr, dummy, oc, perm, E->rowCount.p, nullptr, E->dCnt);
+      E->launches += 2;
+    }
+    else if (nFacets) { k_pairs_fs<false><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, E->counts.p + 3 * n, nullptr, dummy, dummy, oc, perm, E->rowCount.p, nullptr); E->launches++; }
     else CK(cudaMemsetAsync(E->counts.p + 3 * n, 0, (size_t)n * sizeof(int), st));
     CK(cudaMemsetAsync(E->counts.p + 4 * n, 0, sizeof(int), st));
     tb = 0;
@@ -915,7 +922,8 @@ void rebuild(wdem_engine* E) {
       else k_pairs_ws_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dWalls.p, nWalls, pu, vd, c.wallHalfThick, c.loneMask, nullptr, E->offsets.p + 2 * n, T, oc, perm, nullptr, E->srcOld.p, E->dCnt);
       E->launches++;
     }
-    if (nFacets) { k_pairs_fs<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, nullptr, E->offsets.p + 3 * n, T, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
+    if (nFacets && c.periodic) { k_pairs_fs_peri<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, nFacets, E->facetBoxes.p, pu, vd, c.loneMask, nullptr, E->offsets.p + 3 * n, T, oc, perm, nullptr, E->srcOld.p, E->dCnt); E->launches++; }
+    else if (nFacets) { k_pairs_fs<true><<<nb128, 128, 0, st>>>(E->S(), n, E->dFacets.p, E->fgrid, vd, c.loneMask, nullptr, E->offsets.p + 3 * n, T, O, oc, perm, nullptr, E->srcOld.p); E->launches++; }
     if (nC0 > 0) {
       // real-first order inside the sphere-sphere segment (the reference reorders its contacts for the same reason, ContactLoop.cpp:75-91):
       // warps of k_contact_ss then see either all-real or all-potential contacts instead of paying the long path for half-empty warps
@@ -1619,6 +1627,7 @@ int wdem_destroy(wdem_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& s : h->sph) s.release(); for (auto& c : h->con) c.release(); for (auto& r : h->csr) r.release(); h->clumps.release();
   h->dImpSetStart.release(); h->dImpSetOps.release(); h->dImpOfId.release(); h->dImpRing.release(); if (h->hImpRing) cudaFreeHost(h->hImpRing);
+  h->facetBoxes.release(); h->ownedSlot.release(); h->ownedIds.release();
   h->id2slot.release(); h->up2slot.release(); h->dMats.release(); h->dWalls.release(); h->dFacets.release(); h->fgCellStart.release(); h->fgCellFacet.release(); h->fgCursor.release(); h->keys.release(); h->keysAlt.release(); h->idx.release(); h->idxAlt.release();
   h->orphCnt.release(); h->rowCount.release(); h->srcOld.release(); h->candBuf.release(); h->wallBits.release(); h->ioBuf.release(); h->cellStart.release(); h->counts.release(); h->offsets.release(); h->cubTemp.release(); h->blk.release(); h->ckeys.release(); h->ckeysAlt.release(); h->cntScratch.release(); h->cvals.release(); h->cvalsAlt.release(); h->realFlag.release(); h->realPos.release(); for (auto& b : h->tmpCd) b.release();
   peerTeardown(h, false);

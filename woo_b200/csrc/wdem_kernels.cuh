@@ -2021,6 +2021,62 @@ __global__ void __launch_bounds__(128) k_pairs_ws_peri(Spheres S, int n, const W
 
 // carry L6Geom/FrictPhys history of contacts that were real into the new table: one thread per NEW contact.  T holds (pair, kind, cellDist) in
 // emission order; sphere-sphere contacts are placed real-first (stable): dst = realPos[c] for carried-real ones, nReal + (c - realPos[c]) otherwise.
+// Facets in a periodic cell.  Bo1_Facet_Aabb in a periodic cell (Facet.cpp:286-297): the box of the UNSHEARED node positions +- halfThick, enlarged by verletDist
+// (AabbCollider::updateAabb); nodes are never wrapped.  The boxes depend on the cell's shear, so they are refreshed at every full run.
+__global__ void __launch_bounds__(128) k_facet_boxes_peri(const Facet* __restrict__ facets, int nF, PeriU pu, double vd, double* __restrict__ box /*6 per facet: min xyz, max xyz*/) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nF) return;
+  const Facet* F = facets + f; const double ht = F->halfThick;
+  d3 mn, mx;
+  for (int i = 0; i < 3; i++) {
+    const d3 p = mulMV(pu.unshear, mk3(F->v[3 * i], F->v[3 * i + 1], F->v[3 * i + 2]));
+    const d3 lo = mk3(p.x - ht, p.y - ht, p.z - ht), hi = mk3(p.x + ht, p.y + ht, p.z + ht);
+    if (i == 0) { mn = lo; mx = hi; }
+    else { mn = mk3(fmin(mn.x, lo.x), fmin(mn.y, lo.y), fmin(mn.z, lo.z)); mx = mk3(fmax(mx.x, hi.x), fmax(mx.y, hi.y), fmax(mx.z, hi.z)); }
+  }
+  if (vd > 0) { mx = mk3(mx.x + vd, mx.y + vd, mx.z + vd); mn = mk3(mn.x - vd, mn.y - vd, mn.z - vd); }
+  box[6 * f] = mn.x; box[6 * f + 1] = mn.y; box[6 * f + 2] = mn.z; box[6 * f + 3] = mx.x; box[6 * f + 4] = mx.y; box[6 * f + 5] = mx.z;
+}
+// Facet+Sphere candidates in a periodic cell: spatialOverlapPeri of the two boxes (the one of the lower id first) gives Contact.cellDist.  Every sphere visits every
+// facet: meshes in periodic cells are small (a plate, an obstacle); the engine refuses more than WD_MAX_PERI_FACETS of them.
+#define WD_MAX_PERI_FACETS 4096
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_pairs_fs_peri(Spheres S, int n, const Facet* __restrict__ facets, int nF, const double* __restrict__ box, PeriU pu, double vd, uint32_t loneMask,
+                                                      int* counts, const int* __restrict__ offsets, Contacts N, OldCsr oc, const int* __restrict__ perm,
+                                                      int* __restrict__ rowCount, int* __restrict__ srcOld, Counters* cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t fi = S.flags[i];
+  if (fi & F_GHOST) { if (!FILL) counts[i] = 0; return; }
+  const double4 pi = S.posr[i];
+  d3 mnI, mxI; periAabb(pu, pi, vd, mnI, mxI);
+  const uint32_t mi = S.mask[i];
+  const int idI = S.id[i];
+  int cntLocal = 0;
+  long long out = FILL ? offsets[i] : 0;
+  const int oslotI = FILL ? (perm ? perm[i] : i) : 0;
+  for (int f = 0; f < nF; f++) {
+    const Facet* F = facets + f;
+    if (!mayCollide(mi, F->mask, loneMask)) continue;
+    const d3 mnF = mk3(box[6 * f], box[6 * f + 1], box[6 * f + 2]), mxF = mk3(box[6 * f + 3], box[6 * f + 4], box[6 * f + 5]);
+    int per[3];
+    const bool facetLo = F->id < idI;
+    const int ov = facetLo ? overlapPeri(mnF, mxF, mnI, mxI, pu.size, per) : overlapPeri(mnI, mxI, mnF, mxF, pu.size, per);
+    if (ov < 0) { cnt->error = ERR_AMBIGUOUS_PERI; cnt->errA = F->id; cnt->errB = idI; continue; }
+    if (!ov) continue;
+    if (FILL) {
+      const long long c = out + cntLocal;
+      N.pair[c] = make_int2(f, i);
+      const int sg = facetLo ? 1 : -1;      // canonical pA = facet (Contact::swapOrder negates cellDist, Contact.cpp:12-16)
+      N.cdx[c] = sg * per[0]; N.cdy[c] = sg * per[1]; N.cdz[c] = sg * per[2];
+      srcOld[c] = (int)find_old2(oc, oslotI, F->id, fi, F->id, idI);
+      N.flags[c] = (KIND_FS << CF_KIND_SHIFT);
+    }
+    cntLocal++;
+  }
+  if (!FILL) { counts[i] = cntLocal; if (cntLocal) atomicAdd(&rowCount[i], cntLocal); }
+}
+
 __global__ void __launch_bounds__(256) k_was_real(const int* __restrict__ srcOld, const uint32_t* __restrict__ oflags, long long nSS, int* flag) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c > nSS) return;
