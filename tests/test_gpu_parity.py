@@ -181,6 +181,24 @@ def test_periodic_with_static_facets(shear0, world):
     assert fs.sum() > 5 and np.abs(co["cellDist"][fs]).max() > 0, "the test should see facet contacts through the cell boundary"
 
 
+@pytest.mark.parametrize("homo", [sc.HOMO_POS, sc.HOMO_VEL_2ND, sc.HOMO_GRADV2])
+def test_periodic_with_a_moving_facet_group(homo):
+    """A plate clumped to a master node that translates and rotates (ParticleContainer.addClumped with a central node) inside a periodic cell that is being sheared and
+    compressed: the master node is a fully blocked node, so Leapfrog's fixed branch applies the cell's corrections to it (Leapfrog.cpp:206-215,258-273); the members
+    follow, their unsheared boxes are refreshed at the full runs their motion triggers."""
+    S = sc.periodic_gas(400, cell=(.5, .4, .45), r=.02, psd_ratio=2.0, seed=67, gradV=[[-.5, 1.5, 0], [0, -.3, 0], [0, 0, 0]], shear0=.1, homoDeform=homo)
+    z = .2
+    quad = lambda x0, y0, x1, y1: [np.array([(x0, y0, z), (x1, y0, z), (x1, y1, z)]), np.array([(x0, y0, z), (x1, y1, z), (x0, y1, z)])]
+    tris = quad(.1, .05, .25, .2) + quad(.25, .05, .4, .2) + quad(.4, .05, .55, .2)      # the last one leaves the cell
+    S.facets = [dict(v=t, halfThick=0., fakeVel=(0., 0., 0.), mat=0, mask=sc.MASK_BOUNDARY) for t in tris]
+    S.facet_groups = [dict(pos=(.32, .12, z), ori=(0., 0., 0., 1.), vel=(.3, -.2, .5), angVel=(1., 0., 4.), facets=list(range(len(tris))))]
+    S.finalize()
+    O, E = compare(S, 150, check_every=25, label=f"peri moving facets homoDeform={homo}")
+    compare_potential(O, E)
+    assert np.array_equal(O.facets(), E.facets()) and not np.allclose(E.facets()[0], tris[0], atol=1e-3)
+    assert (O.contacts(True)["ids"][:, 0] >= S.n).sum() > 0
+
+
 def test_periodic_with_walls():
     S = sc.periodic_gas(300, cell=(.4, .4, .5), r=.02, psd_ratio=2.0, seed=19, walls=True)
     S.params.gravity = (0, 0, -9.81)

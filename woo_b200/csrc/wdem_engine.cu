@@ -1352,11 +1352,18 @@ StepU stepPrologue(wdem_engine* E, int k) {
     CK(cudaMemsetAsync(u.energy + EN_KINETIC, 0, sizeof(double), E->stream)); CK(cudaMemsetAsync(u.energy + EN_ELAST, 0, sizeof(double), E->stream));
   }
   if (E->groups.n > 0 && !E->hFacets.empty()) {
-    if (c.periodic) throw EngErr{"moving facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    if (c.periodic && (int)E->hFacets.size() > WD_MAX_PERI_FACETS) throw EngErr{"more than " + std::to_string(WD_MAX_PERI_FACETS) + " facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     // master nodes: all DOFs blocked => Leapfrog's fixed-particle branch with the prescribed velocities: leapfrogTranslate + leapfrogSphericalRotate
     // (Leapfrog.cpp:195-199,275-297) on the host (a handful of nodes; libm sin/cos), members on the device (ClumpData::applyToMembers, Clump.cpp:293-307)
     for (int gi = 0; gi < E->groups.n; gi++) {
       GroupU& G = E->groups.g[gi]; const double dt = E->dt;
+      if (c.periodic) {      // a fully blocked node in a deforming cell gets the cell's velocity / position corrections (Leapfrog.cpp:206-215,258-273), no acceleration
+        if (u.homoDeform == 4) G.vel = mulMV(u.ImLL4hInv, mulMV(u.LmL, G.pos) + mulMV(u.IpLL4h, G.vel));
+        else if (u.homoDeform == 2 || u.homoDeform == 3) {
+          if (u.homoDeform == 3) G.vel = G.vel + mulMV(u.midGradV, G.vel - (dt / 2.) * mk3(0, 0, 0)) * dt;
+          G.vel = G.vel + mulMV(u.dGradV, G.pos);
+        } else if (u.homoDeform == 1) G.pos = G.pos + mulMV(u.nextGradV, G.pos) * dt;
+      }
       G.pos = G.pos + G.vel * dt;
       d3 axis = G.angVel;
       if (axis.x != 0. || axis.y != 0. || axis.z != 0.) {
@@ -1399,7 +1406,7 @@ void enqueueIntegrate(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
     k_clumps_step<<<nblk(E->clumps.n, 128), 128, 0, st>>>(E->clumps.view(), E->S(), E->id2slot.p, u, E->dCnt, E->impDev(u.impSlot)); E->launches++;
   }
   if ((E->groups.n > 0 || E->impFacetNodes) && !E->hFacets.empty()) {
-    if (c.periodic) throw EngErr{"moving facets in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
+    if (c.periodic && E->impFacetNodes) throw EngErr{"impositions on facet nodes in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     k_facets_step<<<nblk((long long)E->hFacets.size(), 128), 128, 0, st>>>(E->dFacets.p, (int)E->hFacets.size(), E->groups, u, E->dCnt, 0, E->impDev(u.impSlot)); E->launches++;
   }
   if (E->anyMovingWall) {
