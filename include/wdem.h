@@ -181,7 +181,7 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
                         const int32_t* sphereIds, const int32_t* sphereSet, const int32_t* wallSet, const int32_t* groupSet);
 /* DemData.impose of facet NODES: facetSet[f] = the set of impositions all three nodes of uploaded facet f carry, -1 none.  Such nodes are in DemField.nodes
  * (DemData::guessMoving, Particle.cpp:638-640): Leapfrog's fixed-node branch translates them with their velocity and Impose::velocity at the end of the node's step sets
- * the velocity of the next one (Leapfrog.cpp:195-199,248).  Velocity impositions only; not for facets of a kinematic group; aperiodic scenes.  Call after wdem_upload_imposes. */
+ * the velocity of the next one (Leapfrog.cpp:195-199,248).  Velocity impositions only; not for facets of a kinematic group.  Call after wdem_upload_imposes. */
 int wdem_upload_facet_imposes(wdem_handle h, const int32_t* facetSet);
 /* DemData.impose of the master nodes of clumps of spheres: clumpSet[c] = the set of impositions of uploaded clump c, -1 none.  Leapfrog calls the hooks on the master
  * node like on any other node (velocity after the accelerations and at the end of the node's step, before ClumpData::applyToMembers; force at the reset;

@@ -1477,8 +1477,16 @@ struct Scene {
     // Impose::velocity at the end of the node's step sets the velocity of the next one (Leapfrog.cpp:195-199,248)
     for (Facet& f : facets) {
       if (f.impose < 0) continue;
-      if (P.periodic) throw std::runtime_error("moving facets in a periodic cell are not supported");
-      for (int i = 0; i < 3; i++) { f.v[i] += f.vvel[i] * dt; V3 dummyW; imposeVelocity(f.impose, f.vvel[i], dummyW, f.v[i]); }
+      for (int i = 0; i < 3; i++) {
+        if (P.periodic) {      // the cell's corrections of the fixed branch (Leapfrog.cpp:206-215,258-273)
+          if (homoDeform == HOMO_GRADV2) f.vvel[i] = mulMV(ImLL4hInv, mulMV(LmL, f.v[i]) + mulMV(IpLL4h, f.vvel[i]));
+          else if (homoDeform == HOMO_VEL || homoDeform == HOMO_VEL_2ND) {
+            if (homoDeform == HOMO_VEL_2ND) f.vvel[i] += mulMV(midGradV, f.vvel[i] - (dt / 2.) * V3()) * dt;
+            f.vvel[i] += mulMV(dGradV, f.v[i]);
+          } else if (homoDeform == HOMO_POS) f.v[i] += mulMV(cell.nextGradV, f.v[i]) * dt;
+        }
+        f.v[i] += f.vvel[i] * dt; V3 dummyW; imposeVelocity(f.impose, f.vvel[i], dummyW, f.v[i]);
+      }
     }
     for (Wall& w : walls) {
       if (!w.moving) continue;

@@ -144,6 +144,36 @@ def test_orbit_impositions_on_spheres_and_on_the_nodes_of_a_rotating_cylinder():
     assert len(E.contacts(True)["ids"]) > 0 and E.scalars()["nFullRuns"] > 5
 
 
+def test_axially_periodic_rotating_drum():
+    """A drum without end caps in a cell that is periodic along its axis: the cylinder of woo.triangulated.cylinder(realRot=True) (one StableCircularOrbit on every node,
+    py/triangulated.py:59-64) plus Bo1_Facet_Aabb's periodic branch; spheres leave through one end and come back through the other."""
+    om = 5.
+    S = sc.drum(200, div=10, axial=3, vz0=.3, vfluct=.2, omega=om, rotate=False)
+    R = float(np.hypot(S.facets[0]["v"][0][1], S.facets[0]["v"][0][2])); L = float(max(w["pos"][0] for w in S.walls))
+    for f in S.facets: f["fakeVel"] = (0., 0., 0.)
+    S.walls = []
+    S.vel[:, 0] += 1.0                                                 # drift along the axis: through the periodic boundary
+    S.params.periodic = 1
+    S.cell = dict(hSize=np.diag([L, 3 * R, 3 * R]), gradV=np.zeros((3, 3)), nextGradV=np.zeros((3, 3)), homoDeform=sc.HOMO_GRADV2)
+    q = (0., math.sin(math.pi / 4), 0., math.cos(math.pi / 4))
+    sc.attach_impose(S, [sc.imp_stable_circular_orbit((0., 0., 0.), om, R, node_ori=q)], facets=range(len(S.facets)))
+    S.finalize()
+    O, E = Oracle(S), engine_for(S)
+    seen = 0
+    for k in range(4):
+        O.step(100); E.step(100)
+        fo, fg = O.facets(), E.facets()
+        assert np.allclose(fo, fg, rtol=0, atol=1e-12 * R), f"facet nodes differ at step {100 * (k + 1)}: {np.abs(fo - fg).max()}"
+        so, sg = O.spheres(), E.spheres()
+        for key in ("pos", "vel"):
+            assert np.allclose(so[key], sg[key], rtol=0, atol=(1e-8 if k == 0 else 1e-3) * max(1., np.abs(so[key]).max())), f"sphere {key} differs at step {100 * (k + 1)}: {np.abs(so[key] - sg[key]).max()}"
+        assert O.nFullRuns == E.scalars()["nFullRuns"] and O.dt == E.scalars()["dt"]
+        co = E.contacts(True)
+        if len(co["ids"]): seen = max(seen, int(np.abs(co["cellDist"]).max()))
+    assert (E.spheres()["pos"][:, 0] > L).any(), "spheres should have left the cell along the axis"
+    assert np.allclose(np.hypot(fg[..., 1], fg[..., 2]), R, rtol=1e-12)
+
+
 def test_impose_errors():
     from woo_b200.engine import Engine
     S = _gas(50)

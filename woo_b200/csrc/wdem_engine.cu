@@ -1406,7 +1406,6 @@ void enqueueIntegrate(wdem_engine* E, const StepU& u, cudaEvent_t* ev) {
     k_clumps_step<<<nblk(E->clumps.n, 128), 128, 0, st>>>(E->clumps.view(), E->S(), E->id2slot.p, u, E->dCnt, E->impDev(u.impSlot)); E->launches++;
   }
   if ((E->groups.n > 0 || E->impFacetNodes) && !E->hFacets.empty()) {
-    if (c.periodic && E->impFacetNodes) throw EngErr{"impositions on facet nodes in a periodic cell are not supported by the GPU engine", WDEM_ERR_UNSUPPORTED};
     k_facets_step<<<nblk((long long)E->hFacets.size(), 128), 128, 0, st>>>(E->dFacets.p, (int)E->hFacets.size(), E->groups, u, E->dCnt, 0, E->impDev(u.impSlot)); E->launches++;
   }
   if (E->anyMovingWall) {
@@ -1897,7 +1896,6 @@ int wdem_upload_facet_imposes(wdem_handle h, const int32_t* facetSet) {
   return guarded(h, [&] {
     if (h->imposes.empty() || !facetSet) throw EngErr{"wdem_upload_facet_imposes: call after wdem_upload_imposes", WDEM_ERR_INVALID};
     if (!h->conDirty || h->nC != 0 || h->cur != 0) throw EngErr{"wdem_upload_facet_imposes: call before the first step", WDEM_ERR_INVALID};
-    if (h->cfg.periodic) throw EngErr{"wdem_upload_facet_imposes: moving facets in a periodic cell are not supported", WDEM_ERR_UNSUPPORTED};
     const int nSets = (int)h->impSetStart.size() - 1; bool any = false;
     for (size_t f = 0; f < h->hFacets.size(); f++) {
       const int set = facetSet[f]; h->hFacets[f].nodeImp1 = 0;

@@ -583,7 +583,15 @@ __global__ void __launch_bounds__(128) k_facets_step(Facet* facets, int n, Group
     double d2 = 0;
     for (int i = 0; i < 3; i++) {
       d3 vv = mk3(F->vvel[3 * i], F->vvel[3 * i + 1], F->vvel[3 * i + 2]), wdum = mk3(0, 0, 0);
-      const d3 p = mk3(F->v[3 * i], F->v[3 * i + 1], F->v[3 * i + 2]) + vv * u.dt;
+      d3 p0 = mk3(F->v[3 * i], F->v[3 * i + 1], F->v[3 * i + 2]);
+      if (u.periodic) {      // the cell's corrections of the fixed branch (Leapfrog.cpp:206-215,258-273), as for walls
+        if (u.homoDeform == 4) vv = mulMV(u.ImLL4hInv, mulMV(u.LmL, p0) + mulMV(u.IpLL4h, vv));
+        else if (u.homoDeform == 2 || u.homoDeform == 3) {
+          if (u.homoDeform == 3) vv = vv + mulMV(u.midGradV, vv - (u.dt / 2.) * mk3(0, 0, 0)) * u.dt;
+          vv = vv + mulMV(u.dGradV, p0);
+        } else if (u.homoDeform == 1) p0 = p0 + mulMV(u.nextGradV, p0) * u.dt;
+      }
+      const d3 p = p0 + vv * u.dt;
       impose_velocity(I, F->nodeImp1 - 1, vv, wdum, p);
       F->v[3 * i] = p.x; F->v[3 * i + 1] = p.y; F->v[3 * i + 2] = p.z;
       F->vvel[3 * i] = vv.x; F->vvel[3 * i + 1] = vv.y; F->vvel[3 * i + 2] = vv.z;
