@@ -1990,6 +1990,7 @@ int wdem_add_spheres(wdem_handle h, int64_t m, const int32_t* ids, const double*
     std::vector<char> take(m, 1);
     if (dec) {
       const int W = h->comm->world, R = h->comm->rank; const DomainState& M = h->dom;
+      if ((int)M.cuts.size() != W - 1) throw EngErr{"wdem_add_spheres: call wdem_set_domain first", WDEM_ERR_INVALID};
       for (int64_t i = 0; i < m; i++) {
         int r = (int)(i % W);
         if (!h->cfg.periodic) { const double x = pos[3 * i + M.axis]; r = 0; while (r + 1 < W && x >= M.cuts[r]) r++; }
