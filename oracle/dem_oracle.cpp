@@ -1447,7 +1447,6 @@ struct Scene {
     // prescribed velocities (Leapfrog.cpp:195-199,275-297), then ClumpData::applyToMembers (Clump.cpp:293-307, called from Leapfrog.cpp:252)
     for (FacetGroup& G : groups) {
       if (P.periodic) {      // a fully blocked node in a deforming cell (Leapfrog.cpp:206-215 fixed branch, applyPeriodicCorrections :258-273), no acceleration
-        if (G.impose >= 0) throw std::runtime_error("impositions on facet groups in a periodic cell are not supported");
         if (homoDeform == HOMO_GRADV2) G.vel = mulMV(ImLL4hInv, mulMV(LmL, G.pos) + mulMV(IpLL4h, G.vel));
         else if (homoDeform == HOMO_VEL || homoDeform == HOMO_VEL_2ND) {
           if (homoDeform == HOMO_VEL_2ND) G.vel += mulMV(midGradV, G.vel - (dt / 2.) * V3()) * dt;

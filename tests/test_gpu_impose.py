@@ -144,6 +144,27 @@ def test_orbit_impositions_on_spheres_and_on_the_nodes_of_a_rotating_cylinder():
     assert len(E.contacts(True)["ids"]) > 0 and E.scalars()["nFullRuns"] > 5
 
 
+def test_imposition_on_a_facet_group_in_a_periodic_cell():
+    """A plate that follows a recorded trajectory (InterpolatedMotion on the master node of its clump) and is shaken (AlignedHarmonicOscillations on a second one) inside
+    a sheared periodic cell: host-evaluated, bit-identical."""
+    S = sc.periodic_gas(300, cell=(.5, .4, .45), r=.02, psd_ratio=2.0, seed=71, gradV=[[0, 1.2, 0], [0, 0, 0], [0, 0, 0]], shear0=.1)
+    quad = lambda x0, y0, x1, y1, z: [np.array([(x0, y0, z), (x1, y0, z), (x1, y1, z)]), np.array([(x0, y0, z), (x1, y1, z), (x0, y1, z)])]
+    tris = quad(.1, .05, .25, .2, .15) + quad(.3, .2, .45, .35, .3)
+    S.facets = [dict(v=t, halfThick=0., fakeVel=(0., 0., 0.), mat=0, mask=sc.MASK_BOUNDARY) for t in tris]
+    S.facet_groups = [dict(pos=(.175, .125, .15), ori=(0., 0., 0., 1.), vel=(0., 0., 0.), angVel=(0., 0., 0.), facets=[0, 1]),
+                      dict(pos=(.375, .275, .3), ori=(0., 0., 0., 1.), vel=(0., 0., 0.), angVel=(0., 0., 0.), facets=[2, 3])]
+    S.finalize()
+    qa = lambda a, ax: (*(math.sin(a / 2) * np.asarray(ax, dtype=float) / np.linalg.norm(ax)), math.cos(a / 2))
+    c0 = np.array(S.facet_groups[0]["pos"])
+    sc.attach_impose(S, [sc.imp_interpolated_motion([0., .002, .004], [c0, c0 + (.01, 0, .02), c0 + (.01, .02, 0)], [qa(0, (0, 0, 1)), qa(.3, (0, 0, 1)), qa(.3, (1, 0, 1))])], groups=[0])
+    sc.attach_impose(S, [sc.imp_aligned_harmonic((float("nan"), 200., 150.), (0, 2e-3, 3e-3))], groups=[1])
+    O, E = Oracle(S), engine_for(S)
+    for k in range(6):
+        O.step(25); E.step(25)
+        check(O, E, 25 * (k + 1))
+    assert not np.array_equal(E.facets(), np.array(tris)) and (O.contacts(True)["ids"][:, 0] >= S.n).sum() > 0
+
+
 def test_axially_periodic_rotating_drum():
     """A drum without end caps in a cell that is periodic along its axis: the cylinder of woo.triangulated.cylinder(realRot=True) (one StableCircularOrbit on every node,
     py/triangulated.py:59-64) plus Bo1_Facet_Aabb's periodic branch; spheres leave through one end and come back through the other."""

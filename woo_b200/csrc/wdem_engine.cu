@@ -1811,7 +1811,7 @@ int wdem_upload_imposes(wdem_handle h, int32_t nImp, const wdem_impose* imp, int
     if (nImp < 0 || nImp > WD_MAX_IMPOSE) throw EngErr{"wdem_upload_imposes: at most " + std::to_string(WD_MAX_IMPOSE) + " Impose objects", WDEM_ERR_UNSUPPORTED};
     if (nImp > 0 && (!imp || nSets <= 0 || !setStart || !setOps)) throw EngErr{"wdem_upload_imposes: bad arguments", WDEM_ERR_INVALID};
     if (!h->conDirty || h->nC != 0 || h->cur != 0) throw EngErr{"wdem_upload_imposes: call after the particles are uploaded and before the first step", WDEM_ERR_INVALID};
-    if (h->cfg.periodic && (wallSet || groupSet)) throw EngErr{"wdem_upload_imposes: impositions on walls / facet groups in a periodic cell are not supported", WDEM_ERR_UNSUPPORTED};
+    if (h->cfg.periodic && wallSet) throw EngErr{"wdem_upload_imposes: impositions on walls in a periodic cell are not supported", WDEM_ERR_UNSUPPORTED};
     h->imposes.clear(); h->impSetStart.clear(); h->impSetOps.clear(); h->wallImpSet.clear(); h->groupImpSet.clear(); h->impSpheres = false; h->impRead = false; h->impFacetNodes = false;
     if (nImp == 0) return;
     cudaStream_t st = h->stream;
