@@ -42,7 +42,8 @@ CASES = [(K.test_pwave_dt, ()), (K.test_cundall_kn_and_hertz_force, ()), (K.test
          (K.test_facet_sphere_closest_point, ((1.1, -.1, .05), (1., 0., 0.), "vertex")), (K.test_hertz_collision_time, (1e-2,)),
          (K.test_hertz_restitution_coefficient, (.5,)), (K.test_collision_masks, (0b01, 0b10, False)), (K.test_collision_masks, (0b10, 0b10, False)),
          (K.test_collision_masks, (0b0101, 0b0011, True)), (K.test_collision_masks, (0b0111, 0b0011, False)), (K.test_collision_masks, (0b0101, 0b0111, True)),
-         (K.test_impose_circular_orbits_keep_radius_and_turn_by_omega_t, ()), (K.test_impose_interpolated_motion_reaches_the_given_poses_at_the_given_times, ())]
+         (K.test_impose_circular_orbits_keep_radius_and_turn_by_omega_t, ()), (K.test_impose_interpolated_motion_reaches_the_given_poses_at_the_given_times, ()),
+         (K.test_facet_contact_through_the_periodic_boundary_equals_the_unwrapped_one, ())]
 
 
 @pytest.mark.parametrize("kat,args", CASES, ids=[f"{f.__name__}{list(a) if a else ''}" for f, a in CASES])

@@ -647,3 +647,28 @@ def test_impose_interpolated_motion_reaches_the_given_poses_at_the_given_times()
         assert np.allclose(f, want, rtol=0, atol=1e-12), (k, np.abs(f - want).max())
     O.step(50)                                                              # past the last time point: the pose stays
     assert np.allclose(O.facets()[0], want, rtol=0, atol=1e-12)
+
+
+def test_facet_contact_through_the_periodic_boundary_equals_the_unwrapped_one():
+    """A sphere that touches a facet through the cell boundary (Contact.cellDist != 0; Bo1_Facet_Aabb's periodic branch Facet.cpp:286-297, Cg2_Facet_Sphere with shift2)
+    feels exactly the force of the same sphere placed one period away, next to the facet, in an aperiodic scene."""
+    L = np.array([.5, .4, .45]); r = .03
+    tri = np.array([(.02, .05, .2), (.22, .05, .2), (.02, .3, .2)])
+
+    def scene(periodic):
+        S = _free_spheres(1, r=r)
+        S.pos[0] = (.08, .12, .2 + .9 * r) if not periodic else (.08 + L[0], .12 - L[1], .2 + .9 * r)      # one period away in x and y
+        S.vel[0] = (.1, 0., -.2)
+        S.facets = [dict(v=tri, halfThick=0., fakeVel=(0., 0., 0.), mat=0, mask=sc.MASK_BOUNDARY)]
+        if periodic:
+            S.params.periodic = 1
+            S.cell = dict(hSize=np.diag(L), gradV=np.zeros((3, 3)), nextGradV=np.zeros((3, 3)), homoDeform=sc.HOMO_GRADV2)
+        return S.finalize()
+    A, B = Oracle(scene(False)), Oracle(scene(True))
+    for k in range(5):
+        A.step(3); B.step(3)                                    # the sphere rebounds within ~20 steps
+        ca, cb = A.contacts(True), B.contacts(True)
+        assert len(ca["ids"]) == len(cb["ids"]) == 1
+        assert np.allclose(ca["force"], cb["force"], rtol=1e-12, atol=0) and ca["uN"][0] == pytest.approx(cb["uN"][0], rel=1e-10)
+        assert np.allclose(A.spheres()["force"], B.spheres()["force"], rtol=1e-10, atol=1e-18)
+    assert tuple(np.abs(cb["cellDist"][0])) == (1, 1, 0) and ca["force"][0][0] != 0.
